@@ -1,0 +1,311 @@
+"""CPU oracle -- TEST INFRASTRUCTURE ONLY.
+
+ctypes/numpy front end of ``oracle/_build/liboracle.so`` (sources: oracle/*.cpp, header oracle/oracle.h).
+The oracle is the parity checker for the CUDA path and the timed CPU baseline of bench.py.  It must
+never be imported from ``imagestitch_b200`` (the product); only ``tests/``, ``__graft_entry__.smoke()``
+and ``bench.py``'s cpu_baseline / ``--impl reference`` legs use it.
+
+Parity pin: see oracle/oracle.h (pinned against OpenCV 4.13 fixtures in tests/golden/; the
+hand-written linear blend is "parity unpinned").
+"""
+from __future__ import annotations
+
+import ctypes as C
+import os
+import subprocess
+
+import numpy as np
+
+_DIR = os.path.dirname(os.path.abspath(__file__))
+_SO = os.path.join(_DIR, "_build", "liboracle.so")
+
+PROJ_CYLINDRICAL, PROJ_SPHERICAL = 0, 1
+INTER_NEAREST, INTER_LINEAR = 0, 1
+BORDER_CONSTANT, BORDER_REFLECT = 0, 2
+COST_COLOR, COST_COLOR_GRAD = 0, 1
+WEIGHT_32F, WEIGHT_16S = 5, 3
+
+
+def build(force: bool = False) -> str:
+    srcs = [os.path.join(_DIR, f) for f in os.listdir(_DIR) if f.endswith((".cpp", ".h"))]
+    stale = (not os.path.exists(_SO)) or any(os.path.getmtime(s) > os.path.getmtime(_SO) for s in srcs)
+    if force or stale:
+        subprocess.check_call(["make", "-s", "-C", _DIR] + (["-B"] if force else []))
+    return _SO
+
+
+_lib = None
+
+
+def lib():
+    global _lib
+    if _lib is None:
+        build()
+        L = C.CDLL(_SO)
+        L.orc_get_max_threads.restype = C.c_int
+        L.orc_dp_seam_find.restype = C.c_int
+        L.orc_mb_create.restype = C.c_void_p
+        L.orc_mb_num_bands.restype = C.c_int
+        L.orc_lin_blend.restype = C.c_int
+        L.orc_pipeline_plan.restype = C.c_int
+        L.orc_pipeline_run.restype = C.c_int
+        _lib = L
+    return _lib
+
+
+def _p(a):
+    return a.ctypes.data_as(C.c_void_p)
+
+
+def _f9(m):
+    return np.ascontiguousarray(np.asarray(m, dtype=np.float32).reshape(9))
+
+
+def set_threads(n: int):
+    lib().orc_set_threads(C.c_int(int(n)))
+
+
+def max_threads() -> int:
+    return int(lib().orc_get_max_threads())
+
+
+# ---------------------------------------------------------------- warp
+def camera_params(K, R):
+    k_rinv = np.zeros(9, np.float32)
+    r_kinv = np.zeros(9, np.float32)
+    lib().orc_camera_params(_p(_f9(K)), _p(_f9(R)), _p(k_rinv), _p(r_kinv))
+    return k_rinv.reshape(3, 3), r_kinv.reshape(3, 3)
+
+
+def detect_roi(proj, src_size_wh, K, R, scale, full_scan=True):
+    """-> (tl_x, tl_y, br_x, br_y)   [WARP]:64-88"""
+    roi = np.zeros(4, np.int32)
+    lib().orc_detect_roi(C.c_int(proj), C.c_int(src_size_wh[0]), C.c_int(src_size_wh[1]), _p(_f9(K)), _p(_f9(R)),
+                         C.c_float(scale), C.c_int(1 if full_scan else 0), _p(roi))
+    return tuple(int(v) for v in roi)
+
+
+def build_maps(proj, src_size_wh, K, R, scale, full_scan=True):
+    """-> (roi, xmap, ymap)   [WARP]:122-144.  roi = (tl_x, tl_y, br_x, br_y)."""
+    roi = detect_roi(proj, src_size_wh, K, R, scale, full_scan)
+    h, w = roi[3] - roi[1] + 1, roi[2] - roi[0] + 1
+    xmap = np.empty((h, w), np.float32)
+    ymap = np.empty((h, w), np.float32)
+    r = np.asarray(roi, np.int32)
+    lib().orc_build_maps(C.c_int(proj), _p(_f9(K)), _p(_f9(R)), C.c_float(scale), _p(r), _p(xmap), _p(ymap))
+    return roi, xmap, ymap
+
+
+def remap(src, xmap, ymap, interp, border):
+    src = np.ascontiguousarray(src)
+    assert src.dtype == np.uint8
+    ch = 1 if src.ndim == 2 else src.shape[2]
+    h, w = xmap.shape
+    dst = np.empty((h, w) if src.ndim == 2 else (h, w, ch), np.uint8)
+    xmap = np.ascontiguousarray(xmap, np.float32)
+    ymap = np.ascontiguousarray(ymap, np.float32)
+    lib().orc_remap_u8(_p(src), C.c_int(src.shape[0]), C.c_int(src.shape[1]), C.c_int(ch), C.c_size_t(src.strides[0]),
+                       _p(xmap), _p(ymap), C.c_int(h), C.c_int(w), C.c_int(interp), C.c_int(border), _p(dst))
+    return dst
+
+
+def warp(proj, src, K, R, scale, interp, border, full_scan=True):
+    """-> ((tl_x, tl_y), dst)   [WARP]:145-161"""
+    roi, xmap, ymap = build_maps(proj, (src.shape[1], src.shape[0]), K, R, scale, full_scan)
+    return (roi[0], roi[1]), remap(src, xmap, ymap, interp, border)
+
+
+# ---------------------------------------------------------------- seam
+def dp_seam_find(images, corners, masks, cost_fn=COST_COLOR, want_trace=False):
+    """[SEAM]:87-124.  images: list of HxWx3 float32 or uint8; masks: list of HxW uint8.
+    Returns new masks (inputs are not modified) and, optionally, the seam trace
+    [(i, j, comp, is_horizontal, points Nx2 in pano coords), ...]."""
+    n = len(images)
+    is_u8 = images[0].dtype == np.uint8
+    imgs = [np.ascontiguousarray(im, np.uint8 if is_u8 else np.float32) for im in images]
+    out = [np.ascontiguousarray(m, np.uint8).copy() for m in masks]
+    ip = (C.c_void_p * n)(*[im.ctypes.data for im in imgs])
+    mp = (C.c_void_p * n)(*[m.ctypes.data for m in out])
+    rows = np.asarray([im.shape[0] for im in imgs], np.int32)
+    cols = np.asarray([im.shape[1] for im in imgs], np.int32)
+    cxy = np.asarray(corners, np.int32).reshape(-1).copy()
+    cap = 0
+    trace = None
+    if want_trace:
+        cap = int(sum(5 + 2 * (im.shape[0] + im.shape[1]) for im in imgs) * max(1, n) * 2)
+        trace = np.zeros(cap, np.int32)
+    tlen = C.c_size_t(0)
+    rc = lib().orc_dp_seam_find(C.c_int(n), ip, C.c_int(1 if is_u8 else 0), _p(rows), _p(cols), _p(cxy), mp,
+                                C.c_int(cost_fn), _p(trace) if want_trace else None, C.c_size_t(cap), C.byref(tlen))
+    if rc:
+        raise RuntimeError(f"orc_dp_seam_find failed: {rc}")
+    if not want_trace:
+        return out
+    return out, parse_trace(trace[: min(cap, tlen.value)])
+
+
+def parse_trace(t):
+    res = []
+    k = 0
+    while k + 5 <= len(t):
+        i, j, comp, horiz, npts = (int(v) for v in t[k:k + 5])
+        pts = np.asarray(t[k + 5:k + 5 + 2 * npts]).reshape(-1, 2).copy()
+        res.append((i, j, comp, bool(horiz), pts))
+        k += 5 + 2 * npts
+    return res
+
+
+def seam_costs(img1, img2, tl1, tl2, labels, union_tl, l, roi_xywh):
+    is_u8 = img1.dtype == np.uint8
+    a = np.ascontiguousarray(img1)
+    b = np.ascontiguousarray(img2)
+    labels = np.ascontiguousarray(labels, np.int32)
+    x, y, w, h = roi_xywh
+    costV = np.empty((h, w + 1), np.float32)
+    costH = np.empty((h + 1, w), np.float32)
+    roi = np.asarray(roi_xywh, np.int32)
+    lib().orc_seam_costs(_p(a), _p(b), C.c_int(1 if is_u8 else 0), C.c_int(a.shape[0]), C.c_int(a.shape[1]),
+                         C.c_int(b.shape[0]), C.c_int(b.shape[1]), C.c_int(tl1[0]), C.c_int(tl1[1]),
+                         C.c_int(tl2[0]), C.c_int(tl2[1]), _p(labels), C.c_int(labels.shape[0]), C.c_int(labels.shape[1]),
+                         C.c_int(union_tl[0]), C.c_int(union_tl[1]), C.c_int(l), _p(roi), _p(costV), _p(costH))
+    return costV, costH
+
+
+# ---------------------------------------------------------------- pyramids / blend
+def pyr_down_s16(src):
+    src = np.ascontiguousarray(src, np.int16)
+    ch = 1 if src.ndim == 2 else src.shape[2]
+    h, w = src.shape[:2]
+    dst = np.empty(((h + 1) // 2, (w + 1) // 2) + (() if src.ndim == 2 else (ch,)), np.int16)
+    lib().orc_pyr_down_s16(_p(src), C.c_int(h), C.c_int(w), C.c_int(ch), _p(dst))
+    return dst
+
+
+def pyr_up_s16(src, dsize_hw):
+    src = np.ascontiguousarray(src, np.int16)
+    ch = 1 if src.ndim == 2 else src.shape[2]
+    h, w = src.shape[:2]
+    dst = np.empty(tuple(dsize_hw) + (() if src.ndim == 2 else (ch,)), np.int16)
+    lib().orc_pyr_up_s16(_p(src), C.c_int(h), C.c_int(w), C.c_int(ch), C.c_int(dsize_hw[0]), C.c_int(dsize_hw[1]), _p(dst))
+    return dst
+
+
+def pyr_down_f32(src):
+    src = np.ascontiguousarray(src, np.float32)
+    h, w = src.shape
+    dst = np.empty(((h + 1) // 2, (w + 1) // 2), np.float32)
+    lib().orc_pyr_down_f32(_p(src), C.c_int(h), C.c_int(w), _p(dst))
+    return dst
+
+
+class MultiBandBlender:
+    """Call shape of cv::detail::MultiBandBlender as used at [SEAM]:1244-1252,1271,1280."""
+
+    def __init__(self, num_bands=5, weight_type=WEIGHT_32F):
+        self._h = C.c_void_p(lib().orc_mb_create(C.c_int(num_bands), C.c_int(weight_type)))
+        self._roi = None
+
+    def __del__(self):
+        if getattr(self, "_h", None):
+            lib().orc_mb_destroy(self._h)
+            self._h = None
+
+    def prepare(self, dst_roi_xywh):
+        self._roi = tuple(int(v) for v in dst_roi_xywh)
+        lib().orc_mb_prepare(self._h, _p(np.asarray(self._roi, np.int32)))
+
+    def prepare_corners(self, corners, sizes_wh):
+        self.prepare(result_roi(corners, sizes_wh))
+
+    def num_bands(self):
+        return int(lib().orc_mb_num_bands(self._h))
+
+    def feed(self, img, mask, tl):
+        img = np.ascontiguousarray(img, np.int16)
+        mask = np.ascontiguousarray(mask, np.uint8)
+        lib().orc_mb_feed(self._h, _p(img), _p(mask), C.c_int(img.shape[0]), C.c_int(img.shape[1]), C.c_int(tl[0]), C.c_int(tl[1]))
+
+    def blend(self):
+        x, y, w, h = self._roi
+        dst = np.empty((h, w, 3), np.int16)
+        dmask = np.empty((h, w), np.uint8)
+        lib().orc_mb_blend(self._h, _p(dst), _p(dmask))
+        return dst, dmask
+
+
+def result_roi(corners, sizes_wh):
+    """cv::detail::resultRoi(corners, sizes) -> (x, y, w, h)"""
+    tlx = min(c[0] for c in corners)
+    tly = min(c[1] for c in corners)
+    brx = max(c[0] + s[0] for c, s in zip(corners, sizes_wh))
+    bry = max(c[1] + s[1] for c, s in zip(corners, sizes_wh))
+    return (tlx, tly, brx - tlx, bry - tly)
+
+
+# ---------------------------------------------------------------- linear blend ([BLEND])
+def lin_blend(img1, img2, tl1, tl2, want_cost=False):
+    a = np.ascontiguousarray(img1, np.float32)
+    b = np.ascontiguousarray(img2, np.float32)
+    he = C.c_int(0)
+    br = C.c_int(0)
+    lib().orc_lin_geometry(C.c_int(a.shape[0]), C.c_int(a.shape[1]), C.c_int(b.shape[0]), C.c_int(b.shape[1]),
+                           C.c_int(tl1[0]), C.c_int(tl1[1]), C.c_int(tl2[0]), C.c_int(tl2[1]), C.byref(he), C.byref(br))
+    pano = np.zeros((he.value, br.value, 3), np.float32)
+    seam = np.zeros(he.value, np.int32)
+    ib = a.shape[1] - (tl2[0] - tl1[0])
+    cost = np.zeros((he.value, ib + 2), np.float32) if want_cost else None
+    rc = lib().orc_lin_blend(_p(a), C.c_int(a.shape[0]), C.c_int(a.shape[1]), _p(b), C.c_int(b.shape[0]), C.c_int(b.shape[1]),
+                             C.c_int(tl1[0]), C.c_int(tl1[1]), C.c_int(tl2[0]), C.c_int(tl2[1]), _p(pano), _p(seam),
+                             _p(cost) if want_cost else None)
+    if rc == 1:
+        return None
+    return (pano, seam, cost) if want_cost else (pano, seam)
+
+
+# ---------------------------------------------------------------- whole path
+def pipeline_plan(proj, src_sizes_hw, Ks, Rs, scale):
+    n = len(src_sizes_hw)
+    rows = np.asarray([s[0] for s in src_sizes_hw], np.int32)
+    cols = np.asarray([s[1] for s in src_sizes_hw], np.int32)
+    K = np.ascontiguousarray(np.asarray(Ks, np.float32).reshape(n, 9))
+    R = np.ascontiguousarray(np.asarray(Rs, np.float32).reshape(n, 9))
+    corners = np.zeros(2 * n, np.int32)
+    sizes = np.zeros(2 * n, np.int32)
+    roi = np.zeros(4, np.int32)
+    lib().orc_pipeline_plan(C.c_int(n), C.c_int(proj), _p(rows), _p(cols), _p(K), _p(R), C.c_float(scale), _p(corners), _p(sizes), _p(roi))
+    return corners.reshape(n, 2), sizes.reshape(n, 2), tuple(int(v) for v in roi)
+
+
+def pipeline_run(proj, srcs, Ks, Rs, scale, seam=True, num_bands=5, weight_type=WEIGHT_32F, want_intermediates=False):
+    """warp -> [DP seam] -> multi-band blend.  Returns dict(pano, pano_mask, corners, sizes, roi, seconds[, warped, masks])."""
+    n = len(srcs)
+    srcs = [np.ascontiguousarray(s, np.uint8) for s in srcs]
+    corners, sizes, roi = pipeline_plan(proj, [s.shape[:2] for s in srcs], Ks, Rs, scale)
+    rows = np.asarray([s.shape[0] for s in srcs], np.int32)
+    cols = np.asarray([s.shape[1] for s in srcs], np.int32)
+    K = np.ascontiguousarray(np.asarray(Ks, np.float32).reshape(n, 9))
+    R = np.ascontiguousarray(np.asarray(Rs, np.float32).reshape(n, 9))
+    pano = np.empty((roi[3], roi[2], 3), np.int16)
+    pmask = np.empty((roi[3], roi[2]), np.uint8)
+    secs = np.zeros(4, np.float64)
+    sp = (C.c_void_p * n)(*[s.ctypes.data for s in srcs])
+    warped = masks = None
+    wp = mp = None
+    if want_intermediates:
+        warped = [np.empty((int(sz[1]), int(sz[0]), 3), np.uint8) for sz in sizes]
+        masks = [np.empty((int(sz[1]), int(sz[0])), np.uint8) for sz in sizes]
+        wp = (C.c_void_p * n)(*[a.ctypes.data for a in warped])
+        mp = (C.c_void_p * n)(*[a.ctypes.data for a in masks])
+    c = np.ascontiguousarray(corners.reshape(-1))
+    s = np.ascontiguousarray(sizes.reshape(-1))
+    r = np.asarray(roi, np.int32)
+    rc = lib().orc_pipeline_run(C.c_int(n), C.c_int(proj), sp, _p(rows), _p(cols), _p(K), _p(R), C.c_float(scale),
+                                C.c_int(1 if seam else 0), C.c_int(num_bands), C.c_int(weight_type), _p(c), _p(s), _p(r),
+                                wp, mp, _p(pano), _p(pmask), _p(secs))
+    if rc:
+        raise RuntimeError(f"orc_pipeline_run failed: {rc}")
+    out = dict(pano=pano, pano_mask=pmask, corners=corners, sizes=sizes, roi=roi, seconds=secs)
+    if want_intermediates:
+        out["warped"] = warped
+        out["masks"] = masks
+    return out

@@ -1,0 +1,128 @@
+// oracle/pipeline.cpp -- TEST INFRASTRUCTURE ONLY (see oracle.h).
+//
+// The reference's composite call sequence on the CPU, stage by stage, as every main() runs it
+// ([BLEND]:99-110 warp loop, [SEAM]:1188-1192 convertTo(CV_32F) + find, [SEAM]:1263 convertTo(CV_16S),
+// blender prepare/feed/blend [SEAM]:1252,1271,1280 with the multi-band blender of [SEAM]:1244-1246).
+// Used by tests as the end-to-end checker and by bench.py as the timed CPU baseline ("port").
+#include "oracle.h"
+
+#include <algorithm>
+#include <chrono>
+#include <cstring>
+#include <vector>
+
+#ifdef _OPENMP
+#include <omp.h>
+#endif
+
+extern "C" {
+
+void orc_set_threads(int n) {
+#ifdef _OPENMP
+    omp_set_num_threads(n > 0 ? n : 1);
+#else
+    (void)n;
+#endif
+}
+
+int orc_get_max_threads(void) {
+#ifdef _OPENMP
+    return omp_get_max_threads();
+#else
+    return 1;
+#endif
+}
+
+// corners_xy[2n], sizes_wh[2n], pano_roi[4] (x,y,w,h) = cv::detail::resultRoi(corners, sizes)
+int orc_pipeline_plan(int n, int proj, const int* src_rows, const int* src_cols, const float* K, const float* R,
+                      float scale, int* corners_xy, int* sizes_wh, int* pano_roi) {
+    int tlx = INT32_MAX, tly = INT32_MAX, brx = INT32_MIN, bry = INT32_MIN;
+    for (int i = 0; i < n; ++i) {
+        int roi[4];
+        orc_detect_roi(proj, src_cols[i], src_rows[i], K + 9 * i, R + 9 * i, scale, 0, roi);
+        corners_xy[2 * i] = roi[0];
+        corners_xy[2 * i + 1] = roi[1];
+        sizes_wh[2 * i] = roi[2] - roi[0] + 1;        // dst.create(roi.height + 1, roi.width + 1)  [WARP]:150
+        sizes_wh[2 * i + 1] = roi[3] - roi[1] + 1;
+        tlx = std::min(tlx, roi[0]); tly = std::min(tly, roi[1]);
+        brx = std::max(brx, roi[0] + sizes_wh[2 * i]); bry = std::max(bry, roi[1] + sizes_wh[2 * i + 1]);
+    }
+    pano_roi[0] = tlx; pano_roi[1] = tly; pano_roi[2] = brx - tlx; pano_roi[3] = bry - tly;
+    return 0;
+}
+
+// seam: 0 = none (warped masks fed as they are), 1 = DP seam finder (COLOR).
+// warped_out / masks_out: optional arrays of n caller buffers (sizes from orc_pipeline_plan) receiving
+// the warped 8-bit images and the final (post-seam) masks.  stage_seconds[4] = warp, seam, blend, total.
+int orc_pipeline_run(int n, int proj, const uint8_t* const* srcs, const int* src_rows, const int* src_cols,
+                     const float* K, const float* R, float scale, int seam, int num_bands, int weight_type,
+                     const int* corners_xy, const int* sizes_wh, const int* pano_roi,
+                     uint8_t* const* warped_out, uint8_t* const* masks_out,
+                     int16_t* pano, uint8_t* pano_mask, double* stage_seconds) {
+    using clk = std::chrono::steady_clock;
+    auto t0 = clk::now();
+    std::vector<std::vector<uint8_t>> warped(n), masks(n);
+    for (int i = 0; i < n; ++i) {                                // [BLEND]:100-110
+        const int w = sizes_wh[2 * i], h = sizes_wh[2 * i + 1];
+        int roi[4] = {corners_xy[2 * i], corners_xy[2 * i + 1], corners_xy[2 * i] + w - 1, corners_xy[2 * i + 1] + h - 1};
+        std::vector<float> xmap((size_t)h * w), ymap((size_t)h * w);
+        orc_build_maps(proj, K + 9 * i, R + 9 * i, scale, roi, xmap.data(), ymap.data());
+        warped[i].resize((size_t)h * w * 3);
+        orc_remap_u8(srcs[i], src_rows[i], src_cols[i], 3, (size_t)src_cols[i] * 3, xmap.data(), ymap.data(), h, w,
+                     ORC_INTER_LINEAR, ORC_BORDER_REFLECT, warped[i].data());
+        // second warp call: the all-255 source mask, INTER_NEAREST + BORDER_CONSTANT (maps are rebuilt
+        // by the reference; they are identical so they are reused here)
+        std::vector<uint8_t> ones((size_t)src_rows[i] * src_cols[i], 255);
+        masks[i].resize((size_t)h * w);
+        orc_remap_u8(ones.data(), src_rows[i], src_cols[i], 1, (size_t)src_cols[i], xmap.data(), ymap.data(), h, w,
+                     ORC_INTER_NEAREST, ORC_BORDER_CONSTANT, masks[i].data());
+    }
+    auto t1 = clk::now();
+    std::vector<int> rows(n), cols(n);
+    for (int i = 0; i < n; ++i) { cols[i] = sizes_wh[2 * i]; rows[i] = sizes_wh[2 * i + 1]; }
+    if (seam) {                                                  // [SEAM]:1188-1192
+        std::vector<std::vector<float>> imgf(n);
+        std::vector<const void*> ip(n);
+        std::vector<uint8_t*> mp(n);
+        for (int i = 0; i < n; ++i) {
+            imgf[i].resize(warped[i].size());
+            const uint8_t* s = warped[i].data();
+            float* d = imgf[i].data();
+            const size_t cnt = warped[i].size();
+#pragma omp parallel for schedule(static)
+            for (size_t k = 0; k < cnt; ++k) d[k] = (float)s[k];
+            ip[i] = imgf[i].data();
+            mp[i] = masks[i].data();
+        }
+        int rc = orc_dp_seam_find(n, ip.data(), 0, rows.data(), cols.data(), corners_xy, mp.data(), ORC_COST_COLOR, nullptr, 0, nullptr);
+        if (rc) return rc;
+    }
+    auto t2 = clk::now();
+    orc_mb* mb = orc_mb_create(num_bands, weight_type);
+    orc_mb_prepare(mb, pano_roi);
+    for (int i = 0; i < n; ++i) {                                // [SEAM]:1263,1271
+        std::vector<int16_t> s16(warped[i].size());
+        const uint8_t* s = warped[i].data();
+        int16_t* d = s16.data();
+        const size_t cnt = warped[i].size();
+#pragma omp parallel for schedule(static)
+        for (size_t k = 0; k < cnt; ++k) d[k] = (int16_t)s[k];
+        orc_mb_feed(mb, s16.data(), masks[i].data(), rows[i], cols[i], corners_xy[2 * i], corners_xy[2 * i + 1]);
+    }
+    orc_mb_blend(mb, pano, pano_mask);                           // [SEAM]:1280
+    orc_mb_destroy(mb);
+    auto t3 = clk::now();
+    for (int i = 0; i < n; ++i) {
+        if (warped_out && warped_out[i]) std::memcpy(warped_out[i], warped[i].data(), warped[i].size());
+        if (masks_out && masks_out[i]) std::memcpy(masks_out[i], masks[i].data(), masks[i].size());
+    }
+    if (stage_seconds) {
+        stage_seconds[0] = std::chrono::duration<double>(t1 - t0).count();
+        stage_seconds[1] = std::chrono::duration<double>(t2 - t1).count();
+        stage_seconds[2] = std::chrono::duration<double>(t3 - t2).count();
+        stage_seconds[3] = std::chrono::duration<double>(t3 - t0).count();
+    }
+    return 0;
+}
+
+}  // extern "C"
