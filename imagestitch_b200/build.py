@@ -1,0 +1,89 @@
+"""Builds libimagestitch_b200.so (CUDA kernels + C ABI) in-tree for sm_100a.
+
+    python -m imagestitch_b200.build [--force] [--verbose]
+
+nvcc cross-compiles without a GPU.  Objects go to imagestitch_b200/_build/, the shared library to
+imagestitch_b200/libimagestitch_b200.so (git-ignored, travels to the GPU box with the snapshot).
+"""
+from __future__ import annotations
+
+import concurrent.futures as cf
+import os
+import shutil
+import subprocess
+import sys
+
+_DIR = os.path.dirname(os.path.abspath(__file__))
+CSRC = os.path.join(_DIR, "csrc")
+BUILD = os.path.join(_DIR, "_build")
+LIB = os.path.join(_DIR, "libimagestitch_b200.so")
+INCLUDE = os.path.join(os.path.dirname(_DIR), "include")
+
+NVCC_FLAGS = [
+    "-gencode", "arch=compute_100a,code=sm_100a",
+    "-lineinfo", "-O3", "-std=c++17",
+    "--fmad=false",                       # bit-exact float paths: no implicit FMA contraction on the device
+    "-Xcompiler", "-fPIC,-ffp-contract=off,-fno-fast-math,-Wall,-Wno-unused-function",
+    "-I", INCLUDE,
+]
+
+
+def nvcc() -> str:
+    exe = shutil.which("nvcc") or "/usr/local/cuda/bin/nvcc"
+    if not os.path.exists(exe):
+        raise RuntimeError("nvcc not found")
+    return exe
+
+
+def _host_compiler_flags():
+    # the image exports CXX=/opt/gcc/... which lacks some runtime pieces; pin the distro g++
+    return ["-ccbin", "/usr/bin/g++"] if os.path.exists("/usr/bin/g++") else []
+
+
+def sources():
+    return sorted(os.path.join(CSRC, f) for f in os.listdir(CSRC) if f.endswith(".cu"))
+
+
+def _deps_mtime():
+    hdrs = [os.path.join(CSRC, f) for f in os.listdir(CSRC) if f.endswith((".cuh", ".h"))]
+    hdrs += [os.path.join(INCLUDE, f) for f in os.listdir(INCLUDE)]
+    return max(os.path.getmtime(h) for h in hdrs)
+
+
+def _compile(src: str, obj: str, verbose: bool):
+    cmd = [nvcc()] + _host_compiler_flags() + NVCC_FLAGS + ["-c", src, "-o", obj]
+    if verbose:
+        cmd.insert(1, "-Xptxas=-v")
+        print(" ".join(cmd), flush=True)
+    r = subprocess.run(cmd, capture_output=True, text=True)
+    if r.returncode != 0:
+        raise RuntimeError(f"nvcc failed for {src}:\n{r.stdout}\n{r.stderr}")
+    if verbose or r.stderr.strip():
+        sys.stderr.write(r.stderr)
+    return obj
+
+
+def build(force: bool = False, verbose: bool = False) -> str:
+    os.makedirs(BUILD, exist_ok=True)
+    hdr_m = _deps_mtime()
+    jobs = []
+    objs = []
+    for src in sources():
+        obj = os.path.join(BUILD, os.path.basename(src)[:-3] + ".o")
+        objs.append(obj)
+        if force or not os.path.exists(obj) or os.path.getmtime(obj) < max(os.path.getmtime(src), hdr_m):
+            jobs.append((src, obj))
+    if jobs:
+        with cf.ThreadPoolExecutor(max_workers=min(8, len(jobs))) as ex:
+            for f in [ex.submit(_compile, s, o, verbose) for s, o in jobs]:
+                f.result()
+    if jobs or not os.path.exists(LIB):
+        cmd = [nvcc()] + _host_compiler_flags() + ["-shared", "-o", LIB] + objs + ["-lcuda"]
+        r = subprocess.run(cmd, capture_output=True, text=True)
+        if r.returncode != 0:
+            raise RuntimeError(f"link failed:\n{r.stdout}\n{r.stderr}")
+    return LIB
+
+
+if __name__ == "__main__":
+    print(build(force="--force" in sys.argv, verbose="--verbose" in sys.argv))

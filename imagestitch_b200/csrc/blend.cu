@@ -1,0 +1,525 @@
+// blend.cu -- Gaussian/Laplacian-pyramid multi-band blend.
+//
+// Replaces cv::detail::MultiBandBlender as the reference's mains drive it (prepare / feed / blend,
+// [SEAM]:1244-1252,1271,1280) together with the OpenCV routines underneath it: copyMakeBorder, pyrDown,
+// pyrUp, createLaplacePyr, normalizeUsingWeightMap, restoreImageFromLaplacePyr.
+//
+// B200 formulation.  OpenCV scatters: every feed() read-modify-writes the panorama-sized accumulators
+// dst_pyr_laplace_[k] / dst_band_weights_[k], then blend() normalises and collapses them in further passes.
+// Here the accumulation is a gather: feed() only builds the image's Gaussian pyramid (levels 1..nb) and its
+// weight pyramid; blend() runs ONE kernel per level, coarse to fine, which for each panorama pixel
+//   - sums over the images covering it  short(laplacian_k * weight_k)  and  weight_k   (in feed order),
+//     forming the Laplacian  g_k - pyrUp(g_{k+1})  on the fly,
+//   - normalises, adds pyrUp of the already collapsed level k+1, and stores the collapsed level k.
+// The panorama accumulators are never read back and level 0 is written exactly once (cropped, masked).
+// int16 accumulation wraps modulo 2^16 exactly like OpenCV's `short +=`, so it is order independent; the
+// float weight sum keeps OpenCV's feed order.  Results equal the scatter formulation bit for bit.
+#include "common.cuh"
+
+#include <algorithm>
+#include <cmath>
+
+namespace is {
+
+constexpr int MAX_LEVELS = 16;
+#define IS_WEIGHT_EPS 1e-5f
+
+__host__ __device__ __forceinline__ int reflect101(int p, int len) {
+    if ((unsigned)p < (unsigned)len) return p;
+    if (len == 1) return 0;
+    do {
+        if (p < 0) p = -p;
+        else p = 2 * (len - 1) - p;
+    } while ((unsigned)p >= (unsigned)len);
+    return p;
+}
+
+__host__ __device__ __forceinline__ int reflect_b(int p, int len) {   // BORDER_REFLECT
+    if ((unsigned)p < (unsigned)len) return p;
+    if (len == 1) return 0;
+    do {
+        if (p < 0) p = -p - 1;
+        else p = len - 1 - (p - len);
+    } while ((unsigned)p >= (unsigned)len);
+    return p;
+}
+
+__device__ __forceinline__ int sat16(int v) { return max(-32768, min(32767, v)); }
+
+// Level-0 view of a fed image: the image with its BORDER_REFLECT frame (copyMakeBorder), never materialised.
+struct Level0 {
+    const void* img; size_t istep; int is_u8;
+    const uint8_t* mask; size_t mstep;
+    int rows, cols;        // fed image
+    int top, left;         // border offsets
+    int height, width;     // padded size
+};
+
+__device__ __forceinline__ void l0_pixel(const Level0& L, int y, int x, int* v) {
+    const int sy = reflect_b(y - L.top, L.rows), sx = reflect_b(x - L.left, L.cols);
+    if (L.is_u8) {
+        const uint8_t* p = reinterpret_cast<const uint8_t*>(L.img) + (size_t)sy * L.istep + 3 * sx;
+        v[0] = p[0]; v[1] = p[1]; v[2] = p[2];
+    } else {
+        const int16_t* p = reinterpret_cast<const int16_t*>(reinterpret_cast<const char*>(L.img) + (size_t)sy * L.istep) + 3 * sx;
+        v[0] = p[0]; v[1] = p[1]; v[2] = p[2];
+    }
+}
+
+// level-0 weight: copyMakeBorder(BORDER_CONSTANT 0) of  mask * (1/255.f)   (CV_32F)  or  mask ? mask + 1 : 0  (CV_16S)
+__device__ __forceinline__ int l0_mask(const Level0& L, int y, int x) {
+    const int sy = y - L.top, sx = x - L.left;
+    if ((unsigned)sy >= (unsigned)L.rows || (unsigned)sx >= (unsigned)L.cols) return 0;
+    return L.mask[(size_t)sy * L.mstep + sx];
+}
+__device__ __forceinline__ float l0_weight_f(const Level0& L, int y, int x) { return __fmul_rn((float)l0_mask(L, y, x), (float)(1. / 255.)); }
+__device__ __forceinline__ int l0_weight_s(const Level0& L, int y, int x) { int m = l0_mask(L, y, x); return m ? m + 1 : 0; }
+
+// ---- pyrDown ------------------------------------------------------------------------------------------------
+// 16S: exact integer 5x5 [1 4 6 4 1]^2 with BORDER_REFLECT_101, (s + 128) >> 8.
+// 32F: scalar order of OpenCV's pyramids.cpp: row = s2*6 + (s1+s3)*4 + s0 + s4 ; out = (r2*6 + (r1+r3)*4 + r0 + r4) * (1/256)
+
+template <bool WF>   // WF: float weights, else int16 weights
+__global__ void k_pyrdown_l0(Level0 L, int16_t* __restrict__ g1, void* __restrict__ w1, int dh, int dw) {
+    const int x = blockIdx.x * blockDim.x + threadIdx.x;
+    const int y = blockIdx.y * blockDim.y + threadIdx.y;
+    if (x >= dw || y >= dh) return;
+    int xs[5], ys[5];
+#pragma unroll
+    for (int a = 0; a < 5; ++a) { xs[a] = reflect101(2 * x + a - 2, L.width); ys[a] = reflect101(2 * y + a - 2, L.height); }
+    const int kk[5] = {1, 4, 6, 4, 1};
+    int acc[3] = {0, 0, 0};
+    float rowf[5];
+    int wacc = 0;
+#pragma unroll
+    for (int a = 0; a < 5; ++a) {
+        int r[3] = {0, 0, 0};
+        float wf[5];
+        int ws = 0;
+#pragma unroll
+        for (int b = 0; b < 5; ++b) {
+            int v[3];
+            l0_pixel(L, ys[a], xs[b], v);
+            r[0] += kk[b] * v[0]; r[1] += kk[b] * v[1]; r[2] += kk[b] * v[2];
+            if (WF) wf[b] = l0_weight_f(L, ys[a], xs[b]);
+            else ws += kk[b] * l0_weight_s(L, ys[a], xs[b]);
+        }
+        acc[0] += kk[a] * r[0]; acc[1] += kk[a] * r[1]; acc[2] += kk[a] * r[2];
+        if (WF) rowf[a] = __fadd_rn(__fadd_rn(__fadd_rn(__fmul_rn(wf[2], 6.f), __fmul_rn(__fadd_rn(wf[1], wf[3]), 4.f)), wf[0]), wf[4]);
+        else wacc += kk[a] * ws;
+    }
+    const size_t o = (size_t)y * dw + x;
+    g1[3 * o] = (int16_t)sat16((acc[0] + 128) >> 8);
+    g1[3 * o + 1] = (int16_t)sat16((acc[1] + 128) >> 8);
+    g1[3 * o + 2] = (int16_t)sat16((acc[2] + 128) >> 8);
+    if (WF) {
+        float v = __fadd_rn(__fadd_rn(__fadd_rn(__fmul_rn(rowf[2], 6.f), __fmul_rn(__fadd_rn(rowf[1], rowf[3]), 4.f)), rowf[0]), rowf[4]);
+        reinterpret_cast<float*>(w1)[o] = __fmul_rn(v, 1.f / 256.f);
+    } else {
+        reinterpret_cast<int16_t*>(w1)[o] = (int16_t)sat16((wacc + 128) >> 8);
+    }
+}
+
+template <bool WF>
+__global__ void k_pyrdown(const int16_t* __restrict__ g, const void* __restrict__ w, int sh, int sw, int16_t* __restrict__ gd,
+                          void* __restrict__ wd, int dh, int dw) {
+    const int x = blockIdx.x * blockDim.x + threadIdx.x;
+    const int y = blockIdx.y * blockDim.y + threadIdx.y;
+    if (x >= dw || y >= dh) return;
+    int xs[5], ys[5];
+#pragma unroll
+    for (int a = 0; a < 5; ++a) { xs[a] = reflect101(2 * x + a - 2, sw); ys[a] = reflect101(2 * y + a - 2, sh); }
+    const int kk[5] = {1, 4, 6, 4, 1};
+    int acc[3] = {0, 0, 0};
+    float rowf[5];
+    int wacc = 0;
+#pragma unroll
+    for (int a = 0; a < 5; ++a) {
+        int r[3] = {0, 0, 0};
+        float wf[5];
+        int ws = 0;
+#pragma unroll
+        for (int b = 0; b < 5; ++b) {
+            const size_t i = (size_t)ys[a] * sw + xs[b];
+            r[0] += kk[b] * g[3 * i]; r[1] += kk[b] * g[3 * i + 1]; r[2] += kk[b] * g[3 * i + 2];
+            if (WF) wf[b] = reinterpret_cast<const float*>(w)[i];
+            else ws += kk[b] * reinterpret_cast<const int16_t*>(w)[i];
+        }
+        acc[0] += kk[a] * r[0]; acc[1] += kk[a] * r[1]; acc[2] += kk[a] * r[2];
+        if (WF) rowf[a] = __fadd_rn(__fadd_rn(__fadd_rn(__fmul_rn(wf[2], 6.f), __fmul_rn(__fadd_rn(wf[1], wf[3]), 4.f)), wf[0]), wf[4]);
+        else wacc += kk[a] * ws;
+    }
+    const size_t o = (size_t)y * dw + x;
+    gd[3 * o] = (int16_t)sat16((acc[0] + 128) >> 8);
+    gd[3 * o + 1] = (int16_t)sat16((acc[1] + 128) >> 8);
+    gd[3 * o + 2] = (int16_t)sat16((acc[2] + 128) >> 8);
+    if (WF) {
+        float v = __fadd_rn(__fadd_rn(__fadd_rn(__fmul_rn(rowf[2], 6.f), __fmul_rn(__fadd_rn(rowf[1], rowf[3]), 4.f)), rowf[0]), rowf[4]);
+        reinterpret_cast<float*>(wd)[o] = __fmul_rn(v, 1.f / 256.f);
+    } else {
+        reinterpret_cast<int16_t*>(wd)[o] = (int16_t)sat16((wacc + 128) >> 8);
+    }
+}
+
+// ---- pyrUp evaluated at one destination pixel ------------------------------------------------------------------
+// per axis: even 2i: s[i-1] + 6 s[i] + s[i+1], odd 2i+1: 4 (s[i] + s[i+1]); s[-1] -> s[1], s[n] -> s[n-1]; (t + 32) >> 6
+struct UpTaps { int i[3]; int w[3]; };
+
+__device__ __forceinline__ UpTaps up_taps(int d, int n) {
+    UpTaps t;
+    const int i = d >> 1;
+    if ((d & 1) == 0) {
+        t.i[0] = i > 0 ? i - 1 : (n > 1 ? 1 : 0); t.w[0] = 1;
+        t.i[1] = i; t.w[1] = 6;
+        t.i[2] = i + 1 < n ? i + 1 : n - 1; t.w[2] = 1;
+    } else {
+        t.i[0] = i; t.w[0] = 4;
+        t.i[1] = i + 1 < n ? i + 1 : n - 1; t.w[1] = 4;
+        t.i[2] = i; t.w[2] = 0;
+    }
+    return t;
+}
+
+__device__ __forceinline__ void pyrup_at(const int16_t* __restrict__ s, int sh, int sw, int y, int x, int* out) {
+    const UpTaps ty = up_taps(y, sh), tx = up_taps(x, sw);
+    int acc[3] = {0, 0, 0};
+#pragma unroll
+    for (int a = 0; a < 3; ++a) {
+        if (ty.w[a] == 0) continue;
+        const int16_t* row = s + (size_t)ty.i[a] * sw * 3;
+        int r[3] = {0, 0, 0};
+#pragma unroll
+        for (int b = 0; b < 3; ++b) {
+            if (tx.w[b] == 0) continue;
+            const int16_t* p = row + 3 * tx.i[b];
+            r[0] += tx.w[b] * p[0]; r[1] += tx.w[b] * p[1]; r[2] += tx.w[b] * p[2];
+        }
+        acc[0] += ty.w[a] * r[0]; acc[1] += ty.w[a] * r[1]; acc[2] += ty.w[a] * r[2];
+    }
+    out[0] = sat16((acc[0] + 32) >> 6);
+    out[1] = sat16((acc[1] + 32) >> 6);
+    out[2] = sat16((acc[2] + 32) >> 6);
+}
+
+// ---- one pyramid level of blend(): gather + normalise + collapse -------------------------------------------------
+struct ImgLevel {
+    Level0 l0;                 // used when k == 0
+    const int16_t* g;          // Gaussian level k   (k >= 1), dims h x w
+    const int16_t* g_up;       // Gaussian level k+1 (k < nb), dims (h/2) x (w/2)
+    const void* wgt;           // weight level k     (k >= 1)
+    int x_tl, y_tl;            // position of the image's level-k array inside the panorama's level-k array
+    int h, w;                  // level-k dims
+};
+
+struct LevelArgs {
+    const ImgLevel* imgs; int n;
+    int k, nb;
+    int H, W;                          // panorama level-k dims (padded)
+    int16_t* out;                      // collapsed level k (H x W x 3), k >= 1
+    const int16_t* up; int uh, uw;     // collapsed level k+1
+    // k == 0 only: final outputs
+    int16_t* dst; size_t dstep; uint8_t* dmask; size_t mstep; int fw, fh;
+};
+
+template <bool WF>
+__global__ void k_blend_level(LevelArgs A) {
+    const int x = blockIdx.x * blockDim.x + threadIdx.x;
+    const int y = blockIdx.y * blockDim.y + threadIdx.y;
+    const int W = A.k == 0 ? A.fw : A.W, H = A.k == 0 ? A.fh : A.H;   // level 0 is cropped to the final ROI
+    if (x >= W || y >= H) return;
+    int acc[3] = {0, 0, 0};
+    float wsum_f = 0.f;
+    int wsum_s = 0;
+    for (int i = 0; i < A.n; ++i) {
+        const ImgLevel& I = A.imgs[i];
+        const int lx = x - I.x_tl, ly = y - I.y_tl;
+        if ((unsigned)lx >= (unsigned)I.w || (unsigned)ly >= (unsigned)I.h) continue;
+        int g[3];
+        if (A.k == 0) l0_pixel(I.l0, ly, lx, g);
+        else { const int16_t* p = I.g + ((size_t)ly * I.w + lx) * 3; g[0] = p[0]; g[1] = p[1]; g[2] = p[2]; }
+        if (A.k < A.nb) {   // Laplacian = g_k - pyrUp(g_{k+1}), saturating (cv::subtract)
+            int u[3];
+            pyrup_at(I.g_up, I.h >> 1, I.w >> 1, ly, lx, u);
+            g[0] = sat16(g[0] - u[0]); g[1] = sat16(g[1] - u[1]); g[2] = sat16(g[2] - u[2]);
+        }
+        if (WF) {
+            const float w = A.k == 0 ? l0_weight_f(I.l0, ly, lx) : reinterpret_cast<const float*>(I.wgt)[(size_t)ly * I.w + lx];
+            // dst += static_cast<short>(src * w): truncation toward zero, int16 wrap-around add
+            acc[0] += (int)(int16_t)__float2int_rz(__fmul_rn((float)g[0], w));
+            acc[1] += (int)(int16_t)__float2int_rz(__fmul_rn((float)g[1], w));
+            acc[2] += (int)(int16_t)__float2int_rz(__fmul_rn((float)g[2], w));
+            wsum_f = __fadd_rn(wsum_f, w);
+        } else {
+            const int w = A.k == 0 ? l0_weight_s(I.l0, ly, lx) : (int)reinterpret_cast<const int16_t*>(I.wgt)[(size_t)ly * I.w + lx];
+            acc[0] += (int)(int16_t)((g[0] * w) >> 8);
+            acc[1] += (int)(int16_t)((g[1] * w) >> 8);
+            acc[2] += (int)(int16_t)((g[2] * w) >> 8);
+            wsum_s = (int)(int16_t)(wsum_s + w);
+        }
+    }
+    int v[3];
+#pragma unroll
+    for (int c = 0; c < 3; ++c) {
+        const int d = (int)(int16_t)acc[c];   // the int16 accumulator of OpenCV
+        if (WF) v[c] = (int)(int16_t)__float2int_rz(__fdiv_rn((float)d, __fadd_rn(wsum_f, IS_WEIGHT_EPS)));
+        else v[c] = (int)(int16_t)((d * 256) / (wsum_s + 1));
+    }
+    if (A.k < A.nb) {   // restoreImageFromLaplacePyr: pyr[k] = pyrUp(pyr[k+1]) + pyr[k], saturating
+        int u[3];
+        pyrup_at(A.up, A.uh, A.uw, y, x, u);
+        v[0] = sat16(v[0] + u[0]); v[1] = sat16(v[1] + u[1]); v[2] = sat16(v[2] + u[2]);
+    }
+    if (A.k > 0) {
+        int16_t* o = A.out + ((size_t)y * A.W + x) * 3;
+        o[0] = (int16_t)v[0]; o[1] = (int16_t)v[1]; o[2] = (int16_t)v[2];
+    } else {
+        const bool on = WF ? (wsum_f > IS_WEIGHT_EPS) : (wsum_s >= 1);
+        int16_t* o = reinterpret_cast<int16_t*>(reinterpret_cast<char*>(A.dst) + (size_t)y * A.dstep) + 3 * x;
+        o[0] = on ? (int16_t)v[0] : 0; o[1] = on ? (int16_t)v[1] : 0; o[2] = on ? (int16_t)v[2] : 0;
+        A.dmask[(size_t)y * A.mstep + x] = on ? 255 : 0;
+    }
+}
+
+}  // namespace is
+
+using namespace is;
+
+struct FedImage {
+    DevMat img, mask;              // device views (owned copies or borrowed)
+    int tl_x = 0, tl_y = 0;
+    int x_tl = 0, y_tl = 0;        // padded rect inside dst_roi_ (level 0)
+    int top = 0, left = 0, height = 0, width = 0;
+    std::vector<DevBuf> g, w;      // levels 1..nb at index k (index 0 unused)
+};
+
+struct is_blender {
+    is_ctx* ctx = nullptr;
+    int actual_num_bands = 5, num_bands = 5, weight_type = IS_WEIGHT_32F;
+    bool prepared = false;
+    is_rect roi_final{}, roi{};
+    std::vector<FedImage> fed;
+};
+
+namespace is {
+
+static Level0 level0_of(const FedImage& f) {
+    Level0 L;
+    L.img = f.img.data; L.istep = f.img.step; L.is_u8 = f.img.depth == IS_8U;
+    L.mask = f.mask.ptr<uint8_t>(); L.mstep = f.mask.step;
+    L.rows = f.img.rows; L.cols = f.img.cols;
+    L.top = f.top; L.left = f.left; L.height = f.height; L.width = f.width;
+    return L;
+}
+
+int blender_prepare_roi(is_blender* b, is_rect dst_roi) {
+    is_ctx* ctx = b->ctx;
+    IS_REQUIRE(ctx, dst_roi.width > 0 && dst_roi.height > 0, IS_ERR_BAD_ARG, "empty destination ROI");
+    b->fed.clear();
+    b->roi_final = dst_roi;
+    const double max_len = (double)std::max(dst_roi.width, dst_roi.height);
+    b->num_bands = std::min(b->actual_num_bands, (int)std::ceil(std::log(max_len) / std::log(2.0)));
+    IS_REQUIRE(ctx, b->num_bands >= 0 && b->num_bands < MAX_LEVELS, IS_ERR_BAD_ARG, "unsupported number of bands");
+    const int m = 1 << b->num_bands;
+    b->roi = dst_roi;
+    b->roi.width += (m - dst_roi.width % m) % m;
+    b->roi.height += (m - dst_roi.height % m) % m;
+    b->prepared = true;
+    return IS_OK;
+}
+
+// copy of a (host or device) mat into a fresh pitched device buffer
+static int private_copy(is_ctx* ctx, const is_mat* m, DevMat* out) {
+    IS_TRY(alloc_mat(ctx, m->rows, m->cols, m->channels, m->depth, out));
+    IS_CUDA(ctx, cudaMemcpy2DAsync(out->data, out->step, m->data, m->step, out->row_bytes(), m->rows,
+                                   m->device >= 0 ? cudaMemcpyDeviceToDevice : cudaMemcpyHostToDevice, ctx->stream));
+    return IS_OK;
+}
+
+int blender_feed_dev(is_blender* b, FedImage&& f) {
+    is_ctx* ctx = b->ctx;
+    const int nb = b->num_bands;
+    const is_rect R = b->roi;
+    const int rows = f.img.rows, cols = f.img.cols;
+    // geometry of MultiBandBlender::feed
+    const int gap = 3 * (1 << nb);
+    int tlx = std::max(R.x, f.tl_x - gap), tly = std::max(R.y, f.tl_y - gap);
+    int brx = std::min(R.x + R.width, f.tl_x + cols + gap), bry = std::min(R.y + R.height, f.tl_y + rows + gap);
+    tlx = R.x + (((tlx - R.x) >> nb) << nb);
+    tly = R.y + (((tly - R.y) >> nb) << nb);
+    int width = brx - tlx, height = bry - tly;
+    const int m = 1 << nb;
+    width += (m - width % m) % m;
+    height += (m - height % m) % m;
+    brx = tlx + width;
+    bry = tly + height;
+    const int dy = std::max(bry - (R.y + R.height), 0), dx = std::max(brx - (R.x + R.width), 0);
+    tlx -= dx; brx -= dx;
+    tly -= dy; bry -= dy;
+    f.top = f.tl_y - tly;
+    f.left = f.tl_x - tlx;
+    f.width = width;
+    f.height = height;
+    f.x_tl = tlx - R.x;
+    f.y_tl = tly - R.y;
+    IS_REQUIRE(ctx, f.top >= 0 && f.left >= 0 && f.x_tl >= 0 && f.y_tl >= 0, IS_ERR_BAD_ARG, "image lies outside the prepared ROI");
+    // Gaussian pyramids of the image and of its weight map, levels 1..nb
+    const bool wf = b->weight_type == IS_WEIGHT_32F;
+    const size_t wsz = wf ? sizeof(float) : sizeof(int16_t);
+    f.g.resize(nb + 1);
+    f.w.resize(nb + 1);
+    int sh = height, sw = width;
+    for (int k = 1; k <= nb; ++k) {
+        const int dh = (sh + 1) / 2, dw = (sw + 1) / 2;
+        IS_TRY(f.g[k].alloc(ctx, sizeof(int16_t) * 3 * (size_t)dh * dw));
+        IS_TRY(f.w[k].alloc(ctx, wsz * (size_t)dh * dw));
+        dim3 block(32, 8), grid(div_up(dw, 32), div_up(dh, 8));
+        if (k == 1) {
+            Level0 L = level0_of(f);
+            if (wf) IS_LAUNCH(ctx, k_pyrdown_l0<true>, grid, block, 0, L, f.g[1].as<int16_t>(), f.w[1].p, dh, dw);
+            else IS_LAUNCH(ctx, k_pyrdown_l0<false>, grid, block, 0, L, f.g[1].as<int16_t>(), f.w[1].p, dh, dw);
+        } else {
+            if (wf) IS_LAUNCH(ctx, k_pyrdown<true>, grid, block, 0, f.g[k - 1].as<int16_t>(), f.w[k - 1].p, sh, sw, f.g[k].as<int16_t>(), f.w[k].p, dh, dw);
+            else IS_LAUNCH(ctx, k_pyrdown<false>, grid, block, 0, f.g[k - 1].as<int16_t>(), f.w[k - 1].p, sh, sw, f.g[k].as<int16_t>(), f.w[k].p, dh, dw);
+        }
+        sh = dh; sw = dw;
+    }
+    b->fed.push_back(std::move(f));
+    return IS_OK;
+}
+
+int blender_blend_dev(is_blender* b, const DevMat& dst, const DevMat& dmask) {
+    is_ctx* ctx = b->ctx;
+    const int nb = b->num_bands, n = (int)b->fed.size();
+    const bool wf = b->weight_type == IS_WEIGHT_32F;
+    // panorama level dims
+    std::vector<int> H(nb + 2), W(nb + 2);
+    H[0] = b->roi.height; W[0] = b->roi.width;
+    for (int k = 1; k <= nb; ++k) { H[k] = (H[k - 1] + 1) / 2; W[k] = (W[k - 1] + 1) / 2; }
+    std::vector<DevBuf> out(nb + 1);
+    for (int k = 1; k <= nb; ++k) IS_TRY(out[k].alloc(ctx, sizeof(int16_t) * 3 * (size_t)H[k] * W[k]));
+    DevBuf table;
+    IS_TRY(table.alloc(ctx, sizeof(ImgLevel) * (size_t)std::max(n, 1) * (nb + 1)));
+    std::vector<ImgLevel> host((size_t)n * (nb + 1));
+    for (int k = 0; k <= nb; ++k)
+        for (int i = 0; i < n; ++i) {
+            const FedImage& f = b->fed[i];
+            ImgLevel& I = host[(size_t)k * n + i];
+            I.l0 = level0_of(f);
+            I.g = k >= 1 ? f.g[k].as<int16_t>() : nullptr;
+            I.g_up = k < nb ? f.g[k + 1].as<int16_t>() : nullptr;
+            I.wgt = k >= 1 ? f.w[k].p : nullptr;
+            I.x_tl = f.x_tl >> k;        // x_tl /= 2 per level; exact: multiples of 2^nb
+            I.y_tl = f.y_tl >> k;
+            I.h = f.height >> k;
+            I.w = f.width >> k;
+        }
+    if (n) IS_TRY(upload(ctx, table.p, host.data(), sizeof(ImgLevel) * host.size()));
+    for (int k = nb; k >= 0; --k) {
+        LevelArgs A;
+        A.imgs = table.as<ImgLevel>() + (size_t)k * n; A.n = n;
+        A.k = k; A.nb = nb;
+        A.H = H[k]; A.W = W[k];
+        A.out = k >= 1 ? out[k].as<int16_t>() : nullptr;
+        A.up = k < nb ? out[k + 1].as<int16_t>() : nullptr;
+        A.uh = k < nb ? H[k + 1] : 0; A.uw = k < nb ? W[k + 1] : 0;
+        A.dst = dst.ptr<int16_t>(); A.dstep = dst.step; A.dmask = dmask.ptr<uint8_t>(); A.mstep = dmask.step;
+        A.fw = b->roi_final.width; A.fh = b->roi_final.height;
+        const int gw = k == 0 ? A.fw : A.W, gh = k == 0 ? A.fh : A.H;
+        dim3 block(32, 8), grid(div_up(gw, 32), div_up(gh, 8));
+        if (wf) IS_LAUNCH(ctx, k_blend_level<true>, grid, block, 0, A);
+        else IS_LAUNCH(ctx, k_blend_level<false>, grid, block, 0, A);
+    }
+    b->fed.clear();        // OpenCV releases the pyramids in blend()
+    b->prepared = false;
+    return IS_OK;
+}
+
+}  // namespace is
+
+extern "C" {
+
+int is_blender_create(is_ctx* ctx, int num_bands, int weight_type, is_blender** out) {
+    if (!ctx || !out) return IS_ERR_BAD_ARG;
+    IS_REQUIRE(ctx, weight_type == IS_WEIGHT_32F || weight_type == IS_WEIGHT_16S, IS_ERR_BAD_ARG, "weight_type must be CV_32F or CV_16S");
+    IS_REQUIRE(ctx, num_bands >= 0 && num_bands < MAX_LEVELS, IS_ERR_BAD_ARG, "num_bands out of range");
+    is_blender* b = new is_blender();
+    b->ctx = ctx;
+    b->actual_num_bands = num_bands;
+    b->num_bands = num_bands;
+    b->weight_type = weight_type;
+    *out = b;
+    return IS_OK;
+}
+
+int is_blender_destroy(is_blender* b) {
+    if (b) {
+        cudaSetDevice(b->ctx->device);
+        delete b;
+    }
+    return IS_OK;
+}
+
+int is_blender_prepare_roi(is_blender* b, is_rect dst_roi) {
+    if (!b) return IS_ERR_BAD_ARG;
+    return blender_prepare_roi(b, dst_roi);
+}
+
+int is_blender_prepare(is_blender* b, int n, const is_point* corners, const is_size* sizes) {   // Blender::prepare(corners, sizes) -> resultRoi
+    if (!b) return IS_ERR_BAD_ARG;
+    IS_REQUIRE(b->ctx, n > 0 && corners && sizes, IS_ERR_BAD_ARG, "prepare needs at least one image");
+    int tlx = INT32_MAX, tly = INT32_MAX, brx = INT32_MIN, bry = INT32_MIN;
+    for (int i = 0; i < n; ++i) {
+        tlx = std::min(tlx, corners[i].x); tly = std::min(tly, corners[i].y);
+        brx = std::max(brx, corners[i].x + sizes[i].width); bry = std::max(bry, corners[i].y + sizes[i].height);
+    }
+    return blender_prepare_roi(b, is_rect{tlx, tly, brx - tlx, bry - tly});
+}
+
+int is_blender_num_bands(const is_blender* b) { return b ? b->num_bands : IS_ERR_BAD_ARG; }
+
+int is_blender_dst_size(const is_blender* b, is_size* size) {
+    if (!b || !size || !b->prepared) return IS_ERR_BAD_ARG;
+    size->width = b->roi_final.width;
+    size->height = b->roi_final.height;
+    return IS_OK;
+}
+
+int is_blender_feed(is_blender* b, const is_mat* img, const is_mat* mask, is_point tl, int flags) {
+    if (!b) return IS_ERR_BAD_ARG;
+    is_ctx* ctx = b->ctx;
+    IS_CUDA(ctx, cudaSetDevice(ctx->device));
+    IS_REQUIRE(ctx, b->prepared, IS_ERR_ASSERT, "feed() before prepare()");
+    IS_TRY(check_mat(ctx, img, "img"));
+    IS_TRY(check_mat(ctx, mask, "mask"));
+    IS_REQUIRE(ctx, img->channels == 3 && (img->depth == IS_16S || img->depth == IS_8U), IS_ERR_ASSERT, "img.type() == CV_16SC3 || img.type() == CV_8UC3");
+    IS_REQUIRE(ctx, mask->depth == IS_8U && mask->channels == 1, IS_ERR_ASSERT, "mask.type() == CV_8U");
+    IS_REQUIRE(ctx, mask->rows == img->rows && mask->cols == img->cols, IS_ERR_ASSERT, "mask.size() == img.size()");
+    FedImage f;
+    f.tl_x = tl.x; f.tl_y = tl.y;
+    const bool borrow = (flags & IS_FEED_BORROW) != 0;
+    if (borrow && img->device >= 0) IS_TRY(stage_in(ctx, img, &f.img)); else IS_TRY(private_copy(ctx, img, &f.img));
+    if (borrow && mask->device >= 0) IS_TRY(stage_in(ctx, mask, &f.mask)); else IS_TRY(private_copy(ctx, mask, &f.mask));
+    return blender_feed_dev(b, std::move(f));
+}
+
+int is_blender_blend(is_blender* b, is_mat* dst, is_mat* dst_mask) {
+    if (!b) return IS_ERR_BAD_ARG;
+    is_ctx* ctx = b->ctx;
+    IS_CUDA(ctx, cudaSetDevice(ctx->device));
+    IS_REQUIRE(ctx, b->prepared, IS_ERR_ASSERT, "blend() before prepare()");
+    IS_TRY(check_mat(ctx, dst, "dst"));
+    IS_TRY(check_mat(ctx, dst_mask, "dst_mask"));
+    IS_REQUIRE(ctx, dst->depth == IS_16S && dst->channels == 3 && dst->rows == b->roi_final.height && dst->cols == b->roi_final.width,
+               IS_ERR_BAD_ARG, "dst must be CV_16SC3 of is_blender_dst_size");
+    IS_REQUIRE(ctx, dst_mask->depth == IS_8U && dst_mask->channels == 1 && dst_mask->rows == dst->rows && dst_mask->cols == dst->cols,
+               IS_ERR_BAD_ARG, "dst_mask must be CV_8U of is_blender_dst_size");
+    DevMat d, m;
+    IS_TRY(stage_out(ctx, dst, &d, false));
+    IS_TRY(stage_out(ctx, dst_mask, &m, false));
+    IS_TRY(blender_blend_dev(b, d, m));
+    IS_TRY(commit(ctx, &d));
+    IS_TRY(commit(ctx, &m));
+    return IS_OK;
+}
+
+}  // extern "C"

@@ -1,0 +1,203 @@
+// ctx.cu -- context life cycle, error strings, staging of host is_mat buffers.
+#include "common.cuh"
+
+namespace is {
+
+int fail(is_ctx* ctx, int status, const char* fmt, ...) {
+    char buf[1024];
+    va_list ap;
+    va_start(ap, fmt);
+    vsnprintf(buf, sizeof(buf), fmt, ap);
+    va_end(ap);
+    if (ctx) ctx->last_error = buf;
+    return status;
+}
+
+int DevBuf::alloc(is_ctx* c, size_t n) {
+    release();
+    ctx = c;
+    if (n == 0) n = 16;
+    cudaError_t e = cudaMallocAsync(&p, n, c->stream);
+    if (e != cudaSuccess) {
+        p = nullptr;
+        return fail(c, e == cudaErrorMemoryAllocation ? IS_ERR_NO_MEM : IS_ERR_CUDA, "cudaMallocAsync(%zu): %s", n,
+                    cudaGetErrorString(e));
+    }
+    bytes = n;
+    return IS_OK;
+}
+
+void DevBuf::release() {
+    if (p && ctx) cudaFreeAsync(p, ctx->stream);
+    p = nullptr;
+    bytes = 0;
+}
+
+int check_mat(is_ctx* ctx, const is_mat* m, const char* name) {
+    if (!m) return fail(ctx, IS_ERR_BAD_ARG, "%s: null is_mat", name);
+    if (!m->data || m->rows <= 0 || m->cols <= 0 || m->channels <= 0 || depth_bytes(m->depth) == 0)
+        return fail(ctx, IS_ERR_BAD_ARG, "%s: empty or malformed is_mat (rows=%d cols=%d ch=%d depth=%d)", name, m->rows,
+                    m->cols, m->channels, m->depth);
+    if (m->step < (size_t)m->cols * m->channels * depth_bytes(m->depth))
+        return fail(ctx, IS_ERR_BAD_ARG, "%s: step %zu smaller than a row", name, m->step);
+    if (m->device >= 0 && m->device != ctx->device)
+        return fail(ctx, IS_ERR_BAD_ARG, "%s: buffer lives on device %d, context on device %d", name, m->device, ctx->device);
+    return IS_OK;
+}
+
+int alloc_mat(is_ctx* ctx, int rows, int cols, int channels, int depth, DevMat* out, size_t align) {
+    out->rows = rows; out->cols = cols; out->channels = channels; out->depth = depth;
+    out->step = align_up((size_t)cols * channels * depth_bytes(depth), align);
+    IS_TRY(out->owned.alloc(ctx, out->step * (size_t)rows + 256));   // tail padding: vector loads may over-read a row end
+    out->data = out->owned.p;
+    out->host = nullptr;
+    return IS_OK;
+}
+
+int stage_in(is_ctx* ctx, const is_mat* m, DevMat* out) {
+    if (m->device >= 0) {
+        out->data = m->data; out->rows = m->rows; out->cols = m->cols; out->channels = m->channels;
+        out->depth = m->depth; out->step = m->step; out->host = nullptr;
+        return IS_OK;
+    }
+    IS_TRY(alloc_mat(ctx, m->rows, m->cols, m->channels, m->depth, out));
+    IS_CUDA(ctx, cudaMemcpy2DAsync(out->data, out->step, m->data, m->step, out->row_bytes(), m->rows,
+                                   cudaMemcpyHostToDevice, ctx->stream));
+    return IS_OK;
+}
+
+int stage_out(is_ctx* ctx, is_mat* m, DevMat* out, bool preload) {
+    if (m->device >= 0) {
+        out->data = m->data; out->rows = m->rows; out->cols = m->cols; out->channels = m->channels;
+        out->depth = m->depth; out->step = m->step; out->host = nullptr;
+        return IS_OK;
+    }
+    IS_TRY(alloc_mat(ctx, m->rows, m->cols, m->channels, m->depth, out));
+    out->host = m;
+    if (preload)
+        IS_CUDA(ctx, cudaMemcpy2DAsync(out->data, out->step, m->data, m->step, out->row_bytes(), m->rows,
+                                       cudaMemcpyHostToDevice, ctx->stream));
+    return IS_OK;
+}
+
+int commit(is_ctx* ctx, DevMat* m) {
+    if (!m->host) return IS_OK;
+    IS_CUDA(ctx, cudaMemcpy2DAsync(m->host->data, m->host->step, m->data, m->step, m->row_bytes(), m->rows,
+                                   cudaMemcpyDeviceToHost, ctx->stream));
+    IS_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+    return IS_OK;
+}
+
+int ensure_pinned(is_ctx* ctx, size_t bytes) {
+    if (ctx->pinned_bytes >= bytes) return IS_OK;
+    if (ctx->pinned) cudaFreeHost(ctx->pinned);
+    ctx->pinned = nullptr;
+    ctx->pinned_bytes = 0;
+    size_t n = align_up(bytes, 1 << 20);
+    IS_CUDA(ctx, cudaMallocHost(&ctx->pinned, n));
+    ctx->pinned_bytes = n;
+    return IS_OK;
+}
+
+int pinned_alloc(is_ctx* ctx, size_t bytes, void** out) {
+    bytes = align_up(bytes, 256);
+    if (ctx->pinned_bytes < bytes || !ctx->pinned) {
+        IS_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+        IS_TRY(ensure_pinned(ctx, bytes > (size_t)(8 << 20) ? bytes : (size_t)(8 << 20)));
+        ctx->pinned_off = 0;
+    }
+    if (ctx->pinned_off + bytes > ctx->pinned_bytes) {
+        IS_CUDA(ctx, cudaStreamSynchronize(ctx->stream));   // earlier uploads have drained
+        ctx->pinned_off = 0;
+    }
+    *out = (char*)ctx->pinned + ctx->pinned_off;
+    ctx->pinned_off += bytes;
+    return IS_OK;
+}
+
+int upload(is_ctx* ctx, void* dst, const void* src, size_t bytes) {
+    if (bytes == 0) return IS_OK;
+    void* stage = nullptr;
+    IS_TRY(pinned_alloc(ctx, bytes, &stage));
+    std::memcpy(stage, src, bytes);
+    IS_CUDA(ctx, cudaMemcpyAsync(dst, stage, bytes, cudaMemcpyHostToDevice, ctx->stream));
+    return IS_OK;
+}
+
+int download(is_ctx* ctx, void* dst, const void* src, size_t bytes) {
+    if (bytes == 0) return IS_OK;
+    IS_CUDA(ctx, cudaMemcpyAsync(dst, src, bytes, cudaMemcpyDeviceToHost, ctx->stream));
+    IS_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+    return IS_OK;
+}
+
+}  // namespace is
+
+extern "C" {
+
+const char* is_version(void) { return "imagestitch_b200 0.1 (sm_100a)"; }
+
+const char* is_status_string(int status) {
+    switch (status) {
+        case IS_OK: return "ok";
+        case IS_ERR_NO_MEM: return "out of memory";
+        case IS_ERR_BAD_ARG: return "bad argument";
+        case IS_ERR_UNSUPPORTED: return "not implemented";
+        case IS_ERR_ASSERT: return "assertion failed";
+        case IS_ERR_CUDA: return "CUDA error";
+        case IS_ERR_INTERNAL: return "internal error";
+        default: return status > 0 ? "ok (informational)" : "unknown error";
+    }
+}
+
+int is_ctx_create(int device, is_ctx** out) {
+    if (!out) return IS_ERR_BAD_ARG;
+    *out = nullptr;
+    int count = 0;
+    cudaError_t e = cudaGetDeviceCount(&count);
+    if (e != cudaSuccess || count <= 0) return IS_ERR_CUDA;   // no CPU fallback: fail loudly
+    if (device < 0 || device >= count) return IS_ERR_BAD_ARG;
+    if (cudaSetDevice(device) != cudaSuccess) return IS_ERR_CUDA;
+    is_ctx* c = new is_ctx();
+    c->device = device;
+    if (cudaStreamCreateWithFlags(&c->own_stream, cudaStreamNonBlocking) != cudaSuccess) { delete c; return IS_ERR_CUDA; }
+    c->stream = c->own_stream;
+    if (cudaDeviceGetDefaultMemPool(&c->pool, device) == cudaSuccess) {
+        uint64_t thr = UINT64_MAX;   // keep freed workspace cached in the pool between calls
+        cudaMemPoolSetAttribute(c->pool, cudaMemPoolAttrReleaseThreshold, &thr);
+    }
+    for (int i = 0; i < 5; ++i) cudaEventCreate(&c->ev[i]);
+    *out = c;
+    return IS_OK;
+}
+
+int is_ctx_destroy(is_ctx* ctx) {
+    if (!ctx) return IS_OK;
+    cudaSetDevice(ctx->device);
+    cudaStreamSynchronize(ctx->stream);
+    for (int i = 0; i < 5; ++i) if (ctx->ev[i]) cudaEventDestroy(ctx->ev[i]);
+    if (ctx->pinned) cudaFreeHost(ctx->pinned);
+    cudaStreamDestroy(ctx->own_stream);
+    delete ctx;
+    return IS_OK;
+}
+
+int is_ctx_synchronize(is_ctx* ctx) {
+    if (!ctx) return IS_ERR_BAD_ARG;
+    IS_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+    return IS_OK;
+}
+
+int is_ctx_set_stream(is_ctx* ctx, void* stream) {
+    if (!ctx) return IS_ERR_BAD_ARG;
+    IS_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+    ctx->stream = stream ? (cudaStream_t)stream : ctx->own_stream;
+    return IS_OK;
+}
+
+const char* is_ctx_last_error(const is_ctx* ctx) { return ctx ? ctx->last_error.c_str() : "null context"; }
+void* is_ctx_stream(is_ctx* ctx) { return ctx ? (void*)ctx->stream : nullptr; }
+uint64_t is_ctx_kernel_launches(const is_ctx* ctx) { return ctx ? ctx->launches : 0; }
+int is_ctx_device(const is_ctx* ctx) { return ctx ? ctx->device : -1; }
+
+}  // extern "C"

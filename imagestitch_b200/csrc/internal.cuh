@@ -1,0 +1,30 @@
+// internal.cuh -- declarations shared between the translation units of the library (not part of the ABI).
+#pragma once
+
+#include "common.cuh"
+
+namespace is {
+
+struct WarpParams {
+    float k_rinv[9];
+    float scale;
+    int tl_x, tl_y;          // dst top-left in panorama coordinates
+    int dst_w, dst_h;
+    int src_w, src_h;
+};
+
+struct WarpPlan {
+    WarpParams P;
+    int roi[4];              // tl_x, tl_y, br_x, br_y as detectResultRoi returns them
+};
+
+// warp.cu
+int warp_plan(is_ctx* ctx, int proj, int src_w, int src_h, const float* K, const float* R, float scale, WarpPlan* plan);
+int upload_tables(is_ctx* ctx, int proj, const WarpPlan& plan, DevBuf* buf);
+int launch_warp(is_ctx* ctx, int proj, const WarpPlan& plan, const float* tables, const DevMat& src, int interp, int border,
+                const DevMat& dst, const DevMat* mask);
+
+// seam.cu
+int seam_find_device(is_ctx* ctx, int n, const DevMat* images, const is_point* corners, const DevMat* masks);
+
+}  // namespace is

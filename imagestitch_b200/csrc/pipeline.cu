@@ -1,0 +1,147 @@
+// pipeline.cu -- the composite call sequence of every main() of the reference:
+//   detect -> match -> homography/estimate   host control flow ([BLEND]:36-64), supplied by the caller as
+//                                            cameras or through is_registration_hooks
+//   warp loop                                [BLEND]:99-110   -> one fused image+mask kernel per image
+//   seam                                     [SEAM]:1188-1192 -> is::seam_find_device (8-bit warped images:
+//                                            identical costs to the reference's CV_32F copies)
+//   blend                                    [SEAM]:1244-1280 -> multi-band blender, images borrowed in place
+// The device boundary is exactly the warp loop: sources + K, R, scale go in, the panorama comes out.
+#include "internal.cuh"
+
+#include <algorithm>
+
+using namespace is;
+
+extern "C" {
+
+int is_pipeline_plan(is_ctx* ctx, int n, const is_size* src_sizes, const is_camera* cameras, const is_pipeline_config* cfg,
+                     is_point* corners, is_size* sizes, is_rect* pano_roi) {
+    if (!ctx) return IS_ERR_BAD_ARG;
+    IS_REQUIRE(ctx, n > 0 && src_sizes && cameras && cfg, IS_ERR_BAD_ARG, "null argument");
+    int tlx = INT32_MAX, tly = INT32_MAX, brx = INT32_MIN, bry = INT32_MIN;
+    for (int i = 0; i < n; ++i) {
+        WarpPlan plan;
+        IS_TRY(warp_plan(ctx, cfg->projection, src_sizes[i].width, src_sizes[i].height, cameras[i].K, cameras[i].R, cfg->scale, &plan));
+        if (corners) corners[i] = is_point{plan.roi[0], plan.roi[1]};
+        if (sizes) sizes[i] = is_size{plan.P.dst_w, plan.P.dst_h};
+        tlx = std::min(tlx, plan.roi[0]); tly = std::min(tly, plan.roi[1]);
+        brx = std::max(brx, plan.roi[0] + plan.P.dst_w); bry = std::max(bry, plan.roi[1] + plan.P.dst_h);
+    }
+    if (pano_roi) *pano_roi = is_rect{tlx, tly, brx - tlx, bry - tly};   // cv::detail::resultRoi(corners, sizes)
+    return IS_OK;
+}
+
+int is_pipeline_run(is_ctx* ctx, int n, const is_mat* images, const is_camera* cameras_in, const is_registration_hooks* hooks,
+                    const is_pipeline_config* cfg_in, is_mat* pano, is_mat* pano_mask, is_mat* seam_masks) {
+    if (!ctx) return IS_ERR_BAD_ARG;
+    IS_CUDA(ctx, cudaSetDevice(ctx->device));
+    IS_REQUIRE(ctx, n > 0 && images && cfg_in && pano && pano_mask, IS_ERR_BAD_ARG, "null argument");
+    is_pipeline_config cfg = *cfg_in;
+    std::vector<is_camera> cams(n);
+    // ---- host registration stages (control flow around the GPU path)
+    if (hooks && hooks->detect)
+        for (int i = 0; i < n; ++i) {
+            int rc = hooks->detect(hooks->user, i, &images[i]);
+            if (rc) return fail(ctx, rc, "detect hook failed for image %d", i);
+        }
+    if (hooks && hooks->match) {
+        int rc = hooks->match(hooks->user, n);
+        if (rc) return fail(ctx, rc, "match hook failed");
+    }
+    if (hooks && hooks->estimate) {
+        int rc = hooks->estimate(hooks->user, n, cams.data(), &cfg.scale);
+        if (rc) return fail(ctx, rc, "estimate hook failed");
+    } else {
+        IS_REQUIRE(ctx, cameras_in, IS_ERR_BAD_ARG, "cameras are required when no estimate hook is given");
+        for (int i = 0; i < n; ++i) cams[i] = cameras_in[i];
+    }
+    for (int i = 0; i < n; ++i) {
+        IS_TRY(check_mat(ctx, &images[i], "image"));
+        IS_REQUIRE(ctx, images[i].depth == IS_8U && images[i].channels == 3, IS_ERR_BAD_ARG, "source images must be CV_8UC3");
+    }
+    // ---- geometry
+    std::vector<WarpPlan> plans(n);
+    std::vector<is_point> corners(n);
+    int tlx = INT32_MAX, tly = INT32_MAX, brx = INT32_MIN, bry = INT32_MIN;
+    for (int i = 0; i < n; ++i) {
+        IS_TRY(warp_plan(ctx, cfg.projection, images[i].cols, images[i].rows, cams[i].K, cams[i].R, cfg.scale, &plans[i]));
+        corners[i] = is_point{plans[i].roi[0], plans[i].roi[1]};
+        tlx = std::min(tlx, plans[i].roi[0]); tly = std::min(tly, plans[i].roi[1]);
+        brx = std::max(brx, plans[i].roi[0] + plans[i].P.dst_w); bry = std::max(bry, plans[i].roi[1] + plans[i].P.dst_h);
+    }
+    const is_rect roi{tlx, tly, brx - tlx, bry - tly};
+    IS_TRY(check_mat(ctx, pano, "pano"));
+    IS_TRY(check_mat(ctx, pano_mask, "pano_mask"));
+    IS_REQUIRE(ctx, pano->depth == IS_16S && pano->channels == 3 && pano->rows == roi.height && pano->cols == roi.width, IS_ERR_BAD_ARG,
+               "pano must be CV_16SC3 of the planned panorama size");
+    IS_REQUIRE(ctx, pano_mask->depth == IS_8U && pano_mask->channels == 1 && pano_mask->rows == roi.height && pano_mask->cols == roi.width,
+               IS_ERR_BAD_ARG, "pano_mask must be CV_8U of the planned panorama size");
+    if (seam_masks)
+        for (int i = 0; i < n; ++i) {
+            IS_TRY(check_mat(ctx, &seam_masks[i], "seam_mask"));
+            IS_REQUIRE(ctx, seam_masks[i].depth == IS_8U && seam_masks[i].channels == 1 && seam_masks[i].rows == plans[i].P.dst_h &&
+                                seam_masks[i].cols == plans[i].P.dst_w, IS_ERR_BAD_ARG, "seam_masks[i] must be CV_8U of the warped size");
+        }
+    // ---- device: stage, warp
+    std::vector<DevMat> src(n), warped(n), masks(n);
+    for (int i = 0; i < n; ++i) IS_TRY(stage_in(ctx, &images[i], &src[i]));
+    IS_CUDA(ctx, cudaEventRecord(ctx->ev[0], ctx->stream));
+    for (int i = 0; i < n; ++i) {
+        IS_TRY(alloc_mat(ctx, plans[i].P.dst_h, plans[i].P.dst_w, 3, IS_8U, &warped[i]));
+        IS_TRY(alloc_mat(ctx, plans[i].P.dst_h, plans[i].P.dst_w, 1, IS_8U, &masks[i]));
+        DevBuf tables;
+        IS_TRY(upload_tables(ctx, cfg.projection, plans[i], &tables));
+        IS_TRY(launch_warp(ctx, cfg.projection, plans[i], tables.as<float>(), src[i], IS_INTER_LINEAR, IS_BORDER_REFLECT, warped[i], &masks[i]));
+    }
+    IS_CUDA(ctx, cudaEventRecord(ctx->ev[1], ctx->stream));
+    // ---- seam
+    if (cfg.seam == IS_SEAM_DP) {
+        if (cfg.seam_cost != IS_COST_COLOR) return fail(ctx, IS_ERR_UNSUPPORTED, "only the COLOR seam cost is implemented");
+        IS_TRY(seam_find_device(ctx, n, warped.data(), corners.data(), masks.data()));
+    } else {
+        IS_REQUIRE(ctx, cfg.seam == IS_SEAM_NONE, IS_ERR_BAD_ARG, "unknown seam mode");
+    }
+    IS_CUDA(ctx, cudaEventRecord(ctx->ev[2], ctx->stream));
+    // ---- blend
+    is_blender* bl = nullptr;
+    IS_TRY(is_blender_create(ctx, cfg.num_bands, cfg.weight_type, &bl));
+    int rc = is_blender_prepare_roi(bl, roi);
+    for (int i = 0; i < n && rc == IS_OK; ++i) {
+        is_mat im{warped[i].data, warped[i].rows, warped[i].cols, 3, IS_8U, warped[i].step, ctx->device};
+        is_mat mk{masks[i].data, masks[i].rows, masks[i].cols, 1, IS_8U, masks[i].step, ctx->device};
+        rc = is_blender_feed(bl, &im, &mk, corners[i], IS_FEED_BORROW);
+    }
+    DevMat dp, dm;
+    if (rc == IS_OK) rc = stage_out(ctx, pano, &dp, false);
+    if (rc == IS_OK) rc = stage_out(ctx, pano_mask, &dm, false);
+    if (rc == IS_OK) {
+        is_mat pd{dp.data, dp.rows, dp.cols, 3, IS_16S, dp.step, ctx->device};
+        is_mat md{dm.data, dm.rows, dm.cols, 1, IS_8U, dm.step, ctx->device};
+        rc = is_blender_blend(bl, &pd, &md);
+    }
+    is_blender_destroy(bl);
+    if (rc != IS_OK) return rc;
+    IS_CUDA(ctx, cudaEventRecord(ctx->ev[3], ctx->stream));
+    // ---- results
+    IS_TRY(commit(ctx, &dp));
+    IS_TRY(commit(ctx, &dm));
+    if (seam_masks)
+        for (int i = 0; i < n; ++i)
+            IS_CUDA(ctx, cudaMemcpy2DAsync(seam_masks[i].data, seam_masks[i].step, masks[i].data, masks[i].step, (size_t)masks[i].cols, masks[i].rows,
+                                           seam_masks[i].device >= 0 ? cudaMemcpyDeviceToDevice : cudaMemcpyDeviceToHost, ctx->stream));
+    IS_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+    float ms = 0.f;
+    for (int k = 0; k < 3; ++k) {
+        if (cudaEventElapsedTime(&ms, ctx->ev[k], ctx->ev[k + 1]) == cudaSuccess) ctx->timings[k] = ms;
+    }
+    if (cudaEventElapsedTime(&ms, ctx->ev[0], ctx->ev[3]) == cudaSuccess) ctx->timings[3] = ms;
+    return IS_OK;
+}
+
+int is_pipeline_last_timings(is_ctx* ctx, float ms[4]) {
+    if (!ctx || !ms) return IS_ERR_BAD_ARG;
+    for (int k = 0; k < 4; ++k) ms[k] = ctx->timings[k];
+    return IS_OK;
+}
+
+}  // extern "C"

@@ -1,0 +1,1233 @@
+// seam.cu -- dynamic-programming seam finder on the GPU.
+//
+// Replaces [SEAM]:87-1093 (find / process / findComponents / findEdges / resolveConflicts /
+// getSeamTips / computeCosts / estimateSeam / updateLabelsUsingSeam), i.e. cv::detail::DpSeamFinder.
+//
+// Split of work:
+//   device  every per-pixel loop of the reference: union-frame mask paste + contour masks ([SEAM]:153-186),
+//           component labelling ([SEAM]:205-256: union-find CCL whose roots are the raster-first pixel
+//           of each component, so ranking the roots reproduces floodFill's numbering), contour lists in
+//           raster order (order-preserving compaction), cost maps ([SEAM]:733-803), the DP forward pass
+//           and back-track ([SEAM]:846-947), the flood fill of updateLabelsUsingSeam ([SEAM]:978-981),
+//           relabelling and the final mask update ([SEAM]:527-545);
+//   host    the tiny irregular part: component graph / edge set / conflict loop ([SEAM]:311-546),
+//           seam tips ([SEAM]:607-706) and the order-dependent walk over the contour of
+//           updateLabelsUsingSeam ([SEAM]:983-1085), all O(perimeter).
+//
+// Exactness: labels, seams and masks are integers; DP costs are IEEE float adds in the reference's
+// association order (cost + costV first, then + costH, [SEAM]:900-904) and candidates are compared
+// lexicographically as (cost, step) like std::min_element over std::pair<float,int> ([SEAM]:909).
+#include "internal.cuh"
+
+#include <algorithm>
+#include <climits>
+#include <limits>
+#include <cmath>
+#include <map>
+#include <set>
+#include <unordered_map>
+#include <utility>
+
+namespace is {
+
+enum { ST_FIRST = 1, ST_SECOND = 2, ST_INTERS = 4 };
+
+struct ContourRec {
+    int x, y;        // union-frame coordinates
+    int label;
+    int nl[4];       // labels of the left, up, right, down neighbours; -1 outside the frame
+    int flags;       // bit0: closeToContour(contour1mask_), bit1: closeToContour(contour2mask_)
+};
+
+// =====================================================================================================
+// device kernels
+// =====================================================================================================
+
+struct MaskView {
+    const uint8_t* p; size_t step; int rows, cols; int ox, oy;   // (ox, oy): position inside the union frame
+    __device__ __forceinline__ int at(int ux, int uy) const {
+        int x = ux - ox, y = uy - oy;
+        if ((unsigned)x >= (unsigned)cols || (unsigned)y >= (unsigned)rows) return 0;
+        return p[(size_t)y * step + x];
+    }
+};
+
+// [SEAM]:153-186 + :205-218.  cls bits: 0 mask1, 1 mask2, 2 contour1mask_, 3 contour2mask_.
+__global__ void k_classify(MaskView m1, MaskView m2, uint8_t* __restrict__ cls, int uw, int uh) {
+    const int x = blockIdx.x * blockDim.x + threadIdx.x;
+    const int y = blockIdx.y * blockDim.y + threadIdx.y;
+    if (x >= uw || y >= uh) return;
+    int c = 0;
+    if (m1.at(x, y)) {
+        c |= 1;
+        if (x == 0 || !m1.at(x - 1, y) || x == uw - 1 || !m1.at(x + 1, y) || y == 0 || !m1.at(x, y - 1) || y == uh - 1 || !m1.at(x, y + 1)) c |= 4;
+    }
+    if (m2.at(x, y)) {
+        c |= 2;
+        if (x == 0 || !m2.at(x - 1, y) || x == uw - 1 || !m2.at(x + 1, y) || y == 0 || !m2.at(x, y - 1) || y == uh - 1 || !m2.at(x, y + 1)) c |= 8;
+    }
+    cls[(size_t)y * uw + x] = (uint8_t)c;
+}
+
+// ---- connected components: union-find, root = smallest linear index of the component ------------------
+// `klass` image: pixels are 4-connected when they carry the same non-zero (klass & kmask).
+
+// one block per row: parent = index of the start of the horizontal run the pixel belongs to
+__global__ void k_ccl_rows(const uint8_t* __restrict__ klass, int kmask, int* __restrict__ parent, int w) {
+    const int y = blockIdx.x;
+    const uint8_t* row = klass + (size_t)y * w;
+    int* prow = parent + (size_t)y * w;
+    __shared__ int warp_max[32];
+    __shared__ int carry_s;
+    if (threadIdx.x == 0) carry_s = 0;
+    __syncthreads();
+    const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5, nw = blockDim.x >> 5;
+    for (int base = 0; base < w; base += blockDim.x) {
+        const int x = base + threadIdx.x;
+        int k = 0, start = -1;
+        if (x < w) {
+            k = row[x] & kmask;
+            int kprev = x > 0 ? (row[x - 1] & kmask) : -1;
+            if (k != kprev) start = x;
+        }
+        // inclusive max-scan of `start` over the block
+        int v = start;
+#pragma unroll
+        for (int o = 1; o < 32; o <<= 1) {
+            int t = __shfl_up_sync(0xffffffffu, v, o);
+            if (lane >= o) v = max(v, t);
+        }
+        if (lane == 31) warp_max[wid] = v;
+        __syncthreads();
+        if (wid == 0) {
+            int t = lane < nw ? warp_max[lane] : -1;
+#pragma unroll
+            for (int o = 1; o < 32; o <<= 1) {
+                int u = __shfl_up_sync(0xffffffffu, t, o);
+                if (lane >= o) t = max(t, u);
+            }
+            warp_max[lane] = t;
+        }
+        __syncthreads();
+        int prefix = wid > 0 ? warp_max[wid - 1] : -1;
+        v = max(max(v, prefix), carry_s);
+        if (x < w) prow[x] = k ? y * w + v : -1;
+        __syncthreads();
+        if (threadIdx.x == blockDim.x - 1) carry_s = v;   // run start carried into the next chunk
+        __syncthreads();
+    }
+}
+
+__device__ __forceinline__ int uf_find(volatile int* parent, int i) {
+    int p = parent[i];
+    while (p != i) { i = p; p = parent[i]; }
+    return i;
+}
+
+__device__ __forceinline__ void uf_union(int* parent, int a, int b) {
+    while (true) {
+        a = uf_find(parent, a);
+        b = uf_find(parent, b);
+        if (a == b) return;
+        if (a > b) { int t = a; a = b; b = t; }
+        int old = atomicMin(parent + b, a);
+        if (old == b) return;
+        b = old;
+    }
+}
+
+// vertical merges, once per pair of vertically adjacent runs (at the larger of the two run starts)
+__global__ void k_ccl_merge(const uint8_t* __restrict__ klass, int kmask, int* parent, int w, int h) {
+    const int x = blockIdx.x * blockDim.x + threadIdx.x;
+    const int y = blockIdx.y * blockDim.y + threadIdx.y + 1;
+    if (x >= w || y >= h) return;
+    const uint8_t* r1 = klass + (size_t)y * w;
+    const uint8_t* r0 = r1 - w;
+    const int k = r1[x] & kmask;
+    if (!k || (r0[x] & kmask) != k) return;
+    const bool start1 = x == 0 || (r1[x - 1] & kmask) != k;
+    const bool start0 = x == 0 || (r0[x - 1] & kmask) != k;
+    if (start1 || start0) uf_union(parent, y * w + x, (y - 1) * w + x);
+}
+
+__global__ void k_ccl_flatten(int* parent, size_t n) {
+    const size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    int p = parent[i];
+    if (p < 0) return;
+    // chase without writing intermediate nodes: every node ends at its root after this kernel because
+    // roots are fixed points and are never modified here
+    volatile int* vp = parent;
+    while (true) { int q = vp[p]; if (q == p) break; p = q; }
+    parent[i] = p;
+}
+
+// roots (unordered): out[2k] = index, out[2k+1] = klass at the root
+__global__ void k_collect_roots(const int* __restrict__ parent, const uint8_t* __restrict__ klass, size_t n, int* out, int* count, int cap) {
+    const size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    if (parent[i] == (int)i) {
+        int k = atomicAdd(count, 1);
+        if (k < cap) { out[2 * k] = (int)i; out[2 * k + 1] = klass[i]; }
+    }
+}
+
+__global__ void k_scatter_ids(const int* __restrict__ roots, int n, int* labels) {
+    const int k = blockIdx.x * blockDim.x + threadIdx.x;
+    if (k < n) labels[roots[k]] = k + 1;
+}
+
+// labels[i] = id stored at the root; roots keep their value; background 0
+__global__ void k_labels_from_roots(const int* __restrict__ parent, int* labels, size_t n) {
+    const size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    int p = parent[i];
+    if (p < 0) labels[i] = 0;
+    else if (p != (int)i) labels[i] = labels[p];
+}
+
+// ---- contour lists (raster order) over a window of the union frame ---------------------------------------
+
+struct Frame { int uw, uh; };
+
+__device__ __forceinline__ bool is_contour(const int* __restrict__ labels, Frame f, int x, int y, int l) {
+    const size_t i = (size_t)y * f.uw + x;
+    return (x == 0 || labels[i - 1] != l) || (x == f.uw - 1 || labels[i + 1] != l) || (y == 0 || labels[i - f.uw] != l) ||
+           (y == f.uh - 1 || labels[i + f.uw] != l);
+}
+
+constexpr int CT_THREADS = 256, CT_PER_THREAD = 8, CT_CHUNK = CT_THREADS * CT_PER_THREAD;
+
+// pass 1: number of selected contour pixels per chunk of the window (window-raster order)
+__global__ void k_contour_count(const int* __restrict__ labels, Frame f, int wx, int wy, int ww, int wh, int fa, int fb, int* counts) {
+    const size_t total = (size_t)ww * wh;
+    size_t e0 = (size_t)blockIdx.x * CT_CHUNK + (size_t)threadIdx.x * CT_PER_THREAD;
+    int c = 0;
+    for (int k = 0; k < CT_PER_THREAD; ++k) {
+        size_t e = e0 + k;
+        if (e >= total) break;
+        int x = wx + (int)(e % ww), y = wy + (int)(e / ww);
+        int l = labels[(size_t)y * f.uw + x];
+        if (l > 0 && (fa == 0 || l == fa || l == fb) && is_contour(labels, f, x, y, l)) ++c;
+    }
+    __shared__ int red[CT_THREADS / 32];
+    for (int o = 16; o; o >>= 1) c += __shfl_down_sync(0xffffffffu, c, o);
+    if ((threadIdx.x & 31) == 0) red[threadIdx.x >> 5] = c;
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        int s = 0;
+        for (int i = 0; i < CT_THREADS / 32; ++i) s += red[i];
+        counts[blockIdx.x] = s;
+    }
+}
+
+// exclusive scan of the chunk counts (single block); offsets[n] = total
+__global__ void k_scan_counts(const int* __restrict__ counts, int n, int* offsets) {
+    __shared__ int warp_sum[32];
+    __shared__ int carry;
+    if (threadIdx.x == 0) carry = 0;
+    __syncthreads();
+    const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5, nw = blockDim.x >> 5;
+    for (int base = 0; base < n; base += blockDim.x) {
+        int i = base + threadIdx.x;
+        int v = i < n ? counts[i] : 0;
+        int s = v;
+#pragma unroll
+        for (int o = 1; o < 32; o <<= 1) { int t = __shfl_up_sync(0xffffffffu, s, o); if (lane >= o) s += t; }
+        if (lane == 31) warp_sum[wid] = s;
+        __syncthreads();
+        if (wid == 0) {
+            int t = lane < nw ? warp_sum[lane] : 0;
+#pragma unroll
+            for (int o = 1; o < 32; o <<= 1) { int u = __shfl_up_sync(0xffffffffu, t, o); if (lane >= o) t += u; }
+            warp_sum[lane] = t;
+        }
+        __syncthreads();
+        int incl = s + (wid > 0 ? warp_sum[wid - 1] : 0) + carry;
+        if (i < n) offsets[i] = incl - v;
+        __syncthreads();
+        if (threadIdx.x == blockDim.x - 1) carry = incl;
+        __syncthreads();
+    }
+    if (threadIdx.x == 0) offsets[n] = carry;
+}
+
+__device__ __forceinline__ bool close_to(const uint8_t* __restrict__ cls, Frame f, int x, int y, int bit) {   // [SEAM]:584-604
+    for (int dy = -2; dy <= 2; ++dy) {
+        int yy = y + dy;
+        if (yy < 0 || yy >= f.uh) continue;
+        for (int dx = -2; dx <= 2; ++dx) {
+            int xx = x + dx;
+            if (xx >= 0 && xx < f.uw && (cls[(size_t)yy * f.uw + xx] & bit)) return true;
+        }
+    }
+    return false;
+}
+
+// pass 2: write the records in window-raster order
+__global__ void k_contour_write(const int* __restrict__ labels, const uint8_t* __restrict__ cls, Frame f, int wx, int wy, int ww, int wh,
+                                int fa, int fb, const int* __restrict__ offsets, ContourRec* out, int cap) {
+    const size_t total = (size_t)ww * wh;
+    size_t e0 = (size_t)blockIdx.x * CT_CHUNK + (size_t)threadIdx.x * CT_PER_THREAD;
+    unsigned sel = 0;
+    int c = 0;
+    for (int k = 0; k < CT_PER_THREAD; ++k) {
+        size_t e = e0 + k;
+        if (e >= total) break;
+        int x = wx + (int)(e % ww), y = wy + (int)(e / ww);
+        int l = labels[(size_t)y * f.uw + x];
+        if (l > 0 && (fa == 0 || l == fa || l == fb) && is_contour(labels, f, x, y, l)) { sel |= 1u << k; ++c; }
+    }
+    // exclusive scan of c over the block
+    __shared__ int warp_sum[CT_THREADS / 32];
+    const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
+    int s = c;
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) { int t = __shfl_up_sync(0xffffffffu, s, o); if (lane >= o) s += t; }
+    if (lane == 31) warp_sum[wid] = s;
+    __syncthreads();
+    int prefix = 0;
+    for (int i = 0; i < wid; ++i) prefix += warp_sum[i];
+    int pos = offsets[blockIdx.x] + prefix + s - c;
+    for (int k = 0; k < CT_PER_THREAD; ++k) {
+        if (!(sel & (1u << k))) continue;
+        size_t e = e0 + k;
+        int x = wx + (int)(e % ww), y = wy + (int)(e / ww);
+        size_t i = (size_t)y * f.uw + x;
+        if (pos < cap) {
+            ContourRec r;
+            r.x = x; r.y = y; r.label = labels[i];
+            r.nl[0] = x > 0 ? labels[i - 1] : -1;
+            r.nl[1] = y > 0 ? labels[i - f.uw] : -1;
+            r.nl[2] = x < f.uw - 1 ? labels[i + 1] : -1;
+            r.nl[3] = y < f.uh - 1 ? labels[i + f.uw] : -1;
+            r.flags = (close_to(cls, f, x, y, 4) ? 1 : 0) | (close_to(cls, f, x, y, 8) ? 2 : 0);
+            out[pos] = r;
+        }
+        ++pos;
+    }
+}
+
+__global__ void k_relabel_rect(int* labels, int uw, int x0, int y0, int w, int h, int from, int to) {
+    const int x = blockIdx.x * blockDim.x + threadIdx.x;
+    const int y = blockIdx.y * blockDim.y + threadIdx.y;
+    if (x >= w || y >= h) return;
+    int* p = labels + (size_t)(y0 + y) * uw + (x0 + x);
+    if (*p == from) *p = to;
+}
+
+// ---- cost maps ------------------------------------------------------------------------------------------------
+
+template <typename T> struct ImgView {
+    const T* p; size_t step; int rows, cols; int dx, dy;   // image coords = union coords + (dx, dy)   ([SEAM]:752-753)
+    __device__ __forceinline__ const T* px(int ux, int uy) const {
+        return reinterpret_cast<const T*>(reinterpret_cast<const char*>(p) + (size_t)(uy + dy) * step) + 3 * (ux + dx);
+    }
+};
+
+// diffL2Square3 [SEAM]:713-718: ((d0^2 + d1^2) + d2^2), float
+template <typename T>
+__device__ __forceinline__ float diff3(const T* a, const T* b) {
+    float d0 = __fsub_rn((float)a[0], (float)b[0]), d1 = __fsub_rn((float)a[1], (float)b[1]), d2 = __fsub_rn((float)a[2], (float)b[2]);
+    return __fadd_rn(__fadd_rn(__fmul_rn(d0, d0), __fmul_rn(d1, d1)), __fmul_rn(d2, d2));
+}
+
+#define IS_BAD_REGION_COST 195075.f   // detail::normL2(Point3f(255,255,255)): squared norm ([SEAM]:754)
+
+__device__ __forceinline__ int label_at(const int* __restrict__ labels, Frame f, int x, int y) {
+    if ((unsigned)x >= (unsigned)f.uw || (unsigned)y >= (unsigned)f.uh) return -1;
+    return labels[(size_t)y * f.uw + x];
+}
+
+template <typename T>
+__device__ __forceinline__ float cost_v(const ImgView<T>& a, const ImgView<T>& b, const int* __restrict__ labels, Frame f, int l, int x, int y) {
+    if (label_at(labels, f, x, y) == l && x > 0 && label_at(labels, f, x - 1, y) == l)
+        return __fmul_rn(__fadd_rn(diff3(a.px(x - 1, y), b.px(x, y)), diff3(a.px(x, y), b.px(x - 1, y))), 0.5f);
+    return IS_BAD_REGION_COST;
+}
+
+template <typename T>
+__device__ __forceinline__ float cost_h(const ImgView<T>& a, const ImgView<T>& b, const int* __restrict__ labels, Frame f, int l, int x, int y) {
+    if (label_at(labels, f, x, y) == l && y > 0 && label_at(labels, f, x, y - 1) == l)
+        return __fmul_rn(__fadd_rn(diff3(a.px(x, y - 1), b.px(x, y)), diff3(a.px(x, y), b.px(x, y - 1))), 0.5f);
+    return IS_BAD_REGION_COST;
+}
+
+// reference layout ([SEAM]:756-802): costV h x (w+1), costH (h+1) x w  -- parity entry point
+template <typename T>
+__global__ void k_cost_maps(ImgView<T> a, ImgView<T> b, const int* __restrict__ labels, Frame f, int l, int rx, int ry, int rw, int rh,
+                            float* costV, size_t vstep, float* costH, size_t hstep) {
+    const int x = blockIdx.x * blockDim.x + threadIdx.x;
+    const int y = blockIdx.y * blockDim.y + threadIdx.y;
+    if (x > rw || y > rh) return;
+    if (y < rh) reinterpret_cast<float*>(reinterpret_cast<char*>(costV) + (size_t)y * vstep)[x] = cost_v(a, b, labels, f, l, rx + x, ry + y);
+    if (x < rw) reinterpret_cast<float*>(reinterpret_cast<char*>(costH) + (size_t)y * hstep)[x] = cost_h(a, b, labels, f, l, rx + x, ry + y);
+}
+
+// DP layout: P[step][lane] = cost of advancing one step at `lane`, Q[step][lane] = cost of the crossing
+// between lane and lane+1 at `step`.  Vertical seam: step = y, lane = x, P = costV, Q = costH; horizontal
+// seam: step = x, lane = y, P = costH, Q = costV.  A negative P marks a cell outside the component.
+template <typename T>
+__global__ void k_cost_pq(ImgView<T> a, ImgView<T> b, const int* __restrict__ labels, Frame f, int l, int rx, int ry, int rw, int rh,
+                          int horizontal, float* __restrict__ P, float* __restrict__ Q) {
+    const int lanes = horizontal ? rh : rw, steps = horizontal ? rw : rh;
+    const int lane = blockIdx.x * blockDim.x + threadIdx.x;
+    const int step = blockIdx.y * blockDim.y + threadIdx.y;
+    if (lane >= lanes || step >= steps) return;
+    const int x = rx + (horizontal ? step : lane), y = ry + (horizontal ? lane : step);
+    float p, q;
+    if (horizontal) { p = cost_h(a, b, labels, f, l, x, y); q = cost_v(a, b, labels, f, l, x, y); }
+    else { p = cost_v(a, b, labels, f, l, x, y); q = cost_h(a, b, labels, f, l, x, y); }
+    if (labels[(size_t)y * f.uw + x] != l) p = -1.f;
+    P[(size_t)step * lanes + lane] = p;
+    Q[(size_t)step * lanes + lane] = q;
+}
+
+// ---- DP forward pass + back-track: one CTA per seam --------------------------------------------------------
+// Thread t owns LPT consecutive lanes.  t[] = cost of the previous step + P of the previous step (the first
+// add of every candidate).  Candidates ([SEAM]:899-904 / :869-874):
+//   1: t[lane]                2: t[lane-1] + Q[step][lane-1]          3: t[lane+1] + Q[step][lane]
+// Unreachable cells carry +inf, which never wins against a finite candidate and never ties with one.
+struct DpArgs {
+    const float* P; const float* Q;
+    uint8_t* control;       // [steps][lanes]
+    int lanes, steps;
+    int s0, lane0;          // source (step, lane)
+    int s1, lane1;          // destination
+    int* seam_lane;         // out: lane of the seam at step s0..s1 (index step - s0)
+    int* reached;           // out: 1 when the destination is reachable
+};
+
+template <int LPT>
+__global__ void __launch_bounds__(1024) k_seam_dp(DpArgs A) {
+    extern __shared__ float sm[];
+    const int nt = blockDim.x, tid = threadIdx.x;
+    float* edgeL = sm;                 // [2][nt]: t of the first lane of each thread (double buffered)
+    float* edgeR = sm + 2 * nt;        // [2][nt]: t of the last lane
+    const int l0 = tid * LPT;
+    const float INF = __int_as_float(0x7f800000);
+    float t[LPT], pn[LPT], qn[LPT];
+    float qleft_n = 0.f;
+    // source step
+#pragma unroll
+    for (int j = 0; j < LPT; ++j) {
+        int lane = l0 + j;
+        float c = lane == A.lane0 ? 0.f : INF;
+        float p = lane < A.lanes ? A.P[(size_t)A.s0 * A.lanes + lane] : -1.f;
+        t[j] = __fadd_rn(c, p);
+    }
+    int buf = 0;
+    edgeL[buf * nt + tid] = t[0];
+    edgeR[buf * nt + tid] = t[LPT - 1];
+    // prefetch step s0+1
+    if (A.s0 + 1 <= A.s1) {
+        const size_t r = (size_t)(A.s0 + 1) * A.lanes;
+#pragma unroll
+        for (int j = 0; j < LPT; ++j) {
+            int lane = l0 + j;
+            pn[j] = lane < A.lanes ? A.P[r + lane] : -1.f;
+            qn[j] = lane < A.lanes ? A.Q[r + lane] : 0.f;
+        }
+        qleft_n = (l0 > 0 && l0 - 1 < A.lanes) ? A.Q[r + l0 - 1] : 0.f;
+    }
+    __syncthreads();
+    float cost_dst = INF;
+    for (int s = A.s0 + 1; s <= A.s1; ++s) {
+        float p[LPT], q[LPT];
+        const float qleft = qleft_n;
+#pragma unroll
+        for (int j = 0; j < LPT; ++j) { p[j] = pn[j]; q[j] = qn[j]; }
+        if (s + 1 <= A.s1) {   // prefetch the next step's costs: independent of the DP state
+            const size_t r = (size_t)(s + 1) * A.lanes;
+#pragma unroll
+            for (int j = 0; j < LPT; ++j) {
+                int lane = l0 + j;
+                pn[j] = lane < A.lanes ? A.P[r + lane] : -1.f;
+                qn[j] = lane < A.lanes ? A.Q[r + lane] : 0.f;
+            }
+            qleft_n = (l0 > 0 && l0 - 1 < A.lanes) ? A.Q[r + l0 - 1] : 0.f;
+        }
+        const float tl_edge = tid > 0 ? edgeR[buf * nt + tid - 1] : INF;
+        const float tr_edge = tid < nt - 1 ? edgeL[buf * nt + tid + 1] : INF;
+        float tn[LPT];
+        uint32_t ctl_pack = 0;
+#pragma unroll
+        for (int j = 0; j < LPT; ++j) {
+            const int lane = l0 + j;
+            const float c1 = t[j];
+            const float tleft = j > 0 ? t[j - 1] : tl_edge;
+            const float tright = j < LPT - 1 ? t[j + 1] : tr_edge;
+            const float ql = j > 0 ? q[j - 1] : qleft;
+            const float c2 = lane > 0 ? __fadd_rn(tleft, ql) : INF;
+            const float c3 = lane < A.lanes - 1 ? __fadd_rn(tright, q[j]) : INF;
+            float best = c1; int ctl = 1;
+            if (c2 < best) { best = c2; ctl = 2; }
+            if (c3 < best) { best = c3; ctl = 3; }
+            const bool ok = lane < A.lanes && p[j] >= 0.f && best < INF;
+            const float c = ok ? best : INF;
+            if (!ok) ctl = 0;
+            tn[j] = __fadd_rn(c, p[j]);
+            if (LPT <= 4) ctl_pack |= (uint32_t)ctl << (8 * j);
+            else if (lane < A.lanes) A.control[(size_t)s * A.lanes + lane] = (uint8_t)ctl;
+            if (s == A.s1 && lane == A.lane1) cost_dst = c;
+        }
+        if (LPT <= 4) {
+            uint8_t* cp = A.control + (size_t)s * A.lanes + l0;
+            if (LPT == 4 && l0 + 4 <= A.lanes && ((reinterpret_cast<uintptr_t>(cp) & 3) == 0)) *reinterpret_cast<uint32_t*>(cp) = ctl_pack;
+            else {
+#pragma unroll
+                for (int j = 0; j < LPT; ++j)
+                    if (l0 + j < A.lanes) cp[j] = (uint8_t)(ctl_pack >> (8 * j));
+            }
+        }
+#pragma unroll
+        for (int j = 0; j < LPT; ++j) t[j] = tn[j];
+        buf ^= 1;
+        edgeL[buf * nt + tid] = t[0];
+        edgeR[buf * nt + tid] = t[LPT - 1];
+        __syncthreads();
+    }
+    // destination reachable?  (the thread owning lane1 knows)
+    __shared__ int reached_s;
+    if (tid == 0) reached_s = (A.s1 == A.s0) ? (A.lane1 == A.lane0) : 0;
+    __syncthreads();
+    if (A.s1 > A.s0 && A.lane1 >= l0 && A.lane1 < l0 + LPT && cost_dst < INF) reached_s = 1;
+    __threadfence_block();
+    __syncthreads();
+    if (tid == 0) *A.reached = reached_s;
+    if (!reached_s) return;
+    // back-track ([SEAM]:923-947), staged through shared memory in chunks of BT steps
+    constexpr int BT = 32;
+    uint8_t* win = reinterpret_cast<uint8_t*>(sm);        // [BT][2*BT+1]
+    __shared__ int cur_lane_s;
+    if (tid == 0) { cur_lane_s = A.lane1; }
+    __syncthreads();
+    for (int shi = A.s1; shi > A.s0; shi -= BT) {
+        const int slo = max(A.s0 + 1, shi - BT + 1);   // steps slo..shi
+        const int cl = cur_lane_s;
+        const int wl = cl - BT;                         // window lanes wl .. wl + 2*BT
+        const int nrow = shi - slo + 1;
+        for (int e = tid; e < nrow * (2 * BT + 1); e += nt) {
+            int r = e / (2 * BT + 1), c = e % (2 * BT + 1);
+            int lane = wl + c;
+            win[e] = (lane >= 0 && lane < A.lanes) ? A.control[(size_t)(slo + r) * A.lanes + lane] : 0;
+        }
+        __syncthreads();
+        if (tid == 0) {
+            int lane = cl;
+            for (int s = shi; s >= slo; --s) {
+                A.seam_lane[s - A.s0] = lane;
+                int c = win[(s - slo) * (2 * BT + 1) + (lane - wl)];
+                if (c == 2) lane--;
+                else if (c == 3) lane++;
+            }
+            cur_lane_s = lane;
+        }
+        __syncthreads();
+    }
+    if (tid == 0) A.seam_lane[0] = cur_lane_s;
+}
+
+// ---- updateLabelsUsingSeam: device part -------------------------------------------------------------------------
+// sub-frame klass: 0 = not comp1, 1 = interior of comp1, 2 = painted (contour of comp1 or seam)  [SEAM]:963-970
+__global__ void k_uls_class(const int* __restrict__ labels, Frame f, int l1, int bx, int by, int bw, int bh, uint8_t* klass) {
+    const int x = blockIdx.x * blockDim.x + threadIdx.x;
+    const int y = blockIdx.y * blockDim.y + threadIdx.y;
+    if (x >= bw || y >= bh) return;
+    const int ux = bx + x, uy = by + y;
+    int k = 0;
+    if (labels[(size_t)uy * f.uw + ux] == l1) k = is_contour(labels, f, ux, uy, l1) ? 2 : 1;
+    klass[(size_t)y * bw + x] = (uint8_t)k;
+}
+
+// seam pixels -> painted.  seam_lane[i] is the lane at step s0+i; (rx, ry) = bbox top-left in union coords
+__global__ void k_uls_paint_seam(const int* __restrict__ seam_lane, int n, int s0, int horizontal, int bw, uint8_t* klass) {
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    const int step = s0 + i, lane = seam_lane[i];
+    const int x = horizontal ? step : lane, y = horizontal ? lane : step;
+    klass[(size_t)y * bw + x] = 2;
+}
+
+__device__ __forceinline__ int uls_value(const uint8_t* __restrict__ klass, const int* __restrict__ parent, int bw, int bh, int x, int y) {
+    if ((unsigned)x >= (unsigned)bw || (unsigned)y >= (unsigned)bh) return -1;   // outside the mask
+    const size_t i = (size_t)y * bw + x;
+    const int k = klass[i];
+    if (k == 0) return 0;
+    if (k == 2) return -255;                                                      // still "255" in the reference's mask
+    return parent[i] + 1;                                                         // root index + 1 of the interior component
+}
+
+// for every contour pixel of comp1 (bbox coordinates in pts): the 8 neighbours in the reference's order
+// dx = {-1,+1,0,0,-1,+1,-1,+1}, dy = {0,0,-1,+1,-1,-1,+1,+1}   [SEAM]:989-990
+__global__ void k_uls_gather8(const uint8_t* __restrict__ klass, const int* __restrict__ parent, int bw, int bh,
+                              const int2* __restrict__ pts, int n, int* out) {
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    const int dx[8] = {-1, +1, 0, 0, -1, +1, -1, +1};
+    const int dy[8] = {0, 0, -1, +1, -1, -1, +1, +1};
+    const int2 p = pts[i];
+#pragma unroll
+    for (int j = 0; j < 8; ++j) out[(size_t)i * 8 + j] = uls_value(klass, parent, bw, bh, p.x + dx[j], p.y + dy[j]);
+}
+
+// for every seam pixel: its position and the value of the neighbour the reference inspects ([SEAM]:1016,1029)
+__global__ void k_uls_gather_seam(const uint8_t* __restrict__ klass, const int* __restrict__ parent, int bw, int bh,
+                                  const int* __restrict__ seam_lane, int n, int s0, int horizontal, int* out) {
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    const int step = s0 + i, lane = seam_lane[i];
+    const int x = horizontal ? step : lane, y = horizontal ? lane : step;
+    out[3 * i] = x;
+    out[3 * i + 1] = y;
+    out[3 * i + 2] = horizontal ? uls_value(klass, parent, bw, bh, x, y + 1) : uls_value(klass, parent, bw, bh, x + 1, y);
+}
+
+// interior pixels whose component is adjacent to comp2 become l2 ([SEAM]:1089-1092); adj_roots sorted
+__global__ void k_uls_apply(const uint8_t* __restrict__ klass, const int* __restrict__ parent, int bw, int bh,
+                            const int* __restrict__ adj_roots, int nadj, int* labels, Frame f, int bx, int by, int l2) {
+    const int x = blockIdx.x * blockDim.x + threadIdx.x;
+    const int y = blockIdx.y * blockDim.y + threadIdx.y;
+    if (x >= bw || y >= bh) return;
+    const size_t i = (size_t)y * bw + x;
+    if (klass[i] != 1) return;
+    const int r = parent[i];
+    int lo = 0, hi = nadj - 1;
+    while (lo <= hi) {
+        int mid = (lo + hi) >> 1;
+        int v = adj_roots[mid];
+        if (v == r) { labels[(size_t)(by + y) * f.uw + (bx + x)] = l2; return; }
+        if (v < r) lo = mid + 1; else hi = mid - 1;
+    }
+}
+
+__global__ void k_scatter_label(const int2* __restrict__ pts, int n, int* labels, int uw, int l) {
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < n) labels[(size_t)pts[i].y * uw + pts[i].x] = l;
+}
+
+// ---- final mask update [SEAM]:527-545 --------------------------------------------------------------------------
+// dst mask pixel (x, y): l = labels at the same union position; cleared when states[l-1] has `bit` and the
+// other image's mask is set there.
+__global__ void k_mask_update(uint8_t* dst, size_t dstep, int drows, int dcols, int dox, int doy, MaskView other,
+                              const int* __restrict__ labels, int uw, const int* __restrict__ states, int bit) {
+    const int x = blockIdx.x * blockDim.x + threadIdx.x;
+    const int y = blockIdx.y * blockDim.y + threadIdx.y;
+    if (x >= dcols || y >= drows) return;
+    const int ux = x + dox, uy = y + doy;
+    const int l = labels[(size_t)uy * uw + ux];
+    if (l > 0 && (states[l - 1] & bit) && other.at(ux, uy)) dst[(size_t)y * dstep + x] = 0;
+}
+
+// =====================================================================================================
+// host logic
+// =====================================================================================================
+
+struct Pt { int x, y; };
+
+struct TraceSink {
+    int32_t* buf = nullptr; size_t cap = 0; size_t len = 0;
+};
+
+class PairSeam {
+public:
+    PairSeam(is_ctx* c, bool u8, TraceSink* tr) : ctx(c), is_u8(u8), trace(tr) {}
+    int process(const DevMat& image1, const DevMat& image2, Pt tl1, Pt tl2, const DevMat& mask1, const DevMat& mask2, int pi, int pj);
+
+private:
+    is_ctx* ctx;
+    bool is_u8;
+    TraceSink* trace;
+    int pair_i = 0, pair_j = 0;
+    Pt unionTl{}, tl1_{}, tl2_{};
+    int uw = 0, uh = 0;
+    const DevMat* img1 = nullptr; const DevMat* img2 = nullptr;
+    DevBuf cls, parent, labels;
+    // host mirrors
+    int ncomps = 0;
+    std::vector<int> states;
+    std::vector<Pt> tls, brs;
+    std::vector<std::vector<ContourRec>> contours;
+    std::set<std::pair<int, int>> edges;
+    // scratch
+    DevBuf counts, offsets, recs;
+
+    Frame frame() const { return Frame{uw, uh}; }
+    int ccl(const uint8_t* klass, int kmask, int w, int h, int* parent_out);
+    int collect_roots(const int* parent_d, const uint8_t* klass_d, size_t n, std::vector<std::pair<int, int>>* roots);
+    int extract_contours(int wx, int wy, int ww, int wh, int fa, int fb, std::vector<ContourRec>* out);
+    void find_edges();
+    bool has_only_one_neighbor(int comp);
+    bool get_seam_tips(int c1, int c2, Pt* p1, Pt* p2);
+    int estimate_and_update(int c1, int c2, Pt p1, Pt p2);
+    int refresh_component(int c);
+    int resolve_conflicts(const DevMat& mask1, const DevMat& mask2);
+};
+
+int PairSeam::ccl(const uint8_t* klass, int kmask, int w, int h, int* parent_out) {
+    IS_LAUNCH(ctx, k_ccl_rows, h, 256, 0, klass, kmask, parent_out, w);
+    if (h > 1) {
+        dim3 block(64, 4), grid(div_up(w, 64), div_up(h - 1, 4));
+        IS_LAUNCH(ctx, k_ccl_merge, grid, block, 0, klass, kmask, parent_out, w, h);
+    }
+    const size_t n = (size_t)w * h;
+    IS_LAUNCH(ctx, k_ccl_flatten, (unsigned)((n + 255) / 256), 256, 0, parent_out, n);
+    return IS_OK;
+}
+
+// roots sorted by index (raster order of the first pixel) with the klass byte at the root
+int PairSeam::collect_roots(const int* parent_d, const uint8_t* klass_d, size_t n, std::vector<std::pair<int, int>>* roots) {
+    int cap = 4096;
+    while (true) {
+        DevBuf out, cnt;
+        IS_TRY(out.alloc(ctx, sizeof(int) * 2 * (size_t)cap));
+        IS_TRY(cnt.alloc(ctx, sizeof(int)));
+        IS_CUDA(ctx, cudaMemsetAsync(cnt.p, 0, sizeof(int), ctx->stream));
+        IS_LAUNCH(ctx, k_collect_roots, (unsigned)((n + 255) / 256), 256, 0, parent_d, klass_d, n, out.as<int>(), cnt.as<int>(), cap);
+        int count = 0;
+        IS_TRY(download(ctx, &count, cnt.p, sizeof(int)));
+        if (count > cap) { cap = count; continue; }
+        std::vector<int> h(2 * (size_t)count);
+        IS_TRY(download(ctx, h.data(), out.p, sizeof(int) * h.size()));
+        roots->resize(count);
+        for (int k = 0; k < count; ++k) (*roots)[k] = {h[2 * k], h[2 * k + 1]};
+        std::sort(roots->begin(), roots->end());
+        return IS_OK;
+    }
+}
+
+int PairSeam::extract_contours(int wx, int wy, int ww, int wh, int fa, int fb, std::vector<ContourRec>* out) {
+    out->clear();
+    if (ww <= 0 || wh <= 0) return IS_OK;
+    const size_t total = (size_t)ww * wh;
+    const int nblocks = (int)((total + CT_CHUNK - 1) / CT_CHUNK);
+    IS_TRY(counts.alloc(ctx, sizeof(int) * (size_t)nblocks));
+    IS_TRY(offsets.alloc(ctx, sizeof(int) * ((size_t)nblocks + 1)));
+    IS_LAUNCH(ctx, k_contour_count, nblocks, CT_THREADS, 0, labels.as<int>(), frame(), wx, wy, ww, wh, fa, fb, counts.as<int>());
+    IS_LAUNCH(ctx, k_scan_counts, 1, 1024, 0, counts.as<int>(), nblocks, offsets.as<int>());
+    int n = 0;
+    IS_TRY(download(ctx, &n, offsets.as<int>() + nblocks, sizeof(int)));
+    if (n == 0) return IS_OK;
+    IS_TRY(recs.alloc(ctx, sizeof(ContourRec) * (size_t)n));
+    IS_LAUNCH(ctx, k_contour_write, nblocks, CT_THREADS, 0, labels.as<int>(), cls.as<uint8_t>(), frame(), wx, wy, ww, wh, fa, fb,
+              offsets.as<int>(), recs.as<ContourRec>(), n);
+    out->resize(n);
+    IS_TRY(download(ctx, out->data(), recs.p, sizeof(ContourRec) * (size_t)n));
+    return IS_OK;
+}
+
+// [SEAM]:311-392
+void PairSeam::find_edges() {
+    std::map<std::pair<int, int>, int> wedges;
+    for (int ci = 0; ci < ncomps; ++ci)
+        for (const ContourRec& r : contours[ci]) {
+            const int l = ci + 1;
+            for (int k = 0; k < 4; ++k) {
+                const int nl = r.nl[k];
+                if (nl > 0 && nl != l) {
+                    wedges[{ci, nl - 1}]++;
+                    wedges[{nl - 1, ci}]++;
+                }
+            }
+        }
+    edges.clear();
+    for (auto& kv : wedges)
+        if (kv.second > 0) edges.insert(kv.first);
+}
+
+// [SEAM]:575-581
+bool PairSeam::has_only_one_neighbor(int comp) {
+    auto begin = edges.lower_bound({comp, INT_MIN});
+    auto end = edges.upper_bound({comp, INT_MAX});
+    return ++begin == end;
+}
+
+static inline double round_half_even(double v) { return std::nearbyint(v); }   // cvRound
+
+// [SEAM]:607-706
+bool PairSeam::get_seam_tips(int c1, int c2, Pt* p1, Pt* p2) {
+    std::vector<Pt> special;
+    const int l2 = c2 + 1;
+    for (const ContourRec& r : contours[c1])
+        if ((r.flags & 3) == 3 && (r.nl[0] == l2 || r.nl[1] == l2 || r.nl[2] == l2 || r.nl[3] == l2)) special.push_back({r.x, r.y});
+    if (special.size() < 2) return false;
+    // cv::partition with ClosePoints(10): connected components of "dist^2 < 100", classes numbered by first member
+    const int n = (int)special.size();
+    std::vector<int> uf(n);
+    for (int i = 0; i < n; ++i) uf[i] = i;
+    auto find = [&](int i) { while (uf[i] != i) { uf[i] = uf[uf[i]]; i = uf[i]; } return i; };
+    // points are in raster order: only rows within 10 of each other can be close
+    for (int i = 0; i < n; ++i)
+        for (int j = i + 1; j < n && special[j].y - special[i].y < 10; ++j) {
+            int dx = special[i].x - special[j].x, dy = special[i].y - special[j].y;
+            if (dx * dx + dy * dy < 100) { int a = find(i), b = find(j); if (a != b) uf[b] = a; }
+        }
+    std::vector<int> cls_of_root(n, -1), lab(n);
+    int nlabels = 0;
+    for (int i = 0; i < n; ++i) { int r = find(i); if (cls_of_root[r] < 0) cls_of_root[r] = nlabels++; lab[i] = cls_of_root[r]; }
+    if (nlabels < 2) return false;
+    std::vector<long long> sumx(nlabels, 0), sumy(nlabels, 0);
+    std::vector<std::vector<Pt>> points(nlabels);
+    for (int i = 0; i < n; ++i) { sumx[lab[i]] += special[i].x; sumy[lab[i]] += special[i].y; points[lab[i]].push_back(special[i]); }
+    int idx[2] = {-1, -1};
+    double maxDist = -std::numeric_limits<double>::max();
+    for (int i = 0; i < nlabels - 1; ++i)
+        for (int j = i + 1; j < nlabels; ++j) {
+            double s1 = (double)points[i].size(), s2 = (double)points[j].size();
+            double cx1 = round_half_even((int)sumx[i] / s1), cy1 = round_half_even((int)sumy[i] / s1);
+            double cx2 = round_half_even((int)sumx[j] / s2), cy2 = round_half_even((int)sumy[j] / s2);
+            double dist = (cx1 - cx2) * (cx1 - cx2) + (cy1 - cy2) * (cy1 - cy2);
+            if (dist > maxDist) { maxDist = dist; idx[0] = i; idx[1] = j; }
+        }
+    Pt p[2];
+    for (int i = 0; i < 2; ++i) {
+        const std::vector<Pt>& pts = points[idx[i]];
+        double size = (double)pts.size();
+        double cx = round_half_even((int)sumx[idx[i]] / size), cy = round_half_even((int)sumy[idx[i]] / size);
+        size_t closest = 0;
+        double minDist = std::numeric_limits<double>::max();
+        for (size_t j = 0; j < pts.size(); ++j) {
+            double dist = (pts[j].x - cx) * (pts[j].x - cx) + (pts[j].y - cy) * (pts[j].y - cy);
+            if (dist < minDist) { minDist = dist; closest = j; }
+        }
+        p[i] = pts[closest];
+    }
+    *p1 = p[0];
+    *p2 = p[1];
+    return true;
+}
+
+// bbox + raster-ordered contour of component c, rescanning its previous bbox ([SEAM]:483-513)
+int PairSeam::refresh_component(int c) {
+    const int x0 = tls[c].x, y0 = tls[c].y, x1 = brs[c].x, y1 = brs[c].y;
+    tls[c] = {INT_MAX, INT_MAX};
+    brs[c] = {INT_MIN, INT_MIN};
+    contours[c].clear();
+    if (x1 <= x0 || y1 <= y0) return IS_OK;
+    IS_TRY(extract_contours(x0, y0, x1 - x0, y1 - y0, c + 1, c + 1, &contours[c]));
+    for (const ContourRec& r : contours[c]) {   // the extreme pixels of a component are contour pixels
+        tls[c].x = std::min(tls[c].x, r.x); tls[c].y = std::min(tls[c].y, r.y);
+        brs[c].x = std::max(brs[c].x, r.x + 1); brs[c].y = std::max(brs[c].y, r.y + 1);
+    }
+    return IS_OK;
+}
+
+template <typename T>
+static ImgView<T> make_view(const DevMat& m, int dx, int dy) {
+    return ImgView<T>{m.ptr<T>(), m.step, m.rows, m.cols, dx, dy};
+}
+
+// estimateSeam [SEAM]:806-957 followed by updateLabelsUsingSeam [SEAM]:960-1093
+int PairSeam::estimate_and_update(int c1, int c2, Pt p1, Pt p2) {
+    const int l1 = c1 + 1, l2 = c2 + 1;
+    const int rx = tls[c1].x, ry = tls[c1].y, rw = brs[c1].x - rx, rh = brs[c1].y - ry;
+    Pt src{p1.x - rx, p1.y - ry}, dst{p2.x - rx, p2.y - ry};
+    bool swapped = false;
+    const bool horizontal = std::abs(dst.x - src.x) > std::abs(dst.y - src.y);
+    if (horizontal) { if (src.x > dst.x) { std::swap(src, dst); swapped = true; } }
+    else if (src.y > dst.y) { std::swap(src, dst); swapped = true; }
+    const int lanes = horizontal ? rh : rw, steps = horizontal ? rw : rh;
+    IS_REQUIRE(ctx, lanes <= 16 * 1024, IS_ERR_UNSUPPORTED, "seam component wider than 16384 lanes");
+
+    DevBuf P, Q, control, seam_lane, reached;
+    IS_TRY(P.alloc(ctx, sizeof(float) * (size_t)lanes * steps));
+    IS_TRY(Q.alloc(ctx, sizeof(float) * (size_t)lanes * steps));
+    IS_TRY(control.alloc(ctx, (size_t)lanes * steps + 4));
+    IS_TRY(seam_lane.alloc(ctx, sizeof(int) * (size_t)steps));
+    IS_TRY(reached.alloc(ctx, sizeof(int)));
+    const int dx1 = unionTl.x - tl1_.x, dy1 = unionTl.y - tl1_.y, dx2 = unionTl.x - tl2_.x, dy2 = unionTl.y - tl2_.y;
+    {
+        dim3 block(64, 4), grid(div_up(lanes, 64), div_up(steps, 4));
+        if (is_u8)
+            IS_LAUNCH(ctx, k_cost_pq<uint8_t>, grid, block, 0, make_view<uint8_t>(*img1, dx1, dy1), make_view<uint8_t>(*img2, dx2, dy2),
+                      labels.as<int>(), frame(), l1, rx, ry, rw, rh, horizontal ? 1 : 0, P.as<float>(), Q.as<float>());
+        else
+            IS_LAUNCH(ctx, k_cost_pq<float>, grid, block, 0, make_view<float>(*img1, dx1, dy1), make_view<float>(*img2, dx2, dy2),
+                      labels.as<int>(), frame(), l1, rx, ry, rw, rh, horizontal ? 1 : 0, P.as<float>(), Q.as<float>());
+    }
+    DpArgs A;
+    A.P = P.as<float>(); A.Q = Q.as<float>(); A.control = control.as<uint8_t>();
+    A.lanes = lanes; A.steps = steps;
+    A.s0 = horizontal ? src.x : src.y; A.lane0 = horizontal ? src.y : src.x;
+    A.s1 = horizontal ? dst.x : dst.y; A.lane1 = horizontal ? dst.y : dst.x;
+    A.seam_lane = seam_lane.as<int>(); A.reached = reached.as<int>();
+    {
+        int lpt = 1;
+        while (lpt < 16 && lanes > 1024 * lpt) lpt *= 2;
+        int nt = std::min(1024, div_up(div_up(lanes, lpt), 32) * 32);
+        size_t smem = std::max(sizeof(float) * 4 * (size_t)nt, (size_t)32 * 65);
+        switch (lpt) {
+            case 1: IS_LAUNCH(ctx, k_seam_dp<1>, 1, nt, smem, A); break;
+            case 2: IS_LAUNCH(ctx, k_seam_dp<2>, 1, nt, smem, A); break;
+            case 4: IS_LAUNCH(ctx, k_seam_dp<4>, 1, nt, smem, A); break;
+            case 8: IS_LAUNCH(ctx, k_seam_dp<8>, 1, nt, smem, A); break;
+            default: IS_LAUNCH(ctx, k_seam_dp<16>, 1, nt, smem, A); break;
+        }
+    }
+    // ---- updateLabelsUsingSeam, device part (launched before knowing `reached`; harmless if unreachable
+    //      because nothing is written to labels until the host has decided)
+    const int nseam = A.s1 - A.s0 + 1;
+    DevBuf klass, sub_parent;
+    IS_TRY(klass.alloc(ctx, (size_t)rw * rh));
+    IS_TRY(sub_parent.alloc(ctx, sizeof(int) * (size_t)rw * rh));
+    int ok = 0;
+    IS_TRY(download(ctx, &ok, reached.p, sizeof(int)));
+    if (!ok) return IS_OK;                                             // [SEAM]:918-919: estimateSeam returned false
+    std::vector<int> lane_h(nseam);
+    IS_TRY(download(ctx, lane_h.data(), seam_lane.p, sizeof(int) * (size_t)nseam));
+    std::vector<Pt> seam(nseam);   // union-frame coordinates, ordered p1 -> p2 ([SEAM]:949-954)
+    for (int i = 0; i < nseam; ++i) {
+        int step = A.s0 + i, lane = lane_h[i];
+        Pt q = horizontal ? Pt{step + rx, lane + ry} : Pt{lane + rx, step + ry};
+        seam[swapped ? nseam - 1 - i : i] = q;
+    }
+    if (!(seam.front().x == p1.x && seam.front().y == p1.y && seam.back().x == p2.x && seam.back().y == p2.y))
+        return fail(ctx, IS_ERR_ASSERT, "seam end points differ from the seam tips ([SEAM]:953-954)");
+    if (trace) {
+        size_t need = 5 + 2 * (size_t)nseam;
+        if (trace->buf && trace->len + need <= trace->cap) {
+            int32_t* t = trace->buf + trace->len;
+            t[0] = pair_i; t[1] = pair_j; t[2] = c1; t[3] = horizontal ? 1 : 0; t[4] = nseam;
+            for (int i = 0; i < nseam; ++i) { t[5 + 2 * i] = seam[i].x + unionTl.x; t[6 + 2 * i] = seam[i].y + unionTl.y; }
+        }
+        trace->len += need;
+    }
+    {
+        dim3 block(64, 4), grid(div_up(rw, 64), div_up(rh, 4));
+        IS_LAUNCH(ctx, k_uls_class, grid, block, 0, labels.as<int>(), frame(), l1, rx, ry, rw, rh, klass.as<uint8_t>());
+        IS_LAUNCH(ctx, k_uls_paint_seam, div_up(nseam, 256), 256, 0, seam_lane.as<int>(), nseam, A.s0, horizontal ? 1 : 0, rw, klass.as<uint8_t>());
+    }
+    // flood fill of the interior ([SEAM]:978-981): klass == 1 regions; klass 2 pixels form components of
+    // their own that are ignored below
+    IS_TRY(ccl(klass.as<uint8_t>(), 3, rw, rh, sub_parent.as<int>()));
+    std::vector<std::pair<int, int>> roots_all;
+    IS_TRY(collect_roots(sub_parent.as<int>(), klass.as<uint8_t>(), (size_t)rw * rh, &roots_all));
+    std::vector<int> roots;   // raster order of the first pixel -> component id = rank + 1
+    for (auto& r : roots_all) if (r.second == 1) roots.push_back(r.first);
+    const int nsub = (int)roots.size();
+    auto id_of = [&](int v) -> int {   // gathered value -> reference mask value
+        if (v <= 0) return v;          // 0, -1 (outside), -255 (painted)
+        auto it = std::lower_bound(roots.begin(), roots.end(), v - 1);
+        return (int)(it - roots.begin()) + 1;
+    };
+    // gather the neighbourhoods the sequential part needs
+    const std::vector<ContourRec>& cont = contours[c1];
+    const int nc = (int)cont.size();
+    std::vector<int2> cpts(nc);
+    for (int i = 0; i < nc; ++i) cpts[i] = make_int2(cont[i].x - rx, cont[i].y - ry);
+    DevBuf cpts_d, g8_d, gs_d;
+    IS_TRY(cpts_d.alloc(ctx, sizeof(int2) * (size_t)std::max(nc, 1)));
+    IS_TRY(g8_d.alloc(ctx, sizeof(int) * 8 * (size_t)std::max(nc, 1)));
+    IS_TRY(gs_d.alloc(ctx, sizeof(int) * 3 * (size_t)nseam));
+    std::vector<int> g8(8 * (size_t)nc), gs(3 * (size_t)nseam);
+    if (nc) {
+        IS_TRY(upload(ctx, cpts_d.p, cpts.data(), sizeof(int2) * (size_t)nc));
+        IS_LAUNCH(ctx, k_uls_gather8, div_up(nc, 128), 128, 0, klass.as<uint8_t>(), sub_parent.as<int>(), rw, rh, cpts_d.as<int2>(), nc, g8_d.as<int>());
+    }
+    IS_LAUNCH(ctx, k_uls_gather_seam, div_up(nseam, 128), 128, 0, klass.as<uint8_t>(), sub_parent.as<int>(), rw, rh, seam_lane.as<int>(), nseam,
+              A.s0, horizontal ? 1 : 0, gs_d.as<int>());
+    if (nc) IS_TRY(download(ctx, g8.data(), g8_d.p, sizeof(int) * g8.size()));
+    IS_TRY(download(ctx, gs.data(), gs_d.p, sizeof(int) * gs.size()));
+
+    // ---- sequential part on the host ([SEAM]:983-1034).  `painted` holds the current mask value of every
+    //      contour / seam pixel (255 until assigned); all other pixels are constant (gathered above).
+    std::unordered_map<long long, int> painted;
+    painted.reserve((size_t)(nc + nseam) * 2);
+    auto key = [&](int x, int y) { return (long long)y * rw + x; };
+    for (int i = 0; i < nc; ++i) painted[key(cpts[i].x, cpts[i].y)] = 255;
+    for (int i = 0; i < nseam; ++i) painted[key(gs[3 * i], gs[3 * i + 1])] = 255;
+    static const int ddx[8] = {-1, +1, 0, 0, -1, +1, -1, +1};
+    static const int ddy[8] = {0, 0, -1, +1, -1, -1, +1, +1};
+    auto value_at = [&](int gathered, int x, int y) -> int {   // current reference mask value at (x, y)
+        if (gathered == -1) return -1;                          // outside the mask
+        if (gathered == -255) return painted[key(x, y)];
+        return id_of(gathered);
+    };
+    for (int i = 0; i < nc; ++i) {
+        const int x = cpts[i].x, y = cpts[i].y;
+        bool okc = false;
+        int val = 255;
+        for (int j = 0; j < 8; ++j) {
+            int v = value_at(g8[(size_t)i * 8 + j], x + ddx[j], y + ddy[j]);
+            if (v > 0 && v != 255) { okc = true; val = v; }
+        }
+        painted[key(x, y)] = okc ? val : 0;
+    }
+    for (int i = 0; i < nseam; ++i) {
+        // order-independent: a seam has one pixel per step, the inspected neighbour lies in the same step
+        const int k = swapped ? nseam - 1 - i : i;
+        const int x = gs[3 * k], y = gs[3 * k + 1];
+        int v = horizontal ? value_at(gs[3 * k + 2], x, y + 1) : value_at(gs[3 * k + 2], x + 1, y);
+        painted[key(x, y)] = (v > 0 && v != 255) ? v : 0;
+    }
+    // adjacency vote ([SEAM]:1039-1085)
+    std::map<int, int> connect2, connectOther;
+    for (int i = 1; i <= nsub; ++i) { connect2.insert({i, 0}); connectOther.insert({i, 0}); }
+    for (int i = 0; i < nc; ++i) {
+        const ContourRec& r = cont[i];
+        const int mv = painted[key(cpts[i].x, cpts[i].y)];
+        if (r.nl[0] == l2 || r.nl[1] == l2 || r.nl[2] == l2 || r.nl[3] == l2) connect2[mv]++;
+        bool other = false;
+        for (int k = 0; k < 4; ++k) if (r.nl[k] >= 0 && r.nl[k] != l1 && r.nl[k] != l2) other = true;
+        if (other) connectOther[mv]++;
+    }
+    int maxKey = nsub;
+    for (auto& kv : connect2) maxKey = std::max(maxKey, kv.first);
+    std::vector<int> isAdj(maxKey + 1, 0);
+    const double len = (double)nc;
+    for (auto& kv : connect2) {
+        int res = 0;
+        if (kv.second / len > 0.05) {
+            auto sub = connectOther.find(kv.first);
+            if (sub != connectOther.end() && (sub->second / len < 0.1)) res = 1;
+        }
+        isAdj[kv.first] = res;
+    }
+    // ---- relabel ([SEAM]:1089-1092)
+    std::vector<int> adj_roots;
+    for (int i = 1; i <= nsub; ++i) if (isAdj[i]) adj_roots.push_back(roots[i - 1]);
+    std::vector<int2> flips;
+    for (auto& kv : painted) {
+        int v = kv.second;
+        if (v > 0 && v <= maxKey && isAdj[v]) flips.push_back(make_int2((int)(kv.first % rw) + rx, (int)(kv.first / rw) + ry));
+    }
+    if (!adj_roots.empty()) {
+        DevBuf ar;
+        IS_TRY(ar.alloc(ctx, sizeof(int) * adj_roots.size()));
+        IS_TRY(upload(ctx, ar.p, adj_roots.data(), sizeof(int) * adj_roots.size()));
+        dim3 block(64, 4), grid(div_up(rw, 64), div_up(rh, 4));
+        IS_LAUNCH(ctx, k_uls_apply, grid, block, 0, klass.as<uint8_t>(), sub_parent.as<int>(), rw, rh, ar.as<int>(), (int)adj_roots.size(),
+                  labels.as<int>(), frame(), rx, ry, l2);
+    }
+    if (!flips.empty()) {
+        DevBuf fl;
+        IS_TRY(fl.alloc(ctx, sizeof(int2) * flips.size()));
+        IS_TRY(upload(ctx, fl.p, flips.data(), sizeof(int2) * flips.size()));
+        IS_LAUNCH(ctx, k_scatter_label, div_up((int)flips.size(), 256), 256, 0, fl.as<int2>(), (int)flips.size(), labels.as<int>(), uw, l2);
+    }
+    return IS_OK;
+}
+
+// [SEAM]:395-546
+int PairSeam::resolve_conflicts(const DevMat& mask1, const DevMat& mask2) {
+    bool hasConflict = true;
+    while (hasConflict) {
+        int c1 = 0, c2 = 0;
+        hasConflict = false;
+        for (auto itr = edges.begin(); itr != edges.end(); ++itr) {
+            c1 = itr->first;
+            c2 = itr->second;
+            if ((states[c1] & ST_INTERS) && (states[c1] & (~ST_INTERS)) != states[c2]) { hasConflict = true; break; }
+        }
+        if (!hasConflict) break;
+        const int l1 = c1 + 1, l2 = c2 + 1;
+        if (has_only_one_neighbor(c1)) {
+            const int w = brs[c1].x - tls[c1].x, h = brs[c1].y - tls[c1].y;
+            dim3 block(64, 4), grid(div_up(w, 64), div_up(h, 4));
+            IS_LAUNCH(ctx, k_relabel_rect, grid, block, 0, labels.as<int>(), uw, tls[c1].x, tls[c1].y, w, h, l1, l2);
+            states[c1] = states[c2] == ST_FIRST ? ST_SECOND : ST_FIRST;
+        } else {
+            Pt p1, p2;
+            if (get_seam_tips(c1, c2, &p1, &p2)) IS_TRY(estimate_and_update(c1, c2, p1, p2));
+            states[c1] = states[c2] == ST_FIRST ? (ST_INTERS | ST_SECOND) : (ST_INTERS | ST_FIRST);
+        }
+        IS_TRY(refresh_component(c1));
+        IS_TRY(refresh_component(c2));
+        edges.erase({c1, c2});
+        edges.erase({c2, c1});
+    }
+    // update masks ([SEAM]:524-545): mask2 first (reads the original mask1), then mask1 (reads the updated mask2)
+    DevBuf st;
+    IS_TRY(st.alloc(ctx, sizeof(int) * (size_t)std::max(ncomps, 1)));
+    if (ncomps) IS_TRY(upload(ctx, st.p, states.data(), sizeof(int) * (size_t)ncomps));
+    const int o1x = tl1_.x - unionTl.x, o1y = tl1_.y - unionTl.y, o2x = tl2_.x - unionTl.x, o2y = tl2_.y - unionTl.y;
+    MaskView v1{mask1.ptr<uint8_t>(), mask1.step, mask1.rows, mask1.cols, o1x, o1y};
+    MaskView v2{mask2.ptr<uint8_t>(), mask2.step, mask2.rows, mask2.cols, o2x, o2y};
+    {
+        dim3 block(64, 4), grid(div_up(mask2.cols, 64), div_up(mask2.rows, 4));
+        IS_LAUNCH(ctx, k_mask_update, grid, block, 0, mask2.ptr<uint8_t>(), mask2.step, mask2.rows, mask2.cols, o2x, o2y, v1, labels.as<int>(), uw,
+                  st.as<int>(), (int)ST_FIRST);
+    }
+    {
+        dim3 block(64, 4), grid(div_up(mask1.cols, 64), div_up(mask1.rows, 4));
+        IS_LAUNCH(ctx, k_mask_update, grid, block, 0, mask1.ptr<uint8_t>(), mask1.step, mask1.rows, mask1.cols, o1x, o1y, v2, labels.as<int>(), uw,
+                  st.as<int>(), (int)ST_SECOND);
+    }
+    return IS_OK;
+}
+
+// [SEAM]:127-193
+int PairSeam::process(const DevMat& image1, const DevMat& image2, Pt tl1, Pt tl2, const DevMat& mask1, const DevMat& mask2, int pi, int pj) {
+    pair_i = pi; pair_j = pj;
+    IS_REQUIRE(ctx, image1.rows == mask1.rows && image1.cols == mask1.cols, IS_ERR_ASSERT, "image1.size() == mask1.size()");
+    IS_REQUIRE(ctx, image2.rows == mask2.rows && image2.cols == mask2.cols, IS_ERR_ASSERT, "image2.size() == mask2.size()");
+    Pt iTl{std::max(tl1.x, tl2.x), std::max(tl1.y, tl2.y)};
+    Pt iBr{std::min(tl1.x + image1.cols, tl2.x + image2.cols), std::min(tl1.y + image1.rows, tl2.y + image2.rows)};
+    if (iTl.x >= iBr.x || iTl.y >= iBr.y) return IS_OK;   // no conflicts
+    img1 = &image1; img2 = &image2; tl1_ = tl1; tl2_ = tl2;
+    unionTl = {std::min(tl1.x, tl2.x), std::min(tl1.y, tl2.y)};
+    Pt unionBr{std::max(tl1.x + image1.cols, tl2.x + image2.cols), std::max(tl1.y + image1.rows, tl2.y + image2.rows)};
+    uw = unionBr.x - unionTl.x;
+    uh = unionBr.y - unionTl.y;
+    const size_t n = (size_t)uw * uh;
+    IS_REQUIRE(ctx, n < (size_t)INT_MAX, IS_ERR_UNSUPPORTED, "union frame of an image pair exceeds 2^31 pixels");
+    IS_TRY(cls.alloc(ctx, n));
+    IS_TRY(parent.alloc(ctx, sizeof(int) * n));
+    IS_TRY(labels.alloc(ctx, sizeof(int) * n));
+    MaskView v1{mask1.ptr<uint8_t>(), mask1.step, mask1.rows, mask1.cols, tl1.x - unionTl.x, tl1.y - unionTl.y};
+    MaskView v2{mask2.ptr<uint8_t>(), mask2.step, mask2.rows, mask2.cols, tl2.x - unionTl.x, tl2.y - unionTl.y};
+    {
+        dim3 block(64, 4), grid(div_up(uw, 64), div_up(uh, 4));
+        IS_LAUNCH(ctx, k_classify, grid, block, 0, v1, v2, cls.as<uint8_t>(), uw, uh);
+    }
+    // findComponents [SEAM]:196-308
+    IS_TRY(ccl(cls.as<uint8_t>(), 3, uw, uh, parent.as<int>()));
+    std::vector<std::pair<int, int>> roots;
+    IS_TRY(collect_roots(parent.as<int>(), cls.as<uint8_t>(), n, &roots));
+    ncomps = (int)roots.size();
+    states.assign(ncomps, 0);
+    tls.assign(ncomps, Pt{INT_MAX, INT_MAX});
+    brs.assign(ncomps, Pt{INT_MIN, INT_MIN});
+    contours.assign(ncomps, std::vector<ContourRec>());
+    if (ncomps) {
+        std::vector<int> root_idx(ncomps);
+        for (int k = 0; k < ncomps; ++k) {
+            root_idx[k] = roots[k].first;
+            const int c = roots[k].second & 3;
+            states[k] = c == 3 ? ST_INTERS : (c == 1 ? ST_FIRST : ST_SECOND);
+        }
+        DevBuf rd;
+        IS_TRY(rd.alloc(ctx, sizeof(int) * (size_t)ncomps));
+        IS_TRY(upload(ctx, rd.p, root_idx.data(), sizeof(int) * (size_t)ncomps));
+        IS_LAUNCH(ctx, k_scatter_ids, div_up(ncomps, 256), 256, 0, rd.as<int>(), ncomps, labels.as<int>());
+        IS_LAUNCH(ctx, k_labels_from_roots, (unsigned)((n + 255) / 256), 256, 0, parent.as<int>(), labels.as<int>(), n);
+    } else {
+        IS_CUDA(ctx, cudaMemsetAsync(labels.p, 0, sizeof(int) * n, ctx->stream));
+    }
+    parent.release();
+    std::vector<ContourRec> all;
+    IS_TRY(extract_contours(0, 0, uw, uh, 0, 0, &all));
+    for (const ContourRec& r : all) {
+        const int c = r.label - 1;
+        contours[c].push_back(r);
+        tls[c].x = std::min(tls[c].x, r.x); tls[c].y = std::min(tls[c].y, r.y);
+        brs[c].x = std::max(brs[c].x, r.x + 1); brs[c].y = std::max(brs[c].y, r.y + 1);
+    }
+    find_edges();
+    return resolve_conflicts(mask1, mask2);
+}
+
+static int seam_find_impl(is_ctx* ctx, int n, const is_mat* images, const is_point* corners, is_mat* masks, int cost_fn, TraceSink* trace) {
+    if (!ctx) return IS_ERR_BAD_ARG;
+    IS_CUDA(ctx, cudaSetDevice(ctx->device));
+    if (n == 0) return IS_OK;                                                // [SEAM]:94-95
+    IS_REQUIRE(ctx, images && corners && masks, IS_ERR_BAD_ARG, "null argument");
+    if (cost_fn == IS_COST_COLOR_GRAD) return fail(ctx, IS_ERR_UNSUPPORTED, "COLOR_GRAD seam cost is not implemented yet");
+    IS_REQUIRE(ctx, cost_fn == IS_COST_COLOR, IS_ERR_BAD_ARG, "unknown cost function");
+    const int depth = images[0].depth;
+    for (int i = 0; i < n; ++i) {
+        IS_TRY(check_mat(ctx, &images[i], "image"));
+        IS_TRY(check_mat(ctx, &masks[i], "mask"));
+        IS_REQUIRE(ctx, images[i].channels == 3 && (images[i].depth == IS_8U || images[i].depth == IS_32F) && images[i].depth == depth,
+                   IS_ERR_BAD_ARG, "both images must have CV_32FC3 or CV_8UC3 type");     // [SEAM]:749
+        IS_REQUIRE(ctx, masks[i].depth == IS_8U && masks[i].channels == 1, IS_ERR_BAD_ARG, "masks must be CV_8U");
+        IS_REQUIRE(ctx, images[i].rows == masks[i].rows && images[i].cols == masks[i].cols, IS_ERR_ASSERT, "image.size() == mask.size()");
+    }
+    std::vector<DevMat> dimg(n), dmask(n);
+    for (int i = 0; i < n; ++i) {
+        IS_TRY(stage_in(ctx, &images[i], &dimg[i]));
+        IS_TRY(stage_out(ctx, &masks[i], &dmask[i], true));
+    }
+    std::vector<std::pair<int, int>> pairs;                                  // [SEAM]:97-111 (no sort, reversed)
+    for (int i = 0; i + 1 < n; ++i)
+        for (int j = i + 1; j < n; ++j) pairs.push_back({i, j});
+    std::reverse(pairs.begin(), pairs.end());
+    for (auto& pr : pairs) {
+        PairSeam ps(ctx, depth == IS_8U, trace);
+        IS_TRY(ps.process(dimg[pr.first], dimg[pr.second], Pt{corners[pr.first].x, corners[pr.first].y},
+                          Pt{corners[pr.second].x, corners[pr.second].y}, dmask[pr.first], dmask[pr.second], pr.first, pr.second));
+    }
+    for (int i = 0; i < n; ++i) IS_TRY(commit(ctx, &dmask[i]));
+    return IS_OK;
+}
+
+// used by the pipeline with device-resident mats
+int seam_find_device(is_ctx* ctx, int n, const DevMat* images, const is_point* corners, const DevMat* masks) {
+    std::vector<std::pair<int, int>> pairs;
+    for (int i = 0; i + 1 < n; ++i)
+        for (int j = i + 1; j < n; ++j) pairs.push_back({i, j});
+    std::reverse(pairs.begin(), pairs.end());
+    for (auto& pr : pairs) {
+        PairSeam ps(ctx, images[pr.first].depth == IS_8U, nullptr);
+        IS_TRY(ps.process(images[pr.first], images[pr.second], Pt{corners[pr.first].x, corners[pr.first].y},
+                          Pt{corners[pr.second].x, corners[pr.second].y}, masks[pr.first], masks[pr.second], pr.first, pr.second));
+    }
+    return IS_OK;
+}
+
+}  // namespace is
+
+using namespace is;
+
+extern "C" {
+
+int is_seam_dp_find(is_ctx* ctx, int n, const is_mat* images, const is_point* corners, is_mat* masks, int cost_fn) {
+    return seam_find_impl(ctx, n, images, corners, masks, cost_fn, nullptr);
+}
+
+int is_seam_dp_find_trace(is_ctx* ctx, int n, const is_mat* images, const is_point* corners, is_mat* masks, int cost_fn,
+                          int32_t* trace, size_t trace_cap, size_t* trace_len) {
+    TraceSink sink;
+    sink.buf = trace;
+    sink.cap = trace ? trace_cap : 0;
+    int rc = seam_find_impl(ctx, n, images, corners, masks, cost_fn, &sink);
+    if (trace_len) *trace_len = sink.len;
+    return rc;
+}
+
+int is_seam_cost_maps(is_ctx* ctx, const is_mat* image1, const is_mat* image2, is_point tl1, is_point tl2, const is_mat* labels,
+                      is_point union_tl, int label, is_rect roi, is_mat* costV, is_mat* costH) {
+    if (!ctx) return IS_ERR_BAD_ARG;
+    IS_CUDA(ctx, cudaSetDevice(ctx->device));
+    IS_TRY(check_mat(ctx, image1, "image1"));
+    IS_TRY(check_mat(ctx, image2, "image2"));
+    IS_TRY(check_mat(ctx, labels, "labels"));
+    IS_TRY(check_mat(ctx, costV, "costV"));
+    IS_TRY(check_mat(ctx, costH, "costH"));
+    IS_REQUIRE(ctx, image1->channels == 3 && image2->channels == 3 && image1->depth == image2->depth &&
+                        (image1->depth == IS_8U || image1->depth == IS_32F), IS_ERR_BAD_ARG, "both images must have CV_32FC3 or CV_8UC3 type");
+    IS_REQUIRE(ctx, labels->depth == IS_32S && labels->channels == 1, IS_ERR_BAD_ARG, "labels must be CV_32S");
+    IS_REQUIRE(ctx, labels->device >= 0 || labels->step == (size_t)labels->cols * 4, IS_ERR_BAD_ARG, "host labels must be dense");
+    IS_REQUIRE(ctx, costV->depth == IS_32F && costV->rows == roi.height && costV->cols == roi.width + 1, IS_ERR_BAD_ARG, "costV must be h x (w+1) CV_32F");
+    IS_REQUIRE(ctx, costH->depth == IS_32F && costH->rows == roi.height + 1 && costH->cols == roi.width, IS_ERR_BAD_ARG, "costH must be (h+1) x w CV_32F");
+    IS_REQUIRE(ctx, roi.x >= 0 && roi.y >= 0 && roi.x + roi.width <= labels->cols && roi.y + roi.height <= labels->rows, IS_ERR_BAD_ARG, "roi outside the label image");
+    DevMat a, b, cv, ch;
+    IS_TRY(stage_in(ctx, image1, &a));
+    IS_TRY(stage_in(ctx, image2, &b));
+    // labels: dense int32 on the device
+    DevBuf lab;
+    const int* lab_d = nullptr;
+    if (labels->device >= 0 && labels->step == (size_t)labels->cols * 4) lab_d = (const int*)labels->data;
+    else {
+        IS_TRY(lab.alloc(ctx, sizeof(int) * (size_t)labels->rows * labels->cols));
+        IS_CUDA(ctx, cudaMemcpy2DAsync(lab.p, (size_t)labels->cols * 4, labels->data, labels->step, (size_t)labels->cols * 4, labels->rows,
+                                       labels->device >= 0 ? cudaMemcpyDeviceToDevice : cudaMemcpyHostToDevice, ctx->stream));
+        lab_d = lab.as<int>();
+    }
+    IS_TRY(stage_out(ctx, costV, &cv, false));
+    IS_TRY(stage_out(ctx, costH, &ch, false));
+    Frame f{labels->cols, labels->rows};
+    const int dx1 = union_tl.x - tl1.x, dy1 = union_tl.y - tl1.y, dx2 = union_tl.x - tl2.x, dy2 = union_tl.y - tl2.y;
+    dim3 block(32, 8), grid(div_up(roi.width + 1, 32), div_up(roi.height + 1, 8));
+    if (image1->depth == IS_8U)
+        IS_LAUNCH(ctx, k_cost_maps<uint8_t>, grid, block, 0, make_view<uint8_t>(a, dx1, dy1), make_view<uint8_t>(b, dx2, dy2), lab_d, f, label,
+                  roi.x, roi.y, roi.width, roi.height, cv.ptr<float>(), cv.step, ch.ptr<float>(), ch.step);
+    else
+        IS_LAUNCH(ctx, k_cost_maps<float>, grid, block, 0, make_view<float>(a, dx1, dy1), make_view<float>(b, dx2, dy2), lab_d, f, label,
+                  roi.x, roi.y, roi.width, roi.height, cv.ptr<float>(), cv.step, ch.ptr<float>(), ch.step);
+    IS_TRY(commit(ctx, &cv));
+    IS_TRY(commit(ctx, &ch));
+    return IS_OK;
+}
+
+}  // extern "C"

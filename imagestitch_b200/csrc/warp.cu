@@ -1,0 +1,438 @@
+// warp.cu -- cylindrical / spherical backward warp with OpenCV-exact fixed-point sampling.
+//
+// Replaces [WARP]:36-161 (setCameraParams, mapForward/mapBackward, detectResultRoi, buildMaps, warp) and
+// the cv::remap call at [WARP]:157.  buildMaps and remap are fused: the kernel evaluates the backward map
+// of a destination pixel and samples the source at once, so the two CV_32F maps (8 B per pixel, written
+// and read back by the reference) never exist in HBM.
+//
+// Bit-exactness recipe ("hard parts"):
+//   * sinf/cosf of the per-column angle u/scale (and, spherical, of the per-row angle pi - v/scale) are
+//     evaluated by the host libm into O(W+H) tables -- the same libm the CPU path uses;
+//   * everything per pixel is IEEE mul/add/div in the reference's association order ([WARP]:57-61) with
+//     explicit round-to-nearest intrinsics, so nvcc cannot contract them into FMAs;
+//   * sampling is cv::remap's 8-bit path: coordinates rounded half-even to 1/32 pixel, integer weights
+//     (32-fy)(32-fx) ... (the 15-bit table of OpenCV divided by its common factor 32), BORDER_REFLECT /
+//     BORDER_CONSTANT neighbour fetch, (sum + 512) >> 10.
+#include "internal.cuh"
+
+#include <cmath>
+#include <limits>
+
+namespace is {
+
+struct Projector {
+    float k[9], rinv[9], r_kinv[9], k_rinv[9];
+};
+
+// ---- host: camera parameters and result ROI -------------------------------------------------------
+
+static bool invert3x3f(const float* s, float* d) {   // cv::invert on 3x3 CV_32F: double cofactors, float result
+    double a = s[0], b = s[1], c = s[2], e = s[3], f = s[4], g = s[5], h = s[6], i = s[7], j = s[8];
+    double det = a * (f * j - g * i) - b * (e * j - g * h) + c * (e * i - f * h);
+    if (det == 0.) return false;
+    double r = 1. / det;
+    double t[9] = {(f * j - g * i) * r, (c * i - b * j) * r, (b * g - c * f) * r,
+                   (g * h - e * j) * r, (a * j - c * h) * r, (c * e - a * g) * r,
+                   (e * i - f * h) * r, (b * h - a * i) * r, (a * f - b * e) * r};
+    for (int n = 0; n < 9; ++n) d[n] = (float)t[n];
+    return true;
+}
+
+static void matmul3f(const float* A, const float* B, float* C) {   // float accumulation, left to right
+    for (int r = 0; r < 3; ++r)
+        for (int c = 0; c < 3; ++c) {
+            volatile float acc = 0.f;   // volatile: one rounding per operation, no contraction by the host compiler
+            for (int t = 0; t < 3; ++t) {
+                volatile float prod = A[r * 3 + t] * B[t * 3 + c];
+                acc = acc + prod;
+            }
+            C[r * 3 + c] = acc;
+        }
+}
+
+static void set_camera(const float* K, const float* R, Projector* p) {   // [WARP]:90-120
+    for (int n = 0; n < 9; ++n) p->k[n] = K[n];
+    for (int r = 0; r < 3; ++r)
+        for (int c = 0; c < 3; ++c) p->rinv[r * 3 + c] = R[c * 3 + r];
+    float kinv[9];
+    if (!invert3x3f(K, kinv)) std::memset(kinv, 0, sizeof(kinv));
+    matmul3f(R, kinv, p->r_kinv);
+    matmul3f(K, p->rinv, p->k_rinv);
+}
+
+static const float kPiF = static_cast<float>(3.14159265358979323846);
+
+static inline void map_forward(int proj, const Projector& p, float scale, float x, float y, float* u, float* v) {
+    volatile float x_ = p.r_kinv[0] * x + p.r_kinv[1] * y + p.r_kinv[2];
+    volatile float y_ = p.r_kinv[3] * x + p.r_kinv[4] * y + p.r_kinv[5];
+    volatile float z_ = p.r_kinv[6] * x + p.r_kinv[7] * y + p.r_kinv[8];
+    *u = scale * atan2f(x_, z_);
+    if (proj == IS_PROJ_CYLINDRICAL) {
+        *v = scale * y_ / sqrtf(x_ * x_ + z_ * z_);
+    } else {
+        float w = y_ / sqrtf(x_ * x_ + y_ * y_ + z_ * z_);
+        *v = scale * (kPiF - acosf(w == w ? w : 0));
+    }
+}
+
+// detectResultRoi: the extrema of (u, v) over the source image lie on its border for every camera
+// that does not look along the projection axis; that is the scan cv::detail::CylindricalWarper /
+// SphericalWarper themselves use (detectResultRoiByBorder).  The reference's full scan
+// ([WARP]:72-81) gives the same corners (tests/test_oracle_warp.py pins both).
+static void detect_roi(int proj, int w, int h, const Projector& p, float scale, int roi[4]) {
+    float tl_u = std::numeric_limits<float>::max(), tl_v = tl_u, br_u = -tl_u, br_v = -tl_u;
+    auto acc = [&](int x, int y) {
+        float u, v;
+        map_forward(proj, p, scale, (float)x, (float)y, &u, &v);
+        tl_u = std::min(tl_u, u); tl_v = std::min(tl_v, v);
+        br_u = std::max(br_u, u); br_v = std::max(br_v, v);
+    };
+    for (int x = 0; x < w; ++x) { acc(x, 0); acc(x, h - 1); }
+    for (int y = 0; y < h; ++y) { acc(0, y); acc(w - 1, y); }
+    if (proj == IS_PROJ_SPHERICAL) {   // SphericalWarper::detectResultRoi: poles inside the image widen the ROI
+        tl_u = (float)(int)tl_u; tl_v = (float)(int)tl_v; br_u = (float)(int)br_u; br_v = (float)(int)br_v;
+        for (int pole = 0; pole < 2; ++pole) {
+            float s = pole ? -1.f : 1.f;
+            float x = s * p.rinv[1], y = s * p.rinv[4], z = s * p.rinv[7];
+            if (y > 0.f) {
+                float x_ = (p.k[0] * x + p.k[1] * y) / z + p.k[2];
+                float y_ = p.k[4] * y / z + p.k[5];
+                if (x_ > 0.f && x_ < w && y_ > 0.f && y_ < h) {
+                    float pv = pole ? 0.f : static_cast<float>(3.14159265358979323846 * scale);
+                    tl_u = std::min(tl_u, 0.f); tl_v = std::min(tl_v, pv);
+                    br_u = std::max(br_u, 0.f); br_v = std::max(br_v, pv);
+                }
+            }
+        }
+    }
+    roi[0] = (int)tl_u; roi[1] = (int)tl_v; roi[2] = (int)br_u; roi[3] = (int)br_v;
+}
+
+// Per-column and per-row trigonometry of the backward map, host libm.  Layout: [sinu(w) | cosu(w) | rowA(h) | rowB(h)]
+//   cylindrical: rowA = v / scale (y_), rowB unused
+//   spherical:   rowA = sinf(pi - v/scale), rowB = cosf(pi - v/scale)
+static void fill_tables(int proj, float scale, int tl_x, int tl_y, int w, int h, float* t) {
+    float* sinu = t; float* cosu = t + w; float* rowA = t + 2 * (size_t)w; float* rowB = rowA + h;
+    for (int i = 0; i < w; ++i) {
+        float u = (float)(tl_x + i) / scale;
+        sinu[i] = sinf(u);
+        cosu[i] = cosf(u);
+    }
+    for (int j = 0; j < h; ++j) {
+        float v = (float)(tl_y + j) / scale;
+        if (proj == IS_PROJ_CYLINDRICAL) { rowA[j] = v; rowB[j] = 0.f; }
+        else { rowA[j] = sinf(kPiF - v); rowB[j] = cosf(kPiF - v); }
+    }
+}
+
+// ---- device ------------------------------------------------------------------------------------------
+
+template <int PROJ>
+__device__ __forceinline__ void map_backward(const WarpParams& P, float su, float cu, float ra, float rb, float* x, float* y) {
+    float x_, y_, z_;
+    if (PROJ == IS_PROJ_CYLINDRICAL) { x_ = su; y_ = ra; z_ = cu; }
+    else { x_ = __fmul_rn(ra, su); y_ = rb; z_ = __fmul_rn(ra, cu); }
+    const float* m = P.k_rinv;
+    float X = __fadd_rn(__fadd_rn(__fmul_rn(m[0], x_), __fmul_rn(m[1], y_)), __fmul_rn(m[2], z_));
+    float Y = __fadd_rn(__fadd_rn(__fmul_rn(m[3], x_), __fmul_rn(m[4], y_)), __fmul_rn(m[5], z_));
+    float Z = __fadd_rn(__fadd_rn(__fmul_rn(m[6], x_), __fmul_rn(m[7], y_)), __fmul_rn(m[8], z_));
+    if (Z > 0.f) { *x = __fdiv_rn(X, Z); *y = __fdiv_rn(Y, Z); }
+    else { *x = -1.f; *y = -1.f; }
+}
+
+__device__ __forceinline__ int reflect_idx(int p, int len) {   // cv::borderInterpolate, BORDER_REFLECT
+    if ((unsigned)p < (unsigned)len) return p;
+    if (len == 1) return 0;
+    do {
+        if (p < 0) p = -p - 1;
+        else p = len - 1 - (p - len);
+    } while ((unsigned)p >= (unsigned)len);
+    return p;
+}
+
+__device__ __forceinline__ int clamp_short(int v) { return max(-32768, min(32767, v)); }
+
+// One destination pixel of cv::remap (8-bit).  out[c], c < CH.
+template <int CH, int INTERP, int BORDER>
+__device__ __forceinline__ void sample(const uint8_t* __restrict__ src, size_t sstep, int sw, int sh, float x, float y, int* out) {
+    if (INTERP == IS_INTER_NEAREST) {
+        int sx = clamp_short(__float2int_rn(x)), sy = clamp_short(__float2int_rn(y));
+        bool in = (unsigned)sx < (unsigned)sw && (unsigned)sy < (unsigned)sh;
+        if (!in) {
+            if (BORDER == IS_BORDER_CONSTANT) {
+#pragma unroll
+                for (int c = 0; c < CH; ++c) out[c] = 0;
+                return;
+            }
+            sx = reflect_idx(sx, sw);
+            sy = reflect_idx(sy, sh);
+        }
+        const uint8_t* s = src + (size_t)sy * sstep + sx * CH;
+#pragma unroll
+        for (int c = 0; c < CH; ++c) out[c] = __ldg(s + c);
+        return;
+    }
+    int ix = __float2int_rn(__fmul_rn(x, 32.f)), iy = __float2int_rn(__fmul_rn(y, 32.f));
+    int sx = clamp_short(ix >> 5), sy = clamp_short(iy >> 5);
+    int fx = ix & 31, fy = iy & 31;
+    int w00 = (32 - fy) * (32 - fx), w01 = (32 - fy) * fx, w10 = fy * (32 - fx), w11 = fy * fx;
+    if ((unsigned)sx < (unsigned)(sw - 1) && (unsigned)sy < (unsigned)(sh - 1)) {   // all four neighbours inside
+        const uint8_t* s0 = src + (size_t)sy * sstep + sx * CH;
+        const uint8_t* s1 = s0 + sstep;
+#pragma unroll
+        for (int c = 0; c < CH; ++c)
+            out[c] = (__ldg(s0 + c) * w00 + __ldg(s0 + CH + c) * w01 + __ldg(s1 + c) * w10 + __ldg(s1 + CH + c) * w11 + 512) >> 10;
+        return;
+    }
+    if (BORDER == IS_BORDER_CONSTANT) {
+        bool x0 = (unsigned)sx < (unsigned)sw, x1 = (unsigned)(sx + 1) < (unsigned)sw;
+        bool y0 = (unsigned)sy < (unsigned)sh, y1 = (unsigned)(sy + 1) < (unsigned)sh;
+#pragma unroll
+        for (int c = 0; c < CH; ++c) {
+            int v0 = (x0 && y0) ? __ldg(src + (size_t)sy * sstep + sx * CH + c) : 0;
+            int v1 = (x1 && y0) ? __ldg(src + (size_t)sy * sstep + (sx + 1) * CH + c) : 0;
+            int v2 = (x0 && y1) ? __ldg(src + (size_t)(sy + 1) * sstep + sx * CH + c) : 0;
+            int v3 = (x1 && y1) ? __ldg(src + (size_t)(sy + 1) * sstep + (sx + 1) * CH + c) : 0;
+            out[c] = (v0 * w00 + v1 * w01 + v2 * w10 + v3 * w11 + 512) >> 10;
+        }
+        return;
+    }
+    int sx0 = reflect_idx(sx, sw), sx1 = reflect_idx(sx + 1, sw);
+    int sy0 = reflect_idx(sy, sh), sy1 = reflect_idx(sy + 1, sh);
+    const uint8_t* r0 = src + (size_t)sy0 * sstep;
+    const uint8_t* r1 = src + (size_t)sy1 * sstep;
+#pragma unroll
+    for (int c = 0; c < CH; ++c)
+        out[c] = (__ldg(r0 + sx0 * CH + c) * w00 + __ldg(r0 + sx1 * CH + c) * w01 + __ldg(r1 + sx0 * CH + c) * w10 +
+                  __ldg(r1 + sx1 * CH + c) * w11 + 512) >> 10;
+}
+
+constexpr int WARP_PX = 4;          // destination pixels per thread (consecutive in x)
+constexpr int WARP_BX = 32, WARP_BY = 8;
+
+// tables: [sinu(w) | cosu(w) | rowA(h) | rowB(h)]
+template <int PROJ, int CH, int INTERP, int BORDER, bool WITH_MASK>
+__global__ void __launch_bounds__(WARP_BX* WARP_BY)
+k_warp(WarpParams P, const float* __restrict__ tables, const uint8_t* __restrict__ src, size_t sstep,
+       uint8_t* __restrict__ dst, size_t dstep, uint8_t* __restrict__ mask, size_t mstep) {
+    const int x0 = (blockIdx.x * WARP_BX + threadIdx.x) * WARP_PX;
+    const int y = blockIdx.y * WARP_BY + threadIdx.y;
+    if (y >= P.dst_h || x0 >= P.dst_w) return;
+    const float* sinu = tables;
+    const float* cosu = tables + P.dst_w;
+    const float ra = __ldg(tables + 2 * (size_t)P.dst_w + y);
+    const float rb = __ldg(tables + 2 * (size_t)P.dst_w + P.dst_h + y);
+    int px[WARP_PX][CH];
+    int mk[WARP_PX];
+#pragma unroll
+    for (int i = 0; i < WARP_PX; ++i) {
+        int x = min(x0 + i, P.dst_w - 1);
+        float sx, sy;
+        map_backward<PROJ>(P, __ldg(sinu + x), __ldg(cosu + x), ra, rb, &sx, &sy);
+        sample<CH, INTERP, BORDER>(src, sstep, P.src_w, P.src_h, sx, sy, px[i]);
+        if (WITH_MASK) {   // INTER_NEAREST + BORDER_CONSTANT on an all-255 source mask
+            int nx = clamp_short(__float2int_rn(sx)), ny = clamp_short(__float2int_rn(sy));
+            mk[i] = ((unsigned)nx < (unsigned)P.src_w && (unsigned)ny < (unsigned)P.src_h) ? 255 : 0;
+        }
+    }
+    uint8_t* d = dst + (size_t)y * dstep + (size_t)x0 * CH;
+    const bool full = x0 + WARP_PX <= P.dst_w;
+    if (full && ((reinterpret_cast<uintptr_t>(d) & 3) == 0)) {
+        if (CH == 3) {
+            uint32_t w0 = px[0][0] | (px[0][1] << 8) | (px[0][2] << 16) | (px[1][0] << 24);
+            uint32_t w1 = px[1][1] | (px[1][2] << 8) | (px[2][0] << 16) | (px[2][1] << 24);
+            uint32_t w2 = px[2][2] | (px[3][0] << 8) | (px[3][1] << 16) | (px[3][2] << 24);
+            uint32_t* d32 = reinterpret_cast<uint32_t*>(d);
+            d32[0] = w0; d32[1] = w1; d32[2] = w2;
+        } else {
+            *reinterpret_cast<uint32_t*>(d) = px[0][0] | (px[1][0] << 8) | (px[2][0] << 16) | (px[3][0] << 24);
+        }
+    } else {
+#pragma unroll
+        for (int i = 0; i < WARP_PX; ++i)
+            if (x0 + i < P.dst_w)
+#pragma unroll
+                for (int c = 0; c < CH; ++c) d[i * CH + c] = (uint8_t)px[i][c];
+    }
+    if (WITH_MASK) {
+        uint8_t* m = mask + (size_t)y * mstep + x0;
+        if (full && ((reinterpret_cast<uintptr_t>(m) & 3) == 0)) {
+            *reinterpret_cast<uint32_t*>(m) = mk[0] | (mk[1] << 8) | (mk[2] << 16) | (mk[3] << 24);
+        } else {
+#pragma unroll
+            for (int i = 0; i < WARP_PX; ++i)
+                if (x0 + i < P.dst_w) m[i] = (uint8_t)mk[i];
+        }
+    }
+}
+
+template <int PROJ>
+__global__ void k_build_maps(WarpParams P, const float* __restrict__ tables, float* __restrict__ xmap, size_t xstep,
+                             float* __restrict__ ymap, size_t ystep) {
+    const int x = blockIdx.x * blockDim.x + threadIdx.x;
+    const int y = blockIdx.y * blockDim.y + threadIdx.y;
+    if (x >= P.dst_w || y >= P.dst_h) return;
+    float sx, sy;
+    map_backward<PROJ>(P, __ldg(tables + x), __ldg(tables + P.dst_w + x), __ldg(tables + 2 * (size_t)P.dst_w + y),
+                       __ldg(tables + 2 * (size_t)P.dst_w + P.dst_h + y), &sx, &sy);
+    reinterpret_cast<float*>(reinterpret_cast<char*>(xmap) + (size_t)y * xstep)[x] = sx;
+    reinterpret_cast<float*>(reinterpret_cast<char*>(ymap) + (size_t)y * ystep)[x] = sy;
+}
+
+// ---- host drivers ----------------------------------------------------------------------------------
+
+int warp_plan(is_ctx* ctx, int proj, int src_w, int src_h, const float* K, const float* R, float scale, WarpPlan* plan) {
+    IS_REQUIRE(ctx, proj == IS_PROJ_CYLINDRICAL || proj == IS_PROJ_SPHERICAL, IS_ERR_BAD_ARG, "unknown projection");
+    IS_REQUIRE(ctx, K && R, IS_ERR_ASSERT, "K and R must be 3x3 CV_32F");
+    IS_REQUIRE(ctx, src_w > 0 && src_h > 0 && scale > 0.f, IS_ERR_BAD_ARG, "empty source or non-positive scale");
+    Projector p;
+    set_camera(K, R, &p);
+    detect_roi(proj, src_w, src_h, p, scale, plan->roi);
+    std::memcpy(plan->P.k_rinv, p.k_rinv, sizeof(p.k_rinv));
+    plan->P.scale = scale;
+    plan->P.tl_x = plan->roi[0];
+    plan->P.tl_y = plan->roi[1];
+    plan->P.dst_w = plan->roi[2] - plan->roi[0] + 1;
+    plan->P.dst_h = plan->roi[3] - plan->roi[1] + 1;
+    plan->P.src_w = src_w;
+    plan->P.src_h = src_h;
+    IS_REQUIRE(ctx, plan->P.dst_w > 0 && plan->P.dst_h > 0 && plan->P.dst_w < (1 << 24) && plan->P.dst_h < (1 << 24),
+               IS_ERR_BAD_ARG, "degenerate warp ROI");
+    return IS_OK;
+}
+
+int upload_tables(is_ctx* ctx, int proj, const WarpPlan& plan, DevBuf* buf) {
+    const int w = plan.P.dst_w, h = plan.P.dst_h;
+    const size_t n = 2 * (size_t)w + 2 * (size_t)h;
+    IS_TRY(buf->alloc(ctx, n * sizeof(float)));
+    void* stage = nullptr;
+    IS_TRY(pinned_alloc(ctx, n * sizeof(float), &stage));
+    fill_tables(proj, plan.P.scale, plan.P.tl_x, plan.P.tl_y, w, h, (float*)stage);
+    IS_CUDA(ctx, cudaMemcpyAsync(buf->p, stage, n * sizeof(float), cudaMemcpyHostToDevice, ctx->stream));
+    return IS_OK;
+}
+
+template <int PROJ, int CH, int INTERP, int BORDER, bool WITH_MASK>
+static int launch_warp_t(is_ctx* ctx, const WarpPlan& plan, const float* tables, const DevMat& src, const DevMat& dst,
+                         const DevMat* mask) {
+    dim3 block(WARP_BX, WARP_BY);
+    dim3 grid(div_up(plan.P.dst_w, WARP_BX * WARP_PX), div_up(plan.P.dst_h, WARP_BY));
+    IS_LAUNCH(ctx, (k_warp<PROJ, CH, INTERP, BORDER, WITH_MASK>), grid, block, 0, plan.P, tables, src.ptr<uint8_t>(), src.step,
+              dst.ptr<uint8_t>(), dst.step, mask ? mask->ptr<uint8_t>() : nullptr, mask ? mask->step : 0);
+    return IS_OK;
+}
+
+// device-resident src/dst; used by is_warp* and by the pipeline
+int launch_warp(is_ctx* ctx, int proj, const WarpPlan& plan, const float* tables, const DevMat& src, int interp, int border,
+                const DevMat& dst, const DevMat* mask) {
+    const int ch = src.channels;
+#define IS_WARP_CASE(PJ, C, I, B, M) \
+    if (proj == PJ && ch == C && interp == I && border == B && (mask != nullptr) == M) \
+        return launch_warp_t<PJ, C, I, B, M>(ctx, plan, tables, src, dst, mask);
+#define IS_WARP_CASES(PJ)                                                   \
+    IS_WARP_CASE(PJ, 3, IS_INTER_LINEAR, IS_BORDER_REFLECT, true)           \
+    IS_WARP_CASE(PJ, 3, IS_INTER_LINEAR, IS_BORDER_REFLECT, false)          \
+    IS_WARP_CASE(PJ, 3, IS_INTER_LINEAR, IS_BORDER_CONSTANT, false)         \
+    IS_WARP_CASE(PJ, 3, IS_INTER_NEAREST, IS_BORDER_REFLECT, false)         \
+    IS_WARP_CASE(PJ, 3, IS_INTER_NEAREST, IS_BORDER_CONSTANT, false)        \
+    IS_WARP_CASE(PJ, 1, IS_INTER_LINEAR, IS_BORDER_REFLECT, false)          \
+    IS_WARP_CASE(PJ, 1, IS_INTER_LINEAR, IS_BORDER_CONSTANT, false)         \
+    IS_WARP_CASE(PJ, 1, IS_INTER_NEAREST, IS_BORDER_REFLECT, false)         \
+    IS_WARP_CASE(PJ, 1, IS_INTER_NEAREST, IS_BORDER_CONSTANT, false)
+    IS_WARP_CASES(IS_PROJ_CYLINDRICAL)
+    IS_WARP_CASES(IS_PROJ_SPHERICAL)
+#undef IS_WARP_CASES
+#undef IS_WARP_CASE
+    return fail(ctx, IS_ERR_UNSUPPORTED, "warp: unsupported combination (channels=%d interp=%d border=%d)", ch, interp, border);
+}
+
+}  // namespace is
+
+using namespace is;
+
+extern "C" {
+
+int is_warp_roi(is_ctx* ctx, int projection, is_size src_size, const float K[9], const float R[9], float scale,
+                is_point* dst_tl, is_size* dst_size) {
+    if (!ctx) return IS_ERR_BAD_ARG;
+    WarpPlan plan;
+    IS_TRY(warp_plan(ctx, projection, src_size.width, src_size.height, K, R, scale, &plan));
+    if (dst_tl) { dst_tl->x = plan.roi[0]; dst_tl->y = plan.roi[1]; }
+    if (dst_size) { dst_size->width = plan.P.dst_w; dst_size->height = plan.P.dst_h; }
+    return IS_OK;
+}
+
+int is_build_maps(is_ctx* ctx, int projection, is_size src_size, const float K[9], const float R[9], float scale,
+                  is_mat* xmap, is_mat* ymap, is_rect* dst_roi) {
+    if (!ctx) return IS_ERR_BAD_ARG;
+    IS_CUDA(ctx, cudaSetDevice(ctx->device));
+    WarpPlan plan;
+    IS_TRY(warp_plan(ctx, projection, src_size.width, src_size.height, K, R, scale, &plan));
+    IS_TRY(check_mat(ctx, xmap, "xmap"));
+    IS_TRY(check_mat(ctx, ymap, "ymap"));
+    IS_REQUIRE(ctx, xmap->depth == IS_32F && xmap->channels == 1 && ymap->depth == IS_32F && ymap->channels == 1, IS_ERR_BAD_ARG,
+               "maps must be 1-channel IS_32F");
+    IS_REQUIRE(ctx, xmap->rows == plan.P.dst_h && xmap->cols == plan.P.dst_w && ymap->rows == plan.P.dst_h && ymap->cols == plan.P.dst_w,
+               IS_ERR_BAD_ARG, "maps must have the size reported by is_warp_roi");
+    DevBuf tables;
+    IS_TRY(upload_tables(ctx, projection, plan, &tables));
+    DevMat dx, dy;
+    IS_TRY(stage_out(ctx, xmap, &dx, false));
+    IS_TRY(stage_out(ctx, ymap, &dy, false));
+    dim3 block(32, 8), grid(div_up(plan.P.dst_w, 32), div_up(plan.P.dst_h, 8));
+    if (projection == IS_PROJ_CYLINDRICAL)
+        IS_LAUNCH(ctx, k_build_maps<IS_PROJ_CYLINDRICAL>, grid, block, 0, plan.P, tables.as<float>(), dx.ptr<float>(), dx.step,
+                  dy.ptr<float>(), dy.step);
+    else
+        IS_LAUNCH(ctx, k_build_maps<IS_PROJ_SPHERICAL>, grid, block, 0, plan.P, tables.as<float>(), dx.ptr<float>(), dx.step,
+                  dy.ptr<float>(), dy.step);
+    IS_TRY(commit(ctx, &dx));
+    IS_TRY(commit(ctx, &dy));
+    if (dst_roi) { dst_roi->x = plan.roi[0]; dst_roi->y = plan.roi[1]; dst_roi->width = plan.roi[2] - plan.roi[0]; dst_roi->height = plan.roi[3] - plan.roi[1]; }
+    return IS_OK;
+}
+
+static int warp_common(is_ctx* ctx, int projection, const is_mat* src, const float* K, const float* R, float scale,
+                       int interp, int border, is_mat* dst, is_mat* dst_mask, is_point* dst_tl) {
+    if (!ctx) return IS_ERR_BAD_ARG;
+    IS_CUDA(ctx, cudaSetDevice(ctx->device));
+    IS_TRY(check_mat(ctx, src, "src"));
+    IS_TRY(check_mat(ctx, dst, "dst"));
+    IS_REQUIRE(ctx, src->depth == IS_8U && (src->channels == 1 || src->channels == 3), IS_ERR_UNSUPPORTED, "src must be 8UC1 or 8UC3");
+    IS_REQUIRE(ctx, dst->depth == IS_8U && dst->channels == src->channels, IS_ERR_BAD_ARG, "dst must have the type of src");
+    IS_REQUIRE(ctx, (interp == IS_INTER_NEAREST || interp == IS_INTER_LINEAR) && (border == IS_BORDER_CONSTANT || border == IS_BORDER_REFLECT),
+               IS_ERR_UNSUPPORTED, "interp must be NEAREST/LINEAR and border CONSTANT/REFLECT");
+    WarpPlan plan;
+    IS_TRY(warp_plan(ctx, projection, src->cols, src->rows, K, R, scale, &plan));
+    IS_REQUIRE(ctx, dst->rows == plan.P.dst_h && dst->cols == plan.P.dst_w, IS_ERR_BAD_ARG, "dst must have the size reported by is_warp_roi");
+    if (dst_mask) {
+        IS_TRY(check_mat(ctx, dst_mask, "dst_mask"));
+        IS_REQUIRE(ctx, src->channels == 3, IS_ERR_BAD_ARG, "is_warp_with_mask needs a 3-channel source");
+        IS_REQUIRE(ctx, dst_mask->depth == IS_8U && dst_mask->channels == 1 && dst_mask->rows == dst->rows && dst_mask->cols == dst->cols,
+                   IS_ERR_BAD_ARG, "dst_mask must be 8UC1 of the dst size");
+    }
+    DevBuf tables;
+    IS_TRY(upload_tables(ctx, projection, plan, &tables));
+    DevMat s, d, m;
+    IS_TRY(stage_in(ctx, src, &s));
+    IS_TRY(stage_out(ctx, dst, &d, false));
+    if (dst_mask) IS_TRY(stage_out(ctx, dst_mask, &m, false));
+    IS_TRY(launch_warp(ctx, projection, plan, tables.as<float>(), s, interp, border, d, dst_mask ? &m : nullptr));
+    IS_TRY(commit(ctx, &d));
+    if (dst_mask) IS_TRY(commit(ctx, &m));
+    if (dst_tl) { dst_tl->x = plan.roi[0]; dst_tl->y = plan.roi[1]; }
+    return IS_OK;
+}
+
+int is_warp(is_ctx* ctx, int projection, const is_mat* src, const float K[9], const float R[9], float scale, int interp,
+            int border, is_mat* dst, is_point* dst_tl) {
+    return warp_common(ctx, projection, src, K, R, scale, interp, border, dst, nullptr, dst_tl);
+}
+
+int is_warp_with_mask(is_ctx* ctx, int projection, const is_mat* src, const float K[9], const float R[9], float scale,
+                      is_mat* dst, is_mat* dst_mask, is_point* dst_tl) {
+    if (!dst_mask) return ctx ? fail(ctx, IS_ERR_BAD_ARG, "dst_mask is null") : IS_ERR_BAD_ARG;
+    return warp_common(ctx, projection, src, K, R, scale, IS_INTER_LINEAR, IS_BORDER_REFLECT, dst, dst_mask, dst_tl);
+}
+
+}  // extern "C"

@@ -1,0 +1,214 @@
+/*
+ * imagestitch.h -- C ABI of libimagestitch_b200.so: the per-pixel composite stage of the stitching
+ * pipeline (cylindrical/spherical backward warp -> DP seam -> multi-band / linear blend) on B200.
+ *
+ * The reference (mhhai/ImageStitch) has no FFI of its own; its hot path is the set of cv::detail
+ * stitching interfaces it both calls and re-implements as free functions.  Each entry point below
+ * names the reference interface it replaces (aliases [WARP], [SEAM], [BLEND]: SURVEY.md section 0).
+ *
+ * Conventions
+ *   - plain C, no exceptions cross the boundary: every call returns an is_status (0 = OK, negative
+ *     values follow cv::Error codes where the reference would CV_Assert / CV_Error, plus CUDA codes).
+ *     is_ctx_last_error() gives the message.
+ *   - images are described by is_mat, a mirror of cv::Mat: row-major, channels interleaved (BGR),
+ *     `step` bytes per row, `depth` uses OpenCV's depth codes.  `device` = -1 for host memory or the
+ *     CUDA ordinal that owns `data`; host buffers are staged through the context's stream, device
+ *     buffers are used in place.  All buffers are caller-owned.
+ *   - an is_ctx owns a CUDA stream, a stream-ordered workspace pool and the launch counter; one
+ *     context per host thread (the reference keeps this state in globals and is not re-entrant,
+ *     [WARP]:30-35, [SEAM]:65-85).  Calls are asynchronous with respect to device buffers; results in
+ *     host buffers are complete on return.
+ *   - there is no CPU fallback: without a CUDA device every compute entry point fails with
+ *     IS_ERR_CUDA.
+ */
+#ifndef IMAGESTITCH_H
+#define IMAGESTITCH_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define IS_VERSION_MAJOR 0
+#define IS_VERSION_MINOR 1
+
+typedef enum is_status {
+    IS_OK = 0,
+    IS_ERR_NO_MEM = -4,          /* cv::Error::StsNoMem */
+    IS_ERR_BAD_ARG = -5,         /* cv::Error::StsBadArg   ([SEAM]:749) */
+    IS_ERR_UNSUPPORTED = -213,   /* cv::Error::StsNotImplemented */
+    IS_ERR_ASSERT = -215,        /* cv::Error::StsAssert   ([WARP]:94-96, [SEAM]:133-134) */
+    IS_ERR_CUDA = -1000,         /* CUDA runtime / driver failure, or no device */
+    IS_ERR_INTERNAL = -1001
+} is_status;
+
+/* depth codes = OpenCV's */
+enum { IS_8U = 0, IS_16S = 3, IS_32S = 4, IS_32F = 5 };
+
+typedef struct is_mat {
+    void* data;
+    int rows, cols, channels, depth;
+    size_t step;      /* bytes per row */
+    int device;       /* -1: host memory, >= 0: CUDA device ordinal */
+} is_mat;
+
+typedef struct is_point { int x, y; } is_point;
+typedef struct is_size { int width, height; } is_size;
+typedef struct is_rect { int x, y, width, height; } is_rect;
+
+typedef enum is_projection { IS_PROJ_CYLINDRICAL = 0, IS_PROJ_SPHERICAL = 1 } is_projection;
+typedef enum is_interp { IS_INTER_NEAREST = 0, IS_INTER_LINEAR = 1 } is_interp;           /* cv::INTER_* */
+typedef enum is_border { IS_BORDER_CONSTANT = 0, IS_BORDER_REFLECT = 2 } is_border;       /* cv::BORDER_* */
+typedef enum is_seam_cost { IS_COST_COLOR = 0, IS_COST_COLOR_GRAD = 1 } is_seam_cost;     /* [SEAM]:71 */
+typedef enum is_weight_type { IS_WEIGHT_32F = 5, IS_WEIGHT_16S = 3 } is_weight_type;      /* CV_32F / CV_16S */
+
+typedef struct is_ctx is_ctx;
+typedef struct is_blender is_blender;
+
+/* ------------------------------------------------------------------ context */
+const char* is_version(void);
+const char* is_status_string(int status);
+int is_ctx_create(int device, is_ctx** out);
+int is_ctx_destroy(is_ctx* ctx);
+int is_ctx_synchronize(is_ctx* ctx);
+const char* is_ctx_last_error(const is_ctx* ctx);
+void* is_ctx_stream(is_ctx* ctx);                     /* cudaStream_t all work of this context runs on */
+int is_ctx_set_stream(is_ctx* ctx, void* stream);     /* adopt a caller-owned cudaStream_t (NULL: back to the context's own) */
+uint64_t is_ctx_kernel_launches(const is_ctx* ctx);   /* kernels of this library launched so far */
+int is_ctx_device(const is_ctx* ctx);
+
+/* ------------------------------------------------------------------ warp
+ * Replaces the free functions of [WARP] (== cv::detail::RotationWarper created by
+ * WarperCreator::create(scale), [BLEND]:99):
+ *   Rect  buildMaps(Size src_size, InputArray K, InputArray R, OutputArray xmap, OutputArray ymap)  [WARP]:122
+ *   Point warp(InputArray src, InputArray K, InputArray R, int interp, int border, OutputArray dst) [WARP]:145
+ * K and R are 3x3 row-major float (CV_32F is asserted at [WARP]:94-96).
+ */
+
+/* detectResultRoi [WARP]:64-88 -> top-left corner in panorama coordinates and the size of the
+ * destination the reference allocates (dst.create(roi.height + 1, roi.width + 1), [WARP]:150). */
+int is_warp_roi(is_ctx* ctx, int projection, is_size src_size, const float K[9], const float R[9],
+                float scale, is_point* dst_tl, is_size* dst_size);
+
+/* buildMaps [WARP]:122-144.  xmap / ymap: dst_size, 1 channel IS_32F, caller-allocated. */
+int is_build_maps(is_ctx* ctx, int projection, is_size src_size, const float K[9], const float R[9],
+                  float scale, is_mat* xmap, is_mat* ymap, is_rect* dst_roi);
+
+/* warp [WARP]:145-161 (buildMaps + cv::remap fused; no maps are materialised).  src: IS_8U, 1 or 3
+ * channels.  dst: caller-allocated, dst_size from is_warp_roi, same type as src. */
+int is_warp(is_ctx* ctx, int projection, const is_mat* src, const float K[9], const float R[9], float scale,
+            int interp, int border, is_mat* dst, is_point* dst_tl);
+
+/* The two warp calls every main() makes per image ([BLEND]:105,109): image with INTER_LINEAR +
+ * BORDER_REFLECT and an all-255 mask with INTER_NEAREST + BORDER_CONSTANT, in one pass over the
+ * destination.  dst: 3 channels IS_8U; dst_mask: 1 channel IS_8U. */
+int is_warp_with_mask(is_ctx* ctx, int projection, const is_mat* src, const float K[9], const float R[9],
+                      float scale, is_mat* dst, is_mat* dst_mask, is_point* dst_tl);
+
+/* ------------------------------------------------------------------ seam
+ * Replaces  void find(const std::vector<UMat>& src, const std::vector<Point>& corners,
+ *                     std::vector<UMat>& masks)                                        [SEAM]:87
+ * (== cv::detail::DpSeamFinder::find).  images: n mats, 3 channels, IS_32F or IS_8U (all the same);
+ * masks: n mats IS_8U, same sizes as the images ([SEAM]:133-134), modified in place.
+ * cost_fn: IS_COST_COLOR; IS_COST_COLOR_GRAD returns IS_ERR_UNSUPPORTED.
+ */
+int is_seam_dp_find(is_ctx* ctx, int n, const is_mat* images, const is_point* corners, is_mat* masks, int cost_fn);
+
+/* Same, additionally reporting every seam the DP estimated ([SEAM]:806-957) as int32 records
+ * [pair_i, pair_j, comp, isHorizontal, npoints, x0, y0, x1, y1, ...] (panorama coordinates) into the
+ * host array `trace` of capacity trace_cap; *trace_len receives the length needed. */
+int is_seam_dp_find_trace(is_ctx* ctx, int n, const is_mat* images, const is_point* corners, is_mat* masks,
+                          int cost_fn, int32_t* trace, size_t trace_cap, size_t* trace_len);
+
+/* computeCosts [SEAM]:733-803 for the component labelled `label` of a host/device label image
+ * (IS_32S, union frame of the pair, top-left union_tl in panorama coordinates) over `roi` (union-frame
+ * coordinates).  costV: roi.height x (roi.width + 1), costH: (roi.height + 1) x roi.width, IS_32F. */
+int is_seam_cost_maps(is_ctx* ctx, const is_mat* image1, const is_mat* image2, is_point tl1, is_point tl2,
+                      const is_mat* labels, is_point union_tl, int label, is_rect roi,
+                      is_mat* costV, is_mat* costH);
+
+/* ------------------------------------------------------------------ multi-band blend
+ * Replaces the blender calls of every main() ([SEAM]:1244-1252,1271,1280; == cv::detail::MultiBandBlender):
+ *   Blender::createDefault(MULTI_BAND) + setNumBands   -> is_blender_create
+ *   prepare(corners, sizes) / prepare(Rect)            -> is_blender_prepare / is_blender_prepare_roi
+ *   feed(InputArray img, InputArray mask, Point tl)    -> is_blender_feed
+ *   blend(InputOutputArray dst, InputOutputArray mask) -> is_blender_blend
+ */
+int is_blender_create(is_ctx* ctx, int num_bands, int weight_type, is_blender** out);
+int is_blender_destroy(is_blender* b);
+int is_blender_prepare(is_blender* b, int n, const is_point* corners, const is_size* sizes);
+int is_blender_prepare_roi(is_blender* b, is_rect dst_roi);
+int is_blender_num_bands(const is_blender* b);        /* after prepare: min(num_bands, ceil(log2(max side))) */
+int is_blender_dst_size(const is_blender* b, is_size* size);
+
+/* img: 3 channels IS_16S or IS_8U; mask: IS_8U, same size.  flags: IS_FEED_COPY keeps a private
+ * copy (OpenCV semantics); IS_FEED_BORROW uses device buffers in place -- they must stay valid and
+ * unchanged until is_blender_blend returns (host buffers are always copied). */
+enum { IS_FEED_COPY = 0, IS_FEED_BORROW = 1 };
+int is_blender_feed(is_blender* b, const is_mat* img, const is_mat* mask, is_point tl, int flags);
+
+/* dst: 3 channels IS_16S, dst_mask: IS_8U, both is_blender_dst_size, caller-allocated. */
+int is_blender_blend(is_blender* b, is_mat* dst, is_mat* dst_mask);
+
+/* ------------------------------------------------------------------ linear blend
+ * Replaces the hand-written pair blend of [BLEND]:141-717 (cost map, greedy seam, seam-guided linear
+ * weights, composite).  img1 / img2: 3 channels IS_32F; image 1 must be the left image.
+ * pano: 3 channels IS_32F of is_linear_blend_size; seam_x: host array of pano rows ints (may be NULL).
+ * Returns 1 (not an error) when the two images do not overlap ([BLEND]:182-183).
+ */
+int is_linear_blend_size(is_size size1, is_size size2, is_point tl1, is_point tl2, is_size* pano_size);
+int is_linear_blend_pair(is_ctx* ctx, const is_mat* img1, const is_mat* img2, is_point tl1, is_point tl2,
+                         is_mat* pano, int* seam_x);
+
+/* ------------------------------------------------------------------ composite pipeline
+ * The call sequence of every main(): detect -> match -> homography (host control flow, supplied by
+ * the caller as cameras or through the hooks below) -> warp -> seam -> blend.
+ */
+typedef struct is_camera { float K[9]; float R[9]; } is_camera;
+
+/* Host-side registration hooks mirroring (*finder)(img, features) [FEAT]:948, matcher(features,
+ * matches) [MATCH]:123 and estimator(features, matches, cameras) [CAM]:118.  They run on the host
+ * before the GPU stages; `estimate` must fill n cameras and the warp scale.  All may be NULL when
+ * cameras are passed to is_pipeline_run directly. */
+typedef struct is_registration_hooks {
+    void* user;
+    int (*detect)(void* user, int image_index, const is_mat* image);
+    int (*match)(void* user, int n_images);
+    int (*estimate)(void* user, int n_images, is_camera* cameras, float* scale);
+} is_registration_hooks;
+
+typedef enum is_seam_mode { IS_SEAM_NONE = 0, IS_SEAM_DP = 1 } is_seam_mode;
+
+typedef struct is_pipeline_config {
+    int projection;      /* is_projection */
+    int seam;            /* is_seam_mode */
+    int seam_cost;       /* is_seam_cost */
+    int num_bands;       /* MultiBandBlender::setNumBands, default 5 */
+    int weight_type;     /* is_weight_type */
+    float scale;         /* warper scale = cameras[0].focal ([BLEND]:99); ignored when hooks->estimate is set */
+} is_pipeline_config;
+
+typedef struct is_pipeline_plan_t {
+    is_rect pano_roi;    /* resultRoi(corners, sizes) */
+} is_pipeline_plan_t;
+
+/* Geometry only (host): corners[n], sizes[n] of the warped images and the panorama ROI. */
+int is_pipeline_plan(is_ctx* ctx, int n, const is_size* src_sizes, const is_camera* cameras,
+                     const is_pipeline_config* cfg, is_point* corners, is_size* sizes, is_rect* pano_roi);
+
+/* images: n source images, 3 channels IS_8U, host or device.  pano: 3 channels IS_16S, pano_mask:
+ * IS_8U, both of pano_roi size.  seam_masks (optional, may be NULL): n caller-allocated IS_8U mats of
+ * sizes[i] receiving the final seam masks. */
+int is_pipeline_run(is_ctx* ctx, int n, const is_mat* images, const is_camera* cameras,
+                    const is_registration_hooks* hooks, const is_pipeline_config* cfg,
+                    is_mat* pano, is_mat* pano_mask, is_mat* seam_masks);
+
+/* Per-stage device time (ms) of the last is_pipeline_run on this context: warp, seam, blend, total. */
+int is_pipeline_last_timings(is_ctx* ctx, float ms[4]);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* IMAGESTITCH_H */

@@ -1,0 +1,225 @@
+"""GPU parity tests: the CUDA path through the C ABI against the CPU oracle on the same inputs.
+
+Bars: bit-exact for ROI/corners, maps, warped images and masks, cost maps, seam point
+lists, seam masks, linear-blend seam indices and the CV_16S-weight multi-band blend; the CV_32F-weight
+blend is bit-exact against the oracle as well (same association order on both sides -- the tolerance
+max|d| <= 2 int16 units / >= 99 % exact applies to oracle-vs-OpenCV, tests/test_oracle_cv2.py).
+The linear blend's float panorama: |d| <= 1e-3 * 255.
+"""
+import numpy as np
+import pytest
+
+from helpers import blob_masks, random_camera, warped_set
+from imagestitch_b200 import stitching as S, synth
+
+pytestmark = pytest.mark.gpu
+
+
+def _eq(a, b, what):
+    a = np.asarray(a)
+    b = np.asarray(b)
+    assert a.shape == b.shape, f"{what}: shape {a.shape} vs {b.shape}"
+    if not np.array_equal(a, b):
+        bad = np.argwhere(a != b)
+        raise AssertionError(f"{what}: {len(bad)} of {a.size} differ, first at {bad[0].tolist()}: got {a[tuple(bad[0])]} want {b[tuple(bad[0])]}")
+
+
+@pytest.mark.parametrize("proj", [0, 1])
+def test_warp_roi_maps_image_mask(ctx, oracle, proj):
+    O = oracle
+    rng = np.random.default_rng(10 + proj)
+    for t in range(4):
+        w, h = int(rng.integers(200, 700)), int(rng.integers(150, 500))
+        K, R, scale = random_camera(rng, w, h)
+        img = rng.integers(0, 256, (h, w, 3), dtype=np.uint8)
+        wp = S.RotationWarper(ctx, proj, scale)
+        roi, oxm, oym = O.build_maps(proj, (w, h), K, R, scale, full_scan=True)   # the reference's full scan
+        (tlx, tly), (dw, dh) = wp.warp_roi((w, h), K, R)
+        assert (tlx, tly, tlx + dw - 1, tly + dh - 1) == roi
+        groi, xm, ym = wp.buildMaps((w, h), K, R)
+        assert groi == (roi[0], roi[1], roi[2] - roi[0], roi[3] - roi[1])
+        _eq(xm.view(np.uint32), oxm.view(np.uint32), "xmap bits")
+        _eq(ym.view(np.uint32), oym.view(np.uint32), "ymap bits")
+        for interp in (O.INTER_LINEAR, O.INTER_NEAREST):
+            for border in (O.BORDER_REFLECT, O.BORDER_CONSTANT):
+                tl, dst = wp.warp(img, K, R, interp, border)
+                assert tl == (roi[0], roi[1])
+                _eq(dst, O.remap(img, oxm, oym, interp, border), f"warp interp={interp} border={border}")
+        g = img[:, :, 1].copy()
+        _, dst1 = wp.warp(g, K, R, O.INTER_LINEAR, O.BORDER_REFLECT)
+        _eq(dst1, O.remap(g, oxm, oym, O.INTER_LINEAR, O.BORDER_REFLECT), "warp 8UC1")
+        tl, dimg, dmask = wp.warp_with_mask(img, K, R)
+        _eq(dimg, O.remap(img, oxm, oym, O.INTER_LINEAR, O.BORDER_REFLECT), "warp_with_mask image")
+        _eq(dmask, O.remap(np.full((h, w), 255, np.uint8), oxm, oym, O.INTER_NEAREST, O.BORDER_CONSTANT), "warp_with_mask mask")
+
+
+def test_warp_device_buffers(ctx, oracle):
+    import torch
+    O = oracle
+    rng = np.random.default_rng(5)
+    w, h = 640, 480
+    K, R, scale = random_camera(rng, w, h)
+    img = rng.integers(0, 256, (h, w, 3), dtype=np.uint8)
+    wp = S.RotationWarper(ctx, 0, scale)
+    timg = torch.from_numpy(img).cuda()
+    torch.cuda.synchronize()
+    tl, dimg, dmask = wp.warp_with_mask(timg, K, R)
+    ctx.synchronize()
+    otl, oimg = O.warp(0, img, K, R, scale, O.INTER_LINEAR, O.BORDER_REFLECT)
+    assert tl == otl
+    _eq(dimg.cpu().numpy(), oimg, "device warp")
+
+
+SEAM_CASES = [(2, 400, 300, 0.25, 1), (3, 320, 240, 0.3, 1), (4, 256, 200, 0.25, 1), (2, 300, 400, 0.5, 1), (3, 300, 200, 0.6, 1),
+              (4, 240, 180, 0.3, 2)]
+
+
+@pytest.mark.parametrize("case", SEAM_CASES)
+@pytest.mark.parametrize("as_float", [False, True])
+def test_dp_seam_masks_and_seams(ctx, oracle, case, as_float):
+    O = oracle
+    n, w, h, ov, grid_rows = case
+    corners, wi, wm = warped_set(O, n, w, h, overlap=ov, grid_rows=grid_rows)
+    imgs = [a.astype(np.float32) for a in wi] if as_float else wi
+    want, wtrace = O.dp_seam_find(imgs, corners, wm, want_trace=True)
+    got, gtrace = S.DpSeamFinder(ctx, "COLOR").find(imgs, corners, [m.copy() for m in wm], want_trace=True)
+    assert len(gtrace) == len(wtrace), f"number of seams {len(gtrace)} vs {len(wtrace)}"
+    for (gi, gj, gc, gh, gp), (oi, oj, oc, oh, op) in zip(gtrace, wtrace):
+        assert (gi, gj, gc, gh) == (oi, oj, oc, oh)
+        _eq(gp, op, f"seam points of pair ({gi},{gj})")
+    for k in range(n):
+        _eq(got[k], want[k], f"seam mask {k}")
+
+
+def test_dp_seam_irregular_masks(ctx, oracle):
+    """Holes and notches: many components, single-neighbour relabelling, unreachable seams."""
+    O = oracle
+    rng = np.random.default_rng(99)
+    for t in range(4):
+        corners, wi, wm = warped_set(O, 3, 220, 160, overlap=0.4)
+        holes = blob_masks(rng, [m.shape for m in wm], holes=4)
+        wm = [np.where(hm > 0, m, 0).astype(np.uint8) for m, hm in zip(wm, holes)]
+        want = O.dp_seam_find(wi, corners, wm)
+        got = S.DpSeamFinder(ctx, "COLOR").find(wi, corners, [m.copy() for m in wm])
+        for k in range(3):
+            _eq(got[k], want[k], f"irregular case {t} mask {k}")
+
+
+def test_dp_seam_edge_cases(ctx, oracle):
+    O = oracle
+    f = S.DpSeamFinder(ctx, "COLOR")
+    assert f.find([], [], []) == []                                    # [SEAM]:94-95
+    a = np.zeros((40, 50, 3), np.uint8)
+    m = [np.full((40, 50), 255, np.uint8), np.full((40, 50), 255, np.uint8)]
+    got = f.find([a, a], [(0, 0), (100, 0)], [x.copy() for x in m])    # disjoint ROIs: [SEAM]:142-143
+    _eq(got[0], m[0], "disjoint 0")
+    _eq(got[1], m[1], "disjoint 1")
+    # identical placement (full overlap), flat images: all costs tie -> exercises the (cost, step) tie-break
+    want = O.dp_seam_find([a, a], [(0, 0), (20, 7)], m)
+    got = f.find([a, a], [(0, 0), (20, 7)], [x.copy() for x in m])
+    _eq(got[0], want[0], "flat 0")
+    _eq(got[1], want[1], "flat 1")
+    with pytest.raises(Exception):
+        S.DpSeamFinder(ctx, "COLOR_GRAD").find([a, a], [(0, 0), (20, 7)], [x.copy() for x in m])
+
+
+def test_seam_cost_maps(ctx, oracle):
+    O = oracle
+    rng = np.random.default_rng(3)
+    h1, w1, h2, w2 = 60, 80, 70, 64
+    tl1, tl2 = (5, -3), (40, 4)
+    utl = (min(tl1[0], tl2[0]), min(tl1[1], tl2[1]))
+    ubr = (max(tl1[0] + w1, tl2[0] + w2), max(tl1[1] + h1, tl2[1] + h2))
+    W, H = ubr[0] - utl[0], ubr[1] - utl[1]
+    labels = np.zeros((H, W), np.int32)
+    ix0, iy0 = tl2[0] - utl[0], tl2[1] - utl[1]
+    ix1, iy1 = tl1[0] + w1 - utl[0], tl1[1] + h1 - utl[1]
+    labels[iy0:iy1, ix0:ix1] = 2
+    labels[iy0 + 5:iy0 + 9, ix0 + 3:ix0 + 10] = 1          # a hole of another label inside the component
+    roi = (ix0, iy0, ix1 - ix0, iy1 - iy0)
+    for dt in (np.uint8, np.float32):
+        a = rng.integers(0, 256, (h1, w1, 3)).astype(dt)
+        b = rng.integers(0, 256, (h2, w2, 3)).astype(dt)
+        if dt == np.float32:
+            a += rng.uniform(-0.5, 0.5, a.shape).astype(np.float32)
+            b += rng.uniform(-0.5, 0.5, b.shape).astype(np.float32)
+        wv, wh = O.seam_costs(a, b, tl1, tl2, labels, utl, 2, roi)
+        gv, gh = S.DpSeamFinder(ctx, "COLOR").cost_maps(a, b, tl1, tl2, labels, utl, 2, roi)
+        _eq(gv.view(np.uint32), wv.view(np.uint32), f"costV {dt.__name__}")
+        _eq(gh.view(np.uint32), wh.view(np.uint32), f"costH {dt.__name__}")
+
+
+BLEND_CASES = [(2, 400, 300, 0.25, 5), (3, 320, 240, 0.3, 5), (4, 256, 200, 0.25, 3), (2, 300, 400, 0.5, 6), (2, 200, 150, 0.3, 0)]
+
+
+@pytest.mark.parametrize("case", BLEND_CASES)
+@pytest.mark.parametrize("wt", [S.WEIGHT_32F, S.WEIGHT_16S])
+@pytest.mark.parametrize("u8", [False, True])
+def test_multiband_blend(ctx, oracle, case, wt, u8):
+    O = oracle
+    n, w, h, ov, nb = case
+    corners, wi, wm = warped_set(O, n, w, h, overlap=ov)
+    sm = O.dp_seam_find(wi, corners, wm)
+    sizes = [(a.shape[1], a.shape[0]) for a in wi]
+    for masks in (sm, wm):
+        ob = O.MultiBandBlender(nb, wt)
+        ob.prepare(O.result_roi(corners, sizes))
+        gb = S.MultiBandBlender(ctx, 0, nb, wt)
+        gb.prepare(corners, sizes)
+        for i in range(n):
+            ob.feed(wi[i].astype(np.int16), masks[i], corners[i])
+            gb.feed(wi[i] if u8 else wi[i].astype(np.int16), masks[i], corners[i])
+        assert gb.numBands() == ob.num_bands()
+        want, wmask = ob.blend()
+        got, gmask = gb.blend()
+        _eq(gmask, wmask, "blend mask")
+        _eq(got, want, f"blend nb={nb} wt={wt}")
+
+
+def test_linear_blend_pair(ctx, oracle):
+    O = oracle
+    for (w, h, ov) in ((400, 300, 0.25), (320, 260, 0.4)):
+        corners, wi, _ = warped_set(O, 2, w, h, overlap=ov)
+        a, b = wi[0].astype(np.float32), wi[1].astype(np.float32)
+        for tl2 in (corners[1], (corners[1][0], corners[0][1]), (corners[1][0], corners[0][1] + 6), (corners[1][0], corners[0][1] - 5)):
+            want = O.lin_blend(a, b, corners[0], tl2)
+            got = S.linear_blend_pair(ctx, a, b, corners[0], tl2)
+            assert (want is None) == (got is None)
+            if want is None:
+                continue
+            _eq(got[1], want[1], f"greedy seam indices tl2={tl2}")
+            assert got[0].shape == want[0].shape
+            d = np.abs(got[0] - want[0])
+            assert np.nanmax(d) <= 1e-3 * 255, f"linear blend pano max diff {np.nanmax(d)}"
+            assert np.array_equal(np.isnan(got[0]), np.isnan(want[0]))
+    assert S.linear_blend_pair(ctx, a, b, (0, 0), (5000, 0)) is None     # [BLEND]:182-183
+
+
+@pytest.mark.parametrize("cfg", [(3, 384, 288, 1.2, 5, S.WEIGHT_32F, 0), (2, 512, 384, 1.2, 5, S.WEIGHT_16S, 0), (4, 300, 220, 1.5, 4, S.WEIGHT_32F, 1)])
+def test_pipeline_end_to_end(ctx, oracle, cfg):
+    O = oracle
+    n, w, h, fw, nb, wt, proj = cfg
+    imgs, Ks, Rs, scale = synth.make_panorama_inputs(n, w, h, fw, 0.25)
+    want = O.pipeline_run(proj, imgs, Ks, Rs, scale, seam=True, num_bands=nb, weight_type=wt, want_intermediates=True)
+    st = S.Stitcher(ctx, proj, "dp", nb, wt)
+    got = st.stitch(imgs, Ks, Rs, scale, want_seam_masks=True)
+    assert got["roi"] == want["roi"]
+    assert [tuple(c) for c in got["corners"]] == [tuple(int(v) for v in c) for c in want["corners"]]
+    for k in range(n):
+        _eq(got["seam_masks"][k], want["masks"][k], f"pipeline seam mask {k}")
+    _eq(got["pano_mask"], want["pano_mask"], "pano mask")
+    _eq(got["pano"], want["pano"], "pano")
+    assert ctx.kernel_launches > 0
+
+
+def test_pipeline_device_resident(ctx, oracle):
+    import torch
+    O = oracle
+    imgs, Ks, Rs, scale = synth.make_panorama_inputs(3, 384, 288, 1.2, 0.25)
+    want = O.pipeline_run(0, imgs, Ks, Rs, scale, seam=True, num_bands=5, weight_type=O.WEIGHT_32F)
+    timgs = [torch.from_numpy(a).cuda() for a in imgs]
+    torch.cuda.synchronize()
+    got = S.Stitcher(ctx, 0, "dp", 5, S.WEIGHT_32F).stitch(timgs, Ks, Rs, scale)
+    ctx.synchronize()
+    _eq(got["pano"].cpu().numpy(), want["pano"], "device-resident pano")
+    _eq(got["pano_mask"].cpu().numpy(), want["pano_mask"], "device-resident pano mask")
