@@ -1,0 +1,151 @@
+"""Generates the golden fixtures under tests/golden/ from OpenCV (python cv2 4.13.0), the library whose
+arithmetic the reference delegates to on this path (remap, DpSeamFinder, MultiBandBlender, pyrDown/pyrUp;
+reference pin: OpenCV 3.4.2, un-vendored).  The reference itself ships no golden vectors.
+
+    python tests/golden/make_golden.py
+
+Inputs are generated with numpy / imagestitch_b200.synth only; every *_cv entry is an OpenCV output.
+The oracle is NOT used here.
+"""
+import os
+import sys
+
+import cv2
+import numpy as np
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, os.path.dirname(os.path.dirname(HERE)))
+sys.path.insert(0, os.path.dirname(HERE))
+from helpers import blob_masks, random_camera  # noqa: E402
+from imagestitch_b200 import synth  # noqa: E402
+
+cv2.setNumThreads(1)
+cv2.ocl.setUseOpenCL(False)
+
+
+def warp_cases():
+    rng = np.random.default_rng(2026)
+    out = {}
+    k = 0
+    for name in ("cylindrical", "spherical"):
+        for _ in range(3):
+            w, h = int(rng.integers(60, 120)), int(rng.integers(50, 100))
+            K, R, scale = random_camera(rng, w, h)
+            img = rng.integers(0, 256, (h, w, 3), dtype=np.uint8)
+            wp = cv2.PyRotationWarper(name, scale)
+            roi, xm, ym = wp.buildMaps((w, h), K, R)
+            tl, wi = wp.warp(img, K, R, cv2.INTER_LINEAR, cv2.BORDER_REFLECT)
+            _, wm = wp.warp(np.full((h, w), 255, np.uint8), K, R, cv2.INTER_NEAREST, cv2.BORDER_CONSTANT)
+            p = f"c{k}_"
+            out.update({p + "proj": np.int32(0 if name == "cylindrical" else 1), p + "K": K, p + "R": R, p + "scale": np.float32(scale),
+                        p + "img": img, p + "roi_cv": np.asarray(roi, np.int32), p + "tl_cv": np.asarray(tl, np.int32),
+                        p + "xmap_cv": xm, p + "ymap_cv": ym, p + "warped_cv": wi, p + "mask_cv": wm})
+            k += 1
+    out["n"] = np.int32(k)
+    np.savez_compressed(os.path.join(HERE, "warp_cases.npz"), **out)
+
+
+def remap_cases():
+    rng = np.random.default_rng(7)
+    out = {}
+    src = rng.integers(0, 256, (40, 50, 3), dtype=np.uint8)
+    xm = rng.uniform(-120, 170, (48, 64)).astype(np.float32)
+    ym = rng.uniform(-90, 130, (48, 64)).astype(np.float32)
+    xm[0, :8] = -1
+    ym[0, :8] = -1
+    xm[1, :16] = np.arange(16, dtype=np.float32)          # exact integer coordinates: the (0,0) weight entry
+    ym[1, :16] = np.arange(16, dtype=np.float32) + 2
+    out.update(src=src, xmap=xm, ymap=ym)
+    for iname, ci in (("linear", cv2.INTER_LINEAR), ("nearest", cv2.INTER_NEAREST)):
+        for bname, cb in (("reflect", cv2.BORDER_REFLECT), ("constant", cv2.BORDER_CONSTANT)):
+            out[f"{iname}_{bname}_c3_cv"] = cv2.remap(src, xm, ym, ci, borderMode=cb)
+            out[f"{iname}_{bname}_c1_cv"] = cv2.remap(src[:, :, 0].copy(), xm, ym, ci, borderMode=cb)
+    np.savez_compressed(os.path.join(HERE, "remap_cases.npz"), **out)
+
+
+def _cv_warped_set(n, w, h, ov, grid_rows=1):
+    imgs, Ks, Rs, scale = synth.make_panorama_inputs(n, w, h, 1.2, ov, grid_rows=grid_rows)
+    wp = cv2.PyRotationWarper("cylindrical", scale)
+    corners, wi, wm = [], [], []
+    for i in range(n):
+        tl, a = wp.warp(imgs[i], Ks[i], Rs[i], cv2.INTER_LINEAR, cv2.BORDER_REFLECT)
+        _, m = wp.warp(np.full(imgs[i].shape[:2], 255, np.uint8), Ks[i], Rs[i], cv2.INTER_NEAREST, cv2.BORDER_CONSTANT)
+        corners.append(tuple(tl))
+        wi.append(a)
+        wm.append(m)
+    return corners, wi, wm
+
+
+def _cv_seam_pairwise(wi, corners, masks):
+    """cv2.detail_DpSeamFinder driven one pair at a time in the reference's order ([SEAM]:100-111)."""
+    n = len(wi)
+    masks = [m.copy() for m in masks]
+    pairs = [(i, j) for i in range(n) for j in range(i + 1, n)][::-1]
+    for (i, j) in pairs:
+        sf = cv2.detail_DpSeamFinder("COLOR")
+        res = sf.find([cv2.UMat(wi[i].astype(np.float32)), cv2.UMat(wi[j].astype(np.float32))], [corners[i], corners[j]],
+                      [cv2.UMat(masks[i]), cv2.UMat(masks[j])])
+        masks[i], masks[j] = res[0].get(), res[1].get()
+    return masks
+
+
+def seam_blend_cases():
+    rng = np.random.default_rng(11)
+    out = {}
+    cases = [(2, 160, 120, 0.25, 1, False), (3, 128, 96, 0.35, 1, False), (3, 128, 96, 0.4, 1, True), (4, 112, 84, 0.3, 2, False)]
+    for k, (n, w, h, ov, rows, irregular) in enumerate(cases):
+        corners, wi, wm = _cv_warped_set(n, w, h, ov, rows)
+        if irregular:
+            holes = blob_masks(rng, [m.shape for m in wm], holes=4)
+            wm = [np.where(hm > 0, m, 0).astype(np.uint8) for m, hm in zip(wm, holes)]
+        sm = _cv_seam_pairwise(wi, corners, wm)
+        p = f"s{k}_"
+        out[p + "n"] = np.int32(n)
+        out[p + "corners"] = np.asarray(corners, np.int32)
+        for i in range(n):
+            out[p + f"img{i}"] = wi[i]
+            out[p + f"mask{i}"] = wm[i]
+            out[p + f"seam_mask{i}_cv"] = sm[i]
+        sizes = [(a.shape[1], a.shape[0]) for a in wi]
+        tlx = min(c[0] for c in corners); tly = min(c[1] for c in corners)
+        brx = max(c[0] + s[0] for c, s in zip(corners, sizes)); bry = max(c[1] + s[1] for c, s in zip(corners, sizes))
+        roi = (tlx, tly, brx - tlx, bry - tly)
+        for nb in (3, 5):
+            for wname, cwt in (("f32", cv2.CV_32F), ("s16", cv2.CV_16S)):
+                mb = cv2.detail_MultiBandBlender(0, nb, cwt)
+                mb.prepare(roi)
+                for i in range(n):
+                    mb.feed(wi[i].astype(np.int16), sm[i], corners[i])
+                d, dm = mb.blend(None, None)
+                out[p + f"blend_nb{nb}_{wname}_cv"] = d
+                out[p + f"blend_nb{nb}_{wname}_mask_cv"] = dm
+                out[p + f"blend_nb{nb}_numbands_cv"] = np.int32(mb.numBands())
+    out["n_cases"] = np.int32(len(cases))
+    np.savez_compressed(os.path.join(HERE, "seam_blend_cases.npz"), **out)
+
+
+def pyr_cases():
+    rng = np.random.default_rng(5)
+    out = {}
+    for k, (h, w) in enumerate(((17, 23), (32, 48), (5, 9), (41, 6))):
+        a = rng.integers(-3000, 3000, (h, w, 3)).astype(np.int16)
+        out[f"p{k}_src"] = a
+        out[f"p{k}_down_cv"] = cv2.pyrDown(a)
+        out[f"p{k}_up_cv"] = cv2.pyrUp(a, dstsize=(2 * w, 2 * h))
+        out[f"p{k}_up_odd_cv"] = cv2.pyrUp(a, dstsize=(2 * w - 1, 2 * h - 1))
+        f = rng.uniform(0, 1, (h, w)).astype(np.float32)
+        out[f"p{k}_f32"] = f
+        out[f"p{k}_f32_down_cv"] = cv2.pyrDown(f)
+    out["n"] = np.int32(4)
+    np.savez_compressed(os.path.join(HERE, "pyr_cases.npz"), **out)
+
+
+if __name__ == "__main__":
+    warp_cases()
+    remap_cases()
+    seam_blend_cases()
+    pyr_cases()
+    for f in sorted(os.listdir(HERE)):
+        if f.endswith(".npz"):
+            print(f, os.path.getsize(os.path.join(HERE, f)))
+    print("cv2", cv2.__version__)

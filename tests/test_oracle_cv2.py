@@ -1,0 +1,80 @@
+"""Live cross-check of the oracle against OpenCV (python cv2) on fresh random cases; skipped when cv2 is
+not importable.  Complements tests/test_oracle_golden.py, which needs neither cv2 nor a GPU."""
+import numpy as np
+import pytest
+
+from helpers import blob_masks, random_camera, warped_set
+
+cv2 = pytest.importorskip("cv2")
+
+
+def test_warp_vs_cv2(oracle):
+    O = oracle
+    rng = np.random.default_rng(1234)
+    for proj, name in ((0, "cylindrical"), (1, "spherical")):
+        for _ in range(4):
+            w, h = int(rng.integers(120, 360)), int(rng.integers(100, 300))
+            K, R, scale = random_camera(rng, w, h)
+            wp = cv2.PyRotationWarper(name, scale)
+            roi, xm, ym = wp.buildMaps((w, h), K, R)
+            oroi, oxm, oym = O.build_maps(proj, (w, h), K, R, scale, full_scan=True)
+            assert (roi[0], roi[1], roi[0] + roi[2], roi[1] + roi[3]) == oroi
+            assert O.detect_roi(proj, (w, h), K, R, scale, full_scan=False) == oroi
+            assert np.array_equal(xm.view(np.uint32), oxm.view(np.uint32)) and np.array_equal(ym.view(np.uint32), oym.view(np.uint32))
+            img = rng.integers(0, 256, (h, w, 3), dtype=np.uint8)
+            tl, wi = wp.warp(img, K, R, cv2.INTER_LINEAR, cv2.BORDER_REFLECT)
+            otl, owi = O.warp(proj, img, K, R, scale, O.INTER_LINEAR, O.BORDER_REFLECT)
+            assert tuple(tl) == otl and np.array_equal(wi, owi)
+
+
+def test_remap_vs_cv2(oracle):
+    O = oracle
+    rng = np.random.default_rng(4321)
+    img = rng.integers(0, 256, (60, 80, 3), dtype=np.uint8)
+    xm = rng.uniform(-200, 300, (100, 120)).astype(np.float32)
+    ym = rng.uniform(-150, 250, (100, 120)).astype(np.float32)
+    for interp, ci in ((O.INTER_LINEAR, cv2.INTER_LINEAR), (O.INTER_NEAREST, cv2.INTER_NEAREST)):
+        for border, cb in ((O.BORDER_REFLECT, cv2.BORDER_REFLECT), (O.BORDER_CONSTANT, cv2.BORDER_CONSTANT)):
+            assert np.array_equal(cv2.remap(img, xm, ym, ci, borderMode=cb), O.remap(img, xm, ym, interp, border))
+
+
+def _cv_pairwise(wi, corners, masks):
+    n = len(wi)
+    masks = [m.copy() for m in masks]
+    for (i, j) in [(i, j) for i in range(n) for j in range(i + 1, n)][::-1]:      # [SEAM]:100-111
+        res = cv2.detail_DpSeamFinder("COLOR").find([cv2.UMat(wi[i].astype(np.float32)), cv2.UMat(wi[j].astype(np.float32))],
+                                                    [corners[i], corners[j]], [cv2.UMat(masks[i]), cv2.UMat(masks[j])])
+        masks[i], masks[j] = res[0].get(), res[1].get()
+    return masks
+
+
+@pytest.mark.parametrize("case", [(2, 260, 200, 0.25, 1, False), (3, 200, 150, 0.6, 1, False), (4, 160, 120, 0.3, 2, False), (3, 180, 130, 0.4, 1, True)])
+def test_seam_and_blend_vs_cv2(oracle, case):
+    O = oracle
+    n, w, h, ov, rows, irregular = case
+    corners, wi, wm = warped_set(O, n, w, h, overlap=ov, grid_rows=rows)
+    if irregular:
+        holes = blob_masks(np.random.default_rng(8), [m.shape for m in wm], holes=4)
+        wm = [np.where(hm > 0, m, 0).astype(np.uint8) for m, hm in zip(wm, holes)]
+    want = _cv_pairwise(wi, corners, wm)
+    got = O.dp_seam_find(wi, corners, wm)
+    for i in range(n):
+        assert np.array_equal(got[i], want[i])
+    sizes = [(a.shape[1], a.shape[0]) for a in wi]
+    roi = O.result_roi(corners, sizes)
+    for wt, cwt in ((O.WEIGHT_16S, cv2.CV_16S), (O.WEIGHT_32F, cv2.CV_32F)):
+        mb = cv2.detail_MultiBandBlender(0, 5, cwt)
+        mb.prepare(roi)
+        ob = O.MultiBandBlender(5, wt)
+        ob.prepare(roi)
+        for i in range(n):
+            mb.feed(wi[i].astype(np.int16), got[i], corners[i])
+            ob.feed(wi[i].astype(np.int16), got[i], corners[i])
+        cd, cm = mb.blend(None, None)
+        od, om = ob.blend()
+        assert np.array_equal(cm, om)
+        if wt == O.WEIGHT_16S:
+            assert np.array_equal(cd, od)
+        else:
+            d = np.abs(cd.astype(np.int32) - od.astype(np.int32))
+            assert d.max() <= 2 and (d == 0).mean() >= 0.99
