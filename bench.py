@@ -1,0 +1,361 @@
+#!/usr/bin/env python
+"""bench.py -- stitched megapixels/s of the composite path (warp -> DP seam -> 5-band blend).
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference] [--workload c2|c1|c3|tiny]
+
+One "step" = one pass of the whole hot path over one synthetic panorama (BASELINE.json configs[1] at N=1:
+6 x (4000 x 6000) RGB strip, cylindrical warp, DP seam masks, multi-band blend with 5 bands).
+
+  value     input megapixels / s with the sources already resident in HBM when the timed region starts and
+            the panorama left in HBM (CUDA events on the stream the kernels run on, max over ranks)
+  e2e       the same metric through the C ABI with HOST buffers (pinned): H2D of the sources and D2H of the
+            panorama + mask inside the timed region
+  roofline  the dominant kernel of the step: algorithmic bytes per launch / CUDA-event duration per launch
+            (per-launch events recorded by the library in a second timed region of the same K steps)
+  cpu_baseline   the oracle's CPU restatement of the same path on the host cores, bounded sample
+
+--impl reference times the CPU port (oracle/, all host threads) on the same workload definition; the
+reference's own sources cannot be compiled here (OpenCV C++ headers/libs absent), see DESIGN.md.
+"""
+from __future__ import annotations
+
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+WORKLOADS = {
+    # name: (n_images, rows, cols, f_over_w, overlap, grid_rows, description)
+    "c2": (6, 4000, 6000, 1.2, 0.25, 1, "6x(4000x6000) RGB strip, cylindrical warp + DP seam masks + multi-band blend (5 bands)"),
+    "c3": (12, 4000, 6000, 1.5, 0.25, 1, "12x(4000x6000) RGB strip, cylindrical warp + DP seam + multi-band blend (5 bands)"),
+    "c1": (2, 768, 1024, 1.2, 0.25, 1, "2x(768x1024) RGB pair, cylindrical warp + DP seam + multi-band blend (5 bands)"),
+    "tiny": (3, 384, 512, 1.2, 0.25, 1, "3x(384x512) debug strip"),
+}
+NUM_BANDS = 5
+L2_BYTES = 126 * 1024 * 1024
+
+
+class ClockSampler:
+    """nvidia-smi clocks / throttle reasons sampled every 200 ms while the timed regions run."""
+
+    Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,clocks_event_reasons.hw_slowdown,"
+         "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, gpu_index):
+        self.gpu = gpu_index
+        self.rows = []
+        self.proc = None
+        self.thread = None
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", f"--id={self.gpu}", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits", "-lms", "200"],
+                                         stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+        except Exception:
+            self.proc = None
+            return
+        self.thread = threading.Thread(target=self._pump, daemon=True)
+        self.thread.start()
+
+    def _pump(self):
+        for line in self.proc.stdout:
+            self.rows.append((time.perf_counter(), line.strip()))
+
+    def stop(self):
+        if self.proc:
+            self.proc.terminate()            # the exact process we started
+            try:
+                self.proc.wait(timeout=5)
+            except Exception:
+                pass
+
+    def summary(self, windows):
+        sm, smax, reasons = [], [], set()
+        for t, line in self.rows:
+            if not any(a <= t <= b for a, b in windows):
+                continue
+            f = [x.strip() for x in line.split(",")]
+            if len(f) < 9:
+                continue
+            try:
+                sm.append(float(f[1]))
+                smax.append(float(f[2]))
+            except ValueError:
+                continue
+            for name, v in zip(("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"), f[5:9]):
+                if v.lower().startswith("active"):
+                    reasons.add(name)
+        if not sm:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": [], "samples": 0}
+        sm.sort()
+        return {"sm_mhz": sm[len(sm) // 2], "sm_max_mhz": max(smax), "reasons": sorted(reasons), "samples": len(sm)}
+
+
+def algorithmic_bytes(n, rows, cols, sizes, roi):
+    """compulsory traffic of the path, implementation independent."""
+    src = n * 3 * rows * cols
+    area = sum(w * h for (w, h) in sizes)
+    pano = roi[2] * roi[3]
+    return {"warp": src + 4 * area,                    # u8 source read, u8x3 warped + u8 mask written
+            "warp_blend_fused": src + area + 7 * pano,  # B_warp+blend: source + seam mask read, s16x3 pano + u8 mask written
+            "blend_level0": 4 * area + 7 * pano,       # warped u8x3 + mask read once, pano + mask written once
+            "pyrdown_level0": 4 * area + (6 + 4) * area // 4}
+
+
+def cpu_port_run(workload, threads, sample_rows=None, n_sample=2, steps=1, warmup=0):
+    """The oracle's CPU restatement of the path on a bounded sample: n_sample neighbouring images (full
+    width, sample_rows rows).  Returns (MP/s, description, seconds per step, per-stage seconds)."""
+    import numpy as np
+
+    import oracle as O
+    from imagestitch_b200 import synth
+    n, rows, cols, fw, ov, grid_rows, _ = WORKLOADS[workload]
+    rows_s = min(rows, sample_rows or rows)
+    n_s = min(n, n_sample)
+    Ks, Rs, scale = synth.strip_cameras(n, cols, rows_s, fw * 1.0, ov, grid_rows=grid_rows)
+    # keep the focal length of the full workload: f = f_over_w * cols
+    imgs = [synth.make_image(i, cols, rows_s, Ks[i], Rs[i], device="cpu").numpy() for i in range(n_s)]
+    O.set_threads(threads)
+    best = None
+    stages = None
+    for it in range(warmup + steps):
+        t0 = time.perf_counter()
+        r = O.pipeline_run(O.PROJ_CYLINDRICAL, imgs, Ks[:n_s], Rs[:n_s], scale, seam=True, num_bands=NUM_BANDS, weight_type=O.WEIGHT_32F)
+        dt = time.perf_counter() - t0
+        if it >= warmup and (best is None or dt < best):
+            best, stages = dt, [float(v) for v in r["seconds"]]
+    mp = n_s * rows_s * cols / 1e6
+    desc = f"{n_s} neighbouring images of the workload, {rows_s}x{cols} each (warp + DP seam + {NUM_BANDS}-band blend), {threads} OpenMP threads, best of {steps}"
+    return mp / best, desc, best, stages
+
+
+def run_reference(args):
+    """--impl reference: the CPU port of the reference path, all host threads, bounded sample per step."""
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return 0
+    import oracle as O
+    O.build()
+    threads = os.cpu_count() or 1
+    n, rows, cols, fw, ov, grid_rows, desc = WORKLOADS[args.workload]
+    # size the sample so that (steps + warmup) steps stay within a few minutes: probe at 1/8 of the rows
+    probe_rows = max(64, rows // 8)
+    v, _, dt, _ = cpu_port_run(args.workload, threads, sample_rows=probe_rows)
+    budget = 150.0 / max(1, args.steps + args.warmup)
+    rows_s = int(min(rows, max(probe_rows, probe_rows * budget / max(dt, 1e-3))))
+    rows_s -= rows_s % 32
+    rows_s = max(rows_s, 64)
+    import numpy as np
+    from imagestitch_b200 import synth
+    n_s = min(n, 2)
+    Ks, Rs, scale = synth.strip_cameras(n, cols, rows_s, fw, ov, grid_rows=grid_rows)
+    imgs = [synth.make_image(i, cols, rows_s, Ks[i], Rs[i], device="cpu").numpy() for i in range(n_s)]
+    O.set_threads(threads)
+    times = []
+    for it in range(args.warmup + args.steps):
+        t0 = time.perf_counter()
+        O.pipeline_run(O.PROJ_CYLINDRICAL, imgs, Ks[:n_s], Rs[:n_s], scale, seam=True, num_bands=NUM_BANDS, weight_type=O.WEIGHT_32F)
+        if it >= args.warmup:
+            times.append(time.perf_counter() - t0)
+    ms = 1e3 * sum(times) / len(times)
+    mp = n_s * rows_s * cols / 1e6
+    value = mp / (ms / 1e3)
+    sample = f"{n_s} neighbouring images of the workload at {rows_s}x{cols} per step (bounded sample), {threads} OpenMP threads"
+    line = {"impl": "reference", "metric": "stitched_megapixels_per_sec", "value": value, "unit": "MP/s", "n_gpus": args.gpus, "steps": args.steps,
+            "warmup": args.warmup, "ms_per_step": ms, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "s16",
+            "data": "synthetic", "config": {"workload": desc, "sample": sample},
+            "cpu_baseline": {"value": value, "unit": "MP/s", "cores": threads, "kind": "port", "sample": sample},
+            "e2e": {"value": value, "unit": "MP/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
+    print(json.dumps(line), flush=True)
+    return 0
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=10)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--workload", default="c2", choices=sorted(WORKLOADS))
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--kernel-report", default=None, help="write the per-kernel timing table (JSON) to this file")
+    args = ap.parse_args()
+    args.warmup = max(args.warmup, 0)
+    if args.impl == "reference":
+        return run_reference(args)
+
+    import numpy as np
+    import torch
+
+    from imagestitch_b200 import build as B, stitching as S, synth
+
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py needs a CUDA device (there is no CPU fallback)")
+    torch.cuda.set_device(local_rank)
+    dist = None
+    if world > 1:
+        import torch.distributed as dist
+        os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
+        dist.init_process_group("nccl", rank=rank, world_size=world, device_id=torch.device("cuda", local_rank))
+    if rank == 0:
+        B.build()
+    if dist:
+        dist.barrier()
+
+    n, rows, cols, fw, ov, grid_rows, desc = WORKLOADS[args.workload]
+    dev = f"cuda:{local_rank}"
+    # weak scaling: every rank stitches its own strip of n images (the cameras of rank r continue the strip)
+    Ks_all, Rs_all, scale = synth.strip_cameras(n * world, cols, rows, fw, ov, grid_rows=grid_rows)
+    idx = list(range(rank * n, rank * n + n))
+    Ks, Rs = Ks_all[idx], Rs_all[idx]
+    imgs_dev = [synth.make_image(i, cols, rows, Ks_all[i], Rs_all[i], device=dev) for i in idx]
+    torch.cuda.synchronize()
+
+    ctx = S.Context(local_rank, use_torch_stream=True)     # kernels run on torch's current stream -> torch events see them
+    st = S.Stitcher(ctx, "cylindrical", "dp", NUM_BANDS, S.WEIGHT_32F)
+    corners, sizes, roi = st.plan([(cols, rows)] * n, Ks, Rs, scale)
+    pano_dev = torch.empty((roi[3], roi[2], 3), dtype=torch.int16, device=dev)
+    pmask_dev = torch.empty((roi[3], roi[2]), dtype=torch.uint8, device=dev)
+    in_mp = n * rows * cols / 1e6
+
+    def barrier():
+        if dist:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    def step_device():
+        st.stitch(imgs_dev, Ks, Rs, scale, out=(pano_dev, pmask_dev))
+
+    sampler = ClockSampler(local_rank) if rank == 0 else None
+    if sampler:
+        sampler.start()
+    windows = []
+
+    def timed(fn, steps):
+        barrier()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        t0 = time.perf_counter()
+        l0 = ctx.kernel_launches
+        e0.record()
+        for _ in range(steps):
+            fn()
+        e1.record()
+        barrier()
+        windows.append((t0, time.perf_counter()))
+        ms = e0.elapsed_time(e1) / steps
+        launches = (ctx.kernel_launches - l0) // steps
+        if dist:
+            t = torch.tensor([ms], device=dev)
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+            ms = float(t.item())
+        return ms, launches
+
+    for _ in range(max(args.warmup, 3)):
+        step_device()
+    ms_dev, launches = timed(step_device, args.steps)
+    stage_ms = dict(st.timings_ms)
+
+    # second timed region with per-launch events for the roofline figure
+    ctx.kernel_timing(True)
+    ctx.kernel_timing_report()
+    ms_dev_ev, _ = timed(step_device, args.steps)
+    ktable = ctx.kernel_timing_report()
+    ctx.kernel_timing(False)
+
+    # end to end through the C ABI with pinned host buffers
+    imgs_pin = [torch.empty((rows, cols, 3), dtype=torch.uint8, pin_memory=True) for _ in range(n)]
+    for p, d in zip(imgs_pin, imgs_dev):
+        p.copy_(d)
+    pano_pin = torch.empty((roi[3], roi[2], 3), dtype=torch.int16, pin_memory=True)
+    pmask_pin = torch.empty((roi[3], roi[2]), dtype=torch.uint8, pin_memory=True)
+    imgs_host = [p.numpy() for p in imgs_pin]
+    out_host = (pano_pin.numpy(), pmask_pin.numpy())
+    torch.cuda.synchronize()
+
+    def step_host():
+        st.stitch(imgs_host, Ks, Rs, scale, out=out_host)
+
+    step_host()
+    ms_e2e, _ = timed(step_host, max(1, min(args.steps, 5)))
+    # the device-resident and the host path must produce the same panorama
+    same = bool(torch.equal(pano_dev.cpu(), pano_pin)) and bool(torch.equal(pmask_dev.cpu(), pmask_pin))
+    if sampler:
+        sampler.stop()
+
+    if rank != 0:
+        if dist:
+            dist.destroy_process_group()
+        return 0
+
+    alg = algorithmic_bytes(n, rows, cols, sizes, roi)
+    peaks = {}
+    try:
+        peaks = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))
+    except Exception:
+        pass
+    peak = float(peaks.get("hbm_gbs", 6650.0))
+    peak_src = "measured (MEASURED_PEAKS.json hbm_gbs)" if "hbm_gbs" in peaks else "fallback (B200_PROFILING.md 6.65 TB/s)"
+    ktable.sort(key=lambda r: -r["ms"])
+    total_k_ms = sum(r["ms"] for r in ktable) or 1.0
+    top = ktable[0] if ktable else None
+    roofline = None
+    if top:
+        per_launch_ms = top["ms"] / top["launches"]
+        bytes_per_launch = top["bytes"] / top["launches"] if top["bytes"] else None
+        achieved = (bytes_per_launch / (per_launch_ms * 1e-3) / 1e9) if bytes_per_launch else None
+        roofline = {"bound": "hbm", "kernel": top["name"], "achieved": achieved, "peak": peak, "unit": "GB/s",
+                    "frac": (achieved / peak) if achieved else None, "traffic": None, "peak_source": peak_src,
+                    "launches_per_step": top["launches"] // args.steps, "ms_per_launch": per_launch_ms,
+                    "algorithmic_bytes_per_launch": bytes_per_launch, "share_of_kernel_time": top["ms"] / total_k_ms,
+                    "path_algorithmic_bytes_per_step": alg["warp_blend_fused"],
+                    "path_achieved_gbs": alg["warp_blend_fused"] / (ms_dev * 1e-3) / 1e9}
+    if args.kernel_report:
+        os.makedirs(os.path.dirname(os.path.abspath(args.kernel_report)), exist_ok=True)
+        with open(args.kernel_report, "w") as f:
+            json.dump({"steps": args.steps, "ms_per_step": ms_dev, "ms_per_step_with_events": ms_dev_ev, "kernels": ktable}, f, indent=1)
+
+    cpu = None
+    if not args.no_cpu_baseline and world == 1:
+        import oracle as O
+        O.build()
+        threads = os.cpu_count() or 1
+        sample_rows = rows if rows * cols <= 8e6 else rows // 4
+        v, sdesc, dt, stages = cpu_port_run(args.workload, threads, sample_rows=sample_rows)
+        cpu = {"value": v, "unit": "MP/s", "cores": threads, "kind": "port", "sample": sdesc, "seconds": dt,
+               "stage_seconds": dict(zip(("warp", "seam", "blend", "total"), stages))}
+
+    h2d = n * rows * cols * 3
+    d2h = roi[2] * roi[3] * 7
+    line = {
+        "metric": "stitched_megapixels_per_sec", "value": world * in_mp / (ms_dev * 1e-3), "unit": "MP/s", "n_gpus": world, "steps": args.steps,
+        "warmup": max(args.warmup, 3), "ms_per_step": ms_dev, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+        "dtype": "s16", "data": "synthetic",
+        "config": {"workload": desc, "images_per_gpu": n, "image_rows": rows, "image_cols": cols, "num_bands": NUM_BANDS, "weight_type": "CV_32F",
+                   "seam": "dp_color", "projection": "cylindrical", "f_over_w": fw, "overlap": ov, "pano_roi": list(roi),
+                   "l2_policy": f"inputs ({h2d >> 20} MiB) and panorama exceed the {L2_BYTES >> 20} MiB L2; no flush needed",
+                   "parallelism": "single GPU" if world == 1 else f"{world} independent strips (one per GPU), no exchange"},
+        "clocks": sampler.summary(windows) if sampler else None,
+        "e2e": {"value": world * in_mp / (ms_e2e * 1e-3), "unit": "MP/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
+                "ms_per_step": ms_e2e, "matches_device_path": same},
+        "gpu_launches": int(launches),
+        "stage_ms": stage_ms, "ms_per_step_with_kernel_events": ms_dev_ev,
+        "roofline": roofline, "cpu_baseline": cpu,
+        "top_kernels": [{"name": r["name"], "ms_per_step": r["ms"] / args.steps, "launches_per_step": r["launches"] / args.steps} for r in ktable[:8]],
+    }
+    print(json.dumps(line), flush=True)
+    if dist:
+        dist.destroy_process_group()
+    return 0
+
+
+if __name__ == "__main__":
+    sys.exit(main())

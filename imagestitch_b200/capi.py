@@ -73,6 +73,8 @@ SYMBOLS = {
     "is_ctx_set_stream": (C.c_int, [C.c_void_p, C.c_void_p]),
     "is_ctx_kernel_launches": (C.c_uint64, [C.c_void_p]),
     "is_ctx_device": (C.c_int, [C.c_void_p]),
+    "is_ctx_kernel_timing": (C.c_int, [C.c_void_p, C.c_int]),
+    "is_ctx_kernel_timing_report": (C.c_int, [C.c_void_p, C.c_char_p, C.c_size_t]),
     "is_warp_roi": (C.c_int, [C.c_void_p, C.c_int, Size, _F9, _F9, C.c_float, _P(Point), _P(Size)]),
     "is_build_maps": (C.c_int, [C.c_void_p, C.c_int, Size, _F9, _F9, C.c_float, _P(Mat), _P(Mat), _P(Rect)]),
     "is_warp": (C.c_int, [C.c_void_p, C.c_int, _P(Mat), _F9, _F9, C.c_float, C.c_int, C.c_int, _P(Mat), _P(Point)]),

@@ -373,6 +373,9 @@ int blender_feed_dev(is_blender* b, FedImage&& f) {
         IS_TRY(f.g[k].alloc(ctx, sizeof(int16_t) * 3 * (size_t)dh * dw));
         IS_TRY(f.w[k].alloc(ctx, wsz * (size_t)dh * dw));
         dim3 block(32, 8), grid(div_up(dw, 32), div_up(dh, 8));
+        // algorithmic bytes: level k-1 (image + weight) read once, level k written once
+        const double in_px = k == 1 ? (double)rows * cols : (double)sh * sw;
+        ctx->next_bytes = in_px * (k == 1 ? (f.img.depth == IS_8U ? 3 : 6) + 1 : 6 + (double)wsz) + (double)dh * dw * (6 + (double)wsz);
         if (k == 1) {
             Level0 L = level0_of(f);
             if (wf) IS_LAUNCH(ctx, k_pyrdown_l0<true>, grid, block, 0, L, f.g[1].as<int16_t>(), f.w[1].p, dh, dw);
@@ -426,6 +429,19 @@ int blender_blend_dev(is_blender* b, const DevMat& dst, const DevMat& dmask) {
         A.fw = b->roi_final.width; A.fh = b->roi_final.height;
         const int gw = k == 0 ? A.fw : A.W, gh = k == 0 ? A.fh : A.H;
         dim3 block(32, 8), grid(div_up(gw, 32), div_up(gh, 8));
+        {   // algorithmic bytes: every input of the level read once, the collapsed level written once
+            const double wsz = wf ? 4 : 2;
+            double bytes = 0;
+            for (int i = 0; i < n; ++i) {
+                const FedImage& f = b->fed[i];
+                if (k == 0) bytes += (double)f.img.rows * f.img.cols * ((f.img.depth == IS_8U ? 3 : 6) + 1);
+                else bytes += (double)(f.height >> k) * (f.width >> k) * (6 + wsz);
+                if (k < nb) bytes += (double)(f.height >> (k + 1)) * (f.width >> (k + 1)) * 6;
+            }
+            if (k < nb) bytes += (double)H[k + 1] * W[k + 1] * 6;
+            bytes += k == 0 ? (double)A.fw * A.fh * 7 : (double)H[k] * W[k] * 6;
+            ctx->next_bytes = bytes;
+        }
         if (wf) IS_LAUNCH(ctx, k_blend_level<true>, grid, block, 0, A);
         else IS_LAUNCH(ctx, k_blend_level<false>, grid, block, 0, A);
     }

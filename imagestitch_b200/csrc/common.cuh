@@ -23,13 +23,22 @@ struct is_ctx {
     void* pinned = nullptr;
     size_t pinned_bytes = 0;
     size_t pinned_off = 0;
+    void* pinned_dl = nullptr;           // bounce buffer for downloads
+    size_t pinned_dl_bytes = 0;
     float timings[4] = {0, 0, 0, 0};
     cudaEvent_t ev[5] = {nullptr, nullptr, nullptr, nullptr, nullptr};
+    // optional per-launch CUDA-event timing (is_ctx_kernel_timing): one (start, stop) pair per launch
+    bool ktiming = false;
+    struct KRec { const char* name; cudaEvent_t e0, e1; double bytes; };
+    std::vector<KRec> krecs;
+    std::vector<cudaEvent_t> kpool;
+    double next_bytes = 0;   // algorithmic bytes the next launch accounts for (set by the host code, optional)
 };
 
 namespace is {
 
 int fail(is_ctx* ctx, int status, const char* fmt, ...);
+cudaEvent_t ktiming_begin(is_ctx* ctx, const char* name);   // records the start event, returns the stop event
 
 #define IS_CUDA(ctx, expr)                                                                            \
     do {                                                                                              \
@@ -54,7 +63,10 @@ int fail(is_ctx* ctx, int status, const char* fmt, ...);
 // gpu_launches) and surfaces launch-configuration errors immediately.
 #define IS_LAUNCH(ctx, kernel, grid, block, smem, ...)                                  \
     do {                                                                                \
+        cudaEvent_t _k1 = nullptr;                                                      \
+        if ((ctx)->ktiming) _k1 = is::ktiming_begin((ctx), #kernel);                    \
         kernel<<<(grid), (block), (smem), (ctx)->stream>>>(__VA_ARGS__);                \
+        if (_k1) cudaEventRecord(_k1, (ctx)->stream);                                   \
         (ctx)->launches++;                                                              \
         IS_CUDA((ctx), cudaGetLastError());                                             \
     } while (0)

@@ -1,6 +1,8 @@
 // ctx.cu -- context life cycle, error strings, staging of host is_mat buffers.
 #include "common.cuh"
 
+#include <algorithm>
+
 namespace is {
 
 int fail(is_ctx* ctx, int status, const char* fmt, ...) {
@@ -11,6 +13,25 @@ int fail(is_ctx* ctx, int status, const char* fmt, ...) {
     va_end(ap);
     if (ctx) ctx->last_error = buf;
     return status;
+}
+
+static cudaEvent_t pool_event(is_ctx* ctx) {
+    if (!ctx->kpool.empty()) { cudaEvent_t e = ctx->kpool.back(); ctx->kpool.pop_back(); return e; }
+    cudaEvent_t e = nullptr;
+    cudaEventCreate(&e);
+    return e;
+}
+
+cudaEvent_t ktiming_begin(is_ctx* ctx, const char* name) {
+    is_ctx::KRec r;
+    r.name = name;
+    r.e0 = pool_event(ctx);
+    r.e1 = pool_event(ctx);
+    r.bytes = ctx->next_bytes;
+    ctx->next_bytes = 0;
+    cudaEventRecord(r.e0, ctx->stream);
+    ctx->krecs.push_back(r);
+    return r.e1;
 }
 
 int DevBuf::alloc(is_ctx* c, size_t n) {
@@ -126,8 +147,17 @@ int upload(is_ctx* ctx, void* dst, const void* src, size_t bytes) {
 
 int download(is_ctx* ctx, void* dst, const void* src, size_t bytes) {
     if (bytes == 0) return IS_OK;
-    IS_CUDA(ctx, cudaMemcpyAsync(dst, src, bytes, cudaMemcpyDeviceToHost, ctx->stream));
+    if (ctx->pinned_dl_bytes < bytes) {
+        if (ctx->pinned_dl) { IS_CUDA(ctx, cudaStreamSynchronize(ctx->stream)); cudaFreeHost(ctx->pinned_dl); }
+        ctx->pinned_dl = nullptr;
+        ctx->pinned_dl_bytes = 0;
+        const size_t n = align_up(bytes > (size_t)(4 << 20) ? bytes : (size_t)(4 << 20), 1 << 20);
+        IS_CUDA(ctx, cudaMallocHost(&ctx->pinned_dl, n));
+        ctx->pinned_dl_bytes = n;
+    }
+    IS_CUDA(ctx, cudaMemcpyAsync(ctx->pinned_dl, src, bytes, cudaMemcpyDeviceToHost, ctx->stream));
     IS_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+    std::memcpy(dst, ctx->pinned_dl, bytes);
     return IS_OK;
 }
 
@@ -176,7 +206,10 @@ int is_ctx_destroy(is_ctx* ctx) {
     cudaSetDevice(ctx->device);
     cudaStreamSynchronize(ctx->stream);
     for (int i = 0; i < 5; ++i) if (ctx->ev[i]) cudaEventDestroy(ctx->ev[i]);
+    for (auto& r : ctx->krecs) { cudaEventDestroy(r.e0); cudaEventDestroy(r.e1); }
+    for (auto e : ctx->kpool) cudaEventDestroy(e);
     if (ctx->pinned) cudaFreeHost(ctx->pinned);
+    if (ctx->pinned_dl) cudaFreeHost(ctx->pinned_dl);
     cudaStreamDestroy(ctx->own_stream);
     delete ctx;
     return IS_OK;
@@ -193,6 +226,49 @@ int is_ctx_set_stream(is_ctx* ctx, void* stream) {
     IS_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
     ctx->stream = stream ? (cudaStream_t)stream : ctx->own_stream;
     return IS_OK;
+}
+
+int is_ctx_kernel_timing(is_ctx* ctx, int enable) {
+    if (!ctx) return IS_ERR_BAD_ARG;
+    ctx->ktiming = enable != 0;
+    return IS_OK;
+}
+
+// JSON array [{"name": ..., "launches": n, "ms": total, "bytes": algorithmic bytes}, ...] of the launches recorded
+// since the last report; synchronises the stream.  Returns the length needed (including the NUL).
+int is_ctx_kernel_timing_report(is_ctx* ctx, char* buf, size_t cap) {
+    if (!ctx) return IS_ERR_BAD_ARG;
+    IS_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+    struct Agg { std::string name; int n; double ms; double bytes; };
+    std::vector<Agg> agg;
+    for (auto& r : ctx->krecs) {
+        float ms = 0.f;
+        cudaEventElapsedTime(&ms, r.e0, r.e1);
+        std::string nm = r.name;
+        size_t i = 0;
+        for (; i < agg.size(); ++i) if (agg[i].name == nm) break;
+        if (i == agg.size()) agg.push_back(Agg{nm, 0, 0., 0.});
+        agg[i].n++; agg[i].ms += ms; agg[i].bytes += r.bytes;
+        ctx->kpool.push_back(r.e0);
+        ctx->kpool.push_back(r.e1);
+    }
+    ctx->krecs.clear();
+    std::string out = "[";
+    for (size_t i = 0; i < agg.size(); ++i) {
+        char line[512];
+        std::string nm;
+        for (char c : agg[i].name) if (c != '"' && c != '\\') nm += c;
+        snprintf(line, sizeof(line), "%s{\"name\": \"%s\", \"launches\": %d, \"ms\": %.6f, \"bytes\": %.0f}", i ? ", " : "", nm.c_str(),
+                 agg[i].n, agg[i].ms, agg[i].bytes);
+        out += line;
+    }
+    out += "]";
+    if (buf && cap) {
+        size_t n = std::min(cap - 1, out.size());
+        std::memcpy(buf, out.data(), n);
+        buf[n] = 0;
+    }
+    return (int)out.size() + 1;
 }
 
 const char* is_ctx_last_error(const is_ctx* ctx) { return ctx ? ctx->last_error.c_str() : "null context"; }

@@ -20,12 +20,13 @@
 #include "internal.cuh"
 
 #include <algorithm>
+#include <chrono>
 #include <climits>
+#include <cstdlib>
 #include <limits>
 #include <cmath>
 #include <map>
 #include <set>
-#include <unordered_map>
 #include <utility>
 
 namespace is {
@@ -197,9 +198,17 @@ __device__ __forceinline__ bool is_contour(const int* __restrict__ labels, Frame
 }
 
 constexpr int CT_THREADS = 256, CT_PER_THREAD = 8, CT_CHUNK = CT_THREADS * CT_PER_THREAD;
+constexpr int CT_FILTER_INTERS = -3;   // select the pixels lying in both masks (the INTERS components at labelling time)
+
+__device__ __forceinline__ bool ct_select(int l, int fa, int fb, const uint8_t* __restrict__ cls, size_t i) {
+    if (l <= 0) return false;
+    if (fa == CT_FILTER_INTERS) return (cls[i] & 3) == 3;
+    return fa == 0 || l == fa || l == fb;
+}
 
 // pass 1: number of selected contour pixels per chunk of the window (window-raster order)
-__global__ void k_contour_count(const int* __restrict__ labels, Frame f, int wx, int wy, int ww, int wh, int fa, int fb, int* counts) {
+__global__ void k_contour_count(const int* __restrict__ labels, const uint8_t* __restrict__ cls, Frame f, int wx, int wy, int ww, int wh, int fa,
+                                int fb, int* counts) {
     const size_t total = (size_t)ww * wh;
     size_t e0 = (size_t)blockIdx.x * CT_CHUNK + (size_t)threadIdx.x * CT_PER_THREAD;
     int c = 0;
@@ -207,8 +216,9 @@ __global__ void k_contour_count(const int* __restrict__ labels, Frame f, int wx,
         size_t e = e0 + k;
         if (e >= total) break;
         int x = wx + (int)(e % ww), y = wy + (int)(e / ww);
-        int l = labels[(size_t)y * f.uw + x];
-        if (l > 0 && (fa == 0 || l == fa || l == fb) && is_contour(labels, f, x, y, l)) ++c;
+        const size_t i = (size_t)y * f.uw + x;
+        int l = labels[i];
+        if (ct_select(l, fa, fb, cls, i) && is_contour(labels, f, x, y, l)) ++c;
     }
     __shared__ int red[CT_THREADS / 32];
     for (int o = 16; o; o >>= 1) c += __shfl_down_sync(0xffffffffu, c, o);
@@ -275,8 +285,9 @@ __global__ void k_contour_write(const int* __restrict__ labels, const uint8_t* _
         size_t e = e0 + k;
         if (e >= total) break;
         int x = wx + (int)(e % ww), y = wy + (int)(e / ww);
-        int l = labels[(size_t)y * f.uw + x];
-        if (l > 0 && (fa == 0 || l == fa || l == fb) && is_contour(labels, f, x, y, l)) { sel |= 1u << k; ++c; }
+        const size_t i = (size_t)y * f.uw + x;
+        int l = labels[i];
+        if (ct_select(l, fa, fb, cls, i) && is_contour(labels, f, x, y, l)) { sel |= 1u << k; ++c; }
     }
     // exclusive scan of c over the block
     __shared__ int warp_sum[CT_THREADS / 32];
@@ -369,18 +380,23 @@ __global__ void k_cost_maps(ImgView<T> a, ImgView<T> b, const int* __restrict__ 
 // seam: step = x, lane = y, P = costH, Q = costV.  A negative P marks a cell outside the component.
 template <typename T>
 __global__ void k_cost_pq(ImgView<T> a, ImgView<T> b, const int* __restrict__ labels, Frame f, int l, int rx, int ry, int rw, int rh,
-                          int horizontal, float* __restrict__ P, float* __restrict__ Q) {
+                          int horizontal, float* __restrict__ P, float* __restrict__ Q, int pitch) {
     const int lanes = horizontal ? rh : rw, steps = horizontal ? rw : rh;
     const int lane = blockIdx.x * blockDim.x + threadIdx.x;
     const int step = blockIdx.y * blockDim.y + threadIdx.y;
-    if (lane >= lanes || step >= steps) return;
+    if (lane >= pitch || step >= steps) return;
+    if (lane >= lanes) {   // padding lanes: outside the component
+        P[(size_t)step * pitch + lane] = -1.f;
+        Q[(size_t)step * pitch + lane] = 0.f;
+        return;
+    }
     const int x = rx + (horizontal ? step : lane), y = ry + (horizontal ? lane : step);
     float p, q;
     if (horizontal) { p = cost_h(a, b, labels, f, l, x, y); q = cost_v(a, b, labels, f, l, x, y); }
     else { p = cost_v(a, b, labels, f, l, x, y); q = cost_h(a, b, labels, f, l, x, y); }
     if (labels[(size_t)y * f.uw + x] != l) p = -1.f;
-    P[(size_t)step * lanes + lane] = p;
-    Q[(size_t)step * lanes + lane] = q;
+    P[(size_t)step * pitch + lane] = p;
+    Q[(size_t)step * pitch + lane] = q;
 }
 
 // ---- DP forward pass + back-track: one CTA per seam --------------------------------------------------------
@@ -388,117 +404,164 @@ __global__ void k_cost_pq(ImgView<T> a, ImgView<T> b, const int* __restrict__ la
 // add of every candidate).  Candidates ([SEAM]:899-904 / :869-874):
 //   1: t[lane]                2: t[lane-1] + Q[step][lane-1]          3: t[lane+1] + Q[step][lane]
 // Unreachable cells carry +inf, which never wins against a finite candidate and never ties with one.
+//
+// The pass is latency bound (one dependent step per row of the overlap), so the cost rows are taken off the
+// critical path: they stream from HBM/L2 into a shared-memory ring with TMA bulk copies (cp.async.bulk +
+// mbarrier complete_tx), G rows of P and Q per stage, D stages in flight, issued by one thread.  Inside a step
+// neighbouring threads exchange the running cost of their edge lanes through shared memory; one
+// __syncthreads per step is the only synchronisation on the chain.
 struct DpArgs {
-    const float* P; const float* Q;
-    uint8_t* control;       // [steps][lanes]
-    int lanes, steps;
-    int s0, lane0;          // source (step, lane)
-    int s1, lane1;          // destination
-    int* seam_lane;         // out: lane of the seam at step s0..s1 (index step - s0)
-    int* reached;           // out: 1 when the destination is reachable
+    const float* P; const float* Q;   // [steps][pitch]
+    uint8_t* control;                 // [steps][lanes]
+    int lanes, pitch, steps;
+    int s0, lane0;                    // source (step, lane)
+    int s1, lane1;                    // destination
+    int* seam_lane;                   // out: lane of the seam at step s0..s1 (index step - s0)
+    int* reached;                     // out: 1 when the destination is reachable
+    int G, D;                         // rows per ring stage, number of stages
 };
 
+__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+
+__device__ __forceinline__ void mbar_init(uint64_t* bar, int count) {
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count) : "memory");
+}
+__device__ __forceinline__ void mbar_expect_tx(uint64_t* bar, uint32_t bytes) {
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
+    asm volatile(
+        "{\n"
+        ".reg .pred p;\n"
+        "WAIT_%=:\n"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n"
+        "@p bra DONE_%=;\n"
+        "bra WAIT_%=;\n"
+        "DONE_%=:\n"
+        "}\n" ::"r"(smem_u32(bar)), "r"(parity) : "memory");
+}
+// 1-D TMA bulk copy global -> shared, completion signalled on an mbarrier (SASS: UBLKCP)
+__device__ __forceinline__ void bulk_g2s(void* dst, const void* src, uint32_t bytes, uint64_t* bar) {
+    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(smem_u32(dst)), "l"(src),
+                 "r"(bytes), "r"(smem_u32(bar))
+                 : "memory");
+}
+
+// Rows of P, Q and control are padded to `pitch` = nt * LPT lanes.  Padding lanes carry P = -1 (outside the
+// component) so they stay unreachable (+inf) and need no bounds checks in the loop: a neighbour outside
+// [0, lanes) always contributes +inf, exactly like the reference's `x > 0` / `x < roi.width - 1` guards.
 template <int LPT>
 __global__ void __launch_bounds__(1024) k_seam_dp(DpArgs A) {
-    extern __shared__ float sm[];
+    extern __shared__ __align__(128) unsigned char sm_raw[];
     const int nt = blockDim.x, tid = threadIdx.x;
-    float* edgeL = sm;                 // [2][nt]: t of the first lane of each thread (double buffered)
-    float* edgeR = sm + 2 * nt;        // [2][nt]: t of the last lane
+    const int row_f = A.pitch;                             // floats per row
+    const int stage_f = 2 * A.G * row_f;                   // floats per stage: G rows of P, then G rows of Q
+    float* ring = reinterpret_cast<float*>(sm_raw);
+    float* edgeL = ring + (size_t)A.D * stage_f;           // [2][nt]: t of the first lane of each thread (double buffered)
+    float* edgeR = edgeL + 2 * nt;                         // [2][nt]: t of the last lane
+    uint64_t* bars = reinterpret_cast<uint64_t*>(edgeR + 2 * nt);
     const int l0 = tid * LPT;
     const float INF = __int_as_float(0x7f800000);
-    float t[LPT], pn[LPT], qn[LPT];
-    float qleft_n = 0.f;
+    const int R = A.s1 - A.s0;                             // DP steps to run: rows s0+1 .. s1
+    const int NG = (R + A.G - 1) / A.G;
+
+    auto issue = [&](int g) {                              // thread 0: load group g into stage g % D
+        const int stage = g % A.D;
+        const int rows = min(A.G, R - g * A.G);
+        const uint32_t bytes = (uint32_t)(rows * row_f) * (uint32_t)sizeof(float);
+        const size_t goff = (size_t)(A.s0 + 1 + g * A.G) * row_f;
+        mbar_expect_tx(&bars[stage], 2 * bytes);
+        bulk_g2s(ring + (size_t)stage * stage_f, A.P + goff, bytes, &bars[stage]);
+        bulk_g2s(ring + (size_t)stage * stage_f + A.G * row_f, A.Q + goff, bytes, &bars[stage]);
+    };
+    if (tid == 0) {
+        for (int d = 0; d < A.D; ++d) mbar_init(&bars[d], 1);
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    __syncthreads();
+    if (tid == 0)
+        for (int g = 0; g < min(A.D, NG); ++g) issue(g);
+
+    float t[LPT];
     // source step
 #pragma unroll
     for (int j = 0; j < LPT; ++j) {
-        int lane = l0 + j;
-        float c = lane == A.lane0 ? 0.f : INF;
-        float p = lane < A.lanes ? A.P[(size_t)A.s0 * A.lanes + lane] : -1.f;
-        t[j] = __fadd_rn(c, p);
+        const int lane = l0 + j;
+        const float c = lane == A.lane0 ? 0.f : INF;
+        t[j] = __fadd_rn(c, A.P[(size_t)A.s0 * row_f + lane]);
     }
-    int buf = 0;
-    edgeL[buf * nt + tid] = t[0];
-    edgeR[buf * nt + tid] = t[LPT - 1];
-    // prefetch step s0+1
-    if (A.s0 + 1 <= A.s1) {
-        const size_t r = (size_t)(A.s0 + 1) * A.lanes;
-#pragma unroll
-        for (int j = 0; j < LPT; ++j) {
-            int lane = l0 + j;
-            pn[j] = lane < A.lanes ? A.P[r + lane] : -1.f;
-            qn[j] = lane < A.lanes ? A.Q[r + lane] : 0.f;
-        }
-        qleft_n = (l0 > 0 && l0 - 1 < A.lanes) ? A.Q[r + l0 - 1] : 0.f;
-    }
+    // double-buffered edge exchange: this thread writes its own slots, reads its neighbours' slots
+    float* eLw = edgeL + tid;
+    float* eRw = edgeR + tid;
+    const float* eLr = edgeL + min(tid + 1, nt - 1);       // first lane of the right neighbour
+    const float* eRr = edgeR + max(tid - 1, 0);            // last lane of the left neighbour
+    const bool has_left = tid > 0, has_right = tid < nt - 1;
+    int boff = 0;                                          // 0 or nt: which of the two edge buffers is current
+    eLw[boff] = t[0];
+    eRw[boff] = t[LPT - 1];
     __syncthreads();
-    float cost_dst = INF;
-    for (int s = A.s0 + 1; s <= A.s1; ++s) {
-        float p[LPT], q[LPT];
-        const float qleft = qleft_n;
+    uint8_t* ctl_row = A.control + (size_t)(A.s0 + 1) * row_f + l0;
+    for (int g = 0; g < NG; ++g) {
+        const int stage = g % A.D;
+        mbar_wait(&bars[stage], (uint32_t)((g / A.D) & 1));
+        const float* Pr = ring + (size_t)stage * stage_f + l0;
+        const float* Qr = Pr + A.G * row_f;
+        const int rows = min(A.G, R - g * A.G);
+        for (int rr = 0; rr < rows; ++rr, Pr += row_f, Qr += row_f, ctl_row += row_f) {
+            float p[LPT], q[LPT];
 #pragma unroll
-        for (int j = 0; j < LPT; ++j) { p[j] = pn[j]; q[j] = qn[j]; }
-        if (s + 1 <= A.s1) {   // prefetch the next step's costs: independent of the DP state
-            const size_t r = (size_t)(s + 1) * A.lanes;
+            for (int j = 0; j < LPT; j += 4) {
+                const float4 pv = *reinterpret_cast<const float4*>(Pr + j);
+                const float4 qv = *reinterpret_cast<const float4*>(Qr + j);
+                p[j] = pv.x; p[j + 1] = pv.y; p[j + 2] = pv.z; p[j + 3] = pv.w;
+                q[j] = qv.x; q[j + 1] = qv.y; q[j + 2] = qv.z; q[j + 3] = qv.w;
+            }
+            const float qleft = has_left ? Qr[-1] : 0.f;
+            const float tl_edge = has_left ? eRr[boff] : INF;
+            const float tr_edge = has_right ? eLr[boff] : INF;
+            float tn[LPT];
+            uint32_t ctl_pack[LPT / 4];
+#pragma unroll
+            for (int j = 0; j < LPT / 4; ++j) ctl_pack[j] = 0;
 #pragma unroll
             for (int j = 0; j < LPT; ++j) {
-                int lane = l0 + j;
-                pn[j] = lane < A.lanes ? A.P[r + lane] : -1.f;
-                qn[j] = lane < A.lanes ? A.Q[r + lane] : 0.f;
+                const float tleft = j > 0 ? t[j - 1] : tl_edge;
+                const float tright = j < LPT - 1 ? t[j + 1] : tr_edge;
+                const float ql = j > 0 ? q[j - 1] : qleft;
+                const float c2 = __fadd_rn(tleft, ql);
+                const float c3 = __fadd_rn(tright, q[j]);
+                float best = t[j]; uint32_t ctl = 1;
+                if (c2 < best) { best = c2; ctl = 2; }
+                if (c3 < best) { best = c3; ctl = 3; }
+                const float c = p[j] >= 0.f ? best : INF;        // cells outside the component stay unreachable
+                if (!(c < INF)) ctl = 0;
+                tn[j] = __fadd_rn(c, p[j]);
+                ctl_pack[j / 4] |= ctl << (8 * (j & 3));
             }
-            qleft_n = (l0 > 0 && l0 - 1 < A.lanes) ? A.Q[r + l0 - 1] : 0.f;
-        }
-        const float tl_edge = tid > 0 ? edgeR[buf * nt + tid - 1] : INF;
-        const float tr_edge = tid < nt - 1 ? edgeL[buf * nt + tid + 1] : INF;
-        float tn[LPT];
-        uint32_t ctl_pack = 0;
 #pragma unroll
-        for (int j = 0; j < LPT; ++j) {
-            const int lane = l0 + j;
-            const float c1 = t[j];
-            const float tleft = j > 0 ? t[j - 1] : tl_edge;
-            const float tright = j < LPT - 1 ? t[j + 1] : tr_edge;
-            const float ql = j > 0 ? q[j - 1] : qleft;
-            const float c2 = lane > 0 ? __fadd_rn(tleft, ql) : INF;
-            const float c3 = lane < A.lanes - 1 ? __fadd_rn(tright, q[j]) : INF;
-            float best = c1; int ctl = 1;
-            if (c2 < best) { best = c2; ctl = 2; }
-            if (c3 < best) { best = c3; ctl = 3; }
-            const bool ok = lane < A.lanes && p[j] >= 0.f && best < INF;
-            const float c = ok ? best : INF;
-            if (!ok) ctl = 0;
-            tn[j] = __fadd_rn(c, p[j]);
-            if (LPT <= 4) ctl_pack |= (uint32_t)ctl << (8 * j);
-            else if (lane < A.lanes) A.control[(size_t)s * A.lanes + lane] = (uint8_t)ctl;
-            if (s == A.s1 && lane == A.lane1) cost_dst = c;
-        }
-        if (LPT <= 4) {
-            uint8_t* cp = A.control + (size_t)s * A.lanes + l0;
-            if (LPT == 4 && l0 + 4 <= A.lanes && ((reinterpret_cast<uintptr_t>(cp) & 3) == 0)) *reinterpret_cast<uint32_t*>(cp) = ctl_pack;
-            else {
+            for (int j = 0; j < LPT / 4; ++j) reinterpret_cast<uint32_t*>(ctl_row)[j] = ctl_pack[j];
 #pragma unroll
-                for (int j = 0; j < LPT; ++j)
-                    if (l0 + j < A.lanes) cp[j] = (uint8_t)(ctl_pack >> (8 * j));
-            }
+            for (int j = 0; j < LPT; ++j) t[j] = tn[j];
+            boff = nt - boff;
+            eLw[boff] = t[0];
+            eRw[boff] = t[LPT - 1];
+            __syncthreads();
         }
-#pragma unroll
-        for (int j = 0; j < LPT; ++j) t[j] = tn[j];
-        buf ^= 1;
-        edgeL[buf * nt + tid] = t[0];
-        edgeR[buf * nt + tid] = t[LPT - 1];
-        __syncthreads();
+        // every thread is past its reads of this stage (barrier above): refill it with group g + D
+        if (tid == 0 && g + A.D < NG) issue(g + A.D);
     }
-    // destination reachable?  (the thread owning lane1 knows)
+    // destination reachable <=> a control value was recorded for it ([SEAM]:918)
     __shared__ int reached_s;
-    if (tid == 0) reached_s = (A.s1 == A.s0) ? (A.lane1 == A.lane0) : 0;
+    if (tid == 0) {
+        if (A.s1 == A.s0) reached_s = A.lane1 == A.lane0;
+        else reached_s = A.control[(size_t)A.s1 * row_f + A.lane1] != 0;
+        *A.reached = reached_s;
+    }
     __syncthreads();
-    if (A.s1 > A.s0 && A.lane1 >= l0 && A.lane1 < l0 + LPT && cost_dst < INF) reached_s = 1;
-    __threadfence_block();
-    __syncthreads();
-    if (tid == 0) *A.reached = reached_s;
     if (!reached_s) return;
     // back-track ([SEAM]:923-947), staged through shared memory in chunks of BT steps
     constexpr int BT = 32;
-    uint8_t* win = reinterpret_cast<uint8_t*>(sm);        // [BT][2*BT+1]
+    uint8_t* win = reinterpret_cast<uint8_t*>(sm_raw);    // [BT][2*BT+1]; the ring is idle now
     __shared__ int cur_lane_s;
     if (tid == 0) { cur_lane_s = A.lane1; }
     __syncthreads();
@@ -510,7 +573,7 @@ __global__ void __launch_bounds__(1024) k_seam_dp(DpArgs A) {
         for (int e = tid; e < nrow * (2 * BT + 1); e += nt) {
             int r = e / (2 * BT + 1), c = e % (2 * BT + 1);
             int lane = wl + c;
-            win[e] = (lane >= 0 && lane < A.lanes) ? A.control[(size_t)(slo + r) * A.lanes + lane] : 0;
+            win[e] = (lane >= 0 && lane < A.lanes) ? A.control[(size_t)(slo + r) * row_f + lane] : 0;
         }
         __syncthreads();
         if (tid == 0) {
@@ -625,6 +688,40 @@ __global__ void k_mask_update(uint8_t* dst, size_t dstep, int drows, int dcols, 
 
 struct Pt { int x, y; };
 
+// open-addressing (key -> int) map for the few thousand contour / seam pixels of updateLabelsUsingSeam
+struct FlatMap {
+    std::vector<long long> keys;
+    std::vector<int> vals;
+    size_t mask = 0;
+    explicit FlatMap(size_t expected) {
+        size_t cap = 64;
+        while (cap < expected * 4) cap <<= 1;
+        keys.assign(cap, -1);
+        vals.assign(cap, 0);
+        mask = cap - 1;
+    }
+    inline int& operator[](long long k) {
+        size_t h = ((unsigned long long)k * 0x9E3779B97F4A7C15ull) >> 20 & mask;
+        while (keys[h] != k) {
+            if (keys[h] < 0) { keys[h] = k; vals[h] = 0; break; }
+            h = (h + 1) & mask;
+        }
+        return vals[h];
+    }
+};
+
+struct DbgTimer {   // IS_SEAM_DEBUG=1: host wall-clock per section (includes the device work it waits for)
+    bool on; std::chrono::steady_clock::time_point t;
+    DbgTimer() : on(getenv("IS_SEAM_DEBUG") != nullptr), t(std::chrono::steady_clock::now()) {}
+    void lap(const char* what) {
+        if (!on) return;
+        auto n = std::chrono::steady_clock::now();
+        fprintf(stderr, "[seam] %-28s %8.3f ms\n", what, std::chrono::duration<double, std::milli>(n - t).count());
+        t = n;
+    }
+};
+
+
 struct TraceSink {
     int32_t* buf = nullptr; size_t cap = 0; size_t len = 0;
 };
@@ -703,7 +800,7 @@ int PairSeam::extract_contours(int wx, int wy, int ww, int wh, int fa, int fb, s
     const int nblocks = (int)((total + CT_CHUNK - 1) / CT_CHUNK);
     IS_TRY(counts.alloc(ctx, sizeof(int) * (size_t)nblocks));
     IS_TRY(offsets.alloc(ctx, sizeof(int) * ((size_t)nblocks + 1)));
-    IS_LAUNCH(ctx, k_contour_count, nblocks, CT_THREADS, 0, labels.as<int>(), frame(), wx, wy, ww, wh, fa, fb, counts.as<int>());
+    IS_LAUNCH(ctx, k_contour_count, nblocks, CT_THREADS, 0, labels.as<int>(), cls.as<uint8_t>(), frame(), wx, wy, ww, wh, fa, fb, counts.as<int>());
     IS_LAUNCH(ctx, k_scan_counts, 1, 1024, 0, counts.as<int>(), nblocks, offsets.as<int>());
     int n = 0;
     IS_TRY(download(ctx, &n, offsets.as<int>() + nblocks, sizeof(int)));
@@ -827,41 +924,60 @@ int PairSeam::estimate_and_update(int c1, int c2, Pt p1, Pt p2) {
     if (horizontal) { if (src.x > dst.x) { std::swap(src, dst); swapped = true; } }
     else if (src.y > dst.y) { std::swap(src, dst); swapped = true; }
     const int lanes = horizontal ? rh : rw, steps = horizontal ? rw : rh;
-    IS_REQUIRE(ctx, lanes <= 16 * 1024, IS_ERR_UNSUPPORTED, "seam component wider than 16384 lanes");
 
     DevBuf P, Q, control, seam_lane, reached;
-    IS_TRY(P.alloc(ctx, sizeof(float) * (size_t)lanes * steps));
-    IS_TRY(Q.alloc(ctx, sizeof(float) * (size_t)lanes * steps));
-    IS_TRY(control.alloc(ctx, (size_t)lanes * steps + 4));
+    int lpt = lanes <= 4096 ? 4 : (lanes <= 8192 ? 8 : 16);
+    if (const char* e = getenv("IS_DP_LPT")) {             // tuning knob (4, 8 or 16 lanes per thread)
+        const int v = atoi(e);
+        if ((v == 4 || v == 8 || v == 16) && lanes <= 1024 * v) lpt = v;
+    }
+    const int nt = std::min(1024, div_up(div_up(lanes, lpt), 32) * 32);
+    const int pitch = nt * lpt;                            // padded row length (multiple of 128 lanes)
+    IS_REQUIRE(ctx, pitch >= lanes && pitch <= 12 * 1024, IS_ERR_UNSUPPORTED, "seam component wider than 12288 lanes");
+    IS_TRY(P.alloc(ctx, sizeof(float) * (size_t)pitch * steps + 64));
+    IS_TRY(Q.alloc(ctx, sizeof(float) * (size_t)pitch * steps + 64));
+    IS_TRY(control.alloc(ctx, (size_t)pitch * steps + 64));
     IS_TRY(seam_lane.alloc(ctx, sizeof(int) * (size_t)steps));
     IS_TRY(reached.alloc(ctx, sizeof(int)));
     const int dx1 = unionTl.x - tl1_.x, dy1 = unionTl.y - tl1_.y, dx2 = unionTl.x - tl2_.x, dy2 = unionTl.y - tl2_.y;
     {
-        dim3 block(64, 4), grid(div_up(lanes, 64), div_up(steps, 4));
+        dim3 block(64, 4), grid(div_up(pitch, 64), div_up(steps, 4));
+        ctx->next_bytes = (double)lanes * steps * (is_u8 ? 6 : 24) + (double)lanes * steps * 12;   // two image overlaps + labels read, P and Q written
         if (is_u8)
             IS_LAUNCH(ctx, k_cost_pq<uint8_t>, grid, block, 0, make_view<uint8_t>(*img1, dx1, dy1), make_view<uint8_t>(*img2, dx2, dy2),
-                      labels.as<int>(), frame(), l1, rx, ry, rw, rh, horizontal ? 1 : 0, P.as<float>(), Q.as<float>());
+                      labels.as<int>(), frame(), l1, rx, ry, rw, rh, horizontal ? 1 : 0, P.as<float>(), Q.as<float>(), pitch);
         else
             IS_LAUNCH(ctx, k_cost_pq<float>, grid, block, 0, make_view<float>(*img1, dx1, dy1), make_view<float>(*img2, dx2, dy2),
-                      labels.as<int>(), frame(), l1, rx, ry, rw, rh, horizontal ? 1 : 0, P.as<float>(), Q.as<float>());
+                      labels.as<int>(), frame(), l1, rx, ry, rw, rh, horizontal ? 1 : 0, P.as<float>(), Q.as<float>(), pitch);
     }
     DpArgs A;
     A.P = P.as<float>(); A.Q = Q.as<float>(); A.control = control.as<uint8_t>();
-    A.lanes = lanes; A.steps = steps;
+    A.lanes = lanes; A.pitch = pitch; A.steps = steps;
     A.s0 = horizontal ? src.x : src.y; A.lane0 = horizontal ? src.y : src.x;
     A.s1 = horizontal ? dst.x : dst.y; A.lane1 = horizontal ? dst.y : dst.x;
     A.seam_lane = seam_lane.as<int>(); A.reached = reached.as<int>();
     {
-        int lpt = 1;
-        while (lpt < 16 && lanes > 1024 * lpt) lpt *= 2;
-        int nt = std::min(1024, div_up(div_up(lanes, lpt), 32) * 32);
-        size_t smem = std::max(sizeof(float) * 4 * (size_t)nt, (size_t)32 * 65);
+        const size_t row_pair = 2 * sizeof(float) * (size_t)pitch;            // one row of P + one of Q
+        const size_t budget = 192 * 1024;
+        A.D = 3;
+        A.G = (int)std::min<size_t>(16, budget / (A.D * row_pair));
+        if (A.G < 1) { A.D = 2; A.G = 1; }
+        const size_t smem = (size_t)A.D * A.G * row_pair + sizeof(float) * 4 * (size_t)nt + 8 * (size_t)A.D + 16;
+        IS_REQUIRE(ctx, smem <= 220 * 1024 && smem >= (size_t)32 * 65, IS_ERR_INTERNAL, "DP shared-memory budget");
+        ctx->next_bytes = (double)(A.s1 - A.s0) * lanes * 9;                    // P, Q read once, control written once
         switch (lpt) {
-            case 1: IS_LAUNCH(ctx, k_seam_dp<1>, 1, nt, smem, A); break;
-            case 2: IS_LAUNCH(ctx, k_seam_dp<2>, 1, nt, smem, A); break;
-            case 4: IS_LAUNCH(ctx, k_seam_dp<4>, 1, nt, smem, A); break;
-            case 8: IS_LAUNCH(ctx, k_seam_dp<8>, 1, nt, smem, A); break;
-            default: IS_LAUNCH(ctx, k_seam_dp<16>, 1, nt, smem, A); break;
+            case 4:
+                IS_CUDA(ctx, cudaFuncSetAttribute(k_seam_dp<4>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+                IS_LAUNCH(ctx, k_seam_dp<4>, 1, nt, smem, A);
+                break;
+            case 8:
+                IS_CUDA(ctx, cudaFuncSetAttribute(k_seam_dp<8>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+                IS_LAUNCH(ctx, k_seam_dp<8>, 1, nt, smem, A);
+                break;
+            default:
+                IS_CUDA(ctx, cudaFuncSetAttribute(k_seam_dp<16>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+                IS_LAUNCH(ctx, k_seam_dp<16>, 1, nt, smem, A);
+                break;
         }
     }
     // ---- updateLabelsUsingSeam, device part (launched before knowing `reached`; harmless if unreachable
@@ -870,8 +986,10 @@ int PairSeam::estimate_and_update(int c1, int c2, Pt p1, Pt p2) {
     DevBuf klass, sub_parent;
     IS_TRY(klass.alloc(ctx, (size_t)rw * rh));
     IS_TRY(sub_parent.alloc(ctx, sizeof(int) * (size_t)rw * rh));
+    DbgTimer dbg;
     int ok = 0;
     IS_TRY(download(ctx, &ok, reached.p, sizeof(int)));
+    dbg.lap("  cost+dp (sync)");
     if (!ok) return IS_OK;                                             // [SEAM]:918-919: estimateSeam returned false
     std::vector<int> lane_h(nseam);
     IS_TRY(download(ctx, lane_h.data(), seam_lane.p, sizeof(int) * (size_t)nseam));
@@ -928,11 +1046,11 @@ int PairSeam::estimate_and_update(int c1, int c2, Pt p1, Pt p2) {
               A.s0, horizontal ? 1 : 0, gs_d.as<int>());
     if (nc) IS_TRY(download(ctx, g8.data(), g8_d.p, sizeof(int) * g8.size()));
     IS_TRY(download(ctx, gs.data(), gs_d.p, sizeof(int) * gs.size()));
+    dbg.lap("  uls device part (sync)");
 
     // ---- sequential part on the host ([SEAM]:983-1034).  `painted` holds the current mask value of every
     //      contour / seam pixel (255 until assigned); all other pixels are constant (gathered above).
-    std::unordered_map<long long, int> painted;
-    painted.reserve((size_t)(nc + nseam) * 2);
+    FlatMap painted((size_t)(nc + nseam));
     auto key = [&](int x, int y) { return (long long)y * rw + x; };
     for (int i = 0; i < nc; ++i) painted[key(cpts[i].x, cpts[i].y)] = 255;
     for (int i = 0; i < nseam; ++i) painted[key(gs[3 * i], gs[3 * i + 1])] = 255;
@@ -983,13 +1101,16 @@ int PairSeam::estimate_and_update(int c1, int c2, Pt p1, Pt p2) {
         }
         isAdj[kv.first] = res;
     }
+    dbg.lap("  uls host walk");
     // ---- relabel ([SEAM]:1089-1092)
     std::vector<int> adj_roots;
     for (int i = 1; i <= nsub; ++i) if (isAdj[i]) adj_roots.push_back(roots[i - 1]);
     std::vector<int2> flips;
-    for (auto& kv : painted) {
-        int v = kv.second;
-        if (v > 0 && v <= maxKey && isAdj[v]) flips.push_back(make_int2((int)(kv.first % rw) + rx, (int)(kv.first / rw) + ry));
+    for (size_t h = 0; h < painted.keys.size(); ++h) {
+        const long long k = painted.keys[h];
+        if (k < 0) continue;
+        const int v = painted.vals[h];
+        if (v > 0 && v <= maxKey && isAdj[v]) flips.push_back(make_int2((int)(k % rw) + rx, (int)(k / rw) + ry));
     }
     if (!adj_roots.empty()) {
         DevBuf ar;
@@ -1032,7 +1153,7 @@ int PairSeam::resolve_conflicts(const DevMat& mask1, const DevMat& mask2) {
             states[c1] = states[c2] == ST_FIRST ? (ST_INTERS | ST_SECOND) : (ST_INTERS | ST_FIRST);
         }
         IS_TRY(refresh_component(c1));
-        IS_TRY(refresh_component(c2));
+        if (states[c2] & ST_INTERS) IS_TRY(refresh_component(c2));   // geometry of a non-INTERS component is never read again
         edges.erase({c1, c2});
         edges.erase({c2, c1});
     }
@@ -1059,6 +1180,7 @@ int PairSeam::resolve_conflicts(const DevMat& mask1, const DevMat& mask2) {
 // [SEAM]:127-193
 int PairSeam::process(const DevMat& image1, const DevMat& image2, Pt tl1, Pt tl2, const DevMat& mask1, const DevMat& mask2, int pi, int pj) {
     pair_i = pi; pair_j = pj;
+    DbgTimer dbg;
     IS_REQUIRE(ctx, image1.rows == mask1.rows && image1.cols == mask1.cols, IS_ERR_ASSERT, "image1.size() == mask1.size()");
     IS_REQUIRE(ctx, image2.rows == mask2.rows && image2.cols == mask2.cols, IS_ERR_ASSERT, "image2.size() == mask2.size()");
     Pt iTl{std::max(tl1.x, tl2.x), std::max(tl1.y, tl2.y)};
@@ -1084,6 +1206,7 @@ int PairSeam::process(const DevMat& image1, const DevMat& image2, Pt tl1, Pt tl2
     IS_TRY(ccl(cls.as<uint8_t>(), 3, uw, uh, parent.as<int>()));
     std::vector<std::pair<int, int>> roots;
     IS_TRY(collect_roots(parent.as<int>(), cls.as<uint8_t>(), n, &roots));
+    dbg.lap("classify+ccl+roots");
     ncomps = (int)roots.size();
     states.assign(ncomps, 0);
     tls.assign(ncomps, Pt{INT_MAX, INT_MAX});
@@ -1105,16 +1228,26 @@ int PairSeam::process(const DevMat& image1, const DevMat& image2, Pt tl1, Pt tl2
         IS_CUDA(ctx, cudaMemsetAsync(labels.p, 0, sizeof(int) * n, ctx->stream));
     }
     parent.release();
+    // Contour lists, bounding boxes and edges are only ever consulted for INTERS components (the conflict loop
+    // picks edges whose first component is INTERS, [SEAM]:427; getSeamTips / updateLabelsUsingSeam walk
+    // contours_[comp1] with comp1 INTERS), and every adjacency of an INTERS component is witnessed by one of
+    // its own contour pixels.  INTERS components lie inside the intersection rectangle, so only that window is
+    // scanned -- the raster order of the extracted lists is the same as in a full-frame scan.
     std::vector<ContourRec> all;
-    IS_TRY(extract_contours(0, 0, uw, uh, 0, 0, &all));
+    IS_TRY(extract_contours(iTl.x - unionTl.x, iTl.y - unionTl.y, iBr.x - iTl.x, iBr.y - iTl.y, CT_FILTER_INTERS, 0, &all));
     for (const ContourRec& r : all) {
         const int c = r.label - 1;
         contours[c].push_back(r);
         tls[c].x = std::min(tls[c].x, r.x); tls[c].y = std::min(tls[c].y, r.y);
         brs[c].x = std::max(brs[c].x, r.x + 1); brs[c].y = std::max(brs[c].y, r.y + 1);
     }
+    dbg.lap("labels+contours");
     find_edges();
-    return resolve_conflicts(mask1, mask2);
+    dbg.lap("find_edges");
+    int rc = resolve_conflicts(mask1, mask2);
+    if (dbg.on) cudaStreamSynchronize(ctx->stream);
+    dbg.lap("resolve_conflicts+masks");
+    return rc;
 }
 
 static int seam_find_impl(is_ctx* ctx, int n, const is_mat* images, const is_point* corners, is_mat* masks, int cost_fn, TraceSink* trace) {

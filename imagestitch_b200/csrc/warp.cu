@@ -317,6 +317,8 @@ static int launch_warp_t(is_ctx* ctx, const WarpPlan& plan, const float* tables,
                          const DevMat* mask) {
     dim3 block(WARP_BX, WARP_BY);
     dim3 grid(div_up(plan.P.dst_w, WARP_BX * WARP_PX), div_up(plan.P.dst_h, WARP_BY));
+    // algorithmic bytes (B_warp_only): source read once, warped image (+ mask) written once
+    ctx->next_bytes = (double)CH * plan.P.src_w * plan.P.src_h + (double)(CH + (WITH_MASK ? 1 : 0)) * plan.P.dst_w * plan.P.dst_h;
     IS_LAUNCH(ctx, (k_warp<PROJ, CH, INTERP, BORDER, WITH_MASK>), grid, block, 0, plan.P, tables, src.ptr<uint8_t>(), src.step,
               dst.ptr<uint8_t>(), dst.step, mask ? mask->ptr<uint8_t>() : nullptr, mask ? mask->step : 0);
     return IS_OK;

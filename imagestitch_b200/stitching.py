@@ -105,6 +105,16 @@ class Context:
     def set_stream(self, cuda_stream_ptr):
         self.check(self.lib.is_ctx_set_stream(self.h, C.c_void_p(cuda_stream_ptr)))
 
+    def kernel_timing(self, enable: bool):
+        self.check(self.lib.is_ctx_kernel_timing(self.h, 1 if enable else 0))
+
+    def kernel_timing_report(self):
+        """[{name, launches, ms, bytes}] per kernel since the last report (CUDA events on the context's stream)."""
+        import json
+        buf = C.create_string_buffer(1 << 20)      # one call: the report clears the records
+        self.lib.is_ctx_kernel_timing_report(self.h, buf, len(buf))
+        return json.loads(buf.value.decode() or "[]")
+
     @property
     def kernel_launches(self) -> int:
         return int(self.lib.is_ctx_kernel_launches(self.h))

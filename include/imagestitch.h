@@ -78,6 +78,12 @@ void* is_ctx_stream(is_ctx* ctx);                     /* cudaStream_t all work o
 int is_ctx_set_stream(is_ctx* ctx, void* stream);     /* adopt a caller-owned cudaStream_t (NULL: back to the context's own) */
 uint64_t is_ctx_kernel_launches(const is_ctx* ctx);   /* kernels of this library launched so far */
 int is_ctx_device(const is_ctx* ctx);
+/* Per-launch CUDA-event timing for measurement (bench.py's roofline figure): when enabled every kernel launch
+ * of this context is bracketed by two events on the context's stream.  The report is a JSON array
+ * [{"name", "launches", "ms", "bytes"}] aggregated per kernel since the last report; it synchronises the
+ * stream, clears the records and returns the buffer length needed. */
+int is_ctx_kernel_timing(is_ctx* ctx, int enable);
+int is_ctx_kernel_timing_report(is_ctx* ctx, char* buf, size_t cap);
 
 /* ------------------------------------------------------------------ warp
  * Replaces the free functions of [WARP] (== cv::detail::RotationWarper created by
