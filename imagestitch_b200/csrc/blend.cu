@@ -280,6 +280,200 @@ __global__ void k_blend_level(LevelArgs A) {
     }
 }
 
+
+// ---- quad variant: one thread per 2x2 block of level-k pixels (k < nb) --------------------------------------------
+// The four pixels of an even-aligned 2x2 block share one 3x3 neighbourhood of the next coarser level, so pyrUp
+// costs 9 coarse loads per block instead of 9 per pixel (per axis: even = s[i-1] + 6 s[i] + s[i+1], odd =
+// 4 (s[i] + s[i+1]); s[-1] -> s[1], s[n] -> s[n-1]).  Image rectangles are even-aligned on every level below the
+// top one (offsets and sizes are multiples of 2^(nb-k)), so a block is entirely inside or outside an image.
+__device__ __forceinline__ void pyrup_quad(const int16_t* __restrict__ s, int sh, int sw, int cy, int cx, int out[4][3]) {
+    const int r0 = cy > 0 ? cy - 1 : (sh > 1 ? 1 : 0), r2 = cy + 1 < sh ? cy + 1 : sh - 1;
+    const int c0 = cx > 0 ? cx - 1 : (sw > 1 ? 1 : 0), c2 = cx + 1 < sw ? cx + 1 : sw - 1;
+    const int rows[3] = {r0, cy, r2};
+    int e[3][3], o[3][3];   // per row: even-column and odd-column horizontal sums
+#pragma unroll
+    for (int a = 0; a < 3; ++a) {
+        const int16_t* row = s + (size_t)rows[a] * sw * 3;
+        const int16_t* p0 = row + 3 * c0;
+        const int16_t* p1 = row + 3 * cx;
+        const int16_t* p2 = row + 3 * c2;
+#pragma unroll
+        for (int c = 0; c < 3; ++c) {
+            const int v0 = p0[c], v1 = p1[c], v2 = p2[c];
+            e[a][c] = v0 + 6 * v1 + v2;
+            o[a][c] = 4 * (v1 + v2);
+        }
+    }
+#pragma unroll
+    for (int c = 0; c < 3; ++c) {
+        out[0][c] = sat16((e[0][c] + 6 * e[1][c] + e[2][c] + 32) >> 6);   // (even y, even x)
+        out[1][c] = sat16((o[0][c] + 6 * o[1][c] + o[2][c] + 32) >> 6);   // (even y, odd x)
+        out[2][c] = sat16((4 * (e[1][c] + e[2][c]) + 32) >> 6);           // (odd y, even x)
+        out[3][c] = sat16((4 * (o[1][c] + o[2][c]) + 32) >> 6);           // (odd y, odd x)
+    }
+}
+
+template <bool WF>
+__global__ void __launch_bounds__(256) k_blend_level_quad(LevelArgs A) {
+    const int qx = blockIdx.x * blockDim.x + threadIdx.x;
+    const int qy = blockIdx.y * blockDim.y + threadIdx.y;
+    const int W = A.k == 0 ? A.fw : A.W, H = A.k == 0 ? A.fh : A.H;   // level 0 is cropped to the final ROI
+    const int x = 2 * qx, y = 2 * qy;
+    if (x >= W || y >= H) return;
+    int acc[4][3];
+    float wsum_f[4] = {0.f, 0.f, 0.f, 0.f};
+    int wsum_s[4] = {0, 0, 0, 0};
+#pragma unroll
+    for (int q = 0; q < 4; ++q) { acc[q][0] = 0; acc[q][1] = 0; acc[q][2] = 0; }
+    for (int i = 0; i < A.n; ++i) {
+        const ImgLevel& I = A.imgs[i];
+        const int lx = x - I.x_tl, ly = y - I.y_tl;
+        if ((unsigned)lx >= (unsigned)I.w || (unsigned)ly >= (unsigned)I.h) continue;
+        int u[4][3];
+        pyrup_quad(I.g_up, I.h >> 1, I.w >> 1, ly >> 1, lx >> 1, u);
+#pragma unroll
+        for (int q = 0; q < 4; ++q) {
+            const int px = lx + (q & 1), py = ly + (q >> 1);
+            int g[3];
+            if (A.k == 0) l0_pixel(I.l0, py, px, g);
+            else { const int16_t* p = I.g + ((size_t)py * I.w + px) * 3; g[0] = p[0]; g[1] = p[1]; g[2] = p[2]; }
+            g[0] = sat16(g[0] - u[q][0]); g[1] = sat16(g[1] - u[q][1]); g[2] = sat16(g[2] - u[q][2]);
+            if (WF) {
+                const float w = A.k == 0 ? l0_weight_f(I.l0, py, px) : reinterpret_cast<const float*>(I.wgt)[(size_t)py * I.w + px];
+                acc[q][0] += (int)(int16_t)__float2int_rz(__fmul_rn((float)g[0], w));
+                acc[q][1] += (int)(int16_t)__float2int_rz(__fmul_rn((float)g[1], w));
+                acc[q][2] += (int)(int16_t)__float2int_rz(__fmul_rn((float)g[2], w));
+                wsum_f[q] = __fadd_rn(wsum_f[q], w);
+            } else {
+                const int w = A.k == 0 ? l0_weight_s(I.l0, py, px) : (int)reinterpret_cast<const int16_t*>(I.wgt)[(size_t)py * I.w + px];
+                acc[q][0] += (int)(int16_t)((g[0] * w) >> 8);
+                acc[q][1] += (int)(int16_t)((g[1] * w) >> 8);
+                acc[q][2] += (int)(int16_t)((g[2] * w) >> 8);
+                wsum_s[q] = (int)(int16_t)(wsum_s[q] + w);
+            }
+        }
+    }
+    int up[4][3];
+    pyrup_quad(A.up, A.uh, A.uw, qy, qx, up);
+    int v[4][3];
+    bool on[4];
+#pragma unroll
+    for (int q = 0; q < 4; ++q) {
+#pragma unroll
+        for (int c = 0; c < 3; ++c) {
+            const int d = (int)(int16_t)acc[q][c];
+            int n;
+            if (WF) n = (int)(int16_t)__float2int_rz(__fdiv_rn((float)d, __fadd_rn(wsum_f[q], IS_WEIGHT_EPS)));
+            else n = (int)(int16_t)((d * 256) / (wsum_s[q] + 1));
+            v[q][c] = sat16(n + up[q][c]);
+        }
+        on[q] = WF ? (wsum_f[q] > IS_WEIGHT_EPS) : (wsum_s[q] >= 1);
+    }
+    if (A.k > 0) {   // W and H are even on these levels: the block is complete
+#pragma unroll
+        for (int r = 0; r < 2; ++r) {
+            uint32_t* o = reinterpret_cast<uint32_t*>(A.out + ((size_t)(y + r) * A.W + x) * 3);
+            const int a = 2 * r, b = 2 * r + 1;
+            o[0] = (uint32_t)(uint16_t)v[a][0] | ((uint32_t)(uint16_t)v[a][1] << 16);
+            o[1] = (uint32_t)(uint16_t)v[a][2] | ((uint32_t)(uint16_t)v[b][0] << 16);
+            o[2] = (uint32_t)(uint16_t)v[b][1] | ((uint32_t)(uint16_t)v[b][2] << 16);
+        }
+    } else {
+#pragma unroll
+        for (int r = 0; r < 2; ++r) {
+            if (y + r >= H) break;
+            int16_t* o = reinterpret_cast<int16_t*>(reinterpret_cast<char*>(A.dst) + (size_t)(y + r) * A.dstep) + 3 * x;
+            uint8_t* m = A.dmask + (size_t)(y + r) * A.mstep + x;
+            const int a = 2 * r, b = 2 * r + 1;
+            int va[3], vb[3];
+#pragma unroll
+            for (int c = 0; c < 3; ++c) { va[c] = on[a] ? v[a][c] : 0; vb[c] = on[b] ? v[b][c] : 0; }
+            if (x + 1 < W && ((reinterpret_cast<uintptr_t>(o) & 3) == 0)) {
+                uint32_t* o32 = reinterpret_cast<uint32_t*>(o);
+                o32[0] = (uint32_t)(uint16_t)va[0] | ((uint32_t)(uint16_t)va[1] << 16);
+                o32[1] = (uint32_t)(uint16_t)va[2] | ((uint32_t)(uint16_t)vb[0] << 16);
+                o32[2] = (uint32_t)(uint16_t)vb[1] | ((uint32_t)(uint16_t)vb[2] << 16);
+            } else {
+                o[0] = (int16_t)va[0]; o[1] = (int16_t)va[1]; o[2] = (int16_t)va[2];
+                if (x + 1 < W) { o[3] = (int16_t)vb[0]; o[4] = (int16_t)vb[1]; o[5] = (int16_t)vb[2]; }
+            }
+            m[0] = on[a] ? 255 : 0;
+            if (x + 1 < W) m[1] = on[b] ? 255 : 0;
+        }
+    }
+}
+
+// ---- pyrDown of level 0 through shared memory -------------------------------------------------------------------------
+// One block = PD_TX x PD_TY outputs.  The (2 PD_TX + 3) x (2 PD_TY + 3) input tile is fetched once through the
+// reflect-border view (REFLECT_101 of the padded frame, then BORDER_REFLECT into the fed image), packed as
+// (b, g, r, mask) in one 32-bit word; the horizontal 5-tap sums go to shared memory, the vertical pass finishes.
+constexpr int PD_TX = 32, PD_TY = 8, PD_IW = 2 * PD_TX + 3, PD_IH = 2 * PD_TY + 3;
+
+template <bool WF>
+__global__ void __launch_bounds__(PD_TX* PD_TY) k_pyrdown_l0_tiled(Level0 L, int16_t* __restrict__ g1, void* __restrict__ w1, int dh, int dw) {
+    __shared__ uint32_t tile[PD_IH][PD_IW + 1];
+    __shared__ int hsum[PD_IH][PD_TX][3];
+    __shared__ float hw_f[PD_IH][PD_TX];
+    const int tid = threadIdx.y * PD_TX + threadIdx.x;
+    const int ox0 = blockIdx.x * PD_TX, oy0 = blockIdx.y * PD_TY;
+    for (int e = tid; e < PD_IH * PD_IW; e += PD_TX * PD_TY) {
+        const int r = e / PD_IW, c = e % PD_IW;
+        const int y = reflect101(2 * oy0 - 2 + r, L.height), x = reflect101(2 * ox0 - 2 + c, L.width);
+        int v[3];
+        l0_pixel(L, y, x, v);
+        tile[r][c] = (uint32_t)v[0] | ((uint32_t)v[1] << 8) | ((uint32_t)v[2] << 16) | ((uint32_t)l0_mask(L, y, x) << 24);
+    }
+    __syncthreads();
+    for (int e = tid; e < PD_IH * PD_TX; e += PD_TX * PD_TY) {
+        const int r = e / PD_TX, ox = e % PD_TX;
+        uint32_t p[5];
+#pragma unroll
+        for (int b = 0; b < 5; ++b) p[b] = tile[r][2 * ox + b];
+        const int kk[5] = {1, 4, 6, 4, 1};
+        int s0 = 0, s1 = 0, s2 = 0;
+#pragma unroll
+        for (int b = 0; b < 5; ++b) { s0 += kk[b] * (int)(p[b] & 255); s1 += kk[b] * (int)((p[b] >> 8) & 255); s2 += kk[b] * (int)((p[b] >> 16) & 255); }
+        hsum[r][ox][0] = s0; hsum[r][ox][1] = s1; hsum[r][ox][2] = s2;
+        if (WF) {
+            float wv[5];
+#pragma unroll
+            for (int b = 0; b < 5; ++b) wv[b] = __fmul_rn((float)(p[b] >> 24), (float)(1. / 255.));
+            hw_f[r][ox] = __fadd_rn(__fadd_rn(__fadd_rn(__fmul_rn(wv[2], 6.f), __fmul_rn(__fadd_rn(wv[1], wv[3]), 4.f)), wv[0]), wv[4]);
+        } else {
+            int ws = 0;
+#pragma unroll
+            for (int b = 0; b < 5; ++b) { const int m = (int)(p[b] >> 24); ws += kk[b] * (m ? m + 1 : 0); }
+            hw_f[r][ox] = __int_as_float(ws);
+        }
+    }
+    __syncthreads();
+    const int ox = threadIdx.x, oy = threadIdx.y;
+    const int x = ox0 + ox, y = oy0 + oy;
+    if (x >= dw || y >= dh) return;
+    const int kk[5] = {1, 4, 6, 4, 1};
+    int acc[3] = {0, 0, 0};
+#pragma unroll
+    for (int a = 0; a < 5; ++a) {
+        acc[0] += kk[a] * hsum[2 * oy + a][ox][0];
+        acc[1] += kk[a] * hsum[2 * oy + a][ox][1];
+        acc[2] += kk[a] * hsum[2 * oy + a][ox][2];
+    }
+    const size_t o = (size_t)y * dw + x;
+    g1[3 * o] = (int16_t)sat16((acc[0] + 128) >> 8);
+    g1[3 * o + 1] = (int16_t)sat16((acc[1] + 128) >> 8);
+    g1[3 * o + 2] = (int16_t)sat16((acc[2] + 128) >> 8);
+    if (WF) {
+        const float r0 = hw_f[2 * oy][ox], r1 = hw_f[2 * oy + 1][ox], r2 = hw_f[2 * oy + 2][ox], r3 = hw_f[2 * oy + 3][ox], r4 = hw_f[2 * oy + 4][ox];
+        const float v = __fadd_rn(__fadd_rn(__fadd_rn(__fmul_rn(r2, 6.f), __fmul_rn(__fadd_rn(r1, r3), 4.f)), r0), r4);
+        reinterpret_cast<float*>(w1)[o] = __fmul_rn(v, 1.f / 256.f);
+    } else {
+        int wacc = 0;
+#pragma unroll
+        for (int a = 0; a < 5; ++a) wacc += kk[a] * __float_as_int(hw_f[2 * oy + a][ox]);
+        reinterpret_cast<int16_t*>(w1)[o] = (int16_t)sat16((wacc + 128) >> 8);
+    }
+}
+
 }  // namespace is
 
 using namespace is;
@@ -378,8 +572,9 @@ int blender_feed_dev(is_blender* b, FedImage&& f) {
         ctx->next_bytes = in_px * (k == 1 ? (f.img.depth == IS_8U ? 3 : 6) + 1 : 6 + (double)wsz) + (double)dh * dw * (6 + (double)wsz);
         if (k == 1) {
             Level0 L = level0_of(f);
-            if (wf) IS_LAUNCH(ctx, k_pyrdown_l0<true>, grid, block, 0, L, f.g[1].as<int16_t>(), f.w[1].p, dh, dw);
-            else IS_LAUNCH(ctx, k_pyrdown_l0<false>, grid, block, 0, L, f.g[1].as<int16_t>(), f.w[1].p, dh, dw);
+            dim3 tb(PD_TX, PD_TY), tg(div_up(dw, PD_TX), div_up(dh, PD_TY));
+            if (wf) IS_LAUNCH(ctx, k_pyrdown_l0_tiled<true>, tg, tb, 0, L, f.g[1].as<int16_t>(), f.w[1].p, dh, dw);
+            else IS_LAUNCH(ctx, k_pyrdown_l0_tiled<false>, tg, tb, 0, L, f.g[1].as<int16_t>(), f.w[1].p, dh, dw);
         } else {
             if (wf) IS_LAUNCH(ctx, k_pyrdown<true>, grid, block, 0, f.g[k - 1].as<int16_t>(), f.w[k - 1].p, sh, sw, f.g[k].as<int16_t>(), f.w[k].p, dh, dw);
             else IS_LAUNCH(ctx, k_pyrdown<false>, grid, block, 0, f.g[k - 1].as<int16_t>(), f.w[k - 1].p, sh, sw, f.g[k].as<int16_t>(), f.w[k].p, dh, dw);
@@ -442,8 +637,14 @@ int blender_blend_dev(is_blender* b, const DevMat& dst, const DevMat& dmask) {
             bytes += k == 0 ? (double)A.fw * A.fh * 7 : (double)H[k] * W[k] * 6;
             ctx->next_bytes = bytes;
         }
-        if (wf) IS_LAUNCH(ctx, k_blend_level<true>, grid, block, 0, A);
-        else IS_LAUNCH(ctx, k_blend_level<false>, grid, block, 0, A);
+        if (k < nb) {   // 2x2 blocks share their pyrUp neighbourhood
+            dim3 qgrid(div_up(div_up(gw, 2), 32), div_up(div_up(gh, 2), 8));
+            if (wf) IS_LAUNCH(ctx, k_blend_level_quad<true>, qgrid, block, 0, A);
+            else IS_LAUNCH(ctx, k_blend_level_quad<false>, qgrid, block, 0, A);
+        } else {
+            if (wf) IS_LAUNCH(ctx, k_blend_level<true>, grid, block, 0, A);
+            else IS_LAUNCH(ctx, k_blend_level<false>, grid, block, 0, A);
+        }
     }
     b->fed.clear();        // OpenCV releases the pyramids in blend()
     b->prepared = false;
