@@ -205,6 +205,8 @@ int is_ctx_destroy(is_ctx* ctx) {
     if (!ctx) return IS_OK;
     cudaSetDevice(ctx->device);
     cudaStreamSynchronize(ctx->stream);
+    for (is_ctx* c : ctx->children) is_ctx_destroy(c);
+    ctx->children.clear();
     for (int i = 0; i < 5; ++i) if (ctx->ev[i]) cudaEventDestroy(ctx->ev[i]);
     for (auto& r : ctx->krecs) { cudaEventDestroy(r.e0); cudaEventDestroy(r.e1); }
     for (auto e : ctx->kpool) cudaEventDestroy(e);
@@ -270,6 +272,8 @@ int is_ctx_kernel_timing_report(is_ctx* ctx, char* buf, size_t cap) {
     }
     return (int)out.size() + 1;
 }
+
+int is_ctx_seam_speculation(const is_ctx* ctx) { return ctx ? ctx->seam_speculation_accepted : -1; }
 
 const char* is_ctx_last_error(const is_ctx* ctx) { return ctx ? ctx->last_error.c_str() : "null context"; }
 void* is_ctx_stream(is_ctx* ctx) { return ctx ? (void*)ctx->stream : nullptr; }

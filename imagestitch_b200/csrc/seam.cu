@@ -27,6 +27,7 @@
 #include <cmath>
 #include <map>
 #include <set>
+#include <thread>
 #include <utility>
 
 namespace is {
@@ -729,7 +730,16 @@ struct TraceSink {
 class PairSeam {
 public:
     PairSeam(is_ctx* c, bool u8, TraceSink* tr) : ctx(c), is_u8(u8), trace(tr) {}
-    int process(const DevMat& image1, const DevMat& image2, Pt tl1, Pt tl2, const DevMat& mask1, const DevMat& mask2, int pi, int pj);
+    // in1/in2: masks as the pair sees them; out1/out2: where the masks with this pair's clears go (may alias in1/in2).
+    // structure_only: stop after the component / contour analysis (used to validate a speculative run).
+    int process(const DevMat& image1, const DevMat& image2, Pt tl1, Pt tl2, const DevMat& in1, const DevMat& in2, const DevMat& out1,
+                const DevMat& out2, int pi, int pj, bool structure_only = false);
+    // Everything the pair does after labelling is a function of these two (and of the images): the raster-ordered
+    // contour records of the INTERS components (pixels, labels, neighbour labels, contour-proximity flags) and the
+    // states of the components they mention.
+    std::vector<ContourRec> fp_records;
+    std::vector<int> fp_states;
+    bool same_structure(const PairSeam& o) const;
 
 private:
     is_ctx* ctx;
@@ -750,6 +760,7 @@ private:
     DevBuf counts, offsets, recs;
 
     Frame frame() const { return Frame{uw, uh}; }
+    void release_device() { cls.release(); parent.release(); labels.release(); counts.release(); offsets.release(); recs.release(); }
     int ccl(const uint8_t* klass, int kmask, int w, int h, int* parent_out);
     int collect_roots(const int* parent_d, const uint8_t* klass_d, size_t n, std::vector<std::pair<int, int>>* roots);
     int extract_contours(int wx, int wy, int ww, int wh, int fa, int fb, std::vector<ContourRec>* out);
@@ -758,8 +769,20 @@ private:
     bool get_seam_tips(int c1, int c2, Pt* p1, Pt* p2);
     int estimate_and_update(int c1, int c2, Pt p1, Pt p2);
     int refresh_component(int c);
-    int resolve_conflicts(const DevMat& mask1, const DevMat& mask2);
+    int resolve_conflicts(const DevMat& in1, const DevMat& in2, const DevMat& out1, const DevMat& out2);
 };
+
+bool PairSeam::same_structure(const PairSeam& o) const {
+    if (fp_records.size() != o.fp_records.size()) return false;
+    if (!fp_records.empty() && std::memcmp(fp_records.data(), o.fp_records.data(), sizeof(ContourRec) * fp_records.size()) != 0) return false;
+    auto state_of = [](const std::vector<int>& st, int label) { return (label >= 1 && label <= (int)st.size()) ? st[label - 1] : -1; };
+    for (const ContourRec& r : fp_records) {
+        if (state_of(fp_states, r.label) != state_of(o.fp_states, r.label)) return false;
+        for (int k = 0; k < 4; ++k)
+            if (r.nl[k] > 0 && state_of(fp_states, r.nl[k]) != state_of(o.fp_states, r.nl[k])) return false;
+    }
+    return true;
+}
 
 int PairSeam::ccl(const uint8_t* klass, int kmask, int w, int h, int* parent_out) {
     IS_LAUNCH(ctx, k_ccl_rows, h, 256, 0, klass, kmask, parent_out, w);
@@ -1130,7 +1153,7 @@ int PairSeam::estimate_and_update(int c1, int c2, Pt p1, Pt p2) {
 }
 
 // [SEAM]:395-546
-int PairSeam::resolve_conflicts(const DevMat& mask1, const DevMat& mask2) {
+int PairSeam::resolve_conflicts(const DevMat& in1, const DevMat& in2, const DevMat& mask1, const DevMat& mask2) {
     bool hasConflict = true;
     while (hasConflict) {
         int c1 = 0, c2 = 0;
@@ -1158,6 +1181,10 @@ int PairSeam::resolve_conflicts(const DevMat& mask1, const DevMat& mask2) {
         edges.erase({c2, c1});
     }
     // update masks ([SEAM]:524-545): mask2 first (reads the original mask1), then mask1 (reads the updated mask2)
+    if (mask1.data != in1.data)
+        IS_CUDA(ctx, cudaMemcpy2DAsync(mask1.data, mask1.step, in1.data, in1.step, (size_t)in1.cols, in1.rows, cudaMemcpyDeviceToDevice, ctx->stream));
+    if (mask2.data != in2.data)
+        IS_CUDA(ctx, cudaMemcpy2DAsync(mask2.data, mask2.step, in2.data, in2.step, (size_t)in2.cols, in2.rows, cudaMemcpyDeviceToDevice, ctx->stream));
     DevBuf st;
     IS_TRY(st.alloc(ctx, sizeof(int) * (size_t)std::max(ncomps, 1)));
     if (ncomps) IS_TRY(upload(ctx, st.p, states.data(), sizeof(int) * (size_t)ncomps));
@@ -1178,7 +1205,8 @@ int PairSeam::resolve_conflicts(const DevMat& mask1, const DevMat& mask2) {
 }
 
 // [SEAM]:127-193
-int PairSeam::process(const DevMat& image1, const DevMat& image2, Pt tl1, Pt tl2, const DevMat& mask1, const DevMat& mask2, int pi, int pj) {
+int PairSeam::process(const DevMat& image1, const DevMat& image2, Pt tl1, Pt tl2, const DevMat& mask1, const DevMat& mask2, const DevMat& out1,
+                      const DevMat& out2, int pi, int pj, bool structure_only) {
     pair_i = pi; pair_j = pj;
     DbgTimer dbg;
     IS_REQUIRE(ctx, image1.rows == mask1.rows && image1.cols == mask1.cols, IS_ERR_ASSERT, "image1.size() == mask1.size()");
@@ -1242,12 +1270,228 @@ int PairSeam::process(const DevMat& image1, const DevMat& image2, Pt tl1, Pt tl2
         brs[c].x = std::max(brs[c].x, r.x + 1); brs[c].y = std::max(brs[c].y, r.y + 1);
     }
     dbg.lap("labels+contours");
+    fp_records = all;
+    fp_states = states;
+    if (structure_only) { release_device(); return IS_OK; }
     find_edges();
     dbg.lap("find_edges");
-    int rc = resolve_conflicts(mask1, mask2);
+    int rc = resolve_conflicts(mask1, mask2, out1, out2);
     if (dbg.on) cudaStreamSynchronize(ctx->stream);
     dbg.lap("resolve_conflicts+masks");
+    release_device();
     return rc;
+}
+
+// dst keeps its value where src is non-zero and becomes 0 where src is 0 (intersection of two clear sets)
+__global__ void k_mask_and(uint8_t* dst, size_t dstep, const uint8_t* __restrict__ src, size_t sstep, int rows, int cols) {
+    const int x = blockIdx.x * blockDim.x + threadIdx.x;
+    const int y = blockIdx.y * blockDim.y + threadIdx.y;
+    if (x >= cols || y >= rows) return;
+    if (src[(size_t)y * sstep + x] == 0) dst[(size_t)y * dstep + x] = 0;
+}
+
+static int mask_and(is_ctx* ctx, const DevMat& dst, const DevMat& src) {
+    dim3 block(64, 4), grid(div_up(dst.cols, 64), div_up(dst.rows, 4));
+    IS_LAUNCH(ctx, k_mask_and, grid, block, 0, dst.ptr<uint8_t>(), dst.step, src.ptr<uint8_t>(), src.step, dst.rows, dst.cols);
+    return IS_OK;
+}
+
+static int mask_copy(is_ctx* ctx, const DevMat& dst, const DevMat& src) {
+    IS_CUDA(ctx, cudaMemcpy2DAsync(dst.data, dst.step, src.data, src.step, (size_t)src.cols, src.rows, cudaMemcpyDeviceToDevice, ctx->stream));
+    return IS_OK;
+}
+
+// The reference's order ([SEAM]:97-121): pairs (i, j), i < j, lexicographic, reversed; masks updated in place.
+static int seam_find_sequential(is_ctx* ctx, const std::vector<std::pair<int, int>>& pairs, const DevMat* images, const is_point* corners,
+                                const DevMat* masks, TraceSink* trace) {
+    for (auto& pr : pairs) {
+        PairSeam ps(ctx, images[pr.first].depth == IS_8U, trace);
+        IS_TRY(ps.process(images[pr.first], images[pr.second], Pt{corners[pr.first].x, corners[pr.first].y},
+                          Pt{corners[pr.second].x, corners[pr.second].y}, masks[pr.first], masks[pr.second], masks[pr.first], masks[pr.second],
+                          pr.first, pr.second));
+    }
+    return IS_OK;
+}
+
+// ---- speculative concurrent execution ------------------------------------------------------------------------------
+// Every pair modifies its two masks in place, so the reference's loop is a dependency chain: pair p must see the
+// clears of every earlier pair that shares an image with it.  In a panorama those clears almost never reach the
+// part of the mask pair p looks at, but that is a property of the data, not of the algorithm.  So:
+//   1. all overlapping pairs run CONCURRENTLY (one host thread + CUDA stream each) on the masks as they were at
+//      entry, each writing its clears into private copies, and each keeping its structural fingerprint
+//      (PairSeam::fp_records / fp_states: everything the pair computes after labelling is a function of it);
+//   2. every pair with an earlier neighbour recomputes ONLY that fingerprint on the masks it would really have
+//      seen (entry masks minus the clears of the earlier pairs) -- also concurrently;
+//   3. if all fingerprints agree, the speculative clears are exactly what the sequential loop produces and the
+//      final masks are their intersection; otherwise everything is redone sequentially.
+// The DP passes (one CTA each, latency bound) and the host/device round trips of different pairs overlap.
+struct PairJob {
+    int i, j;
+    DevMat out_i, out_j;          // private result masks
+    PairSeam* spec = nullptr;
+    TraceSink trace;
+    std::vector<int32_t> trace_buf;
+    int status = IS_OK;
+    bool needs_check = false, valid = true;
+};
+
+static int child_ctx(is_ctx* parent, size_t k, is_ctx** out) {
+    while (parent->children.size() <= k) {
+        is_ctx* c = new is_ctx();
+        c->device = parent->device;
+        if (cudaStreamCreateWithFlags(&c->own_stream, cudaStreamNonBlocking) != cudaSuccess) { delete c; return fail(parent, IS_ERR_CUDA, "cudaStreamCreate failed"); }
+        c->stream = c->own_stream;
+        c->pool = parent->pool;
+        for (int e = 0; e < 5; ++e) cudaEventCreateWithFlags(&c->ev[e], cudaEventDisableTiming);
+        parent->children.push_back(c);
+    }
+    *out = parent->children[k];
+    return IS_OK;
+}
+
+template <typename F>
+static void run_on_workers(is_ctx* parent, std::vector<is_ctx*>& workers, size_t njobs, F&& fn) {
+    std::vector<std::thread> th;
+    const size_t T = std::min(workers.size(), njobs);
+    for (size_t t = 0; t < T; ++t)
+        th.emplace_back([&, t] {
+            cudaSetDevice(parent->device);
+            for (size_t k = t; k < njobs; k += T) fn(workers[t], k);
+        });
+    for (auto& x : th) x.join();
+}
+
+static int seam_find_concurrent(is_ctx* ctx, const std::vector<std::pair<int, int>>& active, int n, const DevMat* images, const is_point* corners,
+                                const DevMat* masks, TraceSink* trace, bool* accepted) {
+    *accepted = false;
+    const size_t np = active.size();
+    std::vector<PairJob> jobs(np);
+    size_t T = std::min<size_t>(np, 8);
+    if (const char* e = getenv("IS_SEAM_WORKERS")) T = std::max<size_t>(1, std::min<size_t>(np, (size_t)atoi(e)));
+    std::vector<is_ctx*> workers(T);
+    for (size_t t = 0; t < T; ++t) {
+        IS_TRY(child_ctx(ctx, t, &workers[t]));
+        workers[t]->ktiming = ctx->ktiming;
+        workers[t]->launches = 0;
+    }
+    for (size_t k = 0; k < np; ++k) {
+        jobs[k].i = active[k].first; jobs[k].j = active[k].second;
+        IS_TRY(alloc_mat(ctx, masks[jobs[k].i].rows, masks[jobs[k].i].cols, 1, IS_8U, &jobs[k].out_i));
+        IS_TRY(alloc_mat(ctx, masks[jobs[k].j].rows, masks[jobs[k].j].cols, 1, IS_8U, &jobs[k].out_j));
+        if (trace) { jobs[k].trace_buf.resize(5 + 2 * (size_t)(images[jobs[k].i].rows + images[jobs[k].i].cols + images[jobs[k].j].rows + images[jobs[k].j].cols) * 4);
+                     jobs[k].trace.buf = jobs[k].trace_buf.data(); jobs[k].trace.cap = jobs[k].trace_buf.size(); }
+    }
+    // fork: the workers' streams start after everything queued on the caller's stream
+    IS_CUDA(ctx, cudaEventRecord(ctx->ev[4], ctx->stream));
+    for (size_t t = 0; t < T; ++t) IS_CUDA(ctx, cudaStreamWaitEvent(workers[t]->stream, ctx->ev[4], 0));
+    DbgTimer dbg;
+    // 1. speculative runs on the entry masks
+    run_on_workers(ctx, workers, np, [&](is_ctx* w, size_t k) {
+        PairJob& J = jobs[k];
+        J.spec = new PairSeam(w, images[J.i].depth == IS_8U, trace ? &J.trace : nullptr);
+        J.status = J.spec->process(images[J.i], images[J.j], Pt{corners[J.i].x, corners[J.i].y}, Pt{corners[J.j].x, corners[J.j].y}, masks[J.i],
+                                   masks[J.j], J.out_i, J.out_j, J.i, J.j);
+        if (J.status == IS_OK && cudaStreamSynchronize(w->stream) != cudaSuccess) J.status = IS_ERR_CUDA;
+    });
+    dbg.lap("concurrent: speculative runs");
+    // 2. validate the pairs that had an earlier neighbour
+    auto earlier = [&](size_t k, int img) {   // results of earlier pairs for image img
+        std::vector<const DevMat*> v;
+        for (size_t q = 0; q < k; ++q) {
+            if (jobs[q].i == img) v.push_back(&jobs[q].out_i);
+            if (jobs[q].j == img) v.push_back(&jobs[q].out_j);
+        }
+        return v;
+    };
+    bool failed = false;
+    for (size_t k = 0; k < np; ++k) {
+        if (jobs[k].status != IS_OK) failed = true;
+        jobs[k].needs_check = !earlier(k, jobs[k].i).empty() || !earlier(k, jobs[k].j).empty();
+    }
+    if (!failed)
+        run_on_workers(ctx, workers, np, [&](is_ctx* w, size_t k) {
+            PairJob& J = jobs[k];
+            if (!J.needs_check) return;
+            DevMat true_i, true_j;
+            const DevMat* in[2] = {&masks[J.i], &masks[J.j]};
+            DevMat* tmp[2] = {&true_i, &true_j};
+            const int img[2] = {J.i, J.j};
+            for (int s2 = 0; s2 < 2 && J.status == IS_OK; ++s2) {
+                auto ev = earlier(k, img[s2]);
+                if (ev.empty()) continue;
+                J.status = alloc_mat(w, in[s2]->rows, in[s2]->cols, 1, IS_8U, tmp[s2]);
+                if (J.status == IS_OK) J.status = mask_copy(w, *tmp[s2], *ev[0]);
+                for (size_t q = 1; q < ev.size() && J.status == IS_OK; ++q) J.status = mask_and(w, *tmp[s2], *ev[q]);
+                in[s2] = tmp[s2];
+            }
+            if (J.status != IS_OK) return;
+            PairSeam chk(w, images[J.i].depth == IS_8U, nullptr);
+            J.status = chk.process(images[J.i], images[J.j], Pt{corners[J.i].x, corners[J.i].y}, Pt{corners[J.j].x, corners[J.j].y}, *in[0], *in[1],
+                                   *in[0], *in[1], J.i, J.j, /*structure_only=*/true);
+            if (J.status == IS_OK) J.valid = chk.same_structure(*J.spec);
+            cudaStreamSynchronize(w->stream);
+        });
+    dbg.lap("concurrent: validation");
+    int rc = IS_OK;
+    bool all_valid = !failed;
+    for (size_t k = 0; k < np; ++k) {
+        if (jobs[k].status != IS_OK && rc == IS_OK) { rc = jobs[k].status; }
+        if (!jobs[k].valid) all_valid = false;
+        delete jobs[k].spec;
+        jobs[k].spec = nullptr;
+    }
+    // join: account the workers' launches / timing records to the caller's context
+    for (size_t t = 0; t < T; ++t) {
+        if (rc != IS_OK && !workers[t]->last_error.empty() && ctx->last_error.empty()) ctx->last_error = workers[t]->last_error;
+        ctx->launches += workers[t]->launches;
+        for (auto& r : workers[t]->krecs) ctx->krecs.push_back(r);
+        workers[t]->krecs.clear();
+        IS_CUDA(ctx, cudaEventRecord(workers[t]->ev[0], workers[t]->stream));
+        IS_CUDA(ctx, cudaStreamWaitEvent(ctx->stream, workers[t]->ev[0], 0));
+    }
+    if (rc != IS_OK) {
+        for (size_t t = 0; t < T; ++t) if (!workers[t]->last_error.empty()) { ctx->last_error = workers[t]->last_error; break; }
+        return rc;
+    }
+    if (!all_valid) return IS_OK;                        // caller falls back to the sequential loop
+    // 3. final masks = entry masks minus every pair's clears
+    for (size_t k = 0; k < np; ++k) {
+        IS_TRY(mask_and(ctx, masks[jobs[k].i], jobs[k].out_i));
+        IS_TRY(mask_and(ctx, masks[jobs[k].j], jobs[k].out_j));
+        if (trace) {
+            const size_t len = jobs[k].trace.len;
+            if (trace->buf && trace->len + len <= trace->cap && len <= jobs[k].trace.cap) std::memcpy(trace->buf + trace->len, jobs[k].trace_buf.data(), len * sizeof(int32_t));
+            trace->len += len;
+        }
+    }
+    (void)n;
+    *accepted = true;
+    return IS_OK;
+}
+
+// device-resident images / masks (masks in-out); used by is_seam_dp_find* and by the pipeline
+int seam_find_core(is_ctx* ctx, int n, const DevMat* images, const is_point* corners, const DevMat* masks, TraceSink* trace) {
+    std::vector<std::pair<int, int>> pairs;                                  // [SEAM]:97-111 (no sort, reversed)
+    for (int i = 0; i + 1 < n; ++i)
+        for (int j = i + 1; j < n; ++j) pairs.push_back({i, j});
+    std::reverse(pairs.begin(), pairs.end());
+    std::vector<std::pair<int, int>> active;                                 // pairs that do not return at [SEAM]:142-143
+    for (auto& pr : pairs) {
+        const int i = pr.first, j = pr.second;
+        const int x0 = std::max(corners[i].x, corners[j].x), y0 = std::max(corners[i].y, corners[j].y);
+        const int x1 = std::min(corners[i].x + images[i].cols, corners[j].x + images[j].cols);
+        const int y1 = std::min(corners[i].y + images[i].rows, corners[j].y + images[j].rows);
+        if (x0 < x1 && y0 < y1) active.push_back(pr);
+    }
+    const char* seq = getenv("IS_SEAM_SEQUENTIAL");
+    ctx->seam_speculation_accepted = -1;
+    if (active.size() >= 2 && !(seq && seq[0] == '1')) {
+        bool accepted = false;
+        IS_TRY(seam_find_concurrent(ctx, active, n, images, corners, masks, trace, &accepted));
+        ctx->seam_speculation_accepted = accepted ? 1 : 0;
+        if (accepted) return IS_OK;
+    }
+    return seam_find_sequential(ctx, active, images, corners, masks, trace);
 }
 
 static int seam_find_impl(is_ctx* ctx, int n, const is_mat* images, const is_point* corners, is_mat* masks, int cost_fn, TraceSink* trace) {
@@ -1271,31 +1515,14 @@ static int seam_find_impl(is_ctx* ctx, int n, const is_mat* images, const is_poi
         IS_TRY(stage_in(ctx, &images[i], &dimg[i]));
         IS_TRY(stage_out(ctx, &masks[i], &dmask[i], true));
     }
-    std::vector<std::pair<int, int>> pairs;                                  // [SEAM]:97-111 (no sort, reversed)
-    for (int i = 0; i + 1 < n; ++i)
-        for (int j = i + 1; j < n; ++j) pairs.push_back({i, j});
-    std::reverse(pairs.begin(), pairs.end());
-    for (auto& pr : pairs) {
-        PairSeam ps(ctx, depth == IS_8U, trace);
-        IS_TRY(ps.process(dimg[pr.first], dimg[pr.second], Pt{corners[pr.first].x, corners[pr.first].y},
-                          Pt{corners[pr.second].x, corners[pr.second].y}, dmask[pr.first], dmask[pr.second], pr.first, pr.second));
-    }
+    IS_TRY(seam_find_core(ctx, n, dimg.data(), corners, dmask.data(), trace));
     for (int i = 0; i < n; ++i) IS_TRY(commit(ctx, &dmask[i]));
     return IS_OK;
 }
 
 // used by the pipeline with device-resident mats
 int seam_find_device(is_ctx* ctx, int n, const DevMat* images, const is_point* corners, const DevMat* masks) {
-    std::vector<std::pair<int, int>> pairs;
-    for (int i = 0; i + 1 < n; ++i)
-        for (int j = i + 1; j < n; ++j) pairs.push_back({i, j});
-    std::reverse(pairs.begin(), pairs.end());
-    for (auto& pr : pairs) {
-        PairSeam ps(ctx, images[pr.first].depth == IS_8U, nullptr);
-        IS_TRY(ps.process(images[pr.first], images[pr.second], Pt{corners[pr.first].x, corners[pr.first].y},
-                          Pt{corners[pr.second].x, corners[pr.second].y}, masks[pr.first], masks[pr.second], pr.first, pr.second));
-    }
-    return IS_OK;
+    return seam_find_core(ctx, n, images, corners, masks, nullptr);
 }
 
 }  // namespace is

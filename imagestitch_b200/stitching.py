@@ -116,6 +116,11 @@ class Context:
         return json.loads(buf.value.decode() or "[]")
 
     @property
+    def seam_speculation(self) -> int:
+        """1: concurrent pair execution accepted, 0: fell back to the sequential loop, -1: sequential by construction."""
+        return int(self.lib.is_ctx_seam_speculation(self.h))
+
+    @property
     def kernel_launches(self) -> int:
         return int(self.lib.is_ctx_kernel_launches(self.h))
 

@@ -128,6 +128,11 @@ int is_seam_dp_find(is_ctx* ctx, int n, const is_mat* images, const is_point* co
 int is_seam_dp_find_trace(is_ctx* ctx, int n, const is_mat* images, const is_point* corners, is_mat* masks,
                           int cost_fn, int32_t* trace, size_t trace_cap, size_t* trace_len);
 
+/* How the last is_seam_dp_find / is_pipeline_run on this context executed the pair loop: 1 = the pairs ran
+ * concurrently and their results were proven equal to the reference's sequential loop, 0 = the proof failed and
+ * the sequential loop was run, -1 = sequential (fewer than two overlapping pairs, or IS_SEAM_SEQUENTIAL=1). */
+int is_ctx_seam_speculation(const is_ctx* ctx);
+
 /* computeCosts [SEAM]:733-803 for the component labelled `label` of a host/device label image
  * (IS_32S, union frame of the pair, top-left union_tl in panorama coordinates) over `roi` (union-frame
  * coordinates).  costV: roi.height x (roi.width + 1), costH: (roi.height + 1) x roi.width, IS_32F. */

@@ -223,3 +223,28 @@ def test_pipeline_device_resident(ctx, oracle):
     ctx.synchronize()
     _eq(got["pano"].cpu().numpy(), want["pano"], "device-resident pano")
     _eq(got["pano_mask"].cpu().numpy(), want["pano_mask"], "device-resident pano mask")
+
+
+def test_seam_concurrent_pairs_are_proven_or_redone(ctx, oracle, monkeypatch):
+    """The pair loop runs concurrently and is accepted only when proven equal to the sequential loop
+    (is_ctx_seam_speculation); mutually overlapping images (rho = 0.6) exercise the dependent case."""
+    O = oracle
+    f = S.DpSeamFinder(ctx, "COLOR")
+    corners, wi, wm = warped_set(O, 4, 256, 200, overlap=0.25)          # strip: independent pairs
+    want = O.dp_seam_find(wi, corners, wm)
+    got = f.find(wi, corners, [m.copy() for m in wm])
+    assert ctx.seam_speculation == 1
+    for k in range(4):
+        _eq(got[k], want[k], f"concurrent mask {k}")
+    monkeypatch.setenv("IS_SEAM_SEQUENTIAL", "1")
+    got = f.find(wi, corners, [m.copy() for m in wm])
+    assert ctx.seam_speculation == -1
+    for k in range(4):
+        _eq(got[k], want[k], f"sequential mask {k}")
+    monkeypatch.delenv("IS_SEAM_SEQUENTIAL")
+    corners, wi, wm = warped_set(O, 3, 300, 200, overlap=0.6)           # images 0 and 2 overlap as well
+    want = O.dp_seam_find(wi, corners, wm)
+    got = f.find(wi, corners, [m.copy() for m in wm])
+    assert ctx.seam_speculation in (0, 1)
+    for k in range(3):
+        _eq(got[k], want[k], f"dependent mask {k}")
