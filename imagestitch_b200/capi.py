@@ -82,6 +82,12 @@ SYMBOLS = {
     "is_seam_dp_find": (C.c_int, [C.c_void_p, C.c_int, _P(Mat), _P(Point), _P(Mat), C.c_int]),
     "is_seam_dp_find_trace": (C.c_int, [C.c_void_p, C.c_int, _P(Mat), _P(Point), _P(Mat), C.c_int, _P(C.c_int32), C.c_size_t, _P(C.c_size_t)]),
     "is_ctx_seam_speculation": (C.c_int, [C.c_void_p]),
+    "is_seam_pair_run": (C.c_int, [C.c_void_p, _P(Mat), _P(Mat), Point, Point, _P(Mat), _P(Mat), _P(Mat), _P(Mat), _P(C.c_void_p)]),
+    "is_seam_pair_check": (C.c_int, [C.c_void_p, _P(Mat), _P(Mat), Point, Point, _P(Mat), _P(Mat), C.c_void_p, _P(C.c_int)]),
+    "is_seam_pair_destroy": (C.c_int, [C.c_void_p]),
+    "is_mask_and": (C.c_int, [C.c_void_p, _P(Mat), _P(Mat)]),
+    "is_blender_strip_needs": (C.c_int, [C.c_void_p, Size, Point, C.c_int, C.c_int, _P(C.c_int)]),
+    "is_blender_blend_strip": (C.c_int, [C.c_void_p, C.c_int, C.c_int, _P(Mat), _P(Mat)]),
     "is_seam_cost_maps": (C.c_int, [C.c_void_p, _P(Mat), _P(Mat), Point, Point, _P(Mat), Point, C.c_int, Rect, _P(Mat), _P(Mat)]),
     "is_blender_create": (C.c_int, [C.c_void_p, C.c_int, C.c_int, _P(C.c_void_p)]),
     "is_blender_destroy": (C.c_int, [C.c_void_p]),

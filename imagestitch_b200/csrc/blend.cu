@@ -219,14 +219,16 @@ struct LevelArgs {
     const int16_t* up; int uh, uw;     // collapsed level k+1
     // k == 0 only: final outputs
     int16_t* dst; size_t dstep; uint8_t* dmask; size_t mstep; int fw, fh;
+    int xb, xe;                        // columns of this level computed by the launch (xb even)
+    int sx0, sx1;                      // level 0: columns of the final ROI stored (dst column = x - sx0)
 };
 
 template <bool WF>
 __global__ void k_blend_level(LevelArgs A) {
-    const int x = blockIdx.x * blockDim.x + threadIdx.x;
+    const int x = A.xb + blockIdx.x * blockDim.x + threadIdx.x;
     const int y = blockIdx.y * blockDim.y + threadIdx.y;
-    const int W = A.k == 0 ? A.fw : A.W, H = A.k == 0 ? A.fh : A.H;   // level 0 is cropped to the final ROI
-    if (x >= W || y >= H) return;
+    const int W = A.k == 0 ? min(A.fw, A.sx1) : min(A.W, A.xe), H = A.k == 0 ? A.fh : A.H;   // level 0 is cropped to the final ROI
+    if (x >= W || y >= H || (A.k == 0 && x < A.sx0)) return;
     int acc[3] = {0, 0, 0};
     float wsum_f = 0.f;
     int wsum_s = 0;
@@ -274,9 +276,9 @@ __global__ void k_blend_level(LevelArgs A) {
         o[0] = (int16_t)v[0]; o[1] = (int16_t)v[1]; o[2] = (int16_t)v[2];
     } else {
         const bool on = WF ? (wsum_f > IS_WEIGHT_EPS) : (wsum_s >= 1);
-        int16_t* o = reinterpret_cast<int16_t*>(reinterpret_cast<char*>(A.dst) + (size_t)y * A.dstep) + 3 * x;
+        int16_t* o = reinterpret_cast<int16_t*>(reinterpret_cast<char*>(A.dst) + (size_t)y * A.dstep) + 3 * (x - A.sx0);
         o[0] = on ? (int16_t)v[0] : 0; o[1] = on ? (int16_t)v[1] : 0; o[2] = on ? (int16_t)v[2] : 0;
-        A.dmask[(size_t)y * A.mstep + x] = on ? 255 : 0;
+        A.dmask[(size_t)y * A.mstep + (x - A.sx0)] = on ? 255 : 0;
     }
 }
 
@@ -317,8 +319,8 @@ template <bool WF>
 __global__ void __launch_bounds__(256) k_blend_level_quad(LevelArgs A) {
     const int qx = blockIdx.x * blockDim.x + threadIdx.x;
     const int qy = blockIdx.y * blockDim.y + threadIdx.y;
-    const int W = A.k == 0 ? A.fw : A.W, H = A.k == 0 ? A.fh : A.H;   // level 0 is cropped to the final ROI
-    const int x = 2 * qx, y = 2 * qy;
+    const int W = A.k == 0 ? min(A.fw, A.sx1) : min(A.W, A.xe), H = A.k == 0 ? A.fh : A.H;   // level 0 is cropped to the final ROI
+    const int x = A.xb + 2 * qx, y = 2 * qy;
     if (x >= W || y >= H) return;
     int acc[4][3];
     float wsum_f[4] = {0.f, 0.f, 0.f, 0.f};
@@ -354,7 +356,7 @@ __global__ void __launch_bounds__(256) k_blend_level_quad(LevelArgs A) {
         }
     }
     int up[4][3];
-    pyrup_quad(A.up, A.uh, A.uw, qy, qx, up);
+    pyrup_quad(A.up, A.uh, A.uw, qy, x >> 1, up);
     int v[4][3];
     bool on[4];
 #pragma unroll
@@ -382,12 +384,16 @@ __global__ void __launch_bounds__(256) k_blend_level_quad(LevelArgs A) {
 #pragma unroll
         for (int r = 0; r < 2; ++r) {
             if (y + r >= H) break;
-            int16_t* o = reinterpret_cast<int16_t*>(reinterpret_cast<char*>(A.dst) + (size_t)(y + r) * A.dstep) + 3 * x;
-            uint8_t* m = A.dmask + (size_t)(y + r) * A.mstep + x;
+            int16_t* o = reinterpret_cast<int16_t*>(reinterpret_cast<char*>(A.dst) + (size_t)(y + r) * A.dstep) + 3 * (x - A.sx0);
+            uint8_t* m = A.dmask + (size_t)(y + r) * A.mstep + (x - A.sx0);
             const int a = 2 * r, b = 2 * r + 1;
             int va[3], vb[3];
 #pragma unroll
             for (int c = 0; c < 3; ++c) { va[c] = on[a] ? v[a][c] : 0; vb[c] = on[b] ? v[b][c] : 0; }
+            if (x < A.sx0) {          // strip starting at an odd column: only the second pixel of the block belongs to it
+                if (x + 1 < W) { o[3] = (int16_t)vb[0]; o[4] = (int16_t)vb[1]; o[5] = (int16_t)vb[2]; m[1] = on[b] ? 255 : 0; }
+                continue;
+            }
             if (x + 1 < W && ((reinterpret_cast<uintptr_t>(o) & 3) == 0)) {
                 uint32_t* o32 = reinterpret_cast<uint32_t*>(o);
                 o32[0] = (uint32_t)(uint16_t)va[0] | ((uint32_t)(uint16_t)va[1] << 16);
@@ -529,6 +535,43 @@ static int private_copy(is_ctx* ctx, const is_mat* m, DevMat* out) {
     return IS_OK;
 }
 
+// per-level column ranges [xb, xe) a blend of the final-ROI columns [x0, x1) has to compute (pyrUp halo, even starts)
+static void strip_ranges(const is_blender* b, int x0, int x1, std::vector<int>* xb, std::vector<int>* xe) {
+    const int nb = b->num_bands;
+    std::vector<int> W(nb + 1);
+    W[0] = b->roi.width;
+    for (int k = 1; k <= nb; ++k) W[k] = (W[k - 1] + 1) / 2;
+    xb->assign(nb + 1, 0);
+    xe->assign(nb + 1, 0);
+    (*xb)[0] = x0 & ~1;
+    (*xe)[0] = std::min(W[0], (x1 + 1) & ~1);
+    for (int k = 1; k <= nb; ++k) {
+        (*xb)[k] = std::max(0, ((*xb)[k - 1] >> 1) - 1) & ~1;
+        (*xe)[k] = std::min(W[k], ((((*xe)[k - 1] - 1) >> 1) + 3) & ~1);
+        if (W[k] & 1) (*xe)[k] = std::min(W[k], (((*xe)[k - 1] - 1) >> 1) + 2);   // only the top level can be odd
+    }
+}
+
+// padded rectangle of a fed image inside dst_roi_ (MultiBandBlender::feed geometry): x_tl, y_tl, width, height, top, left
+static void feed_geometry(const is_blender* b, int rows, int cols, int tl_x, int tl_y, int g[6]) {
+    const int nb = b->num_bands;
+    const is_rect R = b->roi;
+    const int gap = 3 * (1 << nb);
+    int tlx = std::max(R.x, tl_x - gap), tly = std::max(R.y, tl_y - gap);
+    int brx = std::min(R.x + R.width, tl_x + cols + gap), bry = std::min(R.y + R.height, tl_y + rows + gap);
+    tlx = R.x + (((tlx - R.x) >> nb) << nb);
+    tly = R.y + (((tly - R.y) >> nb) << nb);
+    int width = brx - tlx, height = bry - tly;
+    const int m = 1 << nb;
+    width += (m - width % m) % m;
+    height += (m - height % m) % m;
+    brx = tlx + width;
+    bry = tly + height;
+    const int dy = std::max(bry - (R.y + R.height), 0), dx = std::max(brx - (R.x + R.width), 0);
+    tlx -= dx; tly -= dy;
+    g[0] = tlx - R.x; g[1] = tly - R.y; g[2] = width; g[3] = height; g[4] = tl_y - tly; g[5] = tl_x - tlx;
+}
+
 int blender_feed_dev(is_blender* b, FedImage&& f) {
     is_ctx* ctx = b->ctx;
     const int nb = b->num_bands;
@@ -585,8 +628,10 @@ int blender_feed_dev(is_blender* b, FedImage&& f) {
     return IS_OK;
 }
 
-int blender_blend_dev(is_blender* b, const DevMat& dst, const DevMat& dmask) {
+int blender_blend_dev(is_blender* b, const DevMat& dst, const DevMat& dmask, int sx0, int sx1) {
     is_ctx* ctx = b->ctx;
+    std::vector<int> xb, xe;
+    strip_ranges(b, sx0, sx1, &xb, &xe);
     const int nb = b->num_bands, n = (int)b->fed.size();
     const bool wf = b->weight_type == IS_WEIGHT_32F;
     // panorama level dims
@@ -622,7 +667,9 @@ int blender_blend_dev(is_blender* b, const DevMat& dst, const DevMat& dmask) {
         A.uh = k < nb ? H[k + 1] : 0; A.uw = k < nb ? W[k + 1] : 0;
         A.dst = dst.ptr<int16_t>(); A.dstep = dst.step; A.dmask = dmask.ptr<uint8_t>(); A.mstep = dmask.step;
         A.fw = b->roi_final.width; A.fh = b->roi_final.height;
-        const int gw = k == 0 ? A.fw : A.W, gh = k == 0 ? A.fh : A.H;
+        A.xb = xb[k]; A.xe = xe[k]; A.sx0 = sx0; A.sx1 = sx1;
+        const int gw = std::max(0, xe[k] - xb[k]), gh = k == 0 ? A.fh : A.H;
+        if (gw == 0) continue;
         dim3 block(32, 8), grid(div_up(gw, 32), div_up(gh, 8));
         {   // algorithmic bytes: every input of the level read once, the collapsed level written once
             const double wsz = wf ? 4 : 2;
@@ -635,7 +682,7 @@ int blender_blend_dev(is_blender* b, const DevMat& dst, const DevMat& dmask) {
             }
             if (k < nb) bytes += (double)H[k + 1] * W[k + 1] * 6;
             bytes += k == 0 ? (double)A.fw * A.fh * 7 : (double)H[k] * W[k] * 6;
-            ctx->next_bytes = bytes;
+            ctx->next_bytes = bytes * ((double)gw / (double)W[k]);   // strip: the share of the level this launch covers
         }
         if (k < nb) {   // 2x2 blocks share their pyrUp neighbourhood
             dim3 qgrid(div_up(div_up(gw, 2), 32), div_up(div_up(gh, 2), 8));
@@ -719,6 +766,41 @@ int is_blender_feed(is_blender* b, const is_mat* img, const is_mat* mask, is_poi
     return blender_feed_dev(b, std::move(f));
 }
 
+int is_blender_strip_needs(const is_blender* b, is_size img_size, is_point tl, int x0, int x1, int* needed) {
+    if (!b || !needed || !b->prepared) return IS_ERR_BAD_ARG;
+    std::vector<int> xb, xe;
+    strip_ranges(b, x0, x1, &xb, &xe);
+    int g[6];
+    feed_geometry(b, img_size.height, img_size.width, tl.x, tl.y, g);
+    *needed = 0;
+    for (int k = 0; k <= b->num_bands; ++k) {
+        const int lo = g[0] >> k, hi = (g[0] + g[2]) >> k;
+        if (lo < xe[k] && hi > xb[k]) { *needed = 1; break; }
+    }
+    return IS_OK;
+}
+
+int is_blender_blend_strip(is_blender* b, int x0, int x1, is_mat* dst, is_mat* dst_mask) {
+    if (!b) return IS_ERR_BAD_ARG;
+    is_ctx* ctx = b->ctx;
+    IS_CUDA(ctx, cudaSetDevice(ctx->device));
+    IS_REQUIRE(ctx, b->prepared, IS_ERR_ASSERT, "blend() before prepare()");
+    IS_REQUIRE(ctx, 0 <= x0 && x0 < x1 && x1 <= b->roi_final.width, IS_ERR_BAD_ARG, "strip must lie inside the destination ROI");
+    IS_TRY(check_mat(ctx, dst, "dst"));
+    IS_TRY(check_mat(ctx, dst_mask, "dst_mask"));
+    IS_REQUIRE(ctx, dst->depth == IS_16S && dst->channels == 3 && dst->rows == b->roi_final.height && dst->cols == x1 - x0, IS_ERR_BAD_ARG,
+               "dst must be CV_16SC3, ROI height x strip width");
+    IS_REQUIRE(ctx, dst_mask->depth == IS_8U && dst_mask->channels == 1 && dst_mask->rows == dst->rows && dst_mask->cols == dst->cols,
+               IS_ERR_BAD_ARG, "dst_mask must be CV_8U of the strip size");
+    DevMat d, m;
+    IS_TRY(stage_out(ctx, dst, &d, false));
+    IS_TRY(stage_out(ctx, dst_mask, &m, false));
+    IS_TRY(blender_blend_dev(b, d, m, x0, x1));
+    IS_TRY(commit(ctx, &d));
+    IS_TRY(commit(ctx, &m));
+    return IS_OK;
+}
+
 int is_blender_blend(is_blender* b, is_mat* dst, is_mat* dst_mask) {
     if (!b) return IS_ERR_BAD_ARG;
     is_ctx* ctx = b->ctx;
@@ -733,7 +815,7 @@ int is_blender_blend(is_blender* b, is_mat* dst, is_mat* dst_mask) {
     DevMat d, m;
     IS_TRY(stage_out(ctx, dst, &d, false));
     IS_TRY(stage_out(ctx, dst_mask, &m, false));
-    IS_TRY(blender_blend_dev(b, d, m));
+    IS_TRY(blender_blend_dev(b, d, m, 0, b->roi_final.width));
     IS_TRY(commit(ctx, &d));
     IS_TRY(commit(ctx, &m));
     return IS_OK;

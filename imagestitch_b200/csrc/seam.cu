@@ -1545,6 +1545,93 @@ int is_seam_dp_find_trace(is_ctx* ctx, int n, const is_mat* images, const is_poi
     return rc;
 }
 
+// ---- single-pair primitives for sharded execution (one strip of the panorama per GPU) ---------------------------
+struct is_seam_pair_impl { std::vector<ContourRec> records; std::vector<int> states; };
+
+static int pair_common(is_ctx* ctx, const is_mat* image_i, const is_mat* image_j, const is_mat* mask_i, const is_mat* mask_j) {
+    IS_TRY(check_mat(ctx, image_i, "image_i"));
+    IS_TRY(check_mat(ctx, image_j, "image_j"));
+    IS_TRY(check_mat(ctx, mask_i, "mask_i"));
+    IS_TRY(check_mat(ctx, mask_j, "mask_j"));
+    IS_REQUIRE(ctx, image_i->channels == 3 && image_j->channels == 3 && image_i->depth == image_j->depth &&
+                        (image_i->depth == IS_8U || image_i->depth == IS_32F), IS_ERR_BAD_ARG, "both images must have CV_32FC3 or CV_8UC3 type");
+    IS_REQUIRE(ctx, mask_i->depth == IS_8U && mask_i->channels == 1 && mask_j->depth == IS_8U && mask_j->channels == 1, IS_ERR_BAD_ARG, "masks must be CV_8U");
+    return IS_OK;
+}
+
+int is_seam_pair_run(is_ctx* ctx, const is_mat* image_i, const is_mat* image_j, is_point tl_i, is_point tl_j, const is_mat* mask_i,
+                     const is_mat* mask_j, is_mat* out_i, is_mat* out_j, is_seam_pair** result) {
+    if (!ctx || !result) return IS_ERR_BAD_ARG;
+    IS_CUDA(ctx, cudaSetDevice(ctx->device));
+    IS_TRY(pair_common(ctx, image_i, image_j, mask_i, mask_j));
+    IS_TRY(check_mat(ctx, out_i, "out_i"));
+    IS_TRY(check_mat(ctx, out_j, "out_j"));
+    IS_REQUIRE(ctx, out_i->rows == mask_i->rows && out_i->cols == mask_i->cols && out_j->rows == mask_j->rows && out_j->cols == mask_j->cols &&
+                        out_i->depth == IS_8U && out_j->depth == IS_8U, IS_ERR_BAD_ARG, "out masks must match the input masks");
+    DevMat di, dj, mi, mj, oi, oj;
+    IS_TRY(stage_in(ctx, image_i, &di));
+    IS_TRY(stage_in(ctx, image_j, &dj));
+    IS_TRY(stage_in(ctx, mask_i, &mi));
+    IS_TRY(stage_in(ctx, mask_j, &mj));
+    IS_TRY(stage_out(ctx, out_i, &oi, false));
+    IS_TRY(stage_out(ctx, out_j, &oj, false));
+    PairSeam ps(ctx, image_i->depth == IS_8U, nullptr);
+    const bool overlap = std::max(tl_i.x, tl_j.x) < std::min(tl_i.x + image_i->cols, tl_j.x + image_j->cols) &&
+                         std::max(tl_i.y, tl_j.y) < std::min(tl_i.y + image_i->rows, tl_j.y + image_j->rows);
+    if (overlap) IS_TRY(ps.process(di, dj, Pt{tl_i.x, tl_i.y}, Pt{tl_j.x, tl_j.y}, mi, mj, oi, oj, 0, 1));
+    else { IS_TRY(mask_copy(ctx, oi, mi)); IS_TRY(mask_copy(ctx, oj, mj)); }
+    IS_TRY(commit(ctx, &oi));
+    IS_TRY(commit(ctx, &oj));
+    is_seam_pair_impl* r = new is_seam_pair_impl();
+    r->records = ps.fp_records;
+    r->states = ps.fp_states;
+    *result = reinterpret_cast<is_seam_pair*>(r);
+    return IS_OK;
+}
+
+int is_seam_pair_check(is_ctx* ctx, const is_mat* image_i, const is_mat* image_j, is_point tl_i, is_point tl_j, const is_mat* mask_i,
+                       const is_mat* mask_j, const is_seam_pair* spec, int* same) {
+    if (!ctx || !spec || !same) return IS_ERR_BAD_ARG;
+    IS_CUDA(ctx, cudaSetDevice(ctx->device));
+    IS_TRY(pair_common(ctx, image_i, image_j, mask_i, mask_j));
+    DevMat di, dj, mi, mj;
+    IS_TRY(stage_in(ctx, image_i, &di));
+    IS_TRY(stage_in(ctx, image_j, &dj));
+    IS_TRY(stage_in(ctx, mask_i, &mi));
+    IS_TRY(stage_in(ctx, mask_j, &mj));
+    PairSeam chk(ctx, image_i->depth == IS_8U, nullptr);
+    const bool overlap = std::max(tl_i.x, tl_j.x) < std::min(tl_i.x + image_i->cols, tl_j.x + image_j->cols) &&
+                         std::max(tl_i.y, tl_j.y) < std::min(tl_i.y + image_i->rows, tl_j.y + image_j->rows);
+    if (overlap) IS_TRY(chk.process(di, dj, Pt{tl_i.x, tl_i.y}, Pt{tl_j.x, tl_j.y}, mi, mj, mi, mj, 0, 1, /*structure_only=*/true));
+    const is_seam_pair_impl* sp = reinterpret_cast<const is_seam_pair_impl*>(spec);
+    PairSeam ref(ctx, true, nullptr);
+    ref.fp_records = sp->records;
+    ref.fp_states = sp->states;
+    *same = chk.same_structure(ref) ? 1 : 0;
+    IS_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+    return IS_OK;
+}
+
+int is_seam_pair_destroy(is_seam_pair* p) {
+    delete reinterpret_cast<is_seam_pair_impl*>(p);
+    return IS_OK;
+}
+
+int is_mask_and(is_ctx* ctx, is_mat* dst, const is_mat* src) {
+    if (!ctx) return IS_ERR_BAD_ARG;
+    IS_CUDA(ctx, cudaSetDevice(ctx->device));
+    IS_TRY(check_mat(ctx, dst, "dst"));
+    IS_TRY(check_mat(ctx, src, "src"));
+    IS_REQUIRE(ctx, dst->depth == IS_8U && src->depth == IS_8U && dst->channels == 1 && src->channels == 1 && dst->rows == src->rows &&
+                        dst->cols == src->cols, IS_ERR_BAD_ARG, "masks must be CV_8U of equal size");
+    DevMat d, sm;
+    IS_TRY(stage_out(ctx, dst, &d, true));
+    IS_TRY(stage_in(ctx, src, &sm));
+    IS_TRY(mask_and(ctx, d, sm));
+    IS_TRY(commit(ctx, &d));
+    return IS_OK;
+}
+
 int is_seam_cost_maps(is_ctx* ctx, const is_mat* image1, const is_mat* image2, is_point tl1, is_point tl2, const is_mat* labels,
                       is_point union_tl, int label, is_rect roi, is_mat* costV, is_mat* costH) {
     if (!ctx) return IS_ERR_BAD_ARG;

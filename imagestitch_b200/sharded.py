@@ -1,0 +1,328 @@
+"""Column-strip sharding of one panorama across the GPUs of a box.
+
+One process per GPU (torch.distributed: NCCL on GPUs, gloo in the CPU tests).  Rank r owns a contiguous group of
+the strip's images and the panorama columns [cut[r], cut[r+1]).  Per step:
+
+  warp        local (each rank warps its own images)
+  X1          the right image of every pair that straddles a strip boundary travels to the owner of the left image
+              (warped u8x3 + warped mask) -- neighbour-only P2P
+  seam        every rank runs the pairs it owns CONCURRENTLY and speculatively on the entry masks
+              (is_seam_pair_run); results needed elsewhere travel (X2: mask-sized messages); each pair with an
+              earlier neighbour in the reference's order proves its result on the masks it would really have seen
+              (is_seam_pair_check); one all-reduce of the verdict; if any proof fails every rank falls back to the
+              reference's sequential loop on all-gathered inputs
+  X3          blend halo: images that reach into a neighbour's strip travel with their final masks
+  blend       is_blender_blend_strip on the rank's columns; the panorama stays sharded
+
+The host logic here (ownership, exchange schedule, strip cuts) is pure Python over a small `backend` object, so the
+N > 1 path is covered on CPU with gloo (tests/test_sharded_gloo.py) while the GPU backend calls the C ABI.
+"""
+from __future__ import annotations
+
+import threading
+from dataclasses import dataclass, field
+
+import numpy as np
+
+
+def _overlap(c1, s1, c2, s2):
+    return max(c1[0], c2[0]) < min(c1[0] + s1[0], c2[0] + s2[0]) and max(c1[1], c2[1]) < min(c1[1] + s1[1], c2[1] + s2[1])
+
+
+@dataclass
+class ShardPlan:
+    """Everything every rank can derive from the geometry alone (deterministic, identical on all ranks)."""
+    corners: list
+    sizes: list
+    roi: tuple
+    world: int
+    num_bands: int
+    owner: list = field(default_factory=list)
+    pairs: list = field(default_factory=list)        # active pairs in the reference's order ([SEAM]:100-111)
+    cuts: list = field(default_factory=list)         # panorama columns (relative to roi.x): rank r owns [cuts[r], cuts[r+1])
+
+    @staticmethod
+    def build(corners, sizes, roi, world, num_bands):
+        n = len(corners)
+        assert n % world == 0, "images must divide evenly over the ranks"
+        m = n // world
+        p = ShardPlan([tuple(int(v) for v in c) for c in corners], [tuple(int(v) for v in s) for s in sizes], tuple(int(v) for v in roi), world, num_bands)
+        p.owner = [i // m for i in range(n)]
+        allp = [(i, j) for i in range(n) for j in range(i + 1, n)][::-1]
+        p.pairs = [(i, j) for (i, j) in allp if _overlap(p.corners[i], p.sizes[i], p.corners[j], p.sizes[j])]
+        nb = min(num_bands, int(np.ceil(np.log(max(roi[2], roi[3])) / np.log(2.0))))
+        q = 1 << nb
+        cuts = [0]
+        for r in range(1, world):
+            a, b = r * m - 1, r * m                   # last image of rank r-1, first image of rank r
+            lo = p.corners[b][0]
+            hi = p.corners[a][0] + p.sizes[a][0]
+            mid = (lo + hi) // 2 - roi[0]
+            mid = max(cuts[-1] + q, min(roi[2] - q, (mid // q) * q))
+            cuts.append(mid)
+        cuts.append(roi[2])
+        p.cuts = cuts
+        return p
+
+    def pair_owner(self, k):
+        return self.owner[self.pairs[k][0]]           # the rank that owns the left (lower-index) image
+
+    def earlier(self, k, img):
+        """indices of the earlier pairs (reference order) that contain image img"""
+        return [q for q in range(k) if img in self.pairs[q]]
+
+
+class Comm:
+    """Neighbour exchange over torch.distributed (batch_isend_irecv); world == 1 degenerates to nothing."""
+
+    def __init__(self, dist=None):
+        self.dist = dist
+        self.rank = dist.get_rank() if dist else 0
+        self.world = dist.get_world_size() if dist else 1
+
+    def exchange(self, sends, recvs):
+        """sends: [(dst_rank, tensor)], recvs: [(src_rank, tensor)] -- matched by order per peer."""
+        if not self.dist or (not sends and not recvs):
+            return
+        ops = [self.dist.P2POp(self.dist.isend, t, dst) for dst, t in sends] + [self.dist.P2POp(self.dist.irecv, t, src) for src, t in recvs]
+        for req in self.dist.batch_isend_irecv(ops):
+            req.wait()
+
+    def all_min(self, value: int, device):
+        if not self.dist:
+            return value
+        import torch
+        t = torch.tensor([value], dtype=torch.int32, device=device)
+        self.dist.all_reduce(t, op=self.dist.ReduceOp.MIN)
+        return int(t.item())
+
+
+class ShardedStitcher:
+    """backend: object with warp / pair_run / pair_check / mask_and / clone / empty / strip_needs / blend_strip /
+    run_concurrently / sync / device (see GpuBackend below and the oracle-backed double in the tests)."""
+
+    def __init__(self, backend, comm: Comm, num_bands=5):
+        self.be, self.comm, self.num_bands = backend, comm, num_bands
+        self.info = {}
+
+    def stitch(self, my_images, Ks_all, Rs_all, scale, plan: ShardPlan):
+        be, comm, rank = self.be, self.comm, self.comm.rank
+        n = len(plan.corners)
+        mine = [i for i in range(n) if plan.owner[i] == rank]
+        assert len(mine) == len(my_images)
+        # ---- warp (local)
+        warped, mask0 = {}, {}
+        for i, img in zip(mine, my_images):
+            warped[i], mask0[i] = be.warp(img, Ks_all[i], Rs_all[i], scale)
+        be.sync()
+        # ---- X1: right images of boundary pairs -> owner of the left image
+        sends, recvs = [], []
+        seen = set()
+        for k, (i, j) in enumerate(plan.pairs):
+            src, dst = plan.owner[j], plan.pair_owner(k)
+            if src == dst or (j, dst) in seen:
+                continue
+            seen.add((j, dst))
+            if rank == src:
+                sends += [(dst, warped[j]), (dst, mask0[j])]
+            if rank == dst:
+                warped[j] = be.empty((plan.sizes[j][1], plan.sizes[j][0], 3), np.uint8)
+                mask0[j] = be.empty((plan.sizes[j][1], plan.sizes[j][0]), np.uint8)
+                recvs += [(src, warped[j]), (src, mask0[j])]
+        comm.exchange(sends, recvs)
+        # ---- seam: speculative runs of the pairs this rank owns
+        my_pairs = [k for k in range(len(plan.pairs)) if plan.pair_owner(k) == rank]
+        outs, handles = {}, {}
+
+        def run(k):
+            i, j = plan.pairs[k]
+            oi, oj, h = be.pair_run(warped[i], warped[j], plan.corners[i], plan.corners[j], mask0[i], mask0[j])
+            outs[(k, i)], outs[(k, j)], handles[k] = oi, oj, h
+
+        be.run_concurrently(run, my_pairs)
+        be.sync()
+        # ---- X2: pair results to whoever needs them (final masks of the images' owners, validation of later pairs)
+        sends, recvs = [], []
+        for k, (i, j) in enumerate(plan.pairs):
+            src = plan.pair_owner(k)
+            for img in (i, j):
+                dsts = {plan.owner[img]} | {plan.pair_owner(k2) for k2 in range(k + 1, len(plan.pairs)) if img in plan.pairs[k2]}
+                for dst in sorted(dsts - {src}):
+                    if rank == src:
+                        sends.append((dst, outs[(k, img)]))
+                    if rank == dst:
+                        outs[(k, img)] = be.empty((plan.sizes[img][1], plan.sizes[img][0]), np.uint8)
+                        recvs.append((src, outs[(k, img)]))
+        comm.exchange(sends, recvs)
+        # ---- validation of the owned pairs that have an earlier neighbour
+        verdict = {}
+
+        def check(k):
+            i, j = plan.pairs[k]
+            true = {}
+            for img in (i, j):
+                ev = plan.earlier(k, img)
+                if not ev:
+                    true[img] = mask0[img]
+                    continue
+                t = be.clone(outs[(ev[0], img)])
+                for q in ev[1:]:
+                    be.mask_and(t, outs[(q, img)])
+                true[img] = t
+            if true[i] is mask0[i] and true[j] is mask0[j]:
+                verdict[k] = True
+                return
+            verdict[k] = be.pair_check(warped[i], warped[j], plan.corners[i], plan.corners[j], true[i], true[j], handles[k])
+
+        be.run_concurrently(check, my_pairs)
+        be.sync()
+        ok = comm.all_min(1 if all(verdict.values()) else 0, be.device)
+        self.info["seam_speculation"] = ok
+        for k in my_pairs:
+            be.pair_free(handles[k])
+        final = {}
+        if ok:
+            for i in mine:                            # final mask = entry mask minus the clears of every pair it is in
+                t = be.clone(mask0[i])
+                for k, pr in enumerate(plan.pairs):
+                    if i in pr:
+                        be.mask_and(t, outs[(k, i)])
+                final[i] = t
+        else:
+            final, warped = self._sequential_fallback(plan, mine, warped, mask0)
+        be.sync()
+        # ---- X3: blend halo
+        x0, x1 = plan.cuts[rank], plan.cuts[rank + 1]
+        needed_by = [[i for i in range(n) if be.strip_needs(plan.sizes[i], plan.corners[i], plan.roi, self.num_bands, plan.cuts[r], plan.cuts[r + 1])]
+                     for r in range(comm.world)]
+        sends, recvs = [], []
+        for r in range(comm.world):
+            for i in needed_by[r]:
+                src = plan.owner[i]
+                if src == r:
+                    continue
+                if rank == src:
+                    sends += [(r, warped[i]), (r, final[i])]
+                if rank == r:
+                    warped[i] = be.empty((plan.sizes[i][1], plan.sizes[i][0], 3), np.uint8)
+                    final[i] = be.empty((plan.sizes[i][1], plan.sizes[i][0]), np.uint8)
+                    recvs += [(src, warped[i]), (src, final[i])]
+        comm.exchange(sends, recvs)
+        # ---- blend my strip (feed order = global image order)
+        feed = [(warped[i], final[i], plan.corners[i]) for i in needed_by[rank]]
+        pano, pmask = be.blend_strip(feed, plan.roi, self.num_bands, x0, x1)
+        self.info["needed_images"] = needed_by[rank]
+        return dict(pano=pano, pano_mask=pmask, x0=x0, x1=x1, seam_masks={i: final[i] for i in mine})
+
+    def _sequential_fallback(self, plan, mine, warped, mask0):
+        """A proof failed somewhere: all-gather the warped images + entry masks and run the reference's loop on every
+        rank (redundantly); rare by construction (the pairs of a panorama are independent in practice)."""
+        be, comm = self.be, self.comm
+        n = len(plan.corners)
+        allw, allm = {}, {}
+        for i in range(n):
+            src = plan.owner[i]
+            sends, recvs = [], []
+            if comm.rank == src:
+                allw[i], allm[i] = warped[i], mask0[i]
+                sends = [(r, t) for r in range(comm.world) if r != src for t in (warped[i], mask0[i])]
+            else:
+                allw[i] = be.empty((plan.sizes[i][1], plan.sizes[i][0], 3), np.uint8)
+                allm[i] = be.empty((plan.sizes[i][1], plan.sizes[i][0]), np.uint8)
+                recvs = [(src, allw[i]), (src, allm[i])]
+            comm.exchange(sends, recvs)
+        masks = be.seam_find_all([allw[i] for i in range(n)], plan.corners, [be.clone(allm[i]) for i in range(n)])
+        return {i: masks[i] for i in range(n)}, allw
+
+
+class GpuBackend:
+    """The C ABI on one GPU; arrays are torch CUDA tensors."""
+
+    def __init__(self, device_index, projection="cylindrical", weight_type=None, workers=6):
+        import torch
+
+        from . import stitching as S
+        self.torch, self.S = torch, S
+        self.device = torch.device("cuda", device_index)
+        self.proj = projection
+        self.wt = S.WEIGHT_32F if weight_type is None else weight_type
+        self.ctx = S.Context(device_index, use_torch_stream=True)
+        self.workers = [S.Context(device_index) for _ in range(workers)]
+        self.tls = threading.local()
+
+    def _ctx(self):
+        return getattr(self.tls, "ctx", self.ctx)
+
+    def sync(self):
+        self.torch.cuda.synchronize(self.device)
+
+    def empty(self, shape, dtype):
+        return self.torch.empty(shape, dtype={np.uint8: self.torch.uint8, np.int16: self.torch.int16}[dtype], device=self.device)
+
+    def clone(self, t):
+        return t.clone()
+
+    def warp(self, img, K, R, scale):
+        _, w, m = self.S.RotationWarper(self.ctx, self.proj, scale).warp_with_mask(img, K, R)
+        return w, m
+
+    def pair_run(self, wi, wj, ci, cj, mi, mj):
+        return self.S.DpSeamFinder(self._ctx(), "COLOR").pair_run(wi, wj, ci, cj, mi, mj)
+
+    def pair_check(self, wi, wj, ci, cj, mi, mj, h):
+        return self.S.DpSeamFinder(self._ctx(), "COLOR").pair_check(wi, wj, ci, cj, mi, mj, h)
+
+    def pair_free(self, h):
+        self.S.DpSeamFinder(self.ctx, "COLOR").pair_free(h)
+
+    def mask_and(self, dst, src):
+        c = self._ctx()
+        self.S.DpSeamFinder(c, "COLOR").mask_and(dst, src)
+        if c is not self.ctx:
+            c.synchronize()
+
+    def seam_find_all(self, images, corners, masks):
+        return self.S.DpSeamFinder(self.ctx, "COLOR").find(images, corners, masks)
+
+    def run_concurrently(self, fn, items):
+        """fn(item) on worker threads, each bound to its own context / CUDA stream (ctypes releases the GIL)."""
+        self.sync()
+        if len(items) <= 1:
+            for it in items:
+                fn(it)
+            return
+        errs = []
+
+        def work(t):
+            self.tls.ctx = self.workers[t]
+            try:
+                for it in items[t::len(self.workers)]:
+                    fn(it)
+                self.workers[t].synchronize()
+            except Exception as e:      # noqa: BLE001 - re-raised below
+                errs.append(e)
+
+        th = [threading.Thread(target=work, args=(t,)) for t in range(min(len(self.workers), len(items)))]
+        for x in th:
+            x.start()
+        for x in th:
+            x.join()
+        if errs:
+            raise errs[0]
+
+    def _blender(self, roi, num_bands):
+        b = self.S.MultiBandBlender(self.ctx, 0, num_bands, self.wt)
+        b.prepare(roi)
+        return b
+
+    def strip_needs(self, size_wh, corner, roi, num_bands, x0, x1):
+        key = (tuple(roi), num_bands)
+        if getattr(self, "_needs_key", None) != key:
+            self._needs_b, self._needs_key = self._blender(roi, num_bands), key
+        return self._needs_b.strip_needs(size_wh, corner, x0, x1)
+
+    def blend_strip(self, feed, roi, num_bands, x0, x1):
+        b = self._blender(roi, num_bands)
+        for (img, mask, corner) in feed:
+            b.feed(img, mask, corner, borrow=True)
+        return b.blend_strip(x0, x1)

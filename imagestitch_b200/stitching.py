@@ -224,6 +224,43 @@ class DpSeamFinder:
             k += 5 + 2 * npts
         return masks, res
 
+    def pair_run(self, image_i, image_j, tl_i, tl_j, mask_i, mask_j):
+        """One pair of the loop on the given input masks -> (out_i, out_j, handle).  The inputs are not modified."""
+        mi, _a = as_mat(image_i)
+        mj, _b = as_mat(image_j)
+        ki, _c = as_mat(mask_i)
+        kj, _d = as_mat(mask_j)
+        out_i = _alloc_like(mask_i, (ki.rows, ki.cols), np.uint8)
+        out_j = _alloc_like(mask_j, (kj.rows, kj.cols), np.uint8)
+        oi, _e = as_mat(out_i)
+        oj, _f = as_mat(out_j)
+        h = C.c_void_p()
+        self.ctx.check(self.ctx.lib.is_seam_pair_run(self.ctx.h, C.byref(mi), C.byref(mj), capi.Point(int(tl_i[0]), int(tl_i[1])),
+                                                     capi.Point(int(tl_j[0]), int(tl_j[1])), C.byref(ki), C.byref(kj), C.byref(oi), C.byref(oj),
+                                                     C.byref(h)))
+        return out_i, out_j, h
+
+    def pair_check(self, image_i, image_j, tl_i, tl_j, mask_i, mask_j, handle) -> bool:
+        """True when the pair run that produced `handle` is proven equal to a run on these (true) input masks."""
+        mi, _a = as_mat(image_i)
+        mj, _b = as_mat(image_j)
+        ki, _c = as_mat(mask_i)
+        kj, _d = as_mat(mask_j)
+        same = C.c_int(0)
+        self.ctx.check(self.ctx.lib.is_seam_pair_check(self.ctx.h, C.byref(mi), C.byref(mj), capi.Point(int(tl_i[0]), int(tl_i[1])),
+                                                       capi.Point(int(tl_j[0]), int(tl_j[1])), C.byref(ki), C.byref(kj), handle, C.byref(same)))
+        return bool(same.value)
+
+    def pair_free(self, handle):
+        self.ctx.lib.is_seam_pair_destroy(handle)
+
+    def mask_and(self, dst, src):
+        """dst = 0 where src == 0 (intersection of clear sets), in place."""
+        md, _a = as_mat(dst)
+        ms, _b = as_mat(src)
+        self.ctx.check(self.ctx.lib.is_mask_and(self.ctx.h, C.byref(md), C.byref(ms)))
+        return dst
+
     def cost_maps(self, image1, image2, tl1, tl2, labels, union_tl, label, roi_xywh):
         """computeCosts [SEAM]:733-803 -> (costV h x (w+1), costH (h+1) x w)"""
         x, y, w, h = (int(v) for v in roi_xywh)
@@ -279,6 +316,29 @@ class MultiBandBlender:
             self._keep += [ki, km]
         self.ctx.check(self.ctx.lib.is_blender_feed(self.h, C.byref(mi), C.byref(mm), capi.Point(int(tl[0]), int(tl[1])),
                                                     FEED_BORROW if borrow else FEED_COPY))
+
+    def strip_needs(self, size_wh, tl, x0, x1) -> bool:
+        """Does an image of this size / corner contribute to the destination columns [x0, x1)?"""
+        needed = C.c_int(0)
+        self.ctx.check(self.ctx.lib.is_blender_strip_needs(self.h, capi.Size(int(size_wh[0]), int(size_wh[1])), capi.Point(int(tl[0]), int(tl[1])),
+                                                           int(x0), int(x1), C.byref(needed)))
+        return bool(needed.value)
+
+    def blend_strip(self, x0, x1, out=None):
+        """Columns [x0, x1) of the destination ROI -> (dst H x (x1-x0) x 3 int16, mask)."""
+        sz = capi.Size()
+        self.ctx.check(self.ctx.lib.is_blender_dst_size(self.h, C.byref(sz)))
+        like = self._like if self._like is not None else np.empty(0)
+        if out is None:
+            dst = _alloc_like(like, (sz.height, x1 - x0, 3), np.int16)
+            dmask = _alloc_like(like, (sz.height, x1 - x0), np.uint8)
+        else:
+            dst, dmask = out
+        md, _a = as_mat(dst)
+        mm, _b = as_mat(dmask)
+        self.ctx.check(self.ctx.lib.is_blender_blend_strip(self.h, int(x0), int(x1), C.byref(md), C.byref(mm)))
+        self._keep = []
+        return dst, dmask
 
     def blend(self):
         sz = capi.Size()

@@ -128,6 +128,20 @@ int is_seam_dp_find(is_ctx* ctx, int n, const is_mat* images, const is_point* co
 int is_seam_dp_find_trace(is_ctx* ctx, int n, const is_mat* images, const is_point* corners, is_mat* masks,
                           int cost_fn, int32_t* trace, size_t trace_cap, size_t* trace_len);
 
+/* Single-pair primitives for sharded execution (one strip of the panorama per GPU, pairs of a strip boundary run
+ * on the GPU that owns the left image).  is_seam_pair_run = process() [SEAM]:127-193 for ONE pair on the given
+ * input masks, writing the masks with this pair's clears to out_i / out_j and returning a handle on the pair's
+ * structural fingerprint.  is_seam_pair_check recomputes only that fingerprint on the masks the pair would have
+ * seen in the reference's sequential loop (entry masks minus the clears of earlier pairs); *same = 1 proves that
+ * the speculative result is the sequential one.  is_mask_and intersects clear sets: dst = 0 where src == 0. */
+typedef struct is_seam_pair is_seam_pair;
+int is_seam_pair_run(is_ctx* ctx, const is_mat* image_i, const is_mat* image_j, is_point tl_i, is_point tl_j, const is_mat* mask_i,
+                     const is_mat* mask_j, is_mat* out_i, is_mat* out_j, is_seam_pair** result);
+int is_seam_pair_check(is_ctx* ctx, const is_mat* image_i, const is_mat* image_j, is_point tl_i, is_point tl_j, const is_mat* mask_i,
+                       const is_mat* mask_j, const is_seam_pair* spec, int* same);
+int is_seam_pair_destroy(is_seam_pair* p);
+int is_mask_and(is_ctx* ctx, is_mat* dst, const is_mat* src);
+
 /* How the last is_seam_dp_find / is_pipeline_run on this context executed the pair loop: 1 = the pairs ran
  * concurrently and their results were proven equal to the reference's sequential loop, 0 = the proof failed and
  * the sequential loop was run, -1 = sequential (fewer than two overlapping pairs, or IS_SEAM_SEQUENTIAL=1). */
@@ -162,6 +176,12 @@ int is_blender_feed(is_blender* b, const is_mat* img, const is_mat* mask, is_poi
 
 /* dst: 3 channels IS_16S, dst_mask: IS_8U, both is_blender_dst_size, caller-allocated. */
 int is_blender_blend(is_blender* b, is_mat* dst, is_mat* dst_mask);
+
+/* Column-strip sharding (one strip of the panorama per GPU): blend only the columns [x0, x1) of the destination
+ * ROI.  dst / dst_mask: ROI height x (x1 - x0).  The result equals the same columns of is_blender_blend provided
+ * every image for which is_blender_strip_needs reports 1 was fed, in the same order as for the full blend. */
+int is_blender_strip_needs(const is_blender* b, is_size img_size, is_point tl, int x0, int x1, int* needed);
+int is_blender_blend_strip(is_blender* b, int x0, int x1, is_mat* dst, is_mat* dst_mask);
 
 /* ------------------------------------------------------------------ linear blend
  * Replaces the hand-written pair blend of [BLEND]:141-717 (cost map, greedy seam, seam-guided linear

@@ -248,3 +248,68 @@ def test_seam_concurrent_pairs_are_proven_or_redone(ctx, oracle, monkeypatch):
     assert ctx.seam_speculation in (0, 1)
     for k in range(3):
         _eq(got[k], want[k], f"dependent mask {k}")
+
+
+def test_blend_strips_equal_full_blend(ctx, oracle):
+    """Column-strip blending (one strip per GPU): strips fed only with the images is_blender_strip_needs asks for
+    must reproduce the same columns of the full blend, for odd / unaligned cuts too."""
+    O = oracle
+    corners, wi, wm = warped_set(O, 4, 256, 200, overlap=0.25)
+    sm = O.dp_seam_find(wi, corners, wm)
+    sizes = [(a.shape[1], a.shape[0]) for a in wi]
+    roi = O.result_roi(corners, sizes)
+    for wt in (S.WEIGHT_32F, S.WEIGHT_16S):
+        ob = O.MultiBandBlender(5, wt)
+        ob.prepare(roi)
+        for i in range(4):
+            ob.feed(wi[i].astype(np.int16), sm[i], corners[i])
+        want, wmask = ob.blend()
+        for cuts in ([0, 256, roi[2]], [0, 97, 301, 555, roi[2]], [0, 1, roi[2] - 1, roi[2]]):
+            for x0, x1 in zip(cuts, cuts[1:]):
+                gb = S.MultiBandBlender(ctx, 0, 5, wt)
+                gb.prepare(roi)
+                fed = [i for i in range(4) if gb.strip_needs(sizes[i], corners[i], x0, x1)]
+                assert fed, "a strip inside the ROI needs at least one image"
+                for i in fed:
+                    gb.feed(wi[i], sm[i], corners[i])
+                got, gmask = gb.blend_strip(x0, x1)
+                _eq(gmask, wmask[:, x0:x1], f"strip mask [{x0},{x1})")
+                _eq(got, want[:, x0:x1], f"strip [{x0},{x1}) fed {fed}")
+
+
+def test_seam_pair_primitives(ctx, oracle):
+    O = oracle
+    corners, wi, wm = warped_set(O, 3, 320, 240, overlap=0.3)
+    want = O.dp_seam_find(wi, corners, wm)
+    f = S.DpSeamFinder(ctx, "COLOR")
+    # reference order: (1,2) then (0,1); run both on the entry masks, then prove (0,1) on the mask it would have seen
+    o1, o2, h12 = f.pair_run(wi[1], wi[2], corners[1], corners[2], wm[1], wm[2])
+    p0, p1, h01 = f.pair_run(wi[0], wi[1], corners[0], corners[1], wm[0], wm[1])
+    assert f.pair_check(wi[0], wi[1], corners[0], corners[1], wm[0], o1, h01)
+    assert not f.pair_check(wi[0], wi[1], corners[0], corners[1], wm[0], np.zeros_like(wm[1]), h01)   # a different structure is detected
+    m1 = wm[1].copy()
+    f.mask_and(m1, o1)
+    f.mask_and(m1, p1)
+    _eq(p0, want[0], "mask 0")
+    _eq(m1, want[1], "mask 1")
+    _eq(o2, want[2], "mask 2")
+    f.pair_free(h12)
+    f.pair_free(h01)
+
+
+def test_sharded_stitcher_single_rank(oracle):
+    import torch
+
+    from imagestitch_b200 import sharded
+    O = oracle
+    imgs, Ks, Rs, scale = synth.make_panorama_inputs(4, 300, 220, 1.2, 0.25)
+    want = O.pipeline_run(0, imgs, Ks, Rs, scale, seam=True, num_bands=4, weight_type=O.WEIGHT_32F, want_intermediates=True)
+    be = sharded.GpuBackend(0)
+    plan = sharded.ShardPlan.build(want["corners"], want["sizes"], want["roi"], 1, 4)
+    st = sharded.ShardedStitcher(be, sharded.Comm(None), 4)
+    res = st.stitch([torch.from_numpy(a).cuda() for a in imgs], Ks, Rs, scale, plan)
+    assert st.info["seam_speculation"] == 1
+    _eq(res["pano"].cpu().numpy(), want["pano"], "sharded (1 rank) pano")
+    _eq(res["pano_mask"].cpu().numpy(), want["pano_mask"], "sharded (1 rank) pano mask")
+    for i in range(4):
+        _eq(res["seam_masks"][i].cpu().numpy(), want["masks"][i], f"sharded (1 rank) seam mask {i}")
