@@ -71,6 +71,7 @@ SYMBOLS = {
     "is_ctx_last_error": (C.c_char_p, [C.c_void_p]),
     "is_ctx_stream": (C.c_void_p, [C.c_void_p]),
     "is_ctx_set_stream": (C.c_int, [C.c_void_p, C.c_void_p]),
+    "is_ctx_reset_stream": (C.c_int, [C.c_void_p]),
     "is_ctx_kernel_launches": (C.c_uint64, [C.c_void_p]),
     "is_ctx_device": (C.c_int, [C.c_void_p]),
     "is_ctx_kernel_timing": (C.c_int, [C.c_void_p, C.c_int]),

@@ -226,7 +226,14 @@ int is_ctx_synchronize(is_ctx* ctx) {
 int is_ctx_set_stream(is_ctx* ctx, void* stream) {
     if (!ctx) return IS_ERR_BAD_ARG;
     IS_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
-    ctx->stream = stream ? (cudaStream_t)stream : ctx->own_stream;
+    ctx->stream = (cudaStream_t)stream;     // NULL is a stream too: the legacy default stream (torch's default)
+    return IS_OK;
+}
+
+int is_ctx_reset_stream(is_ctx* ctx) {
+    if (!ctx) return IS_ERR_BAD_ARG;
+    IS_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+    ctx->stream = ctx->own_stream;
     return IS_OK;
 }
 

@@ -19,6 +19,7 @@ N > 1 path is covered on CPU with gloo (tests/test_sharded_gloo.py) while the GP
 """
 from __future__ import annotations
 
+import os
 import threading
 from dataclasses import dataclass, field
 
@@ -177,6 +178,8 @@ class ShardedStitcher:
         be.run_concurrently(check, my_pairs)
         be.sync()
         ok = comm.all_min(1 if all(verdict.values()) else 0, be.device)
+        if os.environ.get("IS_SHARDED_FORCE_FALLBACK") == "1":      # test hook: exercise the sequential fallback
+            ok = 0
         self.info["seam_speculation"] = ok
         for k in my_pairs:
             be.pair_free(handles[k])
@@ -260,7 +263,10 @@ class GpuBackend:
         return self.torch.empty(shape, dtype={np.uint8: self.torch.uint8, np.int16: self.torch.int16}[dtype], device=self.device)
 
     def clone(self, t):
-        return t.clone()
+        r = t.clone()
+        # the copy runs on torch's stream of the calling thread; the library may touch it next on another stream
+        self.torch.cuda.current_stream(self.device).synchronize()
+        return r
 
     def warp(self, img, K, R, scale):
         _, w, m = self.S.RotationWarper(self.ctx, self.proj, scale).warp_with_mask(img, K, R)

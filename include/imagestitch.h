@@ -75,7 +75,8 @@ int is_ctx_destroy(is_ctx* ctx);
 int is_ctx_synchronize(is_ctx* ctx);
 const char* is_ctx_last_error(const is_ctx* ctx);
 void* is_ctx_stream(is_ctx* ctx);                     /* cudaStream_t all work of this context runs on */
-int is_ctx_set_stream(is_ctx* ctx, void* stream);     /* adopt a caller-owned cudaStream_t (NULL: back to the context's own) */
+int is_ctx_set_stream(is_ctx* ctx, void* stream);     /* adopt a caller-owned cudaStream_t; NULL = the legacy default stream */
+int is_ctx_reset_stream(is_ctx* ctx);                  /* back to the context's own stream */
 uint64_t is_ctx_kernel_launches(const is_ctx* ctx);   /* kernels of this library launched so far */
 int is_ctx_device(const is_ctx* ctx);
 /* Per-launch CUDA-event timing for measurement (bench.py's roofline figure): when enabled every kernel launch

@@ -33,16 +33,35 @@ if rank == 0:
     print(f"sharded: world={world} images={n} {rows}x{cols} pano={roi[3]}x{roi[2]} cuts={plan.cuts} step={dt * 1e3:.2f} ms "
           f"speculation={sh.info['seam_speculation']} needed={sh.info['needed_images']}", flush=True)
 # assemble on rank 0 and compare with the single-GPU pipeline
+sums = [None] * world
+dist.all_gather_object(sums, {i: int(t.to(torch.int64).sum().item()) for i, t in zip([k for k in range(n) if plan.owner[k] == rank], mine)})
 parts = [None] * world
-dist.all_gather_object(parts, (res["x0"], res["x1"], res["pano"].cpu().numpy(), res["pano_mask"].cpu().numpy()))
+dist.all_gather_object(parts, (res["x0"], res["x1"], res["pano"].cpu().numpy(), res["pano_mask"].cpu().numpy(),
+                               {i: m.cpu().numpy() for i, m in res["seam_masks"].items()}))
 if rank == 0:
     parts.sort(key=lambda p: p[0])
     pano = np.concatenate([p[2] for p in parts], axis=1)
     pmask = np.concatenate([p[3] for p in parts], axis=1)
     imgs = [synth.make_image(i, cols, rows, Ks[i], Rs[i], device="cuda:0") for i in range(n)]
-    ref = st0.stitch(imgs, Ks, Rs, scale)
-    ok = np.array_equal(pano, ref["pano"].cpu().numpy()) and np.array_equal(pmask, ref["pano_mask"].cpu().numpy())
-    print("SHARDED == SINGLE GPU:", ok, flush=True)
+    for d_ in sums:
+        for i, v in d_.items():
+            v0 = int(imgs[i].to(torch.int64).sum().item())
+            if v != v0:
+                print(f"SOURCE image {i} differs between GPUs: byte sum {v} vs {v0}", flush=True)
+    ref = st0.stitch(imgs, Ks, Rs, scale, want_seam_masks=True)
+    for p_ in parts:
+        for i, m in p_[4].items():
+            rmk = ref["seam_masks"][i].cpu().numpy()
+            if not np.array_equal(m, rmk):
+                d = np.argwhere(m != rmk)
+                print(f"seam mask {i} differs: {len(d)} px, cols {d[:,1].min()}..{d[:,1].max()} rows {d[:,0].min()}..{d[:,0].max()}", flush=True)
+    rp, rm = ref["pano"].cpu().numpy(), ref["pano_mask"].cpu().numpy()
+    ok = np.array_equal(pano, rp) and np.array_equal(pmask, rm)
+    print("SHARDED == SINGLE GPU:", ok, "single-GPU speculation:", be.ctx.seam_speculation, flush=True)
+    if not ok:
+        bad = np.argwhere((pano != rp).any(axis=2))
+        print("mismatching pixels:", len(bad), "columns", bad[:, 1].min(), "..", bad[:, 1].max(), "rows", bad[:, 0].min(), "..", bad[:, 0].max(),
+              "mask mismatches:", int((pmask != rm).sum()), flush=True)
     if not ok:
         sys.exit(1)
 dist.barrier()

@@ -113,16 +113,21 @@ def _worker(rank, world, port, case, result_path):
     dist.destroy_process_group()
 
 
-@pytest.mark.parametrize("case", [(4, 192, 144, 0.25, 3), (6, 160, 120, 0.3, 4), (4, 200, 150, 0.6, 3)])
-def test_two_rank_sharded_matches_single_process(tmp_path, case):
+@pytest.mark.parametrize("case", [(4, 192, 144, 0.25, 3), (6, 160, 120, 0.3, 4), (4, 200, 150, 0.6, 3), (4, 192, 144, 0.25, 3, "fallback")])
+def test_two_rank_sharded_matches_single_process(tmp_path, case, monkeypatch):
     import oracle
     oracle.build()
+    if len(case) > 5:
+        monkeypatch.setenv("IS_SHARDED_FORCE_FALLBACK", "1")
+        case = case[:5]
     port = 29500 + (os.getpid() + case[0] * 7 + int(case[3] * 100)) % 2000
     out = tmp_path / "result.txt"
     mp.spawn(_worker, args=(2, port, case, str(out)), nprocs=2, join=True)
     ok, spec = out.read_text().split()
     assert ok == "1", "sharded panorama / seam masks differ from the single-process oracle"
-    if case[3] < 0.5:
+    if os.environ.get("IS_SHARDED_FORCE_FALLBACK") == "1":
+        assert spec == "0"
+    elif case[3] < 0.5:
         assert spec == "1"     # independent pairs: the speculative results are accepted
 
 
