@@ -213,27 +213,54 @@ def main():
 
     n, rows, cols, fw, ov, grid_rows, desc = WORKLOADS[args.workload]
     dev = f"cuda:{local_rank}"
-    # weak scaling: every rank stitches its own strip of n images (the cameras of rank r continue the strip)
-    Ks_all, Rs_all, scale = synth.strip_cameras(n * world, cols, rows, fw, ov, grid_rows=grid_rows)
+    # Weak scaling: every GPU brings n images; for N > 1 they form ONE strip panorama of n*N images that is sharded by
+    # column strip (imagestitch_b200.sharded: NCCL halo exchange at the strip boundaries).  A cylinder cannot hold more
+    # than 360 degrees, so the focal length grows with N to keep the strip below ~340 degrees.
+    import math
+    n_all = n * world
+    fw = max(fw, 1.0 / (2.0 * math.tan(5.9 / (2.0 * (1.0 - ov) * n_all)))) if world > 1 else fw
+    Ks_all, Rs_all, scale = synth.strip_cameras(n_all, cols, rows, fw, ov, grid_rows=grid_rows)
     idx = list(range(rank * n, rank * n + n))
     Ks, Rs = Ks_all[idx], Rs_all[idx]
     imgs_dev = [synth.make_image(i, cols, rows, Ks_all[i], Rs_all[i], device=dev) for i in idx]
     torch.cuda.synchronize()
-
-    ctx = S.Context(local_rank, use_torch_stream=True)     # kernels run on torch's current stream -> torch events see them
-    st = S.Stitcher(ctx, "cylindrical", "dp", NUM_BANDS, S.WEIGHT_32F)
-    corners, sizes, roi = st.plan([(cols, rows)] * n, Ks, Rs, scale)
-    pano_dev = torch.empty((roi[3], roi[2], 3), dtype=torch.int16, device=dev)
-    pmask_dev = torch.empty((roi[3], roi[2]), dtype=torch.uint8, device=dev)
     in_mp = n * rows * cols / 1e6
+
+    if world == 1:
+        ctx = S.Context(local_rank, use_torch_stream=True)     # kernels run on torch's current stream -> torch events see them
+        st = S.Stitcher(ctx, "cylindrical", "dp", NUM_BANDS, S.WEIGHT_32F)
+        corners, sizes, roi = st.plan([(cols, rows)] * n, Ks, Rs, scale)
+        out_shape = (roi[3], roi[2])
+        pano_dev = torch.empty(out_shape + (3,), dtype=torch.int16, device=dev)
+        pmask_dev = torch.empty(out_shape, dtype=torch.uint8, device=dev)
+        contexts = [ctx]
+
+        def step_device():
+            st.stitch(imgs_dev, Ks, Rs, scale, out=(pano_dev, pmask_dev))
+            return pano_dev, pmask_dev
+    else:
+        from imagestitch_b200 import sharded
+        be = sharded.GpuBackend(local_rank)
+        ctx = be.ctx
+        contexts = [be.ctx] + be.workers
+        st = S.Stitcher(ctx, "cylindrical", "dp", NUM_BANDS, S.WEIGHT_32F)
+        corners_all, sizes_all, roi = st.plan([(cols, rows)] * n_all, Ks_all, Rs_all, scale)
+        plan = sharded.ShardPlan.build(corners_all, sizes_all, roi, world, NUM_BANDS)
+        sizes = [sizes_all[i] for i in idx]
+        sh = sharded.ShardedStitcher(be, sharded.Comm(dist), NUM_BANDS)
+        out_shape = (roi[3], plan.cuts[rank + 1] - plan.cuts[rank])
+
+        def step_device():
+            r = sh.stitch(imgs_dev, Ks_all, Rs_all, scale, plan)
+            return r["pano"], r["pano_mask"]
 
     def barrier():
         if dist:
             dist.barrier()
         torch.cuda.synchronize()
 
-    def step_device():
-        st.stitch(imgs_dev, Ks, Rs, scale, out=(pano_dev, pmask_dev))
+    def total_launches():
+        return sum(c.kernel_launches for c in contexts)
 
     sampler = ClockSampler(local_rank) if rank == 0 else None
     if sampler:
@@ -244,7 +271,7 @@ def main():
         barrier()
         e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         t0 = time.perf_counter()
-        l0 = ctx.kernel_launches
+        l0 = total_launches()
         e0.record()
         for _ in range(steps):
             fn()
@@ -252,7 +279,7 @@ def main():
         barrier()
         windows.append((t0, time.perf_counter()))
         ms = e0.elapsed_time(e1) / steps
-        launches = (ctx.kernel_launches - l0) // steps
+        launches = (total_launches() - l0) // steps
         if dist:
             t = torch.tensor([ms], device=dev)
             dist.all_reduce(t, op=dist.ReduceOp.MAX)
@@ -262,32 +289,53 @@ def main():
     for _ in range(max(args.warmup, 3)):
         step_device()
     ms_dev, launches = timed(step_device, args.steps)
-    stage_ms = dict(st.timings_ms)
+    stage_ms = dict(st.timings_ms) if world == 1 else None
+    speculation = ctx.seam_speculation if world == 1 else sh.info.get("seam_speculation")
+    dev_pano, dev_pmask = step_device()
+    dev_pano, dev_pmask = dev_pano.clone(), dev_pmask.clone()
 
     # second timed region with per-launch events for the roofline figure
-    ctx.kernel_timing(True)
-    ctx.kernel_timing_report()
+    for c in contexts:
+        c.kernel_timing(True)
+        c.kernel_timing_report()
     ms_dev_ev, _ = timed(step_device, args.steps)
-    ktable = ctx.kernel_timing_report()
-    ctx.kernel_timing(False)
+    ktable = {}
+    for c in contexts:
+        for r in c.kernel_timing_report():
+            a = ktable.setdefault(r["name"], {"name": r["name"], "launches": 0, "ms": 0.0, "bytes": 0.0})
+            a["launches"] += r["launches"]; a["ms"] += r["ms"]; a["bytes"] += r["bytes"]
+        c.kernel_timing(False)
+    ktable = list(ktable.values())
 
-    # end to end through the C ABI with pinned host buffers
+    # end to end with HOST buffers (pinned): H2D of the sources and D2H of the panorama (strip) inside the timed region
     imgs_pin = [torch.empty((rows, cols, 3), dtype=torch.uint8, pin_memory=True) for _ in range(n)]
     for p, d in zip(imgs_pin, imgs_dev):
         p.copy_(d)
-    pano_pin = torch.empty((roi[3], roi[2], 3), dtype=torch.int16, pin_memory=True)
-    pmask_pin = torch.empty((roi[3], roi[2]), dtype=torch.uint8, pin_memory=True)
-    imgs_host = [p.numpy() for p in imgs_pin]
-    out_host = (pano_pin.numpy(), pmask_pin.numpy())
+    pano_pin = torch.empty(out_shape + (3,), dtype=torch.int16, pin_memory=True)
+    pmask_pin = torch.empty(out_shape, dtype=torch.uint8, pin_memory=True)
     torch.cuda.synchronize()
+    if world == 1:
+        imgs_host = [p.numpy() for p in imgs_pin]
+        out_host = (pano_pin.numpy(), pmask_pin.numpy())
 
-    def step_host():
-        st.stitch(imgs_host, Ks, Rs, scale, out=out_host)
+        def step_host():                                  # host buffers straight through the C ABI (is_pipeline_run)
+            st.stitch(imgs_host, Ks, Rs, scale, out=out_host)
+    else:
+        def step_host():                                  # per rank: its sources up, its strip of the panorama down
+            up = [p.to(dev, non_blocking=True) for p in imgs_pin]
+            r = sh.stitch(up, Ks_all, Rs_all, scale, plan)
+            pano_pin.copy_(r["pano"], non_blocking=True)
+            pmask_pin.copy_(r["pano_mask"], non_blocking=True)
+            torch.cuda.synchronize()
 
     step_host()
     ms_e2e, _ = timed(step_host, max(1, min(args.steps, 5)))
     # the device-resident and the host path must produce the same panorama
-    same = bool(torch.equal(pano_dev.cpu(), pano_pin)) and bool(torch.equal(pmask_dev.cpu(), pmask_pin))
+    same = bool(torch.equal(dev_pano.cpu(), pano_pin)) and bool(torch.equal(dev_pmask.cpu(), pmask_pin))
+    if dist:
+        t = torch.tensor([1 if same else 0], device=dev)
+        dist.all_reduce(t, op=dist.ReduceOp.MIN)
+        same = bool(t.item())
     if sampler:
         sampler.stop()
 
@@ -296,7 +344,7 @@ def main():
             dist.destroy_process_group()
         return 0
 
-    alg = algorithmic_bytes(n, rows, cols, sizes, roi)
+    alg = algorithmic_bytes(n, rows, cols, sizes, (roi[0], roi[1], out_shape[1], out_shape[0]))   # this rank's share of the panorama
     peaks = {}
     try:
         peaks = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))
@@ -333,16 +381,18 @@ def main():
         cpu = {"value": v, "unit": "MP/s", "cores": threads, "kind": "port", "sample": sdesc, "seconds": dt,
                "stage_seconds": dict(zip(("warp", "seam", "blend", "total"), stages))}
 
-    h2d = n * rows * cols * 3
+    h2d = world * n * rows * cols * 3
     d2h = roi[2] * roi[3] * 7
     line = {
         "metric": "stitched_megapixels_per_sec", "value": world * in_mp / (ms_dev * 1e-3), "unit": "MP/s", "n_gpus": world, "steps": args.steps,
         "warmup": max(args.warmup, 3), "ms_per_step": ms_dev, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
         "dtype": "s16", "data": "synthetic",
-        "config": {"workload": desc, "images_per_gpu": n, "image_rows": rows, "image_cols": cols, "num_bands": NUM_BANDS, "weight_type": "CV_32F",
-                   "seam": "dp_color", "projection": "cylindrical", "f_over_w": fw, "overlap": ov, "pano_roi": list(roi),
-                   "l2_policy": f"inputs ({h2d >> 20} MiB) and panorama exceed the {L2_BYTES >> 20} MiB L2; no flush needed",
-                   "parallelism": "single GPU" if world == 1 else f"{world} independent strips (one per GPU), no exchange"},
+        "config": {"workload": desc if world == 1 else f"{n_all}x({rows}x{cols}) RGB strip ({n} images per GPU), cylindrical warp + DP seam masks + multi-band blend (5 bands)", "images_per_gpu": n, "image_rows": rows, "image_cols": cols, "num_bands": NUM_BANDS, "weight_type": "CV_32F",
+                   "seam": "dp_color", "projection": "cylindrical", "f_over_w": round(fw, 4), "overlap": ov, "pano_roi": list(roi),
+                   "l2_policy": f"inputs ({(h2d // world) >> 20} MiB per GPU) and panorama exceed the {L2_BYTES >> 20} MiB L2; no flush needed",
+                   "parallelism": "single GPU" if world == 1 else
+                   f"one {n_all}-image strip panorama sharded by column strip over {world} GPUs, NCCL P2P halo exchange at strip boundaries",
+                   "seam_pairs": "concurrent, proven equal to the sequential loop" if speculation == 1 else "sequential loop"},
         "clocks": sampler.summary(windows) if sampler else None,
         "e2e": {"value": world * in_mp / (ms_e2e * 1e-3), "unit": "MP/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
                 "ms_per_step": ms_e2e, "matches_device_path": same},
