@@ -190,26 +190,40 @@ __global__ void k_labels_from_roots(const int* __restrict__ parent, int* labels,
 
 // ---- contour lists (raster order) over a window of the union frame ---------------------------------------
 
-struct Frame { int uw, uh; };
+// The union frame of a pair.  Component labels are stored only for a window of it (the intersection rectangle grown
+// by one pixel when the run-based labelling is used, the whole frame in the dense fallback): every label the
+// algorithm reads after labelling lies there (INTERS components and the 4-neighbours of their pixels).
+struct Frame {
+    int uw, uh;              // union frame size
+    int wx, wy, ww, wh;      // label window: labels[(y - wy) * ww + (x - wx)]
+    MaskView m1, m2;         // the two masks placed in the frame
+};
 
-__device__ __forceinline__ bool is_contour(const int* __restrict__ labels, Frame f, int x, int y, int l) {
-    const size_t i = (size_t)y * f.uw + x;
-    return (x == 0 || labels[i - 1] != l) || (x == f.uw - 1 || labels[i + 1] != l) || (y == 0 || labels[i - f.uw] != l) ||
-           (y == f.uh - 1 || labels[i + f.uw] != l);
+__device__ __forceinline__ size_t lidx(const Frame& f, int x, int y) { return (size_t)(y - f.wy) * f.ww + (x - f.wx); }
+
+__device__ __forceinline__ int lab(const int* __restrict__ labels, const Frame& f, int x, int y) {
+    if ((unsigned)(x - f.wx) >= (unsigned)f.ww || (unsigned)(y - f.wy) >= (unsigned)f.wh) return -2;   // never a label
+    return labels[lidx(f, x, y)];
+}
+
+__device__ __forceinline__ int class_at(const Frame& f, int x, int y) { return (f.m1.at(x, y) ? 1 : 0) | (f.m2.at(x, y) ? 2 : 0); }
+
+__device__ __forceinline__ bool is_contour(const int* __restrict__ labels, const Frame& f, int x, int y, int l) {
+    return (x == 0 || lab(labels, f, x - 1, y) != l) || (x == f.uw - 1 || lab(labels, f, x + 1, y) != l) ||
+           (y == 0 || lab(labels, f, x, y - 1) != l) || (y == f.uh - 1 || lab(labels, f, x, y + 1) != l);
 }
 
 constexpr int CT_THREADS = 256, CT_PER_THREAD = 8, CT_CHUNK = CT_THREADS * CT_PER_THREAD;
 constexpr int CT_FILTER_INTERS = -3;   // select the pixels lying in both masks (the INTERS components at labelling time)
 
-__device__ __forceinline__ bool ct_select(int l, int fa, int fb, const uint8_t* __restrict__ cls, size_t i) {
+__device__ __forceinline__ bool ct_select(int l, int fa, int fb, const Frame& f, int x, int y) {
     if (l <= 0) return false;
-    if (fa == CT_FILTER_INTERS) return (cls[i] & 3) == 3;
+    if (fa == CT_FILTER_INTERS) return class_at(f, x, y) == 3;
     return fa == 0 || l == fa || l == fb;
 }
 
 // pass 1: number of selected contour pixels per chunk of the window (window-raster order)
-__global__ void k_contour_count(const int* __restrict__ labels, const uint8_t* __restrict__ cls, Frame f, int wx, int wy, int ww, int wh, int fa,
-                                int fb, int* counts) {
+__global__ void k_contour_count(const int* __restrict__ labels, Frame f, int wx, int wy, int ww, int wh, int fa, int fb, int* counts) {
     const size_t total = (size_t)ww * wh;
     size_t e0 = (size_t)blockIdx.x * CT_CHUNK + (size_t)threadIdx.x * CT_PER_THREAD;
     int c = 0;
@@ -217,9 +231,8 @@ __global__ void k_contour_count(const int* __restrict__ labels, const uint8_t* _
         size_t e = e0 + k;
         if (e >= total) break;
         int x = wx + (int)(e % ww), y = wy + (int)(e / ww);
-        const size_t i = (size_t)y * f.uw + x;
-        int l = labels[i];
-        if (ct_select(l, fa, fb, cls, i) && is_contour(labels, f, x, y, l)) ++c;
+        int l = lab(labels, f, x, y);
+        if (ct_select(l, fa, fb, f, x, y) && is_contour(labels, f, x, y, l)) ++c;
     }
     __shared__ int red[CT_THREADS / 32];
     for (int o = 16; o; o >>= 1) c += __shfl_down_sync(0xffffffffu, c, o);
@@ -263,21 +276,26 @@ __global__ void k_scan_counts(const int* __restrict__ counts, int n, int* offset
     if (threadIdx.x == 0) offsets[n] = carry;
 }
 
-__device__ __forceinline__ bool close_to(const uint8_t* __restrict__ cls, Frame f, int x, int y, int bit) {   // [SEAM]:584-604
+// contour{1,2}mask_ of [SEAM]:165-186, evaluated on demand: a mask pixel with a 4-neighbour outside the mask or the frame
+__device__ __forceinline__ bool mask_contour(const MaskView& m, const Frame& f, int x, int y) {
+    return m.at(x, y) && (x == 0 || !m.at(x - 1, y) || x == f.uw - 1 || !m.at(x + 1, y) || y == 0 || !m.at(x, y - 1) || y == f.uh - 1 || !m.at(x, y + 1));
+}
+
+__device__ __forceinline__ bool close_to(const MaskView& m, const Frame& f, int x, int y) {   // closeToContour [SEAM]:584-604
     for (int dy = -2; dy <= 2; ++dy) {
         int yy = y + dy;
         if (yy < 0 || yy >= f.uh) continue;
         for (int dx = -2; dx <= 2; ++dx) {
             int xx = x + dx;
-            if (xx >= 0 && xx < f.uw && (cls[(size_t)yy * f.uw + xx] & bit)) return true;
+            if (xx >= 0 && xx < f.uw && mask_contour(m, f, xx, yy)) return true;
         }
     }
     return false;
 }
 
 // pass 2: write the records in window-raster order
-__global__ void k_contour_write(const int* __restrict__ labels, const uint8_t* __restrict__ cls, Frame f, int wx, int wy, int ww, int wh,
-                                int fa, int fb, const int* __restrict__ offsets, ContourRec* out, int cap) {
+__global__ void k_contour_write(const int* __restrict__ labels, Frame f, int wx, int wy, int ww, int wh, int fa, int fb,
+                                const int* __restrict__ offsets, ContourRec* out, int cap) {
     const size_t total = (size_t)ww * wh;
     size_t e0 = (size_t)blockIdx.x * CT_CHUNK + (size_t)threadIdx.x * CT_PER_THREAD;
     unsigned sel = 0;
@@ -286,9 +304,8 @@ __global__ void k_contour_write(const int* __restrict__ labels, const uint8_t* _
         size_t e = e0 + k;
         if (e >= total) break;
         int x = wx + (int)(e % ww), y = wy + (int)(e / ww);
-        const size_t i = (size_t)y * f.uw + x;
-        int l = labels[i];
-        if (ct_select(l, fa, fb, cls, i) && is_contour(labels, f, x, y, l)) { sel |= 1u << k; ++c; }
+        int l = lab(labels, f, x, y);
+        if (ct_select(l, fa, fb, f, x, y) && is_contour(labels, f, x, y, l)) { sel |= 1u << k; ++c; }
     }
     // exclusive scan of c over the block
     __shared__ int warp_sum[CT_THREADS / 32];
@@ -305,26 +322,25 @@ __global__ void k_contour_write(const int* __restrict__ labels, const uint8_t* _
         if (!(sel & (1u << k))) continue;
         size_t e = e0 + k;
         int x = wx + (int)(e % ww), y = wy + (int)(e / ww);
-        size_t i = (size_t)y * f.uw + x;
         if (pos < cap) {
             ContourRec r;
-            r.x = x; r.y = y; r.label = labels[i];
-            r.nl[0] = x > 0 ? labels[i - 1] : -1;
-            r.nl[1] = y > 0 ? labels[i - f.uw] : -1;
-            r.nl[2] = x < f.uw - 1 ? labels[i + 1] : -1;
-            r.nl[3] = y < f.uh - 1 ? labels[i + f.uw] : -1;
-            r.flags = (close_to(cls, f, x, y, 4) ? 1 : 0) | (close_to(cls, f, x, y, 8) ? 2 : 0);
+            r.x = x; r.y = y; r.label = lab(labels, f, x, y);
+            r.nl[0] = x > 0 ? lab(labels, f, x - 1, y) : -1;
+            r.nl[1] = y > 0 ? lab(labels, f, x, y - 1) : -1;
+            r.nl[2] = x < f.uw - 1 ? lab(labels, f, x + 1, y) : -1;
+            r.nl[3] = y < f.uh - 1 ? lab(labels, f, x, y + 1) : -1;
+            r.flags = (close_to(f.m1, f, x, y) ? 1 : 0) | (close_to(f.m2, f, x, y) ? 2 : 0);
             out[pos] = r;
         }
         ++pos;
     }
 }
 
-__global__ void k_relabel_rect(int* labels, int uw, int x0, int y0, int w, int h, int from, int to) {
+__global__ void k_relabel_rect(int* labels, Frame f, int x0, int y0, int w, int h, int from, int to) {
     const int x = blockIdx.x * blockDim.x + threadIdx.x;
     const int y = blockIdx.y * blockDim.y + threadIdx.y;
     if (x >= w || y >= h) return;
-    int* p = labels + (size_t)(y0 + y) * uw + (x0 + x);
+    int* p = labels + lidx(f, x0 + x, y0 + y);
     if (*p == from) *p = to;
 }
 
@@ -348,7 +364,7 @@ __device__ __forceinline__ float diff3(const T* a, const T* b) {
 
 __device__ __forceinline__ int label_at(const int* __restrict__ labels, Frame f, int x, int y) {
     if ((unsigned)x >= (unsigned)f.uw || (unsigned)y >= (unsigned)f.uh) return -1;
-    return labels[(size_t)y * f.uw + x];
+    return lab(labels, f, x, y);
 }
 
 template <typename T>
@@ -395,7 +411,7 @@ __global__ void k_cost_pq(ImgView<T> a, ImgView<T> b, const int* __restrict__ la
     float p, q;
     if (horizontal) { p = cost_h(a, b, labels, f, l, x, y); q = cost_v(a, b, labels, f, l, x, y); }
     else { p = cost_v(a, b, labels, f, l, x, y); q = cost_h(a, b, labels, f, l, x, y); }
-    if (labels[(size_t)y * f.uw + x] != l) p = -1.f;
+    if (lab(labels, f, x, y) != l) p = -1.f;
     P[(size_t)step * pitch + lane] = p;
     Q[(size_t)step * pitch + lane] = q;
 }
@@ -600,7 +616,7 @@ __global__ void k_uls_class(const int* __restrict__ labels, Frame f, int l1, int
     if (x >= bw || y >= bh) return;
     const int ux = bx + x, uy = by + y;
     int k = 0;
-    if (labels[(size_t)uy * f.uw + ux] == l1) k = is_contour(labels, f, ux, uy, l1) ? 2 : 1;
+    if (lab(labels, f, ux, uy) == l1) k = is_contour(labels, f, ux, uy, l1) ? 2 : 1;
     klass[(size_t)y * bw + x] = (uint8_t)k;
 }
 
@@ -660,27 +676,81 @@ __global__ void k_uls_apply(const uint8_t* __restrict__ klass, const int* __rest
     while (lo <= hi) {
         int mid = (lo + hi) >> 1;
         int v = adj_roots[mid];
-        if (v == r) { labels[(size_t)(by + y) * f.uw + (bx + x)] = l2; return; }
+        if (v == r) { labels[lidx(f, bx + x, by + y)] = l2; return; }
         if (v < r) lo = mid + 1; else hi = mid - 1;
     }
 }
 
-__global__ void k_scatter_label(const int2* __restrict__ pts, int n, int* labels, int uw, int l) {
+__global__ void k_scatter_label(const int2* __restrict__ pts, int n, int* labels, Frame f, int l) {
     const int i = blockIdx.x * blockDim.x + threadIdx.x;
-    if (i < n) labels[(size_t)pts[i].y * uw + pts[i].x] = l;
+    if (i < n) labels[lidx(f, pts[i].x, pts[i].y)] = l;
 }
 
 // ---- final mask update [SEAM]:527-545 --------------------------------------------------------------------------
-// dst mask pixel (x, y): l = labels at the same union position; cleared when states[l-1] has `bit` and the
-// other image's mask is set there.
-__global__ void k_mask_update(uint8_t* dst, size_t dstep, int drows, int dcols, int dox, int doy, MaskView other,
-                              const int* __restrict__ labels, int uw, const int* __restrict__ states, int bit) {
+// A pixel of `dst` is cleared when its label's state has `bit` and the other image's mask is set there; both masks
+// being set means the pixel lies in the intersection rectangle (ix, iy, iw, ih in frame coordinates), so only that is
+// visited.  dst: mask placed at (dox, doy) in the frame.
+__global__ void k_mask_update(uint8_t* dst, size_t dstep, int dox, int doy, MaskView other, const int* __restrict__ labels, Frame f,
+                              const int* __restrict__ states, int bit, int ix, int iy, int iw, int ih) {
     const int x = blockIdx.x * blockDim.x + threadIdx.x;
     const int y = blockIdx.y * blockDim.y + threadIdx.y;
-    if (x >= dcols || y >= drows) return;
-    const int ux = x + dox, uy = y + doy;
-    const int l = labels[(size_t)uy * uw + ux];
-    if (l > 0 && (states[l - 1] & bit) && other.at(ux, uy)) dst[(size_t)y * dstep + x] = 0;
+    if (x >= iw || y >= ih) return;
+    const int ux = ix + x, uy = iy + y;
+    const int l = lab(labels, f, ux, uy);
+    if (l > 0 && (states[l - 1] & bit) && other.at(ux, uy)) dst[(size_t)(uy - doy) * dstep + (ux - dox)] = 0;
+}
+
+// ---- run-based component labelling ---------------------------------------------------------------------------------
+// Warped masks are made of a few long horizontal runs per row.  Instead of labelling every pixel of the union frame
+// (3 x int32 passes over tens of megapixels per pair) the rows are reduced to their class change points on the device
+// (class = mask1 | mask2 << 1), the host unites the runs of adjacent rows (a few thousand runs), and labels are
+// materialised only in the window the algorithm reads.  Component numbering = rank of the component's first run in
+// raster order = floodFill's numbering ([SEAM]:222-256).
+struct ChangePt { int x, cls; };
+
+// one block per frame row; out == nullptr: count only.  Change points of a row are written in increasing x.
+__global__ void k_row_changes(Frame f, int* __restrict__ counts, const int* __restrict__ offsets, ChangePt* __restrict__ out) {
+    const int y = blockIdx.x;
+    __shared__ int warp_cnt[32];
+    __shared__ int carry;
+    if (threadIdx.x == 0) carry = 0;
+    __syncthreads();
+    const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5, nw = blockDim.x >> 5;
+    const int base_out = out ? offsets[y] : 0;
+    for (int base = 0; base < f.uw; base += blockDim.x) {
+        const int x = base + threadIdx.x;
+        int c = 0, flag = 0;
+        if (x < f.uw) {
+            c = class_at(f, x, y);
+            const int prev = x > 0 ? class_at(f, x - 1, y) : 0;
+            flag = c != prev;
+        }
+        const unsigned ballot = __ballot_sync(0xffffffffu, flag);
+        const int within = __popc(ballot & ((1u << lane) - 1));
+        if (lane == 0) warp_cnt[wid] = __popc(ballot);
+        __syncthreads();
+        int prefix = 0, total = 0;
+        for (int w = 0; w < nw; ++w) { const int v = warp_cnt[w]; if (w < wid) prefix += v; total += v; }
+        if (flag && out) out[base_out + carry + prefix + within] = ChangePt{x, c};
+        __syncthreads();
+        if (threadIdx.x == 0) carry += total;
+        __syncthreads();
+    }
+    if (threadIdx.x == 0 && !out) counts[y] = carry;
+}
+
+// labels of the window from the change points: label of the last change point at or before x in row y
+__global__ void k_label_window(Frame f, const int* __restrict__ row_off, const ChangePt* __restrict__ cps, const int* __restrict__ cp_label,
+                               int* __restrict__ labels) {
+    const int x = f.wx + blockIdx.x * blockDim.x + threadIdx.x;
+    const int y = f.wy + blockIdx.y * blockDim.y + threadIdx.y;
+    if (x >= f.wx + f.ww || y >= f.wy + f.wh) return;
+    int lo = row_off[y], hi = row_off[y + 1] - 1, best = -1;
+    while (lo <= hi) {
+        const int mid = (lo + hi) >> 1;
+        if (cps[mid].x <= x) { best = mid; lo = mid + 1; } else hi = mid - 1;
+    }
+    labels[lidx(f, x, y)] = best >= 0 ? cp_label[best] : 0;
 }
 
 // =====================================================================================================
@@ -759,7 +829,10 @@ private:
     // scratch
     DevBuf counts, offsets, recs;
 
-    Frame frame() const { return Frame{uw, uh}; }
+    Frame fr{};
+    Frame frame() const { return fr; }
+    int label_runs(const Pt& iTl, const Pt& iBr, bool* done);
+    int label_dense();
     void release_device() { cls.release(); parent.release(); labels.release(); counts.release(); offsets.release(); recs.release(); }
     int ccl(const uint8_t* klass, int kmask, int w, int h, int* parent_out);
     int collect_roots(const int* parent_d, const uint8_t* klass_d, size_t n, std::vector<std::pair<int, int>>* roots);
@@ -823,14 +896,14 @@ int PairSeam::extract_contours(int wx, int wy, int ww, int wh, int fa, int fb, s
     const int nblocks = (int)((total + CT_CHUNK - 1) / CT_CHUNK);
     IS_TRY(counts.alloc(ctx, sizeof(int) * (size_t)nblocks));
     IS_TRY(offsets.alloc(ctx, sizeof(int) * ((size_t)nblocks + 1)));
-    IS_LAUNCH(ctx, k_contour_count, nblocks, CT_THREADS, 0, labels.as<int>(), cls.as<uint8_t>(), frame(), wx, wy, ww, wh, fa, fb, counts.as<int>());
+    IS_LAUNCH(ctx, k_contour_count, nblocks, CT_THREADS, 0, labels.as<int>(), frame(), wx, wy, ww, wh, fa, fb, counts.as<int>());
     IS_LAUNCH(ctx, k_scan_counts, 1, 1024, 0, counts.as<int>(), nblocks, offsets.as<int>());
     int n = 0;
     IS_TRY(download(ctx, &n, offsets.as<int>() + nblocks, sizeof(int)));
     if (n == 0) return IS_OK;
     IS_TRY(recs.alloc(ctx, sizeof(ContourRec) * (size_t)n));
-    IS_LAUNCH(ctx, k_contour_write, nblocks, CT_THREADS, 0, labels.as<int>(), cls.as<uint8_t>(), frame(), wx, wy, ww, wh, fa, fb,
-              offsets.as<int>(), recs.as<ContourRec>(), n);
+    IS_LAUNCH(ctx, k_contour_write, nblocks, CT_THREADS, 0, labels.as<int>(), frame(), wx, wy, ww, wh, fa, fb, offsets.as<int>(),
+              recs.as<ContourRec>(), n);
     out->resize(n);
     IS_TRY(download(ctx, out->data(), recs.p, sizeof(ContourRec) * (size_t)n));
     return IS_OK;
@@ -1147,7 +1220,7 @@ int PairSeam::estimate_and_update(int c1, int c2, Pt p1, Pt p2) {
         DevBuf fl;
         IS_TRY(fl.alloc(ctx, sizeof(int2) * flips.size()));
         IS_TRY(upload(ctx, fl.p, flips.data(), sizeof(int2) * flips.size()));
-        IS_LAUNCH(ctx, k_scatter_label, div_up((int)flips.size(), 256), 256, 0, fl.as<int2>(), (int)flips.size(), labels.as<int>(), uw, l2);
+        IS_LAUNCH(ctx, k_scatter_label, div_up((int)flips.size(), 256), 256, 0, fl.as<int2>(), (int)flips.size(), labels.as<int>(), frame(), l2);
     }
     return IS_OK;
 }
@@ -1168,7 +1241,7 @@ int PairSeam::resolve_conflicts(const DevMat& in1, const DevMat& in2, const DevM
         if (has_only_one_neighbor(c1)) {
             const int w = brs[c1].x - tls[c1].x, h = brs[c1].y - tls[c1].y;
             dim3 block(64, 4), grid(div_up(w, 64), div_up(h, 4));
-            IS_LAUNCH(ctx, k_relabel_rect, grid, block, 0, labels.as<int>(), uw, tls[c1].x, tls[c1].y, w, h, l1, l2);
+            IS_LAUNCH(ctx, k_relabel_rect, grid, block, 0, labels.as<int>(), frame(), tls[c1].x, tls[c1].y, w, h, l1, l2);
             states[c1] = states[c2] == ST_FIRST ? ST_SECOND : ST_FIRST;
         } else {
             Pt p1, p2;
@@ -1191,16 +1264,109 @@ int PairSeam::resolve_conflicts(const DevMat& in1, const DevMat& in2, const DevM
     const int o1x = tl1_.x - unionTl.x, o1y = tl1_.y - unionTl.y, o2x = tl2_.x - unionTl.x, o2y = tl2_.y - unionTl.y;
     MaskView v1{mask1.ptr<uint8_t>(), mask1.step, mask1.rows, mask1.cols, o1x, o1y};
     MaskView v2{mask2.ptr<uint8_t>(), mask2.step, mask2.rows, mask2.cols, o2x, o2y};
+    const int ix = std::max(o1x, o2x), iy = std::max(o1y, o2y);
+    const int iw = std::min(o1x + mask1.cols, o2x + mask2.cols) - ix, ih = std::min(o1y + mask1.rows, o2y + mask2.rows) - iy;
+    dim3 mblock(64, 4), mgrid(div_up(iw, 64), div_up(ih, 4));
+    IS_LAUNCH(ctx, k_mask_update, mgrid, mblock, 0, mask2.ptr<uint8_t>(), mask2.step, o2x, o2y, v1, labels.as<int>(), frame(), st.as<int>(),
+              (int)ST_FIRST, ix, iy, iw, ih);
+    IS_LAUNCH(ctx, k_mask_update, mgrid, mblock, 0, mask1.ptr<uint8_t>(), mask1.step, o1x, o1y, v2, labels.as<int>(), frame(), st.as<int>(),
+              (int)ST_SECOND, ix, iy, iw, ih);
+    return IS_OK;
+}
+
+// Dense fallback (masks with very many runs): per-pixel union-find over the whole frame.
+int PairSeam::label_dense() {
+    const size_t n = (size_t)uw * uh;
+    fr.wx = 0; fr.wy = 0; fr.ww = uw; fr.wh = uh;
+    IS_TRY(cls.alloc(ctx, n));
+    IS_TRY(parent.alloc(ctx, sizeof(int) * n));
+    IS_TRY(labels.alloc(ctx, sizeof(int) * n));
     {
-        dim3 block(64, 4), grid(div_up(mask2.cols, 64), div_up(mask2.rows, 4));
-        IS_LAUNCH(ctx, k_mask_update, grid, block, 0, mask2.ptr<uint8_t>(), mask2.step, mask2.rows, mask2.cols, o2x, o2y, v1, labels.as<int>(), uw,
-                  st.as<int>(), (int)ST_FIRST);
+        dim3 block(64, 4), grid(div_up(uw, 64), div_up(uh, 4));
+        IS_LAUNCH(ctx, k_classify, grid, block, 0, fr.m1, fr.m2, cls.as<uint8_t>(), uw, uh);
     }
+    IS_TRY(ccl(cls.as<uint8_t>(), 3, uw, uh, parent.as<int>()));
+    std::vector<std::pair<int, int>> roots;
+    IS_TRY(collect_roots(parent.as<int>(), cls.as<uint8_t>(), n, &roots));
+    ncomps = (int)roots.size();
+    states.assign(ncomps, 0);
+    if (ncomps) {
+        std::vector<int> root_idx(ncomps);
+        for (int k = 0; k < ncomps; ++k) {
+            root_idx[k] = roots[k].first;
+            const int c = roots[k].second & 3;
+            states[k] = c == 3 ? ST_INTERS : (c == 1 ? ST_FIRST : ST_SECOND);
+        }
+        DevBuf rd;
+        IS_TRY(rd.alloc(ctx, sizeof(int) * (size_t)ncomps));
+        IS_TRY(upload(ctx, rd.p, root_idx.data(), sizeof(int) * (size_t)ncomps));
+        IS_LAUNCH(ctx, k_scatter_ids, div_up(ncomps, 256), 256, 0, rd.as<int>(), ncomps, labels.as<int>());
+        IS_LAUNCH(ctx, k_labels_from_roots, (unsigned)((n + 255) / 256), 256, 0, parent.as<int>(), labels.as<int>(), n);
+    } else {
+        IS_CUDA(ctx, cudaMemsetAsync(labels.p, 0, sizeof(int) * n, ctx->stream));
+    }
+    parent.release();
+    cls.release();
+    return IS_OK;
+}
+
+// Run-based labelling (see k_row_changes).  *done stays false when the masks have too many runs for it to pay off.
+int PairSeam::label_runs(const Pt& iTl, const Pt& iBr, bool* done) {
+    *done = false;
+    DevBuf cnt, off, cps_d;
+    IS_TRY(cnt.alloc(ctx, sizeof(int) * (size_t)uh));
+    IS_TRY(off.alloc(ctx, sizeof(int) * ((size_t)uh + 1)));
+    IS_LAUNCH(ctx, k_row_changes, uh, 256, 0, fr, cnt.as<int>(), (const int*)nullptr, (ChangePt*)nullptr);
+    IS_LAUNCH(ctx, k_scan_counts, 1, 1024, 0, cnt.as<int>(), uh, off.as<int>());
+    std::vector<int> row_off((size_t)uh + 1);
+    IS_TRY(download(ctx, row_off.data(), off.p, sizeof(int) * row_off.size()));
+    const int R = row_off[uh];
+    if ((size_t)R > 16 * (size_t)uh + 4096) return IS_OK;                   // noisy masks: dense path
+    std::vector<ChangePt> cps((size_t)std::max(R, 1));
+    IS_TRY(cps_d.alloc(ctx, sizeof(ChangePt) * cps.size()));
+    if (R) {
+        IS_LAUNCH(ctx, k_row_changes, uh, 256, 0, fr, (int*)nullptr, off.as<int>(), cps_d.as<ChangePt>());
+        IS_TRY(download(ctx, cps.data(), cps_d.p, sizeof(ChangePt) * (size_t)R));
+    }
+    // union-find over the runs (run k = change point k with cls != 0, spanning [x, next change point or uw))
+    std::vector<int> uf((size_t)R);
+    for (int k = 0; k < R; ++k) uf[k] = k;
+    auto find = [&](int k) { while (uf[k] != k) { uf[k] = uf[uf[k]]; k = uf[k]; } return k; };
+    auto run_end = [&](int k, int y) { return k + 1 < row_off[y + 1] ? cps[k + 1].x : uw; };
+    for (int y = 1; y < uh; ++y) {
+        int a = row_off[y - 1], ae = row_off[y], b = row_off[y], be = row_off[y + 1];
+        while (a < ae && b < be) {
+            const int ax1 = run_end(a, y - 1), bx1 = run_end(b, y);
+            if (cps[a].cls && cps[a].cls == cps[b].cls && cps[a].x < bx1 && cps[b].x < ax1) {
+                int ra = find(a), rb = find(b);
+                if (ra != rb) { if (ra < rb) uf[rb] = ra; else uf[ra] = rb; }   // the root is the raster-first run
+            }
+            if (ax1 <= bx1) ++a; else ++b;
+        }
+    }
+    std::vector<int> cp_label((size_t)std::max(R, 1), 0), id_of_root((size_t)std::max(R, 1), 0);
+    ncomps = 0;
+    states.clear();
+    for (int k = 0; k < R; ++k) {               // roots in increasing index = raster order of the first pixel
+        if (!cps[k].cls || find(k) != k) continue;
+        id_of_root[k] = ++ncomps;
+        states.push_back(cps[k].cls == 3 ? ST_INTERS : (cps[k].cls == 1 ? ST_FIRST : ST_SECOND));
+    }
+    for (int k = 0; k < R; ++k) cp_label[k] = cps[k].cls ? id_of_root[find(k)] : 0;
+    // labels only where they are read: the intersection rectangle grown by one pixel
+    fr.wx = std::max(0, iTl.x - unionTl.x - 1);
+    fr.wy = std::max(0, iTl.y - unionTl.y - 1);
+    fr.ww = std::min(uw, iBr.x - unionTl.x + 1) - fr.wx;
+    fr.wh = std::min(uh, iBr.y - unionTl.y + 1) - fr.wy;
+    IS_TRY(labels.alloc(ctx, sizeof(int) * (size_t)fr.ww * fr.wh));
+    DevBuf lab_d;
+    IS_TRY(lab_d.alloc(ctx, sizeof(int) * cp_label.size()));
+    IS_TRY(upload(ctx, lab_d.p, cp_label.data(), sizeof(int) * cp_label.size()));
     {
-        dim3 block(64, 4), grid(div_up(mask1.cols, 64), div_up(mask1.rows, 4));
-        IS_LAUNCH(ctx, k_mask_update, grid, block, 0, mask1.ptr<uint8_t>(), mask1.step, mask1.rows, mask1.cols, o1x, o1y, v2, labels.as<int>(), uw,
-                  st.as<int>(), (int)ST_SECOND);
+        dim3 block(64, 4), grid(div_up(fr.ww, 64), div_up(fr.wh, 4));
+        IS_LAUNCH(ctx, k_label_window, grid, block, 0, fr, off.as<int>(), cps_d.as<ChangePt>(), lab_d.as<int>(), labels.as<int>());
     }
+    *done = true;
     return IS_OK;
 }
 
@@ -1221,41 +1387,18 @@ int PairSeam::process(const DevMat& image1, const DevMat& image2, Pt tl1, Pt tl2
     uh = unionBr.y - unionTl.y;
     const size_t n = (size_t)uw * uh;
     IS_REQUIRE(ctx, n < (size_t)INT_MAX, IS_ERR_UNSUPPORTED, "union frame of an image pair exceeds 2^31 pixels");
-    IS_TRY(cls.alloc(ctx, n));
-    IS_TRY(parent.alloc(ctx, sizeof(int) * n));
-    IS_TRY(labels.alloc(ctx, sizeof(int) * n));
     MaskView v1{mask1.ptr<uint8_t>(), mask1.step, mask1.rows, mask1.cols, tl1.x - unionTl.x, tl1.y - unionTl.y};
     MaskView v2{mask2.ptr<uint8_t>(), mask2.step, mask2.rows, mask2.cols, tl2.x - unionTl.x, tl2.y - unionTl.y};
-    {
-        dim3 block(64, 4), grid(div_up(uw, 64), div_up(uh, 4));
-        IS_LAUNCH(ctx, k_classify, grid, block, 0, v1, v2, cls.as<uint8_t>(), uw, uh);
-    }
+    fr = Frame{uw, uh, 0, 0, uw, uh, v1, v2};
     // findComponents [SEAM]:196-308
-    IS_TRY(ccl(cls.as<uint8_t>(), 3, uw, uh, parent.as<int>()));
-    std::vector<std::pair<int, int>> roots;
-    IS_TRY(collect_roots(parent.as<int>(), cls.as<uint8_t>(), n, &roots));
-    dbg.lap("classify+ccl+roots");
-    ncomps = (int)roots.size();
-    states.assign(ncomps, 0);
+    bool done = false;
+    const char* dense = getenv("IS_SEAM_DENSE");
+    if (!(dense && dense[0] == '1')) IS_TRY(label_runs(iTl, iBr, &done));
+    if (!done) IS_TRY(label_dense());
+    dbg.lap("component labelling");
     tls.assign(ncomps, Pt{INT_MAX, INT_MAX});
     brs.assign(ncomps, Pt{INT_MIN, INT_MIN});
     contours.assign(ncomps, std::vector<ContourRec>());
-    if (ncomps) {
-        std::vector<int> root_idx(ncomps);
-        for (int k = 0; k < ncomps; ++k) {
-            root_idx[k] = roots[k].first;
-            const int c = roots[k].second & 3;
-            states[k] = c == 3 ? ST_INTERS : (c == 1 ? ST_FIRST : ST_SECOND);
-        }
-        DevBuf rd;
-        IS_TRY(rd.alloc(ctx, sizeof(int) * (size_t)ncomps));
-        IS_TRY(upload(ctx, rd.p, root_idx.data(), sizeof(int) * (size_t)ncomps));
-        IS_LAUNCH(ctx, k_scatter_ids, div_up(ncomps, 256), 256, 0, rd.as<int>(), ncomps, labels.as<int>());
-        IS_LAUNCH(ctx, k_labels_from_roots, (unsigned)((n + 255) / 256), 256, 0, parent.as<int>(), labels.as<int>(), n);
-    } else {
-        IS_CUDA(ctx, cudaMemsetAsync(labels.p, 0, sizeof(int) * n, ctx->stream));
-    }
-    parent.release();
     // Contour lists, bounding boxes and edges are only ever consulted for INTERS components (the conflict loop
     // picks edges whose first component is INTERS, [SEAM]:427; getSeamTips / updateLabelsUsingSeam walk
     // contours_[comp1] with comp1 INTERS), and every adjacency of an INTERS component is witnessed by one of
@@ -1663,7 +1806,7 @@ int is_seam_cost_maps(is_ctx* ctx, const is_mat* image1, const is_mat* image2, i
     }
     IS_TRY(stage_out(ctx, costV, &cv, false));
     IS_TRY(stage_out(ctx, costH, &ch, false));
-    Frame f{labels->cols, labels->rows};
+    Frame f{labels->cols, labels->rows, 0, 0, labels->cols, labels->rows, MaskView{nullptr, 0, 0, 0, 0, 0}, MaskView{nullptr, 0, 0, 0, 0, 0}};   // dense labels: window = frame
     const int dx1 = union_tl.x - tl1.x, dy1 = union_tl.y - tl1.y, dx2 = union_tl.x - tl2.x, dy2 = union_tl.y - tl2.y;
     dim3 block(32, 8), grid(div_up(roi.width + 1, 32), div_up(roi.height + 1, 8));
     if (image1->depth == IS_8U)

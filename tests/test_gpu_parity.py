@@ -313,3 +313,22 @@ def test_sharded_stitcher_single_rank(oracle):
     _eq(res["pano_mask"].cpu().numpy(), want["pano_mask"], "sharded (1 rank) pano mask")
     for i in range(4):
         _eq(res["seam_masks"][i].cpu().numpy(), want["masks"][i], f"sharded (1 rank) seam mask {i}")
+
+
+def test_dp_seam_noisy_masks_take_the_dense_labelling_path(ctx, oracle, monkeypatch):
+    """Salt-and-pepper masks have far too many runs for the run-based labelling: the dense union-find fallback must
+    give the same masks, and forcing it (IS_SEAM_DENSE=1) on clean masks must change nothing either."""
+    O = oracle
+    rng = np.random.default_rng(4)
+    corners, wi, wm = warped_set(O, 2, 160, 120, overlap=0.4)
+    noisy = [np.where(rng.random(m.shape) < 0.35, 0, m).astype(np.uint8) for m in wm]
+    want = O.dp_seam_find(wi, corners, noisy)
+    got = S.DpSeamFinder(ctx, "COLOR").find(wi, corners, [m.copy() for m in noisy])
+    for k in range(2):
+        _eq(got[k], want[k], f"noisy mask {k}")
+    corners, wi, wm = warped_set(O, 3, 256, 200, overlap=0.3)
+    want = O.dp_seam_find(wi, corners, wm)
+    monkeypatch.setenv("IS_SEAM_DENSE", "1")
+    got = S.DpSeamFinder(ctx, "COLOR").find(wi, corners, [m.copy() for m in wm])
+    for k in range(3):
+        _eq(got[k], want[k], f"dense-path mask {k}")
