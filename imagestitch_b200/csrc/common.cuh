@@ -33,6 +33,8 @@ struct is_ctx {
     std::vector<KRec> krecs;
     std::vector<cudaEvent_t> kpool;
     double next_bytes = 0;   // algorithmic bytes the next launch accounts for (set by the host code, optional)
+    // memo of warp_plan results (camera -> ROI): detectResultRoi is a few hundred microseconds of host libm per image
+    std::vector<unsigned char> plan_cache;
     // worker contexts (own stream + staging) for the concurrent seam pairs; owned by this context
     std::vector<is_ctx*> children;
     int seam_speculation_accepted = -1;   // last is_seam_dp_find: 1 concurrent result accepted, 0 fell back, -1 not attempted

@@ -329,11 +329,23 @@ __global__ void k_contour_write(const int* __restrict__ labels, Frame f, int wx,
             r.nl[1] = y > 0 ? lab(labels, f, x, y - 1) : -1;
             r.nl[2] = x < f.uw - 1 ? lab(labels, f, x + 1, y) : -1;
             r.nl[3] = y < f.uh - 1 ? lab(labels, f, x, y + 1) : -1;
-            r.flags = (close_to(f.m1, f, x, y) ? 1 : 0) | (close_to(f.m2, f, x, y) ? 2 : 0);
+            r.flags = 0;                                  // filled by k_contour_flags
             out[pos] = r;
         }
         ++pos;
     }
+}
+
+// closeToContour flags of the records: one warp per record, lanes 0..24 test one position of the 5x5 window each
+__global__ void k_contour_flags(ContourRec* recs, int n, Frame f) {
+    const int r = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+    if (r >= n) return;
+    const int lane = threadIdx.x & 31;
+    const int x = recs[r].x + (lane % 5) - 2, y = recs[r].y + (lane / 5) - 2;
+    const bool in = lane < 25 && x >= 0 && x < f.uw && y >= 0 && y < f.uh;
+    const unsigned b1 = __ballot_sync(0xffffffffu, in && mask_contour(f.m1, f, x, y));
+    const unsigned b2 = __ballot_sync(0xffffffffu, in && mask_contour(f.m2, f, x, y));
+    if (lane == 0) recs[r].flags = (b1 ? 1 : 0) | (b2 ? 2 : 0);
 }
 
 __global__ void k_relabel_rect(int* labels, Frame f, int x0, int y0, int w, int h, int from, int to) {
@@ -708,44 +720,44 @@ __global__ void k_mask_update(uint8_t* dst, size_t dstep, int dox, int doy, Mask
 // raster order = floodFill's numbering ([SEAM]:222-256).
 struct ChangePt { int x, cls; };
 
-// one block per frame row; out == nullptr: count only.  Change points of a row are written in increasing x.
-__global__ void k_row_changes(Frame f, int* __restrict__ counts, const int* __restrict__ offsets, ChangePt* __restrict__ out) {
-    const int y = blockIdx.x;
-    __shared__ int warp_cnt[32];
-    __shared__ int carry;
-    if (threadIdx.x == 0) carry = 0;
-    __syncthreads();
-    const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5, nw = blockDim.x >> 5;
-    const int base_out = out ? offsets[y] : 0;
-    for (int base = 0; base < f.uw; base += blockDim.x) {
-        const int x = base + threadIdx.x;
-        int c = 0, flag = 0;
-        if (x < f.uw) {
-            c = class_at(f, x, y);
-            const int prev = x > 0 ? class_at(f, x - 1, y) : 0;
-            flag = c != prev;
-        }
+// One warp per frame row.  The change points of row y go to out[y * cap ...] in increasing x; counts[y] is the true
+// number (rows with more than `cap` set *overflow and the caller falls back to the dense labelling).
+constexpr int ROW_CAP = 32;
+
+__global__ void k_row_changes(Frame f, int cap, int* __restrict__ counts, ChangePt* __restrict__ out, int* __restrict__ overflow) {
+    const int y = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+    if (y >= f.uh) return;
+    const int lane = threadIdx.x & 31;
+    ChangePt* row = out + (size_t)y * cap;
+    int n = 0;
+    int prev_last = 0;                                   // class of the pixel left of the current 32-pixel group
+    for (int base = 0; base < f.uw; base += 32) {
+        const int x = base + lane;
+        const int c = x < f.uw ? class_at(f, x, y) : 0;
+        int prev = __shfl_up_sync(0xffffffffu, c, 1);
+        if (lane == 0) prev = prev_last;
+        const bool flag = x < f.uw && c != prev;
         const unsigned ballot = __ballot_sync(0xffffffffu, flag);
-        const int within = __popc(ballot & ((1u << lane) - 1));
-        if (lane == 0) warp_cnt[wid] = __popc(ballot);
-        __syncthreads();
-        int prefix = 0, total = 0;
-        for (int w = 0; w < nw; ++w) { const int v = warp_cnt[w]; if (w < wid) prefix += v; total += v; }
-        if (flag && out) out[base_out + carry + prefix + within] = ChangePt{x, c};
-        __syncthreads();
-        if (threadIdx.x == 0) carry += total;
-        __syncthreads();
+        if (flag) {
+            const int k = n + __popc(ballot & ((1u << lane) - 1));
+            if (k < cap) row[k] = ChangePt{x, c};
+        }
+        n += __popc(ballot);
+        prev_last = __shfl_sync(0xffffffffu, c, 31);
     }
-    if (threadIdx.x == 0 && !out) counts[y] = carry;
+    if (lane == 0) {
+        counts[y] = n;
+        if (n > cap) *overflow = 1;
+    }
 }
 
 // labels of the window from the change points: label of the last change point at or before x in row y
-__global__ void k_label_window(Frame f, const int* __restrict__ row_off, const ChangePt* __restrict__ cps, const int* __restrict__ cp_label,
+__global__ void k_label_window(Frame f, int cap, const int* __restrict__ counts, const ChangePt* __restrict__ cps, const int* __restrict__ cp_label,
                                int* __restrict__ labels) {
     const int x = f.wx + blockIdx.x * blockDim.x + threadIdx.x;
     const int y = f.wy + blockIdx.y * blockDim.y + threadIdx.y;
     if (x >= f.wx + f.ww || y >= f.wy + f.wh) return;
-    int lo = row_off[y], hi = row_off[y + 1] - 1, best = -1;
+    int lo = y * cap, hi = y * cap + counts[y] - 1, best = -1;
     while (lo <= hi) {
         const int mid = (lo + hi) >> 1;
         if (cps[mid].x <= x) { best = mid; lo = mid + 1; } else hi = mid - 1;
@@ -904,6 +916,7 @@ int PairSeam::extract_contours(int wx, int wy, int ww, int wh, int fa, int fb, s
     IS_TRY(recs.alloc(ctx, sizeof(ContourRec) * (size_t)n));
     IS_LAUNCH(ctx, k_contour_write, nblocks, CT_THREADS, 0, labels.as<int>(), frame(), wx, wy, ww, wh, fa, fb, offsets.as<int>(),
               recs.as<ContourRec>(), n);
+    IS_LAUNCH(ctx, k_contour_flags, div_up(n, 8), 256, 0, recs.as<ContourRec>(), n, frame());
     out->resize(n);
     IS_TRY(download(ctx, out->data(), recs.p, sizeof(ContourRec) * (size_t)n));
     return IS_OK;
@@ -1313,21 +1326,24 @@ int PairSeam::label_dense() {
 // Run-based labelling (see k_row_changes).  *done stays false when the masks have too many runs for it to pay off.
 int PairSeam::label_runs(const Pt& iTl, const Pt& iBr, bool* done) {
     *done = false;
-    DevBuf cnt, off, cps_d;
+    DevBuf cnt, cps_d, ovf;
     IS_TRY(cnt.alloc(ctx, sizeof(int) * (size_t)uh));
-    IS_TRY(off.alloc(ctx, sizeof(int) * ((size_t)uh + 1)));
-    IS_LAUNCH(ctx, k_row_changes, uh, 256, 0, fr, cnt.as<int>(), (const int*)nullptr, (ChangePt*)nullptr);
-    IS_LAUNCH(ctx, k_scan_counts, 1, 1024, 0, cnt.as<int>(), uh, off.as<int>());
-    std::vector<int> row_off((size_t)uh + 1);
-    IS_TRY(download(ctx, row_off.data(), off.p, sizeof(int) * row_off.size()));
+    IS_TRY(cps_d.alloc(ctx, sizeof(ChangePt) * (size_t)uh * ROW_CAP));
+    IS_TRY(ovf.alloc(ctx, sizeof(int)));
+    IS_CUDA(ctx, cudaMemsetAsync(ovf.p, 0, sizeof(int), ctx->stream));
+    IS_LAUNCH(ctx, k_row_changes, div_up(uh, 8), 256, 0, fr, ROW_CAP, cnt.as<int>(), cps_d.as<ChangePt>(), ovf.as<int>());
+    std::vector<int> cnt_h((size_t)uh);
+    std::vector<ChangePt> raw((size_t)uh * ROW_CAP);
+    int overflow = 0;
+    IS_CUDA(ctx, cudaMemcpyAsync(&overflow, ovf.p, sizeof(int), cudaMemcpyDeviceToHost, ctx->stream));
+    IS_TRY(download(ctx, cnt_h.data(), cnt.p, sizeof(int) * cnt_h.size()));
+    if (overflow) return IS_OK;                                             // noisy masks: dense path
+    IS_TRY(download(ctx, raw.data(), cps_d.p, sizeof(ChangePt) * raw.size()));
+    std::vector<int> row_off((size_t)uh + 1, 0);
+    for (int y = 0; y < uh; ++y) row_off[y + 1] = row_off[y] + cnt_h[y];
     const int R = row_off[uh];
-    if ((size_t)R > 16 * (size_t)uh + 4096) return IS_OK;                   // noisy masks: dense path
     std::vector<ChangePt> cps((size_t)std::max(R, 1));
-    IS_TRY(cps_d.alloc(ctx, sizeof(ChangePt) * cps.size()));
-    if (R) {
-        IS_LAUNCH(ctx, k_row_changes, uh, 256, 0, fr, (int*)nullptr, off.as<int>(), cps_d.as<ChangePt>());
-        IS_TRY(download(ctx, cps.data(), cps_d.p, sizeof(ChangePt) * (size_t)R));
-    }
+    for (int y = 0; y < uh; ++y) std::copy(raw.begin() + (size_t)y * ROW_CAP, raw.begin() + (size_t)y * ROW_CAP + cnt_h[y], cps.begin() + row_off[y]);
     // union-find over the runs (run k = change point k with cls != 0, spanning [x, next change point or uw))
     std::vector<int> uf((size_t)R);
     for (int k = 0; k < R; ++k) uf[k] = k;
@@ -1359,12 +1375,17 @@ int PairSeam::label_runs(const Pt& iTl, const Pt& iBr, bool* done) {
     fr.ww = std::min(uw, iBr.x - unionTl.x + 1) - fr.wx;
     fr.wh = std::min(uh, iBr.y - unionTl.y + 1) - fr.wy;
     IS_TRY(labels.alloc(ctx, sizeof(int) * (size_t)fr.ww * fr.wh));
+    // labels of the change points in the device layout (row y at y * ROW_CAP); only the window's rows are needed
+    std::vector<int> lab_rows((size_t)fr.wh * ROW_CAP, 0);
+    for (int y = fr.wy; y < fr.wy + fr.wh; ++y)
+        std::copy(cp_label.begin() + row_off[y], cp_label.begin() + row_off[y + 1], lab_rows.begin() + (size_t)(y - fr.wy) * ROW_CAP);
     DevBuf lab_d;
-    IS_TRY(lab_d.alloc(ctx, sizeof(int) * cp_label.size()));
-    IS_TRY(upload(ctx, lab_d.p, cp_label.data(), sizeof(int) * cp_label.size()));
+    IS_TRY(lab_d.alloc(ctx, sizeof(int) * lab_rows.size()));
+    IS_TRY(upload(ctx, lab_d.p, lab_rows.data(), sizeof(int) * lab_rows.size()));
     {
         dim3 block(64, 4), grid(div_up(fr.ww, 64), div_up(fr.wh, 4));
-        IS_LAUNCH(ctx, k_label_window, grid, block, 0, fr, off.as<int>(), cps_d.as<ChangePt>(), lab_d.as<int>(), labels.as<int>());
+        IS_LAUNCH(ctx, k_label_window, grid, block, 0, fr, ROW_CAP, cnt.as<int>(), cps_d.as<ChangePt>(), lab_d.as<int>() - (size_t)fr.wy * ROW_CAP,
+                  labels.as<int>());
     }
     *done = true;
     return IS_OK;

@@ -285,6 +285,18 @@ int warp_plan(is_ctx* ctx, int proj, int src_w, int src_h, const float* K, const
     IS_REQUIRE(ctx, proj == IS_PROJ_CYLINDRICAL || proj == IS_PROJ_SPHERICAL, IS_ERR_BAD_ARG, "unknown projection");
     IS_REQUIRE(ctx, K && R, IS_ERR_ASSERT, "K and R must be 3x3 CV_32F");
     IS_REQUIRE(ctx, src_w > 0 && src_h > 0 && scale > 0.f, IS_ERR_BAD_ARG, "empty source or non-positive scale");
+    struct Key { int proj, w, h; float K[9], R[9], scale; };
+    struct Entry { Key key; WarpPlan plan; };
+    Key key;
+    std::memset(&key, 0, sizeof(key));
+    key.proj = proj; key.w = src_w; key.h = src_h; key.scale = scale;
+    std::memcpy(key.K, K, sizeof(key.K));
+    std::memcpy(key.R, R, sizeof(key.R));
+    const size_t nent = ctx->plan_cache.size() / sizeof(Entry);
+    for (size_t e = 0; e < nent; ++e) {
+        const Entry* ent = reinterpret_cast<const Entry*>(ctx->plan_cache.data()) + e;
+        if (std::memcmp(&ent->key, &key, sizeof(Key)) == 0) { *plan = ent->plan; return IS_OK; }
+    }
     Projector p;
     set_camera(K, R, &p);
     detect_roi(proj, src_w, src_h, p, scale, plan->roi);
@@ -298,6 +310,13 @@ int warp_plan(is_ctx* ctx, int proj, int src_w, int src_h, const float* K, const
     plan->P.src_h = src_h;
     IS_REQUIRE(ctx, plan->P.dst_w > 0 && plan->P.dst_h > 0 && plan->P.dst_w < (1 << 24) && plan->P.dst_h < (1 << 24),
                IS_ERR_BAD_ARG, "degenerate warp ROI");
+    if (nent >= 256) ctx->plan_cache.clear();
+    Entry ent;
+    std::memset(&ent, 0, sizeof(ent));
+    ent.key = key;
+    ent.plan = *plan;
+    const unsigned char* raw = reinterpret_cast<const unsigned char*>(&ent);
+    ctx->plan_cache.insert(ctx->plan_cache.end(), raw, raw + sizeof(Entry));
     return IS_OK;
 }
 
