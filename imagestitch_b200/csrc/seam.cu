@@ -406,7 +406,7 @@ __global__ void k_cost_maps(ImgView<T> a, ImgView<T> b, const int* __restrict__ 
 
 // DP layout: P[step][lane] = cost of advancing one step at `lane`, Q[step][lane] = cost of the crossing
 // between lane and lane+1 at `step`.  Vertical seam: step = y, lane = x, P = costV, Q = costH; horizontal
-// seam: step = x, lane = y, P = costH, Q = costV.  A negative P marks a cell outside the component.
+// seam: step = x, lane = y, P = costH, Q = costV.  P = +inf marks a cell outside the component.
 template <typename T>
 __global__ void k_cost_pq(ImgView<T> a, ImgView<T> b, const int* __restrict__ labels, Frame f, int l, int rx, int ry, int rw, int rh,
                           int horizontal, float* __restrict__ P, float* __restrict__ Q, int pitch) {
@@ -415,7 +415,7 @@ __global__ void k_cost_pq(ImgView<T> a, ImgView<T> b, const int* __restrict__ la
     const int step = blockIdx.y * blockDim.y + threadIdx.y;
     if (lane >= pitch || step >= steps) return;
     if (lane >= lanes) {   // padding lanes: outside the component
-        P[(size_t)step * pitch + lane] = -1.f;
+        P[(size_t)step * pitch + lane] = __int_as_float(0x7f800000);
         Q[(size_t)step * pitch + lane] = 0.f;
         return;
     }
@@ -423,7 +423,7 @@ __global__ void k_cost_pq(ImgView<T> a, ImgView<T> b, const int* __restrict__ la
     float p, q;
     if (horizontal) { p = cost_h(a, b, labels, f, l, x, y); q = cost_v(a, b, labels, f, l, x, y); }
     else { p = cost_v(a, b, labels, f, l, x, y); q = cost_h(a, b, labels, f, l, x, y); }
-    if (lab(labels, f, x, y) != l) p = -1.f;
+    if (lab(labels, f, x, y) != l) p = __int_as_float(0x7f800000);   // +inf: the cell can never be on a path
     P[(size_t)step * pitch + lane] = p;
     Q[(size_t)step * pitch + lane] = q;
 }
@@ -476,9 +476,10 @@ __device__ __forceinline__ void bulk_g2s(void* dst, const void* src, uint32_t by
                  : "memory");
 }
 
-// Rows of P, Q and control are padded to `pitch` = nt * LPT lanes.  Padding lanes carry P = -1 (outside the
-// component) so they stay unreachable (+inf) and need no bounds checks in the loop: a neighbour outside
-// [0, lanes) always contributes +inf, exactly like the reference's `x > 0` / `x < roi.width - 1` guards.
+// Rows of P, Q and control are padded to `pitch` = nt * LPT lanes.  Cells outside the component (and the padding
+// lanes) carry P = +inf: whatever cost reaches them, the running value t = cost + P leaving them is +inf, so no path
+// continues through them and the back-track never visits them -- the reference's `labels_ == l` test ([SEAM]:897) and
+// its `x > 0` / `x < roi.width - 1` guards without a branch.  (Their own control byte is arbitrary and never read.)
 template <int LPT>
 __global__ void __launch_bounds__(1024) k_seam_dp(DpArgs A) {
     extern __shared__ __align__(128) unsigned char sm_raw[];
@@ -486,9 +487,10 @@ __global__ void __launch_bounds__(1024) k_seam_dp(DpArgs A) {
     const int row_f = A.pitch;                             // floats per row
     const int stage_f = 2 * A.G * row_f;                   // floats per stage: G rows of P, then G rows of Q
     float* ring = reinterpret_cast<float*>(sm_raw);
-    float* edgeL = ring + (size_t)A.D * stage_f;           // [2][nt]: t of the first lane of each thread (double buffered)
-    float* edgeR = edgeL + 2 * nt;                         // [2][nt]: t of the last lane
-    uint64_t* bars = reinterpret_cast<uint64_t*>(edgeR + 2 * nt);
+    uint64_t* bars = reinterpret_cast<uint64_t*>(ring + (size_t)A.D * stage_f);
+    // running value of the first / last lane of every thread, double buffered (static: plain LDS/STS addressing)
+    __shared__ float edgeL[2][1024];
+    __shared__ float edgeR[2][1024];
     const int l0 = tid * LPT;
     const float INF = __int_as_float(0x7f800000);
     const int R = A.s1 - A.s0;                             // DP steps to run: rows s0+1 .. s1
@@ -520,14 +522,11 @@ __global__ void __launch_bounds__(1024) k_seam_dp(DpArgs A) {
         t[j] = __fadd_rn(c, A.P[(size_t)A.s0 * row_f + lane]);
     }
     // double-buffered edge exchange: this thread writes its own slots, reads its neighbours' slots
-    float* eLw = edgeL + tid;
-    float* eRw = edgeR + tid;
-    const float* eLr = edgeL + min(tid + 1, nt - 1);       // first lane of the right neighbour
-    const float* eRr = edgeR + max(tid - 1, 0);            // last lane of the left neighbour
     const bool has_left = tid > 0, has_right = tid < nt - 1;
-    int boff = 0;                                          // 0 or nt: which of the two edge buffers is current
-    eLw[boff] = t[0];
-    eRw[boff] = t[LPT - 1];
+    const int tl_i = max(tid - 1, 0), tr_i = min(tid + 1, nt - 1);
+    int cur = 0;
+    edgeL[cur][tid] = t[0];
+    edgeR[cur][tid] = t[LPT - 1];
     __syncthreads();
     uint8_t* ctl_row = A.control + (size_t)(A.s0 + 1) * row_f + l0;
     for (int g = 0; g < NG; ++g) {
@@ -537,6 +536,9 @@ __global__ void __launch_bounds__(1024) k_seam_dp(DpArgs A) {
         const float* Qr = Pr + A.G * row_f;
         const int rows = min(A.G, R - g * A.G);
         for (int rr = 0; rr < rows; ++rr, Pr += row_f, Qr += row_f, ctl_row += row_f) {
+            const float el = edgeR[cur][tl_i], er = edgeL[cur][tr_i];
+            const float tl_edge = has_left ? el : INF;
+            const float tr_edge = has_right ? er : INF;
             float p[LPT], q[LPT];
 #pragma unroll
             for (int j = 0; j < LPT; j += 4) {
@@ -546,8 +548,6 @@ __global__ void __launch_bounds__(1024) k_seam_dp(DpArgs A) {
                 q[j] = qv.x; q[j + 1] = qv.y; q[j + 2] = qv.z; q[j + 3] = qv.w;
             }
             const float qleft = has_left ? Qr[-1] : 0.f;
-            const float tl_edge = has_left ? eRr[boff] : INF;
-            const float tr_edge = has_right ? eLr[boff] : INF;
             float tn[LPT];
             uint32_t ctl_pack[LPT / 4];
 #pragma unroll
@@ -562,31 +562,34 @@ __global__ void __launch_bounds__(1024) k_seam_dp(DpArgs A) {
                 float best = t[j]; uint32_t ctl = 1;
                 if (c2 < best) { best = c2; ctl = 2; }
                 if (c3 < best) { best = c3; ctl = 3; }
-                const float c = p[j] >= 0.f ? best : INF;        // cells outside the component stay unreachable
-                if (!(c < INF)) ctl = 0;
-                tn[j] = __fadd_rn(c, p[j]);
+                tn[j] = __fadd_rn(best, p[j]);
                 ctl_pack[j / 4] |= ctl << (8 * (j & 3));
             }
 #pragma unroll
             for (int j = 0; j < LPT / 4; ++j) reinterpret_cast<uint32_t*>(ctl_row)[j] = ctl_pack[j];
 #pragma unroll
             for (int j = 0; j < LPT; ++j) t[j] = tn[j];
-            boff = nt - boff;
-            eLw[boff] = t[0];
-            eRw[boff] = t[LPT - 1];
+            cur ^= 1;
+            edgeL[cur][tid] = t[0];
+            edgeR[cur][tid] = t[LPT - 1];
             __syncthreads();
         }
         // every thread is past its reads of this stage (barrier above): refill it with group g + D
         if (tid == 0 && g + A.D < NG) issue(g + A.D);
     }
-    // destination reachable <=> a control value was recorded for it ([SEAM]:918)
+    // destination reachable ([SEAM]:918) <=> its running value is finite (the destination is a cell of the component,
+    // so its own P is finite)
     __shared__ int reached_s;
-    if (tid == 0) {
-        if (A.s1 == A.s0) reached_s = A.lane1 == A.lane0;
-        else reached_s = A.control[(size_t)A.s1 * row_f + A.lane1] != 0;
-        *A.reached = reached_s;
+    if (tid == 0) reached_s = (A.s1 == A.s0) ? (A.lane1 == A.lane0) : 0;
+    __syncthreads();
+    if (A.s1 > A.s0 && A.lane1 >= l0 && A.lane1 < l0 + LPT) {
+        float tv = INF;
+#pragma unroll
+        for (int j = 0; j < LPT; ++j) if (l0 + j == A.lane1) tv = t[j];
+        if (tv < INF) reached_s = 1;
     }
     __syncthreads();
+    if (tid == 0) *A.reached = reached_s;
     if (!reached_s) return;
     // back-track ([SEAM]:923-947), staged through shared memory in chunks of BT steps
     constexpr int BT = 32;
@@ -922,23 +925,24 @@ int PairSeam::extract_contours(int wx, int wy, int ww, int wh, int fa, int fb, s
     return IS_OK;
 }
 
-// [SEAM]:311-392
+// [SEAM]:311-392.  An edge exists when at least one contour pixel touches the other component; consecutive contour
+// pixels mostly repeat the same neighbour, so repeated inserts are skipped.
 void PairSeam::find_edges() {
-    std::map<std::pair<int, int>, int> wedges;
-    for (int ci = 0; ci < ncomps; ++ci)
+    edges.clear();
+    for (int ci = 0; ci < ncomps; ++ci) {
+        int last = -1;
         for (const ContourRec& r : contours[ci]) {
             const int l = ci + 1;
             for (int k = 0; k < 4; ++k) {
                 const int nl = r.nl[k];
-                if (nl > 0 && nl != l) {
-                    wedges[{ci, nl - 1}]++;
-                    wedges[{nl - 1, ci}]++;
+                if (nl > 0 && nl != l && nl != last) {
+                    edges.insert({ci, nl - 1});
+                    edges.insert({nl - 1, ci});
+                    last = nl;
                 }
             }
         }
-    edges.clear();
-    for (auto& kv : wedges)
-        if (kv.second > 0) edges.insert(kv.first);
+    }
 }
 
 // [SEAM]:575-581
@@ -1071,8 +1075,8 @@ int PairSeam::estimate_and_update(int c1, int c2, Pt p1, Pt p2) {
         A.D = 3;
         A.G = (int)std::min<size_t>(16, budget / (A.D * row_pair));
         if (A.G < 1) { A.D = 2; A.G = 1; }
-        const size_t smem = (size_t)A.D * A.G * row_pair + sizeof(float) * 4 * (size_t)nt + 8 * (size_t)A.D + 16;
-        IS_REQUIRE(ctx, smem <= 220 * 1024 && smem >= (size_t)32 * 65, IS_ERR_INTERNAL, "DP shared-memory budget");
+        const size_t smem = std::max<size_t>((size_t)A.D * A.G * row_pair + 8 * (size_t)A.D + 16, (size_t)32 * 65 + 16);
+        IS_REQUIRE(ctx, smem <= 200 * 1024, IS_ERR_INTERNAL, "DP shared-memory budget");
         ctx->next_bytes = (double)(A.s1 - A.s0) * lanes * 9;                    // P, Q read once, control written once
         switch (lpt) {
             case 4:
@@ -1187,28 +1191,29 @@ int PairSeam::estimate_and_update(int c1, int c2, Pt p1, Pt p2) {
         int v = horizontal ? value_at(gs[3 * k + 2], x, y + 1) : value_at(gs[3 * k + 2], x + 1, y);
         painted[key(x, y)] = (v > 0 && v != 255) ? v : 0;
     }
-    // adjacency vote ([SEAM]:1039-1085)
-    std::map<int, int> connect2, connectOther;
-    for (int i = 1; i <= nsub; ++i) { connect2.insert({i, 0}); connectOther.insert({i, 0}); }
+    // adjacency vote ([SEAM]:1039-1085).  The reference's std::map<int,int> counters hold the keys 1..ncomps plus key 0
+    // when a contour pixel ended up unassigned; plain arrays with a "key 0 present" flag are equivalent.
+    std::vector<int> connect2(nsub + 1, 0), connectOther(nsub + 1, 0);
+    bool c2_has0 = false, co_has0 = false;
     for (int i = 0; i < nc; ++i) {
         const ContourRec& r = cont[i];
-        const int mv = painted[key(cpts[i].x, cpts[i].y)];
-        if (r.nl[0] == l2 || r.nl[1] == l2 || r.nl[2] == l2 || r.nl[3] == l2) connect2[mv]++;
+        int mv = painted[key(cpts[i].x, cpts[i].y)];
+        if (mv < 0 || mv > nsub) mv = 0;
+        if (r.nl[0] == l2 || r.nl[1] == l2 || r.nl[2] == l2 || r.nl[3] == l2) { connect2[mv]++; if (mv == 0) c2_has0 = true; }
         bool other = false;
         for (int k = 0; k < 4; ++k) if (r.nl[k] >= 0 && r.nl[k] != l1 && r.nl[k] != l2) other = true;
-        if (other) connectOther[mv]++;
+        if (other) { connectOther[mv]++; if (mv == 0) co_has0 = true; }
     }
-    int maxKey = nsub;
-    for (auto& kv : connect2) maxKey = std::max(maxKey, kv.first);
+    const int maxKey = nsub;
     std::vector<int> isAdj(maxKey + 1, 0);
     const double len = (double)nc;
-    for (auto& kv : connect2) {
+    for (int k = c2_has0 ? 0 : 1; k <= nsub; ++k) {
         int res = 0;
-        if (kv.second / len > 0.05) {
-            auto sub = connectOther.find(kv.first);
-            if (sub != connectOther.end() && (sub->second / len < 0.1)) res = 1;
+        if (connect2[k] / len > 0.05) {
+            const bool sub_exists = k >= 1 || co_has0;
+            if (sub_exists && (connectOther[k] / len < 0.1)) res = 1;
         }
-        isAdj[kv.first] = res;
+        isAdj[k] = res;
     }
     dbg.lap("  uls host walk");
     // ---- relabel ([SEAM]:1089-1092)
@@ -1460,6 +1465,15 @@ static int mask_and(is_ctx* ctx, const DevMat& dst, const DevMat& src) {
     return IS_OK;
 }
 
+// same, restricted to the rectangle (x0, y0, w, h) of the masks: a pair only clears pixels inside its intersection
+static int mask_and_rect(is_ctx* ctx, const DevMat& dst, const DevMat& src, int x0, int y0, int w, int h) {
+    if (w <= 0 || h <= 0) return IS_OK;
+    dim3 block(64, 4), grid(div_up(w, 64), div_up(h, 4));
+    IS_LAUNCH(ctx, k_mask_and, grid, block, 0, dst.ptr<uint8_t>() + (size_t)y0 * dst.step + x0, dst.step,
+              src.ptr<uint8_t>() + (size_t)y0 * src.step + x0, src.step, h, w);
+    return IS_OK;
+}
+
 static int mask_copy(is_ctx* ctx, const DevMat& dst, const DevMat& src) {
     IS_CUDA(ctx, cudaMemcpy2DAsync(dst.data, dst.step, src.data, src.step, (size_t)src.cols, src.rows, cudaMemcpyDeviceToDevice, ctx->stream));
     return IS_OK;
@@ -1620,8 +1634,12 @@ static int seam_find_concurrent(is_ctx* ctx, const std::vector<std::pair<int, in
     if (!all_valid) return IS_OK;                        // caller falls back to the sequential loop
     // 3. final masks = entry masks minus every pair's clears
     for (size_t k = 0; k < np; ++k) {
-        IS_TRY(mask_and(ctx, masks[jobs[k].i], jobs[k].out_i));
-        IS_TRY(mask_and(ctx, masks[jobs[k].j], jobs[k].out_j));
+        const int i = jobs[k].i, j = jobs[k].j;
+        const int x0 = std::max(corners[i].x, corners[j].x), y0 = std::max(corners[i].y, corners[j].y);
+        const int x1 = std::min(corners[i].x + images[i].cols, corners[j].x + images[j].cols);
+        const int y1 = std::min(corners[i].y + images[i].rows, corners[j].y + images[j].rows);
+        IS_TRY(mask_and_rect(ctx, masks[i], jobs[k].out_i, x0 - corners[i].x, y0 - corners[i].y, x1 - x0, y1 - y0));
+        IS_TRY(mask_and_rect(ctx, masks[j], jobs[k].out_j, x0 - corners[j].x, y0 - corners[j].y, x1 - x0, y1 - y0));
         if (trace) {
             const size_t len = jobs[k].trace.len;
             if (trace->buf && trace->len + len <= trace->cap && len <= jobs[k].trace.cap) std::memcpy(trace->buf + trace->len, jobs[k].trace_buf.data(), len * sizeof(int32_t));
