@@ -15,9 +15,11 @@
 // int16 accumulation wraps modulo 2^16 exactly like OpenCV's `short +=`, so it is order independent; the
 // float weight sum keeps OpenCV's feed order.  Results equal the scatter formulation bit for bit.
 #include "common.cuh"
+#include "tma.cuh"
 
 #include <algorithm>
 #include <cmath>
+#include <cstdlib>
 
 namespace is {
 
@@ -409,6 +411,300 @@ __global__ void __launch_bounds__(256) k_blend_level_quad(LevelArgs A) {
     }
 }
 
+// ---- level 0 of blend(), tiled: TMA-staged 2-D tiles, one CTA per 64 x 32 panorama pixels ----------------------------
+// Level 0 carries most of the blend's bytes (u8 image + mask in, int16 panorama + mask out).  Facts used here:
+//   * the level-0 weight of an image is its mask (x 1/255, or +1 for CV_16S) inside the image and 0 in the
+//     copyMakeBorder frame; a pixel whose weight is 0 adds  short(laplacian * 0) = 0  and  w = 0  to the sums, so only
+//     pixels with a non-zero mask matter and the BORDER_REFLECT view of the image is never needed;
+//   * a coarse occupancy map of every mask (one byte per 64 x 32 cell, k_mask_summary) tells which images can
+//     contribute to a tile at all, so the overlap zones do not fetch the image that lost the seam;
+//   * mask 255 gives w = 255 * (1/255.f) = 1.0f exactly, and with a weight sum of exactly 1.0f the normalisation
+//     short(d / (1.0f + 1e-5f)) equals d - sign(d) for every int16 d (checked exhaustively in tests/test_blend_math.py):
+//     the common pixel needs no floating point at all.
+// The tiles (collapsed level 1, and per contributing image: mask, u8 image, Gaussian level 1) arrive by
+// cp.async.bulk.tensor.2d into shared memory, out-of-range parts zero-filled by the TMA unit; every thread owns two
+// vertically adjacent 2 x 2 quads and walks the four level-1 rows they share (pyrUp is separable: horizontal sums once
+// per level-1 row, vertical combination per output row).
+constexpr int L0_TW = 64, L0_TH = 32;                        // level-0 pixels per tile
+constexpr int L0_UW = L0_TW / 2 + 2, L0_UH = L0_TH / 2 + 2;  // level-1 pixels per tile incl. the pyrUp halo: 34 x 18
+// TMA wants the innermost box start 16-byte aligned (probed on B200: an unaligned start raises "illegal instruction"), so every
+// box starts at the aligned address below the tile and is up to 15 bytes wider; the kernel indexes with the shift.
+constexpr int L0_UROW = 112;                                 // int16 per shared-memory row of a level-1 tile: 3 * 34 = 102, + 7 shift, padded to 16 B
+constexpr int L0_UBYTES = L0_UH * L0_UROW * 2;               // 4032
+constexpr int L0_UALLOC = 4096;                              // ... rounded up to 128 B
+constexpr int L0_IROW = 208;                                 // bytes per row of a u8 x 3 image tile: 192 + 15 shift, padded to 16 B
+constexpr int L0_IBYTES = L0_TH * L0_IROW;                   // 6656
+constexpr int L0_MROW = 80;                                  // bytes per row of a mask tile: 64 + 15 shift, padded to 16 B
+constexpr int L0_MBYTES = L0_TH * L0_MROW;                   // 2560
+constexpr int SUM_CW = 64, SUM_CH = 32;                      // cell of the mask occupancy map
+
+struct L0Img {
+    int X0, Y0;            // image origin (the real image, not the padded frame) in panorama level-0 coordinates
+    int rows, cols;        // real image size
+    int fx, fy;            // padded frame origin in panorama level-0 coordinates (multiples of 2^nb)
+    int h1, w1;            // Gaussian level-1 dims of the frame
+    const uint8_t* summary; int sum_w, sum_h;
+};
+
+struct L0Args {
+    const CUtensorMap* maps;   // [0] collapsed level 1; [1 + 3 i ...]: mask, image, Gaussian level 1 of image i
+    const L0Img* imgs; int n;
+    int uh, uw;                // collapsed level-1 dims
+    int16_t* dst; size_t dstep; uint8_t* dmask; size_t mstep;
+    int W, H;                  // panorama columns [sx0, W) and rows [0, H) are stored
+    int xb, sx0;               // first computed column (even), first stored column
+};
+
+__global__ void k_mask_summary(const uint8_t* __restrict__ mask, size_t step, int rows, int cols, uint8_t* __restrict__ out, int sw) {
+    const int cx = blockIdx.x, cy = blockIdx.y;
+    const int tx = threadIdx.x & 63, ty = threadIdx.x >> 6;   // 64 x 4 threads
+    int any = 0;
+    const int x = cx * SUM_CW + tx;
+    if (x < cols)
+        for (int r = ty; r < SUM_CH; r += 4) {
+            const int y = cy * SUM_CH + r;
+            if (y < rows) any |= mask[(size_t)y * step + x];
+        }
+    any = __syncthreads_or(any);
+    if (threadIdx.x == 0) out[(size_t)cy * sw + cx] = any ? 1 : 0;
+}
+
+// horizontal pyrUp sums of one level-1 row at three (border-mapped) columns: E = s[i-1] + 6 s[i] + s[i+1], O = s[i] + s[i+1]
+// (the odd output is 4 * O; the factor is folded into the final shifts)
+__device__ __forceinline__ void l0_hsum(const int16_t* __restrict__ row, int cm, int cc, int cp, int E[3], int O[3]) {
+#pragma unroll
+    for (int c = 0; c < 3; ++c) {
+        const int v0 = row[3 * cm + c], v1 = row[3 * cc + c], v2 = row[3 * cp + c];
+        E[c] = v0 + 6 * v1 + v2;
+        O[c] = v1 + v2;
+    }
+}
+// pyrUp of a 2 x 2 quad from the horizontal sums of its three level-1 rows; u[q]: q = 0 (even y, even x), 1 (even y, odd x),
+// 2 (odd y, even x), 3 (odd y, odd x).  Same integers as (t + 32) >> 6 of the separable [1 6 1] / [4 4] taps.
+__device__ __forceinline__ void l0_quad_up(const int Ea[3], const int Oa[3], const int Eb[3], const int Ob[3], const int Ec[3], const int Oc[3],
+                                           int u[4][3]) {
+#pragma unroll
+    for (int c = 0; c < 3; ++c) {
+        u[0][c] = (Ea[c] + 6 * Eb[c] + Ec[c] + 32) >> 6;
+        u[1][c] = (Oa[c] + 6 * Ob[c] + Oc[c] + 8) >> 4;
+        u[2][c] = (Eb[c] + Ec[c] + 8) >> 4;
+        u[3][c] = (Ob[c] + Oc[c] + 2) >> 2;
+    }
+}
+
+template <bool WF>
+__global__ void __launch_bounds__(256, 3) k_blend_l0_tiled(L0Args A) {
+    __shared__ __align__(128) unsigned char s_c1[L0_UALLOC];
+    __shared__ __align__(128) unsigned char s_img[2][L0_IBYTES];
+    __shared__ __align__(128) unsigned char s_g1[2][L0_UALLOC];
+    __shared__ __align__(128) unsigned char s_msk[2][L0_MBYTES];
+    __shared__ __align__(8) uint64_t bars[3];   // 0: collapsed level 1, 1 / 2: image slots
+    __shared__ unsigned s_cmask;
+
+    const int tid = threadIdx.x, tx = tid & 31, ty = tid >> 5;
+    const int x0t = A.xb + blockIdx.x * L0_TW, y0t = blockIdx.y * L0_TH;
+    if (tid == 0) {
+        mbar_init(&bars[0], 1); mbar_init(&bars[1], 1); mbar_init(&bars[2], 1);
+        mbar_fence_init();
+    }
+    __syncthreads();
+    if (tid == 0) {   // collapsed level 1: needed last, requested first
+        tensormap_acquire(&A.maps[0]);
+        mbar_expect_tx(&bars[0], L0_UBYTES);
+        tma_load_2d(s_c1, &A.maps[0], ((6 * ((x0t >> 1) - 1)) & ~15) >> 1, (y0t >> 1) - 1, &bars[0]);
+    }
+
+    // accumulators of this thread's 8 pixels: p = 4 * quad + 2 * (row in quad) + (column in quad)
+    int acc[8][3];
+    float wsum_f[8];
+    int wsum_s[8];
+#pragma unroll
+    for (int p = 0; p < 8; ++p) { acc[p][0] = acc[p][1] = acc[p][2] = 0; wsum_f[p] = 0.f; wsum_s[p] = 0; }
+
+    uint32_t ph[2] = {0, 0};
+    for (int base = 0; base < A.n; base += 32) {
+        if (tid < 32) {   // which of the images base .. base + 31 can contribute to this tile
+            bool cand = false;
+            const int i = base + tid;
+            if (i < A.n) {
+                const L0Img I = A.imgs[i];
+                const int lx_lo = max(x0t - I.X0, 0), lx_hi = min(x0t + L0_TW, I.X0 + I.cols) - I.X0 - 1;
+                const int ly_lo = max(y0t - I.Y0, 0), ly_hi = min(y0t + L0_TH, I.Y0 + I.rows) - I.Y0 - 1;
+                if (lx_lo <= lx_hi && ly_lo <= ly_hi) {
+                    for (int cy = ly_lo / SUM_CH; cy <= ly_hi / SUM_CH; ++cy)
+                        for (int cx = lx_lo / SUM_CW; cx <= lx_hi / SUM_CW; ++cx) cand = cand || I.summary[(size_t)cy * I.sum_w + cx] != 0;
+                }
+            }
+            const unsigned b = __ballot_sync(0xffffffffu, cand);
+            if (tid == 0) s_cmask = b;
+        }
+        __syncthreads();
+        unsigned cm = s_cmask;
+        while (cm) {   // batches of up to two images: both requested at once, consumed in feed order
+            int ci[2];
+            ci[0] = base + __ffs(cm) - 1; cm &= cm - 1;
+            ci[1] = -1;
+            if (cm) { ci[1] = base + __ffs(cm) - 1; cm &= cm - 1; }
+            if (tid == 0) {
+#pragma unroll
+                for (int s = 0; s < 2; ++s) {
+                    if (ci[s] < 0) continue;
+                    const L0Img I = A.imgs[ci[s]];
+                    const CUtensorMap* m = A.maps + 1 + 3 * ci[s];
+                    tensormap_acquire(m); tensormap_acquire(m + 1); tensormap_acquire(m + 2);
+                    mbar_expect_tx(&bars[1 + s], L0_MBYTES + L0_IBYTES + L0_UBYTES);
+                    tma_load_2d(s_msk[s], m, (x0t - I.X0) & ~15, y0t - I.Y0, &bars[1 + s]);
+                    tma_load_2d(s_img[s], m + 1, (3 * (x0t - I.X0)) & ~15, y0t - I.Y0, &bars[1 + s]);
+                    tma_load_2d(s_g1[s], m + 2, ((6 * (((x0t - I.fx) >> 1) - 1)) & ~15) >> 1, ((y0t - I.fy) >> 1) - 1, &bars[1 + s]);
+                }
+            }
+#pragma unroll
+            for (int s = 0; s < 2; ++s) {
+                if (ci[s] < 0) continue;
+                mbar_wait(&bars[1 + s], ph[s]);
+                ph[s] ^= 1;
+                // masks of the 8 pixels: rows 4 ty .. 4 ty + 3, columns 2 tx, 2 tx + 1
+                const L0Img I = A.imgs[ci[s]];
+                const int lx0 = x0t - I.X0;                      // tile origin in image coordinates
+                const int msh = lx0 - (lx0 & ~15);               // byte shifts of the tiles inside their aligned boxes
+                const int ish = 3 * lx0 - ((3 * lx0) & ~15);
+                uint32_t mk[4];
+                uint32_t anym = 0;
+#pragma unroll
+                for (int r = 0; r < 4; ++r) {
+                    const uint8_t* mp = &s_msk[s][(4 * ty + r) * L0_MROW + msh + 2 * tx];
+                    mk[r] = (uint32_t)mp[0] | ((uint32_t)mp[1] << 8);
+                    anym |= mk[r];
+                }
+                if (anym) {
+                    // level-1 coordinates inside the image's frame; the tile starts at an even frame coordinate
+                    const int cx = ((x0t - I.fx) >> 1) + tx, cy = ((y0t - I.fy) >> 1) + 2 * ty;
+                    const int ox = ((x0t - I.fx) >> 1) - 1, oy = ((y0t - I.fy) >> 1) - 1;   // level-1 origin of the tile in shared memory
+                    const int cm_ = min(max((cx > 0 ? cx - 1 : 1) - ox, 0), L0_UW - 1);
+                    const int cc_ = min(max(cx - ox, 0), L0_UW - 1);
+                    const int cp_ = min(max(min(cx + 1, I.w1 - 1) - ox, 0), L0_UW - 1);
+                    int rr[4];
+                    rr[0] = (cy > 0 ? cy - 1 : 1) - oy;
+                    rr[1] = cy - oy;
+                    rr[2] = min(cy + 1, I.h1 - 1) - oy;
+                    rr[3] = min(cy + 2, I.h1 - 1) - oy;
+                    const int16_t* g1 = reinterpret_cast<const int16_t*>(s_g1[s]) + ((6 * ox - ((6 * ox) & ~15)) >> 1);
+                    int E[4][3], O[4][3];
+#pragma unroll
+                    for (int j = 0; j < 4; ++j) l0_hsum(g1 + min(max(rr[j], 0), L0_UH - 1) * L0_UROW, cm_, cc_, cp_, E[j], O[j]);
+#pragma unroll
+                    for (int q = 0; q < 2; ++q) {
+                        int u[4][3];
+                        l0_quad_up(E[q], O[q], E[q + 1], O[q + 1], E[q + 2], O[q + 2], u);
+#pragma unroll
+                        for (int r = 0; r < 2; ++r) {
+                            const int row = 4 * ty + 2 * q + r;
+                            const uint8_t* px = &s_img[s][row * L0_IROW + ish + 6 * tx];
+#pragma unroll
+                            for (int c2 = 0; c2 < 2; ++c2) {
+                                const int m = (int)((mk[2 * q + r] >> (8 * c2)) & 255u);
+                                if (m == 0) continue;
+                                const int p = 4 * q + 2 * r + c2;
+                                int lap[3];
+#pragma unroll
+                                for (int c = 0; c < 3; ++c) lap[c] = min((int)px[3 * c2 + c] - u[2 * r + c2][c], 32767);   // cv::subtract saturates
+                                if (WF) {
+                                    const float w = __fmul_rn((float)m, (float)(1. / 255.));
+                                    if (m == 255) {   // w == 1.0f: short(lap * 1.0f) == lap
+                                        acc[p][0] += lap[0]; acc[p][1] += lap[1]; acc[p][2] += lap[2];
+                                    } else {
+                                        acc[p][0] += (int)(int16_t)__float2int_rz(__fmul_rn((float)lap[0], w));
+                                        acc[p][1] += (int)(int16_t)__float2int_rz(__fmul_rn((float)lap[1], w));
+                                        acc[p][2] += (int)(int16_t)__float2int_rz(__fmul_rn((float)lap[2], w));
+                                    }
+                                    wsum_f[p] = __fadd_rn(wsum_f[p], w);
+                                } else {
+                                    const int w = m + 1;
+                                    acc[p][0] += (int)(int16_t)((lap[0] * w) >> 8);
+                                    acc[p][1] += (int)(int16_t)((lap[1] * w) >> 8);
+                                    acc[p][2] += (int)(int16_t)((lap[2] * w) >> 8);
+                                    wsum_s[p] = (int)(int16_t)(wsum_s[p] + w);
+                                }
+                            }
+                        }
+                    }
+                }
+            }
+            __syncthreads();   // every thread is done with both slots before the next batch lands in them
+        }
+        __syncthreads();       // s_cmask is rewritten by the next round
+    }
+
+    // ---- normalise, add pyrUp of the collapsed level 1, crop, mask, store
+    mbar_wait(&bars[0], 0);
+    {
+        const int cx = (x0t >> 1) + tx, cy = (y0t >> 1) + 2 * ty;
+        const int ox = (x0t >> 1) - 1, oy = (y0t >> 1) - 1;
+        const int cm_ = min(max((cx > 0 ? cx - 1 : 1) - ox, 0), L0_UW - 1);
+        const int cc_ = min(max(cx - ox, 0), L0_UW - 1);
+        const int cp_ = min(max(min(cx + 1, A.uw - 1) - ox, 0), L0_UW - 1);
+        int rr[4];
+        rr[0] = (cy > 0 ? cy - 1 : 1) - oy;
+        rr[1] = cy - oy;
+        rr[2] = min(cy + 1, A.uh - 1) - oy;
+        rr[3] = min(cy + 2, A.uh - 1) - oy;
+        const int16_t* c1 = reinterpret_cast<const int16_t*>(s_c1) + ((6 * ox - ((6 * ox) & ~15)) >> 1);
+        int E[4][3], O[4][3];
+#pragma unroll
+        for (int j = 0; j < 4; ++j) l0_hsum(c1 + min(max(rr[j], 0), L0_UH - 1) * L0_UROW, cm_, cc_, cp_, E[j], O[j]);
+        const int x = x0t + 2 * tx;
+#pragma unroll
+        for (int q = 0; q < 2; ++q) {
+            int u[4][3];
+            l0_quad_up(E[q], O[q], E[q + 1], O[q + 1], E[q + 2], O[q + 2], u);
+#pragma unroll
+            for (int r = 0; r < 2; ++r) {
+                const int y = y0t + 4 * ty + 2 * q + r;
+                if (y >= A.H) continue;
+                int v[2][3];
+                bool on[2];
+#pragma unroll
+                for (int c2 = 0; c2 < 2; ++c2) {
+                    const int p = 4 * q + 2 * r + c2;
+                    on[c2] = WF ? (wsum_f[p] > IS_WEIGHT_EPS) : (wsum_s[p] >= 1);
+#pragma unroll
+                    for (int c = 0; c < 3; ++c) {
+                        const int d = (int)(int16_t)acc[p][c];   // the int16 accumulator of OpenCV
+                        int nrm;
+                        if (WF) {
+                            if (wsum_f[p] == 1.0f) nrm = d - (d > 0) + (d < 0);
+                            else if (wsum_f[p] == 0.f) nrm = 0;
+                            else nrm = (int)(int16_t)__float2int_rz(__fdiv_rn((float)d, __fadd_rn(wsum_f[p], IS_WEIGHT_EPS)));
+                        } else {
+                            nrm = (int)(int16_t)((d * 256) / (wsum_s[p] + 1));
+                        }
+                        const int t = sat16(nrm + u[2 * r + c2][c]);
+                        v[c2][c] = on[c2] ? t : 0;
+                    }
+                }
+                const bool va = x >= A.sx0 && x < A.W, vb = x + 1 >= A.sx0 && x + 1 < A.W;
+                int16_t* o = reinterpret_cast<int16_t*>(reinterpret_cast<char*>(A.dst) + (size_t)y * A.dstep) + 3 * (x - A.sx0);
+                uint8_t* mo = A.dmask + (size_t)y * A.mstep + (x - A.sx0);
+                if (va && vb && ((reinterpret_cast<uintptr_t>(o) & 3) == 0)) {
+                    uint32_t* o32 = reinterpret_cast<uint32_t*>(o);
+                    o32[0] = (uint32_t)(uint16_t)v[0][0] | ((uint32_t)(uint16_t)v[0][1] << 16);
+                    o32[1] = (uint32_t)(uint16_t)v[0][2] | ((uint32_t)(uint16_t)v[1][0] << 16);
+                    o32[2] = (uint32_t)(uint16_t)v[1][1] | ((uint32_t)(uint16_t)v[1][2] << 16);
+                } else {
+                    if (va) { o[0] = (int16_t)v[0][0]; o[1] = (int16_t)v[0][1]; o[2] = (int16_t)v[0][2]; }
+                    if (vb) { o[3] = (int16_t)v[1][0]; o[4] = (int16_t)v[1][1]; o[5] = (int16_t)v[1][2]; }
+                }
+                if (va && vb && ((reinterpret_cast<uintptr_t>(mo) & 1) == 0)) {
+                    *reinterpret_cast<uint16_t*>(mo) = (uint16_t)((on[0] ? 255u : 0u) | (on[1] ? 0xff00u : 0u));
+                } else {
+                    if (va) mo[0] = on[0] ? 255 : 0;
+                    if (vb) mo[1] = on[1] ? 255 : 0;
+                }
+            }
+        }
+    }
+}
+
 // ---- pyrDown of level 0 through shared memory -------------------------------------------------------------------------
 // One block = PD_TX x PD_TY outputs.  The (2 PD_TX + 3) x (2 PD_TY + 3) input tile is fetched once through the
 // reflect-border view (REFLECT_101 of the padded frame, then BORDER_REFLECT into the fed image), packed as
@@ -490,6 +786,8 @@ struct FedImage {
     int x_tl = 0, y_tl = 0;        // padded rect inside dst_roi_ (level 0)
     int top = 0, left = 0, height = 0, width = 0;
     std::vector<DevBuf> g, w;      // levels 1..nb at index k (index 0 unused)
+    DevBuf summary;                // occupancy of the mask per 64 x 32 cell (k_mask_summary)
+    int sum_w = 0, sum_h = 0;
 };
 
 struct is_blender {
@@ -624,7 +922,81 @@ int blender_feed_dev(is_blender* b, FedImage&& f) {
         }
         sh = dh; sw = dw;
     }
+    if (nb >= 1) {   // which 64 x 32 cells of the mask hold anything: lets the level-0 blend skip images per tile
+        f.sum_w = div_up(cols, SUM_CW); f.sum_h = div_up(rows, SUM_CH);
+        IS_TRY(f.summary.alloc(ctx, (size_t)f.sum_w * f.sum_h));
+        ctx->next_bytes = (double)rows * cols;
+        IS_LAUNCH(ctx, k_mask_summary, dim3(f.sum_w, f.sum_h), 256, 0, f.mask.ptr<uint8_t>(), f.mask.step, rows, cols, f.summary.as<uint8_t>(), f.sum_w);
+    }
     b->fed.push_back(std::move(f));
+    return IS_OK;
+}
+
+static int make_map_2d(is_ctx* ctx, CUtensorMap* m, CUtensorMapDataType dt, const void* base, uint64_t inner, uint64_t rows, uint64_t stride_bytes,
+                       uint32_t box_inner, uint32_t box_rows) {
+    const cuuint64_t dims[2] = {inner, rows};
+    const cuuint64_t strides[1] = {stride_bytes};
+    const cuuint32_t box[2] = {box_inner, box_rows};
+    const cuuint32_t estr[2] = {1, 1};
+    const CUresult r = cuTensorMapEncodeTiled(m, dt, 2, const_cast<void*>(base), dims, strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
+                                              CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_128B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    if (r != CUDA_SUCCESS) return fail(ctx, IS_ERR_CUDA, "cuTensorMapEncodeTiled failed (%d)", (int)r);
+    return IS_OK;
+}
+
+static bool tma_ok(const void* base, size_t stride) { return (reinterpret_cast<uintptr_t>(base) & 15) == 0 && (stride & 15) == 0; }
+
+// level 0 through the tiled TMA kernel when every operand meets the TMA alignment rules (16-byte base and pitch);
+// *done = false leaves the level to the generic quad kernel
+static int blend_level0_tiled(is_blender* b, const DevMat& dst, const DevMat& dmask, const int16_t* c1, int uh, int uw, int xb, int xe, int sx0,
+                              int sx1, double bytes, bool* done) {
+    is_ctx* ctx = b->ctx;
+    *done = false;
+    const int n = (int)b->fed.size();
+    if (getenv("IS_BLEND_L0_GENERIC")) return IS_OK;
+    if (b->num_bands < 1 || !tma_ok(c1, (size_t)uw * 6)) return IS_OK;
+    for (const FedImage& f : b->fed) {
+        if (f.img.depth != IS_8U || !tma_ok(f.img.data, f.img.step) || !tma_ok(f.mask.data, f.mask.step)) return IS_OK;
+        if (!tma_ok(f.g[1].p, (size_t)(f.width >> 1) * 6) || !f.summary.p) return IS_OK;
+    }
+    const size_t maps_bytes = sizeof(CUtensorMap) * (size_t)(1 + 3 * n);
+    std::vector<unsigned char> host(maps_bytes + sizeof(L0Img) * (size_t)std::max(n, 1));
+    CUtensorMap* maps = reinterpret_cast<CUtensorMap*>(host.data());
+    L0Img* imgs = reinterpret_cast<L0Img*>(host.data() + maps_bytes);
+    IS_TRY(make_map_2d(ctx, &maps[0], CU_TENSOR_MAP_DATA_TYPE_UINT16, c1, (uint64_t)uw * 3, (uint64_t)uh, (uint64_t)uw * 6, L0_UROW, L0_UH));
+    for (int i = 0; i < n; ++i) {
+        const FedImage& f = b->fed[i];
+        const int h1 = f.height >> 1, w1 = f.width >> 1;
+        IS_TRY(make_map_2d(ctx, &maps[1 + 3 * i], CU_TENSOR_MAP_DATA_TYPE_UINT8, f.mask.data, (uint64_t)f.mask.cols, (uint64_t)f.mask.rows, f.mask.step,
+                           L0_MROW, L0_TH));
+        IS_TRY(make_map_2d(ctx, &maps[2 + 3 * i], CU_TENSOR_MAP_DATA_TYPE_UINT8, f.img.data, (uint64_t)f.img.cols * 3, (uint64_t)f.img.rows, f.img.step,
+                           L0_IROW, L0_TH));
+        IS_TRY(make_map_2d(ctx, &maps[3 + 3 * i], CU_TENSOR_MAP_DATA_TYPE_UINT16, f.g[1].p, (uint64_t)w1 * 3, (uint64_t)h1, (uint64_t)w1 * 6, L0_UROW, L0_UH));
+        L0Img& I = imgs[i];
+        I.fx = f.x_tl; I.fy = f.y_tl;
+        I.X0 = f.x_tl + f.left; I.Y0 = f.y_tl + f.top;
+        I.rows = f.img.rows; I.cols = f.img.cols;
+        I.h1 = h1; I.w1 = w1;
+        I.summary = f.summary.as<uint8_t>(); I.sum_w = f.sum_w; I.sum_h = f.sum_h;
+    }
+    DevBuf table;
+    IS_TRY(table.alloc(ctx, host.size()));
+    IS_TRY(upload(ctx, table.p, host.data(), host.size()));
+    L0Args A;
+    A.maps = table.as<CUtensorMap>();
+    A.imgs = reinterpret_cast<const L0Img*>(table.as<unsigned char>() + maps_bytes);
+    A.n = n;
+    A.uh = uh; A.uw = uw;
+    A.dst = dst.ptr<int16_t>(); A.dstep = dst.step; A.dmask = dmask.ptr<uint8_t>(); A.mstep = dmask.step;
+    A.W = std::min(b->roi_final.width, sx1); A.H = b->roi_final.height;
+    A.xb = xb; A.sx0 = sx0;
+    const int gw = std::min(xe, A.W) - xb;
+    if (gw <= 0) { *done = true; return IS_OK; }
+    dim3 grid(div_up(gw, L0_TW), div_up(A.H, L0_TH));
+    ctx->next_bytes = bytes;
+    if (b->weight_type == IS_WEIGHT_32F) IS_LAUNCH(ctx, k_blend_l0_tiled<true>, grid, 256, 0, A);
+    else IS_LAUNCH(ctx, k_blend_l0_tiled<false>, grid, 256, 0, A);
+    *done = true;
     return IS_OK;
 }
 
@@ -683,6 +1055,13 @@ int blender_blend_dev(is_blender* b, const DevMat& dst, const DevMat& dmask, int
             if (k < nb) bytes += (double)H[k + 1] * W[k + 1] * 6;
             bytes += k == 0 ? (double)A.fw * A.fh * 7 : (double)H[k] * W[k] * 6;
             ctx->next_bytes = bytes * ((double)gw / (double)W[k]);   // strip: the share of the level this launch covers
+        }
+        if (k == 0 && nb >= 1) {
+            bool done = false;
+            const double bytes = ctx->next_bytes;
+            IS_TRY(blend_level0_tiled(b, dst, dmask, out[1].as<int16_t>(), H[1], W[1], xb[0], xe[0], sx0, sx1, bytes, &done));
+            if (done) continue;
+            ctx->next_bytes = bytes;
         }
         if (k < nb) {   // 2x2 blocks share their pyrUp neighbourhood
             dim3 qgrid(div_up(div_up(gw, 2), 32), div_up(div_up(gh, 2), 8));

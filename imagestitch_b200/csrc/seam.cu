@@ -18,6 +18,7 @@
 // association order (cost + costV first, then + costH, [SEAM]:900-904) and candidates are compared
 // lexicographically as (cost, step) like std::min_element over std::pair<float,int> ([SEAM]:909).
 #include "internal.cuh"
+#include "tma.cuh"
 
 #include <algorithm>
 #include <chrono>
@@ -450,32 +451,6 @@ struct DpArgs {
     int G, D;                         // rows per ring stage, number of stages
 };
 
-__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
-
-__device__ __forceinline__ void mbar_init(uint64_t* bar, int count) {
-    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count) : "memory");
-}
-__device__ __forceinline__ void mbar_expect_tx(uint64_t* bar, uint32_t bytes) {
-    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
-}
-__device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
-    asm volatile(
-        "{\n"
-        ".reg .pred p;\n"
-        "WAIT_%=:\n"
-        "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n"
-        "@p bra DONE_%=;\n"
-        "bra WAIT_%=;\n"
-        "DONE_%=:\n"
-        "}\n" ::"r"(smem_u32(bar)), "r"(parity) : "memory");
-}
-// 1-D TMA bulk copy global -> shared, completion signalled on an mbarrier (SASS: UBLKCP)
-__device__ __forceinline__ void bulk_g2s(void* dst, const void* src, uint32_t bytes, uint64_t* bar) {
-    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(smem_u32(dst)), "l"(src),
-                 "r"(bytes), "r"(smem_u32(bar))
-                 : "memory");
-}
-
 // Rows of P, Q and control are padded to `pitch` = nt * LPT lanes.  Cells outside the component (and the padding
 // lanes) carry P = +inf: whatever cost reaches them, the running value t = cost + P leaving them is +inf, so no path
 // continues through them and the back-track never visits them -- the reference's `labels_ == l` test ([SEAM]:897) and
@@ -507,7 +482,7 @@ __global__ void __launch_bounds__(1024) k_seam_dp(DpArgs A) {
     };
     if (tid == 0) {
         for (int d = 0; d < A.D; ++d) mbar_init(&bars[d], 1);
-        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+        mbar_fence_init();
     }
     __syncthreads();
     if (tid == 0)

@@ -176,6 +176,33 @@ def test_multiband_blend(ctx, oracle, case, wt, u8):
         _eq(got, want, f"blend nb={nb} wt={wt}")
 
 
+@pytest.mark.parametrize("wt", [S.WEIGHT_32F, S.WEIGHT_16S])
+def test_multiband_blend_gray_masks(ctx, oracle, wt):
+    """Masks with arbitrary byte values (fractional level-0 weights), overlapping everywhere: the general
+    multiply / divide path of the tiled level-0 kernel next to its mask == 255 fast path."""
+    O = oracle
+    rng = np.random.default_rng(5)
+    corners, wi, wm = warped_set(O, 3, 320, 240, overlap=0.3)
+    sizes = [(a.shape[1], a.shape[0]) for a in wi]
+    vals = np.array([0, 1, 77, 128, 254, 255, 255, 255], np.uint8)
+    masks = []
+    for m in wm:
+        blocks = vals[rng.integers(0, len(vals), (m.shape[0] // 16 + 1, m.shape[1] // 16 + 1))]
+        g = np.kron(blocks, np.ones((16, 16), np.uint8))[:m.shape[0], :m.shape[1]]
+        masks.append(np.where(m > 0, g, 0).astype(np.uint8))
+    ob = O.MultiBandBlender(5, wt)
+    ob.prepare(O.result_roi(corners, sizes))
+    gb = S.MultiBandBlender(ctx, 0, 5, wt)
+    gb.prepare(corners, sizes)
+    for i in range(3):
+        ob.feed(wi[i].astype(np.int16), masks[i], corners[i])
+        gb.feed(wi[i], masks[i], corners[i])
+    want, wmask = ob.blend()
+    got, gmask = gb.blend()
+    _eq(gmask, wmask, "blend mask (gray masks)")
+    _eq(got, want, f"blend gray masks wt={wt}")
+
+
 def test_linear_blend_pair(ctx, oracle):
     O = oracle
     for (w, h, ov) in ((400, 300, 0.25), (320, 260, 0.4)):
