@@ -453,6 +453,7 @@ struct L0Args {
     int16_t* dst; size_t dstep; uint8_t* dmask; size_t mstep;
     int W, H;                  // panorama columns [sx0, W) and rows [0, H) are stored
     int xb, sx0;               // first computed column (even), first stored column
+    int ntx, ntiles;           // tiles per row, tiles in total
 };
 
 __global__ void k_mask_summary(const uint8_t* __restrict__ mask, size_t step, int rows, int cols, uint8_t* __restrict__ out, int sw) {
@@ -469,16 +470,8 @@ __global__ void k_mask_summary(const uint8_t* __restrict__ mask, size_t step, in
     if (threadIdx.x == 0) out[(size_t)cy * sw + cx] = any ? 1 : 0;
 }
 
-// horizontal pyrUp sums of one level-1 row at three (border-mapped) columns: E = s[i-1] + 6 s[i] + s[i+1], O = s[i] + s[i+1]
-// (the odd output is 4 * O; the factor is folded into the final shifts)
-__device__ __forceinline__ void l0_hsum(const int16_t* __restrict__ row, int cm, int cc, int cp, int E[3], int O[3]) {
-#pragma unroll
-    for (int c = 0; c < 3; ++c) {
-        const int v0 = row[3 * cm + c], v1 = row[3 * cc + c], v2 = row[3 * cp + c];
-        E[c] = v0 + 6 * v1 + v2;
-        O[c] = v1 + v2;
-    }
-}
+// pyrUp is separable.  Horizontal sums of a level-1 row at three (border-mapped) columns: E = s[i-1] + 6 s[i] + s[i+1],
+// O = s[i] + s[i+1] (the odd output is 4 * O; the factor is folded into the final shifts).
 // pyrUp of a 2 x 2 quad from the horizontal sums of its three level-1 rows; u[q]: q = 0 (even y, even x), 1 (even y, odd x),
 // 2 (odd y, even x), 3 (odd y, odd x).  Same integers as (t + 32) >> 6 of the separable [1 6 1] / [4 4] taps.
 __device__ __forceinline__ void l0_quad_up(const int Ea[3], const int Oa[3], const int Eb[3], const int Ob[3], const int Ec[3], const int Oc[3],
@@ -492,216 +485,307 @@ __device__ __forceinline__ void l0_quad_up(const int Ea[3], const int Oa[3], con
     }
 }
 
-template <bool WF>
-__global__ void __launch_bounds__(256, 3) k_blend_l0_tiled(L0Args A) {
-    __shared__ __align__(128) unsigned char s_c1[L0_UALLOC];
-    __shared__ __align__(128) unsigned char s_img[2][L0_IBYTES];
-    __shared__ __align__(128) unsigned char s_g1[2][L0_UALLOC];
-    __shared__ __align__(128) unsigned char s_msk[2][L0_MBYTES];
-    __shared__ __align__(8) uint64_t bars[3];   // 0: collapsed level 1, 1 / 2: image slots
-    __shared__ unsigned s_cmask;
+// Persistent, warp-specialised pipeline: 8 consumer warps (one 64 x 4 pixel band of the tile each) + 1 producer warp.
+// The producer finds the images that can contribute to the next tile (occupancy maps), then issues the tile's TMA loads
+// into the free stage while the consumers still compute the previous one; full[] / empty[] mbarriers hand the two
+// stages back and forth, no __syncthreads in steady state.  A tile with more than two contributing images takes
+// several rounds through the stages (the consumers keep their accumulators between rounds).
+constexpr int L0_SLOT_BYTES = L0_MBYTES + L0_IBYTES + L0_UALLOC;      // mask | image | Gaussian level 1
+constexpr int L0_STAGE_BYTES = L0_UALLOC + 2 * L0_SLOT_BYTES;         // collapsed level 1 + two image slots = 30720
+constexpr int L0_CONSUMERS = 256, L0_THREADS = L0_CONSUMERS + 32;
+constexpr int L0_MAXCAND = 32;                                        // contributing images per tile (the host checks the bound)
 
-    const int tid = threadIdx.x, tx = tid & 31, ty = tid >> 5;
-    const int x0t = A.xb + blockIdx.x * L0_TW, y0t = blockIdx.y * L0_TH;
+struct L0Round {         // producer -> consumers, one per stage
+    int x0t, y0t;        // tile origin (level-0 panorama coordinates)
+    int ncand;           // images in this round (0..2); -1: no more work
+    int flags;           // 1: first round of the tile, 2: last round (the collapsed level-1 tile is in the stage), 4: nothing contributes
+    int lx0[2];          // tile origin in image coordinates
+    int ox[2], oy[2];    // level-1 origin of the Gaussian tile inside the image's frame
+    int w1[2], h1[2];    // level-1 frame dims
+};
+constexpr int L0_SMEM_BYTES = 2 * L0_STAGE_BYTES + 64 + 2 * 64 + L0_MAXCAND * 4;
+
+__device__ __forceinline__ void mbar_arrive(uint64_t* bar) {
+    asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory");
+}
+
+// three column pointers + four row offsets of a thread's level-1 neighbourhood (pyrUp border rule: s[-1] -> s[1], s[n] -> s[n-1])
+struct L0Nbr { const int16_t* pm; const int16_t* pc; const int16_t* pp; int ro[4]; };
+
+__device__ __forceinline__ L0Nbr l0_nbr(const unsigned char* tile, int ox, int oy, int w1, int h1, int tx, int ty) {
+    const int cx = ox + 1 + tx, cy = oy + 1 + 2 * ty;   // this thread's level-1 column, first of its two level-1 rows
+    const int16_t* base = reinterpret_cast<const int16_t*>(tile) + ((6 * ox - ((6 * ox) & ~15)) >> 1);
+    L0Nbr n;
+    n.pm = base + 3 * min(max((cx > 0 ? cx - 1 : 1) - ox, 0), L0_UW - 1);
+    n.pc = base + 3 * min(max(cx - ox, 0), L0_UW - 1);
+    n.pp = base + 3 * min(max(min(cx + 1, w1 - 1) - ox, 0), L0_UW - 1);
+    n.ro[0] = min(max((cy > 0 ? cy - 1 : 1) - oy, 0), L0_UH - 1) * L0_UROW;
+    n.ro[1] = min(max(cy - oy, 0), L0_UH - 1) * L0_UROW;
+    n.ro[2] = min(max(min(cy + 1, h1 - 1) - oy, 0), L0_UH - 1) * L0_UROW;
+    n.ro[3] = min(max(min(cy + 2, h1 - 1) - oy, 0), L0_UH - 1) * L0_UROW;
+    return n;
+}
+
+__device__ __forceinline__ void l0_hsum4(const L0Nbr& n, int E[4][3], int O[4][3]) {
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+        const int16_t* a = n.pm + n.ro[j];
+        const int16_t* b = n.pc + n.ro[j];
+        const int16_t* c = n.pp + n.ro[j];
+#pragma unroll
+        for (int ch = 0; ch < 3; ++ch) {
+            const int v0 = a[ch], v1 = b[ch], v2 = c[ch];
+            E[j][ch] = v0 + 6 * v1 + v2;
+            O[j][ch] = v1 + v2;
+        }
+    }
+}
+
+template <bool WF>
+__global__ void __launch_bounds__(L0_THREADS, 3) k_blend_l0_tiled(L0Args A) {
+    extern __shared__ __align__(128) unsigned char sm[];
+    uint64_t* full = reinterpret_cast<uint64_t*>(sm + 2 * L0_STAGE_BYTES);   // [2]
+    uint64_t* empty = full + 2;                                                // [2]
+    L0Round* info = reinterpret_cast<L0Round*>(sm + 2 * L0_STAGE_BYTES + 64);  // [2], 64 bytes apart
+    int* s_list = reinterpret_cast<int*>(sm + 2 * L0_STAGE_BYTES + 64 + 2 * 64);
+    static_assert(sizeof(L0Round) <= 64, "L0Round must fit its slot");
+
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     if (tid == 0) {
-        mbar_init(&bars[0], 1); mbar_init(&bars[1], 1); mbar_init(&bars[2], 1);
+        mbar_init(&full[0], 1); mbar_init(&full[1], 1);
+        mbar_init(&empty[0], L0_CONSUMERS / 32); mbar_init(&empty[1], L0_CONSUMERS / 32);
         mbar_fence_init();
     }
     __syncthreads();
-    if (tid == 0) {   // collapsed level 1: needed last, requested first
-        tensormap_acquire(&A.maps[0]);
-        mbar_expect_tx(&bars[0], L0_UBYTES);
-        tma_load_2d(s_c1, &A.maps[0], ((6 * ((x0t >> 1) - 1)) & ~15) >> 1, (y0t >> 1) - 1, &bars[0]);
+
+    if (warp == L0_CONSUMERS / 32) {
+        // ================================ producer warp ================================
+        int uses[2] = {0, 0};
+        int stage = 0;
+        for (int t = blockIdx.x; t < A.ntiles; t += gridDim.x) {
+            const int x0t = A.xb + (t % A.ntx) * L0_TW, y0t = (t / A.ntx) * L0_TH;
+            // images whose mask has something inside this tile, in feed order
+            int count = 0;
+            for (int base = 0; base < A.n; base += 32) {
+                bool cand = false;
+                const int i = base + lane;
+                if (i < A.n) {
+                    const L0Img I = A.imgs[i];
+                    const int lx_lo = max(x0t - I.X0, 0), lx_hi = min(x0t + L0_TW, I.X0 + I.cols) - I.X0 - 1;
+                    const int ly_lo = max(y0t - I.Y0, 0), ly_hi = min(y0t + L0_TH, I.Y0 + I.rows) - I.Y0 - 1;
+                    if (lx_lo <= lx_hi && ly_lo <= ly_hi) {
+                        for (int cy = ly_lo / SUM_CH; cy <= ly_hi / SUM_CH; ++cy)
+                            for (int cx = lx_lo / SUM_CW; cx <= lx_hi / SUM_CW; ++cx) cand = cand || I.summary[(size_t)cy * I.sum_w + cx] != 0;
+                    }
+                }
+                const unsigned b = __ballot_sync(0xffffffffu, cand);
+                if (cand) {
+                    const int pos = count + __popc(b & ((1u << lane) - 1u));
+                    if (pos < L0_MAXCAND) s_list[pos] = i;
+                }
+                count += __popc(b);
+            }
+            count = min(count, L0_MAXCAND);
+            __syncwarp();
+            const int rounds = max(1, (count + 1) >> 1);
+            for (int r = 0; r < rounds; ++r) {
+                if (uses[stage] > 0) mbar_wait(&empty[stage], (uint32_t)((uses[stage] - 1) & 1));   // the consumers are done with the stage
+                if (lane == 0) {
+                    unsigned char* st = sm + stage * L0_STAGE_BYTES;
+                    L0Round& R = info[stage];
+                    const int nc = max(0, min(2, count - 2 * r));
+                    const bool with_c1 = (r == rounds - 1) && count > 0;
+                    R.x0t = x0t; R.y0t = y0t; R.ncand = nc;
+                    R.flags = (r == 0 ? 1 : 0) | (r == rounds - 1 ? 2 : 0) | (count == 0 ? 4 : 0);
+                    const uint32_t bytes = (with_c1 ? L0_UBYTES : 0) + nc * (L0_MBYTES + L0_IBYTES + L0_UBYTES);
+                    if (bytes == 0) {
+                        mbar_arrive(&full[stage]);
+                    } else {
+                        int idx[2];
+                        L0Img I[2];
+                        for (int s2 = 0; s2 < nc; ++s2) {
+                            idx[s2] = s_list[2 * r + s2];
+                            I[s2] = A.imgs[idx[s2]];
+                            R.lx0[s2] = x0t - I[s2].X0;
+                            R.ox[s2] = ((x0t - I[s2].fx) >> 1) - 1;
+                            R.oy[s2] = ((y0t - I[s2].fy) >> 1) - 1;
+                            R.w1[s2] = I[s2].w1; R.h1[s2] = I[s2].h1;
+                        }
+                        mbar_expect_tx(&full[stage], bytes);   // also publishes R (release)
+                        if (with_c1) {
+                            tensormap_acquire(&A.maps[0]);
+                            tma_load_2d(st, &A.maps[0], ((6 * ((x0t >> 1) - 1)) & ~15) >> 1, (y0t >> 1) - 1, &full[stage]);
+                        }
+                        for (int s2 = 0; s2 < nc; ++s2) {
+                            const CUtensorMap* m = A.maps + 1 + 3 * idx[s2];
+                            unsigned char* slot = st + L0_UALLOC + s2 * L0_SLOT_BYTES;
+                            tensormap_acquire(m); tensormap_acquire(m + 1); tensormap_acquire(m + 2);
+                            tma_load_2d(slot, m, (x0t - I[s2].X0) & ~15, y0t - I[s2].Y0, &full[stage]);
+                            tma_load_2d(slot + L0_MBYTES, m + 1, (3 * (x0t - I[s2].X0)) & ~15, y0t - I[s2].Y0, &full[stage]);
+                            tma_load_2d(slot + L0_MBYTES + L0_IBYTES, m + 2, ((6 * R.ox[s2]) & ~15) >> 1, R.oy[s2], &full[stage]);
+                        }
+                    }
+                }
+                uses[stage]++;
+                stage ^= 1;
+            }
+            __syncwarp();   // lane 0 is done with s_list before the next tile's list is written
+        }
+        if (uses[stage] > 0) mbar_wait(&empty[stage], (uint32_t)((uses[stage] - 1) & 1));
+        if (lane == 0) { info[stage].ncand = -1; mbar_arrive(&full[stage]); }
+        return;
     }
 
+    // ================================ consumer warps ================================
+    const int tx = lane, ty = warp;
     // accumulators of this thread's 8 pixels: p = 4 * quad + 2 * (row in quad) + (column in quad)
     int acc[8][3];
     float wsum_f[8];
     int wsum_s[8];
+    int fuse[2] = {0, 0};
+    int stage = 0;
+    for (;;) {
+        mbar_wait(&full[stage], (uint32_t)(fuse[stage] & 1));
+        fuse[stage]++;
+        const L0Round& R = info[stage];
+        const int ncand = R.ncand;
+        if (ncand < 0) break;
+        const int flags = R.flags;
+        const int x0t = R.x0t, y0t = R.y0t;
+        const unsigned char* st = sm + stage * L0_STAGE_BYTES;
+        if (flags & 1) {
 #pragma unroll
-    for (int p = 0; p < 8; ++p) { acc[p][0] = acc[p][1] = acc[p][2] = 0; wsum_f[p] = 0.f; wsum_s[p] = 0; }
-
-    uint32_t ph[2] = {0, 0};
-    for (int base = 0; base < A.n; base += 32) {
-        if (tid < 32) {   // which of the images base .. base + 31 can contribute to this tile
-            bool cand = false;
-            const int i = base + tid;
-            if (i < A.n) {
-                const L0Img I = A.imgs[i];
-                const int lx_lo = max(x0t - I.X0, 0), lx_hi = min(x0t + L0_TW, I.X0 + I.cols) - I.X0 - 1;
-                const int ly_lo = max(y0t - I.Y0, 0), ly_hi = min(y0t + L0_TH, I.Y0 + I.rows) - I.Y0 - 1;
-                if (lx_lo <= lx_hi && ly_lo <= ly_hi) {
-                    for (int cy = ly_lo / SUM_CH; cy <= ly_hi / SUM_CH; ++cy)
-                        for (int cx = lx_lo / SUM_CW; cx <= lx_hi / SUM_CW; ++cx) cand = cand || I.summary[(size_t)cy * I.sum_w + cx] != 0;
-                }
-            }
-            const unsigned b = __ballot_sync(0xffffffffu, cand);
-            if (tid == 0) s_cmask = b;
+            for (int p = 0; p < 8; ++p) { acc[p][0] = acc[p][1] = acc[p][2] = 0; wsum_f[p] = 0.f; wsum_s[p] = 0; }
         }
-        __syncthreads();
-        unsigned cm = s_cmask;
-        while (cm) {   // batches of up to two images: both requested at once, consumed in feed order
-            int ci[2];
-            ci[0] = base + __ffs(cm) - 1; cm &= cm - 1;
-            ci[1] = -1;
-            if (cm) { ci[1] = base + __ffs(cm) - 1; cm &= cm - 1; }
-            if (tid == 0) {
+#pragma unroll 1
+        for (int s2 = 0; s2 < ncand; ++s2) {
+            const unsigned char* slot = st + L0_UALLOC + s2 * L0_SLOT_BYTES;
+            const int lx0 = R.lx0[s2];
+            const int msh = lx0 - (lx0 & ~15);               // byte shifts of the tiles inside their 16-byte aligned boxes
+            const int ish = 3 * lx0 - ((3 * lx0) & ~15);
+            // masks of the 8 pixels: rows 4 ty .. 4 ty + 3, columns 2 tx, 2 tx + 1
+            const unsigned char* mp = slot + (4 * ty) * L0_MROW + msh + 2 * tx;
+            const uint32_t m01 = (uint32_t)mp[0] | ((uint32_t)mp[1] << 8) | ((uint32_t)mp[L0_MROW] << 16) | ((uint32_t)mp[L0_MROW + 1] << 24);
+            const uint32_t m23 = (uint32_t)mp[2 * L0_MROW] | ((uint32_t)mp[2 * L0_MROW + 1] << 8) | ((uint32_t)mp[3 * L0_MROW] << 16) |
+                                 ((uint32_t)mp[3 * L0_MROW + 1] << 24);
+            // every mask byte 0 or 255?  (b & 0x7f) == 0x7f * (b >> 7) per byte
+            const bool binary = ((m01 & 0x7f7f7f7fu) == ((m01 >> 7) & 0x01010101u) * 0x7fu) && ((m23 & 0x7f7f7f7fu) == ((m23 >> 7) & 0x01010101u) * 0x7fu);
+            const bool fast = __all_sync(0xffffffffu, binary);
+            if ((m01 | m23) == 0) continue;
+            const L0Nbr nb = l0_nbr(slot + L0_MBYTES + L0_IBYTES, R.ox[s2], R.oy[s2], R.w1[s2], R.h1[s2], tx, ty);
+            int E[4][3], O[4][3];
+            l0_hsum4(nb, E, O);
+            const unsigned char* ip = slot + L0_MBYTES + (4 * ty) * L0_IROW + ish + 6 * tx;
 #pragma unroll
-                for (int s = 0; s < 2; ++s) {
-                    if (ci[s] < 0) continue;
-                    const L0Img I = A.imgs[ci[s]];
-                    const CUtensorMap* m = A.maps + 1 + 3 * ci[s];
-                    tensormap_acquire(m); tensormap_acquire(m + 1); tensormap_acquire(m + 2);
-                    mbar_expect_tx(&bars[1 + s], L0_MBYTES + L0_IBYTES + L0_UBYTES);
-                    tma_load_2d(s_msk[s], m, (x0t - I.X0) & ~15, y0t - I.Y0, &bars[1 + s]);
-                    tma_load_2d(s_img[s], m + 1, (3 * (x0t - I.X0)) & ~15, y0t - I.Y0, &bars[1 + s]);
-                    tma_load_2d(s_g1[s], m + 2, ((6 * (((x0t - I.fx) >> 1) - 1)) & ~15) >> 1, ((y0t - I.fy) >> 1) - 1, &bars[1 + s]);
-                }
-            }
+            for (int q = 0; q < 2; ++q) {
+                int u[4][3];
+                l0_quad_up(E[q], O[q], E[q + 1], O[q + 1], E[q + 2], O[q + 2], u);
+                const uint32_t mq = q == 0 ? m01 : m23;
 #pragma unroll
-            for (int s = 0; s < 2; ++s) {
-                if (ci[s] < 0) continue;
-                mbar_wait(&bars[1 + s], ph[s]);
-                ph[s] ^= 1;
-                // masks of the 8 pixels: rows 4 ty .. 4 ty + 3, columns 2 tx, 2 tx + 1
-                const L0Img I = A.imgs[ci[s]];
-                const int lx0 = x0t - I.X0;                      // tile origin in image coordinates
-                const int msh = lx0 - (lx0 & ~15);               // byte shifts of the tiles inside their aligned boxes
-                const int ish = 3 * lx0 - ((3 * lx0) & ~15);
-                uint32_t mk[4];
-                uint32_t anym = 0;
+                for (int r = 0; r < 2; ++r) {
+                    const unsigned char* px = ip + (2 * q + r) * L0_IROW;
 #pragma unroll
-                for (int r = 0; r < 4; ++r) {
-                    const uint8_t* mp = &s_msk[s][(4 * ty + r) * L0_MROW + msh + 2 * tx];
-                    mk[r] = (uint32_t)mp[0] | ((uint32_t)mp[1] << 8);
-                    anym |= mk[r];
-                }
-                if (anym) {
-                    // level-1 coordinates inside the image's frame; the tile starts at an even frame coordinate
-                    const int cx = ((x0t - I.fx) >> 1) + tx, cy = ((y0t - I.fy) >> 1) + 2 * ty;
-                    const int ox = ((x0t - I.fx) >> 1) - 1, oy = ((y0t - I.fy) >> 1) - 1;   // level-1 origin of the tile in shared memory
-                    const int cm_ = min(max((cx > 0 ? cx - 1 : 1) - ox, 0), L0_UW - 1);
-                    const int cc_ = min(max(cx - ox, 0), L0_UW - 1);
-                    const int cp_ = min(max(min(cx + 1, I.w1 - 1) - ox, 0), L0_UW - 1);
-                    int rr[4];
-                    rr[0] = (cy > 0 ? cy - 1 : 1) - oy;
-                    rr[1] = cy - oy;
-                    rr[2] = min(cy + 1, I.h1 - 1) - oy;
-                    rr[3] = min(cy + 2, I.h1 - 1) - oy;
-                    const int16_t* g1 = reinterpret_cast<const int16_t*>(s_g1[s]) + ((6 * ox - ((6 * ox) & ~15)) >> 1);
-                    int E[4][3], O[4][3];
+                    for (int c2 = 0; c2 < 2; ++c2) {
+                        const int m = (int)((mq >> (16 * r + 8 * c2)) & 255u);
+                        const int p = 4 * q + 2 * r + c2;
+                        int lap[3];
 #pragma unroll
-                    for (int j = 0; j < 4; ++j) l0_hsum(g1 + min(max(rr[j], 0), L0_UH - 1) * L0_UROW, cm_, cc_, cp_, E[j], O[j]);
-#pragma unroll
-                    for (int q = 0; q < 2; ++q) {
-                        int u[4][3];
-                        l0_quad_up(E[q], O[q], E[q + 1], O[q + 1], E[q + 2], O[q + 2], u);
-#pragma unroll
-                        for (int r = 0; r < 2; ++r) {
-                            const int row = 4 * ty + 2 * q + r;
-                            const uint8_t* px = &s_img[s][row * L0_IROW + ish + 6 * tx];
-#pragma unroll
-                            for (int c2 = 0; c2 < 2; ++c2) {
-                                const int m = (int)((mk[2 * q + r] >> (8 * c2)) & 255u);
-                                if (m == 0) continue;
-                                const int p = 4 * q + 2 * r + c2;
-                                int lap[3];
-#pragma unroll
-                                for (int c = 0; c < 3; ++c) lap[c] = min((int)px[3 * c2 + c] - u[2 * r + c2][c], 32767);   // cv::subtract saturates
-                                if (WF) {
-                                    const float w = __fmul_rn((float)m, (float)(1. / 255.));
-                                    if (m == 255) {   // w == 1.0f: short(lap * 1.0f) == lap
-                                        acc[p][0] += lap[0]; acc[p][1] += lap[1]; acc[p][2] += lap[2];
-                                    } else {
-                                        acc[p][0] += (int)(int16_t)__float2int_rz(__fmul_rn((float)lap[0], w));
-                                        acc[p][1] += (int)(int16_t)__float2int_rz(__fmul_rn((float)lap[1], w));
-                                        acc[p][2] += (int)(int16_t)__float2int_rz(__fmul_rn((float)lap[2], w));
-                                    }
-                                    wsum_f[p] = __fadd_rn(wsum_f[p], w);
-                                } else {
-                                    const int w = m + 1;
-                                    acc[p][0] += (int)(int16_t)((lap[0] * w) >> 8);
-                                    acc[p][1] += (int)(int16_t)((lap[1] * w) >> 8);
-                                    acc[p][2] += (int)(int16_t)((lap[2] * w) >> 8);
-                                    wsum_s[p] = (int)(int16_t)(wsum_s[p] + w);
-                                }
+                        for (int c = 0; c < 3; ++c) lap[c] = min((int)px[3 * c2 + c] - u[2 * r + c2][c], 32767);   // cv::subtract saturates
+                        if (fast) {   // warp-uniform: weights are exactly 0 or 1 (1.0f = 255 * (1/255.f); 256 for CV_16S)
+                            const int keep = m ? -1 : 0;
+                            acc[p][0] += lap[0] & keep; acc[p][1] += lap[1] & keep; acc[p][2] += lap[2] & keep;
+                            if (WF) wsum_f[p] = __fadd_rn(wsum_f[p], m ? 1.0f : 0.f);
+                            else wsum_s[p] = (int)(int16_t)(wsum_s[p] + (m ? 256 : 0));
+                        } else if (m) {
+                            if (WF) {
+                                const float w = __fmul_rn((float)m, (float)(1. / 255.));
+                                // dst += static_cast<short>(src * w): truncation toward zero, int16 wrap-around add
+                                acc[p][0] += (int)(int16_t)__float2int_rz(__fmul_rn((float)lap[0], w));
+                                acc[p][1] += (int)(int16_t)__float2int_rz(__fmul_rn((float)lap[1], w));
+                                acc[p][2] += (int)(int16_t)__float2int_rz(__fmul_rn((float)lap[2], w));
+                                wsum_f[p] = __fadd_rn(wsum_f[p], w);
+                            } else {
+                                const int w = m + 1;
+                                acc[p][0] += (int)(int16_t)((lap[0] * w) >> 8);
+                                acc[p][1] += (int)(int16_t)((lap[1] * w) >> 8);
+                                acc[p][2] += (int)(int16_t)((lap[2] * w) >> 8);
+                                wsum_s[p] = (int)(int16_t)(wsum_s[p] + w);
                             }
                         }
                     }
                 }
             }
-            __syncthreads();   // every thread is done with both slots before the next batch lands in them
         }
-        __syncthreads();       // s_cmask is rewritten by the next round
-    }
-
-    // ---- normalise, add pyrUp of the collapsed level 1, crop, mask, store
-    mbar_wait(&bars[0], 0);
-    {
-        const int cx = (x0t >> 1) + tx, cy = (y0t >> 1) + 2 * ty;
-        const int ox = (x0t >> 1) - 1, oy = (y0t >> 1) - 1;
-        const int cm_ = min(max((cx > 0 ? cx - 1 : 1) - ox, 0), L0_UW - 1);
-        const int cc_ = min(max(cx - ox, 0), L0_UW - 1);
-        const int cp_ = min(max(min(cx + 1, A.uw - 1) - ox, 0), L0_UW - 1);
-        int rr[4];
-        rr[0] = (cy > 0 ? cy - 1 : 1) - oy;
-        rr[1] = cy - oy;
-        rr[2] = min(cy + 1, A.uh - 1) - oy;
-        rr[3] = min(cy + 2, A.uh - 1) - oy;
-        const int16_t* c1 = reinterpret_cast<const int16_t*>(s_c1) + ((6 * ox - ((6 * ox) & ~15)) >> 1);
-        int E[4][3], O[4][3];
+        if (flags & 2) {
+            // ---- normalise, add pyrUp of the collapsed level 1, crop, mask, store
+            int E[4][3], O[4][3];
+            if (!(flags & 4)) {
+                const L0Nbr nb = l0_nbr(st, (x0t >> 1) - 1, (y0t >> 1) - 1, A.uw, A.uh, tx, ty);
+                l0_hsum4(nb, E, O);
+            } else {
 #pragma unroll
-        for (int j = 0; j < 4; ++j) l0_hsum(c1 + min(max(rr[j], 0), L0_UH - 1) * L0_UROW, cm_, cc_, cp_, E[j], O[j]);
-        const int x = x0t + 2 * tx;
+                for (int j = 0; j < 4; ++j) { E[j][0] = E[j][1] = E[j][2] = 0; O[j][0] = O[j][1] = O[j][2] = 0; }
+            }
+            // warp-uniform fast path: every weight sum is exactly 0 or 1 -> d / (1 + 1e-5f) truncates to d - sign(d), and a
+            // single contribution cannot have wrapped the int16 accumulator
+            bool unit = true;
 #pragma unroll
-        for (int q = 0; q < 2; ++q) {
-            int u[4][3];
-            l0_quad_up(E[q], O[q], E[q + 1], O[q + 1], E[q + 2], O[q + 2], u);
+            for (int p = 0; p < 8; ++p) unit = unit && (WF ? (wsum_f[p] == 1.0f || wsum_f[p] == 0.f) : false);
+            const bool fastn = __all_sync(0xffffffffu, unit);
+            const int x = x0t + 2 * tx;
+            const bool va = x >= A.sx0 && x < A.W, vb = x + 1 >= A.sx0 && x + 1 < A.W;
 #pragma unroll
-            for (int r = 0; r < 2; ++r) {
-                const int y = y0t + 4 * ty + 2 * q + r;
-                if (y >= A.H) continue;
-                int v[2][3];
-                bool on[2];
+            for (int q = 0; q < 2; ++q) {
+                int u[4][3];
+                l0_quad_up(E[q], O[q], E[q + 1], O[q + 1], E[q + 2], O[q + 2], u);
 #pragma unroll
-                for (int c2 = 0; c2 < 2; ++c2) {
-                    const int p = 4 * q + 2 * r + c2;
-                    on[c2] = WF ? (wsum_f[p] > IS_WEIGHT_EPS) : (wsum_s[p] >= 1);
+                for (int r = 0; r < 2; ++r) {
+                    const int y = y0t + 4 * ty + 2 * q + r;
+                    if (y >= A.H) continue;
+                    int v[2][3];
+                    bool on[2];
 #pragma unroll
-                    for (int c = 0; c < 3; ++c) {
-                        const int d = (int)(int16_t)acc[p][c];   // the int16 accumulator of OpenCV
-                        int nrm;
-                        if (WF) {
-                            if (wsum_f[p] == 1.0f) nrm = d - (d > 0) + (d < 0);
-                            else if (wsum_f[p] == 0.f) nrm = 0;
-                            else nrm = (int)(int16_t)__float2int_rz(__fdiv_rn((float)d, __fadd_rn(wsum_f[p], IS_WEIGHT_EPS)));
-                        } else {
-                            nrm = (int)(int16_t)((d * 256) / (wsum_s[p] + 1));
+                    for (int c2 = 0; c2 < 2; ++c2) {
+                        const int p = 4 * q + 2 * r + c2;
+                        on[c2] = WF ? (wsum_f[p] > IS_WEIGHT_EPS) : (wsum_s[p] >= 1);
+#pragma unroll
+                        for (int c = 0; c < 3; ++c) {
+                            int nrm;
+                            if (fastn) {
+                                const int d = acc[p][c];
+                                nrm = max(d - 1, min(d + 1, 0));   // d - sign(d)
+                            } else {
+                                const int d = (int)(int16_t)acc[p][c];   // the int16 accumulator of OpenCV
+                                if (WF) nrm = (int)(int16_t)__float2int_rz(__fdiv_rn((float)d, __fadd_rn(wsum_f[p], IS_WEIGHT_EPS)));
+                                else nrm = (int)(int16_t)((d * 256) / (wsum_s[p] + 1));
+                            }
+                            const int t = sat16(nrm + u[2 * r + c2][c]);
+                            v[c2][c] = on[c2] ? t : 0;
                         }
-                        const int t = sat16(nrm + u[2 * r + c2][c]);
-                        v[c2][c] = on[c2] ? t : 0;
                     }
-                }
-                const bool va = x >= A.sx0 && x < A.W, vb = x + 1 >= A.sx0 && x + 1 < A.W;
-                int16_t* o = reinterpret_cast<int16_t*>(reinterpret_cast<char*>(A.dst) + (size_t)y * A.dstep) + 3 * (x - A.sx0);
-                uint8_t* mo = A.dmask + (size_t)y * A.mstep + (x - A.sx0);
-                if (va && vb && ((reinterpret_cast<uintptr_t>(o) & 3) == 0)) {
-                    uint32_t* o32 = reinterpret_cast<uint32_t*>(o);
-                    o32[0] = (uint32_t)(uint16_t)v[0][0] | ((uint32_t)(uint16_t)v[0][1] << 16);
-                    o32[1] = (uint32_t)(uint16_t)v[0][2] | ((uint32_t)(uint16_t)v[1][0] << 16);
-                    o32[2] = (uint32_t)(uint16_t)v[1][1] | ((uint32_t)(uint16_t)v[1][2] << 16);
-                } else {
-                    if (va) { o[0] = (int16_t)v[0][0]; o[1] = (int16_t)v[0][1]; o[2] = (int16_t)v[0][2]; }
-                    if (vb) { o[3] = (int16_t)v[1][0]; o[4] = (int16_t)v[1][1]; o[5] = (int16_t)v[1][2]; }
-                }
-                if (va && vb && ((reinterpret_cast<uintptr_t>(mo) & 1) == 0)) {
-                    *reinterpret_cast<uint16_t*>(mo) = (uint16_t)((on[0] ? 255u : 0u) | (on[1] ? 0xff00u : 0u));
-                } else {
-                    if (va) mo[0] = on[0] ? 255 : 0;
-                    if (vb) mo[1] = on[1] ? 255 : 0;
+                    int16_t* o = reinterpret_cast<int16_t*>(reinterpret_cast<char*>(A.dst) + (size_t)y * A.dstep) + 3 * (x - A.sx0);
+                    uint8_t* mo = A.dmask + (size_t)y * A.mstep + (x - A.sx0);
+                    if (va && vb && ((reinterpret_cast<uintptr_t>(o) & 3) == 0)) {
+                        uint32_t* o32 = reinterpret_cast<uint32_t*>(o);
+                        o32[0] = (uint32_t)(uint16_t)v[0][0] | ((uint32_t)(uint16_t)v[0][1] << 16);
+                        o32[1] = (uint32_t)(uint16_t)v[0][2] | ((uint32_t)(uint16_t)v[1][0] << 16);
+                        o32[2] = (uint32_t)(uint16_t)v[1][1] | ((uint32_t)(uint16_t)v[1][2] << 16);
+                    } else {
+                        if (va) { o[0] = (int16_t)v[0][0]; o[1] = (int16_t)v[0][1]; o[2] = (int16_t)v[0][2]; }
+                        if (vb) { o[3] = (int16_t)v[1][0]; o[4] = (int16_t)v[1][1]; o[5] = (int16_t)v[1][2]; }
+                    }
+                    if (va && vb && ((reinterpret_cast<uintptr_t>(mo) & 1) == 0)) {
+                        *reinterpret_cast<uint16_t*>(mo) = (uint16_t)((on[0] ? 255u : 0u) | (on[1] ? 0xff00u : 0u));
+                    } else {
+                        if (va) mo[0] = on[0] ? 255 : 0;
+                        if (vb) mo[1] = on[1] ? 255 : 0;
+                    }
                 }
             }
         }
+        __syncwarp();
+        if (lane == 0) mbar_arrive(&empty[stage]);
+        stage ^= 1;
     }
 }
 
@@ -959,6 +1043,19 @@ static int blend_level0_tiled(is_blender* b, const DevMat& dst, const DevMat& dm
         if (f.img.depth != IS_8U || !tma_ok(f.img.data, f.img.step) || !tma_ok(f.mask.data, f.mask.step)) return IS_OK;
         if (!tma_ok(f.g[1].p, (size_t)(f.width >> 1) * 6) || !f.summary.p) return IS_OK;
     }
+    if (n > L0_MAXCAND) {   // the kernel lists at most L0_MAXCAND contributing images per tile: bound it by rectangle overlap
+        for (int i = 0; i < n; ++i) {
+            const FedImage& a = b->fed[i];
+            int cnt = 0;
+            for (int j = 0; j < n; ++j) {
+                const FedImage& c = b->fed[j];
+                const bool apart = a.tl_x - L0_TW >= c.tl_x + c.img.cols + L0_TW || c.tl_x - L0_TW >= a.tl_x + a.img.cols + L0_TW ||
+                                   a.tl_y - L0_TH >= c.tl_y + c.img.rows + L0_TH || c.tl_y - L0_TH >= a.tl_y + a.img.rows + L0_TH;
+                if (!apart) ++cnt;
+            }
+            if (cnt > L0_MAXCAND) return IS_OK;
+        }
+    }
     const size_t maps_bytes = sizeof(CUtensorMap) * (size_t)(1 + 3 * n);
     std::vector<unsigned char> host(maps_bytes + sizeof(L0Img) * (size_t)std::max(n, 1));
     CUtensorMap* maps = reinterpret_cast<CUtensorMap*>(host.data());
@@ -992,10 +1089,28 @@ static int blend_level0_tiled(is_blender* b, const DevMat& dst, const DevMat& dm
     A.xb = xb; A.sx0 = sx0;
     const int gw = std::min(xe, A.W) - xb;
     if (gw <= 0) { *done = true; return IS_OK; }
-    dim3 grid(div_up(gw, L0_TW), div_up(A.H, L0_TH));
+    A.ntx = div_up(gw, L0_TW);
+    A.ntiles = A.ntx * div_up(A.H, L0_TH);
+    static int bps_table[64][2], sms_table[64];   // per device: resident CTAs per SM for the two instantiations
+    const int wi = b->weight_type == IS_WEIGHT_32F ? 0 : 1;
+    int* blocks_per_sm = bps_table[ctx->device & 63];
+    int& sms = sms_table[ctx->device & 63];
+    if (!blocks_per_sm[wi]) {
+        const int dev = ctx->device;
+        IS_CUDA(ctx, cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev));
+        if (wi == 0) {
+            IS_CUDA(ctx, cudaFuncSetAttribute(k_blend_l0_tiled<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, L0_SMEM_BYTES));
+            IS_CUDA(ctx, cudaOccupancyMaxActiveBlocksPerMultiprocessor(&blocks_per_sm[wi], k_blend_l0_tiled<true>, L0_THREADS, L0_SMEM_BYTES));
+        } else {
+            IS_CUDA(ctx, cudaFuncSetAttribute(k_blend_l0_tiled<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, L0_SMEM_BYTES));
+            IS_CUDA(ctx, cudaOccupancyMaxActiveBlocksPerMultiprocessor(&blocks_per_sm[wi], k_blend_l0_tiled<false>, L0_THREADS, L0_SMEM_BYTES));
+        }
+        if (blocks_per_sm[wi] < 1) blocks_per_sm[wi] = 1;
+    }
+    const int grid = std::min(A.ntiles, sms * blocks_per_sm[wi]);   // persistent: every CTA walks tiles grid apart
     ctx->next_bytes = bytes;
-    if (b->weight_type == IS_WEIGHT_32F) IS_LAUNCH(ctx, k_blend_l0_tiled<true>, grid, 256, 0, A);
-    else IS_LAUNCH(ctx, k_blend_l0_tiled<false>, grid, 256, 0, A);
+    if (wi == 0) IS_LAUNCH(ctx, k_blend_l0_tiled<true>, grid, L0_THREADS, L0_SMEM_BYTES, A);
+    else IS_LAUNCH(ctx, k_blend_l0_tiled<false>, grid, L0_THREADS, L0_SMEM_BYTES, A);
     *done = true;
     return IS_OK;
 }
