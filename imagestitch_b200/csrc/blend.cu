@@ -318,11 +318,9 @@ __device__ __forceinline__ void pyrup_quad(const int16_t* __restrict__ s, int sh
 }
 
 template <bool WF>
-__global__ void __launch_bounds__(256) k_blend_level_quad(LevelArgs A) {
-    const int qx = blockIdx.x * blockDim.x + threadIdx.x;
-    const int qy = blockIdx.y * blockDim.y + threadIdx.y;
+__device__ __forceinline__ void blend_quad_at(const LevelArgs& A, int x, int y) {   // the 2 x 2 block at even (x, y)
+    const int qy = y >> 1;
     const int W = A.k == 0 ? min(A.fw, A.sx1) : min(A.W, A.xe), H = A.k == 0 ? A.fh : A.H;   // level 0 is cropped to the final ROI
-    const int x = A.xb + 2 * qx, y = 2 * qy;
     if (x >= W || y >= H) return;
     int acc[4][3];
     float wsum_f[4] = {0.f, 0.f, 0.f, 0.f};
@@ -411,7 +409,26 @@ __global__ void __launch_bounds__(256) k_blend_level_quad(LevelArgs A) {
     }
 }
 
-// ---- level 0 of blend(), tiled: TMA-staged 2-D tiles, one CTA per 64 x 32 panorama pixels ----------------------------
+template <bool WF>
+__global__ void __launch_bounds__(256) k_blend_level_quad(LevelArgs A) {
+    const int qx = blockIdx.x * blockDim.x + threadIdx.x;
+    const int qy = blockIdx.y * blockDim.y + threadIdx.y;
+    blend_quad_at<WF>(A, A.xb + 2 * qx, 2 * qy);
+}
+
+// Level-0 bands (64 x 8 pixels at (x, y)) the tiled kernel below handed back: several contributing images or masks other
+// than 0 / 255.  Same arithmetic as k_blend_level_quad; the list is produced on the device, so the grid is fixed and
+// every CTA walks the list.
+template <bool WF>
+__global__ void __launch_bounds__(128) k_blend_l0_bands(LevelArgs A, const int2* __restrict__ bands, const int* __restrict__ count) {
+    const int n = *count;
+    for (int b = blockIdx.x; b < n; b += gridDim.x) {
+        const int2 o = bands[b];
+        blend_quad_at<WF>(A, o.x + 2 * (threadIdx.x & 31), o.y + 2 * (threadIdx.x >> 5));
+    }
+}
+
+// ---- level 0 of blend(), tiled: TMA-staged 2-D tiles, persistent CTAs walking 64 x 64 panorama tiles ------------------
 // Level 0 carries most of the blend's bytes (u8 image + mask in, int16 panorama + mask out).  Facts used here:
 //   * the level-0 weight of an image is its mask (x 1/255, or +1 for CV_16S) inside the image and 0 in the
 //     copyMakeBorder frame; a pixel whose weight is 0 adds  short(laplacian * 0) = 0  and  w = 0  to the sums, so only
@@ -422,20 +439,22 @@ __global__ void __launch_bounds__(256) k_blend_level_quad(LevelArgs A) {
 //     short(d / (1.0f + 1e-5f)) equals d - sign(d) for every int16 d (checked exhaustively in tests/test_blend_math.py):
 //     the common pixel needs no floating point at all.
 // The tiles (collapsed level 1, and per contributing image: mask, u8 image, Gaussian level 1) arrive by
-// cp.async.bulk.tensor.2d into shared memory, out-of-range parts zero-filled by the TMA unit; every thread owns two
-// vertically adjacent 2 x 2 quads and walks the four level-1 rows they share (pyrUp is separable: horizontal sums once
-// per level-1 row, vertical combination per output row).
-constexpr int L0_TW = 64, L0_TH = 32;                        // level-0 pixels per tile
-constexpr int L0_UW = L0_TW / 2 + 2, L0_UH = L0_TH / 2 + 2;  // level-1 pixels per tile incl. the pyrUp halo: 34 x 18
+// cp.async.bulk.tensor.2d into shared memory, out-of-range parts zero-filled by the TMA unit.  Every thread owns a
+// column of four vertically adjacent 2 x 2 quads and walks the six level-1 rows under them (pyrUp is separable:
+// horizontal sums once per level-1 row, vertical combination per output row) in a rolled loop small enough for the
+// instruction cache.
+constexpr int L0_TW = 64, L0_TH = 64;                        // level-0 pixels per tile
+constexpr int L0_QN = L0_TH / 16;                            // quads per thread: 8 consumer warps x 4 quads x 2 rows
+constexpr int L0_UW = L0_TW / 2 + 2, L0_UH = L0_TH / 2 + 2;  // level-1 pixels per tile incl. the pyrUp halo: 34 x 34
 // TMA wants the innermost box start 16-byte aligned (probed on B200: an unaligned start raises "illegal instruction"), so every
 // box starts at the aligned address below the tile and is up to 15 bytes wider; the kernel indexes with the shift.
 constexpr int L0_UROW = 112;                                 // int16 per shared-memory row of a level-1 tile: 3 * 34 = 102, + 7 shift, padded to 16 B
-constexpr int L0_UBYTES = L0_UH * L0_UROW * 2;               // 4032
-constexpr int L0_UALLOC = 4096;                              // ... rounded up to 128 B
+constexpr int L0_UBYTES = L0_UH * L0_UROW * 2;               // 7616
+constexpr int L0_UALLOC = 7680;                              // ... rounded up to 128 B
 constexpr int L0_IROW = 208;                                 // bytes per row of a u8 x 3 image tile: 192 + 15 shift, padded to 16 B
-constexpr int L0_IBYTES = L0_TH * L0_IROW;                   // 6656
+constexpr int L0_IBYTES = L0_TH * L0_IROW;                   // 13312
 constexpr int L0_MROW = 80;                                  // bytes per row of a mask tile: 64 + 15 shift, padded to 16 B
-constexpr int L0_MBYTES = L0_TH * L0_MROW;                   // 2560
+constexpr int L0_MBYTES = L0_TH * L0_MROW;                   // 5120
 constexpr int SUM_CW = 64, SUM_CH = 32;                      // cell of the mask occupancy map
 
 struct L0Img {
@@ -454,6 +473,7 @@ struct L0Args {
     int W, H;                  // panorama columns [sx0, W) and rows [0, H) are stored
     int xb, sx0;               // first computed column (even), first stored column
     int ntx, ntiles;           // tiles per row, tiles in total
+    int2* bands; int* nbands;  // out: 64 x 8 bands left to k_blend_l0_bands (several contributing images, masks other than 0 / 255)
 };
 
 __global__ void k_mask_summary(const uint8_t* __restrict__ mask, size_t step, int rows, int cols, uint8_t* __restrict__ out, int sw) {
@@ -484,24 +504,32 @@ __device__ __forceinline__ void l0_quad_up(const int Ea[3], const int Oa[3], con
         u[3][c] = (Ob[c] + Oc[c] + 2) >> 2;
     }
 }
+__device__ __forceinline__ void l0_hrow(const int16_t* a, const int16_t* b, const int16_t* c, int E[3], int O[3]) {
+#pragma unroll
+    for (int ch = 0; ch < 3; ++ch) {
+        const int v0 = a[ch], v1 = b[ch], v2 = c[ch];
+        E[ch] = v0 + 6 * v1 + v2;
+        O[ch] = v1 + v2;
+    }
+}
 
-// Persistent, warp-specialised pipeline: 8 consumer warps (one 64 x 4 pixel band of the tile each) + 1 producer warp.
+// Persistent, warp-specialised pipeline: 8 consumer warps (one 64 x 8 pixel band of the tile each) + 1 producer warp.
 // The producer finds the images that can contribute to the next tile (occupancy maps), then issues the tile's TMA loads
 // into the free stage while the consumers still compute the previous one; full[] / empty[] mbarriers hand the two
-// stages back and forth, no __syncthreads in steady state.  A tile with more than two contributing images takes
-// several rounds through the stages (the consumers keep their accumulators between rounds).
-constexpr int L0_SLOT_BYTES = L0_MBYTES + L0_IBYTES + L0_UALLOC;      // mask | image | Gaussian level 1
-constexpr int L0_STAGE_BYTES = L0_UALLOC + 2 * L0_SLOT_BYTES;         // collapsed level 1 + two image slots = 30720
+// stages back and forth, no __syncthreads in steady state.  Tiles with several contributing images, and bands whose
+// masks are not 0 / 255, are not computed here: they go on a device-side work list for k_blend_l0_bands.
+constexpr int L0_STAGE_BYTES = L0_UALLOC + L0_MBYTES + L0_IBYTES + L0_UALLOC;   // collapsed level 1 | mask | image | Gaussian level 1 = 33792
+constexpr int L0_OFF_MASK = L0_UALLOC, L0_OFF_IMG = L0_UALLOC + L0_MBYTES, L0_OFF_G1 = L0_UALLOC + L0_MBYTES + L0_IBYTES;
 constexpr int L0_CONSUMERS = 256, L0_THREADS = L0_CONSUMERS + 32;
-constexpr int L0_MAXCAND = 32;                                        // contributing images per tile (the host checks the bound)
+constexpr int L0_MAXCAND = 32;                                        // capacity of the per-tile candidate list (only its head is used)
 
 struct L0Round {         // producer -> consumers, one per stage
     int x0t, y0t;        // tile origin (level-0 panorama coordinates)
-    int ncand;           // images in this round (0..2); -1: no more work
-    int flags;           // 1: first round of the tile, 2: last round (the collapsed level-1 tile is in the stage), 4: nothing contributes
-    int lx0[2];          // tile origin in image coordinates
-    int ox[2], oy[2];    // level-1 origin of the Gaussian tile inside the image's frame
-    int w1[2], h1[2];    // level-1 frame dims
+    int ncand;           // contributing images (0 or 1); -1: no more work
+    int flags;           // 8 / 16: the collapsed / the Gaussian level-1 neighbourhood lies inside its array (no border rule)
+    int lx0;             // tile origin in image coordinates
+    int ox, oy;          // level-1 origin of the Gaussian tile inside the image's frame
+    int w1, h1;          // level-1 frame dims
 };
 constexpr int L0_SMEM_BYTES = 2 * L0_STAGE_BYTES + 64 + 2 * 64 + L0_MAXCAND * 4;
 
@@ -509,36 +537,29 @@ __device__ __forceinline__ void mbar_arrive(uint64_t* bar) {
     asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory");
 }
 
-// three column pointers + four row offsets of a thread's level-1 neighbourhood (pyrUp border rule: s[-1] -> s[1], s[n] -> s[n-1])
-struct L0Nbr { const int16_t* pm; const int16_t* pc; const int16_t* pp; int ro[4]; };
+// consumer-only barrier (the producer warp never joins)
+__device__ __forceinline__ void l0_consumer_sync() { asm volatile("bar.sync 1, %0;" ::"n"(L0_CONSUMERS) : "memory"); }
 
-__device__ __forceinline__ L0Nbr l0_nbr(const unsigned char* tile, int ox, int oy, int w1, int h1, int tx, int ty) {
-    const int cx = ox + 1 + tx, cy = oy + 1 + 2 * ty;   // this thread's level-1 column, first of its two level-1 rows
-    const int16_t* base = reinterpret_cast<const int16_t*>(tile) + ((6 * ox - ((6 * ox) & ~15)) >> 1);
-    L0Nbr n;
-    n.pm = base + 3 * min(max((cx > 0 ? cx - 1 : 1) - ox, 0), L0_UW - 1);
-    n.pc = base + 3 * min(max(cx - ox, 0), L0_UW - 1);
-    n.pp = base + 3 * min(max(min(cx + 1, w1 - 1) - ox, 0), L0_UW - 1);
-    n.ro[0] = min(max((cy > 0 ? cy - 1 : 1) - oy, 0), L0_UH - 1) * L0_UROW;
-    n.ro[1] = min(max(cy - oy, 0), L0_UH - 1) * L0_UROW;
-    n.ro[2] = min(max(min(cy + 1, h1 - 1) - oy, 0), L0_UH - 1) * L0_UROW;
-    n.ro[3] = min(max(min(cy + 2, h1 - 1) - oy, 0), L0_UH - 1) * L0_UROW;
-    return n;
-}
-
-__device__ __forceinline__ void l0_hsum4(const L0Nbr& n, int E[4][3], int O[4][3]) {
-#pragma unroll
-    for (int j = 0; j < 4; ++j) {
-        const int16_t* a = n.pm + n.ro[j];
-        const int16_t* b = n.pc + n.ro[j];
-        const int16_t* c = n.pp + n.ro[j];
-#pragma unroll
-        for (int ch = 0; ch < 3; ++ch) {
-            const int v0 = a[ch], v1 = b[ch], v2 = c[ch];
-            E[j][ch] = v0 + 6 * v1 + v2;
-            O[j][ch] = v1 + v2;
-        }
+// pyrUp border rule (s[-1] -> s[1], s[n] -> s[n-1]) applied to a level-1 tile in shared memory, so that every thread can use
+// the fixed-offset neighbourhood: the halo row / column that falls outside the array is overwritten with its mirror.
+// (ox, oy): level-1 origin of the tile inside an array of w1 x h1.  All consumer threads call this.
+__device__ __forceinline__ void l0_patch_border(unsigned char* tile, int ox, int oy, int w1, int h1, int ctid) {
+    int16_t* base = reinterpret_cast<int16_t*>(tile) + ((6 * ox - ((6 * ox) & ~15)) >> 1);
+    // rows
+    if (ctid < 3 * L0_UW) {
+        if (oy < 0 && 1 - oy < L0_UH) base[(-1 - oy) * L0_UROW + ctid] = base[(1 - oy) * L0_UROW + ctid];
+        const int rb = h1 - oy;                        // first row below the array
+        if (rb >= 1 && rb < L0_UH) base[rb * L0_UROW + ctid] = base[(rb - 1) * L0_UROW + ctid];
     }
+    l0_consumer_sync();
+    // columns
+    if (ctid < 3 * L0_UH) {
+        const int r = ctid / 3, c = ctid % 3;
+        if (ox < 0 && 1 - ox < L0_UW) base[r * L0_UROW + 3 * (-1 - ox) + c] = base[r * L0_UROW + 3 * (1 - ox) + c];
+        const int cb = w1 - ox;                        // first column right of the array
+        if (cb >= 1 && cb < L0_UW) base[r * L0_UROW + 3 * cb + c] = base[r * L0_UROW + 3 * (cb - 1) + c];
+    }
+    l0_consumer_sync();
 }
 
 template <bool WF>
@@ -585,50 +606,48 @@ __global__ void __launch_bounds__(L0_THREADS, 3) k_blend_l0_tiled(L0Args A) {
                 }
                 count += __popc(b);
             }
-            count = min(count, L0_MAXCAND);
             __syncwarp();
-            const int rounds = max(1, (count + 1) >> 1);
-            for (int r = 0; r < rounds; ++r) {
-                if (uses[stage] > 0) mbar_wait(&empty[stage], (uint32_t)((uses[stage] - 1) & 1));   // the consumers are done with the stage
-                if (lane == 0) {
-                    unsigned char* st = sm + stage * L0_STAGE_BYTES;
-                    L0Round& R = info[stage];
-                    const int nc = max(0, min(2, count - 2 * r));
-                    const bool with_c1 = (r == rounds - 1) && count > 0;
-                    R.x0t = x0t; R.y0t = y0t; R.ncand = nc;
-                    R.flags = (r == 0 ? 1 : 0) | (r == rounds - 1 ? 2 : 0) | (count == 0 ? 4 : 0);
-                    const uint32_t bytes = (with_c1 ? L0_UBYTES : 0) + nc * (L0_MBYTES + L0_IBYTES + L0_UBYTES);
-                    if (bytes == 0) {
-                        mbar_arrive(&full[stage]);
-                    } else {
-                        int idx[2];
-                        L0Img I[2];
-                        for (int s2 = 0; s2 < nc; ++s2) {
-                            idx[s2] = s_list[2 * r + s2];
-                            I[s2] = A.imgs[idx[s2]];
-                            R.lx0[s2] = x0t - I[s2].X0;
-                            R.ox[s2] = ((x0t - I[s2].fx) >> 1) - 1;
-                            R.oy[s2] = ((y0t - I[s2].fy) >> 1) - 1;
-                            R.w1[s2] = I[s2].w1; R.h1[s2] = I[s2].h1;
-                        }
-                        mbar_expect_tx(&full[stage], bytes);   // also publishes R (release)
-                        if (with_c1) {
-                            tensormap_acquire(&A.maps[0]);
-                            tma_load_2d(st, &A.maps[0], ((6 * ((x0t >> 1) - 1)) & ~15) >> 1, (y0t >> 1) - 1, &full[stage]);
-                        }
-                        for (int s2 = 0; s2 < nc; ++s2) {
-                            const CUtensorMap* m = A.maps + 1 + 3 * idx[s2];
-                            unsigned char* slot = st + L0_UALLOC + s2 * L0_SLOT_BYTES;
-                            tensormap_acquire(m); tensormap_acquire(m + 1); tensormap_acquire(m + 2);
-                            tma_load_2d(slot, m, (x0t - I[s2].X0) & ~15, y0t - I[s2].Y0, &full[stage]);
-                            tma_load_2d(slot + L0_MBYTES, m + 1, (3 * (x0t - I[s2].X0)) & ~15, y0t - I[s2].Y0, &full[stage]);
-                            tma_load_2d(slot + L0_MBYTES + L0_IBYTES, m + 2, ((6 * R.ox[s2]) & ~15) >> 1, R.oy[s2], &full[stage]);
-                        }
-                    }
+            if (count > 1) {   // several contributing images: the whole tile goes to the general kernel, nothing is loaded
+                if (lane < L0_TH / 8) {
+                    const int pos = atomicAdd(A.nbands, 1);
+                    A.bands[pos] = make_int2(x0t, y0t + 8 * lane);
                 }
-                uses[stage]++;
-                stage ^= 1;
+                continue;
             }
+            if (uses[stage] > 0) mbar_wait(&empty[stage], (uint32_t)((uses[stage] - 1) & 1));   // the consumers are done with the stage
+            if (lane == 0) {
+                unsigned char* st = sm + stage * L0_STAGE_BYTES;
+                L0Round& R = info[stage];
+                R.x0t = x0t; R.y0t = y0t; R.ncand = count;
+                int flags = 0;
+                {
+                    const int ox = (x0t >> 1) - 1, oy = (y0t >> 1) - 1;
+                    if (ox >= 0 && oy >= 0 && ox + L0_UW <= A.uw && oy + L0_UH <= A.uh) flags |= 8;
+                }
+                if (count == 0) {
+                    R.flags = flags;
+                    mbar_arrive(&full[stage]);
+                } else {
+                    const int idx = s_list[0];
+                    const L0Img I = A.imgs[idx];
+                    R.lx0 = x0t - I.X0;
+                    R.ox = ((x0t - I.fx) >> 1) - 1;
+                    R.oy = ((y0t - I.fy) >> 1) - 1;
+                    R.w1 = I.w1; R.h1 = I.h1;
+                    if (R.ox >= 0 && R.oy >= 0 && R.ox + L0_UW <= I.w1 && R.oy + L0_UH <= I.h1) flags |= 16;
+                    R.flags = flags;
+                    mbar_expect_tx(&full[stage], L0_UBYTES + L0_MBYTES + L0_IBYTES + L0_UBYTES);   // also publishes R (release)
+                    tensormap_acquire(&A.maps[0]);
+                    tma_load_2d(st, &A.maps[0], ((6 * ((x0t >> 1) - 1)) & ~15) >> 1, (y0t >> 1) - 1, &full[stage]);
+                    const CUtensorMap* m = A.maps + 1 + 3 * idx;
+                    tensormap_acquire(m); tensormap_acquire(m + 1); tensormap_acquire(m + 2);
+                    tma_load_2d(st + L0_OFF_MASK, m, (x0t - I.X0) & ~15, y0t - I.Y0, &full[stage]);
+                    tma_load_2d(st + L0_OFF_IMG, m + 1, (3 * (x0t - I.X0)) & ~15, y0t - I.Y0, &full[stage]);
+                    tma_load_2d(st + L0_OFF_G1, m + 2, ((6 * R.ox) & ~15) >> 1, R.oy, &full[stage]);
+                }
+            }
+            uses[stage]++;
+            stage ^= 1;
             __syncwarp();   // lane 0 is done with s_list before the next tile's list is written
         }
         if (uses[stage] > 0) mbar_wait(&empty[stage], (uint32_t)((uses[stage] - 1) & 1));
@@ -637,11 +656,9 @@ __global__ void __launch_bounds__(L0_THREADS, 3) k_blend_l0_tiled(L0Args A) {
     }
 
     // ================================ consumer warps ================================
+    // this thread's pixels: columns 2 tx, 2 tx + 1; rows 8 ty .. 8 ty + 7 as four quads; p = 4 * quad + 2 * (row in quad) + (column in quad)
     const int tx = lane, ty = warp;
-    // accumulators of this thread's 8 pixels: p = 4 * quad + 2 * (row in quad) + (column in quad)
-    int acc[8][3];
-    float wsum_f[8];
-    int wsum_s[8];
+    const int nbr_off = 3 * tx + L0_QN * ty * L0_UROW;        // level-1 neighbourhood of a quad column: fixed offsets from here
     int fuse[2] = {0, 0};
     int stage = 0;
     for (;;) {
@@ -652,136 +669,117 @@ __global__ void __launch_bounds__(L0_THREADS, 3) k_blend_l0_tiled(L0Args A) {
         if (ncand < 0) break;
         const int flags = R.flags;
         const int x0t = R.x0t, y0t = R.y0t;
-        const unsigned char* st = sm + stage * L0_STAGE_BYTES;
-        if (flags & 1) {
-#pragma unroll
-            for (int p = 0; p < 8; ++p) { acc[p][0] = acc[p][1] = acc[p][2] = 0; wsum_f[p] = 0.f; wsum_s[p] = 0; }
-        }
+        unsigned char* st = sm + stage * L0_STAGE_BYTES;
+        const int x = x0t + 2 * tx;
+        const bool va = x >= A.sx0 && x < A.W, vb = x + 1 >= A.sx0 && x + 1 < A.W;
+        int y = y0t + 2 * L0_QN * ty;
+        char* orow = reinterpret_cast<char*>(A.dst) + (size_t)y * A.dstep + 6 * (ptrdiff_t)(x - A.sx0);
+        uint8_t* mrow = A.dmask + (size_t)y * A.mstep + (x - A.sx0);
+        if (ncand == 0) {
+            // ---- nothing contributes: zeros
 #pragma unroll 1
-        for (int s2 = 0; s2 < ncand; ++s2) {
-            const unsigned char* slot = st + L0_UALLOC + s2 * L0_SLOT_BYTES;
-            const int lx0 = R.lx0[s2];
+            for (int r = 0; r < 2 * L0_QN; ++r, orow += A.dstep, mrow += A.mstep) {
+                if (y + r >= A.H) break;
+                int16_t* o = reinterpret_cast<int16_t*>(orow);
+                if (va) { o[0] = 0; o[1] = 0; o[2] = 0; mrow[0] = 0; }
+                if (vb) { o[3] = 0; o[4] = 0; o[5] = 0; mrow[1] = 0; }
+            }
+        } else {
+            // ---- one contributing image
+            if ((flags & (8 | 16)) != (8 | 16)) {   // tile on the border of a level-1 array: mirror the halo in place (uniform per tile)
+                if (!(flags & 8)) l0_patch_border(st, (x0t >> 1) - 1, (y0t >> 1) - 1, A.uw, A.uh, tid);
+                if (!(flags & 16)) l0_patch_border(st + L0_OFF_G1, R.ox, R.oy, R.w1, R.h1, tid);
+            }
+            const int lx0 = R.lx0;
             const int msh = lx0 - (lx0 & ~15);               // byte shifts of the tiles inside their 16-byte aligned boxes
             const int ish = 3 * lx0 - ((3 * lx0) & ~15);
-            // masks of the 8 pixels: rows 4 ty .. 4 ty + 3, columns 2 tx, 2 tx + 1
-            const unsigned char* mp = slot + (4 * ty) * L0_MROW + msh + 2 * tx;
-            const uint32_t m01 = (uint32_t)mp[0] | ((uint32_t)mp[1] << 8) | ((uint32_t)mp[L0_MROW] << 16) | ((uint32_t)mp[L0_MROW + 1] << 24);
-            const uint32_t m23 = (uint32_t)mp[2 * L0_MROW] | ((uint32_t)mp[2 * L0_MROW + 1] << 8) | ((uint32_t)mp[3 * L0_MROW] << 16) |
-                                 ((uint32_t)mp[3 * L0_MROW + 1] << 24);
-            // every mask byte 0 or 255?  (b & 0x7f) == 0x7f * (b >> 7) per byte
-            const bool binary = ((m01 & 0x7f7f7f7fu) == ((m01 >> 7) & 0x01010101u) * 0x7fu) && ((m23 & 0x7f7f7f7fu) == ((m23 >> 7) & 0x01010101u) * 0x7fu);
-            const bool fast = __all_sync(0xffffffffu, binary);
-            if ((m01 | m23) == 0) continue;
-            const L0Nbr nb = l0_nbr(slot + L0_MBYTES + L0_IBYTES, R.ox[s2], R.oy[s2], R.w1[s2], R.h1[s2], tx, ty);
-            int E[4][3], O[4][3];
-            l0_hsum4(nb, E, O);
-            const unsigned char* ip = slot + L0_MBYTES + (4 * ty) * L0_IROW + ish + 6 * tx;
+            const unsigned char* mp = st + L0_OFF_MASK + (2 * L0_QN * ty) * L0_MROW + msh + 2 * tx;
+            uint32_t mw[L0_QN];                              // four mask bytes per quad
+            bool binary = true;
 #pragma unroll
-            for (int q = 0; q < 2; ++q) {
-                int u[4][3];
-                l0_quad_up(E[q], O[q], E[q + 1], O[q + 1], E[q + 2], O[q + 2], u);
-                const uint32_t mq = q == 0 ? m01 : m23;
-#pragma unroll
-                for (int r = 0; r < 2; ++r) {
-                    const unsigned char* px = ip + (2 * q + r) * L0_IROW;
-#pragma unroll
-                    for (int c2 = 0; c2 < 2; ++c2) {
-                        const int m = (int)((mq >> (16 * r + 8 * c2)) & 255u);
-                        const int p = 4 * q + 2 * r + c2;
-                        int lap[3];
-#pragma unroll
-                        for (int c = 0; c < 3; ++c) lap[c] = min((int)px[3 * c2 + c] - u[2 * r + c2][c], 32767);   // cv::subtract saturates
-                        if (fast) {   // warp-uniform: weights are exactly 0 or 1 (1.0f = 255 * (1/255.f); 256 for CV_16S)
-                            const int keep = m ? -1 : 0;
-                            acc[p][0] += lap[0] & keep; acc[p][1] += lap[1] & keep; acc[p][2] += lap[2] & keep;
-                            if (WF) wsum_f[p] = __fadd_rn(wsum_f[p], m ? 1.0f : 0.f);
-                            else wsum_s[p] = (int)(int16_t)(wsum_s[p] + (m ? 256 : 0));
-                        } else if (m) {
-                            if (WF) {
-                                const float w = __fmul_rn((float)m, (float)(1. / 255.));
-                                // dst += static_cast<short>(src * w): truncation toward zero, int16 wrap-around add
-                                acc[p][0] += (int)(int16_t)__float2int_rz(__fmul_rn((float)lap[0], w));
-                                acc[p][1] += (int)(int16_t)__float2int_rz(__fmul_rn((float)lap[1], w));
-                                acc[p][2] += (int)(int16_t)__float2int_rz(__fmul_rn((float)lap[2], w));
-                                wsum_f[p] = __fadd_rn(wsum_f[p], w);
-                            } else {
-                                const int w = m + 1;
-                                acc[p][0] += (int)(int16_t)((lap[0] * w) >> 8);
-                                acc[p][1] += (int)(int16_t)((lap[1] * w) >> 8);
-                                acc[p][2] += (int)(int16_t)((lap[2] * w) >> 8);
-                                wsum_s[p] = (int)(int16_t)(wsum_s[p] + w);
-                            }
-                        }
-                    }
-                }
+            for (int q = 0; q < L0_QN; ++q) {
+                mw[q] = (uint32_t)mp[(2 * q) * L0_MROW] | ((uint32_t)mp[(2 * q) * L0_MROW + 1] << 8) | ((uint32_t)mp[(2 * q + 1) * L0_MROW] << 16) |
+                        ((uint32_t)mp[(2 * q + 1) * L0_MROW + 1] << 24);
+                // every byte 0 or 255?  (b & 0x7f) == 0x7f * (b >> 7) per byte
+                binary = binary && ((mw[q] & 0x7f7f7f7fu) == ((mw[q] >> 7) & 0x01010101u) * 0x7fu);
             }
-        }
-        if (flags & 2) {
-            // ---- normalise, add pyrUp of the collapsed level 1, crop, mask, store
-            int E[4][3], O[4][3];
-            if (!(flags & 4)) {
-                const L0Nbr nb = l0_nbr(st, (x0t >> 1) - 1, (y0t >> 1) - 1, A.uw, A.uh, tx, ty);
-                l0_hsum4(nb, E, O);
+            if (!__all_sync(0xffffffffu, binary)) {
+                // fractional weights: this warp's band goes to the general kernel
+                if (lane == 0) {
+                    const int pos = atomicAdd(A.nbands, 1);
+                    A.bands[pos] = make_int2(x0t, y);
+                }
             } else {
+                // weight 1.0f (= 255 * (1/255.f)) where the mask is set: the accumulator is the Laplacian itself and
+                // short(d / (1 + 1e-5f)) = d - sign(d).  CV_16S: weight 256, accumulator (d * 256) >> 8 = d, normalised (d << 8) / 257.
+                const int oxg = R.ox, oxc = (x0t >> 1) - 1;
+                const int16_t* g = reinterpret_cast<const int16_t*>(st + L0_OFF_G1) + ((6 * oxg - ((6 * oxg) & ~15)) >> 1) + nbr_off;
+                const int16_t* k = reinterpret_cast<const int16_t*>(st) + ((6 * oxc - ((6 * oxc) & ~15)) >> 1) + nbr_off;
+                const unsigned char* ip = st + L0_OFF_IMG + (2 * L0_QN * ty) * L0_IROW + ish + 6 * tx;
+                // rolling horizontal sums of the Gaussian (G) and the collapsed (K) level-1 rows
+                int GE0[3], GO0[3], GE1[3], GO1[3], KE0[3], KO0[3], KE1[3], KO1[3];
+                l0_hrow(g, g + 3, g + 6, GE0, GO0);
+                l0_hrow(g + L0_UROW, g + L0_UROW + 3, g + L0_UROW + 6, GE1, GO1);
+                l0_hrow(k, k + 3, k + 6, KE0, KO0);
+                l0_hrow(k + L0_UROW, k + L0_UROW + 3, k + L0_UROW + 6, KE1, KO1);
+#pragma unroll 1
+                for (int q = 0; q < L0_QN; ++q) {
+                    g += L0_UROW; k += L0_UROW;
+                    int GE2[3], GO2[3], KE2[3], KO2[3];
+                    l0_hrow(g + L0_UROW, g + L0_UROW + 3, g + L0_UROW + 6, GE2, GO2);
+                    l0_hrow(k + L0_UROW, k + L0_UROW + 3, k + L0_UROW + 6, KE2, KO2);
+                    int ug[4][3], uk[4][3];
+                    l0_quad_up(GE0, GO0, GE1, GO1, GE2, GO2, ug);
+                    l0_quad_up(KE0, KO0, KE1, KO1, KE2, KO2, uk);
+                    const uint32_t mq = mw[0];
 #pragma unroll
-                for (int j = 0; j < 4; ++j) { E[j][0] = E[j][1] = E[j][2] = 0; O[j][0] = O[j][1] = O[j][2] = 0; }
-            }
-            // warp-uniform fast path: every weight sum is exactly 0 or 1 -> d / (1 + 1e-5f) truncates to d - sign(d), and a
-            // single contribution cannot have wrapped the int16 accumulator
-            bool unit = true;
+                    for (int r = 0; r < 2; ++r) {
+                        int v[2][3];
 #pragma unroll
-            for (int p = 0; p < 8; ++p) unit = unit && (WF ? (wsum_f[p] == 1.0f || wsum_f[p] == 0.f) : false);
-            const bool fastn = __all_sync(0xffffffffu, unit);
-            const int x = x0t + 2 * tx;
-            const bool va = x >= A.sx0 && x < A.W, vb = x + 1 >= A.sx0 && x + 1 < A.W;
+                        for (int c2 = 0; c2 < 2; ++c2) {
+                            const bool on = ((mq >> (16 * r + 8 * c2)) & 255u) != 0;
 #pragma unroll
-            for (int q = 0; q < 2; ++q) {
-                int u[4][3];
-                l0_quad_up(E[q], O[q], E[q + 1], O[q + 1], E[q + 2], O[q + 2], u);
-#pragma unroll
-                for (int r = 0; r < 2; ++r) {
-                    const int y = y0t + 4 * ty + 2 * q + r;
-                    if (y >= A.H) continue;
-                    int v[2][3];
-                    bool on[2];
-#pragma unroll
-                    for (int c2 = 0; c2 < 2; ++c2) {
-                        const int p = 4 * q + 2 * r + c2;
-                        on[c2] = WF ? (wsum_f[p] > IS_WEIGHT_EPS) : (wsum_s[p] >= 1);
-#pragma unroll
-                        for (int c = 0; c < 3; ++c) {
-                            int nrm;
-                            if (fastn) {
-                                const int d = acc[p][c];
-                                nrm = max(d - 1, min(d + 1, 0));   // d - sign(d)
-                            } else {
-                                const int d = (int)(int16_t)acc[p][c];   // the int16 accumulator of OpenCV
-                                if (WF) nrm = (int)(int16_t)__float2int_rz(__fdiv_rn((float)d, __fadd_rn(wsum_f[p], IS_WEIGHT_EPS)));
-                                else nrm = (int)(int16_t)((d * 256) / (wsum_s[p] + 1));
+                            for (int c = 0; c < 3; ++c) {
+                                const int d = min((int)ip[r * L0_IROW + 3 * c2 + c] - ug[2 * r + c2][c], 32767);   // cv::subtract saturates
+                                const int nrm = WF ? max(d - 1, min(d + 1, 0)) : (d * 256) / 257;                 // d - sign(d)
+                                const int t = sat16(nrm + uk[2 * r + c2][c]);
+                                v[c2][c] = on ? t : 0;
                             }
-                            const int t = sat16(nrm + u[2 * r + c2][c]);
-                            v[c2][c] = on[c2] ? t : 0;
+                        }
+                        if (y + r < A.H) {
+                            const uint32_t mm = (mq >> (16 * r)) & 0xffffu;   // the two mask bytes of this row (0 or 255 each)
+                            int16_t* o = reinterpret_cast<int16_t*>(orow + (size_t)r * A.dstep);
+                            uint8_t* mo = mrow + (size_t)r * A.mstep;
+                            if (va && vb && ((reinterpret_cast<uintptr_t>(o) & 3) == 0)) {
+                                uint32_t* o32 = reinterpret_cast<uint32_t*>(o);
+                                o32[0] = (uint32_t)(uint16_t)v[0][0] | ((uint32_t)(uint16_t)v[0][1] << 16);
+                                o32[1] = (uint32_t)(uint16_t)v[0][2] | ((uint32_t)(uint16_t)v[1][0] << 16);
+                                o32[2] = (uint32_t)(uint16_t)v[1][1] | ((uint32_t)(uint16_t)v[1][2] << 16);
+                            } else {
+                                if (va) { o[0] = (int16_t)v[0][0]; o[1] = (int16_t)v[0][1]; o[2] = (int16_t)v[0][2]; }
+                                if (vb) { o[3] = (int16_t)v[1][0]; o[4] = (int16_t)v[1][1]; o[5] = (int16_t)v[1][2]; }
+                            }
+                            if (va && vb && ((reinterpret_cast<uintptr_t>(mo) & 1) == 0)) {
+                                *reinterpret_cast<uint16_t*>(mo) = (uint16_t)mm;
+                            } else {
+                                if (va) mo[0] = (uint8_t)(mm & 255u);
+                                if (vb) mo[1] = (uint8_t)(mm >> 8);
+                            }
                         }
                     }
-                    int16_t* o = reinterpret_cast<int16_t*>(reinterpret_cast<char*>(A.dst) + (size_t)y * A.dstep) + 3 * (x - A.sx0);
-                    uint8_t* mo = A.dmask + (size_t)y * A.mstep + (x - A.sx0);
-                    if (va && vb && ((reinterpret_cast<uintptr_t>(o) & 3) == 0)) {
-                        uint32_t* o32 = reinterpret_cast<uint32_t*>(o);
-                        o32[0] = (uint32_t)(uint16_t)v[0][0] | ((uint32_t)(uint16_t)v[0][1] << 16);
-                        o32[1] = (uint32_t)(uint16_t)v[0][2] | ((uint32_t)(uint16_t)v[1][0] << 16);
-                        o32[2] = (uint32_t)(uint16_t)v[1][1] | ((uint32_t)(uint16_t)v[1][2] << 16);
-                    } else {
-                        if (va) { o[0] = (int16_t)v[0][0]; o[1] = (int16_t)v[0][1]; o[2] = (int16_t)v[0][2]; }
-                        if (vb) { o[3] = (int16_t)v[1][0]; o[4] = (int16_t)v[1][1]; o[5] = (int16_t)v[1][2]; }
+                    // roll on: next quad, next level-1 row
+                    ip += 2 * L0_IROW; y += 2;
+                    orow += 2 * A.dstep; mrow += 2 * A.mstep;
+#pragma unroll
+                    for (int c = 0; c < 3; ++c) {
+                        GE0[c] = GE1[c]; GO0[c] = GO1[c]; GE1[c] = GE2[c]; GO1[c] = GO2[c];
+                        KE0[c] = KE1[c]; KO0[c] = KO1[c]; KE1[c] = KE2[c]; KO1[c] = KO2[c];
                     }
-                    if (va && vb && ((reinterpret_cast<uintptr_t>(mo) & 1) == 0)) {
-                        *reinterpret_cast<uint16_t*>(mo) = (uint16_t)((on[0] ? 255u : 0u) | (on[1] ? 0xff00u : 0u));
-                    } else {
-                        if (va) mo[0] = on[0] ? 255 : 0;
-                        if (vb) mo[1] = on[1] ? 255 : 0;
-                    }
+#pragma unroll
+                    for (int j = 0; j + 1 < L0_QN; ++j) mw[j] = mw[j + 1];
                 }
             }
+            if ((flags & (8 | 16)) != (8 | 16)) asm volatile("fence.proxy.async.shared::cta;" ::: "memory");   // patched bytes vs the next TMA write
         }
         __syncwarp();
         if (lane == 0) mbar_arrive(&empty[stage]);
@@ -1032,8 +1030,8 @@ static bool tma_ok(const void* base, size_t stride) { return (reinterpret_cast<u
 
 // level 0 through the tiled TMA kernel when every operand meets the TMA alignment rules (16-byte base and pitch);
 // *done = false leaves the level to the generic quad kernel
-static int blend_level0_tiled(is_blender* b, const DevMat& dst, const DevMat& dmask, const int16_t* c1, int uh, int uw, int xb, int xe, int sx0,
-                              int sx1, double bytes, bool* done) {
+static int blend_level0_tiled(is_blender* b, const LevelArgs& generic, const DevMat& dst, const DevMat& dmask, const int16_t* c1, int uh, int uw,
+                              int xb, int xe, int sx0, int sx1, double bytes, bool* done) {
     is_ctx* ctx = b->ctx;
     *done = false;
     const int n = (int)b->fed.size();
@@ -1042,19 +1040,6 @@ static int blend_level0_tiled(is_blender* b, const DevMat& dst, const DevMat& dm
     for (const FedImage& f : b->fed) {
         if (f.img.depth != IS_8U || !tma_ok(f.img.data, f.img.step) || !tma_ok(f.mask.data, f.mask.step)) return IS_OK;
         if (!tma_ok(f.g[1].p, (size_t)(f.width >> 1) * 6) || !f.summary.p) return IS_OK;
-    }
-    if (n > L0_MAXCAND) {   // the kernel lists at most L0_MAXCAND contributing images per tile: bound it by rectangle overlap
-        for (int i = 0; i < n; ++i) {
-            const FedImage& a = b->fed[i];
-            int cnt = 0;
-            for (int j = 0; j < n; ++j) {
-                const FedImage& c = b->fed[j];
-                const bool apart = a.tl_x - L0_TW >= c.tl_x + c.img.cols + L0_TW || c.tl_x - L0_TW >= a.tl_x + a.img.cols + L0_TW ||
-                                   a.tl_y - L0_TH >= c.tl_y + c.img.rows + L0_TH || c.tl_y - L0_TH >= a.tl_y + a.img.rows + L0_TH;
-                if (!apart) ++cnt;
-            }
-            if (cnt > L0_MAXCAND) return IS_OK;
-        }
     }
     const size_t maps_bytes = sizeof(CUtensorMap) * (size_t)(1 + 3 * n);
     std::vector<unsigned char> host(maps_bytes + sizeof(L0Img) * (size_t)std::max(n, 1));
@@ -1107,10 +1092,19 @@ static int blend_level0_tiled(is_blender* b, const DevMat& dst, const DevMat& dm
         }
         if (blocks_per_sm[wi] < 1) blocks_per_sm[wi] = 1;
     }
+    // bands the tiled kernel leaves to the general one (device-side work list)
+    DevBuf bands;
+    IS_TRY(bands.alloc(ctx, sizeof(int2) * (size_t)A.ntiles * (L0_TH / 8) + 16));
+    A.nbands = bands.as<int>();                                           // counter in the first 16 bytes
+    A.bands = reinterpret_cast<int2*>(bands.as<unsigned char>() + 16);
+    IS_CUDA(ctx, cudaMemsetAsync(bands.p, 0, 16, ctx->stream));
     const int grid = std::min(A.ntiles, sms * blocks_per_sm[wi]);   // persistent: every CTA walks tiles grid apart
     ctx->next_bytes = bytes;
     if (wi == 0) IS_LAUNCH(ctx, k_blend_l0_tiled<true>, grid, L0_THREADS, L0_SMEM_BYTES, A);
     else IS_LAUNCH(ctx, k_blend_l0_tiled<false>, grid, L0_THREADS, L0_SMEM_BYTES, A);
+    const int ggrid = std::min(A.ntiles * (L0_TH / 8), sms * 8);
+    if (wi == 0) IS_LAUNCH(ctx, k_blend_l0_bands<true>, ggrid, 128, 0, generic, A.bands, A.nbands);
+    else IS_LAUNCH(ctx, k_blend_l0_bands<false>, ggrid, 128, 0, generic, A.bands, A.nbands);
     *done = true;
     return IS_OK;
 }
@@ -1174,7 +1168,7 @@ int blender_blend_dev(is_blender* b, const DevMat& dst, const DevMat& dmask, int
         if (k == 0 && nb >= 1) {
             bool done = false;
             const double bytes = ctx->next_bytes;
-            IS_TRY(blend_level0_tiled(b, dst, dmask, out[1].as<int16_t>(), H[1], W[1], xb[0], xe[0], sx0, sx1, bytes, &done));
+            IS_TRY(blend_level0_tiled(b, A, dst, dmask, out[1].as<int16_t>(), H[1], W[1], xb[0], xe[0], sx0, sx1, bytes, &done));
             if (done) continue;
             ctx->next_bytes = bytes;
         }
