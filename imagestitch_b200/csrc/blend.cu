@@ -81,48 +81,11 @@ __device__ __forceinline__ int l0_weight_s(const Level0& L, int y, int x) { int 
 // 16S: exact integer 5x5 [1 4 6 4 1]^2 with BORDER_REFLECT_101, (s + 128) >> 8.
 // 32F: scalar order of OpenCV's pyramids.cpp: row = s2*6 + (s1+s3)*4 + s0 + s4 ; out = (r2*6 + (r1+r3)*4 + r0 + r4) * (1/256)
 
-template <bool WF>   // WF: float weights, else int16 weights
-__global__ void k_pyrdown_l0(Level0 L, int16_t* __restrict__ g1, void* __restrict__ w1, int dh, int dw) {
-    const int x = blockIdx.x * blockDim.x + threadIdx.x;
-    const int y = blockIdx.y * blockDim.y + threadIdx.y;
-    if (x >= dw || y >= dh) return;
-    int xs[5], ys[5];
-#pragma unroll
-    for (int a = 0; a < 5; ++a) { xs[a] = reflect101(2 * x + a - 2, L.width); ys[a] = reflect101(2 * y + a - 2, L.height); }
-    const int kk[5] = {1, 4, 6, 4, 1};
-    int acc[3] = {0, 0, 0};
-    float rowf[5];
-    int wacc = 0;
-#pragma unroll
-    for (int a = 0; a < 5; ++a) {
-        int r[3] = {0, 0, 0};
-        float wf[5];
-        int ws = 0;
-#pragma unroll
-        for (int b = 0; b < 5; ++b) {
-            int v[3];
-            l0_pixel(L, ys[a], xs[b], v);
-            r[0] += kk[b] * v[0]; r[1] += kk[b] * v[1]; r[2] += kk[b] * v[2];
-            if (WF) wf[b] = l0_weight_f(L, ys[a], xs[b]);
-            else ws += kk[b] * l0_weight_s(L, ys[a], xs[b]);
-        }
-        acc[0] += kk[a] * r[0]; acc[1] += kk[a] * r[1]; acc[2] += kk[a] * r[2];
-        if (WF) rowf[a] = __fadd_rn(__fadd_rn(__fadd_rn(__fmul_rn(wf[2], 6.f), __fmul_rn(__fadd_rn(wf[1], wf[3]), 4.f)), wf[0]), wf[4]);
-        else wacc += kk[a] * ws;
-    }
-    const size_t o = (size_t)y * dw + x;
-    g1[3 * o] = (int16_t)sat16((acc[0] + 128) >> 8);
-    g1[3 * o + 1] = (int16_t)sat16((acc[1] + 128) >> 8);
-    g1[3 * o + 2] = (int16_t)sat16((acc[2] + 128) >> 8);
-    if (WF) {
-        float v = __fadd_rn(__fadd_rn(__fadd_rn(__fmul_rn(rowf[2], 6.f), __fmul_rn(__fadd_rn(rowf[1], rowf[3]), 4.f)), rowf[0]), rowf[4]);
-        reinterpret_cast<float*>(w1)[o] = __fmul_rn(v, 1.f / 256.f);
-    } else {
-        reinterpret_cast<int16_t*>(w1)[o] = (int16_t)sat16((wacc + 128) >> 8);
-    }
-}
+// PART selects what a launch produces: the image level, the weight level, or both.  The image pyramid does not depend on
+// the mask, so the pipeline builds it while the seam stage is still running and adds the weights afterwards.
+enum { PD_BOTH = 0, PD_IMAGE = 1, PD_WEIGHT = 2 };
 
-template <bool WF>
+template <bool WF, int PART>   // WF: float weights, else int16 weights
 __global__ void k_pyrdown(const int16_t* __restrict__ g, const void* __restrict__ w, int sh, int sw, int16_t* __restrict__ gd,
                           void* __restrict__ wd, int dh, int dw) {
     const int x = blockIdx.x * blockDim.x + threadIdx.x;
@@ -143,23 +106,31 @@ __global__ void k_pyrdown(const int16_t* __restrict__ g, const void* __restrict_
 #pragma unroll
         for (int b = 0; b < 5; ++b) {
             const size_t i = (size_t)ys[a] * sw + xs[b];
-            r[0] += kk[b] * g[3 * i]; r[1] += kk[b] * g[3 * i + 1]; r[2] += kk[b] * g[3 * i + 2];
-            if (WF) wf[b] = reinterpret_cast<const float*>(w)[i];
-            else ws += kk[b] * reinterpret_cast<const int16_t*>(w)[i];
+            if (PART != PD_WEIGHT) { r[0] += kk[b] * g[3 * i]; r[1] += kk[b] * g[3 * i + 1]; r[2] += kk[b] * g[3 * i + 2]; }
+            if (PART != PD_IMAGE) {
+                if (WF) wf[b] = reinterpret_cast<const float*>(w)[i];
+                else ws += kk[b] * reinterpret_cast<const int16_t*>(w)[i];
+            }
         }
         acc[0] += kk[a] * r[0]; acc[1] += kk[a] * r[1]; acc[2] += kk[a] * r[2];
-        if (WF) rowf[a] = __fadd_rn(__fadd_rn(__fadd_rn(__fmul_rn(wf[2], 6.f), __fmul_rn(__fadd_rn(wf[1], wf[3]), 4.f)), wf[0]), wf[4]);
-        else wacc += kk[a] * ws;
+        if (PART != PD_IMAGE) {
+            if (WF) rowf[a] = __fadd_rn(__fadd_rn(__fadd_rn(__fmul_rn(wf[2], 6.f), __fmul_rn(__fadd_rn(wf[1], wf[3]), 4.f)), wf[0]), wf[4]);
+            else wacc += kk[a] * ws;
+        }
     }
     const size_t o = (size_t)y * dw + x;
-    gd[3 * o] = (int16_t)sat16((acc[0] + 128) >> 8);
-    gd[3 * o + 1] = (int16_t)sat16((acc[1] + 128) >> 8);
-    gd[3 * o + 2] = (int16_t)sat16((acc[2] + 128) >> 8);
-    if (WF) {
-        float v = __fadd_rn(__fadd_rn(__fadd_rn(__fmul_rn(rowf[2], 6.f), __fmul_rn(__fadd_rn(rowf[1], rowf[3]), 4.f)), rowf[0]), rowf[4]);
-        reinterpret_cast<float*>(wd)[o] = __fmul_rn(v, 1.f / 256.f);
-    } else {
-        reinterpret_cast<int16_t*>(wd)[o] = (int16_t)sat16((wacc + 128) >> 8);
+    if (PART != PD_WEIGHT) {
+        gd[3 * o] = (int16_t)sat16((acc[0] + 128) >> 8);
+        gd[3 * o + 1] = (int16_t)sat16((acc[1] + 128) >> 8);
+        gd[3 * o + 2] = (int16_t)sat16((acc[2] + 128) >> 8);
+    }
+    if (PART != PD_IMAGE) {
+        if (WF) {
+            float v = __fadd_rn(__fadd_rn(__fadd_rn(__fmul_rn(rowf[2], 6.f), __fmul_rn(__fadd_rn(rowf[1], rowf[3]), 4.f)), rowf[0]), rowf[4]);
+            reinterpret_cast<float*>(wd)[o] = __fmul_rn(v, 1.f / 256.f);
+        } else {
+            reinterpret_cast<int16_t*>(wd)[o] = (int16_t)sat16((wacc + 128) >> 8);
+        }
     }
 }
 
@@ -793,19 +764,24 @@ __global__ void __launch_bounds__(L0_THREADS, 3) k_blend_l0_tiled(L0Args A) {
 // (b, g, r, mask) in one 32-bit word; the horizontal 5-tap sums go to shared memory, the vertical pass finishes.
 constexpr int PD_TX = 32, PD_TY = 8, PD_IW = 2 * PD_TX + 3, PD_IH = 2 * PD_TY + 3;
 
-template <bool WF>
+template <bool WF, int PART>
 __global__ void __launch_bounds__(PD_TX* PD_TY) k_pyrdown_l0_tiled(Level0 L, int16_t* __restrict__ g1, void* __restrict__ w1, int dh, int dw) {
     __shared__ uint32_t tile[PD_IH][PD_IW + 1];
-    __shared__ int hsum[PD_IH][PD_TX][3];
-    __shared__ float hw_f[PD_IH][PD_TX];
+    __shared__ int hsum[PART != PD_WEIGHT ? PD_IH : 1][PD_TX][3];
+    __shared__ float hw_f[PART != PD_IMAGE ? PD_IH : 1][PD_TX];
     const int tid = threadIdx.y * PD_TX + threadIdx.x;
     const int ox0 = blockIdx.x * PD_TX, oy0 = blockIdx.y * PD_TY;
     for (int e = tid; e < PD_IH * PD_IW; e += PD_TX * PD_TY) {
         const int r = e / PD_IW, c = e % PD_IW;
         const int y = reflect101(2 * oy0 - 2 + r, L.height), x = reflect101(2 * ox0 - 2 + c, L.width);
-        int v[3];
-        l0_pixel(L, y, x, v);
-        tile[r][c] = (uint32_t)v[0] | ((uint32_t)v[1] << 8) | ((uint32_t)v[2] << 16) | ((uint32_t)l0_mask(L, y, x) << 24);
+        uint32_t word = 0;
+        if (PART != PD_WEIGHT) {
+            int v[3];
+            l0_pixel(L, y, x, v);
+            word = (uint32_t)v[0] | ((uint32_t)v[1] << 8) | ((uint32_t)v[2] << 16);
+        }
+        if (PART != PD_IMAGE) word |= (uint32_t)l0_mask(L, y, x) << 24;
+        tile[r][c] = word;
     }
     __syncthreads();
     for (int e = tid; e < PD_IH * PD_TX; e += PD_TX * PD_TY) {
@@ -814,20 +790,24 @@ __global__ void __launch_bounds__(PD_TX* PD_TY) k_pyrdown_l0_tiled(Level0 L, int
 #pragma unroll
         for (int b = 0; b < 5; ++b) p[b] = tile[r][2 * ox + b];
         const int kk[5] = {1, 4, 6, 4, 1};
-        int s0 = 0, s1 = 0, s2 = 0;
+        if (PART != PD_WEIGHT) {
+            int s0 = 0, s1 = 0, s2 = 0;
 #pragma unroll
-        for (int b = 0; b < 5; ++b) { s0 += kk[b] * (int)(p[b] & 255); s1 += kk[b] * (int)((p[b] >> 8) & 255); s2 += kk[b] * (int)((p[b] >> 16) & 255); }
-        hsum[r][ox][0] = s0; hsum[r][ox][1] = s1; hsum[r][ox][2] = s2;
-        if (WF) {
-            float wv[5];
+            for (int b = 0; b < 5; ++b) { s0 += kk[b] * (int)(p[b] & 255); s1 += kk[b] * (int)((p[b] >> 8) & 255); s2 += kk[b] * (int)((p[b] >> 16) & 255); }
+            hsum[r][ox][0] = s0; hsum[r][ox][1] = s1; hsum[r][ox][2] = s2;
+        }
+        if (PART != PD_IMAGE) {
+            if (WF) {
+                float wv[5];
 #pragma unroll
-            for (int b = 0; b < 5; ++b) wv[b] = __fmul_rn((float)(p[b] >> 24), (float)(1. / 255.));
-            hw_f[r][ox] = __fadd_rn(__fadd_rn(__fadd_rn(__fmul_rn(wv[2], 6.f), __fmul_rn(__fadd_rn(wv[1], wv[3]), 4.f)), wv[0]), wv[4]);
-        } else {
-            int ws = 0;
+                for (int b = 0; b < 5; ++b) wv[b] = __fmul_rn((float)(p[b] >> 24), (float)(1. / 255.));
+                hw_f[r][ox] = __fadd_rn(__fadd_rn(__fadd_rn(__fmul_rn(wv[2], 6.f), __fmul_rn(__fadd_rn(wv[1], wv[3]), 4.f)), wv[0]), wv[4]);
+            } else {
+                int ws = 0;
 #pragma unroll
-            for (int b = 0; b < 5; ++b) { const int m = (int)(p[b] >> 24); ws += kk[b] * (m ? m + 1 : 0); }
-            hw_f[r][ox] = __int_as_float(ws);
+                for (int b = 0; b < 5; ++b) { const int m = (int)(p[b] >> 24); ws += kk[b] * (m ? m + 1 : 0); }
+                hw_f[r][ox] = __int_as_float(ws);
+            }
         }
     }
     __syncthreads();
@@ -835,26 +815,30 @@ __global__ void __launch_bounds__(PD_TX* PD_TY) k_pyrdown_l0_tiled(Level0 L, int
     const int x = ox0 + ox, y = oy0 + oy;
     if (x >= dw || y >= dh) return;
     const int kk[5] = {1, 4, 6, 4, 1};
-    int acc[3] = {0, 0, 0};
-#pragma unroll
-    for (int a = 0; a < 5; ++a) {
-        acc[0] += kk[a] * hsum[2 * oy + a][ox][0];
-        acc[1] += kk[a] * hsum[2 * oy + a][ox][1];
-        acc[2] += kk[a] * hsum[2 * oy + a][ox][2];
-    }
     const size_t o = (size_t)y * dw + x;
-    g1[3 * o] = (int16_t)sat16((acc[0] + 128) >> 8);
-    g1[3 * o + 1] = (int16_t)sat16((acc[1] + 128) >> 8);
-    g1[3 * o + 2] = (int16_t)sat16((acc[2] + 128) >> 8);
-    if (WF) {
-        const float r0 = hw_f[2 * oy][ox], r1 = hw_f[2 * oy + 1][ox], r2 = hw_f[2 * oy + 2][ox], r3 = hw_f[2 * oy + 3][ox], r4 = hw_f[2 * oy + 4][ox];
-        const float v = __fadd_rn(__fadd_rn(__fadd_rn(__fmul_rn(r2, 6.f), __fmul_rn(__fadd_rn(r1, r3), 4.f)), r0), r4);
-        reinterpret_cast<float*>(w1)[o] = __fmul_rn(v, 1.f / 256.f);
-    } else {
-        int wacc = 0;
+    if (PART != PD_WEIGHT) {
+        int acc[3] = {0, 0, 0};
 #pragma unroll
-        for (int a = 0; a < 5; ++a) wacc += kk[a] * __float_as_int(hw_f[2 * oy + a][ox]);
-        reinterpret_cast<int16_t*>(w1)[o] = (int16_t)sat16((wacc + 128) >> 8);
+        for (int a = 0; a < 5; ++a) {
+            acc[0] += kk[a] * hsum[2 * oy + a][ox][0];
+            acc[1] += kk[a] * hsum[2 * oy + a][ox][1];
+            acc[2] += kk[a] * hsum[2 * oy + a][ox][2];
+        }
+        g1[3 * o] = (int16_t)sat16((acc[0] + 128) >> 8);
+        g1[3 * o + 1] = (int16_t)sat16((acc[1] + 128) >> 8);
+        g1[3 * o + 2] = (int16_t)sat16((acc[2] + 128) >> 8);
+    }
+    if (PART != PD_IMAGE) {
+        if (WF) {
+            const float r0 = hw_f[2 * oy][ox], r1 = hw_f[2 * oy + 1][ox], r2 = hw_f[2 * oy + 2][ox], r3 = hw_f[2 * oy + 3][ox], r4 = hw_f[2 * oy + 4][ox];
+            const float v = __fadd_rn(__fadd_rn(__fadd_rn(__fmul_rn(r2, 6.f), __fmul_rn(__fadd_rn(r1, r3), 4.f)), r0), r4);
+            reinterpret_cast<float*>(w1)[o] = __fmul_rn(v, 1.f / 256.f);
+        } else {
+            int wacc = 0;
+#pragma unroll
+            for (int a = 0; a < 5; ++a) wacc += kk[a] * __float_as_int(hw_f[2 * oy + a][ox]);
+            reinterpret_cast<int16_t*>(w1)[o] = (int16_t)sat16((wacc + 128) >> 8);
+        }
     }
 }
 
@@ -952,12 +936,12 @@ static void feed_geometry(const is_blender* b, int rows, int cols, int tl_x, int
     g[0] = tlx - R.x; g[1] = tly - R.y; g[2] = width; g[3] = height; g[4] = tl_y - tly; g[5] = tl_x - tlx;
 }
 
-int blender_feed_dev(is_blender* b, FedImage&& f) {
+// geometry of MultiBandBlender::feed + the (stream-ordered) allocation of the image's pyramid levels on the blender's stream
+static int feed_prepare(is_blender* b, FedImage& f) {
     is_ctx* ctx = b->ctx;
     const int nb = b->num_bands;
     const is_rect R = b->roi;
     const int rows = f.img.rows, cols = f.img.cols;
-    // geometry of MultiBandBlender::feed
     const int gap = 3 * (1 << nb);
     int tlx = std::max(R.x, f.tl_x - gap), tly = std::max(R.y, f.tl_y - gap);
     int brx = std::min(R.x + R.width, f.tl_x + cols + gap), bry = std::min(R.y + R.height, f.tl_y + rows + gap);
@@ -979,9 +963,7 @@ int blender_feed_dev(is_blender* b, FedImage&& f) {
     f.x_tl = tlx - R.x;
     f.y_tl = tly - R.y;
     IS_REQUIRE(ctx, f.top >= 0 && f.left >= 0 && f.x_tl >= 0 && f.y_tl >= 0, IS_ERR_BAD_ARG, "image lies outside the prepared ROI");
-    // Gaussian pyramids of the image and of its weight map, levels 1..nb
-    const bool wf = b->weight_type == IS_WEIGHT_32F;
-    const size_t wsz = wf ? sizeof(float) : sizeof(int16_t);
+    const size_t wsz = b->weight_type == IS_WEIGHT_32F ? sizeof(float) : sizeof(int16_t);
     f.g.resize(nb + 1);
     f.w.resize(nb + 1);
     int sh = height, sw = width;
@@ -989,28 +971,86 @@ int blender_feed_dev(is_blender* b, FedImage&& f) {
         const int dh = (sh + 1) / 2, dw = (sw + 1) / 2;
         IS_TRY(f.g[k].alloc(ctx, sizeof(int16_t) * 3 * (size_t)dh * dw));
         IS_TRY(f.w[k].alloc(ctx, wsz * (size_t)dh * dw));
-        dim3 block(32, 8), grid(div_up(dw, 32), div_up(dh, 8));
-        // algorithmic bytes: level k-1 (image + weight) read once, level k written once
-        const double in_px = k == 1 ? (double)rows * cols : (double)sh * sw;
-        ctx->next_bytes = in_px * (k == 1 ? (f.img.depth == IS_8U ? 3 : 6) + 1 : 6 + (double)wsz) + (double)dh * dw * (6 + (double)wsz);
+        sh = dh; sw = dw;
+    }
+    if (nb >= 1) {
+        f.sum_w = div_up(cols, SUM_CW); f.sum_h = div_up(rows, SUM_CH);
+        IS_TRY(f.summary.alloc(ctx, (size_t)f.sum_w * f.sum_h));
+    }
+    return IS_OK;
+}
+
+template <bool WF, int PART>
+static int feed_pyramid_t(is_ctx* sctx, const FedImage& f, int nb) {
+    const size_t wsz = WF ? sizeof(float) : sizeof(int16_t);
+    const double ib = PART != PD_WEIGHT ? 1. : 0., wb = PART != PD_IMAGE ? 1. : 0.;   // which bytes this launch accounts for
+    int sh = f.height, sw = f.width;
+    for (int k = 1; k <= nb; ++k) {
+        const int dh = (sh + 1) / 2, dw = (sw + 1) / 2;
+        // algorithmic bytes: level k-1 read once, level k written once
+        const double in_px = k == 1 ? (double)f.img.rows * f.img.cols : (double)sh * sw;
+        sctx->next_bytes = in_px * (k == 1 ? ib * (f.img.depth == IS_8U ? 3 : 6) + wb : ib * 6 + wb * (double)wsz) + (double)dh * dw * (ib * 6 + wb * (double)wsz);
         if (k == 1) {
             Level0 L = level0_of(f);
             dim3 tb(PD_TX, PD_TY), tg(div_up(dw, PD_TX), div_up(dh, PD_TY));
-            if (wf) IS_LAUNCH(ctx, k_pyrdown_l0_tiled<true>, tg, tb, 0, L, f.g[1].as<int16_t>(), f.w[1].p, dh, dw);
-            else IS_LAUNCH(ctx, k_pyrdown_l0_tiled<false>, tg, tb, 0, L, f.g[1].as<int16_t>(), f.w[1].p, dh, dw);
+            IS_LAUNCH(sctx, (k_pyrdown_l0_tiled<WF, PART>), tg, tb, 0, L, f.g[1].as<int16_t>(), f.w[1].p, dh, dw);
         } else {
-            if (wf) IS_LAUNCH(ctx, k_pyrdown<true>, grid, block, 0, f.g[k - 1].as<int16_t>(), f.w[k - 1].p, sh, sw, f.g[k].as<int16_t>(), f.w[k].p, dh, dw);
-            else IS_LAUNCH(ctx, k_pyrdown<false>, grid, block, 0, f.g[k - 1].as<int16_t>(), f.w[k - 1].p, sh, sw, f.g[k].as<int16_t>(), f.w[k].p, dh, dw);
+            dim3 block(32, 8), grid(div_up(dw, 32), div_up(dh, 8));
+            IS_LAUNCH(sctx, (k_pyrdown<WF, PART>), grid, block, 0, f.g[k - 1].as<int16_t>(), f.w[k - 1].p, sh, sw, f.g[k].as<int16_t>(), f.w[k].p, dh, dw);
         }
         sh = dh; sw = dw;
     }
-    if (nb >= 1) {   // which 64 x 32 cells of the mask hold anything: lets the level-0 blend skip images per tile
-        f.sum_w = div_up(cols, SUM_CW); f.sum_h = div_up(rows, SUM_CH);
-        IS_TRY(f.summary.alloc(ctx, (size_t)f.sum_w * f.sum_h));
-        ctx->next_bytes = (double)rows * cols;
-        IS_LAUNCH(ctx, k_mask_summary, dim3(f.sum_w, f.sum_h), 256, 0, f.mask.ptr<uint8_t>(), f.mask.step, rows, cols, f.summary.as<uint8_t>(), f.sum_w);
+    return IS_OK;
+}
+
+// Gaussian pyramids (levels 1..nb) of the image and / or of its weight map, launched on sctx's stream
+static int feed_pyramid(is_ctx* sctx, const is_blender* b, const FedImage& f, int part) {
+    const bool wf = b->weight_type == IS_WEIGHT_32F;
+    const int nb = b->num_bands;
+    switch (part) {
+        case PD_BOTH: return wf ? feed_pyramid_t<true, PD_BOTH>(sctx, f, nb) : feed_pyramid_t<false, PD_BOTH>(sctx, f, nb);
+        case PD_IMAGE: return wf ? feed_pyramid_t<true, PD_IMAGE>(sctx, f, nb) : feed_pyramid_t<false, PD_IMAGE>(sctx, f, nb);
+        default: return wf ? feed_pyramid_t<true, PD_WEIGHT>(sctx, f, nb) : feed_pyramid_t<false, PD_WEIGHT>(sctx, f, nb);
     }
+}
+
+// which 64 x 32 cells of the mask hold anything: lets the level-0 blend skip images per tile
+static int feed_summary(is_ctx* ctx, const FedImage& f) {
+    if (!f.summary.p) return IS_OK;
+    ctx->next_bytes = (double)f.img.rows * f.img.cols;
+    IS_LAUNCH(ctx, k_mask_summary, dim3(f.sum_w, f.sum_h), 256, 0, f.mask.ptr<uint8_t>(), f.mask.step, f.img.rows, f.img.cols, f.summary.as<uint8_t>(), f.sum_w);
+    return IS_OK;
+}
+
+int blender_feed_dev(is_blender* b, FedImage&& f) {
+    IS_TRY(feed_prepare(b, f));
+    IS_TRY(feed_pyramid(b->ctx, b, f, PD_BOTH));
+    IS_TRY(feed_summary(b->ctx, f));
     b->fed.push_back(std::move(f));
+    return IS_OK;
+}
+
+// Pipeline variant of feed(): the image pyramid is built on `side` (its stream must already be ordered after the image and
+// after the blender's stream at this point); the mask is only read by blender_feed_weights().
+int blender_feed_image(is_blender* b, is_ctx* side, const DevMat& img, const DevMat& mask, is_point tl) {
+    FedImage f;
+    f.tl_x = tl.x; f.tl_y = tl.y;
+    f.img.data = img.data; f.img.rows = img.rows; f.img.cols = img.cols; f.img.channels = img.channels; f.img.depth = img.depth; f.img.step = img.step;
+    f.mask.data = mask.data; f.mask.rows = mask.rows; f.mask.cols = mask.cols; f.mask.channels = 1; f.mask.depth = IS_8U; f.mask.step = mask.step;
+    IS_TRY(feed_prepare(b, f));
+    if (side != b->ctx) IS_TRY(stream_after(b->ctx, side->stream, b->ctx->stream));   // the allocations above are ordered on the blender's stream
+    const int rc = feed_pyramid(side, b, f, PD_IMAGE);
+    if (rc != IS_OK) { if (b->ctx->last_error.empty()) b->ctx->last_error = side->last_error; return rc; }
+    b->fed.push_back(std::move(f));
+    return IS_OK;
+}
+
+// weight pyramids + occupancy maps of everything fed with blender_feed_image(), on the blender's stream
+int blender_feed_weights(is_blender* b) {
+    for (const FedImage& f : b->fed) {
+        IS_TRY(feed_pyramid(b->ctx, b, f, PD_WEIGHT));
+        IS_TRY(feed_summary(b->ctx, f));
+    }
     return IS_OK;
 }
 

@@ -37,6 +37,9 @@ struct is_ctx {
     std::vector<unsigned char> plan_cache;
     // worker contexts (own stream + staging) for the concurrent seam pairs; owned by this context
     std::vector<is_ctx*> children;
+    // events for stream_after(): reused round-robin per call sequence (sync_next is reset by the pipeline entry points)
+    std::vector<cudaEvent_t> sync_events;
+    size_t sync_next = 0;
     int seam_speculation_accepted = -1;   // last is_seam_dp_find: 1 concurrent result accepted, 0 fell back, -1 not attempted
 };
 
@@ -137,7 +140,13 @@ int pinned_alloc(is_ctx* ctx, size_t bytes, void** out);
 // small control transfers through the pinned staging buffer (synchronous with the stream)
 int upload(is_ctx* ctx, void* dst, const void* src, size_t bytes);
 int download(is_ctx* ctx, void* dst, const void* src, size_t bytes);
+int download2d(is_ctx* ctx, void* dst, size_t dpitch, const void* src, size_t spitch, size_t width, size_t height);
 
 int check_mat(is_ctx* ctx, const is_mat* m, const char* name);
+
+enum { SIDE_PYRAMID = 8, SIDE_COPY = 9 };
+int child_ctx(is_ctx* parent, size_t k, is_ctx** out);
+int stream_after(is_ctx* ctx, cudaStream_t to, cudaStream_t from);
+void merge_child(is_ctx* parent, is_ctx* child);
 
 }  // namespace is

@@ -54,6 +54,48 @@ void DevBuf::release() {
     bytes = 0;
 }
 
+// Worker contexts: own stream + staging, sharing the parent's device and memory pool.  Indices 0..7 serve the
+// concurrent seam pairs, SIDE_PYRAMID / SIDE_COPY the pipeline's side streams.
+int child_ctx(is_ctx* parent, size_t k, is_ctx** out) {
+    while (parent->children.size() <= k) {
+        is_ctx* c = new is_ctx();
+        c->device = parent->device;
+        // the seam workers' short kernels go ahead of the bulk work of the side streams
+        int lo = 0, hi = 0;
+        cudaDeviceGetStreamPriorityRange(&lo, &hi);
+        const int prio = parent->children.size() < (size_t)SIDE_PYRAMID ? hi : lo;
+        if (cudaStreamCreateWithPriority(&c->own_stream, cudaStreamNonBlocking, prio) != cudaSuccess) { delete c; return fail(parent, IS_ERR_CUDA, "cudaStreamCreate failed"); }
+        c->stream = c->own_stream;
+        c->pool = parent->pool;
+        for (int e = 0; e < 5; ++e) cudaEventCreateWithFlags(&c->ev[e], cudaEventDisableTiming);
+        parent->children.push_back(c);
+    }
+    *out = parent->children[k];
+    return IS_OK;
+}
+
+// `to` waits for everything queued on `from` so far
+int stream_after(is_ctx* ctx, cudaStream_t to, cudaStream_t from) {
+    if (ctx->sync_next >= ctx->sync_events.size()) {
+        cudaEvent_t e = nullptr;
+        IS_CUDA(ctx, cudaEventCreateWithFlags(&e, cudaEventDisableTiming));
+        ctx->sync_events.push_back(e);
+    }
+    cudaEvent_t e = ctx->sync_events[ctx->sync_next++];
+    IS_CUDA(ctx, cudaEventRecord(e, from));
+    IS_CUDA(ctx, cudaStreamWaitEvent(to, e, 0));
+    return IS_OK;
+}
+
+// account a worker's launches / timing records / error to the parent
+void merge_child(is_ctx* parent, is_ctx* child) {
+    parent->launches += child->launches;
+    child->launches = 0;
+    for (auto& r : child->krecs) parent->krecs.push_back(r);
+    child->krecs.clear();
+    if (!child->last_error.empty() && parent->last_error.empty()) parent->last_error = child->last_error;
+}
+
 int check_mat(is_ctx* ctx, const is_mat* m, const char* name) {
     if (!m) return fail(ctx, IS_ERR_BAD_ARG, "%s: null is_mat", name);
     if (!m->data || m->rows <= 0 || m->cols <= 0 || m->channels <= 0 || depth_bytes(m->depth) == 0)
@@ -161,6 +203,24 @@ int download(is_ctx* ctx, void* dst, const void* src, size_t bytes) {
     return IS_OK;
 }
 
+// pitched download (rows of `width` bytes) through the pinned bounce buffer; dst is packed with dpitch
+int download2d(is_ctx* ctx, void* dst, size_t dpitch, const void* src, size_t spitch, size_t width, size_t height) {
+    if (width == 0 || height == 0) return IS_OK;
+    const size_t bytes = width * height;
+    if (ctx->pinned_dl_bytes < bytes) {
+        if (ctx->pinned_dl) { IS_CUDA(ctx, cudaStreamSynchronize(ctx->stream)); cudaFreeHost(ctx->pinned_dl); }
+        ctx->pinned_dl = nullptr;
+        ctx->pinned_dl_bytes = 0;
+        const size_t n = align_up(bytes > (size_t)(4 << 20) ? bytes : (size_t)(4 << 20), 1 << 20);
+        IS_CUDA(ctx, cudaMallocHost(&ctx->pinned_dl, n));
+        ctx->pinned_dl_bytes = n;
+    }
+    IS_CUDA(ctx, cudaMemcpy2DAsync(ctx->pinned_dl, width, src, spitch, width, height, cudaMemcpyDeviceToHost, ctx->stream));
+    IS_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+    for (size_t r = 0; r < height; ++r) std::memcpy((char*)dst + r * dpitch, (const char*)ctx->pinned_dl + r * width, width);
+    return IS_OK;
+}
+
 }  // namespace is
 
 extern "C" {
@@ -210,6 +270,7 @@ int is_ctx_destroy(is_ctx* ctx) {
     for (int i = 0; i < 5; ++i) if (ctx->ev[i]) cudaEventDestroy(ctx->ev[i]);
     for (auto& r : ctx->krecs) { cudaEventDestroy(r.e0); cudaEventDestroy(r.e1); }
     for (auto e : ctx->kpool) cudaEventDestroy(e);
+    for (auto e : ctx->sync_events) cudaEventDestroy(e);
     if (ctx->pinned) cudaFreeHost(ctx->pinned);
     if (ctx->pinned_dl) cudaFreeHost(ctx->pinned_dl);
     cudaStreamDestroy(ctx->own_stream);

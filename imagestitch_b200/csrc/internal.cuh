@@ -24,6 +24,11 @@ int upload_tables(is_ctx* ctx, int proj, const WarpPlan& plan, DevBuf* buf);
 int launch_warp(is_ctx* ctx, int proj, const WarpPlan& plan, const float* tables, const DevMat& src, int interp, int border,
                 const DevMat& dst, const DevMat* mask);
 
+// blend.cu
+int blender_feed_image(is_blender* b, is_ctx* side, const DevMat& img, const DevMat& mask, is_point tl);
+int blender_feed_weights(is_blender* b);
+int blender_blend_dev(is_blender* b, const DevMat& dst, const DevMat& dmask, int sx0, int sx1);
+
 // seam.cu
 int seam_find_device(is_ctx* ctx, int n, const DevMat* images, const is_point* corners, const DevMat* masks);
 

@@ -9,6 +9,7 @@
 #include "internal.cuh"
 
 #include <algorithm>
+#include <cstdlib>
 
 using namespace is;
 
@@ -82,16 +83,45 @@ int is_pipeline_run(is_ctx* ctx, int n, const is_mat* images, const is_camera* c
             IS_REQUIRE(ctx, seam_masks[i].depth == IS_8U && seam_masks[i].channels == 1 && seam_masks[i].rows == plans[i].P.dst_h &&
                                 seam_masks[i].cols == plans[i].P.dst_w, IS_ERR_BAD_ARG, "seam_masks[i] must be CV_8U of the warped size");
         }
-    // ---- device: stage, warp
+    // ---- device.  Three streams: the caller's (warp, seam, weights, blend), a copy stream that uploads host sources one
+    //      image ahead of the warp, and a side stream that builds the Gaussian image pyramids (they do not depend on the
+    //      seam masks) while the latency-bound seam stage leaves the SMs mostly idle.
+    ctx->sync_next = 0;
+    is_ctx *side = nullptr, *copy = nullptr;
+    IS_TRY(child_ctx(ctx, SIDE_PYRAMID, &side));
+    IS_TRY(child_ctx(ctx, SIDE_COPY, &copy));
+    if (getenv("IS_PIPELINE_SERIAL")) side = ctx;           // tuning knob: everything on the caller's stream
+    side->ktiming = ctx->ktiming;
     std::vector<DevMat> src(n), warped(n), masks(n);
-    for (int i = 0; i < n; ++i) IS_TRY(stage_in(ctx, &images[i], &src[i]));
+    is_blender* bl = nullptr;
+    IS_TRY(is_blender_create(ctx, cfg.num_bands, cfg.weight_type, &bl));
+    // destroyed before the buffers above: on an error path the side streams may still be using them
+    struct Guard {
+        is_blender* b; is_ctx* side; is_ctx* copy;
+        ~Guard() { cudaStreamSynchronize(side->stream); cudaStreamSynchronize(copy->stream); is_blender_destroy(b); }
+    } guard{bl, side, copy};
+    IS_TRY(is_blender_prepare_roi(bl, roi));
     IS_CUDA(ctx, cudaEventRecord(ctx->ev[0], ctx->stream));
+    bool any_host = false;
     for (int i = 0; i < n; ++i) {
+        if (images[i].device >= 0) { IS_TRY(stage_in(ctx, &images[i], &src[i])); continue; }
+        any_host = true;
+        IS_TRY(alloc_mat(ctx, images[i].rows, images[i].cols, images[i].channels, images[i].depth, &src[i]));
+    }
+    if (any_host) IS_TRY(stream_after(ctx, copy->stream, ctx->stream));   // the allocations are ordered on the caller's stream
+    for (int i = 0; i < n; ++i) {
+        if (images[i].device < 0) {
+            IS_CUDA(ctx, cudaMemcpy2DAsync(src[i].data, src[i].step, images[i].data, images[i].step, src[i].row_bytes(), images[i].rows,
+                                           cudaMemcpyHostToDevice, copy->stream));
+            IS_TRY(stream_after(ctx, ctx->stream, copy->stream));
+        }
         IS_TRY(alloc_mat(ctx, plans[i].P.dst_h, plans[i].P.dst_w, 3, IS_8U, &warped[i]));
         IS_TRY(alloc_mat(ctx, plans[i].P.dst_h, plans[i].P.dst_w, 1, IS_8U, &masks[i]));
         DevBuf tables;
         IS_TRY(upload_tables(ctx, cfg.projection, plans[i], &tables));
         IS_TRY(launch_warp(ctx, cfg.projection, plans[i], tables.as<float>(), src[i], IS_INTER_LINEAR, IS_BORDER_REFLECT, warped[i], &masks[i]));
+        // feed(): geometry + image pyramid now (side stream, ordered after this warp), weights after the seam stage
+        IS_TRY(blender_feed_image(bl, side, warped[i], masks[i], corners[i]));
     }
     IS_CUDA(ctx, cudaEventRecord(ctx->ev[1], ctx->stream));
     // ---- seam
@@ -103,24 +133,15 @@ int is_pipeline_run(is_ctx* ctx, int n, const is_mat* images, const is_camera* c
     }
     IS_CUDA(ctx, cudaEventRecord(ctx->ev[2], ctx->stream));
     // ---- blend
-    is_blender* bl = nullptr;
-    IS_TRY(is_blender_create(ctx, cfg.num_bands, cfg.weight_type, &bl));
-    int rc = is_blender_prepare_roi(bl, roi);
-    for (int i = 0; i < n && rc == IS_OK; ++i) {
-        is_mat im{warped[i].data, warped[i].rows, warped[i].cols, 3, IS_8U, warped[i].step, ctx->device};
-        is_mat mk{masks[i].data, masks[i].rows, masks[i].cols, 1, IS_8U, masks[i].step, ctx->device};
-        rc = is_blender_feed(bl, &im, &mk, corners[i], IS_FEED_BORROW);
+    IS_TRY(blender_feed_weights(bl));
+    if (side != ctx) {
+        IS_TRY(stream_after(ctx, ctx->stream, side->stream));   // join: the image pyramids are complete
+        merge_child(ctx, side);
     }
     DevMat dp, dm;
-    if (rc == IS_OK) rc = stage_out(ctx, pano, &dp, false);
-    if (rc == IS_OK) rc = stage_out(ctx, pano_mask, &dm, false);
-    if (rc == IS_OK) {
-        is_mat pd{dp.data, dp.rows, dp.cols, 3, IS_16S, dp.step, ctx->device};
-        is_mat md{dm.data, dm.rows, dm.cols, 1, IS_8U, dm.step, ctx->device};
-        rc = is_blender_blend(bl, &pd, &md);
-    }
-    is_blender_destroy(bl);
-    if (rc != IS_OK) return rc;
+    IS_TRY(stage_out(ctx, pano, &dp, false));
+    IS_TRY(stage_out(ctx, pano_mask, &dm, false));
+    IS_TRY(blender_blend_dev(bl, dp, dm, 0, roi.width));
     IS_CUDA(ctx, cudaEventRecord(ctx->ev[3], ctx->stream));
     // ---- results
     IS_TRY(commit(ctx, &dp));

@@ -702,26 +702,52 @@ struct ChangePt { int x, cls; };
 // number (rows with more than `cap` set *overflow and the caller falls back to the dense labelling).
 constexpr int ROW_CAP = 32;
 
-__global__ void k_row_changes(Frame f, int cap, int* __restrict__ counts, ChangePt* __restrict__ out, int* __restrict__ overflow) {
+// One warp per mask row: the x positions where (mask != 0) toggles, in increasing x; the state left of x = 0 is "outside".
+// 16 pixels per lane and trip (one 16-byte load when the row allows it), so a 6000-pixel row is 12 dependent trips.
+// counts[y] is the true number of toggles; rows with more than `cap` set *overflow (the caller falls back to the dense
+// labelling).  The union-frame class change points of a pair are the merge of its two masks' toggles (host, label_runs).
+__global__ void k_mask_row_toggles(const uint8_t* __restrict__ mask, size_t step, int rows, int cols, int cap, int* __restrict__ counts,
+                                   int* __restrict__ xs, int* __restrict__ overflow) {
     const int y = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
-    if (y >= f.uh) return;
+    if (y >= rows) return;
     const int lane = threadIdx.x & 31;
-    ChangePt* row = out + (size_t)y * cap;
+    const uint8_t* row = mask + (size_t)y * step;
+    const bool aligned = (reinterpret_cast<uintptr_t>(row) & 15) == 0;
+    int* out = xs + (size_t)y * cap;
     int n = 0;
-    int prev_last = 0;                                   // class of the pixel left of the current 32-pixel group
-    for (int base = 0; base < f.uw; base += 32) {
-        const int x = base + lane;
-        const int c = x < f.uw ? class_at(f, x, y) : 0;
-        int prev = __shfl_up_sync(0xffffffffu, c, 1);
-        if (lane == 0) prev = prev_last;
-        const bool flag = x < f.uw && c != prev;
-        const unsigned ballot = __ballot_sync(0xffffffffu, flag);
-        if (flag) {
-            const int k = n + __popc(ballot & ((1u << lane) - 1));
-            if (k < cap) row[k] = ChangePt{x, c};
+    unsigned carry = 0;                                  // state of the pixel left of the current 512-pixel chunk
+    for (int base = 0; base < cols; base += 512) {
+        const int x0 = base + 16 * lane;
+        unsigned bits = 0;                               // bit i: pixel x0 + i is inside the mask
+        if (x0 + 16 <= cols && aligned) {
+            const uint4 v = *reinterpret_cast<const uint4*>(row + x0);
+            const unsigned w[4] = {v.x, v.y, v.z, v.w};
+#pragma unroll
+            for (int k = 0; k < 4; ++k) {
+                const unsigned t = ((((w[k] & 0x7f7f7f7fu) + 0x7f7f7f7fu) | w[k]) & 0x80808080u) >> 7;   // 1 in every non-zero byte
+                bits |= (((t * 0x01020408u) >> 24) & 0xfu) << (4 * k);
+            }
+        } else {
+            for (int i = 0; i < 16; ++i)
+                if (x0 + i < cols && row[x0 + i]) bits |= 1u << i;
         }
-        n += __popc(ballot);
-        prev_last = __shfl_sync(0xffffffffu, c, 31);
+        unsigned left = __shfl_up_sync(0xffffffffu, bits >> 15, 1);
+        if (lane == 0) left = carry;
+        unsigned tg = (bits ^ ((bits << 1) | (left & 1u))) & 0xffffu;
+        if (x0 + 16 > cols) tg &= x0 < cols ? (1u << (cols - x0)) - 1u : 0u;   // nothing is reported at or beyond the row end
+        const int c = __popc(tg);
+        int incl = c;
+#pragma unroll
+        for (int o = 1; o < 32; o <<= 1) { const int t = __shfl_up_sync(0xffffffffu, incl, o); if (lane >= o) incl += t; }
+        int k = n + incl - c;
+        while (tg) {
+            const int i = __ffs(tg) - 1;
+            tg &= tg - 1;
+            if (k < cap) out[k] = x0 + i;
+            ++k;
+        }
+        n += __shfl_sync(0xffffffffu, incl, 31);
+        carry = __shfl_sync(0xffffffffu, bits >> 15, 31);
     }
     if (lane == 0) {
         counts[y] = n;
@@ -822,6 +848,7 @@ private:
     Frame fr{};
     Frame frame() const { return fr; }
     int label_runs(const Pt& iTl, const Pt& iBr, bool* done);
+    std::vector<char> stale;   // components whose bbox / contour recomputation is pending (resolve_conflicts)
     int label_dense();
     void release_device() { cls.release(); parent.release(); labels.release(); counts.release(); offsets.release(); recs.release(); }
     int ccl(const uint8_t* klass, int kmask, int w, int h, int* parent_out);
@@ -1231,17 +1258,27 @@ int PairSeam::resolve_conflicts(const DevMat& in1, const DevMat& in2, const DevM
         }
         if (!hasConflict) break;
         const int l1 = c1 + 1, l2 = c2 + 1;
+        // The reference recomputes the bbox and the contour of c1 (and of an INTERS c2) after every conflict ([SEAM]:483-513).
+        // c1 only ever loses pixels, so its recomputation is deferred until something reads it: a stale bbox is a superset
+        // (good enough to relabel the whole component) and scanning the superset later finds the same pixels in the same
+        // raster order.  A component that is about to gain pixels is brought up to date first, because the reference scans
+        // the bbox it had at that moment.
+        if (stale.size() < (size_t)ncomps) stale.resize((size_t)ncomps, 0);
+        if ((states[c2] & ST_INTERS) && stale[c2]) { IS_TRY(refresh_component(c2)); stale[c2] = 0; }
         if (has_only_one_neighbor(c1)) {
             const int w = brs[c1].x - tls[c1].x, h = brs[c1].y - tls[c1].y;
-            dim3 block(64, 4), grid(div_up(w, 64), div_up(h, 4));
-            IS_LAUNCH(ctx, k_relabel_rect, grid, block, 0, labels.as<int>(), frame(), tls[c1].x, tls[c1].y, w, h, l1, l2);
+            if (w > 0 && h > 0) {
+                dim3 block(64, 4), grid(div_up(w, 64), div_up(h, 4));
+                IS_LAUNCH(ctx, k_relabel_rect, grid, block, 0, labels.as<int>(), frame(), tls[c1].x, tls[c1].y, w, h, l1, l2);
+            }
             states[c1] = states[c2] == ST_FIRST ? ST_SECOND : ST_FIRST;
         } else {
+            if (stale[c1]) { IS_TRY(refresh_component(c1)); stale[c1] = 0; }
             Pt p1, p2;
             if (get_seam_tips(c1, c2, &p1, &p2)) IS_TRY(estimate_and_update(c1, c2, p1, p2));
             states[c1] = states[c2] == ST_FIRST ? (ST_INTERS | ST_SECOND) : (ST_INTERS | ST_FIRST);
         }
-        IS_TRY(refresh_component(c1));
+        stale[c1] = 1;
         if (states[c2] & ST_INTERS) IS_TRY(refresh_component(c2));   // geometry of a non-INTERS component is never read again
         edges.erase({c1, c2});
         edges.erase({c2, c1});
@@ -1306,24 +1343,59 @@ int PairSeam::label_dense() {
 // Run-based labelling (see k_row_changes).  *done stays false when the masks have too many runs for it to pay off.
 int PairSeam::label_runs(const Pt& iTl, const Pt& iBr, bool* done) {
     *done = false;
-    DevBuf cnt, cps_d, ovf;
-    IS_TRY(cnt.alloc(ctx, sizeof(int) * (size_t)uh));
-    IS_TRY(cps_d.alloc(ctx, sizeof(ChangePt) * (size_t)uh * ROW_CAP));
-    IS_TRY(ovf.alloc(ctx, sizeof(int)));
-    IS_CUDA(ctx, cudaMemsetAsync(ovf.p, 0, sizeof(int), ctx->stream));
-    IS_LAUNCH(ctx, k_row_changes, div_up(uh, 8), 256, 0, fr, ROW_CAP, cnt.as<int>(), cps_d.as<ChangePt>(), ovf.as<int>());
-    std::vector<int> cnt_h((size_t)uh);
-    std::vector<ChangePt> raw((size_t)uh * ROW_CAP);
-    int overflow = 0;
-    IS_CUDA(ctx, cudaMemcpyAsync(&overflow, ovf.p, sizeof(int), cudaMemcpyDeviceToHost, ctx->stream));
-    IS_TRY(download(ctx, cnt_h.data(), cnt.p, sizeof(int) * cnt_h.size()));
-    if (overflow) return IS_OK;                                             // noisy masks: dense path
-    IS_TRY(download(ctx, raw.data(), cps_d.p, sizeof(ChangePt) * raw.size()));
+    // toggles of both masks (own coordinates), one launch each, one download for all of it
+    const MaskView mv[2] = {fr.m1, fr.m2};
+    const size_t nrow[2] = {(size_t)mv[0].rows, (size_t)mv[1].rows};
+    const size_t ints = 1 + nrow[0] + nrow[1] + (nrow[0] + nrow[1]) * ROW_CAP;   // overflow flag | counts1 | counts2 | xs1 | xs2
+    DevBuf tg;
+    IS_TRY(tg.alloc(ctx, sizeof(int) * ints));
+    int* tg_d = tg.as<int>();
+    IS_CUDA(ctx, cudaMemsetAsync(tg_d, 0, sizeof(int), ctx->stream));
+    int* cnt_d[2] = {tg_d + 1, tg_d + 1 + nrow[0]};
+    int* xs_d[2] = {tg_d + 1 + nrow[0] + nrow[1], tg_d + 1 + nrow[0] + nrow[1] + nrow[0] * ROW_CAP};
+    for (int k = 0; k < 2; ++k) {
+        ctx->next_bytes = (double)mv[k].rows * mv[k].cols;
+        IS_LAUNCH(ctx, k_mask_row_toggles, div_up(mv[k].rows, 8), 256, 0, mv[k].p, mv[k].step, mv[k].rows, mv[k].cols, ROW_CAP, cnt_d[k], xs_d[k], tg_d);
+    }
+    // counts first (tiny), then only as many slots per row as the fullest row uses
+    const size_t head = 1 + nrow[0] + nrow[1];
+    std::vector<int> tg_h(head);
+    IS_TRY(download(ctx, tg_h.data(), tg_d, sizeof(int) * head));
+    if (tg_h[0]) return IS_OK;                                              // noisy masks: dense path
+    const int* cnt_h[2] = {tg_h.data() + 1, tg_h.data() + 1 + nrow[0]};
+    int slots = 1;
+    for (size_t r = 0; r < nrow[0] + nrow[1]; ++r) slots = std::max(slots, tg_h[1 + r]);
+    std::vector<int> xs_all((nrow[0] + nrow[1]) * (size_t)slots);
+    IS_TRY(download2d(ctx, xs_all.data(), sizeof(int) * (size_t)slots, xs_d[0], sizeof(int) * ROW_CAP, sizeof(int) * (size_t)slots, nrow[0] + nrow[1]));
+    const int* xs_h[2] = {xs_all.data(), xs_all.data() + nrow[0] * (size_t)slots};
+    // merge per union-frame row: class = (inside mask1) | (inside mask2) << 1, a change point wherever it differs from the pixel
+    // on its left (class 0 left of x = 0) -- the run-length form of [SEAM]:205-218
     std::vector<int> row_off((size_t)uh + 1, 0);
-    for (int y = 0; y < uh; ++y) row_off[y + 1] = row_off[y] + cnt_h[y];
+    std::vector<ChangePt> cps;
+    cps.reserve((size_t)uh * 6);
+    for (int y = 0; y < uh; ++y) {
+        int na[2] = {0, 0};
+        const int* xa[2] = {nullptr, nullptr};
+        for (int k = 0; k < 2; ++k) {
+            const int my = y - mv[k].oy;
+            if (my >= 0 && my < mv[k].rows) { na[k] = cnt_h[k][my]; xa[k] = xs_h[k] + (size_t)my * slots; }
+        }
+        // position i of mask k: xa[k][i] + ox for i < na[k], then (when the row ends inside the mask) the closing toggle at ox + cols
+        auto pos = [&](int k, int i) { return i < na[k] ? xa[k][i] + mv[k].ox : ((na[k] & 1) && i == na[k] ? mv[k].ox + mv[k].cols : INT_MAX); };
+        int i0 = 0, i1 = 0, st = 0, prev_cls = 0, emitted = 0;
+        for (;;) {
+            const int p0 = pos(0, i0), p1 = pos(1, i1);
+            const int x = std::min(p0, p1);
+            if (x >= uw) break;                     // INT_MAX (both exhausted) or a closing toggle on the frame's right edge
+            if (p0 == x) { st ^= 1; ++i0; }
+            if (p1 == x) { st ^= 2; ++i1; }
+            if (st != prev_cls) { cps.push_back(ChangePt{x, st}); prev_cls = st; ++emitted; }
+        }
+        if (emitted > ROW_CAP) return IS_OK;        // more runs than the window kernel's per-row table holds: dense path
+        row_off[y + 1] = row_off[y] + emitted;
+    }
     const int R = row_off[uh];
-    std::vector<ChangePt> cps((size_t)std::max(R, 1));
-    for (int y = 0; y < uh; ++y) std::copy(raw.begin() + (size_t)y * ROW_CAP, raw.begin() + (size_t)y * ROW_CAP + cnt_h[y], cps.begin() + row_off[y]);
+    if (cps.empty()) cps.push_back(ChangePt{0, 0});
     // union-find over the runs (run k = change point k with cls != 0, spanning [x, next change point or uw))
     std::vector<int> uf((size_t)R);
     for (int k = 0; k < R; ++k) uf[k] = k;
@@ -1355,17 +1427,29 @@ int PairSeam::label_runs(const Pt& iTl, const Pt& iBr, bool* done) {
     fr.ww = std::min(uw, iBr.x - unionTl.x + 1) - fr.wx;
     fr.wh = std::min(uh, iBr.y - unionTl.y + 1) - fr.wy;
     IS_TRY(labels.alloc(ctx, sizeof(int) * (size_t)fr.ww * fr.wh));
-    // labels of the change points in the device layout (row y at y * ROW_CAP); only the window's rows are needed
-    std::vector<int> lab_rows((size_t)fr.wh * ROW_CAP, 0);
-    for (int y = fr.wy; y < fr.wy + fr.wh; ++y)
-        std::copy(cp_label.begin() + row_off[y], cp_label.begin() + row_off[y + 1], lab_rows.begin() + (size_t)(y - fr.wy) * ROW_CAP);
-    DevBuf lab_d;
-    IS_TRY(lab_d.alloc(ctx, sizeof(int) * lab_rows.size()));
-    IS_TRY(upload(ctx, lab_d.p, lab_rows.data(), sizeof(int) * lab_rows.size()));
+    // change points + their labels of the window's rows in the window kernel's layout: per row a count, then ROW_CAP slots
+    const size_t wrows = (size_t)fr.wh;
+    size_t wcap = 1;                                           // slots per row: the fullest window row
+    for (int y = fr.wy; y < fr.wy + fr.wh; ++y) wcap = std::max(wcap, (size_t)(row_off[y + 1] - row_off[y]));
+    std::vector<int> tab(wrows + wrows * wcap * 3, 0);         // counts | ChangePt (x, cls) | labels
+    int* t_cnt = tab.data();
+    ChangePt* t_cps = reinterpret_cast<ChangePt*>(tab.data() + wrows);
+    int* t_lab = tab.data() + wrows + wrows * wcap * 2;
+    for (int y = fr.wy; y < fr.wy + fr.wh; ++y) {
+        const size_t r = (size_t)(y - fr.wy);
+        t_cnt[r] = row_off[y + 1] - row_off[y];
+        std::copy(cps.begin() + row_off[y], cps.begin() + row_off[y + 1], t_cps + r * wcap);
+        std::copy(cp_label.begin() + row_off[y], cp_label.begin() + row_off[y + 1], t_lab + r * wcap);
+    }
+    DevBuf tab_d;
+    IS_TRY(tab_d.alloc(ctx, sizeof(int) * tab.size()));
+    IS_TRY(upload(ctx, tab_d.p, tab.data(), sizeof(int) * tab.size()));
     {
         dim3 block(64, 4), grid(div_up(fr.ww, 64), div_up(fr.wh, 4));
-        IS_LAUNCH(ctx, k_label_window, grid, block, 0, fr, ROW_CAP, cnt.as<int>(), cps_d.as<ChangePt>(), lab_d.as<int>() - (size_t)fr.wy * ROW_CAP,
-                  labels.as<int>());
+        const int* d = tab_d.as<int>();
+        // the kernel indexes its tables with the frame row: bias the pointers by the window's first row
+        IS_LAUNCH(ctx, k_label_window, grid, block, 0, fr, (int)wcap, d - fr.wy, reinterpret_cast<const ChangePt*>(d + wrows) - (size_t)fr.wy * wcap,
+                  d + wrows + wrows * wcap * 2 - (size_t)fr.wy * wcap, labels.as<int>());
     }
     *done = true;
     return IS_OK;
@@ -1487,20 +1571,6 @@ struct PairJob {
     int status = IS_OK;
     bool needs_check = false, valid = true;
 };
-
-static int child_ctx(is_ctx* parent, size_t k, is_ctx** out) {
-    while (parent->children.size() <= k) {
-        is_ctx* c = new is_ctx();
-        c->device = parent->device;
-        if (cudaStreamCreateWithFlags(&c->own_stream, cudaStreamNonBlocking) != cudaSuccess) { delete c; return fail(parent, IS_ERR_CUDA, "cudaStreamCreate failed"); }
-        c->stream = c->own_stream;
-        c->pool = parent->pool;
-        for (int e = 0; e < 5; ++e) cudaEventCreateWithFlags(&c->ev[e], cudaEventDisableTiming);
-        parent->children.push_back(c);
-    }
-    *out = parent->children[k];
-    return IS_OK;
-}
 
 template <typename F>
 static void run_on_workers(is_ctx* parent, std::vector<is_ctx*>& workers, size_t njobs, F&& fn) {
