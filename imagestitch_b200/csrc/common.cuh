@@ -7,6 +7,7 @@
 #include <cstdint>
 #include <cstdio>
 #include <cstring>
+#include <map>
 #include <string>
 #include <vector>
 
@@ -37,6 +38,11 @@ struct is_ctx {
     std::vector<unsigned char> plan_cache;
     // worker contexts (own stream + staging) for the concurrent seam pairs; owned by this context
     std::vector<is_ctx*> children;
+    // Free blocks of this context's stream-ordered allocations, by size.  A step allocates the same few dozen sizes over and
+    // over; reusing them here skips the driver's allocator (a lock shared with every other stream) in steady state.  Safe
+    // because a block is only handed out again on the stream it was released on.
+    std::multimap<size_t, void*> block_cache;
+    size_t block_cache_bytes = 0;
     // events for stream_after(): reused round-robin per call sequence (sync_next is reset by the pipeline entry points)
     std::vector<cudaEvent_t> sync_events;
     size_t sync_next = 0;

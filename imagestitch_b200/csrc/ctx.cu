@@ -34,11 +34,29 @@ cudaEvent_t ktiming_begin(is_ctx* ctx, const char* name) {
     return r.e1;
 }
 
+constexpr size_t BLOCK_CACHE_LIMIT = (size_t)6 << 30;   // per context
+
 int DevBuf::alloc(is_ctx* c, size_t n) {
     release();
     ctx = c;
     if (n == 0) n = 16;
+    n = align_up(n, 256);
+    auto it = c->block_cache.lower_bound(n);
+    if (it != c->block_cache.end() && it->first <= n + n / 4 + 4096) {   // close enough in size: reuse
+        p = it->second;
+        bytes = it->first;
+        c->block_cache_bytes -= bytes;
+        c->block_cache.erase(it);
+        return IS_OK;
+    }
     cudaError_t e = cudaMallocAsync(&p, n, c->stream);
+    if (e != cudaSuccess && !c->block_cache.empty()) {   // out of memory with blocks parked here: give them back and retry
+        cudaGetLastError();
+        for (auto& kv : c->block_cache) cudaFreeAsync(kv.second, c->stream);
+        c->block_cache.clear();
+        c->block_cache_bytes = 0;
+        e = cudaMallocAsync(&p, n, c->stream);
+    }
     if (e != cudaSuccess) {
         p = nullptr;
         return fail(c, e == cudaErrorMemoryAllocation ? IS_ERR_NO_MEM : IS_ERR_CUDA, "cudaMallocAsync(%zu): %s", n,
@@ -49,7 +67,14 @@ int DevBuf::alloc(is_ctx* c, size_t n) {
 }
 
 void DevBuf::release() {
-    if (p && ctx) cudaFreeAsync(p, ctx->stream);
+    if (p && ctx) {
+        if (ctx->block_cache_bytes + bytes <= BLOCK_CACHE_LIMIT) {
+            ctx->block_cache.emplace(bytes, p);
+            ctx->block_cache_bytes += bytes;
+        } else {
+            cudaFreeAsync(p, ctx->stream);
+        }
+    }
     p = nullptr;
     bytes = 0;
 }
@@ -271,6 +296,9 @@ int is_ctx_destroy(is_ctx* ctx) {
     for (auto& r : ctx->krecs) { cudaEventDestroy(r.e0); cudaEventDestroy(r.e1); }
     for (auto e : ctx->kpool) cudaEventDestroy(e);
     for (auto e : ctx->sync_events) cudaEventDestroy(e);
+    for (auto& kv : ctx->block_cache) cudaFreeAsync(kv.second, ctx->stream);
+    ctx->block_cache.clear();
+    cudaStreamSynchronize(ctx->stream);
     if (ctx->pinned) cudaFreeHost(ctx->pinned);
     if (ctx->pinned_dl) cudaFreeHost(ctx->pinned_dl);
     cudaStreamDestroy(ctx->own_stream);
