@@ -14,3 +14,11 @@ for it in range(int(os.environ.get("ITERS", 2))):
     r = st.stitch(imgs, Ks, Rs, scale)
     torch.cuda.synchronize()
     print(it, st.timings_ms)
+if os.environ.get("KT"):      # per-kernel CUDA-event times of a few more steps
+    ctx.kernel_timing(True); ctx.kernel_timing_report()
+    k = int(os.environ.get("KT"))
+    for it in range(k):
+        st.stitch(imgs, Ks, Rs, scale)
+    rep = sorted(ctx.kernel_timing_report(), key=lambda r: -r["ms"])
+    for r in rep[:int(os.environ.get("KT_TOP", 12))]:
+        print(f'{r["name"]:50s} {r["launches"] / k:6.1f} launches/step {r["ms"] / k:8.4f} ms/step')
