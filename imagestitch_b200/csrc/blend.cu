@@ -55,6 +55,7 @@ struct Level0 {
     int rows, cols;        // fed image
     int top, left;         // border offsets
     int height, width;     // padded size
+    const uint8_t* summary; int sum_w;   // k_mask_summary of the mask (may be null)
 };
 
 __device__ __forceinline__ void l0_pixel(const Level0& L, int y, int x, int* v) {
@@ -447,18 +448,37 @@ struct L0Args {
     int2* bands; int* nbands;  // out: 64 x 8 bands left to k_blend_l0_bands (several contributing images, masks other than 0 / 255)
 };
 
-__global__ void k_mask_summary(const uint8_t* __restrict__ mask, size_t step, int rows, int cols, uint8_t* __restrict__ out, int sw) {
-    const int cx = blockIdx.x, cy = blockIdx.y;
-    const int tx = threadIdx.x & 63, ty = threadIdx.x >> 6;   // 64 x 4 threads
-    int any = 0;
-    const int x = cx * SUM_CW + tx;
-    if (x < cols)
-        for (int r = ty; r < SUM_CH; r += 4) {
-            const int y = cy * SUM_CH + r;
-            if (y < rows) any |= mask[(size_t)y * step + x];
+// One warp per 64 x 32 cell (lane = row of the cell, 64 bytes as four 16-byte loads when the mask allows it).
+// out[cell]: bit 0 = some pixel of the cell is non-zero, bit 1 = every pixel of the cell (inside the image) is 255.
+__global__ void __launch_bounds__(256) k_mask_summary(const uint8_t* __restrict__ mask, size_t step, int rows, int cols, uint8_t* __restrict__ out,
+                                                      int sw, int sh) {
+    const int cell = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+    if (cell >= sw * sh) return;
+    const int lane = threadIdx.x & 31;
+    const int cx = cell % sw, cy = cell / sw;
+    const int y = cy * SUM_CH + lane, x0 = cx * SUM_CW;
+    unsigned any = 0, all = 0xffffffffu;
+    if (y < rows) {
+        const uint8_t* p = mask + (size_t)y * step + x0;
+        if (x0 + SUM_CW <= cols && (reinterpret_cast<uintptr_t>(p) & 15) == 0) {
+            const uint4* q = reinterpret_cast<const uint4*>(p);
+#pragma unroll
+            for (int k = 0; k < SUM_CW / 16; ++k) {
+                const uint4 v = __ldg(q + k);
+                any |= v.x | v.y | v.z | v.w;
+                all &= v.x & v.y & v.z & v.w;
+            }
+        } else {
+            for (int x = x0; x < min(x0 + SUM_CW, cols); ++x) {
+                const unsigned m = p[x - x0];
+                any |= m;
+                if (m != 255u) all = 0u;
+            }
         }
-    any = __syncthreads_or(any);
-    if (threadIdx.x == 0) out[(size_t)cy * sw + cx] = any ? 1 : 0;
+    }
+    const bool w_any = __any_sync(0xffffffffu, any != 0);
+    const bool w_all = __all_sync(0xffffffffu, all == 0xffffffffu);
+    if (lane == 0) out[cell] = (uint8_t)((w_any ? 1 : 0) | (w_all ? 2 : 0));
 }
 
 // pyrUp is separable.  Horizontal sums of a level-1 row at three (border-mapped) columns: E = s[i-1] + 6 s[i] + s[i+1],
@@ -567,7 +587,7 @@ __global__ void __launch_bounds__(L0_THREADS, 3) k_blend_l0_tiled(L0Args A) {
                     const int ly_lo = max(y0t - I.Y0, 0), ly_hi = min(y0t + L0_TH, I.Y0 + I.rows) - I.Y0 - 1;
                     if (lx_lo <= lx_hi && ly_lo <= ly_hi) {
                         for (int cy = ly_lo / SUM_CH; cy <= ly_hi / SUM_CH; ++cy)
-                            for (int cx = lx_lo / SUM_CW; cx <= lx_hi / SUM_CW; ++cx) cand = cand || I.summary[(size_t)cy * I.sum_w + cx] != 0;
+                            for (int cx = lx_lo / SUM_CW; cx <= lx_hi / SUM_CW; ++cx) cand = cand || (I.summary[(size_t)cy * I.sum_w + cx] & 1) != 0;
                     }
                 }
                 const unsigned b = __ballot_sync(0xffffffffu, cand);
@@ -771,6 +791,42 @@ __global__ void __launch_bounds__(PD_TX* PD_TY) k_pyrdown_l0_tiled(Level0 L, int
     __shared__ float hw_f[PART != PD_IMAGE ? PD_IH : 1][PD_TX];
     const int tid = threadIdx.y * PD_TX + threadIdx.x;
     const int ox0 = blockIdx.x * PD_TX, oy0 = blockIdx.y * PD_TY;
+    if (PART == PD_WEIGHT && L.summary) {
+        // Weights only: a tile whose whole 5 x 5 support is uniform needs no arithmetic.  All 255 -> every weight is exactly
+        // 1.0f (255 * (1/255.f) = 1, row sums 16, (16 * 16) * (1/256) = 1; CV_16S: 256), all zero -> 0.  Uniformity comes from
+        // the occupancy map; tiles that touch the frame border (reflection) take the general path.
+        __shared__ int s_uni;
+        if (tid == 0) {
+            int uni = -1;                                           // -1: general path, 0 / 1: constant weight
+            const int fx0 = 2 * ox0 - 2, fx1 = 2 * ox0 + 2 * PD_TX, fy0 = 2 * oy0 - 2, fy1 = 2 * oy0 + 2 * PD_TY;   // support in frame coordinates
+            if (fx0 >= 0 && fy0 >= 0 && fx1 < L.width && fy1 < L.height) {
+                const int mx0 = fx0 - L.left, mx1 = fx1 - L.left, my0 = fy0 - L.top, my1 = fy1 - L.top;            // ... in mask coordinates
+                const int cx0 = max(mx0, 0), cx1 = min(mx1, L.cols - 1), cy0 = max(my0, 0), cy1 = min(my1, L.rows - 1);
+                if (cx0 > cx1 || cy0 > cy1) {
+                    uni = 0;                                        // entirely in the zero border
+                } else {
+                    unsigned orv = 0, andv = 3;
+                    for (int cy = cy0 / SUM_CH; cy <= cy1 / SUM_CH; ++cy)
+                        for (int cx = cx0 / SUM_CW; cx <= cx1 / SUM_CW; ++cx) { const unsigned v = L.summary[(size_t)cy * L.sum_w + cx]; orv |= v; andv &= v; }
+                    const bool inside = mx0 >= 0 && my0 >= 0 && mx1 < L.cols && my1 < L.rows;
+                    if (!(orv & 1)) uni = 0;
+                    else if (inside && (andv & 2)) uni = 1;
+                }
+            }
+            s_uni = uni;
+        }
+        __syncthreads();
+        const int uni = s_uni;
+        if (uni >= 0) {
+            const int x = ox0 + threadIdx.x, y = oy0 + threadIdx.y;
+            if (x < dw && y < dh) {
+                const size_t o = (size_t)y * dw + x;
+                if (WF) reinterpret_cast<float*>(w1)[o] = uni ? 1.0f : 0.f;
+                else reinterpret_cast<int16_t*>(w1)[o] = uni ? (int16_t)256 : (int16_t)0;
+            }
+            return;
+        }
+    }
     for (int e = tid; e < PD_IH * PD_IW; e += PD_TX * PD_TY) {
         const int r = e / PD_IW, c = e % PD_IW;
         const int y = reflect101(2 * oy0 - 2 + r, L.height), x = reflect101(2 * ox0 - 2 + c, L.width);
@@ -872,6 +928,7 @@ static Level0 level0_of(const FedImage& f) {
     L.mask = f.mask.ptr<uint8_t>(); L.mstep = f.mask.step;
     L.rows = f.img.rows; L.cols = f.img.cols;
     L.top = f.top; L.left = f.left; L.height = f.height; L.width = f.width;
+    L.summary = f.summary.as<uint8_t>(); L.sum_w = f.sum_w;
     return L;
 }
 
@@ -1018,14 +1075,15 @@ static int feed_pyramid(is_ctx* sctx, const is_blender* b, const FedImage& f, in
 static int feed_summary(is_ctx* ctx, const FedImage& f) {
     if (!f.summary.p) return IS_OK;
     ctx->next_bytes = (double)f.img.rows * f.img.cols;
-    IS_LAUNCH(ctx, k_mask_summary, dim3(f.sum_w, f.sum_h), 256, 0, f.mask.ptr<uint8_t>(), f.mask.step, f.img.rows, f.img.cols, f.summary.as<uint8_t>(), f.sum_w);
+    IS_LAUNCH(ctx, k_mask_summary, div_up(f.sum_w * f.sum_h, 8), 256, 0, f.mask.ptr<uint8_t>(), f.mask.step, f.img.rows, f.img.cols, f.summary.as<uint8_t>(),
+              f.sum_w, f.sum_h);
     return IS_OK;
 }
 
 int blender_feed_dev(is_blender* b, FedImage&& f) {
     IS_TRY(feed_prepare(b, f));
-    IS_TRY(feed_pyramid(b->ctx, b, f, PD_BOTH));
     IS_TRY(feed_summary(b->ctx, f));
+    IS_TRY(feed_pyramid(b->ctx, b, f, PD_BOTH));
     b->fed.push_back(std::move(f));
     return IS_OK;
 }
@@ -1048,8 +1106,8 @@ int blender_feed_image(is_blender* b, is_ctx* side, const DevMat& img, const Dev
 // weight pyramids + occupancy maps of everything fed with blender_feed_image(), on the blender's stream
 int blender_feed_weights(is_blender* b) {
     for (const FedImage& f : b->fed) {
-        IS_TRY(feed_pyramid(b->ctx, b, f, PD_WEIGHT));
         IS_TRY(feed_summary(b->ctx, f));
+        IS_TRY(feed_pyramid(b->ctx, b, f, PD_WEIGHT));
     }
     return IS_OK;
 }
