@@ -507,8 +507,11 @@ __device__ __forceinline__ void l0_hrow(const int16_t* a, const int16_t* b, cons
 // Persistent, warp-specialised pipeline: 8 consumer warps (one 64 x 8 pixel band of the tile each) + 1 producer warp.
 // The producer finds the images that can contribute to the next tile (occupancy maps), then issues the tile's TMA loads
 // into the free stage while the consumers still compute the previous one; full[] / empty[] mbarriers hand the two
-// stages back and forth, no __syncthreads in steady state.  Tiles with several contributing images, and bands whose
-// masks are not 0 / 255, are not computed here: they go on a device-side work list for k_blend_l0_bands.
+// stages back and forth, no __syncthreads in steady state.  A tile with several contributing images (along a seam) takes one
+// round per image: the first round stores every pixel (zeros where its mask is clear), the later rounds store the pixels
+// of their own mask.  That is exact as long as the masks are 0 / 255 and no pixel is claimed twice; a band (64 x 8) that
+// sees a fractional mask, or a pixel claimed by two images, goes on a device-side work list for k_blend_l0_bands, which
+// runs afterwards and overwrites it with the general arithmetic.
 constexpr int L0_STAGE_BYTES = L0_UALLOC + L0_MBYTES + L0_IBYTES + L0_UALLOC;   // collapsed level 1 | mask | image | Gaussian level 1 = 33792
 constexpr int L0_OFF_MASK = L0_UALLOC, L0_OFF_IMG = L0_UALLOC + L0_MBYTES, L0_OFF_G1 = L0_UALLOC + L0_MBYTES + L0_IBYTES;
 constexpr int L0_CONSUMERS = 256, L0_THREADS = L0_CONSUMERS + 32;
@@ -516,8 +519,8 @@ constexpr int L0_MAXCAND = 32;                                        // capacit
 
 struct L0Round {         // producer -> consumers, one per stage
     int x0t, y0t;        // tile origin (level-0 panorama coordinates)
-    int ncand;           // contributing images (0 or 1); -1: no more work
-    int flags;           // 8 / 16: the collapsed / the Gaussian level-1 neighbourhood lies inside its array (no border rule)
+    int ncand;           // image in this round (0 or 1); -1: no more work
+    int flags;           // 1: first round of the tile; 8 / 16: the collapsed / the Gaussian level-1 neighbourhood lies inside its array
     int lx0;             // tile origin in image coordinates
     int ox, oy;          // level-1 origin of the Gaussian tile inside the image's frame
     int w1, h1;          // level-1 frame dims
@@ -598,47 +601,51 @@ __global__ void __launch_bounds__(L0_THREADS, 3) k_blend_l0_tiled(L0Args A) {
                 count += __popc(b);
             }
             __syncwarp();
-            if (count > 1) {   // several contributing images: the whole tile goes to the general kernel, nothing is loaded
+            if (count > L0_MAXCAND) {   // more contributing images than the list holds: the whole tile goes to the general kernel
                 if (lane < L0_TH / 8) {
                     const int pos = atomicAdd(A.nbands, 1);
                     A.bands[pos] = make_int2(x0t, y0t + 8 * lane);
                 }
                 continue;
             }
-            if (uses[stage] > 0) mbar_wait(&empty[stage], (uint32_t)((uses[stage] - 1) & 1));   // the consumers are done with the stage
-            if (lane == 0) {
-                unsigned char* st = sm + stage * L0_STAGE_BYTES;
-                L0Round& R = info[stage];
-                R.x0t = x0t; R.y0t = y0t; R.ncand = count;
-                int flags = 0;
-                {
-                    const int ox = (x0t >> 1) - 1, oy = (y0t >> 1) - 1;
-                    if (ox >= 0 && oy >= 0 && ox + L0_UW <= A.uw && oy + L0_UH <= A.uh) flags |= 8;
+            // one round through a stage per contributing image (a tile nothing contributes to takes one round without loads)
+            const int rounds = max(1, count);
+            for (int r = 0; r < rounds; ++r) {
+                if (uses[stage] > 0) mbar_wait(&empty[stage], (uint32_t)((uses[stage] - 1) & 1));   // the consumers are done with the stage
+                if (lane == 0) {
+                    unsigned char* st = sm + stage * L0_STAGE_BYTES;
+                    L0Round& R = info[stage];
+                    R.x0t = x0t; R.y0t = y0t; R.ncand = count > 0 ? 1 : 0;
+                    int flags = r == 0 ? 1 : 0;
+                    {
+                        const int ox = (x0t >> 1) - 1, oy = (y0t >> 1) - 1;
+                        if (ox >= 0 && oy >= 0 && ox + L0_UW <= A.uw && oy + L0_UH <= A.uh) flags |= 8;
+                    }
+                    if (count == 0) {
+                        R.flags = flags;
+                        mbar_arrive(&full[stage]);
+                    } else {
+                        const int idx = s_list[r];
+                        const L0Img I = A.imgs[idx];
+                        R.lx0 = x0t - I.X0;
+                        R.ox = ((x0t - I.fx) >> 1) - 1;
+                        R.oy = ((y0t - I.fy) >> 1) - 1;
+                        R.w1 = I.w1; R.h1 = I.h1;
+                        if (R.ox >= 0 && R.oy >= 0 && R.ox + L0_UW <= I.w1 && R.oy + L0_UH <= I.h1) flags |= 16;
+                        R.flags = flags;
+                        mbar_expect_tx(&full[stage], L0_UBYTES + L0_MBYTES + L0_IBYTES + L0_UBYTES);   // also publishes R (release)
+                        tensormap_acquire(&A.maps[0]);
+                        tma_load_2d(st, &A.maps[0], ((6 * ((x0t >> 1) - 1)) & ~15) >> 1, (y0t >> 1) - 1, &full[stage]);
+                        const CUtensorMap* m = A.maps + 1 + 3 * idx;
+                        tensormap_acquire(m); tensormap_acquire(m + 1); tensormap_acquire(m + 2);
+                        tma_load_2d(st + L0_OFF_MASK, m, (x0t - I.X0) & ~15, y0t - I.Y0, &full[stage]);
+                        tma_load_2d(st + L0_OFF_IMG, m + 1, (3 * (x0t - I.X0)) & ~15, y0t - I.Y0, &full[stage]);
+                        tma_load_2d(st + L0_OFF_G1, m + 2, ((6 * R.ox) & ~15) >> 1, R.oy, &full[stage]);
+                    }
                 }
-                if (count == 0) {
-                    R.flags = flags;
-                    mbar_arrive(&full[stage]);
-                } else {
-                    const int idx = s_list[0];
-                    const L0Img I = A.imgs[idx];
-                    R.lx0 = x0t - I.X0;
-                    R.ox = ((x0t - I.fx) >> 1) - 1;
-                    R.oy = ((y0t - I.fy) >> 1) - 1;
-                    R.w1 = I.w1; R.h1 = I.h1;
-                    if (R.ox >= 0 && R.oy >= 0 && R.ox + L0_UW <= I.w1 && R.oy + L0_UH <= I.h1) flags |= 16;
-                    R.flags = flags;
-                    mbar_expect_tx(&full[stage], L0_UBYTES + L0_MBYTES + L0_IBYTES + L0_UBYTES);   // also publishes R (release)
-                    tensormap_acquire(&A.maps[0]);
-                    tma_load_2d(st, &A.maps[0], ((6 * ((x0t >> 1) - 1)) & ~15) >> 1, (y0t >> 1) - 1, &full[stage]);
-                    const CUtensorMap* m = A.maps + 1 + 3 * idx;
-                    tensormap_acquire(m); tensormap_acquire(m + 1); tensormap_acquire(m + 2);
-                    tma_load_2d(st + L0_OFF_MASK, m, (x0t - I.X0) & ~15, y0t - I.Y0, &full[stage]);
-                    tma_load_2d(st + L0_OFF_IMG, m + 1, (3 * (x0t - I.X0)) & ~15, y0t - I.Y0, &full[stage]);
-                    tma_load_2d(st + L0_OFF_G1, m + 2, ((6 * R.ox) & ~15) >> 1, R.oy, &full[stage]);
-                }
+                uses[stage]++;
+                stage ^= 1;
             }
-            uses[stage]++;
-            stage ^= 1;
             __syncwarp();   // lane 0 is done with s_list before the next tile's list is written
         }
         if (uses[stage] > 0) mbar_wait(&empty[stage], (uint32_t)((uses[stage] - 1) & 1));
@@ -652,6 +659,8 @@ __global__ void __launch_bounds__(L0_THREADS, 3) k_blend_l0_tiled(L0Args A) {
     const int nbr_off = 3 * tx + L0_QN * ty * L0_UROW;        // level-1 neighbourhood of a quad column: fixed offsets from here
     int fuse[2] = {0, 0};
     int stage = 0;
+    uint32_t claimed[L0_QN] = {};   // per quad: the mask bytes of the pixels an earlier round of this tile has stored
+    bool dead = false;              // this warp's band is on the work list: the remaining rounds of the tile skip it
     for (;;) {
         mbar_wait(&full[stage], (uint32_t)(fuse[stage] & 1));
         fuse[stage]++;
@@ -659,6 +668,12 @@ __global__ void __launch_bounds__(L0_THREADS, 3) k_blend_l0_tiled(L0Args A) {
         const int ncand = R.ncand;
         if (ncand < 0) break;
         const int flags = R.flags;
+        const bool first = (flags & 1) != 0;
+        if (first) {
+            dead = false;
+#pragma unroll
+            for (int q = 0; q < L0_QN; ++q) claimed[q] = 0;
+        }
         const int x0t = R.x0t, y0t = R.y0t;
         unsigned char* st = sm + stage * L0_STAGE_BYTES;
         const int x = x0t + 2 * tx;
@@ -694,13 +709,25 @@ __global__ void __launch_bounds__(L0_THREADS, 3) k_blend_l0_tiled(L0Args A) {
                 // every byte 0 or 255?  (b & 0x7f) == 0x7f * (b >> 7) per byte
                 binary = binary && ((mw[q] & 0x7f7f7f7fu) == ((mw[q] >> 7) & 0x01010101u) * 0x7fu);
             }
-            if (!__all_sync(0xffffffffu, binary)) {
-                // fractional weights: this warp's band goes to the general kernel
+            bool clash = false;                              // a pixel of this round's mask already stored by an earlier round
+            uint32_t anyset = 0;
+#pragma unroll
+            for (int q = 0; q < L0_QN; ++q) { clash = clash || (mw[q] & claimed[q]) != 0; anyset |= mw[q]; }
+            const bool ok = __all_sync(0xffffffffu, binary && !clash);
+            if (dead) {
+                // on the work list already
+            } else if (!ok) {
+                // fractional weights, or two images claim a pixel: this warp's band goes to the general kernel
+                dead = true;
                 if (lane == 0) {
                     const int pos = atomicAdd(A.nbands, 1);
                     A.bands[pos] = make_int2(x0t, y);
                 }
+            } else if (!first && __all_sync(0xffffffffu, anyset == 0)) {
+                // a later round with nothing for this band
             } else {
+#pragma unroll
+                for (int q = 0; q < L0_QN; ++q) claimed[q] |= mw[q];
                 // weight 1.0f (= 255 * (1/255.f)) where the mask is set: the accumulator is the Laplacian itself and
                 // short(d / (1 + 1e-5f)) = d - sign(d).  CV_16S: weight 256, accumulator (d * 256) >> 8 = d, normalised (d << 8) / 257.
                 const int oxg = R.ox, oxc = (x0t >> 1) - 1;
@@ -741,20 +768,25 @@ __global__ void __launch_bounds__(L0_THREADS, 3) k_blend_l0_tiled(L0Args A) {
                             const uint32_t mm = (mq >> (16 * r)) & 0xffffu;   // the two mask bytes of this row (0 or 255 each)
                             int16_t* o = reinterpret_cast<int16_t*>(orow + (size_t)r * A.dstep);
                             uint8_t* mo = mrow + (size_t)r * A.mstep;
-                            if (va && vb && ((reinterpret_cast<uintptr_t>(o) & 3) == 0)) {
-                                uint32_t* o32 = reinterpret_cast<uint32_t*>(o);
-                                o32[0] = (uint32_t)(uint16_t)v[0][0] | ((uint32_t)(uint16_t)v[0][1] << 16);
-                                o32[1] = (uint32_t)(uint16_t)v[0][2] | ((uint32_t)(uint16_t)v[1][0] << 16);
-                                o32[2] = (uint32_t)(uint16_t)v[1][1] | ((uint32_t)(uint16_t)v[1][2] << 16);
+                            if (!first) {   // a later round of the tile: only the pixels of this image's mask
+                                if (va && (mm & 0xffu)) { o[0] = (int16_t)v[0][0]; o[1] = (int16_t)v[0][1]; o[2] = (int16_t)v[0][2]; mo[0] = 255; }
+                                if (vb && (mm >> 8)) { o[3] = (int16_t)v[1][0]; o[4] = (int16_t)v[1][1]; o[5] = (int16_t)v[1][2]; mo[1] = 255; }
                             } else {
-                                if (va) { o[0] = (int16_t)v[0][0]; o[1] = (int16_t)v[0][1]; o[2] = (int16_t)v[0][2]; }
-                                if (vb) { o[3] = (int16_t)v[1][0]; o[4] = (int16_t)v[1][1]; o[5] = (int16_t)v[1][2]; }
-                            }
-                            if (va && vb && ((reinterpret_cast<uintptr_t>(mo) & 1) == 0)) {
-                                *reinterpret_cast<uint16_t*>(mo) = (uint16_t)mm;
-                            } else {
-                                if (va) mo[0] = (uint8_t)(mm & 255u);
-                                if (vb) mo[1] = (uint8_t)(mm >> 8);
+                                if (va && vb && ((reinterpret_cast<uintptr_t>(o) & 3) == 0)) {
+                                    uint32_t* o32 = reinterpret_cast<uint32_t*>(o);
+                                    o32[0] = (uint32_t)(uint16_t)v[0][0] | ((uint32_t)(uint16_t)v[0][1] << 16);
+                                    o32[1] = (uint32_t)(uint16_t)v[0][2] | ((uint32_t)(uint16_t)v[1][0] << 16);
+                                    o32[2] = (uint32_t)(uint16_t)v[1][1] | ((uint32_t)(uint16_t)v[1][2] << 16);
+                                } else {
+                                    if (va) { o[0] = (int16_t)v[0][0]; o[1] = (int16_t)v[0][1]; o[2] = (int16_t)v[0][2]; }
+                                    if (vb) { o[3] = (int16_t)v[1][0]; o[4] = (int16_t)v[1][1]; o[5] = (int16_t)v[1][2]; }
+                                }
+                                if (va && vb && ((reinterpret_cast<uintptr_t>(mo) & 1) == 0)) {
+                                    *reinterpret_cast<uint16_t*>(mo) = (uint16_t)mm;
+                                } else {
+                                    if (va) mo[0] = (uint8_t)(mm & 255u);
+                                    if (vb) mo[1] = (uint8_t)(mm >> 8);
+                                }
                             }
                         }
                     }
