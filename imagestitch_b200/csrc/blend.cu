@@ -135,6 +135,44 @@ __global__ void k_pyrdown(const int16_t* __restrict__ g, const void* __restrict_
     }
 }
 
+// Weight levels >= 2 of all fed images in one launch per level (blockIdx.z = image): the levels are small, and thirty
+// dependent launches cost more than their arithmetic.  Same float association order as k_pyrdown.
+struct WeightLevel { const void* w_in; void* w_out; int sh, sw, dh, dw; };
+
+template <bool WF>
+__global__ void k_pyrdown_weights_batch(const WeightLevel* __restrict__ table) {
+    const WeightLevel T = table[blockIdx.z];
+    const int x = blockIdx.x * blockDim.x + threadIdx.x;
+    const int y = blockIdx.y * blockDim.y + threadIdx.y;
+    if (x >= T.dw || y >= T.dh) return;
+    int xs[5], ys[5];
+#pragma unroll
+    for (int a = 0; a < 5; ++a) { xs[a] = reflect101(2 * x + a - 2, T.sw); ys[a] = reflect101(2 * y + a - 2, T.sh); }
+    const int kk[5] = {1, 4, 6, 4, 1};
+    float rowf[5];
+    int wacc = 0;
+#pragma unroll
+    for (int a = 0; a < 5; ++a) {
+        float wf[5];
+        int ws = 0;
+#pragma unroll
+        for (int b = 0; b < 5; ++b) {
+            const size_t i = (size_t)ys[a] * T.sw + xs[b];
+            if (WF) wf[b] = reinterpret_cast<const float*>(T.w_in)[i];
+            else ws += kk[b] * reinterpret_cast<const int16_t*>(T.w_in)[i];
+        }
+        if (WF) rowf[a] = __fadd_rn(__fadd_rn(__fadd_rn(__fmul_rn(wf[2], 6.f), __fmul_rn(__fadd_rn(wf[1], wf[3]), 4.f)), wf[0]), wf[4]);
+        else wacc += kk[a] * ws;
+    }
+    const size_t o = (size_t)y * T.dw + x;
+    if (WF) {
+        const float v = __fadd_rn(__fadd_rn(__fadd_rn(__fmul_rn(rowf[2], 6.f), __fmul_rn(__fadd_rn(rowf[1], rowf[3]), 4.f)), rowf[0]), rowf[4]);
+        reinterpret_cast<float*>(T.w_out)[o] = __fmul_rn(v, 1.f / 256.f);
+    } else {
+        reinterpret_cast<int16_t*>(T.w_out)[o] = (int16_t)sat16((wacc + 128) >> 8);
+    }
+}
+
 // ---- pyrUp evaluated at one destination pixel ------------------------------------------------------------------
 // per axis: even 2i: s[i-1] + 6 s[i] + s[i+1], odd 2i+1: 4 (s[i] + s[i+1]); s[-1] -> s[1], s[n] -> s[n-1]; (t + 32) >> 6
 struct UpTaps { int i[3]; int w[3]; };
@@ -1137,9 +1175,46 @@ int blender_feed_image(is_blender* b, is_ctx* side, const DevMat& img, const Dev
 
 // weight pyramids + occupancy maps of everything fed with blender_feed_image(), on the blender's stream
 int blender_feed_weights(is_blender* b) {
+    is_ctx* ctx = b->ctx;
+    const int nb = b->num_bands, n = (int)b->fed.size();
+    const bool wf = b->weight_type == IS_WEIGHT_32F;
+    const size_t wsz = wf ? sizeof(float) : sizeof(int16_t);
     for (const FedImage& f : b->fed) {
-        IS_TRY(feed_summary(b->ctx, f));
-        IS_TRY(feed_pyramid(b->ctx, b, f, PD_WEIGHT));
+        IS_TRY(feed_summary(ctx, f));
+        if (nb >= 1) {   // level 1 from the mask (tiled kernel, constants for uniform tiles)
+            const int dh = (f.height + 1) / 2, dw = (f.width + 1) / 2;
+            ctx->next_bytes = (double)f.img.rows * f.img.cols + (double)dh * dw * (double)wsz;
+            Level0 L = level0_of(f);
+            dim3 tb(PD_TX, PD_TY), tg(div_up(dw, PD_TX), div_up(dh, PD_TY));
+            if (wf) IS_LAUNCH(ctx, (k_pyrdown_l0_tiled<true, PD_WEIGHT>), tg, tb, 0, L, f.g[1].as<int16_t>(), f.w[1].p, dh, dw);
+            else IS_LAUNCH(ctx, (k_pyrdown_l0_tiled<false, PD_WEIGHT>), tg, tb, 0, L, f.g[1].as<int16_t>(), f.w[1].p, dh, dw);
+        }
+    }
+    if (nb < 2 || n == 0) return IS_OK;
+    // levels 2..nb: one launch per level over all images
+    std::vector<WeightLevel> host((size_t)n * (nb - 1));
+    std::vector<int> gx(nb + 1, 0), gy(nb + 1, 0);
+    std::vector<double> bytes(nb + 1, 0.);
+    for (int i = 0; i < n; ++i) {
+        const FedImage& f = b->fed[i];
+        int sh = (f.height + 1) / 2, sw = (f.width + 1) / 2;
+        for (int k = 2; k <= nb; ++k) {
+            const int dh = (sh + 1) / 2, dw = (sw + 1) / 2;
+            host[(size_t)(k - 2) * n + i] = WeightLevel{f.w[k - 1].p, f.w[k].p, sh, sw, dh, dw};
+            gx[k] = std::max(gx[k], div_up(dw, 32)); gy[k] = std::max(gy[k], div_up(dh, 8));
+            bytes[k] += ((double)sh * sw + (double)dh * dw) * (double)wsz;
+            sh = dh; sw = dw;
+        }
+    }
+    DevBuf table;
+    IS_TRY(table.alloc(ctx, sizeof(WeightLevel) * host.size()));
+    IS_TRY(upload(ctx, table.p, host.data(), sizeof(WeightLevel) * host.size()));
+    for (int k = 2; k <= nb; ++k) {
+        dim3 block(32, 8), grid(gx[k], gy[k], n);
+        ctx->next_bytes = bytes[k];
+        const WeightLevel* t = table.as<WeightLevel>() + (size_t)(k - 2) * n;
+        if (wf) IS_LAUNCH(ctx, k_pyrdown_weights_batch<true>, grid, block, 0, t);
+        else IS_LAUNCH(ctx, k_pyrdown_weights_batch<false>, grid, block, 0, t);
     }
     return IS_OK;
 }

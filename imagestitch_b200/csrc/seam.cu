@@ -889,16 +889,15 @@ int PairSeam::ccl(const uint8_t* klass, int kmask, int w, int h, int* parent_out
 int PairSeam::collect_roots(const int* parent_d, const uint8_t* klass_d, size_t n, std::vector<std::pair<int, int>>* roots) {
     int cap = 4096;
     while (true) {
-        DevBuf out, cnt;
-        IS_TRY(out.alloc(ctx, sizeof(int) * 2 * (size_t)cap));
-        IS_TRY(cnt.alloc(ctx, sizeof(int)));
-        IS_CUDA(ctx, cudaMemsetAsync(cnt.p, 0, sizeof(int), ctx->stream));
-        IS_LAUNCH(ctx, k_collect_roots, (unsigned)((n + 255) / 256), 256, 0, parent_d, klass_d, n, out.as<int>(), cnt.as<int>(), cap);
-        int count = 0;
-        IS_TRY(download(ctx, &count, cnt.p, sizeof(int)));
-        if (count > cap) { cap = count; continue; }
-        std::vector<int> h(2 * (size_t)count);
+        DevBuf out;
+        IS_TRY(out.alloc(ctx, sizeof(int) * (2 * (size_t)cap + 1)));   // [2 cap] = number of roots found: one download for both
+        int* cnt = out.as<int>() + 2 * (size_t)cap;
+        IS_CUDA(ctx, cudaMemsetAsync(cnt, 0, sizeof(int), ctx->stream));
+        IS_LAUNCH(ctx, k_collect_roots, (unsigned)((n + 255) / 256), 256, 0, parent_d, klass_d, n, out.as<int>(), cnt, cap);
+        std::vector<int> h(2 * (size_t)cap + 1);
         IS_TRY(download(ctx, h.data(), out.p, sizeof(int) * h.size()));
+        const int count = h[2 * (size_t)cap];
+        if (count > cap) { cap = count; continue; }
         roots->resize(count);
         for (int k = 0; k < count; ++k) (*roots)[k] = {h[2 * k], h[2 * k + 1]};
         std::sort(roots->begin(), roots->end());
@@ -1040,7 +1039,7 @@ int PairSeam::estimate_and_update(int c1, int c2, Pt p1, Pt p2) {
     else if (src.y > dst.y) { std::swap(src, dst); swapped = true; }
     const int lanes = horizontal ? rh : rw, steps = horizontal ? rw : rh;
 
-    DevBuf P, Q, control, seam_lane, reached;
+    DevBuf P, Q, control, seam_lane;
     int lpt = lanes <= 4096 ? 4 : (lanes <= 8192 ? 8 : 16);
     if (const char* e = getenv("IS_DP_LPT")) {             // tuning knob (4, 8 or 16 lanes per thread)
         const int v = atoi(e);
@@ -1052,8 +1051,7 @@ int PairSeam::estimate_and_update(int c1, int c2, Pt p1, Pt p2) {
     IS_TRY(P.alloc(ctx, sizeof(float) * (size_t)pitch * steps + 64));
     IS_TRY(Q.alloc(ctx, sizeof(float) * (size_t)pitch * steps + 64));
     IS_TRY(control.alloc(ctx, (size_t)pitch * steps + 64));
-    IS_TRY(seam_lane.alloc(ctx, sizeof(int) * (size_t)steps));
-    IS_TRY(reached.alloc(ctx, sizeof(int)));
+    IS_TRY(seam_lane.alloc(ctx, sizeof(int) * ((size_t)steps + 1)));   // [steps] = "destination reached" flag: one download for both
     const int dx1 = unionTl.x - tl1_.x, dy1 = unionTl.y - tl1_.y, dx2 = unionTl.x - tl2_.x, dy2 = unionTl.y - tl2_.y;
     {
         dim3 block(64, 4), grid(div_up(pitch, 64), div_up(steps, 4));
@@ -1070,7 +1068,7 @@ int PairSeam::estimate_and_update(int c1, int c2, Pt p1, Pt p2) {
     A.lanes = lanes; A.pitch = pitch; A.steps = steps;
     A.s0 = horizontal ? src.x : src.y; A.lane0 = horizontal ? src.y : src.x;
     A.s1 = horizontal ? dst.x : dst.y; A.lane1 = horizontal ? dst.y : dst.x;
-    A.seam_lane = seam_lane.as<int>(); A.reached = reached.as<int>();
+    A.seam_lane = seam_lane.as<int>(); A.reached = seam_lane.as<int>() + steps;
     {
         const size_t row_pair = 2 * sizeof(float) * (size_t)pitch;            // one row of P + one of Q
         const size_t budget = 192 * 1024;
@@ -1107,12 +1105,12 @@ int PairSeam::estimate_and_update(int c1, int c2, Pt p1, Pt p2) {
     IS_TRY(klass.alloc(ctx, (size_t)rw * rh));
     IS_TRY(sub_parent.alloc(ctx, sizeof(int) * (size_t)rw * rh));
     DbgTimer dbg;
-    int ok = 0;
-    IS_TRY(download(ctx, &ok, reached.p, sizeof(int)));
+    std::vector<int> lane_all((size_t)steps + 1);
+    IS_TRY(download(ctx, lane_all.data(), seam_lane.p, sizeof(int) * lane_all.size()));
+    const int ok = lane_all[steps];
     dbg.lap("  cost+dp (sync)");
     if (!ok) return IS_OK;                                             // [SEAM]:918-919: estimateSeam returned false
-    std::vector<int> lane_h(nseam);
-    IS_TRY(download(ctx, lane_h.data(), seam_lane.p, sizeof(int) * (size_t)nseam));
+    const int* lane_h = lane_all.data();
     std::vector<Pt> seam(nseam);   // union-frame coordinates, ordered p1 -> p2 ([SEAM]:949-954)
     for (int i = 0; i < nseam; ++i) {
         int step = A.s0 + i, lane = lane_h[i];
@@ -1153,19 +1151,21 @@ int PairSeam::estimate_and_update(int c1, int c2, Pt p1, Pt p2) {
     const int nc = (int)cont.size();
     std::vector<int2> cpts(nc);
     for (int i = 0; i < nc; ++i) cpts[i] = make_int2(cont[i].x - rx, cont[i].y - ry);
-    DevBuf cpts_d, g8_d, gs_d;
+    DevBuf cpts_d, gath_d;                                   // gathered neighbourhoods: 8 ints per contour pixel, then 3 per seam pixel
     IS_TRY(cpts_d.alloc(ctx, sizeof(int2) * (size_t)std::max(nc, 1)));
-    IS_TRY(g8_d.alloc(ctx, sizeof(int) * 8 * (size_t)std::max(nc, 1)));
-    IS_TRY(gs_d.alloc(ctx, sizeof(int) * 3 * (size_t)nseam));
-    std::vector<int> g8(8 * (size_t)nc), gs(3 * (size_t)nseam);
+    std::vector<int> gath(8 * (size_t)nc + 3 * (size_t)nseam);
+    IS_TRY(gath_d.alloc(ctx, sizeof(int) * gath.size()));
+    int* g8_dp = gath_d.as<int>();
+    int* gs_dp = gath_d.as<int>() + 8 * (size_t)nc;
     if (nc) {
         IS_TRY(upload(ctx, cpts_d.p, cpts.data(), sizeof(int2) * (size_t)nc));
-        IS_LAUNCH(ctx, k_uls_gather8, div_up(nc, 128), 128, 0, klass.as<uint8_t>(), sub_parent.as<int>(), rw, rh, cpts_d.as<int2>(), nc, g8_d.as<int>());
+        IS_LAUNCH(ctx, k_uls_gather8, div_up(nc, 128), 128, 0, klass.as<uint8_t>(), sub_parent.as<int>(), rw, rh, cpts_d.as<int2>(), nc, g8_dp);
     }
     IS_LAUNCH(ctx, k_uls_gather_seam, div_up(nseam, 128), 128, 0, klass.as<uint8_t>(), sub_parent.as<int>(), rw, rh, seam_lane.as<int>(), nseam,
-              A.s0, horizontal ? 1 : 0, gs_d.as<int>());
-    if (nc) IS_TRY(download(ctx, g8.data(), g8_d.p, sizeof(int) * g8.size()));
-    IS_TRY(download(ctx, gs.data(), gs_d.p, sizeof(int) * gs.size()));
+              A.s0, horizontal ? 1 : 0, gs_dp);
+    IS_TRY(download(ctx, gath.data(), gath_d.p, sizeof(int) * gath.size()));   // one round trip for both
+    const int* g8 = gath.data();
+    const int* gs = gath.data() + 8 * (size_t)nc;
     dbg.lap("  uls device part (sync)");
 
     // ---- sequential part on the host ([SEAM]:983-1034).  `painted` holds the current mask value of every
