@@ -78,7 +78,7 @@ def build(force: bool = False, verbose: bool = False) -> str:
             for f in [ex.submit(_compile, s, o, verbose) for s, o in jobs]:
                 f.result()
     if jobs or not os.path.exists(LIB):
-        cmd = [nvcc()] + _host_compiler_flags() + ["-shared", "-o", LIB] + objs + ["-lcuda"]
+        cmd = [nvcc()] + _host_compiler_flags() + ["-shared", "-o", LIB] + objs
         r = subprocess.run(cmd, capture_output=True, text=True)
         if r.returncode != 0:
             raise RuntimeError(f"link failed:\n{r.stdout}\n{r.stderr}")

@@ -22,6 +22,7 @@ COST_COLOR, COST_COLOR_GRAD = 0, 1
 WEIGHT_32F, WEIGHT_16S = 5, 3
 FEED_COPY, FEED_BORROW = 0, 1
 SEAM_NONE, SEAM_DP = 0, 1
+EXPOSURE_NONE, EXPOSURE_GAIN = 0, 1
 
 
 class Mat(C.Structure):
@@ -56,7 +57,7 @@ class RegistrationHooks(C.Structure):
 
 class PipelineConfig(C.Structure):
     _fields_ = [("projection", C.c_int), ("seam", C.c_int), ("seam_cost", C.c_int), ("num_bands", C.c_int),
-                ("weight_type", C.c_int), ("scale", C.c_float)]
+                ("weight_type", C.c_int), ("scale", C.c_float), ("exposure", C.c_int)]
 
 
 # every symbol include/imagestitch.h declares: name -> (restype, argtypes)
@@ -100,8 +101,11 @@ SYMBOLS = {
     "is_blender_blend": (C.c_int, [C.c_void_p, _P(Mat), _P(Mat)]),
     "is_linear_blend_size": (C.c_int, [Size, Size, Point, Point, _P(Size)]),
     "is_linear_blend_pair": (C.c_int, [C.c_void_p, _P(Mat), _P(Mat), Point, Point, _P(Mat), _P(C.c_int)]),
+    "is_gain_feed": (C.c_int, [C.c_void_p, C.c_int, _P(Point), _P(Mat), _P(Mat), _P(C.c_double)]),
+    "is_gain_apply": (C.c_int, [C.c_void_p, _P(Mat), C.c_double]),
     "is_pipeline_plan": (C.c_int, [C.c_void_p, C.c_int, _P(Size), _P(Camera), _P(PipelineConfig), _P(Point), _P(Size), _P(Rect)]),
     "is_pipeline_run": (C.c_int, [C.c_void_p, C.c_int, _P(Mat), _P(Camera), _P(RegistrationHooks), _P(PipelineConfig), _P(Mat), _P(Mat), _P(Mat)]),
+    "is_pipeline_last_gains": (C.c_int, [C.c_void_p, C.c_int, _P(C.c_double)]),
     "is_pipeline_last_timings": (C.c_int, [C.c_void_p, _P(C.c_float)]),
 }
 

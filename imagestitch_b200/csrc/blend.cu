@@ -1225,8 +1225,20 @@ static int make_map_2d(is_ctx* ctx, CUtensorMap* m, CUtensorMapDataType dt, cons
     const cuuint64_t strides[1] = {stride_bytes};
     const cuuint32_t box[2] = {box_inner, box_rows};
     const cuuint32_t estr[2] = {1, 1};
-    const CUresult r = cuTensorMapEncodeTiled(m, dt, 2, const_cast<void*>(base), dims, strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
-                                              CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_128B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    // the driver entry point is looked up at run time: the library has no link-time dependency on libcuda.so.1, so it loads
+    // (and exports its symbols) on a box without a GPU driver
+    typedef CUresult (*encode_fn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*, const cuuint32_t*,
+                                  const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+    static encode_fn encode = nullptr;
+    if (!encode) {
+        void* f = nullptr;
+        cudaDriverEntryPointQueryResult q = cudaDriverEntryPointSymbolNotFound;
+        const cudaError_t e = cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &f, cudaEnableDefault, &q);
+        if (e != cudaSuccess || q != cudaDriverEntryPointSuccess || !f) return fail(ctx, IS_ERR_CUDA, "cuTensorMapEncodeTiled is not available from this driver");
+        encode = reinterpret_cast<encode_fn>(f);
+    }
+    const CUresult r = encode(m, dt, 2, const_cast<void*>(base), dims, strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE,
+                              CU_TENSOR_MAP_L2_PROMOTION_L2_128B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
     if (r != CUDA_SUCCESS) return fail(ctx, IS_ERR_CUDA, "cuTensorMapEncodeTiled failed (%d)", (int)r);
     return IS_OK;
 }

@@ -46,6 +46,7 @@ struct is_ctx {
     // events for stream_after(): reused round-robin per call sequence (sync_next is reset by the pipeline entry points)
     std::vector<cudaEvent_t> sync_events;
     size_t sync_next = 0;
+    std::vector<double> last_gains;       // exposure gains of the last is_pipeline_run (is_pipeline_last_gains)
     int seam_speculation_accepted = -1;   // last is_seam_dp_find: 1 concurrent result accepted, 0 fell back, -1 not attempted
 };
 

@@ -87,12 +87,13 @@ int is_pipeline_run(is_ctx* ctx, int n, const is_mat* images, const is_camera* c
     //      image ahead of the warp, and a side stream that builds the Gaussian image pyramids (they do not depend on the
     //      seam masks) while the latency-bound seam stage leaves the SMs mostly idle.
     ctx->sync_next = 0;
+    ctx->last_gains.clear();
     is_ctx *side = nullptr, *copy = nullptr;
     IS_TRY(child_ctx(ctx, SIDE_PYRAMID, &side));
     IS_TRY(child_ctx(ctx, SIDE_COPY, &copy));
     if (getenv("IS_PIPELINE_SERIAL")) side = ctx;           // tuning knob: everything on the caller's stream
     side->ktiming = ctx->ktiming;
-    std::vector<DevMat> src(n), warped(n), masks(n);
+    std::vector<DevMat> src(n), warped(n), masks(n), comp(cfg.exposure == IS_EXPOSURE_GAIN ? n : 0);
     is_blender* bl = nullptr;
     IS_TRY(is_blender_create(ctx, cfg.num_bands, cfg.weight_type, &bl));
     // destroyed before the buffers above: on an error path the side streams may still be using them
@@ -121,7 +122,24 @@ int is_pipeline_run(is_ctx* ctx, int n, const is_mat* images, const is_camera* c
         IS_TRY(upload_tables(ctx, cfg.projection, plans[i], &tables));
         IS_TRY(launch_warp(ctx, cfg.projection, plans[i], tables.as<float>(), src[i], IS_INTER_LINEAR, IS_BORDER_REFLECT, warped[i], &masks[i]));
         // feed(): geometry + image pyramid now (side stream, ordered after this warp), weights after the seam stage
-        IS_TRY(blender_feed_image(bl, side, warped[i], masks[i], corners[i]));
+        if (cfg.exposure == IS_EXPOSURE_NONE) IS_TRY(blender_feed_image(bl, side, warped[i], masks[i], corners[i]));
+    }
+    // ---- exposure: compensator->feed(corners, images_warped, masks_warped) [BLEND]:117-123.  The seam finder keeps the
+    //      uncompensated images ([BLEND]:138-140); apply() goes into copies that only the blender reads ([SEAM]:1165-1171),
+    //      on the side stream together with their pyramids.
+    if (cfg.exposure == IS_EXPOSURE_GAIN) {
+        std::vector<double> gains(n, 1.0);
+        IS_TRY(gain_feed_device(ctx, n, warped.data(), masks.data(), corners.data(), gains.data()));
+        for (int i = 0; i < n; ++i) {
+            IS_TRY(alloc_mat(ctx, warped[i].rows, warped[i].cols, 3, IS_8U, &comp[i]));
+            if (side != ctx) IS_TRY(stream_after(ctx, side->stream, ctx->stream));
+            const int rc = gain_apply_device(side, warped[i], comp[i], gains[i]);
+            if (rc != IS_OK) { if (ctx->last_error.empty()) ctx->last_error = side->last_error; return rc; }
+            IS_TRY(blender_feed_image(bl, side, comp[i], masks[i], corners[i]));
+        }
+        ctx->last_gains = gains;
+    } else {
+        IS_REQUIRE(ctx, cfg.exposure == IS_EXPOSURE_NONE, IS_ERR_BAD_ARG, "unknown exposure mode");
     }
     IS_CUDA(ctx, cudaEventRecord(ctx->ev[1], ctx->stream));
     // ---- seam
@@ -156,6 +174,13 @@ int is_pipeline_run(is_ctx* ctx, int n, const is_mat* images, const is_camera* c
         if (cudaEventElapsedTime(&ms, ctx->ev[k], ctx->ev[k + 1]) == cudaSuccess) ctx->timings[k] = ms;
     }
     if (cudaEventElapsedTime(&ms, ctx->ev[0], ctx->ev[3]) == cudaSuccess) ctx->timings[3] = ms;
+    return IS_OK;
+}
+
+int is_pipeline_last_gains(is_ctx* ctx, int n, double* gains) {
+    if (!ctx || !gains || n < 0) return IS_ERR_BAD_ARG;
+    IS_REQUIRE(ctx, (size_t)n == ctx->last_gains.size(), IS_ERR_BAD_ARG, "the last is_pipeline_run did not compute gains for n images");
+    for (int i = 0; i < n; ++i) gains[i] = ctx->last_gains[i];
     return IS_OK;
 }
 

@@ -20,8 +20,8 @@ import ctypes as C
 import numpy as np
 
 from . import capi
-from .capi import (BORDER_CONSTANT, BORDER_REFLECT, COST_COLOR, COST_COLOR_GRAD, FEED_BORROW, FEED_COPY, INTER_LINEAR,
-                   INTER_NEAREST, PROJ_CYLINDRICAL, PROJ_SPHERICAL, SEAM_DP, SEAM_NONE, WEIGHT_16S, WEIGHT_32F)
+from .capi import (BORDER_CONSTANT, BORDER_REFLECT, COST_COLOR, COST_COLOR_GRAD, EXPOSURE_GAIN, EXPOSURE_NONE, FEED_BORROW, FEED_COPY,
+                   INTER_LINEAR, INTER_NEAREST, PROJ_CYLINDRICAL, PROJ_SPHERICAL, SEAM_DP, SEAM_NONE, WEIGHT_16S, WEIGHT_32F)
 
 _NP_DEPTH = {np.dtype(np.uint8): capi.IS_8U, np.dtype(np.int16): capi.IS_16S, np.dtype(np.int32): capi.IS_32S,
              np.dtype(np.float32): capi.IS_32F}
@@ -189,6 +189,37 @@ def _mat_array(arrs):
         mats.append(m)
         keep.append(k)
     return (capi.Mat * len(mats))(*mats), keep
+
+
+class GainCompensator:
+    """cv::detail::GainCompensator (ExposureCompensator::createDefault(GAIN)), the compensator of every main:
+    feed(corners, images_warped, masks_warped) [BLEND]:117-123, apply(index, corner, image, mask) [SEAM]:1165-1171."""
+
+    def __init__(self, ctx: Context):
+        self.ctx = ctx
+        self._gains = None
+
+    def feed(self, corners, images, masks):
+        n = len(images)
+        im, _k1 = _mat_array(images)
+        mk, _k2 = _mat_array(masks)
+        pts = (capi.Point * n)(*[capi.Point(int(c[0]), int(c[1])) for c in corners])
+        g = (C.c_double * n)()
+        self.ctx.check(self.ctx.lib.is_gain_feed(self.ctx.h, n, pts, im, mk, g))
+        self._gains = np.array(list(g), np.float64)
+        return self._gains
+
+    def gains(self):
+        """getMatGains()"""
+        return self._gains
+
+    def apply(self, index, corner, image, mask=None):
+        """in place, like the reference; also returns the image"""
+        if not _is_torch(image) and not image.flags["C_CONTIGUOUS"]:
+            raise ValueError("apply() works in place: pass a contiguous array")
+        m, _k = as_mat(image)
+        self.ctx.check(self.ctx.lib.is_gain_apply(self.ctx.h, C.byref(m), float(self._gains[index])))
+        return image
 
 
 class DpSeamFinder:
@@ -373,10 +404,10 @@ class Stitcher:
     """The composite call sequence detect -> match -> homography -> warp -> seam -> blend (is_pipeline_run).
     Registration stages are host control flow: pass cameras, or Python callables as hooks."""
 
-    def __init__(self, ctx: Context, projection="cylindrical", seam="dp", num_bands=5, weight_type=WEIGHT_32F):
+    def __init__(self, ctx: Context, projection="cylindrical", seam="dp", num_bands=5, weight_type=WEIGHT_32F, exposure=None):
         self.ctx = ctx
         self.cfg = capi.PipelineConfig(_PROJ[projection], SEAM_DP if seam in ("dp", SEAM_DP, True) else SEAM_NONE, COST_COLOR,
-                                       int(num_bands), int(weight_type), 1.0)
+                                       int(num_bands), int(weight_type), 1.0, EXPOSURE_GAIN if exposure in ("gain", EXPOSURE_GAIN, True) else EXPOSURE_NONE)
         self.timings_ms = None
 
     @staticmethod
@@ -423,6 +454,10 @@ class Stitcher:
         self.ctx.lib.is_pipeline_last_timings(self.ctx.h, t)
         self.timings_ms = dict(warp=t[0], seam=t[1], blend=t[2], total=t[3])
         res = dict(pano=pano, pano_mask=pmask, corners=corners, sizes=sizes, roi=roi)
+        if self.cfg.exposure == EXPOSURE_GAIN:
+            g = (C.c_double * n)()
+            self.ctx.check(self.ctx.lib.is_pipeline_last_gains(self.ctx.h, n, g))
+            res["gains"] = np.array(list(g), np.float64)
         if want_seam_masks:
             res["seam_masks"] = seam_masks
         return res

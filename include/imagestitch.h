@@ -212,6 +212,15 @@ typedef struct is_registration_hooks {
 } is_registration_hooks;
 
 typedef enum is_seam_mode { IS_SEAM_NONE = 0, IS_SEAM_DP = 1 } is_seam_mode;
+typedef enum is_exposure_mode { IS_EXPOSURE_NONE = 0, IS_EXPOSURE_GAIN = 1 } is_exposure_mode;
+
+/* ---- gain exposure compensation: cv::detail::GainCompensator (ExposureCompensator::GAIN), the compensator of every main:
+ *      compensator->feed(corners, images_warped, masks_warped)   [BLEND]:117-123 / [SEAM]:1165-1171
+ *      compensator->apply(img_idx, corner, img_warped, mask)     compositing loop, before Blender::feed
+ * images: n CV_8UC3, masks: n CV_8U (255 = inside), host or device.  gains[n] receives what getMatGains() would return. */
+int is_gain_feed(is_ctx* ctx, int n, const is_point* corners, const is_mat* images, const is_mat* masks, double* gains);
+/* image (CV_8U, any channel count, in place) = saturate_cast<uchar>(image * gain) */
+int is_gain_apply(is_ctx* ctx, is_mat* image, double gain);
 
 typedef struct is_pipeline_config {
     int projection;      /* is_projection */
@@ -220,6 +229,7 @@ typedef struct is_pipeline_config {
     int num_bands;       /* MultiBandBlender::setNumBands, default 5 */
     int weight_type;     /* is_weight_type */
     float scale;         /* warper scale = cameras[0].focal ([BLEND]:99); ignored when hooks->estimate is set */
+    int exposure;        /* is_exposure_mode: gains from the warped images, applied before the blender's feed */
 } is_pipeline_config;
 
 typedef struct is_pipeline_plan_t {
@@ -236,6 +246,9 @@ int is_pipeline_plan(is_ctx* ctx, int n, const is_size* src_sizes, const is_came
 int is_pipeline_run(is_ctx* ctx, int n, const is_mat* images, const is_camera* cameras,
                     const is_registration_hooks* hooks, const is_pipeline_config* cfg,
                     is_mat* pano, is_mat* pano_mask, is_mat* seam_masks);
+
+/* Exposure gains of the last is_pipeline_run with cfg.exposure == IS_EXPOSURE_GAIN (compensator->getMatGains()). */
+int is_pipeline_last_gains(is_ctx* ctx, int n, double* gains);
 
 /* Per-stage device time (ms) of the last is_pipeline_run on this context: warp, seam, blend, total. */
 int is_pipeline_last_timings(is_ctx* ctx, float ms[4]);

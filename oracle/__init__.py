@@ -49,6 +49,8 @@ def lib():
         L.orc_lin_blend.restype = C.c_int
         L.orc_pipeline_plan.restype = C.c_int
         L.orc_pipeline_run.restype = C.c_int
+        L.orc_pipeline_run_ex.restype = C.c_int
+        L.orc_gain_feed.restype = C.c_int
         _lib = L
     return _lib
 
@@ -276,8 +278,32 @@ def pipeline_plan(proj, src_sizes_hw, Ks, Rs, scale):
     return corners.reshape(n, 2), sizes.reshape(n, 2), tuple(int(v) for v in roi)
 
 
-def pipeline_run(proj, srcs, Ks, Rs, scale, seam=True, num_bands=5, weight_type=WEIGHT_32F, want_intermediates=False):
-    """warp -> [DP seam] -> multi-band blend.  Returns dict(pano, pano_mask, corners, sizes, roi, seconds[, warped, masks])."""
+def gain_feed(corners, images, masks):
+    """cv::detail::GainCompensator::feed -> gains (float64[n]); images u8 BGR, masks u8"""
+    n = len(images)
+    images = [np.ascontiguousarray(a, np.uint8) for a in images]
+    masks = [np.ascontiguousarray(a, np.uint8) for a in masks]
+    rows = np.asarray([a.shape[0] for a in images], np.int32)
+    cols = np.asarray([a.shape[1] for a in images], np.int32)
+    c = np.ascontiguousarray(np.asarray(corners, np.int32).reshape(-1))
+    gains = np.zeros(n, np.float64)
+    ip = (C.c_void_p * n)(*[a.ctypes.data for a in images])
+    mp = (C.c_void_p * n)(*[a.ctypes.data for a in masks])
+    rc = lib().orc_gain_feed(C.c_int(n), ip, mp, _p(rows), _p(cols), _p(c), _p(gains))
+    if rc:
+        raise RuntimeError("orc_gain_feed: singular system")
+    return gains
+
+
+def gain_apply(image, gain):
+    """cv::detail::GainCompensator::apply = multiply(image, gain) on CV_8UC3 -> new array"""
+    out = np.ascontiguousarray(image, np.uint8).copy()
+    lib().orc_gain_apply(_p(out), C.c_size_t(out.size), C.c_double(float(gain)))
+    return out
+
+
+def pipeline_run(proj, srcs, Ks, Rs, scale, seam=True, num_bands=5, weight_type=WEIGHT_32F, want_intermediates=False, exposure_gain=False):
+    """warp -> [gain exposure] -> [DP seam] -> multi-band blend.  Returns dict(pano, pano_mask, corners, sizes, roi, seconds, gains[, warped, masks])."""
     n = len(srcs)
     srcs = [np.ascontiguousarray(s, np.uint8) for s in srcs]
     corners, sizes, roi = pipeline_plan(proj, [s.shape[:2] for s in srcs], Ks, Rs, scale)
@@ -299,12 +325,13 @@ def pipeline_run(proj, srcs, Ks, Rs, scale, seam=True, num_bands=5, weight_type=
     c = np.ascontiguousarray(corners.reshape(-1))
     s = np.ascontiguousarray(sizes.reshape(-1))
     r = np.asarray(roi, np.int32)
-    rc = lib().orc_pipeline_run(C.c_int(n), C.c_int(proj), sp, _p(rows), _p(cols), _p(K), _p(R), C.c_float(scale),
-                                C.c_int(1 if seam else 0), C.c_int(num_bands), C.c_int(weight_type), _p(c), _p(s), _p(r),
-                                wp, mp, _p(pano), _p(pmask), _p(secs))
+    gains = np.ones(n, np.float64)
+    rc = lib().orc_pipeline_run_ex(C.c_int(n), C.c_int(proj), sp, _p(rows), _p(cols), _p(K), _p(R), C.c_float(scale),
+                                   C.c_int(1 if seam else 0), C.c_int(num_bands), C.c_int(weight_type), C.c_int(1 if exposure_gain else 0),
+                                   _p(c), _p(s), _p(r), wp, mp, _p(pano), _p(pmask), _p(secs), _p(gains))
     if rc:
         raise RuntimeError(f"orc_pipeline_run failed: {rc}")
-    out = dict(pano=pano, pano_mask=pmask, corners=corners, sizes=sizes, roi=roi, seconds=secs)
+    out = dict(pano=pano, pano_mask=pmask, corners=corners, sizes=sizes, roi=roi, seconds=secs, gains=gains)
     if want_intermediates:
         out["warped"] = warped
         out["masks"] = masks

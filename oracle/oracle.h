@@ -98,7 +98,12 @@ int orc_lin_blend(const float* img1, int rows1, int cols1, const float* img2, in
                   int tl1x, int tl1y, int tl2x, int tl2y, float* pano, int* seam_x,
                   float* costV_out /* panoHe x (interSectBr+2), may be NULL */);
 
-/* ---- whole composite path (oracle/pipeline.cpp): warp -> [DP seam] -> multi-band blend ---- */
+/* ---- gain exposure compensation (oracle/exposure.cpp): cv::detail::GainCompensator feed / apply ---- */
+int orc_gain_feed(int n, const uint8_t* const* images, const uint8_t* const* masks, const int* rows, const int* cols, const int* corners_xy,
+                  double* gains);
+void orc_gain_apply(uint8_t* image, size_t count, double gain);
+
+/* ---- whole composite path (oracle/pipeline.cpp): warp -> [gain exposure] -> [DP seam] -> multi-band blend ---- */
 void orc_set_threads(int n);
 int orc_get_max_threads(void);
 int orc_pipeline_plan(int n, int proj, const int* src_rows, const int* src_cols, const float* K, const float* R,
@@ -108,6 +113,13 @@ int orc_pipeline_run(int n, int proj, const uint8_t* const* srcs, const int* src
                      const int* corners_xy, const int* sizes_wh, const int* pano_roi,
                      uint8_t* const* warped_out, uint8_t* const* masks_out,
                      int16_t* pano, uint8_t* pano_mask, double* stage_seconds);
+/* the same with the gain exposure compensator of the mains: gains from the warped images and masks ([BLEND]:117-123), the
+ * seam finder sees the uncompensated images, apply() before the blender's feed ([SEAM]:1165-1171); gains_out[n] optional */
+int orc_pipeline_run_ex(int n, int proj, const uint8_t* const* srcs, const int* src_rows, const int* src_cols,
+                        const float* K, const float* R, float scale, int seam, int num_bands, int weight_type, int exposure_gain,
+                        const int* corners_xy, const int* sizes_wh, const int* pano_roi,
+                        uint8_t* const* warped_out, uint8_t* const* masks_out,
+                        int16_t* pano, uint8_t* pano_mask, double* stage_seconds, double* gains_out);
 
 #ifdef __cplusplus
 }

@@ -59,6 +59,15 @@ int orc_pipeline_run(int n, int proj, const uint8_t* const* srcs, const int* src
                      const int* corners_xy, const int* sizes_wh, const int* pano_roi,
                      uint8_t* const* warped_out, uint8_t* const* masks_out,
                      int16_t* pano, uint8_t* pano_mask, double* stage_seconds) {
+    return orc_pipeline_run_ex(n, proj, srcs, src_rows, src_cols, K, R, scale, seam, num_bands, weight_type, 0, corners_xy, sizes_wh, pano_roi,
+                               warped_out, masks_out, pano, pano_mask, stage_seconds, nullptr);
+}
+
+int orc_pipeline_run_ex(int n, int proj, const uint8_t* const* srcs, const int* src_rows, const int* src_cols,
+                        const float* K, const float* R, float scale, int seam, int num_bands, int weight_type, int exposure_gain,
+                        const int* corners_xy, const int* sizes_wh, const int* pano_roi,
+                        uint8_t* const* warped_out, uint8_t* const* masks_out,
+                        int16_t* pano, uint8_t* pano_mask, double* stage_seconds, double* gains_out) {
     using clk = std::chrono::steady_clock;
     auto t0 = clk::now();
     std::vector<std::vector<uint8_t>> warped(n), masks(n);
@@ -77,9 +86,16 @@ int orc_pipeline_run(int n, int proj, const uint8_t* const* srcs, const int* src
         orc_remap_u8(ones.data(), src_rows[i], src_cols[i], 1, (size_t)src_cols[i], xmap.data(), ymap.data(), h, w,
                      ORC_INTER_NEAREST, ORC_BORDER_CONSTANT, masks[i].data());
     }
-    auto t1 = clk::now();
     std::vector<int> rows(n), cols(n);
     for (int i = 0; i < n; ++i) { cols[i] = sizes_wh[2 * i]; rows[i] = sizes_wh[2 * i + 1]; }
+    std::vector<double> gains(n, 1.0);
+    if (exposure_gain) {                                         // compensator->feed(corners, images_warped, masks_warped)  [BLEND]:117-123
+        std::vector<const uint8_t*> ip(n), mp(n);
+        for (int i = 0; i < n; ++i) { ip[i] = warped[i].data(); mp[i] = masks[i].data(); }
+        if (orc_gain_feed(n, ip.data(), mp.data(), rows.data(), cols.data(), corners_xy, gains.data())) return -1;
+    }
+    if (gains_out) for (int i = 0; i < n; ++i) gains_out[i] = gains[i];
+    auto t1 = clk::now();
     if (seam) {                                                  // [SEAM]:1188-1192
         std::vector<std::vector<float>> imgf(n);
         std::vector<const void*> ip(n);
@@ -101,6 +117,7 @@ int orc_pipeline_run(int n, int proj, const uint8_t* const* srcs, const int* src
     orc_mb* mb = orc_mb_create(num_bands, weight_type);
     orc_mb_prepare(mb, pano_roi);
     for (int i = 0; i < n; ++i) {                                // [SEAM]:1263,1271
+        if (exposure_gain) orc_gain_apply(warped[i].data(), warped[i].size(), gains[i]);   // compensator->apply  [SEAM]:1165-1171
         std::vector<int16_t> s16(warped[i].size());
         const uint8_t* s = warped[i].data();
         int16_t* d = s16.data();

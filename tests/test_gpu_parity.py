@@ -203,6 +203,51 @@ def test_multiband_blend_gray_masks(ctx, oracle, wt):
     _eq(got, want, f"blend gray masks wt={wt}")
 
 
+def test_gain_compensator(ctx, oracle):
+    """GainCompensator feed / apply through the C ABI vs the oracle: gains to 1e-12 relative (tree sum on the device, raster
+    sum on the CPU), applied images bit for bit; host and device buffers."""
+    import torch
+    O = oracle
+    corners, wi, wm = warped_set(O, 4, 320, 240, overlap=0.3)
+    rng = np.random.default_rng(3)
+    wi = [np.clip(a.astype(np.float32) * g, 0, 255).astype(np.uint8) for a, g in zip(wi, (0.8, 1.0, 1.15, 0.95))]
+    wm = [m.copy() for m in wm]
+    wm[1][10:40, 5:60] = 0
+    wm[2][::9, ::4] = 77                                   # only mask == 255 counts
+    want = O.gain_feed(corners, wi, wm)
+    gc = S.GainCompensator(ctx)
+    got = gc.feed(corners, wi, wm)
+    assert np.max(np.abs(got - want) / np.abs(want)) < 1e-12, (got, want)
+    dev = S.GainCompensator(ctx).feed(corners, [torch.from_numpy(a).cuda() for a in wi], [torch.from_numpy(m).cuda() for m in wm])
+    assert np.array_equal(dev, got), "device buffers give different gains than host buffers"
+    for i in range(4):
+        a = wi[i].copy()
+        gc.apply(i, corners[i], a, wm[i])
+        _eq(a, O.gain_apply(wi[i], got[i]), f"apply {i}")
+    vals = np.arange(256, dtype=np.uint8).reshape(1, 256, 1).repeat(3, 2)
+    for g in list(rng.uniform(0.3, 3.0, 200)) + [1.2208333386655252, 0.5, 1.5]:
+        gc._gains = np.array([g])
+        t = torch.from_numpy(vals.copy()).cuda()
+        gc.apply(0, (0, 0), t)
+        torch.cuda.synchronize()
+        _eq(t.cpu().numpy(), O.gain_apply(vals, g), f"apply gain {g!r}")
+
+
+def test_pipeline_with_gain_exposure(ctx, oracle):
+    O = oracle
+    imgs, Ks, Rs, scale = synth.make_panorama_inputs(4, 384, 288, 1.2, 0.25)
+    imgs = [np.clip(a.astype(np.float32) * g, 0, 255).astype(np.uint8) for a, g in zip(imgs, (0.85, 1.0, 1.1, 0.9))]
+    want = O.pipeline_run(O.PROJ_CYLINDRICAL, imgs, Ks, Rs, scale, seam=True, num_bands=5, weight_type=O.WEIGHT_32F, want_intermediates=True,
+                          exposure_gain=True)
+    got = S.Stitcher(ctx, "cylindrical", "dp", 5, S.WEIGHT_32F, exposure="gain").stitch(imgs, Ks, Rs, scale, want_seam_masks=True)
+    assert np.max(np.abs(got["gains"] - want["gains"]) / want["gains"]) < 1e-12
+    assert np.ptp(want["gains"]) > 0.05, "the test images should need visibly different gains"
+    for k in range(4):
+        _eq(got["seam_masks"][k], want["masks"][k], f"seam mask {k}")
+    _eq(got["pano_mask"], want["pano_mask"], "panorama mask")
+    _eq(got["pano"], want["pano"], "panorama (gain compensated)")
+
+
 def test_linear_blend_pair(ctx, oracle):
     O = oracle
     for (w, h, ov) in ((400, 300, 0.25), (320, 260, 0.4)):

@@ -78,3 +78,36 @@ def test_seam_and_blend_vs_cv2(oracle, case):
         else:
             d = np.abs(cd.astype(np.int32) - od.astype(np.int32))
             assert d.max() <= 2 and (d == 0).mean() >= 0.99
+
+
+def test_gain_compensator_vs_cv2(oracle):
+    """cv::detail::GainCompensator (feed / apply): gains to 1e-12 relative (the sums are doubles in raster order on both sides;
+    OpenCV 4.13 agrees to the last bit or two), apply() bit for bit."""
+    O = oracle
+    rng = np.random.default_rng(99)
+    for trial in range(6):
+        n = int(rng.integers(2, 6))
+        imgs, masks, corners, x = [], [], [], 0
+        for i in range(n):
+            h, w = int(rng.integers(40, 90)), int(rng.integers(60, 120))
+            imgs.append(np.clip(rng.integers(0, 256, (h, w, 3)).astype(np.float32) * rng.uniform(0.6, 1.2), 0, 255).astype(np.uint8))
+            m = np.full((h, w), 255, np.uint8)
+            m[int(rng.integers(0, h // 2)):, :int(rng.integers(1, w // 3))] = 0
+            if trial % 2:
+                m[::7, ::5] = 128                      # only mask == 255 counts
+            masks.append(m)
+            corners.append((x, int(rng.integers(-8, 8))))
+            x += int(w * rng.uniform(0.5, 0.9))
+        c = cv2.detail.ExposureCompensator_createDefault(cv2.detail.ExposureCompensator_GAIN)
+        c.feed(corners, imgs, masks)
+        g_cv = np.array([float(g[0, 0]) for g in c.getMatGains()])
+        g_or = O.gain_feed(corners, imgs, masks)
+        assert np.max(np.abs(g_cv - g_or) / np.abs(g_cv)) < 1e-12
+        for i in range(n):
+            assert np.array_equal(c.apply(i, corners[i], imgs[i].copy(), masks[i]), O.gain_apply(imgs[i], g_cv[i]))
+    # apply(): every 8-bit value under many gains, including products that land on .5 in float but not in double
+    vals = np.arange(256, dtype=np.uint8).reshape(1, 256, 1).repeat(3, 2)
+    for g in list(rng.uniform(0.3, 3.0, 1500)) + [1.0, 0.5, 2.0, 1.5, 1.2208333386655252]:
+        c = cv2.detail.ExposureCompensator_createDefault(cv2.detail.ExposureCompensator_GAIN)
+        c.setMatGains([np.array([[g]], np.float64)])
+        assert np.array_equal(c.apply(0, (0, 0), vals.copy(), np.full((1, 256), 255, np.uint8)), O.gain_apply(vals, g)), g
