@@ -23,6 +23,7 @@ WEIGHT_32F, WEIGHT_16S = 5, 3
 FEED_COPY, FEED_BORROW = 0, 1
 SEAM_NONE, SEAM_DP = 0, 1
 EXPOSURE_NONE, EXPOSURE_GAIN = 0, 1
+BLEND_MULTI_BAND, BLEND_FEATHER = 0, 1
 
 
 class Mat(C.Structure):
@@ -57,7 +58,8 @@ class RegistrationHooks(C.Structure):
 
 class PipelineConfig(C.Structure):
     _fields_ = [("projection", C.c_int), ("seam", C.c_int), ("seam_cost", C.c_int), ("num_bands", C.c_int),
-                ("weight_type", C.c_int), ("scale", C.c_float), ("exposure", C.c_int)]
+                ("weight_type", C.c_int), ("scale", C.c_float), ("exposure", C.c_int), ("blender", C.c_int), ("sharpness", C.c_float),
+                ("seam_dilate", C.c_int)]
 
 
 # every symbol include/imagestitch.h declares: name -> (restype, argtypes)
@@ -101,6 +103,15 @@ SYMBOLS = {
     "is_blender_blend": (C.c_int, [C.c_void_p, _P(Mat), _P(Mat)]),
     "is_linear_blend_size": (C.c_int, [Size, Size, Point, Point, _P(Size)]),
     "is_linear_blend_pair": (C.c_int, [C.c_void_p, _P(Mat), _P(Mat), Point, Point, _P(Mat), _P(C.c_int)]),
+    "is_mask_dilate_and": (C.c_int, [C.c_void_p, _P(Mat), C.c_int, C.c_int, _P(Mat)]),
+    "is_feather_weight_map": (C.c_int, [C.c_void_p, _P(Mat), C.c_float, _P(Mat)]),
+    "is_feather_create": (C.c_int, [C.c_void_p, C.c_float, _P(C.c_void_p)]),
+    "is_feather_destroy": (C.c_int, [C.c_void_p]),
+    "is_feather_prepare": (C.c_int, [C.c_void_p, C.c_int, _P(Point), _P(Size)]),
+    "is_feather_prepare_roi": (C.c_int, [C.c_void_p, Rect]),
+    "is_feather_dst_size": (C.c_int, [C.c_void_p, _P(Size)]),
+    "is_feather_feed": (C.c_int, [C.c_void_p, _P(Mat), _P(Mat), Point]),
+    "is_feather_blend": (C.c_int, [C.c_void_p, _P(Mat), _P(Mat)]),
     "is_gain_feed": (C.c_int, [C.c_void_p, C.c_int, _P(Point), _P(Mat), _P(Mat), _P(C.c_double)]),
     "is_gain_apply": (C.c_int, [C.c_void_p, _P(Mat), C.c_double]),
     "is_pipeline_plan": (C.c_int, [C.c_void_p, C.c_int, _P(Size), _P(Camera), _P(PipelineConfig), _P(Point), _P(Size), _P(Rect)]),

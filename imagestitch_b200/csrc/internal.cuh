@@ -29,6 +29,11 @@ int blender_feed_image(is_blender* b, is_ctx* side, const DevMat& img, const Dev
 int blender_feed_weights(is_blender* b);
 int blender_blend_dev(is_blender* b, const DevMat& dst, const DevMat& dmask, int sx0, int sx1);
 
+// feather.cu
+int mask_dilate_and_device(is_ctx* ctx, const DevMat& mask, int kw, int kh, const DevMat* andm);
+int feather_blend_device(is_ctx* ctx, float sharpness, is_rect roi, int n, const DevMat* imgs, const DevMat* masks, const is_point* corners,
+                         const DevMat& dst, const DevMat& dmask);
+
 // exposure.cu
 int gain_feed_device(is_ctx* ctx, int n, const DevMat* images, const DevMat* masks, const is_point* corners, double* gains);
 int gain_apply_device(is_ctx* ctx, const DevMat& src, const DevMat& dst, double gain);

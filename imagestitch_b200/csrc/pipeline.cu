@@ -93,7 +93,7 @@ int is_pipeline_run(is_ctx* ctx, int n, const is_mat* images, const is_camera* c
     IS_TRY(child_ctx(ctx, SIDE_COPY, &copy));
     if (getenv("IS_PIPELINE_SERIAL")) side = ctx;           // tuning knob: everything on the caller's stream
     side->ktiming = ctx->ktiming;
-    std::vector<DevMat> src(n), warped(n), masks(n), comp(cfg.exposure == IS_EXPOSURE_GAIN ? n : 0);
+    std::vector<DevMat> src(n), warped(n), masks(n), comp(cfg.exposure == IS_EXPOSURE_GAIN ? n : 0), wmask0(cfg.seam_dilate > 0 ? n : 0);
     is_blender* bl = nullptr;
     IS_TRY(is_blender_create(ctx, cfg.num_bands, cfg.weight_type, &bl));
     // destroyed before the buffers above: on an error path the side streams may still be using them
@@ -102,6 +102,9 @@ int is_pipeline_run(is_ctx* ctx, int n, const is_mat* images, const is_camera* c
         ~Guard() { cudaStreamSynchronize(side->stream); cudaStreamSynchronize(copy->stream); is_blender_destroy(b); }
     } guard{bl, side, copy};
     IS_TRY(is_blender_prepare_roi(bl, roi));
+    const bool multiband = cfg.blender == IS_BLEND_MULTI_BAND;
+    IS_REQUIRE(ctx, multiband || cfg.blender == IS_BLEND_FEATHER, IS_ERR_BAD_ARG, "unknown blender type");
+    IS_REQUIRE(ctx, cfg.seam_dilate >= 0 && cfg.seam_dilate <= 64, IS_ERR_BAD_ARG, "seam_dilate must be 0..64");
     IS_CUDA(ctx, cudaEventRecord(ctx->ev[0], ctx->stream));
     bool any_host = false;
     for (int i = 0; i < n; ++i) {
@@ -122,7 +125,7 @@ int is_pipeline_run(is_ctx* ctx, int n, const is_mat* images, const is_camera* c
         IS_TRY(upload_tables(ctx, cfg.projection, plans[i], &tables));
         IS_TRY(launch_warp(ctx, cfg.projection, plans[i], tables.as<float>(), src[i], IS_INTER_LINEAR, IS_BORDER_REFLECT, warped[i], &masks[i]));
         // feed(): geometry + image pyramid now (side stream, ordered after this warp), weights after the seam stage
-        if (cfg.exposure == IS_EXPOSURE_NONE) IS_TRY(blender_feed_image(bl, side, warped[i], masks[i], corners[i]));
+        if (multiband && cfg.exposure == IS_EXPOSURE_NONE) IS_TRY(blender_feed_image(bl, side, warped[i], masks[i], corners[i]));
     }
     // ---- exposure: compensator->feed(corners, images_warped, masks_warped) [BLEND]:117-123.  The seam finder keeps the
     //      uncompensated images ([BLEND]:138-140); apply() goes into copies that only the blender reads ([SEAM]:1165-1171),
@@ -135,12 +138,18 @@ int is_pipeline_run(is_ctx* ctx, int n, const is_mat* images, const is_camera* c
             if (side != ctx) IS_TRY(stream_after(ctx, side->stream, ctx->stream));
             const int rc = gain_apply_device(side, warped[i], comp[i], gains[i]);
             if (rc != IS_OK) { if (ctx->last_error.empty()) ctx->last_error = side->last_error; return rc; }
-            IS_TRY(blender_feed_image(bl, side, comp[i], masks[i], corners[i]));
+            if (multiband) IS_TRY(blender_feed_image(bl, side, comp[i], masks[i], corners[i]));
         }
         ctx->last_gains = gains;
     } else {
         IS_REQUIRE(ctx, cfg.exposure == IS_EXPOSURE_NONE, IS_ERR_BAD_ARG, "unknown exposure mode");
     }
+    if (cfg.seam_dilate > 0)   // masks_warped of [SEAM]:1267: the seam finder changes `masks` in place
+        for (int i = 0; i < n; ++i) {
+            IS_TRY(alloc_mat(ctx, masks[i].rows, masks[i].cols, 1, IS_8U, &wmask0[i]));
+            IS_CUDA(ctx, cudaMemcpy2DAsync(wmask0[i].data, wmask0[i].step, masks[i].data, masks[i].step, (size_t)masks[i].cols, masks[i].rows,
+                                           cudaMemcpyDeviceToDevice, ctx->stream));
+        }
     IS_CUDA(ctx, cudaEventRecord(ctx->ev[1], ctx->stream));
     // ---- seam
     if (cfg.seam == IS_SEAM_DP) {
@@ -150,16 +159,21 @@ int is_pipeline_run(is_ctx* ctx, int n, const is_mat* images, const is_camera* c
         IS_REQUIRE(ctx, cfg.seam == IS_SEAM_NONE, IS_ERR_BAD_ARG, "unknown seam mode");
     }
     IS_CUDA(ctx, cudaEventRecord(ctx->ev[2], ctx->stream));
-    // ---- blend
-    IS_TRY(blender_feed_weights(bl));
+    // ---- blend.  masks_seam[k] = dilate(masks_seam[k]) & masks_warped[k] ([SEAM]:1264-1269) opens a band on either side of
+    //      the seam for the blender to work in; the seam masks handed back to the caller are the dilated ones, as in the mains.
+    if (cfg.seam_dilate > 0)
+        for (int i = 0; i < n; ++i) IS_TRY(mask_dilate_and_device(ctx, masks[i], cfg.seam_dilate, cfg.seam_dilate, &wmask0[i]));
+    if (multiband) IS_TRY(blender_feed_weights(bl));
     if (side != ctx) {
-        IS_TRY(stream_after(ctx, ctx->stream, side->stream));   // join: the image pyramids are complete
+        IS_TRY(stream_after(ctx, ctx->stream, side->stream));   // join: the image pyramids / compensated copies are complete
         merge_child(ctx, side);
     }
     DevMat dp, dm;
     IS_TRY(stage_out(ctx, pano, &dp, false));
     IS_TRY(stage_out(ctx, pano_mask, &dm, false));
-    IS_TRY(blender_blend_dev(bl, dp, dm, 0, roi.width));
+    if (multiband) IS_TRY(blender_blend_dev(bl, dp, dm, 0, roi.width));
+    else IS_TRY(feather_blend_device(ctx, cfg.sharpness, roi, n, cfg.exposure == IS_EXPOSURE_GAIN ? comp.data() : warped.data(), masks.data(),
+                                     corners.data(), dp, dm));
     IS_CUDA(ctx, cudaEventRecord(ctx->ev[3], ctx->stream));
     // ---- results
     IS_TRY(commit(ctx, &dp));

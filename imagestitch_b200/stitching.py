@@ -384,6 +384,74 @@ class MultiBandBlender:
         return dst, dmask
 
 
+def dilate_and(ctx: Context, mask, ksize_wh=(20, 20), and_mask=None):
+    """dilate(mask, mask, getStructuringElement(MORPH_RECT, ksize)); mask &= and_mask   ([SEAM]:1258-1269).  In place."""
+    if not _is_torch(mask) and not mask.flags["C_CONTIGUOUS"]:
+        raise ValueError("dilate_and() works in place: pass a contiguous array")
+    m, _k = as_mat(mask)
+    if and_mask is None:
+        ctx.check(ctx.lib.is_mask_dilate_and(ctx.h, C.byref(m), int(ksize_wh[0]), int(ksize_wh[1]), None))
+    else:
+        a, _k2 = as_mat(and_mask)
+        ctx.check(ctx.lib.is_mask_dilate_and(ctx.h, C.byref(m), int(ksize_wh[0]), int(ksize_wh[1]), C.byref(a)))
+    return mask
+
+
+def feather_weight_map(ctx: Context, mask, sharpness):
+    """createWeightMap(mask, sharpness, weight) of the feather blender -> float32 map"""
+    w = _alloc_like(mask, tuple(mask.shape[:2]), np.float32)
+    m, _k = as_mat(mask)
+    mw, _k2 = as_mat(w)
+    ctx.check(ctx.lib.is_feather_weight_map(ctx.h, C.byref(m), float(sharpness), C.byref(mw)))
+    return w
+
+
+class FeatherBlender:
+    """cv::detail::FeatherBlender as the reference's mains call it ([SEAM]:1249-1252,1271,1280)."""
+
+    def __init__(self, ctx: Context, sharpness=0.02):
+        self.ctx = ctx
+        h = C.c_void_p()
+        ctx.check(ctx.lib.is_feather_create(ctx.h, float(sharpness), C.byref(h)))
+        self.h = h
+        self._like = None
+
+    def __del__(self):
+        try:
+            if getattr(self, "h", None) and getattr(self.ctx, "h", None):
+                self.ctx.lib.is_feather_destroy(self.h)
+            self.h = None
+        except Exception:
+            pass
+
+    def prepare(self, corners_or_roi, sizes=None):
+        if sizes is None:
+            x, y, w, h = (int(v) for v in corners_or_roi)
+            self.ctx.check(self.ctx.lib.is_feather_prepare_roi(self.h, capi.Rect(x, y, w, h)))
+        else:
+            n = len(sizes)
+            pts = (capi.Point * n)(*[capi.Point(int(c[0]), int(c[1])) for c in corners_or_roi])
+            szs = (capi.Size * n)(*[capi.Size(int(s[0]), int(s[1])) for s in sizes])
+            self.ctx.check(self.ctx.lib.is_feather_prepare(self.h, n, pts, szs))
+
+    def feed(self, img, mask, tl):
+        mi, ki = as_mat(img)
+        mm, _km = as_mat(mask)
+        self._like = ki
+        self.ctx.check(self.ctx.lib.is_feather_feed(self.h, C.byref(mi), C.byref(mm), capi.Point(int(tl[0]), int(tl[1]))))
+
+    def blend(self):
+        sz = capi.Size()
+        self.ctx.check(self.ctx.lib.is_feather_dst_size(self.h, C.byref(sz)))
+        like = self._like if self._like is not None else np.empty(0)
+        dst = _alloc_like(like, (sz.height, sz.width, 3), np.int16)
+        dmask = _alloc_like(like, (sz.height, sz.width), np.uint8)
+        md, _a = as_mat(dst)
+        mm, _b = as_mat(dmask)
+        self.ctx.check(self.ctx.lib.is_feather_blend(self.h, C.byref(md), C.byref(mm)))
+        return dst, dmask
+
+
 def linear_blend_pair(ctx: Context, img1, img2, tl1, tl2):
     """The reference's hand-written pair blend [BLEND]:141-717 -> (pano float32 HxWx3, seam_x) or None."""
     m1, k1 = as_mat(img1)
@@ -404,10 +472,14 @@ class Stitcher:
     """The composite call sequence detect -> match -> homography -> warp -> seam -> blend (is_pipeline_run).
     Registration stages are host control flow: pass cameras, or Python callables as hooks."""
 
-    def __init__(self, ctx: Context, projection="cylindrical", seam="dp", num_bands=5, weight_type=WEIGHT_32F, exposure=None):
+    def __init__(self, ctx: Context, projection="cylindrical", seam="dp", num_bands=5, weight_type=WEIGHT_32F, exposure=None,
+                 blender="multiband", sharpness=0.02, seam_dilate=0):
+        """blender="feather", sharpness=0.1, seam_dilate=20, exposure="gain" is the configuration the reference's mains run."""
         self.ctx = ctx
         self.cfg = capi.PipelineConfig(_PROJ[projection], SEAM_DP if seam in ("dp", SEAM_DP, True) else SEAM_NONE, COST_COLOR,
-                                       int(num_bands), int(weight_type), 1.0, EXPOSURE_GAIN if exposure in ("gain", EXPOSURE_GAIN, True) else EXPOSURE_NONE)
+                                       int(num_bands), int(weight_type), 1.0, EXPOSURE_GAIN if exposure in ("gain", EXPOSURE_GAIN, True) else EXPOSURE_NONE,
+                                       capi.BLEND_FEATHER if blender in ("feather", capi.BLEND_FEATHER) else capi.BLEND_MULTI_BAND, float(sharpness),
+                                       int(seam_dilate))
         self.timings_ms = None
 
     @staticmethod

@@ -211,8 +211,26 @@ typedef struct is_registration_hooks {
     int (*estimate)(void* user, int n_images, is_camera* cameras, float* scale);
 } is_registration_hooks;
 
+/* ---- mask preparation + feather blend: the blend path the reference's mains execute ([SEAM]:1249-1280)
+ *   Mat element = getStructuringElement(MORPH_RECT, Size(20, 20)); dilate(masks_seam[k], masks_seam[k], element);
+ *   masks_seam[k] = masks_seam[k] & masks_warped[k];                       -> is_mask_dilate_and(mask, 20, 20, masks_warped)
+ *   Blender::createDefault(Blender::FEATHER) + setSharpness(0.1)           -> is_feather_create
+ *   prepare(corners, sizes) / feed(img_s, mask, corner) / blend(dst, mask) -> is_feather_prepare / _feed / _blend
+ * img: 3 channels IS_16S or IS_8U; masks IS_8U; dst: 3 channels IS_16S, dst_mask: IS_8U, of is_feather_dst_size. */
+typedef struct is_feather_blender is_feather_blender;
+int is_mask_dilate_and(is_ctx* ctx, is_mat* mask /* in-out */, int kw, int kh, const is_mat* and_mask /* may be NULL */);
+int is_feather_weight_map(is_ctx* ctx, const is_mat* mask, float sharpness, is_mat* weight /* IS_32F: createWeightMap */);
+int is_feather_create(is_ctx* ctx, float sharpness, is_feather_blender** out);
+int is_feather_destroy(is_feather_blender* b);
+int is_feather_prepare(is_feather_blender* b, int n, const is_point* corners, const is_size* sizes);
+int is_feather_prepare_roi(is_feather_blender* b, is_rect dst_roi);
+int is_feather_dst_size(const is_feather_blender* b, is_size* size);
+int is_feather_feed(is_feather_blender* b, const is_mat* img, const is_mat* mask, is_point tl);
+int is_feather_blend(is_feather_blender* b, is_mat* dst, is_mat* dst_mask);
+
 typedef enum is_seam_mode { IS_SEAM_NONE = 0, IS_SEAM_DP = 1 } is_seam_mode;
 typedef enum is_exposure_mode { IS_EXPOSURE_NONE = 0, IS_EXPOSURE_GAIN = 1 } is_exposure_mode;
+typedef enum is_blender_type { IS_BLEND_MULTI_BAND = 0, IS_BLEND_FEATHER = 1 } is_blender_type;
 
 /* ---- gain exposure compensation: cv::detail::GainCompensator (ExposureCompensator::GAIN), the compensator of every main:
  *      compensator->feed(corners, images_warped, masks_warped)   [BLEND]:117-123 / [SEAM]:1165-1171
@@ -230,6 +248,10 @@ typedef struct is_pipeline_config {
     int weight_type;     /* is_weight_type */
     float scale;         /* warper scale = cameras[0].focal ([BLEND]:99); ignored when hooks->estimate is set */
     int exposure;        /* is_exposure_mode: gains from the warped images, applied before the blender's feed */
+    int blender;         /* is_blender_type: IS_BLEND_MULTI_BAND (num_bands, weight_type) or IS_BLEND_FEATHER (sharpness) */
+    float sharpness;     /* FeatherBlender::setSharpness ([SEAM]:1251: 0.1) */
+    int seam_dilate;     /* > 0: masks_seam = dilate(masks_seam, seam_dilate x seam_dilate rectangle) & masks_warped before the
+                            blender's feed ([SEAM]:1257-1270: 20); 0: the seam masks are fed as they are */
 } is_pipeline_config;
 
 typedef struct is_pipeline_plan_t {

@@ -118,6 +118,52 @@ private:
     is_blender* h_ = nullptr;
 };
 
+// cv::detail::GainCompensator (ExposureCompensator::createDefault(GAIN)): feed [BLEND]:117-123, apply [SEAM]:1165-1171
+class GainCompensator {
+public:
+    explicit GainCompensator(Context& ctx) : ctx_(ctx) {}
+    void feed(const std::vector<is_point>& corners, const std::vector<is_mat>& images, const std::vector<is_mat>& masks) {
+        if (images.size() != corners.size() || images.size() != masks.size()) throw Error(IS_ERR_BAD_ARG, "feed: size mismatch");
+        gains_.assign(images.size(), 1.0);
+        ctx_.check(is_gain_feed(ctx_.get(), (int)images.size(), corners.data(), images.data(), masks.data(), gains_.data()));
+    }
+    void apply(int index, is_point /*corner*/, is_mat& image, const is_mat& /*mask*/) const { ctx_.check(is_gain_apply(ctx_.get(), &image, gains_.at(index))); }
+    const std::vector<double>& gains() const { return gains_; }
+
+private:
+    Context& ctx_;
+    std::vector<double> gains_;
+};
+
+// dilate(mask, mask, getStructuringElement(MORPH_RECT, Size(kw, kh))); mask &= and_mask   ([SEAM]:1258-1269)
+inline void dilateAnd(Context& ctx, is_mat& mask, int kw, int kh, const is_mat* and_mask = nullptr) {
+    ctx.check(is_mask_dilate_and(ctx.get(), &mask, kw, kh, and_mask));
+}
+
+// cv::detail::FeatherBlender (Blender::createDefault(FEATHER) + setSharpness), the blender the mains run: [SEAM]:1249-1252,1271,1280
+class FeatherBlender {
+public:
+    explicit FeatherBlender(Context& ctx, float sharpness = 0.02f) : ctx_(ctx) { ctx_.check(is_feather_create(ctx_.get(), sharpness, &h_)); }
+    ~FeatherBlender() { is_feather_destroy(h_); }
+    FeatherBlender(const FeatherBlender&) = delete;
+    FeatherBlender& operator=(const FeatherBlender&) = delete;
+    void prepare(const std::vector<is_point>& corners, const std::vector<is_size>& sizes) {
+        ctx_.check(is_feather_prepare(h_, (int)corners.size(), corners.data(), sizes.data()));
+    }
+    void prepare(is_rect dst_roi) { ctx_.check(is_feather_prepare_roi(h_, dst_roi)); }
+    is_size dstSize() const {
+        is_size s{};
+        ctx_.check(is_feather_dst_size(h_, &s));
+        return s;
+    }
+    void feed(const is_mat& img, const is_mat& mask, is_point tl) { ctx_.check(is_feather_feed(h_, &img, &mask, tl)); }
+    void blend(is_mat& dst, is_mat& dst_mask) { ctx_.check(is_feather_blend(h_, &dst, &dst_mask)); }
+
+private:
+    Context& ctx_;
+    is_feather_blender* h_ = nullptr;
+};
+
 // the whole composite sequence (every main() of the reference)
 inline void stitch(Context& ctx, const std::vector<is_mat>& images, const std::vector<is_camera>& cameras, const is_pipeline_config& cfg,
                    is_mat& pano, is_mat& pano_mask, const is_registration_hooks* hooks = nullptr) {

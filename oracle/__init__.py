@@ -50,7 +50,9 @@ def lib():
         L.orc_pipeline_plan.restype = C.c_int
         L.orc_pipeline_run.restype = C.c_int
         L.orc_pipeline_run_ex.restype = C.c_int
+        L.orc_pipeline_run_ex2.restype = C.c_int
         L.orc_gain_feed.restype = C.c_int
+        L.orc_fb_create.restype = C.c_void_p
         _lib = L
     return _lib
 
@@ -278,6 +280,57 @@ def pipeline_plan(proj, src_sizes_hw, Ks, Rs, scale):
     return corners.reshape(n, 2), sizes.reshape(n, 2), tuple(int(v) for v in roi)
 
 
+def dilate_rect(mask, ksize_wh=(20, 20)):
+    """cv::dilate with getStructuringElement(MORPH_RECT, ksize) ([SEAM]:1258,1264)"""
+    m = np.ascontiguousarray(mask, np.uint8)
+    out = np.empty_like(m)
+    lib().orc_dilate_rect(_p(m), C.c_int(m.shape[0]), C.c_int(m.shape[1]), C.c_int(ksize_wh[0]), C.c_int(ksize_wh[1]), _p(out))
+    return out
+
+
+def distance_l1(mask):
+    m = np.ascontiguousarray(mask, np.uint8)
+    out = np.empty(m.shape, np.float32)
+    lib().orc_distance_l1(_p(m), C.c_int(m.shape[0]), C.c_int(m.shape[1]), _p(out))
+    return out
+
+
+def feather_weight(mask, sharpness):
+    m = np.ascontiguousarray(mask, np.uint8)
+    out = np.empty(m.shape, np.float32)
+    lib().orc_feather_weight(_p(m), C.c_int(m.shape[0]), C.c_int(m.shape[1]), C.c_float(sharpness), _p(out))
+    return out
+
+
+class FeatherBlender:
+    """cv::detail::FeatherBlender ([SEAM]:1249-1252,1271,1280)"""
+
+    def __init__(self, sharpness=0.02):
+        self.h = C.c_void_p(lib().orc_fb_create(C.c_float(sharpness)))
+        self.roi = None
+
+    def __del__(self):
+        if getattr(self, "h", None):
+            lib().orc_fb_destroy(self.h)
+            self.h = None
+
+    def prepare(self, dst_roi_xywh):
+        self.roi = tuple(int(v) for v in dst_roi_xywh)
+        r = np.asarray(self.roi, np.int32)
+        lib().orc_fb_prepare(self.h, _p(r))
+
+    def feed(self, img, mask, tl):
+        img = np.ascontiguousarray(img, np.int16)
+        mask = np.ascontiguousarray(mask, np.uint8)
+        lib().orc_fb_feed(self.h, _p(img), _p(mask), C.c_int(img.shape[0]), C.c_int(img.shape[1]), C.c_int(int(tl[0])), C.c_int(int(tl[1])))
+
+    def blend(self):
+        pano = np.empty((self.roi[3], self.roi[2], 3), np.int16)
+        pmask = np.empty((self.roi[3], self.roi[2]), np.uint8)
+        lib().orc_fb_blend(self.h, _p(pano), _p(pmask))
+        return pano, pmask
+
+
 def gain_feed(corners, images, masks):
     """cv::detail::GainCompensator::feed -> gains (float64[n]); images u8 BGR, masks u8"""
     n = len(images)
@@ -302,7 +355,8 @@ def gain_apply(image, gain):
     return out
 
 
-def pipeline_run(proj, srcs, Ks, Rs, scale, seam=True, num_bands=5, weight_type=WEIGHT_32F, want_intermediates=False, exposure_gain=False):
+def pipeline_run(proj, srcs, Ks, Rs, scale, seam=True, num_bands=5, weight_type=WEIGHT_32F, want_intermediates=False, exposure_gain=False,
+                 blender="multiband", sharpness=0.02, seam_dilate=0):
     """warp -> [gain exposure] -> [DP seam] -> multi-band blend.  Returns dict(pano, pano_mask, corners, sizes, roi, seconds, gains[, warped, masks])."""
     n = len(srcs)
     srcs = [np.ascontiguousarray(s, np.uint8) for s in srcs]
@@ -326,9 +380,10 @@ def pipeline_run(proj, srcs, Ks, Rs, scale, seam=True, num_bands=5, weight_type=
     s = np.ascontiguousarray(sizes.reshape(-1))
     r = np.asarray(roi, np.int32)
     gains = np.ones(n, np.float64)
-    rc = lib().orc_pipeline_run_ex(C.c_int(n), C.c_int(proj), sp, _p(rows), _p(cols), _p(K), _p(R), C.c_float(scale),
-                                   C.c_int(1 if seam else 0), C.c_int(num_bands), C.c_int(weight_type), C.c_int(1 if exposure_gain else 0),
-                                   _p(c), _p(s), _p(r), wp, mp, _p(pano), _p(pmask), _p(secs), _p(gains))
+    rc = lib().orc_pipeline_run_ex2(C.c_int(n), C.c_int(proj), sp, _p(rows), _p(cols), _p(K), _p(R), C.c_float(scale),
+                                    C.c_int(1 if seam else 0), C.c_int(num_bands), C.c_int(weight_type), C.c_int(1 if exposure_gain else 0),
+                                    C.c_int(1 if blender == "feather" else 0), C.c_float(sharpness), C.c_int(int(seam_dilate)),
+                                    _p(c), _p(s), _p(r), wp, mp, _p(pano), _p(pmask), _p(secs), _p(gains))
     if rc:
         raise RuntimeError(f"orc_pipeline_run failed: {rc}")
     out = dict(pano=pano, pano_mask=pmask, corners=corners, sizes=sizes, roi=roi, seconds=secs, gains=gains)

@@ -98,6 +98,17 @@ int orc_lin_blend(const float* img1, int rows1, int cols1, const float* img2, in
                   int tl1x, int tl1y, int tl2x, int tl2y, float* pano, int* seam_x,
                   float* costV_out /* panoHe x (interSectBr+2), may be NULL */);
 
+/* ---- feather blend + mask preparation (oracle/feather.cpp): dilate / distanceTransform / cv::detail::FeatherBlender ---- */
+void orc_dilate_rect(const uint8_t* src, int rows, int cols, int kw, int kh, uint8_t* dst);
+void orc_distance_l1(const uint8_t* mask, int rows, int cols, float* dist);
+void orc_feather_weight(const uint8_t* mask, int rows, int cols, float sharpness, float* weight);
+typedef struct orc_fb orc_fb;
+orc_fb* orc_fb_create(float sharpness);
+void orc_fb_destroy(orc_fb* f);
+void orc_fb_prepare(orc_fb* f, const int* roi_xywh);
+void orc_fb_feed(orc_fb* f, const int16_t* img, const uint8_t* mask, int rows, int cols, int tlx, int tly);
+void orc_fb_blend(orc_fb* f, int16_t* pano, uint8_t* pano_mask);
+
 /* ---- gain exposure compensation (oracle/exposure.cpp): cv::detail::GainCompensator feed / apply ---- */
 int orc_gain_feed(int n, const uint8_t* const* images, const uint8_t* const* masks, const int* rows, const int* cols, const int* corners_xy,
                   double* gains);
@@ -120,6 +131,14 @@ int orc_pipeline_run_ex(int n, int proj, const uint8_t* const* srcs, const int* 
                         const int* corners_xy, const int* sizes_wh, const int* pano_roi,
                         uint8_t* const* warped_out, uint8_t* const* masks_out,
                         int16_t* pano, uint8_t* pano_mask, double* stage_seconds, double* gains_out);
+/* ... and with the blender of the mains' live path: blender 0 = multi-band, 1 = feather (sharpness); seam_dilate > 0:
+ * masks = dilate(masks, d x d) & warped masks before the blender's feed ([SEAM]:1257-1270) */
+int orc_pipeline_run_ex2(int n, int proj, const uint8_t* const* srcs, const int* src_rows, const int* src_cols,
+                         const float* K, const float* R, float scale, int seam, int num_bands, int weight_type, int exposure_gain,
+                         int blender, float sharpness, int seam_dilate,
+                         const int* corners_xy, const int* sizes_wh, const int* pano_roi,
+                         uint8_t* const* warped_out, uint8_t* const* masks_out,
+                         int16_t* pano, uint8_t* pano_mask, double* stage_seconds, double* gains_out);
 
 #ifdef __cplusplus
 }

@@ -68,6 +68,19 @@ int orc_pipeline_run_ex(int n, int proj, const uint8_t* const* srcs, const int* 
                         const int* corners_xy, const int* sizes_wh, const int* pano_roi,
                         uint8_t* const* warped_out, uint8_t* const* masks_out,
                         int16_t* pano, uint8_t* pano_mask, double* stage_seconds, double* gains_out) {
+    return orc_pipeline_run_ex2(n, proj, srcs, src_rows, src_cols, K, R, scale, seam, num_bands, weight_type, exposure_gain, 0, 0.02f, 0, corners_xy,
+                                sizes_wh, pano_roi, warped_out, masks_out, pano, pano_mask, stage_seconds, gains_out);
+}
+
+// blender: 0 = multi-band (num_bands, weight_type), 1 = feather (sharpness).  seam_dilate > 0: masks = dilate(masks, d x d) & warped
+// masks before the blender's feed ([SEAM]:1257-1270).  With blender = 1, seam_dilate = 20, sharpness = 0.1 this is the sequence the
+// reference's mains execute.
+int orc_pipeline_run_ex2(int n, int proj, const uint8_t* const* srcs, const int* src_rows, const int* src_cols,
+                         const float* K, const float* R, float scale, int seam, int num_bands, int weight_type, int exposure_gain,
+                         int blender, float sharpness, int seam_dilate,
+                         const int* corners_xy, const int* sizes_wh, const int* pano_roi,
+                         uint8_t* const* warped_out, uint8_t* const* masks_out,
+                         int16_t* pano, uint8_t* pano_mask, double* stage_seconds, double* gains_out) {
     using clk = std::chrono::steady_clock;
     auto t0 = clk::now();
     std::vector<std::vector<uint8_t>> warped(n), masks(n);
@@ -96,6 +109,8 @@ int orc_pipeline_run_ex(int n, int proj, const uint8_t* const* srcs, const int* 
     }
     if (gains_out) for (int i = 0; i < n; ++i) gains_out[i] = gains[i];
     auto t1 = clk::now();
+    std::vector<std::vector<uint8_t>> wmask0;                    // masks_warped: the seam finder changes `masks` in place
+    if (seam_dilate > 0) wmask0 = masks;
     if (seam) {                                                  // [SEAM]:1188-1192
         std::vector<std::vector<float>> imgf(n);
         std::vector<const void*> ip(n);
@@ -114,20 +129,27 @@ int orc_pipeline_run_ex(int n, int proj, const uint8_t* const* srcs, const int* 
         if (rc) return rc;
     }
     auto t2 = clk::now();
-    orc_mb* mb = orc_mb_create(num_bands, weight_type);
-    orc_mb_prepare(mb, pano_roi);
+    orc_mb* mb = blender == 0 ? orc_mb_create(num_bands, weight_type) : nullptr;
+    orc_fb* fb = blender == 1 ? orc_fb_create(sharpness) : nullptr;
+    if (mb) orc_mb_prepare(mb, pano_roi); else orc_fb_prepare(fb, pano_roi);
     for (int i = 0; i < n; ++i) {                                // [SEAM]:1263,1271
         if (exposure_gain) orc_gain_apply(warped[i].data(), warped[i].size(), gains[i]);   // compensator->apply  [SEAM]:1165-1171
+        if (seam_dilate > 0) {                                   // dilate(masks_seam) & masks_warped  [SEAM]:1264-1269
+            std::vector<uint8_t> dil(masks[i].size());
+            orc_dilate_rect(masks[i].data(), rows[i], cols[i], seam_dilate, seam_dilate, dil.data());
+            for (size_t k = 0; k < dil.size(); ++k) masks[i][k] = dil[k] & wmask0[i][k];
+        }
         std::vector<int16_t> s16(warped[i].size());
         const uint8_t* s = warped[i].data();
         int16_t* d = s16.data();
         const size_t cnt = warped[i].size();
 #pragma omp parallel for schedule(static)
         for (size_t k = 0; k < cnt; ++k) d[k] = (int16_t)s[k];
-        orc_mb_feed(mb, s16.data(), masks[i].data(), rows[i], cols[i], corners_xy[2 * i], corners_xy[2 * i + 1]);
+        if (mb) orc_mb_feed(mb, s16.data(), masks[i].data(), rows[i], cols[i], corners_xy[2 * i], corners_xy[2 * i + 1]);
+        else orc_fb_feed(fb, s16.data(), masks[i].data(), rows[i], cols[i], corners_xy[2 * i], corners_xy[2 * i + 1]);
     }
-    orc_mb_blend(mb, pano, pano_mask);                           // [SEAM]:1280
-    orc_mb_destroy(mb);
+    if (mb) { orc_mb_blend(mb, pano, pano_mask); orc_mb_destroy(mb); }   // [SEAM]:1280
+    else { orc_fb_blend(fb, pano, pano_mask); orc_fb_destroy(fb); }
     auto t3 = clk::now();
     for (int i = 0; i < n; ++i) {
         if (warped_out && warped_out[i]) std::memcpy(warped_out[i], warped[i].data(), warped[i].size());

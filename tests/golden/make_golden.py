@@ -140,11 +140,54 @@ def pyr_cases():
     np.savez_compressed(os.path.join(HERE, "pyr_cases.npz"), **out)
 
 
+def exposure_feather_cases():
+    """GainCompensator feed / apply, dilate 20x20, distanceTransform(L1, 3), FeatherBlender (the mains' live blend path)."""
+    rng = np.random.default_rng(77)
+    out = {}
+    for k in range(3):
+        n = 3
+        imgs, masks, corners, x = [], [], [], 0
+        for i in range(n):
+            h, w = int(rng.integers(50, 80)), int(rng.integers(70, 110))
+            imgs.append(np.clip(rng.integers(0, 256, (h, w, 3)).astype(np.float32) * rng.uniform(0.6, 1.2), 0, 255).astype(np.uint8))
+            m = blob_masks(rng, [(h, w)])[0]
+            masks.append(m)
+            corners.append((x, int(rng.integers(-6, 6))))
+            x += int(w * rng.uniform(0.5, 0.8))
+        c = cv2.detail.ExposureCompensator_createDefault(cv2.detail.ExposureCompensator_GAIN)
+        c.feed(corners, imgs, masks)
+        gains = np.array([float(g[0, 0]) for g in c.getMatGains()])
+        sizes = [(a.shape[1], a.shape[0]) for a in imgs]
+        x0 = min(cc[0] for cc in corners); y0 = min(cc[1] for cc in corners)
+        x1 = max(cc[0] + sz[0] for cc, sz in zip(corners, sizes)); y1 = max(cc[1] + sz[1] for cc, sz in zip(corners, sizes))
+        roi = (x0, y0, x1 - x0, y1 - y0)
+        fb = cv2.detail_FeatherBlender(0.1)
+        fb.prepare(roi)
+        e = cv2.getStructuringElement(cv2.MORPH_RECT, (20, 20))
+        out[f"e{k}_corners"] = np.asarray(corners, np.int32)
+        out[f"e{k}_gains_cv"] = gains
+        out[f"e{k}_roi"] = np.asarray(roi, np.int32)
+        for i in range(n):
+            out[f"e{k}_img{i}"] = imgs[i]
+            out[f"e{k}_mask{i}"] = masks[i]
+            out[f"e{k}_applied{i}_cv"] = c.apply(i, corners[i], imgs[i].copy(), masks[i])
+            out[f"e{k}_dilated{i}_cv"] = cv2.dilate(masks[i], e)
+            out[f"e{k}_dist{i}_cv"] = cv2.distanceTransform(masks[i], cv2.DIST_L1, 3)
+            fb.feed(imgs[i].astype(np.int16), masks[i], corners[i])
+        pano, pmask = fb.blend(None, None)
+        out[f"e{k}_feather_cv"] = pano
+        out[f"e{k}_feather_mask_cv"] = pmask
+    out["n"] = np.int32(3)
+    np.savez_compressed(os.path.join(HERE, "exposure_feather_cases.npz"), **out)
+
+
 if __name__ == "__main__":
-    warp_cases()
-    remap_cases()
-    seam_blend_cases()
-    pyr_cases()
+    if "--only-new" not in sys.argv:
+        warp_cases()
+        remap_cases()
+        seam_blend_cases()
+        pyr_cases()
+    exposure_feather_cases()
     for f in sorted(os.listdir(HERE)):
         if f.endswith(".npz"):
             print(f, os.path.getsize(os.path.join(HERE, f)))

@@ -248,6 +248,73 @@ def test_pipeline_with_gain_exposure(ctx, oracle):
     _eq(got["pano"], want["pano"], "panorama (gain compensated)")
 
 
+def test_dilate_and_feather_weights(ctx, oracle):
+    """Mask preparation of the mains ([SEAM]:1257-1270) and createWeightMap: dilate / & / L1 distance weights, bit for bit."""
+    import torch
+    O = oracle
+    rng = np.random.default_rng(8)
+    for t in range(5):
+        h, w = int(rng.integers(30, 300)), int(rng.integers(30, 400))
+        m = ((rng.random((h, w)) > 0.6).astype(np.uint8) * 255) if t % 2 else blob_masks(rng, [(h, w)])[0]
+        other = blob_masks(rng, [(h, w)])[0]
+        for k in ((20, 20), (3, 5), (1, 1), (33, 7)):
+            a = m.copy()
+            S.dilate_and(ctx, a, k, other)
+            _eq(a, O.dilate_rect(m, k) & other, f"dilate {k} & mask")
+            b = torch.from_numpy(m.copy()).cuda()
+            S.dilate_and(ctx, b, k)
+            torch.cuda.synchronize()
+            _eq(b.cpu().numpy(), O.dilate_rect(m, k), f"dilate {k} (device buffer)")
+        for sharp in (0.02, 0.1, 5.0):
+            _eq(S.feather_weight_map(ctx, m, sharp).view(np.uint32), O.feather_weight(m, sharp).view(np.uint32), f"weight map sharpness {sharp}")
+    full = np.full((40, 50), 255, np.uint8)          # no zero pixel anywhere: distance FLT_MAX, weight 1
+    _eq(S.feather_weight_map(ctx, full, 0.1), O.feather_weight(full, 0.1), "weight map of a mask without zeros")
+
+
+@pytest.mark.parametrize("sharp", [0.02, 0.1])
+@pytest.mark.parametrize("u8", [False, True])
+def test_feather_blend(ctx, oracle, sharp, u8):
+    """The mains' live blend path: dilated seam masks & warped masks, FeatherBlender(sharpness) prepare / feed / blend."""
+    O = oracle
+    corners, wi, wm = warped_set(O, 4, 320, 240, overlap=0.3)
+    sm = O.dp_seam_find(wi, corners, wm)
+    sizes = [(a.shape[1], a.shape[0]) for a in wi]
+    for masks in ([O.dilate_rect(s) & m for s, m in zip(sm, wm)], wm):
+        ob = O.FeatherBlender(sharp)
+        ob.prepare(O.result_roi(corners, sizes))
+        gb = S.FeatherBlender(ctx, sharp)
+        gb.prepare(corners, sizes)
+        for i in range(4):
+            ob.feed(wi[i].astype(np.int16), masks[i], corners[i])
+            gb.feed(wi[i] if u8 else wi[i].astype(np.int16), masks[i], corners[i])
+        want, wmask = ob.blend()
+        got, gmask = gb.blend()
+        _eq(gmask, wmask, "feather mask")
+        _eq(got, want, f"feather blend sharpness={sharp}")
+
+
+@pytest.mark.parametrize("cfg", [dict(blender="feather", sharpness=0.1, seam_dilate=20, exposure_gain=True),      # what the reference's mains run
+                                 dict(blender="feather", sharpness=0.02, seam_dilate=0, exposure_gain=False),
+                                 dict(blender="multiband", sharpness=0.02, seam_dilate=20, exposure_gain=True)])
+def test_pipeline_reference_configuration(ctx, oracle, cfg):
+    """warp -> gain exposure -> DP seam -> dilate(20x20) & warped mask -> feather blend(0.1): the sequence of [SEAM]:1094-1285."""
+    O = oracle
+    imgs, Ks, Rs, scale = synth.make_panorama_inputs(4, 384, 288, 1.2, 0.25)
+    imgs = [np.clip(a.astype(np.float32) * g, 0, 255).astype(np.uint8) for a, g in zip(imgs, (0.85, 1.0, 1.1, 0.9))]
+    want = O.pipeline_run(O.PROJ_CYLINDRICAL, imgs, Ks, Rs, scale, seam=True, num_bands=5, weight_type=O.WEIGHT_32F, want_intermediates=True, **cfg)
+    st = S.Stitcher(ctx, "cylindrical", "dp", 5, S.WEIGHT_32F, exposure="gain" if cfg["exposure_gain"] else None, blender=cfg["blender"],
+                    sharpness=cfg["sharpness"], seam_dilate=cfg["seam_dilate"])
+    got = st.stitch(imgs, Ks, Rs, scale, want_seam_masks=True)
+    for k in range(4):
+        _eq(got["seam_masks"][k], want["masks"][k], f"seam mask {k}")
+    _eq(got["pano_mask"], want["pano_mask"], "panorama mask")
+    _eq(got["pano"], want["pano"], f"panorama {cfg}")
+    import torch
+    dev = st.stitch([torch.from_numpy(a).cuda() for a in imgs], Ks, Rs, scale)
+    torch.cuda.synchronize()
+    _eq(dev["pano"].cpu().numpy(), want["pano"], "panorama (device buffers)")
+
+
 def test_linear_blend_pair(ctx, oracle):
     O = oracle
     for (w, h, ov) in ((400, 300, 0.25), (320, 260, 0.4)):

@@ -111,3 +111,33 @@ def test_gain_compensator_vs_cv2(oracle):
         c = cv2.detail.ExposureCompensator_createDefault(cv2.detail.ExposureCompensator_GAIN)
         c.setMatGains([np.array([[g]], np.float64)])
         assert np.array_equal(c.apply(0, (0, 0), vals.copy(), np.full((1, 256), 255, np.uint8)), O.gain_apply(vals, g)), g
+
+
+def test_dilate_distance_feather_vs_cv2(oracle):
+    """The mains' live blend path ([SEAM]:1249-1280): dilate 20x20, distanceTransform(L1, 3), FeatherBlender -- bit for bit."""
+    O = oracle
+    rng = np.random.default_rng(5)
+    for t in range(6):
+        h, w = int(rng.integers(30, 90)), int(rng.integers(30, 120))
+        m = ((rng.random((h, w)) > 0.7).astype(np.uint8) * 255) if t % 2 else blob_masks(rng, [(h, w)])[0]
+        for k in ((20, 20), (3, 3), (5, 8), (1, 1)):
+            assert np.array_equal(cv2.dilate(m, cv2.getStructuringElement(cv2.MORPH_RECT, k)), O.dilate_rect(m, k)), (t, k)
+        assert np.array_equal(cv2.distanceTransform(m, cv2.DIST_L1, 3), O.distance_l1(m)), t
+    full = np.full((20, 30), 255, np.uint8)
+    assert np.array_equal(cv2.distanceTransform(full, cv2.DIST_L1, 3), O.distance_l1(full))      # FLT_MAX everywhere
+    corners, wi, wm = warped_set(O, 3, 320, 240, overlap=0.3)
+    sm = O.dp_seam_find(wi, corners, wm)
+    sizes = [(a.shape[1], a.shape[0]) for a in wi]
+    roi = O.result_roi(corners, sizes)
+    for sharp in (0.02, 0.1, 5.0):
+        for masks in ([O.dilate_rect(s) & m for s, m in zip(sm, wm)], wm):
+            fb = cv2.detail_FeatherBlender(sharp)
+            fb.prepare(roi)
+            ob = O.FeatherBlender(sharp)
+            ob.prepare(roi)
+            for i in range(3):
+                fb.feed(wi[i].astype(np.int16), masks[i], corners[i])
+                ob.feed(wi[i].astype(np.int16), masks[i], corners[i])
+            a, am = fb.blend(None, None)
+            b, bm = ob.blend()
+            assert np.array_equal(am, bm) and np.array_equal(a, b), sharp

@@ -100,3 +100,24 @@ def test_pyramid_fixtures(oracle):
         assert np.array_equal(O.pyr_up_s16(a, (2 * h, 2 * w)), z[f"p{k}_up_cv"])
         assert np.array_equal(O.pyr_up_s16(a, (2 * h - 1, 2 * w - 1)), z[f"p{k}_up_odd_cv"])
         assert np.abs(O.pyr_down_f32(z[f"p{k}_f32"]) - z[f"p{k}_f32_down_cv"]).max() <= 2.4e-7
+
+
+def test_exposure_and_feather_fixtures(oracle):
+    """GainCompensator, dilate, L1 distance and FeatherBlender outputs of OpenCV 4.13 (the mains' exposure + live blend path)."""
+    O = oracle
+    z = _load("exposure_feather_cases.npz")
+    for k in range(int(z["n"])):
+        corners = [tuple(int(v) for v in c) for c in z[f"e{k}_corners"]]
+        imgs = [z[f"e{k}_img{i}"] for i in range(3)]
+        masks = [z[f"e{k}_mask{i}"] for i in range(3)]
+        g = O.gain_feed(corners, imgs, masks)
+        assert np.max(np.abs(g - z[f"e{k}_gains_cv"]) / z[f"e{k}_gains_cv"]) < 1e-12
+        fb = O.FeatherBlender(0.1)
+        fb.prepare(tuple(int(v) for v in z[f"e{k}_roi"]))
+        for i in range(3):
+            assert np.array_equal(O.gain_apply(imgs[i], z[f"e{k}_gains_cv"][i]), z[f"e{k}_applied{i}_cv"])
+            assert np.array_equal(O.dilate_rect(masks[i], (20, 20)), z[f"e{k}_dilated{i}_cv"])
+            assert np.array_equal(O.distance_l1(masks[i]), z[f"e{k}_dist{i}_cv"])
+            fb.feed(imgs[i].astype(np.int16), masks[i], corners[i])
+        pano, pmask = fb.blend()
+        assert np.array_equal(pmask, z[f"e{k}_feather_mask_cv"]) and np.array_equal(pano, z[f"e{k}_feather_cv"])
