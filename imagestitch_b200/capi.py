@@ -20,7 +20,7 @@ INTER_NEAREST, INTER_LINEAR = 0, 1
 BORDER_CONSTANT, BORDER_REFLECT = 0, 2
 COST_COLOR, COST_COLOR_GRAD = 0, 1
 WEIGHT_32F, WEIGHT_16S = 5, 3
-FEED_COPY, FEED_BORROW = 0, 1
+FEED_COPY, FEED_BORROW, FEED_DEFER_WEIGHTS = 0, 1, 2
 SEAM_NONE, SEAM_DP = 0, 1
 EXPOSURE_NONE, EXPOSURE_GAIN = 0, 1
 BLEND_MULTI_BAND, BLEND_FEATHER = 0, 1
@@ -100,6 +100,7 @@ SYMBOLS = {
     "is_blender_num_bands": (C.c_int, [C.c_void_p]),
     "is_blender_dst_size": (C.c_int, [C.c_void_p, _P(Size)]),
     "is_blender_feed": (C.c_int, [C.c_void_p, _P(Mat), _P(Mat), Point, C.c_int]),
+    "is_blender_feed_ex": (C.c_int, [C.c_void_p, _P(Mat), _P(Mat), Point, C.c_int, C.c_longlong]),
     "is_blender_blend": (C.c_int, [C.c_void_p, _P(Mat), _P(Mat)]),
     "is_linear_blend_size": (C.c_int, [Size, Size, Point, Point, _P(Size)]),
     "is_linear_blend_pair": (C.c_int, [C.c_void_p, _P(Mat), _P(Mat), Point, Point, _P(Mat), _P(C.c_int)]),

@@ -980,6 +980,8 @@ struct FedImage {
     std::vector<DevBuf> g, w;      // levels 1..nb at index k (index 0 unused)
     DevBuf summary;                // occupancy of the mask per 64 x 32 cell (k_mask_summary)
     int sum_w = 0, sum_h = 0;
+    bool weights_pending = false;  // fed with the image pyramid only: weights + occupancy map are built when blend() starts
+    long long key = 0;             // feed order of the reference (ascending key, ties in call order)
 };
 
 struct is_blender {
@@ -988,6 +990,8 @@ struct is_blender {
     bool prepared = false;
     is_rect roi_final{}, roi{};
     std::vector<FedImage> fed;
+    is_ctx* side = nullptr;        // side stream with image pyramids in flight (deferred feeds), joined when blend() starts
+    long long next_key = 0;
 };
 
 namespace is {
@@ -1151,6 +1155,7 @@ static int feed_summary(is_ctx* ctx, const FedImage& f) {
 }
 
 int blender_feed_dev(is_blender* b, FedImage&& f) {
+    if (f.key == 0) f.key = ++b->next_key; else b->next_key = std::max(b->next_key, f.key);
     IS_TRY(feed_prepare(b, f));
     IS_TRY(feed_summary(b->ctx, f));
     IS_TRY(feed_pyramid(b->ctx, b, f, PD_BOTH));
@@ -1165,10 +1170,13 @@ int blender_feed_image(is_blender* b, is_ctx* side, const DevMat& img, const Dev
     f.tl_x = tl.x; f.tl_y = tl.y;
     f.img.data = img.data; f.img.rows = img.rows; f.img.cols = img.cols; f.img.channels = img.channels; f.img.depth = img.depth; f.img.step = img.step;
     f.mask.data = mask.data; f.mask.rows = mask.rows; f.mask.cols = mask.cols; f.mask.channels = 1; f.mask.depth = IS_8U; f.mask.step = mask.step;
+    f.key = ++b->next_key;
+    f.weights_pending = true;
     IS_TRY(feed_prepare(b, f));
     if (side != b->ctx) IS_TRY(stream_after(b->ctx, side->stream, b->ctx->stream));   // the allocations above are ordered on the blender's stream
     const int rc = feed_pyramid(side, b, f, PD_IMAGE);
     if (rc != IS_OK) { if (b->ctx->last_error.empty()) b->ctx->last_error = side->last_error; return rc; }
+    if (side != b->ctx) b->side = side;
     b->fed.push_back(std::move(f));
     return IS_OK;
 }
@@ -1179,7 +1187,11 @@ int blender_feed_weights(is_blender* b) {
     const int nb = b->num_bands, n = (int)b->fed.size();
     const bool wf = b->weight_type == IS_WEIGHT_32F;
     const size_t wsz = wf ? sizeof(float) : sizeof(int16_t);
-    for (const FedImage& f : b->fed) {
+    std::vector<int> pend;
+    for (int i = 0; i < n; ++i) if (b->fed[i].weights_pending) pend.push_back(i);
+    if (pend.empty()) return IS_OK;
+    for (int pi : pend) {
+        const FedImage& f = b->fed[pi];
         IS_TRY(feed_summary(ctx, f));
         if (nb >= 1) {   // level 1 from the mask (tiled kernel, constants for uniform tiles)
             const int dh = (f.height + 1) / 2, dw = (f.width + 1) / 2;
@@ -1190,17 +1202,19 @@ int blender_feed_weights(is_blender* b) {
             else IS_LAUNCH(ctx, (k_pyrdown_l0_tiled<false, PD_WEIGHT>), tg, tb, 0, L, f.g[1].as<int16_t>(), f.w[1].p, dh, dw);
         }
     }
-    if (nb < 2 || n == 0) return IS_OK;
-    // levels 2..nb: one launch per level over all images
-    std::vector<WeightLevel> host((size_t)n * (nb - 1));
+    for (int pi : pend) b->fed[pi].weights_pending = false;
+    if (nb < 2) return IS_OK;
+    // levels 2..nb: one launch per level over all pending images
+    const int np = (int)pend.size();
+    std::vector<WeightLevel> host((size_t)np * (nb - 1));
     std::vector<int> gx(nb + 1, 0), gy(nb + 1, 0);
     std::vector<double> bytes(nb + 1, 0.);
-    for (int i = 0; i < n; ++i) {
-        const FedImage& f = b->fed[i];
+    for (int i = 0; i < np; ++i) {
+        const FedImage& f = b->fed[pend[i]];
         int sh = (f.height + 1) / 2, sw = (f.width + 1) / 2;
         for (int k = 2; k <= nb; ++k) {
             const int dh = (sh + 1) / 2, dw = (sw + 1) / 2;
-            host[(size_t)(k - 2) * n + i] = WeightLevel{f.w[k - 1].p, f.w[k].p, sh, sw, dh, dw};
+            host[(size_t)(k - 2) * np + i] = WeightLevel{f.w[k - 1].p, f.w[k].p, sh, sw, dh, dw};
             gx[k] = std::max(gx[k], div_up(dw, 32)); gy[k] = std::max(gy[k], div_up(dh, 8));
             bytes[k] += ((double)sh * sw + (double)dh * dw) * (double)wsz;
             sh = dh; sw = dw;
@@ -1210,9 +1224,9 @@ int blender_feed_weights(is_blender* b) {
     IS_TRY(table.alloc(ctx, sizeof(WeightLevel) * host.size()));
     IS_TRY(upload(ctx, table.p, host.data(), sizeof(WeightLevel) * host.size()));
     for (int k = 2; k <= nb; ++k) {
-        dim3 block(32, 8), grid(gx[k], gy[k], n);
+        dim3 block(32, 8), grid(gx[k], gy[k], np);
         ctx->next_bytes = bytes[k];
-        const WeightLevel* t = table.as<WeightLevel>() + (size_t)(k - 2) * n;
+        const WeightLevel* t = table.as<WeightLevel>() + (size_t)(k - 2) * np;
         if (wf) IS_LAUNCH(ctx, k_pyrdown_weights_batch<true>, grid, block, 0, t);
         else IS_LAUNCH(ctx, k_pyrdown_weights_batch<false>, grid, block, 0, t);
     }
@@ -1328,6 +1342,15 @@ static int blend_level0_tiled(is_blender* b, const LevelArgs& generic, const Dev
 
 int blender_blend_dev(is_blender* b, const DevMat& dst, const DevMat& dmask, int sx0, int sx1) {
     is_ctx* ctx = b->ctx;
+    // deferred feeds: weights + occupancy maps from the masks as they are now, image pyramids of the side stream joined,
+    // images in the reference's feed order
+    IS_TRY(blender_feed_weights(b));
+    if (b->side) {
+        IS_TRY(stream_after(ctx, ctx->stream, b->side->stream));
+        merge_child(ctx, b->side);
+        b->side = nullptr;
+    }
+    std::stable_sort(b->fed.begin(), b->fed.end(), [](const FedImage& a, const FedImage& c) { return a.key < c.key; });
     std::vector<int> xb, xe;
     strip_ranges(b, sx0, sx1, &xb, &xe);
     const int nb = b->num_bands, n = (int)b->fed.size();
@@ -1399,6 +1422,7 @@ int blender_blend_dev(is_blender* b, const DevMat& dst, const DevMat& dmask, int
         }
     }
     b->fed.clear();        // OpenCV releases the pyramids in blend()
+    b->next_key = 0;
     b->prepared = false;
     return IS_OK;
 }
@@ -1469,6 +1493,37 @@ int is_blender_feed(is_blender* b, const is_mat* img, const is_mat* mask, is_poi
     if (borrow && img->device >= 0) IS_TRY(stage_in(ctx, img, &f.img)); else IS_TRY(private_copy(ctx, img, &f.img));
     if (borrow && mask->device >= 0) IS_TRY(stage_in(ctx, mask, &f.mask)); else IS_TRY(private_copy(ctx, mask, &f.mask));
     return blender_feed_dev(b, std::move(f));
+}
+
+int is_blender_feed_ex(is_blender* b, const is_mat* img, const is_mat* mask, is_point tl, int flags, long long key) {
+    if (!b) return IS_ERR_BAD_ARG;
+    is_ctx* ctx = b->ctx;
+    IS_CUDA(ctx, cudaSetDevice(ctx->device));
+    IS_REQUIRE(ctx, b->prepared, IS_ERR_ASSERT, "feed() before prepare()");
+    IS_REQUIRE(ctx, key > 0, IS_ERR_BAD_ARG, "key must be positive");
+    if (!(flags & IS_FEED_DEFER_WEIGHTS)) {
+        const size_t before = b->fed.size();
+        IS_TRY(is_blender_feed(b, img, mask, tl, flags & IS_FEED_BORROW));
+        if (b->fed.size() > before) b->fed.back().key = key;
+        b->next_key = std::max(b->next_key, key);
+        return IS_OK;
+    }
+    IS_TRY(check_mat(ctx, img, "img"));
+    IS_TRY(check_mat(ctx, mask, "mask"));
+    IS_REQUIRE(ctx, img->device >= 0 && mask->device >= 0, IS_ERR_BAD_ARG, "deferred feeds borrow device buffers");
+    IS_REQUIRE(ctx, img->channels == 3 && (img->depth == IS_16S || img->depth == IS_8U), IS_ERR_ASSERT, "img.type() == CV_16SC3 || img.type() == CV_8UC3");
+    IS_REQUIRE(ctx, mask->depth == IS_8U && mask->channels == 1 && mask->rows == img->rows && mask->cols == img->cols, IS_ERR_ASSERT,
+               "mask.type() == CV_8U && mask.size() == img.size()");
+    is_ctx* side = nullptr;
+    IS_TRY(child_ctx(ctx, SIDE_PYRAMID, &side));
+    side->ktiming = ctx->ktiming;
+    DevMat im, mk;
+    IS_TRY(stage_in(ctx, img, &im));
+    IS_TRY(stage_in(ctx, mask, &mk));
+    IS_TRY(blender_feed_image(b, side, im, mk, tl));
+    b->fed.back().key = key;
+    b->next_key = std::max(b->next_key, key);
+    return IS_OK;
 }
 
 int is_blender_strip_needs(const is_blender* b, is_size img_size, is_point tl, int x0, int x1, int* needed) {

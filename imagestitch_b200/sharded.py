@@ -108,6 +108,17 @@ class ShardedStitcher:
 
     def stitch(self, my_images, Ks_all, Rs_all, scale, plan: ShardPlan):
         be, comm, rank = self.be, self.comm, self.comm.rank
+        import time
+        dbg = os.environ.get("IS_SHARD_DEBUG") == "1"
+        t_last = [time.perf_counter()]
+        laps = {}
+
+        def lap(name):               # wall clock per phase (the phases end with a device sync already)
+            if dbg:
+                be.sync()
+                t = time.perf_counter()
+                laps[name] = laps.get(name, 0.0) + (t - t_last[0]) * 1e3
+                t_last[0] = t
         n = len(plan.corners)
         mine = [i for i in range(n) if plan.owner[i] == rank]
         assert len(mine) == len(my_images)
@@ -116,6 +127,20 @@ class ShardedStitcher:
         for i, img in zip(mine, my_images):
             warped[i], mask0[i] = be.warp(img, Ks_all[i], Rs_all[i], scale)
         be.sync()
+        lap("warp")
+        # which images every strip needs is geometry only; with a backend that can take feeds early, this rank's own images go
+        # to the blender now (image pyramids on a side stream while the seam stage runs) with their final masks still to come
+        x0, x1 = plan.cuts[rank], plan.cuts[rank + 1]
+        needed_by = [[i for i in range(n) if be.strip_needs(plan.sizes[i], plan.corners[i], plan.roi, self.num_bands, plan.cuts[r], plan.cuts[r + 1])]
+                     for r in range(comm.world)]
+        early = hasattr(be, "blend_begin")
+        final_buf, bh = {}, None
+        if early:
+            bh = be.blend_begin(plan.roi, self.num_bands)
+            for i in mine:
+                final_buf[i] = be.empty((plan.sizes[i][1], plan.sizes[i][0]), np.uint8)
+                if i in needed_by[rank]:
+                    be.blend_feed_early(bh, warped[i], final_buf[i], plan.corners[i], i + 1)
         # ---- X1: right images of boundary pairs -> owner of the left image
         sends, recvs = [], []
         seen = set()
@@ -131,6 +156,7 @@ class ShardedStitcher:
                 mask0[j] = be.empty((plan.sizes[j][1], plan.sizes[j][0]), np.uint8)
                 recvs += [(src, warped[j]), (src, mask0[j])]
         comm.exchange(sends, recvs)
+        lap("x1")
         # ---- seam: speculative runs of the pairs this rank owns
         my_pairs = [k for k in range(len(plan.pairs)) if plan.pair_owner(k) == rank]
         outs, handles = {}, {}
@@ -142,6 +168,7 @@ class ShardedStitcher:
 
         be.run_concurrently(run, my_pairs)
         be.sync()
+        lap("seam_runs")
         # ---- X2: pair results to whoever needs them (final masks of the images' owners, validation of later pairs)
         sends, recvs = [], []
         for k, (i, j) in enumerate(plan.pairs):
@@ -155,6 +182,7 @@ class ShardedStitcher:
                         outs[(k, img)] = be.empty((plan.sizes[img][1], plan.sizes[img][0]), np.uint8)
                         recvs.append((src, outs[(k, img)]))
         comm.exchange(sends, recvs)
+        lap("x2")
         # ---- validation of the owned pairs that have an earlier neighbour
         verdict = {}
 
@@ -177,6 +205,7 @@ class ShardedStitcher:
 
         be.run_concurrently(check, my_pairs)
         be.sync()
+        lap("seam_checks")
         ok = comm.all_min(1 if all(verdict.values()) else 0, be.device)
         if os.environ.get("IS_SHARDED_FORCE_FALLBACK") == "1":      # test hook: exercise the sequential fallback
             ok = 0
@@ -186,18 +215,29 @@ class ShardedStitcher:
         final = {}
         if ok:
             for i in mine:                            # final mask = entry mask minus the clears of every pair it is in
-                t = be.clone(mask0[i])
+                if early:
+                    t = final_buf[i]
+                    be.copy_into(t, mask0[i])
+                else:
+                    t = be.clone(mask0[i])
                 for k, pr in enumerate(plan.pairs):
                     if i in pr:
                         be.mask_and(t, outs[(k, i)])
                 final[i] = t
         else:
-            final, warped = self._sequential_fallback(plan, mine, warped, mask0)
+            final, warped_all = self._sequential_fallback(plan, mine, warped, mask0)
+            if early:                                 # the blender already holds this rank's images and mask buffers
+                for i in mine:
+                    be.copy_into(final_buf[i], final[i])
+                    final[i] = final_buf[i]
+                for i in range(n):
+                    if i not in mine:
+                        warped[i] = warped_all[i]
+            else:
+                warped = warped_all
         be.sync()
+        lap("final_masks")
         # ---- X3: blend halo
-        x0, x1 = plan.cuts[rank], plan.cuts[rank + 1]
-        needed_by = [[i for i in range(n) if be.strip_needs(plan.sizes[i], plan.corners[i], plan.roi, self.num_bands, plan.cuts[r], plan.cuts[r + 1])]
-                     for r in range(comm.world)]
         sends, recvs = [], []
         for r in range(comm.world):
             for i in needed_by[r]:
@@ -211,10 +251,21 @@ class ShardedStitcher:
                     final[i] = be.empty((plan.sizes[i][1], plan.sizes[i][0]), np.uint8)
                     recvs += [(src, warped[i]), (src, final[i])]
         comm.exchange(sends, recvs)
+        lap("x3")
         # ---- blend my strip (feed order = global image order)
-        feed = [(warped[i], final[i], plan.corners[i]) for i in needed_by[rank]]
-        pano, pmask = be.blend_strip(feed, plan.roi, self.num_bands, x0, x1)
+        if early:
+            for i in needed_by[rank]:
+                if i not in mine:
+                    be.blend_feed(bh, warped[i], final[i], plan.corners[i], i + 1)
+            pano, pmask = be.blend_finish(bh, x0, x1)
+        else:
+            feed = [(warped[i], final[i], plan.corners[i]) for i in needed_by[rank]]
+            pano, pmask = be.blend_strip(feed, plan.roi, self.num_bands, x0, x1)
         self.info["needed_images"] = needed_by[rank]
+        lap("blend")
+        if dbg:
+            self.info["laps_ms"] = laps
+            print(f"[shard rank {rank}] " + " ".join(f"{k}={v:.2f}" for k, v in laps.items()), flush=True)
         return dict(pano=pano, pano_mask=pmask, x0=x0, x1=x1, seam_masks={i: final[i] for i in mine})
 
     def _sequential_fallback(self, plan, mine, warped, mask0):
@@ -332,3 +383,19 @@ class GpuBackend:
         for (img, mask, corner) in feed:
             b.feed(img, mask, corner, borrow=True)
         return b.blend_strip(x0, x1)
+
+    # feeds spread over the step: own images early (image pyramid on a side stream, mask buffer filled in later), halo images late
+    def blend_begin(self, roi, num_bands):
+        return self._blender(roi, num_bands)
+
+    def blend_feed_early(self, b, img, mask_buffer, corner, key):
+        b.feed(img, mask_buffer, corner, defer=True, key=key)
+
+    def blend_feed(self, b, img, mask, corner, key):
+        b.feed(img, mask, corner, borrow=True, key=key)
+
+    def blend_finish(self, b, x0, x1):
+        return b.blend_strip(x0, x1)
+
+    def copy_into(self, dst, src):
+        dst.copy_(src)          # torch's current stream = the stream the library's main context adopted

@@ -339,14 +339,22 @@ class MultiBandBlender:
     def numBands(self):
         return int(self.ctx.lib.is_blender_num_bands(self.h))
 
-    def feed(self, img, mask, tl, borrow=False):
+    def feed(self, img, mask, tl, borrow=False, defer=False, key=None):
+        """key: position in the feed order (1-based, ascending).  defer=True (device buffers): only the image pyramid is built
+        now, on a side stream; the mask is read when blend() / blend_strip() is called and may change until then."""
         mi, ki = as_mat(img)
         mm, km = as_mat(mask)
         self._like = ki
-        if borrow:
+        if borrow or defer:
             self._keep += [ki, km]
-        self.ctx.check(self.ctx.lib.is_blender_feed(self.h, C.byref(mi), C.byref(mm), capi.Point(int(tl[0]), int(tl[1])),
-                                                    FEED_BORROW if borrow else FEED_COPY))
+        if key is None and not defer:
+            self.ctx.check(self.ctx.lib.is_blender_feed(self.h, C.byref(mi), C.byref(mm), capi.Point(int(tl[0]), int(tl[1])),
+                                                        FEED_BORROW if borrow else FEED_COPY))
+            return
+        self._auto_key = getattr(self, "_auto_key", 0) + 1
+        flags = (FEED_BORROW if (borrow or defer) else FEED_COPY) | (capi.FEED_DEFER_WEIGHTS if defer else 0)
+        self.ctx.check(self.ctx.lib.is_blender_feed_ex(self.h, C.byref(mi), C.byref(mm), capi.Point(int(tl[0]), int(tl[1])), flags,
+                                                       int(key) if key is not None else self._auto_key))
 
     def strip_needs(self, size_wh, tl, x0, x1) -> bool:
         """Does an image of this size / corner contribute to the destination columns [x0, x1)?"""

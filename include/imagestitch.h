@@ -172,8 +172,13 @@ int is_blender_dst_size(const is_blender* b, is_size* size);
 /* img: 3 channels IS_16S or IS_8U; mask: IS_8U, same size.  flags: IS_FEED_COPY keeps a private
  * copy (OpenCV semantics); IS_FEED_BORROW uses device buffers in place -- they must stay valid and
  * unchanged until is_blender_blend returns (host buffers are always copied). */
-enum { IS_FEED_COPY = 0, IS_FEED_BORROW = 1 };
+enum { IS_FEED_COPY = 0, IS_FEED_BORROW = 1, IS_FEED_DEFER_WEIGHTS = 2 };
 int is_blender_feed(is_blender* b, const is_mat* img, const is_mat* mask, is_point tl, int flags);
+/* feed() with an explicit position in the feed order (ascending key > 0; the float weight sums of the blender depend on the
+ * order).  IS_FEED_DEFER_WEIGHTS (device buffers, borrowed): the image's Gaussian pyramid is built now on a side stream; the
+ * mask may still change and is only read when is_blender_blend / is_blender_blend_strip is called -- lets the caller feed
+ * the images before its seam stage has produced the final masks. */
+int is_blender_feed_ex(is_blender* b, const is_mat* img, const is_mat* mask, is_point tl, int flags, long long key);
 
 /* dst: 3 channels IS_16S, dst_mask: IS_8U, both is_blender_dst_size, caller-allocated. */
 int is_blender_blend(is_blender* b, is_mat* dst, is_mat* dst_mask);

@@ -80,6 +80,26 @@ class OracleBackend:
         return torch.from_numpy(d[:, x0:x1].copy()), torch.from_numpy(m[:, x0:x1].copy())
 
 
+class OracleBackendEarly(OracleBackend):
+    """... with the early-feed interface of GpuBackend (images fed before the seam stage, masks filled in later, keyed order)."""
+
+    def blend_begin(self, roi, num_bands):
+        return dict(roi=roi, nb=num_bands, fed=[])
+
+    def blend_feed_early(self, b, img, mask_buffer, corner, key):
+        b["fed"].append((key, img, mask_buffer, corner))      # the buffer is read at blend time
+
+    def blend_feed(self, b, img, mask, corner, key):
+        b["fed"].append((key, img, mask, corner))
+
+    def blend_finish(self, b, x0, x1):
+        feed = [(img, mask, corner) for (_k, img, mask, corner) in sorted(b["fed"], key=lambda t: t[0])]
+        return self.blend_strip(feed, b["roi"], b["nb"], x0, x1)
+
+    def copy_into(self, dst, src):
+        dst.copy_(src)
+
+
 def _worker(rank, world, port, case, result_path):
     sys.path.insert(0, ROOT)
     os.environ["MASTER_ADDR"] = "127.0.0.1"
@@ -92,7 +112,7 @@ def _worker(rank, world, port, case, result_path):
     corners, sizes, roi = O.pipeline_plan(0, [(h, w)] * n, Ks, Rs, scale)
     plan = sharded.ShardPlan.build(corners, sizes, roi, world, nb)
     mine = [torch.from_numpy(imgs[i]) for i in range(n) if plan.owner[i] == rank]
-    st = sharded.ShardedStitcher(OracleBackend(O), sharded.Comm(dist), nb)
+    st = sharded.ShardedStitcher((OracleBackendEarly if os.environ.get("IS_TEST_EARLY_FEED") == "1" else OracleBackend)(O), sharded.Comm(dist), nb)
     res = st.stitch(mine, Ks, Rs, scale, plan)
     strips = [None] * world
     dist.all_gather_object(strips, (res["x0"], res["x1"], res["pano"].numpy(), res["pano_mask"].numpy(),
@@ -113,10 +133,12 @@ def _worker(rank, world, port, case, result_path):
     dist.destroy_process_group()
 
 
+@pytest.mark.parametrize("early", [False, True])
 @pytest.mark.parametrize("case", [(4, 192, 144, 0.25, 3), (6, 160, 120, 0.3, 4), (4, 200, 150, 0.6, 3), (4, 192, 144, 0.25, 3, "fallback")])
-def test_two_rank_sharded_matches_single_process(tmp_path, case, monkeypatch):
+def test_two_rank_sharded_matches_single_process(tmp_path, case, monkeypatch, early):
     import oracle
     oracle.build()
+    monkeypatch.setenv("IS_TEST_EARLY_FEED", "1" if early else "0")
     if len(case) > 5:
         monkeypatch.setenv("IS_SHARDED_FORCE_FALLBACK", "1")
         case = case[:5]
