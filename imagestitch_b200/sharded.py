@@ -221,8 +221,13 @@ class ShardedStitcher:
                 else:
                     t = be.clone(mask0[i])
                 for k, pr in enumerate(plan.pairs):
-                    if i in pr:
-                        be.mask_and(t, outs[(k, i)])
+                    if i in pr:                       # a pair only clears pixels inside the intersection of its two images
+                        a, b2 = pr
+                        rx0 = max(plan.corners[a][0], plan.corners[b2][0]) - plan.corners[i][0]
+                        ry0 = max(plan.corners[a][1], plan.corners[b2][1]) - plan.corners[i][1]
+                        rx1 = min(plan.corners[a][0] + plan.sizes[a][0], plan.corners[b2][0] + plan.sizes[b2][0]) - plan.corners[i][0]
+                        ry1 = min(plan.corners[a][1] + plan.sizes[a][1], plan.corners[b2][1] + plan.sizes[b2][1]) - plan.corners[i][1]
+                        be.mask_and(t, outs[(k, i)], rect=(rx0, ry0, rx1, ry1))
                 final[i] = t
         else:
             final, warped_all = self._sequential_fallback(plan, mine, warped, mask0)
@@ -332,7 +337,12 @@ class GpuBackend:
     def pair_free(self, h):
         self.S.DpSeamFinder(self.ctx, "COLOR").pair_free(h)
 
-    def mask_and(self, dst, src):
+    def mask_and(self, dst, src, rect=None):
+        if rect is not None:      # dst[src == 0] = 0 inside rect = (x0, y0, x1, y1): one small torch op on the main stream
+            x0, y0, x1, y1 = rect
+            if x1 > x0 and y1 > y0:
+                dst[y0:y1, x0:x1].masked_fill_(src[y0:y1, x0:x1] == 0, 0)
+            return
         c = self._ctx()
         self.S.DpSeamFinder(c, "COLOR").mask_and(dst, src)
         if c is not self.ctx:

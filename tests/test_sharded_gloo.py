@@ -55,7 +55,11 @@ class OracleBackend:
     def pair_free(self, h):
         pass
 
-    def mask_and(self, dst, src):
+    def mask_and(self, dst, src, rect=None):
+        if rect is not None:
+            x0, y0, x1, y1 = rect
+            dst[y0:y1, x0:x1][src[y0:y1, x0:x1] == 0] = 0
+            return
         dst[src == 0] = 0
 
     def seam_find_all(self, images, corners, masks):
