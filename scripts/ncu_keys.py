@@ -1,8 +1,10 @@
 """Key metrics + stall / opcode histograms of the first kernel in an ncu report.  usage: python scripts/ncu_keys.py report.ncu-rep"""
 import csv, subprocess, sys
 from collections import Counter
+import os
 rep = sys.argv[1]
-raw = subprocess.run(["ncu", "-i", rep, "--page", "raw", "--csv"], capture_output=True, text=True).stdout
+KSEL = ["-k", "regex:" + os.environ["NCU_KERNEL"]] if os.environ.get("NCU_KERNEL") else []   # NCU_KERNEL=regex selects the kernel
+raw = subprocess.run(["ncu", "-i", rep] + KSEL + ["--page", "raw", "--csv"], capture_output=True, text=True).stdout
 rows = list(csv.reader(raw.splitlines()))
 hdr, units, vals = rows[0], rows[1], rows[2]
 keys = ['gpu__time_duration.sum', 'dram__bytes_read.sum', 'dram__bytes_write.sum', 'gpu__dram_throughput.avg.pct_of_peak_sustained_elapsed',
@@ -13,10 +15,16 @@ keys = ['gpu__time_duration.sum', 'dram__bytes_read.sum', 'dram__bytes_write.sum
         'sm__cycles_elapsed.avg', 'launch__grid_size', 'launch__block_size', 'smsp__thread_inst_executed.sum']
 for k in keys:
     if k in hdr: print(f"{k:70s} {vals[hdr.index(k)]} {units[hdr.index(k)]}")
-src = subprocess.run(["ncu", "-i", rep, "--page", "source", "--csv", "--print-source", "sass"], capture_output=True, text=True).stdout
+src = subprocess.run(["ncu", "-i", rep] + KSEL + ["--page", "source", "--csv", "--print-source", "sass"], capture_output=True, text=True).stdout
 rows = list(csv.reader(src.splitlines()))
 hi = next(i for i, r in enumerate(rows) if r and r[0] == "Address")
-h = rows[hi]; ix = {k: i for i, k in enumerate(h)}; data = [r for r in rows[hi + 1:] if len(r) == len(h)]
+h = rows[hi]; ix = {k: i for i, k in enumerate(h)}
+data = []
+for r in rows[hi + 1:]:            # first kernel of the report only
+    if r and r[0] in ("Kernel Name", "Address"):
+        break
+    if len(r) == len(h):
+        data.append(r)
 ti = sum(float(r[ix['Instructions Executed']] or 0) for r in data); ts = sum(float(r[ix['# Samples']] or 0) for r in data)
 c = Counter(); s = Counter()
 for r in data:

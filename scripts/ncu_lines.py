@@ -1,8 +1,11 @@
 """Per-source-line instruction / stall-sample shares from `ncu --page source --csv --print-source cuda,sass`.
 usage: python scripts/ncu_lines.py report.ncu-rep [min_pct]"""
 import csv, subprocess, sys
-rep = sys.argv[1]; thr = float(sys.argv[2]) if len(sys.argv) > 2 else 1.0
-txt = subprocess.run(["ncu", "-i", rep, "--page", "source", "--csv", "--print-source", "cuda,sass"], capture_output=True, text=True).stdout
+import os
+rep = sys.argv[1]
+KSEL = ["-k", "regex:" + os.environ["NCU_KERNEL"]] if os.environ.get("NCU_KERNEL") else []   # NCU_KERNEL=regex selects the kernel
+thr = float(sys.argv[2]) if len(sys.argv) > 2 else 1.0
+txt = subprocess.run(["ncu", "-i", rep] + KSEL + ["--page", "source", "--csv", "--print-source", "cuda,sass"], capture_output=True, text=True).stdout
 rows = list(csv.reader(txt.splitlines()))
 hi = next(i for i, r in enumerate(rows) if r and r[0] == "Line No")
 hdr = rows[hi]
