@@ -1269,8 +1269,29 @@ static int blend_level0_tiled(is_blender* b, const LevelArgs& generic, const Dev
     if (getenv("IS_BLEND_L0_GENERIC")) return IS_OK;
     if (b->num_bands < 1 || !tma_ok(c1, (size_t)uw * 6)) return IS_OK;
     for (const FedImage& f : b->fed) {
-        if (f.img.depth != IS_8U || !tma_ok(f.img.data, f.img.step) || !tma_ok(f.mask.data, f.mask.step)) return IS_OK;
+        if (f.img.depth != IS_8U) return IS_OK;
         if (!tma_ok(f.g[1].p, (size_t)(f.width >> 1) * 6) || !f.summary.p) return IS_OK;
+    }
+    // Borrowed caller buffers (e.g. dense torch tensors: pitch = 3 * cols) may miss TMA's 16-byte base / pitch rule: such an
+    // image or mask is copied once into a pitched buffer (96 MB at HBM speed is ~30 us; the generic kernel would cost 1.4 ms)
+    std::vector<DevMat> aligned_img((size_t)n), aligned_mask((size_t)n);
+    std::vector<const void*> img_ptr((size_t)n), mask_ptr((size_t)n);
+    std::vector<size_t> img_step((size_t)n), mask_step((size_t)n);
+    for (int i = 0; i < n; ++i) {
+        const FedImage& f = b->fed[i];
+        img_ptr[i] = f.img.data; img_step[i] = f.img.step; mask_ptr[i] = f.mask.data; mask_step[i] = f.mask.step;
+        if (!tma_ok(f.img.data, f.img.step)) {
+            IS_TRY(alloc_mat(ctx, f.img.rows, f.img.cols, 3, IS_8U, &aligned_img[i]));
+            IS_CUDA(ctx, cudaMemcpy2DAsync(aligned_img[i].data, aligned_img[i].step, f.img.data, f.img.step, (size_t)f.img.cols * 3, f.img.rows,
+                                           cudaMemcpyDeviceToDevice, ctx->stream));
+            img_ptr[i] = aligned_img[i].data; img_step[i] = aligned_img[i].step;
+        }
+        if (!tma_ok(f.mask.data, f.mask.step)) {
+            IS_TRY(alloc_mat(ctx, f.mask.rows, f.mask.cols, 1, IS_8U, &aligned_mask[i]));
+            IS_CUDA(ctx, cudaMemcpy2DAsync(aligned_mask[i].data, aligned_mask[i].step, f.mask.data, f.mask.step, (size_t)f.mask.cols, f.mask.rows,
+                                           cudaMemcpyDeviceToDevice, ctx->stream));
+            mask_ptr[i] = aligned_mask[i].data; mask_step[i] = aligned_mask[i].step;
+        }
     }
     const size_t maps_bytes = sizeof(CUtensorMap) * (size_t)(1 + 3 * n);
     std::vector<unsigned char> host(maps_bytes + sizeof(L0Img) * (size_t)std::max(n, 1));
@@ -1280,9 +1301,9 @@ static int blend_level0_tiled(is_blender* b, const LevelArgs& generic, const Dev
     for (int i = 0; i < n; ++i) {
         const FedImage& f = b->fed[i];
         const int h1 = f.height >> 1, w1 = f.width >> 1;
-        IS_TRY(make_map_2d(ctx, &maps[1 + 3 * i], CU_TENSOR_MAP_DATA_TYPE_UINT8, f.mask.data, (uint64_t)f.mask.cols, (uint64_t)f.mask.rows, f.mask.step,
+        IS_TRY(make_map_2d(ctx, &maps[1 + 3 * i], CU_TENSOR_MAP_DATA_TYPE_UINT8, mask_ptr[i], (uint64_t)f.mask.cols, (uint64_t)f.mask.rows, mask_step[i],
                            L0_MROW, L0_TH));
-        IS_TRY(make_map_2d(ctx, &maps[2 + 3 * i], CU_TENSOR_MAP_DATA_TYPE_UINT8, f.img.data, (uint64_t)f.img.cols * 3, (uint64_t)f.img.rows, f.img.step,
+        IS_TRY(make_map_2d(ctx, &maps[2 + 3 * i], CU_TENSOR_MAP_DATA_TYPE_UINT8, img_ptr[i], (uint64_t)f.img.cols * 3, (uint64_t)f.img.rows, img_step[i],
                            L0_IROW, L0_TH));
         IS_TRY(make_map_2d(ctx, &maps[3 + 3 * i], CU_TENSOR_MAP_DATA_TYPE_UINT16, f.g[1].p, (uint64_t)w1 * 3, (uint64_t)h1, (uint64_t)w1 * 6, L0_UROW, L0_UH));
         L0Img& I = imgs[i];
