@@ -159,7 +159,17 @@ def parse_trace(t):
     return res
 
 
-def seam_costs(img1, img2, tl1, tl2, labels, union_tl, l, roi_xywh):
+def seam_gradients(img):
+    """[SEAM]:549-572: Sobel x / y (CV_32F, ksize 3) of cvtColor(BGR2GRAY) of the image taken as CV_32F"""
+    is_u8 = img.dtype == np.uint8
+    a = np.ascontiguousarray(img, np.uint8 if is_u8 else np.float32)
+    gx = np.empty(a.shape[:2], np.float32)
+    gy = np.empty(a.shape[:2], np.float32)
+    lib().orc_seam_gradients(_p(a), C.c_int(1 if is_u8 else 0), C.c_int(a.shape[0]), C.c_int(a.shape[1]), _p(gx), _p(gy))
+    return gx, gy
+
+
+def seam_costs(img1, img2, tl1, tl2, labels, union_tl, l, roi_xywh, cost_fn=COST_COLOR):
     is_u8 = img1.dtype == np.uint8
     a = np.ascontiguousarray(img1)
     b = np.ascontiguousarray(img2)
@@ -168,10 +178,10 @@ def seam_costs(img1, img2, tl1, tl2, labels, union_tl, l, roi_xywh):
     costV = np.empty((h, w + 1), np.float32)
     costH = np.empty((h + 1, w), np.float32)
     roi = np.asarray(roi_xywh, np.int32)
-    lib().orc_seam_costs(_p(a), _p(b), C.c_int(1 if is_u8 else 0), C.c_int(a.shape[0]), C.c_int(a.shape[1]),
+    lib().orc_seam_costs_ex(_p(a), _p(b), C.c_int(1 if is_u8 else 0), C.c_int(a.shape[0]), C.c_int(a.shape[1]),
                          C.c_int(b.shape[0]), C.c_int(b.shape[1]), C.c_int(tl1[0]), C.c_int(tl1[1]),
                          C.c_int(tl2[0]), C.c_int(tl2[1]), _p(labels), C.c_int(labels.shape[0]), C.c_int(labels.shape[1]),
-                         C.c_int(union_tl[0]), C.c_int(union_tl[1]), C.c_int(l), _p(roi), _p(costV), _p(costH))
+                         C.c_int(union_tl[0]), C.c_int(union_tl[1]), C.c_int(l), _p(roi), C.c_int(cost_fn), _p(costV), _p(costH))
     return costV, costH
 
 

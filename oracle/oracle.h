@@ -71,6 +71,14 @@ void orc_seam_costs(const void* img1, const void* img2, int is_u8,
                     int tl1x, int tl1y, int tl2x, int tl2y,
                     const int32_t* labels, int H, int W, int union_tlx, int union_tly,
                     int l, const int roi[4], float* costV, float* costH);
+/* ... with the cost function selectable (ORC_COST_COLOR_GRAD: [SEAM]:767-772, :792-797) */
+void orc_seam_costs_ex(const void* img1, const void* img2, int is_u8,
+                       int rows1, int cols1, int rows2, int cols2,
+                       int tl1x, int tl1y, int tl2x, int tl2y,
+                       const int32_t* labels, int H, int W, int union_tlx, int union_tly,
+                       int l, const int roi[4], int cost_fn, float* costV, float* costH);
+/* [SEAM]:549-572 computeGradients for one image: Sobel x / y of its gray conversion (rows x cols f32 each) */
+void orc_seam_gradients(const void* img, int is_u8, int rows, int cols, float* gradx, float* grady);
 
 /* ---- pyramids (cv::pyrDown / cv::pyrUp) ---- */
 void orc_pyr_down_s16(const int16_t* src, int h, int w, int ch, int16_t* dst);      /* dst ((h+1)/2,(w+1)/2) */

@@ -2,7 +2,9 @@
 //
 // CPU restatement of the reference's dynamic-programming seam finder ([SEAM]:87-1093, itself a
 // free-function copy of cv::detail::DpSeamFinder).  Function-by-function citations below.
-// COLOR_GRAD ([SEAM]:549-572, needs cv::Sobel) is not restated: SURVEY.md 8f rank 4 ("next").
+// COLOR_GRAD ([SEAM]:549-572, :769-771, :794-796) is restated with cvtColor(BGR2GRAY) + Sobel(3x3, CV_32F) written out:
+// OpenCV's float results for these two depend on the SIMD dispatch (FMA or not, vector body or scalar tail), so the
+// gradients are pinned against cv2 to a few ulp, the seam masks exactly (tests/test_oracle_cv2.py).
 //
 // Compile with -ffp-contract=off.
 #include "oracle.h"
@@ -303,6 +305,42 @@ struct DpSeam {
         return d0 * d0 + d1 * d1 + d2 * d2;
     }
 
+    // [SEAM]:549-572 computeGradients: gray = cvtColor(BGR2GRAY) of the CV_32F image (coefficients 0.114/0.587/0.299,
+    // association of OpenCV's FMA vector body), gradx/grady = Sobel(gray, CV_32F, 1,0 / 0,1), ksize 3, BORDER_REFLECT_101:
+    // separable, row filter first; [1 2 1] is evaluated as (a + c) + 2b, [-1 0 1] as c - a.
+    // 8-bit images are taken as their CV_32F conversion (what the mains pass to find(): images_warped_f, [SEAM]:1188-1190).
+    Grid<float> gradx1_, grady1_, gradx2_, grady2_;
+    static void sobelPair(const Img& im, Grid<float>& gx, Grid<float>& gy) {
+        const int H = im.rows, W = im.cols;
+        Grid<float> gray, dxr, smr;
+        gray.create(H, W);
+        for (int y = 0; y < H; ++y)
+            for (int x = 0; x < W; ++x)
+                gray(y, x) = std::fmaf(im.at(y, x, 2), 0.299f, std::fmaf(im.at(y, x, 0), 0.114f, im.at(y, x, 1) * 0.587f));
+        auto refl = [](int i, int n) { return n == 1 ? 0 : (i < 0 ? -i : (i >= n ? 2 * n - 2 - i : i)); };
+        dxr.create(H, W);
+        smr.create(H, W);
+        for (int y = 0; y < H; ++y)
+            for (int x = 0; x < W; ++x) {
+                float a = gray(y, refl(x - 1, W)), b = gray(y, x), c = gray(y, refl(x + 1, W));
+                dxr(y, x) = c - a;
+                smr(y, x) = (a + c) + b * 2.f;
+            }
+        gx.create(H, W);
+        gy.create(H, W);
+        for (int y = 0; y < H; ++y) {
+            int ya = refl(y - 1, H), yc = refl(y + 1, H);
+            for (int x = 0; x < W; ++x) {
+                gx(y, x) = (dxr(ya, x) + dxr(yc, x)) + dxr(y, x) * 2.f;
+                gy(y, x) = smr(yc, x) - smr(ya, x);
+            }
+        }
+    }
+    void computeGradients(const Img& image1, const Img& image2) {
+        sobelPair(image1, gradx1_, grady1_);
+        sobelPair(image2, gradx2_, grady2_);
+    }
+
     // [SEAM]:733-803
     void computeCosts(const Img& image1, const Img& image2, Pt tl1, Pt tl2, int comp,
                       Grid<float>& costV, Grid<float>& costH) {
@@ -318,6 +356,11 @@ struct DpSeam {
                 if (label(y, x) == l && x > 0 && label(y, x - 1) == l) {
                     float costColor = (diff3(image1, y + dy1, x + dx1 - 1, image2, y + dy2, x + dx2) +
                                        diff3(image1, y + dy1, x + dx1, image2, y + dy2, x + dx2 - 1)) / 2;
+                    if (costFunc == ORC_COST_COLOR_GRAD) {                                   // :767-772
+                        float costGrad = std::fabs(gradx1_(y + dy1, x + dx1)) + std::fabs(gradx1_(y + dy1, x + dx1 - 1)) +
+                                         std::fabs(gradx2_(y + dy2, x + dx2)) + std::fabs(gradx2_(y + dy2, x + dx2 - 1)) + 1.f;
+                        costColor = costColor / costGrad;
+                    }
                     costV(y - ry, x - rx) = costColor;
                 } else
                     costV(y - ry, x - rx) = badRegionCost;
@@ -328,6 +371,11 @@ struct DpSeam {
                 if (label(y, x) == l && y > 0 && label(y - 1, x) == l) {
                     float costColor = (diff3(image1, y + dy1 - 1, x + dx1, image2, y + dy2, x + dx2) +
                                        diff3(image1, y + dy1, x + dx1, image2, y + dy2 - 1, x + dx2)) / 2;
+                    if (costFunc == ORC_COST_COLOR_GRAD) {                                   // :792-797
+                        float costGrad = std::fabs(grady1_(y + dy1, x + dx1)) + std::fabs(grady1_(y + dy1 - 1, x + dx1)) +
+                                         std::fabs(grady2_(y + dy2, x + dx2)) + std::fabs(grady2_(y + dy2 - 1, x + dx2)) + 1.f;
+                        costColor = costColor / costGrad;
+                    }
                     costH(y - ry, x - rx) = costColor;
                 } else
                     costH(y - ry, x - rx) = badRegionCost;
@@ -498,6 +546,7 @@ struct DpSeam {
 
     // [SEAM]:395-546
     void resolveConflicts(const Img& image1, const Img& image2, Pt tl1, Pt tl2, uint8_t* mask1, uint8_t* mask2) {
+        if (costFunc == ORC_COST_COLOR_GRAD) computeGradients(image1, image2);           // :398-399
         bool hasConflict = true;
         while (hasConflict) {
             int c1 = 0, c2 = 0;
@@ -594,7 +643,7 @@ int orc_dp_seam_find(int n, const void* const* images, int is_u8, const int* row
                      int32_t* trace, size_t trace_cap, size_t* trace_len) {
     if (trace_len) *trace_len = 0;
     if (n == 0) return 0;                                    // [SEAM]:94-95
-    if (cost_fn != ORC_COST_COLOR) return -5;                // StsBadArg: COLOR_GRAD not restated
+    if (cost_fn != ORC_COST_COLOR && cost_fn != ORC_COST_COLOR_GRAD) return -5;   // StsBadArg
     std::vector<std::pair<int, int>> pairs;                  // [SEAM]:97-111
     for (int i = 0; i + 1 < n; ++i)
         for (int j = i + 1; j < n; ++j) pairs.push_back({i, j});
@@ -621,7 +670,25 @@ void orc_seam_costs(const void* img1, const void* img2, int is_u8,
                     int tl1x, int tl1y, int tl2x, int tl2y,
                     const int32_t* labels, int H, int W, int union_tlx, int union_tly,
                     int l, const int roi[4], float* costV, float* costH) {
+    orc_seam_costs_ex(img1, img2, is_u8, rows1, cols1, rows2, cols2, tl1x, tl1y, tl2x, tl2y, labels, H, W, union_tlx, union_tly, l, roi,
+                      ORC_COST_COLOR, costV, costH);
+}
+
+void orc_seam_gradients(const void* img, int is_u8, int rows, int cols, float* gradx, float* grady) {
+    Img a{img, rows, cols, is_u8 != 0};
+    Grid<float> gx, gy;
+    DpSeam::sobelPair(a, gx, gy);
+    std::memcpy(gradx, gx.v.data(), sizeof(float) * gx.v.size());
+    std::memcpy(grady, gy.v.data(), sizeof(float) * gy.v.size());
+}
+
+void orc_seam_costs_ex(const void* img1, const void* img2, int is_u8,
+                       int rows1, int cols1, int rows2, int cols2,
+                       int tl1x, int tl1y, int tl2x, int tl2y,
+                       const int32_t* labels, int H, int W, int union_tlx, int union_tly,
+                       int l, const int roi[4], int cost_fn, float* costV, float* costH) {
     DpSeam f;
+    f.costFunc = cost_fn;
     f.uw = W; f.uh = H;
     f.unionTl = {union_tlx, union_tly};
     f.labels_.create(H, W, 0);
@@ -633,6 +700,7 @@ void orc_seam_costs(const void* img1, const void* img2, int is_u8,
     f.tls_[comp] = {roi[0], roi[1]};
     f.brs_[comp] = {roi[0] + roi[2], roi[1] + roi[3]};
     Img a{img1, rows1, cols1, is_u8 != 0}, b{img2, rows2, cols2, is_u8 != 0};
+    if (cost_fn == ORC_COST_COLOR_GRAD) f.computeGradients(a, b);
     Grid<float> cv, ch;
     f.computeCosts(a, b, Pt{tl1x, tl1y}, Pt{tl2x, tl2y}, comp, cv, ch);
     std::memcpy(costV, cv.v.data(), sizeof(float) * cv.v.size());

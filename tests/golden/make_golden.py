@@ -181,13 +181,41 @@ def exposure_feather_cases():
     np.savez_compressed(os.path.join(HERE, "exposure_feather_cases.npz"), **out)
 
 
+def color_grad_cases():
+    """DpSeamFinder("COLOR_GRAD") masks for the inputs already stored in seam_blend_cases.npz, plus cvtColor + Sobel gradients."""
+    z = np.load(os.path.join(HERE, "seam_blend_cases.npz"))
+    out = {}
+    for k in range(int(z["n_cases"])):
+        p = f"s{k}_"
+        n = int(z[p + "n"])
+        corners = [tuple(int(v) for v in c) for c in z[p + "corners"]]
+        wi = [z[p + f"img{i}"] for i in range(n)]
+        masks = [z[p + f"mask{i}"].copy() for i in range(n)]
+        for (i, j) in [(i, j) for i in range(n) for j in range(i + 1, n)][::-1]:
+            res = cv2.detail_DpSeamFinder("COLOR_GRAD").find([cv2.UMat(wi[i].astype(np.float32)), cv2.UMat(wi[j].astype(np.float32))],
+                                                         [corners[i], corners[j]], [cv2.UMat(masks[i]), cv2.UMat(masks[j])])
+            masks[i], masks[j] = res[0].get(), res[1].get()
+        for i in range(n):
+            out[p + f"seam_mask{i}_grad_cv"] = masks[i]
+    rng = np.random.default_rng(5)
+    for k, shape in enumerate([(48, 64), (37, 53)]):
+        a = rng.integers(0, 256, shape + (3,), dtype=np.uint8)
+        g = cv2.cvtColor(a.astype(np.float32), cv2.COLOR_BGR2GRAY)
+        out[f"g{k}_img"] = a
+        out[f"g{k}_gradx_cv"] = cv2.Sobel(g, cv2.CV_32F, 1, 0)
+        out[f"g{k}_grady_cv"] = cv2.Sobel(g, cv2.CV_32F, 0, 1)
+    np.savez_compressed(os.path.join(HERE, "color_grad_cases.npz"), **out)
+
+
 if __name__ == "__main__":
     if "--only-new" not in sys.argv:
         warp_cases()
         remap_cases()
         seam_blend_cases()
         pyr_cases()
-    exposure_feather_cases()
+    if "--only-color-grad" not in sys.argv:
+        exposure_feather_cases()
+    color_grad_cases()
     for f in sorted(os.listdir(HERE)):
         if f.endswith(".npz"):
             print(f, os.path.getsize(os.path.join(HERE, f)))

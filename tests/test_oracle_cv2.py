@@ -38,11 +38,11 @@ def test_remap_vs_cv2(oracle):
             assert np.array_equal(cv2.remap(img, xm, ym, ci, borderMode=cb), O.remap(img, xm, ym, interp, border))
 
 
-def _cv_pairwise(wi, corners, masks):
+def _cv_pairwise(wi, corners, masks, cost="COLOR"):
     n = len(wi)
     masks = [m.copy() for m in masks]
     for (i, j) in [(i, j) for i in range(n) for j in range(i + 1, n)][::-1]:      # [SEAM]:100-111
-        res = cv2.detail_DpSeamFinder("COLOR").find([cv2.UMat(wi[i].astype(np.float32)), cv2.UMat(wi[j].astype(np.float32))],
+        res = cv2.detail_DpSeamFinder(cost).find([cv2.UMat(wi[i].astype(np.float32)), cv2.UMat(wi[j].astype(np.float32))],
                                                     [corners[i], corners[j]], [cv2.UMat(masks[i]), cv2.UMat(masks[j])])
         masks[i], masks[j] = res[0].get(), res[1].get()
     return masks
@@ -78,6 +78,27 @@ def test_seam_and_blend_vs_cv2(oracle, case):
         else:
             d = np.abs(cd.astype(np.int32) - od.astype(np.int32))
             assert d.max() <= 2 and (d == 0).mean() >= 0.99
+
+
+@pytest.mark.parametrize("case", [(2, 260, 200, 0.25, 1, False), (3, 200, 150, 0.6, 1, False), (4, 160, 120, 0.3, 2, False),
+                                  (5, 220, 160, 0.35, 1, True)])
+def test_color_grad_seam_vs_cv2(oracle, case):
+    O = oracle
+    n, w, h, ov, rows, irregular = case
+    corners, wi, wm = warped_set(O, n, w, h, overlap=ov, grid_rows=rows)
+    if irregular:
+        holes = blob_masks(np.random.default_rng(8), [m.shape for m in wm], holes=4)
+        wm = [np.where(hm > 0, m, 0).astype(np.uint8) for m, hm in zip(wm, holes)]
+    want = _cv_pairwise(wi, corners, wm, "COLOR_GRAD")
+    for imgs in (wi, [a.astype(np.float32) for a in wi]):
+        got = O.dp_seam_find(imgs, corners, wm, cost_fn=O.COST_COLOR_GRAD)
+        for i in range(n):
+            assert np.array_equal(got[i], want[i])
+    rng = np.random.default_rng(n)
+    a = (rng.random((h, w, 3)) * 255).astype(np.float32)
+    g = cv2.cvtColor(a, cv2.COLOR_BGR2GRAY)
+    gx, gy = O.seam_gradients(a)
+    assert np.abs(gx - cv2.Sobel(g, cv2.CV_32F, 1, 0)).max() <= 2.5e-4 and np.abs(gy - cv2.Sobel(g, cv2.CV_32F, 0, 1)).max() <= 2.5e-4
 
 
 def test_gain_compensator_vs_cv2(oracle):

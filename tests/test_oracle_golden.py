@@ -121,3 +121,25 @@ def test_exposure_and_feather_fixtures(oracle):
             fb.feed(imgs[i].astype(np.int16), masks[i], corners[i])
         pano, pmask = fb.blend()
         assert np.array_equal(pmask, z[f"e{k}_feather_mask_cv"]) and np.array_equal(pano, z[f"e{k}_feather_cv"])
+
+
+def test_color_grad_fixtures(oracle):
+    """COLOR_GRAD cost ([SEAM]:549-572,:767-772,:792-797): seam masks of cv2.detail_DpSeamFinder("COLOR_GRAD") exactly; the
+    gradients to a few ulp (OpenCV's vector body and scalar tail associate differently, so its own result is not
+    position-independent)."""
+    O = oracle
+    z = _load("seam_blend_cases.npz")
+    g = _load("color_grad_cases.npz")
+    differs = 0
+    for k in range(int(z["n_cases"])):
+        p, n, corners, wi, wm = _case(z, k)
+        for imgs in (wi, [a.astype(np.float32) for a in wi]):
+            got = O.dp_seam_find(imgs, corners, wm, cost_fn=O.COST_COLOR_GRAD)
+            for i in range(n):
+                assert np.array_equal(got[i], g[p + f"seam_mask{i}_grad_cv"]), f"case {k} mask {i}"
+        differs += sum(int(np.any(g[p + f"seam_mask{i}_grad_cv"] != z[p + f"seam_mask{i}_cv"])) for i in range(n))
+    assert differs > 0                      # the fixtures do separate COLOR_GRAD from COLOR
+    for k in range(2):
+        gx, gy = O.seam_gradients(g[f"g{k}_img"])
+        for got, want in ((gx, g[f"g{k}_gradx_cv"]), (gy, g[f"g{k}_grady_cv"])):
+            assert np.abs(got - want).max() <= 2.5e-4 and (got == want).mean() >= 0.9     # inexact only in OpenCV's scalar tail columns
