@@ -380,17 +380,71 @@ __device__ __forceinline__ int label_at(const int* __restrict__ labels, Frame f,
     return lab(labels, f, x, y);
 }
 
+// COLOR_GRAD ([SEAM]:549-572): Sobel gradients of the gray images over the intersection rectangle of the pair (every cell
+// with the component's label lies inside it).  Window coordinates = union coordinates - (ox, oy).
+struct GradView {
+    const float* gx1; const float* gy1; const float* gx2; const float* gy2;
+    int pitch, ox, oy;
+    __device__ __forceinline__ size_t at(int ux, int uy) const { return (size_t)(uy - oy) * pitch + (ux - ox); }
+};
+
+// cvtColor(BGR2GRAY) on CV_32F in the association of OpenCV's FMA vector body (the oracle's `sobelPair`)
 template <typename T>
-__device__ __forceinline__ float cost_v(const ImgView<T>& a, const ImgView<T>& b, const int* __restrict__ labels, Frame f, int l, int x, int y) {
-    if (label_at(labels, f, x, y) == l && x > 0 && label_at(labels, f, x - 1, y) == l)
-        return __fmul_rn(__fadd_rn(diff3(a.px(x - 1, y), b.px(x, y)), diff3(a.px(x, y), b.px(x - 1, y))), 0.5f);
+__device__ __forceinline__ float gray_at(const ImgView<T>& a, int ix, int iy) {   // image coordinates
+    const T* p = reinterpret_cast<const T*>(reinterpret_cast<const char*>(a.p) + (size_t)iy * a.step) + 3 * ix;
+    return __fmaf_rn((float)p[2], 0.299f, __fmaf_rn((float)p[0], 0.114f, __fmul_rn((float)p[1], 0.587f)));
+}
+
+__device__ __forceinline__ int reflect101(int i, int n) { return n == 1 ? 0 : (i < 0 ? -i : (i >= n ? 2 * n - 2 - i : i)); }
+
+// Sobel(gray, CV_32F, 1, 0) and (0, 1), ksize 3, BORDER_REFLECT_101 at the IMAGE border: row filter first,
+// [1 2 1] as (a + c) + 2b, [-1 0 1] as c - a.  One thread per window pixel; the 3x3 gray values are recomputed.
+template <typename T>
+__global__ void k_sobel_window(ImgView<T> a, int ox, int oy, int ww, int wh, float* __restrict__ gx, float* __restrict__ gy, int pitch) {
+    const int x = blockIdx.x * blockDim.x + threadIdx.x;
+    const int y = blockIdx.y * blockDim.y + threadIdx.y;
+    if (x >= ww || y >= wh) return;
+    const int ix = ox + x + a.dx, iy = oy + y + a.dy;
+    const int xs0 = reflect101(ix - 1, a.cols), xs2 = reflect101(ix + 1, a.cols);
+    const int ys[3] = {reflect101(iy - 1, a.rows), iy, reflect101(iy + 1, a.rows)};
+    float d[3], sm[3];
+#pragma unroll
+    for (int k = 0; k < 3; ++k) {
+        const float l = gray_at(a, xs0, ys[k]), c = gray_at(a, ix, ys[k]), r = gray_at(a, xs2, ys[k]);
+        d[k] = __fsub_rn(r, l);
+        sm[k] = __fadd_rn(__fadd_rn(l, r), __fmul_rn(c, 2.f));
+    }
+    gx[(size_t)y * pitch + x] = __fadd_rn(__fadd_rn(d[0], d[2]), __fmul_rn(d[1], 2.f));
+    gy[(size_t)y * pitch + x] = __fsub_rn(sm[2], sm[0]);
+}
+
+template <typename T, bool GRAD>
+__device__ __forceinline__ float cost_v(const ImgView<T>& a, const ImgView<T>& b, const int* __restrict__ labels, Frame f, int l, int x, int y,
+                                        const GradView& g) {
+    if (label_at(labels, f, x, y) == l && x > 0 && label_at(labels, f, x - 1, y) == l) {
+        float c = __fmul_rn(__fadd_rn(diff3(a.px(x - 1, y), b.px(x, y)), diff3(a.px(x, y), b.px(x - 1, y))), 0.5f);
+        if (GRAD) {                                                                        // [SEAM]:767-772
+            const size_t i = g.at(x, y);
+            const float cg = __fadd_rn(__fadd_rn(__fadd_rn(__fadd_rn(fabsf(g.gx1[i]), fabsf(g.gx1[i - 1])), fabsf(g.gx2[i])), fabsf(g.gx2[i - 1])), 1.f);
+            c = __fdiv_rn(c, cg);
+        }
+        return c;
+    }
     return IS_BAD_REGION_COST;
 }
 
-template <typename T>
-__device__ __forceinline__ float cost_h(const ImgView<T>& a, const ImgView<T>& b, const int* __restrict__ labels, Frame f, int l, int x, int y) {
-    if (label_at(labels, f, x, y) == l && y > 0 && label_at(labels, f, x, y - 1) == l)
-        return __fmul_rn(__fadd_rn(diff3(a.px(x, y - 1), b.px(x, y)), diff3(a.px(x, y), b.px(x, y - 1))), 0.5f);
+template <typename T, bool GRAD>
+__device__ __forceinline__ float cost_h(const ImgView<T>& a, const ImgView<T>& b, const int* __restrict__ labels, Frame f, int l, int x, int y,
+                                        const GradView& g) {
+    if (label_at(labels, f, x, y) == l && y > 0 && label_at(labels, f, x, y - 1) == l) {
+        float c = __fmul_rn(__fadd_rn(diff3(a.px(x, y - 1), b.px(x, y)), diff3(a.px(x, y), b.px(x, y - 1))), 0.5f);
+        if (GRAD) {                                                                        // [SEAM]:792-797
+            const size_t i = g.at(x, y);
+            const float cg = __fadd_rn(__fadd_rn(__fadd_rn(__fadd_rn(fabsf(g.gy1[i]), fabsf(g.gy1[i - g.pitch])), fabsf(g.gy2[i])), fabsf(g.gy2[i - g.pitch])), 1.f);
+            c = __fdiv_rn(c, cg);
+        }
+        return c;
+    }
     return IS_BAD_REGION_COST;
 }
 
@@ -401,16 +455,17 @@ __global__ void k_cost_maps(ImgView<T> a, ImgView<T> b, const int* __restrict__ 
     const int x = blockIdx.x * blockDim.x + threadIdx.x;
     const int y = blockIdx.y * blockDim.y + threadIdx.y;
     if (x > rw || y > rh) return;
-    if (y < rh) reinterpret_cast<float*>(reinterpret_cast<char*>(costV) + (size_t)y * vstep)[x] = cost_v(a, b, labels, f, l, rx + x, ry + y);
-    if (x < rw) reinterpret_cast<float*>(reinterpret_cast<char*>(costH) + (size_t)y * hstep)[x] = cost_h(a, b, labels, f, l, rx + x, ry + y);
+    const GradView g{};
+    if (y < rh) reinterpret_cast<float*>(reinterpret_cast<char*>(costV) + (size_t)y * vstep)[x] = cost_v<T, false>(a, b, labels, f, l, rx + x, ry + y, g);
+    if (x < rw) reinterpret_cast<float*>(reinterpret_cast<char*>(costH) + (size_t)y * hstep)[x] = cost_h<T, false>(a, b, labels, f, l, rx + x, ry + y, g);
 }
 
 // DP layout: P[step][lane] = cost of advancing one step at `lane`, Q[step][lane] = cost of the crossing
 // between lane and lane+1 at `step`.  Vertical seam: step = y, lane = x, P = costV, Q = costH; horizontal
 // seam: step = x, lane = y, P = costH, Q = costV.  P = +inf marks a cell outside the component.
-template <typename T>
+template <typename T, bool GRAD>
 __global__ void k_cost_pq(ImgView<T> a, ImgView<T> b, const int* __restrict__ labels, Frame f, int l, int rx, int ry, int rw, int rh,
-                          int horizontal, float* __restrict__ P, float* __restrict__ Q, int pitch) {
+                          int horizontal, float* __restrict__ P, float* __restrict__ Q, int pitch, GradView g) {
     const int lanes = horizontal ? rh : rw, steps = horizontal ? rw : rh;
     const int lane = blockIdx.x * blockDim.x + threadIdx.x;
     const int step = blockIdx.y * blockDim.y + threadIdx.y;
@@ -422,8 +477,8 @@ __global__ void k_cost_pq(ImgView<T> a, ImgView<T> b, const int* __restrict__ la
     }
     const int x = rx + (horizontal ? step : lane), y = ry + (horizontal ? lane : step);
     float p, q;
-    if (horizontal) { p = cost_h(a, b, labels, f, l, x, y); q = cost_v(a, b, labels, f, l, x, y); }
-    else { p = cost_v(a, b, labels, f, l, x, y); q = cost_h(a, b, labels, f, l, x, y); }
+    if (horizontal) { p = cost_h<T, GRAD>(a, b, labels, f, l, x, y, g); q = cost_v<T, GRAD>(a, b, labels, f, l, x, y, g); }
+    else { p = cost_v<T, GRAD>(a, b, labels, f, l, x, y, g); q = cost_h<T, GRAD>(a, b, labels, f, l, x, y, g); }
     if (lab(labels, f, x, y) != l) p = __int_as_float(0x7f800000);   // +inf: the cell can never be on a path
     P[(size_t)step * pitch + lane] = p;
     Q[(size_t)step * pitch + lane] = q;
@@ -815,7 +870,7 @@ struct TraceSink {
 
 class PairSeam {
 public:
-    PairSeam(is_ctx* c, bool u8, TraceSink* tr) : ctx(c), is_u8(u8), trace(tr) {}
+    PairSeam(is_ctx* c, bool u8, TraceSink* tr, int cost = IS_COST_COLOR) : ctx(c), is_u8(u8), trace(tr), cost_fn(cost) {}
     // in1/in2: masks as the pair sees them; out1/out2: where the masks with this pair's clears go (may alias in1/in2).
     // structure_only: stop after the component / contour analysis (used to validate a speculative run).
     int process(const DevMat& image1, const DevMat& image2, Pt tl1, Pt tl2, const DevMat& in1, const DevMat& in2, const DevMat& out1,
@@ -831,6 +886,10 @@ private:
     is_ctx* ctx;
     bool is_u8;
     TraceSink* trace;
+    int cost_fn;
+    DevBuf grad;                          // COLOR_GRAD: gx1, gy1, gx2, gy2 over the intersection window
+    GradView gview{};
+    int compute_gradients(const Pt& iTl, const Pt& iBr);
     int pair_i = 0, pair_j = 0;
     Pt unionTl{}, tl1_{}, tl2_{};
     int uw = 0, uh = 0;
@@ -850,7 +909,7 @@ private:
     int label_runs(const Pt& iTl, const Pt& iBr, bool* done);
     std::vector<char> stale;   // components whose bbox / contour recomputation is pending (resolve_conflicts)
     int label_dense();
-    void release_device() { cls.release(); parent.release(); labels.release(); counts.release(); offsets.release(); recs.release(); }
+    void release_device() { cls.release(); parent.release(); labels.release(); counts.release(); offsets.release(); recs.release(); grad.release(); }
     int ccl(const uint8_t* klass, int kmask, int w, int h, int* parent_out);
     int collect_roots(const int* parent_d, const uint8_t* klass_d, size_t n, std::vector<std::pair<int, int>>* roots);
     int extract_contours(int wx, int wy, int ww, int wh, int fa, int fb, std::vector<ContourRec>* out);
@@ -1028,6 +1087,29 @@ static ImgView<T> make_view(const DevMat& m, int dx, int dy) {
     return ImgView<T>{m.ptr<T>(), m.step, m.rows, m.cols, dx, dy};
 }
 
+// computeGradients [SEAM]:549-572, restricted to the intersection rectangle (the only place costs are evaluated)
+int PairSeam::compute_gradients(const Pt& iTl, const Pt& iBr) {
+    const int ww = iBr.x - iTl.x, wh = iBr.y - iTl.y;
+    const int pitch = (ww + 31) & ~31;
+    const size_t plane = (size_t)pitch * wh;
+    IS_TRY(grad.alloc(ctx, sizeof(float) * plane * 4));
+    float* g = grad.as<float>();
+    gview = GradView{g, g + plane, g + 2 * plane, g + 3 * plane, pitch, iTl.x - unionTl.x, iTl.y - unionTl.y};
+    const int dx1 = unionTl.x - tl1_.x, dy1 = unionTl.y - tl1_.y, dx2 = unionTl.x - tl2_.x, dy2 = unionTl.y - tl2_.y;
+    dim3 block(64, 4), grid(div_up(ww, 64), div_up(wh, 4));
+    ctx->next_bytes = (double)ww * wh * ((is_u8 ? 3 : 12) + 8);
+    if (is_u8) {
+        IS_LAUNCH(ctx, k_sobel_window<uint8_t>, grid, block, 0, make_view<uint8_t>(*img1, dx1, dy1), gview.ox, gview.oy, ww, wh, g, g + plane, pitch);
+        ctx->next_bytes = (double)ww * wh * (3 + 8);
+        IS_LAUNCH(ctx, k_sobel_window<uint8_t>, grid, block, 0, make_view<uint8_t>(*img2, dx2, dy2), gview.ox, gview.oy, ww, wh, g + 2 * plane, g + 3 * plane, pitch);
+    } else {
+        IS_LAUNCH(ctx, k_sobel_window<float>, grid, block, 0, make_view<float>(*img1, dx1, dy1), gview.ox, gview.oy, ww, wh, g, g + plane, pitch);
+        ctx->next_bytes = (double)ww * wh * (12 + 8);
+        IS_LAUNCH(ctx, k_sobel_window<float>, grid, block, 0, make_view<float>(*img2, dx2, dy2), gview.ox, gview.oy, ww, wh, g + 2 * plane, g + 3 * plane, pitch);
+    }
+    return IS_OK;
+}
+
 // estimateSeam [SEAM]:806-957 followed by updateLabelsUsingSeam [SEAM]:960-1093
 int PairSeam::estimate_and_update(int c1, int c2, Pt p1, Pt p2) {
     const int l1 = c1 + 1, l2 = c2 + 1;
@@ -1056,12 +1138,23 @@ int PairSeam::estimate_and_update(int c1, int c2, Pt p1, Pt p2) {
     {
         dim3 block(64, 4), grid(div_up(pitch, 64), div_up(steps, 4));
         ctx->next_bytes = (double)lanes * steps * (is_u8 ? 6 : 24) + (double)lanes * steps * 12;   // two image overlaps + labels read, P and Q written
-        if (is_u8)
-            IS_LAUNCH(ctx, k_cost_pq<uint8_t>, grid, block, 0, make_view<uint8_t>(*img1, dx1, dy1), make_view<uint8_t>(*img2, dx2, dy2),
-                      labels.as<int>(), frame(), l1, rx, ry, rw, rh, horizontal ? 1 : 0, P.as<float>(), Q.as<float>(), pitch);
+        const auto v1u = make_view<uint8_t>(*img1, dx1, dy1), v2u = make_view<uint8_t>(*img2, dx2, dy2);
+        const auto v1f = make_view<float>(*img1, dx1, dy1), v2f = make_view<float>(*img2, dx2, dy2);
+        const int hz = horizontal ? 1 : 0;
+        if (cost_fn == IS_COST_COLOR_GRAD) {
+            ctx->next_bytes += (double)lanes * steps * 16;                                   // four gradient planes
+            if (is_u8)
+                IS_LAUNCH(ctx, (k_cost_pq<uint8_t, true>), grid, block, 0, v1u, v2u, labels.as<int>(), frame(), l1, rx, ry, rw, rh, hz, P.as<float>(),
+                          Q.as<float>(), pitch, gview);
+            else
+                IS_LAUNCH(ctx, (k_cost_pq<float, true>), grid, block, 0, v1f, v2f, labels.as<int>(), frame(), l1, rx, ry, rw, rh, hz, P.as<float>(),
+                          Q.as<float>(), pitch, gview);
+        } else if (is_u8)
+            IS_LAUNCH(ctx, (k_cost_pq<uint8_t, false>), grid, block, 0, v1u, v2u, labels.as<int>(), frame(), l1, rx, ry, rw, rh, hz, P.as<float>(),
+                      Q.as<float>(), pitch, gview);
         else
-            IS_LAUNCH(ctx, k_cost_pq<float>, grid, block, 0, make_view<float>(*img1, dx1, dy1), make_view<float>(*img2, dx2, dy2),
-                      labels.as<int>(), frame(), l1, rx, ry, rw, rh, horizontal ? 1 : 0, P.as<float>(), Q.as<float>(), pitch);
+            IS_LAUNCH(ctx, (k_cost_pq<float, false>), grid, block, 0, v1f, v2f, labels.as<int>(), frame(), l1, rx, ry, rw, rh, hz, P.as<float>(),
+                      Q.as<float>(), pitch, gview);
     }
     DpArgs A;
     A.P = P.as<float>(); A.Q = Q.as<float>(); A.control = control.as<uint8_t>();
@@ -1508,6 +1601,7 @@ int PairSeam::process(const DevMat& image1, const DevMat& image2, Pt tl1, Pt tl2
     if (structure_only) { release_device(); return IS_OK; }
     find_edges();
     dbg.lap("find_edges");
+    if (cost_fn == IS_COST_COLOR_GRAD) IS_TRY(compute_gradients(iTl, iBr));                 // [SEAM]:398-399
     int rc = resolve_conflicts(mask1, mask2, out1, out2);
     if (dbg.on) cudaStreamSynchronize(ctx->stream);
     dbg.lap("resolve_conflicts+masks");
@@ -1545,9 +1639,9 @@ static int mask_copy(is_ctx* ctx, const DevMat& dst, const DevMat& src) {
 
 // The reference's order ([SEAM]:97-121): pairs (i, j), i < j, lexicographic, reversed; masks updated in place.
 static int seam_find_sequential(is_ctx* ctx, const std::vector<std::pair<int, int>>& pairs, const DevMat* images, const is_point* corners,
-                                const DevMat* masks, TraceSink* trace) {
+                                const DevMat* masks, TraceSink* trace, int cost_fn = IS_COST_COLOR) {
     for (auto& pr : pairs) {
-        PairSeam ps(ctx, images[pr.first].depth == IS_8U, trace);
+        PairSeam ps(ctx, images[pr.first].depth == IS_8U, trace, cost_fn);
         IS_TRY(ps.process(images[pr.first], images[pr.second], Pt{corners[pr.first].x, corners[pr.first].y},
                           Pt{corners[pr.second].x, corners[pr.second].y}, masks[pr.first], masks[pr.second], masks[pr.first], masks[pr.second],
                           pr.first, pr.second));
@@ -1702,7 +1796,8 @@ static int seam_find_concurrent(is_ctx* ctx, const std::vector<std::pair<int, in
 }
 
 // device-resident images / masks (masks in-out); used by is_seam_dp_find* and by the pipeline
-int seam_find_core(is_ctx* ctx, int n, const DevMat* images, const is_point* corners, const DevMat* masks, TraceSink* trace) {
+int seam_find_core(is_ctx* ctx, int n, const DevMat* images, const is_point* corners, const DevMat* masks, TraceSink* trace,
+                   int cost_fn = IS_COST_COLOR) {
     std::vector<std::pair<int, int>> pairs;                                  // [SEAM]:97-111 (no sort, reversed)
     for (int i = 0; i + 1 < n; ++i)
         for (int j = i + 1; j < n; ++j) pairs.push_back({i, j});
@@ -1717,6 +1812,7 @@ int seam_find_core(is_ctx* ctx, int n, const DevMat* images, const is_point* cor
     }
     const char* seq = getenv("IS_SEAM_SEQUENTIAL");
     ctx->seam_speculation_accepted = -1;
+    if (cost_fn != IS_COST_COLOR) return seam_find_sequential(ctx, active, images, corners, masks, trace, cost_fn);   // not yet on the concurrent path
     if (active.size() >= 2 && !(seq && seq[0] == '1')) {
         bool accepted = false;
         IS_TRY(seam_find_concurrent(ctx, active, n, images, corners, masks, trace, &accepted));
@@ -1731,8 +1827,13 @@ static int seam_find_impl(is_ctx* ctx, int n, const is_mat* images, const is_poi
     IS_CUDA(ctx, cudaSetDevice(ctx->device));
     if (n == 0) return IS_OK;                                                // [SEAM]:94-95
     IS_REQUIRE(ctx, images && corners && masks, IS_ERR_BAD_ARG, "null argument");
-    if (cost_fn == IS_COST_COLOR_GRAD) return fail(ctx, IS_ERR_UNSUPPORTED, "COLOR_GRAD seam cost is not implemented yet");
-    IS_REQUIRE(ctx, cost_fn == IS_COST_COLOR, IS_ERR_BAD_ARG, "unknown cost function");
+    IS_REQUIRE(ctx, cost_fn == IS_COST_COLOR || cost_fn == IS_COST_COLOR_GRAD, IS_ERR_BAD_ARG, "unknown cost function");
+    if (cost_fn == IS_COST_COLOR_GRAD) {
+        // Written against the oracle's restatement but not yet run on a device (no GPU time was left in the round it was
+        // written in): kept behind a switch until tests/test_gpu_color_grad.py has passed on hardware.
+        const char* e = getenv("IS_EXPERIMENTAL_COLOR_GRAD");
+        if (!(e && e[0] == '1')) return fail(ctx, IS_ERR_UNSUPPORTED, "COLOR_GRAD seam cost is not enabled (IS_EXPERIMENTAL_COLOR_GRAD=1)");
+    }
     const int depth = images[0].depth;
     for (int i = 0; i < n; ++i) {
         IS_TRY(check_mat(ctx, &images[i], "image"));
@@ -1747,7 +1848,7 @@ static int seam_find_impl(is_ctx* ctx, int n, const is_mat* images, const is_poi
         IS_TRY(stage_in(ctx, &images[i], &dimg[i]));
         IS_TRY(stage_out(ctx, &masks[i], &dmask[i], true));
     }
-    IS_TRY(seam_find_core(ctx, n, dimg.data(), corners, dmask.data(), trace));
+    IS_TRY(seam_find_core(ctx, n, dimg.data(), corners, dmask.data(), trace, cost_fn));
     for (int i = 0; i < n; ++i) IS_TRY(commit(ctx, &dmask[i]));
     return IS_OK;
 }
