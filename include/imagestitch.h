@@ -119,7 +119,9 @@ int is_warp_with_mask(is_ctx* ctx, int projection, const is_mat* src, const floa
  *                     std::vector<UMat>& masks)                                        [SEAM]:87
  * (== cv::detail::DpSeamFinder::find).  images: n mats, 3 channels, IS_32F or IS_8U (all the same);
  * masks: n mats IS_8U, same sizes as the images ([SEAM]:133-134), modified in place.
- * cost_fn: IS_COST_COLOR; IS_COST_COLOR_GRAD returns IS_ERR_UNSUPPORTED.
+ * cost_fn: IS_COST_COLOR.  IS_COST_COLOR_GRAD ([SEAM]:549-572, :767-772, :792-797; 8-bit images are taken as their
+ * CV_32F conversion, which is what the mains pass) returns IS_ERR_UNSUPPORTED unless the environment sets
+ * IS_EXPERIMENTAL_COLOR_GRAD=1: the device path exists but has not been through the hardware parity run yet.
  */
 int is_seam_dp_find(is_ctx* ctx, int n, const is_mat* images, const is_point* corners, is_mat* masks, int cost_fn);
 
