@@ -1,11 +1,12 @@
 """Column-strip sharding of one panorama across the GPUs of a box.
 
-One process per GPU (torch.distributed: NCCL on GPUs, gloo in the CPU tests).  Rank r owns a contiguous group of
-the strip's images and the panorama columns [cut[r], cut[r+1]).  Per step:
+One process per GPU (torch.distributed: NCCL on GPUs, gloo in the CPU tests).  Rank r owns the images whose centres
+fall into its group of panorama columns (a contiguous run of a strip's images; whole columns of a 2-D mosaic) and the
+panorama columns [cut[r], cut[r+1]).  Per step:
 
   warp        local (each rank warps its own images)
   X1          the right image of every pair that straddles a strip boundary travels to the owner of the left image
-              (warped u8x3 + warped mask) -- neighbour-only P2P
+              (warped u8x3 + warped mask) -- P2P between column neighbours
   seam        every rank runs the pairs it owns CONCURRENTLY and speculatively on the entry masks
               (is_seam_pair_run); results needed elsewhere travel (X2: mask-sized messages); each pair with an
               earlier neighbour in the reference's order proves its result on the masks it would really have seen
@@ -48,16 +49,20 @@ class ShardPlan:
         assert n % world == 0, "images must divide evenly over the ranks"
         m = n // world
         p = ShardPlan([tuple(int(v) for v in c) for c in corners], [tuple(int(v) for v in s) for s in sizes], tuple(int(v) for v in roi), world, num_bands)
-        p.owner = [i // m for i in range(n)]
+        # ownership by panorama column: images ordered by the x of their centre, n/world of them per rank.  For a strip
+        # that is rank = i // m; for a 2-D mosaic (several rows of images) every rank gets the images of its columns.
+        order = sorted(range(n), key=lambda i: (2 * p.corners[i][0] + p.sizes[i][0], i))
+        p.owner = [0] * n
+        for k, i in enumerate(order):
+            p.owner[i] = k // m
         allp = [(i, j) for i in range(n) for j in range(i + 1, n)][::-1]
         p.pairs = [(i, j) for (i, j) in allp if _overlap(p.corners[i], p.sizes[i], p.corners[j], p.sizes[j])]
         nb = min(num_bands, int(np.ceil(np.log(max(roi[2], roi[3])) / np.log(2.0))))
         q = 1 << nb
         cuts = [0]
         for r in range(1, world):
-            a, b = r * m - 1, r * m                   # last image of rank r-1, first image of rank r
-            lo = p.corners[b][0]
-            hi = p.corners[a][0] + p.sizes[a][0]
+            lo = min(p.corners[i][0] for i in range(n) if p.owner[i] == r)                       # leftmost column of rank r
+            hi = max(p.corners[i][0] + p.sizes[i][0] for i in range(n) if p.owner[i] == r - 1)   # rightmost of rank r-1
             mid = (lo + hi) // 2 - roi[0]
             mid = max(cuts[-1] + q, min(roi[2] - q, (mid // q) * q))
             cuts.append(mid)

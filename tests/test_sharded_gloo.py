@@ -112,7 +112,7 @@ def _worker(rank, world, port, case, result_path):
     import oracle as O
     from imagestitch_b200 import sharded, synth
     n, w, h, ov, nb = case
-    imgs, Ks, Rs, scale = synth.make_panorama_inputs(n, w, h, 1.2, ov)
+    imgs, Ks, Rs, scale = synth.make_panorama_inputs(n, w, h, 1.2, ov, grid_rows=int(os.environ.get("IS_TEST_GRID_ROWS", "1")))
     corners, sizes, roi = O.pipeline_plan(0, [(h, w)] * n, Ks, Rs, scale)
     plan = sharded.ShardPlan.build(corners, sizes, roi, world, nb)
     mine = [torch.from_numpy(imgs[i]) for i in range(n) if plan.owner[i] == rank]
@@ -138,13 +138,16 @@ def _worker(rank, world, port, case, result_path):
 
 
 @pytest.mark.parametrize("early", [False, True])
-@pytest.mark.parametrize("case", [(4, 192, 144, 0.25, 3), (6, 160, 120, 0.3, 4), (4, 200, 150, 0.6, 3), (4, 192, 144, 0.25, 3, "fallback")])
+@pytest.mark.parametrize("case", [(4, 192, 144, 0.25, 3), (6, 160, 120, 0.3, 4), (4, 200, 150, 0.6, 3), (4, 192, 144, 0.25, 3, "fallback"),
+                                  (8, 128, 96, 0.3, 3, "mosaic")])
 def test_two_rank_sharded_matches_single_process(tmp_path, case, monkeypatch, early):
     import oracle
     oracle.build()
     monkeypatch.setenv("IS_TEST_EARLY_FEED", "1" if early else "0")
-    if len(case) > 5:
+    monkeypatch.setenv("IS_TEST_GRID_ROWS", "2" if case[-1] == "mosaic" else "1")
+    if case[-1] == "fallback":
         monkeypatch.setenv("IS_SHARDED_FORCE_FALLBACK", "1")
+    if len(case) > 5:
         case = case[:5]
     port = 29500 + (os.getpid() + case[0] * 7 + int(case[3] * 100)) % 2000
     out = tmp_path / "result.txt"
@@ -153,8 +156,19 @@ def test_two_rank_sharded_matches_single_process(tmp_path, case, monkeypatch, ea
     assert ok == "1", "sharded panorama / seam masks differ from the single-process oracle"
     if os.environ.get("IS_SHARDED_FORCE_FALLBACK") == "1":
         assert spec == "0"
-    elif case[3] < 0.5:
+    elif case[3] < 0.5 and os.environ.get("IS_TEST_GRID_ROWS") != "2":
         assert spec == "1"     # independent pairs: the speculative results are accepted
+
+
+def test_three_rank_mosaic(tmp_path, monkeypatch):
+    """2 x 6 mosaic over three ranks: ownership by panorama column, pairs between the rows and across strip boundaries."""
+    import oracle
+    oracle.build()
+    monkeypatch.setenv("IS_TEST_EARLY_FEED", "1")
+    monkeypatch.setenv("IS_TEST_GRID_ROWS", "2")
+    out = tmp_path / "result.txt"
+    mp.spawn(_worker, args=(3, 29500 + (os.getpid() + 977) % 2000, (12, 112, 84, 0.3, 3), str(out)), nprocs=3, join=True)
+    assert out.read_text().split()[0] == "1", "sharded mosaic differs from the single-process oracle"
 
 
 def test_shard_plan_geometry():
@@ -168,3 +182,9 @@ def test_shard_plan_geometry():
     assert p.cuts[0] == 0 and p.cuts[-1] == 475 and all(c % 8 == 0 for c in p.cuts[1:-1]) and p.cuts == sorted(p.cuts)
     assert [p.pair_owner(k) for k in range(5)] == [2, 1, 1, 0, 0]
     assert p.earlier(1, 4) == [0] and p.earlier(0, 4) == []
+    # 2 x 4 mosaic, row-major image order: ranks own panorama columns, not index ranges
+    corners = [(-193, -13), (-108, -14), (-23, -13), (61, -13), (-193, -87), (-108, -87), (-23, -86), (61, -86)]
+    p = sharded.ShardPlan.build(corners, [(130, 100)] * 8, (-193, -87, 384, 174), 2, 3)
+    assert p.owner == [0, 0, 1, 1, 0, 0, 1, 1]
+    assert p.cuts[0] == 0 and p.cuts[-1] == 384 and p.cuts[1] % 8 == 0 and -23 + 193 <= p.cuts[1] <= -108 + 130 + 193
+    assert any(p.owner[i] != p.owner[j] for (i, j) in p.pairs) and any(abs(i - j) == 4 for (i, j) in p.pairs)
