@@ -1,6 +1,7 @@
 """Launched with torchrun on N GPUs: stitches one strip panorama sharded by column strip (NCCL halo exchange) and
 checks the assembled strips against the single-GPU pipeline on rank 0.
-    python -m torch.distributed.run --nnodes=1 --nproc-per-node N --master-addr 127.0.0.1 --master-port 29511 scripts/sharded_check.py [rows cols per_rank]"""
+    python -m torch.distributed.run --nnodes=1 --nproc-per-node N --master-addr 127.0.0.1 --master-port 29511 scripts/sharded_check.py [rows cols per_rank [grid_rows]]
+grid_rows > 1: a grid_rows x (N*per_rank/grid_rows) mosaic instead of a strip (per_rank must be a multiple of grid_rows)."""
 import os
 import sys
 import time
@@ -13,12 +14,13 @@ import torch.distributed as dist
 from imagestitch_b200 import sharded, stitching as S, synth
 
 rows, cols, per_rank = (int(v) for v in (sys.argv[1:4] + ["800", "1200", "3"])[:3])
+grid_rows = int(sys.argv[4]) if len(sys.argv) > 4 else 1
 rank, world, local = int(os.environ["RANK"]), int(os.environ["WORLD_SIZE"]), int(os.environ["LOCAL_RANK"])
 torch.cuda.set_device(local)
 dist.init_process_group("nccl", device_id=torch.device("cuda", local))
 n = per_rank * world
-fw = max(1.2, 0.75 * n / (2 * 5.9) / 0.5)       # keep the strip below ~340 degrees
-Ks, Rs, scale = synth.strip_cameras(n, cols, rows, fw, 0.25)
+fw = max(1.2, 0.75 * (n // grid_rows) / (2 * 5.9) / 0.5)       # keep the strip below ~340 degrees
+Ks, Rs, scale = synth.strip_cameras(n, cols, rows, fw, 0.25, grid_rows=grid_rows)
 be = sharded.GpuBackend(local)
 st0 = S.Stitcher(be.ctx, "cylindrical", "dp", 5, S.WEIGHT_32F)
 corners, sizes, roi = st0.plan([(cols, rows)] * n, Ks, Rs, scale)
