@@ -246,6 +246,8 @@ def main():
         st = S.Stitcher(ctx, "cylindrical", "dp", NUM_BANDS, S.WEIGHT_32F)
         corners_all, sizes_all, roi = st.plan([(cols, rows)] * n_all, Ks_all, Rs_all, scale)
         plan = sharded.ShardPlan.build(corners_all, sizes_all, roi, world, NUM_BANDS)
+        if [i for i in range(n_all) if plan.owner[i] == rank] != idx:
+            raise RuntimeError("shard plan does not assign images rank*n .. rank*n+n-1 to this rank (the workload is not a left-to-right strip)")
         sizes = [sizes_all[i] for i in idx]
         sh = sharded.ShardedStitcher(be, sharded.Comm(dist), NUM_BANDS)
         out_shape = (roi[3], plan.cuts[rank + 1] - plan.cuts[rank])
