@@ -6,7 +6,7 @@ never be imported from ``imagestitch_b200`` (the product); only ``tests/``, ``__
 and ``bench.py``'s cpu_baseline / ``--impl reference`` legs use it.
 
 Parity pin: see oracle/oracle.h (pinned against OpenCV 4.13 fixtures in tests/golden/; the
-hand-written linear blend is "parity unpinned").
+hand-written linear blend against the reference's own block compiled into oracle/_ref, `build_ref()`).
 """
 from __future__ import annotations
 
@@ -274,6 +274,51 @@ def lin_blend(img1, img2, tl1, tl2, want_cost=False):
     if rc == 1:
         return None
     return (pano, seam, cost) if want_cost else (pano, seam)
+
+
+# ---------------------------------------------------------------- oracle/_ref: the reference's own code
+_REF_SO = os.path.join(_DIR, "_ref", "libref_linblend.so")
+_ref = None
+
+
+def build_ref() -> str | None:
+    """Compiles the reference's own hand-written pair blend ([BLEND]:141-717) from /root/reference against
+    oracle/ref_shim/cvshim.h (recipe: `make -C oracle ref`).  Returns the .so path, or None where neither the
+    reference sources nor a prebuilt oracle/_ref exist."""
+    if os.path.isdir("/root/reference"):
+        srcs = [os.path.join(_DIR, "ref_shim", f) for f in ("cvshim.h", "linblend_ref.cpp")] + [os.path.join(_DIR, "Makefile")]
+        if not os.path.exists(_REF_SO) or any(os.path.getmtime(x) > os.path.getmtime(_REF_SO) for x in srcs):
+            subprocess.check_call(["make", "-s", "-C", _DIR, "ref"], stdout=subprocess.DEVNULL)
+    return _REF_SO if os.path.exists(_REF_SO) else None
+
+
+def ref_lin_blend(img1, img2, tl1, tl2):
+    """The reference's compiled block on two CV_32FC3 images -> (pano, seam_x, costV), None for its early return
+    ([BLEND]:182-183).  Raises if oracle/_ref is not available."""
+    global _ref
+    if _ref is None:
+        so = build_ref()
+        if so is None:
+            raise RuntimeError("oracle/_ref/libref_linblend.so is not available (no /root/reference here)")
+        _ref = C.CDLL(so)
+        _ref.ref_lin_blend.restype = C.c_int
+    a = np.ascontiguousarray(img1, np.float32)
+    b = np.ascontiguousarray(img2, np.float32)
+    he, br = C.c_int(0), C.c_int(0)
+    lib().orc_lin_geometry(C.c_int(a.shape[0]), C.c_int(a.shape[1]), C.c_int(b.shape[0]), C.c_int(b.shape[1]),
+                           C.c_int(tl1[0]), C.c_int(tl1[1]), C.c_int(tl2[0]), C.c_int(tl2[1]), C.byref(he), C.byref(br))
+    ib = a.shape[1] - (tl2[0] - tl1[0])
+    pano = np.zeros((max(he.value, 0), max(br.value, 0), 3), np.float32)
+    seam = np.zeros(max(he.value, 0), np.int32)
+    cost = np.zeros((max(he.value, 0), max(ib + 2, 0)), np.float32)
+    rc = _ref.ref_lin_blend(_p(a), C.c_int(a.shape[0]), C.c_int(a.shape[1]), _p(b), C.c_int(b.shape[0]), C.c_int(b.shape[1]),
+                            C.c_int(int(tl1[0])), C.c_int(int(tl1[1])), C.c_int(int(tl2[0])), C.c_int(int(tl2[1])),
+                            _p(pano), C.c_int(pano.shape[0]), C.c_int(pano.shape[1]), _p(seam), _p(cost), C.c_int(cost.shape[1]))
+    if rc == 1:
+        return None
+    if rc != 0:
+        raise RuntimeError(f"ref_lin_blend: geometry mismatch between the reference block and orc_lin_geometry ({rc})")
+    return pano, seam, cost
 
 
 # ---------------------------------------------------------------- whole path

@@ -4,8 +4,12 @@
 // map costV, greedy per-row seam, overlap classification masks, per-row left/right scan, seam-guided
 // linear weights and the three-region composite.
 //
-// PARITY UNPINNED: the reference main() cannot be built here (needs OpenCV C++ and the author's
-// images) and OpenCV has no equivalent routine, so no executable pin exists for this function.
+// Parity pin: the reference's OWN block -- [BLEND]:141-717 cut out of its main() at build time and compiled against
+// oracle/ref_shim/cvshim.h (`make -C oracle ref` -> oracle/_ref/libref_linblend.so).  This restatement reproduces it bit
+// for bit (panorama incl. its NaNs, greedy seam, cost map): tests/test_oracle_reference_build.py, live where
+// /root/reference exists and against tests/golden/linblend_ref_cases.npz everywhere.  Not covered by the pin: OpenCV's
+// own cvtColor (the shim uses the scalar formula below; a gray value exactly at a threshold may round differently in
+// OpenCV 3.4.2's SIMD body) and the out-of-buffer reads listed next.
 //
 // Defined behaviour where the reference reads out of bounds:
 //   * cv::Mat_ buffers are continuous, so row-relative out-of-row reads of costV / mask_r2

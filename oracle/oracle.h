@@ -11,8 +11,9 @@
  * delegates to is OpenCV (pinned 3.4.2, un-vendored); this oracle is pinned against
  * OpenCV 4.13 (python cv2) outputs stored under tests/golden/ (generator:
  * tests/golden/make_golden.py) and, when cv2 is importable, against cv2 directly.
- * The hand-written linear blend (oracle/linblend.cpp) has no executable reference:
- * "parity unpinned" for that function.
+ * The hand-written linear blend (oracle/linblend.cpp) is pinned against the reference's own
+ * code: [BLEND]:141-717 compiled from /root/reference with a small cv::Mat shim into
+ * oracle/_ref/libref_linblend.so (`make ref`), golden outputs in tests/golden/linblend_ref_cases.npz.
  *
  * Reference aliases ([WARP], [SEAM], [BLEND]) are defined in SURVEY.md section 0.
  */

@@ -1,0 +1,55 @@
+"""Golden vectors of the hand-written pair blend, produced by the REFERENCE'S OWN code ([BLEND]:141-717 compiled from
+/root/reference against oracle/ref_shim/cvshim.h, `make -C oracle ref`).  Runs only where /root/reference exists; the
+resulting tests/golden/linblend_ref_cases.npz travels, the reference does not.
+    python tests/golden/make_linblend_ref.py"""
+import os
+import sys
+
+import numpy as np
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, os.path.dirname(os.path.dirname(HERE)))
+sys.path.insert(0, os.path.dirname(HERE))
+
+import oracle as O  # noqa: E402
+from helpers import warped_set  # noqa: E402
+
+
+def cases():
+    """(img1 u8, img2 u8, tl1, tl2): warped synthetic pairs with their black borders (dy < 0, == 0, > 0) and noise
+    pairs with dark patches around the classification thresholds 10 / 20 ([BLEND]:331-460)."""
+    out = []
+    corners, wi, _ = warped_set(O, 2, 120, 90, overlap=0.3)
+    for dy in (None, 0, 4, -3):
+        tl2 = corners[1] if dy is None else (corners[1][0], corners[0][1] + dy)
+        out.append((wi[0], wi[1], tuple(int(v) for v in corners[0]), tuple(int(v) for v in tl2)))
+    # (image heights are chosen so that the block never reads image rows past the end of an image: for panoHe - dy2 > rows
+    #  [BLEND]:216-219 does, and what it finds there is whatever follows the buffer)
+    rng = np.random.default_rng(41)
+    for k, (h1, w1, h2, w2, tl2) in enumerate([(70, 100, 70, 96, (60, 0)), (66, 90, 64, 90, (41, 2)), (72, 88, 70, 92, (50, -2))]):
+        a = rng.integers(0, 256, (h1, w1, 3), dtype=np.uint8)
+        b = rng.integers(0, 256, (h2, w2, 3), dtype=np.uint8)
+        for im in (a, b):                                   # dark patches: values 0..40 straddle both thresholds
+            for _ in range(6):
+                y, x = int(rng.integers(0, im.shape[0] - 12)), int(rng.integers(0, im.shape[1] - 12))
+                im[y:y + 12, x:x + 12] = rng.integers(0, 41, (12, 12, 3), dtype=np.uint8)
+        a[:, :3] = 0
+        b[:, -3:] = 0
+        out.append((a, b, (0, 0), tl2))
+    return out
+
+
+if __name__ == "__main__":
+    if O.build_ref() is None:
+        sys.exit("oracle/_ref is not available here")
+    z = {}
+    cs = cases()
+    for k, (a, b, tl1, tl2) in enumerate(cs):
+        pano, seam, cost = O.ref_lin_blend(a.astype(np.float32), b.astype(np.float32), tl1, tl2)
+        z[f"c{k}_img1"], z[f"c{k}_img2"] = a, b
+        z[f"c{k}_tl"] = np.asarray([tl1, tl2], np.int32)
+        z[f"c{k}_pano_ref"], z[f"c{k}_seam_ref"], z[f"c{k}_cost_ref"] = pano, seam, cost
+    z["n"] = np.int32(len(cs))
+    path = os.path.join(HERE, "linblend_ref_cases.npz")
+    np.savez_compressed(path, **z)
+    print(path, os.path.getsize(path), "bytes,", len(cs), "cases")
