@@ -278,7 +278,9 @@ def lin_blend(img1, img2, tl1, tl2, want_cost=False):
 
 # ---------------------------------------------------------------- oracle/_ref: the reference's own code
 _REF_SO = os.path.join(_DIR, "_ref", "libref_linblend.so")
+_REF_WARP_SO = os.path.join(_DIR, "_ref", "libref_warp.so")
 _ref = None
+_ref_warp = None
 
 
 def build_ref() -> str | None:
@@ -286,10 +288,30 @@ def build_ref() -> str | None:
     oracle/ref_shim/cvshim.h (recipe: `make -C oracle ref`).  Returns the .so path, or None where neither the
     reference sources nor a prebuilt oracle/_ref exist."""
     if os.path.isdir("/root/reference"):
-        srcs = [os.path.join(_DIR, "ref_shim", f) for f in ("cvshim.h", "linblend_ref.cpp")] + [os.path.join(_DIR, "Makefile")]
-        if not os.path.exists(_REF_SO) or any(os.path.getmtime(x) > os.path.getmtime(_REF_SO) for x in srcs):
+        srcs = [os.path.join(_DIR, "ref_shim", f) for f in ("cvshim.h", "linblend_ref.cpp", "warp_ref.cpp")] + [os.path.join(_DIR, "Makefile")]
+        outs = (_REF_SO, _REF_WARP_SO)
+        if not all(os.path.exists(o) for o in outs) or any(os.path.getmtime(x) > min(os.path.getmtime(o) for o in outs) for x in srcs):
             subprocess.check_call(["make", "-s", "-C", _DIR, "ref"], stdout=subprocess.DEVNULL)
-    return _REF_SO if os.path.exists(_REF_SO) else None
+    return _REF_SO if os.path.exists(_REF_SO) and os.path.exists(_REF_WARP_SO) else None
+
+
+def ref_cylindrical_maps(src_size_wh, K, R, scale):
+    """The reference's own detectResultRoi + mapBackward ([WARP]:47-88) -> (roi (tlx, tly, brx, bry), xmap, ymap).
+    k_rinv / r_kinv are the oracle's (setCameraParams forms them with OpenCV matrix operators, pinned against cv2)."""
+    global _ref_warp
+    if _ref_warp is None:
+        if build_ref() is None:
+            raise RuntimeError("oracle/_ref/libref_warp.so is not available (no /root/reference here)")
+        _ref_warp = C.CDLL(_REF_WARP_SO)
+    k_rinv, r_kinv = camera_params(K, R)
+    _ref_warp.ref_warp_set(_p(np.ascontiguousarray(k_rinv.reshape(9))), _p(np.ascontiguousarray(r_kinv.reshape(9))), C.c_float(scale))
+    roi = np.zeros(4, np.int32)
+    _ref_warp.ref_detect_roi(C.c_int(src_size_wh[0]), C.c_int(src_size_wh[1]), _p(roi))
+    h, w = int(roi[3] - roi[1] + 1), int(roi[2] - roi[0] + 1)
+    xmap = np.empty((h, w), np.float32)
+    ymap = np.empty((h, w), np.float32)
+    _ref_warp.ref_build_maps(C.c_int(int(roi[0])), C.c_int(int(roi[1])), C.c_int(int(roi[2])), C.c_int(int(roi[3])), _p(xmap), _p(ymap))
+    return tuple(int(v) for v in roi), xmap, ymap
 
 
 def ref_lin_blend(img1, img2, tl1, tl2):

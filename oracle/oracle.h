@@ -13,7 +13,9 @@
  * tests/golden/make_golden.py) and, when cv2 is importable, against cv2 directly.
  * The hand-written linear blend (oracle/linblend.cpp) is pinned against the reference's own
  * code: [BLEND]:141-717 compiled from /root/reference with a small cv::Mat shim into
- * oracle/_ref/libref_linblend.so (`make ref`), golden outputs in tests/golden/linblend_ref_cases.npz.
+ * oracle/_ref/libref_linblend.so (`make ref`), golden outputs in tests/golden/linblend_ref_cases.npz;
+ * ROI + backward maps of the cylindrical warp likewise against the reference's own detectResultRoi /
+ * mapBackward ([WARP]:47-88, oracle/_ref/libref_warp.so, tests/golden/warp_ref_cases.npz).
  *
  * Reference aliases ([WARP], [SEAM], [BLEND]) are defined in SURVEY.md section 0.
  */

@@ -25,6 +25,12 @@ struct Point {
     Point(int x_, int y_) : x(x_), y(y_) {}
 };
 
+struct Size {
+    int width = 0, height = 0;
+    Size() {}
+    Size(int w, int h) : width(w), height(h) {}
+};
+
 class Mat {
 public:
     int rows = 0, cols = 0;

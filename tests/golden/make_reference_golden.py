@@ -1,7 +1,8 @@
-"""Golden vectors of the hand-written pair blend, produced by the REFERENCE'S OWN code ([BLEND]:141-717 compiled from
-/root/reference against oracle/ref_shim/cvshim.h, `make -C oracle ref`).  Runs only where /root/reference exists; the
-resulting tests/golden/linblend_ref_cases.npz travels, the reference does not.
-    python tests/golden/make_linblend_ref.py"""
+"""Golden vectors produced by the REFERENCE'S OWN code, compiled from /root/reference against oracle/ref_shim/cvshim.h
+(`make -C oracle ref`): the hand-written pair blend ([BLEND]:141-717) -> linblend_ref_cases.npz, and the cylindrical
+projector (detectResultRoi + mapBackward, [WARP]:47-88) -> warp_ref_cases.npz.  Runs only where /root/reference exists; the
+resulting files travel, the reference does not.
+    python tests/golden/make_reference_golden.py"""
 import os
 import sys
 
@@ -12,7 +13,7 @@ sys.path.insert(0, os.path.dirname(os.path.dirname(HERE)))
 sys.path.insert(0, os.path.dirname(HERE))
 
 import oracle as O  # noqa: E402
-from helpers import warped_set  # noqa: E402
+from helpers import random_camera, warped_set  # noqa: E402
 
 
 def cases():
@@ -53,3 +54,16 @@ if __name__ == "__main__":
     path = os.path.join(HERE, "linblend_ref_cases.npz")
     np.savez_compressed(path, **z)
     print(path, os.path.getsize(path), "bytes,", len(cs), "cases")
+    rng = np.random.default_rng(2024)
+    z = {}
+    for k in range(6):
+        w, h = int(rng.integers(60, 140)), int(rng.integers(50, 120))
+        K, R, scale = random_camera(rng, w, h)
+        roi, xm, ym = O.ref_cylindrical_maps((w, h), K, R, scale)
+        z[f"w{k}_size"] = np.asarray([w, h], np.int32)
+        z[f"w{k}_K"], z[f"w{k}_R"], z[f"w{k}_scale"] = np.asarray(K, np.float32), np.asarray(R, np.float32), np.float32(scale)
+        z[f"w{k}_roi_ref"], z[f"w{k}_xmap_ref"], z[f"w{k}_ymap_ref"] = np.asarray(roi, np.int32), xm, ym
+    z["n"] = np.int32(6)
+    path = os.path.join(HERE, "warp_ref_cases.npz")
+    np.savez_compressed(path, **z)
+    print(path, os.path.getsize(path), "bytes")

@@ -1,7 +1,8 @@
-"""The hand-written pair blend ([BLEND]:141-717) against the reference's OWN code.
+"""The oracle against the reference's OWN code: the hand-written pair blend ([BLEND]:141-717) and the cylindrical
+projector (detectResultRoi + mapBackward, [WARP]:47-88).
 
 tests/golden/linblend_ref_cases.npz holds outputs of the reference's block compiled from /root/reference
-(`make -C oracle ref`, generator tests/golden/make_linblend_ref.py); the oracle's restatement must reproduce them bit
+(`make -C oracle ref`, generator tests/golden/make_reference_golden.py); the oracle's restatement must reproduce them bit
 for bit -- panorama including its NaNs (0/0 weights where a row's left == seam + 1), greedy seam, cost map.  Where the
 reference build is available (this container, or a prebuilt oracle/_ref on the GPU box) the same is checked live on
 further cases."""
@@ -10,7 +11,7 @@ import os
 import numpy as np
 import pytest
 
-from helpers import warped_set
+from helpers import random_camera, warped_set
 
 GOLD = os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "linblend_ref_cases.npz")
 
@@ -47,3 +48,31 @@ def test_linear_blend_matches_reference_build_live(oracle):
             if want is not None:
                 _same(got, want, f"{w}x{h} tl2={tuple(int(v) for v in tl2)}")
     assert O.ref_lin_blend(a, b, (0, 0), (5000, 0)) is None and O.lin_blend(a, b, (0, 0), (5000, 0)) is None     # [BLEND]:182-183
+
+
+def test_cylindrical_maps_match_reference_golden(oracle):
+    """ROI (the reference's full forward scan and the oracle's border scan) and backward maps, bit for bit"""
+    O = oracle
+    z = np.load(os.path.join(os.path.dirname(GOLD), "warp_ref_cases.npz"))
+    for k in range(int(z["n"])):
+        w, h = (int(v) for v in z[f"w{k}_size"])
+        K, R, scale = z[f"w{k}_K"], z[f"w{k}_R"], float(z[f"w{k}_scale"])
+        roi, xm, ym = O.build_maps(O.PROJ_CYLINDRICAL, (w, h), K, R, scale, full_scan=True)
+        assert roi == tuple(int(v) for v in z[f"w{k}_roi_ref"])
+        assert O.detect_roi(O.PROJ_CYLINDRICAL, (w, h), K, R, scale, full_scan=False) == roi
+        assert np.array_equal(xm.view(np.uint32), z[f"w{k}_xmap_ref"].view(np.uint32))
+        assert np.array_equal(ym.view(np.uint32), z[f"w{k}_ymap_ref"].view(np.uint32))
+
+
+def test_cylindrical_maps_match_reference_build_live(oracle):
+    O = oracle
+    if O.build_ref() is None:
+        pytest.skip("oracle/_ref (the compiled reference block) is not available on this machine")
+    rng = np.random.default_rng(77)
+    for _ in range(8):
+        w, h = int(rng.integers(100, 500)), int(rng.integers(80, 400))
+        K, R, scale = random_camera(rng, w, h)
+        roi, xm, ym = O.ref_cylindrical_maps((w, h), K, R, scale)
+        oroi, oxm, oym = O.build_maps(O.PROJ_CYLINDRICAL, (w, h), K, R, scale, full_scan=True)
+        assert roi == oroi and O.detect_roi(O.PROJ_CYLINDRICAL, (w, h), K, R, scale, full_scan=False) == roi
+        assert np.array_equal(xm.view(np.uint32), oxm.view(np.uint32)) and np.array_equal(ym.view(np.uint32), oym.view(np.uint32))
