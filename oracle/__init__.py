@@ -279,8 +279,10 @@ def lin_blend(img1, img2, tl1, tl2, want_cost=False):
 # ---------------------------------------------------------------- oracle/_ref: the reference's own code
 _REF_SO = os.path.join(_DIR, "_ref", "libref_linblend.so")
 _REF_WARP_SO = os.path.join(_DIR, "_ref", "libref_warp.so")
+_REF_SEAM_SO = os.path.join(_DIR, "_ref", "libref_seam.so")
 _ref = None
 _ref_warp = None
+_ref_seam = None
 
 
 def build_ref() -> str | None:
@@ -288,11 +290,35 @@ def build_ref() -> str | None:
     oracle/ref_shim/cvshim.h (recipe: `make -C oracle ref`).  Returns the .so path, or None where neither the
     reference sources nor a prebuilt oracle/_ref exist."""
     if os.path.isdir("/root/reference"):
-        srcs = [os.path.join(_DIR, "ref_shim", f) for f in ("cvshim.h", "linblend_ref.cpp", "warp_ref.cpp")] + [os.path.join(_DIR, "Makefile")]
-        outs = (_REF_SO, _REF_WARP_SO)
+        srcs = [os.path.join(_DIR, "ref_shim", f) for f in os.listdir(os.path.join(_DIR, "ref_shim"))] + [os.path.join(_DIR, "Makefile")]
+        outs = (_REF_SO, _REF_WARP_SO, _REF_SEAM_SO)
         if not all(os.path.exists(o) for o in outs) or any(os.path.getmtime(x) > min(os.path.getmtime(o) for o in outs) for x in srcs):
             subprocess.check_call(["make", "-s", "-C", _DIR, "ref"], stdout=subprocess.DEVNULL)
-    return _REF_SO if os.path.exists(_REF_SO) and os.path.exists(_REF_WARP_SO) else None
+    return _REF_SO if all(os.path.exists(o) for o in (_REF_SO, _REF_WARP_SO, _REF_SEAM_SO)) else None
+
+
+def ref_dp_seam_find(images, corners, masks, cost_fn=COST_COLOR):
+    """The reference's own find() ([SEAM]:87-1093, compiled into oracle/_ref) -> new masks.  COLOR_GRAD on 8-bit images goes
+    through an 8-bit gray image there (cv::cvtColor on CV_8U), unlike the CV_32F images the mains pass."""
+    global _ref_seam
+    if _ref_seam is None:
+        if build_ref() is None:
+            raise RuntimeError("oracle/_ref/libref_seam.so is not available (no /root/reference here)")
+        _ref_seam = C.CDLL(_REF_SEAM_SO)
+        _ref_seam.ref_dp_seam_find.restype = C.c_int
+    n = len(images)
+    is_u8 = images[0].dtype == np.uint8
+    imgs = [np.ascontiguousarray(im, np.uint8 if is_u8 else np.float32) for im in images]
+    out = [np.ascontiguousarray(m, np.uint8).copy() for m in masks]
+    ip = (C.c_void_p * n)(*[im.ctypes.data for im in imgs])
+    mp = (C.c_void_p * n)(*[m.ctypes.data for m in out])
+    rows = np.asarray([im.shape[0] for im in imgs], np.int32)
+    cols = np.asarray([im.shape[1] for im in imgs], np.int32)
+    cxy = np.asarray(corners, np.int32).reshape(-1).copy()
+    rc = _ref_seam.ref_dp_seam_find(C.c_int(n), ip, C.c_int(1 if is_u8 else 0), _p(rows), _p(cols), _p(cxy), mp, C.c_int(cost_fn))
+    if rc:
+        raise RuntimeError(f"the reference's find() raised cv::Error {rc}")
+    return out
 
 
 def ref_cylindrical_maps(src_size_wh, K, R, scale):

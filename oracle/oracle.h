@@ -15,7 +15,9 @@
  * code: [BLEND]:141-717 compiled from /root/reference with a small cv::Mat shim into
  * oracle/_ref/libref_linblend.so (`make ref`), golden outputs in tests/golden/linblend_ref_cases.npz;
  * ROI + backward maps of the cylindrical warp likewise against the reference's own detectResultRoi /
- * mapBackward ([WARP]:47-88, oracle/_ref/libref_warp.so, tests/golden/warp_ref_cases.npz).
+ * mapBackward ([WARP]:47-88, oracle/_ref/libref_warp.so, tests/golden/warp_ref_cases.npz), and the DP
+ * seam finder against the reference's own find() ... updateLabelsUsingSeam ([SEAM]:29-1093,
+ * oracle/_ref/libref_seam.so, tests/golden/seam_ref_cases.npz).
  *
  * Reference aliases ([WARP], [SEAM], [BLEND]) are defined in SURVEY.md section 0.
  */

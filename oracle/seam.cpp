@@ -6,6 +6,10 @@
 // OpenCV's float results for these two depend on the SIMD dispatch (FMA or not, vector body or scalar tail), so the
 // gradients are pinned against cv2 to a few ulp, the seam masks exactly (tests/test_oracle_cv2.py).
 //
+// Parity pin: cv2.detail_DpSeamFinder (tests/golden/seam_blend_cases.npz, color_grad_cases.npz, tests/test_oracle_cv2.py)
+// and the reference's own find() compiled into oracle/_ref/libref_seam.so (tests/test_oracle_reference_build.py,
+// tests/golden/seam_ref_cases.npz): seam masks bit for bit.
+//
 // Compile with -ffp-contract=off.
 #include "oracle.h"
 

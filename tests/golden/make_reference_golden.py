@@ -1,6 +1,7 @@
 """Golden vectors produced by the REFERENCE'S OWN code, compiled from /root/reference against oracle/ref_shim/cvshim.h
-(`make -C oracle ref`): the hand-written pair blend ([BLEND]:141-717) -> linblend_ref_cases.npz, and the cylindrical
-projector (detectResultRoi + mapBackward, [WARP]:47-88) -> warp_ref_cases.npz.  Runs only where /root/reference exists; the
+(`make -C oracle ref`): the hand-written pair blend ([BLEND]:141-717) -> linblend_ref_cases.npz, the cylindrical
+projector (detectResultRoi + mapBackward, [WARP]:47-88) -> warp_ref_cases.npz, and the refactored DP seam finder
+(find() ... updateLabelsUsingSeam, [SEAM]:87-1093) on the inputs of seam_blend_cases.npz -> seam_ref_cases.npz.  Runs only where /root/reference exists; the
 resulting files travel, the reference does not.
     python tests/golden/make_reference_golden.py"""
 import os
@@ -65,5 +66,23 @@ if __name__ == "__main__":
         z[f"w{k}_roi_ref"], z[f"w{k}_xmap_ref"], z[f"w{k}_ymap_ref"] = np.asarray(roi, np.int32), xm, ym
     z["n"] = np.int32(6)
     path = os.path.join(HERE, "warp_ref_cases.npz")
+    np.savez_compressed(path, **z)
+    print(path, os.path.getsize(path), "bytes")
+    zin = np.load(os.path.join(HERE, "seam_blend_cases.npz"))
+    z = {}
+    for k in range(int(zin["n_cases"])):
+        p = f"s{k}_"
+        n = int(zin[p + "n"])
+        corners = [tuple(int(v) for v in c) for c in zin[p + "corners"]]
+        wi = [zin[p + f"img{i}"] for i in range(n)]
+        wm = [zin[p + f"mask{i}"] for i in range(n)]
+        color = O.ref_dp_seam_find([a.astype(np.float32) for a in wi], corners, wm, O.COST_COLOR)
+        color_u8 = O.ref_dp_seam_find(wi, corners, wm, O.COST_COLOR)
+        assert all(np.array_equal(a, b) for a, b in zip(color, color_u8))
+        grad = O.ref_dp_seam_find([a.astype(np.float32) for a in wi], corners, wm, O.COST_COLOR_GRAD)
+        for i in range(n):
+            z[p + f"seam_mask{i}_ref"] = color[i]
+            z[p + f"seam_mask{i}_grad_ref"] = grad[i]
+    path = os.path.join(HERE, "seam_ref_cases.npz")
     np.savez_compressed(path, **z)
     print(path, os.path.getsize(path), "bytes")
