@@ -307,6 +307,8 @@ def ref_dp_seam_find(images, corners, masks, cost_fn=COST_COLOR):
         _ref_seam = C.CDLL(_REF_SEAM_SO)
         _ref_seam.ref_dp_seam_find.restype = C.c_int
     n = len(images)
+    if n == 0:
+        return []
     is_u8 = images[0].dtype == np.uint8
     imgs = [np.ascontiguousarray(im, np.uint8 if is_u8 else np.float32) for im in images]
     out = [np.ascontiguousarray(m, np.uint8).copy() for m in masks]
@@ -367,6 +369,28 @@ def ref_lin_blend(img1, img2, tl1, tl2):
     if rc != 0:
         raise RuntimeError(f"ref_lin_blend: geometry mismatch between the reference block and orc_lin_geometry ({rc})")
     return pano, seam, cost
+
+
+def ref_seam_costs(img1, img2, tl1, tl2, labels, union_tl, l, roi_xywh, cost_fn=COST_COLOR):
+    """The reference's own computeCosts ([SEAM]:733-803) -> (costV, costH); same arguments as seam_costs()."""
+    global _ref_seam
+    if _ref_seam is None:
+        ref_dp_seam_find([], [], [])
+    is_u8 = img1.dtype == np.uint8
+    a = np.ascontiguousarray(img1)
+    b = np.ascontiguousarray(img2)
+    labels = np.ascontiguousarray(labels, np.int32)
+    x, y, w, h = roi_xywh
+    costV = np.empty((h, w + 1), np.float32)
+    costH = np.empty((h + 1, w), np.float32)
+    roi = np.asarray(roi_xywh, np.int32)
+    rc = _ref_seam.ref_seam_costs(_p(a), _p(b), C.c_int(1 if is_u8 else 0), C.c_int(a.shape[0]), C.c_int(a.shape[1]),
+                                  C.c_int(b.shape[0]), C.c_int(b.shape[1]), C.c_int(tl1[0]), C.c_int(tl1[1]), C.c_int(tl2[0]), C.c_int(tl2[1]),
+                                  _p(labels), C.c_int(labels.shape[0]), C.c_int(labels.shape[1]), C.c_int(union_tl[0]), C.c_int(union_tl[1]),
+                                  C.c_int(l), _p(roi), C.c_int(cost_fn), _p(costV), _p(costH))
+    if rc:
+        raise RuntimeError(f"the reference's computeCosts raised cv::Error {rc}")
+    return costV, costH
 
 
 # ---------------------------------------------------------------- whole path

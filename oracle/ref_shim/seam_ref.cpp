@@ -35,3 +35,37 @@ extern "C" int ref_dp_seam_find(int n, const void* const* images, int is_u8, con
         return e.code;
     }
 }
+
+// computeCosts ([SEAM]:733-803) alone: the globals it reads are set from the arguments (labels: H x W int32 in the union
+// frame, component label l with bounding box roi = x, y, w, h).  costV: h x (w+1), costH: (h+1) x w.
+extern "C" int ref_seam_costs(const void* img1, const void* img2, int is_u8, int rows1, int cols1, int rows2, int cols2, int tl1x, int tl1y,
+                              int tl2x, int tl2y, const int32_t* labels, int H, int W, int union_tlx, int union_tly, int l, const int roi[4],
+                              int cost_fn, float* costV_out, float* costH_out) {
+    try {
+        const int type = is_u8 ? CV_8UC3 : CV_32FC3;
+        const size_t es = is_u8 ? 1 : 4;
+        Mat image1(rows1, cols1, type, const_cast<void*>(img1), (size_t)cols1 * 3 * es);
+        Mat image2(rows2, cols2, type, const_cast<void*>(img2), (size_t)cols2 * 3 * es);
+        unionTl_ = Point(union_tlx, union_tly);
+        unionBr_ = Point(union_tlx + W, union_tly + H);
+        unionSize_ = Size(W, H);
+        labels_.create(unionSize_);
+        for (int y = 0; y < H; ++y) std::memcpy(labels_.ptr<int>(y), labels + (size_t)y * W, sizeof(int) * (size_t)W);
+        const int comp = l - 1;
+        states_.assign(comp + 1, INTERS);
+        tls_.assign(comp + 1, Point(0, 0));
+        brs_.assign(comp + 1, Point(0, 0));
+        tls_[comp] = Point(roi[0], roi[1]);
+        brs_[comp] = Point(roi[0] + roi[2], roi[1] + roi[3]);
+        costFunc_ = cost_fn ? COLOR_GRAD : COLOR;
+        if (costFunc_ == COLOR_GRAD) computeGradients(image1, image2);
+        Mat_<float> costV, costH;
+        computeCosts(image1, image2, Point(tl1x, tl1y), Point(tl2x, tl2y), comp, costV, costH);
+        for (int y = 0; y < costV.rows; ++y) std::memcpy(costV_out + (size_t)y * costV.cols, costV.ptr<float>(y), sizeof(float) * (size_t)costV.cols);
+        for (int y = 0; y < costH.rows; ++y) std::memcpy(costH_out + (size_t)y * costH.cols, costH.ptr<float>(y), sizeof(float) * (size_t)costH.cols);
+        return 0;
+    } catch (const RefError& e) {
+        return e.code;
+    }
+}
+

@@ -135,3 +135,34 @@ def test_reference_find_on_its_own_artefacts(oracle):
     want = O.ref_dp_seam_find(imgs, [(0, 5), (799, 0)], masks)
     got = O.dp_seam_find(imgs, [(0, 5), (799, 0)], masks)
     assert np.array_equal(got[0], want[0]) and np.array_equal(got[1], want[1])
+
+
+def test_seam_cost_maps_match_reference_build_live(oracle):
+    """computeCosts ([SEAM]:733-803): costV / costH of the oracle against the reference's own function, bit for bit, with
+    fractional float images (sums that do round), a hole of another label in the component, COLOR and COLOR_GRAD"""
+    O = oracle
+    if O.build_ref() is None:
+        pytest.skip("oracle/_ref (the compiled reference block) is not available on this machine")
+    rng = np.random.default_rng(3)
+    h1, w1, h2, w2 = 60, 80, 70, 64
+    tl1, tl2 = (5, -3), (40, 4)
+    utl = (min(tl1[0], tl2[0]), min(tl1[1], tl2[1]))
+    ubr = (max(tl1[0] + w1, tl2[0] + w2), max(tl1[1] + h1, tl2[1] + h2))
+    W, H = ubr[0] - utl[0], ubr[1] - utl[1]
+    labels = np.zeros((H, W), np.int32)
+    ix0, iy0 = tl2[0] - utl[0], tl2[1] - utl[1]
+    ix1, iy1 = tl1[0] + w1 - utl[0], tl1[1] + h1 - utl[1]
+    labels[iy0:iy1, ix0:ix1] = 2
+    labels[iy0 + 5:iy0 + 9, ix0 + 3:ix0 + 10] = 1
+    roi = (ix0, iy0, ix1 - ix0, iy1 - iy0)
+    for dt in (np.uint8, np.float32):
+        a = rng.integers(0, 256, (h1, w1, 3)).astype(dt)
+        b = rng.integers(0, 256, (h2, w2, 3)).astype(dt)
+        if dt == np.float32:
+            a += rng.uniform(-0.5, 0.5, a.shape).astype(np.float32)
+            b += rng.uniform(-0.5, 0.5, b.shape).astype(np.float32)
+        for cost in ((O.COST_COLOR, O.COST_COLOR_GRAD) if dt == np.float32 else (O.COST_COLOR,)):
+            wv, wh = O.ref_seam_costs(a, b, tl1, tl2, labels, utl, 2, roi, cost)
+            gv, gh = O.seam_costs(a, b, tl1, tl2, labels, utl, 2, roi, cost)
+            assert np.array_equal(gv.view(np.uint32), wv.view(np.uint32)), f"costV {dt.__name__} cost {cost}"
+            assert np.array_equal(gh.view(np.uint32), wh.view(np.uint32)), f"costH {dt.__name__} cost {cost}"
