@@ -135,6 +135,46 @@ def cpu_port_run(workload, threads, sample_rows=None, n_sample=2, steps=1, warmu
     return mp / best, desc, best, stages
 
 
+def opencv_run(workload, sample_rows, n_sample=2):
+    """Informational: the reference-equivalent OpenCV path through python cv2 on the host cores, same bounded
+    sample as cpu_port_run: PyRotationWarper.warp x2 per image -> float32 -> detail_DpSeamFinder -> int16 ->
+    MultiBandBlender(5 bands).  Returns None when cv2 (or its stitching module) is not importable."""
+    try:
+        import cv2
+        import numpy as np
+
+        from imagestitch_b200 import synth
+        n, rows, cols, fw, ov, grid_rows, _ = WORKLOADS[workload]
+        rows_s = min(rows, sample_rows or rows)
+        n_s = min(n, n_sample)
+        Ks, Rs, scale = synth.strip_cameras(n, cols, rows_s, fw * 1.0, ov, grid_rows=grid_rows)
+        imgs = [synth.make_image(i, cols, rows_s, Ks[i], Rs[i], device="cpu").numpy() for i in range(n_s)]
+        t0 = time.perf_counter()
+        wp = cv2.PyRotationWarper("cylindrical", float(scale))
+        corners, wi, wm = [], [], []
+        for i in range(n_s):
+            K, R = np.asarray(Ks[i], np.float32), np.asarray(Rs[i], np.float32)
+            tl, a = wp.warp(imgs[i], K, R, cv2.INTER_LINEAR, cv2.BORDER_REFLECT)
+            _, m = wp.warp(np.full(imgs[i].shape[:2], 255, np.uint8), K, R, cv2.INTER_NEAREST, cv2.BORDER_CONSTANT)
+            corners.append(tuple(int(v) for v in tl)); wi.append(a); wm.append(m)
+        t1 = time.perf_counter()
+        masks = cv2.detail_DpSeamFinder("COLOR").find([cv2.UMat(a.astype(np.float32)) for a in wi], corners, [cv2.UMat(m) for m in wm])
+        masks = [m.get() for m in masks]
+        t2 = time.perf_counter()
+        x0 = min(c[0] for c in corners); y0 = min(c[1] for c in corners)
+        x1 = max(c[0] + a.shape[1] for c, a in zip(corners, wi)); y1 = max(c[1] + a.shape[0] for c, a in zip(corners, wi))
+        mb = cv2.detail_MultiBandBlender(0, NUM_BANDS, cv2.CV_32F)
+        mb.prepare((x0, y0, x1 - x0, y1 - y0))
+        for i in range(n_s):
+            mb.feed(wi[i].astype(np.int16), masks[i], corners[i])
+        mb.blend(None, None)
+        t3 = time.perf_counter()
+        return {"value": n_s * rows_s * cols / 1e6 / (t3 - t0), "unit": "MP/s", "threads": int(cv2.getNumThreads()), "version": cv2.__version__,
+                "stage_seconds": {"warp": t1 - t0, "seam": t2 - t1, "blend": t3 - t2, "total": t3 - t0}}
+    except Exception as e:                      # informational only: never fail the bench over it
+        return {"unavailable": f"{type(e).__name__}: {e}"[:200]}
+
+
 def run_reference(args):
     """--impl reference: the CPU port of the reference path, all host threads, bounded sample per step."""
     rank = int(os.environ.get("RANK", "0"))
@@ -418,7 +458,8 @@ def main():
         sample_rows = rows if rows * cols <= 8e6 else rows // 4
         v, sdesc, dt, stages = cpu_port_run(args.workload, threads, sample_rows=sample_rows)
         cpu = {"value": v, "unit": "MP/s", "cores": threads, "kind": "port", "sample": sdesc, "seconds": dt,
-               "stage_seconds": dict(zip(("warp", "seam", "blend", "total"), stages))}
+               "stage_seconds": dict(zip(("warp", "seam", "blend", "total"), stages)),
+               "opencv_cv2_same_sample": opencv_run(args.workload, sample_rows)}
 
     h2d = world * n * rows * cols * 3
     d2h = roi[2] * roi[3] * 7
