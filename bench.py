@@ -135,7 +135,22 @@ def cpu_port_run(workload, threads, sample_rows=None, n_sample=2, steps=1, warmu
     return mp / best, desc, best, stages
 
 
-def opencv_run(workload, sample_rows, n_sample=2):
+def opencv_run(workload, sample_rows):
+    """opencv_run_inline in a process of its own (cv2 brings its own threading runtime; nothing it does can disturb or end
+    the bench).  Returns its dict, or {"unavailable": why}."""
+    import subprocess
+    try:
+        r = subprocess.run([sys.executable, os.path.abspath(__file__), "--opencv-sample", str(int(sample_rows)), "--workload", workload],
+                           capture_output=True, text=True, timeout=600)
+        for ln in reversed(r.stdout.strip().splitlines()):
+            if ln.startswith("{"):
+                return json.loads(ln)
+        return {"unavailable": f"no output (exit {r.returncode}): {r.stderr.strip()[-160:]}"}
+    except Exception as e:
+        return {"unavailable": f"{type(e).__name__}: {e}"[:200]}
+
+
+def opencv_run_inline(workload, sample_rows, n_sample=2):
     """Informational: the reference-equivalent OpenCV path through python cv2 on the host cores, same bounded
     sample as cpu_port_run: PyRotationWarper.warp x2 per image -> float32 -> detail_DpSeamFinder -> int16 ->
     MultiBandBlender(5 bands).  Returns None when cv2 (or its stitching module) is not importable."""
@@ -225,7 +240,11 @@ def main():
     ap.add_argument("--workload", default="c2", choices=sorted(WORKLOADS))
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--kernel-report", default=None, help="write the per-kernel timing table (JSON) to this file")
+    ap.add_argument("--opencv-sample", type=int, default=None, help="internal: time python cv2's path on a sample of this many rows, print JSON")
     args = ap.parse_args()
+    if args.opencv_sample is not None:
+        print(json.dumps(opencv_run_inline(args.workload, args.opencv_sample)), flush=True)
+        return 0
     args.warmup = max(args.warmup, 0)
     if args.impl == "reference":
         return run_reference(args)
