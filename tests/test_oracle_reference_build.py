@@ -102,7 +102,8 @@ def test_dp_seam_matches_reference_golden(oracle):
 
 
 @pytest.mark.parametrize("case", [(2, 260, 200, 0.25, 1, False), (3, 200, 150, 0.6, 1, False), (4, 160, 120, 0.3, 2, False),
-                                  (3, 180, 130, 0.4, 1, True), (5, 220, 160, 0.35, 1, True), (6, 128, 96, 0.3, 2, True)])
+                                  (3, 180, 130, 0.4, 1, True), (5, 220, 160, 0.35, 1, True), (6, 128, 96, 0.3, 2, True),
+                                  (2, 1500, 1000, 0.3, 1, False)])
 def test_dp_seam_matches_reference_build_live(oracle, case):
     O = oracle
     if O.build_ref() is None:
