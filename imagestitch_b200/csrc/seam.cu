@@ -1830,7 +1830,7 @@ static int seam_find_impl(is_ctx* ctx, int n, const is_mat* images, const is_poi
     IS_REQUIRE(ctx, cost_fn == IS_COST_COLOR || cost_fn == IS_COST_COLOR_GRAD, IS_ERR_BAD_ARG, "unknown cost function");
     if (cost_fn == IS_COST_COLOR_GRAD) {
         // Written against the oracle's restatement but not yet run on a device (no GPU time was left in the round it was
-        // written in): kept behind a switch until tests/test_gpu_color_grad.py has passed on hardware.
+        // written in): kept behind a switch until tests/test_gpu_zz_reports.py has passed on hardware.
         const char* e = getenv("IS_EXPERIMENTAL_COLOR_GRAD");
         if (!(e && e[0] == '1')) return fail(ctx, IS_ERR_UNSUPPORTED, "COLOR_GRAD seam cost is not enabled (IS_EXPERIMENTAL_COLOR_GRAD=1)");
     }

@@ -1,6 +1,6 @@
 """COLOR_GRAD seam cost on the device against the CPU oracle (bit-exact seam masks and seam point lists).
 
-The device path is switched on by IS_EXPERIMENTAL_COLOR_GRAD=1 (set here); tests/test_gpu_color_grad.py runs this
+The device path is switched on by IS_EXPERIMENTAL_COLOR_GRAD=1 (set here); tests/test_gpu_zz_reports.py runs this
 script in a process of its own so that a fault cannot take the test session's CUDA context with it.
 usage: python scripts/check_color_grad.py          exit code 0 = parity on every case
 """

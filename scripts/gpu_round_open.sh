@@ -9,6 +9,8 @@ timeout 900 python -m pytest tests -m gpu -x -q > gpurun_out/open_pytest_gpu.log
 echo "pytest -m gpu: exit $?" | tee gpurun_out/open_status.txt
 timeout 600 python scripts/check_color_grad.py > gpurun_out/open_color_grad.log 2>&1
 echo "COLOR_GRAD device parity: exit $?" | tee -a gpurun_out/open_status.txt
+timeout 600 python scripts/check_seam_edge_cases.py > gpurun_out/open_seam_edge_cases.log 2>&1
+echo "seam edge cases on the device: exit $?" | tee -a gpurun_out/open_status.txt
 timeout 300 python scripts/check_linblend_exact.py > gpurun_out/open_linblend_exact.log 2>&1
 echo "pair blend exactness report: exit $?" | tee -a gpurun_out/open_status.txt
 timeout 300 python -c "import __graft_entry__ as g; g.smoke(); print('smoke ok')" > gpurun_out/open_smoke.log 2>&1
@@ -21,4 +23,5 @@ echo "ncu launch list: exit $?" | tee -a gpurun_out/open_status.txt
 tail -3 gpurun_out/open_pytest_gpu.log
 tail -8 gpurun_out/open_color_grad.log
 tail -2 gpurun_out/open_linblend_exact.log
+grep -v ': ok' gpurun_out/open_seam_edge_cases.log | tail -12
 cat gpurun_out/open_bench.json

@@ -11,7 +11,7 @@ import os
 import numpy as np
 import pytest
 
-from helpers import blob_masks, random_camera, warped_set
+from helpers import blob_masks, random_camera, seam_edge_cases, warped_set
 
 GOLD = os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "linblend_ref_cases.npz")
 
@@ -167,3 +167,21 @@ def test_seam_cost_maps_match_reference_build_live(oracle):
             gv, gh = O.seam_costs(a, b, tl1, tl2, labels, utl, 2, roi, cost)
             assert np.array_equal(gv.view(np.uint32), wv.view(np.uint32)), f"costV {dt.__name__} cost {cost}"
             assert np.array_equal(gh.view(np.uint32), wh.view(np.uint32)), f"costH {dt.__name__} cost {cost}"
+
+
+def test_dp_seam_edge_cases_match_reference(oracle):
+    """ties everywhere, containment, one-pixel overlaps, empty / gray / checkerboard masks, noise with irregular masks:
+    against the masks the reference's own find() wrote for the same inputs (golden), and live where oracle/_ref exists"""
+    O = oracle
+    z = np.load(os.path.join(os.path.dirname(GOLD), "seam_ref_edge_cases.npz"))
+    live = O.build_ref() is not None
+    for k, (name, imgs, cs, ms, cost) in enumerate(seam_edge_cases()):
+        got = O.dp_seam_find(imgs, cs, ms, cost_fn=cost)
+        want = O.ref_dp_seam_find(imgs, cs, ms, cost) if live else None
+        for i in range(len(imgs)):
+            assert np.array_equal(got[i], z[f"e{k}_mask{i}_ref"]), f"{name}: mask {i} differs from the reference's (golden)"
+            if live:
+                assert np.array_equal(got[i], want[i]), f"{name}: mask {i} differs from the reference's (live)"
+        if cost == 0:                                          # 8-bit images: identical costs, identical masks ([SEAM]:742-743)
+            got8 = O.dp_seam_find([a.astype(np.uint8) for a in imgs], cs, ms)
+            assert all(np.array_equal(a, b) for a, b in zip(got8, got)), name
