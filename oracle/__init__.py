@@ -483,7 +483,7 @@ def gain_apply(image, gain):
 
 
 def pipeline_run(proj, srcs, Ks, Rs, scale, seam=True, num_bands=5, weight_type=WEIGHT_32F, want_intermediates=False, exposure_gain=False,
-                 blender="multiband", sharpness=0.02, seam_dilate=0):
+                 blender="multiband", sharpness=0.02, seam_dilate=0, seam_cost=COST_COLOR):
     """warp -> [gain exposure] -> [DP seam] -> multi-band blend.  Returns dict(pano, pano_mask, corners, sizes, roi, seconds, gains[, warped, masks])."""
     n = len(srcs)
     srcs = [np.ascontiguousarray(s, np.uint8) for s in srcs]
@@ -508,7 +508,7 @@ def pipeline_run(proj, srcs, Ks, Rs, scale, seam=True, num_bands=5, weight_type=
     r = np.asarray(roi, np.int32)
     gains = np.ones(n, np.float64)
     rc = lib().orc_pipeline_run_ex2(C.c_int(n), C.c_int(proj), sp, _p(rows), _p(cols), _p(K), _p(R), C.c_float(scale),
-                                    C.c_int(1 if seam else 0), C.c_int(num_bands), C.c_int(weight_type), C.c_int(1 if exposure_gain else 0),
+                                    C.c_int((2 if seam_cost == COST_COLOR_GRAD else 1) if seam else 0), C.c_int(num_bands), C.c_int(weight_type), C.c_int(1 if exposure_gain else 0),
                                     C.c_int(1 if blender == "feather" else 0), C.c_float(sharpness), C.c_int(int(seam_dilate)),
                                     _p(c), _p(s), _p(r), wp, mp, _p(pano), _p(pmask), _p(secs), _p(gains))
     if rc:

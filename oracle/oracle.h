@@ -146,6 +146,7 @@ int orc_pipeline_run_ex(int n, int proj, const uint8_t* const* srcs, const int* 
                         int16_t* pano, uint8_t* pano_mask, double* stage_seconds, double* gains_out);
 /* ... and with the blender of the mains' live path: blender 0 = multi-band, 1 = feather (sharpness); seam_dilate > 0:
  * masks = dilate(masks, d x d) & warped masks before the blender's feed ([SEAM]:1257-1270) */
+/* seam: 0 = keep the warped masks, 1 = DP seam finder with COLOR, 2 = with COLOR_GRAD */
 int orc_pipeline_run_ex2(int n, int proj, const uint8_t* const* srcs, const int* src_rows, const int* src_cols,
                          const float* K, const float* R, float scale, int seam, int num_bands, int weight_type, int exposure_gain,
                          int blender, float sharpness, int seam_dilate,

@@ -125,7 +125,8 @@ int orc_pipeline_run_ex2(int n, int proj, const uint8_t* const* srcs, const int*
             ip[i] = imgf[i].data();
             mp[i] = masks[i].data();
         }
-        int rc = orc_dp_seam_find(n, ip.data(), 0, rows.data(), cols.data(), corners_xy, mp.data(), ORC_COST_COLOR, nullptr, 0, nullptr);
+        int rc = orc_dp_seam_find(n, ip.data(), 0, rows.data(), cols.data(), corners_xy, mp.data(), seam == 2 ? ORC_COST_COLOR_GRAD : ORC_COST_COLOR,
+                                  nullptr, 0, nullptr);        // seam: 1 = DP with COLOR, 2 = DP with COLOR_GRAD
         if (rc) return rc;
     }
     auto t2 = clk::now();

@@ -143,3 +143,17 @@ def test_color_grad_fixtures(oracle):
         gx, gy = O.seam_gradients(g[f"g{k}_img"])
         for got, want in ((gx, g[f"g{k}_gradx_cv"]), (gy, g[f"g{k}_grady_cv"])):
             assert np.abs(got - want).max() <= 2.5e-4 and (got == want).mean() >= 0.9     # inexact only in OpenCV's scalar tail columns
+
+
+def test_pipeline_color_grad_consistent(oracle):
+    """pipeline_run(seam_cost=COLOR_GRAD) == warp, then dp_seam_find(COLOR_GRAD) on the warped intermediates"""
+    O = oracle
+    from imagestitch_b200 import synth
+    imgs, Ks, Rs, scale = synth.make_panorama_inputs(3, 256, 192, 1.2, 0.3)
+    r = O.pipeline_run(0, imgs, Ks, Rs, scale, seam=True, num_bands=4, want_intermediates=True, seam_cost=O.COST_COLOR_GRAD)
+    r0 = O.pipeline_run(0, imgs, Ks, Rs, scale, seam=True, num_bands=4, want_intermediates=True)
+    wm = [O.warp(0, np.full(im.shape[:2], 255, np.uint8), Ks[i], Rs[i], scale, O.INTER_NEAREST, O.BORDER_CONSTANT, full_scan=False)[1]
+          for i, im in enumerate(imgs)]
+    want = O.dp_seam_find([a.astype(np.float32) for a in r["warped"]], [tuple(c) for c in r["corners"]], wm, cost_fn=O.COST_COLOR_GRAD)
+    assert all(np.array_equal(a, b) for a, b in zip(r["masks"], want))
+    assert any(np.any(a != b) for a, b in zip(r["masks"], r0["masks"]))
