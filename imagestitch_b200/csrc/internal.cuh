@@ -39,6 +39,6 @@ int gain_feed_device(is_ctx* ctx, int n, const DevMat* images, const DevMat* mas
 int gain_apply_device(is_ctx* ctx, const DevMat& src, const DevMat& dst, double gain);
 
 // seam.cu
-int seam_find_device(is_ctx* ctx, int n, const DevMat* images, const is_point* corners, const DevMat* masks);
+int seam_find_device(is_ctx* ctx, int n, const DevMat* images, const is_point* corners, const DevMat* masks, int cost_fn = IS_COST_COLOR);
 
 }  // namespace is

@@ -153,8 +153,12 @@ int is_pipeline_run(is_ctx* ctx, int n, const is_mat* images, const is_camera* c
     IS_CUDA(ctx, cudaEventRecord(ctx->ev[1], ctx->stream));
     // ---- seam
     if (cfg.seam == IS_SEAM_DP) {
-        if (cfg.seam_cost != IS_COST_COLOR) return fail(ctx, IS_ERR_UNSUPPORTED, "only the COLOR seam cost is implemented");
-        IS_TRY(seam_find_device(ctx, n, warped.data(), corners.data(), masks.data()));
+        IS_REQUIRE(ctx, cfg.seam_cost == IS_COST_COLOR || cfg.seam_cost == IS_COST_COLOR_GRAD, IS_ERR_BAD_ARG, "unknown seam cost function");
+        if (cfg.seam_cost == IS_COST_COLOR_GRAD) {                     // same switch as is_seam_dp_find (seam.cu): not yet run on hardware
+            const char* e = getenv("IS_EXPERIMENTAL_COLOR_GRAD");
+            if (!(e && e[0] == '1')) return fail(ctx, IS_ERR_UNSUPPORTED, "COLOR_GRAD seam cost is not enabled (IS_EXPERIMENTAL_COLOR_GRAD=1)");
+        }
+        IS_TRY(seam_find_device(ctx, n, warped.data(), corners.data(), masks.data(), cfg.seam_cost));
     } else {
         IS_REQUIRE(ctx, cfg.seam == IS_SEAM_NONE, IS_ERR_BAD_ARG, "unknown seam mode");
     }

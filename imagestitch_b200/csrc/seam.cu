@@ -1854,8 +1854,8 @@ static int seam_find_impl(is_ctx* ctx, int n, const is_mat* images, const is_poi
 }
 
 // used by the pipeline with device-resident mats
-int seam_find_device(is_ctx* ctx, int n, const DevMat* images, const is_point* corners, const DevMat* masks) {
-    return seam_find_core(ctx, n, images, corners, masks, nullptr);
+int seam_find_device(is_ctx* ctx, int n, const DevMat* images, const is_point* corners, const DevMat* masks, int cost_fn) {
+    return seam_find_core(ctx, n, images, corners, masks, nullptr, cost_fn);
 }
 
 }  // namespace is

@@ -481,10 +481,11 @@ class Stitcher:
     Registration stages are host control flow: pass cameras, or Python callables as hooks."""
 
     def __init__(self, ctx: Context, projection="cylindrical", seam="dp", num_bands=5, weight_type=WEIGHT_32F, exposure=None,
-                 blender="multiband", sharpness=0.02, seam_dilate=0):
+                 blender="multiband", sharpness=0.02, seam_dilate=0, seam_cost="COLOR"):
         """blender="feather", sharpness=0.1, seam_dilate=20, exposure="gain" is the configuration the reference's mains run."""
         self.ctx = ctx
-        self.cfg = capi.PipelineConfig(_PROJ[projection], SEAM_DP if seam in ("dp", SEAM_DP, True) else SEAM_NONE, COST_COLOR,
+        self.cfg = capi.PipelineConfig(_PROJ[projection], SEAM_DP if seam in ("dp", SEAM_DP, True) else SEAM_NONE,
+                                       COST_COLOR_GRAD if seam_cost in ("COLOR_GRAD", COST_COLOR_GRAD) else COST_COLOR,
                                        int(num_bands), int(weight_type), 1.0, EXPOSURE_GAIN if exposure in ("gain", EXPOSURE_GAIN, True) else EXPOSURE_NONE,
                                        capi.BLEND_FEATHER if blender in ("feather", capi.BLEND_FEATHER) else capi.BLEND_MULTI_BAND, float(sharpness),
                                        int(seam_dilate))

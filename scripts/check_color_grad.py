@@ -41,6 +41,14 @@ def main():
             print(f"case {case} {kind}: masks {'ok' if ok else 'DIFFER'}, seam points {'ok' if ok_trace else 'DIFFER'}, "
                   f"differs from COLOR in {sum(int((a != b).sum()) for a, b in zip(want, color))} px", flush=True)
             bad += (not ok) + (not ok_trace)
+    # the whole sequence with the COLOR_GRAD cost (is_pipeline_run -> seam_find_device)
+    from imagestitch_b200 import synth
+    imgs, Ks, Rs, scale = synth.make_panorama_inputs(3, 384, 288, 1.2, 0.25)
+    want = O.pipeline_run(0, imgs, Ks, Rs, scale, seam=True, num_bands=5, weight_type=O.WEIGHT_32F, want_intermediates=True, seam_cost=O.COST_COLOR_GRAD)
+    got = S.Stitcher(ctx, "cylindrical", "dp", 5, S.WEIGHT_32F, seam_cost="COLOR_GRAD").stitch(imgs, Ks, Rs, scale, want_seam_masks=True)
+    okp = all(np.array_equal(a, b) for a, b in zip(got["seam_masks"], want["masks"])) and np.array_equal(got["pano"], want["pano"])
+    print(f"pipeline with COLOR_GRAD: {'ok' if okp else 'DIFFERS'}", flush=True)
+    bad += not okp
     ctx.close()
     print("COLOR_GRAD parity:", "PASS" if bad == 0 else f"FAIL ({bad})")
     return 1 if bad else 0
