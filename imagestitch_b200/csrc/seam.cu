@@ -46,6 +46,7 @@ struct ContourRec {
 // device kernels
 // =====================================================================================================
 
+// @emu-begin (tests/test_kernel_host_emulation.py compiles the marked regions for the host)
 struct MaskView {
     const uint8_t* p; size_t step; int rows, cols; int ox, oy;   // (ox, oy): position inside the union frame
     __device__ __forceinline__ int at(int ux, int uy) const {
@@ -54,6 +55,7 @@ struct MaskView {
         return p[(size_t)y * step + x];
     }
 };
+// @emu-end
 
 // [SEAM]:153-186 + :205-218.  cls bits: 0 mask1, 1 mask2, 2 contour1mask_, 3 contour2mask_.
 __global__ void k_classify(MaskView m1, MaskView m2, uint8_t* __restrict__ cls, int uw, int uh) {
@@ -194,6 +196,7 @@ __global__ void k_labels_from_roots(const int* __restrict__ parent, int* labels,
 // The union frame of a pair.  Component labels are stored only for a window of it (the intersection rectangle grown
 // by one pixel when the run-based labelling is used, the whole frame in the dense fallback): every label the
 // algorithm reads after labelling lies there (INTERS components and the 4-neighbours of their pixels).
+// @emu-begin
 struct Frame {
     int uw, uh;              // union frame size
     int wx, wy, ww, wh;      // label window: labels[(y - wy) * ww + (x - wx)]
@@ -207,6 +210,7 @@ __device__ __forceinline__ int lab(const int* __restrict__ labels, const Frame& 
     return labels[lidx(f, x, y)];
 }
 
+// @emu-end
 __device__ __forceinline__ int class_at(const Frame& f, int x, int y) { return (f.m1.at(x, y) ? 1 : 0) | (f.m2.at(x, y) ? 2 : 0); }
 
 __device__ __forceinline__ bool is_contour(const int* __restrict__ labels, const Frame& f, int x, int y, int l) {
@@ -359,6 +363,7 @@ __global__ void k_relabel_rect(int* labels, Frame f, int x0, int y0, int w, int 
 
 // ---- cost maps ------------------------------------------------------------------------------------------------
 
+// @emu-begin
 template <typename T> struct ImgView {
     const T* p; size_t step; int rows, cols; int dx, dy;   // image coords = union coords + (dx, dy)   ([SEAM]:752-753)
     __device__ __forceinline__ const T* px(int ux, int uy) const {
@@ -484,6 +489,7 @@ __global__ void k_cost_pq(ImgView<T> a, ImgView<T> b, const int* __restrict__ la
     Q[(size_t)step * pitch + lane] = q;
 }
 
+// @emu-end
 // ---- DP forward pass + back-track: one CTA per seam --------------------------------------------------------
 // Thread t owns LPT consecutive lanes.  t[] = cost of the previous step + P of the previous step (the first
 // add of every candidate).  Candidates ([SEAM]:899-904 / :869-874):
