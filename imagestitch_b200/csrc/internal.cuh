@@ -5,6 +5,7 @@
 
 namespace is {
 
+// @emu-begin (tests/test_kernel_host_emulation.py compiles the marked regions for the host)
 struct WarpParams {
     float k_rinv[9];
     float scale;
@@ -18,6 +19,7 @@ struct WarpPlan {
     int roi[4];              // tl_x, tl_y, br_x, br_y as detectResultRoi returns them
 };
 
+// @emu-end
 // warp.cu
 int warp_plan(is_ctx* ctx, int proj, int src_w, int src_h, const float* K, const float* R, float scale, WarpPlan* plan);
 int upload_tables(is_ctx* ctx, int proj, const WarpPlan& plan, DevBuf* buf);

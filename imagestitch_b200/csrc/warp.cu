@@ -20,6 +20,7 @@
 
 namespace is {
 
+// @emu-begin (tests/test_kernel_host_emulation.py compiles the marked regions for the host)
 struct Projector {
     float k[9], rinv[9], r_kinv[9], k_rinv[9];
 };
@@ -279,6 +280,7 @@ __global__ void k_build_maps(WarpParams P, const float* __restrict__ tables, flo
     reinterpret_cast<float*>(reinterpret_cast<char*>(ymap) + (size_t)y * ystep)[x] = sy;
 }
 
+// @emu-end
 // ---- host drivers ----------------------------------------------------------------------------------
 
 int warp_plan(is_ctx* ctx, int proj, int src_w, int src_h, const float* K, const float* R, float scale, WarpPlan* plan) {

@@ -31,6 +31,14 @@ inline float __fmul_rn(float a, float b) { return a * b; }
 inline float __fdiv_rn(float a, float b) { return a / b; }
 inline float __fmaf_rn(float a, float b, float c) { return std::fmaf(a, b, c); }
 inline float __int_as_float(int v) { float f; std::memcpy(&f, &v, 4); return f; }
+inline int __float2int_rn(float v) {                      // cvt.rni.s32.f32: round half even, saturate, NaN -> 0
+    if (v != v) return 0;
+    if (v >= 2147483648.f) return 2147483647;
+    if (v <= -2147483648.f) return -2147483647 - 1;
+    return (int)std::nearbyintf(v);
+}
+template <typename T> inline T __ldg(const T* p) { return *p; }
+#define __launch_bounds__(...)
 using std::max;
 using std::min;
 

@@ -1,5 +1,6 @@
-"""Host emulation of device code that could not be run on hardware when it was written (the COLOR_GRAD additions to the
-seam cost kernels): the regions of imagestitch_b200/csrc/seam.cu marked @emu-begin / @emu-end are compiled for the host
+"""Host emulation of device code: the warp path (camera products, ROI scan, trig tables, k_warp, k_build_maps -- the product's
+source checked against the oracle without a GPU) and the code that could not be run on hardware when it was written (the
+COLOR_GRAD additions to the seam cost kernels).  The regions of imagestitch_b200/csrc/the .cu files marked @emu-begin / @emu-end are compiled for the host
 (tests/emu/cuda_host_emul.h: qualifiers vanish, *_rn intrinsics are the IEEE operations, threadIdx/blockIdx are stepped by
 a loop) and their results compared with the oracle bit for bit.  This checks the per-thread arithmetic and every index
 computation of k_sobel_window and k_cost_pq<T, GRAD>; it does not check the launch plumbing around them."""
@@ -16,18 +17,29 @@ EMU = os.path.join(ROOT, "tests", "emu")
 OUT = os.path.join(EMU, "_build")
 
 
+def _build(name, sources, n_regions, inc_name):
+    text = "\n".join(open(os.path.join(ROOT, "imagestitch_b200", "csrc", f)).read() for f in sources)
+    regions = re.findall(r"// @emu-begin[^\n]*\n(.*?)// @emu-end", text, flags=re.S)
+    assert len(regions) == n_regions, f"expected {n_regions} marked regions in {sources}, found {len(regions)}"
+    os.makedirs(OUT, exist_ok=True)
+    with open(os.path.join(OUT, inc_name), "w") as f:
+        f.write("\n".join(regions))
+    so = os.path.join(OUT, f"lib{name}.so")
+    subprocess.check_call(["g++", "-O1", "-fPIC", "-std=c++17", "-ffp-contract=off", "-fno-fast-math", "-w", "-I", EMU, "-I", OUT, "-shared", "-o", so,
+                           os.path.join(EMU, f"{name}.cpp")])
+    return C.CDLL(so)
+
+
 @pytest.fixture(scope="module")
 def emu():
-    src = open(os.path.join(ROOT, "imagestitch_b200", "csrc", "seam.cu")).read()
-    regions = re.findall(r"// @emu-begin[^\n]*\n(.*?)// @emu-end", src, flags=re.S)
-    assert len(regions) == 3, "expected three marked regions in seam.cu"
-    os.makedirs(OUT, exist_ok=True)
-    with open(os.path.join(OUT, "seam_regions.inc"), "w") as f:
-        f.write("\n".join(regions))
-    so = os.path.join(OUT, "libseam_cost_emul.so")
-    subprocess.check_call(["g++", "-O1", "-fPIC", "-std=c++17", "-ffp-contract=off", "-fno-fast-math", "-w", "-I", EMU, "-I", OUT, "-shared", "-o", so,
-                           os.path.join(EMU, "seam_cost_emul.cpp")])
-    return C.CDLL(so)
+    return _build("seam_cost_emul", ["seam.cu"], 3, "seam_regions.inc")
+
+
+@pytest.fixture(scope="module")
+def emu_warp():
+    lib = _build("warp_emul", ["internal.cuh", "warp.cu"], 2, "warp_regions.inc")
+    lib.emu_warp.restype = C.c_int
+    return lib
 
 
 def _p(a):
@@ -103,3 +115,58 @@ def test_cost_pq_kernel_matches_oracle(emu, oracle, dtype, grad, horizontal):
     assert np.array_equal(gotP[ins].view(np.uint32), wantP[ins].view(np.uint32))
     assert np.isinf(gotP[~ins]).all()                                    # cells outside the component can never be on a path
     assert np.isinf(P[:, lanes:]).all() and (Q[:, lanes:] == 0).all()    # padding lanes
+
+
+def _f9(m):
+    return np.ascontiguousarray(np.asarray(m, np.float32).reshape(9))
+
+
+@pytest.mark.parametrize("proj", [0, 1])
+def test_warp_kernels_match_oracle(emu_warp, oracle, proj):
+    """ROI, backward maps, warped image and warped mask of the product's warp source == the oracle (== cv2 / the reference)"""
+    from helpers import random_camera
+    O = oracle
+    rng = np.random.default_rng(10 + proj)
+    for t in range(3):
+        w, h = int(rng.integers(90, 260)), int(rng.integers(70, 200))
+        K, R, scale = random_camera(rng, w, h)
+        img = rng.integers(0, 256, (h, w, 3), dtype=np.uint8)
+        roi = np.zeros(4, np.int32)
+        emu_warp.emu_warp_roi(proj, w, h, _p(_f9(K)), _p(_f9(R)), C.c_float(scale), _p(roi))
+        oroi, oxm, oym = O.build_maps(proj, (w, h), K, R, scale, full_scan=True)
+        assert tuple(int(v) for v in roi) == oroi
+        dh, dw = oroi[3] - oroi[1] + 1, oroi[2] - oroi[0] + 1
+        xm = np.empty((dh, dw), np.float32)
+        ym = np.empty((dh, dw), np.float32)
+        emu_warp.emu_build_maps(proj, w, h, _p(_f9(K)), _p(_f9(R)), C.c_float(scale), _p(xm), _p(ym))
+        assert np.array_equal(xm.view(np.uint32), oxm.view(np.uint32)) and np.array_equal(ym.view(np.uint32), oym.view(np.uint32))
+        dst = np.zeros((dh, dw, 3), np.uint8)
+        msk = np.zeros((dh, dw), np.uint8)
+        assert emu_warp.emu_warp(proj, _p(img), h, w, 3, C.c_size_t(w * 3), _p(_f9(K)), _p(_f9(R)), C.c_float(scale), O.INTER_LINEAR, O.BORDER_REFLECT,
+                                 _p(dst), C.c_size_t(dw * 3), _p(msk), C.c_size_t(dw)) == 0
+        _, want = O.warp(proj, img, K, R, scale, O.INTER_LINEAR, O.BORDER_REFLECT)
+        _, wmask = O.warp(proj, np.full((h, w), 255, np.uint8), K, R, scale, O.INTER_NEAREST, O.BORDER_CONSTANT)
+        assert np.array_equal(dst, want) and np.array_equal(msk, wmask)
+        # the stand-alone mask warp (1 channel, nearest, constant border) through the same kernel
+        m1 = np.zeros((dh, dw), np.uint8)
+        assert emu_warp.emu_warp(proj, _p(np.full((h, w), 255, np.uint8)), h, w, 1, C.c_size_t(w), _p(_f9(K)), _p(_f9(R)), C.c_float(scale),
+                                 O.INTER_NEAREST, O.BORDER_CONSTANT, _p(m1), C.c_size_t(dw), None, C.c_size_t(0)) == 0
+        assert np.array_equal(m1, wmask)
+
+
+def test_warp_kernel_other_sampling_modes(emu_warp, oracle):
+    from helpers import random_camera
+    O = oracle
+    rng = np.random.default_rng(77)
+    w, h = 150, 110
+    K, R, scale = random_camera(rng, w, h)
+    img = rng.integers(0, 256, (h, w, 3), dtype=np.uint8)
+    oroi = O.detect_roi(0, (w, h), K, R, scale)
+    dh, dw = oroi[3] - oroi[1] + 1, oroi[2] - oroi[0] + 1
+    for ch, interp, border in ((3, O.INTER_LINEAR, O.BORDER_CONSTANT), (3, O.INTER_NEAREST, O.BORDER_REFLECT), (1, O.INTER_LINEAR, O.BORDER_REFLECT)):
+        src = img if ch == 3 else np.ascontiguousarray(img[:, :, 0])
+        dst = np.zeros((dh, dw, 3) if ch == 3 else (dh, dw), np.uint8)
+        assert emu_warp.emu_warp(0, _p(src), h, w, ch, C.c_size_t(w * ch), _p(_f9(K)), _p(_f9(R)), C.c_float(scale), interp, border, _p(dst),
+                                 C.c_size_t(dw * ch), None, C.c_size_t(0)) == 0
+        _, want = O.warp(0, src, K, R, scale, interp, border)
+        assert np.array_equal(dst, want), (ch, interp, border)
