@@ -190,6 +190,37 @@ def opencv_run_inline(workload, sample_rows, n_sample=2):
         return {"unavailable": f"{type(e).__name__}: {e}"[:200]}
 
 
+def reference_find_check(workload, sample_rows, n_sample=2):
+    """Informational: the reference's OWN find() ([SEAM]:87-1093 compiled into oracle/_ref, single-threaded as in the reference)
+    beside the port's seam finder on the CPU baseline's sample, and whether their masks agree.  None when oracle/_ref is absent."""
+    try:
+        import numpy as np
+
+        import oracle as O
+        from imagestitch_b200 import synth
+        if O.build_ref() is None:
+            return {"unavailable": "oracle/_ref not present"}
+        n, rows, cols, fw, ov, grid_rows, _ = WORKLOADS[workload]
+        rows_s = min(rows, sample_rows or rows)
+        n_s = min(n, n_sample)
+        Ks, Rs, scale = synth.strip_cameras(n, cols, rows_s, fw * 1.0, ov, grid_rows=grid_rows)
+        wi, wm, cs = [], [], []
+        for i in range(n_s):
+            img = synth.make_image(i, cols, rows_s, Ks[i], Rs[i], device="cpu").numpy()
+            tl, a = O.warp(O.PROJ_CYLINDRICAL, img, Ks[i], Rs[i], scale, O.INTER_LINEAR, O.BORDER_REFLECT, full_scan=False)
+            _, m = O.warp(O.PROJ_CYLINDRICAL, np.full(img.shape[:2], 255, np.uint8), Ks[i], Rs[i], scale, O.INTER_NEAREST, O.BORDER_CONSTANT, full_scan=False)
+            wi.append(a.astype(np.float32)); wm.append(m); cs.append(tl)
+        t0 = time.perf_counter()
+        ref = O.ref_dp_seam_find(wi, cs, wm)
+        t1 = time.perf_counter()
+        port = O.dp_seam_find(wi, cs, wm)
+        t2 = time.perf_counter()
+        return {"find_seconds_reference_1_thread": t1 - t0, "find_seconds_port": t2 - t1,
+                "masks_equal": bool(all(np.array_equal(a, b) for a, b in zip(ref, port)))}
+    except Exception as e:                      # informational only
+        return {"unavailable": f"{type(e).__name__}: {e}"[:200]}
+
+
 def run_reference(args):
     """--impl reference: the CPU port of the reference path, all host threads, bounded sample per step."""
     rank = int(os.environ.get("RANK", "0"))
@@ -478,7 +509,8 @@ def main():
         v, sdesc, dt, stages = cpu_port_run(args.workload, threads, sample_rows=sample_rows)
         cpu = {"value": v, "unit": "MP/s", "cores": threads, "kind": "port", "sample": sdesc, "seconds": dt,
                "stage_seconds": dict(zip(("warp", "seam", "blend", "total"), stages)),
-               "opencv_cv2_same_sample": opencv_run(args.workload, sample_rows)}
+               "opencv_cv2_same_sample": opencv_run(args.workload, sample_rows),
+               "reference_find_same_sample": reference_find_check(args.workload, sample_rows)}
 
     h2d = world * n * rows * cols * 3
     d2h = roi[2] * roi[3] * 7
