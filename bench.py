@@ -135,12 +135,12 @@ def cpu_port_run(workload, threads, sample_rows=None, n_sample=2, steps=1, warmu
     return mp / best, desc, best, stages
 
 
-def opencv_run(workload, sample_rows):
-    """opencv_run_inline in a process of its own (cv2 brings its own threading runtime; nothing it does can disturb or end
-    the bench).  Returns its dict, or {"unavailable": why}."""
+def _informational_leg(flag, workload, sample_rows):
+    """An informational CPU leg in a process of its own: nothing it does (cv2's threading runtime, the reference's code reading
+    past a buffer) can disturb or end the bench.  Returns its dict, or {"unavailable": why}."""
     import subprocess
     try:
-        r = subprocess.run([sys.executable, os.path.abspath(__file__), "--opencv-sample", str(int(sample_rows)), "--workload", workload],
+        r = subprocess.run([sys.executable, os.path.abspath(__file__), flag, str(int(sample_rows)), "--workload", workload],
                            capture_output=True, text=True, timeout=600)
         for ln in reversed(r.stdout.strip().splitlines()):
             if ln.startswith("{"):
@@ -148,6 +148,14 @@ def opencv_run(workload, sample_rows):
         return {"unavailable": f"no output (exit {r.returncode}): {r.stderr.strip()[-160:]}"}
     except Exception as e:
         return {"unavailable": f"{type(e).__name__}: {e}"[:200]}
+
+
+def opencv_run(workload, sample_rows):
+    return _informational_leg("--opencv-sample", workload, sample_rows)
+
+
+def reference_find_check(workload, sample_rows):
+    return _informational_leg("--reference-find-sample", workload, sample_rows)
 
 
 def opencv_run_inline(workload, sample_rows, n_sample=2):
@@ -190,7 +198,7 @@ def opencv_run_inline(workload, sample_rows, n_sample=2):
         return {"unavailable": f"{type(e).__name__}: {e}"[:200]}
 
 
-def reference_find_check(workload, sample_rows, n_sample=2):
+def reference_find_check_inline(workload, sample_rows, n_sample=2):
     """Informational: the reference's OWN find() ([SEAM]:87-1093 compiled into oracle/_ref, single-threaded as in the reference)
     beside the port's seam finder on the CPU baseline's sample, and whether their masks agree.  None when oracle/_ref is absent."""
     try:
@@ -272,9 +280,13 @@ def main():
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--kernel-report", default=None, help="write the per-kernel timing table (JSON) to this file")
     ap.add_argument("--opencv-sample", type=int, default=None, help="internal: time python cv2's path on a sample of this many rows, print JSON")
+    ap.add_argument("--reference-find-sample", type=int, default=None, help="internal: the reference's own find() vs the port on such a sample, print JSON")
     args = ap.parse_args()
     if args.opencv_sample is not None:
         print(json.dumps(opencv_run_inline(args.workload, args.opencv_sample)), flush=True)
+        return 0
+    if args.reference_find_sample is not None:
+        print(json.dumps(reference_find_check_inline(args.workload, args.reference_find_sample)), flush=True)
         return 0
     args.warmup = max(args.warmup, 0)
     if args.impl == "reference":
