@@ -323,6 +323,21 @@ def ref_dp_seam_find(images, corners, masks, cost_fn=COST_COLOR):
     return out
 
 
+def ref_last_seams():
+    """Seams the reference's estimateSeam() produced during the last ref_dp_seam_find call, in order:
+    [(comp, is_horizontal, points Nx2 in pano coords), ...] -- compare with dp_seam_find(..., want_trace=True)[1]."""
+    _ref_seam.ref_last_seam_trace.restype = C.c_size_t
+    n = int(_ref_seam.ref_last_seam_trace(None, C.c_size_t(0)))
+    t = np.zeros(max(n, 1), np.int32)
+    _ref_seam.ref_last_seam_trace(_p(t), C.c_size_t(n))
+    res, k = [], 0
+    while k + 3 <= n:
+        comp, horiz, npts = (int(v) for v in t[k:k + 3])
+        res.append((comp, bool(horiz), t[k + 3:k + 3 + 2 * npts].reshape(-1, 2).copy()))
+        k += 3 + 2 * npts
+    return res
+
+
 def ref_cylindrical_maps(src_size_wh, K, R, scale):
     """The reference's own detectResultRoi + mapBackward ([WARP]:47-88) -> (roi (tlx, tly, brx, bry), xmap, ymap).
     k_rinv / r_kinv are the oracle's (setCameraParams forms them with OpenCV matrix operators, pinned against cv2)."""

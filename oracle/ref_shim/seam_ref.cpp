@@ -13,7 +13,26 @@ using namespace cv;
 using namespace std;
 using namespace detail;
 
+// Seam capture without touching the reference's text: its resolveConflicts() calls
+//     updateLabelsUsingSeam(c1, c2, seam, isHorizontalSeam)          [SEAM]:470
+// with a NON-const std::vector<Point> lvalue, while its own function takes a const reference.  The overload declared
+// here takes a non-const reference, so overload resolution picks it at that call site; it records the seam (the
+// vector estimateSeam() produced) and forwards to the reference's function.
+static std::vector<int32_t> g_seam_trace;   // per seam: comp, horizontal, npts, then npts x (x, y) in panorama coordinates
+void updateLabelsUsingSeam(int comp1, int comp2, std::vector<Point>& seam, bool isHorizontalSeam);
+
 #include "seam_block.inc"
+
+void updateLabelsUsingSeam(int comp1, int comp2, std::vector<Point>& seam, bool isHorizontalSeam) {
+    g_seam_trace.push_back(comp1);
+    g_seam_trace.push_back(isHorizontalSeam ? 1 : 0);
+    g_seam_trace.push_back((int32_t)seam.size());
+    for (const Point& p : seam) {
+        g_seam_trace.push_back(p.x + unionTl_.x);
+        g_seam_trace.push_back(p.y + unionTl_.y);
+    }
+    updateLabelsUsingSeam(comp1, comp2, static_cast<const std::vector<Point>&>(seam), isHorizontalSeam);
+}
 
 // images: n pointers to tightly packed rows x cols x 3 (uint8 or float32); masks: n pointers, modified in place.
 // returns 0, or the cv::Error code the reference's CV_Assert / CV_Error raised.
@@ -29,11 +48,20 @@ extern "C" int ref_dp_seam_find(int n, const void* const* images, int is_u8, con
             corners[i] = Point(corners_xy[2 * i], corners_xy[2 * i + 1]);
         }
         costFunc_ = cost_fn ? COLOR_GRAD : COLOR;
+        g_seam_trace.clear();
         find(src, corners, msk);
         return 0;
     } catch (const RefError& e) {
         return e.code;
     }
+}
+
+// the seams of the last ref_dp_seam_find call, in the order they were estimated: returns the number of int32 values and
+// copies at most cap of them
+extern "C" size_t ref_last_seam_trace(int32_t* out, size_t cap) {
+    const size_t n = g_seam_trace.size();
+    if (out) std::memcpy(out, g_seam_trace.data(), sizeof(int32_t) * std::min(n, cap));
+    return n;
 }
 
 // computeCosts ([SEAM]:733-803) alone: the globals it reads are set from the arguments (labels: H x W int32 in the union

@@ -17,6 +17,15 @@ import oracle as O  # noqa: E402
 from helpers import random_camera, seam_edge_cases, warped_set  # noqa: E402
 
 
+def _flat(seams):
+    """[(comp, horizontal, points Nx2)] -> int32 vector comp, horizontal, npts, x0, y0, ... (the layout of the oracle's trace
+    without the pair indices)"""
+    out = []
+    for comp, horiz, pts in seams:
+        out += [comp, int(horiz), len(pts)] + [int(v) for v in pts.reshape(-1)]
+    return np.asarray(out, np.int32)
+
+
 def cases():
     """(img1 u8, img2 u8, tl1, tl2): warped synthetic pairs with their black borders (dy < 0, == 0, > 0) and noise
     pairs with dark patches around the classification thresholds 10 / 20 ([BLEND]:331-460)."""
@@ -79,7 +88,10 @@ if __name__ == "__main__":
         color = O.ref_dp_seam_find([a.astype(np.float32) for a in wi], corners, wm, O.COST_COLOR)
         color_u8 = O.ref_dp_seam_find(wi, corners, wm, O.COST_COLOR)
         assert all(np.array_equal(a, b) for a, b in zip(color, color_u8))
+        color = O.ref_dp_seam_find([a.astype(np.float32) for a in wi], corners, wm, O.COST_COLOR)
+        z[p + "seams_ref"] = _flat(O.ref_last_seams())
         grad = O.ref_dp_seam_find([a.astype(np.float32) for a in wi], corners, wm, O.COST_COLOR_GRAD)
+        z[p + "seams_grad_ref"] = _flat(O.ref_last_seams())
         for i in range(n):
             z[p + f"seam_mask{i}_ref"] = color[i]
             z[p + f"seam_mask{i}_grad_ref"] = grad[i]
@@ -89,6 +101,7 @@ if __name__ == "__main__":
     z = {}
     for k, (name, imgs, cs, ms, cost) in enumerate(seam_edge_cases()):
         ref = O.ref_dp_seam_find(imgs, cs, ms, cost)
+        z[f"e{k}_seams_ref"] = _flat(O.ref_last_seams())
         for i, m in enumerate(ref):
             z[f"e{k}_mask{i}_ref"] = m
     path = os.path.join(HERE, "seam_ref_edge_cases.npz")       # inputs are regenerated by tests/helpers.seam_edge_cases()

@@ -16,6 +16,14 @@ from helpers import blob_masks, random_camera, seam_edge_cases, warped_set
 GOLD = os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "linblend_ref_cases.npz")
 
 
+def _flat_trace(trace):
+    """oracle trace [(i, j, comp, horizontal, points)] -> the flat layout of tests/golden/make_reference_golden._flat"""
+    out = []
+    for _i, _j, comp, horiz, pts in trace:
+        out += [comp, int(horiz), len(pts)] + [int(v) for v in np.asarray(pts).reshape(-1)]
+    return np.asarray(out, np.int32)
+
+
 def _same(got, want, what):
     pano, seam, cost = got
     assert np.array_equal(seam, want[1]), f"{what}: greedy seam differs"
@@ -91,10 +99,13 @@ def test_dp_seam_matches_reference_golden(oracle):
         wi = [zin[p + f"img{i}"] for i in range(n)]
         wm = [zin[p + f"mask{i}"] for i in range(n)]
         for imgs in (wi, [a.astype(np.float32) for a in wi]):
-            got = O.dp_seam_find(imgs, corners, wm)
+            got, trace = O.dp_seam_find(imgs, corners, wm, want_trace=True)
             for i in range(n):
                 assert np.array_equal(got[i], z[p + f"seam_mask{i}_ref"]), f"case {k} mask {i}"
-        got = O.dp_seam_find([a.astype(np.float32) for a in wi], corners, wm, cost_fn=O.COST_COLOR_GRAD)
+            # every seam estimateSeam() produced in the reference: component, orientation, each point, in order
+            assert np.array_equal(_flat_trace(trace), z[p + "seams_ref"]), f"case {k}: seam point lists differ"
+        got, trace = O.dp_seam_find([a.astype(np.float32) for a in wi], corners, wm, cost_fn=O.COST_COLOR_GRAD, want_trace=True)
+        assert np.array_equal(_flat_trace(trace), z[p + "seams_grad_ref"]), f"case {k}: seam point lists differ (COLOR_GRAD)"
         for i in range(n):
             assert np.array_equal(got[i], z[p + f"seam_mask{i}_grad_ref"]), f"case {k} mask {i} (COLOR_GRAD)"
             # the reference's copy and OpenCV's class agree with each other as well
@@ -116,9 +127,13 @@ def test_dp_seam_matches_reference_build_live(oracle, case):
     wf = [a.astype(np.float32) for a in wi]
     for imgs, cost in ((wi, O.COST_COLOR), (wf, O.COST_COLOR), (wf, O.COST_COLOR_GRAD)):
         want = O.ref_dp_seam_find(imgs, corners, wm, cost)
-        got = O.dp_seam_find(imgs, corners, wm, cost_fn=cost)
+        want_seams = O.ref_last_seams()
+        got, trace = O.dp_seam_find(imgs, corners, wm, cost_fn=cost, want_trace=True)
         for i in range(n):
             assert np.array_equal(got[i], want[i]), f"mask {i}, cost {cost}, {imgs[0].dtype}"
+        assert len(trace) == len(want_seams) and len(trace) >= 1
+        for a, b in zip(want_seams, trace):
+            assert a[0] == b[2] and a[1] == b[3] and np.array_equal(a[2], b[4]), f"seam point list differs, cost {cost}, {imgs[0].dtype}"
 
 
 def test_reference_find_on_its_own_artefacts(oracle):
@@ -176,7 +191,8 @@ def test_dp_seam_edge_cases_match_reference(oracle):
     z = np.load(os.path.join(os.path.dirname(GOLD), "seam_ref_edge_cases.npz"))
     live = O.build_ref() is not None
     for k, (name, imgs, cs, ms, cost) in enumerate(seam_edge_cases()):
-        got = O.dp_seam_find(imgs, cs, ms, cost_fn=cost)
+        got, trace = O.dp_seam_find(imgs, cs, ms, cost_fn=cost, want_trace=True)
+        assert np.array_equal(_flat_trace(trace), z[f"e{k}_seams_ref"]), f"{name}: seam point lists differ from the reference's (golden)"
         want = O.ref_dp_seam_find(imgs, cs, ms, cost) if live else None
         for i in range(len(imgs)):
             assert np.array_equal(got[i], z[f"e{k}_mask{i}_ref"]), f"{name}: mask {i} differs from the reference's (golden)"
