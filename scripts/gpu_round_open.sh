@@ -7,11 +7,11 @@ mkdir -p gpurun_out
 python -c "import __graft_entry__ as g; g.build()" > gpurun_out/open_build.log 2>&1
 timeout 900 python -m pytest tests -m gpu -x -q --deselect tests/test_gpu_zz_reports.py > gpurun_out/open_pytest_gpu.log 2>&1   # the report scripts run directly below
 echo "pytest -m gpu: exit $?" | tee gpurun_out/open_status.txt
-timeout 600 python scripts/check_color_grad.py > gpurun_out/open_color_grad.log 2>&1
+timeout 600 python tests/tools/check_color_grad.py > gpurun_out/open_color_grad.log 2>&1
 echo "COLOR_GRAD device parity: exit $?" | tee -a gpurun_out/open_status.txt
-timeout 600 python scripts/check_seam_edge_cases.py > gpurun_out/open_seam_edge_cases.log 2>&1
+timeout 600 python tests/tools/check_seam_edge_cases.py > gpurun_out/open_seam_edge_cases.log 2>&1
 echo "seam edge cases on the device: exit $?" | tee -a gpurun_out/open_status.txt
-timeout 300 python scripts/check_linblend_exact.py > gpurun_out/open_linblend_exact.log 2>&1
+timeout 300 python tests/tools/check_linblend_exact.py > gpurun_out/open_linblend_exact.log 2>&1
 echo "pair blend exactness report: exit $?" | tee -a gpurun_out/open_status.txt
 timeout 300 python -c "import __graft_entry__ as g; g.smoke(); print('smoke ok')" > gpurun_out/open_smoke.log 2>&1
 echo "smoke: exit $?" | tee -a gpurun_out/open_status.txt

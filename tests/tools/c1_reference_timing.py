@@ -1,13 +1,13 @@
 """BASELINE.json configs[0]: 2x(1024x768) RGB pair, cylindrical warp + the reference's hand-written linear blend, CPU, one core.
 The blend is timed twice: the reference's OWN block ([BLEND]:141-717 compiled into oracle/_ref, when available) and the
 oracle's restatement of it; the warp is the oracle's (the reference calls OpenCV's warper for it).  Prints one JSON line.
-    python scripts/c1_reference_timing.py"""
+    python tests/tools/c1_reference_timing.py"""
 import json
 import os
 import sys
 import time
 
-sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.dirname(os.path.abspath(__file__)))))
 
 import numpy as np  # noqa: E402
 

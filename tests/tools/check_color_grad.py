@@ -2,13 +2,13 @@
 
 The device path is switched on by IS_EXPERIMENTAL_COLOR_GRAD=1 (set here); tests/test_gpu_zz_reports.py runs this
 script in a process of its own so that a fault cannot take the test session's CUDA context with it.
-usage: python scripts/check_color_grad.py          exit code 0 = parity on every case
+usage: python tests/tools/check_color_grad.py          exit code 0 = parity on every case
 """
 import os
 import sys
 
 os.environ["IS_EXPERIMENTAL_COLOR_GRAD"] = "1"
-ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+ROOT = os.path.dirname(os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 sys.path.insert(0, ROOT)
 sys.path.insert(0, os.path.join(ROOT, "tests"))
 

@@ -1,10 +1,10 @@
 """Is the device pair blend (is_linear_blend_pair) bit-exact against the oracle -- which is bit-exact against the reference's
 own compiled block?  tests/test_gpu_parity.py only asserts |d| <= 1e-3 * 255 for the panorama; this reports the exact
-figure so that the test can be tightened.   python scripts/check_linblend_exact.py   (needs a GPU)"""
+figure so that the test can be tightened.   python tests/tools/check_linblend_exact.py   (needs a GPU)"""
 import os
 import sys
 
-ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+ROOT = os.path.dirname(os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 sys.path.insert(0, ROOT)
 sys.path.insert(0, os.path.join(ROOT, "tests"))
 

@@ -1,12 +1,12 @@
 """Degenerate / adversarial DP-seam inputs (tests/helpers.seam_edge_cases: ties everywhere, containment, one-pixel overlaps,
 empty / gray / checkerboard masks, noise with irregular masks) on the device against the oracle -- which equals the
 reference's own find() on every one of them (tests/test_oracle_reference_build.py).  COLOR cases go through the shipped
-path; COLOR_GRAD cases through the experimental switch.   python scripts/check_seam_edge_cases.py   (needs a GPU)"""
+path; COLOR_GRAD cases through the experimental switch.   python tests/tools/check_seam_edge_cases.py   (needs a GPU)"""
 import os
 import sys
 
 os.environ["IS_EXPERIMENTAL_COLOR_GRAD"] = "1"
-ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+ROOT = os.path.dirname(os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 sys.path.insert(0, ROOT)
 sys.path.insert(0, os.path.join(ROOT, "tests"))
 

@@ -1,6 +1,6 @@
 """Single-GPU pipeline vs the CPU oracle at larger sizes; prints the seam speculation verdict."""
 import os, sys, time
-sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.dirname(os.path.abspath(__file__)))))
 import numpy as np
 import oracle as O
 from imagestitch_b200 import stitching as S, synth
