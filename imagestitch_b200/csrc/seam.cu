@@ -501,6 +501,7 @@ __global__ void k_cost_pq(ImgView<T> a, ImgView<T> b, const int* __restrict__ la
 // mbarrier complete_tx), G rows of P and Q per stage, D stages in flight, issued by one thread.  Inside a step
 // neighbouring threads exchange the running cost of their edge lanes through shared memory; one
 // __syncthreads per step is the only synchronisation on the chain.
+// @emu-dp-begin (tests/test_kernel_host_emulation.py runs this region on the multi-threaded block emulator)
 struct DpArgs {
     const float* P; const float* Q;   // [steps][pitch]
     uint8_t* control;                 // [steps][lanes]
@@ -659,6 +660,7 @@ __global__ void __launch_bounds__(1024) k_seam_dp(DpArgs A) {
     if (tid == 0) A.seam_lane[0] = cur_lane_s;
 }
 
+// @emu-dp-end
 // ---- updateLabelsUsingSeam: device part -------------------------------------------------------------------------
 // sub-frame klass: 0 = not comp1, 1 = interior of comp1, 2 = painted (contour of comp1 or seam)  [SEAM]:963-970
 __global__ void k_uls_class(const int* __restrict__ labels, Frame f, int l1, int bx, int by, int bw, int bh, uint8_t* klass) {

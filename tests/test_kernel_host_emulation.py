@@ -42,6 +42,26 @@ def emu_warp():
     return lib
 
 
+@pytest.fixture(scope="module")
+def emu_dp():
+    """the DP kernel on the multi-threaded block emulator (tests/emu/cuda_host_emul_mt.h, tests/emu/tma.cuh)"""
+    src = open(os.path.join(ROOT, "imagestitch_b200", "csrc", "seam.cu")).read()
+    regions = re.findall(r"// @emu-dp-begin[^\n]*\n(.*?)// @emu-dp-end", src, flags=re.S)
+    assert len(regions) == 1
+    # dynamic shared memory: `extern __shared__ ... unsigned char name[];` becomes a pointer to the emulator's buffer
+    text, n = re.subn(r"extern\s+__shared__[^;]*?unsigned char (\w+)\[\];", r"unsigned char* \1 = emu_dynamic_smem;", regions[0])
+    assert n == 1
+    os.makedirs(OUT, exist_ok=True)
+    with open(os.path.join(OUT, "seam_dp_region.inc"), "w") as f:
+        f.write(text)
+    so = os.path.join(OUT, "libseam_dp_emul.so")
+    subprocess.check_call(["g++", "-O1", "-fPIC", "-std=c++20", "-pthread", "-ffp-contract=off", "-fno-fast-math", "-w", "-I", EMU, "-I", OUT, "-shared",
+                           "-o", so, os.path.join(EMU, "seam_dp_emul.cpp")])
+    lib = C.CDLL(so)
+    lib.emu_seam_dp.restype = C.c_int
+    return lib
+
+
 def _p(a):
     return a.ctypes.data_as(C.c_void_p)
 
@@ -170,3 +190,52 @@ def test_warp_kernel_other_sampling_modes(emu_warp, oracle):
                                  C.c_size_t(dw * ch), None, C.c_size_t(0)) == 0
         _, want = O.warp(0, src, K, R, scale, interp, border)
         assert np.array_equal(dst, want), (ch, interp, border)
+
+
+@pytest.mark.parametrize("case", [(200, 150, 0.3, 0, 4, 8, 2), (180, 140, 0.45, 3, 4, 3, 2), (150, 110, 0.35, -4, 8, 16, 2), (260, 120, 0.3, 2, 4, 5, 3)])
+def test_dp_kernel_matches_oracle(emu, emu_dp, oracle, case):
+    """k_seam_dp (forward pass over the TMA ring, reachability, back-track) fed by k_cost_pq, both from the product's source and
+    both emulated on the host, against the seam the oracle traces for the same pair (== the reference's estimateSeam)."""
+    from helpers import warped_set
+    O = oracle
+    w, h, ov, dy, lpt, G, D = case
+    corners, wi, wm = warped_set(O, 2, w, h, overlap=ov)
+    corners = [tuple(int(v) for v in corners[0]), (int(corners[1][0]), int(corners[0][1]) + dy)]
+    got_masks, trace = O.dp_seam_find(wi, corners, wm, want_trace=True)
+    assert len(trace) == 1
+    _i, _j, _comp, horizontal, pts = trace[0]
+    assert not horizontal
+    (h1, w1), (h2, w2) = wi[0].shape[:2], wi[1].shape[:2]
+    utl = (min(corners[0][0], corners[1][0]), min(corners[0][1], corners[1][1]))
+    ubr = (max(corners[0][0] + w1, corners[1][0] + w2), max(corners[0][1] + h1, corners[1][1] + h2))
+    W, H = ubr[0] - utl[0], ubr[1] - utl[1]
+    m1 = np.zeros((H, W), np.uint8)
+    m2 = np.zeros((H, W), np.uint8)
+    m1[corners[0][1] - utl[1]:corners[0][1] - utl[1] + h1, corners[0][0] - utl[0]:corners[0][0] - utl[0] + w1] = wm[0]
+    m2[corners[1][1] - utl[1]:corners[1][1] - utl[1] + h2, corners[1][0] - utl[0]:corners[1][0] - utl[0] + w2] = wm[1]
+    inters = (m1 > 0) & (m2 > 0)                                           # the INTERS component of a two-image strip
+    ys, xs = np.nonzero(inters)
+    rx, ry, rw, rh = int(xs.min()), int(ys.min()), int(xs.max() - xs.min() + 1), int(ys.max() - ys.min() + 1)
+    labels = np.where(inters, 2, 0).astype(np.int32)
+    dx1, dy1, dx2, dy2 = utl[0] - corners[0][0], utl[1] - corners[0][1], utl[0] - corners[1][0], utl[1] - corners[1][1]
+    nt = ((rw + lpt - 1) // lpt + 31) // 32 * 32
+    pitch = nt * lpt
+    P = np.zeros((rh, pitch), np.float32)
+    Q = np.zeros((rh, pitch), np.float32)
+    emu.emu_cost_pq(_p(wi[0]), _p(wi[1]), 1, h1, w1, h2, w2, dx1, dy1, dx2, dy2, _p(labels), H, W, 2, rx, ry, rw, rh, 0, None, 0, 0, 0, 0, _p(P), _p(Q), pitch)
+    seam = np.asarray(pts) - np.asarray(utl) - np.asarray([rx, ry])           # bbox coordinates (x = lane, y = step)
+    order = np.argsort(seam[:, 1])
+    seam = seam[order]
+    s0, lane0, s1, lane1 = int(seam[0, 1]), int(seam[0, 0]), int(seam[-1, 1]), int(seam[-1, 0])
+    assert np.array_equal(seam[:, 1], np.arange(s0, s1 + 1))                # a vertical seam has one point per step
+    control = np.zeros((rh, pitch), np.uint8)
+    seam_lane = np.full(rh + 1, -1, np.int32)
+    reached = np.zeros(1, np.int32)
+    assert emu_dp.emu_seam_dp(_p(P), _p(Q), rw, pitch, rh, s0, lane0, s1, lane1, lpt, G, D, _p(control), _p(seam_lane), _p(reached)) == 0
+    assert reached[0] == 1
+    assert np.array_equal(seam_lane[:s1 - s0 + 1], seam[:, 0]), "DP kernel seam differs from the oracle's"
+    # an unreachable destination: a wall of +inf across the component
+    P2 = P.copy()
+    P2[(s0 + s1) // 2, :] = np.inf
+    assert emu_dp.emu_seam_dp(_p(P2), _p(Q), rw, pitch, rh, s0, lane0, s1, lane1, lpt, G, D, _p(control), _p(seam_lane), _p(reached)) == 0
+    assert reached[0] == 0
