@@ -12,6 +12,7 @@
 
 namespace is {
 
+// @emu-begin (tests/test_kernel_host_emulation.py compiles the marked region for the host)
 struct LinGeo {
     int panoBr, panoHe, dx2, dy, dy1, dy2, height, width, IB;
     int rows1, cols1, rows2, cols2;
@@ -204,6 +205,7 @@ __global__ void k_lin_composite(FImg a, FImg b, LinGeo g, const float* __restric
     o[0] = o0; o[1] = o1; o[2] = o2;
 }
 
+// @emu-end
 }  // namespace is
 
 using namespace is;

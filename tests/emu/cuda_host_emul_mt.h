@@ -6,7 +6,8 @@
 //   __syncthreads()               -> a reusable barrier over the block's threads
 //   mbarrier / bulk copies        -> tests/emu/tma.cuh (same names as imagestitch_b200/csrc/tma.cuh): the copy happens at
 //                                    issue time, the transaction count and phase bookkeeping follow the PTX semantics
-// Not emulated: warp shuffles / votes, clusters, 2-D tensor maps.
+//   __shfl_xor_sync (full mask)   -> exchange through a per-warp slot array between two per-warp barriers
+// Not emulated: other shuffles / votes, clusters, 2-D tensor maps.
 #pragma once
 
 #include <algorithm>
@@ -53,7 +54,30 @@ using std::min;
 
 alignas(128) static unsigned char emu_dynamic_smem[256 * 1024];
 static std::unique_ptr<std::barrier<>> emu_block_barrier;
+static std::unique_ptr<std::barrier<>> emu_warp_barrier[32];
+static uint32_t emu_shfl_slot[32][32];
 inline void __syncthreads() { emu_block_barrier->arrive_and_wait(); }
+
+template <typename T> inline T __shfl_xor_sync(unsigned /*full mask*/, T v, int lane_mask) {
+    static_assert(sizeof(T) == 4, "32-bit shuffles only");
+    const unsigned w = threadIdx.x >> 5, l = threadIdx.x & 31;
+    std::memcpy(&emu_shfl_slot[w][l], &v, 4);
+    emu_warp_barrier[w]->arrive_and_wait();
+    T r;
+    std::memcpy(&r, &emu_shfl_slot[w][l ^ (unsigned)lane_mask], 4);
+    emu_warp_barrier[w]->arrive_and_wait();
+    return r;
+}
+
+// kernels without barriers or shuffles: one host thread steps through the grid
+template <typename F> inline void emu_launch(dim3 grid, dim3 block, F&& kernel_call) {
+    gridDim = grid; blockDim = block;
+    for (unsigned bz = 0; bz < grid.z; ++bz) for (unsigned by = 0; by < grid.y; ++by) for (unsigned bx = 0; bx < grid.x; ++bx)
+        for (unsigned tz = 0; tz < block.z; ++tz) for (unsigned ty = 0; ty < block.y; ++ty) for (unsigned tx = 0; tx < block.x; ++tx) {
+            blockIdx = EmuDim3(bx, by, bz); threadIdx = EmuDim3(tx, ty, tz);
+            kernel_call();
+        }
+}
 
 // one block after the other; the threads of a block concurrently (1-D blocks are enough for the kernels covered)
 template <typename F> inline void emu_launch_mt(unsigned grid_x, unsigned block_x, F&& kernel_call) {
@@ -61,6 +85,7 @@ template <typename F> inline void emu_launch_mt(unsigned grid_x, unsigned block_
     for (unsigned b = 0; b < grid_x; ++b) {
         blockIdx = EmuDim3(b);
         emu_block_barrier = std::make_unique<std::barrier<>>((std::ptrdiff_t)block_x);
+        for (unsigned w = 0; w * 32 < block_x; ++w) emu_warp_barrier[w] = std::make_unique<std::barrier<>>((std::ptrdiff_t)std::min(32u, block_x - w * 32));
         std::vector<std::thread> th;
         th.reserve(block_x);
         for (unsigned t = 0; t < block_x; ++t)
@@ -68,6 +93,7 @@ template <typename F> inline void emu_launch_mt(unsigned grid_x, unsigned block_
                 threadIdx = EmuDim3(t);
                 kernel_call();
                 emu_block_barrier->arrive_and_drop();          // a thread that returned early no longer takes part in barriers
+                emu_warp_barrier[t >> 5]->arrive_and_drop();
             });
         for (auto& x : th) x.join();
     }

@@ -62,6 +62,22 @@ def emu_dp():
     return lib
 
 
+@pytest.fixture(scope="module")
+def emu_linblend():
+    text = open(os.path.join(ROOT, "imagestitch_b200", "csrc", "linblend.cu")).read()
+    regions = re.findall(r"// @emu-begin[^\n]*\n(.*?)// @emu-end", text, flags=re.S)
+    assert len(regions) == 1
+    os.makedirs(OUT, exist_ok=True)
+    with open(os.path.join(OUT, "linblend_region.inc"), "w") as f:
+        f.write(regions[0])
+    so = os.path.join(OUT, "liblinblend_emul.so")
+    subprocess.check_call(["g++", "-O1", "-fPIC", "-std=c++20", "-pthread", "-ffp-contract=off", "-fno-fast-math", "-w", "-I", EMU, "-I", OUT, "-shared",
+                           "-o", so, os.path.join(EMU, "linblend_emul.cpp")])
+    lib = C.CDLL(so)
+    lib.emu_linear_blend_pair.restype = C.c_int
+    return lib
+
+
 def _p(a):
     return a.ctypes.data_as(C.c_void_p)
 
@@ -239,3 +255,31 @@ def test_dp_kernel_matches_oracle(emu, emu_dp, oracle, case):
     P2[(s0 + s1) // 2, :] = np.inf
     assert emu_dp.emu_seam_dp(_p(P2), _p(Q), rw, pitch, rh, s0, lane0, s1, lane1, lpt, G, D, _p(control), _p(seam_lane), _p(reached)) == 0
     assert reached[0] == 0
+
+
+def test_pair_blend_kernels_match_oracle(emu_linblend, oracle):
+    """the six kernels of is_linear_blend_pair, emulated, against the oracle -- which equals the reference's own compiled block
+    bit for bit (tests/test_oracle_reference_build.py): greedy seam, panorama and its NaN pattern"""
+    from helpers import warped_set
+    O = oracle
+    exact = total = 0
+    for (w, h, ov) in ((240, 180, 0.25), (200, 160, 0.4)):
+        corners, wi, _ = warped_set(O, 2, w, h, overlap=ov)
+        a, b = wi[0].astype(np.float32), wi[1].astype(np.float32)
+        for tl2 in (corners[1], (corners[1][0], corners[0][1]), (corners[1][0], corners[0][1] + 6), (corners[1][0], corners[0][1] - 5)):
+            want = O.lin_blend(a, b, corners[0], tl2)
+            pano = np.zeros_like(want[0])
+            seam = np.zeros(want[0].shape[0], np.int32)
+            rc = emu_linblend.emu_linear_blend_pair(_p(a), a.shape[0], a.shape[1], _p(b), b.shape[0], b.shape[1], int(corners[0][0]), int(corners[0][1]),
+                                                    int(tl2[0]), int(tl2[1]), _p(pano), _p(seam))
+            assert rc == 0
+            assert np.array_equal(seam, want[1]), f"greedy seam differs, tl2={tl2}"
+            assert np.array_equal(np.isnan(pano), np.isnan(want[0]))
+            d = np.nanmax(np.abs(pano - want[0]))
+            assert d <= 1e-3 * 255, d                                         # the bar of tests/test_gpu_parity.py
+            total += 1
+            exact += int(np.array_equal(np.nan_to_num(pano).view(np.uint32), np.nan_to_num(want[0]).view(np.uint32)))
+    print(f"pair blend kernels: {exact} of {total} panoramas bit-exact against the oracle")
+    assert exact == total, f"only {exact} of {total} panoramas are bit-exact"
+    z = np.zeros((40, 50, 3), np.float32)
+    assert emu_linblend.emu_linear_blend_pair(_p(z), 40, 50, _p(z), 40, 50, 0, 0, 5000, 0, _p(np.zeros(3, np.float32)), _p(np.zeros(1, np.int32))) == 1
