@@ -10,6 +10,7 @@ if ROOT not in sys.path:
 
 def pytest_configure(config):
     config.addinivalue_line("markers", "gpu: needs a CUDA device (run on the B200 box with -m gpu)")
+    config.addinivalue_line("markers", "timeout: per-test time limit (pytest-timeout; a no-op marker when the plugin is absent)")
 
 
 @pytest.fixture(scope="session")

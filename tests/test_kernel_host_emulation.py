@@ -12,6 +12,8 @@ import subprocess
 import numpy as np
 import pytest
 
+pytestmark = pytest.mark.timeout(600)      # the multi-threaded emulator spins on emulated mbarriers: never let a bug hang the suite
+
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 EMU = os.path.join(ROOT, "tests", "emu")
 OUT = os.path.join(EMU, "_build")
