@@ -23,6 +23,7 @@
 
 namespace is {
 
+// @emu-begin (tests/test_kernel_host_emulation.py compiles the marked regions for the host)
 constexpr int DT_INF = INT_MAX / 4;
 
 // ---- dilate (rectangular element kw x kh, anchor (kw/2, kh/2)): dst(x,y) = max src over x - kw/2 .. x - kw/2 + kw - 1 ----------
@@ -113,6 +114,7 @@ __global__ void k_dt_cols_up_weight(const int* __restrict__ dh, int rows, int co
     }
 }
 
+// @emu-end
 int feather_weight_device(is_ctx* ctx, const DevMat& mask, float sharpness, float* w, size_t wstep_f) {
     DevBuf dh;
     IS_TRY(dh.alloc(ctx, sizeof(int) * (size_t)mask.rows * mask.cols));
@@ -126,6 +128,7 @@ int feather_weight_device(is_ctx* ctx, const DevMat& mask, float sharpness, floa
 }
 
 // ---- blend(): gather over the fed images -------------------------------------------------------------------------------
+// @emu-begin
 struct FeatherImg {
     const void* img; size_t istep; int is_u8;
     const float* w;          // dense rows x cols
@@ -164,6 +167,7 @@ __global__ void k_feather_blend(const FeatherImg* __restrict__ imgs, int n, int 
     dmask[(size_t)y * mstep + x] = on ? 255 : 0;
 }
 
+// @emu-end
 // dilate (kw x kh rectangle, anchor at the centre) in place, optionally followed by `& andm`
 int mask_dilate_and_device(is_ctx* ctx, const DevMat& m, int kw, int kh, const DevMat* andm) {
     IS_REQUIRE(ctx, kw >= 1 && kh >= 1 && kw <= DIL_MAXK && kh <= DIL_MAXK, IS_ERR_BAD_ARG, "structuring element must be 1..64 wide / high");

@@ -6,8 +6,8 @@
 //   __syncthreads()               -> a reusable barrier over the block's threads
 //   mbarrier / bulk copies        -> tests/emu/tma.cuh (same names as imagestitch_b200/csrc/tma.cuh): the copy happens at
 //                                    issue time, the transaction count and phase bookkeeping follow the PTX semantics
-//   __shfl_xor_sync (full mask)   -> exchange through a per-warp slot array between two per-warp barriers
-// Not emulated: other shuffles / votes, clusters, 2-D tensor maps.
+//   __shfl_{xor,up,down,}_sync    -> (full mask) exchange through a per-warp slot array between two per-warp barriers
+// Not emulated: votes, clusters, 2-D tensor maps.
 #pragma once
 
 #include <algorithm>
@@ -67,6 +67,27 @@ template <typename T> inline T __shfl_xor_sync(unsigned /*full mask*/, T v, int 
     std::memcpy(&r, &emu_shfl_slot[w][l ^ (unsigned)lane_mask], 4);
     emu_warp_barrier[w]->arrive_and_wait();
     return r;
+}
+
+template <typename T, typename Pick> inline T emu_shfl(T v, Pick pick) {          // pick(lane) -> source lane (or lane itself: keep own value)
+    static_assert(sizeof(T) == 4, "32-bit shuffles only");
+    const unsigned w = threadIdx.x >> 5, l = threadIdx.x & 31;
+    std::memcpy(&emu_shfl_slot[w][l], &v, 4);
+    emu_warp_barrier[w]->arrive_and_wait();
+    T r;
+    std::memcpy(&r, &emu_shfl_slot[w][pick(l)], 4);
+    emu_warp_barrier[w]->arrive_and_wait();
+    return r;
+}
+template <typename T> inline T __shfl_up_sync(unsigned, T v, unsigned d) { return emu_shfl(v, [d](unsigned l) { return l >= d ? l - d : l; }); }
+template <typename T> inline T __shfl_down_sync(unsigned, T v, unsigned d) { return emu_shfl(v, [d](unsigned l) { return l + d < 32 ? l + d : l; }); }
+template <typename T> inline T __shfl_sync(unsigned, T v, int src) { return emu_shfl(v, [src](unsigned) { return (unsigned)src & 31; }); }
+
+inline int __float2int_rz(float v) {                        // cvt.rzi.s32.f32: truncate, saturate, NaN -> 0
+    if (v != v) return 0;
+    if (v >= 2147483648.f) return 2147483647;
+    if (v <= -2147483648.f) return -2147483647 - 1;
+    return (int)v;
 }
 
 // kernels without barriers or shuffles: one host thread steps through the grid

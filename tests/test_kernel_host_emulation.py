@@ -80,6 +80,20 @@ def emu_linblend():
     return lib
 
 
+@pytest.fixture(scope="module")
+def emu_feather():
+    text = open(os.path.join(ROOT, "imagestitch_b200", "csrc", "feather.cu")).read()
+    regions = re.findall(r"// @emu-begin[^\n]*\n(.*?)// @emu-end", text, flags=re.S)
+    assert len(regions) == 2
+    os.makedirs(OUT, exist_ok=True)
+    with open(os.path.join(OUT, "feather_regions.inc"), "w") as f:
+        f.write("\n".join(regions))
+    so = os.path.join(OUT, "libfeather_emul.so")
+    subprocess.check_call(["g++", "-O1", "-fPIC", "-std=c++20", "-pthread", "-ffp-contract=off", "-fno-fast-math", "-w", "-I", EMU, "-I", OUT, "-shared",
+                           "-o", so, os.path.join(EMU, "feather_emul.cpp")])
+    return C.CDLL(so)
+
+
 def _p(a):
     return a.ctypes.data_as(C.c_void_p)
 
@@ -285,3 +299,53 @@ def test_pair_blend_kernels_match_oracle(emu_linblend, oracle):
     assert exact == total, f"only {exact} of {total} panoramas are bit-exact"
     z = np.zeros((40, 50, 3), np.float32)
     assert emu_linblend.emu_linear_blend_pair(_p(z), 40, 50, _p(z), 40, 50, 0, 0, 5000, 0, _p(np.zeros(3, np.float32)), _p(np.zeros(1, np.int32))) == 1
+
+
+def test_feather_path_kernels_match_oracle(emu_feather, oracle):
+    """the blend path the reference's mains execute ([SEAM]:1249-1282): dilate 20x20 & mask, distance-transform weight map,
+    feather blend -- the product's kernels, emulated, against the oracle (== cv2, tests/test_oracle_cv2.py)"""
+    from helpers import blob_masks
+    O = oracle
+    rng = np.random.default_rng(21)
+    n = 3
+    imgs, masks, corners, x = [], [], [], 0
+    for i in range(n):
+        h, w = int(rng.integers(50, 80)), int(rng.integers(70, 110))
+        imgs.append(rng.integers(0, 256, (h, w, 3), dtype=np.uint8))
+        masks.append(blob_masks(rng, [(h, w)])[0])
+        corners.append((x, int(rng.integers(0, 9))))
+        x += int(w * rng.uniform(0.5, 0.8))
+    for k, m in enumerate(masks + [np.zeros((9, 40), np.uint8), np.full((30, 33), 255, np.uint8)]):
+        for (kw, kh) in (((20, 20), (3, 7)) if k < 2 else ((20, 20),)):  # dilation, with and without the `&`
+            stripes = np.where(np.arange(m.shape[1])[None, :] % 5 > 0, 255, 0).astype(np.uint8).repeat(m.shape[0], 0)
+            for andm in ((None, stripes) if kw == 20 else (None,)):
+                got = m.copy()
+                emu_feather.emu_mask_dilate_and(_p(got), m.shape[0], m.shape[1], kw, kh, _p(andm) if andm is not None else None)
+                want = O.dilate_rect(m, (kw, kh))
+                if andm is not None:
+                    want = want & andm
+                assert np.array_equal(got, want), (m.shape, kw, kh, andm is not None)
+        for sharp in (0.02, 0.1, 5.0):                                   # weight map; no zero pixel -> FLT_MAX * sharpness, clamped to 1
+            got = np.zeros(m.shape, np.float32)
+            emu_feather.emu_feather_weight(_p(m), m.shape[0], m.shape[1], C.c_float(sharp), _p(got))
+            assert np.array_equal(got.view(np.uint32), O.feather_weight(m, sharp).view(np.uint32)), (m.shape, sharp)
+    sizes = [(a.shape[1], a.shape[0]) for a in imgs]
+    roi = O.result_roi(corners, sizes)
+    for dtype in (np.uint8, np.int16):
+        fb = O.FeatherBlender(0.1)
+        fb.prepare(roi)
+        src = [a.astype(dtype) for a in imgs]
+        for i in range(n):
+            fb.feed(src[i].astype(np.int16), masks[i], corners[i])
+        want, wmask = fb.blend()
+        dst = np.zeros((roi[3], roi[2], 3), np.int16)
+        dmask = np.zeros((roi[3], roi[2]), np.uint8)
+        ip = (C.c_void_p * n)(*[a.ctypes.data for a in src])
+        mp = (C.c_void_p * n)(*[m.ctypes.data for m in masks])
+        rows = np.asarray([a.shape[0] for a in src], np.int32)
+        cols = np.asarray([a.shape[1] for a in src], np.int32)
+        x0 = np.asarray([c[0] - roi[0] for c in corners], np.int32)
+        y0 = np.asarray([c[1] - roi[1] for c in corners], np.int32)
+        emu_feather.emu_feather_blend(n, ip, 1 if dtype == np.uint8 else 0, mp, _p(rows), _p(cols), _p(x0), _p(y0), C.c_float(0.1), roi[2], roi[3],
+                                      _p(dst), _p(dmask))
+        assert np.array_equal(dmask, wmask) and np.array_equal(dst, want), dtype
