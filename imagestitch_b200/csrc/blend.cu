@@ -1006,9 +1006,20 @@ static Level0 level0_of(const FedImage& f) {
     return L;
 }
 
+// The pyramid buffers of deferred feeds are written on the side stream but released into the block cache of the blender's
+// context, which hands them out again on ctx->stream: that stream must first wait for the side stream (common.cuh: "only
+// handed out again on the stream it was released on").
+static void join_side(is_blender* b) {
+    if (!b->side) return;
+    if (stream_after(b->ctx, b->ctx->stream, b->side->stream) != IS_OK) cudaStreamSynchronize(b->side->stream);
+    merge_child(b->ctx, b->side);
+    b->side = nullptr;
+}
+
 int blender_prepare_roi(is_blender* b, is_rect dst_roi) {
     is_ctx* ctx = b->ctx;
     IS_REQUIRE(ctx, dst_roi.width > 0 && dst_roi.height > 0, IS_ERR_BAD_ARG, "empty destination ROI");
+    join_side(b);          // pyramids of deferred feeds may still be in flight on the side stream: order their release after it
     b->fed.clear();
     b->roi_final = dst_roi;
     const double max_len = (double)std::max(dst_roi.width, dst_roi.height);
@@ -1366,11 +1377,7 @@ int blender_blend_dev(is_blender* b, const DevMat& dst, const DevMat& dmask, int
     // deferred feeds: weights + occupancy maps from the masks as they are now, image pyramids of the side stream joined,
     // images in the reference's feed order
     IS_TRY(blender_feed_weights(b));
-    if (b->side) {
-        IS_TRY(stream_after(ctx, ctx->stream, b->side->stream));
-        merge_child(ctx, b->side);
-        b->side = nullptr;
-    }
+    join_side(b);
     std::stable_sort(b->fed.begin(), b->fed.end(), [](const FedImage& a, const FedImage& c) { return a.key < c.key; });
     std::vector<int> xb, xe;
     strip_ranges(b, sx0, sx1, &xb, &xe);
@@ -1468,6 +1475,7 @@ int is_blender_create(is_ctx* ctx, int num_bands, int weight_type, is_blender** 
 int is_blender_destroy(is_blender* b) {
     if (b) {
         cudaSetDevice(b->ctx->device);
+        is::join_side(b);
         delete b;
     }
     return IS_OK;

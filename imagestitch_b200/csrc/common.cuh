@@ -13,6 +13,8 @@
 
 #include "../../include/imagestitch.h"
 
+namespace is { class HostPool; }
+
 struct is_ctx {
     int device = 0;
     cudaStream_t stream = nullptr;       // stream in use (own_stream or an adopted one)
@@ -43,11 +45,13 @@ struct is_ctx {
     // because a block is only handed out again on the stream it was released on.
     std::multimap<size_t, void*> block_cache;
     size_t block_cache_bytes = 0;
-    // events for stream_after(): reused round-robin per call sequence (sync_next is reset by the pipeline entry points)
+    // events for stream_after(): a fixed ring, reused round-robin
     std::vector<cudaEvent_t> sync_events;
     size_t sync_next = 0;
     std::vector<double> last_gains;       // exposure gains of the last is_pipeline_run (is_pipeline_last_gains)
     int seam_speculation_accepted = -1;   // last is_seam_dp_find: 1 concurrent result accepted, 0 fell back, -1 not attempted
+    int seam_path = 0;                    // last is_seam_dp_find: 2 batched path, 1 per-pair concurrent path, 0 sequential loop
+    is::HostPool* hpool = nullptr;        // host threads for the per-pair control work of the seam stage (hostpool.h)
 };
 
 namespace is {
@@ -148,6 +152,8 @@ int pinned_alloc(is_ctx* ctx, size_t bytes, void** out);
 int upload(is_ctx* ctx, void* dst, const void* src, size_t bytes);
 int download(is_ctx* ctx, void* dst, const void* src, size_t bytes);
 int download2d(is_ctx* ctx, void* dst, size_t dpitch, const void* src, size_t spitch, size_t width, size_t height);
+// download into the pinned bounce buffer and hand out a view of it (valid until the next download on this context)
+int download_view(is_ctx* ctx, const void* src, size_t bytes, const void** view);
 
 int check_mat(is_ctx* ctx, const is_mat* m, const char* name);
 

@@ -1,5 +1,6 @@
 // ctx.cu -- context life cycle, error strings, staging of host is_mat buffers.
 #include "common.cuh"
+#include "hostpool.h"
 
 #include <algorithm>
 
@@ -99,14 +100,18 @@ int child_ctx(is_ctx* parent, size_t k, is_ctx** out) {
     return IS_OK;
 }
 
-// `to` waits for everything queued on `from` so far
+// `to` waits for everything queued on `from` so far.  The events come from a fixed ring: an event that has been recorded and
+// waited on may be re-recorded (the wait already captured the earlier record), so a long-running job never grows the pool.
 int stream_after(is_ctx* ctx, cudaStream_t to, cudaStream_t from) {
-    if (ctx->sync_next >= ctx->sync_events.size()) {
+    constexpr size_t RING = 64;
+    if (ctx->sync_events.size() < RING) {
         cudaEvent_t e = nullptr;
         IS_CUDA(ctx, cudaEventCreateWithFlags(&e, cudaEventDisableTiming));
         ctx->sync_events.push_back(e);
+        ctx->sync_next = ctx->sync_events.size() - 1;
     }
-    cudaEvent_t e = ctx->sync_events[ctx->sync_next++];
+    cudaEvent_t e = ctx->sync_events[ctx->sync_next % ctx->sync_events.size()];
+    ctx->sync_next = (ctx->sync_next + 1) % RING;
     IS_CUDA(ctx, cudaEventRecord(e, from));
     IS_CUDA(ctx, cudaStreamWaitEvent(to, e, 0));
     return IS_OK;
@@ -228,6 +233,21 @@ int download(is_ctx* ctx, void* dst, const void* src, size_t bytes) {
     return IS_OK;
 }
 
+int download_view(is_ctx* ctx, const void* src, size_t bytes, const void** view) {
+    if (ctx->pinned_dl_bytes < bytes || !ctx->pinned_dl) {
+        if (ctx->pinned_dl) { IS_CUDA(ctx, cudaStreamSynchronize(ctx->stream)); cudaFreeHost(ctx->pinned_dl); }
+        ctx->pinned_dl = nullptr;
+        ctx->pinned_dl_bytes = 0;
+        const size_t n = align_up(bytes > (size_t)(4 << 20) ? bytes : (size_t)(4 << 20), 1 << 20);
+        IS_CUDA(ctx, cudaMallocHost(&ctx->pinned_dl, n));
+        ctx->pinned_dl_bytes = n;
+    }
+    if (bytes) IS_CUDA(ctx, cudaMemcpyAsync(ctx->pinned_dl, src, bytes, cudaMemcpyDeviceToHost, ctx->stream));
+    IS_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+    *view = ctx->pinned_dl;
+    return IS_OK;
+}
+
 // pitched download (rows of `width` bytes) through the pinned bounce buffer; dst is packed with dpitch
 int download2d(is_ctx* ctx, void* dst, size_t dpitch, const void* src, size_t spitch, size_t width, size_t height) {
     if (width == 0 || height == 0) return IS_OK;
@@ -290,6 +310,8 @@ int is_ctx_destroy(is_ctx* ctx) {
     if (!ctx) return IS_OK;
     cudaSetDevice(ctx->device);
     cudaStreamSynchronize(ctx->stream);
+    delete ctx->hpool;
+    ctx->hpool = nullptr;
     for (is_ctx* c : ctx->children) is_ctx_destroy(c);
     ctx->children.clear();
     for (int i = 0; i < 5; ++i) if (ctx->ev[i]) cudaEventDestroy(ctx->ev[i]);
@@ -370,6 +392,7 @@ int is_ctx_kernel_timing_report(is_ctx* ctx, char* buf, size_t cap) {
 }
 
 int is_ctx_seam_speculation(const is_ctx* ctx) { return ctx ? ctx->seam_speculation_accepted : -1; }
+int is_ctx_seam_path(const is_ctx* ctx) { return ctx ? ctx->seam_path : -1; }
 
 const char* is_ctx_last_error(const is_ctx* ctx) { return ctx ? ctx->last_error.c_str() : "null context"; }
 void* is_ctx_stream(is_ctx* ctx) { return ctx ? (void*)ctx->stream : nullptr; }

@@ -86,14 +86,13 @@ int is_pipeline_run(is_ctx* ctx, int n, const is_mat* images, const is_camera* c
     // ---- device.  Three streams: the caller's (warp, seam, weights, blend), a copy stream that uploads host sources one
     //      image ahead of the warp, and a side stream that builds the Gaussian image pyramids (they do not depend on the
     //      seam masks) while the latency-bound seam stage leaves the SMs mostly idle.
-    ctx->sync_next = 0;
     ctx->last_gains.clear();
     is_ctx *side = nullptr, *copy = nullptr;
     IS_TRY(child_ctx(ctx, SIDE_PYRAMID, &side));
     IS_TRY(child_ctx(ctx, SIDE_COPY, &copy));
     if (getenv("IS_PIPELINE_SERIAL")) side = ctx;           // tuning knob: everything on the caller's stream
     side->ktiming = ctx->ktiming;
-    std::vector<DevMat> src(n), warped(n), masks(n), comp(cfg.exposure == IS_EXPOSURE_GAIN ? n : 0), wmask0(cfg.seam_dilate > 0 ? n : 0);
+    std::vector<DevMat> src(n), warped(n), masks(n), wmask0(cfg.seam_dilate > 0 ? n : 0);
     is_blender* bl = nullptr;
     IS_TRY(is_blender_create(ctx, cfg.num_bands, cfg.weight_type, &bl));
     // destroyed before the buffers above: on an error path the side streams may still be using them
@@ -127,18 +126,15 @@ int is_pipeline_run(is_ctx* ctx, int n, const is_mat* images, const is_camera* c
         // feed(): geometry + image pyramid now (side stream, ordered after this warp), weights after the seam stage
         if (multiband && cfg.exposure == IS_EXPOSURE_NONE) IS_TRY(blender_feed_image(bl, side, warped[i], masks[i], corners[i]));
     }
-    // ---- exposure: compensator->feed(corners, images_warped, masks_warped) [BLEND]:117-123.  The seam finder keeps the
-    //      uncompensated images ([BLEND]:138-140); apply() goes into copies that only the blender reads ([SEAM]:1165-1171),
-    //      on the side stream together with their pyramids.
+    // ---- exposure: compensator->feed(corners, images_warped, masks_warped), then compensator->apply(i, ...) IN PLACE on
+    //      images_warped[i] ([BLEND]:117-123, [SEAM]:1165-1171) -- before convertTo(CV_32F) and find(): the seam finder and the
+    //      blender both see the compensated images.  The image pyramids follow on the side stream.
     if (cfg.exposure == IS_EXPOSURE_GAIN) {
         std::vector<double> gains(n, 1.0);
         IS_TRY(gain_feed_device(ctx, n, warped.data(), masks.data(), corners.data(), gains.data()));
         for (int i = 0; i < n; ++i) {
-            IS_TRY(alloc_mat(ctx, warped[i].rows, warped[i].cols, 3, IS_8U, &comp[i]));
-            if (side != ctx) IS_TRY(stream_after(ctx, side->stream, ctx->stream));
-            const int rc = gain_apply_device(side, warped[i], comp[i], gains[i]);
-            if (rc != IS_OK) { if (ctx->last_error.empty()) ctx->last_error = side->last_error; return rc; }
-            if (multiband) IS_TRY(blender_feed_image(bl, side, comp[i], masks[i], corners[i]));
+            IS_TRY(gain_apply_device(ctx, warped[i], warped[i], gains[i]));
+            if (multiband) IS_TRY(blender_feed_image(bl, side, warped[i], masks[i], corners[i]));
         }
         ctx->last_gains = gains;
     } else {
@@ -154,10 +150,6 @@ int is_pipeline_run(is_ctx* ctx, int n, const is_mat* images, const is_camera* c
     // ---- seam
     if (cfg.seam == IS_SEAM_DP) {
         IS_REQUIRE(ctx, cfg.seam_cost == IS_COST_COLOR || cfg.seam_cost == IS_COST_COLOR_GRAD, IS_ERR_BAD_ARG, "unknown seam cost function");
-        if (cfg.seam_cost == IS_COST_COLOR_GRAD) {                     // same switch as is_seam_dp_find (seam.cu): not yet run on hardware
-            const char* e = getenv("IS_EXPERIMENTAL_COLOR_GRAD");
-            if (!(e && e[0] == '1')) return fail(ctx, IS_ERR_UNSUPPORTED, "COLOR_GRAD seam cost is not enabled (IS_EXPERIMENTAL_COLOR_GRAD=1)");
-        }
         IS_TRY(seam_find_device(ctx, n, warped.data(), corners.data(), masks.data(), cfg.seam_cost));
     } else {
         IS_REQUIRE(ctx, cfg.seam == IS_SEAM_NONE, IS_ERR_BAD_ARG, "unknown seam mode");
@@ -176,7 +168,7 @@ int is_pipeline_run(is_ctx* ctx, int n, const is_mat* images, const is_camera* c
     IS_TRY(stage_out(ctx, pano, &dp, false));
     IS_TRY(stage_out(ctx, pano_mask, &dm, false));
     if (multiband) IS_TRY(blender_blend_dev(bl, dp, dm, 0, roi.width));
-    else IS_TRY(feather_blend_device(ctx, cfg.sharpness, roi, n, cfg.exposure == IS_EXPOSURE_GAIN ? comp.data() : warped.data(), masks.data(),
+    else IS_TRY(feather_blend_device(ctx, cfg.sharpness, roi, n, warped.data(), masks.data(),
                                      corners.data(), dp, dm));
     IS_CUDA(ctx, cudaEventRecord(ctx->ev[3], ctx->stream));
     // ---- results

@@ -18,6 +18,7 @@
 // association order (cost + costV first, then + costH, [SEAM]:900-904) and candidates are compared
 // lexicographically as (cost, step) like std::min_element over std::pair<float,int> ([SEAM]:909).
 #include "internal.cuh"
+#include "hostpool.h"
 #include "tma.cuh"
 
 #include <algorithm>
@@ -518,7 +519,7 @@ struct DpArgs {
 // continues through them and the back-track never visits them -- the reference's `labels_ == l` test ([SEAM]:897) and
 // its `x > 0` / `x < roi.width - 1` guards without a branch.  (Their own control byte is arbitrary and never read.)
 template <int LPT>
-__global__ void __launch_bounds__(1024) k_seam_dp(DpArgs A) {
+__device__ __forceinline__ void seam_dp_body(const DpArgs& A) {
     extern __shared__ __align__(128) unsigned char sm_raw[];
     const int nt = blockDim.x, tid = threadIdx.x;
     const int row_f = A.pitch;                             // floats per row
@@ -659,6 +660,13 @@ __global__ void __launch_bounds__(1024) k_seam_dp(DpArgs A) {
     }
     if (tid == 0) A.seam_lane[0] = cur_lane_s;
 }
+
+template <int LPT>
+__global__ void __launch_bounds__(1024) k_seam_dp(DpArgs A) { seam_dp_body<LPT>(A); }
+
+// all seams of a call in one launch: one CTA per seam (the seams of a launch share LPT and the block size)
+template <int LPT>
+__global__ void __launch_bounds__(1024) k_seam_dp_batch(const DpArgs* __restrict__ table) { seam_dp_body<LPT>(table[blockIdx.x]); }
 
 // @emu-dp-end
 // ---- updateLabelsUsingSeam: device part -------------------------------------------------------------------------
@@ -1803,6 +1811,9 @@ static int seam_find_concurrent(is_ctx* ctx, const std::vector<std::pair<int, in
     return IS_OK;
 }
 
+#include "seam_runs.inl"
+#include "seam_batch.inl"
+
 // device-resident images / masks (masks in-out); used by is_seam_dp_find* and by the pipeline
 int seam_find_core(is_ctx* ctx, int n, const DevMat* images, const is_point* corners, const DevMat* masks, TraceSink* trace,
                    int cost_fn = IS_COST_COLOR) {
@@ -1819,13 +1830,22 @@ int seam_find_core(is_ctx* ctx, int n, const DevMat* images, const is_point* cor
         if (x0 < x1 && y0 < y1) active.push_back(pr);
     }
     const char* seq = getenv("IS_SEAM_SEQUENTIAL");
+    const char* mode = getenv("IS_SEAM_PATH");            // tuning / test knob: "pairs" = per-pair concurrent path, "seq" = sequential loop
     ctx->seam_speculation_accepted = -1;
-    if (cost_fn != IS_COST_COLOR) return seam_find_sequential(ctx, active, images, corners, masks, trace, cost_fn);   // not yet on the concurrent path
-    if (active.size() >= 2 && !(seq && seq[0] == '1')) {
+    ctx->seam_path = 0;
+    const bool want_seq = (seq && seq[0] == '1') || (mode && !strcmp(mode, "seq"));
+    if (!active.empty() && !want_seq && !(mode && !strcmp(mode, "pairs"))) {
+        // all pairs through every kernel at once, three host consultations per call (seam_batch.inl)
+        bool accepted = false;
+        IS_TRY(seam_find_batched(ctx, active, n, images, corners, masks, trace, cost_fn, &accepted));
+        if (accepted) { ctx->seam_speculation_accepted = 1; ctx->seam_path = 2; return IS_OK; }
+    }
+    if (cost_fn != IS_COST_COLOR) return seam_find_sequential(ctx, active, images, corners, masks, trace, cost_fn);   // not on the per-pair concurrent path
+    if (active.size() >= 2 && !want_seq) {
         bool accepted = false;
         IS_TRY(seam_find_concurrent(ctx, active, n, images, corners, masks, trace, &accepted));
         ctx->seam_speculation_accepted = accepted ? 1 : 0;
-        if (accepted) return IS_OK;
+        if (accepted) { ctx->seam_path = 1; return IS_OK; }
     }
     return seam_find_sequential(ctx, active, images, corners, masks, trace);
 }
@@ -1836,12 +1856,6 @@ static int seam_find_impl(is_ctx* ctx, int n, const is_mat* images, const is_poi
     if (n == 0) return IS_OK;                                                // [SEAM]:94-95
     IS_REQUIRE(ctx, images && corners && masks, IS_ERR_BAD_ARG, "null argument");
     IS_REQUIRE(ctx, cost_fn == IS_COST_COLOR || cost_fn == IS_COST_COLOR_GRAD, IS_ERR_BAD_ARG, "unknown cost function");
-    if (cost_fn == IS_COST_COLOR_GRAD) {
-        // Written against the oracle's restatement but not yet run on a device (no GPU time was left in the round it was
-        // written in): kept behind a switch until tests/test_gpu_zz_reports.py has passed on hardware.
-        const char* e = getenv("IS_EXPERIMENTAL_COLOR_GRAD");
-        if (!(e && e[0] == '1')) return fail(ctx, IS_ERR_UNSUPPORTED, "COLOR_GRAD seam cost is not enabled (IS_EXPERIMENTAL_COLOR_GRAD=1)");
-    }
     const int depth = images[0].depth;
     for (int i = 0; i < n; ++i) {
         IS_TRY(check_mat(ctx, &images[i], "image"));
@@ -1970,6 +1984,55 @@ int is_mask_and(is_ctx* ctx, is_mat* dst, const is_mat* src) {
     IS_TRY(stage_in(ctx, src, &sm));
     IS_TRY(mask_and(ctx, d, sm));
     IS_TRY(commit(ctx, &d));
+    return IS_OK;
+}
+
+// Host-only diagnostic (no device needed): the run-domain structure and plan of ONE pair, computed by the same code the
+// batched path runs between its kernels (PairRuns), with the device-side inputs (row toggles, special points) produced by
+// host loops.  out (int32): [too_many_runs, unsupported, ncomps, nops, nrecords, union_tl.x, union_tl.y, states[ncomps],
+// ops[nops][11] = (kind, c1, c2, p1.x, p1.y, p2.x, p2.y, rx, ry, rw, rh), records[nrecords][7] = (x, y, label, nl[4])];
+// coordinates are union-frame.
+int is_debug_seam_pair_plan(const uint8_t* mask1, int rows1, int cols1, size_t step1, int tl1x, int tl1y, const uint8_t* mask2, int rows2, int cols2,
+                            size_t step2, int tl2x, int tl2y, int32_t* out, size_t cap, size_t* len) {
+    if (!mask1 || !mask2 || !len) return IS_ERR_BAD_ARG;
+    MaskRuns r1, r2;
+    mask_runs_from_host(mask1, step1, rows1, cols1, &r1);
+    mask_runs_from_host(mask2, step2, rows2, cols2, &r2);
+    PairRuns P;
+    P.setup(0, 1, Pt{tl1x, tl1y}, Pt{tl2x, tl2y}, &r1, &r2);
+    if (P.iTl.x < P.iBr.x && P.iTl.y < P.iBr.y) {
+        // special points: host restatement of k_special_points_batch
+        auto at = [&](int k, int x, int y) { return k == 0 ? r1.inside(x - P.o1x, y - P.o1y) : r2.inside(x - P.o2x, y - P.o2y); };
+        auto contour = [&](int k, int x, int y) { return at(k, x, y) && !(at(k, x - 1, y) && at(k, x + 1, y) && at(k, x, y - 1) && at(k, x, y + 1)); };
+        auto close_to = [&](int k, int x, int y) {
+            for (int dy = -2; dy <= 2; ++dy)
+                for (int dx = -2; dx <= 2; ++dx) {
+                    const int xx = x + dx, yy = y + dy;
+                    if (xx >= 0 && xx < P.uw && yy >= 0 && yy < P.uh && contour(k, xx, yy)) return true;
+                }
+            return false;
+        };
+        for (int y = P.iTl.y - P.unionTl.y; y < P.iBr.y - P.unionTl.y; ++y)
+            for (int x = P.iTl.x - P.unionTl.x; x < P.iBr.x - P.unionTl.x; ++x) {
+                if (!at(0, x, y) || !at(1, x, y)) continue;
+                const int nx[4] = {x - 1, x, x + 1, x}, ny[4] = {y, y - 1, y, y + 1};
+                bool touches = false;
+                for (int k = 0; k < 4; ++k) touches = touches || (at(0, nx[k], ny[k]) != at(1, nx[k], ny[k]));
+                if (touches && close_to(0, x, y) && close_to(1, x, y)) P.specials.push_back(Pt{x, y});
+            }
+        P.build();
+        if (!P.too_many_runs) P.plan();
+    }
+    std::vector<int32_t> v;
+    size_t nrec = 0;
+    for (auto& c : P.contours) nrec += c.size();
+    v.push_back(P.too_many_runs); v.push_back(P.unsupported); v.push_back(P.ncomps); v.push_back((int)P.ops.size()); v.push_back((int)nrec);
+    v.push_back(P.unionTl.x); v.push_back(P.unionTl.y);
+    for (int st : P.states) v.push_back(st);
+    for (auto& op : P.ops) for (int q : {op.kind, op.c1, op.c2, op.p1.x, op.p1.y, op.p2.x, op.p2.y, op.rx, op.ry, op.rw, op.rh}) v.push_back(q);
+    for (auto& c : P.contours) for (auto& r : c) for (int q : {r.x, r.y, r.label, r.nl[0], r.nl[1], r.nl[2], r.nl[3]}) v.push_back(q);
+    *len = v.size();
+    if (out && cap >= v.size()) std::memcpy(out, v.data(), v.size() * sizeof(int32_t));
     return IS_OK;
 }
 

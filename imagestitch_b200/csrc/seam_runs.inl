@@ -1,0 +1,426 @@
+// seam_runs.inl -- host side of the batched seam path: the structure of an image pair in the RUN domain.
+// (included by seam.cu inside namespace is, after PairSeam)
+//
+// Warped masks are a few horizontal runs per row.  k_row_toggles_batch reduces every mask to its per-row toggle positions once
+// per call; everything the reference derives from the masks before the first seam estimation -- the class image and its
+// connected components ([SEAM]:196-308), bounding boxes and raster-ordered contour lists of the INTERS components, the edge
+// set ([SEAM]:311-392), the seam tips ([SEAM]:607-706) and the order of the conflict loop ([SEAM]:395-546) -- is computed
+// here from those runs, without a labels image and without a device round trip.  What it produces is a PLAN: the list of
+// relabel operations and seam estimations (component, orientation, tips) the device then executes for all pairs at once.
+
+struct MaskRuns {                     // toggles of one mask in its own coordinates
+    int rows = 0, cols = 0, slots = 0;
+    std::vector<unsigned char> counts;   // [rows]
+    std::vector<unsigned short> xs;      // [rows][slots]
+    int count(int y) const { return counts[(size_t)y]; }
+    const unsigned short* row(int y) const { return xs.data() + (size_t)y * slots; }
+    // number of intervals of row y and the i-th one [a, b)
+    int nint(int y) const { return (count(y) + 1) >> 1; }
+    void interval(int y, int i, int* a, int* b) const {
+        const unsigned short* r = row(y);
+        *a = r[2 * i];
+        *b = 2 * i + 1 < count(y) ? r[2 * i + 1] : cols;
+    }
+    bool inside(int x, int y) const {
+        if ((unsigned)y >= (unsigned)rows || (unsigned)x >= (unsigned)cols) return false;
+        const unsigned short* r = row(y);
+        const int n = count(y);
+        int k = 0;
+        while (k < n && r[k] <= x) ++k;      // rows hold a handful of toggles
+        return (k & 1) != 0;
+    }
+};
+
+// host reference of k_row_toggles_batch (used by the CPU-side structure check, tests/test_seam_runs_host.py)
+static void mask_runs_from_host(const uint8_t* mask, size_t step, int rows, int cols, MaskRuns* out) {
+    out->rows = rows; out->cols = cols;
+    out->counts.assign((size_t)rows, 0);
+    std::vector<std::vector<int>> tmp((size_t)rows);
+    int slots = 1;
+    for (int y = 0; y < rows; ++y) {
+        int prev = 0;
+        for (int x = 0; x < cols; ++x) {
+            const int v = mask[(size_t)y * step + x] != 0;
+            if (v != prev) { tmp[(size_t)y].push_back(x); prev = v; }
+        }
+        out->counts[(size_t)y] = (unsigned char)std::min<size_t>(tmp[(size_t)y].size(), 255);
+        slots = std::max(slots, (int)tmp[(size_t)y].size());
+    }
+    out->slots = slots;
+    out->xs.assign((size_t)rows * slots, 0);
+    for (int y = 0; y < rows; ++y) std::copy(tmp[(size_t)y].begin(), tmp[(size_t)y].end(), out->xs.begin() + (size_t)y * slots);
+}
+
+struct SeamOp {                       // one step of the conflict loop ([SEAM]:423-520)
+    int kind;                         // 0: relabel the whole component c1 -> label of c2 ([SEAM]:440-450); 1: estimateSeam + updateLabelsUsingSeam
+    int c1, c2;
+    Pt p1, p2;                        // seam tips (kind 1), union-frame coordinates
+    int rx, ry, rw, rh;               // bounding box of c1 at that moment
+};
+
+class PairRuns {
+public:
+    int pi = 0, pj = 0;
+    Pt tl1{}, tl2{}, unionTl{}, iTl{}, iBr{};
+    int uw = 0, uh = 0;
+    int rows1 = 0, cols1 = 0, rows2 = 0, cols2 = 0;
+    int o1x = 0, o1y = 0, o2x = 0, o2y = 0;          // mask origins in the union frame
+    const MaskRuns* mr[2] = {nullptr, nullptr};
+    // class change points of every union-frame row, their labels
+    std::vector<int> row_off;
+    std::vector<ChangePt> cps;
+    std::vector<int> cp_label;
+    int ncomps = 0;
+    std::vector<int> states;                          // initial states ([SEAM]:240-250)
+    std::vector<int> final_states;                    // after the conflict loop
+    int wx = 0, wy = 0, ww = 0, wh = 0;               // label window: intersection rectangle grown by one pixel
+    size_t wcap = 1;
+    std::vector<int> tab;                             // counts | ChangePt (x, cls) | labels of the window rows (k_label_window layout)
+    std::vector<Pt> tls, brs;
+    std::vector<std::vector<ContourRec>> contours;    // INTERS components only, raster order; flags are NOT filled here
+    std::set<std::pair<int, int>> edges;
+    std::vector<SeamOp> ops;
+    std::vector<Pt> specials;                         // see get_seam_tips
+    bool too_many_runs = false;                       // a row has more change points than the window kernel's table holds
+    bool unsupported = false;                         // the conflict loop needs device results the plan cannot anticipate
+
+    void setup(int i, int j, Pt t1, Pt t2, const MaskRuns* m1, const MaskRuns* m2);
+    void build();                                     // merge, components, contours, edges
+    void plan();                                      // conflict loop -> ops, final_states
+    bool same_structure(const PairRuns& o) const;
+
+private:
+    int label_at(int x, int y) const;                 // label of a frame pixel from the runs (0 background, -1 outside the frame)
+    void contour_rows();
+    void find_edges();
+    bool has_only_one_neighbor(int comp) const;
+    bool get_seam_tips(int c1, int c2, Pt* p1, Pt* p2) const;
+};
+
+void PairRuns::setup(int i, int j, Pt t1, Pt t2, const MaskRuns* m1, const MaskRuns* m2) {
+    pi = i; pj = j; tl1 = t1; tl2 = t2; mr[0] = m1; mr[1] = m2;
+    rows1 = m1->rows; cols1 = m1->cols; rows2 = m2->rows; cols2 = m2->cols;
+    iTl = {std::max(tl1.x, tl2.x), std::max(tl1.y, tl2.y)};
+    iBr = {std::min(tl1.x + cols1, tl2.x + cols2), std::min(tl1.y + rows1, tl2.y + rows2)};
+    unionTl = {std::min(tl1.x, tl2.x), std::min(tl1.y, tl2.y)};
+    const Pt unionBr{std::max(tl1.x + cols1, tl2.x + cols2), std::max(tl1.y + rows1, tl2.y + rows2)};
+    uw = unionBr.x - unionTl.x;
+    uh = unionBr.y - unionTl.y;
+    o1x = tl1.x - unionTl.x; o1y = tl1.y - unionTl.y; o2x = tl2.x - unionTl.x; o2y = tl2.y - unionTl.y;
+}
+
+int PairRuns::label_at(int x, int y) const {
+    if ((unsigned)x >= (unsigned)uw || (unsigned)y >= (unsigned)uh) return -1;
+    const int b = row_off[(size_t)y], e = row_off[(size_t)y + 1];
+    int k = b;
+    while (k < e && cps[(size_t)k].x <= x) ++k;
+    return k == b ? 0 : cp_label[(size_t)k - 1];
+}
+
+// [SEAM]:196-308 in run-length form
+void PairRuns::build() {
+    const int ox[2] = {o1x, o2x}, oy[2] = {o1y, o2y};
+    row_off.assign((size_t)uh + 1, 0);
+    cps.clear();
+    cps.reserve((size_t)uh * 6);
+    too_many_runs = false;
+    for (int y = 0; y < uh; ++y) {
+        int na[2] = {0, 0};
+        const unsigned short* xa[2] = {nullptr, nullptr};
+        for (int k = 0; k < 2; ++k) {
+            const int my = y - oy[k];
+            if (my >= 0 && my < mr[k]->rows) { na[k] = mr[k]->count(my); xa[k] = mr[k]->row(my); }
+        }
+        // position i of mask k: xa[k][i] + ox for i < na[k], then (when the row ends inside the mask) the closing toggle at ox + cols
+        auto pos = [&](int k, int i) { return i < na[k] ? xa[k][i] + ox[k] : ((na[k] & 1) && i == na[k] ? ox[k] + mr[k]->cols : INT_MAX); };
+        int i0 = 0, i1 = 0, st = 0, prev_cls = 0, emitted = 0;
+        for (;;) {
+            const int p0 = pos(0, i0), p1 = pos(1, i1);
+            const int x = std::min(p0, p1);
+            if (x >= uw) break;                     // INT_MAX (both exhausted) or a closing toggle on the frame's right edge
+            if (p0 == x) { st ^= 1; ++i0; }
+            if (p1 == x) { st ^= 2; ++i1; }
+            if (st != prev_cls) { cps.push_back(ChangePt{x, st}); prev_cls = st; ++emitted; }
+        }
+        if (emitted > ROW_CAP) too_many_runs = true;
+        row_off[(size_t)y + 1] = row_off[(size_t)y] + emitted;
+    }
+    const int R = row_off[(size_t)uh];
+    // union-find over the runs (run k = change point k with cls != 0, spanning [x, next change point or uw))
+    std::vector<int> uf((size_t)std::max(R, 1));
+    for (int k = 0; k < R; ++k) uf[(size_t)k] = k;
+    auto find = [&](int k) { while (uf[(size_t)k] != k) { uf[(size_t)k] = uf[(size_t)uf[(size_t)k]]; k = uf[(size_t)k]; } return k; };
+    auto run_end = [&](int k, int y) { return k + 1 < row_off[(size_t)y + 1] ? cps[(size_t)k + 1].x : uw; };
+    for (int y = 1; y < uh; ++y) {
+        int a = row_off[(size_t)y - 1], ae = row_off[(size_t)y], b = row_off[(size_t)y], be = row_off[(size_t)y + 1];
+        while (a < ae && b < be) {
+            const int ax1 = run_end(a, y - 1), bx1 = run_end(b, y);
+            if (cps[(size_t)a].cls && cps[(size_t)a].cls == cps[(size_t)b].cls && cps[(size_t)a].x < bx1 && cps[(size_t)b].x < ax1) {
+                const int ra = find(a), rb = find(b);
+                if (ra != rb) { if (ra < rb) uf[(size_t)rb] = ra; else uf[(size_t)ra] = rb; }   // the root is the raster-first run
+            }
+            if (ax1 <= bx1) ++a; else ++b;
+        }
+    }
+    cp_label.assign((size_t)std::max(R, 1), 0);
+    std::vector<int> id_of_root((size_t)std::max(R, 1), 0);
+    ncomps = 0;
+    states.clear();
+    for (int k = 0; k < R; ++k) {               // roots in increasing index = raster order of the first pixel
+        if (!cps[(size_t)k].cls || find(k) != k) continue;
+        id_of_root[(size_t)k] = ++ncomps;
+        states.push_back(cps[(size_t)k].cls == 3 ? ST_INTERS : (cps[(size_t)k].cls == 1 ? ST_FIRST : ST_SECOND));
+    }
+    for (int k = 0; k < R; ++k) cp_label[(size_t)k] = cps[(size_t)k].cls ? id_of_root[(size_t)find(k)] : 0;
+    // labels are materialised on the device only where they are read: the intersection rectangle grown by one pixel
+    wx = std::max(0, iTl.x - unionTl.x - 1);
+    wy = std::max(0, iTl.y - unionTl.y - 1);
+    ww = std::min(uw, iBr.x - unionTl.x + 1) - wx;
+    wh = std::min(uh, iBr.y - unionTl.y + 1) - wy;
+    wcap = 1;
+    for (int y = wy; y < wy + wh; ++y) wcap = std::max(wcap, (size_t)(row_off[(size_t)y + 1] - row_off[(size_t)y]));
+    const size_t wrows = (size_t)wh;
+    tab.assign(wrows + wrows * wcap * 3, 0);
+    int* t_cnt = tab.data();
+    ChangePt* t_cps = reinterpret_cast<ChangePt*>(tab.data() + wrows);
+    int* t_lab = tab.data() + wrows + wrows * wcap * 2;
+    for (int y = wy; y < wy + wh; ++y) {
+        const size_t r = (size_t)(y - wy);
+        t_cnt[r] = row_off[(size_t)y + 1] - row_off[(size_t)y];
+        std::copy(cps.begin() + row_off[(size_t)y], cps.begin() + row_off[(size_t)y + 1], t_cps + r * wcap);
+        std::copy(cp_label.begin() + row_off[(size_t)y], cp_label.begin() + row_off[(size_t)y + 1], t_lab + r * wcap);
+    }
+    tls.assign((size_t)ncomps, Pt{INT_MAX, INT_MAX});
+    brs.assign((size_t)ncomps, Pt{INT_MIN, INT_MIN});
+    contours.assign((size_t)ncomps, std::vector<ContourRec>());
+    contour_rows();
+    find_edges();
+}
+
+// Raster-ordered contour records of the INTERS components: a pixel of an INTERS run is a contour pixel when one of its
+// 4-neighbours lies outside the frame or carries another label ([SEAM]:262-273).  Inside a run only the two end pixels can
+// have a different left / right neighbour; the up / down neighbours are constant over the segments into which the runs of
+// the rows above and below cut the run.
+void PairRuns::contour_rows() {
+    struct Seg { int x0, x1, lab; };      // [x0, x1): label of row r over that range
+    std::vector<Seg> up, dn;
+    auto row_segs = [&](int r, int a, int b, std::vector<Seg>& out) {      // labels of row r over [a, b)
+        out.clear();
+        if (r < 0 || r >= uh) { out.push_back(Seg{a, b, -1}); return; }
+        const int rb = row_off[(size_t)r], re = row_off[(size_t)r + 1];
+        int k = rb;
+        while (k < re && cps[(size_t)k].x <= a) ++k;                       // k: first change point right of a
+        int x = a;
+        while (x < b) {
+            const int lab = k == rb ? 0 : cp_label[(size_t)k - 1];
+            const int nx = k < re ? std::min(cps[(size_t)k].x, b) : b;
+            out.push_back(Seg{x, nx, lab});
+            x = nx;
+            ++k;
+        }
+    };
+    for (int y = std::max(0, iTl.y - unionTl.y); y < std::min(uh, iBr.y - unionTl.y); ++y) {
+        const int rb = row_off[(size_t)y], re = row_off[(size_t)y + 1];
+        for (int k = rb; k < re; ++k) {
+            if (cps[(size_t)k].cls != 3) continue;
+            const int a = cps[(size_t)k].x, b = k + 1 < re ? cps[(size_t)k + 1].x : uw;
+            const int l = cp_label[(size_t)k];
+            const int left = a == 0 ? -1 : (k == rb ? 0 : cp_label[(size_t)k - 1]);
+            const int right = b == uw ? -1 : (k + 1 < re ? cp_label[(size_t)k + 1] : 0);   // b < uw implies a following change point
+            row_segs(y - 1, a, b, up);
+            row_segs(y + 1, a, b, dn);
+            std::vector<ContourRec>& out = contours[(size_t)l - 1];
+            Pt& tl = tls[(size_t)l - 1];
+            Pt& br = brs[(size_t)l - 1];
+            size_t iu = 0, id = 0;
+            int x = a;
+            while (x < b) {
+                while (up[iu].x1 <= x) ++iu;
+                while (dn[id].x1 <= x) ++id;
+                const int e = std::min(up[iu].x1, dn[id].x1);          // [x, e): constant up / down labels
+                const int ul = up[iu].lab, dl = dn[id].lab;
+                auto emit = [&](int px) {
+                    ContourRec r;
+                    r.x = px; r.y = y; r.label = l;
+                    r.nl[0] = px == a ? left : l;
+                    r.nl[1] = ul;
+                    r.nl[2] = px == b - 1 ? right : l;
+                    r.nl[3] = dl;
+                    r.flags = 0;
+                    out.push_back(r);
+                    tl.x = std::min(tl.x, px); tl.y = std::min(tl.y, y);
+                    br.x = std::max(br.x, px + 1); br.y = std::max(br.y, y + 1);
+                };
+                if (ul != l || dl != l) {
+                    for (int px = x; px < e; ++px) emit(px);
+                } else {
+                    if (x == a) emit(a);                                   // the end pixels of a run always differ from their outer neighbour
+                    if (b - 1 != a && b - 1 >= x && b - 1 < e) emit(b - 1);
+                }
+                x = e;
+            }
+        }
+    }
+}
+
+// [SEAM]:311-392 (edges whose first component is INTERS, both directions; the only ones the conflict loop reads)
+void PairRuns::find_edges() {
+    edges.clear();
+    for (int ci = 0; ci < ncomps; ++ci) {
+        int last = -1;
+        const int l = ci + 1;
+        for (const ContourRec& r : contours[(size_t)ci])
+            for (int k = 0; k < 4; ++k) {
+                const int nl = r.nl[k];
+                if (nl > 0 && nl != l && nl != last) {
+                    edges.insert({ci, nl - 1});
+                    edges.insert({nl - 1, ci});
+                    last = nl;
+                }
+            }
+    }
+}
+
+bool PairRuns::has_only_one_neighbor(int comp) const {   // [SEAM]:575-581
+    auto begin = edges.lower_bound({comp, INT_MIN});
+    auto end = edges.upper_bound({comp, INT_MAX});
+    return ++begin == end;
+}
+
+// [SEAM]:607-706.  `specials`: the pixels of the pair's INTERS class that touch a pixel of exactly one mask and lie within
+// two pixels of both masks' contours (closeToContour, [SEAM]:584-604), in raster order -- found on the device by
+// k_special_points_batch straight from the masks; the labels come from the runs.
+bool PairRuns::get_seam_tips(int c1, int c2, Pt* p1, Pt* p2) const {
+    const int l1 = c1 + 1, l2 = c2 + 1;
+    std::vector<Pt> special;
+    for (const Pt& p : specials) {
+        if (label_at(p.x, p.y) != l1) continue;
+        if (label_at(p.x - 1, p.y) == l2 || label_at(p.x, p.y - 1) == l2 || label_at(p.x + 1, p.y) == l2 || label_at(p.x, p.y + 1) == l2) special.push_back(p);
+    }
+    if (special.size() < 2) return false;
+    // cv::partition with ClosePoints(10): connected components of "dist^2 < 100", classes numbered by first member
+    const int n = (int)special.size();
+    std::vector<int> uf((size_t)n);
+    for (int i = 0; i < n; ++i) uf[(size_t)i] = i;
+    auto find = [&](int i) { while (uf[(size_t)i] != i) { uf[(size_t)i] = uf[(size_t)uf[(size_t)i]]; i = uf[(size_t)i]; } return i; };
+    for (int i = 0; i < n; ++i)                                   // raster order: only rows within 10 of each other can be close
+        for (int j = i + 1; j < n && special[(size_t)j].y - special[(size_t)i].y < 10; ++j) {
+            const int dx = special[(size_t)i].x - special[(size_t)j].x, dy = special[(size_t)i].y - special[(size_t)j].y;
+            if (dx * dx + dy * dy < 100) { const int a = find(i), b = find(j); if (a != b) uf[(size_t)b] = a; }
+        }
+    std::vector<int> cls_of_root((size_t)n, -1), lab((size_t)n);
+    int nlabels = 0;
+    for (int i = 0; i < n; ++i) { const int r = find(i); if (cls_of_root[(size_t)r] < 0) cls_of_root[(size_t)r] = nlabels++; lab[(size_t)i] = cls_of_root[(size_t)r]; }
+    if (nlabels < 2) return false;
+    std::vector<long long> sumx((size_t)nlabels, 0), sumy((size_t)nlabels, 0);
+    std::vector<std::vector<Pt>> points((size_t)nlabels);
+    for (int i = 0; i < n; ++i) { sumx[(size_t)lab[(size_t)i]] += special[(size_t)i].x; sumy[(size_t)lab[(size_t)i]] += special[(size_t)i].y; points[(size_t)lab[(size_t)i]].push_back(special[(size_t)i]); }
+    int idx[2] = {-1, -1};
+    double maxDist = -std::numeric_limits<double>::max();
+    for (int i = 0; i < nlabels - 1; ++i)
+        for (int j = i + 1; j < nlabels; ++j) {
+            const double s1 = (double)points[(size_t)i].size(), s2 = (double)points[(size_t)j].size();
+            const double cx1 = round_half_even((int)sumx[(size_t)i] / s1), cy1 = round_half_even((int)sumy[(size_t)i] / s1);
+            const double cx2 = round_half_even((int)sumx[(size_t)j] / s2), cy2 = round_half_even((int)sumy[(size_t)j] / s2);
+            const double dist = (cx1 - cx2) * (cx1 - cx2) + (cy1 - cy2) * (cy1 - cy2);
+            if (dist > maxDist) { maxDist = dist; idx[0] = i; idx[1] = j; }
+        }
+    Pt p[2];
+    for (int i = 0; i < 2; ++i) {
+        const std::vector<Pt>& pts = points[(size_t)idx[i]];
+        const double size = (double)pts.size();
+        const double cx = round_half_even((int)sumx[(size_t)idx[i]] / size), cy = round_half_even((int)sumy[(size_t)idx[i]] / size);
+        size_t closest = 0;
+        double minDist = std::numeric_limits<double>::max();
+        for (size_t j = 0; j < pts.size(); ++j) {
+            const double dist = (pts[j].x - cx) * (pts[j].x - cx) + (pts[j].y - cy) * (pts[j].y - cy);
+            if (dist < minDist) { minDist = dist; closest = j; }
+        }
+        p[i] = pts[closest];
+    }
+    *p1 = p[0];
+    *p2 = p[1];
+    return true;
+}
+
+// The conflict loop [SEAM]:395-546 as far as it can be decided before any seam is known.  Everything it decides -- which
+// component meets which, who is relabelled wholesale, which seams are estimated between which tips, the final states -- depends
+// on the run structure only; what a seam estimation changes (part of c1 becomes l2) is never read again by the loop unless the
+// same component enters a second estimation, or an INTERS component is on the receiving side (neither happens with warped
+// panorama masks; both are reported as `unsupported` and take the general path of PairSeam).
+void PairRuns::plan() {
+    ops.clear();
+    unsupported = false;
+    final_states = states;
+    std::vector<int>& st = final_states;
+    std::set<std::pair<int, int>> ed = edges;
+    std::vector<char> stale((size_t)ncomps, 0);
+    auto only_one = [&](int comp) {
+        auto begin = ed.lower_bound({comp, INT_MIN});
+        auto end = ed.upper_bound({comp, INT_MAX});
+        return ++begin == end;
+    };
+    for (;;) {
+        int c1 = 0, c2 = 0;
+        bool hasConflict = false;
+        for (auto itr = ed.begin(); itr != ed.end(); ++itr) {
+            c1 = itr->first;
+            c2 = itr->second;
+            if ((st[(size_t)c1] & ST_INTERS) && (st[(size_t)c1] & (~ST_INTERS)) != st[(size_t)c2]) { hasConflict = true; break; }
+        }
+        if (!hasConflict) break;
+        if (st[(size_t)c2] & ST_INTERS) { unsupported = true; return; }   // c2's geometry would have to be refreshed ([SEAM]:499-513)
+        SeamOp op;
+        op.c1 = c1; op.c2 = c2;
+        op.rx = tls[(size_t)c1].x; op.ry = tls[(size_t)c1].y;
+        op.rw = brs[(size_t)c1].x - tls[(size_t)c1].x; op.rh = brs[(size_t)c1].y - tls[(size_t)c1].y;
+        op.p1 = op.p2 = Pt{0, 0};
+        if (only_one(c1)) {
+            op.kind = 0;                                                     // a stale bounding box is a superset: good enough
+            if (op.rw > 0 && op.rh > 0) ops.push_back(op);
+            st[(size_t)c1] = st[(size_t)c2] == ST_FIRST ? ST_SECOND : ST_FIRST;
+        } else {
+            if (stale[(size_t)c1]) { unsupported = true; return; }           // tips of a component a seam has already cut
+            op.kind = 1;
+            if (get_seam_tips(c1, c2, &op.p1, &op.p2)) ops.push_back(op);
+            st[(size_t)c1] = st[(size_t)c2] == ST_FIRST ? (ST_INTERS | ST_SECOND) : (ST_INTERS | ST_FIRST);
+        }
+        stale[(size_t)c1] = 1;
+        ed.erase({c1, c2});
+        ed.erase({c2, c1});
+    }
+}
+
+// Everything a pair computes after labelling is a function of the contour records of its INTERS components (position, label,
+// neighbour labels), the states of the labels they mention, and -- through the seam tips -- the contour-proximity flags of the
+// candidate points; the latter are compared through the planned operations themselves.
+bool PairRuns::same_structure(const PairRuns& o) const {
+    auto state_of = [](const std::vector<int>& st, int label) { return (label >= 1 && label <= (int)st.size()) ? st[(size_t)label - 1] : -1; };
+    // INTERS components in label order, records in raster order
+    std::vector<const std::vector<ContourRec>*> a, b;
+    std::vector<int> la, lb;
+    for (size_t c = 0; c < contours.size(); ++c) if (!contours[c].empty()) { a.push_back(&contours[c]); la.push_back((int)c + 1); }
+    for (size_t c = 0; c < o.contours.size(); ++c) if (!o.contours[c].empty()) { b.push_back(&o.contours[c]); lb.push_back((int)c + 1); }
+    if (la != lb) return false;
+    for (size_t k = 0; k < a.size(); ++k) {
+        const auto& ra = *a[k];
+        const auto& rb = *b[k];
+        if (ra.size() != rb.size()) return false;
+        for (size_t i = 0; i < ra.size(); ++i) {
+            const ContourRec& x = ra[i];
+            const ContourRec& y = rb[i];
+            if (x.x != y.x || x.y != y.y || x.label != y.label || x.nl[0] != y.nl[0] || x.nl[1] != y.nl[1] || x.nl[2] != y.nl[2] || x.nl[3] != y.nl[3]) return false;
+            if (state_of(states, x.label) != state_of(o.states, x.label)) return false;
+            for (int q = 0; q < 4; ++q)
+                if (x.nl[q] > 0 && state_of(states, x.nl[q]) != state_of(o.states, x.nl[q])) return false;
+        }
+    }
+    if (unsupported != o.unsupported || ops.size() != o.ops.size()) return false;
+    for (size_t k = 0; k < ops.size(); ++k) {
+        const SeamOp& x = ops[k];
+        const SeamOp& y = o.ops[k];
+        if (x.kind != y.kind || x.c1 != y.c1 || x.c2 != y.c2 || x.p1.x != y.p1.x || x.p1.y != y.p1.y || x.p2.x != y.p2.x || x.p2.y != y.p2.y ||
+            x.rx != y.rx || x.ry != y.ry || x.rw != y.rw || x.rh != y.rh) return false;
+    }
+    return true;
+}

@@ -119,9 +119,8 @@ int is_warp_with_mask(is_ctx* ctx, int projection, const is_mat* src, const floa
  *                     std::vector<UMat>& masks)                                        [SEAM]:87
  * (== cv::detail::DpSeamFinder::find).  images: n mats, 3 channels, IS_32F or IS_8U (all the same);
  * masks: n mats IS_8U, same sizes as the images ([SEAM]:133-134), modified in place.
- * cost_fn: IS_COST_COLOR.  IS_COST_COLOR_GRAD ([SEAM]:549-572, :767-772, :792-797; 8-bit images are taken as their
- * CV_32F conversion, which is what the mains pass) returns IS_ERR_UNSUPPORTED unless the environment sets
- * IS_EXPERIMENTAL_COLOR_GRAD=1: the device path exists but has not been through the hardware parity run yet.
+ * cost_fn: IS_COST_COLOR or IS_COST_COLOR_GRAD ([SEAM]:549-572, :767-772, :792-797; 8-bit images are taken as their
+ * CV_32F conversion, which is what the mains pass).
  */
 int is_seam_dp_find(is_ctx* ctx, int n, const is_mat* images, const is_point* corners, is_mat* masks, int cost_fn);
 
@@ -149,6 +148,18 @@ int is_mask_and(is_ctx* ctx, is_mat* dst, const is_mat* src);
  * concurrently and their results were proven equal to the reference's sequential loop, 0 = the proof failed and
  * the sequential loop was run, -1 = sequential (fewer than two overlapping pairs, or IS_SEAM_SEQUENTIAL=1). */
 int is_ctx_seam_speculation(const is_ctx* ctx);
+
+/* Which implementation of the pair loop the last call took: 2 = batched (all pairs through each kernel in one launch,
+ * csrc/seam_batch.inl), 1 = one host thread + stream per pair, 0 = the reference's sequential loop [SEAM]:100-121.
+ * The results are identical; the batched path hands inputs it does not cover (noisy masks with more than 8 toggles
+ * per row, a component cut by two seams) to the other two. */
+int is_ctx_seam_path(const is_ctx* ctx);
+
+/* Host-only diagnostic, no device needed: structure and plan of one image pair as the batched path computes them
+ * between its kernels (components, states, conflict-loop operations with seam tips, contour records).  See seam.cu. */
+int is_debug_seam_pair_plan(const uint8_t* mask1, int rows1, int cols1, size_t step1, int tl1x, int tl1y,
+                            const uint8_t* mask2, int rows2, int cols2, size_t step2, int tl2x, int tl2y,
+                            int32_t* out, size_t cap, size_t* len);
 
 /* computeCosts [SEAM]:733-803 for the component labelled `label` of a host/device label image
  * (IS_32S, union frame of the pair, top-left union_tl in panorama coordinates) over `roi` (union-frame

@@ -108,6 +108,10 @@ int orc_pipeline_run_ex2(int n, int proj, const uint8_t* const* srcs, const int*
         if (orc_gain_feed(n, ip.data(), mp.data(), rows.data(), cols.data(), corners_xy, gains.data())) return -1;
     }
     if (gains_out) for (int i = 0; i < n; ++i) gains_out[i] = gains[i];
+    // compensator->apply(i, corners[i], images_warped[i], masks_warped[i]) in place, BEFORE convertTo(CV_32F) and find():
+    // the seam finder and the blender both see the compensated images ([SEAM]:1165-1171, 1188-1192; [BLEND]:117-123, 138-140)
+    if (exposure_gain)
+        for (int i = 0; i < n; ++i) orc_gain_apply(warped[i].data(), warped[i].size(), gains[i]);
     auto t1 = clk::now();
     std::vector<std::vector<uint8_t>> wmask0;                    // masks_warped: the seam finder changes `masks` in place
     if (seam_dilate > 0) wmask0 = masks;
@@ -134,7 +138,6 @@ int orc_pipeline_run_ex2(int n, int proj, const uint8_t* const* srcs, const int*
     orc_fb* fb = blender == 1 ? orc_fb_create(sharpness) : nullptr;
     if (mb) orc_mb_prepare(mb, pano_roi); else orc_fb_prepare(fb, pano_roi);
     for (int i = 0; i < n; ++i) {                                // [SEAM]:1263,1271
-        if (exposure_gain) orc_gain_apply(warped[i].data(), warped[i].size(), gains[i]);   // compensator->apply  [SEAM]:1165-1171
         if (seam_dilate > 0) {                                   // dilate(masks_seam) & masks_warped  [SEAM]:1264-1269
             std::vector<uint8_t> dil(masks[i].size());
             orc_dilate_rect(masks[i].data(), rows[i], cols[i], seam_dilate, seam_dilate, dil.data());

@@ -207,7 +207,49 @@ def color_grad_cases():
     np.savez_compressed(os.path.join(HERE, "color_grad_cases.npz"), **out)
 
 
+def mains_sequence_case():
+    """The composite sequence of the reference's main() ([SEAM]:1150-1285) through OpenCV: warp -> GAIN feed -> apply in place
+    -> DpSeamFinder(COLOR) on the compensated images -> dilate(20x20) & warped mask -> FeatherBlender(0.1).  The inputs are
+    regenerated by the test from imagestitch_b200.synth (same call), only OpenCV's outputs are stored."""
+    n = 3
+    imgs, Ks, Rs, scale = synth.make_panorama_inputs(n, 256, 192, 1.2, 0.25)
+    gains_in = (0.7, 1.0, 1.25)
+    imgs = [np.clip(a.astype(np.float32) * g, 0, 255).astype(np.uint8) for a, g in zip(imgs, gains_in)]
+    warper = cv2.PyRotationWarper("cylindrical", scale)
+    corners, wi, wm = [], [], []
+    for i in range(n):
+        tl, a = warper.warp(imgs[i], Ks[i], Rs[i], cv2.INTER_LINEAR, cv2.BORDER_REFLECT)
+        _, m = warper.warp(np.full(imgs[i].shape[:2], 255, np.uint8), Ks[i], Rs[i], cv2.INTER_NEAREST, cv2.BORDER_CONSTANT)
+        corners.append(tuple(int(v) for v in tl)); wi.append(a); wm.append(m)
+    comp = cv2.detail.ExposureCompensator_createDefault(cv2.detail.ExposureCompensator_GAIN)
+    comp.feed(corners, wi, wm)
+    wi = [comp.apply(i, corners[i], wi[i], wm[i]) for i in range(n)]
+    masks = [m.copy() for m in wm]
+    for (i, j) in [(i, j) for i in range(n) for j in range(i + 1, n)][::-1]:
+        res = cv2.detail_DpSeamFinder("COLOR").find([cv2.UMat(wi[i].astype(np.float32)), cv2.UMat(wi[j].astype(np.float32))],
+                                                    [corners[i], corners[j]], [cv2.UMat(masks[i]), cv2.UMat(masks[j])])
+        masks[i], masks[j] = res[0].get(), res[1].get()
+    el = cv2.getStructuringElement(cv2.MORPH_RECT, (20, 20))
+    masks = [cv2.dilate(s, el) & m for s, m in zip(masks, wm)]
+    sizes = [(a.shape[1], a.shape[0]) for a in wi]
+    tl = (min(c[0] for c in corners), min(c[1] for c in corners))
+    br = (max(c[0] + s[0] for c, s in zip(corners, sizes)), max(c[1] + s[1] for c, s in zip(corners, sizes)))
+    fb = cv2.detail_FeatherBlender(0.1)
+    fb.prepare((tl[0], tl[1], br[0] - tl[0], br[1] - tl[1]))
+    for i in range(n):
+        fb.feed(wi[i].astype(np.int16), masks[i], corners[i])
+    pano, pmask = fb.blend(None, None)
+    out = {"gains_in": np.asarray(gains_in), "pano_cv": pano, "pano_mask_cv": pmask}
+    for i in range(n):
+        out[f"seam_mask{i}_cv"] = masks[i]
+    np.savez_compressed(os.path.join(HERE, "mains_sequence_case.npz"), **out)
+
+
 if __name__ == "__main__":
+    if "--only-mains" in sys.argv:
+        mains_sequence_case()
+        sys.exit(0)
+    mains_sequence_case()
     if "--only-new" not in sys.argv:
         warp_cases()
         remap_cases()

@@ -1,0 +1,57 @@
+"""More DP-seam parity on the device (hard assertions; these ran as reports in round 1 and passed on hardware):
+COLOR_GRAD seam cost ([SEAM]:549-572, 767-772, 792-797) and the degenerate / adversarial inputs of tests/helpers.seam_edge_cases
+(pinned against the reference's own compiled find() on the CPU side, tests/test_oracle_reference_build.py)."""
+import numpy as np
+import pytest
+
+from helpers import blob_masks, seam_edge_cases, warped_set
+from imagestitch_b200 import stitching as S, synth
+
+pytestmark = pytest.mark.gpu
+
+
+def _traces_equal(a, b):
+    return len(a) == len(b) and all(x[:4] == y[:4] and np.array_equal(x[4], y[4]) for x, y in zip(a, b))
+
+
+@pytest.mark.parametrize("case", [(2, 260, 200, 0.25, 1, False), (3, 200, 150, 0.6, 1, False), (4, 160, 120, 0.3, 2, False), (3, 180, 130, 0.4, 1, True),
+                                  (5, 220, 160, 0.35, 1, True), (2, 1500, 1000, 0.3, 1, False)])
+@pytest.mark.parametrize("kind", ["u8", "f32"])
+def test_color_grad_masks_and_seams(ctx, oracle, case, kind):
+    O = oracle
+    n, w, h, ov, rows, irregular = case
+    corners, wi, wm = warped_set(O, n, w, h, overlap=ov, grid_rows=rows)
+    if irregular:
+        holes = blob_masks(np.random.default_rng(8), [m.shape for m in wm], holes=4)
+        wm = [np.where(hm > 0, m, 0).astype(np.uint8) for m, hm in zip(wm, holes)]
+    imgs = wi if kind == "u8" else [a.astype(np.float32) for a in wi]
+    want, wtrace = O.dp_seam_find(imgs, corners, wm, cost_fn=O.COST_COLOR_GRAD, want_trace=True)
+    got, gtrace = S.DpSeamFinder(ctx, "COLOR_GRAD").find(imgs, corners, [m.copy() for m in wm], want_trace=True)
+    for i in range(n):
+        assert np.array_equal(got[i], want[i]), f"COLOR_GRAD seam mask {i}"
+    assert _traces_equal(wtrace, gtrace), "COLOR_GRAD seam point lists"
+
+
+def test_pipeline_color_grad(ctx, oracle):
+    O = oracle
+    imgs, Ks, Rs, scale = synth.make_panorama_inputs(3, 384, 288, 1.2, 0.25)
+    want = O.pipeline_run(0, imgs, Ks, Rs, scale, seam=True, num_bands=5, weight_type=O.WEIGHT_32F, want_intermediates=True, seam_cost=O.COST_COLOR_GRAD)
+    got = S.Stitcher(ctx, "cylindrical", "dp", 5, S.WEIGHT_32F, seam_cost="COLOR_GRAD").stitch(imgs, Ks, Rs, scale, want_seam_masks=True)
+    for a, b in zip(got["seam_masks"], want["masks"]):
+        assert np.array_equal(a, b)
+    assert np.array_equal(got["pano"], want["pano"])
+
+
+_EDGE = seam_edge_cases()
+
+
+@pytest.mark.parametrize("idx", range(len(_EDGE)), ids=[c[0].replace(" ", "_") for c in _EDGE])
+def test_seam_edge_case(ctx, oracle, idx):
+    O = oracle
+    name, imgs, cs, ms, cost = _EDGE[idx]
+    want = O.dp_seam_find(imgs, cs, ms, cost_fn=cost)
+    variants = [("f32", imgs)] + ([("u8", [a.astype(np.uint8) for a in imgs])] if cost == 0 else [])
+    for kind, im in variants:
+        got = S.DpSeamFinder(ctx, "COLOR_GRAD" if cost else "COLOR").find(im, cs, [m.copy() for m in ms])
+        for i, (a, b) in enumerate(zip(got, want)):
+            assert np.array_equal(a, b), f"{name} [{kind}] mask {i}: {int((a != b).sum())} px differ"

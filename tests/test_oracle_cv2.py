@@ -4,6 +4,7 @@ import numpy as np
 import pytest
 
 from helpers import blob_masks, random_camera, warped_set
+from imagestitch_b200 import synth
 
 cv2 = pytest.importorskip("cv2")
 
@@ -162,3 +163,41 @@ def test_dilate_distance_feather_vs_cv2(oracle):
             a, am = fb.blend(None, None)
             b, bm = ob.blend()
             assert np.array_equal(am, bm) and np.array_equal(a, b), sharp
+
+
+def test_mains_sequence_gain_before_seam_vs_cv2(oracle):
+    """The whole composite sequence of the reference's main() ([SEAM]:1150-1285) driven through cv2: warp -> GAIN feed ->
+    apply IN PLACE -> convertTo(CV_32F) -> DpSeamFinder -> dilate(20x20) & warped mask -> FeatherBlender(0.1).  The seam
+    finder must see the COMPENSATED images ([SEAM]:1165-1171 precede :1188-1192); with gains this far from 1 the seam masks
+    differ from those of the uncompensated images, which the last assertion checks."""
+    O = oracle
+    n = 4
+    imgs, Ks, Rs, scale = synth.make_panorama_inputs(n, 384, 288, 1.2, 0.25)
+    imgs = [np.clip(a.astype(np.float32) * g, 0, 255).astype(np.uint8) for a, g in zip(imgs, (0.7, 1.0, 1.25, 0.85))]
+    warper = cv2.PyRotationWarper("cylindrical", scale)
+    corners, wi, wm = [], [], []
+    for i in range(n):
+        tl, a = warper.warp(imgs[i], Ks[i], Rs[i], cv2.INTER_LINEAR, cv2.BORDER_REFLECT)
+        _, m = warper.warp(np.full(imgs[i].shape[:2], 255, np.uint8), Ks[i], Rs[i], cv2.INTER_NEAREST, cv2.BORDER_CONSTANT)
+        corners.append(tuple(int(v) for v in tl)); wi.append(a); wm.append(m)
+    comp = cv2.detail.ExposureCompensator_createDefault(cv2.detail.ExposureCompensator_GAIN)
+    comp.feed(corners, wi, wm)
+    raw = [a.copy() for a in wi]
+    wi = [comp.apply(i, corners[i], wi[i], wm[i]) for i in range(n)]
+    seam = _cv_pairwise(wi, corners, [m.copy() for m in wm], "COLOR")
+    seam_raw = _cv_pairwise(raw, corners, [m.copy() for m in wm], "COLOR")
+    el = cv2.getStructuringElement(cv2.MORPH_RECT, (20, 20))
+    masks = [cv2.dilate(s, el) & m for s, m in zip(seam, wm)]
+    sizes = [(a.shape[1], a.shape[0]) for a in wi]
+    fb = cv2.detail_FeatherBlender(0.1)
+    fb.prepare(O.result_roi(corners, sizes))
+    for i in range(n):
+        fb.feed(wi[i].astype(np.int16), masks[i], corners[i])
+    pano, pmask = fb.blend(None, None)
+    got = O.pipeline_run(O.PROJ_CYLINDRICAL, imgs, Ks, Rs, scale, seam=True, want_intermediates=True, exposure_gain=True, blender="feather",
+                         sharpness=0.1, seam_dilate=20)
+    for i in range(n):
+        assert np.array_equal(got["warped"][i], wi[i]), f"compensated image {i}"
+        assert np.array_equal(got["masks"][i], masks[i]), f"seam mask {i} (dilated & warped)"
+    assert np.array_equal(got["pano_mask"], pmask) and np.array_equal(got["pano"], pano)
+    assert any(not np.array_equal(a, b) for a, b in zip(seam, seam_raw)), "the case must distinguish compensated from raw seam inputs"

@@ -123,6 +123,21 @@ def test_exposure_and_feather_fixtures(oracle):
         assert np.array_equal(pmask, z[f"e{k}_feather_mask_cv"]) and np.array_equal(pano, z[f"e{k}_feather_cv"])
 
 
+def test_mains_sequence_fixture(oracle):
+    """The reference's main() sequence with GAIN exposure through OpenCV 4.13 (generator: make_golden.py mains_sequence_case):
+    apply() precedes find(), so the seam masks are those of the compensated images ([SEAM]:1165-1171, 1188-1192)."""
+    O = oracle
+    from imagestitch_b200 import synth
+    z = _load("mains_sequence_case.npz")
+    imgs, Ks, Rs, scale = synth.make_panorama_inputs(3, 256, 192, 1.2, 0.25)
+    imgs = [np.clip(a.astype(np.float32) * g, 0, 255).astype(np.uint8) for a, g in zip(imgs, [float(v) for v in z["gains_in"]])]
+    got = O.pipeline_run(O.PROJ_CYLINDRICAL, imgs, Ks, Rs, scale, seam=True, want_intermediates=True, exposure_gain=True, blender="feather",
+                         sharpness=0.1, seam_dilate=20)
+    for i in range(3):
+        assert np.array_equal(got["masks"][i], z[f"seam_mask{i}_cv"]), f"seam mask {i}"
+    assert np.array_equal(got["pano_mask"], z["pano_mask_cv"]) and np.array_equal(got["pano"], z["pano_cv"])
+
+
 def test_color_grad_fixtures(oracle):
     """COLOR_GRAD cost ([SEAM]:549-572,:767-772,:792-797): seam masks of cv2.detail_DpSeamFinder("COLOR_GRAD") exactly; the
     gradients to a few ulp (OpenCV's vector body and scalar tail associate differently, so its own result is not
