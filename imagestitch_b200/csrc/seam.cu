@@ -30,6 +30,7 @@
 #include <map>
 #include <set>
 #include <thread>
+#include <tuple>
 #include <utility>
 
 namespace is {
@@ -669,6 +670,200 @@ template <int LPT>
 __global__ void __launch_bounds__(1024) k_seam_dp_batch(const DpArgs* __restrict__ table) { seam_dp_body<LPT>(table[blockIdx.x]); }
 
 // @emu-dp-end
+
+// ---- DP forward pass, second formulation: warp-private windows with redundant halos -------------------------------------
+// The pass above pays one __syncthreads per step (~420 cycles per step measured on B200, whatever the number of warps).
+// The arithmetic itself is ~11 instructions per lane and step, i.e. ~130 issue cycles per step for a 1500-lane overlap on one
+// SM -- so the barrier, not the work, sets the pace.  Here every warp owns OWN = 32 LPT - 2 H lanes but computes a window of
+// 32 LPT lanes: H lanes of halo on either side, recomputed redundantly from the same inputs (bit-identical by construction).
+// A lane at the rim of a window has no valid neighbour, which invalidates one more halo lane per step, so after K = H steps
+// the owned lanes are still exact and the halos are spent: only then do the warps meet (one __syncthreads per H steps) and
+// refresh their windows from each other's owned lanes through shared memory.  Inside a window neighbours talk through warp
+// shuffles; the cost rows come straight from L2 into a register ring R steps ahead (every thread reads only its own lanes'
+// costs, so no staging through shared memory is needed); the control bytes of the owned lanes go out as one 32-bit store.
+// The back-track is a separate, parallel pair of kernels (k_bt_compose / k_bt_walk).
+__device__ unsigned g_dp_inf_row[16] = {0x7f800000u, 0x7f800000u, 0x7f800000u, 0x7f800000u, 0x7f800000u, 0x7f800000u, 0x7f800000u, 0x7f800000u,
+                                        0x7f800000u, 0x7f800000u, 0x7f800000u, 0x7f800000u, 0x7f800000u, 0x7f800000u, 0x7f800000u, 0x7f800000u};
+
+template <int LPT, int H, int R>
+__global__ void __launch_bounds__(512) k_seam_fwd(const DpArgs* __restrict__ table) {
+    static_assert(H % LPT == 0 && H % R == 0 && LPT % 4 == 0 && LPT <= 16, "halo / ring shapes");
+    extern __shared__ __align__(16) float T_sm[];             // [2][pitch + 2 H]: running costs of all lanes at the last exchange
+    const DpArgs A = table[blockIdx.x];
+    constexpr int WIN = 32 * LPT, OWN = WIN - 2 * H, K = H;
+    const int tid = threadIdx.x, lane_id = tid & 31, warp = tid >> 5;
+    const int l0 = warp * OWN - H + lane_id * LPT;            // first lane of this thread (may lie outside the table)
+    const bool live = l0 >= 0 && l0 < A.lanes;                // lanes [l0, l0 + LPT) exist (pitch is a multiple of LPT)
+    const bool owned = live && lane_id * LPT >= H && lane_id * LPT < WIN - H;
+    const float INF = __int_as_float(0x7f800000);
+    const int tstride = A.pitch + 2 * H;
+    const size_t pitch = (size_t)A.pitch;
+    const int lc = live ? l0 : 0;
+    // Threads outside the table read a constant row of +inf with stride 0: their lanes stay unreachable without a branch.
+    const float4* fp = live ? reinterpret_cast<const float4*>(A.P + (size_t)(A.s0 + 1) * pitch + lc) : reinterpret_cast<const float4*>(g_dp_inf_row);
+    const float4* fq = live ? reinterpret_cast<const float4*>(A.Q + (size_t)(A.s0 + 1) * pitch + lc) : reinterpret_cast<const float4*>(g_dp_inf_row);
+    const int row4 = live ? (A.pitch >> 2) : 0;               // float4 per row
+    uint32_t* cp = reinterpret_cast<uint32_t*>(A.control + (size_t)(A.s0 + 1) * pitch + lc);
+    const int crow = A.pitch >> 2;
+    float t[LPT];
+#pragma unroll
+    for (int j = 0; j < LPT; ++j) {
+        const float c = l0 + j == A.lane0 ? 0.f : INF;
+        t[j] = live ? __fadd_rn(c, __ldg(A.P + (size_t)A.s0 * pitch + l0 + j)) : INF;
+    }
+    // one DP step from the cost rows (pv, qv) of this thread's lanes
+    auto dp_step = [&](const float4* pv, const float4* qv) {
+        float p[LPT], q[LPT];
+#pragma unroll
+        for (int v = 0; v < LPT / 4; ++v) {
+            p[4 * v] = pv[v].x; p[4 * v + 1] = pv[v].y; p[4 * v + 2] = pv[v].z; p[4 * v + 3] = pv[v].w;
+            q[4 * v] = qv[v].x; q[4 * v + 1] = qv[v].y; q[4 * v + 2] = qv[v].z; q[4 * v + 3] = qv[v].w;
+        }
+        float tl_edge = __shfl_up_sync(0xffffffffu, t[LPT - 1], 1);
+        float tr_edge = __shfl_down_sync(0xffffffffu, t[0], 1);
+        const float qleft = __shfl_up_sync(0xffffffffu, q[LPT - 1], 1);
+        if (lane_id == 0) tl_edge = INF;
+        if (lane_id == 31) tr_edge = INF;
+        float tn[LPT];
+        uint32_t ctl_pack[LPT / 4];
+#pragma unroll
+        for (int j = 0; j < LPT / 4; ++j) ctl_pack[j] = 0;
+#pragma unroll
+        for (int j = 0; j < LPT; ++j) {
+            const float tleft = j > 0 ? t[j - 1] : tl_edge;
+            const float tright = j < LPT - 1 ? t[j + 1] : tr_edge;
+            const float ql = j > 0 ? q[j - 1] : qleft;
+            const float c2 = __fadd_rn(tleft, ql);
+            const float c3 = __fadd_rn(tright, q[j]);
+            // Costs are non-negative floats or +inf (never NaN, never -0): their bit patterns order like signed integers, and
+            // the DPX minimum hands back "first operand <= second" with the minimum -- (cost, step) lexicographic as in
+            // std::min_element over pair<float, int> ([SEAM]:909): a later candidate wins only when strictly smaller.
+            bool keep1, keep2;
+            const int b1 = __vibmin_s32(__float_as_int(t[j]), __float_as_int(c2), &keep1);
+            const int b2 = __vibmin_s32(b1, __float_as_int(c3), &keep2);
+            uint32_t ctl = keep1 ? 1u << (8 * (j & 3)) : 2u << (8 * (j & 3));
+            ctl = keep2 ? ctl : 3u << (8 * (j & 3));
+            tn[j] = __fadd_rn(__int_as_float(b2), p[j]);
+            ctl_pack[j / 4] |= ctl;
+        }
+        if (owned) {
+#pragma unroll
+            for (int j = 0; j < LPT / 4; ++j) cp[j] = ctl_pack[j];
+        }
+        cp += crow;
+#pragma unroll
+        for (int j = 0; j < LPT; ++j) t[j] = tn[j];
+    };
+    // refresh every window from the owners of its lanes (one __syncthreads)
+    int buf = 0;
+    auto exchange = [&]() {
+        float* T = T_sm + buf * tstride + H;                  // T[lane], lane in [-H, pitch + H)
+        if (owned) {
+#pragma unroll
+            for (int v = 0; v < LPT / 4; ++v) reinterpret_cast<float4*>(T + l0)[v] = make_float4(t[4 * v], t[4 * v + 1], t[4 * v + 2], t[4 * v + 3]);
+        }
+        __syncthreads();
+        if (live) {
+#pragma unroll
+            for (int v = 0; v < LPT / 4; ++v) {
+                const float4 x = reinterpret_cast<const float4*>(T + l0)[v];
+                t[4 * v] = x.x; t[4 * v + 1] = x.y; t[4 * v + 2] = x.z; t[4 * v + 3] = x.w;
+            }
+        }
+        buf ^= 1;
+    };
+    const int nsteps = A.s1 - A.s0;
+    const int rem = nsteps % K, ngroups = nsteps / K;
+    // The odd steps come FIRST (plain loads, their latency exposed once per seam), so that every later group is complete and
+    // runs fully unrolled over the register ring without a bounds test.
+    if (rem) {
+        for (int i = 0; i < rem; ++i) {
+            float4 pv[LPT / 4], qv[LPT / 4];
+#pragma unroll
+            for (int v = 0; v < LPT / 4; ++v) { pv[v] = __ldg(fp + v); qv[v] = __ldg(fq + v); }
+            fp += row4; fq += row4;
+            dp_step(pv, qv);
+        }
+        if (ngroups) exchange();
+    }
+    // register ring of cost rows, R steps ahead; the fetch pointers never stop: the tables carry DP_ROW_PAD spare rows
+    float4 rp[R][LPT / 4], rq[R][LPT / 4];
+    auto fetch = [&](int slot) {
+#pragma unroll
+        for (int v = 0; v < LPT / 4; ++v) { rp[slot][v] = __ldg(fp + v); rq[slot][v] = __ldg(fq + v); }
+        fp += row4; fq += row4;
+    };
+    if (ngroups) {
+#pragma unroll
+        for (int r = 0; r < R; ++r) fetch(r);
+    }
+    for (int g = 0; g < ngroups; ++g) {
+#pragma unroll
+        for (int k = 0; k < K; ++k) {
+            float4 pv[LPT / 4], qv[LPT / 4];
+#pragma unroll
+            for (int v = 0; v < LPT / 4; ++v) { pv[v] = rp[k % R][v]; qv[v] = rq[k % R][v]; }
+            fetch(k % R);
+            dp_step(pv, qv);
+        }
+        if (g + 1 < ngroups) exchange();
+    }
+    // destination reachable ([SEAM]:918) <=> its running value is finite
+    if (nsteps == 0) { if (tid == 0) *A.reached = (A.lane1 == A.lane0) ? 1 : 0; }
+    else if (owned && A.lane1 >= l0 && A.lane1 < l0 + LPT) {
+        float tv = INF;
+#pragma unroll
+        for (int j = 0; j < LPT; ++j) if (l0 + j == A.lane1) tv = t[j];
+        *A.reached = tv < INF ? 1 : 0;
+    }
+}
+
+// Back-track ([SEAM]:923-947) in parallel.  Steps s0+1 .. s1 are cut into chunks of BT_CHUNK; k_bt_compose walks every lane
+// of every chunk upwards through the control bytes (BT_CHUNK dependent byte loads per thread, all chunks of all seams at
+// once) and records where it leaves the chunk; k_bt_walk chains the chunk maps from the destination (one short serial chain
+// per seam) and then lets one thread per chunk write the seam lanes of its steps.
+constexpr int BT_CHUNK = 64;
+constexpr int DP_ROW_PAD = 8;                                 // spare rows behind the cost tables (k_seam_fwd prefetches past the last step)
+struct BtArgs { DpArgs A; short* map; int nchunks; };         // map[chunk][pitch]: lane at the step below the chunk, given the lane at its top step
+
+__device__ __forceinline__ int bt_step(const uint8_t* __restrict__ control, size_t pitch, int lanes, int step, int lane) {
+    const int c = control[(size_t)step * pitch + lane];
+    lane += (c == 3) - (c == 2);
+    return min(max(lane, 0), lanes - 1);                      // lanes off the optimal path may hold anything: stay inside the table
+}
+
+__global__ void __launch_bounds__(256) k_bt_compose(const BtArgs* __restrict__ table) {
+    const BtArgs& B = table[blockIdx.z];
+    const int c = blockIdx.y;
+    if (c >= B.nchunks || !*B.A.reached) return;
+    const int lane = blockIdx.x * blockDim.x + threadIdx.x;
+    if (lane >= B.A.lanes) return;
+    const int hi = B.A.s1 - c * BT_CHUNK, lo = max(B.A.s0, hi - BT_CHUNK);   // steps hi, hi-1, ..., lo+1
+    int cur = lane;
+    for (int s = hi; s > lo; --s) cur = bt_step(B.A.control, (size_t)B.A.pitch, B.A.lanes, s, cur);
+    B.map[(size_t)c * B.A.pitch + lane] = (short)cur;
+}
+
+__global__ void __launch_bounds__(256) k_bt_walk(const BtArgs* __restrict__ table) {
+    const BtArgs& B = table[blockIdx.x];
+    if (!*B.A.reached) return;
+    extern __shared__ int entry[];                            // [nchunks]
+    if (threadIdx.x == 0) {
+        int cur = B.A.lane1;
+        for (int c = 0; c < B.nchunks; ++c) { entry[c] = cur; cur = B.map[(size_t)c * B.A.pitch + cur]; }
+        B.A.seam_lane[0] = cur;                               // lane at the source step
+    }
+    __syncthreads();
+    for (int c = threadIdx.x; c < B.nchunks; c += blockDim.x) {
+        const int hi = B.A.s1 - c * BT_CHUNK, lo = max(B.A.s0, hi - BT_CHUNK);
+        int cur = entry[c];
+        for (int s = hi; s > lo; --s) {
+            B.A.seam_lane[s - B.A.s0] = cur;
+            cur = bt_step(B.A.control, (size_t)B.A.pitch, B.A.lanes, s, cur);
+        }
+    }
+}
+
 // ---- updateLabelsUsingSeam: device part -------------------------------------------------------------------------
 // sub-frame klass: 0 = not comp1, 1 = interior of comp1, 2 = painted (contour of comp1 or seam)  [SEAM]:963-970
 __global__ void k_uls_class(const int* __restrict__ labels, Frame f, int l1, int bx, int by, int bw, int bh, uint8_t* klass) {
@@ -1814,6 +2009,22 @@ static int seam_find_concurrent(is_ctx* ctx, const std::vector<std::pair<int, in
 #include "seam_runs.inl"
 #include "seam_batch.inl"
 
+// synthetic cost rows for is_debug_dp_bench: multiples of 0.5 like real colour costs, a curved band of cells outside the
+// component (+inf) on either side so that the reachability logic is exercised
+__global__ void k_dp_bench_fill(float* P, float* Q, int lanes, int pitch, int steps, unsigned seed) {
+    const int lane = blockIdx.x * blockDim.x + threadIdx.x;
+    const int step = blockIdx.y;
+    if (lane >= pitch || step >= steps) return;
+    unsigned h = (unsigned)lane * 2654435761u ^ ((unsigned)step * 40503u + seed) * 2246822519u;
+    h ^= h >> 15; h *= 2654435761u; h ^= h >> 13;
+    const int margin = 3 + (int)(12.f * (0.5f + 0.5f * __sinf(step * 0.01f)));
+    const bool inside = lane >= margin && lane < lanes - margin;
+    float p = 0.5f * (float)(h % 1500u), q = 0.5f * (float)((h >> 11) % 1500u);
+    if ((h >> 28) == 0) { p = 0.f; q = 0.f; }                       // ties
+    P[(size_t)step * pitch + lane] = (lane < lanes && inside) ? p : __int_as_float(0x7f800000);
+    Q[(size_t)step * pitch + lane] = lane < lanes ? q : 0.f;
+}
+
 // device-resident images / masks (masks in-out); used by is_seam_dp_find* and by the pipeline
 int seam_find_core(is_ctx* ctx, int n, const DevMat* images, const is_point* corners, const DevMat* masks, TraceSink* trace,
                    int cost_fn = IS_COST_COLOR) {
@@ -2033,6 +2244,62 @@ int is_debug_seam_pair_plan(const uint8_t* mask1, int rows1, int cols1, size_t s
     for (auto& c : P.contours) for (auto& r : c) for (int q : {r.x, r.y, r.label, r.nl[0], r.nl[1], r.nl[2], r.nl[3]}) v.push_back(q);
     *len = v.size();
     if (out && cap >= v.size()) std::memcpy(out, v.data(), v.size() * sizeof(int32_t));
+    return IS_OK;
+}
+
+// Diagnostic / tuning entry: `njobs` synthetic seams of lanes x steps through the DP kernels of formulation `variant`
+// (0: barrier per step + in-kernel back-track, 1: halo windows + parallel back-track), `iters` timed launches.
+// seam_out[njobs][steps] receives the seam lanes, ms[0] = mean milliseconds per launch group (CUDA events).
+int is_debug_dp_bench(is_ctx* ctx, int lanes, int steps, int njobs, int variant, unsigned seed, int iters, int32_t* seam_out, float* ms) {
+    if (!ctx || lanes < 8 || steps < 2 || njobs < 1 || iters < 1) return IS_ERR_BAD_ARG;
+    IS_CUDA(ctx, cudaSetDevice(ctx->device));
+    DpShape S;
+    dp_choose_shape(lanes, steps, 0, steps - 1, variant, &S);
+    IS_REQUIRE(ctx, S.pitch >= lanes && S.pitch <= 12 * 1024, IS_ERR_UNSUPPORTED, "too many lanes");
+    const size_t cells = (size_t)S.pitch * (steps + DP_ROW_PAD);
+    const int nchunks = div_up(steps - 1, BT_CHUNK);
+    DevBuf P, Q, ctl, res, map, tab;
+    IS_TRY(P.alloc(ctx, sizeof(float) * cells * njobs + 64));
+    IS_TRY(Q.alloc(ctx, sizeof(float) * cells * njobs + 64));
+    IS_TRY(ctl.alloc(ctx, cells * njobs + 64));
+    IS_TRY(res.alloc(ctx, sizeof(int) * (size_t)(steps + 4) * njobs));
+    IS_TRY(map.alloc(ctx, sizeof(short) * (size_t)nchunks * S.pitch * njobs + 64));
+    std::vector<DpArgs> da((size_t)njobs);
+    std::vector<BtArgs> ba((size_t)njobs);
+    for (int j = 0; j < njobs; ++j) {
+        IS_LAUNCH(ctx, k_dp_bench_fill, dim3(div_up(S.pitch, 256), steps), 256, 0, P.as<float>() + cells * j, Q.as<float>() + cells * j, lanes, S.pitch, steps, seed + 977u * j);
+        DpArgs& A = da[(size_t)j];
+        A.P = P.as<float>() + cells * j; A.Q = Q.as<float>() + cells * j; A.control = ctl.as<uint8_t>() + cells * j;
+        A.lanes = lanes; A.pitch = S.pitch; A.steps = steps;
+        A.s0 = 0; A.lane0 = lanes / 2 - 7 * j; A.s1 = steps - 1; A.lane1 = lanes / 3 + 11 * j;
+        A.seam_lane = res.as<int>() + (size_t)(steps + 4) * j + 4; A.reached = res.as<int>() + (size_t)(steps + 4) * j;
+        A.G = S.G; A.D = S.D;
+        ba[(size_t)j].A = A; ba[(size_t)j].map = map.as<short>() + (size_t)nchunks * S.pitch * j; ba[(size_t)j].nchunks = nchunks;
+    }
+    IS_TRY(tab.alloc(ctx, sizeof(DpArgs) * njobs + sizeof(BtArgs) * njobs + 64));
+    IS_TRY(upload(ctx, tab.p, da.data(), sizeof(DpArgs) * njobs));
+    BtArgs* bt_d = reinterpret_cast<BtArgs*>(tab.as<unsigned char>() + align_up(sizeof(DpArgs) * njobs, 16));
+    IS_TRY(upload(ctx, bt_d, ba.data(), sizeof(BtArgs) * njobs));
+    std::vector<DpShape> shapes((size_t)njobs, S);
+    IS_CUDA(ctx, cudaMemsetAsync(res.p, 0, sizeof(int) * (size_t)(steps + 4) * njobs, ctx->stream));
+    IS_TRY(launch_dp_all(ctx, shapes, tab.as<DpArgs>(), bt_d));                  // warm-up
+    cudaEvent_t e0, e1;
+    IS_CUDA(ctx, cudaEventCreate(&e0));
+    IS_CUDA(ctx, cudaEventCreate(&e1));
+    IS_CUDA(ctx, cudaEventRecord(e0, ctx->stream));
+    for (int it = 0; it < iters; ++it) IS_TRY(launch_dp_all(ctx, shapes, tab.as<DpArgs>(), bt_d));
+    IS_CUDA(ctx, cudaEventRecord(e1, ctx->stream));
+    IS_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+    float t = 0.f;
+    cudaEventElapsedTime(&t, e0, e1);
+    cudaEventDestroy(e0); cudaEventDestroy(e1);
+    if (ms) ms[0] = t / iters;
+    if (seam_out) {
+        std::vector<int> h((size_t)(steps + 4) * njobs);
+        IS_TRY(download(ctx, h.data(), res.p, sizeof(int) * h.size()));
+        for (int j = 0; j < njobs; ++j)
+            for (int k = 0; k < steps; ++k) seam_out[(size_t)j * steps + k] = h[(size_t)(steps + 4) * j] ? h[(size_t)(steps + 4) * j + 4 + k] : -1;
+    }
     return IS_OK;
 }
 

@@ -405,6 +405,103 @@ __global__ void k_apply_clears_batch(const PairDev* __restrict__ pairs) {
     if (c & 2) D.mask2[(size_t)(uy - D.fr.m2.oy) * D.mstep2 + (ux - D.fr.m2.ox)] = 0;
 }
 
+// ---- DP launches ----------------------------------------------------------------------------------------------------------
+// Two formulations of the forward pass (seam.cu): 0 = one __syncthreads per step over a TMA-fed shared-memory ring, back-track
+// inside the kernel; 1 = warp-private halo windows, one __syncthreads per H steps, parallel back-track kernels.
+struct DpShape {
+    int v1 = 0;                        // formulation
+    int tmpl = 0, nwarps = 0;          // v1: template choice, warps per CTA
+    int lpt = 4, nt = 32;              // v0
+    int pitch = 128, G = 1, D = 2;
+    int lanes = 0, s0 = 0, s1 = 0;
+    bool same(const DpShape& o) const { return v1 == o.v1 && (v1 ? (tmpl == o.tmpl && nwarps == o.nwarps) : (lpt == o.lpt && nt == o.nt)); }
+};
+
+static int dp_variant_default() {
+    if (const char* e = getenv("IS_DP_VARIANT")) return atoi(e) ? 1 : 0;
+    return 1;
+}
+
+// window shapes of k_seam_fwd<LPT, H, R>: {LPT, H, owned lanes per warp}
+static const int V1_TMPL[4][3] = {{4, 8, 112}, {8, 16, 224}, {16, 16, 480}, {4, 16, 96}};
+
+static void dp_choose_shape(int lanes, int steps, int s0, int s1, int variant, DpShape* S) {
+    S->lanes = lanes; S->s0 = s0; S->s1 = s1;
+    S->lpt = lanes <= 4096 ? 4 : (lanes <= 8192 ? 8 : 16);
+    if (const char* e = getenv("IS_DP_LPT")) {
+        const int v = atoi(e);
+        if ((v == 4 || v == 8 || v == 16) && lanes <= 1024 * v) S->lpt = v;
+    }
+    S->nt = std::min(1024, div_up(div_up(lanes, S->lpt), 32) * 32);
+    S->pitch = S->nt * S->lpt;
+    const size_t row_pair = 2 * sizeof(float) * (size_t)S->pitch;
+    S->D = 2;
+    S->G = (int)std::min<size_t>(16, (192 * 1024) / (S->D * row_pair));
+    if (S->G < 1) S->G = 1;
+    if (const char* e = getenv("IS_DP_G")) S->G = std::max(1, atoi(e));
+    if (const char* e = getenv("IS_DP_D")) S->D = std::max(2, atoi(e));
+    S->v1 = 0;
+    if (variant == 1) {
+        int forced = -1;
+        if (const char* e = getenv("IS_DP_V1_TMPL")) forced = atoi(e);
+        for (int t = 0; t < 4; ++t) {
+            if (forced >= 0 ? t != forced : t == 3) continue;
+            if (lanes <= 16 * V1_TMPL[t][2]) { S->v1 = 1; S->tmpl = t; S->nwarps = div_up(lanes, V1_TMPL[t][2]); break; }
+        }
+    }
+    (void)steps;
+}
+
+template <int LPT>
+static int launch_dp_v0(is_ctx* ctx, const DpArgs* table_d, int njobs, int nt, size_t smem, double bytes) {
+    IS_CUDA(ctx, cudaFuncSetAttribute(k_seam_dp_batch<LPT>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    ctx->next_bytes = bytes;
+    IS_LAUNCH(ctx, k_seam_dp_batch<LPT>, njobs, nt, smem, table_d);
+    return IS_OK;
+}
+
+// shapes[q] describes table entry q; entries of equal shape are adjacent.  bt_d: BtArgs of the v1 entries (same indices).
+static int launch_dp_all(is_ctx* ctx, const std::vector<DpShape>& shapes, const DpArgs* dp_d, const BtArgs* bt_d) {
+    const size_t nj = shapes.size();
+    int v1_first = -1, v1_count = 0, max_lanes = 0, max_chunks = 0;
+    for (size_t q = 0; q < nj;) {
+        size_t e = q;
+        const DpShape& S0 = shapes[q];
+        double bytes = 0;
+        while (e < nj && shapes[e].same(S0)) { bytes += (double)(shapes[e].s1 - shapes[e].s0) * shapes[e].lanes * 9; ++e; }
+        const int cnt = (int)(e - q);
+        if (!S0.v1) {
+            const size_t row_pair = 2 * sizeof(float) * (size_t)S0.pitch;
+            const size_t smem = std::max<size_t>((size_t)S0.D * S0.G * row_pair + 8 * (size_t)S0.D + 16, (size_t)32 * 65 + 16);
+            IS_REQUIRE(ctx, smem <= 200 * 1024, IS_ERR_INTERNAL, "DP shared-memory budget");
+            switch (S0.lpt) {
+                case 4: IS_TRY(launch_dp_v0<4>(ctx, dp_d + q, cnt, S0.nt, smem, bytes)); break;
+                case 8: IS_TRY(launch_dp_v0<8>(ctx, dp_d + q, cnt, S0.nt, smem, bytes)); break;
+                default: IS_TRY(launch_dp_v0<16>(ctx, dp_d + q, cnt, S0.nt, smem, bytes)); break;
+            }
+        } else {
+            const int H = V1_TMPL[S0.tmpl][1];
+            const size_t smem = 2 * sizeof(float) * (size_t)(S0.pitch + 2 * H);
+            ctx->next_bytes = bytes;
+            switch (S0.tmpl) {
+                case 0: IS_LAUNCH(ctx, (k_seam_fwd<4, 8, 4>), cnt, S0.nwarps * 32, smem, dp_d + q); break;
+                case 1: IS_LAUNCH(ctx, (k_seam_fwd<8, 16, 2>), cnt, S0.nwarps * 32, smem, dp_d + q); break;
+                case 2: IS_LAUNCH(ctx, (k_seam_fwd<16, 16, 1>), cnt, S0.nwarps * 32, smem, dp_d + q); break;
+                default: IS_LAUNCH(ctx, (k_seam_fwd<4, 16, 4>), cnt, S0.nwarps * 32, smem, dp_d + q); break;
+            }
+            if (v1_first < 0) v1_first = (int)q;
+            v1_count = (int)e - v1_first;                               // v1 entries are contiguous (sorted by formulation first)
+            for (size_t k = q; k < e; ++k) { max_lanes = std::max(max_lanes, shapes[k].lanes); max_chunks = std::max(max_chunks, div_up(shapes[k].s1 - shapes[k].s0, BT_CHUNK)); }
+        }
+        q = e;
+    }
+    if (v1_count > 0 && max_chunks > 0) {
+        IS_LAUNCH(ctx, k_bt_compose, dim3(div_up(max_lanes, 256), max_chunks, v1_count), 256, 0, bt_d + v1_first);
+        IS_LAUNCH(ctx, k_bt_walk, v1_count, 256, sizeof(int) * (size_t)max_chunks, bt_d + v1_first);
+    }
+    return IS_OK;
+}
+
 // ---- host ------------------------------------------------------------------------------------------------------------------
 
 // a device arena + its pinned host mirror: everything a phase uploads goes up in ONE copy
@@ -424,6 +521,8 @@ struct SeamJobHost {
     bool horizontal = false, swapped = false;
     int lanes = 0, steps = 0, lpt = 4, nt = 32, pitch = 128;
     int s0 = 0, lane0 = 0, s1 = 0, lane1 = 0, nseam = 0, nc = 0;
+    DpShape shape;
+    size_t off_map = 0;
     size_t off_P = 0, off_Q = 0, off_ctl = 0, off_klass = 0, off_parent = 0, off_res = 0;   // device arena offsets
     size_t res_ints = 0;
     std::vector<int> adj_roots;
@@ -665,14 +764,6 @@ static LayeredMask plain_mask(const DevMat& m) {
     return L;
 }
 
-template <int LPT>
-static int launch_dp_group(is_ctx* ctx, const DpArgs* table_d, int njobs, int nt, size_t smem, double bytes) {
-    IS_CUDA(ctx, cudaFuncSetAttribute(k_seam_dp_batch<LPT>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    ctx->next_bytes = bytes;
-    IS_LAUNCH(ctx, k_seam_dp_batch<LPT>, njobs, nt, smem, table_d);
-    return IS_OK;
-}
-
 static int seam_find_batched(is_ctx* ctx, const std::vector<std::pair<int, int>>& active, int n, const DevMat* images, const is_point* corners,
                              const DevMat* masks, TraceSink* trace, int cost_fn, bool* accepted) {
     *accepted = false;
@@ -709,6 +800,7 @@ static int seam_find_batched(is_ctx* ctx, const std::vector<std::pair<int, int>>
     // ---- C: plan -> device tables
     std::vector<SeamJobHost> jobs;
     std::vector<RelabelDev> pre_relabel, post_relabel;
+    const int dp_variant = dp_variant_default();
     for (size_t k = 0; k < np; ++k) {
         std::vector<char> cut((size_t)PR[k].ncomps, 0);
         for (const SeamOp& op : PR[k].ops) {
@@ -725,16 +817,11 @@ static int seam_find_batched(is_ctx* ctx, const std::vector<std::pair<int, int>>
             if (J.horizontal) { if (src.x > dst.x) { std::swap(src, dst); J.swapped = true; } }
             else if (src.y > dst.y) { std::swap(src, dst); J.swapped = true; }
             J.lanes = J.horizontal ? op.rh : op.rw; J.steps = J.horizontal ? op.rw : op.rh;
-            J.lpt = J.lanes <= 4096 ? 4 : (J.lanes <= 8192 ? 8 : 16);
-            if (const char* e = getenv("IS_DP_LPT")) {
-                const int v = atoi(e);
-                if ((v == 4 || v == 8 || v == 16) && J.lanes <= 1024 * v) J.lpt = v;
-            }
-            J.nt = std::min(1024, div_up(div_up(J.lanes, J.lpt), 32) * 32);
-            J.pitch = J.nt * J.lpt;
-            if (!(J.pitch >= J.lanes && J.pitch <= 12 * 1024)) return IS_OK;                      // wider than the DP kernel handles: general path reports it
             J.s0 = J.horizontal ? src.x : src.y; J.lane0 = J.horizontal ? src.y : src.x;
             J.s1 = J.horizontal ? dst.x : dst.y; J.lane1 = J.horizontal ? dst.y : dst.x;
+            dp_choose_shape(J.lanes, J.steps, J.s0, J.s1, dp_variant, &J.shape);
+            J.lpt = J.shape.lpt; J.nt = J.shape.nt; J.pitch = J.shape.pitch;
+            if (!(J.pitch >= J.lanes && J.pitch <= 12 * 1024)) return IS_OK;                      // wider than the DP kernels handle: general path reports it
             J.nseam = J.s1 - J.s0 + 1;
             J.nc = (int)PR[k].contours[(size_t)op.c1].size();
             jobs.push_back(std::move(J));
@@ -759,11 +846,12 @@ static int seam_find_batched(is_ctx* ctx, const std::vector<std::pair<int, int>>
     }
     size_t res_total_ints = 0;
     for (auto& J : jobs) {
-        J.off_P = take(sizeof(float) * (size_t)J.pitch * J.steps + 64);
-        J.off_Q = take(sizeof(float) * (size_t)J.pitch * J.steps + 64);
+        J.off_P = take(sizeof(float) * (size_t)J.pitch * (J.steps + DP_ROW_PAD) + 64);
+        J.off_Q = take(sizeof(float) * (size_t)J.pitch * (J.steps + DP_ROW_PAD) + 64);
         J.off_ctl = take((size_t)J.pitch * J.steps + 64);
         J.off_klass = take((size_t)J.op.rw * J.op.rh);
         J.off_parent = take(sizeof(int) * (size_t)J.op.rw * J.op.rh);
+        if (J.shape.v1) J.off_map = take(sizeof(short) * (size_t)div_up(J.s1 - J.s0, BT_CHUNK) * J.pitch + 64);
         J.res_ints = 2 + (size_t)J.nseam + 8 * (size_t)J.nc + 3 * (size_t)J.nseam;
         J.off_res = res_total_ints;
         res_total_ints += (J.res_ints + 3) & ~(size_t)3;
@@ -783,6 +871,7 @@ static int seam_find_batched(is_ctx* ctx, const std::vector<std::pair<int, int>>
     const size_t off_pairs = B1.put(nullptr, sizeof(PairDev) * np);
     const size_t off_jobs = B1.put(nullptr, sizeof(JobDev) * std::max<size_t>(nj, 1));
     const size_t off_dp = B1.put(nullptr, sizeof(DpArgs) * std::max<size_t>(nj, 1));
+    const size_t off_bt = B1.put(nullptr, sizeof(BtArgs) * std::max<size_t>(nj, 1));
     const size_t off_pre = B1.put(pre_relabel.data(), sizeof(RelabelDev) * pre_relabel.size());
     const size_t off_b1 = take(B1.host.size());
     // blob 2 (after the host walk): states, adjacency roots, flips, post relabels -- sized now, filled later
@@ -800,7 +889,11 @@ static int seam_find_batched(is_ctx* ctx, const std::vector<std::pair<int, int>>
     // group the seams by DP launch shape
     std::vector<size_t> order(nj);
     for (size_t j = 0; j < nj; ++j) order[j] = j;
-    std::stable_sort(order.begin(), order.end(), [&](size_t a, size_t b) { return std::make_pair(jobs[a].lpt, jobs[a].nt) < std::make_pair(jobs[b].lpt, jobs[b].nt); });
+    std::stable_sort(order.begin(), order.end(), [&](size_t a, size_t b) {
+        const DpShape& x = jobs[a].shape;
+        const DpShape& y = jobs[b].shape;
+        return std::make_tuple(x.v1, x.v1 ? x.tmpl : x.lpt, x.v1 ? x.nwarps : x.nt) < std::make_tuple(y.v1, y.v1 ? y.tmpl : y.lpt, y.v1 ? y.nwarps : y.nt);
+    });
     {
         PairDev* pd = reinterpret_cast<PairDev*>(B1.host.data() + off_pairs);
         for (size_t k = 0; k < np; ++k) {
@@ -835,6 +928,7 @@ static int seam_find_batched(is_ctx* ctx, const std::vector<std::pair<int, int>>
         }
         JobDev* jd = reinterpret_cast<JobDev*>(B1.host.data() + off_jobs);
         DpArgs* da = reinterpret_cast<DpArgs*>(B1.host.data() + off_dp);
+        BtArgs* ba = reinterpret_cast<BtArgs*>(B1.host.data() + off_bt);
         for (size_t q = 0; q < nj; ++q) {
             const SeamJobHost& J = jobs[order[q]];
             JobDev& D = jd[q];
@@ -852,12 +946,10 @@ static int seam_find_batched(is_ctx* ctx, const std::vector<std::pair<int, int>>
             A.lanes = J.lanes; A.pitch = J.pitch; A.steps = J.steps;
             A.s0 = J.s0; A.lane0 = J.lane0; A.s1 = J.s1; A.lane1 = J.lane1;
             A.seam_lane = D.res + 2; A.reached = D.res;
-            const size_t row_pair = 2 * sizeof(float) * (size_t)J.pitch;
-            A.D = 2;
-            A.G = (int)std::min<size_t>(16, (192 * 1024) / (A.D * row_pair));
-            if (A.G < 1) A.G = 1;
-            if (const char* e = getenv("IS_DP_G")) A.G = std::max(1, atoi(e));
-            if (const char* e = getenv("IS_DP_D")) A.D = std::max(2, atoi(e));
+            A.G = J.shape.G; A.D = J.shape.D;
+            ba[q].A = A;
+            ba[q].map = reinterpret_cast<short*>(base + J.off_map);
+            ba[q].nchunks = div_up(J.s1 - J.s0, BT_CHUNK);
         }
     }
     IS_TRY(upload(ctx, b1d, B1.host.data(), B1.host.size()));
@@ -920,21 +1012,10 @@ static int seam_find_batched(is_ctx* ctx, const std::vector<std::pair<int, int>>
                 else IS_LAUNCH(ctx, (k_cost_pq_batch<float, false>), grid, block, 0, pairs_d, jobs_d);
             }
         }
-        for (size_t q = 0; q < nj;) {                                                            // one DP launch per shape, one CTA per seam
-            size_t e = q;
-            const SeamJobHost& J0 = jobs[order[q]];
-            double bytes = 0;
-            while (e < nj && jobs[order[e]].lpt == J0.lpt && jobs[order[e]].nt == J0.nt) { bytes += (double)(jobs[order[e]].s1 - jobs[order[e]].s0) * jobs[order[e]].lanes * 9; ++e; }
-            const DpArgs* A0 = reinterpret_cast<const DpArgs*>(B1.host.data() + off_dp) + q;
-            const size_t row_pair = 2 * sizeof(float) * (size_t)J0.pitch;
-            const size_t smem = std::max<size_t>((size_t)A0->D * A0->G * row_pair + 8 * (size_t)A0->D + 16, (size_t)32 * 65 + 16);
-            IS_REQUIRE(ctx, smem <= 200 * 1024, IS_ERR_INTERNAL, "DP shared-memory budget");
-            switch (J0.lpt) {
-                case 4: IS_TRY(launch_dp_group<4>(ctx, dp_d + q, (int)(e - q), J0.nt, smem, bytes)); break;
-                case 8: IS_TRY(launch_dp_group<8>(ctx, dp_d + q, (int)(e - q), J0.nt, smem, bytes)); break;
-                default: IS_TRY(launch_dp_group<16>(ctx, dp_d + q, (int)(e - q), J0.nt, smem, bytes)); break;
-            }
-            q = e;
+        {                                                                                        // one DP launch per shape, one CTA per seam
+            std::vector<DpShape> shapes(nj);
+            for (size_t q = 0; q < nj; ++q) shapes[q] = jobs[order[q]].shape;
+            IS_TRY(launch_dp_all(ctx, shapes, dp_d, reinterpret_cast<const BtArgs*>(b1d + off_bt)));
         }
         {
             dim3 block(64, 4), grid(div_up(max_rw, 64), div_up(max_rh, 4), (unsigned)nj);

@@ -121,6 +121,11 @@ class Context:
         return int(self.lib.is_ctx_seam_speculation(self.h))
 
     @property
+    def seam_path(self) -> int:
+        """2 = batched pair loop, 1 = one host thread + stream per pair, 0 = the reference's sequential loop (last call)."""
+        return int(self.lib.is_ctx_seam_path(self.h))
+
+    @property
     def kernel_launches(self) -> int:
         return int(self.lib.is_ctx_kernel_launches(self.h))
 

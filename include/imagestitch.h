@@ -155,6 +155,11 @@ int is_ctx_seam_speculation(const is_ctx* ctx);
  * per row, a component cut by two seams) to the other two. */
 int is_ctx_seam_path(const is_ctx* ctx);
 
+/* Tuning diagnostic: njobs synthetic seams (lanes x steps cost tables generated on the device) through the DP forward /
+ * back-track kernels of formulation `variant` (0 or 1, see csrc/seam.cu); seam_out[njobs][steps] = seam lanes (or -1 when the
+ * destination is unreachable), ms[0] = mean milliseconds per launch over `iters` launches. */
+int is_debug_dp_bench(is_ctx* ctx, int lanes, int steps, int njobs, int variant, unsigned seed, int iters, int32_t* seam_out, float* ms);
+
 /* Host-only diagnostic, no device needed: structure and plan of one image pair as the batched path computes them
  * between its kernels (components, states, conflict-loop operations with seam tips, contour records).  See seam.cu. */
 int is_debug_seam_pair_plan(const uint8_t* mask1, int rows1, int cols1, size_t step1, int tl1x, int tl1y,

@@ -55,3 +55,51 @@ def test_seam_edge_case(ctx, oracle, idx):
         got = S.DpSeamFinder(ctx, "COLOR_GRAD" if cost else "COLOR").find(im, cs, [m.copy() for m in ms])
         for i, (a, b) in enumerate(zip(got, want)):
             assert np.array_equal(a, b), f"{name} [{kind}] mask {i}: {int((a != b).sum())} px differ"
+
+
+@pytest.mark.parametrize("case", [(3, 384, 288, 0.25, 1), (4, 320, 240, 0.3, 2), (6, 240, 200, 0.3, 2), (3, 200, 150, 0.6, 1), (2, 1500, 1000, 0.3, 1)])
+@pytest.mark.parametrize("dp_variant", ["0", "1"])
+def test_pair_loop_paths_agree(ctx, oracle, case, dp_variant, monkeypatch):
+    """The three implementations of the pair loop -- batched (all pairs per launch), one thread + stream per pair, the
+    reference's sequential loop -- and both formulations of the DP forward pass give the oracle's masks and seam point lists."""
+    O = oracle
+    n, w, h, ov, rows = case
+    corners, wi, wm = warped_set(O, n, w, h, overlap=ov, grid_rows=rows)
+    want, wtrace = O.dp_seam_find(wi, corners, wm, want_trace=True)
+    monkeypatch.setenv("IS_DP_VARIANT", dp_variant)
+    for mode in ("", "pairs", "seq"):
+        if mode:
+            monkeypatch.setenv("IS_SEAM_PATH", mode)
+        else:
+            monkeypatch.delenv("IS_SEAM_PATH", raising=False)
+        got, gtrace = S.DpSeamFinder(ctx).find(wi, corners, [m.copy() for m in wm], want_trace=True)
+        for i in range(n):
+            assert np.array_equal(got[i], want[i]), f"path '{mode}' DP variant {dp_variant}: seam mask {i}"
+        assert _traces_equal(sorted(wtrace, key=lambda t: t[:3]), sorted(gtrace, key=lambda t: t[:3])), f"path '{mode}': seam point lists"
+        if not mode and ov < 0.5:
+            assert ctx.seam_path == 2, "a plain strip / mosaic must take the batched path"
+    monkeypatch.delenv("IS_SEAM_PATH", raising=False)
+
+
+def test_dp_formulations_agree_on_synthetic_tables(ctx):
+    """is_debug_dp_bench: the halo-window forward pass + parallel back-track against the barrier-per-step kernel on synthetic
+    cost tables (ties, unreachable bands), several shapes and window templates."""
+    import ctypes as C
+    import os
+    lib = ctx.lib
+    for (lanes, steps, njobs) in ((100, 700, 2), (1500, 1200, 3), (1800, 500, 2), (3000, 400, 2), (5000, 300, 1), (40, 37, 3)):
+        base = np.zeros((njobs, steps), np.int32)
+        ms = (C.c_float * 1)()
+        assert lib.is_debug_dp_bench(ctx.h, lanes, steps, njobs, 0, 77, 1, base.ctypes.data_as(C.POINTER(C.c_int32)), ms) == 0
+        assert (base[:, 0] >= 0).any(), "the synthetic tables should be solvable"
+        for tmpl in (None, "1", "2", "3"):
+            if tmpl is None:
+                os.environ.pop("IS_DP_V1_TMPL", None)
+            else:
+                os.environ["IS_DP_V1_TMPL"] = tmpl
+            try:
+                got = np.zeros((njobs, steps), np.int32)
+                assert lib.is_debug_dp_bench(ctx.h, lanes, steps, njobs, 1, 77, 1, got.ctypes.data_as(C.POINTER(C.c_int32)), ms) == 0
+            finally:
+                os.environ.pop("IS_DP_V1_TMPL", None)
+            assert np.array_equal(got, base), f"lanes={lanes} steps={steps} template {tmpl}"
