@@ -543,6 +543,7 @@ def main():
         "stage_ms": stage_ms, "ms_per_step_with_kernel_events": ms_dev_ev,
         "roofline": roofline, "cpu_baseline": cpu,
         "top_kernels": [{"name": r["name"], "ms_per_step": r["ms"] / args.steps, "launches_per_step": r["launches"] / args.steps} for r in ktable[:8]],
+        "all_kernels": [{"name": r["name"], "ms_per_step": round(r["ms"] / args.steps, 5), "launches_per_step": r["launches"] / args.steps} for r in ktable],
     }
     print(json.dumps(line), flush=True)
     if dist:

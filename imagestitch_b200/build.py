@@ -45,7 +45,7 @@ def sources():
 
 
 def _deps_mtime():
-    hdrs = [os.path.join(CSRC, f) for f in os.listdir(CSRC) if f.endswith((".cuh", ".h"))]
+    hdrs = [os.path.join(CSRC, f) for f in os.listdir(CSRC) if f.endswith((".cuh", ".h", ".inl"))]
     hdrs += [os.path.join(INCLUDE, f) for f in os.listdir(INCLUDE)]
     return max(os.path.getmtime(h) for h in hdrs)
 

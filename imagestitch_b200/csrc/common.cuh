@@ -50,6 +50,7 @@ struct is_ctx {
     size_t sync_next = 0;
     std::vector<double> last_gains;       // exposure gains of the last is_pipeline_run (is_pipeline_last_gains)
     int seam_speculation_accepted = -1;   // last is_seam_dp_find: 1 concurrent result accepted, 0 fell back, -1 not attempted
+    int seam_waves = 0;                   // last is_seam_dp_find: waves of the batched path
     int seam_path = 0;                    // last is_seam_dp_find: 2 batched path, 1 per-pair concurrent path, 0 sequential loop
     is::HostPool* hpool = nullptr;        // host threads for the per-pair control work of the seam stage (hostpool.h)
 };

@@ -2046,10 +2046,29 @@ int seam_find_core(is_ctx* ctx, int n, const DevMat* images, const is_point* cor
     ctx->seam_path = 0;
     const bool want_seq = (seq && seq[0] == '1') || (mode && !strcmp(mode, "seq"));
     if (!active.empty() && !want_seq && !(mode && !strcmp(mode, "pairs"))) {
-        // all pairs through every kernel at once, three host consultations per call (seam_batch.inl)
-        bool accepted = false;
-        IS_TRY(seam_find_batched(ctx, active, n, images, corners, masks, trace, cost_fn, &accepted));
-        if (accepted) { ctx->seam_speculation_accepted = 1; ctx->seam_path = 2; return IS_OK; }
+        // all pairs through every kernel at once, three host consultations per wave (seam_batch.inl)
+        size_t done = 0;
+        bool all_batched = true;
+        int waves = 0;
+        while (done < active.size()) {
+            std::vector<std::pair<int, int>> rest(active.begin() + done, active.end());
+            size_t accepted = 0;
+            bool first_unsupported = false;
+            IS_TRY(seam_batch_wave(ctx, rest, n, images, corners, masks, trace, cost_fn, &accepted, &first_unsupported));
+            if (first_unsupported) {                       // this pair alone through the general path, then on with the waves
+                std::vector<std::pair<int, int>> one(1, active[done]);
+                IS_TRY(seam_find_sequential(ctx, one, images, corners, masks, trace, cost_fn));
+                all_batched = false;
+                done += 1;
+                continue;
+            }
+            ++waves;
+            done += accepted;
+        }
+        ctx->seam_speculation_accepted = waves <= 1 ? 1 : 0;
+        ctx->seam_path = all_batched ? 2 : 0;
+        ctx->seam_waves = waves;
+        return IS_OK;
     }
     if (cost_fn != IS_COST_COLOR) return seam_find_sequential(ctx, active, images, corners, masks, trace, cost_fn);   // not on the per-pair concurrent path
     if (active.size() >= 2 && !want_seq) {
@@ -2231,8 +2250,14 @@ int is_debug_seam_pair_plan(const uint8_t* mask1, int rows1, int cols1, size_t s
                 for (int k = 0; k < 4; ++k) touches = touches || (at(0, nx[k], ny[k]) != at(1, nx[k], ny[k]));
                 if (touches && close_to(0, x, y) && close_to(1, x, y)) P.specials.push_back(Pt{x, y});
             }
+        const bool timing = getenv("IS_DEBUG_PLAN_TIMING") != nullptr;
+        auto t0 = std::chrono::steady_clock::now();
         P.build();
+        auto t1 = std::chrono::steady_clock::now();
         if (!P.too_many_runs) P.plan();
+        auto t2 = std::chrono::steady_clock::now();
+        if (timing) fprintf(stderr, "[plan timing] build %.3f ms, plan %.3f ms (uh=%d, runs=%d)\n", std::chrono::duration<double, std::milli>(t1 - t0).count(),
+                            std::chrono::duration<double, std::milli>(t2 - t1).count(), P.uh, P.row_off.empty() ? 0 : P.row_off.back());
     }
     std::vector<int32_t> v;
     size_t nrec = 0;

@@ -12,7 +12,9 @@
 //              masks minus the clears of the earlier pairs)                                   -> one download
 //      host    PairRuns of those masks; identical structure and plan <=> the speculative result is the sequential loop's
 //   G  device  k_apply_clears_batch: the clears go into the real masks
-// Pairs the plan cannot cover (noisy masks, a component cut twice) send the whole call to the general path (PairSeam).
+// Every pair of a wave starts from the same masks; the longest prefix (in the reference's order) proven independent of the
+// earlier pairs' clears is accepted, the rest forms the next wave (a strip needs one wave, a mosaic whose images overlap
+// mutually a few).  A pair the plan cannot cover (noisy masks, a component cut twice) takes the general path (PairSeam) alone.
 
 constexpr int TG_CAP = 8;              // toggles per mask row the batched path handles (rows are a few runs; more -> general path)
 constexpr int MAX_LAYERS = 8;          // earlier pairs whose clears a validation mask can carry
@@ -45,7 +47,7 @@ struct ToggleJob { LayeredMask m; unsigned char* counts; unsigned short* xs; }; 
 
 // One warp per mask row (blockIdx.y = job): the x positions where (mask != 0) toggles, in increasing x; the state left of
 // x = 0 is "outside".  16 pixels per lane and trip.  Rows with more than TG_CAP toggles set *overflow.
-__global__ void __launch_bounds__(256) k_row_toggles_batch(const ToggleJob* __restrict__ jobs, int* __restrict__ overflow) {
+__global__ void __launch_bounds__(256) k_row_toggles_batch(const ToggleJob* __restrict__ jobs, int* __restrict__ overflow) {   // overflow[job]
     const ToggleJob& J = jobs[blockIdx.y];
     const int rows = J.m.rows, cols = J.m.cols;
     const int y = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
@@ -95,7 +97,7 @@ __global__ void __launch_bounds__(256) k_row_toggles_batch(const ToggleJob* __re
     }
     if (lane == 0) {
         J.counts[y] = (unsigned char)min(n, 255);
-        if (n > TG_CAP) *overflow = 1;
+        if (n > TG_CAP) overflow[blockIdx.y] = 1;
     }
 }
 
@@ -104,6 +106,8 @@ struct SpecialJob {
     int o1x, o1y, o2x, o2y;            // mask origins in the union frame
     int uw, uh;
     int ix, iy, iw, ih;                // intersection rectangle (frame coordinates)
+    const unsigned char* cnt1; const unsigned short* xs1;   // the two masks' row toggles (k_row_toggles_batch)
+    const unsigned char* cnt2; const unsigned short* xs2;
     int2* out; int* count;
 };
 
@@ -123,26 +127,58 @@ __device__ __forceinline__ bool sp_close(const LayeredMask& m, int ox, int oy, i
     return false;
 }
 
+// bit i of the result: pixel mx0 + i (own coordinates) of mask row my is set, i < 18 -- from the row's toggles
+__device__ __forceinline__ unsigned row_bits18(const unsigned char* __restrict__ counts, const unsigned short* __restrict__ xs, int rows, int cols, int mx0, int my) {
+    if ((unsigned)my >= (unsigned)rows) return 0u;
+    const int n = min((int)counts[my], TG_CAP);
+    const uint4 v = *reinterpret_cast<const uint4*>(xs + (size_t)my * TG_CAP);
+    const unsigned w[4] = {v.x, v.y, v.z, v.w};
+    unsigned bits = 0;
+    for (int k = 0; k < n; ++k) {
+        const int t = (int)((w[k >> 1] >> (16 * (k & 1))) & 0xffffu) - mx0;      // toggle position inside the window
+        bits ^= t <= 0 ? 0x3ffffu : (t >= 18 ? 0u : (0x3ffffu << t) & 0x3ffffu);
+    }
+    if (mx0 + 18 > cols) bits &= mx0 < cols ? (1u << (cols - mx0)) - 1u : 0u;      // a row that ends inside the mask has no closing toggle
+    return bits;
+}
+
 // The only pixels getSeamTips can ever pick ([SEAM]:621-629): pixels of both masks with a 4-neighbour inside exactly one
 // mask (a contour pixel of an INTERS component touching a FIRST / SECOND component), close to both masks' contours.
-__global__ void __launch_bounds__(256) k_special_points_batch(const SpecialJob* __restrict__ jobs) {
+// The scan works on the row toggles k_row_toggles_batch has just produced (16 pixels of a row per step as bit sets: two
+// 16-byte loads per row instead of ten byte loads per pixel); only the few candidates look at the mask bytes themselves.
+constexpr int SP_ROWS = 8;             // rows per thread
+__global__ void __launch_bounds__(128) k_special_points_batch(const SpecialJob* __restrict__ jobs) {
     const SpecialJob& J = jobs[blockIdx.z];
-    const int lx = blockIdx.x * 64 + (threadIdx.x & 63), ly = blockIdx.y * 4 + (threadIdx.x >> 6);
-    if (lx >= J.iw || ly >= J.ih) return;
-    const int x = J.ix + lx, y = J.iy + ly;
-    // quick reject straight from the mask bytes: the pixel and its four neighbours inside both masks (the layers only remove pixels)
-    if (!sp_at(J.m1, J.o1x, J.o1y, x, y) || !sp_at(J.m2, J.o2x, J.o2y, x, y)) return;
-    bool touches = false;
-    const int nx[4] = {x - 1, x, x + 1, x}, ny[4] = {y, y - 1, y, y + 1};
-#pragma unroll
-    for (int k = 0; k < 4; ++k) {
-        const bool a = sp_at(J.m1, J.o1x, J.o1y, nx[k], ny[k]), b = sp_at(J.m2, J.o2x, J.o2y, nx[k], ny[k]);
-        touches = touches || (a != b);
+    const int cx = blockIdx.x * blockDim.x + threadIdx.x;
+    const int ly0 = blockIdx.y * SP_ROWS;
+    if (16 * cx >= J.iw || ly0 >= J.ih) return;
+    const int x0 = J.ix + 16 * cx;                                               // frame column of bit 1
+    const int m1x = x0 - 1 - J.o1x, m2x = x0 - 1 - J.o2x;
+    auto bits = [&](int y, unsigned* b1, unsigned* b2) {                         // frame row y
+        *b1 = row_bits18(J.cnt1, J.xs1, J.m1.rows, J.m1.cols, m1x, y - J.o1y);
+        *b2 = row_bits18(J.cnt2, J.xs2, J.m2.rows, J.m2.cols, m2x, y - J.o2y);
+    };
+    unsigned p1, p2, c1, c2, n1, n2;
+    bits(J.iy + ly0 - 1, &p1, &p2);
+    bits(J.iy + ly0, &c1, &c2);
+    const int rows = min(SP_ROWS, J.ih - ly0);
+    for (int r = 0; r < rows; ++r) {
+        const int y = J.iy + ly0 + r;
+        bits(y + 1, &n1, &n2);
+        const unsigned both = c1 & c2, x_cur = c1 ^ c2, x_up = p1 ^ p2, x_dn = n1 ^ n2;
+        unsigned cand = both & ((x_cur << 1) | (x_cur >> 1) | x_up | x_dn) & 0x1fffeu;   // bits 1..16: this chunk's pixels
+        while (cand) {
+            const int i = __ffs(cand) - 1;
+            cand &= cand - 1;
+            const int x = x0 - 1 + i;
+            if (x >= J.ix + J.iw) break;
+            if (sp_close(J.m1, J.o1x, J.o1y, J.uw, J.uh, x, y) && sp_close(J.m2, J.o2x, J.o2y, J.uw, J.uh, x, y)) {
+                const int pos = atomicAdd(J.count, 1);
+                if (pos < SPECIAL_CAP) J.out[pos] = make_int2(x, y);
+            }
+        }
+        p1 = c1; p2 = c2; c1 = n1; c2 = n2;
     }
-    if (!touches) return;
-    if (!sp_close(J.m1, J.o1x, J.o1y, J.uw, J.uh, x, y) || !sp_close(J.m2, J.o2x, J.o2y, J.uw, J.uh, x, y)) return;
-    const int pos = atomicAdd(J.count, 1);
-    if (pos < SPECIAL_CAP) J.out[pos] = make_int2(x, y);
 }
 
 // ---- per pair / per seam tables ----------------------------------------------------------------------------------------
@@ -545,7 +581,7 @@ static HostPool* host_pool(is_ctx* ctx) {
 static int uls_host_walk(is_ctx* ctx, const PairRuns& PR, SeamJobHost& J, const int* res, TraceSink* trace_on) {
     const SeamOp& op = J.op;
     const int l1 = op.c1 + 1, l2 = op.c2 + 1;
-    const int rx = op.rx, ry = op.ry, rw = op.rw;
+    const int rx = op.rx, ry = op.ry;
     const int nseam = J.nseam, nc = J.nc;
     J.adj_roots.clear(); J.flips.clear(); J.trace.clear();
     if (!res[0]) return IS_OK;                                        // [SEAM]:918-919: estimateSeam returned false
@@ -574,49 +610,74 @@ static int uls_host_walk(is_ctx* ctx, const PairRuns& PR, SeamJobHost& J, const 
     if (nsub_total >= 255) return IS_ERR_UNSUPPORTED;                 // the reference's mask value 255 would collide with a component id: general path
     // interior components are identified by their root index; ids 1.. in order of first appearance (only equality, "> 0" and
     // "!= 255" are ever asked of them, and there are fewer than 255)
-    std::vector<int> roots;
-    auto id_of = [&](int v) -> int {   // gathered value -> reference mask value
-        if (v <= 0) return v;          // 0, -1 (outside), -255 (painted)
-        for (size_t k = 0; k < roots.size(); ++k) if (roots[k] == v - 1) return (int)k + 1;
-        roots.push_back(v - 1);
-        return (int)roots.size();
+    int roots[256];
+    int nroots = 0;
+    auto id_of = [&](int v) -> int {   // gathered value (> 0: root index + 1) -> reference mask value
+        for (int k = 0; k < nroots; ++k) if (roots[k] == v - 1) return k + 1;
+        roots[nroots] = v - 1;
+        return ++nroots;
     };
     const std::vector<ContourRec>& cont = PR.contours[(size_t)op.c1];
-    FlatMap painted((size_t)(nc + nseam));
-    auto key = [&](int x, int y) { return (long long)y * rw + x; };
-    for (int i = 0; i < nc; ++i) painted[key(cont[(size_t)i].x - rx, cont[(size_t)i].y - ry)] = 255;
-    for (int i = 0; i < nseam; ++i) painted[key(gs[3 * i], gs[3 * i + 1])] = 255;
+    // The reference paints contour and seam pixels 255 and then assigns them one by one.  Contour pixels go first, in raster
+    // order: a painted neighbour counts only once it has been assigned, i.e. when it is a contour pixel EARLIER in raster order
+    // (neighbours 0, 2, 4, 5 of the reference's list: left, up, up-left, up-right); later contour pixels and all seam pixels
+    // still hold 255.  The records are raster ordered, so a neighbour is found by a search inside its row's slice.
+    const int rh = op.rh;
+    std::vector<int> row_first((size_t)rh + 1, 0);
+    for (int i = 0; i < nc; ++i) row_first[(size_t)(cont[(size_t)i].y - ry) + 1]++;
+    for (int y = 0; y < rh; ++y) row_first[(size_t)y + 1] += row_first[(size_t)y];
+    auto find_contour = [&](int x, int y) -> int {                     // index of the contour record at bbox position (x, y), -1 if none
+        if ((unsigned)y >= (unsigned)rh) return -1;
+        int lo = row_first[(size_t)y], hi = row_first[(size_t)y + 1] - 1;
+        while (lo <= hi) {
+            const int mid = (lo + hi) >> 1;
+            const int cx = cont[(size_t)mid].x - rx;
+            if (cx == x) return mid;
+            if (cx < x) lo = mid + 1; else hi = mid - 1;
+        }
+        return -1;
+    };
     static const int ddx[8] = {-1, +1, 0, 0, -1, +1, -1, +1};
     static const int ddy[8] = {0, 0, -1, +1, -1, -1, +1, +1};
-    auto value_at = [&](int gathered, int x, int y) -> int {   // current reference mask value at (x, y)
-        if (gathered == -1) return -1;                          // outside the mask
-        if (gathered == -255) return painted[key(x, y)];
-        return id_of(gathered);
-    };
+    std::vector<int> val((size_t)nc, 255);                             // current mask value of every contour pixel
     for (int i = 0; i < nc; ++i) {
         const int x = cont[(size_t)i].x - rx, y = cont[(size_t)i].y - ry;
-        bool okc = false;
-        int val = 255;
+        int v = 0;
         // the last neighbour (in the reference's order) with an assigned value wins: scan backwards, stop at the first hit
         for (int j = 7; j >= 0; --j) {
-            const int v = value_at(g8[(size_t)i * 8 + j], x + ddx[j], y + ddy[j]);
-            if (v > 0 && v != 255) { okc = true; val = v; break; }
+            const int g = g8[(size_t)i * 8 + j];
+            if (g > 0) { v = id_of(g); break; }                        // interior pixel of a flood-filled component
+            if (g == -255 && (j == 0 || j == 2 || j == 4 || j == 5)) { // painted, earlier in raster order: assigned if it is a contour pixel
+                const int k = find_contour(x + ddx[j], y + ddy[j]);
+                if (k >= 0 && k < i && val[(size_t)k] > 0 && val[(size_t)k] != 255) { v = val[(size_t)k]; break; }
+            }
         }
-        painted[key(x, y)] = okc ? val : 0;
+        val[(size_t)i] = v;
     }
+    // then the seam pixels: each looks at one neighbour of its own step (never a seam pixel itself), so their order is irrelevant;
+    // a seam pixel that is also a contour pixel is assigned a second time
+    std::vector<int> sval((size_t)nseam, 0);
+    std::vector<int> seam_contour((size_t)nseam, -1);
     for (int i = 0; i < nseam; ++i) {
-        // order-independent: a seam has one pixel per step, the inspected neighbour lies in the same step
-        const int x = gs[3 * i], y = gs[3 * i + 1];
-        const int v = horizontal ? value_at(gs[3 * i + 2], x, y + 1) : value_at(gs[3 * i + 2], x + 1, y);
-        painted[key(x, y)] = (v > 0 && v != 255) ? v : 0;
+        const int x = gs[3 * i], y = gs[3 * i + 1], g = gs[3 * i + 2];
+        int v = 0;
+        if (g > 0) v = id_of(g);
+        else if (g == -255) {
+            const int k = horizontal ? find_contour(x, y + 1) : find_contour(x + 1, y);
+            if (k >= 0 && val[(size_t)k] > 0 && val[(size_t)k] != 255) v = val[(size_t)k];
+        }
+        sval[(size_t)i] = v;
+        seam_contour[(size_t)i] = find_contour(x, y);
     }
+    for (int i = 0; i < nseam; ++i)
+        if (seam_contour[(size_t)i] >= 0) val[(size_t)seam_contour[(size_t)i]] = sval[(size_t)i];
     // adjacency vote ([SEAM]:1039-1085)
-    const int nsub = (int)roots.size();
+    const int nsub = nroots;
     std::vector<int> connect2((size_t)nsub + 1, 0), connectOther((size_t)nsub + 1, 0);
     bool c2_has0 = false, co_has0 = false;
     for (int i = 0; i < nc; ++i) {
         const ContourRec& r = cont[(size_t)i];
-        int mv = painted[key(r.x - rx, r.y - ry)];
+        int mv = val[(size_t)i];
         if (mv < 0 || mv > nsub) mv = 0;
         if (r.nl[0] == l2 || r.nl[1] == l2 || r.nl[2] == l2 || r.nl[3] == l2) { connect2[(size_t)mv]++; if (mv == 0) c2_has0 = true; }
         bool other = false;
@@ -633,13 +694,16 @@ static int uls_host_walk(is_ctx* ctx, const PairRuns& PR, SeamJobHost& J, const 
         }
         isAdj[(size_t)k] = r;
     }
-    for (int i = 1; i <= nsub; ++i) if (isAdj[(size_t)i]) J.adj_roots.push_back(roots[(size_t)i - 1]);
+    for (int i = 1; i <= nsub; ++i) if (isAdj[(size_t)i]) J.adj_roots.push_back(roots[i - 1]);
     std::sort(J.adj_roots.begin(), J.adj_roots.end());
-    for (size_t h = 0; h < painted.keys.size(); ++h) {
-        const long long k = painted.keys[h];
-        if (k < 0) continue;
-        const int v = painted.vals[h];
-        if (v > 0 && v <= nsub && isAdj[(size_t)v]) J.flips.push_back(make_int2((int)(k % rw) + rx, (int)(k / rw) + ry));
+    // painted pixels that ended up in an adjacent component are relabelled one by one ([SEAM]:1089-1092 covers them with the rest)
+    for (int i = 0; i < nc; ++i) {
+        const int v = val[(size_t)i];
+        if (v > 0 && v <= nsub && isAdj[(size_t)v]) J.flips.push_back(make_int2(cont[(size_t)i].x, cont[(size_t)i].y));
+    }
+    for (int i = 0; i < nseam; ++i) {
+        const int v = sval[(size_t)i];
+        if (seam_contour[(size_t)i] < 0 && v > 0 && v <= nsub && isAdj[(size_t)v]) J.flips.push_back(make_int2(gs[3 * i] + rx, gs[3 * i + 1] + ry));
     }
     return IS_OK;
 }
@@ -663,23 +727,23 @@ struct StructureQuery {
     // results
     std::vector<MaskRuns> runs;
     std::vector<std::vector<Pt>> specials;
-    bool overflow = false;
+    std::vector<char> mask_overflow, pair_overflow;    // more toggles per row / more candidate tips than the batched path carries
 };
 
 static int run_structure_query(is_ctx* ctx, StructureQuery& Q) {
     const size_t nm = Q.masks.size(), np = Q.pairs.size();
     Q.runs.assign(nm, MaskRuns());
     Q.specials.assign(np, std::vector<Pt>());
-    Q.overflow = false;
+    Q.mask_overflow.assign(nm, 0);
+    Q.pair_overflow.assign(np, 0);
     if (nm == 0) return IS_OK;
-    // device layout: [hdr: overflow, special counts np][counts (bytes)][xs (u16)][special points np x SPECIAL_CAP]   tables at the end
+    // device layout: [hdr: overflow flags nm, special counts np][special points np x SPECIAL_CAP][counts (bytes)][xs (u16)]   tables at the end
     size_t total_rows = 0;
     int max_rows = 0;
     for (auto& m : Q.masks) {
-        IS_REQUIRE(ctx, m.cols < 65535, IS_ERR_UNSUPPORTED, "mask wider than 65534 pixels");
         total_rows += (size_t)m.rows; max_rows = std::max(max_rows, m.rows);
     }
-    const size_t off_hdr = 0, hdr_bytes = align_up(sizeof(int) * (1 + np), 16);
+    const size_t off_hdr = 0, hdr_bytes = align_up(sizeof(int) * (nm + np), 16);
     const size_t off_sp_dl = off_hdr + hdr_bytes, sp_dl_bytes = align_up(sizeof(int2) * SPECIAL_CAP * np, 16);
     const size_t off_cnt = off_sp_dl + sp_dl_bytes, cnt_bytes = align_up(total_rows, 16);
     const size_t off_xs = off_cnt + cnt_bytes, xs_bytes = align_up(total_rows * TG_CAP * sizeof(unsigned short), 16);
@@ -714,8 +778,9 @@ static int run_structure_query(is_ctx* ctx, StructureQuery& Q) {
         S.uw = ubr.x - utl.x; S.uh = ubr.y - utl.y;
         S.ix = std::max(S.o1x, S.o2x); S.iy = std::max(S.o1y, S.o2y);
         S.iw = std::min(S.o1x + a.cols, S.o2x + b.cols) - S.ix; S.ih = std::min(S.o1y + a.rows, S.o2y + b.rows) - S.iy;
+        S.cnt1 = tj[(size_t)pq.m1].counts; S.xs1 = tj[(size_t)pq.m1].xs; S.cnt2 = tj[(size_t)pq.m2].counts; S.xs2 = tj[(size_t)pq.m2].xs;
         S.out = reinterpret_cast<int2*>(base + off_sp_dl) + k * SPECIAL_CAP;
-        S.count = reinterpret_cast<int*>(base + off_hdr) + 1 + k;
+        S.count = reinterpret_cast<int*>(base + off_hdr) + nm + k;
         max_iw = std::max(max_iw, S.iw); max_ih = std::max(max_ih, S.ih);
     }
     IS_CUDA(ctx, cudaMemsetAsync(base + off_hdr, 0, hdr_bytes, ctx->stream));
@@ -730,16 +795,17 @@ static int run_structure_query(is_ctx* ctx, StructureQuery& Q) {
         IS_LAUNCH(ctx, k_row_toggles_batch, grid, 256, 0, tj_d, reinterpret_cast<int*>(base + off_hdr));
     }
     if (np && max_iw > 0 && max_ih > 0) {
-        dim3 grid(div_up(max_iw, 64), div_up(max_ih, 4), (unsigned)np);
-        IS_LAUNCH(ctx, k_special_points_batch, grid, 256, 0, sj_d);
+        dim3 grid(div_up(div_up(max_iw, 16), 128), div_up(max_ih, SP_ROWS), (unsigned)np);
+        IS_LAUNCH(ctx, k_special_points_batch, grid, 128, 0, sj_d);
     }
     const unsigned char* h = nullptr;                                   // view of the pinned bounce buffer, valid until the next download
     IS_TRY(download_view(ctx, base, dl_bytes, reinterpret_cast<const void**>(&h)));
     const int* hdr = reinterpret_cast<const int*>(h + off_hdr);
-    if (hdr[0]) { Q.overflow = true; return IS_OK; }
-    for (size_t k = 0; k < np; ++k)
-        if (hdr[1 + k] > SPECIAL_CAP) { Q.overflow = true; return IS_OK; }   // more candidate tips than any panorama mask produces: general path
+    for (size_t k = 0; k < nm; ++k) Q.mask_overflow[k] = hdr[k] != 0 || Q.masks[k].cols >= 65535;
+    for (size_t k = 0; k < np; ++k)   // more candidate tips than any panorama mask produces, or a mask the run tables cannot hold: general path
+        Q.pair_overflow[k] = hdr[nm + k] > SPECIAL_CAP || Q.mask_overflow[(size_t)Q.pairs[k].m1] || Q.mask_overflow[(size_t)Q.pairs[k].m2];
     for (size_t k = 0; k < nm; ++k) {
+        if (Q.mask_overflow[k]) continue;
         MaskRuns& R = Q.runs[k];
         R.rows = Q.masks[k].rows; R.cols = Q.masks[k].cols; R.slots = TG_CAP;
         R.counts.assign(h + off_cnt + row0[k], h + off_cnt + row0[k] + (size_t)R.rows);
@@ -747,7 +813,8 @@ static int run_structure_query(is_ctx* ctx, StructureQuery& Q) {
         R.xs.assign(x, x + (size_t)R.rows * TG_CAP);
     }
     for (size_t k = 0; k < np; ++k) {
-        const int n = hdr[1 + k];
+        if (Q.pair_overflow[k]) continue;
+        const int n = hdr[nm + k];
         const int2* p = reinterpret_cast<const int2*>(h + off_sp_dl) + k * SPECIAL_CAP;
         std::vector<Pt>& out = Q.specials[k];
         out.resize((size_t)n);
@@ -764,11 +831,16 @@ static LayeredMask plain_mask(const DevMat& m) {
     return L;
 }
 
-static int seam_find_batched(is_ctx* ctx, const std::vector<std::pair<int, int>>& active, int n, const DevMat* images, const is_point* corners,
-                             const DevMat* masks, TraceSink* trace, int cost_fn, bool* accepted) {
-    *accepted = false;
-    const size_t np = active.size();
-    if (np == 0) { *accepted = true; return IS_OK; }
+// One wave: the pairs `active_in` (the reference's order) all start from the masks as they are now.  The longest prefix of them
+// whose speculative results are proven to be the sequential loop's is applied to the masks; *accepted_n is its length (at
+// least 1, unless the FIRST pair is outside what the batched path covers: then *first_unsupported is set and nothing is done).
+static int seam_batch_wave(is_ctx* ctx, const std::vector<std::pair<int, int>>& active_in, int n, const DevMat* images, const is_point* corners,
+                           const DevMat* masks, TraceSink* trace, int cost_fn, size_t* accepted_n, bool* first_unsupported) {
+    *accepted_n = 0;
+    *first_unsupported = false;
+    std::vector<std::pair<int, int>> active = active_in;
+    size_t np = active.size();
+    if (np == 0) return IS_OK;
     const bool is_u8 = images[active[0].first].depth == IS_8U;
     BatchTimer tm;
     HostPool* pool = host_pool(ctx);
@@ -783,20 +855,32 @@ static int seam_find_batched(is_ctx* ctx, const std::vector<std::pair<int, int>>
                                                 Pt{corners[pr.second].x, corners[pr.second].y}});
     IS_TRY(run_structure_query(ctx, Q));
     tm.lap("A toggles + special points");
-    if (Q.overflow) return IS_OK;
     std::vector<PairRuns> PR(np);
     pool->run(np, [&](size_t k) {
         PairRuns& P = PR[k];
+        if (Q.pair_overflow[k]) { P.unsupported = true; return; }
         P.setup(active[k].first, active[k].second, Q.pairs[k].tl1, Q.pairs[k].tl2, &Q.runs[(size_t)Q.pairs[k].m1], &Q.runs[(size_t)Q.pairs[k].m2]);
         P.specials = Q.specials[k];
+        if ((size_t)P.uw * P.uh >= (size_t)INT_MAX) { P.unsupported = true; return; }
         P.build();
-        if (!P.too_many_runs) P.plan();
+        if (P.too_many_runs) return;
+        P.plan();
+        for (const SeamOp& op : P.ops) {                               // seams wider than the DP kernels' tables: general path (it reports the limit)
+            if (op.kind != 1) continue;
+            const bool horizontal = std::abs(op.p2.x - op.p1.x) > std::abs(op.p2.y - op.p1.y);
+            if ((horizontal ? op.rh : op.rw) > 12 * 1024 - 128) P.unsupported = true;
+        }
     });
     tm.lap("A host: runs, contours, plan");
-    for (auto& P : PR) {
-        if (P.too_many_runs || P.unsupported) return IS_OK;
-        IS_REQUIRE(ctx, (size_t)P.uw * P.uh < (size_t)INT_MAX, IS_ERR_UNSUPPORTED, "union frame of an image pair exceeds 2^31 pixels");
-    }
+    // a pair the plan does not cover ends the wave in front of it (it goes through the general path, PairSeam, on its own)
+    for (size_t k = 0; k < np; ++k)
+        if (PR[k].too_many_runs || PR[k].unsupported) {
+            if (k == 0) { *first_unsupported = true; return IS_OK; }
+            np = k;
+            active.resize(np);
+            PR.resize(np);
+            break;
+        }
     // ---- C: plan -> device tables
     std::vector<SeamJobHost> jobs;
     std::vector<RelabelDev> pre_relabel, post_relabel;
@@ -821,7 +905,7 @@ static int seam_find_batched(is_ctx* ctx, const std::vector<std::pair<int, int>>
             J.s1 = J.horizontal ? dst.x : dst.y; J.lane1 = J.horizontal ? dst.y : dst.x;
             dp_choose_shape(J.lanes, J.steps, J.s0, J.s1, dp_variant, &J.shape);
             J.lpt = J.shape.lpt; J.nt = J.shape.nt; J.pitch = J.shape.pitch;
-            if (!(J.pitch >= J.lanes && J.pitch <= 12 * 1024)) return IS_OK;                      // wider than the DP kernels handle: general path reports it
+            IS_REQUIRE(ctx, J.pitch >= J.lanes && J.pitch <= 12 * 1024, IS_ERR_INTERNAL, "seam wider than planned");
             J.nseam = J.s1 - J.s0 + 1;
             J.nc = (int)PR[k].contours[(size_t)op.c1].size();
             jobs.push_back(std::move(J));
@@ -1039,10 +1123,12 @@ static int seam_find_batched(is_ctx* ctx, const std::vector<std::pair<int, int>>
         SeamJobHost& J = jobs[j];
         J.status = uls_host_walk(ctx, PR[(size_t)J.pair], J, res_h + J.off_res, trace);
     });
+    size_t limit = np;                                                 // pairs [0, limit) can still be accepted
     for (auto& J : jobs) {
-        if (J.status == IS_ERR_UNSUPPORTED) return IS_OK;                                         // general path
+        if (J.status == IS_ERR_UNSUPPORTED) { limit = std::min(limit, (size_t)J.pair); continue; }   // that pair takes the general path
         if (J.status != IS_OK) return J.status;
     }
+    if (limit == 0) { *first_unsupported = true; return IS_OK; }
     tm.lap("D host: uls walk + vote");
     // ---- E: relabel by the seams, clears per pair (private)
     {
@@ -1083,20 +1169,19 @@ static int seam_find_batched(is_ctx* ctx, const std::vector<std::pair<int, int>>
         IS_LAUNCH(ctx, k_pair_clears_batch, grid, block, 0, pairs_d);
     }
     // ---- F: validation -- the masks every pair would have seen in the sequential loop
-    bool all_valid = true;
     {
         StructureQuery V;
         std::vector<int> vpair;                                        // active index of every validation pair
-        for (size_t k = 0; k < np && all_valid; ++k) {
+        for (size_t k = 0; k < limit; ++k) {
             const int img[2] = {active[k].first, active[k].second};
             LayeredMask lm[2] = {plain_mask(masks[img[0]]), plain_mask(masks[img[1]])};
-            bool any = false;
-            for (int s = 0; s < 2; ++s)
+            bool any = false, too_many = false;
+            for (int s = 0; s < 2 && !too_many; ++s)
                 for (size_t q = 0; q < k; ++q) {
                     int bit = 0;
                     if (active[q].first == img[s]) bit = 1; else if (active[q].second == img[s]) bit = 2;
                     if (!bit) continue;
-                    if (lm[s].nlayers == MAX_LAYERS) { all_valid = false; break; }       // more earlier neighbours than a mask carries: sequential loop
+                    if (lm[s].nlayers == MAX_LAYERS) { too_many = true; break; }       // more earlier neighbours than a mask carries
                     const PairRuns& E = PR[q];
                     ClearLayer& L = lm[s].layer[lm[s].nlayers++];
                     L.p = base + off_clear[q]; L.pitch = cpitch[q];
@@ -1104,41 +1189,41 @@ static int seam_find_batched(is_ctx* ctx, const std::vector<std::pair<int, int>>
                     L.w = E.iBr.x - E.iTl.x; L.h = E.iBr.y - E.iTl.y; L.bit = bit;
                     any = true;
                 }
+            if (too_many) { limit = k; break; }                        // ends the wave here: the pair starts the next one with fewer layers
             if (!any) continue;
             V.pairs.push_back(StructureQuery::PairQ{(int)V.masks.size(), (int)V.masks.size() + 1, PR[k].tl1, PR[k].tl2});
             V.masks.push_back(lm[0]);
             V.masks.push_back(lm[1]);
             vpair.push_back((int)k);
         }
-        if (all_valid && !V.pairs.empty()) {
+        if (!V.pairs.empty()) {
             IS_TRY(run_structure_query(ctx, V));
             tm.lap("F toggles + special points (check)");
-            if (V.overflow) all_valid = false;
-            else {
-                std::vector<char> ok(vpair.size(), 0);
-                pool->run(vpair.size(), [&](size_t v) {
-                    PairRuns C;
-                    const size_t k = (size_t)vpair[v];
-                    C.setup(active[k].first, active[k].second, PR[k].tl1, PR[k].tl2, &V.runs[(size_t)V.pairs[v].m1], &V.runs[(size_t)V.pairs[v].m2]);
-                    C.specials = V.specials[v];
-                    C.build();
-                    if (C.too_many_runs) return;
-                    C.plan();
-                    ok[v] = C.same_structure(PR[k]) ? 1 : 0;
-                });
-                for (char c : ok) if (!c) all_valid = false;
-                tm.lap("F host: check structures");
-            }
+            std::vector<char> ok(vpair.size(), 0);
+            pool->run(vpair.size(), [&](size_t v) {
+                if (V.pair_overflow[v]) return;
+                PairRuns C;
+                const size_t k = (size_t)vpair[v];
+                C.setup(active[k].first, active[k].second, PR[k].tl1, PR[k].tl2, &V.runs[(size_t)V.pairs[v].m1], &V.runs[(size_t)V.pairs[v].m2]);
+                C.specials = V.specials[v];
+                C.build();
+                if (C.too_many_runs) return;
+                C.plan();
+                ok[v] = C.same_structure(PR[k]) ? 1 : 0;
+            });
+            for (size_t v = 0; v < vpair.size(); ++v)
+                if (!ok[v]) { limit = std::min(limit, (size_t)vpair[v]); break; }   // the first pair the earlier clears change starts the next wave
+            tm.lap("F host: check structures");
         }
     }
-    if (!all_valid) return IS_OK;                                      // caller falls back to the sequential loop; the masks are untouched
-    // ---- G: the clears go into the masks
+    // ---- G: the clears of the accepted prefix go into the masks
+    IS_REQUIRE(ctx, limit >= 1, IS_ERR_INTERNAL, "seam wave without progress");
     {
-        dim3 block(64, 4), grid(div_up(max_iw, 64), div_up(max_ih, 4), (unsigned)np);
+        dim3 block(64, 4), grid(div_up(max_iw, 64), div_up(max_ih, 4), (unsigned)limit);
         IS_LAUNCH(ctx, k_apply_clears_batch, grid, block, 0, pairs_d);
     }
     if (trace)
-        for (size_t k = 0; k < np; ++k)
+        for (size_t k = 0; k < limit; ++k)
             for (auto& J : jobs) {
                 if ((size_t)J.pair != k || J.trace.empty()) continue;
                 const size_t len = J.trace.size();
@@ -1148,6 +1233,6 @@ static int seam_find_batched(is_ctx* ctx, const std::vector<std::pair<int, int>>
     if (tm.on) cudaStreamSynchronize(ctx->stream);
     tm.lap("G apply");
     (void)n;
-    *accepted = true;
+    *accepted_n = limit;
     return IS_OK;
 }

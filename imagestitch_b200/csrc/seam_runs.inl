@@ -119,6 +119,9 @@ int PairRuns::label_at(int x, int y) const {
 
 // [SEAM]:196-308 in run-length form
 void PairRuns::build() {
+    const bool tim = getenv("IS_DEBUG_PLAN_TIMING") != nullptr;
+    auto T0 = std::chrono::steady_clock::now();
+    auto lapt = [&](const char* w) { if (!tim) return; auto n = std::chrono::steady_clock::now(); fprintf(stderr, "   [build] %-16s %.3f ms\n", w, std::chrono::duration<double, std::milli>(n - T0).count()); T0 = n; };
     const int ox[2] = {o1x, o2x}, oy[2] = {o1y, o2y};
     row_off.assign((size_t)uh + 1, 0);
     cps.clear();
@@ -145,6 +148,7 @@ void PairRuns::build() {
         if (emitted > ROW_CAP) too_many_runs = true;
         row_off[(size_t)y + 1] = row_off[(size_t)y] + emitted;
     }
+    lapt("merge");
     const int R = row_off[(size_t)uh];
     // union-find over the runs (run k = change point k with cls != 0, spanning [x, next change point or uw))
     std::vector<int> uf((size_t)std::max(R, 1));
@@ -162,6 +166,7 @@ void PairRuns::build() {
             if (ax1 <= bx1) ++a; else ++b;
         }
     }
+    lapt("union-find");
     cp_label.assign((size_t)std::max(R, 1), 0);
     std::vector<int> id_of_root((size_t)std::max(R, 1), 0);
     ncomps = 0;
@@ -172,6 +177,7 @@ void PairRuns::build() {
         states.push_back(cps[(size_t)k].cls == 3 ? ST_INTERS : (cps[(size_t)k].cls == 1 ? ST_FIRST : ST_SECOND));
     }
     for (int k = 0; k < R; ++k) cp_label[(size_t)k] = cps[(size_t)k].cls ? id_of_root[(size_t)find(k)] : 0;
+    lapt("labels");
     // labels are materialised on the device only where they are read: the intersection rectangle grown by one pixel
     wx = std::max(0, iTl.x - unionTl.x - 1);
     wy = std::max(0, iTl.y - unionTl.y - 1);
@@ -190,11 +196,14 @@ void PairRuns::build() {
         std::copy(cps.begin() + row_off[(size_t)y], cps.begin() + row_off[(size_t)y + 1], t_cps + r * wcap);
         std::copy(cp_label.begin() + row_off[(size_t)y], cp_label.begin() + row_off[(size_t)y + 1], t_lab + r * wcap);
     }
+    lapt("tab");
     tls.assign((size_t)ncomps, Pt{INT_MAX, INT_MAX});
     brs.assign((size_t)ncomps, Pt{INT_MIN, INT_MIN});
     contours.assign((size_t)ncomps, std::vector<ContourRec>());
     contour_rows();
+    lapt("contours");
     find_edges();
+    lapt("edges");
 }
 
 // Raster-ordered contour records of the INTERS components: a pixel of an INTERS run is a contour pixel when one of its
@@ -230,6 +239,7 @@ void PairRuns::contour_rows() {
             row_segs(y - 1, a, b, up);
             row_segs(y + 1, a, b, dn);
             std::vector<ContourRec>& out = contours[(size_t)l - 1];
+            if (out.capacity() == 0) out.reserve(4 * (size_t)((iBr.x - iTl.x) + (iBr.y - iTl.y)) + 64);
             Pt& tl = tls[(size_t)l - 1];
             Pt& br = brs[(size_t)l - 1];
             size_t iu = 0, id = 0;
@@ -266,18 +276,22 @@ void PairRuns::contour_rows() {
 // [SEAM]:311-392 (edges whose first component is INTERS, both directions; the only ones the conflict loop reads)
 void PairRuns::find_edges() {
     edges.clear();
+    std::vector<char> seen((size_t)ncomps + 1, 0);
+    std::vector<int> touched;
     for (int ci = 0; ci < ncomps; ++ci) {
-        int last = -1;
+        if (contours[(size_t)ci].empty()) continue;
         const int l = ci + 1;
+        touched.clear();
         for (const ContourRec& r : contours[(size_t)ci])
             for (int k = 0; k < 4; ++k) {
                 const int nl = r.nl[k];
-                if (nl > 0 && nl != l && nl != last) {
-                    edges.insert({ci, nl - 1});
-                    edges.insert({nl - 1, ci});
-                    last = nl;
-                }
+                if (nl > 0 && nl != l && !seen[(size_t)nl]) { seen[(size_t)nl] = 1; touched.push_back(nl); }
             }
+        for (int nl : touched) {
+            edges.insert({ci, nl - 1});
+            edges.insert({nl - 1, ci});
+            seen[(size_t)nl] = 0;
+        }
     }
 }
 

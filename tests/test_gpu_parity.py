@@ -119,8 +119,10 @@ def test_dp_seam_edge_cases(ctx, oracle):
     got = f.find([a, a], [(0, 0), (20, 7)], [x.copy() for x in m])
     _eq(got[0], want[0], "flat 0")
     _eq(got[1], want[1], "flat 1")
-    with pytest.raises(Exception):
-        S.DpSeamFinder(ctx, "COLOR_GRAD").find([a, a], [(0, 0), (20, 7)], [x.copy() for x in m])
+    want = O.dp_seam_find([a, a], [(0, 0), (20, 7)], m, cost_fn=O.COST_COLOR_GRAD)
+    got = S.DpSeamFinder(ctx, "COLOR_GRAD").find([a, a], [(0, 0), (20, 7)], [x.copy() for x in m])
+    _eq(got[0], want[0], "flat 0 (COLOR_GRAD)")
+    _eq(got[1], want[1], "flat 1 (COLOR_GRAD)")
 
 
 def test_seam_cost_maps(ctx, oracle):
