@@ -87,6 +87,8 @@ SYMBOLS = {
     "is_seam_dp_find_trace": (C.c_int, [C.c_void_p, C.c_int, _P(Mat), _P(Point), _P(Mat), C.c_int, _P(C.c_int32), C.c_size_t, _P(C.c_size_t)]),
     "is_ctx_seam_speculation": (C.c_int, [C.c_void_p]),
     "is_ctx_seam_path": (C.c_int, [C.c_void_p]),
+    "is_debug_seam_pair_finish": (C.c_int, [C.c_void_p, C.c_int, C.c_int, C.c_size_t, C.c_int, C.c_int, C.c_void_p, C.c_int, C.c_int, C.c_size_t, C.c_int, C.c_int,
+                                            _P(C.c_int32), C.c_size_t]),
     "is_debug_dp_bench": (C.c_int, [C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_int, C.c_uint, C.c_int, _P(C.c_int32), _P(C.c_float)]),
     "is_debug_seam_pair_plan": (C.c_int, [C.c_void_p, C.c_int, C.c_int, C.c_size_t, C.c_int, C.c_int, C.c_void_p, C.c_int, C.c_int, C.c_size_t, C.c_int, C.c_int,
                                           _P(C.c_int32), C.c_size_t, _P(C.c_size_t)]),

@@ -2272,6 +2272,94 @@ int is_debug_seam_pair_plan(const uint8_t* mask1, int rows1, int cols1, size_t s
     return IS_OK;
 }
 
+// Host-only diagnostic: finishes ONE pair on the CPU with the batched path's host code, given the seams (as the oracle / the
+// reference trace them): plan -> run-domain updateLabelsUsingSeam (UlsRuns) -> clear intervals -> masks.  seams: for every
+// kind-1 operation of the plan, in order, [npts, x0, y0, x1, y1, ...] in panorama coordinates ordered tip 1 -> tip 2
+// (npts = 0: estimateSeam failed).  mask1 / mask2 are updated in place.  Returns IS_ERR_UNSUPPORTED when the plan does not
+// cover the pair.
+int is_debug_seam_pair_finish(uint8_t* mask1, int rows1, int cols1, size_t step1, int tl1x, int tl1y, uint8_t* mask2, int rows2, int cols2,
+                              size_t step2, int tl2x, int tl2y, const int32_t* seams, size_t seams_len) {
+    if (!mask1 || !mask2) return IS_ERR_BAD_ARG;
+    MaskRuns r1, r2;
+    mask_runs_from_host(mask1, step1, rows1, cols1, &r1);
+    mask_runs_from_host(mask2, step2, rows2, cols2, &r2);
+    PairRuns P;
+    P.setup(0, 1, Pt{tl1x, tl1y}, Pt{tl2x, tl2y}, &r1, &r2);
+    if (!(P.iTl.x < P.iBr.x && P.iTl.y < P.iBr.y)) return IS_OK;
+    {
+        auto at = [&](int k, int x, int y) { return k == 0 ? r1.inside(x - P.o1x, y - P.o1y) : r2.inside(x - P.o2x, y - P.o2y); };
+        auto contour = [&](int k, int x, int y) { return at(k, x, y) && !(at(k, x - 1, y) && at(k, x + 1, y) && at(k, x, y - 1) && at(k, x, y + 1)); };
+        auto close_to = [&](int k, int x, int y) {
+            for (int dy = -2; dy <= 2; ++dy)
+                for (int dx = -2; dx <= 2; ++dx) {
+                    const int xx = x + dx, yy = y + dy;
+                    if (xx >= 0 && xx < P.uw && yy >= 0 && yy < P.uh && contour(k, xx, yy)) return true;
+                }
+            return false;
+        };
+        for (int y = P.iTl.y - P.unionTl.y; y < P.iBr.y - P.unionTl.y; ++y)
+            for (int x = P.iTl.x - P.unionTl.x; x < P.iBr.x - P.unionTl.x; ++x) {
+                if (!at(0, x, y) || !at(1, x, y)) continue;
+                const int nx[4] = {x - 1, x, x + 1, x}, ny[4] = {y, y - 1, y, y + 1};
+                bool touches = false;
+                for (int k = 0; k < 4; ++k) touches = touches || (at(0, nx[k], ny[k]) != at(1, nx[k], ny[k]));
+                if (touches && close_to(0, x, y) && close_to(1, x, y)) P.specials.push_back(Pt{x, y});
+            }
+    }
+    P.build();
+    if (P.too_many_runs) return IS_ERR_UNSUPPORTED;
+    P.plan();
+    if (P.unsupported) return IS_ERR_UNSUPPORTED;
+    std::vector<UlsRuns> uls;
+    uls.reserve(P.ops.size());
+    std::vector<std::vector<int>> lanes;
+    lanes.reserve(P.ops.size());
+    std::vector<const std::vector<Interval>*> flips;
+    size_t pos = 0;
+    for (const SeamOp& op : P.ops) {
+        if (op.kind != 1) continue;
+        if (pos >= seams_len) return IS_ERR_BAD_ARG;
+        const int npts = seams[pos++];
+        if (npts == 0) { flips.push_back(nullptr); continue; }
+        if (pos + 2 * (size_t)npts > seams_len) return IS_ERR_BAD_ARG;
+        Pt src{op.p1.x - op.rx, op.p1.y - op.ry}, dst{op.p2.x - op.rx, op.p2.y - op.ry};
+        const bool horizontal = std::abs(dst.x - src.x) > std::abs(dst.y - src.y);
+        bool swapped = false;
+        if (horizontal) { if (src.x > dst.x) { std::swap(src, dst); swapped = true; } }
+        else if (src.y > dst.y) { std::swap(src, dst); swapped = true; }
+        const int s0 = horizontal ? src.x : src.y, s1 = horizontal ? dst.x : dst.y;
+        if (npts != s1 - s0 + 1) return IS_ERR_BAD_ARG;
+        lanes.emplace_back((size_t)npts);
+        for (int i = 0; i < npts; ++i) {
+            const int k = swapped ? npts - 1 - i : i;                          // trace order tip 1 -> tip 2; steps ascend from the (swapped) source
+            const int x = seams[pos + 2 * (size_t)k] - P.unionTl.x - op.rx, y = seams[pos + 2 * (size_t)k + 1] - P.unionTl.y - op.ry;
+            lanes.back()[(size_t)i] = horizontal ? y : x;
+            if ((horizontal ? x : y) != s0 + i) return IS_ERR_BAD_ARG;
+        }
+        pos += 2 * (size_t)npts;
+        uls.emplace_back();
+        UlsRuns& U = uls.back();
+        U.P = &P; U.op = op; U.horizontal = horizontal; U.s0 = s0; U.nseam = npts; U.lane = lanes.back().data();
+        auto t0 = std::chrono::steady_clock::now();
+        U.run();
+        if (getenv("IS_DEBUG_PLAN_TIMING")) fprintf(stderr, "[finish timing] UlsRuns::run %.3f ms (nc=%zu, nseam=%d, flips=%zu)\n",
+                                                    std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - t0).count(), P.contours[(size_t)op.c1].size(), npts, U.flips.size());
+        if (U.too_many_regions) return IS_ERR_UNSUPPORTED;
+        flips.push_back(&U.flips);
+    }
+    std::vector<ClearIv> clears;
+    auto t1 = std::chrono::steady_clock::now();
+    pair_clear_intervals(P, flips, &clears);
+    if (getenv("IS_DEBUG_PLAN_TIMING")) fprintf(stderr, "[finish timing] pair_clear_intervals %.3f ms (%zu intervals)\n",
+                                                std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - t1).count(), clears.size());
+    for (const ClearIv& c : clears)
+        for (int x = c.x0; x < c.x1; ++x) {
+            if (c.bits & 1) mask1[(size_t)(c.y - P.o1y) * step1 + (x - P.o1x)] = 0;
+            if (c.bits & 2) mask2[(size_t)(c.y - P.o2y) * step2 + (x - P.o2x)] = 0;
+        }
+    return IS_OK;
+}
+
 // Diagnostic / tuning entry: `njobs` synthetic seams of lanes x steps through the DP kernels of formulation `variant`
 // (0: barrier per step + in-kernel back-track, 1: halo windows + parallel back-track), `iters` timed launches.
 // seam_out[njobs][steps] receives the seam lanes, ms[0] = mean milliseconds per launch group (CUDA events).

@@ -1,17 +1,18 @@
-// seam_batch.inl -- the batched seam path: ALL image pairs of a call go through each kernel in one launch, the host is
-// consulted three times per call instead of ~15 times per pair.  (included by seam.cu inside namespace is)
+// seam_batch.inl -- the batched seam path: ALL image pairs of a call go through each kernel in one launch, and everything the
+// reference derives from masks and labels is done in the RUN domain on the host (seam_runs.inl); the device keeps what is
+// per-pixel arithmetic: cost maps and the DP.  (included by seam.cu inside namespace is)
 //
 //   A  device  k_row_toggles_batch (every mask -> per-row toggle positions), k_special_points_batch (per pair: the handful of
-//              pixels that can become seam tips)                                            -> one download
+//              pixels that can become seam tips)                                            -> one download (~1 MB)
 //      host    PairRuns::build / plan per pair (thread pool): components, contours, edges, conflict loop -> operations
-//   C  device  k_label_window_batch, k_relabel_batch, k_cost_pq_batch, k_seam_dp_batch (one CTA per seam), the device part of
-//              updateLabelsUsingSeam (class, paint, flood fill as CCL, neighbourhood gathers)  -> one download
-//      host    the order-dependent walk + adjacency vote of updateLabelsUsingSeam per seam (thread pool)
-//   E  device  k_uls_apply_batch, k_scatter_label_batch, k_pair_clears_batch (each pair's mask clears as bits, private)
+//   C  device  k_label_window_batch (labels of the overlap for the cost kernel), k_cost_pq_batch, DP forward + back-track (one
+//              CTA per seam)                                                                  -> one download (the seam lanes)
+//      host    UlsRuns per seam (thread pool): updateLabelsUsingSeam on runs -> the pixels that change sides;
+//              pair_clear_intervals per pair: the final mask update as clear intervals per row -> one upload
 //   F  device  toggles + special points of the masks every pair WOULD have seen in the reference's sequential loop (entry
-//              masks minus the clears of the earlier pairs)                                   -> one download
+//              masks minus the clear intervals of the earlier pairs)                          -> one download
 //      host    PairRuns of those masks; identical structure and plan <=> the speculative result is the sequential loop's
-//   G  device  k_apply_clears_batch: the clears go into the real masks
+//   G  device  k_apply_clear_runs_batch: the clear intervals go into the real masks
 // Every pair of a wave starts from the same masks; the longest prefix (in the reference's order) proven independent of the
 // earlier pairs' clears is accepted, the rest forms the next wave (a strip needs one wave, a mosaic whose images overlap
 // mutually a few).  A pair the plan cannot cover (noisy masks, a component cut twice) takes the general path (PairSeam) alone.
@@ -20,7 +21,14 @@ constexpr int TG_CAP = 8;              // toggles per mask row the batched path 
 constexpr int MAX_LAYERS = 8;          // earlier pairs whose clears a validation mask can carry
 constexpr int SPECIAL_CAP = 512;       // candidate seam tips per pair (a panorama pair has a few dozen; more -> general path)
 
-struct ClearLayer { const uint8_t* p; int pitch; int x0, y0, w, h; int bit; };   // rectangle in the mask's own coordinates
+// clear intervals of one pair over the rows of its intersection rectangle: ivs[row_start[r] .. row_start[r + 1]) = (x0, x1, bits, -)
+// in the pair's FRAME coordinates, row r = frame y - iy; bits: 1 = the first image's mask loses the pixels, 2 = the second's
+struct ClearLayer {
+    const int* row_start; const int4* ivs;
+    int dx, dy;                        // mask coordinates = frame coordinates + (dx, dy)
+    int iy, ih;
+    int bit;
+};
 
 struct LayeredMask {                   // a mask minus the clears of some pairs
     const uint8_t* p; size_t step; int rows, cols;
@@ -31,8 +39,12 @@ struct LayeredMask {                   // a mask minus the clears of some pairs
 __device__ __forceinline__ bool lm_cleared(const LayeredMask& m, int x, int y) {
     for (int k = 0; k < m.nlayers; ++k) {
         const ClearLayer& L = m.layer[k];
-        const int lx = x - L.x0, ly = y - L.y0;
-        if ((unsigned)lx < (unsigned)L.w && (unsigned)ly < (unsigned)L.h && (L.p[(size_t)ly * L.pitch + lx] & L.bit)) return true;
+        const int r = y - L.dy - L.iy, fx = x - L.dx;
+        if ((unsigned)r >= (unsigned)L.ih) continue;
+        for (int q = L.row_start[r]; q < L.row_start[r + 1]; ++q) {
+            const int4 iv = L.ivs[q];
+            if (fx >= iv.x && fx < iv.y && (iv.z & L.bit)) return true;
+        }
     }
     return false;
 }
@@ -46,8 +58,8 @@ __device__ __forceinline__ bool lm_at(const LayeredMask& m, int x, int y) {     
 struct ToggleJob { LayeredMask m; unsigned char* counts; unsigned short* xs; };   // counts[rows], xs[rows][TG_CAP]
 
 // One warp per mask row (blockIdx.y = job): the x positions where (mask != 0) toggles, in increasing x; the state left of
-// x = 0 is "outside".  16 pixels per lane and trip.  Rows with more than TG_CAP toggles set *overflow.
-__global__ void __launch_bounds__(256) k_row_toggles_batch(const ToggleJob* __restrict__ jobs, int* __restrict__ overflow) {   // overflow[job]
+// x = 0 is "outside".  16 pixels per lane and trip.  Rows with more than TG_CAP toggles set overflow[job].
+__global__ void __launch_bounds__(256) k_row_toggles_batch(const ToggleJob* __restrict__ jobs, int* __restrict__ overflow) {
     const ToggleJob& J = jobs[blockIdx.y];
     const int rows = J.m.rows, cols = J.m.cols;
     const int y = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
@@ -73,9 +85,18 @@ __global__ void __launch_bounds__(256) k_row_toggles_batch(const ToggleJob* __re
             for (int i = 0; i < 16; ++i)
                 if (x0 + i < cols && row[x0 + i]) bits |= 1u << i;
         }
-        if (J.m.nlayers && bits) {                       // validation masks: drop the pixels an earlier pair has cleared
-            for (int i = 0; i < 16; ++i)
-                if ((bits >> i & 1u) && lm_cleared(J.m, x0 + i, y)) bits &= ~(1u << i);
+        if (J.m.nlayers && bits) {                       // validation masks: drop the pixels an earlier pair has cleared (a few intervals per row)
+            for (int k = 0; k < J.m.nlayers; ++k) {
+                const ClearLayer& L = J.m.layer[k];
+                const int r = y - L.dy - L.iy;
+                if ((unsigned)r >= (unsigned)L.ih) continue;
+                for (int q = L.row_start[r]; q < L.row_start[r + 1]; ++q) {
+                    const int4 iv = L.ivs[q];
+                    if (!(iv.z & L.bit)) continue;
+                    const int a = max(iv.x + L.dx - x0, 0), b = min(iv.y + L.dx - x0, 16);   // cleared bits [a, b) of this chunk
+                    if (a < b) bits &= ~(((1u << (b - a)) - 1u) << a);
+                }
+            }
         }
         unsigned left = __shfl_up_sync(0xffffffffu, bits >> 15, 1);
         if (lane == 0) left = carry;
@@ -115,17 +136,6 @@ __device__ __forceinline__ bool sp_at(const LayeredMask& m, int ox, int oy, int 
 __device__ __forceinline__ bool sp_contour(const LayeredMask& m, int ox, int oy, int x, int y) {   // contour{1,2}mask_ [SEAM]:165-186
     return sp_at(m, ox, oy, x, y) && !(sp_at(m, ox, oy, x - 1, y) && sp_at(m, ox, oy, x + 1, y) && sp_at(m, ox, oy, x, y - 1) && sp_at(m, ox, oy, x, y + 1));
 }
-__device__ __forceinline__ bool sp_close(const LayeredMask& m, int ox, int oy, int uw, int uh, int x, int y) {   // closeToContour [SEAM]:584-604
-    for (int dy = -2; dy <= 2; ++dy) {
-        const int yy = y + dy;
-        if (yy < 0 || yy >= uh) continue;
-        for (int dx = -2; dx <= 2; ++dx) {
-            const int xx = x + dx;
-            if (xx >= 0 && xx < uw && sp_contour(m, ox, oy, xx, yy)) return true;
-        }
-    }
-    return false;
-}
 
 // bit i of the result: pixel mx0 + i (own coordinates) of mask row my is set, i < 18 -- from the row's toggles
 __device__ __forceinline__ unsigned row_bits18(const unsigned char* __restrict__ counts, const unsigned short* __restrict__ xs, int rows, int cols, int mx0, int my) {
@@ -147,37 +157,60 @@ __device__ __forceinline__ unsigned row_bits18(const unsigned char* __restrict__
 // The scan works on the row toggles k_row_toggles_batch has just produced (16 pixels of a row per step as bit sets: two
 // 16-byte loads per row instead of ten byte loads per pixel); only the few candidates look at the mask bytes themselves.
 constexpr int SP_ROWS = 8;             // rows per thread
+constexpr int SP_QUEUE = 4096;         // candidates a block can hold (8 rows x 128 chunks of 16 pixels could make 16384: beyond the queue the pair overflows)
 __global__ void __launch_bounds__(128) k_special_points_batch(const SpecialJob* __restrict__ jobs) {
+    __shared__ int2 queue[SP_QUEUE];
+    __shared__ int qn;
     const SpecialJob& J = jobs[blockIdx.z];
+    if (threadIdx.x == 0) qn = 0;
+    __syncthreads();
     const int cx = blockIdx.x * blockDim.x + threadIdx.x;
     const int ly0 = blockIdx.y * SP_ROWS;
-    if (16 * cx >= J.iw || ly0 >= J.ih) return;
-    const int x0 = J.ix + 16 * cx;                                               // frame column of bit 1
-    const int m1x = x0 - 1 - J.o1x, m2x = x0 - 1 - J.o2x;
-    auto bits = [&](int y, unsigned* b1, unsigned* b2) {                         // frame row y
-        *b1 = row_bits18(J.cnt1, J.xs1, J.m1.rows, J.m1.cols, m1x, y - J.o1y);
-        *b2 = row_bits18(J.cnt2, J.xs2, J.m2.rows, J.m2.cols, m2x, y - J.o2y);
-    };
-    unsigned p1, p2, c1, c2, n1, n2;
-    bits(J.iy + ly0 - 1, &p1, &p2);
-    bits(J.iy + ly0, &c1, &c2);
-    const int rows = min(SP_ROWS, J.ih - ly0);
-    for (int r = 0; r < rows; ++r) {
-        const int y = J.iy + ly0 + r;
-        bits(y + 1, &n1, &n2);
-        const unsigned both = c1 & c2, x_cur = c1 ^ c2, x_up = p1 ^ p2, x_dn = n1 ^ n2;
-        unsigned cand = both & ((x_cur << 1) | (x_cur >> 1) | x_up | x_dn) & 0x1fffeu;   // bits 1..16: this chunk's pixels
-        while (cand) {
-            const int i = __ffs(cand) - 1;
-            cand &= cand - 1;
-            const int x = x0 - 1 + i;
-            if (x >= J.ix + J.iw) break;
-            if (sp_close(J.m1, J.o1x, J.o1y, J.uw, J.uh, x, y) && sp_close(J.m2, J.o2x, J.o2y, J.uw, J.uh, x, y)) {
-                const int pos = atomicAdd(J.count, 1);
-                if (pos < SPECIAL_CAP) J.out[pos] = make_int2(x, y);
+    if (ly0 >= J.ih) return;                                                     // uniform over the block
+    if (16 * cx < J.iw) {
+        const int x0 = J.ix + 16 * cx;                                           // frame column of bit 1
+        const int m1x = x0 - 1 - J.o1x, m2x = x0 - 1 - J.o2x;
+        auto bits = [&](int y, unsigned* b1, unsigned* b2) {                     // frame row y
+            *b1 = row_bits18(J.cnt1, J.xs1, J.m1.rows, J.m1.cols, m1x, y - J.o1y);
+            *b2 = row_bits18(J.cnt2, J.xs2, J.m2.rows, J.m2.cols, m2x, y - J.o2y);
+        };
+        unsigned p1, p2, c1, c2, n1, n2;
+        bits(J.iy + ly0 - 1, &p1, &p2);
+        bits(J.iy + ly0, &c1, &c2);
+        const int rows = min(SP_ROWS, J.ih - ly0);
+        for (int r = 0; r < rows; ++r) {
+            const int y = J.iy + ly0 + r;
+            bits(y + 1, &n1, &n2);
+            const unsigned both = c1 & c2, x_cur = c1 ^ c2, x_up = p1 ^ p2, x_dn = n1 ^ n2;
+            unsigned cand = both & ((x_cur << 1) | (x_cur >> 1) | x_up | x_dn) & 0x1fffeu;   // bits 1..16: this chunk's pixels
+            if (cand) {
+                const int base = atomicAdd(&qn, __popc(cand));
+                int k = base;
+                while (cand) {
+                    const int i = __ffs(cand) - 1;
+                    cand &= cand - 1;
+                    if (k < SP_QUEUE) queue[k] = make_int2(x0 - 1 + i, y);
+                    ++k;
+                }
             }
+            p1 = c1; p2 = c2; c1 = n1; c2 = n2;
         }
-        p1 = c1; p2 = c2; c1 = n1; c2 = n2;
+    }
+    __syncthreads();
+    const int n = qn;
+    if (n > SP_QUEUE) { if (threadIdx.x == 0) atomicAdd(J.count, SPECIAL_CAP + 1); return; }   // overflow: the pair takes the general path
+    // closeToContour of both masks for every candidate: one warp per candidate, one window position per lane
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nw = blockDim.x >> 5;
+    for (int q = warp; q < n; q += nw) {
+        const int2 c = queue[q];
+        const int x = c.x + (lane % 5) - 2, y = c.y + (lane / 5) - 2;
+        const bool in = lane < 25 && x >= 0 && x < J.uw && y >= 0 && y < J.uh;
+        const unsigned b1 = __ballot_sync(0xffffffffu, in && sp_contour(J.m1, J.o1x, J.o1y, x, y));
+        const unsigned b2 = __ballot_sync(0xffffffffu, in && sp_contour(J.m2, J.o2x, J.o2y, x, y));
+        if (lane == 0 && b1 && b2 && c.x < J.ix + J.iw) {
+            const int pos = atomicAdd(J.count, 1);
+            if (pos < SPECIAL_CAP) J.out[pos] = c;
+        }
     }
 }
 
@@ -187,26 +220,23 @@ struct PairDev {
     int* labels;
     const int* tab_cnt; const ChangePt* tab_cps; const int* tab_lab; int wcap;   // biased by the window's first row (k_label_window)
     const void* img1; const void* img2; size_t step1, step2; int rows1, cols1, rows2, cols2; int dx1, dy1, dx2, dy2;
-    uint8_t* clear; int cpitch; int ix, iy, iw, ih;     // clear bits over the intersection rectangle: 1 = first mask, 2 = second mask
-    const int* states;                 // final states of the components
-    uint8_t* mask1; size_t mstep1; uint8_t* mask2; size_t mstep2;   // the real masks (written by k_apply_clears_batch only)
     GradView g;
 };
 
 struct JobDev {
     int pair;
-    int l1, l2;
+    int l1;
     int rx, ry, rw, rh;
     int horizontal, lanes, steps, pitch;
     float* P; float* Q;
-    int s0, s1;
-    int* res;                          // [0] destination reached, [1] interior components, [2 .. 2 + nseam) seam lanes, gathers of the contour (8 nc), of the seam (3 nseam)
-    uint8_t* klass; int* sub_parent;
-    const int2* cpts; int nc;
 };
 
-struct JobDevE { const int* adj_roots; int nadj; const int2* flips; int nflips; };
-struct RelabelDev { int pair, x0, y0, w, h, from, to; };
+struct ClearTabDev {                   // the clear intervals of a pair and the two masks they go into
+    const int* row_start; const int4* ivs;
+    int iy, ih;
+    uint8_t* mask1; size_t mstep1; int o1x, o1y;
+    uint8_t* mask2; size_t mstep2; int o2x, o2y;
+};
 
 __global__ void k_label_window_batch(const PairDev* __restrict__ pairs) {
     const PairDev& D = pairs[blockIdx.z];
@@ -220,16 +250,6 @@ __global__ void k_label_window_batch(const PairDev* __restrict__ pairs) {
         if (D.tab_cps[mid].x <= x) { best = mid; lo = mid + 1; } else hi = mid - 1;
     }
     D.labels[lidx(f, x, y)] = best >= 0 ? D.tab_lab[best] : 0;
-}
-
-__global__ void k_relabel_batch(const PairDev* __restrict__ pairs, const RelabelDev* __restrict__ ops) {
-    const RelabelDev R = ops[blockIdx.z];
-    const PairDev& D = pairs[R.pair];
-    const int x = blockIdx.x * blockDim.x + threadIdx.x;
-    const int y = blockIdx.y * blockDim.y + threadIdx.y;
-    if (x >= R.w || y >= R.h) return;
-    int* p = D.labels + lidx(D.fr, R.x0 + x, R.y0 + y);
-    if (*p == R.from) *p = R.to;
 }
 
 template <typename T, bool GRAD>
@@ -257,188 +277,28 @@ __global__ void k_cost_pq_batch(const PairDev* __restrict__ pairs, const JobDev*
     Q[(size_t)step * J.pitch + lane] = q;
 }
 
-// ---- updateLabelsUsingSeam, device part, all seams at once (same arithmetic as the k_uls_* kernels) -----------------------
-__global__ void k_uls_class_batch(const PairDev* __restrict__ pairs, const JobDev* __restrict__ jobs) {
-    const JobDev& J = jobs[blockIdx.z];
-    if (!J.res[0]) return;                                                       // estimateSeam failed: nothing to update
-    const PairDev& D = pairs[J.pair];
-    const int x = blockIdx.x * blockDim.x + threadIdx.x;
-    const int y = blockIdx.y * blockDim.y + threadIdx.y;
-    if (x >= J.rw || y >= J.rh) return;
-    const int ux = J.rx + x, uy = J.ry + y;
-    int k = 0;
-    if (lab(D.labels, D.fr, ux, uy) == J.l1) k = is_contour(D.labels, D.fr, ux, uy, J.l1) ? 2 : 1;
-    J.klass[(size_t)y * J.rw + x] = (uint8_t)k;
-}
-
-__global__ void k_uls_paint_seam_batch(const JobDev* __restrict__ jobs) {
-    const JobDev& J = jobs[blockIdx.y];
-    if (!J.res[0]) return;
-    const int i = blockIdx.x * blockDim.x + threadIdx.x;
-    if (i > J.s1 - J.s0) return;
-    const int step = J.s0 + i, lane = J.res[2 + i];
-    const int x = J.horizontal ? step : lane, y = J.horizontal ? lane : step;
-    J.klass[(size_t)y * J.rw + x] = 2;
-}
-
-__global__ void k_ccl_rows_batch(const JobDev* __restrict__ jobs) {   // k_ccl_rows, kmask 3
-    const JobDev& J = jobs[blockIdx.y];
-    if (!J.res[0]) return;
-    const int y = blockIdx.x, w = J.rw;
-    if (y >= J.rh) return;
-    const uint8_t* row = J.klass + (size_t)y * w;
-    int* prow = J.sub_parent + (size_t)y * w;
-    __shared__ int warp_max[32];
-    __shared__ int carry_s;
-    if (threadIdx.x == 0) carry_s = 0;
-    __syncthreads();
-    const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5, nw = blockDim.x >> 5;
-    for (int base = 0; base < w; base += blockDim.x) {
-        const int x = base + threadIdx.x;
-        int k = 0, start = -1;
-        if (x < w) {
-            k = row[x] & 3;
-            const int kprev = x > 0 ? (row[x - 1] & 3) : -1;
-            if (k != kprev) start = x;
-        }
-        int v = start;
+// the final mask update: one warp per row of a pair's intersection rectangle writes zeros over its clear intervals
+__global__ void __launch_bounds__(256) k_apply_clear_runs_batch(const ClearTabDev* __restrict__ tabs) {
+    const ClearTabDev& T = tabs[blockIdx.y];
+    const int r = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+    if (r >= T.ih) return;
+    const int lane = threadIdx.x & 31;
+    const int y = T.iy + r;
+    for (int q = T.row_start[r]; q < T.row_start[r + 1]; ++q) {
+        const int4 iv = T.ivs[q];
 #pragma unroll
-        for (int o = 1; o < 32; o <<= 1) {
-            const int t = __shfl_up_sync(0xffffffffu, v, o);
-            if (lane >= o) v = max(v, t);
+        for (int bit = 1; bit <= 2; ++bit) {
+            if (!(iv.z & bit)) continue;
+            uint8_t* m = bit == 1 ? T.mask1 + (size_t)(y - T.o1y) * T.mstep1 - T.o1x : T.mask2 + (size_t)(y - T.o2y) * T.mstep2 - T.o2x;   // indexed by frame x
+            // byte stores up to a 4-byte boundary, then words, then the tail
+            const int body = min(iv.y, (int)(iv.x + ((4 - (int)((uintptr_t)(m + iv.x) & 3)) & 3)));
+            if (iv.x + lane < body) m[iv.x + lane] = 0;
+            const int nwords = (iv.y - body) >> 2;
+            uint32_t* w = reinterpret_cast<uint32_t*>(m + body);
+            for (int k = lane; k < nwords; k += 32) w[k] = 0u;
+            for (int x = body + 4 * nwords + lane; x < iv.y; x += 32) m[x] = 0;
         }
-        if (lane == 31) warp_max[wid] = v;
-        __syncthreads();
-        if (wid == 0) {
-            int t = lane < nw ? warp_max[lane] : -1;
-#pragma unroll
-            for (int o = 1; o < 32; o <<= 1) {
-                const int u = __shfl_up_sync(0xffffffffu, t, o);
-                if (lane >= o) t = max(t, u);
-            }
-            warp_max[lane] = t;
-        }
-        __syncthreads();
-        const int prefix = wid > 0 ? warp_max[wid - 1] : -1;
-        v = max(max(v, prefix), carry_s);
-        if (x < w) prow[x] = k ? y * w + v : -1;
-        __syncthreads();
-        if (threadIdx.x == blockDim.x - 1) carry_s = v;
-        __syncthreads();
     }
-}
-
-__global__ void k_ccl_merge_batch(const JobDev* __restrict__ jobs) {
-    const JobDev& J = jobs[blockIdx.z];
-    if (!J.res[0]) return;
-    const int w = J.rw, h = J.rh;
-    const int x = blockIdx.x * blockDim.x + threadIdx.x;
-    const int y = blockIdx.y * blockDim.y + threadIdx.y + 1;
-    if (x >= w || y >= h) return;
-    const uint8_t* r1 = J.klass + (size_t)y * w;
-    const uint8_t* r0 = r1 - w;
-    const int k = r1[x] & 3;
-    if (!k || (r0[x] & 3) != k) return;
-    const bool start1 = x == 0 || (r1[x - 1] & 3) != k;
-    const bool start0 = x == 0 || (r0[x - 1] & 3) != k;
-    if (start1 || start0) uf_union(J.sub_parent, y * w + x, (y - 1) * w + x);
-}
-
-// flatten + count the interior components (klass 1 roots)
-__global__ void k_ccl_flatten_batch(const JobDev* __restrict__ jobs) {
-    const JobDev& J = jobs[blockIdx.y];
-    if (!J.res[0]) return;
-    const size_t n = (size_t)J.rw * J.rh;
-    const size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
-    if (i >= n) return;
-    int p = J.sub_parent[i];
-    if (p < 0) return;
-    volatile int* vp = J.sub_parent;
-    while (true) { const int q = vp[p]; if (q == p) break; p = q; }
-    J.sub_parent[i] = p;
-    if (p == (int)i && J.klass[i] == 1) atomicAdd(J.res + 1, 1);
-}
-
-// the neighbourhoods the host walk needs: 8 values per contour pixel ([SEAM]:989-990 order), then (x, y, value) per seam pixel
-__global__ void k_uls_gather_batch(const JobDev* __restrict__ jobs) {
-    const JobDev& J = jobs[blockIdx.y];
-    if (!J.res[0]) return;
-    const int i = blockIdx.x * blockDim.x + threadIdx.x;
-    const int nseam = J.s1 - J.s0 + 1;
-    int* g8 = J.res + 2 + nseam;
-    int* gs = g8 + 8 * (size_t)J.nc;
-    if (i < J.nc) {
-        const int dx[8] = {-1, +1, 0, 0, -1, +1, -1, +1};
-        const int dy[8] = {0, 0, -1, +1, -1, -1, +1, +1};
-        const int2 p = J.cpts[i];
-#pragma unroll
-        for (int j = 0; j < 8; ++j) g8[(size_t)i * 8 + j] = uls_value(J.klass, J.sub_parent, J.rw, J.rh, p.x + dx[j], p.y + dy[j]);
-    } else if (i < J.nc + nseam) {
-        const int k = i - J.nc;
-        const int step = J.s0 + k, lane = J.res[2 + k];
-        const int x = J.horizontal ? step : lane, y = J.horizontal ? lane : step;
-        gs[3 * k] = x;
-        gs[3 * k + 1] = y;
-        gs[3 * k + 2] = J.horizontal ? uls_value(J.klass, J.sub_parent, J.rw, J.rh, x, y + 1) : uls_value(J.klass, J.sub_parent, J.rw, J.rh, x + 1, y);
-    }
-}
-
-__global__ void k_uls_apply_batch(const PairDev* __restrict__ pairs, const JobDev* __restrict__ jobs, const JobDevE* __restrict__ ext) {
-    const JobDev& J = jobs[blockIdx.z];
-    const JobDevE E = ext[blockIdx.z];
-    if (!J.res[0] || E.nadj == 0) return;
-    const PairDev& D = pairs[J.pair];
-    const int x = blockIdx.x * blockDim.x + threadIdx.x;
-    const int y = blockIdx.y * blockDim.y + threadIdx.y;
-    if (x >= J.rw || y >= J.rh) return;
-    const size_t i = (size_t)y * J.rw + x;
-    if (J.klass[i] != 1) return;
-    const int r = J.sub_parent[i];
-    int lo = 0, hi = E.nadj - 1;
-    while (lo <= hi) {
-        const int mid = (lo + hi) >> 1;
-        const int v = E.adj_roots[mid];
-        if (v == r) { D.labels[lidx(D.fr, J.rx + x, J.ry + y)] = J.l2; return; }
-        if (v < r) lo = mid + 1; else hi = mid - 1;
-    }
-}
-
-__global__ void k_scatter_label_batch(const PairDev* __restrict__ pairs, const JobDev* __restrict__ jobs, const JobDevE* __restrict__ ext) {
-    const JobDev& J = jobs[blockIdx.y];
-    const JobDevE E = ext[blockIdx.y];
-    const int i = blockIdx.x * blockDim.x + threadIdx.x;
-    if (i >= E.nflips) return;
-    const PairDev& D = pairs[J.pair];
-    D.labels[lidx(D.fr, E.flips[i].x, E.flips[i].y)] = J.l2;
-}
-
-// The final mask update [SEAM]:527-545 of a pair as clear bits over its intersection rectangle: mask2 loses the pixels whose
-// label's state has FIRST where mask1 is set, then mask1 loses those whose state has SECOND where the UPDATED mask2 is set.
-__global__ void k_pair_clears_batch(const PairDev* __restrict__ pairs) {
-    const PairDev& D = pairs[blockIdx.z];
-    const int x = blockIdx.x * blockDim.x + threadIdx.x;
-    const int y = blockIdx.y * blockDim.y + threadIdx.y;
-    if (x >= D.iw || y >= D.ih) return;
-    const int ux = D.ix + x, uy = D.iy + y;
-    const int l = lab(D.labels, D.fr, ux, uy);
-    const int st = l > 0 ? D.states[l - 1] : 0;
-    const int m1 = D.fr.m1.at(ux, uy), m2 = D.fr.m2.at(ux, uy);
-    const bool c2 = (st & ST_FIRST) && m1;
-    const int m2n = c2 ? 0 : m2;
-    const bool c1 = (st & ST_SECOND) && m2n;
-    D.clear[(size_t)y * D.cpitch + x] = (uint8_t)((c1 && m1 ? 1 : 0) | (c2 && m2 ? 2 : 0));
-}
-
-__global__ void k_apply_clears_batch(const PairDev* __restrict__ pairs) {
-    const PairDev& D = pairs[blockIdx.z];
-    const int x = blockIdx.x * blockDim.x + threadIdx.x;
-    const int y = blockIdx.y * blockDim.y + threadIdx.y;
-    if (x >= D.iw || y >= D.ih) return;
-    const int c = D.clear[(size_t)y * D.cpitch + x];
-    if (!c) return;
-    const int ux = D.ix + x, uy = D.iy + y;
-    if (c & 1) D.mask1[(size_t)(uy - D.fr.m1.oy) * D.mstep1 + (ux - D.fr.m1.ox)] = 0;
-    if (c & 2) D.mask2[(size_t)(uy - D.fr.m2.oy) * D.mstep2 + (ux - D.fr.m2.ox)] = 0;
 }
 
 // ---- DP launches ----------------------------------------------------------------------------------------------------------
@@ -552,17 +412,15 @@ struct Blob {
 };
 
 struct SeamJobHost {
-    int pair;                          // index into the active pair list
+    int pair;                          // index into the wave's pair list
     SeamOp op;
     bool horizontal = false, swapped = false;
-    int lanes = 0, steps = 0, lpt = 4, nt = 32, pitch = 128;
-    int s0 = 0, lane0 = 0, s1 = 0, lane1 = 0, nseam = 0, nc = 0;
+    int lanes = 0, steps = 0, pitch = 128;
+    int s0 = 0, lane0 = 0, s1 = 0, lane1 = 0, nseam = 0;
     DpShape shape;
-    size_t off_map = 0;
-    size_t off_P = 0, off_Q = 0, off_ctl = 0, off_klass = 0, off_parent = 0, off_res = 0;   // device arena offsets
-    size_t res_ints = 0;
-    std::vector<int> adj_roots;
-    std::vector<int2> flips;
+    size_t off_map = 0, off_P = 0, off_Q = 0, off_ctl = 0, off_res = 0;   // device arena offsets (off_res in ints)
+    UlsRuns uls;
+    bool reached = false;
     std::vector<int32_t> trace;
     int status = IS_OK;
 };
@@ -577,135 +435,30 @@ static HostPool* host_pool(is_ctx* ctx) {
     return ctx->hpool;
 }
 
-// the order-dependent part of updateLabelsUsingSeam ([SEAM]:983-1085) for one seam, from the gathered neighbourhoods
-static int uls_host_walk(is_ctx* ctx, const PairRuns& PR, SeamJobHost& J, const int* res, TraceSink* trace_on) {
+// one seam back on the host: end points, trace record, updateLabelsUsingSeam on runs.  res: [reached, -, lanes ...]
+static int seam_job_finish(is_ctx* ctx, const PairRuns& PR, SeamJobHost& J, const int* res, bool want_trace) {
     const SeamOp& op = J.op;
-    const int l1 = op.c1 + 1, l2 = op.c2 + 1;
-    const int rx = op.rx, ry = op.ry;
-    const int nseam = J.nseam, nc = J.nc;
-    J.adj_roots.clear(); J.flips.clear(); J.trace.clear();
-    if (!res[0]) return IS_OK;                                        // [SEAM]:918-919: estimateSeam returned false
-    const int nsub_total = res[1];
+    J.trace.clear();
+    J.reached = res[0] != 0;
+    if (!J.reached) return IS_OK;                                      // [SEAM]:918-919: estimateSeam returned false
     const int* lane_h = res + 2;
-    const int* g8 = res + 2 + nseam;
-    const int* gs = g8 + 8 * (size_t)nc;
-    const bool horizontal = J.horizontal, swapped = J.swapped;
-    // seam in union-frame coordinates, ordered p1 -> p2 ([SEAM]:949-954)
-    {
-        const int first = swapped ? nseam - 1 : 0, last = swapped ? 0 : nseam - 1;
-        auto pt = [&](int i) { const int step = J.s0 + i, lane = lane_h[i]; return horizontal ? Pt{step + rx, lane + ry} : Pt{lane + rx, step + ry}; };
-        const Pt a = pt(first), b = pt(last);
-        if (!(a.x == op.p1.x && a.y == op.p1.y && b.x == op.p2.x && b.y == op.p2.y))
-            return fail(ctx, IS_ERR_ASSERT, "seam end points differ from the seam tips ([SEAM]:953-954)");
-        if (trace_on) {
-            J.trace.resize(5 + 2 * (size_t)nseam);
-            int32_t* t = J.trace.data();
-            t[0] = PR.pi; t[1] = PR.pj; t[2] = op.c1; t[3] = horizontal ? 1 : 0; t[4] = nseam;
-            for (int i = 0; i < nseam; ++i) {
-                const Pt q = pt(swapped ? nseam - 1 - i : i);
-                t[5 + 2 * i] = q.x + PR.unionTl.x; t[6 + 2 * i] = q.y + PR.unionTl.y;
-            }
+    const int nseam = J.nseam;
+    auto pt = [&](int i) { const int step = J.s0 + i, lane = lane_h[i]; return J.horizontal ? Pt{step + op.rx, lane + op.ry} : Pt{lane + op.rx, step + op.ry}; };
+    const Pt a = pt(J.swapped ? nseam - 1 : 0), b = pt(J.swapped ? 0 : nseam - 1);   // ordered p1 -> p2 ([SEAM]:949-954)
+    if (!(a.x == op.p1.x && a.y == op.p1.y && b.x == op.p2.x && b.y == op.p2.y))
+        return fail(ctx, IS_ERR_ASSERT, "seam end points differ from the seam tips ([SEAM]:953-954)");
+    if (want_trace) {
+        J.trace.resize(5 + 2 * (size_t)nseam);
+        int32_t* t = J.trace.data();
+        t[0] = PR.pi; t[1] = PR.pj; t[2] = op.c1; t[3] = J.horizontal ? 1 : 0; t[4] = nseam;
+        for (int i = 0; i < nseam; ++i) {
+            const Pt q = pt(J.swapped ? nseam - 1 - i : i);
+            t[5 + 2 * i] = q.x + PR.unionTl.x; t[6 + 2 * i] = q.y + PR.unionTl.y;
         }
     }
-    if (nsub_total >= 255) return IS_ERR_UNSUPPORTED;                 // the reference's mask value 255 would collide with a component id: general path
-    // interior components are identified by their root index; ids 1.. in order of first appearance (only equality, "> 0" and
-    // "!= 255" are ever asked of them, and there are fewer than 255)
-    int roots[256];
-    int nroots = 0;
-    auto id_of = [&](int v) -> int {   // gathered value (> 0: root index + 1) -> reference mask value
-        for (int k = 0; k < nroots; ++k) if (roots[k] == v - 1) return k + 1;
-        roots[nroots] = v - 1;
-        return ++nroots;
-    };
-    const std::vector<ContourRec>& cont = PR.contours[(size_t)op.c1];
-    // The reference paints contour and seam pixels 255 and then assigns them one by one.  Contour pixels go first, in raster
-    // order: a painted neighbour counts only once it has been assigned, i.e. when it is a contour pixel EARLIER in raster order
-    // (neighbours 0, 2, 4, 5 of the reference's list: left, up, up-left, up-right); later contour pixels and all seam pixels
-    // still hold 255.  The records are raster ordered, so a neighbour is found by a search inside its row's slice.
-    const int rh = op.rh;
-    std::vector<int> row_first((size_t)rh + 1, 0);
-    for (int i = 0; i < nc; ++i) row_first[(size_t)(cont[(size_t)i].y - ry) + 1]++;
-    for (int y = 0; y < rh; ++y) row_first[(size_t)y + 1] += row_first[(size_t)y];
-    auto find_contour = [&](int x, int y) -> int {                     // index of the contour record at bbox position (x, y), -1 if none
-        if ((unsigned)y >= (unsigned)rh) return -1;
-        int lo = row_first[(size_t)y], hi = row_first[(size_t)y + 1] - 1;
-        while (lo <= hi) {
-            const int mid = (lo + hi) >> 1;
-            const int cx = cont[(size_t)mid].x - rx;
-            if (cx == x) return mid;
-            if (cx < x) lo = mid + 1; else hi = mid - 1;
-        }
-        return -1;
-    };
-    static const int ddx[8] = {-1, +1, 0, 0, -1, +1, -1, +1};
-    static const int ddy[8] = {0, 0, -1, +1, -1, -1, +1, +1};
-    std::vector<int> val((size_t)nc, 255);                             // current mask value of every contour pixel
-    for (int i = 0; i < nc; ++i) {
-        const int x = cont[(size_t)i].x - rx, y = cont[(size_t)i].y - ry;
-        int v = 0;
-        // the last neighbour (in the reference's order) with an assigned value wins: scan backwards, stop at the first hit
-        for (int j = 7; j >= 0; --j) {
-            const int g = g8[(size_t)i * 8 + j];
-            if (g > 0) { v = id_of(g); break; }                        // interior pixel of a flood-filled component
-            if (g == -255 && (j == 0 || j == 2 || j == 4 || j == 5)) { // painted, earlier in raster order: assigned if it is a contour pixel
-                const int k = find_contour(x + ddx[j], y + ddy[j]);
-                if (k >= 0 && k < i && val[(size_t)k] > 0 && val[(size_t)k] != 255) { v = val[(size_t)k]; break; }
-            }
-        }
-        val[(size_t)i] = v;
-    }
-    // then the seam pixels: each looks at one neighbour of its own step (never a seam pixel itself), so their order is irrelevant;
-    // a seam pixel that is also a contour pixel is assigned a second time
-    std::vector<int> sval((size_t)nseam, 0);
-    std::vector<int> seam_contour((size_t)nseam, -1);
-    for (int i = 0; i < nseam; ++i) {
-        const int x = gs[3 * i], y = gs[3 * i + 1], g = gs[3 * i + 2];
-        int v = 0;
-        if (g > 0) v = id_of(g);
-        else if (g == -255) {
-            const int k = horizontal ? find_contour(x, y + 1) : find_contour(x + 1, y);
-            if (k >= 0 && val[(size_t)k] > 0 && val[(size_t)k] != 255) v = val[(size_t)k];
-        }
-        sval[(size_t)i] = v;
-        seam_contour[(size_t)i] = find_contour(x, y);
-    }
-    for (int i = 0; i < nseam; ++i)
-        if (seam_contour[(size_t)i] >= 0) val[(size_t)seam_contour[(size_t)i]] = sval[(size_t)i];
-    // adjacency vote ([SEAM]:1039-1085)
-    const int nsub = nroots;
-    std::vector<int> connect2((size_t)nsub + 1, 0), connectOther((size_t)nsub + 1, 0);
-    bool c2_has0 = false, co_has0 = false;
-    for (int i = 0; i < nc; ++i) {
-        const ContourRec& r = cont[(size_t)i];
-        int mv = val[(size_t)i];
-        if (mv < 0 || mv > nsub) mv = 0;
-        if (r.nl[0] == l2 || r.nl[1] == l2 || r.nl[2] == l2 || r.nl[3] == l2) { connect2[(size_t)mv]++; if (mv == 0) c2_has0 = true; }
-        bool other = false;
-        for (int k = 0; k < 4; ++k) if (r.nl[k] >= 0 && r.nl[k] != l1 && r.nl[k] != l2) other = true;
-        if (other) { connectOther[(size_t)mv]++; if (mv == 0) co_has0 = true; }
-    }
-    std::vector<int> isAdj((size_t)nsub + 1, 0);
-    const double len = (double)nc;
-    for (int k = c2_has0 ? 0 : 1; k <= nsub; ++k) {
-        int r = 0;
-        if (connect2[(size_t)k] / len > 0.05) {
-            const bool sub_exists = k >= 1 || co_has0;
-            if (sub_exists && (connectOther[(size_t)k] / len < 0.1)) r = 1;
-        }
-        isAdj[(size_t)k] = r;
-    }
-    for (int i = 1; i <= nsub; ++i) if (isAdj[(size_t)i]) J.adj_roots.push_back(roots[i - 1]);
-    std::sort(J.adj_roots.begin(), J.adj_roots.end());
-    // painted pixels that ended up in an adjacent component are relabelled one by one ([SEAM]:1089-1092 covers them with the rest)
-    for (int i = 0; i < nc; ++i) {
-        const int v = val[(size_t)i];
-        if (v > 0 && v <= nsub && isAdj[(size_t)v]) J.flips.push_back(make_int2(cont[(size_t)i].x, cont[(size_t)i].y));
-    }
-    for (int i = 0; i < nseam; ++i) {
-        const int v = sval[(size_t)i];
-        if (seam_contour[(size_t)i] < 0 && v > 0 && v <= nsub && isAdj[(size_t)v]) J.flips.push_back(make_int2(gs[3 * i] + rx, gs[3 * i + 1] + ry));
-    }
-    return IS_OK;
+    J.uls.P = &PR; J.uls.op = op; J.uls.horizontal = J.horizontal; J.uls.s0 = J.s0; J.uls.nseam = nseam; J.uls.lane = lane_h;
+    J.uls.run();
+    return J.uls.too_many_regions ? IS_ERR_UNSUPPORTED : IS_OK;
 }
 
 struct BatchTimer {
@@ -740,9 +493,7 @@ static int run_structure_query(is_ctx* ctx, StructureQuery& Q) {
     // device layout: [hdr: overflow flags nm, special counts np][special points np x SPECIAL_CAP][counts (bytes)][xs (u16)]   tables at the end
     size_t total_rows = 0;
     int max_rows = 0;
-    for (auto& m : Q.masks) {
-        total_rows += (size_t)m.rows; max_rows = std::max(max_rows, m.rows);
-    }
+    for (auto& m : Q.masks) { total_rows += (size_t)m.rows; max_rows = std::max(max_rows, m.rows); }
     const size_t off_hdr = 0, hdr_bytes = align_up(sizeof(int) * (nm + np), 16);
     const size_t off_sp_dl = off_hdr + hdr_bytes, sp_dl_bytes = align_up(sizeof(int2) * SPECIAL_CAP * np, 16);
     const size_t off_cnt = off_sp_dl + sp_dl_bytes, cnt_bytes = align_up(total_rows, 16);
@@ -883,18 +634,12 @@ static int seam_batch_wave(is_ctx* ctx, const std::vector<std::pair<int, int>>& 
         }
     // ---- C: plan -> device tables
     std::vector<SeamJobHost> jobs;
-    std::vector<RelabelDev> pre_relabel, post_relabel;
     const int dp_variant = dp_variant_default();
-    for (size_t k = 0; k < np; ++k) {
-        std::vector<char> cut((size_t)PR[k].ncomps, 0);
+    for (size_t k = 0; k < np; ++k)
         for (const SeamOp& op : PR[k].ops) {
-            if (op.kind == 0) {
-                RelabelDev R{(int)k, op.rx, op.ry, op.rw, op.rh, op.c1 + 1, op.c2 + 1};
-                (cut[(size_t)op.c1] ? post_relabel : pre_relabel).push_back(R);
-                continue;
-            }
-            cut[(size_t)op.c1] = 1;
-            SeamJobHost J;
+            if (op.kind != 1) continue;                                // wholesale relabels never reach the device: the labels only feed the cost kernel
+            jobs.emplace_back();
+            SeamJobHost& J = jobs.back();
             J.pair = (int)k; J.op = op;
             Pt src{op.p1.x - op.rx, op.p1.y - op.ry}, dst{op.p2.x - op.rx, op.p2.y - op.ry};
             J.horizontal = std::abs(dst.x - src.x) > std::abs(dst.y - src.y);                     // [SEAM]:828
@@ -904,26 +649,21 @@ static int seam_batch_wave(is_ctx* ctx, const std::vector<std::pair<int, int>>& 
             J.s0 = J.horizontal ? src.x : src.y; J.lane0 = J.horizontal ? src.y : src.x;
             J.s1 = J.horizontal ? dst.x : dst.y; J.lane1 = J.horizontal ? dst.y : dst.x;
             dp_choose_shape(J.lanes, J.steps, J.s0, J.s1, dp_variant, &J.shape);
-            J.lpt = J.shape.lpt; J.nt = J.shape.nt; J.pitch = J.shape.pitch;
+            J.pitch = J.shape.pitch;
             IS_REQUIRE(ctx, J.pitch >= J.lanes && J.pitch <= 12 * 1024, IS_ERR_INTERNAL, "seam wider than planned");
             J.nseam = J.s1 - J.s0 + 1;
-            J.nc = (int)PR[k].contours[(size_t)op.c1].size();
-            jobs.push_back(std::move(J));
         }
-    }
     const size_t nj = jobs.size();
-    // device arena: per pair labels / clear bits, per job P, Q, control, klass, parent, results; blob 1 = tables + small inputs
+    // device arena: per pair the label window, per seam P, Q, control (+ back-track maps), results; blob 1 = tables + label tables
     size_t arena = 0;
     auto take = [&](size_t bytes) { const size_t o = arena; arena = align_up(arena + bytes, 256); return o; };
-    std::vector<size_t> off_labels(np), off_clear(np), off_grad(np, 0);
-    std::vector<int> cpitch(np), gpitch(np, 0);
+    std::vector<size_t> off_labels(np), off_grad(np, 0);
+    std::vector<int> gpitch(np, 0);
     for (size_t k = 0; k < np; ++k) {
         const PairRuns& P = PR[k];
         off_labels[k] = take(sizeof(int) * (size_t)P.ww * P.wh);
-        const int iw = P.iBr.x - P.iTl.x, ih = P.iBr.y - P.iTl.y;
-        cpitch[k] = (iw + 15) & ~15;
-        off_clear[k] = take((size_t)cpitch[k] * ih);
         if (cost_fn == IS_COST_COLOR_GRAD) {
+            const int iw = P.iBr.x - P.iTl.x, ih = P.iBr.y - P.iTl.y;
             gpitch[k] = (iw + 31) & ~31;
             off_grad[k] = take(sizeof(float) * (size_t)gpitch[k] * ih * 4);
         }
@@ -933,39 +673,19 @@ static int seam_batch_wave(is_ctx* ctx, const std::vector<std::pair<int, int>>& 
         J.off_P = take(sizeof(float) * (size_t)J.pitch * (J.steps + DP_ROW_PAD) + 64);
         J.off_Q = take(sizeof(float) * (size_t)J.pitch * (J.steps + DP_ROW_PAD) + 64);
         J.off_ctl = take((size_t)J.pitch * J.steps + 64);
-        J.off_klass = take((size_t)J.op.rw * J.op.rh);
-        J.off_parent = take(sizeof(int) * (size_t)J.op.rw * J.op.rh);
         if (J.shape.v1) J.off_map = take(sizeof(short) * (size_t)div_up(J.s1 - J.s0, BT_CHUNK) * J.pitch + 64);
-        J.res_ints = 2 + (size_t)J.nseam + 8 * (size_t)J.nc + 3 * (size_t)J.nseam;
         J.off_res = res_total_ints;
-        res_total_ints += (J.res_ints + 3) & ~(size_t)3;
+        res_total_ints += (2 + (size_t)J.nseam + 3) & ~(size_t)3;
     }
     const size_t off_res_all = take(sizeof(int) * std::max<size_t>(res_total_ints, 4));
-    // blob 1
     Blob B1;
-    std::vector<size_t> off_tab(np), off_cpts(nj);
+    std::vector<size_t> off_tab(np);
     for (size_t k = 0; k < np; ++k) off_tab[k] = B1.put(PR[k].tab.data(), sizeof(int) * PR[k].tab.size());
-    for (size_t j = 0; j < nj; ++j) {
-        const SeamJobHost& J = jobs[j];
-        const auto& cont = PR[(size_t)J.pair].contours[(size_t)J.op.c1];
-        std::vector<int2> cpts((size_t)J.nc);
-        for (int i = 0; i < J.nc; ++i) cpts[(size_t)i] = make_int2(cont[(size_t)i].x - J.op.rx, cont[(size_t)i].y - J.op.ry);
-        off_cpts[j] = B1.put(cpts.data(), sizeof(int2) * cpts.size());
-    }
     const size_t off_pairs = B1.put(nullptr, sizeof(PairDev) * np);
     const size_t off_jobs = B1.put(nullptr, sizeof(JobDev) * std::max<size_t>(nj, 1));
     const size_t off_dp = B1.put(nullptr, sizeof(DpArgs) * std::max<size_t>(nj, 1));
     const size_t off_bt = B1.put(nullptr, sizeof(BtArgs) * std::max<size_t>(nj, 1));
-    const size_t off_pre = B1.put(pre_relabel.data(), sizeof(RelabelDev) * pre_relabel.size());
     const size_t off_b1 = take(B1.host.size());
-    // blob 2 (after the host walk): states, adjacency roots, flips, post relabels -- sized now, filled later
-    size_t b2_bytes = 0;
-    std::vector<size_t> off_states(np);
-    for (size_t k = 0; k < np; ++k) { off_states[k] = b2_bytes; b2_bytes = align_up(b2_bytes + sizeof(int) * (size_t)std::max(PR[k].ncomps, 1), 16); }
-    const size_t b2_fixed = b2_bytes;
-    size_t b2_cap = b2_fixed + sizeof(JobDevE) * std::max<size_t>(nj, 1) + sizeof(RelabelDev) * post_relabel.size() + 64;
-    for (auto& J : jobs) b2_cap += sizeof(int) * 256 + sizeof(int2) * ((size_t)J.nc + (size_t)J.nseam) + 64;
-    const size_t off_b2 = take(b2_cap);
     DevBuf dev;
     IS_TRY(dev.alloc(ctx, arena));
     unsigned char* base = dev.as<unsigned char>();
@@ -1000,14 +720,10 @@ static int seam_batch_wave(is_ctx* ctx, const std::vector<std::pair<int, int>>& 
             D.img1 = i1.data; D.img2 = i2.data; D.step1 = i1.step; D.step2 = i2.step;
             D.rows1 = i1.rows; D.cols1 = i1.cols; D.rows2 = i2.rows; D.cols2 = i2.cols;
             D.dx1 = P.unionTl.x - P.tl1.x; D.dy1 = P.unionTl.y - P.tl1.y; D.dx2 = P.unionTl.x - P.tl2.x; D.dy2 = P.unionTl.y - P.tl2.y;
-            D.clear = base + off_clear[k]; D.cpitch = cpitch[k];
-            D.ix = P.iTl.x - P.unionTl.x; D.iy = P.iTl.y - P.unionTl.y; D.iw = P.iBr.x - P.iTl.x; D.ih = P.iBr.y - P.iTl.y;
-            D.states = reinterpret_cast<const int*>(base + off_b2 + off_states[k]);
-            D.mask1 = m1.ptr<uint8_t>(); D.mstep1 = m1.step; D.mask2 = m2.ptr<uint8_t>(); D.mstep2 = m2.step;
             if (cost_fn == IS_COST_COLOR_GRAD) {
                 float* g = reinterpret_cast<float*>(base + off_grad[k]);
-                const size_t plane = (size_t)gpitch[k] * D.ih;
-                D.g = GradView{g, g + plane, g + 2 * plane, g + 3 * plane, gpitch[k], D.ix, D.iy};
+                const size_t plane = (size_t)gpitch[k] * (size_t)(P.iBr.y - P.iTl.y);
+                D.g = GradView{g, g + plane, g + 2 * plane, g + 3 * plane, gpitch[k], P.iTl.x - P.unionTl.x, P.iTl.y - P.unionTl.y};
             }
         }
         JobDev* jd = reinterpret_cast<JobDev*>(B1.host.data() + off_jobs);
@@ -1017,19 +733,16 @@ static int seam_batch_wave(is_ctx* ctx, const std::vector<std::pair<int, int>>& 
             const SeamJobHost& J = jobs[order[q]];
             JobDev& D = jd[q];
             std::memset(&D, 0, sizeof(D));
-            D.pair = J.pair; D.l1 = J.op.c1 + 1; D.l2 = J.op.c2 + 1;
+            D.pair = J.pair; D.l1 = J.op.c1 + 1;
             D.rx = J.op.rx; D.ry = J.op.ry; D.rw = J.op.rw; D.rh = J.op.rh;
             D.horizontal = J.horizontal ? 1 : 0; D.lanes = J.lanes; D.steps = J.steps; D.pitch = J.pitch;
             D.P = reinterpret_cast<float*>(base + J.off_P); D.Q = reinterpret_cast<float*>(base + J.off_Q);
-            D.s0 = J.s0; D.s1 = J.s1;
-            D.res = reinterpret_cast<int*>(base + off_res_all) + J.off_res;
-            D.klass = base + J.off_klass; D.sub_parent = reinterpret_cast<int*>(base + J.off_parent);
-            D.cpts = reinterpret_cast<const int2*>(b1d + off_cpts[order[q]]); D.nc = J.nc;
+            int* res = reinterpret_cast<int*>(base + off_res_all) + J.off_res;
             DpArgs& A = da[q];
             A.P = D.P; A.Q = D.Q; A.control = base + J.off_ctl;
             A.lanes = J.lanes; A.pitch = J.pitch; A.steps = J.steps;
             A.s0 = J.s0; A.lane0 = J.lane0; A.s1 = J.s1; A.lane1 = J.lane1;
-            A.seam_lane = D.res + 2; A.reached = D.res;
+            A.seam_lane = res + 2; A.reached = res;
             A.G = J.shape.G; A.D = J.shape.D;
             ba[q].A = A;
             ba[q].map = reinterpret_cast<short*>(base + J.off_map);
@@ -1037,52 +750,45 @@ static int seam_batch_wave(is_ctx* ctx, const std::vector<std::pair<int, int>>& 
         }
     }
     IS_TRY(upload(ctx, b1d, B1.host.data(), B1.host.size()));
-    IS_CUDA(ctx, cudaMemsetAsync(base + off_res_all, 0, sizeof(int) * std::max<size_t>(res_total_ints, 4), ctx->stream));
     const PairDev* pairs_d = reinterpret_cast<const PairDev*>(b1d + off_pairs);
     const JobDev* jobs_d = reinterpret_cast<const JobDev*>(b1d + off_jobs);
     const DpArgs* dp_d = reinterpret_cast<const DpArgs*>(b1d + off_dp);
-    int max_ww = 0, max_wh = 0, max_iw = 0, max_ih = 0;
-    for (auto& P : PR) {
-        max_ww = std::max(max_ww, P.ww); max_wh = std::max(max_wh, P.wh);
-        max_iw = std::max(max_iw, P.iBr.x - P.iTl.x); max_ih = std::max(max_ih, P.iBr.y - P.iTl.y);
-    }
-    {
-        dim3 block(64, 4), grid(div_up(max_ww, 64), div_up(max_wh, 4), (unsigned)np);
-        IS_LAUNCH(ctx, k_label_window_batch, grid, block, 0, pairs_d);
-    }
-    if (!pre_relabel.empty()) {
-        int mw = 0, mh = 0;
-        for (auto& R : pre_relabel) { mw = std::max(mw, R.w); mh = std::max(mh, R.h); }
-        dim3 block(64, 4), grid(div_up(mw, 64), div_up(mh, 4), (unsigned)pre_relabel.size());
-        IS_LAUNCH(ctx, k_relabel_batch, grid, block, 0, pairs_d, reinterpret_cast<const RelabelDev*>(b1d + off_pre));
-    }
+    const int* res_h = nullptr;                                        // view of the pinned bounce buffer, valid until the next download
     if (nj) {
+        IS_CUDA(ctx, cudaMemsetAsync(base + off_res_all, 0, sizeof(int) * std::max<size_t>(res_total_ints, 4), ctx->stream));
+        // labels only where seams are estimated: the windows of the pairs that have one
+        int max_ww = 0, max_wh = 0;
+        for (auto& J : jobs) { max_ww = std::max(max_ww, PR[(size_t)J.pair].ww); max_wh = std::max(max_wh, PR[(size_t)J.pair].wh); }
+        {
+            dim3 block(64, 4), grid(div_up(max_ww, 64), div_up(max_wh, 4), (unsigned)np);
+            IS_LAUNCH(ctx, k_label_window_batch, grid, block, 0, pairs_d);
+        }
         if (cost_fn == IS_COST_COLOR_GRAD) {                                                      // computeGradients [SEAM]:549-572 over the intersection rectangles
             const PairDev* pd = reinterpret_cast<const PairDev*>(B1.host.data() + off_pairs);
             for (size_t k = 0; k < np; ++k) {
                 const PairDev& D = pd[k];
+                const PairRuns& P = PR[k];
+                const int ix = P.iTl.x - P.unionTl.x, iy = P.iTl.y - P.unionTl.y, iw = P.iBr.x - P.iTl.x, ih = P.iBr.y - P.iTl.y;
                 float* g = reinterpret_cast<float*>(base + off_grad[k]);
-                const size_t plane = (size_t)gpitch[k] * D.ih;
-                dim3 block(64, 4), grid(div_up(D.iw, 64), div_up(D.ih, 4));
+                const size_t plane = (size_t)gpitch[k] * ih;
+                dim3 block(64, 4), grid(div_up(iw, 64), div_up(ih, 4));
                 if (is_u8) {
                     IS_LAUNCH(ctx, k_sobel_window<uint8_t>, grid, block, 0, ImgView<uint8_t>{reinterpret_cast<const uint8_t*>(D.img1), D.step1, D.rows1, D.cols1, D.dx1, D.dy1},
-                              D.ix, D.iy, D.iw, D.ih, g, g + plane, gpitch[k]);
+                              ix, iy, iw, ih, g, g + plane, gpitch[k]);
                     IS_LAUNCH(ctx, k_sobel_window<uint8_t>, grid, block, 0, ImgView<uint8_t>{reinterpret_cast<const uint8_t*>(D.img2), D.step2, D.rows2, D.cols2, D.dx2, D.dy2},
-                              D.ix, D.iy, D.iw, D.ih, g + 2 * plane, g + 3 * plane, gpitch[k]);
+                              ix, iy, iw, ih, g + 2 * plane, g + 3 * plane, gpitch[k]);
                 } else {
                     IS_LAUNCH(ctx, k_sobel_window<float>, grid, block, 0, ImgView<float>{reinterpret_cast<const float*>(D.img1), D.step1, D.rows1, D.cols1, D.dx1, D.dy1},
-                              D.ix, D.iy, D.iw, D.ih, g, g + plane, gpitch[k]);
+                              ix, iy, iw, ih, g, g + plane, gpitch[k]);
                     IS_LAUNCH(ctx, k_sobel_window<float>, grid, block, 0, ImgView<float>{reinterpret_cast<const float*>(D.img2), D.step2, D.rows2, D.cols2, D.dx2, D.dy2},
-                              D.ix, D.iy, D.iw, D.ih, g + 2 * plane, g + 3 * plane, gpitch[k]);
+                              ix, iy, iw, ih, g + 2 * plane, g + 3 * plane, gpitch[k]);
                 }
             }
         }
-        int max_pitch = 0, max_steps = 0, max_rw = 0, max_rh = 0, max_items = 0, max_nseam = 0;
+        int max_pitch = 0, max_steps = 0;
         double cost_bytes = 0;
         for (auto& J : jobs) {
             max_pitch = std::max(max_pitch, J.pitch); max_steps = std::max(max_steps, J.steps);
-            max_rw = std::max(max_rw, J.op.rw); max_rh = std::max(max_rh, J.op.rh);
-            max_items = std::max(max_items, J.nc + J.nseam); max_nseam = std::max(max_nseam, J.nseam);
             cost_bytes += (double)J.lanes * J.steps * ((is_u8 ? 6 : 24) + 12 + (cost_fn == IS_COST_COLOR_GRAD ? 16 : 0));
         }
         {
@@ -1101,27 +807,13 @@ static int seam_batch_wave(is_ctx* ctx, const std::vector<std::pair<int, int>>& 
             for (size_t q = 0; q < nj; ++q) shapes[q] = jobs[order[q]].shape;
             IS_TRY(launch_dp_all(ctx, shapes, dp_d, reinterpret_cast<const BtArgs*>(b1d + off_bt)));
         }
-        {
-            dim3 block(64, 4), grid(div_up(max_rw, 64), div_up(max_rh, 4), (unsigned)nj);
-            IS_LAUNCH(ctx, k_uls_class_batch, grid, block, 0, pairs_d, jobs_d);
-            IS_LAUNCH(ctx, k_uls_paint_seam_batch, dim3(div_up(max_nseam, 256), (unsigned)nj), 256, 0, jobs_d);
-            IS_LAUNCH(ctx, k_ccl_rows_batch, dim3(max_rh, (unsigned)nj), 256, 0, jobs_d);
-            if (max_rh > 1) {
-                dim3 mgrid(div_up(max_rw, 64), div_up(max_rh - 1, 4), (unsigned)nj);
-                IS_LAUNCH(ctx, k_ccl_merge_batch, mgrid, block, 0, jobs_d);
-            }
-            const size_t nmax = (size_t)max_rw * max_rh;
-            IS_LAUNCH(ctx, k_ccl_flatten_batch, dim3((unsigned)((nmax + 255) / 256), (unsigned)nj), 256, 0, jobs_d);
-            IS_LAUNCH(ctx, k_uls_gather_batch, dim3(div_up(max_items, 128), (unsigned)nj), 128, 0, jobs_d);
-        }
+        IS_TRY(download_view(ctx, base + off_res_all, sizeof(int) * res_total_ints, reinterpret_cast<const void**>(&res_h)));
     }
-    const int* res_h = nullptr;                                        // view of the pinned bounce buffer, valid until the next download
-    if (nj) IS_TRY(download_view(ctx, base + off_res_all, sizeof(int) * res_total_ints, reinterpret_cast<const void**>(&res_h)));
-    tm.lap("C labels, costs, DP, uls device part");
-    // ---- host walks
+    tm.lap("C labels, costs, DP");
+    // ---- host: updateLabelsUsingSeam per seam, then the final mask update of every pair as clear intervals
     pool->run(nj, [&](size_t j) {
         SeamJobHost& J = jobs[j];
-        J.status = uls_host_walk(ctx, PR[(size_t)J.pair], J, res_h + J.off_res, trace);
+        J.status = seam_job_finish(ctx, PR[(size_t)J.pair], J, res_h + J.off_res, trace != nullptr);
     });
     size_t limit = np;                                                 // pairs [0, limit) can still be accepted
     for (auto& J : jobs) {
@@ -1129,49 +821,55 @@ static int seam_batch_wave(is_ctx* ctx, const std::vector<std::pair<int, int>>& 
         if (J.status != IS_OK) return J.status;
     }
     if (limit == 0) { *first_unsupported = true; return IS_OK; }
-    tm.lap("D host: uls walk + vote");
-    // ---- E: relabel by the seams, clears per pair (private)
-    {
-        Blob B2;
-        B2.host.resize(b2_fixed);
-        for (size_t k = 0; k < np; ++k)
-            if (PR[k].ncomps) std::memcpy(B2.host.data() + off_states[k], PR[k].final_states.data(), sizeof(int) * (size_t)PR[k].ncomps);
-        std::vector<JobDevE> ext(std::max<size_t>(nj, 1));
-        int max_flips = 0;
-        bool any_adj = false;
-        for (size_t q = 0; q < nj; ++q) {
-            SeamJobHost& J = jobs[order[q]];
-            const size_t oa = B2.put(J.adj_roots.data(), sizeof(int) * J.adj_roots.size());
-            const size_t of = B2.put(J.flips.data(), sizeof(int2) * J.flips.size());
-            ext[q] = JobDevE{reinterpret_cast<const int*>(base + off_b2 + oa), (int)J.adj_roots.size(), reinterpret_cast<const int2*>(base + off_b2 + of), (int)J.flips.size()};
-            max_flips = std::max(max_flips, (int)J.flips.size());
-            any_adj = any_adj || !J.adj_roots.empty();
+    tm.lap("D host: updateLabelsUsingSeam on runs");
+    std::vector<std::vector<ClearIv>> clears(limit);
+    pool->run(limit, [&](size_t k) {
+        std::vector<const std::vector<Interval>*> fl;
+        for (auto& J : jobs) if ((size_t)J.pair == k) fl.push_back(J.reached ? &J.uls.flips : nullptr);   // jobs are in plan order
+        pair_clear_intervals(PR[k], fl, &clears[k]);
+    });
+    // one upload: per pair row_start[ih + 1] and the intervals, then the table
+    Blob B2;
+    std::vector<size_t> off_rs(limit), off_iv(limit);
+    for (size_t k = 0; k < limit; ++k) {
+        const PairRuns& P = PR[k];
+        const int iy = P.iTl.y - P.unionTl.y, ih = P.iBr.y - P.iTl.y;
+        std::vector<int> rs((size_t)ih + 1, 0);
+        std::vector<int4> iv(clears[k].size());
+        for (size_t q = 0; q < clears[k].size(); ++q) {
+            const ClearIv& c = clears[k][q];
+            rs[(size_t)(c.y - iy) + 1]++;
+            iv[q] = make_int4(c.x0, c.x1, c.bits, 0);
         }
-        const size_t off_ext = B2.put(ext.data(), sizeof(JobDevE) * ext.size());
-        const size_t off_post = B2.put(post_relabel.data(), sizeof(RelabelDev) * post_relabel.size());
-        IS_REQUIRE(ctx, B2.host.size() <= b2_cap, IS_ERR_INTERNAL, "seam batch: second upload larger than planned");
-        IS_TRY(upload(ctx, base + off_b2, B2.host.data(), B2.host.size()));
-        const JobDevE* ext_d = reinterpret_cast<const JobDevE*>(base + off_b2 + off_ext);
-        if (nj && any_adj) {
-            int max_rw = 0, max_rh = 0;
-            for (auto& J : jobs) { max_rw = std::max(max_rw, J.op.rw); max_rh = std::max(max_rh, J.op.rh); }
-            dim3 block(64, 4), grid(div_up(max_rw, 64), div_up(max_rh, 4), (unsigned)nj);
-            IS_LAUNCH(ctx, k_uls_apply_batch, grid, block, 0, pairs_d, jobs_d, ext_d);
-        }
-        if (nj && max_flips) IS_LAUNCH(ctx, k_scatter_label_batch, dim3(div_up(max_flips, 256), (unsigned)nj), 256, 0, pairs_d, jobs_d, ext_d);
-        if (!post_relabel.empty()) {
-            int mw = 0, mh = 0;
-            for (auto& R : post_relabel) { mw = std::max(mw, R.w); mh = std::max(mh, R.h); }
-            dim3 block(64, 4), grid(div_up(mw, 64), div_up(mh, 4), (unsigned)post_relabel.size());
-            IS_LAUNCH(ctx, k_relabel_batch, grid, block, 0, pairs_d, reinterpret_cast<const RelabelDev*>(base + off_b2 + off_post));
-        }
-        dim3 block(64, 4), grid(div_up(max_iw, 64), div_up(max_ih, 4), (unsigned)np);
-        IS_LAUNCH(ctx, k_pair_clears_batch, grid, block, 0, pairs_d);
+        for (int r = 0; r < ih; ++r) rs[(size_t)r + 1] += rs[(size_t)r];
+        off_rs[k] = B2.put(rs.data(), sizeof(int) * rs.size());
+        off_iv[k] = B2.put(iv.data(), sizeof(int4) * iv.size());
     }
+    const size_t off_ct = B2.put(nullptr, sizeof(ClearTabDev) * limit);
+    DevBuf dev2;
+    IS_TRY(dev2.alloc(ctx, B2.host.size()));
+    unsigned char* b2d = dev2.as<unsigned char>();
+    int max_ih = 0;
+    {
+        ClearTabDev* ct = reinterpret_cast<ClearTabDev*>(B2.host.data() + off_ct);
+        for (size_t k = 0; k < limit; ++k) {
+            const PairRuns& P = PR[k];
+            const DevMat& m1 = masks[P.pi];
+            const DevMat& m2 = masks[P.pj];
+            ct[k].row_start = reinterpret_cast<const int*>(b2d + off_rs[k]);
+            ct[k].ivs = reinterpret_cast<const int4*>(b2d + off_iv[k]);
+            ct[k].iy = P.iTl.y - P.unionTl.y; ct[k].ih = P.iBr.y - P.iTl.y;
+            ct[k].mask1 = m1.ptr<uint8_t>(); ct[k].mstep1 = m1.step; ct[k].o1x = P.o1x; ct[k].o1y = P.o1y;
+            ct[k].mask2 = m2.ptr<uint8_t>(); ct[k].mstep2 = m2.step; ct[k].o2x = P.o2x; ct[k].o2y = P.o2y;
+            max_ih = std::max(max_ih, ct[k].ih);
+        }
+    }
+    IS_TRY(upload(ctx, b2d, B2.host.data(), B2.host.size()));
+    tm.lap("E host: clear intervals + upload");
     // ---- F: validation -- the masks every pair would have seen in the sequential loop
     {
         StructureQuery V;
-        std::vector<int> vpair;                                        // active index of every validation pair
+        std::vector<int> vpair;                                        // wave index of every validation pair
         for (size_t k = 0; k < limit; ++k) {
             const int img[2] = {active[k].first, active[k].second};
             LayeredMask lm[2] = {plain_mask(masks[img[0]]), plain_mask(masks[img[1]])};
@@ -1181,12 +879,14 @@ static int seam_batch_wave(is_ctx* ctx, const std::vector<std::pair<int, int>>& 
                     int bit = 0;
                     if (active[q].first == img[s]) bit = 1; else if (active[q].second == img[s]) bit = 2;
                     if (!bit) continue;
+                    if (clears[q].empty()) continue;                   // that pair clears nothing
                     if (lm[s].nlayers == MAX_LAYERS) { too_many = true; break; }       // more earlier neighbours than a mask carries
                     const PairRuns& E = PR[q];
                     ClearLayer& L = lm[s].layer[lm[s].nlayers++];
-                    L.p = base + off_clear[q]; L.pitch = cpitch[q];
-                    L.x0 = E.iTl.x - corners[img[s]].x; L.y0 = E.iTl.y - corners[img[s]].y;
-                    L.w = E.iBr.x - E.iTl.x; L.h = E.iBr.y - E.iTl.y; L.bit = bit;
+                    L.row_start = reinterpret_cast<const int*>(b2d + off_rs[q]);
+                    L.ivs = reinterpret_cast<const int4*>(b2d + off_iv[q]);
+                    L.dx = E.unionTl.x - corners[img[s]].x; L.dy = E.unionTl.y - corners[img[s]].y;
+                    L.iy = E.iTl.y - E.unionTl.y; L.ih = E.iBr.y - E.iTl.y; L.bit = bit;
                     any = true;
                 }
             if (too_many) { limit = k; break; }                        // ends the wave here: the pair starts the next one with fewer layers
@@ -1216,11 +916,13 @@ static int seam_batch_wave(is_ctx* ctx, const std::vector<std::pair<int, int>>& 
             tm.lap("F host: check structures");
         }
     }
-    // ---- G: the clears of the accepted prefix go into the masks
+    // ---- G: the clear intervals of the accepted prefix go into the masks
     IS_REQUIRE(ctx, limit >= 1, IS_ERR_INTERNAL, "seam wave without progress");
-    {
-        dim3 block(64, 4), grid(div_up(max_iw, 64), div_up(max_ih, 4), (unsigned)limit);
-        IS_LAUNCH(ctx, k_apply_clears_batch, grid, block, 0, pairs_d);
+    if (max_ih > 0) {
+        double bytes = 0;
+        for (size_t k = 0; k < limit; ++k) for (const ClearIv& c : clears[k]) bytes += c.x1 - c.x0;
+        ctx->next_bytes = bytes;
+        IS_LAUNCH(ctx, k_apply_clear_runs_batch, dim3(div_up(max_ih, 8), (unsigned)limit), 256, 0, reinterpret_cast<const ClearTabDev*>(b2d + off_ct));
     }
     if (trace)
         for (size_t k = 0; k < limit; ++k)
@@ -1232,7 +934,6 @@ static int seam_batch_wave(is_ctx* ctx, const std::vector<std::pair<int, int>>& 
             }
     if (tm.on) cudaStreamSynchronize(ctx->stream);
     tm.lap("G apply");
-    (void)n;
     *accepted_n = limit;
     return IS_OK;
 }

@@ -438,3 +438,281 @@ bool PairRuns::same_structure(const PairRuns& o) const {
     }
     return true;
 }
+
+// ---- updateLabelsUsingSeam ([SEAM]:960-1093) in the run domain ---------------------------------------------------------------
+// The reference paints the contour of comp1 and the seam into a mask of comp1's bounding box, flood-fills what is left of the
+// component (4-connected) and lets every painted pixel join the region of one of its neighbours; the regions that mostly touch
+// comp2 are then relabelled.  Here the bounding box is never rasterised: a row of comp1 is a few runs, the painted pixels cut
+// them into interior runs, a union-find over vertically overlapping runs is the flood fill, and "the value of pixel (x, y)" is
+// a search in its row.
+struct Interval { int y, x0, x1; };                   // pixels [x0, x1) of frame row y
+
+struct UlsRuns {
+    // inputs
+    const PairRuns* P = nullptr;
+    SeamOp op{};
+    bool horizontal = false;
+    int s0 = 0, nseam = 0;
+    const int* lane = nullptr;                        // lane of the seam at step s0 + i (bbox coordinates)
+    // output: the pixels of comp1 that take comp2's label, sorted by (y, x0), disjoint
+    std::vector<Interval> flips;
+    bool too_many_regions = false;                    // 255 or more flood-filled regions: the reference's mask value 255 collides with an id
+
+    void run();
+};
+
+void UlsRuns::run() {
+    const bool tim = getenv("IS_DEBUG_PLAN_TIMING") != nullptr;
+    auto T0 = std::chrono::steady_clock::now();
+    auto lapt = [&](const char* w) { if (!tim) return; auto n = std::chrono::steady_clock::now(); fprintf(stderr, "   [uls] %-16s %.3f ms\n", w, std::chrono::duration<double, std::milli>(n - T0).count()); T0 = n; };
+    const PairRuns& R = *P;
+    const int l1 = op.c1 + 1, l2 = op.c2 + 1;
+    const int rx = op.rx, ry = op.ry, rw = op.rw, rh = op.rh;
+    const std::vector<ContourRec>& cont = R.contours[(size_t)op.c1];
+    const int nc = (int)cont.size();
+    flips.clear();
+    too_many_regions = false;
+    // contour records per bbox row
+    std::vector<int> row_first((size_t)rh + 1, 0);
+    for (int i = 0; i < nc; ++i) row_first[(size_t)(cont[(size_t)i].y - ry) + 1]++;
+    for (int y = 0; y < rh; ++y) row_first[(size_t)y + 1] += row_first[(size_t)y];
+    auto find_contour = [&](int x, int y) -> int {                   // bbox coordinates -> record index, -1 if none
+        if ((unsigned)y >= (unsigned)rh) return -1;
+        int lo = row_first[(size_t)y], hi = row_first[(size_t)y + 1] - 1;
+        while (lo <= hi) {
+            const int mid = (lo + hi) >> 1;
+            const int cx = cont[(size_t)mid].x - rx;
+            if (cx == x) return mid;
+            if (cx < x) lo = mid + 1; else hi = mid - 1;
+        }
+        return -1;
+    };
+    // seam pixels per bbox row (a vertical seam has one per row of its steps, a horizontal seam any number)
+    std::vector<int> seam_first((size_t)rh + 1, 0), seam_x((size_t)nseam);
+    auto seam_px = [&](int i, int* x, int* y) { const int step = s0 + i; if (horizontal) { *x = step; *y = lane[i]; } else { *x = lane[i]; *y = step; } };
+    for (int i = 0; i < nseam; ++i) { int x, y; seam_px(i, &x, &y); seam_first[(size_t)y + 1]++; }
+    for (int y = 0; y < rh; ++y) seam_first[(size_t)y + 1] += seam_first[(size_t)y];
+    {
+        std::vector<int> fill(seam_first.begin(), seam_first.end() - 1);
+        for (int i = 0; i < nseam; ++i) { int x, y; seam_px(i, &x, &y); seam_x[(size_t)fill[(size_t)y]++] = x; }   // increasing i = increasing x within a row of a horizontal seam
+    }
+    auto is_seam = [&](int x, int y) -> bool {
+        if ((unsigned)y >= (unsigned)rh) return false;
+        for (int k = seam_first[(size_t)y]; k < seam_first[(size_t)y + 1]; ++k) if (seam_x[(size_t)k] == x) return true;
+        return false;
+    };
+    // interior runs of every bbox row: comp1's runs minus the painted pixels
+    struct IRun { int x0, x1, parent; };
+    std::vector<IRun> ir;
+    std::vector<int> ir_first((size_t)rh + 1, 0);
+    std::vector<int> painted;                                         // painted x of the current row, sorted
+    ir.reserve((size_t)rh * 3);
+    for (int y = 0; y < rh; ++y) {
+        const int fy = ry + y;
+        painted.clear();
+        {
+            int a = row_first[(size_t)y], ae = row_first[(size_t)y + 1], b = seam_first[(size_t)y], be = seam_first[(size_t)y + 1];
+            // seam xs of a row are increasing for a horizontal seam; a vertical seam has at most one: merge two sorted lists
+            while (a < ae || b < be) {
+                const int xa = a < ae ? cont[(size_t)a].x - rx : INT_MAX, xb = b < be ? seam_x[(size_t)b] : INT_MAX;
+                const int x = std::min(xa, xb);
+                painted.push_back(x);
+                if (xa == x) ++a;
+                if (xb == x) ++b;
+            }
+        }
+        size_t pi = 0;
+        const int rb = R.row_off[(size_t)fy], re = R.row_off[(size_t)fy + 1];
+        for (int k = rb; k < re; ++k) {
+            if (R.cp_label[(size_t)k] != l1) continue;
+            int a = R.cps[(size_t)k].x - rx, b = (k + 1 < re ? R.cps[(size_t)k + 1].x : R.uw) - rx;
+            a = std::max(a, 0); b = std::min(b, rw);
+            int x = a;
+            while (pi < painted.size() && painted[pi] < a) ++pi;
+            while (x < b) {
+                const int nextp = pi < painted.size() && painted[pi] < b ? painted[pi] : b;
+                if (nextp > x) ir.push_back(IRun{x, nextp, (int)ir.size()});
+                x = nextp + 1;
+                if (nextp < b) ++pi;
+            }
+        }
+        ir_first[(size_t)y + 1] = (int)ir.size();
+    }
+    lapt("interior runs");
+    auto find = [&](int k) { while (ir[(size_t)k].parent != k) { ir[(size_t)k].parent = ir[(size_t)ir[(size_t)k].parent].parent; k = ir[(size_t)k].parent; } return k; };
+    for (int y = 1; y < rh; ++y) {
+        int a = ir_first[(size_t)y - 1], ae = ir_first[(size_t)y], b = ir_first[(size_t)y], be = ir_first[(size_t)y + 1];
+        while (a < ae && b < be) {
+            if (ir[(size_t)a].x0 < ir[(size_t)b].x1 && ir[(size_t)b].x0 < ir[(size_t)a].x1) {
+                const int ra = find(a), rb2 = find(b);
+                if (ra != rb2) { if (ra < rb2) ir[(size_t)rb2].parent = ra; else ir[(size_t)ra].parent = rb2; }
+            }
+            if (ir[(size_t)a].x1 <= ir[(size_t)b].x1) ++a; else ++b;
+        }
+    }
+    lapt("union-find");
+    // ids 1.. of the regions in order of first use (only equality, "> 0" and "!= 255" are ever asked of them)
+    int nregions = 0;
+    for (size_t k = 0; k < ir.size(); ++k) if (find((int)k) == (int)k) ++nregions;
+    if (nregions >= 255) { too_many_regions = true; return; }
+    std::vector<int> region_id(ir.size(), 0);
+    int nsub = 0;
+    auto id_of_run = [&](int k) { const int r = find(k); if (!region_id[(size_t)r]) region_id[(size_t)r] = ++nsub; return region_id[(size_t)r]; };
+    // value of the reference's mask at bbox pixel (x, y) BEFORE any painted pixel is assigned: -1 outside, 0 not comp1, -255 painted, else region id
+    auto value = [&](int x, int y) -> int {
+        if ((unsigned)x >= (unsigned)rw || (unsigned)y >= (unsigned)rh) return -1;
+        for (int k = ir_first[(size_t)y]; k < ir_first[(size_t)y + 1]; ++k) {
+            if (x < ir[(size_t)k].x0) break;
+            if (x < ir[(size_t)k].x1) return id_of_run(k);
+        }
+        if (find_contour(x, y) >= 0 || is_seam(x, y)) return -255;
+        return 0;
+    };
+    static const int ddx[8] = {-1, +1, 0, 0, -1, +1, -1, +1};
+    static const int ddy[8] = {0, 0, -1, +1, -1, -1, +1, +1};
+    // contour pixels in raster order ([SEAM]:983-1010): the last neighbour, in the reference's order, holding an assigned value wins.
+    // A painted neighbour is assigned only if it is a contour pixel earlier in raster order (neighbours 0, 2, 4, 5).
+    std::vector<int> val((size_t)nc, 255);
+    for (int i = 0; i < nc; ++i) {
+        const int x = cont[(size_t)i].x - rx, y = cont[(size_t)i].y - ry;
+        int v = 0;
+        for (int j = 7; j >= 0; --j) {
+            const int g = value(x + ddx[j], y + ddy[j]);
+            if (g > 0) { v = g; break; }
+            if (g == -255 && (j == 0 || j == 2 || j == 4 || j == 5)) {
+                const int k = find_contour(x + ddx[j], y + ddy[j]);
+                if (k >= 0 && k < i && val[(size_t)k] > 0 && val[(size_t)k] != 255) { v = val[(size_t)k]; break; }
+            }
+        }
+        val[(size_t)i] = v;
+    }
+    lapt("contour walk");
+    // seam pixels ([SEAM]:1012-1034): each takes the value of one neighbour of its own step
+    std::vector<int> sval((size_t)nseam, 0), seam_contour((size_t)nseam, -1);
+    for (int i = 0; i < nseam; ++i) {
+        int x, y;
+        seam_px(i, &x, &y);
+        const int nx = horizontal ? x : x + 1, ny = horizontal ? y + 1 : y;
+        const int g = value(nx, ny);
+        int v = 0;
+        if (g > 0) v = g;
+        else if (g == -255) {
+            const int k = find_contour(nx, ny);
+            if (k >= 0 && val[(size_t)k] > 0 && val[(size_t)k] != 255) v = val[(size_t)k];
+        }
+        sval[(size_t)i] = v;
+        seam_contour[(size_t)i] = find_contour(x, y);
+    }
+    for (int i = 0; i < nseam; ++i)
+        if (seam_contour[(size_t)i] >= 0) val[(size_t)seam_contour[(size_t)i]] = sval[(size_t)i];
+    lapt("seam walk");
+    // adjacency vote ([SEAM]:1039-1085)
+    std::vector<int> connect2((size_t)nsub + 1, 0), connectOther((size_t)nsub + 1, 0);
+    bool c2_has0 = false, co_has0 = false;
+    for (int i = 0; i < nc; ++i) {
+        const ContourRec& r = cont[(size_t)i];
+        int mv = val[(size_t)i];
+        if (mv < 0 || mv > nsub) mv = 0;
+        if (r.nl[0] == l2 || r.nl[1] == l2 || r.nl[2] == l2 || r.nl[3] == l2) { connect2[(size_t)mv]++; if (mv == 0) c2_has0 = true; }
+        bool other = false;
+        for (int k = 0; k < 4; ++k) if (r.nl[k] >= 0 && r.nl[k] != l1 && r.nl[k] != l2) other = true;
+        if (other) { connectOther[(size_t)mv]++; if (mv == 0) co_has0 = true; }
+    }
+    std::vector<char> isAdj((size_t)nsub + 1, 0);
+    const double len = (double)nc;
+    for (int k = c2_has0 ? 0 : 1; k <= nsub; ++k) {
+        if (connect2[(size_t)k] / len > 0.05) {
+            const bool sub_exists = k >= 1 || co_has0;
+            if (sub_exists && (connectOther[(size_t)k] / len < 0.1)) isAdj[(size_t)k] = 1;
+        }
+    }
+    lapt("vote");
+    // relabel ([SEAM]:1089-1092): the regions voted adjacent and the painted pixels that joined them, as intervals per frame row
+    // per row: three lists sorted by x (interior runs, contour pixels, seam-only pixels) -> merged, touching intervals joined
+    std::vector<int> seam_idx((size_t)nseam);                         // seam pixels in the order of seam_x (per row)
+    {
+        std::vector<int> fill(seam_first.begin(), seam_first.end() - 1);
+        for (int i = 0; i < nseam; ++i) { int x, y; seam_px(i, &x, &y); seam_idx[(size_t)fill[(size_t)y]++] = i; }
+    }
+    auto adj = [&](int v) { return v > 0 && v <= nsub && isAdj[(size_t)v]; };
+    std::vector<std::pair<int, int>> row;                             // (x0, x1) of the current row
+    for (int y = 0; y < rh; ++y) {
+        row.clear();
+        for (int k = ir_first[(size_t)y]; k < ir_first[(size_t)y + 1]; ++k)
+            if (adj(region_id[(size_t)find(k)])) row.push_back({ir[(size_t)k].x0, ir[(size_t)k].x1});
+        const size_t n_runs = row.size();
+        for (int i = row_first[(size_t)y]; i < row_first[(size_t)y + 1]; ++i)
+            if (adj(val[(size_t)i])) row.push_back({cont[(size_t)i].x - rx, cont[(size_t)i].x - rx + 1});
+        const size_t n_cont = row.size();
+        for (int k = seam_first[(size_t)y]; k < seam_first[(size_t)y + 1]; ++k) {
+            const int i = seam_idx[(size_t)k];
+            if (seam_contour[(size_t)i] < 0 && adj(sval[(size_t)i])) row.push_back({seam_x[(size_t)k], seam_x[(size_t)k] + 1});   // contour pixels are covered above
+        }
+        if (row.empty()) continue;
+        std::inplace_merge(row.begin(), row.begin() + (ptrdiff_t)n_runs, row.begin() + (ptrdiff_t)n_cont);
+        std::inplace_merge(row.begin(), row.begin() + (ptrdiff_t)n_cont, row.end());
+        for (auto& iv : row) {
+            if (!flips.empty() && flips.back().y == ry + y && flips.back().x1 >= iv.first + rx) flips.back().x1 = std::max(flips.back().x1, iv.second + rx);
+            else flips.push_back(Interval{ry + y, iv.first + rx, iv.second + rx});
+        }
+    }
+    lapt("flips");
+}
+
+// The pair's final mask update ([SEAM]:524-545) as clear intervals: for every pixel of both masks, the state of its FINAL label
+// decides which mask loses it -- bit 1: the first image's mask, bit 2: the second's (mask2 is updated first and mask1 then looks
+// at the updated mask2, so a pixel is never cleared in both).  `seam_flips[k]`: UlsRuns::flips of the k-th kind-1 operation of
+// the plan that succeeded (nullptr when estimateSeam failed or was not run).
+struct ClearIv { int y, x0, x1, bits; };              // frame coordinates
+
+static void pair_clear_intervals(const PairRuns& R, const std::vector<const std::vector<Interval>*>& seam_flips, std::vector<ClearIv>* out) {
+    out->clear();
+    auto bits_of = [&](int label) {
+        const int st = R.final_states[(size_t)label - 1];
+        if (st & ST_FIRST) return 2;
+        if (st & ST_SECOND) return 1;
+        return 0;
+    };
+    // per INTERS component: label the pixels a seam did not move end up with (a later wholesale relabel), and its seam flips
+    std::vector<int> rest_label((size_t)R.ncomps, 0);
+    std::vector<const std::vector<Interval>*> flips_of((size_t)R.ncomps, nullptr);
+    std::vector<int> flip_label((size_t)R.ncomps, 0);
+    for (int c = 0; c < R.ncomps; ++c) rest_label[(size_t)c] = c + 1;
+    size_t k1 = 0;
+    for (const SeamOp& op : R.ops) {
+        if (op.kind == 0) rest_label[(size_t)op.c1] = op.c2 + 1;
+        else { flips_of[(size_t)op.c1] = seam_flips[k1++]; flip_label[(size_t)op.c1] = op.c2 + 1; }
+    }
+    std::vector<size_t> cursor((size_t)R.ncomps, 0);                  // position in each component's flip list (sorted by row)
+    const int y_lo = std::max(0, R.iTl.y - R.unionTl.y), y_hi = std::min(R.uh, R.iBr.y - R.unionTl.y);
+    auto emit = [&](int y, int x0, int x1, int bits) {
+        if (!bits || x0 >= x1) return;
+        if (!out->empty() && out->back().y == y && out->back().x1 == x0 && out->back().bits == bits) out->back().x1 = x1;
+        else out->push_back(ClearIv{y, x0, x1, bits});
+    };
+    for (int y = y_lo; y < y_hi; ++y) {
+        const int rb = R.row_off[(size_t)y], re = R.row_off[(size_t)y + 1];
+        for (int k = rb; k < re; ++k) {
+            if (R.cps[(size_t)k].cls != 3) continue;
+            const int c = R.cp_label[(size_t)k] - 1;
+            const int a = R.cps[(size_t)k].x, b = k + 1 < re ? R.cps[(size_t)k + 1].x : R.uw;
+            const int rest_bits = bits_of(rest_label[(size_t)c]);
+            const std::vector<Interval>* fl = flips_of[(size_t)c];
+            int x = a;
+            if (fl) {
+                size_t& cu = cursor[(size_t)c];
+                while (cu < fl->size() && ((*fl)[cu].y < y || ((*fl)[cu].y == y && (*fl)[cu].x1 <= a))) ++cu;
+                const int fbits = bits_of(flip_label[(size_t)c]);
+                size_t q = cu;
+                while (q < fl->size() && (*fl)[q].y == y && (*fl)[q].x0 < b) {
+                    const int f0 = std::max((*fl)[q].x0, a), f1 = std::min((*fl)[q].x1, b);
+                    emit(y, x, f0, rest_bits);
+                    emit(y, f0, f1, fbits);
+                    x = f1;
+                    ++q;
+                }
+            }
+            emit(y, x, b, rest_bits);
+        }
+    }
+}

@@ -155,6 +155,13 @@ int is_ctx_seam_speculation(const is_ctx* ctx);
  * per row, a component cut by two seams) to the other two. */
 int is_ctx_seam_path(const is_ctx* ctx);
 
+/* Host-only diagnostic, no device needed: finishes one pair on the CPU with the batched path's host code, given the seams
+ * of its plan ([npts, x0, y0, ...] per seam operation, panorama coordinates, tip 1 -> tip 2; npts = 0 when the estimation
+ * failed): run-domain updateLabelsUsingSeam, clear intervals, masks updated in place. */
+int is_debug_seam_pair_finish(uint8_t* mask1, int rows1, int cols1, size_t step1, int tl1x, int tl1y,
+                              uint8_t* mask2, int rows2, int cols2, size_t step2, int tl2x, int tl2y,
+                              const int32_t* seams, size_t seams_len);
+
 /* Tuning diagnostic: njobs synthetic seams (lanes x steps cost tables generated on the device) through the DP forward /
  * back-track kernels of formulation `variant` (0 or 1, see csrc/seam.cu); seam_out[njobs][steps] = seam lanes (or -1 when the
  * destination is unreachable), ms[0] = mean milliseconds per launch over `iters` launches. */

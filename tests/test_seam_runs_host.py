@@ -84,6 +84,15 @@ def _pairs():
     for name, imgs, cs, ms, cost in seam_edge_cases():
         if cost == 0:
             cases.append((name + " (0,1)", imgs[0].astype(np.uint8), imgs[1].astype(np.uint8), cs[0], cs[1], ms[0], ms[1]))
+    # random rectangles with a notch or a hole each, random placement (horizontal and vertical seams, components that split)
+    for seed in range(40):
+        r = np.random.default_rng(1000 + seed)
+        h1, w1, h2, w2 = (int(v) for v in r.integers(40, 110, 4))
+        a = r.integers(0, 256, (h1, w1, 3)).astype(np.uint8)
+        b = r.integers(0, 256, (h2, w2, 3)).astype(np.uint8)
+        m1, m2 = blob_masks(r, [(h1, w1), (h2, w2)], holes=int(r.integers(0, 3)))
+        c2 = (int(r.integers(-w2 + 8, w1 - 8)), int(r.integers(-h2 + 8, h1 - 8)))
+        cases.append((f"random {seed}", a, b, (0, 0), c2, m1, m2))
     return cases
 
 
@@ -128,3 +137,37 @@ def test_pair_structure_and_plan_against_grid_and_oracle(oracle):
             k += 1
             checked_plans += 1
     assert checked_plans >= 20
+
+
+def test_pair_finish_on_host_equals_oracle(oracle):
+    """The whole pair on the CPU through the batched path's host code -- plan, run-domain updateLabelsUsingSeam, clear intervals --
+    fed with the seams the oracle traces: the resulting masks equal the oracle's (== the reference's own find())."""
+    O = oracle
+    lib = capi.load()
+    done = 0
+    for name, a, b, c1, c2, m1, m2 in _cases():
+        c1 = (int(c1[0]), int(c1[1])); c2 = (int(c2[0]), int(c2[1]))
+        got = plan(m1, c1, m2, c2)
+        if got["too_many"] or got["unsupported"]:
+            continue
+        want, trace = O.dp_seam_find([a, b], [c1, c2], [m1, m2], want_trace=True)
+        ux, uy = got["union_tl"]
+        dp_ops = [op for op in got["ops"] if op[0] == 1]
+        seams, k = [], 0
+        for op in dp_ops:                              # the oracle's seams in the plan's order; a seam that failed leaves no trace
+            p1 = (op[3] + ux, op[4] + uy); p2 = (op[5] + ux, op[6] + uy)
+            if k < len(trace) and trace[k][2] == op[1] and tuple(trace[k][4][0]) == p1 and tuple(trace[k][4][-1]) == p2:
+                pts = trace[k][4]
+                seams += [len(pts)] + [int(v) for v in pts.reshape(-1)]
+                k += 1
+            else:
+                seams.append(0)
+        assert k == len(trace), name
+        o1 = np.ascontiguousarray(m1).copy(); o2 = np.ascontiguousarray(m2).copy()
+        sa = np.asarray(seams if seams else [0], np.int32)
+        rc = lib.is_debug_seam_pair_finish(o1.ctypes.data, o1.shape[0], o1.shape[1], o1.strides[0], c1[0], c1[1], o2.ctypes.data, o2.shape[0], o2.shape[1],
+                                           o2.strides[0], c2[0], c2[1], sa.ctypes.data_as(C.POINTER(C.c_int32)), len(seams))
+        assert rc == 0, (name, rc)
+        assert np.array_equal(o1, want[0]) and np.array_equal(o2, want[1]), f"{name}: masks differ in {int((o1 != want[0]).sum())} + {int((o2 != want[1]).sum())} px"
+        done += 1
+    assert done >= 25
