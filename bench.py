@@ -31,10 +31,14 @@ ROOT = os.path.dirname(os.path.abspath(__file__))
 sys.path.insert(0, ROOT)
 
 WORKLOADS = {
-    # name: (n_images, rows, cols, f_over_w, overlap, grid_rows, description)
+    # name: (n_images per GPU, rows, cols, f_over_w, overlap, grid_rows, description)
     "c2": (6, 4000, 6000, 1.2, 0.25, 1, "6x(4000x6000) RGB strip, cylindrical warp + DP seam masks + multi-band blend (5 bands)"),
     "c3": (12, 4000, 6000, 1.5, 0.25, 1, "12x(4000x6000) RGB strip, cylindrical warp + DP seam + multi-band blend (5 bands)"),
-    "c1": (2, 768, 1024, 1.2, 0.25, 1, "2x(768x1024) RGB pair, cylindrical warp + DP seam + multi-band blend (5 bands)"),
+    "c2_8k": (6, 6000, 8000, 1.2, 0.25, 1, "6x(6000x8000) RGB strip (8K-wide images), cylindrical warp + DP seam masks + multi-band blend (5 bands)"),
+    "c1": (2, 768, 1024, 1.2, 0.25, 1, "2x(768x1024) RGB pair, cylindrical warp + hand-written linear blend ([BLEND]:141-717)"),
+    # BASELINE.json configs[3], configs[4]: per-GPU shares of the 8-GPU panoramas (run with --gpus 8)
+    "c4": (3, 6000, 8000, 3.0, 0.25, 1, "24x(6000x8000) RGB 346-degree strip over 8 GPUs (3 images per GPU), column-strip sharded, NCCL halo exchange"),
+    "c5": (6, 8000, 12000, 1.5, 0.25, 4, "48x(8000x12000) RGB 4x12 mosaic over 8 GPUs (6 images per GPU), column-strip sharded, NCCL halo exchange"),
     "tiny": (3, 384, 512, 1.2, 0.25, 1, "3x(384x512) debug strip"),
 }
 NUM_BANDS = 5
@@ -270,6 +274,101 @@ def run_reference(args):
     return 0
 
 
+PATH_KERNEL_WORDS = ("k_warp", "k_pyrdown", "k_blend", "k_mask_summary", "k_gain", "k_dilate", "k_feather", "k_dt_")   # warp / pyramid / blend side of the path
+SEAM_KERNEL_WORDS = ("k_seam", "k_cost", "k_row_toggles", "k_special", "k_label", "k_bt_", "k_apply_clear", "k_ccl", "k_uls", "k_contour", "k_mask_row",
+                     "k_mask_update", "k_mask_and", "k_collect", "k_scatter", "k_relabel", "k_classify", "k_sobel", "k_scan")
+
+
+def _kernel_group(name):
+    n = name.strip("()")
+    if any(n.startswith(w) for w in PATH_KERNEL_WORDS):
+        return "warp_blend"
+    if any(n.startswith(w) for w in SEAM_KERNEL_WORDS):
+        return "seam"
+    return "other"
+
+
+def run_c1(args, dev, local_rank):
+    """BASELINE.json configs[0]: 2 x (768 x 1024) pair, cylindrical warp + the reference's hand-written linear blend
+    ([BLEND]:141-717, is_linear_blend_pair) -- the configuration the reference's own CPU path (single core) is quoted on."""
+    import numpy as np
+    import torch
+
+    import oracle as O
+    from imagestitch_b200 import stitching as S, synth
+    n, rows, cols, fw, ov, grid_rows, desc = WORKLOADS["c1"]
+    Ks, Rs, scale = synth.strip_cameras(n, cols, rows, fw, ov)
+    imgs = [synth.make_image(i, cols, rows, Ks[i], Rs[i], device="cpu").numpy() for i in range(n)]
+    ctx = S.Context(local_rank, use_torch_stream=True)
+    wp = S.RotationWarper(ctx, "cylindrical", scale)
+    dimgs = [torch.from_numpy(a).to(dev) for a in imgs]
+
+    def step_device():
+        ctx.clear_plan_cache()
+        ws, tls = [], []
+        for i in range(n):
+            tl, w, _m = wp.warp_with_mask(dimgs[i], Ks[i], Rs[i])
+            ws.append(w.float()); tls.append(tl)               # images_warped[i].convertTo(images_warped_f[i], CV_32F)  [BLEND]:140
+        return S.linear_blend_pair(ctx, ws[0], ws[1], tls[0], tls[1])
+
+    def step_host():
+        ctx.clear_plan_cache()
+        ws, tls = [], []
+        for i in range(n):
+            tl, w, _m = wp.warp_with_mask(imgs[i], Ks[i], Rs[i])
+            ws.append(w.astype(np.float32)); tls.append(tl)
+        return S.linear_blend_pair(ctx, ws[0], ws[1], tls[0], tls[1])
+
+    def timed(fn, steps):
+        torch.cuda.synchronize()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        l0 = ctx.kernel_launches
+        e0.record()
+        for _ in range(steps):
+            fn()
+        e1.record()
+        torch.cuda.synchronize()
+        return e0.elapsed_time(e1) / steps, (ctx.kernel_launches - l0) // steps
+
+    for _ in range(max(args.warmup, 3)):
+        step_device()
+    ms_dev, launches = timed(step_device, args.steps)
+    step_host()
+    ms_e2e, _ = timed(step_host, args.steps)
+    got = step_host()
+    # parity + CPU baseline: the oracle's restatement of the same two stages, ONE thread (the reference is single threaded)
+    O.build()
+    O.set_threads(1)
+    best = None
+    for _ in range(3):
+        t0 = time.perf_counter()
+        ws, tls = [], []
+        for i in range(n):
+            tl, w = O.warp(O.PROJ_CYLINDRICAL, imgs[i], Ks[i], Rs[i], scale, O.INTER_LINEAR, O.BORDER_REFLECT, full_scan=False)
+            O.warp(O.PROJ_CYLINDRICAL, np.full(imgs[i].shape[:2], 255, np.uint8), Ks[i], Rs[i], scale, O.INTER_NEAREST, O.BORDER_CONSTANT, full_scan=False)
+            ws.append(w.astype(np.float32)); tls.append(tl)
+        want = O.lin_blend(ws[0], ws[1], tls[0], tls[1])
+        dt = time.perf_counter() - t0
+        best = dt if best is None else min(best, dt)
+    gp = np.asarray(got[0])
+    seam_equal = bool(np.array_equal(np.asarray(got[1]), np.asarray(want[1])))
+    both = np.isfinite(gp) & np.isfinite(want[0])
+    pano_err = float(np.abs(gp[both] - want[0][both]).max()) if both.any() else 0.0
+    in_mp = n * rows * cols / 1e6
+    line = {"metric": "stitched_megapixels_per_sec", "value": in_mp / (ms_dev * 1e-3), "unit": "MP/s", "n_gpus": 1, "steps": args.steps, "warmup": max(args.warmup, 3),
+            "ms_per_step": ms_dev, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+            "config": {"workload": desc, "l2_policy": "inputs (4.7 MB) fit the L2: the plan memo is cleared every step, nothing else is cached between steps"},
+            "e2e": {"value": in_mp / (ms_e2e * 1e-3), "unit": "MP/s", "h2d_bytes_per_step": n * rows * cols * 3, "d2h_bytes_per_step": int(gp.size * 4), "ms_per_step": ms_e2e},
+            "gpu_launches": int(launches),
+            "parity": {"seam_indices_equal_oracle": seam_equal, "pano_max_abs_err": pano_err, "pano_tolerance": 1e-3 * 255},
+            "roofline": None,
+            "cpu_baseline": {"value": in_mp / best, "unit": "MP/s", "cores": 1, "kind": "port", "seconds": best,
+                             "sample": "the whole workload (2 warps with masks + [BLEND]:141-717 pair blend), oracle port, 1 thread, best of 3"}}
+    print(json.dumps(line), flush=True)
+    ctx.close()
+    return 0
+
+
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
@@ -278,6 +377,7 @@ def main():
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--workload", default="c2", choices=sorted(WORKLOADS))
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-parity-check", action="store_true", help="N > 1: skip the sharded-vs-single-GPU comparison on rank 0")
     ap.add_argument("--kernel-report", default=None, help="write the per-kernel timing table (JSON) to this file")
     ap.add_argument("--opencv-sample", type=int, default=None, help="internal: time python cv2's path on a sample of this many rows, print JSON")
     ap.add_argument("--reference-find-sample", type=int, default=None, help="internal: the reference's own find() vs the port on such a sample, print JSON")
@@ -312,25 +412,31 @@ def main():
         B.build()
     if dist:
         dist.barrier()
+    dev = f"cuda:{local_rank}"
+    if args.workload == "c1":
+        if rank == 0:
+            run_c1(args, dev, local_rank)
+        if dist:
+            dist.destroy_process_group()
+        return 0
 
     n, rows, cols, fw, ov, grid_rows, desc = WORKLOADS[args.workload]
-    dev = f"cuda:{local_rank}"
-    # Weak scaling: every GPU brings n images; for N > 1 they form ONE strip panorama of n*N images that is sharded by
-    # column strip (imagestitch_b200.sharded: NCCL halo exchange at the strip boundaries).  A cylinder cannot hold more
-    # than 360 degrees, so the focal length grows with N to keep the strip below ~340 degrees.
+    # Weak scaling: every GPU brings n images; for N > 1 they form ONE panorama of n*N images (a strip, or a grid_rows-row
+    # mosaic) that is sharded by column strip (imagestitch_b200.sharded: NCCL halo exchange at the strip boundaries).  A
+    # cylinder cannot hold more than 360 degrees, so the focal length grows with N to keep a strip below ~340 degrees.
     import math
     n_all = n * world
-    fw = max(fw, 1.0 / (2.0 * math.tan(5.9 / (2.0 * (1.0 - ov) * n_all)))) if world > 1 else fw
+    per_row = n_all // grid_rows
+    fw = max(fw, 1.0 / (2.0 * math.tan(5.9 / (2.0 * (1.0 - ov) * per_row)))) if world > 1 else fw
     Ks_all, Rs_all, scale = synth.strip_cameras(n_all, cols, rows, fw, ov, grid_rows=grid_rows)
-    idx = list(range(rank * n, rank * n + n))
-    Ks, Rs = Ks_all[idx], Rs_all[idx]
-    imgs_dev = [synth.make_image(i, cols, rows, Ks_all[i], Rs_all[i], device=dev) for i in idx]
-    torch.cuda.synchronize()
     in_mp = n * rows * cols / 1e6
-
+    ctx = S.Context(local_rank, use_torch_stream=True)     # kernels run on torch's current stream -> torch events see them
+    st = S.Stitcher(ctx, "cylindrical", "dp", NUM_BANDS, S.WEIGHT_32F)
+    sh = plan = None
     if world == 1:
-        ctx = S.Context(local_rank, use_torch_stream=True)     # kernels run on torch's current stream -> torch events see them
-        st = S.Stitcher(ctx, "cylindrical", "dp", NUM_BANDS, S.WEIGHT_32F)
+        idx = list(range(n))
+        Ks, Rs = Ks_all, Rs_all
+        imgs_dev = [synth.make_image(i, cols, rows, Ks_all[i], Rs_all[i], device=dev) for i in idx]
         corners, sizes, roi = st.plan([(cols, rows)] * n, Ks, Rs, scale)
         out_shape = (roi[3], roi[2])
         pano_dev = torch.empty(out_shape + (3,), dtype=torch.int16, device=dev)
@@ -338,25 +444,28 @@ def main():
         contexts = [ctx]
 
         def step_device():
+            # a stream of different panoramas never finds its cameras in the plan memo: every step scans its image borders
+            # (detectResultRoi, [WARP]:64-88) once -- plan() does it, is_pipeline_run() then reuses it for the same panorama
+            ctx.clear_plan_cache()
             st.stitch(imgs_dev, Ks, Rs, scale, out=(pano_dev, pmask_dev))
             return pano_dev, pmask_dev
     else:
         from imagestitch_b200 import sharded
-        be = sharded.GpuBackend(local_rank)
-        ctx = be.ctx
+        be = sharded.GpuBackend(local_rank, ctx=ctx)
         contexts = [be.ctx] + be.workers
-        st = S.Stitcher(ctx, "cylindrical", "dp", NUM_BANDS, S.WEIGHT_32F)
         corners_all, sizes_all, roi = st.plan([(cols, rows)] * n_all, Ks_all, Rs_all, scale)
         plan = sharded.ShardPlan.build(corners_all, sizes_all, roi, world, NUM_BANDS)
-        if [i for i in range(n_all) if plan.owner[i] == rank] != idx:
-            raise RuntimeError("shard plan does not assign images rank*n .. rank*n+n-1 to this rank (the workload is not a left-to-right strip)")
+        idx = [i for i in range(n_all) if plan.owner[i] == rank]
         sizes = [sizes_all[i] for i in idx]
+        imgs_dev = [synth.make_image(i, cols, rows, Ks_all[i], Rs_all[i], device=dev) for i in idx]
         sh = sharded.ShardedStitcher(be, sharded.Comm(dist), NUM_BANDS)
         out_shape = (roi[3], plan.cuts[rank + 1] - plan.cuts[rank])
 
         def step_device():
+            ctx.clear_plan_cache()
             r = sh.stitch(imgs_dev, Ks_all, Rs_all, scale, plan)
             return r["pano"], r["pano_mask"]
+    torch.cuda.synchronize()
 
     def barrier():
         if dist:
@@ -394,11 +503,11 @@ def main():
         step_device()
     ms_dev, launches = timed(step_device, args.steps)
     stage_ms = dict(st.timings_ms) if world == 1 else None
-    speculation = ctx.seam_speculation if world == 1 else sh.info.get("seam_speculation")
+    seam_info = {"path": ctx.seam_path, "waves": ctx.seam_waves} if world == 1 else dict(sh.info.get("seam", {}))
     dev_pano, dev_pmask = step_device()
     dev_pano, dev_pmask = dev_pano.clone(), dev_pmask.clone()
 
-    # second timed region with per-launch events for the roofline figure
+    # second timed region with per-launch events: the roofline figures
     for c in contexts:
         c.kernel_timing(True)
         c.kernel_timing_report()
@@ -409,7 +518,7 @@ def main():
             a = ktable.setdefault(r["name"], {"name": r["name"], "launches": 0, "ms": 0.0, "bytes": 0.0})
             a["launches"] += r["launches"]; a["ms"] += r["ms"]; a["bytes"] += r["bytes"]
         c.kernel_timing(False)
-    ktable = list(ktable.values())
+    ktable = sorted(ktable.values(), key=lambda r: -r["ms"])
 
     # end to end with HOST buffers (pinned): H2D of the sources and D2H of the panorama (strip) inside the timed region
     imgs_pin = [torch.empty((rows, cols, 3), dtype=torch.uint8, pin_memory=True) for _ in range(n)]
@@ -418,14 +527,17 @@ def main():
     pano_pin = torch.empty(out_shape + (3,), dtype=torch.int16, pin_memory=True)
     pmask_pin = torch.empty(out_shape, dtype=torch.uint8, pin_memory=True)
     torch.cuda.synchronize()
+    e2e_pipe = None
     if world == 1:
         imgs_host = [p.numpy() for p in imgs_pin]
         out_host = (pano_pin.numpy(), pmask_pin.numpy())
 
         def step_host():                                  # host buffers straight through the C ABI (is_pipeline_run)
+            ctx.clear_plan_cache()
             st.stitch(imgs_host, Ks, Rs, scale, out=out_host)
     else:
         def step_host():                                  # per rank: its sources up, its strip of the panorama down
+            ctx.clear_plan_cache()
             up = [p.to(dev, non_blocking=True) for p in imgs_pin]
             r = sh.stitch(up, Ks_all, Rs_all, scale, plan)
             pano_pin.copy_(r["pano"], non_blocking=True)
@@ -433,7 +545,49 @@ def main():
             torch.cuda.synchronize()
 
     step_host()
-    ms_e2e, _ = timed(step_host, max(1, min(args.steps, 5)))
+    e2e_steps = max(2, min(args.steps, 6))
+    ms_e2e_serial, _ = timed(step_host, e2e_steps)
+    same = bool(torch.equal(dev_pano.cpu(), pano_pin)) and bool(torch.equal(dev_pmask.cpu(), pmask_pin))
+    ms_e2e = ms_e2e_serial
+    if world == 1:
+        # Throughput of a STREAM of panoramas through the same synchronous call: two contexts on two host threads (one context per
+        # thread is the library's threading model), each with its own pinned output buffers, so that the D2H of one panorama
+        # runs under the H2D + compute of the next (the host link is full duplex).  Every step still uploads its sources and
+        # downloads its panorama inside the timed region.
+        ctx2 = S.Context(local_rank)
+        st2 = S.Stitcher(ctx2, "cylindrical", "dp", NUM_BANDS, S.WEIGHT_32F)
+        pano_pin2 = torch.empty(out_shape + (3,), dtype=torch.int16, pin_memory=True)
+        pmask_pin2 = torch.empty(out_shape, dtype=torch.uint8, pin_memory=True)
+        lanes = [(ctx, st, out_host), (ctx2, st2, (pano_pin2.numpy(), pmask_pin2.numpy()))]
+
+        def lane_steps(k, count):
+            c, s_, out = lanes[k]
+            for _ in range(count):
+                c.clear_plan_cache()
+                s_.stitch(imgs_host, Ks, Rs, scale, out=out)
+
+        def run_lanes(count_each):
+            th = [threading.Thread(target=lane_steps, args=(k, count_each)) for k in range(2)]
+            for x in th:
+                x.start()
+            for x in th:
+                x.join()
+
+        run_lanes(1)
+        torch.cuda.synchronize()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        t0 = time.perf_counter()
+        e0.record()
+        per_lane = max(2, e2e_steps // 2 + 1)
+        run_lanes(per_lane)
+        e1.record()
+        torch.cuda.synchronize()
+        windows.append((t0, time.perf_counter()))
+        ms_pipe = e0.elapsed_time(e1) / (2 * per_lane)
+        same2 = bool(torch.equal(dev_pano.cpu(), pano_pin2)) and bool(torch.equal(dev_pmask.cpu(), pmask_pin2))
+        e2e_pipe = {"ms_per_step": ms_pipe, "panoramas_in_flight": 2, "steps": 2 * per_lane, "matches_device_path": same2}
+        ms_e2e = min(ms_e2e_serial, ms_pipe)
+        ctx2.close()
     # what the host link of this box delivers for the same buffers (plain pinned copies): the floor of the e2e figure
     pcie = {}
     try:
@@ -447,15 +601,17 @@ def main():
         del tmp
     except Exception:
         pass
-    # the device-resident and the host path must produce the same panorama
-    same = bool(torch.equal(dev_pano.cpu(), pano_pin)) and bool(torch.equal(dev_pmask.cpu(), pmask_pin))
     if dist:
         t = torch.tensor([1 if same else 0], device=dev)
         dist.all_reduce(t, op=dist.ReduceOp.MIN)
         same = bool(t.item())
+
+    # N > 1: the sharded result against the single-GPU pipeline on a bounded subset (rank 0: the images of ranks 0 and 1)
+    sharded_matches = None
+    if world > 1 and not args.no_parity_check:
+        sharded_matches = sharded_parity_check(rank, world, plan, sh, st, ctx, imgs_dev, dev_pano, dev_pmask, Ks_all, Rs_all, scale, rows, cols, dev, dist)
     if sampler:
         sampler.stop()
-
     if rank != 0:
         if dist:
             dist.destroy_process_group()
@@ -469,44 +625,22 @@ def main():
         pass
     peak = float(peaks.get("hbm_gbs", 6650.0))
     peak_src = "measured (MEASURED_PEAKS.json hbm_gbs)" if "hbm_gbs" in peaks else "fallback (B200_PROFILING.md 6.65 TB/s)"
-    ktable.sort(key=lambda r: -r["ms"])
-    total_k_ms = sum(r["ms"] for r in ktable) or 1.0
-    # The DP forward pass is latency bound (one dependent step per overlap row, one CTA per seam): it is reported on
-    # its own; the roofline figure is for the dominant HBM-bound kernel of the step.
-    LATENCY_BOUND = ("k_seam_dp",)
-    hbm = [r for r in ktable if r["bytes"] > 0 and not r["name"].startswith(LATENCY_BOUND)]
-    # dominant HBM kernel = the one that moves most of the step's algorithmic bytes (level 0 of the blend: u8 images + masks in,
-    # int16 panorama + mask out).  The bands it hands to k_blend_l0_bands are part of the same level: their time is added.
-    top = max(hbm, key=lambda r: r["bytes"]) if hbm else None
-    extra_ms = 0.0
-    if top and top["name"].startswith("k_blend_l0_tiled"):
-        extra_ms = sum(r["ms"] for r in ktable if r["name"].startswith("k_blend_l0_bands"))
-    traffic = None
-    try:        # dram__bytes_{read,write}.sum of the same kernel from the committed ncu --set full capture
-        tj = json.load(open(os.path.join(ROOT, "profiles", "r1_ncu_traffic_c2.json")))
-        key = top["name"].split("<")[0] if top else ""
-        for name, v in tj.items():
-            if name.startswith(key) and key:
-                traffic = v["dram_bytes_per_launch"]
-    except Exception:
-        pass
-    roofline = None
-    if top:
-        per_launch_ms = (top["ms"] + extra_ms) / top["launches"]
-        bytes_per_launch = top["bytes"] / top["launches"]
-        achieved = bytes_per_launch / (per_launch_ms * 1e-3) / 1e9
-        roofline = {"bound": "hbm", "kernel": top["name"] + (" (+ k_blend_l0_bands remainder)" if extra_ms else ""), "achieved": achieved, "peak": peak,
-                    "unit": "GB/s", "frac": achieved / peak, "traffic": traffic, "peak_source": peak_src,
-                    "selection": "HBM-bound kernel with the most algorithmic bytes per step",
-                    "launches_per_step": top["launches"] / args.steps, "ms_per_launch": per_launch_ms,
-                    "algorithmic_bytes_per_launch": bytes_per_launch, "share_of_kernel_time": (top["ms"] + extra_ms) / total_k_ms,
-                    "path_algorithmic_bytes_per_step": alg["warp_blend_fused"],
-                    "path_achieved_gbs": alg["warp_blend_fused"] / (ms_dev * 1e-3) / 1e9,
-                    "hbm_kernels": [{"name": r["name"], "ms_per_step": r["ms"] / args.steps, "launches_per_step": r["launches"] / args.steps,
-                                     "achieved_gbs": r["bytes"] / (r["ms"] * 1e-3) / 1e9 if r["ms"] > 0 else None,
-                                     "frac": r["bytes"] / (r["ms"] * 1e-3) / 1e9 / peak if r["ms"] > 0 else None} for r in hbm],
-                    "latency_bound_kernels": [{"name": r["name"], "ms_per_launch": r["ms"] / r["launches"], "launches_per_step": r["launches"] / args.steps}
-                                              for r in ktable if r["name"].startswith(LATENCY_BOUND)]}
+    groups = {"warp_blend": 0.0, "seam": 0.0, "other": 0.0}
+    for r in ktable:
+        groups[_kernel_group(r["name"])] += r["ms"] / args.steps
+    # The roofline figure of the PATH: compulsory bytes of warp + blend (sources and seam masks read once, int16
+    # panorama + mask written once; every intermediate -- warped images, pyramids -- counts against it) over the summed CUDA-event
+    # time of every warp / pyramid / blend kernel of a step.  The DP seam stage is latency bound and reported beside it.
+    wb_ms = groups["warp_blend"]
+    achieved = alg["warp_blend_fused"] / (wb_ms * 1e-3) / 1e9 if wb_ms > 0 else None
+    roofline = {"bound": "hbm", "kernel": "warp + pyramid + blend kernels of a step (summed CUDA-event time)", "achieved": achieved, "peak": peak, "unit": "GB/s",
+                "frac": achieved / peak if achieved else None, "traffic": None, "peak_source": peak_src,
+                "algorithmic_bytes_per_step": alg["warp_blend_fused"],
+                "algorithmic_bytes_formula": "sum 3hw (u8 BGR sources) + sum A (u8 seam masks) + 7P (s16 BGR panorama + u8 mask); no intermediates",
+                "kernel_ms_per_step": {k: round(v, 4) for k, v in groups.items()},
+                "whole_step": {"ms": ms_dev, "achieved_gbs": alg["warp_blend_fused"] / (ms_dev * 1e-3) / 1e9, "frac": alg["warp_blend_fused"] / (ms_dev * 1e-3) / 1e9 / peak},
+                "kernels": [{"name": r["name"], "group": _kernel_group(r["name"]), "ms_per_step": round(r["ms"] / args.steps, 5), "launches_per_step": r["launches"] / args.steps,
+                             "declared_gbs": round(r["bytes"] / (r["ms"] * 1e-3) / 1e9, 1) if r["ms"] > 0 and r["bytes"] > 0 else None} for r in ktable]}
     if args.kernel_report:
         os.makedirs(os.path.dirname(os.path.abspath(args.kernel_report)), exist_ok=True)
         with open(args.kernel_report, "w") as f:
@@ -518,7 +652,7 @@ def main():
         O.build()
         threads = os.cpu_count() or 1
         sample_rows = rows if rows * cols <= 8e6 else rows // 4
-        v, sdesc, dt, stages = cpu_port_run(args.workload, threads, sample_rows=sample_rows)
+        v, sdesc, dt, stages = cpu_port_run(args.workload, threads, sample_rows=sample_rows, steps=3)
         cpu = {"value": v, "unit": "MP/s", "cores": threads, "kind": "port", "sample": sdesc, "seconds": dt,
                "stage_seconds": dict(zip(("warp", "seam", "blend", "total"), stages)),
                "opencv_cv2_same_sample": opencv_run(args.workload, sample_rows),
@@ -526,29 +660,75 @@ def main():
 
     h2d = world * n * rows * cols * 3
     d2h = roi[2] * roi[3] * 7
+    if world == 1:
+        wl = desc
+    elif grid_rows > 1:
+        wl = f"{n_all}x({rows}x{cols}) RGB {grid_rows}x{per_row} mosaic ({n} images per GPU), cylindrical warp + DP seam masks + multi-band blend (5 bands)"
+    else:
+        wl = f"{n_all}x({rows}x{cols}) RGB strip ({n} images per GPU), cylindrical warp + DP seam masks + multi-band blend (5 bands)"
     line = {
         "metric": "stitched_megapixels_per_sec", "value": world * in_mp / (ms_dev * 1e-3), "unit": "MP/s", "n_gpus": world, "steps": args.steps,
         "warmup": max(args.warmup, 3), "ms_per_step": ms_dev, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
         "dtype": "s16", "data": "synthetic",
-        "config": {"workload": desc if world == 1 else f"{n_all}x({rows}x{cols}) RGB strip ({n} images per GPU), cylindrical warp + DP seam masks + multi-band blend (5 bands)", "images_per_gpu": n, "image_rows": rows, "image_cols": cols, "num_bands": NUM_BANDS, "weight_type": "CV_32F",
+        "config": {"workload": wl, "images_per_gpu": n, "image_rows": rows, "image_cols": cols, "num_bands": NUM_BANDS, "weight_type": "CV_32F",
                    "seam": "dp_color", "projection": "cylindrical", "f_over_w": round(fw, 4), "overlap": ov, "pano_roi": list(roi),
                    "l2_policy": f"inputs ({(h2d // world) >> 20} MiB per GPU) and panorama exceed the {L2_BYTES >> 20} MiB L2; no flush needed",
+                   "plan_memo": "cleared at the start of every step: each step scans its image borders (detectResultRoi) once",
                    "parallelism": "single GPU" if world == 1 else
-                   f"one {n_all}-image strip panorama sharded by column strip over {world} GPUs, NCCL P2P halo exchange at strip boundaries",
-                   "seam_pairs": "concurrent, proven equal to the sequential loop" if speculation == 1 else "sequential loop"},
+                   f"one {n_all}-image panorama sharded by column strip over {world} GPUs, NCCL P2P halo exchange at strip boundaries",
+                   "seam_pairs": seam_info},
         "clocks": sampler.summary(windows) if sampler else None,
         "e2e": {"value": world * in_mp / (ms_e2e * 1e-3), "unit": "MP/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
-                "ms_per_step": ms_e2e, "matches_device_path": same, "host_link_pinned_copy": pcie},
+                "ms_per_step": ms_e2e, "one_panorama_at_a_time": {"ms_per_step": ms_e2e_serial, "value": world * in_mp / (ms_e2e_serial * 1e-3)},
+                "two_panoramas_in_flight": e2e_pipe, "matches_device_path": same, "host_link_pinned_copy": pcie},
         "gpu_launches": int(launches),
         "stage_ms": stage_ms, "ms_per_step_with_kernel_events": ms_dev_ev,
         "roofline": roofline, "cpu_baseline": cpu,
-        "top_kernels": [{"name": r["name"], "ms_per_step": r["ms"] / args.steps, "launches_per_step": r["launches"] / args.steps} for r in ktable[:8]],
-        "all_kernels": [{"name": r["name"], "ms_per_step": round(r["ms"] / args.steps, 5), "launches_per_step": r["launches"] / args.steps} for r in ktable],
     }
+    if sharded_matches is not None:
+        line["sharded_matches"] = sharded_matches
     print(json.dumps(line), flush=True)
     if dist:
         dist.destroy_process_group()
     return 0
+
+
+def sharded_parity_check(rank, world, plan, sh, st, ctx, imgs_dev, dev_pano, dev_pmask, Ks_all, Rs_all, scale, rows, cols, dev, dist):
+    """Rank 0 stitches, on its GPU alone, the images of ranks 0 and 1 (every image its strip can see plus their pair partners)
+    with the single-GPU code -- seam finder, then the blender on the GLOBAL panorama ROI restricted to rank 0's columns -- and
+    compares bit for bit: the seam masks of its own images and its strip of the panorama.  The other ranks only send images."""
+    import torch
+
+    from imagestitch_b200 import stitching as S, synth
+    n_all = len(plan.corners)
+    subset = [i for i in range(n_all) if plan.owner[i] in (0, 1)]
+    ok = True
+    if rank == 0:
+        r = sh.stitch(imgs_dev, Ks_all, Rs_all, scale, plan)       # one more step, keeping the seam masks
+        mine = [i for i in range(n_all) if plan.owner[i] == 0]
+        have = dict(zip(mine, imgs_dev))
+        imgs = [have[i] if i in have else synth.make_image(i, cols, rows, Ks_all[i], Rs_all[i], device=dev) for i in subset]
+        wp = S.RotationWarper(ctx, "cylindrical", scale)
+        ws, ms, cs = [], [], []
+        for k, i in enumerate(subset):
+            tl, w, m = wp.warp_with_mask(imgs[k], Ks_all[i], Rs_all[i])
+            ws.append(w); ms.append(m); cs.append(tl)
+        sm = S.DpSeamFinder(ctx, "COLOR").find(ws, cs, ms)
+        for k, i in enumerate(subset):
+            if i in mine:
+                ok = ok and bool(torch.equal(sm[k], r["seam_masks"][i]))
+        b = S.MultiBandBlender(ctx, 0, NUM_BANDS, S.WEIGHT_32F)
+        b.prepare(plan.roi)
+        for k, i in enumerate(subset):
+            if b.strip_needs(plan.sizes[i], plan.corners[i], plan.cuts[0], plan.cuts[1]):
+                b.feed(ws[k], sm[k], cs[k], borrow=True)
+        pano, pmask = b.blend_strip(plan.cuts[0], plan.cuts[1])
+        ok = ok and bool(torch.equal(pano, r["pano"])) and bool(torch.equal(pmask, r["pano_mask"]))
+    else:
+        sh.stitch(imgs_dev, Ks_all, Rs_all, scale, plan)           # the step is collective
+    t = torch.tensor([1 if ok else 0], device=dev)
+    dist.all_reduce(t, op=dist.ReduceOp.MIN)
+    return bool(t.item())
 
 
 if __name__ == "__main__":

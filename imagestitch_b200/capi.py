@@ -87,6 +87,8 @@ SYMBOLS = {
     "is_seam_dp_find_trace": (C.c_int, [C.c_void_p, C.c_int, _P(Mat), _P(Point), _P(Mat), C.c_int, _P(C.c_int32), C.c_size_t, _P(C.c_size_t)]),
     "is_ctx_seam_speculation": (C.c_int, [C.c_void_p]),
     "is_ctx_seam_path": (C.c_int, [C.c_void_p]),
+    "is_ctx_seam_waves": (C.c_int, [C.c_void_p]),
+    "is_ctx_clear_plan_cache": (C.c_int, [C.c_void_p]),
     "is_debug_seam_pair_finish": (C.c_int, [C.c_void_p, C.c_int, C.c_int, C.c_size_t, C.c_int, C.c_int, C.c_void_p, C.c_int, C.c_int, C.c_size_t, C.c_int, C.c_int,
                                             _P(C.c_int32), C.c_size_t]),
     "is_debug_dp_bench": (C.c_int, [C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_int, C.c_uint, C.c_int, _P(C.c_int32), _P(C.c_float)]),
@@ -95,6 +97,7 @@ SYMBOLS = {
     "is_seam_pair_run": (C.c_int, [C.c_void_p, _P(Mat), _P(Mat), Point, Point, _P(Mat), _P(Mat), _P(Mat), _P(Mat), _P(C.c_void_p)]),
     "is_seam_pair_check": (C.c_int, [C.c_void_p, _P(Mat), _P(Mat), Point, Point, _P(Mat), _P(Mat), C.c_void_p, _P(C.c_int)]),
     "is_seam_pair_destroy": (C.c_int, [C.c_void_p]),
+    "is_seam_pair_same_structure": (C.c_int, [C.c_void_p, _P(Mat), _P(Mat), _P(Mat), Point, Point, _P(C.c_int)]),
     "is_mask_and": (C.c_int, [C.c_void_p, _P(Mat), _P(Mat)]),
     "is_blender_strip_needs": (C.c_int, [C.c_void_p, Size, Point, C.c_int, C.c_int, _P(C.c_int)]),
     "is_blender_blend_strip": (C.c_int, [C.c_void_p, C.c_int, C.c_int, _P(Mat), _P(Mat)]),

@@ -157,6 +157,7 @@ int download2d(is_ctx* ctx, void* dst, size_t dpitch, const void* src, size_t sp
 int download_view(is_ctx* ctx, const void* src, size_t bytes, const void** view);
 
 int check_mat(is_ctx* ctx, const is_mat* m, const char* name);
+HostPool* host_pool(is_ctx* ctx);      // the context's host thread pool (created on first use)
 
 enum { SIDE_PYRAMID = 8, SIDE_COPY = 9 };
 int child_ctx(is_ctx* parent, size_t k, is_ctx** out);

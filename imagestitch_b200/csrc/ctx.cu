@@ -3,6 +3,8 @@
 #include "hostpool.h"
 
 #include <algorithm>
+#include <cstdlib>
+#include <thread>
 
 namespace is {
 
@@ -233,6 +235,16 @@ int download(is_ctx* ctx, void* dst, const void* src, size_t bytes) {
     return IS_OK;
 }
 
+HostPool* host_pool(is_ctx* ctx) {
+    if (!ctx->hpool) {
+        unsigned hc = std::thread::hardware_concurrency();
+        size_t w = hc > 2 ? std::min<size_t>(hc - 1, 7) : 0;
+        if (const char* e = getenv("IS_HOST_THREADS")) w = (size_t)std::max(0, atoi(e) - 1);
+        ctx->hpool = new HostPool(w);
+    }
+    return ctx->hpool;
+}
+
 int download_view(is_ctx* ctx, const void* src, size_t bytes, const void** view) {
     if (ctx->pinned_dl_bytes < bytes || !ctx->pinned_dl) {
         if (ctx->pinned_dl) { IS_CUDA(ctx, cudaStreamSynchronize(ctx->stream)); cudaFreeHost(ctx->pinned_dl); }
@@ -393,6 +405,13 @@ int is_ctx_kernel_timing_report(is_ctx* ctx, char* buf, size_t cap) {
 
 int is_ctx_seam_speculation(const is_ctx* ctx) { return ctx ? ctx->seam_speculation_accepted : -1; }
 int is_ctx_seam_path(const is_ctx* ctx) { return ctx ? ctx->seam_path : -1; }
+int is_ctx_seam_waves(const is_ctx* ctx) { return ctx ? ctx->seam_waves : -1; }
+
+int is_ctx_clear_plan_cache(is_ctx* ctx) {
+    if (!ctx) return IS_ERR_BAD_ARG;
+    ctx->plan_cache.clear();
+    return IS_OK;
+}
 
 const char* is_ctx_last_error(const is_ctx* ctx) { return ctx ? ctx->last_error.c_str() : "null context"; }
 void* is_ctx_stream(is_ctx* ctx) { return ctx ? (void*)ctx->stream : nullptr; }

@@ -22,6 +22,7 @@ struct WarpPlan {
 // @emu-end
 // warp.cu
 int warp_plan(is_ctx* ctx, int proj, int src_w, int src_h, const float* K, const float* R, float scale, WarpPlan* plan);
+int warp_plan_many(is_ctx* ctx, int proj, int n, const int* src_w, const int* src_h, const float* const* K, const float* const* R, float scale, WarpPlan* plans);
 int upload_tables(is_ctx* ctx, int proj, const WarpPlan& plan, DevBuf* buf);
 int launch_warp(is_ctx* ctx, int proj, const WarpPlan& plan, const float* tables, const DevMat& src, int interp, int border,
                 const DevMat& dst, const DevMat* mask);

@@ -20,9 +20,15 @@ int is_pipeline_plan(is_ctx* ctx, int n, const is_size* src_sizes, const is_came
     if (!ctx) return IS_ERR_BAD_ARG;
     IS_REQUIRE(ctx, n > 0 && src_sizes && cameras && cfg, IS_ERR_BAD_ARG, "null argument");
     int tlx = INT32_MAX, tly = INT32_MAX, brx = INT32_MIN, bry = INT32_MIN;
+    std::vector<WarpPlan> plans((size_t)n);
+    {
+        std::vector<int> sw((size_t)n), sh((size_t)n);
+        std::vector<const float*> Kp((size_t)n), Rp((size_t)n);
+        for (int i = 0; i < n; ++i) { sw[(size_t)i] = src_sizes[i].width; sh[(size_t)i] = src_sizes[i].height; Kp[(size_t)i] = cameras[i].K; Rp[(size_t)i] = cameras[i].R; }
+        IS_TRY(warp_plan_many(ctx, cfg->projection, n, sw.data(), sh.data(), Kp.data(), Rp.data(), cfg->scale, plans.data()));
+    }
     for (int i = 0; i < n; ++i) {
-        WarpPlan plan;
-        IS_TRY(warp_plan(ctx, cfg->projection, src_sizes[i].width, src_sizes[i].height, cameras[i].K, cameras[i].R, cfg->scale, &plan));
+        const WarpPlan& plan = plans[(size_t)i];
         if (corners) corners[i] = is_point{plan.roi[0], plan.roi[1]};
         if (sizes) sizes[i] = is_size{plan.P.dst_w, plan.P.dst_h};
         tlx = std::min(tlx, plan.roi[0]); tly = std::min(tly, plan.roi[1]);
@@ -64,8 +70,13 @@ int is_pipeline_run(is_ctx* ctx, int n, const is_mat* images, const is_camera* c
     std::vector<WarpPlan> plans(n);
     std::vector<is_point> corners(n);
     int tlx = INT32_MAX, tly = INT32_MAX, brx = INT32_MIN, bry = INT32_MIN;
+    {
+        std::vector<int> sw((size_t)n), sh((size_t)n);
+        std::vector<const float*> Kp((size_t)n), Rp((size_t)n);
+        for (int i = 0; i < n; ++i) { sw[(size_t)i] = images[i].cols; sh[(size_t)i] = images[i].rows; Kp[(size_t)i] = cams[i].K; Rp[(size_t)i] = cams[i].R; }
+        IS_TRY(warp_plan_many(ctx, cfg.projection, n, sw.data(), sh.data(), Kp.data(), Rp.data(), cfg.scale, plans.data()));
+    }
     for (int i = 0; i < n; ++i) {
-        IS_TRY(warp_plan(ctx, cfg.projection, images[i].cols, images[i].rows, cams[i].K, cams[i].R, cfg.scale, &plans[i]));
         corners[i] = is_point{plans[i].roi[0], plans[i].roi[1]};
         tlx = std::min(tlx, plans[i].roi[0]); tly = std::min(tly, plans[i].roi[1]);
         brx = std::max(brx, plans[i].roi[0] + plans[i].P.dst_w); bry = std::max(bry, plans[i].roi[1] + plans[i].P.dst_h);

@@ -2197,6 +2197,45 @@ int is_seam_pair_check(is_ctx* ctx, const is_mat* image_i, const is_mat* image_j
     return IS_OK;
 }
 
+// Would pair (i, j) take the same decisions on (mask_i, mask_j_b) as on (mask_i, mask_j_a)?  Structure and plan of both
+// settings through the batched path's machinery (row toggles + special points on the device, PairRuns on the host).
+// *same = 1: identical; 0: different, or outside what the run tables cover (the caller then takes its general path).
+int is_seam_pair_same_structure(is_ctx* ctx, const is_mat* mask_i, const is_mat* mask_j_a, const is_mat* mask_j_b, is_point tl_i, is_point tl_j, int* same) {
+    if (!ctx || !same) return IS_ERR_BAD_ARG;
+    *same = 0;
+    IS_CUDA(ctx, cudaSetDevice(ctx->device));
+    IS_TRY(check_mat(ctx, mask_i, "mask_i"));
+    IS_TRY(check_mat(ctx, mask_j_a, "mask_j_a"));
+    IS_TRY(check_mat(ctx, mask_j_b, "mask_j_b"));
+    IS_REQUIRE(ctx, mask_i->depth == IS_8U && mask_i->channels == 1 && mask_j_a->depth == IS_8U && mask_j_a->channels == 1 && mask_j_b->depth == IS_8U &&
+                        mask_j_b->channels == 1 && mask_j_a->rows == mask_j_b->rows && mask_j_a->cols == mask_j_b->cols, IS_ERR_BAD_ARG,
+               "masks must be CV_8U, both settings of mask j of equal size");
+    DevMat mi, ma, mb;
+    IS_TRY(stage_in(ctx, mask_i, &mi));
+    IS_TRY(stage_in(ctx, mask_j_a, &ma));
+    IS_TRY(stage_in(ctx, mask_j_b, &mb));
+    const bool overlap = std::max(tl_i.x, tl_j.x) < std::min(tl_i.x + mi.cols, tl_j.x + ma.cols) && std::max(tl_i.y, tl_j.y) < std::min(tl_i.y + mi.rows, tl_j.y + ma.rows);
+    if (!overlap) { *same = 1; return IS_OK; }
+    StructureQuery Q;
+    Q.masks.push_back(plain_mask(mi));
+    Q.masks.push_back(plain_mask(ma));
+    Q.masks.push_back(plain_mask(mb));
+    Q.pairs.push_back(StructureQuery::PairQ{0, 1, Pt{tl_i.x, tl_i.y}, Pt{tl_j.x, tl_j.y}});
+    Q.pairs.push_back(StructureQuery::PairQ{0, 2, Pt{tl_i.x, tl_i.y}, Pt{tl_j.x, tl_j.y}});
+    IS_TRY(run_structure_query(ctx, Q));
+    if (Q.pair_overflow[0] || Q.pair_overflow[1]) return IS_OK;
+    PairRuns P[2];
+    host_pool(ctx)->run(2, [&](size_t k) {
+        P[k].setup(0, 1, Q.pairs[k].tl1, Q.pairs[k].tl2, &Q.runs[(size_t)Q.pairs[k].m1], &Q.runs[(size_t)Q.pairs[k].m2]);
+        P[k].specials = Q.specials[k];
+        P[k].build();
+        if (!P[k].too_many_runs) P[k].plan();
+    });
+    if (P[0].too_many_runs || P[1].too_many_runs || P[0].unsupported || P[1].unsupported) return IS_OK;
+    *same = P[0].same_structure(P[1]) ? 1 : 0;
+    return IS_OK;
+}
+
 int is_seam_pair_destroy(is_seam_pair* p) {
     delete reinterpret_cast<is_seam_pair_impl*>(p);
     return IS_OK;

@@ -132,11 +132,6 @@ struct SpecialJob {
     int2* out; int* count;
 };
 
-__device__ __forceinline__ bool sp_at(const LayeredMask& m, int ox, int oy, int x, int y) { return lm_at(m, x - ox, y - oy); }
-__device__ __forceinline__ bool sp_contour(const LayeredMask& m, int ox, int oy, int x, int y) {   // contour{1,2}mask_ [SEAM]:165-186
-    return sp_at(m, ox, oy, x, y) && !(sp_at(m, ox, oy, x - 1, y) && sp_at(m, ox, oy, x + 1, y) && sp_at(m, ox, oy, x, y - 1) && sp_at(m, ox, oy, x, y + 1));
-}
-
 // bit i of the result: pixel mx0 + i (own coordinates) of mask row my is set, i < 18 -- from the row's toggles
 __device__ __forceinline__ unsigned row_bits18(const unsigned char* __restrict__ counts, const unsigned short* __restrict__ xs, int rows, int cols, int mx0, int my) {
     if ((unsigned)my >= (unsigned)rows) return 0u;
@@ -156,36 +151,54 @@ __device__ __forceinline__ unsigned row_bits18(const unsigned char* __restrict__
 // mask (a contour pixel of an INTERS component touching a FIRST / SECOND component), close to both masks' contours.
 // The scan works on the row toggles k_row_toggles_batch has just produced (16 pixels of a row per step as bit sets: two
 // 16-byte loads per row instead of ten byte loads per pixel); only the few candidates look at the mask bytes themselves.
-constexpr int SP_ROWS = 8;             // rows per thread
-constexpr int SP_QUEUE = 4096;         // candidates a block can hold (8 rows x 128 chunks of 16 pixels could make 16384: beyond the queue the pair overflows)
+constexpr int SP_ROWS = 4;             // rows per thread; a block of 128 threads covers 32 chunks (512 pixels) x 16 rows
+constexpr int SP_QUEUE = 2048;         // candidates a block can hold (its 8192 pixels could all be candidates: beyond the queue the pair overflows)
+struct SpMask { const uint8_t* p; size_t step; int rows, cols, ox, oy, nlayers; };
+__device__ __forceinline__ bool spm_at(const SpMask& M, const LayeredMask& full, int fx, int fy) {   // frame coordinates
+    const int x = fx - M.ox, y = fy - M.oy;
+    if ((unsigned)x >= (unsigned)M.cols || (unsigned)y >= (unsigned)M.rows) return false;
+    if (!M.p[(size_t)y * M.step + x]) return false;
+    return M.nlayers == 0 || !lm_cleared(full, x, y);
+}
+__device__ __forceinline__ bool spm_contour(const SpMask& M, const LayeredMask& full, int x, int y) {   // contour{1,2}mask_ [SEAM]:165-186
+    return spm_at(M, full, x, y) && !(spm_at(M, full, x - 1, y) && spm_at(M, full, x + 1, y) && spm_at(M, full, x, y - 1) && spm_at(M, full, x, y + 1));
+}
+
 __global__ void __launch_bounds__(128) k_special_points_batch(const SpecialJob* __restrict__ jobs) {
     __shared__ int2 queue[SP_QUEUE];
     __shared__ int qn;
+    __shared__ SpMask M1, M2;
+    __shared__ int geo[6];                                                       // uw, uh, ix, iy, iw, ih
     const SpecialJob& J = jobs[blockIdx.z];
-    if (threadIdx.x == 0) qn = 0;
+    if (threadIdx.x == 0) {
+        qn = 0;
+        M1 = SpMask{J.m1.p, J.m1.step, J.m1.rows, J.m1.cols, J.o1x, J.o1y, J.m1.nlayers};
+        M2 = SpMask{J.m2.p, J.m2.step, J.m2.rows, J.m2.cols, J.o2x, J.o2y, J.m2.nlayers};
+        geo[0] = J.uw; geo[1] = J.uh; geo[2] = J.ix; geo[3] = J.iy; geo[4] = J.iw; geo[5] = J.ih;
+    }
     __syncthreads();
-    const int cx = blockIdx.x * blockDim.x + threadIdx.x;
-    const int ly0 = blockIdx.y * SP_ROWS;
-    if (ly0 >= J.ih) return;                                                     // uniform over the block
-    if (16 * cx < J.iw) {
-        const int x0 = J.ix + 16 * cx;                                           // frame column of bit 1
-        const int m1x = x0 - 1 - J.o1x, m2x = x0 - 1 - J.o2x;
+    const int ix = geo[2], iy = geo[3], iw = geo[4], ih = geo[5];
+    const int cx = blockIdx.x * 32 + (threadIdx.x & 31);
+    const int ly0 = (blockIdx.y * 4 + (threadIdx.x >> 5)) * SP_ROWS;
+    if ((int)(blockIdx.y * 4 * SP_ROWS) >= ih || (int)(blockIdx.x * 512) >= iw) return;   // uniform over the block
+    if (16 * cx < iw && ly0 < ih) {
+        const int x0 = ix + 16 * cx;                                             // frame column of bit 1
+        const int m1x = x0 - 1 - M1.ox, m2x = x0 - 1 - M2.ox;
         auto bits = [&](int y, unsigned* b1, unsigned* b2) {                     // frame row y
-            *b1 = row_bits18(J.cnt1, J.xs1, J.m1.rows, J.m1.cols, m1x, y - J.o1y);
-            *b2 = row_bits18(J.cnt2, J.xs2, J.m2.rows, J.m2.cols, m2x, y - J.o2y);
+            *b1 = row_bits18(J.cnt1, J.xs1, M1.rows, M1.cols, m1x, y - M1.oy);
+            *b2 = row_bits18(J.cnt2, J.xs2, M2.rows, M2.cols, m2x, y - M2.oy);
         };
         unsigned p1, p2, c1, c2, n1, n2;
-        bits(J.iy + ly0 - 1, &p1, &p2);
-        bits(J.iy + ly0, &c1, &c2);
-        const int rows = min(SP_ROWS, J.ih - ly0);
+        bits(iy + ly0 - 1, &p1, &p2);
+        bits(iy + ly0, &c1, &c2);
+        const int rows = min(SP_ROWS, ih - ly0);
         for (int r = 0; r < rows; ++r) {
-            const int y = J.iy + ly0 + r;
+            const int y = iy + ly0 + r;
             bits(y + 1, &n1, &n2);
             const unsigned both = c1 & c2, x_cur = c1 ^ c2, x_up = p1 ^ p2, x_dn = n1 ^ n2;
             unsigned cand = both & ((x_cur << 1) | (x_cur >> 1) | x_up | x_dn) & 0x1fffeu;   // bits 1..16: this chunk's pixels
             if (cand) {
-                const int base = atomicAdd(&qn, __popc(cand));
-                int k = base;
+                int k = atomicAdd(&qn, __popc(cand));
                 while (cand) {
                     const int i = __ffs(cand) - 1;
                     cand &= cand - 1;
@@ -199,15 +212,17 @@ __global__ void __launch_bounds__(128) k_special_points_batch(const SpecialJob* 
     __syncthreads();
     const int n = qn;
     if (n > SP_QUEUE) { if (threadIdx.x == 0) atomicAdd(J.count, SPECIAL_CAP + 1); return; }   // overflow: the pair takes the general path
-    // closeToContour of both masks for every candidate: one warp per candidate, one window position per lane
+    // closeToContour of both masks for every candidate ([SEAM]:584-604): one warp per candidate, one window position per lane
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nw = blockDim.x >> 5;
+    const int uw = geo[0], uh = geo[1];
     for (int q = warp; q < n; q += nw) {
         const int2 c = queue[q];
         const int x = c.x + (lane % 5) - 2, y = c.y + (lane / 5) - 2;
-        const bool in = lane < 25 && x >= 0 && x < J.uw && y >= 0 && y < J.uh;
-        const unsigned b1 = __ballot_sync(0xffffffffu, in && sp_contour(J.m1, J.o1x, J.o1y, x, y));
-        const unsigned b2 = __ballot_sync(0xffffffffu, in && sp_contour(J.m2, J.o2x, J.o2y, x, y));
-        if (lane == 0 && b1 && b2 && c.x < J.ix + J.iw) {
+        const bool in = lane < 25 && x >= 0 && x < uw && y >= 0 && y < uh;
+        const unsigned b1 = __ballot_sync(0xffffffffu, in && spm_contour(M1, J.m1, x, y));
+        if (!b1) continue;                                                       // uniform over the warp
+        const unsigned b2 = __ballot_sync(0xffffffffu, in && spm_contour(M2, J.m2, x, y));
+        if (lane == 0 && b2 && c.x < ix + iw) {
             const int pos = atomicAdd(J.count, 1);
             if (pos < SPECIAL_CAP) J.out[pos] = c;
         }
@@ -275,6 +290,69 @@ __global__ void k_cost_pq_batch(const PairDev* __restrict__ pairs, const JobDev*
     if (lab(D.labels, D.fr, x, y) != J.l1) p = __int_as_float(0x7f800000);   // +inf: the cell can never be on a path
     P[(size_t)step * J.pitch + lane] = p;
     Q[(size_t)step * J.pitch + lane] = q;
+}
+
+// COLOR costs of all seams, second formulation: a thread owns one lane and walks COST_WALK steps.  Both costs of a cell pair
+// the cell with one neighbour -- the neighbouring lane of the same step (P) and the same lane of the previous step (Q):
+//   vertical seam    lane = x, step = y:   P = costV(x, y) pairs (x - 1, y),  Q = costH(x, y) pairs (x, y - 1)
+//   horizontal seam  lane = y, step = x:   P = costH(x, y) pairs (x, y - 1),  Q = costV(x, y) pairs (x - 1, y)
+// so the cell's own pixels and label are loaded once, the previous step's stay in registers and the neighbouring lane's come
+// by warp shuffle: 6 pixel bytes + one label per cell instead of ~24 + 5.  Same arithmetic as cost_v / cost_h ([SEAM]:756-802).
+constexpr int COST_WALK = 32;
+template <typename T>
+__global__ void __launch_bounds__(128) k_cost_pq_walk(const PairDev* __restrict__ pairs, const JobDev* __restrict__ jobs) {
+    const JobDev& J = jobs[blockIdx.z];
+    const int s_begin = blockIdx.y * COST_WALK;
+    if (s_begin >= J.steps || (int)(blockIdx.x * blockDim.x) >= J.pitch) return;      // uniform over the block
+    const PairDev& D = pairs[J.pair];
+    const int lane = blockIdx.x * blockDim.x + threadIdx.x;
+    const int lane_id = threadIdx.x & 31;
+    const bool hz = J.horizontal != 0;
+    const int l1 = J.l1;
+    const ImgView<T> A{reinterpret_cast<const T*>(D.img1), D.step1, D.rows1, D.cols1, D.dx1, D.dy1};
+    const ImgView<T> B{reinterpret_cast<const T*>(D.img2), D.step2, D.rows2, D.cols2, D.dx2, D.dy2};
+    struct Cell { float a[3], b[3]; int lab; };
+    auto load = [&](int ln, int st) {                                               // pixels only where the label says both images cover the cell
+        Cell c;
+        const int x = J.rx + (hz ? st : ln), y = J.ry + (hz ? ln : st);
+        c.lab = ln < J.lanes ? label_at(D.labels, D.fr, x, y) : -3;
+        if (c.lab == l1) {
+            const T* pa = A.px(x, y);
+            const T* pb = B.px(x, y);
+            c.a[0] = (float)pa[0]; c.a[1] = (float)pa[1]; c.a[2] = (float)pa[2];
+            c.b[0] = (float)pb[0]; c.b[1] = (float)pb[1]; c.b[2] = (float)pb[2];
+        } else {
+            c.a[0] = c.a[1] = c.a[2] = c.b[0] = c.b[1] = c.b[2] = 0.f;
+        }
+        return c;
+    };
+    auto pair_cost = [&](const Cell& n, const Cell& c) {
+        if (n.lab != l1 || c.lab != l1) return IS_BAD_REGION_COST;
+        return __fmul_rn(__fadd_rn(diff3(n.a, c.b), diff3(c.a, n.b)), 0.5f);
+    };
+    const float INF = __int_as_float(0x7f800000);
+    Cell prev = load(lane, s_begin - 1);                                             // step -1 is the frame row / column in front of the bounding box
+    const int s_end = min(s_begin + COST_WALK, J.steps);
+    for (int st = s_begin; st < s_end; ++st) {
+        const Cell cur = load(lane, st);
+        Cell nb;
+        nb.lab = __shfl_up_sync(0xffffffffu, cur.lab, 1);
+#pragma unroll
+        for (int k = 0; k < 3; ++k) { nb.a[k] = __shfl_up_sync(0xffffffffu, cur.a[k], 1); nb.b[k] = __shfl_up_sync(0xffffffffu, cur.b[k], 1); }
+        if (lane_id == 0) nb = load(lane - 1, st);                                   // the neighbouring lane belongs to another warp (or lies in front of the box)
+        if (lane < J.pitch) {
+            float p, q;
+            if (lane >= J.lanes) { p = INF; q = 0.f; }                               // padding lanes: outside the component
+            else {
+                p = pair_cost(nb, cur);
+                q = pair_cost(prev, cur);
+                if (cur.lab != l1) p = INF;                                          // +inf: the cell can never be on a path
+            }
+            J.P[(size_t)st * J.pitch + lane] = p;
+            J.Q[(size_t)st * J.pitch + lane] = q;
+        }
+        prev = cur;
+    }
 }
 
 // the final mask update: one warp per row of a pair's intersection rectangle writes zeros over its clear intervals
@@ -425,16 +503,6 @@ struct SeamJobHost {
     int status = IS_OK;
 };
 
-static HostPool* host_pool(is_ctx* ctx) {
-    if (!ctx->hpool) {
-        unsigned hc = std::thread::hardware_concurrency();
-        size_t w = hc > 2 ? std::min<size_t>(hc - 1, 7) : 0;
-        if (const char* e = getenv("IS_SEAM_HOST_THREADS")) w = (size_t)std::max(0, atoi(e) - 1);
-        ctx->hpool = new HostPool(w);
-    }
-    return ctx->hpool;
-}
-
 // one seam back on the host: end points, trace record, updateLabelsUsingSeam on runs.  res: [reached, -, lanes ...]
 static int seam_job_finish(is_ctx* ctx, const PairRuns& PR, SeamJobHost& J, const int* res, bool want_trace) {
     const SeamOp& op = J.op;
@@ -546,7 +614,7 @@ static int run_structure_query(is_ctx* ctx, StructureQuery& Q) {
         IS_LAUNCH(ctx, k_row_toggles_batch, grid, 256, 0, tj_d, reinterpret_cast<int*>(base + off_hdr));
     }
     if (np && max_iw > 0 && max_ih > 0) {
-        dim3 grid(div_up(div_up(max_iw, 16), 128), div_up(max_ih, SP_ROWS), (unsigned)np);
+        dim3 grid(div_up(max_iw, 512), div_up(max_ih, 4 * SP_ROWS), (unsigned)np);
         IS_LAUNCH(ctx, k_special_points_batch, grid, 128, 0, sj_d);
     }
     const unsigned char* h = nullptr;                                   // view of the pinned bounce buffer, valid until the next download
@@ -797,9 +865,13 @@ static int seam_batch_wave(is_ctx* ctx, const std::vector<std::pair<int, int>>& 
             if (cost_fn == IS_COST_COLOR_GRAD) {
                 if (is_u8) IS_LAUNCH(ctx, (k_cost_pq_batch<uint8_t, true>), grid, block, 0, pairs_d, jobs_d);
                 else IS_LAUNCH(ctx, (k_cost_pq_batch<float, true>), grid, block, 0, pairs_d, jobs_d);
-            } else {
+            } else if (getenv("IS_COST_KERNEL_CELL")) {                                          // tuning knob: one thread per cell
                 if (is_u8) IS_LAUNCH(ctx, (k_cost_pq_batch<uint8_t, false>), grid, block, 0, pairs_d, jobs_d);
                 else IS_LAUNCH(ctx, (k_cost_pq_batch<float, false>), grid, block, 0, pairs_d, jobs_d);
+            } else {
+                dim3 wgrid(div_up(max_pitch, 128), div_up(max_steps, COST_WALK), (unsigned)nj);
+                if (is_u8) IS_LAUNCH(ctx, k_cost_pq_walk<uint8_t>, wgrid, 128, 0, pairs_d, jobs_d);
+                else IS_LAUNCH(ctx, k_cost_pq_walk<float>, wgrid, 128, 0, pairs_d, jobs_d);
             }
         }
         {                                                                                        // one DP launch per shape, one CTA per seam

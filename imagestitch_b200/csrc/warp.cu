@@ -14,6 +14,7 @@
 //     (32-fy)(32-fx) ... (the 15-bit table of OpenCV divided by its common factor 32), BORDER_REFLECT /
 //     BORDER_CONSTANT neighbour fetch, (sum + 512) >> 10.
 #include "internal.cuh"
+#include "hostpool.h"
 
 #include <cmath>
 #include <limits>
@@ -80,16 +81,23 @@ static inline void map_forward(int proj, const Projector& p, float scale, float 
 // that does not look along the projection axis; that is the scan cv::detail::CylindricalWarper /
 // SphericalWarper themselves use (detectResultRoiByBorder).  The reference's full scan
 // ([WARP]:72-81) gives the same corners (tests/test_oracle_warp.py pins both).
-static void detect_roi(int proj, int w, int h, const Projector& p, float scale, int roi[4]) {
-    float tl_u = std::numeric_limits<float>::max(), tl_v = tl_u, br_u = -tl_u, br_v = -tl_u;
+struct RoiAcc { float tl_u, tl_v, br_u, br_v; };
+
+// extrema over a part of the border: segment 0 / 1 = top + bottom rows [x0, x1), segment 2 / 3 = left + right columns [y0, y1)
+static RoiAcc roi_segment(int proj, int w, int h, const Projector& p, float scale, bool rows, int a0, int a1) {
+    RoiAcc r{std::numeric_limits<float>::max(), std::numeric_limits<float>::max(), -std::numeric_limits<float>::max(), -std::numeric_limits<float>::max()};
     auto acc = [&](int x, int y) {
         float u, v;
         map_forward(proj, p, scale, (float)x, (float)y, &u, &v);
-        tl_u = std::min(tl_u, u); tl_v = std::min(tl_v, v);
-        br_u = std::max(br_u, u); br_v = std::max(br_v, v);
+        r.tl_u = std::min(r.tl_u, u); r.tl_v = std::min(r.tl_v, v);
+        r.br_u = std::max(r.br_u, u); r.br_v = std::max(r.br_v, v);
     };
-    for (int x = 0; x < w; ++x) { acc(x, 0); acc(x, h - 1); }
-    for (int y = 0; y < h; ++y) { acc(0, y); acc(w - 1, y); }
+    if (rows) for (int x = a0; x < a1; ++x) { acc(x, 0); acc(x, h - 1); }
+    else for (int y = a0; y < a1; ++y) { acc(0, y); acc(w - 1, y); }
+    return r;
+}
+
+static void finish_roi(int proj, int w, int h, const Projector& p, float scale, float tl_u, float tl_v, float br_u, float br_v, int roi[4]) {
     if (proj == IS_PROJ_SPHERICAL) {   // SphericalWarper::detectResultRoi: poles inside the image widen the ROI
         tl_u = (float)(int)tl_u; tl_v = (float)(int)tl_v; br_u = (float)(int)br_u; br_v = (float)(int)br_v;
         for (int pole = 0; pole < 2; ++pole) {
@@ -107,6 +115,16 @@ static void detect_roi(int proj, int w, int h, const Projector& p, float scale, 
         }
     }
     roi[0] = (int)tl_u; roi[1] = (int)tl_v; roi[2] = (int)br_u; roi[3] = (int)br_v;
+}
+
+// detectResultRoi: the extrema of (u, v) over the source image lie on its border for every camera
+// that does not look along the projection axis; that is the scan cv::detail::CylindricalWarper /
+// SphericalWarper themselves use (detectResultRoiByBorder).  The reference's full scan
+// ([WARP]:72-81) gives the same corners (tests/test_oracle_warp.py pins both).  min / max are order independent, so the
+// border may be scanned in pieces (detect_roi_parallel below).
+static void detect_roi(int proj, int w, int h, const Projector& p, float scale, int roi[4]) {
+    const RoiAcc a = roi_segment(proj, w, h, p, scale, true, 0, w), b = roi_segment(proj, w, h, p, scale, false, 0, h);
+    finish_roi(proj, w, h, p, scale, std::min(a.tl_u, b.tl_u), std::min(a.tl_v, b.tl_v), std::max(a.br_u, b.br_u), std::max(a.br_v, b.br_v), roi);
 }
 
 // Per-column and per-row trigonometry of the backward map, host libm.  Layout: [sinu(w) | cosu(w) | rowA(h) | rowB(h)]
@@ -283,25 +301,38 @@ __global__ void k_build_maps(WarpParams P, const float* __restrict__ tables, flo
 // @emu-end
 // ---- host drivers ----------------------------------------------------------------------------------
 
-int warp_plan(is_ctx* ctx, int proj, int src_w, int src_h, const float* K, const float* R, float scale, WarpPlan* plan) {
-    IS_REQUIRE(ctx, proj == IS_PROJ_CYLINDRICAL || proj == IS_PROJ_SPHERICAL, IS_ERR_BAD_ARG, "unknown projection");
-    IS_REQUIRE(ctx, K && R, IS_ERR_ASSERT, "K and R must be 3x3 CV_32F");
-    IS_REQUIRE(ctx, src_w > 0 && src_h > 0 && scale > 0.f, IS_ERR_BAD_ARG, "empty source or non-positive scale");
-    struct Key { int proj, w, h; float K[9], R[9], scale; };
-    struct Entry { Key key; WarpPlan plan; };
-    Key key;
+struct PlanKey { int proj, w, h; float K[9], R[9], scale; };
+struct PlanEntry { PlanKey key; WarpPlan plan; };
+
+static PlanKey plan_key(int proj, int src_w, int src_h, const float* K, const float* R, float scale) {
+    PlanKey key;
     std::memset(&key, 0, sizeof(key));
     key.proj = proj; key.w = src_w; key.h = src_h; key.scale = scale;
     std::memcpy(key.K, K, sizeof(key.K));
     std::memcpy(key.R, R, sizeof(key.R));
-    const size_t nent = ctx->plan_cache.size() / sizeof(Entry);
+    return key;
+}
+
+static bool plan_lookup(is_ctx* ctx, const PlanKey& key, WarpPlan* plan) {
+    const size_t nent = ctx->plan_cache.size() / sizeof(PlanEntry);
     for (size_t e = 0; e < nent; ++e) {
-        const Entry* ent = reinterpret_cast<const Entry*>(ctx->plan_cache.data()) + e;
-        if (std::memcmp(&ent->key, &key, sizeof(Key)) == 0) { *plan = ent->plan; return IS_OK; }
+        const PlanEntry* ent = reinterpret_cast<const PlanEntry*>(ctx->plan_cache.data()) + e;
+        if (std::memcmp(&ent->key, &key, sizeof(PlanKey)) == 0) { *plan = ent->plan; return true; }
     }
-    Projector p;
-    set_camera(K, R, &p);
-    detect_roi(proj, src_w, src_h, p, scale, plan->roi);
+    return false;
+}
+
+static void plan_store(is_ctx* ctx, const PlanKey& key, const WarpPlan& plan) {
+    if (ctx->plan_cache.size() / sizeof(PlanEntry) >= 256) ctx->plan_cache.clear();
+    PlanEntry ent;
+    std::memset(&ent, 0, sizeof(ent));
+    ent.key = key;
+    ent.plan = plan;
+    const unsigned char* raw = reinterpret_cast<const unsigned char*>(&ent);
+    ctx->plan_cache.insert(ctx->plan_cache.end(), raw, raw + sizeof(PlanEntry));
+}
+
+static int plan_from_roi(is_ctx* ctx, const Projector& p, int src_w, int src_h, float scale, WarpPlan* plan) {
     std::memcpy(plan->P.k_rinv, p.k_rinv, sizeof(p.k_rinv));
     plan->P.scale = scale;
     plan->P.tl_x = plan->roi[0];
@@ -312,13 +343,59 @@ int warp_plan(is_ctx* ctx, int proj, int src_w, int src_h, const float* K, const
     plan->P.src_h = src_h;
     IS_REQUIRE(ctx, plan->P.dst_w > 0 && plan->P.dst_h > 0 && plan->P.dst_w < (1 << 24) && plan->P.dst_h < (1 << 24),
                IS_ERR_BAD_ARG, "degenerate warp ROI");
-    if (nent >= 256) ctx->plan_cache.clear();
-    Entry ent;
-    std::memset(&ent, 0, sizeof(ent));
-    ent.key = key;
-    ent.plan = *plan;
-    const unsigned char* raw = reinterpret_cast<const unsigned char*>(&ent);
-    ctx->plan_cache.insert(ctx->plan_cache.end(), raw, raw + sizeof(Entry));
+    return IS_OK;
+}
+
+int warp_plan(is_ctx* ctx, int proj, int src_w, int src_h, const float* K, const float* R, float scale, WarpPlan* plan) {
+    IS_REQUIRE(ctx, proj == IS_PROJ_CYLINDRICAL || proj == IS_PROJ_SPHERICAL, IS_ERR_BAD_ARG, "unknown projection");
+    IS_REQUIRE(ctx, K && R, IS_ERR_ASSERT, "K and R must be 3x3 CV_32F");
+    IS_REQUIRE(ctx, src_w > 0 && src_h > 0 && scale > 0.f, IS_ERR_BAD_ARG, "empty source or non-positive scale");
+    const PlanKey key = plan_key(proj, src_w, src_h, K, R, scale);
+    if (plan_lookup(ctx, key, plan)) return IS_OK;
+    Projector p;
+    set_camera(K, R, &p);
+    detect_roi(proj, src_w, src_h, p, scale, plan->roi);
+    IS_TRY(plan_from_roi(ctx, p, src_w, src_h, scale, plan));
+    plan_store(ctx, key, *plan);
+    return IS_OK;
+}
+
+// The plans of all images of a panorama at once: the border scans of the images not yet in the memo are cut into pieces and
+// spread over the context's host threads (libm atan2f / sqrtf per border pixel: ~0.25 ms per 24 MP image on one core).
+int warp_plan_many(is_ctx* ctx, int proj, int n, const int* src_w, const int* src_h, const float* const* K, const float* const* R, float scale, WarpPlan* plans) {
+    IS_REQUIRE(ctx, proj == IS_PROJ_CYLINDRICAL || proj == IS_PROJ_SPHERICAL, IS_ERR_BAD_ARG, "unknown projection");
+    IS_REQUIRE(ctx, scale > 0.f, IS_ERR_BAD_ARG, "non-positive scale");
+    std::vector<int> todo;
+    std::vector<PlanKey> keys((size_t)n);
+    for (int i = 0; i < n; ++i) {
+        IS_REQUIRE(ctx, K[i] && R[i], IS_ERR_ASSERT, "K and R must be 3x3 CV_32F");
+        IS_REQUIRE(ctx, src_w[i] > 0 && src_h[i] > 0, IS_ERR_BAD_ARG, "empty source");
+        keys[(size_t)i] = plan_key(proj, src_w[i], src_h[i], K[i], R[i], scale);
+        if (!plan_lookup(ctx, keys[(size_t)i], &plans[i])) todo.push_back(i);
+    }
+    if (todo.empty()) return IS_OK;
+    constexpr int PIECES = 8;                             // per image: 4 pieces of the rows, 4 of the columns
+    std::vector<Projector> proj_of(todo.size());
+    std::vector<RoiAcc> acc(todo.size() * PIECES);
+    for (size_t t = 0; t < todo.size(); ++t) set_camera(K[todo[t]], R[todo[t]], &proj_of[t]);
+    host_pool(ctx)->run(todo.size() * PIECES, [&](size_t job) {
+        const size_t t = job / PIECES;
+        const int piece = (int)(job % PIECES), i = todo[t];
+        const bool rows = piece < PIECES / 2;
+        const int len = rows ? src_w[i] : src_h[i], q = piece % (PIECES / 2);
+        acc[job] = roi_segment(proj, src_w[i], src_h[i], proj_of[t], scale, rows, (int)((long long)len * q / (PIECES / 2)), (int)((long long)len * (q + 1) / (PIECES / 2)));
+    });
+    for (size_t t = 0; t < todo.size(); ++t) {
+        const int i = todo[t];
+        RoiAcc a = acc[t * PIECES];
+        for (int q = 1; q < PIECES; ++q) {
+            const RoiAcc& b = acc[t * PIECES + q];
+            a.tl_u = std::min(a.tl_u, b.tl_u); a.tl_v = std::min(a.tl_v, b.tl_v); a.br_u = std::max(a.br_u, b.br_u); a.br_v = std::max(a.br_v, b.br_v);
+        }
+        finish_roi(proj, src_w[i], src_h[i], proj_of[t], scale, a.tl_u, a.tl_v, a.br_u, a.br_v, plans[i].roi);
+        IS_TRY(plan_from_roi(ctx, proj_of[t], src_w[i], src_h[i], scale, &plans[i]));
+        plan_store(ctx, keys[(size_t)i], plans[i]);
+    }
     return IS_OK;
 }
 

@@ -111,7 +111,148 @@ class ShardedStitcher:
         self.be, self.comm, self.num_bands = backend, comm, num_bands
         self.info = {}
 
+    def is_strip(self, plan: ShardPlan):
+        """A left-to-right strip whose only cross-rank pairs join the last image of one rank to the first of the next."""
+        n = len(plan.corners)
+        m = n // plan.world
+        if any(plan.owner[i] != i // m for i in range(n)):
+            return False
+        return all(j == i + 1 for (i, j) in plan.pairs)
+
     def stitch(self, my_images, Ks_all, Rs_all, scale, plan: ShardPlan):
+        if hasattr(self.be, "seam_find_list") and self.is_strip(plan) and os.environ.get("IS_SHARD_GENERAL") != "1":
+            return self.stitch_strip(my_images, Ks_all, Rs_all, scale, plan)
+        return self.stitch_general(my_images, Ks_all, Rs_all, scale, plan)
+
+    def stitch_strip(self, my_images, Ks_all, Rs_all, scale, plan: ShardPlan):
+        """Strips: every rank hands its images plus the first image of its right neighbour to the batched seam finder in ONE call
+        (the pair loop of the reference restricted to this rank: its own pairs and the boundary pair, proven equal to the
+        sequential loop inside the library).  What the restriction misses is exactly one dependency per boundary -- in the
+        reference's order the boundary pair (b, b+1) comes after (b+1, b+2), i.e. after the neighbour's own pairs have cleared
+        part of image b+1 -- and that is checked afterwards with the mask the neighbour ends up with
+        (is_seam_pair_same_structure).  Messages: X1 the neighbour's first image + mask, X2 its mask after its own pairs and,
+        the other way, its mask after the boundary pair, one all-reduce of the verdict, X3 the blend halo."""
+        be, comm, rank = self.be, self.comm, self.comm.rank
+        import time
+        dbg = os.environ.get("IS_SHARD_DEBUG") == "1"
+        t_last = [time.perf_counter()]
+        laps = {}
+
+        def lap(name):
+            if dbg:
+                be.sync()
+                t = time.perf_counter()
+                laps[name] = laps.get(name, 0.0) + (t - t_last[0]) * 1e3
+                t_last[0] = t
+        n = len(plan.corners)
+        mine = [i for i in range(n) if plan.owner[i] == rank]
+        a, b = mine[0], mine[-1]
+        warped, mask = {}, {}
+        for i, img in zip(mine, my_images):
+            warped[i], mask[i] = be.warp(img, Ks_all[i], Rs_all[i], scale)
+        lap("warp")
+        x0, x1 = plan.cuts[rank], plan.cuts[rank + 1]
+        needed_by = [[i for i in range(n) if be.strip_needs(plan.sizes[i], plan.corners[i], plan.roi, self.num_bands, plan.cuts[r], plan.cuts[r + 1])]
+                     for r in range(comm.world)]
+        bh = be.blend_begin(plan.roi, self.num_bands)
+        for i in mine:                                # image pyramids on a side stream while the seam stage runs; the masks are read at blend time
+            if i in needed_by[rank]:
+                be.blend_feed_early(bh, warped[i], mask[i], plan.corners[i], i + 1)
+        # ---- X1: my first image + entry mask -> left neighbour (its boundary pair)
+        has_right = b + 1 < n and (b, b + 1) in plan.pairs
+        has_left = a > 0 and (a - 1, a) in plan.pairs
+        sends, recvs = [], []
+        if has_left:
+            sends += [(rank - 1, warped[a]), (rank - 1, mask[a])]
+        if has_right:
+            warped[b + 1] = be.empty((plan.sizes[b + 1][1], plan.sizes[b + 1][0], 3), np.uint8)
+            halo_entry = be.empty((plan.sizes[b + 1][1], plan.sizes[b + 1][0]), np.uint8)
+            recvs += [(rank + 1, warped[b + 1]), (rank + 1, halo_entry)]
+        comm.exchange(sends, recvs)
+        lap("x1")
+        # ---- seam: one batched call over my images + the halo image
+        entry_b = be.copy_of(mask[b]) if has_right else None
+        ids = mine + ([b + 1] if has_right else [])
+        halo_mask = be.copy_of(halo_entry) if has_right else None
+        masks_in = [mask[i] for i in mine] + ([halo_mask] if has_right else [])
+        self.info["seam"] = be.seam_find_list([warped[i] for i in ids], [plan.corners[i] for i in ids], masks_in)
+        lap("seam")
+        # ---- X2: my first image's mask after my own pairs -> left neighbour (its check); the halo's mask after the boundary pair -> its owner
+        sends, recvs = [], []
+        if has_left:
+            after_own = be.copy_of(mask[a])           # mask[a] receives the boundary pair's clears below
+            from_left = be.empty((plan.sizes[a][1], plan.sizes[a][0]), np.uint8)
+            sends.append((rank - 1, after_own))
+            recvs.append((rank - 1, from_left))
+        if has_right:
+            halo_true = be.empty((plan.sizes[b + 1][1], plan.sizes[b + 1][0]), np.uint8)
+            sends.append((rank + 1, halo_mask))
+            recvs.append((rank + 1, halo_true))
+        comm.exchange(sends, recvs)
+        lap("x2")
+        ok = 1
+        if has_right:                                 # the boundary pair on the mask image b+1 really has at that point of the reference's loop
+            ok = 1 if be.pair_same_structure(entry_b, halo_entry, halo_true, plan.corners[b], plan.corners[b + 1]) else 0
+        ok = comm.all_min(ok, be.device)
+        if os.environ.get("IS_SHARDED_FORCE_FALLBACK") == "1":
+            ok = 0
+        self.info["seam_speculation"] = ok
+        lap("check")
+        if not ok:                                    # rare by construction: redo the step through the general path
+            return self.stitch_general(my_images, Ks_all, Rs_all, scale, plan)
+        if has_left:                                  # the boundary pair's clears (computed by the left neighbour) inside its rectangle
+            i, j = a - 1, a
+            rx0 = max(plan.corners[i][0], plan.corners[j][0]) - plan.corners[j][0]
+            ry0 = max(plan.corners[i][1], plan.corners[j][1]) - plan.corners[j][1]
+            rx1 = min(plan.corners[i][0] + plan.sizes[i][0], plan.corners[j][0] + plan.sizes[j][0]) - plan.corners[j][0]
+            ry1 = min(plan.corners[i][1] + plan.sizes[i][1], plan.corners[j][1] + plan.sizes[j][1]) - plan.corners[j][1]
+            be.mask_and(mask[a], from_left, rect=(rx0, ry0, rx1, ry1))
+        final = {i: mask[i] for i in mine}
+        if has_right:
+            final[b + 1] = halo_true                  # completed below by X3 where the blend needs it
+        lap("final_masks")
+        # ---- X3: blend halo (images that reach into a neighbour's strip, with their final masks)
+        # a receiver that already holds the image tells nobody: the sender must skip it too -- decide from the geometry alone
+        sends, recvs = self._strip_x3(plan, needed_by, mine, warped, final, rank, comm, be, has_right, b)
+        comm.exchange(sends, recvs)
+        lap("x3")
+        for i in needed_by[rank]:
+            if i not in mine:
+                be.blend_feed(bh, warped[i], final[i], plan.corners[i], i + 1)
+        pano, pmask = be.blend_finish(bh, x0, x1)
+        self.info["needed_images"] = needed_by[rank]
+        lap("blend")
+        if dbg:
+            self.info["laps_ms"] = laps
+            print(f"[shard rank {rank}] " + " ".join(f"{k}={v:.2f}" for k, v in laps.items()), flush=True)
+        return dict(pano=pano, pano_mask=pmask, x0=x0, x1=x1, seam_masks={i: final[i] for i in mine})
+
+    def _strip_x3(self, plan, needed_by, mine, warped, final, rank, comm, be, has_right, b):
+        """X3 message lists.  Rank r already holds image b_r + 1 (X1), so only that image's FINAL mask travels to it; every other
+        halo image travels whole.  Both sides derive the same schedule from the plan."""
+        n = len(plan.corners)
+        m = n // plan.world
+        sends, recvs = [], []
+        for r in range(comm.world):
+            b_r = (r + 1) * m - 1
+            for i in needed_by[r]:
+                src = plan.owner[i]
+                if src == r:
+                    continue
+                holds = (i == b_r + 1) and ((b_r, b_r + 1) in plan.pairs)
+                if rank == src:
+                    if not holds:
+                        sends.append((r, warped[i]))
+                    sends.append((r, final[i]))
+                if rank == r:
+                    if not holds:
+                        warped[i] = be.empty((plan.sizes[i][1], plan.sizes[i][0], 3), np.uint8)
+                        recvs.append((src, warped[i]))
+                    final[i] = be.empty((plan.sizes[i][1], plan.sizes[i][0]), np.uint8)
+                    recvs.append((src, final[i]))
+        return sends, recvs
+
+    def stitch_general(self, my_images, Ks_all, Rs_all, scale, plan: ShardPlan):
         be, comm, rank = self.be, self.comm, self.comm.rank
         import time
         dbg = os.environ.get("IS_SHARD_DEBUG") == "1"
@@ -302,7 +443,7 @@ class ShardedStitcher:
 class GpuBackend:
     """The C ABI on one GPU; arrays are torch CUDA tensors."""
 
-    def __init__(self, device_index, projection="cylindrical", weight_type=None, workers=6):
+    def __init__(self, device_index, projection="cylindrical", weight_type=None, workers=6, ctx=None):
         import torch
 
         from . import stitching as S
@@ -310,9 +451,27 @@ class GpuBackend:
         self.device = torch.device("cuda", device_index)
         self.proj = projection
         self.wt = S.WEIGHT_32F if weight_type is None else weight_type
-        self.ctx = S.Context(device_index, use_torch_stream=True)
-        self.workers = [S.Context(device_index) for _ in range(workers)]
+        self.ctx = ctx if ctx is not None else S.Context(device_index, use_torch_stream=True)
+        self._nworkers = workers
+        self._workers = None                  # contexts of the general path's worker threads, created on first use
         self.tls = threading.local()
+
+    @property
+    def workers(self):
+        if self._workers is None:
+            self._workers = [self.S.Context(self.device.index) for _ in range(self._nworkers)]
+        return self._workers
+
+    def seam_find_list(self, images, corners, masks):
+        """the batched pair loop over a list of device images; masks are updated in place -> {path, waves}"""
+        self.S.DpSeamFinder(self.ctx, "COLOR").find(images, corners, masks)      # device masks are updated in place
+        return {"path": self.ctx.seam_path, "waves": self.ctx.seam_waves}
+
+    def copy_of(self, t):
+        return t.clone()                      # same stream as everything else of the strip path: no synchronisation
+
+    def pair_same_structure(self, mask_i, mask_j_a, mask_j_b, tl_i, tl_j):
+        return self.S.DpSeamFinder(self.ctx, "COLOR").pair_same_structure(mask_i, mask_j_a, mask_j_b, tl_i, tl_j)
 
     def _ctx(self):
         return getattr(self.tls, "ctx", self.ctx)

@@ -126,6 +126,14 @@ class Context:
         return int(self.lib.is_ctx_seam_path(self.h))
 
     @property
+    def seam_waves(self) -> int:
+        return int(self.lib.is_ctx_seam_waves(self.h))
+
+    def clear_plan_cache(self):
+        """forget the memoised warp plans: the next plan / run scans the image borders again (detectResultRoi)"""
+        self.check(self.lib.is_ctx_clear_plan_cache(self.h))
+
+    @property
     def kernel_launches(self) -> int:
         return int(self.lib.is_ctx_kernel_launches(self.h))
 
@@ -289,6 +297,16 @@ class DpSeamFinder:
 
     def pair_free(self, handle):
         self.ctx.lib.is_seam_pair_destroy(handle)
+
+    def pair_same_structure(self, mask_i, mask_j_a, mask_j_b, tl_i, tl_j) -> bool:
+        """True when pair (i, j) would take the same decisions with mask_j_b in place of mask_j_a (is_seam_pair_same_structure)."""
+        ki, _a = as_mat(mask_i)
+        ka, _b = as_mat(mask_j_a)
+        kb, _c = as_mat(mask_j_b)
+        same = C.c_int(0)
+        self.ctx.check(self.ctx.lib.is_seam_pair_same_structure(self.ctx.h, C.byref(ki), C.byref(ka), C.byref(kb), capi.Point(int(tl_i[0]), int(tl_i[1])),
+                                                                capi.Point(int(tl_j[0]), int(tl_j[1])), C.byref(same)))
+        return bool(same.value)
 
     def mask_and(self, dst, src):
         """dst = 0 where src == 0 (intersection of clear sets), in place."""

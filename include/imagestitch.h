@@ -142,6 +142,11 @@ int is_seam_pair_run(is_ctx* ctx, const is_mat* image_i, const is_mat* image_j, 
 int is_seam_pair_check(is_ctx* ctx, const is_mat* image_i, const is_mat* image_j, is_point tl_i, is_point tl_j, const is_mat* mask_i,
                        const is_mat* mask_j, const is_seam_pair* spec, int* same);
 int is_seam_pair_destroy(is_seam_pair* p);
+/* Sharded strips: would pair (i, j) decide the same (components, contours, conflict loop, seam tips) with mask_j_b in place of
+ * mask_j_a?  Used at a strip boundary: mask_j_a is image j's mask as the pair saw it, mask_j_b the one it would have seen in the
+ * reference's sequential loop (after the owner's own pairs).  *same = 0 also when the masks are outside what the check covers. */
+int is_seam_pair_same_structure(is_ctx* ctx, const is_mat* mask_i, const is_mat* mask_j_a, const is_mat* mask_j_b,
+                                is_point tl_i, is_point tl_j, int* same);
 int is_mask_and(is_ctx* ctx, is_mat* dst, const is_mat* src);
 
 /* How the last is_seam_dp_find / is_pipeline_run on this context executed the pair loop: 1 = the pairs ran
@@ -166,6 +171,14 @@ int is_debug_seam_pair_finish(uint8_t* mask1, int rows1, int cols1, size_t step1
  * back-track kernels of formulation `variant` (0 or 1, see csrc/seam.cu); seam_out[njobs][steps] = seam lanes (or -1 when the
  * destination is unreachable), ms[0] = mean milliseconds per launch over `iters` launches. */
 int is_debug_dp_bench(is_ctx* ctx, int lanes, int steps, int njobs, int variant, unsigned seed, int iters, int32_t* seam_out, float* ms);
+
+/* Waves the batched pair loop needed in the last call (1 for a strip; more when pairs depend on each other's clears). */
+int is_ctx_seam_waves(const is_ctx* ctx);
+
+/* Drops the context's memo of warp plans (camera -> result ROI, detectResultRoi [WARP]:64-88).  The memo lets the
+ * plan -> run sequence of ONE panorama scan the image borders once; a benchmark that repeats the same panorama clears
+ * it at the start of every step so that each step pays for its own scan, as a stream of different panoramas would. */
+int is_ctx_clear_plan_cache(is_ctx* ctx);
 
 /* Host-only diagnostic, no device needed: structure and plan of one image pair as the batched path computes them
  * between its kernels (components, states, conflict-loop operations with seam tips, contour records).  See seam.cu. */

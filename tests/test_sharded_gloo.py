@@ -104,6 +104,28 @@ class OracleBackendEarly(OracleBackend):
         dst.copy_(src)
 
 
+class OracleBackendStrip(OracleBackendEarly):
+    """... plus what the strip path of ShardedStitcher asks for: the pair loop over a list, the boundary check."""
+
+    def copy_of(self, t):
+        return t.clone()
+
+    def seam_find_list(self, images, corners, masks):
+        out = self.O.dp_seam_find([a.numpy() for a in images], corners, [m.numpy() for m in masks])
+        for m, o in zip(masks, out):
+            m.copy_(torch.from_numpy(o))                      # in place, like the device path
+        return {"path": 2, "waves": 1}
+
+    def pair_same_structure(self, mask_i, mask_j_a, mask_j_b, tl_i, tl_j):
+        # the stand-in compares the effect instead of the structure: the clears of the pair inside mask i, and inside mask j where it is still set
+        h, w = mask_i.shape
+        img = [np.zeros((h, w, 3), np.uint8), np.zeros(tuple(mask_j_a.shape) + (3,), np.uint8)]
+        ra = self.O.dp_seam_find(img, [tl_i, tl_j], [mask_i.numpy(), mask_j_a.numpy()])
+        rb = self.O.dp_seam_find(img, [tl_i, tl_j], [mask_i.numpy(), mask_j_b.numpy()])
+        keep = mask_j_b.numpy() != 0
+        return bool(np.array_equal(ra[0], rb[0]) and np.array_equal((ra[1] == 0) & keep, (rb[1] == 0) & keep))
+
+
 def _worker(rank, world, port, case, result_path):
     sys.path.insert(0, ROOT)
     os.environ["MASTER_ADDR"] = "127.0.0.1"
@@ -116,7 +138,8 @@ def _worker(rank, world, port, case, result_path):
     corners, sizes, roi = O.pipeline_plan(0, [(h, w)] * n, Ks, Rs, scale)
     plan = sharded.ShardPlan.build(corners, sizes, roi, world, nb)
     mine = [torch.from_numpy(imgs[i]) for i in range(n) if plan.owner[i] == rank]
-    st = sharded.ShardedStitcher((OracleBackendEarly if os.environ.get("IS_TEST_EARLY_FEED") == "1" else OracleBackend)(O), sharded.Comm(dist), nb)
+    kind = os.environ.get("IS_TEST_EARLY_FEED")
+    st = sharded.ShardedStitcher((OracleBackendStrip if kind == "strip" else OracleBackendEarly if kind == "1" else OracleBackend)(O), sharded.Comm(dist), nb)
     res = st.stitch(mine, Ks, Rs, scale, plan)
     strips = [None] * world
     dist.all_gather_object(strips, (res["x0"], res["x1"], res["pano"].numpy(), res["pano_mask"].numpy(),
@@ -158,6 +181,25 @@ def test_two_rank_sharded_matches_single_process(tmp_path, case, monkeypatch, ea
         assert spec == "0"
     elif case[3] < 0.5 and os.environ.get("IS_TEST_GRID_ROWS") != "2":
         assert spec == "1"     # independent pairs: the speculative results are accepted
+
+
+@pytest.mark.parametrize("case", [(4, 192, 144, 0.25, 3, 2), (6, 160, 120, 0.3, 4, 3), (6, 160, 120, 0.3, 4, 2), (4, 192, 144, 0.25, 3, 2, "fallback")])
+def test_strip_path_matches_single_process(tmp_path, case, monkeypatch):
+    """The strip path (one pair-loop call per rank over its images + the neighbour's first image, boundary check, mask
+    exchange) on 2 and 3 gloo ranks; flat test images make every seam cost tie, the masks still have to come out right."""
+    import oracle
+    oracle.build()
+    monkeypatch.setenv("IS_TEST_EARLY_FEED", "strip")
+    monkeypatch.setenv("IS_TEST_GRID_ROWS", "1")
+    if case[-1] == "fallback":
+        monkeypatch.setenv("IS_SHARDED_FORCE_FALLBACK", "1")
+        case = case[:-1]
+    world = case[5]
+    out = tmp_path / "result.txt"
+    mp.spawn(_worker, args=(world, 29500 + (os.getpid() + case[0] * 13 + world * 101) % 2000, case[:5], str(out)), nprocs=world, join=True)
+    ok, spec = out.read_text().split()
+    assert ok == "1", "strip-path panorama / seam masks differ from the single-process oracle"
+    assert spec == ("0" if os.environ.get("IS_SHARDED_FORCE_FALLBACK") == "1" else "1")
 
 
 def test_three_rank_mosaic(tmp_path, monkeypatch):
