@@ -67,10 +67,10 @@ private:
     void loop() {
         uint64_t seen = 0;
         for (;;) {
-            // spin for a while (the phases of one call follow each other within microseconds), then sleep
+            // spin for a while (the phases of one call follow each other within a millisecond or two of device work), then sleep
             const auto t0 = std::chrono::steady_clock::now();
             bool got = false;
-            while (std::chrono::steady_clock::now() - t0 < std::chrono::microseconds(300)) {
+            while (std::chrono::steady_clock::now() - t0 < std::chrono::microseconds(1500)) {
                 if (gen_.load(std::memory_order_acquire) != seen) { got = true; break; }
                 std::this_thread::yield();
             }

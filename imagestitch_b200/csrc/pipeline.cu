@@ -9,9 +9,21 @@
 #include "internal.cuh"
 
 #include <algorithm>
+#include <chrono>
 #include <cstdlib>
 
 using namespace is;
+
+// IS_PIPELINE_DEBUG=1: host time stamps (ms since the first call in the process) of the phases of is_pipeline_run, per context
+struct PipeStamp {
+    bool on; const void* who;
+    PipeStamp(const void* w) : on(getenv("IS_PIPELINE_DEBUG") != nullptr), who(w) {}
+    static double now() {
+        static const auto t0 = std::chrono::steady_clock::now();
+        return std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - t0).count();
+    }
+    void mark(const char* what) const { if (on) fprintf(stderr, "[pipeline %p] %9.3f ms  %s\n", who, now(), what); }
+};
 
 extern "C" {
 
@@ -44,6 +56,8 @@ int is_pipeline_run(is_ctx* ctx, int n, const is_mat* images, const is_camera* c
     IS_CUDA(ctx, cudaSetDevice(ctx->device));
     IS_REQUIRE(ctx, n > 0 && images && cfg_in && pano && pano_mask, IS_ERR_BAD_ARG, "null argument");
     is_pipeline_config cfg = *cfg_in;
+    const PipeStamp stamp(ctx);
+    stamp.mark("enter");
     std::vector<is_camera> cams(n);
     // ---- host registration stages (control flow around the GPU path)
     if (hooks && hooks->detect)
@@ -158,6 +172,7 @@ int is_pipeline_run(is_ctx* ctx, int n, const is_mat* images, const is_camera* c
                                            cudaMemcpyDeviceToDevice, ctx->stream));
         }
     IS_CUDA(ctx, cudaEventRecord(ctx->ev[1], ctx->stream));
+    stamp.mark("warps queued");
     // ---- seam
     if (cfg.seam == IS_SEAM_DP) {
         IS_REQUIRE(ctx, cfg.seam_cost == IS_COST_COLOR || cfg.seam_cost == IS_COST_COLOR_GRAD, IS_ERR_BAD_ARG, "unknown seam cost function");
@@ -166,6 +181,7 @@ int is_pipeline_run(is_ctx* ctx, int n, const is_mat* images, const is_camera* c
         IS_REQUIRE(ctx, cfg.seam == IS_SEAM_NONE, IS_ERR_BAD_ARG, "unknown seam mode");
     }
     IS_CUDA(ctx, cudaEventRecord(ctx->ev[2], ctx->stream));
+    stamp.mark("seam done");
     // ---- blend.  masks_seam[k] = dilate(masks_seam[k]) & masks_warped[k] ([SEAM]:1264-1269) opens a band on either side of
     //      the seam for the blender to work in; the seam masks handed back to the caller are the dilated ones, as in the mains.
     if (cfg.seam_dilate > 0)
@@ -182,9 +198,12 @@ int is_pipeline_run(is_ctx* ctx, int n, const is_mat* images, const is_camera* c
     else IS_TRY(feather_blend_device(ctx, cfg.sharpness, roi, n, warped.data(), masks.data(),
                                      corners.data(), dp, dm));
     IS_CUDA(ctx, cudaEventRecord(ctx->ev[3], ctx->stream));
+    stamp.mark("blend queued");
+    if (stamp.on) { cudaStreamSynchronize(ctx->stream); stamp.mark("blend done"); }
     // ---- results
     IS_TRY(commit(ctx, &dp));
     IS_TRY(commit(ctx, &dm));
+    stamp.mark("results copied");
     if (seam_masks)
         for (int i = 0; i < n; ++i)
             IS_CUDA(ctx, cudaMemcpy2DAsync(seam_masks[i].data, seam_masks[i].step, masks[i].data, masks[i].step, (size_t)masks[i].cols, masks[i].rows,

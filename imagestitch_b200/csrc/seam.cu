@@ -2423,7 +2423,8 @@ int is_debug_dp_bench(is_ctx* ctx, int lanes, int steps, int njobs, int variant,
         DpArgs& A = da[(size_t)j];
         A.P = P.as<float>() + cells * j; A.Q = Q.as<float>() + cells * j; A.control = ctl.as<uint8_t>() + cells * j;
         A.lanes = lanes; A.pitch = S.pitch; A.steps = steps;
-        A.s0 = 0; A.lane0 = lanes / 2 - 7 * j; A.s1 = steps - 1; A.lane1 = lanes / 3 + 11 * j;
+        A.s0 = 0; A.lane0 = lanes / 2 - 7 * j; A.s1 = steps - 1;
+        A.lane1 = std::min(lanes - 1, std::max(0, A.lane0 + ((j & 1) ? -1 : 1) * std::min(steps / 3, lanes / 5) + 11 * j));   // inside the source's cone
         A.seam_lane = res.as<int>() + (size_t)(steps + 4) * j + 4; A.reached = res.as<int>() + (size_t)(steps + 4) * j;
         A.G = S.G; A.D = S.D;
         ba[(size_t)j].A = A; ba[(size_t)j].map = map.as<short>() + (size_t)nchunks * S.pitch * j; ba[(size_t)j].nchunks = nchunks;

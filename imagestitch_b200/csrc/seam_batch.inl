@@ -882,10 +882,19 @@ static int seam_batch_wave(is_ctx* ctx, const std::vector<std::pair<int, int>>& 
         IS_TRY(download_view(ctx, base + off_res_all, sizeof(int) * res_total_ints, reinterpret_cast<const void**>(&res_h)));
     }
     tm.lap("C labels, costs, DP");
-    // ---- host: updateLabelsUsingSeam per seam, then the final mask update of every pair as clear intervals
-    pool->run(nj, [&](size_t j) {
-        SeamJobHost& J = jobs[j];
-        J.status = seam_job_finish(ctx, PR[(size_t)J.pair], J, res_h + J.off_res, trace != nullptr);
+    // ---- host: updateLabelsUsingSeam per seam, then the final mask update of the pair as clear intervals -- one task per pair
+    std::vector<std::vector<ClearIv>> clears(np);
+    std::vector<std::vector<size_t>> jobs_of(np);
+    for (size_t j = 0; j < nj; ++j) jobs_of[(size_t)jobs[j].pair].push_back(j);   // plan order
+    pool->run(np, [&](size_t k) {
+        std::vector<const std::vector<Interval>*> fl;
+        for (size_t j : jobs_of[k]) {
+            SeamJobHost& J = jobs[j];
+            J.status = seam_job_finish(ctx, PR[k], J, res_h + J.off_res, trace != nullptr);
+            if (J.status != IS_OK) return;
+            fl.push_back(J.reached ? &J.uls.flips : nullptr);
+        }
+        pair_clear_intervals(PR[k], fl, &clears[k]);
     });
     size_t limit = np;                                                 // pairs [0, limit) can still be accepted
     for (auto& J : jobs) {
@@ -893,13 +902,8 @@ static int seam_batch_wave(is_ctx* ctx, const std::vector<std::pair<int, int>>& 
         if (J.status != IS_OK) return J.status;
     }
     if (limit == 0) { *first_unsupported = true; return IS_OK; }
-    tm.lap("D host: updateLabelsUsingSeam on runs");
-    std::vector<std::vector<ClearIv>> clears(limit);
-    pool->run(limit, [&](size_t k) {
-        std::vector<const std::vector<Interval>*> fl;
-        for (auto& J : jobs) if ((size_t)J.pair == k) fl.push_back(J.reached ? &J.uls.flips : nullptr);   // jobs are in plan order
-        pair_clear_intervals(PR[k], fl, &clears[k]);
-    });
+    clears.resize(limit);
+    tm.lap("D host: updateLabelsUsingSeam on runs, clear intervals");
     // one upload: per pair row_start[ih + 1] and the intervals, then the table
     Blob B2;
     std::vector<size_t> off_rs(limit), off_iv(limit);

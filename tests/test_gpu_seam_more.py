@@ -91,7 +91,7 @@ def test_dp_formulations_agree_on_synthetic_tables(ctx):
         base = np.zeros((njobs, steps), np.int32)
         ms = (C.c_float * 1)()
         assert lib.is_debug_dp_bench(ctx.h, lanes, steps, njobs, 0, 77, 1, base.ctypes.data_as(C.POINTER(C.c_int32)), ms) == 0
-        assert lanes < 100 or (base[:, 0] >= 0).any(), "the synthetic tables should be solvable"
+        assert (base[:, 0] >= 0).any(), "the synthetic tables should be solvable"
         for tmpl in (None, "1", "2", "3"):
             if tmpl is None:
                 os.environ.pop("IS_DP_V1_TMPL", None)
