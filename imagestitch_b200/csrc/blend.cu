@@ -14,7 +14,7 @@
 // The panorama accumulators are never read back and level 0 is written exactly once (cropped, masked).
 // int16 accumulation wraps modulo 2^16 exactly like OpenCV's `short +=`, so it is order independent; the
 // float weight sum keeps OpenCV's feed order.  Results equal the scatter formulation bit for bit.
-#include "common.cuh"
+#include "internal.cuh"
 #include "tma.cuh"
 
 #include <algorithm>
@@ -170,6 +170,62 @@ __global__ void k_pyrdown_weights_batch(const WeightLevel* __restrict__ table) {
         reinterpret_cast<float*>(T.w_out)[o] = __fmul_rn(v, 1.f / 256.f);
     } else {
         reinterpret_cast<int16_t*>(T.w_out)[o] = (int16_t)sat16((wacc + 128) >> 8);
+    }
+}
+
+// Image levels >= 2 of all fed images in one launch per level (blockIdx.z = image), through shared memory: a block computes a
+// 32 x 16 tile of the coarser level from the (2 * 32 + 3) x (2 * 16 + 3) tile under it -- loaded once (32-bit words in the
+// interior, element-wise through BORDER_REFLECT_101 on the rim), horizontal 5-tap sums to shared memory, vertical pass.
+struct ImageLevel { const int16_t* g_in; int16_t* g_out; int sh, sw, dh, dw; };
+constexpr int PU_TX = 32, PU_TY = 16, PU_IW = 2 * PU_TX + 3, PU_IH = 2 * PU_TY + 3;
+constexpr int PU_ROW = 3 * PU_IW + 3;                         // int16 per shared-memory row: 201 values + padding to an even count
+
+__global__ void __launch_bounds__(256) k_pyrdown_images_batch(const ImageLevel* __restrict__ table) {
+    const ImageLevel T = table[blockIdx.z];
+    const int ox0 = blockIdx.x * PU_TX, oy0 = blockIdx.y * PU_TY;
+    if (ox0 >= T.dw || oy0 >= T.dh) return;                   // uniform over the block
+    __shared__ __align__(16) int16_t tile[PU_IH][PU_ROW];
+    __shared__ int hsum[PU_IH][PU_TX][3];
+    const int tid = threadIdx.x;
+    const int x_lo = 2 * ox0 - 2, y_lo = 2 * oy0 - 2;
+    const bool interior = x_lo >= 0 && y_lo >= 0 && x_lo + PU_IW <= T.sw && y_lo + PU_IH <= T.sh;
+    if (interior) {
+        // a tile row is 67 pixels = 402 bytes starting at a multiple of 12 bytes: 100 words + one int16
+        constexpr int WORDS = (3 * PU_IW) / 2;                // 100
+        for (int e = tid; e < PU_IH * (WORDS + 1); e += 256) {
+            const int r = e / (WORDS + 1), wd = e % (WORDS + 1);
+            const int16_t* src = T.g_in + ((size_t)(y_lo + r) * T.sw + x_lo) * 3;
+            if (wd < WORDS) reinterpret_cast<uint32_t*>(&tile[r][0])[wd] = reinterpret_cast<const uint32_t*>(src)[wd];
+            else tile[r][3 * PU_IW - 1] = src[3 * PU_IW - 1];
+        }
+    } else {
+        for (int e = tid; e < PU_IH * PU_IW; e += 256) {
+            const int r = e / PU_IW, c = e % PU_IW;
+            const int y = reflect101(y_lo + r, T.sh), x = reflect101(x_lo + c, T.sw);
+            const int16_t* src = T.g_in + ((size_t)y * T.sw + x) * 3;
+            tile[r][3 * c] = src[0]; tile[r][3 * c + 1] = src[1]; tile[r][3 * c + 2] = src[2];
+        }
+    }
+    __syncthreads();
+    for (int e = tid; e < PU_IH * PU_TX; e += 256) {
+        const int r = e / PU_TX, ox = e % PU_TX;
+        const int16_t* p = &tile[r][6 * ox];
+#pragma unroll
+        for (int c = 0; c < 3; ++c) hsum[r][ox][c] = (int)p[c] + 4 * (int)p[3 + c] + 6 * (int)p[6 + c] + 4 * (int)p[9 + c] + (int)p[12 + c];
+    }
+    __syncthreads();
+    const int ox = tid & 31;
+    const int x = ox0 + ox;
+    if (x >= T.dw) return;
+    for (int oy = tid >> 5; oy < PU_TY; oy += 8) {
+        const int y = oy0 + oy;
+        if (y >= T.dh) break;
+        int16_t* o = T.g_out + ((size_t)y * T.dw + x) * 3;
+#pragma unroll
+        for (int c = 0; c < 3; ++c) {
+            const int acc = hsum[2 * oy][ox][c] + 4 * hsum[2 * oy + 1][ox][c] + 6 * hsum[2 * oy + 2][ox][c] + 4 * hsum[2 * oy + 3][ox][c] + hsum[2 * oy + 4][ox][c];
+            o[c] = (int16_t)sat16((acc + 128) >> 8);
+        }
     }
 }
 
@@ -981,6 +1037,7 @@ struct FedImage {
     DevBuf summary;                // occupancy of the mask per 64 x 32 cell (k_mask_summary)
     int sum_w = 0, sum_h = 0;
     bool weights_pending = false;  // fed with the image pyramid only: weights + occupancy map are built when blend() starts
+    bool upper_pending = false;    // image levels >= 2 not built yet (blender_build_upper_levels does all images of a blender at once)
     long long key = 0;             // feed order of the reference (ascending key, ties in call order)
 };
 
@@ -1123,7 +1180,8 @@ static int feed_prepare(is_blender* b, FedImage& f) {
 }
 
 template <bool WF, int PART>
-static int feed_pyramid_t(is_ctx* sctx, const FedImage& f, int nb) {
+static int feed_pyramid_t(is_ctx* sctx, const FedImage& f, int nb_all, bool level1_only) {
+    const int nb = level1_only ? std::min(nb_all, 1) : nb_all;
     const size_t wsz = WF ? sizeof(float) : sizeof(int16_t);
     const double ib = PART != PD_WEIGHT ? 1. : 0., wb = PART != PD_IMAGE ? 1. : 0.;   // which bytes this launch accounts for
     int sh = f.height, sw = f.width;
@@ -1146,14 +1204,49 @@ static int feed_pyramid_t(is_ctx* sctx, const FedImage& f, int nb) {
 }
 
 // Gaussian pyramids (levels 1..nb) of the image and / or of its weight map, launched on sctx's stream
-static int feed_pyramid(is_ctx* sctx, const is_blender* b, const FedImage& f, int part) {
+static int feed_pyramid(is_ctx* sctx, const is_blender* b, const FedImage& f, int part, bool level1_only = false) {
     const bool wf = b->weight_type == IS_WEIGHT_32F;
     const int nb = b->num_bands;
     switch (part) {
-        case PD_BOTH: return wf ? feed_pyramid_t<true, PD_BOTH>(sctx, f, nb) : feed_pyramid_t<false, PD_BOTH>(sctx, f, nb);
-        case PD_IMAGE: return wf ? feed_pyramid_t<true, PD_IMAGE>(sctx, f, nb) : feed_pyramid_t<false, PD_IMAGE>(sctx, f, nb);
-        default: return wf ? feed_pyramid_t<true, PD_WEIGHT>(sctx, f, nb) : feed_pyramid_t<false, PD_WEIGHT>(sctx, f, nb);
+        case PD_BOTH: return wf ? feed_pyramid_t<true, PD_BOTH>(sctx, f, nb, level1_only) : feed_pyramid_t<false, PD_BOTH>(sctx, f, nb, level1_only);
+        case PD_IMAGE: return wf ? feed_pyramid_t<true, PD_IMAGE>(sctx, f, nb, level1_only) : feed_pyramid_t<false, PD_IMAGE>(sctx, f, nb, level1_only);
+        default: return wf ? feed_pyramid_t<true, PD_WEIGHT>(sctx, f, nb, level1_only) : feed_pyramid_t<false, PD_WEIGHT>(sctx, f, nb, level1_only);
     }
+}
+
+// image levels 2..nb of every image fed with the deferred path, one launch per level over all of them, on sctx's stream (which must
+// be ordered after the level-1 launches: the side stream they ran on, or the blender's stream after the join)
+int blender_build_upper_levels(is_blender* b, is_ctx* sctx) {
+    const int nb = b->num_bands;
+    std::vector<int> pend;
+    for (size_t i = 0; i < b->fed.size(); ++i) if (b->fed[i].upper_pending) pend.push_back((int)i);
+    if (pend.empty()) return IS_OK;
+    for (int pi : pend) b->fed[(size_t)pi].upper_pending = false;
+    if (nb < 2) return IS_OK;
+    const int np = (int)pend.size();
+    std::vector<ImageLevel> host((size_t)np * (nb - 1));
+    std::vector<int> gx(nb + 1, 0), gy(nb + 1, 0);
+    std::vector<double> bytes(nb + 1, 0.);
+    for (int i = 0; i < np; ++i) {
+        const FedImage& f = b->fed[(size_t)pend[i]];
+        int sh = (f.height + 1) / 2, sw = (f.width + 1) / 2;
+        for (int k = 2; k <= nb; ++k) {
+            const int dh = (sh + 1) / 2, dw = (sw + 1) / 2;
+            host[(size_t)(k - 2) * np + i] = ImageLevel{f.g[k - 1].as<int16_t>(), f.g[k].as<int16_t>(), sh, sw, dh, dw};
+            gx[k] = std::max(gx[k], div_up(dw, PU_TX)); gy[k] = std::max(gy[k], div_up(dh, PU_TY));
+            bytes[k] += ((double)sh * sw + (double)dh * dw) * 6.;
+            sh = dh; sw = dw;
+        }
+    }
+    DevBuf table;
+    IS_TRY(table.alloc(sctx, sizeof(ImageLevel) * host.size()));
+    IS_TRY(upload(sctx, table.p, host.data(), sizeof(ImageLevel) * host.size()));
+    for (int k = 2; k <= nb; ++k) {
+        dim3 grid(gx[k], gy[k], np);
+        sctx->next_bytes = bytes[k];
+        IS_LAUNCH(sctx, k_pyrdown_images_batch, grid, 256, 0, table.as<ImageLevel>() + (size_t)(k - 2) * np);
+    }
+    return IS_OK;
 }
 
 // which 64 x 32 cells of the mask hold anything: lets the level-0 blend skip images per tile
@@ -1185,9 +1278,29 @@ int blender_feed_image(is_blender* b, is_ctx* side, const DevMat& img, const Dev
     f.weights_pending = true;
     IS_TRY(feed_prepare(b, f));
     if (side != b->ctx) IS_TRY(stream_after(b->ctx, side->stream, b->ctx->stream));   // the allocations above are ordered on the blender's stream
-    const int rc = feed_pyramid(side, b, f, PD_IMAGE);
+    const int rc = feed_pyramid(side, b, f, PD_IMAGE, /*level1_only=*/true);      // levels >= 2: blender_build_upper_levels, all images at once
     if (rc != IS_OK) { if (b->ctx->last_error.empty()) b->ctx->last_error = side->last_error; return rc; }
+    f.upper_pending = true;
     if (side != b->ctx) b->side = side;
+    b->fed.push_back(std::move(f));
+    return IS_OK;
+}
+
+// Pipeline variant of feed() fused with the warp: one kernel (launch_warp_g1, warp.cu) writes the warped image, its all-255 mask
+// and level 1 of the image's Gaussian pyramid; the blender only learns the geometry and allocates the levels.  On the blender's
+// stream; levels >= 2 follow with blender_build_upper_levels, the weights with blender_feed_weights.
+int blender_feed_image_fused(is_blender* b, int proj, const WarpPlan& plan, const float* tables, const DevMat& src, const DevMat& img, const DevMat& mask, is_point tl) {
+    is_ctx* ctx = b->ctx;
+    IS_REQUIRE(ctx, b->num_bands >= 1, IS_ERR_INTERNAL, "fused feed needs at least one band");
+    FedImage f;
+    f.tl_x = tl.x; f.tl_y = tl.y;
+    f.img.data = img.data; f.img.rows = img.rows; f.img.cols = img.cols; f.img.channels = img.channels; f.img.depth = img.depth; f.img.step = img.step;
+    f.mask.data = mask.data; f.mask.rows = mask.rows; f.mask.cols = mask.cols; f.mask.channels = 1; f.mask.depth = IS_8U; f.mask.step = mask.step;
+    f.key = ++b->next_key;
+    f.weights_pending = true;
+    f.upper_pending = true;
+    IS_TRY(feed_prepare(b, f));
+    IS_TRY(launch_warp_g1(ctx, proj, plan, tables, src, img, mask, f.top, f.left, f.height, f.width, f.g[1].as<int16_t>()));
     b->fed.push_back(std::move(f));
     return IS_OK;
 }
@@ -1377,6 +1490,11 @@ int blender_blend_dev(is_blender* b, const DevMat& dst, const DevMat& dmask, int
     // deferred feeds: weights + occupancy maps from the masks as they are now, image pyramids of the side stream joined,
     // images in the reference's feed order
     IS_TRY(blender_feed_weights(b));
+    {
+        is_ctx* up = b->side ? b->side : ctx;
+        const int rc = blender_build_upper_levels(b, up);               // no-op when the caller has done it already
+        if (rc != IS_OK) { if (ctx->last_error.empty()) ctx->last_error = up->last_error; return rc; }
+    }
     join_side(b);
     std::stable_sort(b->fed.begin(), b->fed.end(), [](const FedImage& a, const FedImage& c) { return a.key < c.key; });
     std::vector<int> xb, xe;

@@ -27,9 +27,14 @@ int upload_tables(is_ctx* ctx, int proj, const WarpPlan& plan, DevBuf* buf);
 int launch_warp(is_ctx* ctx, int proj, const WarpPlan& plan, const float* tables, const DevMat& src, int interp, int border,
                 const DevMat& dst, const DevMat* mask);
 
+int launch_warp_g1(is_ctx* ctx, int proj, const WarpPlan& plan, const float* tables, const DevMat& src, const DevMat& dst, const DevMat& mask,
+                   int top, int left, int height, int width, int16_t* g1);
+
 // blend.cu
+int blender_feed_image_fused(is_blender* b, int proj, const WarpPlan& plan, const float* tables, const DevMat& src, const DevMat& img, const DevMat& mask, is_point tl);
 int blender_feed_image(is_blender* b, is_ctx* side, const DevMat& img, const DevMat& mask, is_point tl);
 int blender_feed_weights(is_blender* b);
+int blender_build_upper_levels(is_blender* b, is_ctx* side);
 int blender_blend_dev(is_blender* b, const DevMat& dst, const DevMat& dmask, int sx0, int sx1);
 
 // feather.cu

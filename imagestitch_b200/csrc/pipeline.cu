@@ -147,8 +147,13 @@ int is_pipeline_run(is_ctx* ctx, int n, const is_mat* images, const is_camera* c
         IS_TRY(alloc_mat(ctx, plans[i].P.dst_h, plans[i].P.dst_w, 1, IS_8U, &masks[i]));
         DevBuf tables;
         IS_TRY(upload_tables(ctx, cfg.projection, plans[i], &tables));
+        // feed(): geometry + level 1 of the image pyramid now, the other levels on the side stream, weights after the seam stage
+        const bool fused = multiband && cfg.exposure == IS_EXPOSURE_NONE && is_blender_num_bands(bl) >= 1 && !getenv("IS_WARP_UNFUSED");
+        if (fused) {
+            IS_TRY(blender_feed_image_fused(bl, cfg.projection, plans[i], tables.as<float>(), src[i], warped[i], masks[i], corners[i]));
+            continue;
+        }
         IS_TRY(launch_warp(ctx, cfg.projection, plans[i], tables.as<float>(), src[i], IS_INTER_LINEAR, IS_BORDER_REFLECT, warped[i], &masks[i]));
-        // feed(): geometry + image pyramid now (side stream, ordered after this warp), weights after the seam stage
         if (multiband && cfg.exposure == IS_EXPOSURE_NONE) IS_TRY(blender_feed_image(bl, side, warped[i], masks[i], corners[i]));
     }
     // ---- exposure: compensator->feed(corners, images_warped, masks_warped), then compensator->apply(i, ...) IN PLACE on
@@ -164,6 +169,11 @@ int is_pipeline_run(is_ctx* ctx, int n, const is_mat* images, const is_camera* c
         ctx->last_gains = gains;
     } else {
         IS_REQUIRE(ctx, cfg.exposure == IS_EXPOSURE_NONE, IS_ERR_BAD_ARG, "unknown exposure mode");
+    }
+    if (multiband) {            // image levels >= 2 of all images, one launch per level, behind the level-1 launches on the side stream
+        if (side != ctx) IS_TRY(stream_after(ctx, side->stream, ctx->stream));   // level 1 may have come from the fused warp kernel (caller's stream)
+        const int rc = blender_build_upper_levels(bl, side);
+        if (rc != IS_OK) { if (ctx->last_error.empty()) ctx->last_error = side->last_error; return rc; }
     }
     if (cfg.seam_dilate > 0)   // masks_warped of [SEAM]:1267: the seam finder changes `masks` in place
         for (int i = 0; i < n; ++i) {

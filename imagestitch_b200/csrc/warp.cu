@@ -299,6 +299,158 @@ __global__ void k_build_maps(WarpParams P, const float* __restrict__ tables, flo
 }
 
 // @emu-end
+// ---- fused: warp + all-255 mask + level 1 of the image's Gaussian pyramid ------------------------------------------------
+// What MultiBandBlender::feed does first with a warped image is copyMakeBorder(BORDER_REFLECT) into a frame padded to a
+// multiple of 2^bands, then pyrDown.  A block of this kernel owns a 64 x 32 rectangle of that frame: it evaluates the warp for
+// the 67 x 35 frame pixels under its 32 x 16 level-1 outputs (the 5 x 5 support reaches two pixels beyond; frame pixels in the
+// padding are reflections of image pixels, i.e. the warp evaluated at the reflected image coordinates), keeps them in shared
+// memory, writes the image pixels it owns (u8 x 3 + mask, four pixels = three 32-bit words per thread) and finishes the
+// separable [1 4 6 4 1] reduction from shared memory.  The warped image is therefore never read back for its first pyramid level
+// (489 MB per C2 step in round 1), and the 8 % of a frame that is padding costs warp arithmetic instead of a second kernel.
+// Source pixels: the 2 x 2 neighbourhood is six consecutive bytes per row, fetched as aligned 32-bit words (three per row at
+// most) instead of twelve byte loads.
+struct WarpG1Args {
+    WarpParams P;
+    const float* tables;
+    const uint8_t* src; size_t sstep;
+    uint8_t* dst; size_t dstep; uint8_t* mask; size_t mstep;
+    int top, left, height, width;          // padded frame; the image sits at (left, top) inside it
+    int16_t* g1; int dh, dw;
+    int wide_ok;                           // source base and pitch are 4-byte aligned
+};
+
+__device__ __forceinline__ int reflect101_i(int p, int len) {
+    if ((unsigned)p < (unsigned)len) return p;
+    if (len == 1) return 0;
+    do {
+        if (p < 0) p = -p;
+        else p = 2 * (len - 1) - p;
+    } while ((unsigned)p >= (unsigned)len);
+    return p;
+}
+
+// cv::remap INTER_LINEAR + BORDER_REFLECT on 8UC3: same integers as sample<3, LINEAR, REFLECT>; returns b | g << 8 | r << 16
+__device__ __forceinline__ uint32_t sample3_packed(const uint8_t* __restrict__ src, size_t sstep, int sw, int sh, float x, float y, bool wide_ok) {
+    const int ix = __float2int_rn(__fmul_rn(x, 32.f)), iy = __float2int_rn(__fmul_rn(y, 32.f));
+    const int sx = clamp_short(ix >> 5), sy = clamp_short(iy >> 5);
+    const int fx = ix & 31, fy = iy & 31;
+    const int w00 = (32 - fy) * (32 - fx), w01 = (32 - fy) * fx, w10 = fy * (32 - fx), w11 = fy * fx;
+    int out[3];
+    if (wide_ok && sx >= 0 && sx < sw - 3 && (unsigned)sy < (unsigned)(sh - 1)) {
+        const int o = 3 * sx, a = o & ~3, sh8 = 8 * (o & 3);
+        const uint32_t* r0 = reinterpret_cast<const uint32_t*>(src + (size_t)sy * sstep + a);
+        const uint32_t* r1 = reinterpret_cast<const uint32_t*>(src + (size_t)(sy + 1) * sstep + a);
+        const uint32_t a0 = __ldg(r0), a1 = __ldg(r0 + 1), a2 = __ldg(r0 + 2);
+        const uint32_t b0 = __ldg(r1), b1 = __ldg(r1 + 1), b2 = __ldg(r1 + 2);
+        const uint32_t t0 = __funnelshift_r(a0, a1, sh8), t1 = __funnelshift_r(a1, a2, sh8);   // bytes 0..3 and 4..7 of the top row's window
+        const uint32_t u0 = __funnelshift_r(b0, b1, sh8), u1 = __funnelshift_r(b1, b2, sh8);
+        // window bytes: [0..2] left pixel, [3..5] right pixel
+        const int tl[3] = {(int)(t0 & 255u), (int)((t0 >> 8) & 255u), (int)((t0 >> 16) & 255u)};
+        const int tr[3] = {(int)(t0 >> 24), (int)(t1 & 255u), (int)((t1 >> 8) & 255u)};
+        const int bl[3] = {(int)(u0 & 255u), (int)((u0 >> 8) & 255u), (int)((u0 >> 16) & 255u)};
+        const int br[3] = {(int)(u0 >> 24), (int)(u1 & 255u), (int)((u1 >> 8) & 255u)};
+#pragma unroll
+        for (int c = 0; c < 3; ++c) out[c] = (tl[c] * w00 + tr[c] * w01 + bl[c] * w10 + br[c] * w11 + 512) >> 10;
+    } else if ((unsigned)sx < (unsigned)(sw - 1) && (unsigned)sy < (unsigned)(sh - 1)) {
+        const uint8_t* s0 = src + (size_t)sy * sstep + sx * 3;
+        const uint8_t* s1 = s0 + sstep;
+#pragma unroll
+        for (int c = 0; c < 3; ++c) out[c] = (__ldg(s0 + c) * w00 + __ldg(s0 + 3 + c) * w01 + __ldg(s1 + c) * w10 + __ldg(s1 + 3 + c) * w11 + 512) >> 10;
+    } else {
+        const int sx0 = reflect_idx(sx, sw), sx1 = reflect_idx(sx + 1, sw);
+        const int sy0 = reflect_idx(sy, sh), sy1 = reflect_idx(sy + 1, sh);
+        const uint8_t* r0 = src + (size_t)sy0 * sstep;
+        const uint8_t* r1 = src + (size_t)sy1 * sstep;
+#pragma unroll
+        for (int c = 0; c < 3; ++c)
+            out[c] = (__ldg(r0 + sx0 * 3 + c) * w00 + __ldg(r0 + sx1 * 3 + c) * w01 + __ldg(r1 + sx0 * 3 + c) * w10 + __ldg(r1 + sx1 * 3 + c) * w11 + 512) >> 10;
+    }
+    return (uint32_t)out[0] | ((uint32_t)out[1] << 8) | ((uint32_t)out[2] << 16);
+}
+
+constexpr int WG_TX = 32, WG_TY = 16, WG_IW = 2 * WG_TX + 3, WG_IH = 2 * WG_TY + 3;
+
+template <int PROJ>
+__global__ void __launch_bounds__(256) k_warp_g1(WarpG1Args A) {
+    __shared__ uint32_t tile[WG_IH][WG_IW + 1];                  // b | g << 8 | r << 16 | mask << 24
+    __shared__ int hsum[WG_IH][WG_TX][3];
+    const int tid = threadIdx.x;
+    const int ox0 = blockIdx.x * WG_TX, oy0 = blockIdx.y * WG_TY;
+    const int fx_lo = 2 * ox0 - 2, fy_lo = 2 * oy0 - 2;
+    const int cols = A.P.dst_w, rows = A.P.dst_h;
+    const float* sinu = A.tables;
+    const float* cosu = A.tables + cols;
+    const float* rowA = A.tables + 2 * (size_t)cols;
+    const float* rowB = rowA + rows;
+    for (int e = tid; e < WG_IH * WG_IW; e += 256) {
+        const int r = e / WG_IW, c = e % WG_IW;
+        const int fy = reflect101_i(fy_lo + r, A.height), fx = reflect101_i(fx_lo + c, A.width);     // pyrDown's BORDER_REFLECT_101 on the frame
+        const int iy = reflect_idx(fy - A.top, rows), ix = reflect_idx(fx - A.left, cols);          // copyMakeBorder's BORDER_REFLECT into the image
+        float sx, sy;
+        map_backward<PROJ>(A.P, __ldg(sinu + ix), __ldg(cosu + ix), __ldg(rowA + iy), __ldg(rowB + iy), &sx, &sy);
+        uint32_t w = sample3_packed(A.src, A.sstep, A.P.src_w, A.P.src_h, sx, sy, A.wide_ok != 0);
+        const int nx = clamp_short(__float2int_rn(sx)), ny = clamp_short(__float2int_rn(sy));       // the all-255 mask: INTER_NEAREST + BORDER_CONSTANT
+        if ((unsigned)nx < (unsigned)A.P.src_w && (unsigned)ny < (unsigned)A.P.src_h) w |= 0xff000000u;
+        tile[r][c] = w;
+    }
+    __syncthreads();
+    // the image pixels of this block's 64 x 32 frame rectangle: four pixels (12 bytes) per thread where the address allows it
+    {
+        const int x_img0 = max(2 * ox0 - A.left, 0), x_img1 = min(2 * ox0 + 2 * WG_TX - A.left, cols);   // image columns owned
+        const int y_img0 = max(2 * oy0 - A.top, 0), y_img1 = min(2 * oy0 + 2 * WG_TY - A.top, rows);
+        if (x_img0 < x_img1 && y_img0 < y_img1) {
+            const int q0 = x_img0 >> 2, q1 = (x_img1 + 3) >> 2;                                         // quads of four image columns
+            const int nq = q1 - q0, nrow = y_img1 - y_img0;
+            const bool aligned = ((reinterpret_cast<uintptr_t>(A.dst) | A.dstep) & 3) == 0 && ((reinterpret_cast<uintptr_t>(A.mask) | A.mstep) & 3) == 0;
+            for (int e = tid; e < nq * nrow; e += 256) {
+                const int yy = y_img0 + e / nq, x4 = 4 * (q0 + e % nq);
+                const uint32_t* t = &tile[yy + A.top - fy_lo][0] + (A.left - fx_lo);                    // t[image x] = frame pixel
+                uint8_t* d = A.dst + (size_t)yy * A.dstep + 3 * (size_t)x4;
+                uint8_t* m = A.mask + (size_t)yy * A.mstep + x4;
+                if (aligned && x4 >= x_img0 && x4 + 4 <= x_img1) {
+                    const uint32_t p0 = t[x4], p1 = t[x4 + 1], p2 = t[x4 + 2], p3 = t[x4 + 3];
+                    uint32_t* d32 = reinterpret_cast<uint32_t*>(d);
+                    d32[0] = (p0 & 0xffffffu) | (p1 << 24);
+                    d32[1] = ((p1 >> 8) & 0xffffu) | (p2 << 16);
+                    d32[2] = ((p2 >> 16) & 0xffu) | (p3 << 8);
+                    *reinterpret_cast<uint32_t*>(m) = (p0 >> 24) | ((p1 >> 24) << 8) | ((p2 >> 24) << 16) | ((p3 >> 24) << 24);
+                } else {
+                    for (int k = 0; k < 4; ++k) {
+                        const int x = x4 + k;
+                        if (x < x_img0 || x >= x_img1) continue;
+                        const uint32_t p = t[x];
+                        d[3 * k] = (uint8_t)p; d[3 * k + 1] = (uint8_t)(p >> 8); d[3 * k + 2] = (uint8_t)(p >> 16);
+                        m[k] = (uint8_t)(p >> 24);
+                    }
+                }
+            }
+        }
+    }
+    // pyrDown: horizontal 5-tap sums, then the vertical pass ((s + 128) >> 8, exact integers)
+    for (int e = tid; e < WG_IH * WG_TX; e += 256) {
+        const int r = e / WG_TX, ox = e % WG_TX;
+        const uint32_t* p = &tile[r][2 * ox];
+        int s0 = 0, s1 = 0, s2 = 0;
+        const int kk[5] = {1, 4, 6, 4, 1};
+#pragma unroll
+        for (int b = 0; b < 5; ++b) { s0 += kk[b] * (int)(p[b] & 255u); s1 += kk[b] * (int)((p[b] >> 8) & 255u); s2 += kk[b] * (int)((p[b] >> 16) & 255u); }
+        hsum[r][ox][0] = s0; hsum[r][ox][1] = s1; hsum[r][ox][2] = s2;
+    }
+    __syncthreads();
+    const int ox = tid & 31, x = ox0 + ox;
+    if (x >= A.dw) return;
+    for (int oy = tid >> 5; oy < WG_TY; oy += 8) {
+        const int y = oy0 + oy;
+        if (y >= A.dh) break;
+        int16_t* o = A.g1 + ((size_t)y * A.dw + x) * 3;
+#pragma unroll
+        for (int c = 0; c < 3; ++c) {
+            const int acc = hsum[2 * oy][ox][c] + 4 * hsum[2 * oy + 1][ox][c] + 6 * hsum[2 * oy + 2][ox][c] + 4 * hsum[2 * oy + 3][ox][c] + hsum[2 * oy + 4][ox][c];
+            o[c] = (int16_t)((acc + 128) >> 8);                                                         // at most 255: no saturation needed
+        }
+    }
+}
+
 // ---- host drivers ----------------------------------------------------------------------------------
 
 struct PlanKey { int proj, w, h; float K[9], R[9], scale; };
@@ -419,6 +571,24 @@ static int launch_warp_t(is_ctx* ctx, const WarpPlan& plan, const float* tables,
     ctx->next_bytes = (double)CH * plan.P.src_w * plan.P.src_h + (double)(CH + (WITH_MASK ? 1 : 0)) * plan.P.dst_w * plan.P.dst_h;
     IS_LAUNCH(ctx, (k_warp<PROJ, CH, INTERP, BORDER, WITH_MASK>), grid, block, 0, plan.P, tables, src.ptr<uint8_t>(), src.step,
               dst.ptr<uint8_t>(), dst.step, mask ? mask->ptr<uint8_t>() : nullptr, mask ? mask->step : 0);
+    return IS_OK;
+}
+
+// warp + mask + Gaussian level 1 of the padded frame (top, left, height, width) in one pass; g1: (height / 2) x (width / 2) x 3 int16
+int launch_warp_g1(is_ctx* ctx, int proj, const WarpPlan& plan, const float* tables, const DevMat& src, const DevMat& dst, const DevMat& mask,
+                   int top, int left, int height, int width, int16_t* g1) {
+    WarpG1Args A;
+    A.P = plan.P; A.tables = tables;
+    A.src = src.ptr<uint8_t>(); A.sstep = src.step;
+    A.dst = dst.ptr<uint8_t>(); A.dstep = dst.step; A.mask = mask.ptr<uint8_t>(); A.mstep = mask.step;
+    A.top = top; A.left = left; A.height = height; A.width = width;
+    A.g1 = g1; A.dh = (height + 1) / 2; A.dw = (width + 1) / 2;
+    A.wide_ok = ((reinterpret_cast<uintptr_t>(src.data) | src.step) & 3) == 0 ? 1 : 0;
+    dim3 grid(div_up(A.dw, WG_TX), div_up(A.dh, WG_TY));
+    // algorithmic bytes: source read once, warped image + mask and level 1 written once
+    ctx->next_bytes = 3. * plan.P.src_w * plan.P.src_h + 4. * plan.P.dst_w * plan.P.dst_h + 6. * A.dh * A.dw;
+    if (proj == IS_PROJ_CYLINDRICAL) IS_LAUNCH(ctx, k_warp_g1<IS_PROJ_CYLINDRICAL>, grid, 256, 0, A);
+    else IS_LAUNCH(ctx, k_warp_g1<IS_PROJ_SPHERICAL>, grid, 256, 0, A);
     return IS_OK;
 }
 

@@ -94,6 +94,17 @@ class Comm:
         for req in self.dist.batch_isend_irecv(ops):
             req.wait()
 
+    def post(self, sends, recvs):
+        """start an exchange (same arguments as exchange); finish it with wait()"""
+        if not self.dist or (not sends and not recvs):
+            return []
+        ops = [self.dist.P2POp(self.dist.isend, t, dst) for dst, t in sends] + [self.dist.P2POp(self.dist.irecv, t, src) for src, t in recvs]
+        return self.dist.batch_isend_irecv(ops)
+
+    def wait(self, pending):
+        for req in pending:
+            req.wait()
+
     def all_min(self, value: int, device):
         if not self.dist:
             return value
@@ -148,7 +159,20 @@ class ShardedStitcher:
         mine = [i for i in range(n) if plan.owner[i] == rank]
         a, b = mine[0], mine[-1]
         warped, mask = {}, {}
-        for i, img in zip(mine, my_images):
+        has_right = b + 1 < n and (b, b + 1) in plan.pairs
+        has_left = a > 0 and (a - 1, a) in plan.pairs
+        # ---- warp; X1 (my first image + entry mask -> left neighbour, for its boundary pair) is posted as soon as that image is
+        #      warped, so that it travels while the other images are still being warped
+        warped[a], mask[a] = be.warp(my_images[0], Ks_all[a], Rs_all[a], scale)
+        sends, recvs = [], []
+        if has_left:
+            sends += [(rank - 1, warped[a]), (rank - 1, mask[a])]
+        if has_right:
+            warped[b + 1] = be.empty((plan.sizes[b + 1][1], plan.sizes[b + 1][0], 3), np.uint8)
+            halo_entry = be.empty((plan.sizes[b + 1][1], plan.sizes[b + 1][0]), np.uint8)
+            recvs += [(rank + 1, warped[b + 1]), (rank + 1, halo_entry)]
+        x1_pending = comm.post(sends, recvs)
+        for i, img in zip(mine[1:], my_images[1:]):
             warped[i], mask[i] = be.warp(img, Ks_all[i], Rs_all[i], scale)
         lap("warp")
         x0, x1 = plan.cuts[rank], plan.cuts[rank + 1]
@@ -158,17 +182,7 @@ class ShardedStitcher:
         for i in mine:                                # image pyramids on a side stream while the seam stage runs; the masks are read at blend time
             if i in needed_by[rank]:
                 be.blend_feed_early(bh, warped[i], mask[i], plan.corners[i], i + 1)
-        # ---- X1: my first image + entry mask -> left neighbour (its boundary pair)
-        has_right = b + 1 < n and (b, b + 1) in plan.pairs
-        has_left = a > 0 and (a - 1, a) in plan.pairs
-        sends, recvs = [], []
-        if has_left:
-            sends += [(rank - 1, warped[a]), (rank - 1, mask[a])]
-        if has_right:
-            warped[b + 1] = be.empty((plan.sizes[b + 1][1], plan.sizes[b + 1][0], 3), np.uint8)
-            halo_entry = be.empty((plan.sizes[b + 1][1], plan.sizes[b + 1][0]), np.uint8)
-            recvs += [(rank + 1, warped[b + 1]), (rank + 1, halo_entry)]
-        comm.exchange(sends, recvs)
+        comm.wait(x1_pending)
         lap("x1")
         # ---- seam: one batched call over my images + the halo image
         entry_b = be.copy_of(mask[b]) if has_right else None
