@@ -368,33 +368,81 @@ __device__ __forceinline__ uint32_t sample3_packed(const uint8_t* __restrict__ s
     return (uint32_t)out[0] | ((uint32_t)out[1] << 8) | ((uint32_t)out[2] << 16);
 }
 
-constexpr int WG_TX = 32, WG_TY = 16, WG_IW = 2 * WG_TX + 3, WG_IH = 2 * WG_TY + 3;
+// cv::remap INTER_LINEAR on 8UC3 for a sample whose 2 x 2 neighbourhood lies inside the source, with the interpolation split into
+// its horizontal and vertical step: top = tl (32 - fx) + tr fx, bottom likewise, out = (top (32 - fy) + bottom fy + 512) >> 10 --
+// the same integer as sum(w p) with w = (32 - fy)(32 - fx) ...  A channel's two taps of a row are bytes c and c + 3 of the
+// six-byte window: one funnel shift + one four-way byte dot product (weights 32 - fx, 0, 0, fx) per channel and row.
+__device__ __forceinline__ uint32_t sample3_dp(const uint8_t* __restrict__ src, size_t sstep, int sx, int sy, int fx, int fy) {
+    const int o = 3 * sx, a = o & ~3, sh8 = 8 * (o & 3);
+    const uint32_t* r0 = reinterpret_cast<const uint32_t*>(src + (size_t)sy * sstep + a);
+    const uint32_t* r1 = reinterpret_cast<const uint32_t*>(src + (size_t)(sy + 1) * sstep + a);
+    const uint32_t a0 = __ldg(r0), a1 = __ldg(r0 + 1), a2 = __ldg(r0 + 2);
+    const uint32_t b0 = __ldg(r1), b1 = __ldg(r1 + 1), b2 = __ldg(r1 + 2);
+    const uint32_t t0 = __funnelshift_r(a0, a1, sh8), t1 = __funnelshift_r(a1, a2, sh8);   // window bytes 0..3, 4..7 of the upper row
+    const uint32_t u0 = __funnelshift_r(b0, b1, sh8), u1 = __funnelshift_r(b1, b2, sh8);
+    const uint32_t wx = (uint32_t)(32 - fx) | ((uint32_t)fx << 24);
+    const uint32_t wy = (uint32_t)(32 - fy) | ((uint32_t)fy << 8);                          // dp2a: low halves of a x bytes 0, 1 of b
+    uint32_t out = 0;
+#pragma unroll
+    for (int c = 0; c < 3; ++c) {
+        const uint32_t top = __dp4a(__funnelshift_r(t0, t1, 8 * c), wx, 0u);                 // bytes c .. c + 3 of the window: taps at c and c + 3
+        const uint32_t bot = __dp4a(__funnelshift_r(u0, u1, 8 * c), wx, 0u);
+        const uint32_t v = __dp2a_lo(top | (bot << 16), wy, 512u) >> 10;
+        out |= v << (8 * c);
+    }
+    return out;
+}
+
+// One thread per frame column of the block's tile, walking down its rows: everything that depends on the column only (table
+// entries, the reflected image column, for the cylinder also the products m * sin u and m * cos u of the backward map) is
+// computed once per thread, everything that depends on the row only is uniform over the block.
+constexpr int WG_TX = 62, WG_TY = 16, WG_IW = 2 * WG_TX + 3, WG_IH = 2 * WG_TY + 3;       // 127 x 35 frame pixels under 62 x 16 outputs
+constexpr int WG_THREADS = 128;
 
 template <int PROJ>
-__global__ void __launch_bounds__(256) k_warp_g1(WarpG1Args A) {
+__global__ void __launch_bounds__(WG_THREADS) k_warp_g1(WarpG1Args A) {
     __shared__ uint32_t tile[WG_IH][WG_IW + 1];                  // b | g << 8 | r << 16 | mask << 24
-    __shared__ int hsum[WG_IH][WG_TX][3];
+    __shared__ int16_t hsum[WG_IH][WG_TX][3];                     // at most 16 * 255
     const int tid = threadIdx.x;
     const int ox0 = blockIdx.x * WG_TX, oy0 = blockIdx.y * WG_TY;
     const int fx_lo = 2 * ox0 - 2, fy_lo = 2 * oy0 - 2;
     const int cols = A.P.dst_w, rows = A.P.dst_h;
-    const float* sinu = A.tables;
-    const float* cosu = A.tables + cols;
     const float* rowA = A.tables + 2 * (size_t)cols;
     const float* rowB = rowA + rows;
-    for (int e = tid; e < WG_IH * WG_IW; e += 256) {
-        const int r = e / WG_IW, c = e % WG_IW;
-        const int fy = reflect101_i(fy_lo + r, A.height), fx = reflect101_i(fx_lo + c, A.width);     // pyrDown's BORDER_REFLECT_101 on the frame
-        const int iy = reflect_idx(fy - A.top, rows), ix = reflect_idx(fx - A.left, cols);          // copyMakeBorder's BORDER_REFLECT into the image
-        float sx, sy;
-        map_backward<PROJ>(A.P, __ldg(sinu + ix), __ldg(cosu + ix), __ldg(rowA + iy), __ldg(rowB + iy), &sx, &sy);
-        uint32_t w = sample3_packed(A.src, A.sstep, A.P.src_w, A.P.src_h, sx, sy, A.wide_ok != 0);
-        const int nx = clamp_short(__float2int_rn(sx)), ny = clamp_short(__float2int_rn(sy));       // the all-255 mask: INTER_NEAREST + BORDER_CONSTANT
-        if ((unsigned)nx < (unsigned)A.P.src_w && (unsigned)ny < (unsigned)A.P.src_h) w |= 0xff000000u;
-        tile[r][c] = w;
+    if (tid < WG_IW) {
+        const int fx = reflect101_i(fx_lo + tid, A.width);                                   // pyrDown's BORDER_REFLECT_101 on the frame
+        const int ix = reflect_idx(fx - A.left, cols);                                       // copyMakeBorder's BORDER_REFLECT into the image
+        const float su = __ldg(A.tables + ix), cu = __ldg(A.tables + cols + ix);
+        const float* m = A.P.k_rinv;
+        // cylinder: (x_, y_, z_) = (sin u, v / scale, cos u): the first and third product of every row of k_rinv depend on the column only
+        const float ax = __fmul_rn(m[0], su), cx = __fmul_rn(m[2], cu), ay = __fmul_rn(m[3], su), cy = __fmul_rn(m[5], cu), az = __fmul_rn(m[6], su), cz = __fmul_rn(m[8], cu);
+        const bool wide = A.wide_ok != 0;
+        for (int r = 0; r < WG_IH; ++r) {
+            const int fy = reflect101_i(fy_lo + r, A.height);
+            const int iy = reflect_idx(fy - A.top, rows);
+            const float ra = __ldg(rowA + iy);
+            float sx, sy;
+            if (PROJ == IS_PROJ_CYLINDRICAL) {
+                const float X = __fadd_rn(__fadd_rn(ax, __fmul_rn(m[1], ra)), cx);
+                const float Y = __fadd_rn(__fadd_rn(ay, __fmul_rn(m[4], ra)), cy);
+                const float Z = __fadd_rn(__fadd_rn(az, __fmul_rn(m[7], ra)), cz);
+                if (Z > 0.f) { sx = __fdiv_rn(X, Z); sy = __fdiv_rn(Y, Z); }
+                else { sx = -1.f; sy = -1.f; }
+            } else {
+                map_backward<PROJ>(A.P, su, cu, ra, __ldg(rowB + iy), &sx, &sy);
+            }
+            const int qx = __float2int_rn(__fmul_rn(sx, 32.f)), qy = __float2int_rn(__fmul_rn(sy, 32.f));
+            const int px = clamp_short(qx >> 5), py = clamp_short(qy >> 5);
+            uint32_t w;
+            if (wide && px >= 0 && px < A.P.src_w - 3 && (unsigned)py < (unsigned)(A.P.src_h - 1)) w = sample3_dp(A.src, A.sstep, px, py, qx & 31, qy & 31);
+            else w = sample3_packed(A.src, A.sstep, A.P.src_w, A.P.src_h, sx, sy, false);
+            const int nx = clamp_short(__float2int_rn(sx)), ny = clamp_short(__float2int_rn(sy));   // the all-255 mask: INTER_NEAREST + BORDER_CONSTANT
+            if ((unsigned)nx < (unsigned)A.P.src_w && (unsigned)ny < (unsigned)A.P.src_h) w |= 0xff000000u;
+            tile[r][tid] = w;
+        }
     }
     __syncthreads();
-    // the image pixels of this block's 64 x 32 frame rectangle: four pixels (12 bytes) per thread where the address allows it
+    // the image pixels of this block's frame rectangle: four pixels (12 bytes) per thread where the address allows it
     {
         const int x_img0 = max(2 * ox0 - A.left, 0), x_img1 = min(2 * ox0 + 2 * WG_TX - A.left, cols);   // image columns owned
         const int y_img0 = max(2 * oy0 - A.top, 0), y_img1 = min(2 * oy0 + 2 * WG_TY - A.top, rows);
@@ -402,7 +450,7 @@ __global__ void __launch_bounds__(256) k_warp_g1(WarpG1Args A) {
             const int q0 = x_img0 >> 2, q1 = (x_img1 + 3) >> 2;                                         // quads of four image columns
             const int nq = q1 - q0, nrow = y_img1 - y_img0;
             const bool aligned = ((reinterpret_cast<uintptr_t>(A.dst) | A.dstep) & 3) == 0 && ((reinterpret_cast<uintptr_t>(A.mask) | A.mstep) & 3) == 0;
-            for (int e = tid; e < nq * nrow; e += 256) {
+            for (int e = tid; e < nq * nrow; e += WG_THREADS) {
                 const int yy = y_img0 + e / nq, x4 = 4 * (q0 + e % nq);
                 const uint32_t* t = &tile[yy + A.top - fy_lo][0] + (A.left - fx_lo);                    // t[image x] = frame pixel
                 uint8_t* d = A.dst + (size_t)yy * A.dstep + 3 * (size_t)x4;
@@ -427,21 +475,21 @@ __global__ void __launch_bounds__(256) k_warp_g1(WarpG1Args A) {
         }
     }
     // pyrDown: horizontal 5-tap sums, then the vertical pass ((s + 128) >> 8, exact integers)
-    for (int e = tid; e < WG_IH * WG_TX; e += 256) {
+    for (int e = tid; e < WG_IH * WG_TX; e += WG_THREADS) {
         const int r = e / WG_TX, ox = e % WG_TX;
         const uint32_t* p = &tile[r][2 * ox];
-        int s0 = 0, s1 = 0, s2 = 0;
-        const int kk[5] = {1, 4, 6, 4, 1};
+        const uint32_t p0 = p[0], p1 = p[1], p2 = p[2], p3 = p[3], p4 = p[4];
 #pragma unroll
-        for (int b = 0; b < 5; ++b) { s0 += kk[b] * (int)(p[b] & 255u); s1 += kk[b] * (int)((p[b] >> 8) & 255u); s2 += kk[b] * (int)((p[b] >> 16) & 255u); }
-        hsum[r][ox][0] = s0; hsum[r][ox][1] = s1; hsum[r][ox][2] = s2;
+        for (int c = 0; c < 3; ++c) {
+            const int sft = 8 * c;
+            hsum[r][ox][c] = (int16_t)(((p0 >> sft) & 255u) + 4 * ((p1 >> sft) & 255u) + 6 * ((p2 >> sft) & 255u) + 4 * ((p3 >> sft) & 255u) + ((p4 >> sft) & 255u));
+        }
     }
     __syncthreads();
-    const int ox = tid & 31, x = ox0 + ox;
-    if (x >= A.dw) return;
-    for (int oy = tid >> 5; oy < WG_TY; oy += 8) {
-        const int y = oy0 + oy;
-        if (y >= A.dh) break;
+    for (int e = tid; e < WG_TY * WG_TX; e += WG_THREADS) {
+        const int oy = e / WG_TX, ox = e % WG_TX;
+        const int x = ox0 + ox, y = oy0 + oy;
+        if (x >= A.dw || y >= A.dh) continue;
         int16_t* o = A.g1 + ((size_t)y * A.dw + x) * 3;
 #pragma unroll
         for (int c = 0; c < 3; ++c) {
@@ -587,8 +635,8 @@ int launch_warp_g1(is_ctx* ctx, int proj, const WarpPlan& plan, const float* tab
     dim3 grid(div_up(A.dw, WG_TX), div_up(A.dh, WG_TY));
     // algorithmic bytes: source read once, warped image + mask and level 1 written once
     ctx->next_bytes = 3. * plan.P.src_w * plan.P.src_h + 4. * plan.P.dst_w * plan.P.dst_h + 6. * A.dh * A.dw;
-    if (proj == IS_PROJ_CYLINDRICAL) IS_LAUNCH(ctx, k_warp_g1<IS_PROJ_CYLINDRICAL>, grid, 256, 0, A);
-    else IS_LAUNCH(ctx, k_warp_g1<IS_PROJ_SPHERICAL>, grid, 256, 0, A);
+    if (proj == IS_PROJ_CYLINDRICAL) IS_LAUNCH(ctx, k_warp_g1<IS_PROJ_CYLINDRICAL>, grid, WG_THREADS, 0, A);
+    else IS_LAUNCH(ctx, k_warp_g1<IS_PROJ_SPHERICAL>, grid, WG_THREADS, 0, A);
     return IS_OK;
 }
 
