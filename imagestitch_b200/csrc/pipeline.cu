@@ -11,8 +11,15 @@
 #include <algorithm>
 #include <chrono>
 #include <cstdlib>
+#include <mutex>
 
 using namespace is;
+
+// Result downloads of panoramas stitched concurrently on one device (one context per host thread) take turns on the host link:
+// two 760 MB downloads at once each run at half speed and finish together, which also drags the callers into lock step
+// (upload | compute | download, all at the same time).  One at a time, a download runs under the other caller's upload +
+// compute and the link stays busy in both directions.
+static std::mutex g_d2h_turn[64];
 
 // IS_PIPELINE_DEBUG=1: host time stamps (ms since the first call in the process) of the phases of is_pipeline_run, per context
 struct PipeStamp {
@@ -211,8 +218,14 @@ int is_pipeline_run(is_ctx* ctx, int n, const is_mat* images, const is_camera* c
     stamp.mark("blend queued");
     if (stamp.on) { cudaStreamSynchronize(ctx->stream); stamp.mark("blend done"); }
     // ---- results
-    IS_TRY(commit(ctx, &dp));
-    IS_TRY(commit(ctx, &dm));
+    {
+        const bool to_host = dp.host != nullptr || dm.host != nullptr;
+        if (to_host) IS_CUDA(ctx, cudaStreamSynchronize(ctx->stream));            // wait for the blend outside the turn, hold it for the copy only
+        std::unique_lock<std::mutex> turn(g_d2h_turn[ctx->device & 63], std::defer_lock);
+        if (to_host) turn.lock();
+        IS_TRY(commit(ctx, &dp));
+        IS_TRY(commit(ctx, &dm));
+    }
     stamp.mark("results copied");
     if (seam_masks)
         for (int i = 0; i < n; ++i)

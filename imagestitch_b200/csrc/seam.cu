@@ -682,6 +682,8 @@ __global__ void __launch_bounds__(1024) k_seam_dp_batch(const DpArgs* __restrict
 // shuffles; the cost rows come straight from L2 into a register ring R steps ahead (every thread reads only its own lanes'
 // costs, so no staging through shared memory is needed); the control bytes of the owned lanes go out as one 32-bit store.
 // The back-track is a separate, parallel pair of kernels (k_bt_compose / k_bt_walk).
+constexpr int DP_L2_AHEAD = 24;                              // steps between a cost row's L2 prefetch and its use in k_seam_fwd
+constexpr int DP_ROW_PAD = 8;                                 // spare rows behind the cost tables (k_seam_fwd prefetches past the last step)
 __device__ unsigned g_dp_inf_row[16] = {0x7f800000u, 0x7f800000u, 0x7f800000u, 0x7f800000u, 0x7f800000u, 0x7f800000u, 0x7f800000u, 0x7f800000u,
                                         0x7f800000u, 0x7f800000u, 0x7f800000u, 0x7f800000u, 0x7f800000u, 0x7f800000u, 0x7f800000u, 0x7f800000u};
 
@@ -788,12 +790,29 @@ __global__ void __launch_bounds__(512) k_seam_fwd(const DpArgs* __restrict__ tab
     }
     // register ring of cost rows, R steps ahead; the fetch pointers never stop: the tables carry DP_ROW_PAD spare rows
     float4 rp[R][LPT / 4], rq[R][LPT / 4];
+    // The tables come from DRAM (a call's cost maps exceed the L2): a register ring of R steps covers an L2 hit, not a DRAM access
+    // (ncu: half of the stall samples were the first use of a loaded row).  So the rows are pulled into the L2 DP_L2_AHEAD steps
+    // early with prefetch.global.L2 (one per 128-byte line: every 8 / LPT * 4-th lane), and the ring only has to hide the L2.
+    constexpr int LINE_LANES = 128 / (4 * LPT) > 0 ? 128 / (4 * LPT) : 1;               // threads sharing a 128-byte line of a row
+    const bool pf_lane = live && (lane_id % LINE_LANES) == 0;
+    const size_t pf_off = (size_t)DP_L2_AHEAD * (size_t)(A.pitch >> 2);
+    const float4* table_end_p = reinterpret_cast<const float4*>(A.P + (size_t)(A.s1 + 1) * pitch);
     auto fetch = [&](int slot) {
 #pragma unroll
         for (int v = 0; v < LPT / 4; ++v) { rp[slot][v] = __ldg(fp + v); rq[slot][v] = __ldg(fq + v); }
+        if (pf_lane && fp + pf_off < table_end_p) {
+            asm volatile("prefetch.global.L2 [%0];" ::"l"(fp + pf_off));
+            asm volatile("prefetch.global.L2 [%0];" ::"l"(fq + pf_off));
+        }
         fp += row4; fq += row4;
     };
     if (ngroups) {
+        if (pf_lane)                                                                      // the rows between the ring and the prefetch distance
+            for (int d = R; d < DP_L2_AHEAD; ++d)
+                if (fp + (size_t)d * (size_t)(A.pitch >> 2) < table_end_p) {
+                    asm volatile("prefetch.global.L2 [%0];" ::"l"(fp + (size_t)d * (size_t)(A.pitch >> 2)));
+                    asm volatile("prefetch.global.L2 [%0];" ::"l"(fq + (size_t)d * (size_t)(A.pitch >> 2)));
+                }
 #pragma unroll
         for (int r = 0; r < R; ++r) fetch(r);
     }
@@ -823,7 +842,6 @@ __global__ void __launch_bounds__(512) k_seam_fwd(const DpArgs* __restrict__ tab
 // once) and records where it leaves the chunk; k_bt_walk chains the chunk maps from the destination (one short serial chain
 // per seam) and then lets one thread per chunk write the seam lanes of its steps.
 constexpr int BT_CHUNK = 64;
-constexpr int DP_ROW_PAD = 8;                                 // spare rows behind the cost tables (k_seam_fwd prefetches past the last step)
 struct BtArgs { DpArgs A; short* map; int nchunks; };         // map[chunk][pitch]: lane at the step below the chunk, given the lane at its top step
 
 __device__ __forceinline__ int bt_step(const uint8_t* __restrict__ control, size_t pitch, int lanes, int step, int lane) {

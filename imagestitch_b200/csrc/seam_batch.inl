@@ -132,14 +132,13 @@ struct SpecialJob {
     int2* out; int* count;
 };
 
-// bit i of the result: pixel mx0 + i (own coordinates) of mask row my is set, i < 18 -- from the row's toggles
-__device__ __forceinline__ unsigned row_bits18(const unsigned char* __restrict__ counts, const unsigned short* __restrict__ xs, int rows, int cols, int mx0, int my) {
-    if ((unsigned)my >= (unsigned)rows) return 0u;
-    const int n = min((int)counts[my], TG_CAP);
-    const uint4 v = *reinterpret_cast<const uint4*>(xs + (size_t)my * TG_CAP);
+// bit i of the result: pixel mx0 + i (own coordinates) of a mask row is set, i < 18 -- from the row's toggles (n of them in v)
+__device__ __forceinline__ unsigned toggles_bits18(int n, const uint4& v, int cols, int mx0) {
     const unsigned w[4] = {v.x, v.y, v.z, v.w};
     unsigned bits = 0;
-    for (int k = 0; k < n; ++k) {
+#pragma unroll
+    for (int k = 0; k < TG_CAP; ++k) {
+        if (k >= n) break;
         const int t = (int)((w[k >> 1] >> (16 * (k & 1))) & 0xffffu) - mx0;      // toggle position inside the window
         bits ^= t <= 0 ? 0x3ffffu : (t >= 18 ? 0u : (0x3ffffu << t) & 0x3ffffu);
     }
@@ -152,7 +151,7 @@ __device__ __forceinline__ unsigned row_bits18(const unsigned char* __restrict__
 // The scan works on the row toggles k_row_toggles_batch has just produced (16 pixels of a row per step as bit sets: two
 // 16-byte loads per row instead of ten byte loads per pixel); only the few candidates look at the mask bytes themselves.
 constexpr int SP_ROWS = 4;             // rows per thread; a block of 128 threads covers 32 chunks (512 pixels) x 16 rows
-constexpr int SP_QUEUE = 2048;         // candidates a block can hold (its 8192 pixels could all be candidates: beyond the queue the pair overflows)
+constexpr int SP_QUEUE = 1024;         // candidates a block can hold (its 8192 pixels could all be candidates: beyond the queue the pair overflows)
 struct SpMask { const uint8_t* p; size_t step; int rows, cols, ox, oy, nlayers; };
 __device__ __forceinline__ bool spm_at(const SpMask& M, const LayeredMask& full, int fx, int fy) {   // frame coordinates
     const int x = fx - M.ox, y = fy - M.oy;
@@ -184,18 +183,30 @@ __global__ void __launch_bounds__(128) k_special_points_batch(const SpecialJob* 
     if (16 * cx < iw && ly0 < ih) {
         const int x0 = ix + 16 * cx;                                             // frame column of bit 1
         const int m1x = x0 - 1 - M1.ox, m2x = x0 - 1 - M2.ox;
-        auto bits = [&](int y, unsigned* b1, unsigned* b2) {                     // frame row y
-            *b1 = row_bits18(J.cnt1, J.xs1, M1.rows, M1.cols, m1x, y - M1.oy);
-            *b2 = row_bits18(J.cnt2, J.xs2, M2.rows, M2.cols, m2x, y - M2.oy);
-        };
-        unsigned p1, p2, c1, c2, n1, n2;
-        bits(iy + ly0 - 1, &p1, &p2);
-        bits(iy + ly0, &c1, &c2);
+        // the toggles of the SP_ROWS + 2 rows this thread looks at, both masks: all loads first (they are independent), then the bits
+        int cn1[SP_ROWS + 2], cn2[SP_ROWS + 2];
+        uint4 tv1[SP_ROWS + 2], tv2[SP_ROWS + 2];
+#pragma unroll
+        for (int r = 0; r < SP_ROWS + 2; ++r) {
+            const int y1 = iy + ly0 - 1 + r - M1.oy, y2 = iy + ly0 - 1 + r - M2.oy;
+            const bool in1 = (unsigned)y1 < (unsigned)M1.rows, in2 = (unsigned)y2 < (unsigned)M2.rows;
+            cn1[r] = in1 ? min((int)J.cnt1[y1], TG_CAP) : 0;
+            cn2[r] = in2 ? min((int)J.cnt2[y2], TG_CAP) : 0;
+            tv1[r] = in1 ? *reinterpret_cast<const uint4*>(J.xs1 + (size_t)y1 * TG_CAP) : make_uint4(0, 0, 0, 0);
+            tv2[r] = in2 ? *reinterpret_cast<const uint4*>(J.xs2 + (size_t)y2 * TG_CAP) : make_uint4(0, 0, 0, 0);
+        }
+        unsigned b1[SP_ROWS + 2], b2[SP_ROWS + 2];
+#pragma unroll
+        for (int r = 0; r < SP_ROWS + 2; ++r) {
+            b1[r] = toggles_bits18(cn1[r], tv1[r], M1.cols, m1x);
+            b2[r] = toggles_bits18(cn2[r], tv2[r], M2.cols, m2x);
+        }
         const int rows = min(SP_ROWS, ih - ly0);
-        for (int r = 0; r < rows; ++r) {
+#pragma unroll
+        for (int r = 0; r < SP_ROWS; ++r) {
+            if (r >= rows) break;
             const int y = iy + ly0 + r;
-            bits(y + 1, &n1, &n2);
-            const unsigned both = c1 & c2, x_cur = c1 ^ c2, x_up = p1 ^ p2, x_dn = n1 ^ n2;
+            const unsigned both = b1[r + 1] & b2[r + 1], x_cur = b1[r + 1] ^ b2[r + 1], x_up = b1[r] ^ b2[r], x_dn = b1[r + 2] ^ b2[r + 2];
             unsigned cand = both & ((x_cur << 1) | (x_cur >> 1) | x_up | x_dn) & 0x1fffeu;   // bits 1..16: this chunk's pixels
             if (cand) {
                 int k = atomicAdd(&qn, __popc(cand));
@@ -206,7 +217,6 @@ __global__ void __launch_bounds__(128) k_special_points_batch(const SpecialJob* 
                     ++k;
                 }
             }
-            p1 = c1; p2 = c2; c1 = n1; c2 = n2;
         }
     }
     __syncthreads();
@@ -244,7 +254,9 @@ struct JobDev {
     int rx, ry, rw, rh;
     int horizontal, lanes, steps, pitch;
     float* P; float* Q;
+    const int2* runs;                  // the component's runs per bounding-box row: runs[(y - ry) * COST_RUNS + k] = (x0, x1) in frame coordinates
 };
+constexpr int COST_RUNS = 4;
 
 struct ClearTabDev {                   // the clear intervals of a pair and the two masks they go into
     const int* row_start; const int4* ivs;
@@ -299,6 +311,8 @@ __global__ void k_cost_pq_batch(const PairDev* __restrict__ pairs, const JobDev*
 // so the cell's own pixels and label are loaded once, the previous step's stay in registers and the neighbouring lane's come
 // by warp shuffle: 6 pixel bytes + one label per cell instead of ~24 + 5.  Same arithmetic as cost_v / cost_h ([SEAM]:756-802).
 constexpr int COST_WALK = 32;
+// Membership of a cell in the component comes from the component's runs of that row (a few intervals per row, uploaded with the
+// plan), not from a label image: no k_label_window pass, no 4-byte label per cell.
 template <typename T>
 __global__ void __launch_bounds__(128) k_cost_pq_walk(const PairDev* __restrict__ pairs, const JobDev* __restrict__ jobs) {
     const JobDev& J = jobs[blockIdx.z];
@@ -315,7 +329,13 @@ __global__ void __launch_bounds__(128) k_cost_pq_walk(const PairDev* __restrict_
     auto load = [&](int ln, int st) {                                               // pixels only where the label says both images cover the cell
         Cell c;
         const int x = J.rx + (hz ? st : ln), y = J.ry + (hz ? ln : st);
-        c.lab = ln < J.lanes ? label_at(D.labels, D.fr, x, y) : -3;
+        c.lab = -3;
+        const int by = y - J.ry;
+        if (ln < J.lanes && (unsigned)by < (unsigned)J.rh) {
+            const int4* rr = reinterpret_cast<const int4*>(J.runs + (size_t)by * COST_RUNS);
+            const int4 r01 = __ldg(rr), r23 = __ldg(rr + 1);
+            if ((x >= r01.x && x < r01.y) || (x >= r01.z && x < r01.w) || (x >= r23.x && x < r23.y) || (x >= r23.z && x < r23.w)) c.lab = l1;
+        }
         if (c.lab == l1) {
             const T* pa = A.px(x, y);
             const T* pb = B.px(x, y);
@@ -418,8 +438,10 @@ static void dp_choose_shape(int lanes, int steps, int s0, int s1, int variant, D
     if (variant == 1) {
         int forced = -1;
         if (const char* e = getenv("IS_DP_V1_TMPL")) forced = atoi(e);
-        for (int t = 0; t < 4; ++t) {
-            if (forced >= 0 ? t != forced : t == 3) continue;
+        static const int order[4] = {3, 0, 1, 2};          // the 16-step halo first (half as many block barriers), then by capacity
+        for (int k = 0; k < 4; ++k) {
+            const int t = order[k];
+            if (forced >= 0 && t != forced) continue;
             if (lanes <= 16 * V1_TMPL[t][2]) { S->v1 = 1; S->tmpl = t; S->nwarps = div_up(lanes, V1_TMPL[t][2]); break; }
         }
     }
@@ -497,6 +519,7 @@ struct SeamJobHost {
     int s0 = 0, lane0 = 0, s1 = 0, lane1 = 0, nseam = 0;
     DpShape shape;
     size_t off_map = 0, off_P = 0, off_Q = 0, off_ctl = 0, off_res = 0;   // device arena offsets (off_res in ints)
+    std::vector<int2> runs;            // component_runs of c1 over its bounding box
     UlsRuns uls;
     bool reached = false;
     std::vector<int32_t> trace;
@@ -722,6 +745,13 @@ static int seam_batch_wave(is_ctx* ctx, const std::vector<std::pair<int, int>>& 
             J.nseam = J.s1 - J.s0 + 1;
         }
     const size_t nj = jobs.size();
+    // COLOR costs read the component's runs; the label image (k_label_window_batch) is only built for the cost kernels that still
+    // want it: COLOR_GRAD, or a component with more than COST_RUNS runs in a row
+    std::vector<char> runs_ok(std::max<size_t>(nj, 1), 0);
+    pool->run(nj, [&](size_t j) { runs_ok[j] = jobs[j].runs.empty() && PR[(size_t)jobs[j].pair].component_runs(jobs[j].op.c1, jobs[j].op.ry, jobs[j].op.rh, COST_RUNS, &jobs[j].runs); });
+    bool need_labels = cost_fn == IS_COST_COLOR_GRAD || getenv("IS_COST_KERNEL_CELL") != nullptr;
+    for (size_t j = 0; j < nj; ++j) need_labels = need_labels || !runs_ok[j];
+    if (need_labels) pool->run(np, [&](size_t k) { PR[k].build_tab(); });
     // device arena: per pair the label window, per seam P, Q, control (+ back-track maps), results; blob 1 = tables + label tables
     size_t arena = 0;
     auto take = [&](size_t bytes) { const size_t o = arena; arena = align_up(arena + bytes, 256); return o; };
@@ -729,7 +759,7 @@ static int seam_batch_wave(is_ctx* ctx, const std::vector<std::pair<int, int>>& 
     std::vector<int> gpitch(np, 0);
     for (size_t k = 0; k < np; ++k) {
         const PairRuns& P = PR[k];
-        off_labels[k] = take(sizeof(int) * (size_t)P.ww * P.wh);
+        off_labels[k] = need_labels ? take(sizeof(int) * (size_t)P.ww * P.wh) : 0;
         if (cost_fn == IS_COST_COLOR_GRAD) {
             const int iw = P.iBr.x - P.iTl.x, ih = P.iBr.y - P.iTl.y;
             gpitch[k] = (iw + 31) & ~31;
@@ -748,7 +778,10 @@ static int seam_batch_wave(is_ctx* ctx, const std::vector<std::pair<int, int>>& 
     const size_t off_res_all = take(sizeof(int) * std::max<size_t>(res_total_ints, 4));
     Blob B1;
     std::vector<size_t> off_tab(np);
-    for (size_t k = 0; k < np; ++k) off_tab[k] = B1.put(PR[k].tab.data(), sizeof(int) * PR[k].tab.size());
+    for (size_t k = 0; k < np; ++k) off_tab[k] = need_labels ? B1.put(PR[k].tab.data(), sizeof(int) * PR[k].tab.size()) : 0;
+    std::vector<size_t> off_runs(std::max<size_t>(nj, 1), 0);
+    if (!need_labels)
+        for (size_t j = 0; j < nj; ++j) off_runs[j] = B1.put(jobs[j].runs.data(), sizeof(int2) * jobs[j].runs.size());
     const size_t off_pairs = B1.put(nullptr, sizeof(PairDev) * np);
     const size_t off_jobs = B1.put(nullptr, sizeof(JobDev) * std::max<size_t>(nj, 1));
     const size_t off_dp = B1.put(nullptr, sizeof(DpArgs) * std::max<size_t>(nj, 1));
@@ -778,13 +811,15 @@ static int seam_batch_wave(is_ctx* ctx, const std::vector<std::pair<int, int>>& 
             std::memset(&D, 0, sizeof(D));
             D.fr = Frame{P.uw, P.uh, P.wx, P.wy, P.ww, P.wh, MaskView{m1.ptr<uint8_t>(), m1.step, m1.rows, m1.cols, P.o1x, P.o1y},
                          MaskView{m2.ptr<uint8_t>(), m2.step, m2.rows, m2.cols, P.o2x, P.o2y}};
-            D.labels = reinterpret_cast<int*>(base + off_labels[k]);
-            const int* d = reinterpret_cast<const int*>(b1d + off_tab[k]);
-            const size_t wrows = (size_t)P.wh;
-            D.wcap = (int)P.wcap;
-            D.tab_cnt = d - P.wy;
-            D.tab_cps = reinterpret_cast<const ChangePt*>(d + wrows) - (size_t)P.wy * P.wcap;
-            D.tab_lab = d + wrows + wrows * P.wcap * 2 - (size_t)P.wy * P.wcap;
+            if (need_labels) {
+                D.labels = reinterpret_cast<int*>(base + off_labels[k]);
+                const int* d = reinterpret_cast<const int*>(b1d + off_tab[k]);
+                const size_t wrows = (size_t)P.wh;
+                D.wcap = (int)P.wcap;
+                D.tab_cnt = d - P.wy;
+                D.tab_cps = reinterpret_cast<const ChangePt*>(d + wrows) - (size_t)P.wy * P.wcap;
+                D.tab_lab = d + wrows + wrows * P.wcap * 2 - (size_t)P.wy * P.wcap;
+            }
             D.img1 = i1.data; D.img2 = i2.data; D.step1 = i1.step; D.step2 = i2.step;
             D.rows1 = i1.rows; D.cols1 = i1.cols; D.rows2 = i2.rows; D.cols2 = i2.cols;
             D.dx1 = P.unionTl.x - P.tl1.x; D.dy1 = P.unionTl.y - P.tl1.y; D.dx2 = P.unionTl.x - P.tl2.x; D.dy2 = P.unionTl.y - P.tl2.y;
@@ -805,6 +840,7 @@ static int seam_batch_wave(is_ctx* ctx, const std::vector<std::pair<int, int>>& 
             D.rx = J.op.rx; D.ry = J.op.ry; D.rw = J.op.rw; D.rh = J.op.rh;
             D.horizontal = J.horizontal ? 1 : 0; D.lanes = J.lanes; D.steps = J.steps; D.pitch = J.pitch;
             D.P = reinterpret_cast<float*>(base + J.off_P); D.Q = reinterpret_cast<float*>(base + J.off_Q);
+            D.runs = need_labels ? nullptr : reinterpret_cast<const int2*>(b1d + off_runs[order[q]]);
             int* res = reinterpret_cast<int*>(base + off_res_all) + J.off_res;
             DpArgs& A = da[q];
             A.P = D.P; A.Q = D.Q; A.control = base + J.off_ctl;
@@ -824,10 +860,9 @@ static int seam_batch_wave(is_ctx* ctx, const std::vector<std::pair<int, int>>& 
     const int* res_h = nullptr;                                        // view of the pinned bounce buffer, valid until the next download
     if (nj) {
         IS_CUDA(ctx, cudaMemsetAsync(base + off_res_all, 0, sizeof(int) * std::max<size_t>(res_total_ints, 4), ctx->stream));
-        // labels only where seams are estimated: the windows of the pairs that have one
-        int max_ww = 0, max_wh = 0;
-        for (auto& J : jobs) { max_ww = std::max(max_ww, PR[(size_t)J.pair].ww); max_wh = std::max(max_wh, PR[(size_t)J.pair].wh); }
-        {
+        if (need_labels) {                                                                       // labels only where seams are estimated
+            int max_ww = 0, max_wh = 0;
+            for (auto& J : jobs) { max_ww = std::max(max_ww, PR[(size_t)J.pair].ww); max_wh = std::max(max_wh, PR[(size_t)J.pair].wh); }
             dim3 block(64, 4), grid(div_up(max_ww, 64), div_up(max_wh, 4), (unsigned)np);
             IS_LAUNCH(ctx, k_label_window_batch, grid, block, 0, pairs_d);
         }
@@ -865,7 +900,7 @@ static int seam_batch_wave(is_ctx* ctx, const std::vector<std::pair<int, int>>& 
             if (cost_fn == IS_COST_COLOR_GRAD) {
                 if (is_u8) IS_LAUNCH(ctx, (k_cost_pq_batch<uint8_t, true>), grid, block, 0, pairs_d, jobs_d);
                 else IS_LAUNCH(ctx, (k_cost_pq_batch<float, true>), grid, block, 0, pairs_d, jobs_d);
-            } else if (getenv("IS_COST_KERNEL_CELL")) {                                          // tuning knob: one thread per cell
+            } else if (need_labels) {                                                            // one thread per cell, label image
                 if (is_u8) IS_LAUNCH(ctx, (k_cost_pq_batch<uint8_t, false>), grid, block, 0, pairs_d, jobs_d);
                 else IS_LAUNCH(ctx, (k_cost_pq_batch<float, false>), grid, block, 0, pairs_d, jobs_d);
             } else {

@@ -86,6 +86,10 @@ public:
 
     void setup(int i, int j, Pt t1, Pt t2, const MaskRuns* m1, const MaskRuns* m2);
     void build();                                     // merge, components, contours, edges
+    void build_tab();                                 // the label-window table (only the label-image path of the cost kernels needs it)
+    // the runs of component c (0-based) in the rows [ry, ry + rh) of the frame, at most `cap` per row: out[(y - ry) * cap + k] = (x0, x1),
+    // unused slots (0, 0); false when a row has more runs than cap
+    bool component_runs(int c, int ry, int rh, int cap, std::vector<int2>* out) const;
     void plan();                                      // conflict loop -> ops, final_states
     bool same_structure(const PairRuns& o) const;
 
@@ -183,6 +187,17 @@ void PairRuns::build() {
     wy = std::max(0, iTl.y - unionTl.y - 1);
     ww = std::min(uw, iBr.x - unionTl.x + 1) - wx;
     wh = std::min(uh, iBr.y - unionTl.y + 1) - wy;
+    lapt("tab");
+    tls.assign((size_t)ncomps, Pt{INT_MAX, INT_MAX});
+    brs.assign((size_t)ncomps, Pt{INT_MIN, INT_MIN});
+    contours.assign((size_t)ncomps, std::vector<ContourRec>());
+    contour_rows();
+    lapt("contours");
+    find_edges();
+    lapt("edges");
+}
+
+void PairRuns::build_tab() {
     wcap = 1;
     for (int y = wy; y < wy + wh; ++y) wcap = std::max(wcap, (size_t)(row_off[(size_t)y + 1] - row_off[(size_t)y]));
     const size_t wrows = (size_t)wh;
@@ -196,14 +211,22 @@ void PairRuns::build() {
         std::copy(cps.begin() + row_off[(size_t)y], cps.begin() + row_off[(size_t)y + 1], t_cps + r * wcap);
         std::copy(cp_label.begin() + row_off[(size_t)y], cp_label.begin() + row_off[(size_t)y + 1], t_lab + r * wcap);
     }
-    lapt("tab");
-    tls.assign((size_t)ncomps, Pt{INT_MAX, INT_MAX});
-    brs.assign((size_t)ncomps, Pt{INT_MIN, INT_MIN});
-    contours.assign((size_t)ncomps, std::vector<ContourRec>());
-    contour_rows();
-    lapt("contours");
-    find_edges();
-    lapt("edges");
+}
+
+bool PairRuns::component_runs(int c, int ry, int rh, int cap, std::vector<int2>* out) const {
+    out->assign((size_t)rh * cap, make_int2(0, 0));
+    const int l = c + 1;
+    for (int y = 0; y < rh; ++y) {
+        const int fy = ry + y;
+        const int rb = row_off[(size_t)fy], re = row_off[(size_t)fy + 1];
+        int k = 0;
+        for (int q = rb; q < re; ++q) {
+            if (cp_label[(size_t)q] != l) continue;
+            if (k == cap) return false;
+            (*out)[(size_t)y * cap + k++] = make_int2(cps[(size_t)q].x, q + 1 < re ? cps[(size_t)q + 1].x : uw);
+        }
+    }
+    return true;
 }
 
 // Raster-ordered contour records of the INTERS components: a pixel of an INTERS run is a contour pixel when one of its

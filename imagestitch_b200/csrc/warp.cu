@@ -372,10 +372,10 @@ __device__ __forceinline__ uint32_t sample3_packed(const uint8_t* __restrict__ s
 // its horizontal and vertical step: top = tl (32 - fx) + tr fx, bottom likewise, out = (top (32 - fy) + bottom fy + 512) >> 10 --
 // the same integer as sum(w p) with w = (32 - fy)(32 - fx) ...  A channel's two taps of a row are bytes c and c + 3 of the
 // six-byte window: one funnel shift + one four-way byte dot product (weights 32 - fx, 0, 0, fx) per channel and row.
-__device__ __forceinline__ uint32_t sample3_dp(const uint8_t* __restrict__ src, size_t sstep, int sx, int sy, int fx, int fy) {
+__device__ __forceinline__ uint32_t sample3_dp(const uint8_t* __restrict__ src, unsigned sstep, int sx, int sy, int fx, int fy) {
     const int o = 3 * sx, a = o & ~3, sh8 = 8 * (o & 3);
-    const uint32_t* r0 = reinterpret_cast<const uint32_t*>(src + (size_t)sy * sstep + a);
-    const uint32_t* r1 = reinterpret_cast<const uint32_t*>(src + (size_t)(sy + 1) * sstep + a);
+    const uint32_t* r0 = reinterpret_cast<const uint32_t*>(src + ((size_t)((unsigned)sy * sstep) + (unsigned)a));   // sources are below 4 GB
+    const uint32_t* r1 = reinterpret_cast<const uint32_t*>(reinterpret_cast<const uint8_t*>(r0) + sstep);
     const uint32_t a0 = __ldg(r0), a1 = __ldg(r0 + 1), a2 = __ldg(r0 + 2);
     const uint32_t b0 = __ldg(r1), b1 = __ldg(r1 + 1), b2 = __ldg(r1 + 2);
     const uint32_t t0 = __funnelshift_r(a0, a1, sh8), t1 = __funnelshift_r(a1, a2, sh8);   // window bytes 0..3, 4..7 of the upper row
@@ -403,41 +403,54 @@ template <int PROJ>
 __global__ void __launch_bounds__(WG_THREADS) k_warp_g1(WarpG1Args A) {
     __shared__ uint32_t tile[WG_IH][WG_IW + 1];                  // b | g << 8 | r << 16 | mask << 24
     __shared__ int16_t hsum[WG_IH][WG_TX][3];                     // at most 16 * 255
+    __shared__ float row_t[WG_IH][4];                             // per tile row: the row's terms of the backward map
     const int tid = threadIdx.x;
     const int ox0 = blockIdx.x * WG_TX, oy0 = blockIdx.y * WG_TY;
     const int fx_lo = 2 * ox0 - 2, fy_lo = 2 * oy0 - 2;
     const int cols = A.P.dst_w, rows = A.P.dst_h;
-    const float* rowA = A.tables + 2 * (size_t)cols;
-    const float* rowB = rowA + rows;
+    const float* m = A.P.k_rinv;
+    if (tid < WG_IH) {                                            // what depends on the row only, once per block
+        const int fy = reflect101_i(fy_lo + tid, A.height);      // pyrDown's BORDER_REFLECT_101 on the frame
+        const int iy = reflect_idx(fy - A.top, rows);            // copyMakeBorder's BORDER_REFLECT into the image
+        const float ra = __ldg(A.tables + 2 * (size_t)cols + iy);
+        if (PROJ == IS_PROJ_CYLINDRICAL) {                       // (x_, y_, z_) = (sin u, v / scale, cos u): the middle product of every row of k_rinv
+            row_t[tid][0] = __fmul_rn(m[1], ra); row_t[tid][1] = __fmul_rn(m[4], ra); row_t[tid][2] = __fmul_rn(m[7], ra); row_t[tid][3] = 0.f;
+        } else {
+            row_t[tid][0] = ra; row_t[tid][1] = __ldg(A.tables + 2 * (size_t)cols + rows + iy); row_t[tid][2] = 0.f; row_t[tid][3] = 0.f;
+        }
+    }
+    __syncthreads();
     if (tid < WG_IW) {
-        const int fx = reflect101_i(fx_lo + tid, A.width);                                   // pyrDown's BORDER_REFLECT_101 on the frame
-        const int ix = reflect_idx(fx - A.left, cols);                                       // copyMakeBorder's BORDER_REFLECT into the image
+        const int fx = reflect101_i(fx_lo + tid, A.width);
+        const int ix = reflect_idx(fx - A.left, cols);
         const float su = __ldg(A.tables + ix), cu = __ldg(A.tables + cols + ix);
-        const float* m = A.P.k_rinv;
-        // cylinder: (x_, y_, z_) = (sin u, v / scale, cos u): the first and third product of every row of k_rinv depend on the column only
+        // cylinder: the first and third product of every row of k_rinv depend on the column only
         const float ax = __fmul_rn(m[0], su), cx = __fmul_rn(m[2], cu), ay = __fmul_rn(m[3], su), cy = __fmul_rn(m[5], cu), az = __fmul_rn(m[6], su), cz = __fmul_rn(m[8], cu);
         const bool wide = A.wide_ok != 0;
+        const uint8_t* src = A.src;
+        const unsigned sstep = (unsigned)A.sstep;
+        const int sw = A.P.src_w, sh = A.P.src_h;
+#pragma unroll 1
         for (int r = 0; r < WG_IH; ++r) {
-            const int fy = reflect101_i(fy_lo + r, A.height);
-            const int iy = reflect_idx(fy - A.top, rows);
-            const float ra = __ldg(rowA + iy);
+            const float4 rt = *reinterpret_cast<const float4*>(row_t[r]);
             float sx, sy;
             if (PROJ == IS_PROJ_CYLINDRICAL) {
-                const float X = __fadd_rn(__fadd_rn(ax, __fmul_rn(m[1], ra)), cx);
-                const float Y = __fadd_rn(__fadd_rn(ay, __fmul_rn(m[4], ra)), cy);
-                const float Z = __fadd_rn(__fadd_rn(az, __fmul_rn(m[7], ra)), cz);
+                const float X = __fadd_rn(__fadd_rn(ax, rt.x), cx);
+                const float Y = __fadd_rn(__fadd_rn(ay, rt.y), cy);
+                const float Z = __fadd_rn(__fadd_rn(az, rt.z), cz);
                 if (Z > 0.f) { sx = __fdiv_rn(X, Z); sy = __fdiv_rn(Y, Z); }
                 else { sx = -1.f; sy = -1.f; }
             } else {
-                map_backward<PROJ>(A.P, su, cu, ra, __ldg(rowB + iy), &sx, &sy);
+                map_backward<PROJ>(A.P, su, cu, rt.x, rt.y, &sx, &sy);
             }
             const int qx = __float2int_rn(__fmul_rn(sx, 32.f)), qy = __float2int_rn(__fmul_rn(sy, 32.f));
-            const int px = clamp_short(qx >> 5), py = clamp_short(qy >> 5);
+            const int px = qx >> 5, py = qy >> 5;                 // inside the source here, so the remap's saturation to short is the identity
             uint32_t w;
-            if (wide && px >= 0 && px < A.P.src_w - 3 && (unsigned)py < (unsigned)(A.P.src_h - 1)) w = sample3_dp(A.src, A.sstep, px, py, qx & 31, qy & 31);
-            else w = sample3_packed(A.src, A.sstep, A.P.src_w, A.P.src_h, sx, sy, false);
-            const int nx = clamp_short(__float2int_rn(sx)), ny = clamp_short(__float2int_rn(sy));   // the all-255 mask: INTER_NEAREST + BORDER_CONSTANT
-            if ((unsigned)nx < (unsigned)A.P.src_w && (unsigned)ny < (unsigned)A.P.src_h) w |= 0xff000000u;
+            if (wide && px >= 0 && px < sw - 3 && (unsigned)py < (unsigned)(sh - 1)) w = sample3_dp(src, sstep, px, py, qx & 31, qy & 31);
+            else w = sample3_packed(src, A.sstep, sw, sh, sx, sy, false);
+            // the all-255 mask: INTER_NEAREST + BORDER_CONSTANT (source sizes are below 32768: saturating the rounded coordinate to short changes nothing)
+            const int nx = __float2int_rn(sx), ny = __float2int_rn(sy);
+            if ((unsigned)nx < (unsigned)sw && (unsigned)ny < (unsigned)sh) w |= 0xff000000u;
             tile[r][tid] = w;
         }
     }
@@ -631,6 +644,8 @@ int launch_warp_g1(is_ctx* ctx, int proj, const WarpPlan& plan, const float* tab
     A.dst = dst.ptr<uint8_t>(); A.dstep = dst.step; A.mask = mask.ptr<uint8_t>(); A.mstep = mask.step;
     A.top = top; A.left = left; A.height = height; A.width = width;
     A.g1 = g1; A.dh = (height + 1) / 2; A.dw = (width + 1) / 2;
+    IS_REQUIRE(ctx, plan.P.src_w < 32768 && plan.P.src_h < 32768 && (size_t)src.step * (size_t)plan.P.src_h < ((size_t)1 << 32), IS_ERR_UNSUPPORTED,
+               "fused warp: source larger than 32767 pixels a side or 4 GB");
     A.wide_ok = ((reinterpret_cast<uintptr_t>(src.data) | src.step) & 3) == 0 ? 1 : 0;
     dim3 grid(div_up(A.dw, WG_TX), div_up(A.dh, WG_TY));
     // algorithmic bytes: source read once, warped image + mask and level 1 written once
