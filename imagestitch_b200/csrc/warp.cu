@@ -403,7 +403,7 @@ template <int PROJ>
 __global__ void __launch_bounds__(WG_THREADS) k_warp_g1(WarpG1Args A) {
     __shared__ uint32_t tile[WG_IH][WG_IW + 1];                  // b | g << 8 | r << 16 | mask << 24
     __shared__ int16_t hsum[WG_IH][WG_TX][3];                     // at most 16 * 255
-    __shared__ float row_t[WG_IH][4];                             // per tile row: the row's terms of the backward map
+    __shared__ __align__(16) float row_t[WG_IH][4];                             // per tile row: the row's terms of the backward map
     const int tid = threadIdx.x;
     const int ox0 = blockIdx.x * WG_TX, oy0 = blockIdx.y * WG_TY;
     const int fx_lo = 2 * ox0 - 2, fy_lo = 2 * oy0 - 2;
