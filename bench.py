@@ -377,6 +377,7 @@ def main():
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--workload", default="c2", choices=sorted(WORKLOADS))
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--e2e-lanes", type=int, default=4, help="N = 1: panoramas in flight in the pipelined end-to-end measurement")
     ap.add_argument("--no-parity-check", action="store_true", help="N > 1: skip the sharded-vs-single-GPU comparison on rank 0")
     ap.add_argument("--kernel-report", default=None, help="write the per-kernel timing table (JSON) to this file")
     ap.add_argument("--opencv-sample", type=int, default=None, help="internal: time python cv2's path on a sample of this many rows, print JSON")
@@ -550,26 +551,30 @@ def main():
     same = bool(torch.equal(dev_pano.cpu(), pano_pin)) and bool(torch.equal(dev_pmask.cpu(), pmask_pin))
     ms_e2e = ms_e2e_serial
     if world == 1:
-        # Throughput of a STREAM of panoramas through the same synchronous call: two contexts on two host threads (one context per
-        # thread is the library's threading model), each with its own pinned output buffers, so that the D2H of one panorama
-        # runs under the H2D + compute of the next (the host link is full duplex).  Every step still uploads its sources and
+        # Throughput of a STREAM of panoramas through the same synchronous call: a few contexts on as many host threads (one context
+        # per thread is the library's threading model), each with its own pinned output buffers, so that the D2H of one panorama
+        # runs under the H2D + compute of the next ones (the host link is full duplex).  Every step still uploads its sources and
         # downloads its panorama inside the timed region.
-        ctx2 = S.Context(local_rank)
-        st2 = S.Stitcher(ctx2, "cylindrical", "dp", NUM_BANDS, S.WEIGHT_32F)
-        pano_pin2 = torch.empty(out_shape + (3,), dtype=torch.int16, pin_memory=True)
-        pmask_pin2 = torch.empty(out_shape, dtype=torch.uint8, pin_memory=True)
-        lanes = [(ctx, st, out_host), (ctx2, st2, (pano_pin2.numpy(), pmask_pin2.numpy()))]
+        n_lanes = max(2, args.e2e_lanes)
+        extra = [S.Context(local_rank) for _ in range(n_lanes - 1)]
+        lanes = [(ctx, st, out_host)]
+        pins = []
+        for c in extra:
+            pp = torch.empty(out_shape + (3,), dtype=torch.int16, pin_memory=True)
+            pm = torch.empty(out_shape, dtype=torch.uint8, pin_memory=True)
+            pins.append((pp, pm))
+            lanes.append((c, S.Stitcher(c, "cylindrical", "dp", NUM_BANDS, S.WEIGHT_32F), (pp.numpy(), pm.numpy())))
 
         def lane_steps(k, count):
             c, s_, out = lanes[k]
-            if k:                                         # the second panorama arrives half a step later: its upload + compute run
-                time.sleep(ms_e2e_serial * 0.5e-3)        # under the first one's download instead of competing with its upload
+            if k:                                         # panorama k arrives a fraction of a step later: its upload + compute run
+                time.sleep(ms_e2e_serial * 1e-3 * k / n_lanes)   # under the others' downloads instead of competing with their uploads
             for _ in range(count):
                 c.clear_plan_cache()
                 s_.stitch(imgs_host, Ks, Rs, scale, out=out)
 
         def run_lanes(count_each):
-            th = [threading.Thread(target=lane_steps, args=(k, count_each)) for k in range(2)]
+            th = [threading.Thread(target=lane_steps, args=(k, count_each)) for k in range(n_lanes)]
             for x in th:
                 x.start()
             for x in th:
@@ -585,11 +590,13 @@ def main():
         e1.record()
         torch.cuda.synchronize()
         windows.append((t0, time.perf_counter()))
-        ms_pipe = e0.elapsed_time(e1) / (2 * per_lane)
-        same2 = bool(torch.equal(dev_pano.cpu(), pano_pin2)) and bool(torch.equal(dev_pmask.cpu(), pmask_pin2))
-        e2e_pipe = {"ms_per_step": ms_pipe, "panoramas_in_flight": 2, "steps": 2 * per_lane, "matches_device_path": same2}
+        ms_pipe = e0.elapsed_time(e1) / (n_lanes * per_lane)
+        same2 = all(bool(torch.equal(dev_pano.cpu(), pp)) and bool(torch.equal(dev_pmask.cpu(), pm)) for pp, pm in pins)
+        e2e_pipe = {"ms_per_step": ms_pipe, "panoramas_in_flight": n_lanes, "steps": n_lanes * per_lane, "matches_device_path": same2}
         ms_e2e = min(ms_e2e_serial, ms_pipe)
-        ctx2.close()
+        for c in extra:
+            c.close()
+        del pins
     # what the host link of this box delivers for the same buffers (plain pinned copies): the floor of the e2e figure
     pcie = {}
     try:
@@ -682,7 +689,7 @@ def main():
         "clocks": sampler.summary(windows) if sampler else None,
         "e2e": {"value": world * in_mp / (ms_e2e * 1e-3), "unit": "MP/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
                 "ms_per_step": ms_e2e, "one_panorama_at_a_time": {"ms_per_step": ms_e2e_serial, "value": world * in_mp / (ms_e2e_serial * 1e-3)},
-                "two_panoramas_in_flight": e2e_pipe, "matches_device_path": same, "host_link_pinned_copy": pcie},
+                "panoramas_in_flight": e2e_pipe, "matches_device_path": same, "host_link_pinned_copy": pcie},
         "gpu_launches": int(launches),
         "stage_ms": stage_ms, "ms_per_step_with_kernel_events": ms_dev_ev,
         "roofline": roofline, "cpu_baseline": cpu,

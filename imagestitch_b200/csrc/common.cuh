@@ -151,6 +151,8 @@ int ensure_pinned(is_ctx* ctx, size_t bytes);
 int pinned_alloc(is_ctx* ctx, size_t bytes, void** out);
 // small control transfers through the pinned staging buffer (synchronous with the stream)
 int upload(is_ctx* ctx, void* dst, const void* src, size_t bytes);
+// one side in device memory, the other in pinned (mapped) host memory: moved by a kernel, not by a copy engine (see ctx.cu)
+int copy_small(is_ctx* ctx, void* dst, const void* src, size_t bytes, cudaMemcpyKind kind);
 int download(is_ctx* ctx, void* dst, const void* src, size_t bytes);
 int download2d(is_ctx* ctx, void* dst, size_t dpitch, const void* src, size_t spitch, size_t width, size_t height);
 // download into the pinned bounce buffer and hand out a view of it (valid until the next download on this context)

@@ -210,13 +210,41 @@ int pinned_alloc(is_ctx* ctx, size_t bytes, void** out) {
     return IS_OK;
 }
 
+// Small control transfers do not go through the copy engines: a panorama's bulk copies (hundreds of MB, one DMA queue per
+// direction) would hold them up for milliseconds when several panoramas are in flight on one device -- the seam stage of one
+// panorama waited for the download of another.  The pinned staging buffers are mapped into the device's address space
+// (unified addressing), so a kernel moves the bytes with ordinary loads and stores over the host link instead.
+__global__ void __launch_bounds__(256) k_copy_small(const unsigned char* __restrict__ src, unsigned char* __restrict__ dst, size_t bytes) {
+    const size_t n16 = bytes >> 4;
+    const size_t stride = (size_t)gridDim.x * blockDim.x;
+    const size_t t = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    for (size_t i = t; i < n16; i += stride) reinterpret_cast<uint4*>(dst)[i] = reinterpret_cast<const uint4*>(src)[i];
+    for (size_t i = (n16 << 4) + t; i < bytes; i += stride) dst[i] = src[i];
+}
+
+static bool sm_copy_ok(const void* a, const void* b) {
+    static const bool off = getenv("IS_COPY_ENGINE_SMALL") != nullptr;            // tuning knob: control transfers as cudaMemcpyAsync again
+    return !off && ((reinterpret_cast<uintptr_t>(a) | reinterpret_cast<uintptr_t>(b)) & 15) == 0;
+}
+
+int copy_small(is_ctx* ctx, void* dst, const void* src, size_t bytes, cudaMemcpyKind kind) {
+    if (!sm_copy_ok(dst, src)) {
+        IS_CUDA(ctx, cudaMemcpyAsync(dst, src, bytes, kind, ctx->stream));
+        return IS_OK;
+    }
+    const int blocks = (int)std::min<size_t>(296, (bytes / 16 + 255) / 256 + 1);
+    k_copy_small<<<blocks, 256, 0, ctx->stream>>>(static_cast<const unsigned char*>(src), static_cast<unsigned char*>(dst), bytes);
+    ctx->launches++;
+    IS_CUDA(ctx, cudaGetLastError());
+    return IS_OK;
+}
+
 int upload(is_ctx* ctx, void* dst, const void* src, size_t bytes) {
     if (bytes == 0) return IS_OK;
     void* stage = nullptr;
     IS_TRY(pinned_alloc(ctx, bytes, &stage));
     std::memcpy(stage, src, bytes);
-    IS_CUDA(ctx, cudaMemcpyAsync(dst, stage, bytes, cudaMemcpyHostToDevice, ctx->stream));
-    return IS_OK;
+    return copy_small(ctx, dst, stage, bytes, cudaMemcpyHostToDevice);
 }
 
 int download(is_ctx* ctx, void* dst, const void* src, size_t bytes) {
@@ -229,7 +257,7 @@ int download(is_ctx* ctx, void* dst, const void* src, size_t bytes) {
         IS_CUDA(ctx, cudaMallocHost(&ctx->pinned_dl, n));
         ctx->pinned_dl_bytes = n;
     }
-    IS_CUDA(ctx, cudaMemcpyAsync(ctx->pinned_dl, src, bytes, cudaMemcpyDeviceToHost, ctx->stream));
+    IS_TRY(copy_small(ctx, ctx->pinned_dl, src, bytes, cudaMemcpyDeviceToHost));
     IS_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
     std::memcpy(dst, ctx->pinned_dl, bytes);
     return IS_OK;
@@ -254,7 +282,7 @@ int download_view(is_ctx* ctx, const void* src, size_t bytes, const void** view)
         IS_CUDA(ctx, cudaMallocHost(&ctx->pinned_dl, n));
         ctx->pinned_dl_bytes = n;
     }
-    if (bytes) IS_CUDA(ctx, cudaMemcpyAsync(ctx->pinned_dl, src, bytes, cudaMemcpyDeviceToHost, ctx->stream));
+    if (bytes) IS_TRY(copy_small(ctx, ctx->pinned_dl, src, bytes, cudaMemcpyDeviceToHost));
     IS_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
     *view = ctx->pinned_dl;
     return IS_OK;

@@ -619,7 +619,7 @@ int upload_tables(is_ctx* ctx, int proj, const WarpPlan& plan, DevBuf* buf) {
     void* stage = nullptr;
     IS_TRY(pinned_alloc(ctx, n * sizeof(float), &stage));
     fill_tables(proj, plan.P.scale, plan.P.tl_x, plan.P.tl_y, w, h, (float*)stage);
-    IS_CUDA(ctx, cudaMemcpyAsync(buf->p, stage, n * sizeof(float), cudaMemcpyHostToDevice, ctx->stream));
+    IS_TRY(copy_small(ctx, buf->p, stage, n * sizeof(float), cudaMemcpyHostToDevice));
     return IS_OK;
 }
 
