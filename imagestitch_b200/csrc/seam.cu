@@ -687,18 +687,53 @@ constexpr int DP_ROW_PAD = 8;                                 // spare rows behi
 __device__ unsigned g_dp_inf_row[16] = {0x7f800000u, 0x7f800000u, 0x7f800000u, 0x7f800000u, 0x7f800000u, 0x7f800000u, 0x7f800000u, 0x7f800000u,
                                         0x7f800000u, 0x7f800000u, 0x7f800000u, 0x7f800000u, 0x7f800000u, 0x7f800000u, 0x7f800000u, 0x7f800000u};
 
-template <int LPT, int H, int R>
-__global__ void __launch_bounds__(512) k_seam_fwd(const DpArgs* __restrict__ table) {
+// Thread-block clusters (CL > 1): the windows of one seam are spread over the CL CTAs of a cluster -- a CTA of four warps keeps one
+// window per scheduler, so a step costs the issue slots of ONE window instead of sixteen, and a 1500-lane seam runs on four SMs.
+// At an exchange the owners of a CTA's outermost H lanes also store them into the neighbouring CTA's halo slots through
+// distributed shared memory (st.shared::cluster), and the block barrier becomes a cluster barrier (arrive.release /
+// wait.acquire).  The arithmetic of a lane does not depend on where its window runs: the seams are the same bit for bit.
+__device__ __forceinline__ uint32_t cluster_rank() { uint32_t r; asm volatile("mov.u32 %0, %%cluster_ctarank;" : "=r"(r)); return r; }
+__device__ __forceinline__ void cluster_barrier() {
+    asm volatile("barrier.cluster.arrive.release.aligned;\n\tbarrier.cluster.wait.acquire.aligned;" ::: "memory");
+}
+__device__ __forceinline__ void st_cluster_f4(const float* local, uint32_t rank, const float4& v) {   // the same offset in CTA `rank`'s shared memory
+    uint32_t remote;
+    asm volatile("mapa.shared::cluster.u32 %0, %1, %2;" : "=r"(remote) : "r"(smem_u32(local)), "r"(rank));
+    asm volatile("st.shared::cluster.v4.f32 [%0], {%1, %2, %3, %4};" ::"r"(remote), "f"(v.x), "f"(v.y), "f"(v.z), "f"(v.w) : "memory");
+}
+
+// The same store as an asynchronous one that reports its bytes to an mbarrier of the receiving CTA (st.async ...
+// mbarrier::complete_tx): the receiver waits for the bytes it expects, nobody fences.  A cluster barrier's release has to drain
+// the sender's outstanding global stores (the control bytes) first -- a quarter of the kernel's stall samples were that membar.
+__device__ __forceinline__ void st_async_f4(const float* local, const uint64_t* local_bar, uint32_t rank, const float4& v) {
+    uint32_t remote, rbar;
+    asm volatile("mapa.shared::cluster.u32 %0, %1, %2;" : "=r"(remote) : "r"(smem_u32(local)), "r"(rank));
+    asm volatile("mapa.shared::cluster.u32 %0, %1, %2;" : "=r"(rbar) : "r"(smem_u32(local_bar)), "r"(rank));
+    asm volatile("st.async.weak.shared::cluster.mbarrier::complete_tx::bytes.v4.f32 [%0], {%1, %2, %3, %4}, [%5];" ::"r"(remote), "f"(v.x), "f"(v.y),
+                 "f"(v.z), "f"(v.w), "r"(rbar)
+                 : "memory");
+}
+
+template <int LPT, int H, int R, int CL, bool ASY = false>
+__device__ __forceinline__ void seam_fwd_body(const DpArgs* __restrict__ table) {
     static_assert(H % LPT == 0 && H % R == 0 && LPT % 4 == 0 && LPT <= 16, "halo / ring shapes");
-    extern __shared__ __align__(16) float T_sm[];             // [2][pitch + 2 H]: running costs of all lanes at the last exchange
-    const DpArgs A = table[blockIdx.x];
+    extern __shared__ __align__(16) float T_sm[];             // [2][span + 2 H]: running costs of this CTA's lanes (+ halos) at the last exchange
+    const DpArgs A = table[blockIdx.x / CL];
     constexpr int WIN = 32 * LPT, OWN = WIN - 2 * H, K = H;
     const int tid = threadIdx.x, lane_id = tid & 31, warp = tid >> 5;
-    const int l0 = warp * OWN - H + lane_id * LPT;            // first lane of this thread (may lie outside the table)
+    const int rank = CL > 1 ? (int)cluster_rank() : 0;
+    const int span = CL > 1 ? (int)(blockDim.x >> 5) * OWN : A.pitch;        // lanes this CTA owns (CL == 1: the whole table)
+    const int cta_base = rank * span;
+    const int l0 = cta_base + warp * OWN - H + lane_id * LPT; // first lane of this thread (may lie outside the table)
     const bool live = l0 >= 0 && l0 < A.lanes;                // lanes [l0, l0 + LPT) exist (pitch is a multiple of LPT)
     const bool owned = live && lane_id * LPT >= H && lane_id * LPT < WIN - H;
     const float INF = __int_as_float(0x7f800000);
-    const int tstride = A.pitch + 2 * H;
+    const int tstride = span + 2 * H;
+    __shared__ uint64_t halo_bar[2];                          // ASY: one per buffer, completed by the neighbours' halo bytes
+    if (CL > 1) {
+        if (ASY && tid == 0) { mbar_init(&halo_bar[0], 1); mbar_init(&halo_bar[1], 1); mbar_fence_init(); }
+        cluster_barrier();                                    // every CTA of the cluster is running (and its barriers exist) before anyone stores into its shared memory
+    }
     const size_t pitch = (size_t)A.pitch;
     const int lc = live ? l0 : 0;
     // Threads outside the table read a constant row of +inf with stride 0: their lanes stay unreachable without a branch.
@@ -757,14 +792,39 @@ __global__ void __launch_bounds__(512) k_seam_fwd(const DpArgs* __restrict__ tab
         for (int j = 0; j < LPT; ++j) t[j] = tn[j];
     };
     // refresh every window from the owners of its lanes (one __syncthreads)
-    int buf = 0;
+    int buf = 0, nex = 0;                                     // nex: exchanges so far (the phase of halo_bar[buf] is nex / 2)
     auto exchange = [&]() {
-        float* T = T_sm + buf * tstride + H;                  // T[lane], lane in [-H, pitch + H)
+        float* T = T_sm + buf * tstride + H - cta_base;       // T[lane], lane in [cta_base - H, cta_base + span + H)
         if (owned) {
 #pragma unroll
-            for (int v = 0; v < LPT / 4; ++v) reinterpret_cast<float4*>(T + l0)[v] = make_float4(t[4 * v], t[4 * v + 1], t[4 * v + 2], t[4 * v + 3]);
+            for (int v = 0; v < LPT / 4; ++v) {
+                const float4 x = make_float4(t[4 * v], t[4 * v + 1], t[4 * v + 2], t[4 * v + 3]);
+                reinterpret_cast<float4*>(T + l0)[v] = x;
+                if (CL > 1 && !ASY) {                         // the CTA's outermost H lanes are the neighbours' halos
+                    const int rel = l0 + 4 * v - cta_base;
+                    if (rank > 0 && rel < H) st_cluster_f4(T + cta_base + span + rel, (uint32_t)(rank - 1), x);        // its lanes [base' + span', +H)
+                    if (rank < CL - 1 && rel >= span - H) st_cluster_f4(T + cta_base - span + rel, (uint32_t)(rank + 1), x);   // its lanes [base' - H, base')
+                }
+            }
         }
-        __syncthreads();
+        if (CL > 1 && !ASY) cluster_barrier(); else __syncthreads();
+        if (CL > 1 && ASY) {
+            // After the block barrier every thread of this CTA has read the halos of two exchanges ago: only now may a neighbour be
+            // given cause to overwrite them (it sends exchange e + 1 after it has received this CTA's exchange e).  The senders
+            // are fixed threads -- dead lanes travel as +inf -- so every CTA receives exactly the bytes it expects.
+            uint64_t* bar = &halo_bar[buf];
+            const int wl = lane_id * LPT, nw = (int)(blockDim.x >> 5);
+#pragma unroll
+            for (int v = 0; v < LPT / 4; ++v) {
+                const float4 x = make_float4(t[4 * v], t[4 * v + 1], t[4 * v + 2], t[4 * v + 3]);
+                const int rel = l0 + 4 * v - cta_base;
+                if (rank > 0 && warp == 0 && wl >= H && wl < 2 * H) st_async_f4(T + cta_base + span + rel, bar, (uint32_t)(rank - 1), x);
+                if (rank < CL - 1 && warp == nw - 1 && wl >= WIN - 2 * H && wl < WIN - H) st_async_f4(T + cta_base - span + rel, bar, (uint32_t)(rank + 1), x);
+            }
+            if (tid == 0) mbar_expect_tx(bar, (uint32_t)(((rank > 0) + (rank < CL - 1)) * H * sizeof(float)));
+            mbar_wait(bar, (uint32_t)((nex >> 1) & 1));
+            ++nex;
+        }
         if (live) {
 #pragma unroll
             for (int v = 0; v < LPT / 4; ++v) {
@@ -835,7 +895,17 @@ __global__ void __launch_bounds__(512) k_seam_fwd(const DpArgs* __restrict__ tab
         for (int j = 0; j < LPT; ++j) if (l0 + j == A.lane1) tv = t[j];
         *A.reached = tv < INF ? 1 : 0;
     }
+    if (CL > 1) cluster_barrier();                            // nobody leaves while a neighbour may still store into its shared memory
 }
+
+template <int LPT, int H, int R, int MAXT = 512>
+__global__ void __launch_bounds__(MAXT) k_seam_fwd(const DpArgs* __restrict__ table) { seam_fwd_body<LPT, H, R, 1>(table); }
+
+// MAXT = 128 / 256: at most four / eight windows per CTA, which leaves the registers for a ring of 16 / 8 steps.  With one or two
+// windows per scheduler nothing else hides the latency of a cost row, and the time of a seam falls almost in proportion to the
+// depth of the ring (measured: 1500 lanes x 4029 steps, 4 CTAs: 1.72 / 1.23 / 0.62 ms at 4 / 8 / 16 steps).
+template <int LPT, int H, int R, int CL, int MAXT, bool ASY>
+__global__ void __cluster_dims__(CL, 1, 1) __launch_bounds__(MAXT) k_seam_fwd_cluster(const DpArgs* __restrict__ table) { seam_fwd_body<LPT, H, R, CL, ASY>(table); }
 
 // Back-track ([SEAM]:923-947) in parallel.  Steps s0+1 .. s1 are cut into chunks of BT_CHUNK; k_bt_compose walks every lane
 // of every chunk upwards through the control bytes (BT_CHUNK dependent byte loads per thread, all chunks of all seams at

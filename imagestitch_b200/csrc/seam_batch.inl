@@ -405,10 +405,11 @@ __global__ void __launch_bounds__(256) k_apply_clear_runs_batch(const ClearTabDe
 struct DpShape {
     int v1 = 0;                        // formulation
     int tmpl = 0, nwarps = 0;          // v1: template choice, warps per CTA
+    int cl = 1;                        // v1: CTAs per seam (thread-block cluster), 1 = a single CTA
     int lpt = 4, nt = 32;              // v0
     int pitch = 128, G = 1, D = 2;
     int lanes = 0, s0 = 0, s1 = 0;
-    bool same(const DpShape& o) const { return v1 == o.v1 && (v1 ? (tmpl == o.tmpl && nwarps == o.nwarps) : (lpt == o.lpt && nt == o.nt)); }
+    bool same(const DpShape& o) const { return v1 == o.v1 && (v1 ? (tmpl == o.tmpl && nwarps == o.nwarps && cl == o.cl) : (lpt == o.lpt && nt == o.nt)); }
 };
 
 static int dp_variant_default() {
@@ -443,6 +444,15 @@ static void dp_choose_shape(int lanes, int steps, int s0, int s1, int variant, D
             const int t = order[k];
             if (forced >= 0 && t != forced) continue;
             if (lanes <= 16 * V1_TMPL[t][2]) { S->v1 = 1; S->tmpl = t; S->nwarps = div_up(lanes, V1_TMPL[t][2]); break; }
+        }
+        // a seam of more than four windows is spread over a cluster of 2, 4 or 8 CTAs (k_seam_fwd_cluster, window shape {4, 16, 96}):
+        // as few windows per CTA as the cluster size allows -- one per scheduler up to 3072 lanes
+        int cl = 0;
+        if (const char* e = getenv("IS_DP_CLUSTER")) cl = atoi(e);                  // tuning knob: 1 = never, 2 / 4 / 8 = always that size
+        const int win = div_up(lanes, V1_TMPL[3][2]);
+        if (forced < 0 && cl != 1 && win <= 8 * 16 && (cl == 2 || cl == 4 || cl == 8 || win > 4)) {
+            if (cl != 2 && cl != 4 && cl != 8) cl = win <= 8 ? 2 : (win <= 16 ? 4 : 8);     // four windows per CTA (ring of 16 steps) up to 32 windows
+            if (div_up(win, cl) <= 16) { S->v1 = 1; S->tmpl = 3; S->cl = cl; S->nwarps = div_up(win, cl); }
         }
     }
     (void)steps;
@@ -479,6 +489,33 @@ static int launch_dp_all(is_ctx* ctx, const std::vector<DpShape>& shapes, const 
             const int H = V1_TMPL[S0.tmpl][1];
             const size_t smem = 2 * sizeof(float) * (size_t)(S0.pitch + 2 * H);
             ctx->next_bytes = bytes;
+            if (S0.cl > 1) {
+                const size_t csmem = 2 * sizeof(float) * (size_t)(S0.nwarps * V1_TMPL[3][2] + 2 * H);
+                int ring = S0.nwarps <= 4 ? 16 : (S0.nwarps <= 8 ? 8 : 4);             // steps of cost rows in registers ahead of their use
+                if (const char* e = getenv("IS_DP_CL_RING")) ring = std::min(ring, atoi(e));   // tuning knob: a shallower ring (4, 8)
+                const bool asy = getenv("IS_DP_CL_BARRIER") == nullptr;                   // tuning knob: halo exchange behind cluster barriers instead of st.async
+#define IS_DP_CL_LAUNCH(CLN, RN, MT)                                                                                                             \
+    do {                                                                                                                                         \
+        if (asy) IS_LAUNCH(ctx, (k_seam_fwd_cluster<4, 16, RN, CLN, MT, true>), cnt * CLN, S0.nwarps * 32, csmem, dp_d + q);                     \
+        else IS_LAUNCH(ctx, (k_seam_fwd_cluster<4, 16, RN, CLN, MT, false>), cnt * CLN, S0.nwarps * 32, csmem, dp_d + q);                        \
+    } while (0)
+#define IS_DP_CL_CASE(CLN)                                                                                                                       \
+    case CLN:                                                                                                                                    \
+        if (ring == 16) IS_DP_CL_LAUNCH(CLN, 16, 128);                                                                                           \
+        else if (ring == 8) IS_DP_CL_LAUNCH(CLN, 8, 256);                                                                                        \
+        else IS_DP_CL_LAUNCH(CLN, 4, 512);                                                                                                       \
+        break;
+                switch (S0.cl) {
+                    IS_DP_CL_CASE(2)
+                    IS_DP_CL_CASE(4)
+                    default:
+                    IS_DP_CL_CASE(8)
+                }
+#undef IS_DP_CL_CASE
+#undef IS_DP_CL_LAUNCH
+            } else if (S0.tmpl == 3 && S0.nwarps <= 4 && !getenv("IS_DP_CL_RING")) {             // a single CTA of at most four windows: the deep ring as well
+                IS_LAUNCH(ctx, (k_seam_fwd<4, 16, 16, 128>), cnt, S0.nwarps * 32, smem, dp_d + q);
+            } else
             switch (S0.tmpl) {
                 case 0: IS_LAUNCH(ctx, (k_seam_fwd<4, 8, 4>), cnt, S0.nwarps * 32, smem, dp_d + q); break;
                 case 1: IS_LAUNCH(ctx, (k_seam_fwd<8, 16, 2>), cnt, S0.nwarps * 32, smem, dp_d + q); break;
@@ -921,6 +958,8 @@ static int seam_batch_wave(is_ctx* ctx, const std::vector<std::pair<int, int>>& 
     std::vector<std::vector<ClearIv>> clears(np);
     std::vector<std::vector<size_t>> jobs_of(np);
     for (size_t j = 0; j < nj; ++j) jobs_of[(size_t)jobs[j].pair].push_back(j);   // plan order
+    std::vector<std::vector<int>> rs_all(np);
+    std::vector<std::vector<int4>> iv_all(np);
     pool->run(np, [&](size_t k) {
         std::vector<const std::vector<Interval>*> fl;
         for (size_t j : jobs_of[k]) {
@@ -930,6 +969,19 @@ static int seam_batch_wave(is_ctx* ctx, const std::vector<std::pair<int, int>>& 
             fl.push_back(J.reached ? &J.uls.flips : nullptr);
         }
         pair_clear_intervals(PR[k], fl, &clears[k]);
+        // the pair's upload tables while the task is at it: row_start[ih + 1] and the intervals
+        const PairRuns& P = PR[k];
+        const int iy = P.iTl.y - P.unionTl.y, ih = P.iBr.y - P.iTl.y;
+        std::vector<int>& rs = rs_all[k];
+        std::vector<int4>& iv = iv_all[k];
+        rs.assign((size_t)ih + 1, 0);
+        iv.resize(clears[k].size());
+        for (size_t q = 0; q < clears[k].size(); ++q) {
+            const ClearIv& c = clears[k][q];
+            rs[(size_t)(c.y - iy) + 1]++;
+            iv[q] = make_int4(c.x0, c.x1, c.bits, 0);
+        }
+        for (int r = 0; r < ih; ++r) rs[(size_t)r + 1] += rs[(size_t)r];
     });
     size_t limit = np;                                                 // pairs [0, limit) can still be accepted
     for (auto& J : jobs) {
@@ -942,19 +994,14 @@ static int seam_batch_wave(is_ctx* ctx, const std::vector<std::pair<int, int>>& 
     // one upload: per pair row_start[ih + 1] and the intervals, then the table
     Blob B2;
     std::vector<size_t> off_rs(limit), off_iv(limit);
+    {
+        size_t total = 64 + sizeof(ClearTabDev) * limit;
+        for (size_t k = 0; k < limit; ++k) total += sizeof(int) * rs_all[k].size() + sizeof(int4) * iv_all[k].size() + 32;
+        B2.host.reserve(total);
+    }
     for (size_t k = 0; k < limit; ++k) {
-        const PairRuns& P = PR[k];
-        const int iy = P.iTl.y - P.unionTl.y, ih = P.iBr.y - P.iTl.y;
-        std::vector<int> rs((size_t)ih + 1, 0);
-        std::vector<int4> iv(clears[k].size());
-        for (size_t q = 0; q < clears[k].size(); ++q) {
-            const ClearIv& c = clears[k][q];
-            rs[(size_t)(c.y - iy) + 1]++;
-            iv[q] = make_int4(c.x0, c.x1, c.bits, 0);
-        }
-        for (int r = 0; r < ih; ++r) rs[(size_t)r + 1] += rs[(size_t)r];
-        off_rs[k] = B2.put(rs.data(), sizeof(int) * rs.size());
-        off_iv[k] = B2.put(iv.data(), sizeof(int4) * iv.size());
+        off_rs[k] = B2.put(rs_all[k].data(), sizeof(int) * rs_all[k].size());
+        off_iv[k] = B2.put(iv_all[k].data(), sizeof(int4) * iv_all[k].size());
     }
     const size_t off_ct = B2.put(nullptr, sizeof(ClearTabDev) * limit);
     DevBuf dev2;
@@ -978,10 +1025,68 @@ static int seam_batch_wave(is_ctx* ctx, const std::vector<std::pair<int, int>>& 
     IS_TRY(upload(ctx, b2d, B2.host.data(), B2.host.size()));
     tm.lap("E host: clear intervals + upload");
     // ---- F: validation -- the masks every pair would have seen in the sequential loop
+    //      Where the earlier pairs' clears stay away from a pair's intersection rectangle (every pair of a strip), its special points
+    //      cannot change and the masks it would have seen follow from the entry toggles minus the clear intervals: such a pair is
+    //      validated on the host alone (runs_minus_clears, the first half of build(), same_window); the others ask the device again.
+    std::vector<char> host_checked(limit, 0);
+    std::vector<int> host_decision(limit, -1);
+    const bool check_both = getenv("IS_SEAM_CHECK_BOTH") != nullptr;   // test knob: validate on the device as well and insist on the same verdicts
+    if (!getenv("IS_SEAM_CHECK_DEVICE")) {
+        std::vector<std::vector<RunLayer>> lay(2 * limit);
+        std::vector<size_t> hk;
+        for (size_t k = 0; k < limit; ++k) {
+            const int img[2] = {active[k].first, active[k].second};
+            bool any = false, near = false;
+            for (int s = 0; s < 2; ++s)
+                for (size_t q = 0; q < k; ++q) {
+                    int bit = 0;
+                    if (active[q].first == img[s]) bit = 1; else if (active[q].second == img[s]) bit = 2;
+                    if (!bit || clears[q].empty()) continue;
+                    const PairRuns& E = PR[q];
+                    lay[2 * k + (size_t)s].push_back(RunLayer{&clears[q], bit, E.unionTl.x - corners[img[s]].x, E.unionTl.y - corners[img[s]].y});
+                    any = true;
+                    // the clears of pair q lie inside its intersection rectangle; special points look three pixels around theirs
+                    const PairRuns& P = PR[k];
+                    if (E.iTl.x < P.iBr.x + 3 && P.iTl.x - 3 < E.iBr.x && E.iTl.y < P.iBr.y + 3 && P.iTl.y - 3 < E.iBr.y) near = true;
+                }
+            if (any && !near) { hk.push_back(k); host_checked[k] = 1; }
+        }
+        if (!hk.empty()) {
+            std::vector<char> ok(hk.size(), 0);
+            pool->run(hk.size(), [&](size_t v) {
+                const size_t k = hk[v];
+                MaskRuns nr[2];
+                const MaskRuns* use[2];
+                for (int s = 0; s < 2; ++s) {
+                    const MaskRuns& base = Q.runs[(size_t)(s == 0 ? Q.pairs[k].m1 : Q.pairs[k].m2)];
+                    use[s] = &base;
+                    if (lay[2 * k + (size_t)s].empty()) continue;
+                    if (!runs_minus_clears(base, lay[2 * k + (size_t)s], TG_CAP, &nr[s])) return;   // too many toggles: the pair starts the next wave
+                    use[s] = &nr[s];
+                }
+                PairRuns C;
+                C.setup(active[k].first, active[k].second, PR[k].tl1, PR[k].tl2, use[0], use[1]);
+                C.specials = PR[k].specials;
+                C.build_runs();
+                if (C.too_many_runs) return;
+                if (C.same_window(PR[k])) { ok[v] = 1; return; }
+                C.build_contours();
+                C.plan();
+                ok[v] = C.same_structure(PR[k]) ? 1 : 0;
+            });
+            for (size_t v = 0; v < hk.size(); ++v) host_decision[hk[v]] = ok[v];
+            if (check_both) std::fill(host_checked.begin(), host_checked.end(), 0);
+            else
+                for (size_t v = 0; v < hk.size(); ++v)
+                    if (!ok[v]) { limit = std::min(limit, hk[v]); break; }
+            tm.lap("F host: check structures (runs)");
+        }
+    }
     {
         StructureQuery V;
         std::vector<int> vpair;                                        // wave index of every validation pair
         for (size_t k = 0; k < limit; ++k) {
+            if (host_checked[k]) continue;
             const int img[2] = {active[k].first, active[k].second};
             LayeredMask lm[2] = {plain_mask(masks[img[0]]), plain_mask(masks[img[1]])};
             bool any = false, too_many = false;
@@ -1022,6 +1127,10 @@ static int seam_batch_wave(is_ctx* ctx, const std::vector<std::pair<int, int>>& 
                 C.plan();
                 ok[v] = C.same_structure(PR[k]) ? 1 : 0;
             });
+            if (check_both)
+                for (size_t v = 0; v < vpair.size(); ++v)
+                    if (host_decision[(size_t)vpair[v]] >= 0 && host_decision[(size_t)vpair[v]] != ok[v])
+                        return fail(ctx, IS_ERR_ASSERT, "seam validation: host verdict %d, device verdict %d for pair %d of the wave", host_decision[(size_t)vpair[v]], (int)ok[v], vpair[v]);
             for (size_t v = 0; v < vpair.size(); ++v)
                 if (!ok[v]) { limit = std::min(limit, (size_t)vpair[v]); break; }   // the first pair the earlier clears change starts the next wave
             tm.lap("F host: check structures");

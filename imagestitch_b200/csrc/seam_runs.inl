@@ -86,6 +86,11 @@ public:
 
     void setup(int i, int j, Pt t1, Pt t2, const MaskRuns* m1, const MaskRuns* m2);
     void build();                                     // merge, components, contours, edges
+    void build_runs();                                // the first half: merged runs, components, labels, the label window
+    void build_contours();                            // the second half: contour records of the INTERS components, edges
+    // true when the runs and labels of `o` (same geometry) agree with these on everything the second half, the plan and the seam
+    // tips read: the label window (intersection rectangle grown by one pixel) and the states of the labels in it
+    bool same_window(const PairRuns& o) const;
     void build_tab();                                 // the label-window table (only the label-image path of the cost kernels needs it)
     // the runs of component c (0-based) in the rows [ry, ry + rh) of the frame, at most `cap` per row: out[(y - ry) * cap + k] = (x0, x1),
     // unused slots (0, 0); false when a row has more runs than cap
@@ -123,6 +128,11 @@ int PairRuns::label_at(int x, int y) const {
 
 // [SEAM]:196-308 in run-length form
 void PairRuns::build() {
+    build_runs();
+    build_contours();
+}
+
+void PairRuns::build_runs() {
     const bool tim = getenv("IS_DEBUG_PLAN_TIMING") != nullptr;
     auto T0 = std::chrono::steady_clock::now();
     auto lapt = [&](const char* w) { if (!tim) return; auto n = std::chrono::steady_clock::now(); fprintf(stderr, "   [build] %-16s %.3f ms\n", w, std::chrono::duration<double, std::milli>(n - T0).count()); T0 = n; };
@@ -188,6 +198,12 @@ void PairRuns::build() {
     ww = std::min(uw, iBr.x - unionTl.x + 1) - wx;
     wh = std::min(uh, iBr.y - unionTl.y + 1) - wy;
     lapt("tab");
+}
+
+void PairRuns::build_contours() {
+    const bool tim = getenv("IS_DEBUG_PLAN_TIMING") != nullptr;
+    auto T0 = std::chrono::steady_clock::now();
+    auto lapt = [&](const char* w) { if (!tim) return; auto n = std::chrono::steady_clock::now(); fprintf(stderr, "   [build] %-16s %.3f ms\n", w, std::chrono::duration<double, std::milli>(n - T0).count()); T0 = n; };
     tls.assign((size_t)ncomps, Pt{INT_MAX, INT_MAX});
     brs.assign((size_t)ncomps, Pt{INT_MIN, INT_MIN});
     contours.assign((size_t)ncomps, std::vector<ContourRec>());
@@ -196,6 +212,38 @@ void PairRuns::build() {
     find_edges();
     lapt("edges");
 }
+
+bool PairRuns::same_window(const PairRuns& o) const {
+    if (uw != o.uw || uh != o.uh || wx != o.wx || wy != o.wy || ww != o.ww || wh != o.wh || too_many_runs != o.too_many_runs) return false;
+    auto state_of = [](const std::vector<int>& st, int label) { return (label >= 1 && label <= (int)st.size()) ? st[(size_t)label - 1] : -1; };
+    const int x_lo = wx, x_hi = wx + ww;
+    for (int y = wy; y < wy + wh; ++y) {
+        // the label function of the row over [x_lo, x_hi) as (start, label) pieces, from either structure, walked in step
+        const int ab = row_off[(size_t)y], ae = row_off[(size_t)y + 1], bb = o.row_off[(size_t)y], be = o.row_off[(size_t)y + 1];
+        int ia = ab, ib = bb;
+        while (ia < ae && cps[(size_t)ia].x <= x_lo) ++ia;                  // ia: first change point right of x_lo
+        while (ib < be && o.cps[(size_t)ib].x <= x_lo) ++ib;
+        int x = x_lo;
+        for (;;) {
+            const int la = ia == ab ? 0 : cp_label[(size_t)ia - 1], lb = ib == bb ? 0 : o.cp_label[(size_t)ib - 1];
+            if (la != lb) return false;
+            if (la > 0 && state_of(states, la) != state_of(o.states, la)) return false;
+            const int na = ia < ae ? std::min(cps[(size_t)ia].x, x_hi) : x_hi, nb = ib < be ? std::min(o.cps[(size_t)ib].x, x_hi) : x_hi;
+            if (na != nb) return false;
+            x = na;
+            if (x >= x_hi) break;
+            ++ia; ++ib;
+        }
+    }
+    return true;
+}
+
+// The toggles of a mask after the clear intervals of earlier pairs have been applied to it (what k_row_toggles_batch reports for a
+// layered mask), on the host.  `layers`: per layer the clear list (sorted by row, frame coordinates of the pair that produced
+// it), the bit that selects this mask's intervals and the offset (dx, dy) from those frame coordinates to this mask's own.
+// false: a row ends up with more toggles than the tables hold.
+struct RunLayer { const std::vector<struct ClearIv>* clears; int bit, dx, dy; };
+static bool runs_minus_clears(const MaskRuns& in, const std::vector<RunLayer>& layers, int cap, MaskRuns* out);
 
 void PairRuns::build_tab() {
     wcap = 1;
@@ -687,6 +735,62 @@ void UlsRuns::run() {
 // at the updated mask2, so a pixel is never cleared in both).  `seam_flips[k]`: UlsRuns::flips of the k-th kind-1 operation of
 // the plan that succeeded (nullptr when estimateSeam failed or was not run).
 struct ClearIv { int y, x0, x1, bits; };              // frame coordinates
+
+static bool runs_minus_clears(const MaskRuns& in, const std::vector<RunLayer>& layers, int cap, MaskRuns* out) {
+    *out = in;
+    if (out->slots < cap) return false;
+    const int cols = in.cols, slots = out->slots;
+    for (const RunLayer& L : layers) {
+        const std::vector<ClearIv>& cl = *L.clears;
+        size_t i = 0;
+        while (i < cl.size()) {
+            const int fy = cl[i].y;
+            size_t j = i;
+            while (j < cl.size() && cl[j].y == fy) ++j;
+            const int my = fy + L.dy;
+            if (my >= 0 && my < in.rows) {
+                unsigned short* r = out->xs.data() + (size_t)my * slots;
+                int n = out->counts[(size_t)my];
+                if (n > slots) return false;
+                // intervals of the row
+                int iv[16][2], ni = 0;
+                for (int k = 0; k < n; k += 2) { iv[ni][0] = r[k]; iv[ni][1] = k + 1 < n ? r[k + 1] : cols; ++ni; }
+                bool changed = false;
+                for (size_t q = i; q < j; ++q) {
+                    if (!(cl[q].bits & L.bit)) continue;
+                    const int a = std::max(cl[q].x0 + L.dx, 0), b = std::min(cl[q].x1 + L.dx, cols);
+                    if (a >= b) continue;
+                    for (int k = 0; k < ni; ++k) {
+                        const int s0 = iv[k][0], s1 = iv[k][1];
+                        if (b <= s0 || a >= s1) continue;
+                        changed = true;
+                        if (a <= s0 && b >= s1) { for (int m = k; m + 1 < ni; ++m) { iv[m][0] = iv[m + 1][0]; iv[m][1] = iv[m + 1][1]; } --ni; --k; }
+                        else if (a <= s0) iv[k][0] = b;
+                        else if (b >= s1) iv[k][1] = a;
+                        else {                                                     // a hole: the interval splits
+                            if (ni >= 15) return false;
+                            for (int m = ni; m > k + 1; --m) { iv[m][0] = iv[m - 1][0]; iv[m][1] = iv[m - 1][1]; }
+                            iv[k + 1][0] = b; iv[k + 1][1] = s1; iv[k][1] = a;
+                            ++ni; ++k;
+                        }
+                    }
+                }
+                if (changed) {
+                    n = 0;
+                    for (int k = 0; k < ni; ++k) {
+                        if (n < slots) r[n] = (unsigned short)iv[k][0];
+                        ++n;
+                        if (iv[k][1] < cols) { if (n < slots) r[n] = (unsigned short)iv[k][1]; ++n; }
+                    }
+                    if (n > cap) return false;
+                    out->counts[(size_t)my] = (unsigned char)n;
+                }
+            }
+            i = j;
+        }
+    }
+    return true;
+}
 
 static void pair_clear_intervals(const PairRuns& R, const std::vector<const std::vector<Interval>*>& seam_flips, std::vector<ClearIv>* out) {
     out->clear();

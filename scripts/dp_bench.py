@@ -35,10 +35,14 @@ def run(lanes, steps, njobs, variant, iters=5, env=None):
 
 
 out = []
-for (lanes, steps, njobs) in ((1500, 4029, 1), (1500, 4029, 5), (1500, 4029, 11), (2000, 6029, 5), (3000, 8029, 8), (4029, 1500, 5), (6029, 2000, 4), (300, 12000, 5), (100, 700, 2)):
+for (lanes, steps, njobs) in ((1500, 4029, 1), (1500, 4029, 5), (1500, 4029, 11), (2000, 6029, 5), (3000, 8029, 8), (4029, 1500, 5), (6029, 2000, 4), (300, 12000, 5), (700, 2000, 3), (100, 700, 2)):
     base_ms, base = run(lanes, steps, njobs, 0)
     row = {"lanes": lanes, "steps": steps, "njobs": njobs, "v0_ms": base_ms}
-    for name, env in (("v1", {}), ("v1_h16", {"IS_DP_V1_TMPL": 3}), ("v1_lpt8", {"IS_DP_V1_TMPL": 1}), ("v1_lpt16", {"IS_DP_V1_TMPL": 2})):
+    variants = [("v1", {}), ("v1_barrier", {"IS_DP_CL_BARRIER": 1}), ("v1_cl1", {"IS_DP_CLUSTER": 1}), ("v1_cl1_r4", {"IS_DP_CLUSTER": 1, "IS_DP_CL_RING": 4})]
+    for cl in (2, 4, 8):
+        variants.append((f"v1_cl{cl}", {"IS_DP_CLUSTER": cl}))
+        variants.append((f"v1_cl{cl}_barrier", {"IS_DP_CLUSTER": cl, "IS_DP_CL_BARRIER": 1}))
+    for name, env in variants:
         ms, seam = run(lanes, steps, njobs, 1, env=env)
         row[name + "_ms"] = ms
         row[name + "_equal"] = None if seam is None or base is None else bool(np.array_equal(seam, base))
