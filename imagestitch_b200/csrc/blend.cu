@@ -397,6 +397,23 @@ __device__ __forceinline__ void blend_quad_at(const LevelArgs& A, int x, int y) 
         const ImgLevel& I = A.imgs[i];
         const int lx = x - I.x_tl, ly = y - I.y_tl;
         if ((unsigned)lx >= (unsigned)I.w || (unsigned)ly >= (unsigned)I.h) continue;
+        // An image whose four weights are zero here adds short(g * 0) = 0 and w = 0 exactly: nothing of it needs to be read.  Away
+        // from the seams that is every covering image but one.
+        float wq_f[4] = {0.f, 0.f, 0.f, 0.f};
+        int wq_s[4] = {0, 0, 0, 0};
+        if (A.k > 0) {
+            if (WF) {
+                const float2 w0 = *reinterpret_cast<const float2*>(reinterpret_cast<const float*>(I.wgt) + (size_t)ly * I.w + lx);
+                const float2 w1 = *reinterpret_cast<const float2*>(reinterpret_cast<const float*>(I.wgt) + (size_t)(ly + 1) * I.w + lx);
+                wq_f[0] = w0.x; wq_f[1] = w0.y; wq_f[2] = w1.x; wq_f[3] = w1.y;
+                if (w0.x == 0.f && w0.y == 0.f && w1.x == 0.f && w1.y == 0.f) continue;
+            } else {
+                const short2 w0 = *reinterpret_cast<const short2*>(reinterpret_cast<const int16_t*>(I.wgt) + (size_t)ly * I.w + lx);
+                const short2 w1 = *reinterpret_cast<const short2*>(reinterpret_cast<const int16_t*>(I.wgt) + (size_t)(ly + 1) * I.w + lx);
+                wq_s[0] = w0.x; wq_s[1] = w0.y; wq_s[2] = w1.x; wq_s[3] = w1.y;
+                if ((w0.x | w0.y | w1.x | w1.y) == 0) continue;
+            }
+        }
         int u[4][3];
         pyrup_quad(I.g_up, I.h >> 1, I.w >> 1, ly >> 1, lx >> 1, u);
 #pragma unroll
@@ -407,13 +424,13 @@ __device__ __forceinline__ void blend_quad_at(const LevelArgs& A, int x, int y) 
             else { const int16_t* p = I.g + ((size_t)py * I.w + px) * 3; g[0] = p[0]; g[1] = p[1]; g[2] = p[2]; }
             g[0] = sat16(g[0] - u[q][0]); g[1] = sat16(g[1] - u[q][1]); g[2] = sat16(g[2] - u[q][2]);
             if (WF) {
-                const float w = A.k == 0 ? l0_weight_f(I.l0, py, px) : reinterpret_cast<const float*>(I.wgt)[(size_t)py * I.w + px];
+                const float w = A.k == 0 ? l0_weight_f(I.l0, py, px) : wq_f[q];
                 acc[q][0] += (int)(int16_t)__float2int_rz(__fmul_rn((float)g[0], w));
                 acc[q][1] += (int)(int16_t)__float2int_rz(__fmul_rn((float)g[1], w));
                 acc[q][2] += (int)(int16_t)__float2int_rz(__fmul_rn((float)g[2], w));
                 wsum_f[q] = __fadd_rn(wsum_f[q], w);
             } else {
-                const int w = A.k == 0 ? l0_weight_s(I.l0, py, px) : (int)reinterpret_cast<const int16_t*>(I.wgt)[(size_t)py * I.w + px];
+                const int w = A.k == 0 ? l0_weight_s(I.l0, py, px) : wq_s[q];
                 acc[q][0] += (int)(int16_t)((g[0] * w) >> 8);
                 acc[q][1] += (int)(int16_t)((g[1] * w) >> 8);
                 acc[q][2] += (int)(int16_t)((g[2] * w) >> 8);

@@ -683,6 +683,10 @@ __global__ void __launch_bounds__(1024) k_seam_dp_batch(const DpArgs* __restrict
 // costs, so no staging through shared memory is needed); the control bytes of the owned lanes go out as one 32-bit store.
 // The back-track is a separate, parallel pair of kernels (k_bt_compose / k_bt_walk).
 constexpr int DP_L2_AHEAD = 24;                              // steps between a cost row's L2 prefetch and its use in k_seam_fwd
+// The dynamic shared-memory limit of a kernel is an attribute of the FUNCTION, shared by every context and host thread of the
+// process: it is always set to this one value (setting it to what a launch needs let a concurrent caller with a smaller seam
+// lower it between another thread's cudaFuncSetAttribute and its launch -> "invalid argument").
+constexpr int DP_SMEM_MAX = 200 * 1024;
 constexpr int DP_ROW_PAD = 8;                                 // spare rows behind the cost tables (k_seam_fwd prefetches past the last step)
 __device__ unsigned g_dp_inf_row[16] = {0x7f800000u, 0x7f800000u, 0x7f800000u, 0x7f800000u, 0x7f800000u, 0x7f800000u, 0x7f800000u, 0x7f800000u,
                                         0x7f800000u, 0x7f800000u, 0x7f800000u, 0x7f800000u, 0x7f800000u, 0x7f800000u, 0x7f800000u, 0x7f800000u};
@@ -1473,19 +1477,19 @@ int PairSeam::estimate_and_update(int c1, int c2, Pt p1, Pt p2) {
         if (const char* e = getenv("IS_DP_G")) A.G = std::max(1, atoi(e));     // tuning knobs: rows per ring stage, stages
         if (const char* e = getenv("IS_DP_D")) A.D = std::max(2, atoi(e));
         const size_t smem = std::max<size_t>((size_t)A.D * A.G * row_pair + 8 * (size_t)A.D + 16, (size_t)32 * 65 + 16);
-        IS_REQUIRE(ctx, smem <= 200 * 1024, IS_ERR_INTERNAL, "DP shared-memory budget");
+        IS_REQUIRE(ctx, smem <= (size_t)DP_SMEM_MAX, IS_ERR_INTERNAL, "DP shared-memory budget");
         ctx->next_bytes = (double)(A.s1 - A.s0) * lanes * 9;                    // P, Q read once, control written once
         switch (lpt) {
             case 4:
-                IS_CUDA(ctx, cudaFuncSetAttribute(k_seam_dp<4>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+                IS_CUDA(ctx, cudaFuncSetAttribute(k_seam_dp<4>, cudaFuncAttributeMaxDynamicSharedMemorySize, DP_SMEM_MAX));
                 IS_LAUNCH(ctx, k_seam_dp<4>, 1, nt, smem, A);
                 break;
             case 8:
-                IS_CUDA(ctx, cudaFuncSetAttribute(k_seam_dp<8>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+                IS_CUDA(ctx, cudaFuncSetAttribute(k_seam_dp<8>, cudaFuncAttributeMaxDynamicSharedMemorySize, DP_SMEM_MAX));
                 IS_LAUNCH(ctx, k_seam_dp<8>, 1, nt, smem, A);
                 break;
             default:
-                IS_CUDA(ctx, cudaFuncSetAttribute(k_seam_dp<16>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+                IS_CUDA(ctx, cudaFuncSetAttribute(k_seam_dp<16>, cudaFuncAttributeMaxDynamicSharedMemorySize, DP_SMEM_MAX));
                 IS_LAUNCH(ctx, k_seam_dp<16>, 1, nt, smem, A);
                 break;
         }

@@ -460,7 +460,7 @@ static void dp_choose_shape(int lanes, int steps, int s0, int s1, int variant, D
 
 template <int LPT>
 static int launch_dp_v0(is_ctx* ctx, const DpArgs* table_d, int njobs, int nt, size_t smem, double bytes) {
-    IS_CUDA(ctx, cudaFuncSetAttribute(k_seam_dp_batch<LPT>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    IS_CUDA(ctx, cudaFuncSetAttribute(k_seam_dp_batch<LPT>, cudaFuncAttributeMaxDynamicSharedMemorySize, DP_SMEM_MAX));
     ctx->next_bytes = bytes;
     IS_LAUNCH(ctx, k_seam_dp_batch<LPT>, njobs, nt, smem, table_d);
     return IS_OK;
@@ -479,7 +479,7 @@ static int launch_dp_all(is_ctx* ctx, const std::vector<DpShape>& shapes, const 
         if (!S0.v1) {
             const size_t row_pair = 2 * sizeof(float) * (size_t)S0.pitch;
             const size_t smem = std::max<size_t>((size_t)S0.D * S0.G * row_pair + 8 * (size_t)S0.D + 16, (size_t)32 * 65 + 16);
-            IS_REQUIRE(ctx, smem <= 200 * 1024, IS_ERR_INTERNAL, "DP shared-memory budget");
+            IS_REQUIRE(ctx, smem <= (size_t)DP_SMEM_MAX, IS_ERR_INTERNAL, "DP shared-memory budget");
             switch (S0.lpt) {
                 case 4: IS_TRY(launch_dp_v0<4>(ctx, dp_d + q, cnt, S0.nt, smem, bytes)); break;
                 case 8: IS_TRY(launch_dp_v0<8>(ctx, dp_d + q, cnt, S0.nt, smem, bytes)); break;
