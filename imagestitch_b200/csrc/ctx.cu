@@ -53,11 +53,21 @@ int DevBuf::alloc(is_ctx* c, size_t n) {
         return IS_OK;
     }
     cudaError_t e = cudaMallocAsync(&p, n, c->stream);
-    if (e != cudaSuccess && !c->block_cache.empty()) {   // out of memory with blocks parked here: give them back and retry
+    if (e != cudaSuccess) {
+        // Out of memory: give back the blocks parked in this context and in its idle children (a child is only ever used from the
+        // thread that runs this call or from workers this call has joined), let the pool return what it holds to the device
+        // (the release threshold is "never" in steady state), and try once more.
         cudaGetLastError();
-        for (auto& kv : c->block_cache) cudaFreeAsync(kv.second, c->stream);
-        c->block_cache.clear();
-        c->block_cache_bytes = 0;
+        auto flush = [](is_ctx* x) {
+            for (auto& kv : x->block_cache) cudaFreeAsync(kv.second, x->stream);
+            x->block_cache.clear();
+            x->block_cache_bytes = 0;
+            cudaStreamSynchronize(x->stream);
+        };
+        flush(c);
+        for (is_ctx* ch : c->children) if (ch) flush(ch);
+        if (c->pool) cudaMemPoolTrimTo(c->pool, 0);
+        cudaGetLastError();
         e = cudaMallocAsync(&p, n, c->stream);
     }
     if (e != cudaSuccess) {

@@ -57,16 +57,13 @@ int is_pipeline_plan(is_ctx* ctx, int n, const is_size* src_sizes, const is_came
     return IS_OK;
 }
 
-int is_pipeline_run(is_ctx* ctx, int n, const is_mat* images, const is_camera* cameras_in, const is_registration_hooks* hooks,
-                    const is_pipeline_config* cfg_in, is_mat* pano, is_mat* pano_mask, is_mat* seam_masks) {
-    if (!ctx) return IS_ERR_BAD_ARG;
-    IS_CUDA(ctx, cudaSetDevice(ctx->device));
-    IS_REQUIRE(ctx, n > 0 && images && cfg_in && pano && pano_mask, IS_ERR_BAD_ARG, "null argument");
-    is_pipeline_config cfg = *cfg_in;
-    const PipeStamp stamp(ctx);
-    stamp.mark("enter");
-    std::vector<is_camera> cams(n);
-    // ---- host registration stages (control flow around the GPU path)
+// the images are validated BEFORE any hook sees them; the hooks run in the order of the mains (detect per image, match, estimate)
+static int run_registration(is_ctx* ctx, int n, const is_mat* images, const is_registration_hooks* hooks, is_camera* cams, float* scale, bool* estimated) {
+    for (int i = 0; i < n; ++i) {
+        IS_TRY(check_mat(ctx, &images[i], "image"));
+        IS_REQUIRE(ctx, images[i].depth == IS_8U && images[i].channels == 3, IS_ERR_BAD_ARG, "source images must be CV_8UC3");
+    }
+    *estimated = false;
     if (hooks && hooks->detect)
         for (int i = 0; i < n; ++i) {
             int rc = hooks->detect(hooks->user, i, &images[i]);
@@ -77,15 +74,35 @@ int is_pipeline_run(is_ctx* ctx, int n, const is_mat* images, const is_camera* c
         if (rc) return fail(ctx, rc, "match hook failed");
     }
     if (hooks && hooks->estimate) {
-        int rc = hooks->estimate(hooks->user, n, cams.data(), &cfg.scale);
+        int rc = hooks->estimate(hooks->user, n, cams, scale);
         if (rc) return fail(ctx, rc, "estimate hook failed");
-    } else {
+        *estimated = true;
+    }
+    return IS_OK;
+}
+
+int is_pipeline_estimate(is_ctx* ctx, int n, const is_mat* images, const is_registration_hooks* hooks, is_camera* cameras, float* scale) {
+    if (!ctx) return IS_ERR_BAD_ARG;
+    IS_REQUIRE(ctx, n > 0 && images && hooks && hooks->estimate && cameras && scale, IS_ERR_BAD_ARG, "null argument (an estimate hook is required)");
+    bool estimated = false;
+    return run_registration(ctx, n, images, hooks, cameras, scale, &estimated);
+}
+
+int is_pipeline_run(is_ctx* ctx, int n, const is_mat* images, const is_camera* cameras_in, const is_registration_hooks* hooks,
+                    const is_pipeline_config* cfg_in, is_mat* pano, is_mat* pano_mask, is_mat* seam_masks) {
+    if (!ctx) return IS_ERR_BAD_ARG;
+    IS_CUDA(ctx, cudaSetDevice(ctx->device));
+    IS_REQUIRE(ctx, n > 0 && images && cfg_in && pano && pano_mask, IS_ERR_BAD_ARG, "null argument");
+    is_pipeline_config cfg = *cfg_in;
+    const PipeStamp stamp(ctx);
+    stamp.mark("enter");
+    std::vector<is_camera> cams(n);
+    // ---- host registration stages (control flow around the GPU path)
+    bool estimated = false;
+    IS_TRY(run_registration(ctx, n, images, hooks, cams.data(), &cfg.scale, &estimated));
+    if (!estimated) {
         IS_REQUIRE(ctx, cameras_in, IS_ERR_BAD_ARG, "cameras are required when no estimate hook is given");
         for (int i = 0; i < n; ++i) cams[i] = cameras_in[i];
-    }
-    for (int i = 0; i < n; ++i) {
-        IS_TRY(check_mat(ctx, &images[i], "image"));
-        IS_REQUIRE(ctx, images[i].depth == IS_8U && images[i].channels == 3, IS_ERR_BAD_ARG, "source images must be CV_8UC3");
     }
     // ---- geometry
     std::vector<WarpPlan> plans(n);

@@ -249,7 +249,9 @@ class DpSeamFinder:
         if n == 0:
             return (masks, []) if want_trace else masks
         im, _k1 = _mat_array(src)
-        masks = [m if _is_torch(m) else np.ascontiguousarray(m) for m in masks]
+        for m in masks:
+            if not _is_torch(m) and not (isinstance(m, np.ndarray) and m.flags.c_contiguous and m.dtype == np.uint8):
+                raise ValueError("find() works in place: pass contiguous uint8 masks")
         mk, _k2 = _mat_array(masks)
         pts = (capi.Point * n)(*[capi.Point(int(c[0]), int(c[1])) for c in corners])
         if not want_trace:

@@ -301,6 +301,14 @@ typedef struct is_pipeline_plan_t {
     is_rect pano_roi;    /* resultRoi(corners, sizes) */
 } is_pipeline_plan_t;
 
+/* Registration only (host): validates the images, runs hooks->detect / match / estimate ((*finder)(img, features) [FEAT]:948,
+ * matcher [MATCH]:123, estimator [CAM]:118) and hands back the n cameras and the warper scale they produce.  The two-phase form
+ * of the call sequence: is_pipeline_estimate -> is_pipeline_plan (sizes the panorama) -> is_pipeline_run with those cameras,
+ * cfg.scale = the scale and hooks = NULL.  (is_pipeline_run also accepts hooks directly; the output mats must then already
+ * have the size the estimated geometry leads to.) */
+int is_pipeline_estimate(is_ctx* ctx, int n, const is_mat* images, const is_registration_hooks* hooks,
+                         is_camera* cameras, float* scale);
+
 /* Geometry only (host): corners[n], sizes[n] of the warped images and the panorama ROI. */
 int is_pipeline_plan(is_ctx* ctx, int n, const is_size* src_sizes, const is_camera* cameras,
                      const is_pipeline_config* cfg, is_point* corners, is_size* sizes, is_rect* pano_roi);

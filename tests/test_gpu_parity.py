@@ -473,3 +473,61 @@ def test_dp_seam_noisy_masks_take_the_dense_labelling_path(ctx, oracle, monkeypa
     got = S.DpSeamFinder(ctx, "COLOR").find(wi, corners, [m.copy() for m in wm])
     for k in range(3):
         _eq(got[k], want[k], f"dense-path mask {k}")
+
+
+def test_registration_hooks_two_phase(ctx, oracle):
+    """detect -> match -> estimate as host hooks ([FEAT]:948, [MATCH]:123, [CAM]:118): is_pipeline_estimate hands back the cameras and
+    the scale, is_pipeline_plan sizes the panorama from them, is_pipeline_run with those cameras equals the run with the hooks
+    passed directly -- and the oracle.  An invalid image is rejected before any hook sees it."""
+    import ctypes as C
+
+    from imagestitch_b200 import capi
+    O = oracle
+    n = 3
+    imgs, Ks, Rs, scale = synth.make_panorama_inputs(n, 320, 240, 1.2, 0.3)
+    calls = []
+
+    def detect(user, i, mat):
+        calls.append(("detect", i, mat.contents.rows, mat.contents.cols))
+        return 0
+
+    def match(user, k):
+        calls.append(("match", k))
+        return 0
+
+    def estimate(user, k, cams, sc):
+        calls.append(("estimate", k))
+        for i in range(k):
+            for q in range(9):
+                cams[i].K[q] = float(np.asarray(Ks[i], np.float32).reshape(9)[q])
+                cams[i].R[q] = float(np.asarray(Rs[i], np.float32).reshape(9)[q])
+        sc[0] = float(scale)
+        return 0
+
+    hooks = capi.RegistrationHooks(None, capi.DETECT_FN(detect), capi.MATCH_FN(match), capi.ESTIMATE_FN(estimate))
+    mats = (capi.Mat * n)()
+    keep = []
+    for i, a in enumerate(imgs):
+        a = np.ascontiguousarray(a)
+        keep.append(a)
+        mats[i] = capi.Mat(a.ctypes.data, a.shape[0], a.shape[1], 3, 0, a.strides[0], -1)
+    cams = (capi.Camera * n)()
+    sc = C.c_float(0)
+    ctx.check(ctx.lib.is_pipeline_estimate(ctx.h, n, mats, C.byref(hooks), cams, C.byref(sc)))
+    assert calls == [("detect", i, 240, 320) for i in range(n)] + [("match", n), ("estimate", n)]
+    assert sc.value == np.float32(scale)
+    Ke = [np.asarray(list(cams[i].K), np.float32).reshape(3, 3) for i in range(n)]
+    Re = [np.asarray(list(cams[i].R), np.float32).reshape(3, 3) for i in range(n)]
+    st = S.Stitcher(ctx, "cylindrical", "dp", 3, S.WEIGHT_32F)
+    got = st.stitch(imgs, Ke, Re, sc.value)
+    want = O.pipeline_run(O.PROJ_CYLINDRICAL, imgs, Ks, Rs, scale, seam=True, num_bands=3, weight_type=O.WEIGHT_32F)
+    _eq(got["pano"], want["pano"], "panorama from the estimated cameras")
+    calls.clear()
+    got2 = st.stitch(imgs, Ks, Rs, scale, hooks=C.byref(hooks))        # hooks passed to the run itself: same geometry, same panorama
+    assert [c[0] for c in calls] == ["detect"] * n + ["match", "estimate"]
+    _eq(got2["pano"], want["pano"], "panorama with the hooks in is_pipeline_run")
+    calls.clear()
+    bad = capi.Mat(keep[0].ctypes.data, 240, 320, 1, 0, keep[0].strides[0], -1)     # one channel: rejected before the hooks run
+    mats[1] = bad
+    assert ctx.lib.is_pipeline_estimate(ctx.h, n, mats, C.byref(hooks), cams, C.byref(sc)) < 0
+    assert calls == []
