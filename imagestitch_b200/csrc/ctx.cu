@@ -5,6 +5,7 @@
 #include <algorithm>
 #include <cstdlib>
 #include <thread>
+#include <sched.h>
 
 namespace is {
 
@@ -275,8 +276,16 @@ int download(is_ctx* ctx, void* dst, const void* src, size_t bytes) {
 
 HostPool* host_pool(is_ctx* ctx) {
     if (!ctx->hpool) {
+        // the cores this process may run on, shared with the other ranks of the box (one process per GPU: torchrun exports
+        // LOCAL_WORLD_SIZE) -- eight ranks with eight spinning threads each on a 16-core host only get in each other's way
         unsigned hc = std::thread::hardware_concurrency();
-        size_t w = hc > 2 ? std::min<size_t>(hc - 1, 7) : 0;
+        {
+            cpu_set_t set;
+            CPU_ZERO(&set);
+            if (sched_getaffinity(0, sizeof(set), &set) == 0 && CPU_COUNT(&set) > 0) hc = (unsigned)CPU_COUNT(&set);
+        }
+        if (const char* e = getenv("LOCAL_WORLD_SIZE")) { const int lws = atoi(e); if (lws > 1) hc = std::max(1u, hc / (unsigned)lws); }
+        size_t w = hc > 2 ? std::min<size_t>(hc - 1, 7) : (hc == 2 ? 1 : 0);
         if (const char* e = getenv("IS_HOST_THREADS")) w = (size_t)std::max(0, atoi(e) - 1);
         ctx->hpool = new HostPool(w);
     }

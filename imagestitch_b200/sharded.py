@@ -106,11 +106,23 @@ class Comm:
             req.wait()
 
     def all_min(self, value: int, device):
+        return self.all_min_result(self.all_min_start(value, device))
+
+    def all_min_start(self, value: int, device):
+        """the all-reduce (MIN) of a verdict, started now and read later with all_min_result(): nobody waits for the slowest rank
+        in the middle of a step"""
         if not self.dist:
             return value
         import torch
         t = torch.tensor([value], dtype=torch.int32, device=device)
-        self.dist.all_reduce(t, op=self.dist.ReduceOp.MIN)
+        work = self.dist.all_reduce(t, op=self.dist.ReduceOp.MIN, async_op=True)
+        return (t, work)
+
+    def all_min_result(self, pending):
+        if not self.dist:
+            return pending
+        t, work = pending
+        work.wait()
         return int(t.item())
 
 
@@ -207,13 +219,11 @@ class ShardedStitcher:
         ok = 1
         if has_right:                                 # the boundary pair on the mask image b+1 really has at that point of the reference's loop
             ok = 1 if be.pair_same_structure(entry_b, halo_entry, halo_true, plan.corners[b], plan.corners[b + 1]) else 0
-        ok = comm.all_min(ok, be.device)
-        if os.environ.get("IS_SHARDED_FORCE_FALLBACK") == "1":
-            ok = 0
-        self.info["seam_speculation"] = ok
+        # The verdict of all ranks (MIN) is only READ at the end of the step: the halo exchange and the blend are queued on the
+        # assumption that every boundary pair is proven, which is the rule; a rank that waited here would wait for the slowest
+        # rank of the box in the middle of every step.
+        verdict = comm.all_min_start(ok, be.device)
         lap("check")
-        if not ok:                                    # rare by construction: redo the step through the general path
-            return self.stitch_general(my_images, Ks_all, Rs_all, scale, plan)
         if has_left:                                  # the boundary pair's clears (computed by the left neighbour) inside its rectangle
             i, j = a - 1, a
             rx0 = max(plan.corners[i][0], plan.corners[j][0]) - plan.corners[j][0]
@@ -236,6 +246,12 @@ class ShardedStitcher:
         pano, pmask = be.blend_finish(bh, x0, x1)
         self.info["needed_images"] = needed_by[rank]
         lap("blend")
+        ok = comm.all_min_result(verdict)
+        if os.environ.get("IS_SHARDED_FORCE_FALLBACK") == "1":
+            ok = 0
+        self.info["seam_speculation"] = ok
+        if not ok:                                    # rare by construction: redo the step through the general path
+            return self.stitch_general(my_images, Ks_all, Rs_all, scale, plan)
         if dbg:
             self.info["laps_ms"] = laps
             print(f"[shard rank {rank}] " + " ".join(f"{k}={v:.2f}" for k, v in laps.items()), flush=True)
