@@ -2142,8 +2142,36 @@ int seam_find_core(is_ctx* ctx, int n, const DevMat* images, const is_point* cor
         size_t done = 0;
         bool all_batched = true;
         int waves = 0;
+        // intersection rectangle of a pair (panorama coordinates): the only place its clears fall
+        auto rect_of = [&](const std::pair<int, int>& pr, int* x0, int* y0, int* x1, int* y1) {
+            const int i = pr.first, j = pr.second;
+            *x0 = std::max(corners[i].x, corners[j].x); *y0 = std::max(corners[i].y, corners[j].y);
+            *x1 = std::min(corners[i].x + images[i].cols, corners[j].x + images[j].cols);
+            *y1 = std::min(corners[i].y + images[i].rows, corners[j].y + images[j].rows);
+        };
+        const bool whole = getenv("IS_SEAM_WAVE_ALL") != nullptr;           // tuning knob: every wave takes all remaining pairs
         while (done < active.size()) {
-            std::vector<std::pair<int, int>> rest(active.begin() + done, active.end());
+            // A wave is the longest run of pairs none of which shares an image with an earlier pair of the wave whose intersection
+            // rectangle comes within a few pixels of its own: the clears of such a neighbour would very likely change what the pair
+            // sees, and everything computed for it (costs, DP) would be thrown away by the validation.  In a strip every wave is
+            // the whole pair list; in a mosaic the waves follow the real conflicts instead of recomputing the tail of the list
+            // once per conflict.  The validation still decides what is accepted: this only chooses what is worth speculating on.
+            std::vector<std::pair<int, int>> rest;
+            for (size_t k = done; k < active.size(); ++k) {
+                bool conflict = false;
+                if (!whole) {
+                    int ax0, ay0, ax1, ay1;
+                    rect_of(active[k], &ax0, &ay0, &ax1, &ay1);
+                    for (const auto& q : rest) {
+                        if (q.first != active[k].first && q.first != active[k].second && q.second != active[k].first && q.second != active[k].second) continue;
+                        int bx0, by0, bx1, by1;
+                        rect_of(q, &bx0, &by0, &bx1, &by1);
+                        if (bx0 < ax1 + 4 && ax0 - 4 < bx1 && by0 < ay1 + 4 && ay0 - 4 < by1) { conflict = true; break; }
+                    }
+                }
+                if (conflict) break;
+                rest.push_back(active[k]);
+            }
             size_t accepted = 0;
             bool first_unsupported = false;
             IS_TRY(seam_batch_wave(ctx, rest, n, images, corners, masks, trace, cost_fn, &accepted, &first_unsupported));

@@ -720,8 +720,10 @@ void UlsRuns::run() {
             if (seam_contour[(size_t)i] < 0 && adj(sval[(size_t)i])) row.push_back({seam_x[(size_t)k], seam_x[(size_t)k] + 1});   // contour pixels are covered above
         }
         if (row.empty()) continue;
-        std::inplace_merge(row.begin(), row.begin() + (ptrdiff_t)n_runs, row.begin() + (ptrdiff_t)n_cont);
-        std::inplace_merge(row.begin(), row.begin() + (ptrdiff_t)n_cont, row.end());
+        // three sorted lists of a handful of intervals: one sort (insertion sort at this size, and unlike std::inplace_merge it
+        // does not ask the allocator for a scratch buffer twice per row)
+        if (row.size() > n_runs || n_cont > n_runs) std::sort(row.begin(), row.end());
+        (void)n_cont;
         for (auto& iv : row) {
             if (!flips.empty() && flips.back().y == ry + y && flips.back().x1 >= iv.first + rx) flips.back().x1 = std::max(flips.back().x1, iv.second + rx);
             else flips.push_back(Interval{ry + y, iv.first + rx, iv.second + rx});
