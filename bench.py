@@ -650,6 +650,16 @@ def main():
                 "whole_step": {"ms": ms_dev, "achieved_gbs": alg["warp_blend_fused"] / (ms_dev * 1e-3) / 1e9, "frac": alg["warp_blend_fused"] / (ms_dev * 1e-3) / 1e9 / peak},
                 "kernels": [{"name": r["name"], "group": _kernel_group(r["name"]), "ms_per_step": round(r["ms"] / args.steps, 5), "launches_per_step": r["launches"] / args.steps,
                              "declared_gbs": round(r["bytes"] / (r["ms"] * 1e-3) / 1e9, 1) if r["ms"] > 0 and r["bytes"] > 0 else None} for r in ktable]}
+    # DRAM traffic of the same kernels from one `ncu --set full` capture of a whole step of THIS workload on one GPU (scripts/
+    # ncu_traffic.py -> profiles/r2_ncu_traffic_c2.json): a constant of the profile, not a measurement of this run -- only
+    # attached where it applies (N = 1, C2)
+    if world == 1 and args.workload == "c2":
+        try:
+            tr = json.load(open(os.path.join(ROOT, "profiles", "r2_ncu_traffic_c2.json")))
+            roofline["traffic"] = sum(v["dram_bytes"] for k, v in tr["kernels"].items() if _kernel_group(k) == "warp_blend") / max(1, tr.get("steps", 1))
+            roofline["traffic_source"] = "profiles/r2_ncu_traffic_c2.json: dram__bytes_read.sum + dram__bytes_write.sum of the warp / pyramid / blend kernels of one step (ncu --set full)"
+        except Exception:
+            pass
     if args.kernel_report:
         os.makedirs(os.path.dirname(os.path.abspath(args.kernel_report)), exist_ok=True)
         with open(args.kernel_report, "w") as f:

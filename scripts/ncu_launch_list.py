@@ -1,5 +1,6 @@
 """Aggregates an `ncu --metrics gpu__time_duration.sum --csv` launch list per kernel: launches, total us, us/launch, share.
-usage: python scripts/ncu_launch_list.py launches.csv [out.md] [title]"""
+usage: python scripts/ncu_launch_list.py launches.csv [out.md] [title] [name-prefix]
+name-prefix (e.g. k_): only kernels whose name starts with it -- the library's own (the synthetic inputs are made by torch kernels)"""
 import csv, sys
 from collections import OrderedDict
 rows = [r for r in csv.reader(open(sys.argv[1], errors="replace")) if len(r) > 5]
@@ -9,6 +10,7 @@ agg = OrderedDict()
 for r in rows[hi + 1:]:
     if len(r) <= mv: continue
     name = r[kn].split("(")[0].replace("void ", "").replace("is::", "")
+    if len(sys.argv) > 4 and not name.startswith(sys.argv[4]): continue
     v = float(r[mv].replace(",", "")) * {"ns": 1e-3, "us": 1.0, "ms": 1e3, "usecond": 1.0, "nsecond": 1e-3, "msecond": 1e3}.get(r[mu], 1.0)
     a = agg.setdefault(name, [0, 0.0]); a[0] += 1; a[1] += v
 tot = sum(a[1] for a in agg.values()) or 1.0

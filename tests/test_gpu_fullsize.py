@@ -1,4 +1,4 @@
-"""Parity at BASELINE.json's full sizes (bench workload C2: 6 x (4000 x 6000)) and size-independent properties at C3.
+"""Parity at BASELINE.json's full sizes: bench workloads C2 (6 x (4000 x 6000)) and C3 (12 images) against the oracle, plus size-independent properties.
 
 C2 is small enough for the CPU oracle to finish in seconds with all host threads, so the whole panorama is compared bit
 for bit; on top of that the properties that do not need an oracle: the concurrent (speculative) seam stage equals the
@@ -76,3 +76,20 @@ def test_c3_properties(ctx, monkeypatch):
     # idempotence: a second run on the same inputs gives the same bits
     c = st.stitch(imgs, Ks, Rs, scale)
     assert bool((c["pano"] == a["pano"]).all()) and bool((c["pano_mask"] == a["pano_mask"]).all())
+
+
+def test_c3_full_size_equals_oracle(ctx, oracle):
+    """BASELINE.json configs[2] (12 x (4000 x 6000), DP seam + 5-band blend) against the oracle at full size: seam masks, panorama
+    mask and panorama bit for bit (about half a minute of CPU with all host threads)."""
+    O = oracle
+    O.set_threads(os.cpu_count() or 1)
+    imgs, Ks, Rs, scale = _inputs(12, 4000, 6000, 1.5, "cuda:0")
+    st = S.Stitcher(ctx, "cylindrical", "dp", 5, S.WEIGHT_32F)
+    got = st.stitch(imgs, Ks, Rs, scale, want_seam_masks=True)
+    host = [t.cpu().numpy() for t in imgs]
+    want = O.pipeline_run(O.PROJ_CYLINDRICAL, host, Ks, Rs, scale, seam=True, num_bands=5, weight_type=O.WEIGHT_32F, want_intermediates=True)
+    assert got["roi"] == want["roi"]
+    for k in range(12):
+        assert np.array_equal(got["seam_masks"][k].cpu().numpy(), want["masks"][k]), f"seam mask {k}"
+    assert np.array_equal(got["pano_mask"].cpu().numpy(), want["pano_mask"])
+    assert np.array_equal(got["pano"].cpu().numpy(), want["pano"])
