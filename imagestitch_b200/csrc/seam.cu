@@ -368,8 +368,9 @@ __global__ void k_relabel_rect(int* labels, Frame f, int x0, int y0, int w, int 
 // @emu-begin
 template <typename T> struct ImgView {
     const T* p; size_t step; int rows, cols; int dx, dy;   // image coords = union coords + (dx, dy)   ([SEAM]:752-753)
+    int cn = 3;                                            // elements per pixel: 3, or 4 with the fourth one skipped (diffL2Square4, [SEAM]:722-730)
     __device__ __forceinline__ const T* px(int ux, int uy) const {
-        return reinterpret_cast<const T*>(reinterpret_cast<const char*>(p) + (size_t)(uy + dy) * step) + 3 * (ux + dx);
+        return reinterpret_cast<const T*>(reinterpret_cast<const char*>(p) + (size_t)(uy + dy) * step) + cn * (ux + dx);
     }
 };
 
@@ -398,7 +399,7 @@ struct GradView {
 // cvtColor(BGR2GRAY) on CV_32F in the association of OpenCV's FMA vector body (the oracle's `sobelPair`)
 template <typename T>
 __device__ __forceinline__ float gray_at(const ImgView<T>& a, int ix, int iy) {   // image coordinates
-    const T* p = reinterpret_cast<const T*>(reinterpret_cast<const char*>(a.p) + (size_t)iy * a.step) + 3 * ix;
+    const T* p = reinterpret_cast<const T*>(reinterpret_cast<const char*>(a.p) + (size_t)iy * a.step) + a.cn * ix;
     return __fmaf_rn((float)p[2], 0.299f, __fmaf_rn((float)p[0], 0.114f, __fmul_rn((float)p[1], 0.587f)));
 }
 
@@ -1387,7 +1388,7 @@ int PairSeam::refresh_component(int c) {
 
 template <typename T>
 static ImgView<T> make_view(const DevMat& m, int dx, int dy) {
-    return ImgView<T>{m.ptr<T>(), m.step, m.rows, m.cols, dx, dy};
+    return ImgView<T>{m.ptr<T>(), m.step, m.rows, m.cols, dx, dy, m.channels};
 }
 
 // computeGradients [SEAM]:549-572, restricted to the intersection rectangle (the only place costs are evaluated)
@@ -2210,8 +2211,9 @@ static int seam_find_impl(is_ctx* ctx, int n, const is_mat* images, const is_poi
     for (int i = 0; i < n; ++i) {
         IS_TRY(check_mat(ctx, &images[i], "image"));
         IS_TRY(check_mat(ctx, &masks[i], "mask"));
-        IS_REQUIRE(ctx, images[i].channels == 3 && (images[i].depth == IS_8U || images[i].depth == IS_32F) && images[i].depth == depth,
-                   IS_ERR_BAD_ARG, "both images must have CV_32FC3 or CV_8UC3 type");     // [SEAM]:749
+        IS_REQUIRE(ctx, (images[i].channels == 3 || images[i].channels == 4) && images[i].channels == images[0].channels &&
+                            (images[i].depth == IS_8U || images[i].depth == IS_32F) && images[i].depth == depth,
+                   IS_ERR_BAD_ARG, "both images must have CV_32FC3(4) or CV_8UC3(4) type");     // [SEAM]:741-750
         IS_REQUIRE(ctx, masks[i].depth == IS_8U && masks[i].channels == 1, IS_ERR_BAD_ARG, "masks must be CV_8U");
         IS_REQUIRE(ctx, images[i].rows == masks[i].rows && images[i].cols == masks[i].cols, IS_ERR_ASSERT, "image.size() == mask.size()");
     }
@@ -2258,8 +2260,8 @@ static int pair_common(is_ctx* ctx, const is_mat* image_i, const is_mat* image_j
     IS_TRY(check_mat(ctx, image_j, "image_j"));
     IS_TRY(check_mat(ctx, mask_i, "mask_i"));
     IS_TRY(check_mat(ctx, mask_j, "mask_j"));
-    IS_REQUIRE(ctx, image_i->channels == 3 && image_j->channels == 3 && image_i->depth == image_j->depth &&
-                        (image_i->depth == IS_8U || image_i->depth == IS_32F), IS_ERR_BAD_ARG, "both images must have CV_32FC3 or CV_8UC3 type");
+    IS_REQUIRE(ctx, (image_i->channels == 3 || image_i->channels == 4) && image_j->channels == image_i->channels && image_i->depth == image_j->depth &&
+                        (image_i->depth == IS_8U || image_i->depth == IS_32F), IS_ERR_BAD_ARG, "both images must have CV_32FC3(4) or CV_8UC3(4) type");
     IS_REQUIRE(ctx, mask_i->depth == IS_8U && mask_i->channels == 1 && mask_j->depth == IS_8U && mask_j->channels == 1, IS_ERR_BAD_ARG, "masks must be CV_8U");
     return IS_OK;
 }
@@ -2585,7 +2587,7 @@ int is_seam_cost_maps(is_ctx* ctx, const is_mat* image1, const is_mat* image2, i
     IS_TRY(check_mat(ctx, labels, "labels"));
     IS_TRY(check_mat(ctx, costV, "costV"));
     IS_TRY(check_mat(ctx, costH, "costH"));
-    IS_REQUIRE(ctx, image1->channels == 3 && image2->channels == 3 && image1->depth == image2->depth &&
+    IS_REQUIRE(ctx, (image1->channels == 3 || image1->channels == 4) && image2->channels == image1->channels && image1->depth == image2->depth &&
                         (image1->depth == IS_8U || image1->depth == IS_32F), IS_ERR_BAD_ARG, "both images must have CV_32FC3 or CV_8UC3 type");
     IS_REQUIRE(ctx, labels->depth == IS_32S && labels->channels == 1, IS_ERR_BAD_ARG, "labels must be CV_32S");
     IS_REQUIRE(ctx, labels->device >= 0 || labels->step == (size_t)labels->cols * 4, IS_ERR_BAD_ARG, "host labels must be dense");

@@ -245,6 +245,7 @@ struct PairDev {
     int* labels;
     const int* tab_cnt; const ChangePt* tab_cps; const int* tab_lab; int wcap;   // biased by the window's first row (k_label_window)
     const void* img1; const void* img2; size_t step1, step2; int rows1, cols1, rows2, cols2; int dx1, dy1, dx2, dy2;
+    int cn;                            // elements per pixel of both images (3 or 4)
     GradView g;
 };
 
@@ -293,8 +294,8 @@ __global__ void k_cost_pq_batch(const PairDev* __restrict__ pairs, const JobDev*
         Q[(size_t)step * J.pitch + lane] = 0.f;
         return;
     }
-    const ImgView<T> a{reinterpret_cast<const T*>(D.img1), D.step1, D.rows1, D.cols1, D.dx1, D.dy1};
-    const ImgView<T> b{reinterpret_cast<const T*>(D.img2), D.step2, D.rows2, D.cols2, D.dx2, D.dy2};
+    const ImgView<T> a{reinterpret_cast<const T*>(D.img1), D.step1, D.rows1, D.cols1, D.dx1, D.dy1, D.cn};
+    const ImgView<T> b{reinterpret_cast<const T*>(D.img2), D.step2, D.rows2, D.cols2, D.dx2, D.dy2, D.cn};
     const int x = J.rx + (J.horizontal ? step : lane), y = J.ry + (J.horizontal ? lane : step);
     float p, q;
     if (J.horizontal) { p = cost_h<T, GRAD>(a, b, D.labels, D.fr, J.l1, x, y, D.g); q = cost_v<T, GRAD>(a, b, D.labels, D.fr, J.l1, x, y, D.g); }
@@ -323,8 +324,8 @@ __global__ void __launch_bounds__(128) k_cost_pq_walk(const PairDev* __restrict_
     const int lane_id = threadIdx.x & 31;
     const bool hz = J.horizontal != 0;
     const int l1 = J.l1;
-    const ImgView<T> A{reinterpret_cast<const T*>(D.img1), D.step1, D.rows1, D.cols1, D.dx1, D.dy1};
-    const ImgView<T> B{reinterpret_cast<const T*>(D.img2), D.step2, D.rows2, D.cols2, D.dx2, D.dy2};
+    const ImgView<T> A{reinterpret_cast<const T*>(D.img1), D.step1, D.rows1, D.cols1, D.dx1, D.dy1, D.cn};
+    const ImgView<T> B{reinterpret_cast<const T*>(D.img2), D.step2, D.rows2, D.cols2, D.dx2, D.dy2, D.cn};
     struct Cell { float a[3], b[3]; int lab; };
     auto load = [&](int ln, int st) {                                               // pixels only where the label says both images cover the cell
         Cell c;
@@ -858,7 +859,7 @@ static int seam_batch_wave(is_ctx* ctx, const std::vector<std::pair<int, int>>& 
                 D.tab_lab = d + wrows + wrows * P.wcap * 2 - (size_t)P.wy * P.wcap;
             }
             D.img1 = i1.data; D.img2 = i2.data; D.step1 = i1.step; D.step2 = i2.step;
-            D.rows1 = i1.rows; D.cols1 = i1.cols; D.rows2 = i2.rows; D.cols2 = i2.cols;
+            D.rows1 = i1.rows; D.cols1 = i1.cols; D.rows2 = i2.rows; D.cols2 = i2.cols; D.cn = i1.channels;
             D.dx1 = P.unionTl.x - P.tl1.x; D.dy1 = P.unionTl.y - P.tl1.y; D.dx2 = P.unionTl.x - P.tl2.x; D.dy2 = P.unionTl.y - P.tl2.y;
             if (cost_fn == IS_COST_COLOR_GRAD) {
                 float* g = reinterpret_cast<float*>(base + off_grad[k]);
@@ -913,14 +914,14 @@ static int seam_batch_wave(is_ctx* ctx, const std::vector<std::pair<int, int>>& 
                 const size_t plane = (size_t)gpitch[k] * ih;
                 dim3 block(64, 4), grid(div_up(iw, 64), div_up(ih, 4));
                 if (is_u8) {
-                    IS_LAUNCH(ctx, k_sobel_window<uint8_t>, grid, block, 0, ImgView<uint8_t>{reinterpret_cast<const uint8_t*>(D.img1), D.step1, D.rows1, D.cols1, D.dx1, D.dy1},
+                    IS_LAUNCH(ctx, k_sobel_window<uint8_t>, grid, block, 0, ImgView<uint8_t>{reinterpret_cast<const uint8_t*>(D.img1), D.step1, D.rows1, D.cols1, D.dx1, D.dy1, D.cn},
                               ix, iy, iw, ih, g, g + plane, gpitch[k]);
-                    IS_LAUNCH(ctx, k_sobel_window<uint8_t>, grid, block, 0, ImgView<uint8_t>{reinterpret_cast<const uint8_t*>(D.img2), D.step2, D.rows2, D.cols2, D.dx2, D.dy2},
+                    IS_LAUNCH(ctx, k_sobel_window<uint8_t>, grid, block, 0, ImgView<uint8_t>{reinterpret_cast<const uint8_t*>(D.img2), D.step2, D.rows2, D.cols2, D.dx2, D.dy2, D.cn},
                               ix, iy, iw, ih, g + 2 * plane, g + 3 * plane, gpitch[k]);
                 } else {
-                    IS_LAUNCH(ctx, k_sobel_window<float>, grid, block, 0, ImgView<float>{reinterpret_cast<const float*>(D.img1), D.step1, D.rows1, D.cols1, D.dx1, D.dy1},
+                    IS_LAUNCH(ctx, k_sobel_window<float>, grid, block, 0, ImgView<float>{reinterpret_cast<const float*>(D.img1), D.step1, D.rows1, D.cols1, D.dx1, D.dy1, D.cn},
                               ix, iy, iw, ih, g, g + plane, gpitch[k]);
-                    IS_LAUNCH(ctx, k_sobel_window<float>, grid, block, 0, ImgView<float>{reinterpret_cast<const float*>(D.img2), D.step2, D.rows2, D.cols2, D.dx2, D.dy2},
+                    IS_LAUNCH(ctx, k_sobel_window<float>, grid, block, 0, ImgView<float>{reinterpret_cast<const float*>(D.img2), D.step2, D.rows2, D.cols2, D.dx2, D.dy2, D.cn},
                               ix, iy, iw, ih, g + 2 * plane, g + 3 * plane, gpitch[k]);
                 }
             }

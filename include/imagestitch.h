@@ -117,7 +117,8 @@ int is_warp_with_mask(is_ctx* ctx, int projection, const is_mat* src, const floa
 /* ------------------------------------------------------------------ seam
  * Replaces  void find(const std::vector<UMat>& src, const std::vector<Point>& corners,
  *                     std::vector<UMat>& masks)                                        [SEAM]:87
- * (== cv::detail::DpSeamFinder::find).  images: n mats, 3 channels, IS_32F or IS_8U (all the same);
+ * (== cv::detail::DpSeamFinder::find).  images: n mats, 3 channels -- or 4 with the fourth ignored, diffL2Square4 [SEAM]:722-730,
+ * 745-748 -- IS_32F or IS_8U (all the same);
  * masks: n mats IS_8U, same sizes as the images ([SEAM]:133-134), modified in place.
  * cost_fn: IS_COST_COLOR or IS_COST_COLOR_GRAD ([SEAM]:549-572, :767-772, :792-797; 8-bit images are taken as their
  * CV_32F conversion, which is what the mains pass).

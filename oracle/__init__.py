@@ -121,7 +121,7 @@ def warp(proj, src, K, R, scale, interp, border, full_scan=True):
 
 # ---------------------------------------------------------------- seam
 def dp_seam_find(images, corners, masks, cost_fn=COST_COLOR, want_trace=False):
-    """[SEAM]:87-124.  images: list of HxWx3 float32 or uint8; masks: list of HxW uint8.
+    """[SEAM]:87-124.  images: list of HxWx3 (or HxWx4: the fourth channel is ignored) float32 or uint8; masks: list of HxW uint8.
     Returns new masks (inputs are not modified) and, optionally, the seam trace
     [(i, j, comp, is_horizontal, points Nx2 in pano coords), ...]."""
     n = len(images)
@@ -139,7 +139,8 @@ def dp_seam_find(images, corners, masks, cost_fn=COST_COLOR, want_trace=False):
         cap = int(sum(5 + 2 * (im.shape[0] + im.shape[1]) for im in imgs) * max(1, n) * 2)
         trace = np.zeros(cap, np.int32)
     tlen = C.c_size_t(0)
-    rc = lib().orc_dp_seam_find(C.c_int(n), ip, C.c_int(1 if is_u8 else 0), _p(rows), _p(cols), _p(cxy), mp,
+    flags = (1 if is_u8 else 0) | (2 if imgs[0].ndim == 3 and imgs[0].shape[2] == 4 else 0)      # bit 1: CV_8UC4 / CV_32FC4 ([SEAM]:745-748)
+    rc = lib().orc_dp_seam_find(C.c_int(n), ip, C.c_int(flags), _p(rows), _p(cols), _p(cxy), mp,
                                 C.c_int(cost_fn), _p(trace) if want_trace else None, C.c_size_t(cap), C.byref(tlen))
     if rc:
         raise RuntimeError(f"orc_dp_seam_find failed: {rc}")
@@ -317,7 +318,8 @@ def ref_dp_seam_find(images, corners, masks, cost_fn=COST_COLOR):
     rows = np.asarray([im.shape[0] for im in imgs], np.int32)
     cols = np.asarray([im.shape[1] for im in imgs], np.int32)
     cxy = np.asarray(corners, np.int32).reshape(-1).copy()
-    rc = _ref_seam.ref_dp_seam_find(C.c_int(n), ip, C.c_int(1 if is_u8 else 0), _p(rows), _p(cols), _p(cxy), mp, C.c_int(cost_fn))
+    flags = (1 if is_u8 else 0) | (2 if imgs[0].ndim == 3 and imgs[0].shape[2] == 4 else 0)
+    rc = _ref_seam.ref_dp_seam_find(C.c_int(n), ip, C.c_int(flags), _p(rows), _p(cols), _p(cxy), mp, C.c_int(cost_fn))
     if rc:
         raise RuntimeError(f"the reference's find() raised cv::Error {rc}")
     return out

@@ -217,7 +217,8 @@ template <typename Tp, class Pred> int partition(const std::vector<Tp>& vec, std
 
 // COLOR_GRAD only.  CV_32F: OpenCV's vector-body association; CV_8U: its 14-bit fixed point (B 1868, G 9617, R 4899).
 inline void cvtColor(const Mat& src, Mat& dst, int code) {
-    const int cn = (code == COLOR_BGRA2GRAY) ? 4 : 3;
+    (void)code;
+    const int cn = src.channels();   // cv::cvtColor takes the channel count from the source (BGR2GRAY accepts 3 or 4, alpha ignored)
     if (src.depth() == CV_32F) {
         dst.create(src.rows, src.cols, CV_32FC1);
         for (int y = 0; y < src.rows; ++y)

@@ -34,7 +34,8 @@ void updateLabelsUsingSeam(int comp1, int comp2, std::vector<Point>& seam, bool 
     updateLabelsUsingSeam(comp1, comp2, static_cast<const std::vector<Point>&>(seam), isHorizontalSeam);
 }
 
-// images: n pointers to tightly packed rows x cols x 3 (uint8 or float32); masks: n pointers, modified in place.
+// images: n pointers to tightly packed rows x cols x cn (uint8 or float32); masks: n pointers, modified in place.
+// is_u8: bit 0 = 8-bit images, bit 1 = four channels (CV_8UC4 / CV_32FC4, [SEAM]:745-748) instead of three.
 // returns 0, or the cv::Error code the reference's CV_Assert / CV_Error raised.
 extern "C" int ref_dp_seam_find(int n, const void* const* images, int is_u8, const int* rows, const int* cols, const int* corners_xy,
                                 uint8_t* const* masks, int cost_fn) {
@@ -42,8 +43,10 @@ extern "C" int ref_dp_seam_find(int n, const void* const* images, int is_u8, con
         std::vector<UMat> src(n), msk(n);
         std::vector<Point> corners(n);
         for (int i = 0; i < n; ++i) {
-            const int type = is_u8 ? CV_8UC3 : CV_32FC3;
-            src[i] = Mat(rows[i], cols[i], type, const_cast<void*>(images[i]), (size_t)cols[i] * 3 * (is_u8 ? 1 : 4));
+            const bool u8 = (is_u8 & 1) != 0;
+            const int cn = (is_u8 & 2) ? 4 : 3;
+            const int type = u8 ? (cn == 4 ? CV_8UC4 : CV_8UC3) : (cn == 4 ? CV_32FC4 : CV_32FC3);
+            src[i] = Mat(rows[i], cols[i], type, const_cast<void*>(images[i]), (size_t)cols[i] * cn * (u8 ? 1 : 4));
             msk[i] = Mat(rows[i], cols[i], CV_8UC1, masks[i], (size_t)cols[i]);
             corners[i] = Point(corners_xy[2 * i], corners_xy[2 * i + 1]);
         }
@@ -70,10 +73,12 @@ extern "C" int ref_seam_costs(const void* img1, const void* img2, int is_u8, int
                               int tl2x, int tl2y, const int32_t* labels, int H, int W, int union_tlx, int union_tly, int l, const int roi[4],
                               int cost_fn, float* costV_out, float* costH_out) {
     try {
-        const int type = is_u8 ? CV_8UC3 : CV_32FC3;
-        const size_t es = is_u8 ? 1 : 4;
-        Mat image1(rows1, cols1, type, const_cast<void*>(img1), (size_t)cols1 * 3 * es);
-        Mat image2(rows2, cols2, type, const_cast<void*>(img2), (size_t)cols2 * 3 * es);
+        const bool u8 = (is_u8 & 1) != 0;
+        const int cn = (is_u8 & 2) ? 4 : 3;
+        const int type = u8 ? (cn == 4 ? CV_8UC4 : CV_8UC3) : (cn == 4 ? CV_32FC4 : CV_32FC3);
+        const size_t es = u8 ? 1 : 4;
+        Mat image1(rows1, cols1, type, const_cast<void*>(img1), (size_t)cols1 * cn * es);
+        Mat image2(rows2, cols2, type, const_cast<void*>(img2), (size_t)cols2 * cn * es);
         unionTl_ = Point(union_tlx, union_tly);
         unionBr_ = Point(union_tlx + W, union_tly + H);
         unionSize_ = Size(W, H);

@@ -31,8 +31,9 @@ enum { FIRST = 1, SECOND = 2, INTERS = 4, INTERS_FIRST = 5, INTERS_SECOND = 6 };
 
 struct Img {
     const void* data; int rows, cols; bool u8;
+    int cn = 3;                       // 3, or 4 (CV_8UC4 / CV_32FC4: the fourth channel is skipped, [SEAM]:722-730 diffL2Square4)
     inline float at(int y, int x, int c) const {
-        size_t i = ((size_t)y * cols + x) * 3 + c;
+        size_t i = ((size_t)y * cols + x) * cn + c;
         return u8 ? (float)((const uint8_t*)data)[i] : ((const float*)data)[i];
     }
 };
@@ -294,17 +295,18 @@ struct DpSeam {
         return true;
     }
 
-    // [SEAM]:713-718 diffL2Square3<T>; float: ((d0^2 + d1^2) + d2^2) with d in float. uchar: the
+    // [SEAM]:713-730 diffL2Square3<T> / diffL2Square4<T> (pixel stride 4, the same three channels); float: ((d0^2 + d1^2) + d2^2)
+    // with d in float. uchar: the
     // same sum in int then converted -- identical values for 8-bit data.
     static inline float diff3(const Img& a, int y1, int x1, const Img& b, int y2, int x2) {
         if (a.u8) {
-            const uint8_t* r1 = (const uint8_t*)a.data + ((size_t)y1 * a.cols + x1) * 3;
-            const uint8_t* r2 = (const uint8_t*)b.data + ((size_t)y2 * b.cols + x2) * 3;
+            const uint8_t* r1 = (const uint8_t*)a.data + ((size_t)y1 * a.cols + x1) * a.cn;
+            const uint8_t* r2 = (const uint8_t*)b.data + ((size_t)y2 * b.cols + x2) * b.cn;
             int d0 = r1[0] - r2[0], d1 = r1[1] - r2[1], d2 = r1[2] - r2[2];
             return static_cast<float>(d0 * d0 + d1 * d1 + d2 * d2);
         }
-        const float* r1 = (const float*)a.data + ((size_t)y1 * a.cols + x1) * 3;
-        const float* r2 = (const float*)b.data + ((size_t)y2 * b.cols + x2) * 3;
+        const float* r1 = (const float*)a.data + ((size_t)y1 * a.cols + x1) * a.cn;
+        const float* r2 = (const float*)b.data + ((size_t)y2 * b.cols + x2) * b.cn;
         float d0 = r1[0] - r2[0], d1 = r1[1] - r2[1], d2 = r1[2] - r2[2];
         return d0 * d0 + d1 * d1 + d2 * d2;
     }
@@ -658,8 +660,8 @@ int orc_dp_seam_find(int n, const void* const* images, int is_u8, const int* row
     f.trace_cap = trace_cap;
     for (size_t k = 0; k < pairs.size(); ++k) {              // [SEAM]:115-121
         int i0 = pairs[k].first, i1 = pairs[k].second;
-        Img a{images[i0], rows[i0], cols[i0], is_u8 != 0};
-        Img b{images[i1], rows[i1], cols[i1], is_u8 != 0};
+        Img a{images[i0], rows[i0], cols[i0], (is_u8 & 1) != 0, (is_u8 & 2) ? 4 : 3};     // is_u8: bit 0 = 8-bit, bit 1 = four channels
+        Img b{images[i1], rows[i1], cols[i1], (is_u8 & 1) != 0, (is_u8 & 2) ? 4 : 3};
         f.cur_i = i0;
         f.cur_j = i1;
         f.process(a, b, Pt{corners_xy[2 * i0], corners_xy[2 * i0 + 1]}, Pt{corners_xy[2 * i1], corners_xy[2 * i1 + 1]},
@@ -679,7 +681,7 @@ void orc_seam_costs(const void* img1, const void* img2, int is_u8,
 }
 
 void orc_seam_gradients(const void* img, int is_u8, int rows, int cols, float* gradx, float* grady) {
-    Img a{img, rows, cols, is_u8 != 0};
+    Img a{img, rows, cols, (is_u8 & 1) != 0, (is_u8 & 2) ? 4 : 3};
     Grid<float> gx, gy;
     DpSeam::sobelPair(a, gx, gy);
     std::memcpy(gradx, gx.v.data(), sizeof(float) * gx.v.size());
@@ -703,7 +705,7 @@ void orc_seam_costs_ex(const void* img1, const void* img2, int is_u8,
     f.states_.assign(comp + 1, INTERS);
     f.tls_[comp] = {roi[0], roi[1]};
     f.brs_[comp] = {roi[0] + roi[2], roi[1] + roi[3]};
-    Img a{img1, rows1, cols1, is_u8 != 0}, b{img2, rows2, cols2, is_u8 != 0};
+    Img a{img1, rows1, cols1, (is_u8 & 1) != 0, (is_u8 & 2) ? 4 : 3}, b{img2, rows2, cols2, (is_u8 & 1) != 0, (is_u8 & 2) ? 4 : 3};
     if (cost_fn == ORC_COST_COLOR_GRAD) f.computeGradients(a, b);
     Grid<float> cv, ch;
     f.computeCosts(a, b, Pt{tl1x, tl1y}, Pt{tl2x, tl2y}, comp, cv, ch);

@@ -103,3 +103,26 @@ def test_dp_formulations_agree_on_synthetic_tables(ctx):
             finally:
                 os.environ.pop("IS_DP_V1_TMPL", None)
             assert np.array_equal(got, base), f"lanes={lanes} steps={steps} template {tmpl}"
+
+
+@pytest.mark.parametrize("kind", ["u8", "f32"])
+@pytest.mark.parametrize("cost", ["COLOR", "COLOR_GRAD"])
+def test_four_channel_images(ctx, oracle, kind, cost):
+    """CV_8UC4 / CV_32FC4 ([SEAM]:722-730, 745-748): masks and seam point lists equal the oracle's (which equals the reference's own
+    find() on four channels, tests/test_oracle_reference_build.py), on the batched path (strip) and with irregular masks."""
+    O = oracle
+    rng = np.random.default_rng(11)
+    for (n, w, h, ov, rows, irregular) in ((3, 260, 200, 0.3, 1, False), (4, 160, 120, 0.3, 2, False), (3, 180, 130, 0.4, 1, True)):
+        corners, wi, wm = warped_set(O, n, w, h, overlap=ov, grid_rows=rows)
+        if irregular:
+            holes = blob_masks(np.random.default_rng(8), [m.shape for m in wm], holes=4)
+            wm = [np.where(hm > 0, m, 0).astype(np.uint8) for m, hm in zip(wm, holes)]
+        imgs = [np.concatenate([a, rng.integers(0, 256, a.shape[:2] + (1,)).astype(np.uint8)], axis=2) for a in wi]
+        if kind == "f32":
+            imgs = [a.astype(np.float32) for a in imgs]
+        cf = O.COST_COLOR_GRAD if cost == "COLOR_GRAD" else O.COST_COLOR
+        want, wtrace = O.dp_seam_find(imgs, corners, wm, cost_fn=cf, want_trace=True)
+        got, gtrace = S.DpSeamFinder(ctx, cost).find(imgs, corners, [m.copy() for m in wm], want_trace=True)
+        for i in range(n):
+            assert np.array_equal(got[i], want[i]), f"4-channel {kind} {cost} seam mask {i}"
+        assert _traces_equal(wtrace, gtrace), "seam point lists"

@@ -201,3 +201,36 @@ def test_dp_seam_edge_cases_match_reference(oracle):
         if cost == 0:                                          # 8-bit images: identical costs, identical masks ([SEAM]:742-743)
             got8 = O.dp_seam_find([a.astype(np.uint8) for a in imgs], cs, ms)
             assert all(np.array_equal(a, b) for a, b in zip(got8, got)), name
+
+
+def _with_alpha(a, rng):
+    """HxWx3 -> HxWx4 with a random fourth channel (it must not influence anything)"""
+    return np.concatenate([a, rng.integers(0, 256, a.shape[:2] + (1,)).astype(a.dtype)], axis=2)
+
+
+@pytest.mark.parametrize("case", [(2, 260, 200, 0.25, 1, False), (4, 160, 120, 0.3, 2, False), (3, 180, 130, 0.4, 1, True)])
+def test_dp_seam_four_channels_match_reference_build(oracle, case):
+    """CV_8UC4 / CV_32FC4 images ([SEAM]:722-730 diffL2Square4, 745-748): the oracle equals the reference's own find() on them --
+    masks and seam point lists -- and the three-channel result (the fourth channel is skipped)."""
+    O = oracle
+    if O.build_ref() is None:
+        pytest.skip("oracle/_ref (the compiled reference block) is not available on this machine")
+    n, w, h, ov, rows, irregular = case
+    corners, wi, wm = warped_set(O, n, w, h, overlap=ov, grid_rows=rows)
+    if irregular:
+        holes = blob_masks(np.random.default_rng(8), [m.shape for m in wm], holes=4)
+        wm = [np.where(hm > 0, m, 0).astype(np.uint8) for m, hm in zip(wm, holes)]
+    rng = np.random.default_rng(5)
+    w4 = [_with_alpha(a, rng) for a in wi]
+    f4 = [a.astype(np.float32) for a in w4]
+    for imgs, cost in ((w4, O.COST_COLOR), (f4, O.COST_COLOR), (f4, O.COST_COLOR_GRAD)):
+        want = O.ref_dp_seam_find(imgs, corners, wm, cost)
+        want_seams = O.ref_last_seams()
+        got, trace = O.dp_seam_find(imgs, corners, wm, cost_fn=cost, want_trace=True)
+        three = O.dp_seam_find([np.ascontiguousarray(a[:, :, :3]) for a in imgs], corners, wm, cost_fn=cost)
+        for i in range(n):
+            assert np.array_equal(got[i], want[i]), f"mask {i}, cost {cost}, {imgs[0].dtype}"
+            assert np.array_equal(got[i], three[i]), f"four channels != three channels, mask {i}"
+        assert len(trace) == len(want_seams) and len(trace) >= 1
+        for a, b in zip(want_seams, trace):
+            assert a[0] == b[2] and a[1] == b[3] and np.array_equal(a[2], b[4])
