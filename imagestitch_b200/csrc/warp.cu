@@ -471,15 +471,20 @@ __global__ void __launch_bounds__(WG_THREADS) k_warp_g1(WarpG1Args A) {
             if (T.inside) w |= 0xff000000u;
             tile[r][tid] = w;
         };
-        Taps t0, t1;
+        Taps t0, t1, t2;                                         // the loads of two rows ahead are in flight
         issue(0, t0);
+        issue(1, t1);
 #pragma unroll 1
-        for (int r = 0; r < WG_IH; r += 2) {
-            if (r + 1 < WG_IH) issue(r + 1, t1);
+        for (int r = 0; r < WG_IH; r += 3) {
+            if (r + 2 < WG_IH) issue(r + 2, t2);
             finish(r, t0);
             if (r + 1 < WG_IH) {
-                if (r + 2 < WG_IH) issue(r + 2, t0);
+                if (r + 3 < WG_IH) issue(r + 3, t0);
                 finish(r + 1, t1);
+            }
+            if (r + 2 < WG_IH) {
+                if (r + 4 < WG_IH) issue(r + 4, t1);
+                finish(r + 2, t2);
             }
         }
     }

@@ -26,3 +26,15 @@ def test_pyrup_shift_folding():
     a = np.arange(-8 * 32768 * 8, 8 * 32768 * 8, 37, dtype=np.int64)
     assert np.array_equal((4 * a + 32) >> 6, (a + 8) >> 4)
     assert np.array_equal((16 * a + 32) >> 6, (a + 2) >> 2)
+
+
+def test_pyrup_of_int16_stays_in_int16():
+    # pyrUp outputs are rounded weighted means with weights summing to 64 (k_blend_level_quad drops the saturation there)
+    rng = np.random.default_rng(0)
+    v = rng.integers(-32768, 32768, (200000, 3, 3)).astype(np.int64)
+    v[:4] = np.asarray([-32768, 32767, -32768, 32767]).reshape(4, 1, 1)
+    e = v[:, :, 0] + 6 * v[:, :, 1] + v[:, :, 2]
+    o = 4 * (v[:, :, 1] + v[:, :, 2])
+    outs = [(e[:, 0] + 6 * e[:, 1] + e[:, 2] + 32) >> 6, (o[:, 0] + 6 * o[:, 1] + o[:, 2] + 32) >> 6, (4 * (e[:, 1] + e[:, 2]) + 32) >> 6, (4 * (o[:, 1] + o[:, 2]) + 32) >> 6]
+    for x in outs:
+        assert x.min() >= -32768 and x.max() <= 32767
