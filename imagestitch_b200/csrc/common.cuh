@@ -7,6 +7,7 @@
 #include <cstdint>
 #include <cstdio>
 #include <cstring>
+#include <functional>
 #include <map>
 #include <string>
 #include <vector>
@@ -53,6 +54,10 @@ struct is_ctx {
     int seam_waves = 0;                   // last is_seam_dp_find: waves of the batched path
     int seam_path = 0;                    // last is_seam_dp_find: 2 batched path, 1 per-pair concurrent path, 0 sequential loop
     is::HostPool* hpool = nullptr;        // host threads for the per-pair control work of the seam stage (hostpool.h)
+    // Work for a side stream that should start BEHIND the first kernels of the seam stage (toggles + special points: short, on the
+    // critical path, and five times slower when the pyramid kernels run beside them): the seam stage calls it once, right after
+    // it has queued those kernels; whoever set it runs it afterwards if it is still there.
+    std::function<int()> deferred_side_work;
 };
 
 namespace is {

@@ -194,10 +194,18 @@ int is_pipeline_run(is_ctx* ctx, int n, const is_mat* images, const is_camera* c
     } else {
         IS_REQUIRE(ctx, cfg.exposure == IS_EXPOSURE_NONE, IS_ERR_BAD_ARG, "unknown exposure mode");
     }
-    if (multiband) {            // image levels >= 2 of all images, one launch per level, behind the level-1 launches on the side stream
+    // image levels >= 2 of all images, one launch per level on the side stream.  With a seam stage to come they are queued from
+    // inside it, behind its first two kernels (is_ctx::deferred_side_work); otherwise now.
+    auto upper_levels = [ctx, side, bl]() -> int {
         if (side != ctx) IS_TRY(stream_after(ctx, side->stream, ctx->stream));   // level 1 may have come from the fused warp kernel (caller's stream)
         const int rc = blender_build_upper_levels(bl, side);
-        if (rc != IS_OK) { if (ctx->last_error.empty()) ctx->last_error = side->last_error; return rc; }
+        if (rc != IS_OK && ctx->last_error.empty()) ctx->last_error = side->last_error;
+        return rc;
+    };
+    struct ClearDeferred { is_ctx* c; ~ClearDeferred() { c->deferred_side_work = nullptr; } } clear_deferred{ctx};
+    if (multiband) {
+        if (cfg.seam == IS_SEAM_DP && side != ctx) ctx->deferred_side_work = upper_levels;
+        else IS_TRY(upper_levels());
     }
     if (cfg.seam_dilate > 0)   // masks_warped of [SEAM]:1267: the seam finder changes `masks` in place
         for (int i = 0; i < n; ++i) {
@@ -211,6 +219,11 @@ int is_pipeline_run(is_ctx* ctx, int n, const is_mat* images, const is_camera* c
     if (cfg.seam == IS_SEAM_DP) {
         IS_REQUIRE(ctx, cfg.seam_cost == IS_COST_COLOR || cfg.seam_cost == IS_COST_COLOR_GRAD, IS_ERR_BAD_ARG, "unknown seam cost function");
         IS_TRY(seam_find_device(ctx, n, warped.data(), corners.data(), masks.data(), cfg.seam_cost));
+        if (ctx->deferred_side_work) {                       // the seam stage had nothing to query (no overlapping pair) or took another path
+            std::function<int()> f = std::move(ctx->deferred_side_work);
+            ctx->deferred_side_work = nullptr;
+            IS_TRY(f());
+        }
     } else {
         IS_REQUIRE(ctx, cfg.seam == IS_SEAM_NONE, IS_ERR_BAD_ARG, "unknown seam mode");
     }

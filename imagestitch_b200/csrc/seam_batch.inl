@@ -678,6 +678,11 @@ static int run_structure_query(is_ctx* ctx, StructureQuery& Q) {
         dim3 grid(div_up(max_iw, 512), div_up(max_ih, 4 * SP_ROWS), (unsigned)np);
         IS_LAUNCH(ctx, k_special_points_batch, grid, 128, 0, sj_d);
     }
+    if (ctx->deferred_side_work) {                                      // see common.cuh: the side stream's work goes behind these kernels
+        std::function<int()> f = std::move(ctx->deferred_side_work);
+        ctx->deferred_side_work = nullptr;
+        IS_TRY(f());
+    }
     const unsigned char* h = nullptr;                                   // view of the pinned bounce buffer, valid until the next download
     IS_TRY(download_view(ctx, base, dl_bytes, reinterpret_cast<const void**>(&h)));
     const int* hdr = reinterpret_cast<const int*>(h + off_hdr);

@@ -497,8 +497,11 @@ __global__ void __launch_bounds__(WG_THREADS) k_warp_g1(WarpG1Args A) {
             const int q0 = x_img0 >> 2, q1 = (x_img1 + 3) >> 2;                                         // quads of four image columns
             const int nq = q1 - q0, nrow = y_img1 - y_img0;
             const bool aligned = ((reinterpret_cast<uintptr_t>(A.dst) | A.dstep) & 3) == 0 && ((reinterpret_cast<uintptr_t>(A.mask) | A.mstep) & 3) == 0;
-            for (int e = tid; e < nq * nrow; e += WG_THREADS) {
-                const int yy = y_img0 + e / nq, x4 = 4 * (q0 + e % nq);
+            for (int e = tid >> 5; e < nrow * ((nq + 31) >> 5); e += WG_THREADS >> 5) {        // one warp per row (and per 32 quads of it: a tile row has 31 or 32)
+                const int chunks = (nq + 31) >> 5;
+                const int ry = chunks == 1 ? e : e / chunks, qq = (chunks == 1 ? 0 : (e % chunks) << 5) + (tid & 31);
+                if (qq >= nq) continue;
+                const int yy = y_img0 + ry, x4 = 4 * (q0 + qq);
                 const uint32_t* t = &tile[yy + A.top - fy_lo][0] + (A.left - fx_lo);                    // t[image x] = frame pixel
                 uint8_t* d = A.dst + (size_t)yy * A.dstep + 3 * (size_t)x4;
                 uint8_t* m = A.mask + (size_t)yy * A.mstep + x4;
@@ -526,10 +529,13 @@ __global__ void __launch_bounds__(WG_THREADS) k_warp_g1(WarpG1Args A) {
         const int r = e / WG_TX, ox = e % WG_TX;
         const uint32_t* p = &tile[r][2 * ox];
         const uint32_t p0 = p[0], p1 = p[1], p2 = p[2], p3 = p[3], p4 = p[4];
+        // channel c of four neighbouring pixels gathered into one word (three byte permutes), the taps 1 4 6 4 as one byte dot product
 #pragma unroll
         for (int c = 0; c < 3; ++c) {
-            const int sft = 8 * c;
-            hsum[r][ox][c] = (int16_t)(((p0 >> sft) & 255u) + 4 * ((p1 >> sft) & 255u) + 6 * ((p2 >> sft) & 255u) + 4 * ((p3 >> sft) & 255u) + ((p4 >> sft) & 255u));
+            const uint32_t w01 = __byte_perm(p0, p1, (uint32_t)c | ((uint32_t)(4 + c) << 4));
+            const uint32_t w23 = __byte_perm(p2, p3, (uint32_t)c | ((uint32_t)(4 + c) << 4));
+            const uint32_t w = __byte_perm(w01, w23, 0x5410u);
+            hsum[r][ox][c] = (int16_t)(__dp4a(w, 0x04060401u, (p4 >> (8 * c)) & 255u));
         }
     }
     __syncthreads();
