@@ -1156,6 +1156,8 @@ struct FlatMap {
     }
 };
 
+#include "seam_dp_launch.inl"
+
 struct DbgTimer {   // IS_SEAM_DEBUG=1: host wall-clock per section (includes the device work it waits for)
     bool on; std::chrono::steady_clock::time_point t;
     DbgTimer() : on(getenv("IS_SEAM_DEBUG") != nullptr), t(std::chrono::steady_clock::now()) {}
@@ -1434,8 +1436,8 @@ int PairSeam::estimate_and_update(int c1, int c2, Pt p1, Pt p2) {
     const int nt = std::min(1024, div_up(div_up(lanes, lpt), 32) * 32);
     const int pitch = nt * lpt;                            // padded row length (multiple of 128 lanes)
     IS_REQUIRE(ctx, pitch >= lanes && pitch <= 12 * 1024, IS_ERR_UNSUPPORTED, "seam component wider than 12288 lanes");
-    IS_TRY(P.alloc(ctx, sizeof(float) * (size_t)pitch * steps + 64));
-    IS_TRY(Q.alloc(ctx, sizeof(float) * (size_t)pitch * steps + 64));
+    IS_TRY(P.alloc(ctx, sizeof(float) * (size_t)pitch * (steps + DP_ROW_PAD) + 64));     // spare rows: k_seam_fwd fetches past the last step
+    IS_TRY(Q.alloc(ctx, sizeof(float) * (size_t)pitch * (steps + DP_ROW_PAD) + 64));
     IS_TRY(control.alloc(ctx, (size_t)pitch * steps + 64));
     IS_TRY(seam_lane.alloc(ctx, sizeof(int) * ((size_t)steps + 1)));   // [steps] = "destination reached" flag: one download for both
     const int dx1 = unionTl.x - tl1_.x, dy1 = unionTl.y - tl1_.y, dx2 = unionTl.x - tl2_.x, dy2 = unionTl.y - tl2_.y;
@@ -1466,7 +1468,25 @@ int PairSeam::estimate_and_update(int c1, int c2, Pt p1, Pt p2) {
     A.s0 = horizontal ? src.x : src.y; A.lane0 = horizontal ? src.y : src.x;
     A.s1 = horizontal ? dst.x : dst.y; A.lane1 = horizontal ? dst.y : dst.x;
     A.seam_lane = seam_lane.as<int>(); A.reached = seam_lane.as<int>() + steps;
-    {
+    // the forward pass of the batched path (halo windows, register ring, clusters) + parallel back-track, one seam per launch;
+    // IS_PAIR_DP_V0=1 keeps round 1's kernel (TMA ring, block barrier per step, back-track inside)
+    DpShape shape;
+    dp_choose_shape(lanes, steps, A.s0, A.s1, dp_variant_default(), &shape);
+    DevBuf bt_map, dp_tab;
+    if (shape.v1 && shape.pitch == pitch && !getenv("IS_PAIR_DP_V0")) {
+        const int nchunks = div_up(A.s1 - A.s0, BT_CHUNK);
+        IS_TRY(bt_map.alloc(ctx, sizeof(short) * (size_t)std::max(nchunks, 1) * pitch + 64));
+        A.G = shape.G; A.D = shape.D;
+        struct alignas(16) Tables { DpArgs a; alignas(16) BtArgs b; } tabs;
+        std::memset(&tabs, 0, sizeof(tabs));
+        tabs.a = A;
+        tabs.b.A = A; tabs.b.map = bt_map.as<short>(); tabs.b.nchunks = nchunks;
+        IS_TRY(dp_tab.alloc(ctx, sizeof(Tables)));
+        IS_TRY(upload(ctx, dp_tab.p, &tabs, sizeof(Tables)));
+        IS_CUDA(ctx, cudaMemsetAsync(seam_lane.p, 0, sizeof(int) * ((size_t)steps + 1), ctx->stream));
+        const Tables* td = dp_tab.as<Tables>();
+        IS_TRY(launch_dp_all(ctx, std::vector<DpShape>(1, shape), &td->a, &td->b));
+    } else {
         const size_t row_pair = 2 * sizeof(float) * (size_t)pitch;            // one row of P + one of Q
         const size_t budget = 192 * 1024;
         // Two stages of as many rows as fit: the per-stage work (mbarrier wait, refill issued by thread 0 while the other warps
