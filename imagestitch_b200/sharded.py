@@ -42,6 +42,7 @@ class ShardPlan:
     owner: list = field(default_factory=list)
     pairs: list = field(default_factory=list)        # active pairs in the reference's order ([SEAM]:100-111)
     cuts: list = field(default_factory=list)         # panorama columns (relative to roi.x): rank r owns [cuts[r], cuts[r+1])
+    pairs_depend: bool = False                       # set (on every rank alike) once a step's proofs have failed: see stitch_general
 
     @staticmethod
     def build(corners, sizes, roi, world, num_bands):
@@ -317,10 +318,13 @@ class ShardedStitcher:
                 final_buf[i] = be.empty((plan.sizes[i][1], plan.sizes[i][0]), np.uint8)
                 if i in needed_by[rank]:
                     be.blend_feed_early(bh, warped[i], final_buf[i], plan.corners[i], i + 1)
+        # A panorama geometry whose pairs were found to depend on each other (the overlaps of a mosaic meet at the grid corners) goes
+        # straight to the reference's loop on the following steps: the speculative runs and their proofs would fail again.
+        speculate = not getattr(plan, "pairs_depend", False) or os.environ.get("IS_SHARD_ALWAYS_SPECULATE") == "1"
         # ---- X1: right images of boundary pairs -> owner of the left image
         sends, recvs = [], []
         seen = set()
-        for k, (i, j) in enumerate(plan.pairs):
+        for k, (i, j) in enumerate(plan.pairs if speculate else []):
             src, dst = plan.owner[j], plan.pair_owner(k)
             if src == dst or (j, dst) in seen:
                 continue
@@ -334,7 +338,7 @@ class ShardedStitcher:
         comm.exchange(sends, recvs)
         lap("x1")
         # ---- seam: speculative runs of the pairs this rank owns
-        my_pairs = [k for k in range(len(plan.pairs)) if plan.pair_owner(k) == rank]
+        my_pairs = [k for k in range(len(plan.pairs)) if plan.pair_owner(k) == rank] if speculate else []
         outs, handles = {}, {}
 
         def run(k):
@@ -347,7 +351,7 @@ class ShardedStitcher:
         lap("seam_runs")
         # ---- X2: pair results to whoever needs them (final masks of the images' owners, validation of later pairs)
         sends, recvs = [], []
-        for k, (i, j) in enumerate(plan.pairs):
+        for k, (i, j) in enumerate(plan.pairs if speculate else []):
             src = plan.pair_owner(k)
             for img in (i, j):
                 dsts = {plan.owner[img]} | {plan.pair_owner(k2) for k2 in range(k + 1, len(plan.pairs)) if img in plan.pairs[k2]}
@@ -382,9 +386,11 @@ class ShardedStitcher:
         be.run_concurrently(check, my_pairs)
         be.sync()
         lap("seam_checks")
-        ok = comm.all_min(1 if all(verdict.values()) else 0, be.device)
+        ok = comm.all_min(1 if all(verdict.values()) else 0, be.device) if speculate else 0
         if os.environ.get("IS_SHARDED_FORCE_FALLBACK") == "1":      # test hook: exercise the sequential fallback
             ok = 0
+        if speculate and not ok and os.environ.get("IS_SHARDED_FORCE_FALLBACK") != "1":
+            plan.pairs_depend = True
         self.info["seam_speculation"] = ok
         for k in my_pairs:
             be.pair_free(handles[k])

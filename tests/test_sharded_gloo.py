@@ -141,6 +141,9 @@ def _worker(rank, world, port, case, result_path):
     kind = os.environ.get("IS_TEST_EARLY_FEED")
     st = sharded.ShardedStitcher((OracleBackendStrip if kind == "strip" else OracleBackendEarly if kind == "1" else OracleBackend)(O), sharded.Comm(dist), nb)
     res = st.stitch(mine, Ks, Rs, scale, plan)
+    if os.environ.get("IS_TEST_SECOND_STEP") == "1":      # a second panorama of the same geometry: a plan whose proofs failed skips the speculation
+        plan.pairs_depend = True
+        res = st.stitch(mine, Ks, Rs, scale, plan)
     strips = [None] * world
     dist.all_gather_object(strips, (res["x0"], res["x1"], res["pano"].numpy(), res["pano_mask"].numpy(),
                                     {k: v.numpy() for k, v in res["seam_masks"].items()}, st.info))
@@ -211,6 +214,20 @@ def test_three_rank_mosaic(tmp_path, monkeypatch):
     out = tmp_path / "result.txt"
     mp.spawn(_worker, args=(3, 29500 + (os.getpid() + 977) % 2000, (12, 112, 84, 0.3, 3), str(out)), nprocs=3, join=True)
     assert out.read_text().split()[0] == "1", "sharded mosaic differs from the single-process oracle"
+
+
+def test_three_rank_mosaic_second_step_skips_speculation(tmp_path, monkeypatch):
+    """A plan marked `pairs_depend` (a step's proofs failed) goes straight to the reference's loop: same panorama, same masks."""
+    import oracle
+    oracle.build()
+    monkeypatch.setenv("IS_TEST_EARLY_FEED", "1")
+    monkeypatch.setenv("IS_TEST_GRID_ROWS", "2")
+    monkeypatch.setenv("IS_TEST_SECOND_STEP", "1")
+    out = tmp_path / "result.txt"
+    mp.spawn(_worker, args=(3, 29500 + (os.getpid() + 1201) % 2000, (12, 112, 84, 0.3, 3), str(out)), nprocs=3, join=True)
+    ok, spec = out.read_text().split()
+    assert ok == "1", "second step of the sharded mosaic differs from the single-process oracle"
+    assert spec == "0"
 
 
 def test_shard_plan_geometry():
