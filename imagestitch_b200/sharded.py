@@ -196,6 +196,14 @@ class ShardedStitcher:
             if i in needed_by[rank]:
                 be.blend_feed_early(bh, warped[i], mask[i], plan.corners[i], i + 1)
         comm.wait(x1_pending)
+        # the neighbour's first image is here: if my strip blends it, its pyramid is built during the seam stage as well; its mask
+        # buffer (halo_true) is filled by X2 and completed by X3, in place, before the blend reads it
+        halo_true, halo_fed = None, False
+        if has_right:
+            halo_true = be.empty((plan.sizes[b + 1][1], plan.sizes[b + 1][0]), np.uint8)
+            if (b + 1) in needed_by[rank]:
+                be.blend_feed_early(bh, warped[b + 1], halo_true, plan.corners[b + 1], b + 2)
+                halo_fed = True
         lap("x1")
         # ---- seam: one batched call over my images + the halo image
         entry_b = be.copy_of(mask[b]) if has_right else None
@@ -212,7 +220,6 @@ class ShardedStitcher:
             sends.append((rank - 1, after_own))
             recvs.append((rank - 1, from_left))
         if has_right:
-            halo_true = be.empty((plan.sizes[b + 1][1], plan.sizes[b + 1][0]), np.uint8)
             sends.append((rank + 1, halo_mask))
             recvs.append((rank + 1, halo_true))
         comm.exchange(sends, recvs)
@@ -242,7 +249,7 @@ class ShardedStitcher:
         comm.exchange(sends, recvs)
         lap("x3")
         for i in needed_by[rank]:
-            if i not in mine:
+            if i not in mine and not (halo_fed and i == b + 1):
                 be.blend_feed(bh, warped[i], final[i], plan.corners[i], i + 1)
         pano, pmask = be.blend_finish(bh, x0, x1)
         self.info["needed_images"] = needed_by[rank]
@@ -279,7 +286,8 @@ class ShardedStitcher:
                     if not holds:
                         warped[i] = be.empty((plan.sizes[i][1], plan.sizes[i][0], 3), np.uint8)
                         recvs.append((src, warped[i]))
-                    final[i] = be.empty((plan.sizes[i][1], plan.sizes[i][0]), np.uint8)
+                    if not (holds and i in final):            # the held image's mask buffer is already known to the blender (early feed): fill it in place
+                        final[i] = be.empty((plan.sizes[i][1], plan.sizes[i][0]), np.uint8)
                     recvs.append((src, final[i]))
         return sends, recvs
 
