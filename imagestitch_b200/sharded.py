@@ -224,16 +224,13 @@ class ShardedStitcher:
             recvs.append((rank + 1, halo_true))
         comm.exchange(sends, recvs)
         lap("x2")
-        # The boundary pair on the mask image b+1 really has at that point of the reference's loop: proven beside the rest of the step
-        # (worker thread and stream, on a copy -- X3 completes halo_true in place) where the backend can, and the verdict of all
-        # ranks (MIN) is only formed at the end: the halo exchange and the blend are queued on the assumption that every boundary
-        # pair is proven, which is the rule; a rank that waited here would wait for the slowest rank of the box in every step.
-        ok, check_pending = 1, None
-        if has_right:
-            if hasattr(be, "pair_same_structure_start"):
-                check_pending = be.pair_same_structure_start(entry_b, halo_entry, be.copy_of(halo_true), plan.corners[b], plan.corners[b + 1])
-            else:
-                ok = 1 if be.pair_same_structure(entry_b, halo_entry, halo_true, plan.corners[b], plan.corners[b + 1]) else 0
+        ok = 1
+        if has_right:                                 # the boundary pair on the mask image b+1 really has at that point of the reference's loop
+            ok = 1 if be.pair_same_structure(entry_b, halo_entry, halo_true, plan.corners[b], plan.corners[b + 1]) else 0
+        # The verdict of all ranks (MIN) is only READ at the end of the step: the halo exchange and the blend are queued on the
+        # assumption that every boundary pair is proven, which is the rule; a rank that waited here would wait for the slowest
+        # rank of the box in the middle of every step.
+        verdict = comm.all_min_start(ok, be.device)
         lap("check")
         if has_left:                                  # the boundary pair's clears (computed by the left neighbour) inside its rectangle
             i, j = a - 1, a
@@ -257,9 +254,7 @@ class ShardedStitcher:
         pano, pmask = be.blend_finish(bh, x0, x1)
         self.info["needed_images"] = needed_by[rank]
         lap("blend")
-        if check_pending is not None:
-            ok = 1 if be.pair_same_structure_result(check_pending) else 0
-        ok = comm.all_min(ok, be.device)
+        ok = comm.all_min_result(verdict)
         if os.environ.get("IS_SHARDED_FORCE_FALLBACK") == "1":
             ok = 0
         self.info["seam_speculation"] = ok
@@ -521,28 +516,6 @@ class GpuBackend:
 
     def pair_same_structure(self, mask_i, mask_j_a, mask_j_b, tl_i, tl_j):
         return self.S.DpSeamFinder(self.ctx, "COLOR").pair_same_structure(mask_i, mask_j_a, mask_j_b, tl_i, tl_j)
-
-    def pair_same_structure_start(self, mask_i, mask_j_a, mask_j_b, tl_i, tl_j):
-        """The same check on a worker thread / context / stream, so that the caller can go on queuing the halo exchange and the
-        blend; the masks must not change until pair_same_structure_result() has returned (pass copies)."""
-        self.torch.cuda.current_stream(self.device).synchronize()      # the masks were produced on the caller's stream
-        box = {}
-
-        def work():
-            try:
-                box["ok"] = self.S.DpSeamFinder(self.workers[0], "COLOR").pair_same_structure(mask_i, mask_j_a, mask_j_b, tl_i, tl_j)
-            except Exception as e:      # noqa: BLE001 - re-raised by the caller
-                box["err"] = e
-        th = threading.Thread(target=work)
-        th.start()
-        return th, box
-
-    def pair_same_structure_result(self, pending):
-        th, box = pending
-        th.join()
-        if "err" in box:
-            raise box["err"]
-        return box["ok"]
 
     def _ctx(self):
         return getattr(self.tls, "ctx", self.ctx)
