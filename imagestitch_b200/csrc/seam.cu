@@ -27,7 +27,9 @@
 #include <cstdlib>
 #include <limits>
 #include <cmath>
+#include <deque>
 #include <map>
+#include <memory>
 #include <set>
 #include <thread>
 #include <tuple>
@@ -2443,7 +2445,7 @@ int is_debug_seam_pair_plan(const uint8_t* mask1, int rows1, int cols1, size_t s
     std::vector<int32_t> v;
     size_t nrec = 0;
     for (auto& c : P.contours) nrec += c.size();
-    v.push_back(P.too_many_runs); v.push_back(P.unsupported); v.push_back(P.ncomps); v.push_back((int)P.ops.size()); v.push_back((int)nrec);
+    v.push_back(P.too_many_runs); v.push_back(P.unsupported ? 1 : (P.blocked ? 2 : 0)); v.push_back(P.ncomps); v.push_back((int)P.ops.size()); v.push_back((int)nrec);   // 2: staged plan, only the first round is listed
     v.push_back(P.unionTl.x); v.push_back(P.unionTl.y);
     for (int st : P.states) v.push_back(st);
     for (auto& op : P.ops) for (int q : {op.kind, op.c1, op.c2, op.p1.x, op.p1.y, op.p2.x, op.p2.y, op.rx, op.ry, op.rw, op.rh}) v.push_back(q);
@@ -2491,46 +2493,61 @@ int is_debug_seam_pair_finish(uint8_t* mask1, int rows1, int cols1, size_t step1
     if (P.too_many_runs) return IS_ERR_UNSUPPORTED;
     P.plan();
     if (P.unsupported) return IS_ERR_UNSUPPORTED;
-    std::vector<UlsRuns> uls;
-    uls.reserve(P.ops.size());
+    // rounds of the staged plan: the seams are consumed in the order the operations are planned
+    std::vector<std::unique_ptr<UlsRuns>> uls;
     std::vector<std::vector<int>> lanes;
-    lanes.reserve(P.ops.size());
-    std::vector<const std::vector<Interval>*> flips;
+    lanes.reserve(256);
+    std::vector<const std::vector<Interval>*> flips, round_flips;
     size_t pos = 0;
-    for (const SeamOp& op : P.ops) {
-        if (op.kind != 1) continue;
-        if (pos >= seams_len) return IS_ERR_BAD_ARG;
-        const int npts = seams[pos++];
-        if (npts == 0) { flips.push_back(nullptr); continue; }
-        if (pos + 2 * (size_t)npts > seams_len) return IS_ERR_BAD_ARG;
-        Pt src{op.p1.x - op.rx, op.p1.y - op.ry}, dst{op.p2.x - op.rx, op.p2.y - op.ry};
-        const bool horizontal = std::abs(dst.x - src.x) > std::abs(dst.y - src.y);
-        bool swapped = false;
-        if (horizontal) { if (src.x > dst.x) { std::swap(src, dst); swapped = true; } }
-        else if (src.y > dst.y) { std::swap(src, dst); swapped = true; }
-        const int s0 = horizontal ? src.x : src.y, s1 = horizontal ? dst.x : dst.y;
-        if (npts != s1 - s0 + 1) return IS_ERR_BAD_ARG;
-        lanes.emplace_back((size_t)npts);
-        for (int i = 0; i < npts; ++i) {
-            const int k = swapped ? npts - 1 - i : i;                          // trace order tip 1 -> tip 2; steps ascend from the (swapped) source
-            const int x = seams[pos + 2 * (size_t)k] - P.unionTl.x - op.rx, y = seams[pos + 2 * (size_t)k + 1] - P.unionTl.y - op.ry;
-            lanes.back()[(size_t)i] = horizontal ? y : x;
-            if ((horizontal ? x : y) != s0 + i) return IS_ERR_BAD_ARG;
+    for (;;) {
+        round_flips.clear();
+        for (size_t q = P.round_begin; q < P.ops.size(); ++q) {
+            const SeamOp op = P.ops[q];
+            if (op.kind != 1) continue;
+            if (pos >= seams_len) return IS_ERR_BAD_ARG;
+            const int npts = seams[pos++];
+            if (npts == 0) { flips.push_back(nullptr); round_flips.push_back(nullptr); continue; }
+            if (pos + 2 * (size_t)npts > seams_len) return IS_ERR_BAD_ARG;
+            Pt src{op.p1.x - op.rx, op.p1.y - op.ry}, dst{op.p2.x - op.rx, op.p2.y - op.ry};
+            const bool horizontal = std::abs(dst.x - src.x) > std::abs(dst.y - src.y);
+            bool swapped = false;
+            if (horizontal) { if (src.x > dst.x) { std::swap(src, dst); swapped = true; } }
+            else if (src.y > dst.y) { std::swap(src, dst); swapped = true; }
+            const int s0 = horizontal ? src.x : src.y, s1 = horizontal ? dst.x : dst.y;
+            if (npts != s1 - s0 + 1) return IS_ERR_BAD_ARG;
+            if (lanes.size() == lanes.capacity()) return IS_ERR_UNSUPPORTED;          // the lane arrays must not move
+            lanes.emplace_back((size_t)npts);
+            for (int i = 0; i < npts; ++i) {
+                const int k = swapped ? npts - 1 - i : i;                          // trace order tip 1 -> tip 2; steps ascend from the (swapped) source
+                const int x = seams[pos + 2 * (size_t)k] - P.unionTl.x - op.rx, y = seams[pos + 2 * (size_t)k + 1] - P.unionTl.y - op.ry;
+                lanes.back()[(size_t)i] = horizontal ? y : x;
+                if ((horizontal ? x : y) != s0 + i) return IS_ERR_BAD_ARG;
+            }
+            pos += 2 * (size_t)npts;
+            uls.emplace_back(new UlsRuns());
+            UlsRuns& U = *uls.back();
+            U.P = &P; U.op = op; U.horizontal = horizontal; U.s0 = s0; U.nseam = npts; U.lane = lanes.back().data();
+            auto t0 = std::chrono::steady_clock::now();
+            U.run();
+            if (getenv("IS_DEBUG_PLAN_TIMING")) fprintf(stderr, "[finish timing] UlsRuns::run %.3f ms (nc=%zu, nseam=%d, flips=%zu)\n",
+                                                        std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - t0).count(), P.contours[(size_t)op.c1].size(), npts, U.flips.size());
+            if (U.too_many_regions) return IS_ERR_UNSUPPORTED;
+            flips.push_back(&U.flips);
+            round_flips.push_back(&U.flips);
         }
-        pos += 2 * (size_t)npts;
-        uls.emplace_back();
-        UlsRuns& U = uls.back();
-        U.P = &P; U.op = op; U.horizontal = horizontal; U.s0 = s0; U.nseam = npts; U.lane = lanes.back().data();
-        auto t0 = std::chrono::steady_clock::now();
-        U.run();
-        if (getenv("IS_DEBUG_PLAN_TIMING")) fprintf(stderr, "[finish timing] UlsRuns::run %.3f ms (nc=%zu, nseam=%d, flips=%zu)\n",
-                                                    std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - t0).count(), P.contours[(size_t)op.c1].size(), npts, U.flips.size());
-        if (U.too_many_regions) return IS_ERR_UNSUPPORTED;
-        flips.push_back(&U.flips);
+        if (!P.blocked) break;
+        if (!P.apply_round(round_flips)) return IS_ERR_UNSUPPORTED;
+        P.plan_resume();
+        if (P.unsupported) return IS_ERR_UNSUPPORTED;
     }
     std::vector<ClearIv> clears;
     auto t1 = std::chrono::steady_clock::now();
-    pair_clear_intervals(P, flips, &clears);
+    if (P.staged) {
+        if (!P.apply_round(round_flips)) return IS_ERR_UNSUPPORTED;
+        P.final_clears(&clears);
+    } else {
+        pair_clear_intervals(P, flips, &clears);
+    }
     if (getenv("IS_DEBUG_PLAN_TIMING")) fprintf(stderr, "[finish timing] pair_clear_intervals %.3f ms (%zu intervals)\n",
                                                 std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - t1).count(), clears.size());
     for (const ClearIv& c : clears)

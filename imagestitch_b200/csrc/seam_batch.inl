@@ -630,12 +630,22 @@ static int seam_batch_wave(is_ctx* ctx, const std::vector<std::pair<int, int>>& 
             PR.resize(np);
             break;
         }
-    // ---- C: plan -> device tables
-    std::vector<SeamJobHost> jobs;
+    // ---- C + D, in rounds: normally one; a pair whose plan stopped in front of a second seam on a component already cut (staged
+    //      plan, seam_runs.inl) goes on in the next round with the labels its first seams have left
     const int dp_variant = dp_variant_default();
-    for (size_t k = 0; k < np; ++k)
-        for (const SeamOp& op : PR[k].ops) {
+    std::deque<SeamJobHost> all_jobs;                                  // the finished seams of all rounds: per pair in the order they were estimated
+    std::vector<std::vector<const std::vector<Interval>*>> flips_of(np), round_flips(np);
+    std::vector<char> in_round(np, 1);
+    size_t limit = np;                                                 // pairs [0, limit) can still be accepted
+    for (int round = 0;; ++round) {
+    std::vector<SeamJobHost> jobs;
+    for (size_t k = 0; k < limit; ++k) {
+        if (!in_round[k]) continue;
+        round_flips[k].clear();
+        for (size_t q = PR[k].round_begin; q < PR[k].ops.size(); ++q) {
+            const SeamOp& op = PR[k].ops[q];
             if (op.kind != 1) continue;                                // wholesale relabels never reach the device: the labels only feed the cost kernel
+            if ((std::abs(op.p2.x - op.p1.x) > std::abs(op.p2.y - op.p1.y) ? op.rh : op.rw) > 12 * 1024 - 128) { limit = std::min(limit, k); break; }   // wider than the DP tables: general path
             jobs.emplace_back();
             SeamJobHost& J = jobs.back();
             J.pair = (int)k; J.op = op;
@@ -651,6 +661,9 @@ static int seam_batch_wave(is_ctx* ctx, const std::vector<std::pair<int, int>>& 
             IS_REQUIRE(ctx, J.pitch >= J.lanes && J.pitch <= 12 * 1024, IS_ERR_INTERNAL, "seam wider than planned");
             J.nseam = J.s1 - J.s0 + 1;
         }
+    }
+    if (limit == 0) { *first_unsupported = true; return IS_OK; }
+    while (!jobs.empty() && (size_t)jobs.back().pair >= limit) jobs.pop_back();   // pairs are visited in order: the dropped ones are at the end
     const size_t nj = jobs.size();
     // COLOR costs read the component's runs; the label image (k_label_window_batch) is only built for the cost kernels that still
     // want it: COLOR_GRAD, or a component with more than COST_RUNS runs in a row
@@ -824,21 +837,58 @@ static int seam_batch_wave(is_ctx* ctx, const std::vector<std::pair<int, int>>& 
         IS_TRY(download_view(ctx, base + off_res_all, sizeof(int) * res_total_ints, reinterpret_cast<const void**>(&res_h)));
     }
     tm.lap("C labels, costs, DP");
-    // ---- host: updateLabelsUsingSeam per seam, then the final mask update of the pair as clear intervals -- one task per pair
-    std::vector<std::vector<ClearIv>> clears(np);
+    // ---- host: updateLabelsUsingSeam per seam -- one task per pair
     std::vector<std::vector<size_t>> jobs_of(np);
     for (size_t j = 0; j < nj; ++j) jobs_of[(size_t)jobs[j].pair].push_back(j);   // plan order
-    std::vector<std::vector<int>> rs_all(np);
-    std::vector<std::vector<int4>> iv_all(np);
-    pool->run(np, [&](size_t k) {
-        std::vector<const std::vector<Interval>*> fl;
+    pool->run(limit, [&](size_t k) {
         for (size_t j : jobs_of[k]) {
             SeamJobHost& J = jobs[j];
             J.status = seam_job_finish(ctx, PR[k], J, res_h + J.off_res, trace != nullptr);
             if (J.status != IS_OK) return;
-            fl.push_back(J.reached ? &J.uls.flips : nullptr);
         }
-        pair_clear_intervals(PR[k], fl, &clears[k]);
+    });
+    for (auto& J : jobs) {
+        if (J.status == IS_ERR_UNSUPPORTED) { limit = std::min(limit, (size_t)J.pair); continue; }   // that pair takes the general path
+        if (J.status != IS_OK) return J.status;
+    }
+    if (limit == 0) { *first_unsupported = true; return IS_OK; }
+    for (auto& J : jobs) {                                             // keep the finished seams (their flips must not move any more)
+        if ((size_t)J.pair >= limit) continue;
+        all_jobs.emplace_back(std::move(J));
+        SeamJobHost& K = all_jobs.back();
+        const std::vector<Interval>* f = K.reached ? &K.uls.flips : nullptr;
+        flips_of[(size_t)K.pair].push_back(f);
+        round_flips[(size_t)K.pair].push_back(f);
+    }
+    // staged pairs: the round's relabels into the runs, then on with the conflict loop
+    bool more = false;
+    std::vector<char> next_round(np, 0);
+    pool->run(limit, [&](size_t k) {
+        if (!in_round[k] || !PR[k].blocked) return;
+        if (round >= 32 || !PR[k].apply_round(round_flips[k])) { PR[k].unsupported = true; return; }
+        PR[k].plan_resume();
+        next_round[k] = 1;
+    });
+    for (size_t k = 0; k < limit; ++k) {
+        if (PR[k].unsupported || PR[k].too_many_runs) { limit = k; break; }   // the plan does not cover what came up: general path from this pair on
+        more = more || next_round[k];
+    }
+    if (limit == 0) { *first_unsupported = true; return IS_OK; }
+    in_round = next_round;
+    if (!more) break;
+    }   // rounds
+    // ---- host: the final mask update of every pair as clear intervals + the upload tables -- one task per pair
+    std::vector<std::vector<ClearIv>> clears(np);
+    std::vector<std::vector<int>> rs_all(np);
+    std::vector<std::vector<int4>> iv_all(np);
+    std::vector<char> clears_failed(np, 0);
+    pool->run(limit, [&](size_t k) {
+        if (PR[k].staged) {
+            if (!PR[k].apply_round(round_flips[k])) { clears_failed[k] = 1; return; }     // the last round's relabels
+            PR[k].final_clears(&clears[k]);
+        } else {
+            pair_clear_intervals(PR[k], flips_of[k], &clears[k]);
+        }
         // the pair's upload tables while the task is at it: row_start[ih + 1] and the intervals
         const PairRuns& P = PR[k];
         const int iy = P.iTl.y - P.unionTl.y, ih = P.iBr.y - P.iTl.y;
@@ -853,11 +903,7 @@ static int seam_batch_wave(is_ctx* ctx, const std::vector<std::pair<int, int>>& 
         }
         for (int r = 0; r < ih; ++r) rs[(size_t)r + 1] += rs[(size_t)r];
     });
-    size_t limit = np;                                                 // pairs [0, limit) can still be accepted
-    for (auto& J : jobs) {
-        if (J.status == IS_ERR_UNSUPPORTED) { limit = std::min(limit, (size_t)J.pair); continue; }   // that pair takes the general path
-        if (J.status != IS_OK) return J.status;
-    }
+    for (size_t k = 0; k < limit; ++k) if (clears_failed[k]) { limit = k; break; }
     if (limit == 0) { *first_unsupported = true; return IS_OK; }
     clears.resize(limit);
     tm.lap("D host: updateLabelsUsingSeam on runs, clear intervals");
@@ -1016,7 +1062,7 @@ static int seam_batch_wave(is_ctx* ctx, const std::vector<std::pair<int, int>>& 
     }
     if (trace)
         for (size_t k = 0; k < limit; ++k)
-            for (auto& J : jobs) {
+            for (auto& J : all_jobs) {
                 if ((size_t)J.pair != k || J.trace.empty()) continue;
                 const size_t len = J.trace.size();
                 if (trace->buf && trace->len + len <= trace->cap) std::memcpy(trace->buf + trace->len, J.trace.data(), len * sizeof(int32_t));

@@ -96,9 +96,27 @@ public:
     // unused slots (0, 0); false when a row has more runs than cap
     bool component_runs(int c, int ry, int rh, int cap, std::vector<int2>* out) const;
     void plan();                                      // conflict loop -> ops, final_states
+    // Staged plan.  The conflict loop can decide everything before any seam is known -- except a SECOND seam estimation on a
+    // component a seam of this pair has already cut (curved mosaic masks leave an INTERS component two neighbours of the same
+    // image): its tips and its cost region depend on the first seam.  plan() then stops in front of that operation (`blocked`);
+    // once the seams of the operations planned so far are back, apply_round() writes their relabels into the runs and refreshes
+    // the contours, plan_resume() carries on.  A pair that has been through apply_round() is `staged`: its final mask update comes
+    // from the relabelled runs (final_clears) instead of pair_clear_intervals.
+    bool blocked = false, staged = false;
+    size_t round_begin = 0;                           // first operation of the current round in `ops`
+    std::vector<int> snap_row_off, snap_label;        // staged pairs: the runs as build() left them (what a validation compares with)
+    std::vector<ChangePt> snap_cps;
+    void plan_resume();
+    // seam_flips: UlsRuns::flips of the round's kind-1 operations in order (nullptr: estimateSeam failed); false: a row now has more runs than the tables hold
+    bool apply_round(const std::vector<const std::vector<struct Interval>*>& seam_flips);
+    void final_clears(std::vector<struct ClearIv>* out) const;
     bool same_structure(const PairRuns& o) const;
 
 private:
+    std::set<std::pair<int, int>> ed_;                // conflict-loop state between rounds: remaining edges, components cut by a seam of this round
+    std::vector<char> cut_;
+    void plan_loop();
+    bool relabel(int l_from, int l_to, const std::vector<struct Interval>* fl);   // fl == nullptr: every pixel of l_from
     int label_at(int x, int y) const;                 // label of a frame pixel from the runs (0 background, -1 outside the frame)
     void contour_rows();
     void find_edges();
@@ -217,18 +235,22 @@ bool PairRuns::same_window(const PairRuns& o) const {
     if (uw != o.uw || uh != o.uh || wx != o.wx || wy != o.wy || ww != o.ww || wh != o.wh || too_many_runs != o.too_many_runs) return false;
     auto state_of = [](const std::vector<int>& st, int label) { return (label >= 1 && label <= (int)st.size()) ? st[(size_t)label - 1] : -1; };
     const int x_lo = wx, x_hi = wx + ww;
+    // a staged pair is compared as build() left it, before its own seams were written into its runs
+    const std::vector<int>& o_row_off = o.staged ? o.snap_row_off : o.row_off;
+    const std::vector<ChangePt>& o_cps = o.staged ? o.snap_cps : o.cps;
+    const std::vector<int>& o_label = o.staged ? o.snap_label : o.cp_label;
     for (int y = wy; y < wy + wh; ++y) {
         // the label function of the row over [x_lo, x_hi) as (start, label) pieces, from either structure, walked in step
-        const int ab = row_off[(size_t)y], ae = row_off[(size_t)y + 1], bb = o.row_off[(size_t)y], be = o.row_off[(size_t)y + 1];
+        const int ab = row_off[(size_t)y], ae = row_off[(size_t)y + 1], bb = o_row_off[(size_t)y], be = o_row_off[(size_t)y + 1];
         int ia = ab, ib = bb;
         while (ia < ae && cps[(size_t)ia].x <= x_lo) ++ia;                  // ia: first change point right of x_lo
-        while (ib < be && o.cps[(size_t)ib].x <= x_lo) ++ib;
+        while (ib < be && o_cps[(size_t)ib].x <= x_lo) ++ib;
         int x = x_lo;
         for (;;) {
-            const int la = ia == ab ? 0 : cp_label[(size_t)ia - 1], lb = ib == bb ? 0 : o.cp_label[(size_t)ib - 1];
+            const int la = ia == ab ? 0 : cp_label[(size_t)ia - 1], lb = ib == bb ? 0 : o_label[(size_t)ib - 1];
             if (la != lb) return false;
             if (la > 0 && state_of(states, la) != state_of(o.states, la)) return false;
-            const int na = ia < ae ? std::min(cps[(size_t)ia].x, x_hi) : x_hi, nb = ib < be ? std::min(o.cps[(size_t)ib].x, x_hi) : x_hi;
+            const int na = ia < ae ? std::min(cps[(size_t)ia].x, x_hi) : x_hi, nb = ib < be ? std::min(o_cps[(size_t)ib].x, x_hi) : x_hi;
             if (na != nb) return false;
             x = na;
             if (x >= x_hi) break;
@@ -305,6 +327,7 @@ void PairRuns::contour_rows() {
             if (cps[(size_t)k].cls != 3) continue;
             const int a = cps[(size_t)k].x, b = k + 1 < re ? cps[(size_t)k + 1].x : uw;
             const int l = cp_label[(size_t)k];
+            if (!(states[(size_t)l - 1] & ST_INTERS)) continue;               // staged pairs: pixels a seam has handed to a FIRST / SECOND component
             const int left = a == 0 ? -1 : (k == rb ? 0 : cp_label[(size_t)k - 1]);
             const int right = b == uw ? -1 : (k + 1 < re ? cp_label[(size_t)k + 1] : 0);   // b < uw implies a following change point
             row_segs(y - 1, a, b, up);
@@ -436,10 +459,25 @@ bool PairRuns::get_seam_tips(int c1, int c2, Pt* p1, Pt* p2) const {
 void PairRuns::plan() {
     ops.clear();
     unsupported = false;
+    blocked = false;
+    staged = false;
+    round_begin = 0;
     final_states = states;
+    ed_ = edges;
+    cut_.assign((size_t)ncomps, 0);
+    plan_loop();
+}
+
+void PairRuns::plan_resume() {
+    blocked = false;
+    std::fill(cut_.begin(), cut_.end(), 0);           // the runs and contours are current again
+    plan_loop();
+}
+
+void PairRuns::plan_loop() {
+    const bool no_resume = getenv("IS_SEAM_NO_RESUME") != nullptr;   // test knob: such pairs go to the general path as before
     std::vector<int>& st = final_states;
-    std::set<std::pair<int, int>> ed = edges;
-    std::vector<char> stale((size_t)ncomps, 0);
+    std::set<std::pair<int, int>>& ed = ed_;
     auto only_one = [&](int comp) {
         auto begin = ed.lower_bound({comp, INT_MIN});
         auto end = ed.upper_bound({comp, INT_MAX});
@@ -457,20 +495,25 @@ void PairRuns::plan() {
         if (st[(size_t)c2] & ST_INTERS) { unsupported = true; return; }   // c2's geometry would have to be refreshed ([SEAM]:499-513)
         SeamOp op;
         op.c1 = c1; op.c2 = c2;
-        op.rx = tls[(size_t)c1].x; op.ry = tls[(size_t)c1].y;
-        op.rw = brs[(size_t)c1].x - tls[(size_t)c1].x; op.rh = brs[(size_t)c1].y - tls[(size_t)c1].y;
+        const bool empty_box = tls[(size_t)c1].x >= brs[(size_t)c1].x || tls[(size_t)c1].y >= brs[(size_t)c1].y;   // no pixel of c1 is left
+        op.rx = empty_box ? 0 : tls[(size_t)c1].x; op.ry = empty_box ? 0 : tls[(size_t)c1].y;
+        op.rw = empty_box ? 0 : brs[(size_t)c1].x - tls[(size_t)c1].x; op.rh = empty_box ? 0 : brs[(size_t)c1].y - tls[(size_t)c1].y;
         op.p1 = op.p2 = Pt{0, 0};
         if (only_one(c1)) {
             op.kind = 0;                                                     // a stale bounding box is a superset: good enough
             if (op.rw > 0 && op.rh > 0) ops.push_back(op);
             st[(size_t)c1] = st[(size_t)c2] == ST_FIRST ? ST_SECOND : ST_FIRST;
         } else {
-            if (stale[(size_t)c1]) { unsupported = true; return; }           // tips of a component a seam has already cut
+            if (cut_[(size_t)c1]) {                                          // tips of a component a seam of this round has already cut
+                if (no_resume) { unsupported = true; return; }
+                blocked = true;                                              // the same conflict is found again by plan_resume()
+                return;
+            }
             op.kind = 1;
             if (get_seam_tips(c1, c2, &op.p1, &op.p2)) ops.push_back(op);
             st[(size_t)c1] = st[(size_t)c2] == ST_FIRST ? (ST_INTERS | ST_SECOND) : (ST_INTERS | ST_FIRST);
         }
-        stale[(size_t)c1] = 1;
+        cut_[(size_t)c1] = 1;
         ed.erase({c1, c2});
         ed.erase({c2, c1});
     }
@@ -737,6 +780,97 @@ void UlsRuns::run() {
 // at the updated mask2, so a pixel is never cleared in both).  `seam_flips[k]`: UlsRuns::flips of the k-th kind-1 operation of
 // the plan that succeeded (nullptr when estimateSeam failed or was not run).
 struct ClearIv { int y, x0, x1, bits; };              // frame coordinates
+
+// ---- staged plan: the relabels of a round written into the runs -----------------------------------------------------------------
+bool PairRuns::relabel(int l_from, int l_to, const std::vector<Interval>* fl) {
+    if (!fl) {                                                            // wholesale relabel ([SEAM]:440-450)
+        for (int& l : cp_label) if (l == l_from) l = l_to;
+        return true;
+    }
+    if (fl->empty()) return true;
+    std::vector<ChangePt> ncps;
+    std::vector<int> nlab, nro((size_t)uh + 1, 0);
+    ncps.reserve(cps.size() + 2 * fl->size());
+    nlab.reserve(cps.size() + 2 * fl->size());
+    size_t fi = 0;
+    for (int y = 0; y < uh; ++y) {
+        const int rb = row_off[(size_t)y], re = row_off[(size_t)y + 1];
+        while (fi < fl->size() && (*fl)[fi].y < y) ++fi;
+        size_t fe = fi;
+        while (fe < fl->size() && (*fl)[fe].y == y) ++fe;
+        const size_t row_begin = ncps.size();
+        if (fi == fe) {
+            ncps.insert(ncps.end(), cps.begin() + rb, cps.begin() + re);
+            nlab.insert(nlab.end(), cp_label.begin() + rb, cp_label.begin() + re);
+        } else {
+            size_t f = fi;                                                // flips of a row are sorted by x0 and disjoint
+            for (int k = rb; k < re; ++k) {
+                const int a = cps[(size_t)k].x, b = k + 1 < re ? cps[(size_t)k + 1].x : uw;
+                const int lab = cp_label[(size_t)k], cls = cps[(size_t)k].cls;
+                if (lab != l_from) { ncps.push_back(ChangePt{a, cls}); nlab.push_back(lab); continue; }
+                int x = a;
+                while (f < fe && (*fl)[f].x1 <= a) ++f;
+                for (size_t g = f; g < fe && (*fl)[g].x0 < b; ++g) {
+                    const int s0 = std::max((*fl)[g].x0, a), e0 = std::min((*fl)[g].x1, b);
+                    if (s0 >= e0) continue;
+                    if (s0 > x) { ncps.push_back(ChangePt{x, cls}); nlab.push_back(l_from); }
+                    ncps.push_back(ChangePt{s0, cls}); nlab.push_back(l_to);
+                    x = e0;
+                }
+                if (x < b) { ncps.push_back(ChangePt{x, cls}); nlab.push_back(l_from); }
+            }
+        }
+        if ((int)(ncps.size() - row_begin) > ROW_CAP) { too_many_runs = true; return false; }
+        nro[(size_t)y + 1] = (int)ncps.size();
+        fi = fe;
+    }
+    cps.swap(ncps);
+    cp_label.swap(nlab);
+    row_off.swap(nro);
+    return true;
+}
+
+bool PairRuns::apply_round(const std::vector<const std::vector<Interval>*>& seam_flips) {
+    if (!staged) { snap_row_off = row_off; snap_cps = cps; snap_label = cp_label; }
+    size_t k1 = 0;
+    for (size_t q = round_begin; q < ops.size(); ++q) {
+        const SeamOp& op = ops[q];
+        if (op.kind == 0) { relabel(op.c1 + 1, op.c2 + 1, nullptr); continue; }
+        const std::vector<Interval>* f = k1 < seam_flips.size() ? seam_flips[k1] : nullptr;
+        ++k1;
+        if (f && !relabel(op.c1 + 1, op.c2 + 1, f)) return false;         // nullptr: estimateSeam failed, the labels stay
+    }
+    round_begin = ops.size();
+    staged = true;
+    // what the reference refreshes after an operation ([SEAM]:484-520) for the components the loop can still ask about: bounding
+    // boxes and contours of the INTERS components, from the labels as they are now.  The edge set is NOT recomputed (the reference
+    // only erases from it).
+    tls.assign((size_t)ncomps, Pt{INT_MAX, INT_MAX});
+    brs.assign((size_t)ncomps, Pt{INT_MIN, INT_MIN});
+    contours.assign((size_t)ncomps, std::vector<ContourRec>());
+    contour_rows();
+    return true;
+}
+
+// the final mask update [SEAM]:524-545 of a staged pair: every pixel of both masks takes the bits of the state its label ends up in
+void PairRuns::final_clears(std::vector<ClearIv>* out) const {
+    out->clear();
+    const int y_lo = std::max(0, iTl.y - unionTl.y), y_hi = std::min(uh, iBr.y - unionTl.y);
+    for (int y = y_lo; y < y_hi; ++y) {
+        const int rb = row_off[(size_t)y], re = row_off[(size_t)y + 1];
+        for (int k = rb; k < re; ++k) {
+            if (cps[(size_t)k].cls != 3) continue;
+            const int l = cp_label[(size_t)k];
+            if (l <= 0) continue;
+            const int st = final_states[(size_t)l - 1];
+            const int bits = (st & ST_FIRST) ? 2 : ((st & ST_SECOND) ? 1 : 0);
+            const int a = cps[(size_t)k].x, b = k + 1 < re ? cps[(size_t)k + 1].x : uw;
+            if (!bits || a >= b) continue;
+            if (!out->empty() && out->back().y == y && out->back().x1 == a && out->back().bits == bits) out->back().x1 = b;
+            else out->push_back(ClearIv{y, a, b, bits});
+        }
+    }
+}
 
 static bool runs_minus_clears(const MaskRuns& in, const std::vector<RunLayer>& layers, int cap, MaskRuns* out) {
     *out = in;

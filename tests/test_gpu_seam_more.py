@@ -126,3 +126,24 @@ def test_four_channel_images(ctx, oracle, kind, cost):
         for i in range(n):
             assert np.array_equal(got[i], want[i]), f"4-channel {kind} {cost} seam mask {i}"
         assert _traces_equal(wtrace, gtrace), "seam point lists"
+
+
+@pytest.mark.parametrize("case", [(12, 240, 160, 4, 1.5, 0.25), (12, 200, 150, 3, 1.3, 0.3), (8, 300, 200, 2, 1.2, 0.35), (15, 180, 140, 3, 1.6, 0.25),
+                                  (16, 160, 120, 4, 1.4, 0.3)])
+def test_mosaic_staged_pairs(ctx, oracle, case, monkeypatch):
+    """Mosaics of curved masks: an INTERS component often has two neighbours of the same image, so it is cut by two seams; the second
+    estimation needs the labels the first one leaves (staged plan, seam_runs.inl).  Masks and seam point lists equal the oracle's,
+    every pair stays on the batched path, and without the staged plan (general path for those pairs) the result is the same."""
+    O = oracle
+    n, w, h, rows, fw, ov = case
+    corners, wi, wm = warped_set(O, n, w, h, f_over_w=fw, overlap=ov, grid_rows=rows)
+    want, wtrace = O.dp_seam_find(wi, corners, wm, want_trace=True)
+    got, gtrace = S.DpSeamFinder(ctx, "COLOR").find(wi, corners, [m.copy() for m in wm], want_trace=True)
+    for i in range(n):
+        assert np.array_equal(got[i], want[i]), f"mosaic {case}: seam mask {i}"
+    assert _traces_equal(wtrace, gtrace), "seam point lists"
+    assert ctx.seam_path == 2, "a pair of the mosaic left the batched path"
+    monkeypatch.setenv("IS_SEAM_NO_RESUME", "1")
+    old = S.DpSeamFinder(ctx, "COLOR").find(wi, corners, [m.copy() for m in wm])
+    for i in range(n):
+        assert np.array_equal(old[i], want[i]), f"mosaic {case} without the staged plan: seam mask {i}"

@@ -121,7 +121,7 @@ def test_pair_structure_and_plan_against_grid_and_oracle(oracle):
         assert got["ncomps"] == want["ncomps"], name
         assert np.array_equal(got["states"], want["states"]), name
         assert got["recs"].shape == want["recs"].shape and np.array_equal(got["recs"], want["recs"]), f"{name}: contour records"
-        if got["unsupported"]:
+        if got["unsupported"]:                         # 1: not covered; 2: staged plan (only its first round is listed here)
             continue
         # the seams the reference estimates for this pair: component and end points = the plan's seam operations
         _, trace = O.dp_seam_find([a, b], [c1, c2], [m1, m2], want_trace=True)
@@ -144,11 +144,11 @@ def test_pair_finish_on_host_equals_oracle(oracle):
     fed with the seams the oracle traces: the resulting masks equal the oracle's (== the reference's own find())."""
     O = oracle
     lib = capi.load()
-    done = 0
+    done = staged = staged_done = 0
     for name, a, b, c1, c2, m1, m2 in _cases():
         c1 = (int(c1[0]), int(c1[1])); c2 = (int(c2[0]), int(c2[1]))
         got = plan(m1, c1, m2, c2)
-        if got["too_many"] or got["unsupported"]:
+        if got["too_many"] or got["unsupported"] == 1:
             continue
         want, trace = O.dp_seam_find([a, b], [c1, c2], [m1, m2], want_trace=True)
         ux, uy = got["union_tl"]
@@ -162,12 +162,23 @@ def test_pair_finish_on_host_equals_oracle(oracle):
                 k += 1
             else:
                 seams.append(0)
+        if got["unsupported"] == 2:
+            # staged plan: only the first round is listed; the later rounds take the oracle's remaining seams in order (an operation
+            # whose estimateSeam failed cannot be told apart here: such cases are skipped)
+            staged += 1
+            for t in trace[k:]:
+                seams += [len(t[4])] + [int(v) for v in t[4].reshape(-1)]
+            k = len(trace)
         assert k == len(trace), name
         o1 = np.ascontiguousarray(m1).copy(); o2 = np.ascontiguousarray(m2).copy()
         sa = np.asarray(seams if seams else [0], np.int32)
         rc = lib.is_debug_seam_pair_finish(o1.ctypes.data, o1.shape[0], o1.shape[1], o1.strides[0], c1[0], c1[1], o2.ctypes.data, o2.shape[0], o2.shape[1],
                                            o2.strides[0], c2[0], c2[1], sa.ctypes.data_as(C.POINTER(C.c_int32)), len(seams))
+        if got["unsupported"] == 2 and rc != 0:
+            continue                                   # a later round met what the plan does not cover (or a failed estimateSeam shifted the seam list)
         assert rc == 0, (name, rc)
         assert np.array_equal(o1, want[0]) and np.array_equal(o2, want[1]), f"{name}: masks differ in {int((o1 != want[0]).sum())} + {int((o2 != want[1]).sum())} px"
         done += 1
+        staged_done += 1 if got["unsupported"] == 2 else 0
     assert done >= 25
+    print(f"staged pairs: {staged_done} of {staged} finished on the host")
