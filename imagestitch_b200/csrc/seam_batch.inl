@@ -17,7 +17,8 @@
 // earlier pairs' clears is accepted, the rest forms the next wave (a strip needs one wave, a mosaic whose images overlap
 // mutually a few).  A pair the plan cannot cover (noisy masks, a component cut twice) takes the general path (PairSeam) alone.
 
-constexpr int TG_CAP = 8;              // toggles per mask row the batched path handles (rows are a few runs; more -> general path)
+constexpr int TG_CAP = 16;             // toggles per mask row the batched path handles (rows are a few runs, up to a dozen in a mosaic after several
+                                       // pairs have cut their seams into a mask; more -> general path)
 constexpr int MAX_LAYERS = 8;          // earlier pairs whose clears a validation mask can carry
 constexpr int SPECIAL_CAP = 512;       // candidate seam tips per pair (a panorama pair has a few dozen; more -> general path)
 
@@ -132,16 +133,20 @@ struct SpecialJob {
     int2* out; int* count;
 };
 
-// bit i of the result: pixel mx0 + i (own coordinates) of a mask row is set, i < 18 -- from the row's toggles (n of them in v)
-__device__ __forceinline__ unsigned toggles_bits18(int n, const uint4& v, int cols, int mx0) {
+// bit i of the result: pixel mx0 + i (own coordinates) of a mask row is set, i < 18 -- from the row's toggles.  Every toggle XORs a
+// suffix of the window, so the toggles can be taken eight at a time (n of them in v) and the partial results XORed.
+__device__ __forceinline__ unsigned toggles_xor18(int n, const uint4& v, int mx0) {
     const unsigned w[4] = {v.x, v.y, v.z, v.w};
     unsigned bits = 0;
 #pragma unroll
-    for (int k = 0; k < TG_CAP; ++k) {
+    for (int k = 0; k < 8; ++k) {
         if (k >= n) break;
         const int t = (int)((w[k >> 1] >> (16 * (k & 1))) & 0xffffu) - mx0;      // toggle position inside the window
         bits ^= t <= 0 ? 0x3ffffu : (t >= 18 ? 0u : (0x3ffffu << t) & 0x3ffffu);
     }
+    return bits;
+}
+__device__ __forceinline__ unsigned clamp_bits18(unsigned bits, int cols, int mx0) {
     if (mx0 + 18 > cols) bits &= mx0 < cols ? (1u << (cols - mx0)) - 1u : 0u;      // a row that ends inside the mask has no closing toggle
     return bits;
 }
@@ -198,8 +203,18 @@ __global__ void __launch_bounds__(128) k_special_points_batch(const SpecialJob* 
         unsigned b1[SP_ROWS + 2], b2[SP_ROWS + 2];
 #pragma unroll
         for (int r = 0; r < SP_ROWS + 2; ++r) {
-            b1[r] = toggles_bits18(cn1[r], tv1[r], M1.cols, m1x);
-            b2[r] = toggles_bits18(cn2[r], tv2[r], M2.cols, m2x);
+            b1[r] = toggles_xor18(cn1[r], tv1[r], m1x);
+            b2[r] = toggles_xor18(cn2[r], tv2[r], m2x);
+            if (cn1[r] > 8) {                                                      // rare: the second eight toggles of the row
+                const int y1 = iy + ly0 - 1 + r - M1.oy;
+                b1[r] ^= toggles_xor18(cn1[r] - 8, *reinterpret_cast<const uint4*>(J.xs1 + (size_t)y1 * TG_CAP + 8), m1x);
+            }
+            if (cn2[r] > 8) {
+                const int y2 = iy + ly0 - 1 + r - M2.oy;
+                b2[r] ^= toggles_xor18(cn2[r] - 8, *reinterpret_cast<const uint4*>(J.xs2 + (size_t)y2 * TG_CAP + 8), m2x);
+            }
+            b1[r] = clamp_bits18(b1[r], M1.cols, m1x);
+            b2[r] = clamp_bits18(b2[r], M2.cols, m2x);
         }
         const int rows = min(SP_ROWS, ih - ly0);
 #pragma unroll
@@ -1038,8 +1053,15 @@ static int seam_batch_wave(is_ctx* ctx, const std::vector<std::pair<int, int>>& 
                 const size_t k = (size_t)vpair[v];
                 C.setup(active[k].first, active[k].second, PR[k].tl1, PR[k].tl2, &V.runs[(size_t)V.pairs[v].m1], &V.runs[(size_t)V.pairs[v].m2]);
                 C.specials = V.specials[v];
-                C.build();
+                C.build_runs();
                 if (C.too_many_runs) return;
+                // the same test as on the host path (a staged pair is compared as build() left it), plus the special points, which
+                // were recomputed here; only then the full comparison of contours and plans
+                bool same_specials = C.specials.size() == PR[k].specials.size();
+                for (size_t q = 0; same_specials && q < C.specials.size(); ++q)
+                    same_specials = C.specials[q].x == PR[k].specials[q].x && C.specials[q].y == PR[k].specials[q].y;
+                if (same_specials && C.same_window(PR[k])) { ok[v] = 1; return; }
+                C.build_contours();
                 C.plan();
                 ok[v] = C.same_structure(PR[k]) ? 1 : 0;
             });
