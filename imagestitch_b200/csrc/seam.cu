@@ -2162,7 +2162,6 @@ int seam_find_core(is_ctx* ctx, int n, const DevMat* images, const is_point* cor
     const bool want_seq = (seq && seq[0] == '1') || (mode && !strcmp(mode, "seq"));
     if (!active.empty() && !want_seq && !(mode && !strcmp(mode, "pairs"))) {
         // all pairs through every kernel at once, three host consultations per wave (seam_batch.inl)
-        size_t done = 0;
         bool all_batched = true;
         int waves = 0;
         // intersection rectangle of a pair (panorama coordinates): the only place its clears fall
@@ -2172,41 +2171,85 @@ int seam_find_core(is_ctx* ctx, int n, const DevMat* images, const is_point* cor
             *x1 = std::min(corners[i].x + images[i].cols, corners[j].x + images[j].cols);
             *y1 = std::min(corners[i].y + images[i].rows, corners[j].y + images[j].rows);
         };
-        const bool whole = getenv("IS_SEAM_WAVE_ALL") != nullptr;           // tuning knob: every wave takes all remaining pairs
-        while (done < active.size()) {
-            // A wave is the longest run of pairs none of which shares an image with an earlier pair of the wave whose intersection
-            // rectangle comes within a few pixels of its own: the clears of such a neighbour would very likely change what the pair
-            // sees, and everything computed for it (costs, DP) would be thrown away by the validation.  In a strip every wave is
-            // the whole pair list; in a mosaic the waves follow the real conflicts instead of recomputing the tail of the list
-            // once per conflict.  The validation still decides what is accepted: this only chooses what is worth speculating on.
+        const bool whole = getenv("IS_SEAM_WAVE_ALL") != nullptr;           // tuning knob: every wave takes all remaining pairs, in order
+        const bool in_order = getenv("IS_SEAM_WAVE_PREFIX") != nullptr;     // tuning knob: a wave ends at the first conflict (no pair is taken out of order)
+        // The seams are reported in the reference's pair order whatever order the waves take the pairs in: with a trace buffer the
+        // records are staged and sorted back at the end.
+        std::vector<int32_t> staged;
+        TraceSink stage_sink;
+        TraceSink* tw = trace;
+        if (trace && trace->buf) { staged.resize(trace->cap); stage_sink.buf = staged.data(); stage_sink.cap = staged.size(); tw = &stage_sink; }
+        std::vector<char> finished(active.size(), 0);
+        size_t left = active.size();
+        while (left > 0) {
+            // A wave takes the remaining pairs in the reference's order and leaves out (a) a pair that shares an image with an earlier
+            // pair of the wave whose intersection rectangle comes within a few pixels of its own -- the clears of such a neighbour
+            // would very likely change what the pair sees, and everything computed for it would be thrown away by the validation --
+            // and (b) every later pair that shares an image with a pair left out: two pairs without a common image touch different
+            // masks and commute, so a pair may overtake the pairs it has nothing in common with, but never one it could depend on or
+            // that could depend on it.  In a strip every wave is the whole pair list; in a mosaic the waves follow the real conflicts.
+            // The validation still decides what is accepted: this only chooses what is worth speculating on.
             std::vector<std::pair<int, int>> rest;
-            for (size_t k = done; k < active.size(); ++k) {
-                bool conflict = false;
-                if (!whole) {
+            std::vector<size_t> rest_idx;
+            std::vector<char> blocked_img((size_t)n, 0);
+            for (size_t k = 0; k < active.size(); ++k) {
+                if (finished[k]) continue;
+                const int i = active[k].first, j = active[k].second;
+                bool skip = blocked_img[(size_t)i] || blocked_img[(size_t)j];
+                if (!skip && !whole) {
                     int ax0, ay0, ax1, ay1;
                     rect_of(active[k], &ax0, &ay0, &ax1, &ay1);
                     for (const auto& q : rest) {
-                        if (q.first != active[k].first && q.first != active[k].second && q.second != active[k].first && q.second != active[k].second) continue;
+                        if (q.first != i && q.first != j && q.second != i && q.second != j) continue;
                         int bx0, by0, bx1, by1;
                         rect_of(q, &bx0, &by0, &bx1, &by1);
-                        if (bx0 < ax1 + 4 && ax0 - 4 < bx1 && by0 < ay1 + 4 && ay0 - 4 < by1) { conflict = true; break; }
+                        if (bx0 < ax1 + 4 && ax0 - 4 < bx1 && by0 < ay1 + 4 && ay0 - 4 < by1) { skip = true; break; }
                     }
                 }
-                if (conflict) break;
+                if (skip) {
+                    if (in_order) break;
+                    blocked_img[(size_t)i] = 1; blocked_img[(size_t)j] = 1;
+                    continue;
+                }
                 rest.push_back(active[k]);
+                rest_idx.push_back(k);
             }
             size_t accepted = 0;
             bool first_unsupported = false;
-            IS_TRY(seam_batch_wave(ctx, rest, n, images, corners, masks, trace, cost_fn, &accepted, &first_unsupported));
+            IS_TRY(seam_batch_wave(ctx, rest, n, images, corners, masks, tw, cost_fn, &accepted, &first_unsupported));
             if (first_unsupported) {                       // this pair alone through the general path, then on with the waves
-                std::vector<std::pair<int, int>> one(1, active[done]);
-                IS_TRY(seam_find_sequential(ctx, one, images, corners, masks, trace, cost_fn));
+                std::vector<std::pair<int, int>> one(1, rest[0]);          // the first pair of a wave is the first remaining pair of the reference's order
+                IS_TRY(seam_find_sequential(ctx, one, images, corners, masks, tw, cost_fn));
                 all_batched = false;
-                done += 1;
+                finished[rest_idx[0]] = 1;
+                --left;
                 continue;
             }
             ++waves;
-            done += accepted;
+            // A wave member left behind (validation) keeps its place: it comes before every member after it in the reference's order
+            // and shares no image with the pairs that were skipped in front of it, so taking it up again later is the same loop.
+            // But the members AFTER it must not have been applied either: seam_batch_wave applies a prefix of the wave only.
+            for (size_t q = 0; q < accepted; ++q) { finished[rest_idx[q]] = 1; --left; }
+        }
+        if (tw == &stage_sink) {
+            if (stage_sink.len > stage_sink.cap) {
+                trace->len += stage_sink.len;                              // too small either way: the caller sees the length it needs
+            } else {
+                std::map<std::pair<int, int>, std::vector<std::pair<size_t, size_t>>> by_pair;    // (i, j) -> records (offset, length) in the order they were estimated
+                for (size_t pos = 0; pos + 5 <= stage_sink.len;) {
+                    const size_t len = 5 + 2 * (size_t)staged[pos + 4];
+                    by_pair[{staged[pos], staged[pos + 1]}].push_back({pos, len});
+                    pos += len;
+                }
+                for (const auto& pr : active) {
+                    auto it = by_pair.find(pr);
+                    if (it == by_pair.end()) continue;
+                    for (const auto& rec : it->second) {
+                        if (trace->len + rec.second <= trace->cap) std::memcpy(trace->buf + trace->len, staged.data() + rec.first, rec.second * sizeof(int32_t));
+                        trace->len += rec.second;
+                    }
+                }
+            }
         }
         ctx->seam_speculation_accepted = waves <= 1 ? 1 : 0;
         ctx->seam_path = all_batched ? 2 : 0;

@@ -639,6 +639,11 @@ static int seam_batch_wave(is_ctx* ctx, const std::vector<std::pair<int, int>>& 
     // a pair the plan does not cover ends the wave in front of it (it goes through the general path, PairSeam, on its own)
     for (size_t k = 0; k < np; ++k)
         if (PR[k].too_many_runs || PR[k].unsupported) {
+            if (tm.on)
+                fprintf(stderr, "[seam batch] pair (%d, %d) leaves the batched path: %s%s%s (toggle overflow %d / %d, special points %d)\n", active[k].first, active[k].second,
+                        Q.pair_overflow[k] ? "toggle / special-point tables " : "", PR[k].too_many_runs ? "too many runs in a row " : "",
+                        PR[k].unsupported && !Q.pair_overflow[k] ? "plan (INTERS neighbour / DP width)" : "", (int)Q.mask_overflow[(size_t)Q.pairs[k].m1],
+                        (int)Q.mask_overflow[(size_t)Q.pairs[k].m2], (int)Q.specials[k].size());
             if (k == 0) { *first_unsupported = true; return IS_OK; }
             np = k;
             active.resize(np);
@@ -863,6 +868,7 @@ static int seam_batch_wave(is_ctx* ctx, const std::vector<std::pair<int, int>>& 
         }
     });
     for (auto& J : jobs) {
+        if (J.status == IS_ERR_UNSUPPORTED && tm.on) fprintf(stderr, "[seam batch] pair (%d, %d) leaves the batched path: 255 or more flood-fill regions\n", active[(size_t)J.pair].first, active[(size_t)J.pair].second);
         if (J.status == IS_ERR_UNSUPPORTED) { limit = std::min(limit, (size_t)J.pair); continue; }   // that pair takes the general path
         if (J.status != IS_OK) return J.status;
     }
@@ -885,6 +891,8 @@ static int seam_batch_wave(is_ctx* ctx, const std::vector<std::pair<int, int>>& 
         next_round[k] = 1;
     });
     for (size_t k = 0; k < limit; ++k) {
+        if ((PR[k].unsupported || PR[k].too_many_runs) && tm.on)
+            fprintf(stderr, "[seam batch] pair (%d, %d) leaves the batched path in round %d of its staged plan\n", active[k].first, active[k].second, round);
         if (PR[k].unsupported || PR[k].too_many_runs) { limit = k; break; }   // the plan does not cover what came up: general path from this pair on
         more = more || next_round[k];
     }
