@@ -2445,7 +2445,7 @@ int is_mask_and(is_ctx* ctx, is_mat* dst, const is_mat* src) {
 
 // Host-only diagnostic (no device needed): the run-domain structure and plan of ONE pair, computed by the same code the
 // batched path runs between its kernels (PairRuns), with the device-side inputs (row toggles, special points) produced by
-// host loops.  out (int32): [too_many_runs, unsupported, ncomps, nops, nrecords, union_tl.x, union_tl.y, states[ncomps],
+// host loops.  out (int32): [too_many_runs, unsupported (1; 2 = staged plan: only its first round is listed), ncomps, nops, nrecords, union_tl.x, union_tl.y, states[ncomps],
 // ops[nops][11] = (kind, c1, c2, p1.x, p1.y, p2.x, p2.y, rx, ry, rw, rh), records[nrecords][7] = (x, y, label, nl[4])];
 // coordinates are union-frame.
 int is_debug_seam_pair_plan(const uint8_t* mask1, int rows1, int cols1, size_t step1, int tl1x, int tl1y, const uint8_t* mask2, int rows2, int cols2,
