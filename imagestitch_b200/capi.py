@@ -124,6 +124,7 @@ SYMBOLS = {
     "is_feather_blend": (C.c_int, [C.c_void_p, _P(Mat), _P(Mat)]),
     "is_gain_feed": (C.c_int, [C.c_void_p, C.c_int, _P(Point), _P(Mat), _P(Mat), _P(C.c_double)]),
     "is_gain_apply": (C.c_int, [C.c_void_p, _P(Mat), C.c_double]),
+    "is_debug_seam_wave_schedule": (C.c_int, [C.c_int, _P(Point), _P(Size), _P(C.c_int32), C.c_size_t, _P(C.c_size_t)]),
     "is_pipeline_estimate": (C.c_int, [C.c_void_p, C.c_int, _P(Mat), _P(RegistrationHooks), _P(Camera), _P(C.c_float)]),
     "is_pipeline_plan": (C.c_int, [C.c_void_p, C.c_int, _P(Size), _P(Camera), _P(PipelineConfig), _P(Point), _P(Size), _P(Rect)]),
     "is_pipeline_run": (C.c_int, [C.c_void_p, C.c_int, _P(Mat), _P(Camera), _P(RegistrationHooks), _P(PipelineConfig), _P(Mat), _P(Mat), _P(Mat)]),

@@ -2140,6 +2140,41 @@ __global__ void k_dp_bench_fill(float* P, float* Q, int lanes, int pitch, int st
     Q[(size_t)step * pitch + lane] = lane < lanes ? q : 0.f;
 }
 
+// One wave of the batched seam path: which of the remaining pairs (reference order) start together.  rects[k] = intersection
+// rectangle (x0, y0, x1, y1) of active[k] in panorama coordinates, the only place its clears fall.
+// A wave takes the remaining pairs in the reference's order and leaves out (a) a pair that shares an image with an earlier pair of
+// the wave whose intersection rectangle comes within a few pixels of its own -- the clears of such a neighbour would very likely
+// change what the pair sees, and everything computed for it would be thrown away by the validation -- and (b) every later pair
+// that shares an image with a pair left out: two pairs without a common image touch different masks and commute, so a pair may
+// overtake the pairs it has nothing in common with, but never one it could depend on or that could depend on it.  In a strip
+// every wave is the whole pair list; in a mosaic the waves follow the real conflicts.  The validation still decides what is
+// accepted: this only chooses what is worth speculating on.  The first remaining pair is always in the wave.
+static void choose_wave(const std::vector<std::pair<int, int>>& active, const std::vector<int4>& rects, const std::vector<char>& finished, int n_images,
+                        bool whole, bool in_order, std::vector<size_t>* wave) {
+    wave->clear();
+    std::vector<char> blocked_img((size_t)n_images, 0);
+    for (size_t k = 0; k < active.size(); ++k) {
+        if (finished[k]) continue;
+        const int i = active[k].first, j = active[k].second;
+        bool skip = blocked_img[(size_t)i] || blocked_img[(size_t)j];
+        if (!skip && !whole) {
+            const int4 a = rects[k];
+            for (size_t q : *wave) {
+                const std::pair<int, int>& w = active[q];
+                if (w.first != i && w.first != j && w.second != i && w.second != j) continue;
+                const int4 b = rects[q];
+                if (b.x < a.z + 4 && a.x - 4 < b.z && b.y < a.w + 4 && a.y - 4 < b.w) { skip = true; break; }
+            }
+        }
+        if (skip) {
+            if (in_order) break;
+            blocked_img[(size_t)i] = 1; blocked_img[(size_t)j] = 1;
+            continue;
+        }
+        wave->push_back(k);
+    }
+}
+
 // device-resident images / masks (masks in-out); used by is_seam_dp_find* and by the pipeline
 int seam_find_core(is_ctx* ctx, int n, const DevMat* images, const is_point* corners, const DevMat* masks, TraceSink* trace,
                    int cost_fn = IS_COST_COLOR) {
@@ -2164,13 +2199,12 @@ int seam_find_core(is_ctx* ctx, int n, const DevMat* images, const is_point* cor
         // all pairs through every kernel at once, three host consultations per wave (seam_batch.inl)
         bool all_batched = true;
         int waves = 0;
-        // intersection rectangle of a pair (panorama coordinates): the only place its clears fall
-        auto rect_of = [&](const std::pair<int, int>& pr, int* x0, int* y0, int* x1, int* y1) {
-            const int i = pr.first, j = pr.second;
-            *x0 = std::max(corners[i].x, corners[j].x); *y0 = std::max(corners[i].y, corners[j].y);
-            *x1 = std::min(corners[i].x + images[i].cols, corners[j].x + images[j].cols);
-            *y1 = std::min(corners[i].y + images[i].rows, corners[j].y + images[j].rows);
-        };
+        std::vector<int4> rects(active.size());
+        for (size_t k = 0; k < active.size(); ++k) {
+            const int i = active[k].first, j = active[k].second;
+            rects[k] = make_int4(std::max(corners[i].x, corners[j].x), std::max(corners[i].y, corners[j].y),
+                                 std::min(corners[i].x + images[i].cols, corners[j].x + images[j].cols), std::min(corners[i].y + images[i].rows, corners[j].y + images[j].rows));
+        }
         const bool whole = getenv("IS_SEAM_WAVE_ALL") != nullptr;           // tuning knob: every wave takes all remaining pairs, in order
         const bool in_order = getenv("IS_SEAM_WAVE_PREFIX") != nullptr;     // tuning knob: a wave ends at the first conflict (no pair is taken out of order)
         // The seams are reported in the reference's pair order whatever order the waves take the pairs in: with a trace buffer the
@@ -2182,38 +2216,10 @@ int seam_find_core(is_ctx* ctx, int n, const DevMat* images, const is_point* cor
         std::vector<char> finished(active.size(), 0);
         size_t left = active.size();
         while (left > 0) {
-            // A wave takes the remaining pairs in the reference's order and leaves out (a) a pair that shares an image with an earlier
-            // pair of the wave whose intersection rectangle comes within a few pixels of its own -- the clears of such a neighbour
-            // would very likely change what the pair sees, and everything computed for it would be thrown away by the validation --
-            // and (b) every later pair that shares an image with a pair left out: two pairs without a common image touch different
-            // masks and commute, so a pair may overtake the pairs it has nothing in common with, but never one it could depend on or
-            // that could depend on it.  In a strip every wave is the whole pair list; in a mosaic the waves follow the real conflicts.
-            // The validation still decides what is accepted: this only chooses what is worth speculating on.
-            std::vector<std::pair<int, int>> rest;
             std::vector<size_t> rest_idx;
-            std::vector<char> blocked_img((size_t)n, 0);
-            for (size_t k = 0; k < active.size(); ++k) {
-                if (finished[k]) continue;
-                const int i = active[k].first, j = active[k].second;
-                bool skip = blocked_img[(size_t)i] || blocked_img[(size_t)j];
-                if (!skip && !whole) {
-                    int ax0, ay0, ax1, ay1;
-                    rect_of(active[k], &ax0, &ay0, &ax1, &ay1);
-                    for (const auto& q : rest) {
-                        if (q.first != i && q.first != j && q.second != i && q.second != j) continue;
-                        int bx0, by0, bx1, by1;
-                        rect_of(q, &bx0, &by0, &bx1, &by1);
-                        if (bx0 < ax1 + 4 && ax0 - 4 < bx1 && by0 < ay1 + 4 && ay0 - 4 < by1) { skip = true; break; }
-                    }
-                }
-                if (skip) {
-                    if (in_order) break;
-                    blocked_img[(size_t)i] = 1; blocked_img[(size_t)j] = 1;
-                    continue;
-                }
-                rest.push_back(active[k]);
-                rest_idx.push_back(k);
-            }
+            choose_wave(active, rects, finished, n, whole, in_order, &rest_idx);
+            std::vector<std::pair<int, int>> rest;
+            for (size_t k : rest_idx) rest.push_back(active[k]);
             size_t accepted = 0;
             bool first_unsupported = false;
             IS_TRY(seam_batch_wave(ctx, rest, n, images, corners, masks, tw, cost_fn, &accepted, &first_unsupported));
@@ -2598,6 +2604,37 @@ int is_debug_seam_pair_finish(uint8_t* mask1, int rows1, int cols1, size_t step1
             if (c.bits & 1) mask1[(size_t)(c.y - P.o1y) * step1 + (x - P.o1x)] = 0;
             if (c.bits & 2) mask2[(size_t)(c.y - P.o2y) * step2 + (x - P.o2x)] = 0;
         }
+    return IS_OK;
+}
+
+// Host-only diagnostic: the waves the batched seam path would form for a set of warped image rectangles if every wave were
+// accepted in full.  out (int32): [nwaves, then per wave: count, (i, j) x count].
+int is_debug_seam_wave_schedule(int n, const is_point* corners, const is_size* sizes, int32_t* out, size_t cap, size_t* len) {
+    if (n < 0 || !corners || !sizes || !len) return IS_ERR_BAD_ARG;
+    std::vector<std::pair<int, int>> pairs, active;
+    for (int i = 0; i + 1 < n; ++i)
+        for (int j = i + 1; j < n; ++j) pairs.push_back({i, j});
+    std::reverse(pairs.begin(), pairs.end());
+    std::vector<int4> rects;
+    for (auto& pr : pairs) {
+        const int i = pr.first, j = pr.second;
+        const int4 r = make_int4(std::max(corners[i].x, corners[j].x), std::max(corners[i].y, corners[j].y),
+                                 std::min(corners[i].x + sizes[i].width, corners[j].x + sizes[j].width), std::min(corners[i].y + sizes[i].height, corners[j].y + sizes[j].height));
+        if (r.x < r.z && r.y < r.w) { active.push_back(pr); rects.push_back(r); }
+    }
+    std::vector<char> finished(active.size(), 0);
+    std::vector<int32_t> v(1, 0);
+    size_t left = active.size();
+    while (left > 0) {
+        std::vector<size_t> wave;
+        choose_wave(active, rects, finished, n, false, false, &wave);
+        if (wave.empty()) return IS_ERR_INTERNAL;
+        v[0]++;
+        v.push_back((int32_t)wave.size());
+        for (size_t k : wave) { v.push_back(active[k].first); v.push_back(active[k].second); finished[k] = 1; --left; }
+    }
+    *len = v.size();
+    if (out && cap >= v.size()) std::memcpy(out, v.data(), v.size() * sizeof(int32_t));
     return IS_OK;
 }
 

@@ -181,6 +181,11 @@ int is_ctx_seam_waves(const is_ctx* ctx);
  * it at the start of every step so that each step pays for its own scan, as a stream of different panoramas would. */
 int is_ctx_clear_plan_cache(is_ctx* ctx);
 
+/* Host-only diagnostic, no device needed: the waves of the batched seam path for a set of warped image rectangles (which pairs
+ * start together; pairs without a common image may overtake each other), assuming every wave is accepted in full.
+ * out (int32): [nwaves, then per wave: count, (i, j) x count]; *len = values needed. */
+int is_debug_seam_wave_schedule(int n, const is_point* corners, const is_size* sizes, int32_t* out, size_t cap, size_t* len);
+
 /* Host-only diagnostic, no device needed: structure and plan of one image pair as the batched path computes them
  * between its kernels (components, states, conflict-loop operations with seam tips, contour records).  See seam.cu. */
 int is_debug_seam_pair_plan(const uint8_t* mask1, int rows1, int cols1, size_t step1, int tl1x, int tl1y,

@@ -182,3 +182,64 @@ def test_pair_finish_on_host_equals_oracle(oracle):
         staged_done += 1 if got["unsupported"] == 2 else 0
     assert done >= 25
     print(f"staged pairs: {staged_done} of {staged} finished on the host")
+
+
+def _wave_schedule(corners, sizes):
+    lib = capi.load()
+    n = len(corners)
+    cs = (capi.Point * n)(*[capi.Point(int(c[0]), int(c[1])) for c in corners])
+    ss = (capi.Size * n)(*[capi.Size(int(s[0]), int(s[1])) for s in sizes])
+    need = C.c_size_t(0)
+    assert lib.is_debug_seam_wave_schedule(n, cs, ss, None, 0, C.byref(need)) == 0
+    out = np.zeros(need.value, np.int32)
+    assert lib.is_debug_seam_wave_schedule(n, cs, ss, out.ctypes.data_as(C.POINTER(C.c_int32)), out.size, C.byref(need)) == 0
+    waves, k = [], 1
+    for _ in range(int(out[0])):
+        cnt = int(out[k]); k += 1
+        waves.append([(int(out[k + 2 * q]), int(out[k + 2 * q + 1])) for q in range(cnt)])
+        k += 2 * cnt
+    return waves
+
+
+@pytest.mark.parametrize("case", [(6, 200, 150, 1, 1.2, 0.25), (12, 200, 140, 4, 1.5, 0.25), (12, 180, 140, 3, 1.3, 0.3), (16, 150, 110, 4, 1.4, 0.3), (10, 220, 160, 2, 1.2, 0.35)])
+def test_wave_order_commutes_with_the_reference_order(oracle, case):
+    """The batched path lets pairs overtake pairs they share no image with.  Run through the oracle one pair at a time, the wave
+    order must leave exactly the masks of the reference's order ([SEAM]:100-121); the schedule itself: every overlapping pair once,
+    the first remaining pair always in the wave, no wave member shares an image with a pair that was left out in front of it,
+    a strip is a single wave."""
+    O = oracle
+    n, w, h, rows, fw, ov = case
+    corners, wi, wm = warped_set(O, n, w, h, f_over_w=fw, overlap=ov, grid_rows=rows)
+    corners = [(int(c[0]), int(c[1])) for c in corners]
+    sizes = [(m.shape[1], m.shape[0]) for m in wm]
+    waves = _wave_schedule(corners, sizes)
+    ref_order = [(i, j) for i in range(n - 1) for j in range(i + 1, n)][::-1]
+    overlapping = [(i, j) for (i, j) in ref_order
+                   if max(corners[i][0], corners[j][0]) < min(corners[i][0] + sizes[i][0], corners[j][0] + sizes[j][0])
+                   and max(corners[i][1], corners[j][1]) < min(corners[i][1] + sizes[i][1], corners[j][1] + sizes[j][1])]
+    flat = [p for wv in waves for p in wv]
+    assert sorted(flat) == sorted(overlapping) and len(set(flat)) == len(flat)
+    if rows == 1:
+        assert len(waves) == 1 and waves[0] == overlapping
+    done = set()
+    for wv in waves:
+        remaining = [p for p in overlapping if p not in done]
+        assert wv[0] == remaining[0]
+        pos = {p: k for k, p in enumerate(remaining)}
+        assert [pos[p] for p in wv] == sorted(pos[p] for p in wv), "wave members keep the reference's order among themselves"
+        for p in wv:
+            skipped_before = [q for q in remaining[:pos[p]] if q not in wv]
+            assert not any(set(p) & set(q) for q in skipped_before), f"{p} overtakes a pair it shares an image with"
+        done.update(wv)
+    # the reference's loop vs the wave order, one pair at a time through the oracle
+    def run(order):
+        masks = [m.copy() for m in wm]
+        for (i, j) in order:
+            out = O.dp_seam_find([wi[i], wi[j]], [corners[i], corners[j]], [masks[i], masks[j]])
+            masks[i], masks[j] = out[0], out[1]
+        return masks
+    a, b = run(overlapping), run(flat)
+    for k in range(n):
+        assert np.array_equal(a[k], b[k]), f"mask {k} differs between the reference's order and the wave order"
+    if rows > 1:
+        assert len(waves) < len(overlapping)
