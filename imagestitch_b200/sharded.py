@@ -47,15 +47,18 @@ class ShardPlan:
     @staticmethod
     def build(corners, sizes, roi, world, num_bands):
         n = len(corners)
-        assert n % world == 0, "images must divide evenly over the ranks"
-        m = n // world
+        assert n >= world, "fewer images than ranks"
+        # n images over `world` ranks: the first n % world ranks take one image more
+        counts = [n // world + (1 if r < n % world else 0) for r in range(world)]
+        first = [sum(counts[:r]) for r in range(world + 1)]                  # rank r takes positions [first[r], first[r + 1]) of the x order
         p = ShardPlan([tuple(int(v) for v in c) for c in corners], [tuple(int(v) for v in s) for s in sizes], tuple(int(v) for v in roi), world, num_bands)
         # ownership by panorama column: images ordered by the x of their centre, n/world of them per rank.  For a strip
         # that is rank = i // m; for a 2-D mosaic (several rows of images) every rank gets the images of its columns.
         order = sorted(range(n), key=lambda i: (2 * p.corners[i][0] + p.sizes[i][0], i))
         p.owner = [0] * n
-        for k, i in enumerate(order):
-            p.owner[i] = k // m
+        for r in range(world):
+            for k in range(first[r], first[r + 1]):
+                p.owner[order[k]] = r
         allp = [(i, j) for i in range(n) for j in range(i + 1, n)][::-1]
         p.pairs = [(i, j) for (i, j) in allp if _overlap(p.corners[i], p.sizes[i], p.corners[j], p.sizes[j])]
         nb = min(num_bands, int(np.ceil(np.log(max(roi[2], roi[3])) / np.log(2.0))))
@@ -138,8 +141,7 @@ class ShardedStitcher:
     def is_strip(self, plan: ShardPlan):
         """A left-to-right strip whose only cross-rank pairs join the last image of one rank to the first of the next."""
         n = len(plan.corners)
-        m = n // plan.world
-        if any(plan.owner[i] != i // m for i in range(n)):
+        if any(plan.owner[i] > plan.owner[i + 1] for i in range(n - 1)):       # ranks own consecutive index ranges, in order
             return False
         return all(j == i + 1 for (i, j) in plan.pairs)
 
@@ -269,10 +271,9 @@ class ShardedStitcher:
         """X3 message lists.  Rank r already holds image b_r + 1 (X1), so only that image's FINAL mask travels to it; every other
         halo image travels whole.  Both sides derive the same schedule from the plan."""
         n = len(plan.corners)
-        m = n // plan.world
         sends, recvs = [], []
         for r in range(comm.world):
-            b_r = (r + 1) * m - 1
+            b_r = max(i for i in range(n) if plan.owner[i] == r)              # the last image of rank r
             for i in needed_by[r]:
                 src = plan.owner[i]
                 if src == r:

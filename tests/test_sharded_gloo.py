@@ -165,7 +165,7 @@ def _worker(rank, world, port, case, result_path):
 
 @pytest.mark.parametrize("early", [False, True])
 @pytest.mark.parametrize("case", [(4, 192, 144, 0.25, 3), (6, 160, 120, 0.3, 4), (4, 200, 150, 0.6, 3), (4, 192, 144, 0.25, 3, "fallback"),
-                                  (8, 128, 96, 0.3, 3, "mosaic")])
+                                  (8, 128, 96, 0.3, 3, "mosaic"), (5, 160, 120, 0.3, 3)])
 def test_two_rank_sharded_matches_single_process(tmp_path, case, monkeypatch, early):
     import oracle
     oracle.build()
@@ -186,7 +186,8 @@ def test_two_rank_sharded_matches_single_process(tmp_path, case, monkeypatch, ea
         assert spec == "1"     # independent pairs: the speculative results are accepted
 
 
-@pytest.mark.parametrize("case", [(4, 192, 144, 0.25, 3, 2), (6, 160, 120, 0.3, 4, 3), (6, 160, 120, 0.3, 4, 2), (4, 192, 144, 0.25, 3, 2, "fallback")])
+@pytest.mark.parametrize("case", [(4, 192, 144, 0.25, 3, 2), (6, 160, 120, 0.3, 4, 3), (6, 160, 120, 0.3, 4, 2), (4, 192, 144, 0.25, 3, 2, "fallback"),
+                                  (5, 160, 120, 0.3, 3, 2), (7, 144, 108, 0.3, 3, 3)])      # the last two: image counts that do not divide by the ranks
 def test_strip_path_matches_single_process(tmp_path, case, monkeypatch):
     """The strip path (one pair-loop call per rank over its images + the neighbour's first image, boundary check, mask
     exchange) on 2 and 3 gloo ranks; flat test images make every seam cost tie, the masks still have to come out right."""
@@ -241,6 +242,9 @@ def test_shard_plan_geometry():
     assert p.cuts[0] == 0 and p.cuts[-1] == 475 and all(c % 8 == 0 for c in p.cuts[1:-1]) and p.cuts == sorted(p.cuts)
     assert [p.pair_owner(k) for k in range(5)] == [2, 1, 1, 0, 0]
     assert p.earlier(1, 4) == [0] and p.earlier(0, 4) == []
+    # seven images over three ranks: 3 + 2 + 2
+    p7 = sharded.ShardPlan.build([(75 * k, 0) for k in range(7)], [(100, 80)] * 7, (0, 0, 550, 80), 3, 3)
+    assert p7.owner == [0, 0, 0, 1, 1, 2, 2] and len(p7.cuts) == 4 and p7.cuts == sorted(p7.cuts)
     # 2 x 4 mosaic, row-major image order: ranks own panorama columns, not index ranges
     corners = [(-193, -13), (-108, -14), (-23, -13), (61, -13), (-193, -87), (-108, -87), (-23, -86), (61, -86)]
     p = sharded.ShardPlan.build(corners, [(130, 100)] * 8, (-193, -87, 384, 174), 2, 3)
