@@ -15,7 +15,7 @@ LIB_PATH = os.path.join(_DIR, "libimagestitch_b200.so")
 IS_OK = 0
 IS_ERR_NO_MEM, IS_ERR_BAD_ARG, IS_ERR_UNSUPPORTED, IS_ERR_ASSERT, IS_ERR_CUDA, IS_ERR_INTERNAL = -4, -5, -213, -215, -1000, -1001
 IS_8U, IS_16S, IS_32S, IS_32F = 0, 3, 4, 5
-PROJ_CYLINDRICAL, PROJ_SPHERICAL = 0, 1
+PROJ_CYLINDRICAL, PROJ_SPHERICAL, PROJ_PLANE, PROJ_FISHEYE, PROJ_STEREOGRAPHIC = 0, 1, 2, 3, 4
 INTER_NEAREST, INTER_LINEAR = 0, 1
 BORDER_CONSTANT, BORDER_REFLECT = 0, 2
 COST_COLOR, COST_COLOR_GRAD = 0, 1
@@ -82,6 +82,7 @@ SYMBOLS = {
     "is_warp_roi": (C.c_int, [C.c_void_p, C.c_int, Size, _F9, _F9, C.c_float, _P(Point), _P(Size)]),
     "is_build_maps": (C.c_int, [C.c_void_p, C.c_int, Size, _F9, _F9, C.c_float, _P(Mat), _P(Mat), _P(Rect)]),
     "is_warp": (C.c_int, [C.c_void_p, C.c_int, _P(Mat), _F9, _F9, C.c_float, C.c_int, C.c_int, _P(Mat), _P(Point)]),
+    "is_remap": (C.c_int, [C.c_void_p, _P(Mat), _P(Mat), _P(Mat), C.c_int, C.c_int, _P(Mat)]),
     "is_warp_with_mask": (C.c_int, [C.c_void_p, C.c_int, _P(Mat), _F9, _F9, C.c_float, _P(Mat), _P(Mat), _P(Point)]),
     "is_seam_dp_find": (C.c_int, [C.c_void_p, C.c_int, _P(Mat), _P(Point), _P(Mat), C.c_int]),
     "is_seam_dp_find_trace": (C.c_int, [C.c_void_p, C.c_int, _P(Mat), _P(Point), _P(Mat), C.c_int, _P(C.c_int32), C.c_size_t, _P(C.c_size_t)]),

@@ -27,6 +27,10 @@ int upload_tables(is_ctx* ctx, int proj, const WarpPlan& plan, DevBuf* buf);
 int launch_warp(is_ctx* ctx, int proj, const WarpPlan& plan, const float* tables, const DevMat& src, int interp, int border,
                 const DevMat& dst, const DevMat* mask);
 
+int launch_remap(is_ctx* ctx, const float* xmap, size_t xstep, const float* ymap, size_t ystep, const DevMat& src, int interp, int border, const DevMat& dst,
+                 const DevMat* mask);
+bool warp_fusable(int proj);     // the projector's backward map comes from O(W + H) tables: k_warp_g1 can evaluate it
+
 int launch_warp_g1(is_ctx* ctx, int proj, const WarpPlan& plan, const float* tables, const DevMat& src, const DevMat& dst, const DevMat& mask,
                    int top, int left, int height, int width, int16_t* g1);
 

@@ -172,7 +172,7 @@ int is_pipeline_run(is_ctx* ctx, int n, const is_mat* images, const is_camera* c
         DevBuf tables;
         IS_TRY(upload_tables(ctx, cfg.projection, plans[i], &tables));
         // feed(): geometry + level 1 of the image pyramid now, the other levels on the side stream, weights after the seam stage
-        const bool fused = multiband && cfg.exposure == IS_EXPOSURE_NONE && is_blender_num_bands(bl) >= 1 && !getenv("IS_WARP_UNFUSED");
+        const bool fused = multiband && cfg.exposure == IS_EXPOSURE_NONE && is_blender_num_bands(bl) >= 1 && warp_fusable(cfg.projection) && !getenv("IS_WARP_UNFUSED");
         if (fused) {
             IS_TRY(blender_feed_image_fused(bl, cfg.projection, plans[i], tables.as<float>(), src[i], warped[i], masks[i], corners[i]));
             continue;

@@ -68,6 +68,27 @@ static inline void map_forward(int proj, const Projector& p, float scale, float 
     volatile float x_ = p.r_kinv[0] * x + p.r_kinv[1] * y + p.r_kinv[2];
     volatile float y_ = p.r_kinv[3] * x + p.r_kinv[4] * y + p.r_kinv[5];
     volatile float z_ = p.r_kinv[6] * x + p.r_kinv[7] * y + p.r_kinv[8];
+    if (proj == IS_PROJ_PLANE) {                    // cv::detail::PlaneProjector::mapForward with t = 0
+        volatile float px = 0.f + x_ / z_ * (1 - 0.f), py = 0.f + y_ / z_ * (1 - 0.f);
+        *u = scale * px;
+        *v = scale * py;
+        return;
+    }
+    if (proj == IS_PROJ_FISHEYE || proj == IS_PROJ_STEREOGRAPHIC) {   // FisheyeProjector / StereographicProjector::mapForward
+        float u_ = atan2f(x_, z_);
+        float v_ = kPiF - acosf(y_ / sqrtf(x_ * x_ + y_ * y_ + z_ * z_));
+        if (proj == IS_PROJ_FISHEYE) {
+            volatile float r = scale * v_;
+            *u = r * cosf(u_);
+            *v = r * sinf(u_);
+        } else {
+            volatile float r = sinf(v_) / (1 - cosf(v_));
+            volatile float sr = scale * r;
+            *u = sr * cosf(u_);
+            *v = sr * sinf(u_);
+        }
+        return;
+    }
     *u = scale * atan2f(x_, z_);
     if (proj == IS_PROJ_CYLINDRICAL) {
         *v = scale * y_ / sqrtf(x_ * x_ + z_ * z_);
@@ -75,6 +96,45 @@ static inline void map_forward(int proj, const Projector& p, float scale, float 
         float w = y_ / sqrtf(x_ * x_ + y_ * y_ + z_ * z_);
         *v = scale * (kPiF - acosf(w == w ? w : 0));
     }
+}
+
+// FisheyeProjector / StereographicProjector::mapBackward: atan2f / sinf / cosf of a per-PIXEL angle, so no O(W + H) table of
+// host-libm values can carry them to the device (and the device's own libm rounds differently).  These two projectors --
+// commented-out alternatives in the reference, [BLEND]:94-95 -- build their maps on the host pool with the host's libm,
+// as buildMaps [WARP]:122-144 does, and the device samples through them (k_remap).
+static inline void map_backward_host(int proj, const Projector& p, float scale, float u, float v, float* x, float* y) {
+    u /= scale;
+    v /= scale;
+    float u_ = atan2f(v, u);
+    volatile float rr = u * u + v * v;
+    float r = sqrtf(rr);
+    float v_;
+    if (proj == IS_PROJ_FISHEYE) v_ = r;
+    else { volatile float inv = 1.f / r; v_ = 2 * atanf(inv); }
+    volatile float pv = kPiF - v_;
+    float sinv = sinf(pv);
+    volatile float x_ = sinv * sinf(u_);
+    volatile float y_ = cosf(pv);
+    volatile float z_ = sinv * cosf(u_);
+    const float* m = p.k_rinv;
+    volatile float a0 = m[0] * x_, a1 = m[1] * y_, a2 = m[2] * z_;
+    volatile float b0 = m[3] * x_, b1 = m[4] * y_, b2 = m[5] * z_;
+    volatile float c0 = m[6] * x_, c1 = m[7] * y_, c2 = m[8] * z_;
+    volatile float X = a0 + a1; X = X + a2;
+    volatile float Y = b0 + b1; Y = Y + b2;
+    volatile float Z = c0 + c1; Z = Z + c2;
+    if (Z > 0) { *x = X / Z; *y = Y / Z; }
+    else { *x = -1.f; *y = -1.f; }
+}
+
+static inline bool proj_uses_maps(int proj) { return proj == IS_PROJ_FISHEYE || proj == IS_PROJ_STEREOGRAPHIC; }
+static inline bool proj_known(int proj) { return proj >= IS_PROJ_CYLINDRICAL && proj <= IS_PROJ_STEREOGRAPHIC; }
+
+// rows [y0, y1) of the two maps of a per-pixel projector (dense, w floats per row)
+static void fill_map_rows(int proj, const Projector& p, float scale, int tl_x, int tl_y, int w, int y0, int y1, float* xmap, float* ymap) {
+    for (int j = y0; j < y1; ++j)
+        for (int i = 0; i < w; ++i)
+            map_backward_host(proj, p, scale, (float)(tl_x + i), (float)(tl_y + j), xmap + (size_t)j * w + i, ymap + (size_t)j * w + i);
 }
 
 // detectResultRoi: the extrema of (u, v) over the source image lie on its border for every camera
@@ -94,6 +154,33 @@ static RoiAcc roi_segment(int proj, int w, int h, const Projector& p, float scal
     };
     if (rows) for (int x = a0; x < a1; ++x) { acc(x, 0); acc(x, h - 1); }
     else for (int y = a0; y < a1; ++y) { acc(0, y); acc(w - 1, y); }
+    return r;
+}
+
+// RotationWarperBase::detectResultRoi, the scan over ALL source pixels that FisheyeWarper / StereographicWarper inherit
+// (and that [WARP]:72-81 spells out): rows [y0, y1)
+static RoiAcc roi_rows(int proj, int w, const Projector& p, float scale, int y0, int y1) {
+    RoiAcc r{std::numeric_limits<float>::max(), std::numeric_limits<float>::max(), -std::numeric_limits<float>::max(), -std::numeric_limits<float>::max()};
+    for (int y = y0; y < y1; ++y)
+        for (int x = 0; x < w; ++x) {
+            float u, v;
+            map_forward(proj, p, scale, (float)x, (float)y, &u, &v);
+            r.tl_u = std::min(r.tl_u, u); r.tl_v = std::min(r.tl_v, v);
+            r.br_u = std::max(r.br_u, u); r.br_v = std::max(r.br_v, v);
+        }
+    return r;
+}
+
+// PlaneWarper::detectResultRoi: the four corners of the source
+static RoiAcc roi_corners(int proj, int w, int h, const Projector& p, float scale) {
+    RoiAcc r{std::numeric_limits<float>::max(), std::numeric_limits<float>::max(), -std::numeric_limits<float>::max(), -std::numeric_limits<float>::max()};
+    const int cx[4] = {0, 0, w - 1, w - 1}, cy[4] = {0, h - 1, 0, h - 1};
+    for (int c = 0; c < 4; ++c) {
+        float u, v;
+        map_forward(proj, p, scale, (float)cx[c], (float)cy[c], &u, &v);
+        r.tl_u = std::min(r.tl_u, u); r.tl_v = std::min(r.tl_v, v);
+        r.br_u = std::max(r.br_u, u); r.br_v = std::max(r.br_v, v);
+    }
     return r;
 }
 
@@ -123,6 +210,11 @@ static void finish_roi(int proj, int w, int h, const Projector& p, float scale, 
 // ([WARP]:72-81) gives the same corners (tests/test_oracle_warp.py pins both).  min / max are order independent, so the
 // border may be scanned in pieces (detect_roi_parallel below).
 static void detect_roi(int proj, int w, int h, const Projector& p, float scale, int roi[4]) {
+    if (proj == IS_PROJ_PLANE || proj_uses_maps(proj)) {
+        const RoiAcc a = proj == IS_PROJ_PLANE ? roi_corners(proj, w, h, p, scale) : roi_rows(proj, w, p, scale, 0, h);
+        finish_roi(proj, w, h, p, scale, a.tl_u, a.tl_v, a.br_u, a.br_v, roi);
+        return;
+    }
     const RoiAcc a = roi_segment(proj, w, h, p, scale, true, 0, w), b = roi_segment(proj, w, h, p, scale, false, 0, h);
     finish_roi(proj, w, h, p, scale, std::min(a.tl_u, b.tl_u), std::min(a.tl_v, b.tl_v), std::max(a.br_u, b.br_u), std::max(a.br_v, b.br_v), roi);
 }
@@ -130,16 +222,20 @@ static void detect_roi(int proj, int w, int h, const Projector& p, float scale, 
 // Per-column and per-row trigonometry of the backward map, host libm.  Layout: [sinu(w) | cosu(w) | rowA(h) | rowB(h)]
 //   cylindrical: rowA = v / scale (y_), rowB unused
 //   spherical:   rowA = sinf(pi - v/scale), rowB = cosf(pi - v/scale)
+//   plane:       "sinu" = u / scale - t[0], "cosu" = 1 - t[2], rowA = v / scale - t[1] with t = 0 (PlaneProjector::mapBackward: the
+//                point (u', v', 1 - t[2]) takes the place of the cylinder's (sin u, v', cos u))
 static void fill_tables(int proj, float scale, int tl_x, int tl_y, int w, int h, float* t) {
     float* sinu = t; float* cosu = t + w; float* rowA = t + 2 * (size_t)w; float* rowB = rowA + h;
     for (int i = 0; i < w; ++i) {
         float u = (float)(tl_x + i) / scale;
+        if (proj == IS_PROJ_PLANE) { sinu[i] = u - 0.f; cosu[i] = 1 - 0.f; continue; }
         sinu[i] = sinf(u);
         cosu[i] = cosf(u);
     }
     for (int j = 0; j < h; ++j) {
         float v = (float)(tl_y + j) / scale;
         if (proj == IS_PROJ_CYLINDRICAL) { rowA[j] = v; rowB[j] = 0.f; }
+        else if (proj == IS_PROJ_PLANE) { rowA[j] = v - 0.f; rowB[j] = 0.f; }
         else { rowA[j] = sinf(kPiF - v); rowB[j] = cosf(kPiF - v); }
     }
 }
@@ -149,13 +245,13 @@ static void fill_tables(int proj, float scale, int tl_x, int tl_y, int w, int h,
 template <int PROJ>
 __device__ __forceinline__ void map_backward(const WarpParams& P, float su, float cu, float ra, float rb, float* x, float* y) {
     float x_, y_, z_;
-    if (PROJ == IS_PROJ_CYLINDRICAL) { x_ = su; y_ = ra; z_ = cu; }
+    if (PROJ == IS_PROJ_CYLINDRICAL || PROJ == IS_PROJ_PLANE) { x_ = su; y_ = ra; z_ = cu; }
     else { x_ = __fmul_rn(ra, su); y_ = rb; z_ = __fmul_rn(ra, cu); }
     const float* m = P.k_rinv;
     float X = __fadd_rn(__fadd_rn(__fmul_rn(m[0], x_), __fmul_rn(m[1], y_)), __fmul_rn(m[2], z_));
     float Y = __fadd_rn(__fadd_rn(__fmul_rn(m[3], x_), __fmul_rn(m[4], y_)), __fmul_rn(m[5], z_));
     float Z = __fadd_rn(__fadd_rn(__fmul_rn(m[6], x_), __fmul_rn(m[7], y_)), __fmul_rn(m[8], z_));
-    if (Z > 0.f) { *x = __fdiv_rn(X, Z); *y = __fdiv_rn(Y, Z); }
+    if (PROJ == IS_PROJ_PLANE || Z > 0.f) { *x = __fdiv_rn(X, Z); *y = __fdiv_rn(Y, Z); }   // the plane projector has no z > 0 guard
     else { *x = -1.f; *y = -1.f; }
 }
 
@@ -171,11 +267,20 @@ __device__ __forceinline__ int reflect_idx(int p, int len) {   // cv::borderInte
 
 __device__ __forceinline__ int clamp_short(int v) { return max(-32768, min(32767, v)); }
 
+// cv::cvRound on the CPUs the reference runs on (cvtss2si / cvtps2dq): round half even and INT_MIN -- the "integer indefinite"
+// value -- for NaN and for everything outside the int range, where cvt.rni.s32.f32 saturates and turns NaN into 0.  Only maps
+// that are not bounded by construction need it (caller-supplied maps, the plane projector's unguarded division).
+template <bool SAFE>
+__device__ __forceinline__ int cv_round(float v) {
+    if (SAFE && !(v >= -2147483648.f && v < 2147483648.f)) return -2147483647 - 1;
+    return __float2int_rn(v);
+}
+
 // One destination pixel of cv::remap (8-bit).  out[c], c < CH.
-template <int CH, int INTERP, int BORDER>
+template <int CH, int INTERP, int BORDER, bool SAFE = false>
 __device__ __forceinline__ void sample(const uint8_t* __restrict__ src, size_t sstep, int sw, int sh, float x, float y, int* out) {
     if (INTERP == IS_INTER_NEAREST) {
-        int sx = clamp_short(__float2int_rn(x)), sy = clamp_short(__float2int_rn(y));
+        int sx = clamp_short(cv_round<SAFE>(x)), sy = clamp_short(cv_round<SAFE>(y));
         bool in = (unsigned)sx < (unsigned)sw && (unsigned)sy < (unsigned)sh;
         if (!in) {
             if (BORDER == IS_BORDER_CONSTANT) {
@@ -191,7 +296,7 @@ __device__ __forceinline__ void sample(const uint8_t* __restrict__ src, size_t s
         for (int c = 0; c < CH; ++c) out[c] = __ldg(s + c);
         return;
     }
-    int ix = __float2int_rn(__fmul_rn(x, 32.f)), iy = __float2int_rn(__fmul_rn(y, 32.f));
+    int ix = cv_round<SAFE>(__fmul_rn(x, 32.f)), iy = cv_round<SAFE>(__fmul_rn(y, 32.f));
     int sx = clamp_short(ix >> 5), sy = clamp_short(iy >> 5);
     int fx = ix & 31, fy = iy & 31;
     int w00 = (32 - fy) * (32 - fx), w01 = (32 - fy) * fx, w10 = fy * (32 - fx), w11 = fy * fx;
@@ -248,9 +353,9 @@ k_warp(WarpParams P, const float* __restrict__ tables, const uint8_t* __restrict
         int x = min(x0 + i, P.dst_w - 1);
         float sx, sy;
         map_backward<PROJ>(P, __ldg(sinu + x), __ldg(cosu + x), ra, rb, &sx, &sy);
-        sample<CH, INTERP, BORDER>(src, sstep, P.src_w, P.src_h, sx, sy, px[i]);
+        sample<CH, INTERP, BORDER, PROJ == IS_PROJ_PLANE>(src, sstep, P.src_w, P.src_h, sx, sy, px[i]);
         if (WITH_MASK) {   // INTER_NEAREST + BORDER_CONSTANT on an all-255 source mask
-            int nx = clamp_short(__float2int_rn(sx)), ny = clamp_short(__float2int_rn(sy));
+            int nx = clamp_short(cv_round<PROJ == IS_PROJ_PLANE>(sx)), ny = clamp_short(cv_round<PROJ == IS_PROJ_PLANE>(sy));
             mk[i] = ((unsigned)nx < (unsigned)P.src_w && (unsigned)ny < (unsigned)P.src_h) ? 255 : 0;
         }
     }
@@ -298,6 +403,33 @@ __global__ void k_build_maps(WarpParams P, const float* __restrict__ tables, flo
     reinterpret_cast<float*>(reinterpret_cast<char*>(ymap) + (size_t)y * ystep)[x] = sy;
 }
 
+// cv::remap [WARP]:157 through caller-supplied (or host-built: fisheye / stereographic) CV_32F maps: the sampler of k_warp
+// behind two map loads; WITH_MASK adds the all-255 mask's INTER_NEAREST + BORDER_CONSTANT warp through the same maps.
+template <int CH, int INTERP, int BORDER, bool WITH_MASK>
+__global__ void __launch_bounds__(WARP_BX* WARP_BY)
+k_remap(int dst_w, int dst_h, int src_w, int src_h, const float* __restrict__ xmap, size_t xstep, const float* __restrict__ ymap, size_t ystep,
+        const uint8_t* __restrict__ src, size_t sstep, uint8_t* __restrict__ dst, size_t dstep, uint8_t* __restrict__ mask, size_t mstep) {
+    const int x0 = (blockIdx.x * WARP_BX + threadIdx.x) * WARP_PX;
+    const int y = blockIdx.y * WARP_BY + threadIdx.y;
+    if (y >= dst_h || x0 >= dst_w) return;
+    const float* mx = reinterpret_cast<const float*>(reinterpret_cast<const char*>(xmap) + (size_t)y * xstep);
+    const float* my = reinterpret_cast<const float*>(reinterpret_cast<const char*>(ymap) + (size_t)y * ystep);
+    uint8_t* d = dst + (size_t)y * dstep + (size_t)x0 * CH;
+#pragma unroll
+    for (int i = 0; i < WARP_PX; ++i) {
+        if (x0 + i >= dst_w) break;
+        const float sx = __ldg(mx + x0 + i), sy = __ldg(my + x0 + i);
+        int px[CH];
+        sample<CH, INTERP, BORDER, true>(src, sstep, src_w, src_h, sx, sy, px);
+#pragma unroll
+        for (int c = 0; c < CH; ++c) d[i * CH + c] = (uint8_t)px[c];
+        if (WITH_MASK) {
+            const int nx = clamp_short(cv_round<true>(sx)), ny = clamp_short(cv_round<true>(sy));
+            mask[(size_t)y * mstep + x0 + i] = ((unsigned)nx < (unsigned)src_w && (unsigned)ny < (unsigned)src_h) ? 255 : 0;
+        }
+    }
+}
+
 // @emu-end
 // ---- fused: warp + all-255 mask + level 1 of the image's Gaussian pyramid ------------------------------------------------
 // What MultiBandBlender::feed does first with a warped image is copyMakeBorder(BORDER_REFLECT) into a frame padded to a
@@ -309,6 +441,7 @@ __global__ void k_build_maps(WarpParams P, const float* __restrict__ tables, flo
 // (489 MB per C2 step in round 1), and the 8 % of a frame that is padding costs warp arithmetic instead of a second kernel.
 // Source pixels: the 2 x 2 neighbourhood is six consecutive bytes per row, fetched as aligned 32-bit words (three per row at
 // most) instead of twelve byte loads.
+// @emu-g1-begin (tests/test_kernel_host_emulation.py runs the fused kernel block by block on the multi-threaded host emulator)
 struct WarpG1Args {
     WarpParams P;
     const float* tables;
@@ -330,8 +463,9 @@ __device__ __forceinline__ int reflect101_i(int p, int len) {
 }
 
 // cv::remap INTER_LINEAR + BORDER_REFLECT on 8UC3: same integers as sample<3, LINEAR, REFLECT>; returns b | g << 8 | r << 16
+template <bool SAFE = false>
 __device__ __forceinline__ uint32_t sample3_packed(const uint8_t* __restrict__ src, size_t sstep, int sw, int sh, float x, float y, bool wide_ok) {
-    const int ix = __float2int_rn(__fmul_rn(x, 32.f)), iy = __float2int_rn(__fmul_rn(y, 32.f));
+    const int ix = cv_round<SAFE>(__fmul_rn(x, 32.f)), iy = cv_round<SAFE>(__fmul_rn(y, 32.f));
     const int sx = clamp_short(ix >> 5), sy = clamp_short(iy >> 5);
     const int fx = ix & 31, fy = iy & 31;
     const int w00 = (32 - fy) * (32 - fx), w01 = (32 - fy) * fx, w10 = fy * (32 - fx), w11 = fy * fx;
@@ -416,7 +550,7 @@ __global__ void __launch_bounds__(WG_THREADS) k_warp_g1(WarpG1Args A) {
         const int fy = reflect101_i(fy_lo + tid, A.height);      // pyrDown's BORDER_REFLECT_101 on the frame
         const int iy = reflect_idx(fy - A.top, rows);            // copyMakeBorder's BORDER_REFLECT into the image
         const float ra = __ldg(A.tables + 2 * (size_t)cols + iy);
-        if (PROJ == IS_PROJ_CYLINDRICAL) {                       // (x_, y_, z_) = (sin u, v / scale, cos u): the middle product of every row of k_rinv
+        if (PROJ == IS_PROJ_CYLINDRICAL || PROJ == IS_PROJ_PLANE) {   // (x_, y_, z_) = (sin u, v / scale, cos u) -- plane: (u', v', 1) --: the middle product of every row of k_rinv
             row_t[tid][0] = __fmul_rn(m[1], ra); row_t[tid][1] = __fmul_rn(m[4], ra); row_t[tid][2] = __fmul_rn(m[7], ra); row_t[tid][3] = 0.f;
         } else {
             row_t[tid][0] = ra; row_t[tid][1] = __ldg(A.tables + 2 * (size_t)cols + rows + iy); row_t[tid][2] = 0.f; row_t[tid][3] = 0.f;
@@ -439,21 +573,22 @@ __global__ void __launch_bounds__(WG_THREADS) k_warp_g1(WarpG1Args A) {
         auto issue = [&](int r, Taps& T) {
             const float4 rt = *reinterpret_cast<const float4*>(row_t[r]);
             float sx, sy;
-            if (PROJ == IS_PROJ_CYLINDRICAL) {
+            constexpr bool SAFE = PROJ == IS_PROJ_PLANE;         // no z > 0 guard there: the quotients may be anything
+            if (PROJ == IS_PROJ_CYLINDRICAL || PROJ == IS_PROJ_PLANE) {
                 const float X = __fadd_rn(__fadd_rn(ax, rt.x), cx);
                 const float Y = __fadd_rn(__fadd_rn(ay, rt.y), cy);
                 const float Z = __fadd_rn(__fadd_rn(az, rt.z), cz);
-                if (Z > 0.f) { sx = __fdiv_rn(X, Z); sy = __fdiv_rn(Y, Z); }
+                if (PROJ == IS_PROJ_PLANE || Z > 0.f) { sx = __fdiv_rn(X, Z); sy = __fdiv_rn(Y, Z); }
                 else { sx = -1.f; sy = -1.f; }
             } else {
                 map_backward<PROJ>(A.P, su, cu, rt.x, rt.y, &sx, &sy);
             }
-            const int qx = __float2int_rn(__fmul_rn(sx, 32.f)), qy = __float2int_rn(__fmul_rn(sy, 32.f));
+            const int qx = cv_round<SAFE>(__fmul_rn(sx, 32.f)), qy = cv_round<SAFE>(__fmul_rn(sy, 32.f));
             const int px = qx >> 5, py = qy >> 5;                 // inside the source here, so the remap's saturation to short is the identity
             T.sx = sx; T.sy = sy; T.fx = qx & 31; T.fy = qy & 31;
             T.fast = wide && px >= 0 && px < sw - 3 && (unsigned)py < (unsigned)(sh - 1);
             // the all-255 mask: INTER_NEAREST + BORDER_CONSTANT (source sizes are below 32768: saturating the rounded coordinate to short changes nothing)
-            const int nx = __float2int_rn(sx), ny = __float2int_rn(sy);
+            const int nx = cv_round<SAFE>(sx), ny = cv_round<SAFE>(sy);
             T.inside = (unsigned)nx < (unsigned)sw && (unsigned)ny < (unsigned)sh;
             if (T.fast) {
                 const int o = 3 * px, a = o & ~3;
@@ -467,7 +602,7 @@ __global__ void __launch_bounds__(WG_THREADS) k_warp_g1(WarpG1Args A) {
         auto finish = [&](int r, const Taps& T) {
             uint32_t w;
             if (T.fast) w = sample3_dp_taps(T.a0, T.a1, T.a2, T.b0, T.b1, T.b2, T.sh8, T.fx, T.fy);
-            else w = sample3_packed(src, A.sstep, sw, sh, T.sx, T.sy, false);
+            else w = sample3_packed<PROJ == IS_PROJ_PLANE>(src, A.sstep, sw, sh, T.sx, T.sy, false);
             if (T.inside) w |= 0xff000000u;
             tile[r][tid] = w;
         };
@@ -551,6 +686,7 @@ __global__ void __launch_bounds__(WG_THREADS) k_warp_g1(WarpG1Args A) {
         }
     }
 }
+// @emu-g1-end
 
 // ---- host drivers ----------------------------------------------------------------------------------
 
@@ -599,15 +735,31 @@ static int plan_from_roi(is_ctx* ctx, const Projector& p, int src_w, int src_h, 
     return IS_OK;
 }
 
+// the full forward scan of the per-pixel projectors (fisheye, stereographic), rows spread over the host pool
+static void detect_roi_full_parallel(is_ctx* ctx, int proj, int w, int h, const Projector& p, float scale, int roi[4]) {
+    const size_t pieces = (size_t)std::min(h, 64);
+    std::vector<RoiAcc> acc(pieces);
+    host_pool(ctx)->run(pieces, [&](size_t j) {
+        acc[j] = roi_rows(proj, w, p, scale, (int)((long long)h * (long long)j / (long long)pieces), (int)((long long)h * (long long)(j + 1) / (long long)pieces));
+    });
+    RoiAcc a = acc[0];
+    for (size_t q = 1; q < pieces; ++q) {
+        const RoiAcc& b = acc[q];
+        a.tl_u = std::min(a.tl_u, b.tl_u); a.tl_v = std::min(a.tl_v, b.tl_v); a.br_u = std::max(a.br_u, b.br_u); a.br_v = std::max(a.br_v, b.br_v);
+    }
+    finish_roi(proj, w, h, p, scale, a.tl_u, a.tl_v, a.br_u, a.br_v, roi);
+}
+
 int warp_plan(is_ctx* ctx, int proj, int src_w, int src_h, const float* K, const float* R, float scale, WarpPlan* plan) {
-    IS_REQUIRE(ctx, proj == IS_PROJ_CYLINDRICAL || proj == IS_PROJ_SPHERICAL, IS_ERR_BAD_ARG, "unknown projection");
+    IS_REQUIRE(ctx, proj_known(proj), IS_ERR_BAD_ARG, "unknown projection");
     IS_REQUIRE(ctx, K && R, IS_ERR_ASSERT, "K and R must be 3x3 CV_32F");
     IS_REQUIRE(ctx, src_w > 0 && src_h > 0 && scale > 0.f, IS_ERR_BAD_ARG, "empty source or non-positive scale");
     const PlanKey key = plan_key(proj, src_w, src_h, K, R, scale);
     if (plan_lookup(ctx, key, plan)) return IS_OK;
     Projector p;
     set_camera(K, R, &p);
-    detect_roi(proj, src_w, src_h, p, scale, plan->roi);
+    if (proj_uses_maps(proj)) detect_roi_full_parallel(ctx, proj, src_w, src_h, p, scale, plan->roi);
+    else detect_roi(proj, src_w, src_h, p, scale, plan->roi);
     IS_TRY(plan_from_roi(ctx, p, src_w, src_h, scale, plan));
     plan_store(ctx, key, *plan);
     return IS_OK;
@@ -616,8 +768,12 @@ int warp_plan(is_ctx* ctx, int proj, int src_w, int src_h, const float* K, const
 // The plans of all images of a panorama at once: the border scans of the images not yet in the memo are cut into pieces and
 // spread over the context's host threads (libm atan2f / sqrtf per border pixel: ~0.25 ms per 24 MP image on one core).
 int warp_plan_many(is_ctx* ctx, int proj, int n, const int* src_w, const int* src_h, const float* const* K, const float* const* R, float scale, WarpPlan* plans) {
-    IS_REQUIRE(ctx, proj == IS_PROJ_CYLINDRICAL || proj == IS_PROJ_SPHERICAL, IS_ERR_BAD_ARG, "unknown projection");
+    IS_REQUIRE(ctx, proj_known(proj), IS_ERR_BAD_ARG, "unknown projection");
     IS_REQUIRE(ctx, scale > 0.f, IS_ERR_BAD_ARG, "non-positive scale");
+    if (proj != IS_PROJ_CYLINDRICAL && proj != IS_PROJ_SPHERICAL) {      // four corners (plane) or a scan that is spread over the pool per image
+        for (int i = 0; i < n; ++i) IS_TRY(warp_plan(ctx, proj, src_w[i], src_h[i], K[i], R[i], scale, &plans[i]));
+        return IS_OK;
+    }
     std::vector<int> todo;
     std::vector<PlanKey> keys((size_t)n);
     for (int i = 0; i < n; ++i) {
@@ -652,8 +808,30 @@ int warp_plan_many(is_ctx* ctx, int proj, int n, const int* src_w, const int* sr
     return IS_OK;
 }
 
+// xmap | ymap (dense, dst_h x dst_w floats each) of a per-pixel projector, built by the host pool
+static void build_maps_host(is_ctx* ctx, int proj, const WarpPlan& plan, float* xmap, float* ymap) {
+    Projector p;
+    std::memset(&p, 0, sizeof(p));
+    std::memcpy(p.k_rinv, plan.P.k_rinv, sizeof(p.k_rinv));
+    const int w = plan.P.dst_w, h = plan.P.dst_h;
+    const size_t pieces = (size_t)std::min(h, 256);
+    host_pool(ctx)->run(pieces, [&](size_t j) {
+        fill_map_rows(proj, p, plan.P.scale, plan.P.tl_x, plan.P.tl_y, w, (int)((long long)h * (long long)j / (long long)pieces),
+                      (int)((long long)h * (long long)(j + 1) / (long long)pieces), xmap, ymap);
+    });
+}
+
 int upload_tables(is_ctx* ctx, int proj, const WarpPlan& plan, DevBuf* buf) {
     const int w = plan.P.dst_w, h = plan.P.dst_h;
+    if (proj_uses_maps(proj)) {
+        const size_t px = (size_t)w * (size_t)h;
+        IS_TRY(buf->alloc(ctx, 2 * px * sizeof(float)));
+        std::vector<float> maps(2 * px);
+        build_maps_host(ctx, proj, plan, maps.data(), maps.data() + px);
+        IS_CUDA(ctx, cudaMemcpyAsync(buf->p, maps.data(), 2 * px * sizeof(float), cudaMemcpyHostToDevice, ctx->stream));
+        IS_CUDA(ctx, cudaStreamSynchronize(ctx->stream));          // pageable source: gone when this returns
+        return IS_OK;
+    }
     const size_t n = 2 * (size_t)w + 2 * (size_t)h;
     IS_TRY(buf->alloc(ctx, n * sizeof(float)));
     void* stage = nullptr;
@@ -675,6 +853,39 @@ static int launch_warp_t(is_ctx* ctx, const WarpPlan& plan, const float* tables,
     return IS_OK;
 }
 
+template <int CH, int INTERP, int BORDER, bool WITH_MASK>
+static int launch_remap_t(is_ctx* ctx, int src_w, int src_h, const float* xmap, size_t xstep, const float* ymap, size_t ystep, const DevMat& src, const DevMat& dst,
+                          const DevMat* mask) {
+    dim3 block(WARP_BX, WARP_BY);
+    dim3 grid(div_up(dst.cols, WARP_BX * WARP_PX), div_up(dst.rows, WARP_BY));
+    // algorithmic bytes: the two maps and the source read once, the destination (+ mask) written once
+    ctx->next_bytes = (double)CH * src_w * src_h + (double)(8 + CH + (WITH_MASK ? 1 : 0)) * dst.cols * dst.rows;
+    IS_LAUNCH(ctx, (k_remap<CH, INTERP, BORDER, WITH_MASK>), grid, block, 0, dst.cols, dst.rows, src_w, src_h, xmap, xstep, ymap, ystep, src.ptr<uint8_t>(),
+              src.step, dst.ptr<uint8_t>(), dst.step, mask ? mask->ptr<uint8_t>() : nullptr, mask ? mask->step : 0);
+    return IS_OK;
+}
+
+bool warp_fusable(int proj) { return proj == IS_PROJ_CYLINDRICAL || proj == IS_PROJ_SPHERICAL || proj == IS_PROJ_PLANE; }
+
+// cv::remap of a device-resident 8-bit image through device-resident maps
+int launch_remap(is_ctx* ctx, const float* xmap, size_t xstep, const float* ymap, size_t ystep, const DevMat& src, int interp, int border, const DevMat& dst,
+                 const DevMat* mask) {
+    const int ch = src.channels;
+#define IS_REMAP_CASE(C, I, B, M) \
+    if (ch == C && interp == I && border == B && (mask != nullptr) == M) return launch_remap_t<C, I, B, M>(ctx, src.cols, src.rows, xmap, xstep, ymap, ystep, src, dst, mask);
+    IS_REMAP_CASE(3, IS_INTER_LINEAR, IS_BORDER_REFLECT, true)
+    IS_REMAP_CASE(3, IS_INTER_LINEAR, IS_BORDER_REFLECT, false)
+    IS_REMAP_CASE(3, IS_INTER_LINEAR, IS_BORDER_CONSTANT, false)
+    IS_REMAP_CASE(3, IS_INTER_NEAREST, IS_BORDER_REFLECT, false)
+    IS_REMAP_CASE(3, IS_INTER_NEAREST, IS_BORDER_CONSTANT, false)
+    IS_REMAP_CASE(1, IS_INTER_LINEAR, IS_BORDER_REFLECT, false)
+    IS_REMAP_CASE(1, IS_INTER_LINEAR, IS_BORDER_CONSTANT, false)
+    IS_REMAP_CASE(1, IS_INTER_NEAREST, IS_BORDER_REFLECT, false)
+    IS_REMAP_CASE(1, IS_INTER_NEAREST, IS_BORDER_CONSTANT, false)
+#undef IS_REMAP_CASE
+    return fail(ctx, IS_ERR_UNSUPPORTED, "remap: unsupported combination (channels=%d interp=%d border=%d)", ch, interp, border);
+}
+
 // warp + mask + Gaussian level 1 of the padded frame (top, left, height, width) in one pass; g1: (height / 2) x (width / 2) x 3 int16
 int launch_warp_g1(is_ctx* ctx, int proj, const WarpPlan& plan, const float* tables, const DevMat& src, const DevMat& dst, const DevMat& mask,
                    int top, int left, int height, int width, int16_t* g1) {
@@ -690,7 +901,9 @@ int launch_warp_g1(is_ctx* ctx, int proj, const WarpPlan& plan, const float* tab
     dim3 grid(div_up(A.dw, WG_TX), div_up(A.dh, WG_TY));
     // algorithmic bytes: source read once, warped image + mask and level 1 written once
     ctx->next_bytes = 3. * plan.P.src_w * plan.P.src_h + 4. * plan.P.dst_w * plan.P.dst_h + 6. * A.dh * A.dw;
+    IS_REQUIRE(ctx, proj == IS_PROJ_CYLINDRICAL || proj == IS_PROJ_SPHERICAL || proj == IS_PROJ_PLANE, IS_ERR_UNSUPPORTED, "fused warp: table projectors only");
     if (proj == IS_PROJ_CYLINDRICAL) IS_LAUNCH(ctx, k_warp_g1<IS_PROJ_CYLINDRICAL>, grid, WG_THREADS, 0, A);
+    else if (proj == IS_PROJ_PLANE) IS_LAUNCH(ctx, k_warp_g1<IS_PROJ_PLANE>, grid, WG_THREADS, 0, A);
     else IS_LAUNCH(ctx, k_warp_g1<IS_PROJ_SPHERICAL>, grid, WG_THREADS, 0, A);
     return IS_OK;
 }
@@ -699,6 +912,10 @@ int launch_warp_g1(is_ctx* ctx, int proj, const WarpPlan& plan, const float* tab
 int launch_warp(is_ctx* ctx, int proj, const WarpPlan& plan, const float* tables, const DevMat& src, int interp, int border,
                 const DevMat& dst, const DevMat* mask) {
     const int ch = src.channels;
+    if (proj_uses_maps(proj)) {                              // `tables` = xmap | ymap of upload_tables
+        const size_t step = (size_t)plan.P.dst_w * sizeof(float);
+        return launch_remap(ctx, tables, step, tables + (size_t)plan.P.dst_w * (size_t)plan.P.dst_h, step, src, interp, border, dst, mask);
+    }
 #define IS_WARP_CASE(PJ, C, I, B, M) \
     if (proj == PJ && ch == C && interp == I && border == B && (mask != nullptr) == M) \
         return launch_warp_t<PJ, C, I, B, M>(ctx, plan, tables, src, dst, mask);
@@ -714,6 +931,7 @@ int launch_warp(is_ctx* ctx, int proj, const WarpPlan& plan, const float* tables
     IS_WARP_CASE(PJ, 1, IS_INTER_NEAREST, IS_BORDER_CONSTANT, false)
     IS_WARP_CASES(IS_PROJ_CYLINDRICAL)
     IS_WARP_CASES(IS_PROJ_SPHERICAL)
+    IS_WARP_CASES(IS_PROJ_PLANE)
 #undef IS_WARP_CASES
 #undef IS_WARP_CASE
     return fail(ctx, IS_ERR_UNSUPPORTED, "warp: unsupported combination (channels=%d interp=%d border=%d)", ch, interp, border);
@@ -747,13 +965,33 @@ int is_build_maps(is_ctx* ctx, int projection, is_size src_size, const float K[9
                "maps must be 1-channel IS_32F");
     IS_REQUIRE(ctx, xmap->rows == plan.P.dst_h && xmap->cols == plan.P.dst_w && ymap->rows == plan.P.dst_h && ymap->cols == plan.P.dst_w,
                IS_ERR_BAD_ARG, "maps must have the size reported by is_warp_roi");
+    if (dst_roi) { dst_roi->x = plan.roi[0]; dst_roi->y = plan.roi[1]; dst_roi->width = plan.roi[2] - plan.roi[0]; dst_roi->height = plan.roi[3] - plan.roi[1]; }
+    if (proj_uses_maps(projection)) {                       // host-built maps: straight into host mats, one copy for device mats
+        const size_t px = (size_t)plan.P.dst_w * (size_t)plan.P.dst_h, row = (size_t)plan.P.dst_w * sizeof(float);
+        std::vector<float> maps(2 * px);
+        build_maps_host(ctx, projection, plan, maps.data(), maps.data() + px);
+        is_mat* out[2] = {xmap, ymap};
+        for (int k = 0; k < 2; ++k) {
+            const float* m = maps.data() + (size_t)k * px;
+            if (out[k]->device < 0) {
+                for (int y = 0; y < plan.P.dst_h; ++y) std::memcpy((char*)out[k]->data + (size_t)y * out[k]->step, m + (size_t)y * plan.P.dst_w, row);
+            } else {
+                IS_CUDA(ctx, cudaMemcpy2DAsync(out[k]->data, out[k]->step, m, row, row, (size_t)plan.P.dst_h, cudaMemcpyHostToDevice, ctx->stream));
+            }
+        }
+        IS_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+        return IS_OK;
+    }
     DevBuf tables;
     IS_TRY(upload_tables(ctx, projection, plan, &tables));
     DevMat dx, dy;
     IS_TRY(stage_out(ctx, xmap, &dx, false));
     IS_TRY(stage_out(ctx, ymap, &dy, false));
     dim3 block(32, 8), grid(div_up(plan.P.dst_w, 32), div_up(plan.P.dst_h, 8));
-    if (projection == IS_PROJ_CYLINDRICAL)
+    if (projection == IS_PROJ_PLANE)
+        IS_LAUNCH(ctx, k_build_maps<IS_PROJ_PLANE>, grid, block, 0, plan.P, tables.as<float>(), dx.ptr<float>(), dx.step,
+                  dy.ptr<float>(), dy.step);
+    else if (projection == IS_PROJ_CYLINDRICAL)
         IS_LAUNCH(ctx, k_build_maps<IS_PROJ_CYLINDRICAL>, grid, block, 0, plan.P, tables.as<float>(), dx.ptr<float>(), dx.step,
                   dy.ptr<float>(), dy.step);
     else
@@ -761,7 +999,31 @@ int is_build_maps(is_ctx* ctx, int projection, is_size src_size, const float K[9
                   dy.ptr<float>(), dy.step);
     IS_TRY(commit(ctx, &dx));
     IS_TRY(commit(ctx, &dy));
-    if (dst_roi) { dst_roi->x = plan.roi[0]; dst_roi->y = plan.roi[1]; dst_roi->width = plan.roi[2] - plan.roi[0]; dst_roi->height = plan.roi[3] - plan.roi[1]; }
+    return IS_OK;
+}
+
+int is_remap(is_ctx* ctx, const is_mat* src, const is_mat* xmap, const is_mat* ymap, int interp, int border, is_mat* dst) {
+    if (!ctx) return IS_ERR_BAD_ARG;
+    IS_CUDA(ctx, cudaSetDevice(ctx->device));
+    IS_TRY(check_mat(ctx, src, "src"));
+    IS_TRY(check_mat(ctx, xmap, "xmap"));
+    IS_TRY(check_mat(ctx, ymap, "ymap"));
+    IS_TRY(check_mat(ctx, dst, "dst"));
+    IS_REQUIRE(ctx, src->depth == IS_8U && (src->channels == 1 || src->channels == 3), IS_ERR_UNSUPPORTED, "src must be 8UC1 or 8UC3");
+    IS_REQUIRE(ctx, src->cols < 32768 && src->rows < 32768, IS_ERR_UNSUPPORTED, "cv::remap addresses sources of less than 32768 pixels a side");
+    IS_REQUIRE(ctx, xmap->depth == IS_32F && xmap->channels == 1 && ymap->depth == IS_32F && ymap->channels == 1, IS_ERR_BAD_ARG, "maps must be 1-channel IS_32F");
+    IS_REQUIRE(ctx, xmap->rows == ymap->rows && xmap->cols == ymap->cols, IS_ERR_BAD_ARG, "xmap and ymap must have the same size");
+    IS_REQUIRE(ctx, dst->depth == IS_8U && dst->channels == src->channels && dst->rows == xmap->rows && dst->cols == xmap->cols, IS_ERR_BAD_ARG,
+               "dst must have the type of src and the size of the maps");
+    IS_REQUIRE(ctx, (interp == IS_INTER_NEAREST || interp == IS_INTER_LINEAR) && (border == IS_BORDER_CONSTANT || border == IS_BORDER_REFLECT),
+               IS_ERR_UNSUPPORTED, "interp must be NEAREST/LINEAR and border CONSTANT/REFLECT");
+    DevMat s, mx, my, d;
+    IS_TRY(stage_in(ctx, src, &s));
+    IS_TRY(stage_in(ctx, xmap, &mx));
+    IS_TRY(stage_in(ctx, ymap, &my));
+    IS_TRY(stage_out(ctx, dst, &d, false));
+    IS_TRY(launch_remap(ctx, mx.ptr<float>(), mx.step, my.ptr<float>(), my.step, s, interp, border, d, nullptr));
+    IS_TRY(commit(ctx, &d));
     return IS_OK;
 }
 

@@ -21,12 +21,13 @@ import numpy as np
 
 from . import capi
 from .capi import (BORDER_CONSTANT, BORDER_REFLECT, COST_COLOR, COST_COLOR_GRAD, EXPOSURE_GAIN, EXPOSURE_NONE, FEED_BORROW, FEED_COPY,
-                   INTER_LINEAR, INTER_NEAREST, PROJ_CYLINDRICAL, PROJ_SPHERICAL, SEAM_DP, SEAM_NONE, WEIGHT_16S, WEIGHT_32F)
+                   INTER_LINEAR, INTER_NEAREST, PROJ_CYLINDRICAL, PROJ_FISHEYE, PROJ_PLANE, PROJ_SPHERICAL, PROJ_STEREOGRAPHIC, SEAM_DP, SEAM_NONE, WEIGHT_16S, WEIGHT_32F)
 
 _NP_DEPTH = {np.dtype(np.uint8): capi.IS_8U, np.dtype(np.int16): capi.IS_16S, np.dtype(np.int32): capi.IS_32S,
              np.dtype(np.float32): capi.IS_32F}
-_PROJ = {"cylindrical": PROJ_CYLINDRICAL, "spherical": PROJ_SPHERICAL, PROJ_CYLINDRICAL: PROJ_CYLINDRICAL,
-         PROJ_SPHERICAL: PROJ_SPHERICAL}
+_PROJ = {"cylindrical": PROJ_CYLINDRICAL, "spherical": PROJ_SPHERICAL, "plane": PROJ_PLANE, "fisheye": PROJ_FISHEYE,
+         "stereographic": PROJ_STEREOGRAPHIC}              # the warper creators of [BLEND]:91-95
+_PROJ.update({v: v for v in list(_PROJ.values())})
 
 
 def _is_torch(a):
@@ -193,6 +194,17 @@ class RotationWarper:
         tl = capi.Point()
         self.ctx.check(self.ctx.lib.is_warp_with_mask(self.ctx.h, self.proj, C.byref(ms), kp, rp, self.scale, C.byref(md), C.byref(mm), C.byref(tl)))
         return (tl.x, tl.y), dst, mask
+
+
+def remap(ctx: Context, src, xmap, ymap, interp_mode=INTER_LINEAR, border_mode=BORDER_REFLECT):
+    """cv::remap ([WARP]:157) for 8-bit images with 1 or 3 channels through CV_32F maps -> dst of the maps' size"""
+    ms, src_k = as_mat(src)
+    mx, _x = as_mat(xmap)
+    my, _y = as_mat(ymap)
+    dst = _alloc_like(src_k, (mx.rows, mx.cols) if ms.channels == 1 else (mx.rows, mx.cols, ms.channels), np.uint8)
+    md, _d = as_mat(dst)
+    ctx.check(ctx.lib.is_remap(ctx.h, C.byref(ms), C.byref(mx), C.byref(my), int(interp_mode), int(border_mode), C.byref(md)))
+    return dst
 
 
 def _mat_array(arrs):

@@ -58,7 +58,13 @@ typedef struct is_point { int x, y; } is_point;
 typedef struct is_size { int width, height; } is_size;
 typedef struct is_rect { int x, y, width, height; } is_rect;
 
-typedef enum is_projection { IS_PROJ_CYLINDRICAL = 0, IS_PROJ_SPHERICAL = 1 } is_projection;
+/* cv::CylindricalWarper / SphericalWarper / PlaneWarper / FisheyeWarper / StereographicWarper: the warper creators of
+ * [BLEND]:91-95.  Fisheye and stereographic need libm calls per PIXEL, so their maps are built on the host (as
+ * buildMaps [WARP]:122-144 does) and sampled on the device; the other three are evaluated on the device from O(W + H)
+ * host tables and take the fused warp path of is_pipeline_run. */
+typedef enum is_projection {
+    IS_PROJ_CYLINDRICAL = 0, IS_PROJ_SPHERICAL = 1, IS_PROJ_PLANE = 2, IS_PROJ_FISHEYE = 3, IS_PROJ_STEREOGRAPHIC = 4
+} is_projection;
 typedef enum is_interp { IS_INTER_NEAREST = 0, IS_INTER_LINEAR = 1 } is_interp;           /* cv::INTER_* */
 typedef enum is_border { IS_BORDER_CONSTANT = 0, IS_BORDER_REFLECT = 2 } is_border;       /* cv::BORDER_* */
 typedef enum is_seam_cost { IS_COST_COLOR = 0, IS_COST_COLOR_GRAD = 1 } is_seam_cost;     /* [SEAM]:71 */
@@ -107,6 +113,11 @@ int is_build_maps(is_ctx* ctx, int projection, is_size src_size, const float K[9
  * channels.  dst: caller-allocated, dst_size from is_warp_roi, same type as src. */
 int is_warp(is_ctx* ctx, int projection, const is_mat* src, const float K[9], const float R[9], float scale,
             int interp, int border, is_mat* dst, is_point* dst_tl);
+
+/* cv::remap(src, dst, xmap, ymap, interp, border) -- the call warp() ends in, [WARP]:157 -- on its own: src IS_8U with 1 or
+ * 3 channels, maps 1-channel IS_32F of the destination's size, dst caller-allocated with the type of src.  NaN and
+ * out-of-range map values sample what cv::remap samples on x86 (cvRound's INT_MIN). */
+int is_remap(is_ctx* ctx, const is_mat* src, const is_mat* xmap, const is_mat* ymap, int interp, int border, is_mat* dst);
 
 /* The two warp calls every main() makes per image ([BLEND]:105,109): image with INTER_LINEAR +
  * BORDER_REFLECT and an all-255 mask with INTER_NEAREST + BORDER_CONSTANT, in one pass over the

@@ -62,6 +62,10 @@ public:
         ctx_.check(is_warp(ctx_.get(), proj_, &src, K, R, scale_, interp_mode, border_mode, &dst, &tl));
         return tl;
     }
+    // cv::remap of [WARP]:157 on its own (any maps of the destination's size)
+    static void remap(Context& ctx, const is_mat& src, const is_mat& xmap, const is_mat& ymap, int interp_mode, int border_mode, is_mat& dst) {
+        ctx.check(is_remap(ctx.get(), &src, &xmap, &ymap, interp_mode, border_mode, &dst));
+    }
     // image (INTER_LINEAR, BORDER_REFLECT) and all-255 mask (INTER_NEAREST, BORDER_CONSTANT) of [BLEND]:105,109 in one pass
     is_point warpWithMask(const is_mat& src, const float K[9], const float R[9], is_mat& dst, is_mat& dst_mask) const {
         is_point tl{};

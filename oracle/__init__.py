@@ -19,7 +19,7 @@ import numpy as np
 _DIR = os.path.dirname(os.path.abspath(__file__))
 _SO = os.path.join(_DIR, "_build", "liboracle.so")
 
-PROJ_CYLINDRICAL, PROJ_SPHERICAL = 0, 1
+PROJ_CYLINDRICAL, PROJ_SPHERICAL, PROJ_PLANE, PROJ_FISHEYE, PROJ_STEREOGRAPHIC = 0, 1, 2, 3, 4
 INTER_NEAREST, INTER_LINEAR = 0, 1
 BORDER_CONSTANT, BORDER_REFLECT = 0, 2
 COST_COLOR, COST_COLOR_GRAD = 0, 1

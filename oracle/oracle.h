@@ -31,7 +31,7 @@
 extern "C" {
 #endif
 
-enum { ORC_PROJ_CYLINDRICAL = 0, ORC_PROJ_SPHERICAL = 1 };
+enum { ORC_PROJ_CYLINDRICAL = 0, ORC_PROJ_SPHERICAL = 1, ORC_PROJ_PLANE = 2, ORC_PROJ_FISHEYE = 3, ORC_PROJ_STEREOGRAPHIC = 4 };
 enum { ORC_INTER_NEAREST = 0, ORC_INTER_LINEAR = 1 };
 enum { ORC_BORDER_CONSTANT = 0, ORC_BORDER_REFLECT = 2 };
 enum { ORC_COST_COLOR = 0, ORC_COST_COLOR_GRAD = 1 };

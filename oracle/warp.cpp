@@ -3,6 +3,9 @@
 // CPU restatement of the reference's rotation warper:
 //   setCameraParams   [WARP]:90-120
 //   mapForward        [WARP]:37-45      (cylindrical)   / SURVEY.md a25 (spherical, OpenCV warpers_inl.hpp)
+//   plane / fisheye / stereographic: the projectors behind the warper creators the reference keeps commented out at
+//                     [BLEND]:91-95 (cv::PlaneWarper, FisheyeWarper, StereographicWarper; OpenCV stitching, un-vendored:
+//                     PlaneProjector, FisheyeProjector, StereographicProjector of warpers_inl.hpp, T = 0), pinned to cv2
 //   mapBackward       [WARP]:47-63
 //   detectResultRoi   [WARP]:64-88
 //   buildMaps         [WARP]:122-144
@@ -78,6 +81,23 @@ inline void mapForward(const Projector& p, float x, float y, float& u, float& v)
     if (p.proj == ORC_PROJ_CYLINDRICAL) {          // [WARP]:43-44
         u = p.scale * atan2f(x_, z_);
         v = p.scale * y_ / sqrtf(x_ * x_ + z_ * z_);
+    } else if (p.proj == ORC_PROJ_PLANE) {          // PlaneProjector::mapForward with t = (0, 0, 0)
+        x_ = 0.f + x_ / z_ * (1 - 0.f);
+        y_ = 0.f + y_ / z_ * (1 - 0.f);
+        u = p.scale * x_;
+        v = p.scale * y_;
+    } else if (p.proj == ORC_PROJ_FISHEYE) {        // FisheyeProjector::mapForward
+        float u_ = atan2f(x_, z_);
+        float v_ = PI_F - acosf(y_ / sqrtf(x_ * x_ + y_ * y_ + z_ * z_));
+        float r = p.scale * v_;
+        u = r * cosf(u_);
+        v = r * sinf(u_);
+    } else if (p.proj == ORC_PROJ_STEREOGRAPHIC) {  // StereographicProjector::mapForward
+        float u_ = atan2f(x_, z_);
+        float v_ = PI_F - acosf(y_ / sqrtf(x_ * x_ + y_ * y_ + z_ * z_));
+        float r = sinf(v_) / (1 - cosf(v_));
+        u = p.scale * r * cosf(u_);
+        v = p.scale * r * sinf(u_);
     } else {                                        // SphericalProjector::mapForward
         u = p.scale * atan2f(x_, z_);
         float w = y_ / sqrtf(x_ * x_ + y_ * y_ + z_ * z_);
@@ -93,6 +113,32 @@ inline void mapBackward(const Projector& p, float u, float v, float& x, float& y
         x_ = sinf(u);
         y_ = v;
         z_ = cosf(u);
+    } else if (p.proj == ORC_PROJ_PLANE) {          // PlaneProjector::mapBackward, t = 0: no z > 0 guard
+        const float* m = p.k_rinv;
+        u = u - 0.f;
+        v = v - 0.f;
+        float z;
+        x = m[0] * u + m[1] * v + m[2] * (1 - 0.f);
+        y = m[3] * u + m[4] * v + m[5] * (1 - 0.f);
+        z = m[6] * u + m[7] * v + m[8] * (1 - 0.f);
+        x /= z;
+        y /= z;
+        return;
+    } else if (p.proj == ORC_PROJ_FISHEYE) {        // FisheyeProjector::mapBackward
+        float u_ = atan2f(v, u);
+        float v_ = sqrtf(u * u + v * v);
+        float sinv = sinf(PI_F - v_);
+        x_ = sinv * sinf(u_);
+        y_ = cosf(PI_F - v_);
+        z_ = sinv * cosf(u_);
+    } else if (p.proj == ORC_PROJ_STEREOGRAPHIC) {  // StereographicProjector::mapBackward
+        float u_ = atan2f(v, u);
+        float r = sqrtf(u * u + v * v);
+        float v_ = 2 * atanf(1.f / r);
+        float sinv = sinf(PI_F - v_);
+        x_ = sinv * sinf(u_);
+        y_ = cosf(PI_F - v_);
+        z_ = sinv * cosf(u_);
     } else {                                        // SphericalProjector::mapBackward
         float sinv = sinf(PI_F - v);
         x_ = sinv * sinf(u);
@@ -108,7 +154,12 @@ inline void mapBackward(const Projector& p, float u, float v, float& x, float& y
     else x = y = -1;
 }
 
-inline int cvRound(float v) { return (int)lrintf(v); }   // round-half-even under the default FP mode
+// cv::cvRound on x86 is _mm_cvtss_si32 / cvtps2dq: round-half-even, and the "integer indefinite" value INT_MIN for NaN and for
+// everything outside the int range (lrintf alone would give the 64-bit result's low half there)
+inline int cvRound(float v) {
+    if (!(v >= -2147483648.f && v < 2147483648.f)) return -2147483647 - 1;
+    return (int)lrintf(v);
+}
 
 inline short saturate_short(int v) {
     return (short)(v < -32768 ? -32768 : (v > 32767 ? 32767 : v));
@@ -186,7 +237,9 @@ void orc_detect_roi(int proj, int src_w, int src_h, const float K[9], const floa
         tl_uf = (std::min)(tl_uf, u); tl_vf = (std::min)(tl_vf, v);
         br_uf = (std::max)(br_uf, u); br_vf = (std::max)(br_vf, v);
     };
-    if (full_scan) {                                        // [WARP]:72-81 (min/max are order-independent)
+    if (proj == ORC_PROJ_PLANE) {                           // PlaneWarper::detectResultRoi: the four corners
+        acc(0, 0); acc(0, src_h - 1); acc(src_w - 1, 0); acc(src_w - 1, src_h - 1);
+    } else if (full_scan || proj == ORC_PROJ_FISHEYE || proj == ORC_PROJ_STEREOGRAPHIC) {   // [WARP]:72-81 (min/max are order-independent); RotationWarperBase::detectResultRoi
 #pragma omp parallel for schedule(static) reduction(min : tl_uf, tl_vf) reduction(max : br_uf, br_vf)
         for (int y = 0; y < src_h; ++y)
             for (int x = 0; x < src_w; ++x) {

@@ -83,6 +83,26 @@ template <typename T> inline T __shfl_up_sync(unsigned, T v, unsigned d) { retur
 template <typename T> inline T __shfl_down_sync(unsigned, T v, unsigned d) { return emu_shfl(v, [d](unsigned l) { return l + d < 32 ? l + d : l; }); }
 template <typename T> inline T __shfl_sync(unsigned, T v, int src) { return emu_shfl(v, [src](unsigned) { return (unsigned)src & 31; }); }
 
+inline int __float2int_rn(float v) {                      // cvt.rni.s32.f32: round half even, saturate, NaN -> 0
+    if (v != v) return 0;
+    if (v >= 2147483648.f) return 2147483647;
+    if (v <= -2147483648.f) return -2147483647 - 1;
+    return (int)std::nearbyintf(v);
+}
+// byte dot products, funnel shift and byte permute as PTX defines them (unsigned forms; prmt without the sign-replicating modes)
+inline uint32_t __dp4a(uint32_t a, uint32_t b, uint32_t c) {
+    for (int i = 0; i < 4; ++i) c += ((a >> (8 * i)) & 255u) * ((b >> (8 * i)) & 255u);
+    return c;
+}
+inline uint32_t __dp2a_lo(uint32_t a, uint32_t b, uint32_t c) { return c + (a & 0xffffu) * (b & 255u) + (a >> 16) * ((b >> 8) & 255u); }
+inline uint32_t __funnelshift_r(uint32_t lo, uint32_t hi, uint32_t shift) { return (uint32_t)((((uint64_t)hi << 32) | lo) >> (shift & 31u)); }
+inline uint32_t __byte_perm(uint32_t x, uint32_t y, uint32_t s) {
+    const uint64_t v = ((uint64_t)y << 32) | x;
+    uint32_t r = 0;
+    for (int i = 0; i < 4; ++i) r |= (uint32_t)((v >> (8 * ((s >> (4 * i)) & 7u))) & 255u) << (8 * i);
+    return r;
+}
+
 inline int __float2int_rz(float v) {                        // cvt.rzi.s32.f32: truncate, saturate, NaN -> 0
     if (v != v) return 0;
     if (v >= 2147483648.f) return 2147483647;

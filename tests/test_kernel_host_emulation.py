@@ -45,6 +45,26 @@ def emu_warp():
 
 
 @pytest.fixture(scope="module")
+def emu_warp_g1():
+    """the fused warp + mask + Gaussian level 1 kernel on the multi-threaded block emulator"""
+    regions = []
+    for f in ("internal.cuh", "warp.cu"):
+        regions += re.findall(r"// @emu-begin[^\n]*\n(.*?)// @emu-end", open(os.path.join(ROOT, "imagestitch_b200", "csrc", f)).read(), flags=re.S)
+    g1 = re.findall(r"// @emu-g1-begin[^\n]*\n(.*?)// @emu-g1-end", open(os.path.join(ROOT, "imagestitch_b200", "csrc", "warp.cu")).read(), flags=re.S)
+    assert len(regions) == 2 and len(g1) == 1
+    os.makedirs(OUT, exist_ok=True)
+    with open(os.path.join(OUT, "warp_g1_regions.inc"), "w") as f:
+        # `__shared__ __align__(n) T x` -> `alignas(n) static T x` (standard attributes must come first)
+        f.write(re.sub(r"__shared__\s+__align__\((\d+)\)", r"alignas(\1) static", "\n".join(regions + g1)))
+    so = os.path.join(OUT, "libwarp_g1_emul.so")
+    subprocess.check_call(["g++", "-O1", "-fPIC", "-std=c++20", "-pthread", "-ffp-contract=off", "-fno-fast-math", "-w", "-I", EMU, "-I", OUT, "-shared",
+                           "-o", so, os.path.join(EMU, "warp_g1_emul.cpp")])
+    lib = C.CDLL(so)
+    lib.emu_warp_g1.restype = C.c_int
+    return lib
+
+
+@pytest.fixture(scope="module")
 def emu_dp():
     """the DP kernel on the multi-threaded block emulator (tests/emu/cuda_host_emul_mt.h, tests/emu/tma.cuh)"""
     src = open(os.path.join(ROOT, "imagestitch_b200", "csrc", "seam.cu")).read()
@@ -173,7 +193,7 @@ def _f9(m):
     return np.ascontiguousarray(np.asarray(m, np.float32).reshape(9))
 
 
-@pytest.mark.parametrize("proj", [0, 1])
+@pytest.mark.parametrize("proj", [0, 1, 2, 3, 4])
 def test_warp_kernels_match_oracle(emu_warp, oracle, proj):
     """ROI, backward maps, warped image and warped mask of the product's warp source == the oracle (== cv2 / the reference)"""
     from helpers import random_camera
@@ -204,6 +224,63 @@ def test_warp_kernels_match_oracle(emu_warp, oracle, proj):
         assert emu_warp.emu_warp(proj, _p(np.full((h, w), 255, np.uint8)), h, w, 1, C.c_size_t(w), _p(_f9(K)), _p(_f9(R)), C.c_float(scale),
                                  O.INTER_NEAREST, O.BORDER_CONSTANT, _p(m1), C.c_size_t(dw), None, C.c_size_t(0)) == 0
         assert np.array_equal(m1, wmask)
+
+
+@pytest.mark.parametrize("proj", [0, 1, 2])
+def test_fused_warp_g1_kernel_matches_oracle(emu_warp_g1, oracle, proj):
+    """k_warp_g1 (the pipeline's warp: image + all-255 mask + pyrDown of the BORDER_REFLECT-padded frame, shared-memory tile, dp4a
+    sampling, three-row software pipeline) thread by thread on the host == oracle warp, mask and pyrDown(copyMakeBorder(warp))"""
+    from helpers import random_camera
+    O = oracle
+    rng = np.random.default_rng(40 + proj)
+    ran = 0
+    for t in range(2):
+        w, h = int(rng.integers(100, 200)), int(rng.integers(70, 130))
+        K, R, scale = random_camera(rng, w, h)
+        if proj == 2 and t == 1:
+            R = np.ascontiguousarray(__import__("helpers").rot(1.15, 0.05, 0.02))    # far off axis: the plane's unguarded quotients grow large
+        img = rng.integers(0, 256, (h, w, 3), dtype=np.uint8)
+        if t == 1:
+            img = np.ascontiguousarray(np.concatenate([img, img[:, :1]], axis=1)[:, :w + 1])[:, :w]     # a pitch that is not a multiple of 4
+        _, want = O.warp(proj, img, K, R, scale, O.INTER_LINEAR, O.BORDER_REFLECT)
+        _, wmask = O.warp(proj, np.full((h, w), 255, np.uint8), K, R, scale, O.INTER_NEAREST, O.BORDER_CONSTANT)
+        dh, dw = want.shape[:2]
+        if dh * dw > 400 * 400:
+            continue
+        top, left = (5, 9) if t == 0 else (0, 16)
+        height, width = -(-(dh + top + 3) // 16) * 16, -(-(dw + left + 1) // 16) * 16
+        dst = np.zeros((dh, dw, 3), np.uint8)
+        msk = np.zeros((dh, dw), np.uint8)
+        g1 = np.zeros(((height + 1) // 2, (width + 1) // 2, 3), np.int16)
+        assert emu_warp_g1.emu_warp_g1(proj, _p(img), h, w, C.c_size_t(img.strides[0]), _p(_f9(K)), _p(_f9(R)), C.c_float(scale), _p(dst), _p(msk),
+                                       top, left, height, width, _p(g1)) == 0
+        assert np.array_equal(dst, want) and np.array_equal(msk, wmask), (proj, t)
+        frame = np.pad(want, ((top, height - top - dh), (left, width - left - dw), (0, 0)), mode="symmetric").astype(np.int16)   # copyMakeBorder(BORDER_REFLECT)
+        assert np.array_equal(g1, O.pyr_down_s16(frame)), (proj, t)
+        ran += 1
+    assert ran >= 1
+
+
+def test_remap_kernel_matches_oracle_incl_extreme_maps(emu_warp, oracle):
+    """k_remap (is_remap, and the fisheye / stereographic warps) on caller maps with NaN, infinities and values beyond the int range:
+    cv::remap samples those at cvRound's INT_MIN on x86 (the oracle is pinned to cv2 on exactly these values)."""
+    O = oracle
+    rng = np.random.default_rng(5)
+    img = rng.integers(0, 256, (60, 80, 3), dtype=np.uint8)
+    vals = np.array([np.nan, np.inf, -np.inf, 3e9, -3e9, 1e8, -1e8, 7e7, -7e7, 2 ** 31 / 32, 2 ** 31 / 32 - 4, -2 ** 31 / 32, 1e12, -1e12, 1e20, -1e20,
+                     6.7e7, 40.3, -0.5, 0.5, 1.5, 79.5, 78.999, -1.0, 32767.4, 32768.6, -32768.5], np.float32)
+    xm = np.concatenate([np.tile(vals, (len(vals), 1)), rng.uniform(-200, 300, (len(vals), len(vals))).astype(np.float32)])
+    ym = np.concatenate([np.tile(vals, (len(vals), 1)).T, rng.uniform(-150, 250, (len(vals), len(vals))).astype(np.float32)])
+    xm, ym = np.ascontiguousarray(xm), np.ascontiguousarray(ym)
+    dh, dw = xm.shape
+    for ch in (3, 1):
+        src = img if ch == 3 else np.ascontiguousarray(img[:, :, 1])
+        for interp in (O.INTER_LINEAR, O.INTER_NEAREST):
+            for border in (O.BORDER_REFLECT, O.BORDER_CONSTANT):
+                dst = np.zeros((dh, dw, 3) if ch == 3 else (dh, dw), np.uint8)
+                assert emu_warp.emu_remap(_p(src), 60, 80, ch, C.c_size_t(80 * ch), _p(xm), _p(ym), dh, dw, interp, border, _p(dst), C.c_size_t(dw * ch),
+                                          None, C.c_size_t(0)) == 0
+                assert np.array_equal(dst, O.remap(src, xm, ym, interp, border)), (ch, interp, border)
 
 
 def test_warp_kernel_other_sampling_modes(emu_warp, oracle):

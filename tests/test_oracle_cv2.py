@@ -12,7 +12,7 @@ cv2 = pytest.importorskip("cv2")
 def test_warp_vs_cv2(oracle):
     O = oracle
     rng = np.random.default_rng(1234)
-    for proj, name in ((0, "cylindrical"), (1, "spherical")):
+    for proj, name in ((0, "cylindrical"), (1, "spherical"), (2, "plane"), (3, "fisheye"), (4, "stereographic")):
         for _ in range(4):
             w, h = int(rng.integers(120, 360)), int(rng.integers(100, 300))
             K, R, scale = random_camera(rng, w, h)
@@ -21,6 +21,10 @@ def test_warp_vs_cv2(oracle):
             oroi, oxm, oym = O.build_maps(proj, (w, h), K, R, scale, full_scan=True)
             assert (roi[0], roi[1], roi[0] + roi[2], roi[1] + roi[3]) == oroi
             assert O.detect_roi(proj, (w, h), K, R, scale, full_scan=False) == oroi
+            if proj >= 2:                                     # the mask warp of the mains ([BLEND]:109) through these projectors too
+                tlm, wmk = wp.warp(np.full((h, w), 255, np.uint8), K, R, cv2.INTER_NEAREST, cv2.BORDER_CONSTANT)
+                otlm, owmk = O.warp(proj, np.full((h, w), 255, np.uint8), K, R, scale, O.INTER_NEAREST, O.BORDER_CONSTANT)
+                assert tuple(tlm) == otlm and np.array_equal(wmk, owmk)
             assert np.array_equal(xm.view(np.uint32), oxm.view(np.uint32)) and np.array_equal(ym.view(np.uint32), oym.view(np.uint32))
             img = rng.integers(0, 256, (h, w, 3), dtype=np.uint8)
             tl, wi = wp.warp(img, K, R, cv2.INTER_LINEAR, cv2.BORDER_REFLECT)
@@ -34,6 +38,20 @@ def test_remap_vs_cv2(oracle):
     img = rng.integers(0, 256, (60, 80, 3), dtype=np.uint8)
     xm = rng.uniform(-200, 300, (100, 120)).astype(np.float32)
     ym = rng.uniform(-150, 250, (100, 120)).astype(np.float32)
+    for interp, ci in ((O.INTER_LINEAR, cv2.INTER_LINEAR), (O.INTER_NEAREST, cv2.INTER_NEAREST)):
+        for border, cb in ((O.BORDER_REFLECT, cv2.BORDER_REFLECT), (O.BORDER_CONSTANT, cv2.BORDER_CONSTANT)):
+            assert np.array_equal(cv2.remap(img, xm, ym, ci, borderMode=cb), O.remap(img, xm, ym, interp, border))
+
+
+def test_remap_extreme_maps_vs_cv2(oracle):
+    """NaN, infinities and coordinates beyond the int range: cv::remap rounds them with cvtps2dq (INT_MIN); the oracle follows"""
+    O = oracle
+    rng = np.random.default_rng(1)
+    img = rng.integers(0, 256, (60, 80, 3), dtype=np.uint8)
+    vals = np.array([np.nan, np.inf, -np.inf, 3e9, -3e9, 1e8, -1e8, 7e7, -7e7, 2 ** 31 / 32, 2 ** 31 / 32 - 4, -2 ** 31 / 32, 1e12, -1e12, 1e20, -1e20,
+                     6.7e7, 40.3, -0.5, 0.5, 1.5, 79.5, 78.999, -1.0, 32767.4, 32768.6, -32768.5], np.float32)
+    xm = np.tile(vals, (len(vals), 1))
+    ym = xm.T.copy()
     for interp, ci in ((O.INTER_LINEAR, cv2.INTER_LINEAR), (O.INTER_NEAREST, cv2.INTER_NEAREST)):
         for border, cb in ((O.BORDER_REFLECT, cv2.BORDER_REFLECT), (O.BORDER_CONSTANT, cv2.BORDER_CONSTANT)):
             assert np.array_equal(cv2.remap(img, xm, ym, ci, borderMode=cb), O.remap(img, xm, ym, interp, border))
