@@ -82,6 +82,9 @@ SYMBOLS = {
     "is_warp_roi": (C.c_int, [C.c_void_p, C.c_int, Size, _F9, _F9, C.c_float, _P(Point), _P(Size)]),
     "is_build_maps": (C.c_int, [C.c_void_p, C.c_int, Size, _F9, _F9, C.c_float, _P(Mat), _P(Mat), _P(Rect)]),
     "is_warp": (C.c_int, [C.c_void_p, C.c_int, _P(Mat), _F9, _F9, C.c_float, C.c_int, C.c_int, _P(Mat), _P(Point)]),
+    "is_bmp_info": (C.c_int, [C.c_void_p, C.c_char_p, _P(Size), _P(C.c_int)]),
+    "is_imread_bmp": (C.c_int, [C.c_void_p, C.c_char_p, _P(Mat)]),
+    "is_imwrite_bmp": (C.c_int, [C.c_void_p, C.c_char_p, _P(Mat)]),
     "is_remap": (C.c_int, [C.c_void_p, _P(Mat), _P(Mat), _P(Mat), C.c_int, C.c_int, _P(Mat)]),
     "is_warp_with_mask": (C.c_int, [C.c_void_p, C.c_int, _P(Mat), _F9, _F9, C.c_float, _P(Mat), _P(Mat), _P(Point)]),
     "is_seam_dp_find": (C.c_int, [C.c_void_p, C.c_int, _P(Mat), _P(Point), _P(Mat), C.c_int]),

@@ -16,6 +16,7 @@ All computation happens in libimagestitch_b200.so; nothing here computes pixels.
 from __future__ import annotations
 
 import ctypes as C
+import os
 
 import numpy as np
 
@@ -205,6 +206,22 @@ def remap(ctx: Context, src, xmap, ymap, interp_mode=INTER_LINEAR, border_mode=B
     md, _d = as_mat(dst)
     ctx.check(ctx.lib.is_remap(ctx.h, C.byref(ms), C.byref(mx), C.byref(my), int(interp_mode), int(border_mode), C.byref(md)))
     return dst
+
+
+def imread(ctx: Context, path, like=None):
+    """cv::imread(path) for bitmaps ([BLEND]:31-34) -> HxWx3 uint8 (numpy, or a CUDA tensor when `like` is one)"""
+    sz, bpp = capi.Size(), C.c_int()
+    ctx.check(ctx.lib.is_bmp_info(ctx.h, os.fsencode(path), C.byref(sz), C.byref(bpp)))
+    dst = _alloc_like(like, (sz.height, sz.width, 3), np.uint8) if like is not None else np.empty((sz.height, sz.width, 3), np.uint8)
+    md, _d = as_mat(dst)
+    ctx.check(ctx.lib.is_imread_bmp(ctx.h, os.fsencode(path), C.byref(md)))
+    return dst
+
+
+def imwrite(ctx: Context, path, img):
+    """cv::imwrite(path, img) for bitmaps ([BLEND]:717, [SEAM]:1195-1206): uint8 / int16 / float32 with 1 or 3 channels"""
+    ms, _k = as_mat(img)
+    ctx.check(ctx.lib.is_imwrite_bmp(ctx.h, os.fsencode(path), C.byref(ms)))
 
 
 def _mat_array(arrs):

@@ -125,6 +125,19 @@ int is_remap(is_ctx* ctx, const is_mat* src, const is_mat* xmap, const is_mat* y
 int is_warp_with_mask(is_ctx* ctx, int projection, const is_mat* src, const float K[9], const float R[9],
                       float scale, is_mat* dst, is_mat* dst_mask, is_point* dst_tl);
 
+/* ------------------------------------------------------------------ image files
+ * The on-disk format either side of the path: cv::imread(".bmp") [BLEND]:31-34, [SEAM]:1098-1100 and
+ * cv::imwrite(".bmp", mat) [BLEND]:717, [SEAM]:1195-1206.  The file's bytes go to the device as they are and a kernel
+ * turns them into cv::Mat rows (top-down, BGR interleaved, palette looked up, padding / alpha dropped); writing packs the
+ * rows bottom-up on the device with imwrite's saturating conversion to 8 bit fused in.  Uncompressed 1 / 4 / 8 / 24 /
+ * 32-bit bitmaps; byte-identical to cv2.imread / cv2.imwrite.  dst / src may be host or device memory. */
+int is_bmp_info(is_ctx* ctx, const char* path, is_size* size, int* bits_per_pixel);
+/* imread(path) with the default IMREAD_COLOR: dst is IS_8U with 3 channels of the size is_bmp_info reports */
+int is_imread_bmp(is_ctx* ctx, const char* path, is_mat* dst);
+/* imwrite(path, src): 1 channel (8-bit file with a gray palette) or 3 channels (24-bit file); IS_16S and IS_32F are converted
+ * like cv::Mat::convertTo(CV_8U) -- what imwrite does with images_warped_f, pano and result in the mains */
+int is_imwrite_bmp(is_ctx* ctx, const char* path, const is_mat* src);
+
 /* ------------------------------------------------------------------ seam
  * Replaces  void find(const std::vector<UMat>& src, const std::vector<Point>& corners,
  *                     std::vector<UMat>& masks)                                        [SEAM]:87
