@@ -26,6 +26,15 @@ EXPOSURE_NONE, EXPOSURE_GAIN = 0, 1
 BLEND_MULTI_BAND, BLEND_FEATHER = 0, 1
 
 
+class KeyPoint(C.Structure):
+    _fields_ = [("x", C.c_float), ("y", C.c_float), ("size", C.c_float), ("angle", C.c_float), ("response", C.c_float), ("octave", C.c_int),
+                ("class_id", C.c_int)]
+
+
+class OrbParams(C.Structure):
+    _fields_ = [("nfeatures", C.c_int), ("scale_factor", C.c_float), ("nlevels", C.c_int), ("grid_width", C.c_int), ("grid_height", C.c_int)]
+
+
 class Mat(C.Structure):
     _fields_ = [("data", C.c_void_p), ("rows", C.c_int), ("cols", C.c_int), ("channels", C.c_int), ("depth", C.c_int),
                 ("step", C.c_size_t), ("device", C.c_int)]
@@ -85,6 +94,7 @@ SYMBOLS = {
     "is_bmp_info": (C.c_int, [C.c_void_p, C.c_char_p, _P(Size), _P(C.c_int)]),
     "is_imread_bmp": (C.c_int, [C.c_void_p, C.c_char_p, _P(Mat)]),
     "is_imwrite_bmp": (C.c_int, [C.c_void_p, C.c_char_p, _P(Mat)]),
+    "is_orb_find": (C.c_int, [C.c_void_p, _P(Mat), _P(OrbParams), _P(KeyPoint), C.c_void_p, C.c_int, _P(C.c_int)]),
     "is_remap": (C.c_int, [C.c_void_p, _P(Mat), _P(Mat), _P(Mat), C.c_int, C.c_int, _P(Mat)]),
     "is_warp_with_mask": (C.c_int, [C.c_void_p, C.c_int, _P(Mat), _F9, _F9, C.c_float, _P(Mat), _P(Mat), _P(Point)]),
     "is_seam_dp_find": (C.c_int, [C.c_void_p, C.c_int, _P(Mat), _P(Point), _P(Mat), C.c_int]),

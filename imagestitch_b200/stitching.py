@@ -224,6 +224,20 @@ def imwrite(ctx: Context, path, img):
     ctx.check(ctx.lib.is_imwrite_bmp(ctx.h, os.fsencode(path), C.byref(ms)))
 
 
+def orb_find(ctx: Context, image, grid_wh=(3, 1), nfeatures=510, scale_factor=1.3, nlevels=5):
+    """find(image, features) [FEAT]:948 -> (key points n x 6 float32: x, y, size, angle, response, octave; descriptors n x 32 uint8)"""
+    ms, _k = as_mat(image)
+    prm = capi.OrbParams(int(nfeatures), float(scale_factor), int(nlevels), int(grid_wh[0]), int(grid_wh[1]))
+    cap = (2 * int(nfeatures) + 64) * int(grid_wh[0]) * int(grid_wh[1])
+    kps = (capi.KeyPoint * cap)()
+    desc = np.zeros((cap, 32), np.uint8)
+    n = C.c_int()
+    ctx.check(ctx.lib.is_orb_find(ctx.h, C.byref(ms), C.byref(prm), kps, desc.ctypes.data_as(C.c_void_p), cap, C.byref(n)))
+    assert n.value <= cap
+    out = np.array([(k.x, k.y, k.size, k.angle, k.response, k.octave) for k in kps[:n.value]], np.float32).reshape(-1, 6)
+    return out, desc[:n.value].copy()
+
+
 def _mat_array(arrs):
     mats, keep = [], []
     for a in arrs:

@@ -301,6 +301,18 @@ int is_feather_dst_size(const is_feather_blender* b, is_size* size);
 int is_feather_feed(is_feather_blender* b, const is_mat* img, const is_mat* mask, is_point tl);
 int is_feather_blend(is_feather_blender* b, is_mat* dst, is_mat* dst_mask);
 
+/* ---- ORB features finder: (*finder)(img, features) of every main ([BLEND]:36-41), restated by the reference as
+ *      void find(InputArray image, ImageFeatures& features)   [FEAT]:948-1021
+ * = gray conversion, grid_width x grid_height cells, per cell ORB::detectAndCompute [FEAT]:727-946 (FAST + Harris + orientation +
+ * rBRIEF, wta_k = 2, edgeThreshold = patchSize = 31, fastThreshold = 20).  params == NULL takes the reference's values
+ * (nfeatures 510, scaleFactor 1.3f, nlevels 5, grid 3 x 1; [FEAT]:39-55).  image: IS_8U with 1, 3 or 4 channels, host or device.
+ * keypoints / descriptors (32 bytes each) receive at most `capacity` entries in the reference's order; *count the number found
+ * (at most about nfeatures per cell, ties included).  What a detect hook of is_registration_hooks would call. */
+typedef struct is_keypoint { float x, y, size, angle, response; int octave, class_id; } is_keypoint;   /* cv::KeyPoint */
+typedef struct is_orb_params { int nfeatures; float scale_factor; int nlevels; int grid_width, grid_height; } is_orb_params;
+int is_orb_find(is_ctx* ctx, const is_mat* image, const is_orb_params* params, is_keypoint* keypoints, uint8_t* descriptors,
+                int capacity, int* count);
+
 typedef enum is_seam_mode { IS_SEAM_NONE = 0, IS_SEAM_DP = 1 } is_seam_mode;
 typedef enum is_exposure_mode { IS_EXPOSURE_NONE = 0, IS_EXPOSURE_GAIN = 1 } is_exposure_mode;
 typedef enum is_blender_type { IS_BLEND_MULTI_BAND = 0, IS_BLEND_FEATHER = 1 } is_blender_type;

@@ -535,3 +535,54 @@ def pipeline_run(proj, srcs, Ks, Rs, scale, seam=True, num_bands=5, weight_type=
         out["warped"] = warped
         out["masks"] = masks
     return out
+
+
+# ---------------------------------------------------------------- ORB features finder ([FEAT])
+def bgr2gray(img):
+    img = np.ascontiguousarray(img, np.uint8)
+    out = np.empty(img.shape[:2], np.uint8)
+    lib().orc_bgr2gray(_p(img), C.c_int(img.shape[0]), C.c_int(img.shape[1]), C.c_int(img.shape[2]), C.c_size_t(img.strides[0]), _p(out))
+    return out
+
+
+def resize_linear_exact(gray, dsize_wh):
+    gray = np.ascontiguousarray(gray, np.uint8)
+    out = np.empty((dsize_wh[1], dsize_wh[0]), np.uint8)
+    lib().orc_resize_linear_exact_u8(_p(gray), C.c_int(gray.shape[0]), C.c_int(gray.shape[1]), _p(out), C.c_int(out.shape[0]), C.c_int(out.shape[1]))
+    return out
+
+
+def fast(gray, threshold=20):
+    """cv::FAST(gray, threshold, nonmaxSuppression=true) -> int array n x 3 (x, y, score), raster order"""
+    gray = np.ascontiguousarray(gray, np.uint8)
+    cap = gray.size // 4 + 16
+    out = np.zeros((cap, 3), np.int32)
+    lib().orc_fast.restype = C.c_int
+    n = lib().orc_fast(_p(gray), C.c_int(gray.shape[0]), C.c_int(gray.shape[1]), C.c_int(threshold), _p(out), C.c_int(cap))
+    return out[:n].copy()
+
+
+def gaussian7(gray):
+    gray = np.ascontiguousarray(gray, np.uint8)
+    out = np.empty_like(gray)
+    lib().orc_gaussian7_u8(_p(gray), C.c_int(gray.shape[0]), C.c_int(gray.shape[1]), _p(out))
+    return out
+
+
+def fast_atan2(y, x):
+    lib().orc_fast_atan2.restype = C.c_float
+    return float(lib().orc_fast_atan2(C.c_float(y), C.c_float(x)))
+
+
+def orb_find(img, grid_wh=(3, 1), nfeatures=510, scale_factor=1.3, nlevels=5):
+    """find() [FEAT]:948 -> (keypoints n x 6 float32: x, y, size, angle, response, octave; descriptors n x 32 uint8)"""
+    img = np.ascontiguousarray(img, np.uint8)
+    ch = 1 if img.ndim == 2 else img.shape[2]
+    cap = (nfeatures * 2 + 64) * grid_wh[0] * grid_wh[1]
+    kps = np.zeros((cap, 6), np.float32)
+    desc = np.zeros((cap, 32), np.uint8)
+    lib().orc_orb_find.restype = C.c_int
+    n = lib().orc_orb_find(_p(img), C.c_int(img.shape[0]), C.c_int(img.shape[1]), C.c_int(ch), C.c_size_t(img.strides[0]), C.c_int(grid_wh[0]),
+                           C.c_int(grid_wh[1]), C.c_int(nfeatures), C.c_float(scale_factor), C.c_int(nlevels), _p(kps), _p(desc), C.c_int(cap))
+    assert n <= cap
+    return kps[:n].copy(), desc[:n].copy()

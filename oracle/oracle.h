@@ -154,6 +154,15 @@ int orc_pipeline_run_ex2(int n, int proj, const uint8_t* const* srcs, const int*
                          uint8_t* const* warped_out, uint8_t* const* masks_out,
                          int16_t* pano, uint8_t* pano_mask, double* stage_seconds, double* gains_out);
 
+/* ---- ORB features finder ([FEAT]:56-418, 727-1021; cvtColor, resize(INTER_LINEAR_EXACT), FAST, fastAtan2, GaussianBlur) ---- */
+void orc_bgr2gray(const uint8_t* src, int rows, int cols, int ch, size_t step, uint8_t* dst);
+void orc_resize_linear_exact_u8(const uint8_t* src, int rows, int cols, uint8_t* dst, int drows, int dcols);
+int orc_fast(const uint8_t* src, int rows, int cols, int threshold, int* out, int cap);
+void orc_gaussian7_u8(const uint8_t* src, int rows, int cols, uint8_t* dst);
+float orc_fast_atan2(float y, float x);
+int orc_orb_find(const uint8_t* img, int rows, int cols, int channels, size_t step, int grid_w, int grid_h, int nfeatures, float scale_factor,
+                 int nlevels, float* kps, uint8_t* desc, int cap);
+
 #ifdef __cplusplus
 }
 #endif

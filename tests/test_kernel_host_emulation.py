@@ -65,6 +65,23 @@ def emu_warp_g1():
 
 
 @pytest.fixture(scope="module")
+def emu_orb():
+    """the ORB kernels and their driver (orb_find_core) on the host"""
+    text = open(os.path.join(ROOT, "imagestitch_b200", "csrc", "orb.cu")).read()
+    regions = re.findall(r"// @emu-begin[^\n]*\n(.*?)// @emu-end", text, flags=re.S)
+    assert len(regions) == 1
+    os.makedirs(OUT, exist_ok=True)
+    with open(os.path.join(OUT, "orb_region.inc"), "w") as f:
+        f.write(regions[0])
+    so = os.path.join(OUT, "liborb_emul.so")
+    subprocess.check_call(["g++", "-O2", "-fPIC", "-std=c++17", "-ffp-contract=off", "-fno-fast-math", "-w", "-I", EMU, "-I", OUT, "-I",
+                           os.path.join(ROOT, "imagestitch_b200", "csrc"), "-shared", "-o", so, os.path.join(EMU, "orb_emul.cpp")])
+    lib = C.CDLL(so)
+    lib.emu_orb_find.restype = C.c_int
+    return lib
+
+
+@pytest.fixture(scope="module")
 def emu_dp():
     """the DP kernel on the multi-threaded block emulator (tests/emu/cuda_host_emul_mt.h, tests/emu/tma.cuh)"""
     src = open(os.path.join(ROOT, "imagestitch_b200", "csrc", "seam.cu")).read()
@@ -426,3 +443,31 @@ def test_feather_path_kernels_match_oracle(emu_feather, oracle):
         emu_feather.emu_feather_blend(n, ip, 1 if dtype == np.uint8 else 0, mp, _p(rows), _p(cols), _p(x0), _p(y0), C.c_float(0.1), roi[2], roi[3],
                                       _p(dst), _p(dmask))
         assert np.array_equal(dmask, wmask) and np.array_equal(dst, want), dtype
+
+
+@pytest.mark.parametrize("case", [("synth", (1, 1), 3), ("synth", (3, 1), 3), ("noise", (2, 2), 1), ("gray", (1, 1), 1), ("bgra", (3, 1), 4)])
+def test_orb_kernels_and_driver_match_oracle(emu_orb, oracle, case):
+    """is_orb_find's whole computation -- gray conversion, pyramid, FAST + non-maximum suppression, Harris, orientation, blur,
+    descriptors and the host selections between them -- from the product's source on the host == the oracle (== cv2.ORB): every field
+    of every key point, their order, every descriptor byte"""
+    from imagestitch_b200 import synth
+    O = oracle
+    kind, grid, ch = case
+    rng = np.random.default_rng(21)
+    if kind == "noise":
+        img = rng.integers(0, 256, (260, 330), dtype=np.uint8)
+    else:
+        img = synth.make_panorama_inputs(2, 480, 300, 1.2, 0.25)[0][1]
+        if kind == "gray":
+            img = np.ascontiguousarray(img[:, :, 1])
+        if kind == "bgra":
+            img = np.ascontiguousarray(np.concatenate([img, rng.integers(0, 256, img.shape[:2] + (1,), dtype=np.uint8)], axis=2))
+    want_k, want_d = O.orb_find(img, grid)
+    cap = 1200 * grid[0] * grid[1]
+    kps = np.zeros((cap, 6), np.float32)
+    desc = np.zeros((cap, 32), np.uint8)
+    n = emu_orb.emu_orb_find(_p(img), img.shape[0], img.shape[1], 1 if img.ndim == 2 else img.shape[2], C.c_size_t(img.strides[0]), grid[0], grid[1], 510,
+                             C.c_float(1.3), 5, _p(kps), _p(desc), cap)
+    assert n == len(want_k) and n > 50
+    assert np.array_equal(kps[:n].view(np.uint32), want_k.view(np.uint32))
+    assert np.array_equal(desc[:n], want_d)
