@@ -31,6 +31,17 @@ static int orb_zero(is_ctx* ctx, void* dst, size_t bytes) {
     return IS_OK;
 }
 #define ORB_LAUNCH(ctx, kernel, grid, block, ...) IS_LAUNCH(ctx, kernel, grid, block, 0, __VA_ARGS__)
+// IS_ORB_DUMP=<dir>: the intermediate buffers of a call as raw files (the host emulation writes the same files: diff them)
+static int orb_dump(is_ctx* ctx, const char* name, const void* dev, size_t bytes) {
+    const char* dir = getenv("IS_ORB_DUMP");
+    if (!dir) return IS_OK;
+    std::vector<uint8_t> h(bytes);
+    IS_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+    IS_CUDA(ctx, cudaMemcpy(h.data(), dev, bytes, cudaMemcpyDeviceToHost));
+    const std::string path = std::string(dir) + "/" + name + ".bin";
+    if (FILE* f = std::fopen(path.c_str(), "wb")) { std::fwrite(h.data(), 1, bytes, f); std::fclose(f); }
+    return IS_OK;
+}
 
 // @emu-begin (tests/test_kernel_host_emulation.py compiles the marked region for the host; ORB_LAUNCH / orb_* memory helpers are
 //             defined by whoever includes it)
@@ -162,20 +173,28 @@ __global__ void __launch_bounds__(256) k_orb_fast(OrbTable T, const uint8_t* __r
         d[4] = v - p[3]; d[5] = v - p[-w + 3]; d[6] = v - p[-2 * w + 2]; d[7] = v - p[-3 * w + 1];
         d[8] = v - p[-3 * w]; d[9] = v - p[-3 * w - 1]; d[10] = v - p[-2 * w - 2]; d[11] = v - p[-w - 3];
         d[12] = v - p[-3]; d[13] = v - p[w - 3]; d[14] = v - p[2 * w - 2]; d[15] = v - p[3 * w - 1];
+        int nd[16];                                          // p - v, subtracted on its own: see the note at `best` below
+        nd[0] = p[3 * w] - v; nd[1] = p[3 * w + 1] - v; nd[2] = p[2 * w + 2] - v; nd[3] = p[w + 3] - v;
+        nd[4] = p[3] - v; nd[5] = p[-w + 3] - v; nd[6] = p[-2 * w + 2] - v; nd[7] = p[-3 * w + 1] - v;
+        nd[8] = p[-3 * w] - v; nd[9] = p[-3 * w - 1] - v; nd[10] = p[-2 * w - 2] - v; nd[11] = p[-w - 3] - v;
+        nd[12] = p[-3] - v; nd[13] = p[w - 3] - v; nd[14] = p[2 * w - 2] - v; nd[15] = p[3 * w - 1] - v;
         uint32_t dark = 0, bright = 0;                       // circle pixels darker than v - t / brighter than v + t
 #pragma unroll
-        for (int k = 0; k < 16; ++k) { dark |= (uint32_t)(d[k] > threshold) << k; bright |= (uint32_t)(d[k] < -threshold) << k; }
+        for (int k = 0; k < 16; ++k) { dark |= (uint32_t)(d[k] > threshold) << k; bright |= (uint32_t)(nd[k] > threshold) << k; }
         dark |= dark << 16; bright |= bright << 16;          // nine contiguous set bits somewhere on the ring
         uint32_t a = dark & (dark >> 1); a &= a >> 2; a &= a >> 4; a &= dark >> 8;
         uint32_t b = bright & (bright >> 1); b &= b >> 2; b &= b >> 4; b &= bright >> 8;
         if ((a | b) & 0xffffu) {
+            // score = max over the 16 arcs of nine of max(min d, min -d).  Written as minima over d and over nd = -d: the form
+            // max(min d, -(max d)) is miscompiled by ptxas 12.9 for sm_100a -- it folds the maxima into VIMNMX3 and loses the
+            // negation from the second arc on (seen on a B200: scores came out as max d; scripts/orb_debug.py found it).
             int best = 0;
 #pragma unroll
             for (int k = 0; k < 16; ++k) {
-                int mn = d[k], mx = d[k];
+                int mn = d[k], mn2 = nd[k];
 #pragma unroll
-                for (int j = 1; j < 9; ++j) { mn = min(mn, d[(k + j) & 15]); mx = max(mx, d[(k + j) & 15]); }
-                best = max(best, max(mn, -mx));
+                for (int j = 1; j < 9; ++j) { mn = min(mn, d[(k + j) & 15]); mn2 = min(mn2, nd[(k + j) & 15]); }
+                best = max(best, max(mn, mn2));
             }
             out = (uint8_t)(best - 1);
         }
@@ -384,6 +403,8 @@ static int orb_find_core(is_ctx* ctx, const uint8_t* src, size_t sstep, int rows
     IS_TRY(orb_alloc(ctx, &d_h, total * sizeof(float) + 64)); IS_TRY(orb_alloc(ctx, &d_blur, total + 64));
     ORB_LAUNCH(ctx, k_orb_blur_rows, gall, 256, T, (const uint8_t*)d_pyr.p, C, (float*)d_h.p);
     ORB_LAUNCH(ctx, k_orb_blur_cols, gall, 256, T, (const float*)d_h.p, C, (uint8_t*)d_blur.p);
+    IS_TRY(orb_dump(ctx, "pyr", d_pyr.p, total)); IS_TRY(orb_dump(ctx, "score", d_score.p, total)); IS_TRY(orb_dump(ctx, "blur", d_blur.p, total));
+    IS_TRY(orb_dump(ctx, "hbuf", d_h.p, total * sizeof(float)));
     unsigned found = 0;
     IS_TRY(orb_d2h(ctx, &found, d_count.p, sizeof(found)));
     if (found > cap) return IS_ERR_NO_MEM;
@@ -420,6 +441,7 @@ static int orb_find_core(is_ctx* ctx, const uint8_t* src, size_t sstep, int rows
     ORB_LAUNCH(ctx, k_orb_harris, dim3((unsigned)div_up((int)hk.size(), 128)), 128, T, (const uint8_t*)d_pyr.p, (const OrbKp*)d_kp.p, (int)hk.size(), C, (float*)d_f.p);
     std::vector<float> resp(hk.size());
     IS_TRY(orb_d2h(ctx, resp.data(), d_f.p, resp.size() * sizeof(float)));
+    IS_TRY(orb_dump(ctx, "kp2n", d_kp.p, hk.size() * sizeof(OrbKp))); IS_TRY(orb_dump(ctx, "resp", d_f.p, hk.size() * sizeof(float)));
     {
         size_t at = 0;
         hk.clear();
@@ -433,6 +455,7 @@ static int orb_find_core(is_ctx* ctx, const uint8_t* src, size_t sstep, int rows
     ORB_LAUNCH(ctx, k_orb_angle, dim3((unsigned)div_up((int)hk.size(), 128)), 128, T, (const uint8_t*)d_pyr.p, (const OrbKp*)d_kp.p, (int)hk.size(), C, (float*)d_f.p);
     std::vector<float> ang(hk.size());
     IS_TRY(orb_d2h(ctx, ang.data(), d_f.p, ang.size() * sizeof(float)));
+    IS_TRY(orb_dump(ctx, "kpn", d_kp.p, hk.size() * sizeof(OrbKp))); IS_TRY(orb_dump(ctx, "ang", d_f.p, hk.size() * sizeof(float)));
     // ---- the points in image coordinates, the descriptor inputs (host libm for cosf / sinf, [FEAT]:303-304)
     std::vector<OrbDescIn> din;
     {

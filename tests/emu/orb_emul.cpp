@@ -5,6 +5,9 @@
 #include "cuda_host_emul.h"
 
 #include <cfloat>
+#include <cstdio>
+#include <cstdlib>
+#include <string>
 #include <vector>
 
 #include "../../include/imagestitch.h"
@@ -22,6 +25,13 @@ static int orb_alloc(is_ctx*, OrbBuf* b, size_t bytes) { b->store.assign(bytes +
 static int orb_h2d(is_ctx*, void* dst, const void* src, size_t bytes) { std::memcpy(dst, src, bytes); return IS_OK; }
 static int orb_d2h(is_ctx*, void* dst, const void* src, size_t bytes) { std::memcpy(dst, src, bytes); return IS_OK; }
 static int orb_zero(is_ctx*, void* dst, size_t bytes) { std::memset(dst, 0, bytes); return IS_OK; }
+static int orb_dump(is_ctx*, const char* name, const void* p, size_t bytes) {
+    const char* dir = getenv("IS_ORB_DUMP");
+    if (!dir) return IS_OK;
+    const std::string path = std::string(dir) + "/" + name + ".bin";
+    if (FILE* f = std::fopen(path.c_str(), "wb")) { std::fwrite(p, 1, bytes, f); std::fclose(f); }
+    return IS_OK;
+}
 #define ORB_LAUNCH(ctx, kernel, grid, block, ...) emu_launch(dim3(grid), dim3(block), [&] { kernel(__VA_ARGS__); })
 #include "orb_region.inc"
 }
