@@ -14,9 +14,11 @@
 // round trips.  Frames around the levels ([FEAT]:776-840) are not built: no retained key point reads within 6 pixels of a level's
 // edge (edgeThreshold 31 against a reach of 25).
 #include "internal.cuh"
+#include "hostpool.h"
 
 #include <algorithm>
 #include <cfloat>
+#include <chrono>
 #include <cmath>
 
 namespace is {
@@ -31,6 +33,7 @@ static int orb_zero(is_ctx* ctx, void* dst, size_t bytes) {
     return IS_OK;
 }
 #define ORB_LAUNCH(ctx, kernel, grid, block, ...) IS_LAUNCH(ctx, kernel, grid, block, 0, __VA_ARGS__)
+static void orb_parallel_for(is_ctx* ctx, size_t n, const std::function<void(size_t)>& fn) { host_pool(ctx)->run(n, fn); }
 // IS_ORB_DUMP=<dir>: the intermediate buffers of a call as raw files (the host emulation writes the same files: diff them)
 static int orb_dump(is_ctx* ctx, const char* name, const void* dev, size_t bytes) {
     const char* dir = getenv("IS_ORB_DUMP");
@@ -71,6 +74,7 @@ struct OrbConsts {
 };
 
 struct KeyPt { float x, y, size, angle, response; int octave; };
+struct OrbCand { float response; uint32_t yx; };      // a candidate during the selections: y << 16 | x
 
 static inline int orb_cvround(float v) { return (int)lrintf(v); }
 
@@ -119,12 +123,12 @@ static void orb_consts(int patch, OrbConsts* c) {
 
 // KeyPointsFilter::retainBest: the n strongest and everything that ties with the n-th; the same std:: calls as OpenCV, on the
 // same (raster) input order, so the surviving order is OpenCV's too
-static void orb_retain_best(std::vector<KeyPt>& k, int n) {
+static void orb_retain_best(std::vector<OrbCand>& k, int n) {
     if (n < 0 || k.size() <= (size_t)n) return;
     if (n == 0) { k.clear(); return; }
-    std::nth_element(k.begin(), k.begin() + n - 1, k.end(), [](const KeyPt& a, const KeyPt& b) { return a.response > b.response; });
+    std::nth_element(k.begin(), k.begin() + n - 1, k.end(), [](const OrbCand& a, const OrbCand& b) { return a.response > b.response; });
     const float amb = k[(size_t)n - 1].response;
-    auto e = std::partition(k.begin() + n, k.end(), [amb](const KeyPt& a) { return a.response >= amb; });
+    auto e = std::partition(k.begin() + n, k.end(), [amb](const OrbCand& a) { return a.response >= amb; });
     k.resize((size_t)(e - k.begin()));
 }
 
@@ -338,6 +342,14 @@ struct OrbParams { int nfeatures; float scale_factor; int nlevels, grid_w, grid_
 // src: device image (8UC1 / 8UC3 / 8UC4).  kps / desc: the reference's order (cells row-major, levels ascending).
 static int orb_find_core(is_ctx* ctx, const uint8_t* src, size_t sstep, int rows, int cols, int ch, const OrbParams& P, std::vector<KeyPt>* kps, std::vector<uint8_t>* desc) {
     kps->clear(); desc->clear();
+    const bool laps = getenv("IS_ORB_LAPS") != nullptr;          // phase times on stderr
+    auto t_prev = std::chrono::steady_clock::now();
+    auto lap = [&](const char* what) {
+        if (!laps) return;
+        const auto now = std::chrono::steady_clock::now();
+        std::fprintf(stderr, "[orb] %-28s %8.3f ms\n", what, std::chrono::duration<double, std::milli>(now - t_prev).count());
+        t_prev = now;
+    };
     const int ncells = P.grid_w * P.grid_h, nl = P.nlevels;
     if (ncells * nl > ORB_MAX_ENTRIES || nl < 1 || ncells < 1) return IS_ERR_UNSUPPORTED;
     OrbTable T;
@@ -405,11 +417,14 @@ static int orb_find_core(is_ctx* ctx, const uint8_t* src, size_t sstep, int rows
     ORB_LAUNCH(ctx, k_orb_blur_cols, gall, 256, T, (const float*)d_h.p, C, (uint8_t*)d_blur.p);
     IS_TRY(orb_dump(ctx, "pyr", d_pyr.p, total)); IS_TRY(orb_dump(ctx, "score", d_score.p, total)); IS_TRY(orb_dump(ctx, "blur", d_blur.p, total));
     IS_TRY(orb_dump(ctx, "hbuf", d_h.p, total * sizeof(float)));
+    lap("tables, uploads, launches");
     unsigned found = 0;
     IS_TRY(orb_d2h(ctx, &found, d_count.p, sizeof(found)));
+    lap("pyramid .. blur on the device");
     if (found > cap) return IS_ERR_NO_MEM;
     std::vector<uint32_t> list(2 * (size_t)found);
     if (found) IS_TRY(orb_d2h(ctx, list.data(), d_list.p, list.size() * sizeof(uint32_t)));
+    lap("corner list download");
     // ---- computeKeyPoints [FEAT]:56-191 on the host: per entry the raster-ordered FAST points, retainBest(2 n)
     std::vector<int> per_level((size_t)nl);
     {
@@ -419,21 +434,37 @@ static int orb_find_core(is_ctx* ctx, const uint8_t* src, size_t sstep, int rows
         for (int l = 0; l < nl - 1; ++l) { per_level[(size_t)l] = orb_cvround(ndesired); sum += per_level[(size_t)l]; ndesired *= factor; }
         per_level[(size_t)nl - 1] = std::max(P.nfeatures - sum, 0);
     }
-    std::vector<std::vector<KeyPt>> cand((size_t)T.n);
+    // FAST's raster order back from the unordered list: a counting sort over (entry, row) -- linear in the corners found, which a
+    // textured 24 MP image has by the million --, then the few corners of a row by x.  The selection works on 8-byte records;
+    // std::nth_element / std::partition permute by comparisons and positions only, so the order is the one they give cv::KeyPoints.
+    std::vector<std::vector<OrbCand>> cand((size_t)T.n);
     {
-        std::vector<uint64_t> keys((size_t)found);
-        for (unsigned i = 0; i < found; ++i) keys[i] = ((uint64_t)(list[2 * i + 1] >> 8) << 40) | ((uint64_t)list[2 * i] << 8) | (list[2 * i + 1] & 255u);   // entry, y, x | score
-        std::sort(keys.begin(), keys.end());
-        for (uint64_t k : keys) {
-            const int e = (int)(k >> 40), y = (int)((k >> 24) & 0xffffu), x = (int)((k >> 8) & 0xffffu), s = (int)(k & 255u);
-            cand[(size_t)e].push_back(KeyPt{(float)x, (float)y, 7.f, -1.f, (float)s, e % nl});
-        }
+        std::vector<size_t> ebeg((size_t)T.n + 1, 0);
+        for (unsigned i = 0; i < found; ++i) ++ebeg[(size_t)(list[2 * i + 1] >> 8) + 1];
+        for (int e = 0; e < T.n; ++e) ebeg[(size_t)e + 1] += ebeg[(size_t)e];
+        std::vector<size_t> efill(ebeg.begin(), ebeg.end() - 1);
+        std::vector<OrbCand> by_entry((size_t)found);
+        for (unsigned i = 0; i < found; ++i) by_entry[efill[list[2 * i + 1] >> 8]++] = OrbCand{(float)(list[2 * i + 1] & 255u), list[2 * i]};
+        lap("corners by entry");
+        orb_parallel_for(ctx, (size_t)T.n, [&](size_t e) {       // the levels are independent of each other: one host thread each
+            const OrbCand* in = by_entry.data() + ebeg[e];
+            const size_t n = ebeg[e + 1] - ebeg[e];
+            std::vector<uint32_t> start((size_t)T.e[e].h + 1, 0);
+            for (size_t i = 0; i < n; ++i) ++start[(size_t)(in[i].yx >> 16) + 1];
+            for (size_t r = 1; r < start.size(); ++r) start[r] += start[r - 1];
+            std::vector<uint32_t> fill(start.begin(), start.end() - 1);
+            std::vector<OrbCand>& out = cand[e];
+            out.resize(n);
+            for (size_t i = 0; i < n; ++i) out[fill[in[i].yx >> 16]++] = in[i];
+            for (size_t r = 0; r + 1 < start.size(); ++r)
+                if (start[r + 1] - start[r] > 1) std::sort(out.begin() + start[r], out.begin() + start[r + 1], [](const OrbCand& p, const OrbCand& q) { return p.yx < q.yx; });
+            orb_retain_best(out, 2 * per_level[e % (size_t)nl]);
+        });
     }
     std::vector<OrbKp> hk;
-    for (int e = 0; e < T.n; ++e) {
-        orb_retain_best(cand[(size_t)e], 2 * per_level[(size_t)(e % nl)]);
-        for (const KeyPt& p : cand[(size_t)e]) hk.push_back(OrbKp{e, (int)p.x, (int)p.y});
-    }
+    for (int e = 0; e < T.n; ++e)
+        for (const OrbCand& p : cand[(size_t)e]) hk.push_back(OrbKp{e, (int)(p.yx & 0xffffu), (int)(p.yx >> 16)});
+    lap("raster order, retainBest(2 n)");
     if (hk.empty()) return IS_OK;
     OrbBuf d_kp, d_f;
     IS_TRY(orb_alloc(ctx, &d_kp, hk.size() * sizeof(OrbKp))); IS_TRY(orb_alloc(ctx, &d_f, hk.size() * sizeof(float)));
@@ -446,9 +477,9 @@ static int orb_find_core(is_ctx* ctx, const uint8_t* src, size_t sstep, int rows
         size_t at = 0;
         hk.clear();
         for (int e = 0; e < T.n; ++e) {
-            for (KeyPt& p : cand[(size_t)e]) p.response = resp[at++];
+            for (OrbCand& p : cand[(size_t)e]) p.response = resp[at++];
             orb_retain_best(cand[(size_t)e], per_level[(size_t)(e % nl)]);
-            for (const KeyPt& p : cand[(size_t)e]) hk.push_back(OrbKp{e, (int)p.x, (int)p.y});
+            for (const OrbCand& p : cand[(size_t)e]) hk.push_back(OrbKp{e, (int)(p.yx & 0xffffu), (int)(p.yx >> 16)});
         }
     }
     IS_TRY(orb_h2d(ctx, d_kp.p, hk.data(), hk.size() * sizeof(OrbKp)));
@@ -463,7 +494,8 @@ static int orb_find_core(is_ctx* ctx, const uint8_t* src, size_t sstep, int rows
         for (int e = 0; e < T.n; ++e) {
             const int l = e % nl;
             const float sf = layer_scale[(size_t)l];
-            for (KeyPt p : cand[(size_t)e]) {
+            for (const OrbCand& c : cand[(size_t)e]) {
+                KeyPt p{(float)(c.yx & 0xffffu), (float)(c.yx >> 16), 0.f, 0.f, c.response, l};
                 p.angle = ang[at++];
                 p.octave = l;
                 p.size = P.patch_size * sf;
@@ -488,6 +520,8 @@ static int orb_find_core(is_ctx* ctx, const uint8_t* src, size_t sstep, int rows
                (int)din.size(), (uint8_t*)d_desc.p);
     desc->resize(din.size() * 32);
     IS_TRY(orb_d2h(ctx, desc->data(), d_desc.p, desc->size()));
+    lap("harris .. descriptors");
+    if (laps) std::fprintf(stderr, "[orb] corners after NMS: %u, key points: %zu\n", found, kps->size());
     return IS_OK;
 }
 // @emu-end

@@ -5,6 +5,7 @@
 #include "cuda_host_emul.h"
 
 #include <cfloat>
+#include <chrono>
 #include <cstdio>
 #include <cstdlib>
 #include <string>
@@ -32,6 +33,7 @@ static int orb_dump(is_ctx*, const char* name, const void* p, size_t bytes) {
     if (FILE* f = std::fopen(path.c_str(), "wb")) { std::fwrite(p, 1, bytes, f); std::fclose(f); }
     return IS_OK;
 }
+template <typename F> static void orb_parallel_for(is_ctx*, size_t n, F&& fn) { for (size_t i = 0; i < n; ++i) fn(i); }
 #define ORB_LAUNCH(ctx, kernel, grid, block, ...) emu_launch(dim3(grid), dim3(block), [&] { kernel(__VA_ARGS__); })
 #include "orb_region.inc"
 }
