@@ -10,6 +10,7 @@
 // Errors become is::Error exceptions carrying the status code (the reference's CV_Assert / CV_Error throw too).
 #pragma once
 
+#include <cstdint>
 #include <stdexcept>
 #include <string>
 #include <vector>
@@ -167,6 +168,47 @@ private:
     Context& ctx_;
     is_feather_blender* h_ = nullptr;
 };
+
+// cv::detail::ImageFeatures / OrbFeaturesFinder as the mains use them ([BLEND]:36-41; the reference's own find() is [FEAT]:948):
+// OrbFeaturesFinder(grid_size = Size(3, 1), nfeatures = 1500, scaleFactor = 1.3f, nlevels = 5) hands
+// nfeatures * (99 + grid.area()) / 100 / grid.area() = 510 features per grid cell to ORB ([FEAT]:39-44)
+struct ImageFeatures {
+    int img_idx = -1;
+    is_size img_size{};
+    std::vector<is_keypoint> keypoints;
+    std::vector<uint8_t> descriptors;          // 32 bytes per key point (cv::Mat keypoints.size() x 32, CV_8U)
+};
+
+class OrbFeaturesFinder {
+public:
+    explicit OrbFeaturesFinder(Context& ctx, is_size grid_size = is_size{3, 1}, int nfeatures = 1500, float scaleFactor = 1.3f, int nlevels = 5)
+        : ctx_(ctx), prm_{nfeatures * (99 + grid_size.width * grid_size.height) / 100 / (grid_size.width * grid_size.height), scaleFactor, nlevels,
+                          grid_size.width, grid_size.height} {}
+    void operator()(const is_mat& image, ImageFeatures& features) {
+        const int cap = (2 * prm_.nfeatures + 64) * prm_.grid_width * prm_.grid_height;
+        features.keypoints.resize((size_t)cap);
+        features.descriptors.resize((size_t)cap * 32);
+        int n = 0;
+        ctx_.check(is_orb_find(ctx_.get(), &image, &prm_, features.keypoints.data(), features.descriptors.data(), cap, &n));
+        if (n > cap) n = cap;
+        features.keypoints.resize((size_t)n);
+        features.descriptors.resize((size_t)n * 32);
+        features.img_size = is_size{image.cols, image.rows};
+    }
+
+private:
+    Context& ctx_;
+    is_orb_params prm_;
+};
+
+// cv::imread / cv::imwrite for bitmaps ([BLEND]:31-34, 717): the caller allocates, as everywhere at this boundary
+inline is_size bmpSize(Context& ctx, const std::string& path) {
+    is_size s{};
+    ctx.check(is_bmp_info(ctx.get(), path.c_str(), &s, nullptr));
+    return s;
+}
+inline void imread(Context& ctx, const std::string& path, is_mat& dst) { ctx.check(is_imread_bmp(ctx.get(), path.c_str(), &dst)); }
+inline void imwrite(Context& ctx, const std::string& path, const is_mat& src) { ctx.check(is_imwrite_bmp(ctx.get(), path.c_str(), &src)); }
 
 // the whole composite sequence (every main() of the reference)
 inline void stitch(Context& ctx, const std::vector<is_mat>& images, const std::vector<is_camera>& cameras, const is_pipeline_config& cfg,
