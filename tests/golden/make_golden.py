@@ -245,7 +245,66 @@ def mains_sequence_case():
     np.savez_compressed(os.path.join(HERE, "mains_sequence_case.npz"), **out)
 
 
+def widened_cases():
+    """the rows added last in round 2 (SURVEY.md 8f): plane / fisheye / stereographic projectors, cv::remap on extreme maps, the ORB
+    features finder (cv2.ORB per grid cell, as find() [FEAT]:948 drives it), bitmap files (cv2.imwrite bytes, cv2.imread pixels)"""
+    rng = np.random.default_rng(4242)
+    out = {}
+    k = 0
+    for proj, name in ((2, "plane"), (3, "fisheye"), (4, "stereographic")):
+        for _ in range(2):
+            w, h = int(rng.integers(60, 110)), int(rng.integers(50, 90))
+            K, R, scale = random_camera(rng, w, h)
+            img = rng.integers(0, 256, (h, w, 3), dtype=np.uint8)
+            wp = cv2.PyRotationWarper(name, scale)
+            roi, xm, ym = wp.buildMaps((w, h), K, R)
+            tl, wi = wp.warp(img, K, R, cv2.INTER_LINEAR, cv2.BORDER_REFLECT)
+            _, wm = wp.warp(np.full((h, w), 255, np.uint8), K, R, cv2.INTER_NEAREST, cv2.BORDER_CONSTANT)
+            p = f"w{k}_"
+            out.update({p + "proj": np.int32(proj), p + "K": K, p + "R": R, p + "scale": np.float32(scale), p + "img": img,
+                        p + "roi_cv": np.asarray(roi, np.int32), p + "xmap_cv": xm, p + "ymap_cv": ym, p + "warped_cv": wi, p + "mask_cv": wm})
+            k += 1
+    out["n_warp"] = np.int32(k)
+    src = rng.integers(0, 256, (30, 40, 3), dtype=np.uint8)
+    vals = np.array([np.nan, np.inf, -np.inf, 3e9, -3e9, 1e8, -1e8, 2 ** 31 / 32, -2 ** 31 / 32, 1e20, -1e20, 20.3, -0.5, 0.5, 39.5, 32767.4, 32768.6, -32768.5], np.float32)
+    xm = np.tile(vals, (len(vals), 1))
+    ym = xm.T.copy()
+    out.update(x_src=src, x_xmap=xm, x_ymap=ym)
+    for iname, ci in (("linear", cv2.INTER_LINEAR), ("nearest", cv2.INTER_NEAREST)):
+        for bname, cb in (("reflect", cv2.BORDER_REFLECT), ("constant", cv2.BORDER_CONSTANT)):
+            out[f"x_{iname}_{bname}_cv"] = cv2.remap(src, xm, ym, ci, borderMode=cb)
+    orb = cv2.ORB_create(510, 1.3, 5)
+    smooth = synth.make_panorama_inputs(2, 420, 260, 1.2, 0.25)[0][1]
+    noise = rng.integers(0, 256, (150, 330), dtype=np.uint8)
+    for j, (img, grid) in enumerate(((smooth, (3, 1)), (noise, (2, 1)))):
+        gray = img if img.ndim == 2 else cv2.cvtColor(img, cv2.COLOR_BGR2GRAY)
+        h, w = gray.shape
+        kps, ds = [], []
+        for c in range(grid[0]):
+            xl, xr = c * w // grid[0], (c + 1) * w // grid[0]
+            kk, dd = orb.detectAndCompute(np.ascontiguousarray(gray[:, xl:xr]), None)
+            kps += [(p.pt[0] + xl, p.pt[1], p.size, p.angle, p.response, p.octave) for p in kk]
+            ds.append(dd)
+        out.update({f"o{j}_img": img, f"o{j}_grid": np.asarray(grid, np.int32), f"o{j}_kps_cv": np.array(kps, np.float32).reshape(-1, 6),
+                    f"o{j}_desc_cv": np.concatenate(ds)})
+    out["n_orb"] = np.int32(2)
+    import tempfile
+    with tempfile.TemporaryDirectory() as d:
+        f32 = rng.uniform(-40, 300, (7, 9, 3)).astype(np.float32)
+        f32[0, 0] = (np.nan, np.inf, -3e9)
+        for j, img in enumerate((rng.integers(0, 256, (6, 7, 3), dtype=np.uint8), rng.integers(0, 256, (5, 6), dtype=np.uint8),
+                                 rng.integers(-300, 600, (4, 5, 3)).astype(np.int16), f32)):
+            path = os.path.join(d, f"b{j}.bmp")
+            assert cv2.imwrite(path, img)
+            out.update({f"b{j}_img": img, f"b{j}_file_cv": np.frombuffer(open(path, "rb").read(), np.uint8), f"b{j}_read_cv": cv2.imread(path)})
+    out["n_bmp"] = np.int32(4)
+    np.savez_compressed(os.path.join(HERE, "widened_cases.npz"), **out)
+
+
 if __name__ == "__main__":
+    if "--only-widened" in sys.argv:
+        widened_cases()
+        sys.exit(0)
     if "--only-mains" in sys.argv:
         mains_sequence_case()
         sys.exit(0)
@@ -258,6 +317,7 @@ if __name__ == "__main__":
     if "--only-color-grad" not in sys.argv:
         exposure_feather_cases()
     color_grad_cases()
+    widened_cases()
     for f in sorted(os.listdir(HERE)):
         if f.endswith(".npz"):
             print(f, os.path.getsize(os.path.join(HERE, f)))

@@ -11,7 +11,11 @@ import subprocess
 import numpy as np
 import pytest
 
-cv2 = pytest.importorskip("cv2")
+try:
+    import cv2
+except ImportError:                     # the golden test below needs neither cv2 nor a GPU
+    cv2 = None
+needs_cv2 = pytest.mark.skipif(cv2 is None, reason="cv2 not importable")
 
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 EMU = os.path.join(ROOT, "tests", "emu")
@@ -112,6 +116,7 @@ def _write_cases():
             ("s16c1", rng.integers(-300, 600, (8, 3)).astype(np.int16)), ("f32c3", f), ("f32c1", np.ascontiguousarray(f[:, :, 0]))]
 
 
+@needs_cv2
 def test_bmp_decode_matches_cv2(emu_io, tmp_path):
     for name, path in _files(tmp_path).items():
         want = cv2.imread(path)
@@ -136,6 +141,7 @@ def test_bmp_decode_rejects_what_it_does_not_read(emu_io, tmp_path):
     assert emu_io.emu_bmp_info(_p(rle), C.c_size_t(rle.size), C.byref(rows), C.byref(cols), C.byref(bpp)) == -213
 
 
+@needs_cv2
 def test_bmp_encode_matches_cv2(emu_io, tmp_path):
     depth = {np.dtype(np.uint8): IS_8U, np.dtype(np.int16): IS_16S, np.dtype(np.float32): IS_32F}
     for name, img in _write_cases():
@@ -148,6 +154,23 @@ def test_bmp_encode_matches_cv2(emu_io, tmp_path):
         assert out[:n].tobytes() == want, name
 
 
+def test_bmp_golden_fixtures(emu_io):
+    """committed cv2.imwrite bytes / cv2.imread pixels (tests/golden/widened_cases.npz, made by tests/golden/make_golden.py)"""
+    z = np.load(os.path.join(ROOT, "tests", "golden", "widened_cases.npz"))
+    depth = {np.dtype(np.uint8): IS_8U, np.dtype(np.int16): IS_16S, np.dtype(np.float32): IS_32F}
+    for j in range(int(z["n_bmp"])):
+        img, want = np.ascontiguousarray(z[f"b{j}_img"]), z[f"b{j}_file_cv"]
+        ch = 1 if img.ndim == 2 else img.shape[2]
+        out = np.zeros(54 + 1024 + ((img.shape[1] * ch + 3) & ~3) * img.shape[0], np.uint8)
+        n = emu_io.emu_bmp_write(_p(img), depth[img.dtype], img.shape[0], img.shape[1], ch, C.c_size_t(img.strides[0]), _p(out))
+        assert np.array_equal(out[:n], want), j
+        data = np.ascontiguousarray(want)
+        got = np.zeros(z[f"b{j}_read_cv"].shape, np.uint8)
+        assert emu_io.emu_bmp_read(_p(data), C.c_size_t(data.size), _p(got), C.c_size_t(got.strides[0])) == 0
+        assert np.array_equal(got, z[f"b{j}_read_cv"]), j
+
+
+@needs_cv2
 @pytest.mark.gpu
 def test_bmp_files_through_the_c_abi(ctx, tmp_path):
     import torch

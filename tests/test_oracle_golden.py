@@ -172,3 +172,27 @@ def test_pipeline_color_grad_consistent(oracle):
     want = O.dp_seam_find([a.astype(np.float32) for a in r["warped"]], [tuple(c) for c in r["corners"]], wm, cost_fn=O.COST_COLOR_GRAD)
     assert all(np.array_equal(a, b) for a, b in zip(r["masks"], want))
     assert any(np.any(a != b) for a, b in zip(r["masks"], r0["masks"]))
+
+
+def test_widened_rows_fixtures(oracle):
+    """the rows added last in round 2 against OpenCV 4.13 outputs: plane / fisheye / stereographic projectors (ROI, map bits, warped
+    image and mask), cv::remap on NaN / infinite / out-of-int-range maps, the ORB features finder (cv2.ORB per grid cell)"""
+    O = oracle
+    z = _load("widened_cases.npz")
+    for k in range(int(z["n_warp"])):
+        p = f"w{k}_"
+        proj, K, R, scale, img = int(z[p + "proj"]), z[p + "K"], z[p + "R"], float(z[p + "scale"]), z[p + "img"]
+        h, w = img.shape[:2]
+        roi, xm, ym = O.build_maps(proj, (w, h), K, R, scale)
+        assert (roi[0], roi[1], roi[2] - roi[0], roi[3] - roi[1]) == tuple(int(v) for v in z[p + "roi_cv"])
+        assert np.array_equal(xm.view(np.uint32), z[p + "xmap_cv"].view(np.uint32)) and np.array_equal(ym.view(np.uint32), z[p + "ymap_cv"].view(np.uint32))
+        assert np.array_equal(O.warp(proj, img, K, R, scale, O.INTER_LINEAR, O.BORDER_REFLECT)[1], z[p + "warped_cv"])
+        assert np.array_equal(O.warp(proj, np.full((h, w), 255, np.uint8), K, R, scale, O.INTER_NEAREST, O.BORDER_CONSTANT)[1], z[p + "mask_cv"])
+    for iname, oi in (("linear", O.INTER_LINEAR), ("nearest", O.INTER_NEAREST)):
+        for bname, ob in (("reflect", O.BORDER_REFLECT), ("constant", O.BORDER_CONSTANT)):
+            assert np.array_equal(O.remap(z["x_src"], z["x_xmap"], z["x_ymap"], oi, ob), z[f"x_{iname}_{bname}_cv"]), (iname, bname)
+    for j in range(int(z["n_orb"])):
+        kps, desc = O.orb_find(z[f"o{j}_img"], tuple(int(v) for v in z[f"o{j}_grid"]))
+        assert len(kps) == len(z[f"o{j}_kps_cv"]) and len(kps) > 100
+        assert np.array_equal(kps.view(np.uint32), z[f"o{j}_kps_cv"].view(np.uint32))       # every field, OpenCV's order
+        assert np.array_equal(desc, z[f"o{j}_desc_cv"])
