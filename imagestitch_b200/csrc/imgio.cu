@@ -154,17 +154,17 @@ extern "C" {
 
 int is_bmp_info(is_ctx* ctx, const char* path, is_size* size, int* bits_per_pixel) {
     if (!ctx || !path) return IS_ERR_BAD_ARG;
-    std::vector<uint8_t> head(1078);
+    // the header decides (14 + 40 bytes, the three masks of BI_BITFIELDS behind it); the length checks see the real file size
+    uint8_t head[80] = {0};
     FILE* f = std::fopen(path, "rb");
     if (!f) return fail(ctx, IS_ERR_BAD_ARG, "cannot open %s", path);
-    head.resize(std::fread(head.data(), 1, head.size(), f));
+    const size_t got = std::fread(head, 1, sizeof(head), f);
     std::fseek(f, 0, SEEK_END);
     const long total = std::ftell(f);
     std::fclose(f);
+    if (got < 26 || total < (long)got) return fail(ctx, IS_ERR_BAD_ARG, "%s: not a bitmap or truncated", path);
     BmpInfo info;
-    std::vector<uint8_t> probe(head);
-    // the header alone decides; the length checks of bmp_parse see the real file size
-    const int rc = bmp_parse(probe.data(), (size_t)std::max<long>(total, 0) >= probe.size() ? (size_t)total : probe.size(), &info);
+    const int rc = bmp_parse(head, (size_t)total, &info);
     if (rc == IS_ERR_UNSUPPORTED) return fail(ctx, rc, "%s: only uncompressed 1 / 4 / 8 / 24 / 32-bit bitmaps are decoded", path);
     if (rc != IS_OK) return fail(ctx, rc, "%s: not a bitmap or truncated", path);
     if (size) { size->width = info.width; size->height = info.height; }

@@ -386,7 +386,7 @@ static int orb_find_core(is_ctx* ctx, const uint8_t* src, size_t sstep, int rows
             orb_linear_coeffs(S.h, E.h, coef.data() + E.coef + 2 * E.w, coef.data() + E.coef + 2 * E.w + E.h);
         }
     OrbBuf d_pyr, d_score, d_coef, d_list, d_count, d_h, d_blur, d_pat;
-    const unsigned cap = (unsigned)std::min<size_t>(total / 8 + 1024, (size_t)1 << 26);
+    const unsigned cap = (unsigned)(total / 4 + 1024);    // a corner beats its eight neighbours: at most one per 2 x 2 pixels
     IS_TRY(orb_alloc(ctx, &d_pyr, total + 64)); IS_TRY(orb_alloc(ctx, &d_score, total + 64)); IS_TRY(orb_alloc(ctx, &d_coef, coef_total * sizeof(int) + 16));
     IS_TRY(orb_alloc(ctx, &d_list, (size_t)cap * 8)); IS_TRY(orb_alloc(ctx, &d_count, 16)); IS_TRY(orb_alloc(ctx, &d_pat, 1024));
     IS_TRY(orb_h2d(ctx, d_coef.p, coef.data(), coef_total * sizeof(int)));
@@ -551,9 +551,9 @@ int is_orb_find(is_ctx* ctx, const is_mat* image, const is_orb_params* params, i
     IS_TRY(stage_in(ctx, image, &s));
     std::vector<KeyPt> kps;
     std::vector<uint8_t> desc;
+    ctx->last_error.clear();
     const int rc = orb_find_core(ctx, s.ptr<uint8_t>(), s.step, s.rows, s.cols, s.channels, P, &kps, &desc);
-    if (rc != IS_OK) return ctx->last_error.empty() || rc == IS_ERR_UNSUPPORTED || rc == IS_ERR_BAD_ARG || rc == IS_ERR_NO_MEM
-                                ? fail(ctx, rc, "ORB: image / pyramid too small or too large for this configuration") : rc;
+    if (rc != IS_OK) return ctx->last_error.empty() ? fail(ctx, rc, "ORB: a pyramid level of a grid cell is empty, or the pyramid exceeds 2^31 pixels") : rc;
     IS_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
     *count = (int)kps.size();
     const int n = std::min(capacity, (int)kps.size());
