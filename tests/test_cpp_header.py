@@ -15,12 +15,12 @@ ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 SRC = os.path.join(ROOT, "tests", "cpp", "hpp_stitch.cpp")
 
 
-def _build(tmp_path):
+def _build(tmp_path, src=SRC, name="hpp_stitch"):
     lib = B.build()
-    exe = str(tmp_path / "hpp_stitch")
+    exe = str(tmp_path / name)
     cxx = "/usr/bin/g++" if os.path.exists("/usr/bin/g++") else (shutil.which("g++") or "g++")
     libdir = os.path.dirname(lib)
-    cmd = [cxx, "-std=c++17", "-O1", "-Wall", "-Wextra", "-Werror", "-I", os.path.join(ROOT, "include"), SRC, "-o", exe,
+    cmd = [cxx, "-std=c++17", "-O1", "-Wall", "-Wextra", "-Werror", "-I", os.path.join(ROOT, "include"), src, "-o", exe,
            "-L", libdir, "-l:" + os.path.basename(lib), "-Wl,-rpath," + libdir]
     r = subprocess.run(cmd, capture_output=True, text=True)
     assert r.returncode == 0, r.stderr
@@ -32,6 +32,12 @@ def test_hpp_compiles_and_links(tmp_path):
     assert os.path.exists(exe)
     r = subprocess.run([exe], capture_output=True, text=True)        # no arguments: usage error before any CUDA call
     assert r.returncode == 2
+
+
+def test_hpp_features_and_io_compile_and_link(tmp_path):
+    """OrbFeaturesFinder / ImageFeatures, imread / imwrite and the stand-alone remap of the header, instantiated"""
+    exe = _build(tmp_path, os.path.join(ROOT, "tests", "cpp", "hpp_features_io.cpp"), "hpp_features_io")
+    assert subprocess.run([exe], capture_output=True, text=True).returncode == 2
 
 
 @pytest.mark.gpu
