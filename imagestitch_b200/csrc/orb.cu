@@ -28,6 +28,7 @@ using OrbBuf = DevBuf;
 static int orb_alloc(is_ctx* ctx, OrbBuf* b, size_t bytes) { return b->alloc(ctx, bytes); }
 static int orb_h2d(is_ctx* ctx, void* dst, const void* src, size_t bytes) { return upload(ctx, dst, src, bytes); }
 static int orb_d2h(is_ctx* ctx, void* dst, const void* src, size_t bytes) { return download(ctx, dst, src, bytes); }
+static int orb_d2h_view(is_ctx* ctx, const void* src, size_t bytes, const void** view) { return download_view(ctx, src, bytes, view); }
 static int orb_zero(is_ctx* ctx, void* dst, size_t bytes) {
     IS_CUDA(ctx, cudaMemsetAsync(dst, 0, bytes, ctx->stream));
     return IS_OK;
@@ -422,8 +423,8 @@ static int orb_find_core(is_ctx* ctx, const uint8_t* src, size_t sstep, int rows
     IS_TRY(orb_d2h(ctx, &found, d_count.p, sizeof(found)));
     lap("pyramid .. blur on the device");
     if (found > cap) return IS_ERR_NO_MEM;
-    std::vector<uint32_t> list(2 * (size_t)found);
-    if (found) IS_TRY(orb_d2h(ctx, list.data(), d_list.p, list.size() * sizeof(uint32_t)));
+    const uint32_t* list = nullptr;                          // a view of the staging buffer: valid until the next download (the responses)
+    if (found) IS_TRY(orb_d2h_view(ctx, d_list.p, 2 * (size_t)found * sizeof(uint32_t), reinterpret_cast<const void**>(&list)));
     lap("corner list download");
     // ---- computeKeyPoints [FEAT]:56-191 on the host: per entry the raster-ordered FAST points, retainBest(2 n)
     std::vector<int> per_level((size_t)nl);
@@ -439,12 +440,27 @@ static int orb_find_core(is_ctx* ctx, const uint8_t* src, size_t sstep, int rows
     // std::nth_element / std::partition permute by comparisons and positions only, so the order is the one they give cv::KeyPoints.
     std::vector<std::vector<OrbCand>> cand((size_t)T.n);
     {
+        // split by entry as a parallel counting sort: every slice of the list counts, the counts are scanned slice-major per
+        // entry, every slice scatters to its own places (order inside an entry does not matter yet: it is sorted below)
+        constexpr size_t SLICES = 16;
+        std::vector<size_t> cnt(SLICES * (size_t)T.n, 0);
+        orb_parallel_for(ctx, SLICES, [&](size_t s) {
+            const size_t i0 = (size_t)found * s / SLICES, i1 = (size_t)found * (s + 1) / SLICES;
+            size_t* c = cnt.data() + s * (size_t)T.n;
+            for (size_t i = i0; i < i1; ++i) ++c[list[2 * i + 1] >> 8];
+        });
         std::vector<size_t> ebeg((size_t)T.n + 1, 0);
-        for (unsigned i = 0; i < found; ++i) ++ebeg[(size_t)(list[2 * i + 1] >> 8) + 1];
-        for (int e = 0; e < T.n; ++e) ebeg[(size_t)e + 1] += ebeg[(size_t)e];
-        std::vector<size_t> efill(ebeg.begin(), ebeg.end() - 1);
+        for (int e = 0; e < T.n; ++e) {
+            size_t at = ebeg[(size_t)e];
+            for (size_t s = 0; s < SLICES; ++s) { const size_t c = cnt[s * (size_t)T.n + (size_t)e]; cnt[s * (size_t)T.n + (size_t)e] = at; at += c; }
+            ebeg[(size_t)e + 1] = at;
+        }
         std::vector<OrbCand> by_entry((size_t)found);
-        for (unsigned i = 0; i < found; ++i) by_entry[efill[list[2 * i + 1] >> 8]++] = OrbCand{(float)(list[2 * i + 1] & 255u), list[2 * i]};
+        orb_parallel_for(ctx, SLICES, [&](size_t s) {
+            const size_t i0 = (size_t)found * s / SLICES, i1 = (size_t)found * (s + 1) / SLICES;
+            size_t* at = cnt.data() + s * (size_t)T.n;
+            for (size_t i = i0; i < i1; ++i) by_entry[at[list[2 * i + 1] >> 8]++] = OrbCand{(float)(list[2 * i + 1] & 255u), list[2 * i]};
+        });
         lap("corners by entry");
         orb_parallel_for(ctx, (size_t)T.n, [&](size_t e) {       // the levels are independent of each other: one host thread each
             const OrbCand* in = by_entry.data() + ebeg[e];

@@ -26,7 +26,7 @@ def main():
         os.makedirs(out, exist_ok=True)
         open(os.path.join(out, "orb_region.inc"), "w").write(re.findall(r"// @emu-begin[^\n]*\n(.*?)// @emu-end", text, flags=re.S)[0])
         so = os.path.join(out, "liborb_emul.so")
-        subprocess.check_call(["g++", "-O2", "-fPIC", "-std=c++17", "-ffp-contract=off", "-fno-fast-math", "-w", "-I", emu, "-I", out, "-I",
+        subprocess.check_call(["g++", "-O2", "-fPIC", "-std=c++17", "-ffp-contract=off", "-pthread", "-fno-fast-math", "-w", "-I", emu, "-I", out, "-I",
                                os.path.join(ROOT, "imagestitch_b200", "csrc"), "-shared", "-o", so, os.path.join(emu, "orb_emul.cpp")])
         os.environ["IS_ORB_DUMP"] = EMU_DIR
         os.makedirs(EMU_DIR, exist_ok=True)

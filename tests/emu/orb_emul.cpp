@@ -9,6 +9,7 @@
 #include <cstdio>
 #include <cstdlib>
 #include <string>
+#include <thread>
 #include <vector>
 
 #include "../../include/imagestitch.h"
@@ -25,6 +26,7 @@ struct OrbBuf { void* p = nullptr; std::vector<uint8_t> store; };
 static int orb_alloc(is_ctx*, OrbBuf* b, size_t bytes) { b->store.assign(bytes + 64, 0xcd); b->p = b->store.data(); return IS_OK; }
 static int orb_h2d(is_ctx*, void* dst, const void* src, size_t bytes) { std::memcpy(dst, src, bytes); return IS_OK; }
 static int orb_d2h(is_ctx*, void* dst, const void* src, size_t bytes) { std::memcpy(dst, src, bytes); return IS_OK; }
+static int orb_d2h_view(is_ctx*, const void* src, size_t, const void** view) { *view = src; return IS_OK; }
 static int orb_zero(is_ctx*, void* dst, size_t bytes) { std::memset(dst, 0, bytes); return IS_OK; }
 static int orb_dump(is_ctx*, const char* name, const void* p, size_t bytes) {
     const char* dir = getenv("IS_ORB_DUMP");
@@ -33,7 +35,14 @@ static int orb_dump(is_ctx*, const char* name, const void* p, size_t bytes) {
     if (FILE* f = std::fopen(path.c_str(), "wb")) { std::fwrite(p, 1, bytes, f); std::fclose(f); }
     return IS_OK;
 }
-template <typename F> static void orb_parallel_for(is_ctx*, size_t n, F&& fn) { for (size_t i = 0; i < n; ++i) fn(i); }
+// the host pool's place: one OS thread per index (IS_EMU_SERIAL=1: a plain loop), so that the sections the product runs on its
+// pool are exercised concurrently here as well
+template <typename F> static void orb_parallel_for(is_ctx*, size_t n, F&& fn) {
+    if (getenv("IS_EMU_SERIAL")) { for (size_t i = 0; i < n; ++i) fn(i); return; }
+    std::vector<std::thread> th;
+    for (size_t i = 0; i < n; ++i) th.emplace_back([&fn, i] { fn(i); });
+    for (auto& t : th) t.join();
+}
 #define ORB_LAUNCH(ctx, kernel, grid, block, ...) emu_launch(dim3(grid), dim3(block), [&] { kernel(__VA_ARGS__); })
 #include "orb_region.inc"
 }

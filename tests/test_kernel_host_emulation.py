@@ -74,7 +74,7 @@ def emu_orb():
     with open(os.path.join(OUT, "orb_region.inc"), "w") as f:
         f.write(regions[0])
     so = os.path.join(OUT, "liborb_emul.so")
-    subprocess.check_call(["g++", "-O2", "-fPIC", "-std=c++17", "-ffp-contract=off", "-fno-fast-math", "-w", "-I", EMU, "-I", OUT, "-I",
+    subprocess.check_call(["g++", "-O2", "-fPIC", "-std=c++17", "-pthread", "-ffp-contract=off", "-fno-fast-math", "-w", "-I", EMU, "-I", OUT, "-I",
                            os.path.join(ROOT, "imagestitch_b200", "csrc"), "-shared", "-o", so, os.path.join(EMU, "orb_emul.cpp")])
     lib = C.CDLL(so)
     lib.emu_orb_find.restype = C.c_int
