@@ -394,10 +394,8 @@ static int orb_find_core(is_ctx* ctx, const uint8_t* src, size_t sstep, int rows
     IS_TRY(orb_h2d(ctx, d_pat.p, kOrbPattern, 1024));
     IS_TRY(orb_zero(ctx, d_count.p, 16));
     {   // gray level 0 of every cell, then the levels one after the other (each from the one below)
-        const OrbEntry& E0 = T.e[0];
         int w0 = 0, h0 = 0;
         for (int cell = 0; cell < ncells; ++cell) { w0 = std::max(w0, T.e[cell * nl].w); h0 = std::max(h0, T.e[cell * nl].h); }
-        (void)E0;
         dim3 grid((unsigned)div_up(w0, 256), (unsigned)h0, (unsigned)ncells);
         if (ch == 1) ORB_LAUNCH(ctx, k_orb_gray<1>, grid, 256, src, sstep, T, (uint8_t*)d_pyr.p);
         else if (ch == 3) ORB_LAUNCH(ctx, k_orb_gray<3>, grid, 256, src, sstep, T, (uint8_t*)d_pyr.p);
@@ -412,19 +410,19 @@ static int orb_find_core(is_ctx* ctx, const uint8_t* src, size_t sstep, int rows
     dim3 gall((unsigned)div_up(maxw, 256), (unsigned)maxh, (unsigned)T.n);
     ORB_LAUNCH(ctx, k_orb_fast, gall, 256, T, (const uint8_t*)d_pyr.p, (uint8_t*)d_score.p, P.fast_threshold);
     ORB_LAUNCH(ctx, k_orb_nms, gall, 256, T, (const uint8_t*)d_score.p, P.edge_threshold, (uint32_t*)d_list.p, (unsigned*)d_count.p, cap);
-    // the blur does not depend on the key points: queued now, it runs while the host selects
-    IS_TRY(orb_alloc(ctx, &d_h, total * sizeof(float) + 64)); IS_TRY(orb_alloc(ctx, &d_blur, total + 64));
-    ORB_LAUNCH(ctx, k_orb_blur_rows, gall, 256, T, (const uint8_t*)d_pyr.p, C, (float*)d_h.p);
-    ORB_LAUNCH(ctx, k_orb_blur_cols, gall, 256, T, (const float*)d_h.p, C, (uint8_t*)d_blur.p);
-    IS_TRY(orb_dump(ctx, "pyr", d_pyr.p, total)); IS_TRY(orb_dump(ctx, "score", d_score.p, total)); IS_TRY(orb_dump(ctx, "blur", d_blur.p, total));
-    IS_TRY(orb_dump(ctx, "hbuf", d_h.p, total * sizeof(float)));
+    IS_TRY(orb_dump(ctx, "pyr", d_pyr.p, total)); IS_TRY(orb_dump(ctx, "score", d_score.p, total));
     lap("tables, uploads, launches");
     unsigned found = 0;
     IS_TRY(orb_d2h(ctx, &found, d_count.p, sizeof(found)));
-    lap("pyramid .. blur on the device");
+    lap("pyramid .. corners on the device");
     if (found > cap) return IS_ERR_NO_MEM;
     const uint32_t* list = nullptr;                          // a view of the staging buffer: valid until the next download (the responses)
     if (found) IS_TRY(orb_d2h_view(ctx, d_list.p, 2 * (size_t)found * sizeof(uint32_t), reinterpret_cast<const void**>(&list)));
+    // the blur does not depend on the key points: queued behind the download, it runs while the host selects
+    IS_TRY(orb_alloc(ctx, &d_h, total * sizeof(float) + 64)); IS_TRY(orb_alloc(ctx, &d_blur, total + 64));
+    ORB_LAUNCH(ctx, k_orb_blur_rows, gall, 256, T, (const uint8_t*)d_pyr.p, C, (float*)d_h.p);
+    ORB_LAUNCH(ctx, k_orb_blur_cols, gall, 256, T, (const float*)d_h.p, C, (uint8_t*)d_blur.p);
+    IS_TRY(orb_dump(ctx, "blur", d_blur.p, total)); IS_TRY(orb_dump(ctx, "hbuf", d_h.p, total * sizeof(float)));
     lap("corner list download");
     // ---- computeKeyPoints [FEAT]:56-191 on the host: per entry the raster-ordered FAST points, retainBest(2 n)
     std::vector<int> per_level((size_t)nl);
