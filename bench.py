@@ -139,13 +139,13 @@ def cpu_port_run(workload, threads, sample_rows=None, n_sample=2, steps=1, warmu
     return mp / best, desc, best, stages
 
 
-def _informational_leg(flag, workload, sample_rows):
+def _informational_leg(flag, workload, sample_rows, timeout=600):
     """An informational CPU leg in a process of its own: nothing it does (cv2's threading runtime, the reference's code reading
     past a buffer) can disturb or end the bench.  Returns its dict, or {"unavailable": why}."""
     import subprocess
     try:
         r = subprocess.run([sys.executable, os.path.abspath(__file__), flag, str(int(sample_rows)), "--workload", workload],
-                           capture_output=True, text=True, timeout=600)
+                           capture_output=True, text=True, timeout=timeout)
         for ln in reversed(r.stdout.strip().splitlines()):
             if ln.startswith("{"):
                 return json.loads(ln)
@@ -160,6 +160,39 @@ def opencv_run(workload, sample_rows):
 
 def reference_find_check(workload, sample_rows):
     return _informational_leg("--reference-find-sample", workload, sample_rows)
+
+
+def weights16s_leg_inline(workload, steps):
+    """The device-resident step of `workload` on one GPU with MultiBandBlender's CV_16S weights ("report CV_16S too")."""
+    import torch
+
+    from imagestitch_b200 import stitching as S, synth
+    n, rows, cols, fw, ov, grid_rows, _desc = WORKLOADS[workload]
+    Ks, Rs, scale = synth.strip_cameras(n, cols, rows, fw, ov, grid_rows=grid_rows)
+    dev = "cuda:0"
+    torch.cuda.set_device(0)
+    ctx = S.Context(0, use_torch_stream=True)
+    st = S.Stitcher(ctx, "cylindrical", "dp", NUM_BANDS, S.WEIGHT_16S)
+    imgs = [synth.make_image(i, cols, rows, Ks[i], Rs[i], device=dev) for i in range(n)]
+    _corners, _sizes, roi = st.plan([(cols, rows)] * n, Ks, Rs, scale)
+    pano = torch.empty((roi[3], roi[2], 3), dtype=torch.int16, device=dev)
+    pmask = torch.empty((roi[3], roi[2]), dtype=torch.uint8, device=dev)
+
+    def step():
+        ctx.clear_plan_cache()
+        st.stitch(imgs, Ks, Rs, scale, out=(pano, pmask))
+
+    for _ in range(3):
+        step()
+    torch.cuda.synchronize()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for _ in range(steps):
+        step()
+    e1.record()
+    torch.cuda.synchronize()
+    ms = e0.elapsed_time(e1) / steps
+    return {"ms_per_step": ms, "value": n * rows * cols / 1e6 / (ms * 1e-3), "unit": "MP/s", "steps": steps, "weight_type": "CV_16S"}
 
 
 def opencv_run_inline(workload, sample_rows, n_sample=2):
@@ -382,12 +415,16 @@ def main():
     ap.add_argument("--kernel-report", default=None, help="write the per-kernel timing table (JSON) to this file")
     ap.add_argument("--opencv-sample", type=int, default=None, help="internal: time python cv2's path on a sample of this many rows, print JSON")
     ap.add_argument("--reference-find-sample", type=int, default=None, help="internal: the reference's own find() vs the port on such a sample, print JSON")
+    ap.add_argument("--weights16s-leg", type=int, default=None, help="internal: time this many device-resident steps with CV_16S blend weights, print JSON")
     args = ap.parse_args()
     if args.opencv_sample is not None:
         print(json.dumps(opencv_run_inline(args.workload, args.opencv_sample)), flush=True)
         return 0
     if args.reference_find_sample is not None:
         print(json.dumps(reference_find_check_inline(args.workload, args.reference_find_sample)), flush=True)
+        return 0
+    if args.weights16s_leg is not None:
+        print(json.dumps(weights16s_leg_inline(args.workload, args.weights16s_leg)), flush=True)
         return 0
     args.warmup = max(args.warmup, 0)
     if args.impl == "reference":
@@ -706,6 +743,12 @@ def main():
     }
     if sharded_matches is not None:
         line["sharded_matches"] = sharded_matches
+    if world == 1:                                        # "also output-pano MP/s", and the CV_16S-weight step
+        out_mp = out_shape[0] * out_shape[1] / 1e6
+        line["output_panorama"] = {"megapixels": out_mp, "mp_per_s": out_mp / (ms_dev * 1e-3), "mp_per_s_e2e": out_mp / (ms_e2e * 1e-3)}
+        # "default weight type CV_32F (report CV_16S too)": the same device-resident step with CV_16S blend weights, timed in a
+        # process of its own so that nothing it does can disturb or end this line (informational)
+        line["weights_cv_16s"] = _informational_leg("--weights16s-leg", args.workload, max(3, min(args.steps, 10)), timeout=120) if not args.no_cpu_baseline else None
     print(json.dumps(line), flush=True)
     if dist:
         dist.destroy_process_group()
