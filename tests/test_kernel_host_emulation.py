@@ -471,3 +471,21 @@ def test_orb_kernels_and_driver_match_oracle(emu_orb, oracle, case):
     assert n == len(want_k) and n > 50
     assert np.array_equal(kps[:n].view(np.uint32), want_k.view(np.uint32))
     assert np.array_equal(desc[:n], want_d)
+
+
+@pytest.mark.parametrize("case", [(100, 150, (3, 1)), (70, 210, (3, 1)), (200, 90, (1, 2)), (333, 517, (2, 3)), (129, 1000, (3, 1))])
+def test_orb_edge_sizes_match_oracle(emu_orb, oracle, case):
+    """the product's ORB source on cells / levels around the 2 x 31 pixel border, odd sizes, grids with rows, tie-heavy images"""
+    O = oracle
+    h, w, grid = case
+    rng = np.random.default_rng(9)
+    noise = rng.integers(0, 256, (h, w), dtype=np.uint8)
+    blocks = np.ascontiguousarray(np.kron(rng.integers(0, 256, (h // 3 + 1, w // 3 + 1), dtype=np.uint8), np.ones((3, 3), np.uint8))[:h, :w])
+    for img in (noise, blocks):
+        want_k, want_d = O.orb_find(img, grid)
+        cap = 1200 * grid[0] * grid[1]
+        kps = np.zeros((cap, 6), np.float32)
+        desc = np.zeros((cap, 32), np.uint8)
+        n = emu_orb.emu_orb_find(_p(img), h, w, 1, C.c_size_t(img.strides[0]), grid[0], grid[1], 510, C.c_float(1.3), 5, _p(kps), _p(desc), cap)
+        assert n == len(want_k)
+        assert np.array_equal(kps[:n].view(np.uint32), want_k.view(np.uint32)) and np.array_equal(desc[:n], want_d)

@@ -70,3 +70,19 @@ def test_orb_find_vs_cv2(oracle, case):
     assert len(want_k) == len(got_k) and len(got_k) > 100
     assert np.array_equal(want_k.view(np.uint32), got_k.view(np.uint32)), "key points (x, y, size, angle, response, octave), in OpenCV's order"
     assert np.array_equal(want_d, got_d), f"{int(np.unpackbits(want_d ^ got_d).sum())} descriptor bits differ"
+
+
+@pytest.mark.parametrize("case", [(100, 150, (3, 1)), (70, 210, (3, 1)), (63, 64, (1, 1)), (200, 90, (1, 2)), (333, 517, (2, 3)), (64, 400, (4, 1)), (129, 1000, (3, 1))])
+def test_orb_edge_sizes_vs_cv2(oracle, case):
+    """cells and pyramid levels around the 2 x 31 pixel border (none / some levels too small for a key point), odd sizes, grids with
+    rows, and blocky images whose responses tie by the hundred (retainBest keeps ties; the order is nth_element's)"""
+    O = oracle
+    h, w, grid = case
+    rng = np.random.default_rng(9)
+    noise = rng.integers(0, 256, (h, w), dtype=np.uint8)
+    blocks = np.ascontiguousarray(np.kron(rng.integers(0, 256, (h // 3 + 1, w // 3 + 1), dtype=np.uint8), np.ones((3, 3), np.uint8))[:h, :w])
+    for img in (noise, blocks):
+        want_k, want_d = _cv_find(img, grid)
+        got_k, got_d = O.orb_find(img, grid)
+        assert len(want_k) == len(got_k)
+        assert np.array_equal(want_k.view(np.uint32), got_k.view(np.uint32)) and np.array_equal(want_d, got_d)
