@@ -71,10 +71,18 @@ def _palette_bmp(idx, bpp, palette, top_down=False, clr_used=0, core=False):
     return b"BM" + struct.pack("<IHHI", off + len(body), 0, 0, off) + head + pal + body
 
 
-def _rgb32_bmp(img, bitfields=False):
+def _rgb24_bmp(img, top_down=False):
     h, w = img.shape[:2]
-    body = b"".join(np.concatenate([img[y], np.full((w, 1), 77, np.uint8)], axis=1).tobytes() for y in range(h - 1, -1, -1))
-    head = struct.pack("<IiiHHIIiiII", 40, w, h, 1, 32, 3 if bitfields else 0, 0, 0, 0, 0, 0)
+    pad = b"\0" * ((-3 * w) % 4)
+    body = b"".join(img[y].tobytes() + pad for y in (range(h) if top_down else range(h - 1, -1, -1)))
+    head = struct.pack("<IiiHHIIiiII", 40, w, -h if top_down else h, 1, 24, 0, 0, 0, 0, 0, 0)
+    return b"BM" + struct.pack("<IHHI", 54 + len(body), 0, 0, 54) + head + body
+
+
+def _rgb32_bmp(img, bitfields=False, top_down=False):
+    h, w = img.shape[:2]
+    body = b"".join(np.concatenate([img[y], np.full((w, 1), 77, np.uint8)], axis=1).tobytes() for y in (range(h) if top_down else range(h - 1, -1, -1)))
+    head = struct.pack("<IiiHHIIiiII", 40, w, -h if top_down else h, 1, 32, 3 if bitfields else 0, 0, 0, 0, 0, 0)
     masks = struct.pack("<III", 0x00ff0000, 0x0000ff00, 0x000000ff) if bitfields else b""
     off = 14 + len(head) + len(masks)
     return b"BM" + struct.pack("<IHHI", off + len(body), 0, 0, off) + head + masks + body
@@ -95,6 +103,11 @@ def _files(tmp_path, with_reference=True):
                        ("p4", _palette_bmp(rng.integers(0, 16, (5, 11)), 4, pal)),
                        ("p1", _palette_bmp(rng.integers(0, 2, (4, 19)), 1, pal)),
                        ("p8_core", _palette_bmp(rng.integers(0, 256, (5, 6)), 8, pal, core=True)),
+                       ("p4_odd", _palette_bmp(rng.integers(0, 16, (3, 7)), 4, pal, top_down=True)),
+                       ("p1_w33", _palette_bmp(rng.integers(0, 2, (5, 33)), 1, pal)),
+                       ("rgb24_topdown", _rgb24_bmp(rng.integers(0, 256, (7, 6, 3), dtype=np.uint8), top_down=True)),
+                       ("rgb24_w1", _rgb24_bmp(rng.integers(0, 256, (3, 1, 3), dtype=np.uint8))),
+                       ("rgb32_topdown", _rgb32_bmp(rng.integers(0, 256, (4, 3, 3), dtype=np.uint8), top_down=True)),
                        ("rgb32", _rgb32_bmp(rng.integers(0, 256, (6, 5, 3), dtype=np.uint8))),
                        ("rgb32_bitfields", _rgb32_bmp(rng.integers(0, 256, (6, 5, 3), dtype=np.uint8), bitfields=True))):
         p = str(tmp_path / f"{name}.bmp")
