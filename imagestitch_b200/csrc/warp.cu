@@ -18,6 +18,7 @@
 
 #include <cmath>
 #include <limits>
+#include <new>
 
 namespace is {
 
@@ -825,8 +826,10 @@ int upload_tables(is_ctx* ctx, int proj, const WarpPlan& plan, DevBuf* buf) {
     const int w = plan.P.dst_w, h = plan.P.dst_h;
     if (proj_uses_maps(proj)) {
         const size_t px = (size_t)w * (size_t)h;
+        IS_REQUIRE(ctx, px < ((size_t)1 << 31), IS_ERR_NO_MEM, "maps of a per-pixel projector: destination of 2^31 pixels or more (a pole inside the image?)");
         IS_TRY(buf->alloc(ctx, 2 * px * sizeof(float)));
-        std::vector<float> maps(2 * px);
+        std::vector<float> maps;
+        try { maps.resize(2 * px); } catch (const std::bad_alloc&) { return fail(ctx, IS_ERR_NO_MEM, "host memory for the maps of a per-pixel projector (%zu pixels)", px); }
         build_maps_host(ctx, proj, plan, maps.data(), maps.data() + px);
         IS_CUDA(ctx, cudaMemcpyAsync(buf->p, maps.data(), 2 * px * sizeof(float), cudaMemcpyHostToDevice, ctx->stream));
         IS_CUDA(ctx, cudaStreamSynchronize(ctx->stream));          // pageable source: gone when this returns
@@ -968,7 +971,8 @@ int is_build_maps(is_ctx* ctx, int projection, is_size src_size, const float K[9
     if (dst_roi) { dst_roi->x = plan.roi[0]; dst_roi->y = plan.roi[1]; dst_roi->width = plan.roi[2] - plan.roi[0]; dst_roi->height = plan.roi[3] - plan.roi[1]; }
     if (proj_uses_maps(projection)) {                       // host-built maps: straight into host mats, one copy for device mats
         const size_t px = (size_t)plan.P.dst_w * (size_t)plan.P.dst_h, row = (size_t)plan.P.dst_w * sizeof(float);
-        std::vector<float> maps(2 * px);
+        std::vector<float> maps;
+        try { maps.resize(2 * px); } catch (const std::bad_alloc&) { return fail(ctx, IS_ERR_NO_MEM, "host memory for the maps of a per-pixel projector (%zu pixels)", px); }
         build_maps_host(ctx, projection, plan, maps.data(), maps.data() + px);
         is_mat* out[2] = {xmap, ymap};
         for (int k = 0; k < 2; ++k) {
