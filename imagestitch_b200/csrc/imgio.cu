@@ -10,6 +10,8 @@
 
 #include <cstdio>
 #include <memory>
+#include <new>
+#include <stdexcept>
 
 namespace is {
 
@@ -150,9 +152,9 @@ static int parse_or_fail(is_ctx* ctx, const char* path, const std::vector<uint8_
 
 using namespace is;
 
-extern "C" {
+namespace {
 
-int is_bmp_info(is_ctx* ctx, const char* path, is_size* size, int* bits_per_pixel) {
+int bmp_info_entry(is_ctx* ctx, const char* path, is_size* size, int* bits_per_pixel) {
     if (!ctx || !path) return IS_ERR_BAD_ARG;
     // the header decides (14 + 40 bytes, the three masks of BI_BITFIELDS behind it); the length checks see the real file size
     uint8_t head[80] = {0};
@@ -172,7 +174,7 @@ int is_bmp_info(is_ctx* ctx, const char* path, is_size* size, int* bits_per_pixe
     return IS_OK;
 }
 
-int is_imread_bmp(is_ctx* ctx, const char* path, is_mat* dst) {
+int imread_bmp_entry(is_ctx* ctx, const char* path, is_mat* dst) {
     if (!ctx || !path) return IS_ERR_BAD_ARG;
     IS_CUDA(ctx, cudaSetDevice(ctx->device));
     IS_TRY(check_mat(ctx, dst, "dst"));
@@ -196,7 +198,7 @@ int is_imread_bmp(is_ctx* ctx, const char* path, is_mat* dst) {
     return IS_OK;
 }
 
-int is_imwrite_bmp(is_ctx* ctx, const char* path, const is_mat* src) {
+int imwrite_bmp_entry(is_ctx* ctx, const char* path, const is_mat* src) {
     if (!ctx || !path) return IS_ERR_BAD_ARG;
     IS_CUDA(ctx, cudaSetDevice(ctx->device));
     IS_TRY(check_mat(ctx, src, "src"));
@@ -226,6 +228,31 @@ int is_imwrite_bmp(is_ctx* ctx, const char* path, const is_mat* src) {
     const bool ok = std::fwrite(head, 1, head_bytes, f) == head_bytes && std::fwrite(host.get(), 1, pixels, f) == pixels;
     if (std::fclose(f) != 0 || !ok) return fail(ctx, IS_ERR_INTERNAL, "short write to %s", path);
     return IS_OK;
+}
+
+template <typename F>
+int guarded(is_ctx* ctx, F&& f) {                             // no exception crosses the boundary (the file is read into a vector)
+    try {
+        return f();
+    } catch (const std::bad_alloc&) {
+        return ctx ? fail(ctx, IS_ERR_NO_MEM, "image file: host memory") : IS_ERR_NO_MEM;
+    } catch (const std::exception& e) {
+        return ctx ? fail(ctx, IS_ERR_INTERNAL, "image file: %s", e.what()) : IS_ERR_INTERNAL;
+    }
+}
+
+}  // namespace
+
+extern "C" {
+
+int is_bmp_info(is_ctx* ctx, const char* path, is_size* size, int* bits_per_pixel) {
+    return guarded(ctx, [&] { return bmp_info_entry(ctx, path, size, bits_per_pixel); });
+}
+int is_imread_bmp(is_ctx* ctx, const char* path, is_mat* dst) {
+    return guarded(ctx, [&] { return imread_bmp_entry(ctx, path, dst); });
+}
+int is_imwrite_bmp(is_ctx* ctx, const char* path, const is_mat* src) {
+    return guarded(ctx, [&] { return imwrite_bmp_entry(ctx, path, src); });
 }
 
 }  // extern "C"

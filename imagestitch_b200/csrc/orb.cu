@@ -20,6 +20,8 @@
 #include <cfloat>
 #include <chrono>
 #include <cmath>
+#include <new>
+#include <stdexcept>
 
 namespace is {
 
@@ -544,9 +546,7 @@ static int orb_find_core(is_ctx* ctx, const uint8_t* src, size_t sstep, int rows
 
 using namespace is;
 
-extern "C" {
-
-int is_orb_find(is_ctx* ctx, const is_mat* image, const is_orb_params* params, is_keypoint* keypoints, uint8_t* descriptors, int capacity, int* count) {
+static int orb_find_entry(is_ctx* ctx, const is_mat* image, const is_orb_params* params, is_keypoint* keypoints, uint8_t* descriptors, int capacity, int* count) {
     if (!ctx) return IS_ERR_BAD_ARG;
     IS_CUDA(ctx, cudaSetDevice(ctx->device));
     IS_TRY(check_mat(ctx, image, "image"));
@@ -577,6 +577,18 @@ int is_orb_find(is_ctx* ctx, const is_mat* image, const is_orb_params* params, i
     }
     if (n) std::memcpy(descriptors, desc.data(), (size_t)n * 32);
     return IS_OK;
+}
+
+extern "C" {
+
+int is_orb_find(is_ctx* ctx, const is_mat* image, const is_orb_params* params, is_keypoint* keypoints, uint8_t* descriptors, int capacity, int* count) {
+    try {                                                     // no exception crosses the boundary (host vectors sized by the corner count)
+        return orb_find_entry(ctx, image, params, keypoints, descriptors, capacity, count);
+    } catch (const std::bad_alloc&) {
+        return ctx ? fail(ctx, IS_ERR_NO_MEM, "ORB: host memory") : IS_ERR_NO_MEM;
+    } catch (const std::exception& e) {
+        return ctx ? fail(ctx, IS_ERR_INTERNAL, "ORB: %s", e.what()) : IS_ERR_INTERNAL;
+    }
 }
 
 }  // extern "C"
